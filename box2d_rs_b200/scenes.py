@@ -1,0 +1,149 @@
+"""Scene recipes of BASELINE.json's configs, written against the mirrored
+reference API (world.create_body / body.create_fixture / world.shapes.*), so the same recipe
+drives the GPU engine and — in tests — the CPU oracle.
+
+Randomised scenes use SplitMix64 (the reference's testbed uses unseeded rand::thread_rng,
+examples/testbed/test.rs:27-36); seed = 0xB2D + config id.
+"""
+import math
+
+import numpy as np
+
+from . import abi
+from .abi import BodyDef, FixtureDef
+
+DT = float(np.float32(1.0) / np.float32(60.0))
+VEL_ITERS, POS_ITERS = 8, 3
+
+
+class SplitMix64:
+    def __init__(self, seed):
+        self.s = seed & 0xFFFFFFFFFFFFFFFF
+
+    def next(self):
+        self.s = (self.s + 0x9E3779B97F4A7C15) & 0xFFFFFFFFFFFFFFFF
+        z = self.s
+        z = ((z ^ (z >> 30)) * 0xBF58476D1CE4E5B9) & 0xFFFFFFFFFFFFFFFF
+        z = ((z ^ (z >> 27)) * 0x94D049BB133111EB) & 0xFFFFFFFFFFFFFFFF
+        return z ^ (z >> 31)
+
+    def uniform(self, lo, hi):
+        return lo + (hi - lo) * ((self.next() >> 40) / float(1 << 24))
+
+
+def f32(x):
+    return float(np.float32(x))
+
+
+def hello_world(world):
+    """tests/test.rs:25-102 — returns the dynamic body."""
+    ground = world.create_body(BodyDef(position=(0.0, -10.0)))
+    ground.create_fixture_by_shape(world.shapes.polygon_box(50.0, 10.0), 0.0)
+    body = world.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(0.0, 4.0)))
+    body.create_fixture(FixtureDef(density=1.0, friction=0.3), world.shapes.polygon_box(1.0, 1.0))
+    return body
+
+
+def pyramid(world, count=20, testbed_ground_body=True):
+    """examples/testbed/tests/pyramid.rs:52-88 preceded by the testbed's empty static body
+    (examples/testbed/test.rs:181-182).  212 bodies, 211 proxies for count=20."""
+    if testbed_ground_body:
+        world.create_body(BodyDef())
+    ground = world.create_body(BodyDef())
+    ground.create_fixture_by_shape(world.shapes.edge_two_sided((-40.0, 0.0), (40.0, 0.0)), 0.0)
+    box = world.shapes.polygon_box(0.5, 0.5)
+    x = np.array([-7.0, 0.75], np.float32)
+    delta_x = np.array([0.5625, 1.25], np.float32)
+    delta_y = np.array([1.125, 0.0], np.float32)
+    bodies = []
+    for i in range(count):
+        y = x.copy()
+        for _ in range(i, count):
+            b = world.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(float(y[0]), float(y[1]))))
+            b.create_fixture_by_shape(box, 5.0)
+            bodies.append(b)
+            y = (y + delta_y).astype(np.float32)
+        x = (x + delta_x).astype(np.float32)
+    return bodies
+
+
+def _container(world, half_width, height):
+    """Static open box made of three two-sided edges (floor + walls)."""
+    ground = world.create_body(BodyDef())
+    hw = float(half_width)
+    ground.create_fixture_by_shape(world.shapes.edge_two_sided((-hw, 0.0), (hw, 0.0)), 0.0)
+    ground.create_fixture_by_shape(world.shapes.edge_two_sided((-hw, 0.0), (-hw, float(height))), 0.0)
+    ground.create_fixture_by_shape(world.shapes.edge_two_sided((hw, 0.0), (hw, float(height))), 0.0)
+    return ground
+
+
+def _polygon_archetypes(world):
+    """The five archetypes of examples/testbed/tests/polygon_shapes.rs:106-188."""
+    tri = world.shapes.polygon([(-0.5, 0.0), (0.5, 0.0), (0.0, 1.5)])
+    thin = world.shapes.polygon([(-0.1, 0.0), (0.1, 0.0), (0.0, 1.5)])
+    w = 1.0
+    b = w / (2.0 + math.sqrt(2.0))
+    s = math.sqrt(2.0) * b
+    octagon = world.shapes.polygon([(0.5 * s, 0.0), (0.5 * w, b), (0.5 * w, b + s), (0.5 * s, w), (-0.5 * s, w),
+                                    (-0.5 * w, b + s), (-0.5 * w, b), (-0.5 * s, 0.0)])
+    box = world.shapes.polygon_box(0.5, 0.5)
+    circle = world.shapes.circle(0.5)
+    return [tri, thin, octagon, box, circle]
+
+
+def mixed(world, n=10000, seed=0xB2D + 2, width=100.0):
+    """Config 2: n mixed polygons + circles on a jittered grid above a static container."""
+    rng = SplitMix64(seed)
+    _container(world, width / 2.0, 60.0 if n >= 1000 else 20.0)
+    shapes = _polygon_archetypes(world)
+    cols = max(1, int(width / 2.0) - 2)
+    bodies = []
+    for k in range(n):
+        col, row = k % cols, k // cols
+        px = f32(-width / 2.0 + 2.5 + 2.0 * col + rng.uniform(-0.2, 0.2))
+        py = f32(2.0 + 2.0 * row + rng.uniform(-0.2, 0.2))
+        ang = f32(rng.uniform(-math.pi, math.pi))
+        kind = int(rng.next() % 5)
+        b = world.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(px, py), angle=ang))
+        b.create_fixture(FixtureDef(density=1.0, friction=0.3), shapes[kind])
+        bodies.append(b)
+    return bodies
+
+
+def pile(world, n=100000, seed=0xB2D + 4, width=400.0):
+    """Config 4: n/2 circles r=0.125 (friction 0.1) + n/2 boxes half-extent 0.125 (friction 0.3)."""
+    rng = SplitMix64(seed)
+    _container(world, width / 2.0, 100.0)
+    circle = world.shapes.circle(0.125)
+    box = world.shapes.polygon_box(0.125, 0.125)
+    pitch = 0.3
+    cols = max(1, int((width - 2.0) / pitch))
+    bodies = []
+    for k in range(n):
+        col, row = k % cols, k // cols
+        px = f32(-width / 2.0 + 1.0 + pitch * col + rng.uniform(-0.02, 0.02))
+        py = f32(0.3 + pitch * row + rng.uniform(-0.02, 0.02))
+        b = world.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(px, py)))
+        if k % 2 == 0:
+            b.create_fixture(FixtureDef(density=1.0, friction=0.1), circle)
+        else:
+            b.create_fixture(FixtureDef(density=1.0, friction=0.3), box)
+        bodies.append(b)
+    return bodies
+
+
+def add_pair(world, n=20000, seed=0xB2D + 5):
+    """Config 5: examples/testbed/tests/add_pair.rs:50-89 scaled. The world must have zero gravity."""
+    rng = SplitMix64(seed)
+    circle = world.shapes.circle(0.1)
+    bodies = []
+    for _ in range(n):
+        px, py = f32(rng.uniform(-60.0, 0.0)), f32(rng.uniform(-10.0, 20.0))
+        b = world.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(px, py)))
+        b.create_fixture_by_shape(circle, 0.01)
+        bodies.append(b)
+    box = world.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(-100.0, 5.0), bullet=1))
+    box.create_fixture_by_shape(world.shapes.polygon_box(1.5, 1.5), 1.0)
+    box.set_linear_velocity((100.0, 0.0))
+    bodies.append(box)
+    return bodies

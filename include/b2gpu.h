@@ -1,0 +1,374 @@
+/*
+ * b2gpu.h — C ABI of the B200-native step engine that replaces the hot path of
+ * box2d-rs `B2world::step` (reference: src/b2_world.rs:98 ->
+ * src/private/dynamics/b2_world.rs:903).
+ *
+ * The reference has no FFI of its own (pure safe Rust).  The entry points below
+ * are what a Rust `extern "C"` block in a replaced `private::step` would bind;
+ * every function cites the reference interface it stands in for.  Conventions:
+ *   - plain pointers and sizes only, no C++/torch types;
+ *   - every call returns 0 on success or a negative B2GPU_E_* code, never
+ *     unwinds; `b2gpu_last_error()` gives the message of the last failure on
+ *     the calling thread;
+ *   - a handle is used by one host thread at a time (the reference world is
+ *     `Rc<RefCell<..>>`, i.e. !Send, src/b2_world.rs:19);
+ *   - there is NO CPU fallback: without a CUDA device every stepping call
+ *     fails with B2GPU_E_NO_DEVICE.
+ *
+ * Data model.  World state crosses the boundary as a *snapshot*: flat arrays of
+ * fixed-layout records in creation order.  All intrusive lists of the reference
+ * are push_front lists (src/b2rs_double_linked_list.rs:200-219), so iteration
+ * order == descending creation order; arrays in ascending creation order carry
+ * the same information.
+ */
+#ifndef B2GPU_H
+#define B2GPU_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2GPU_ABI_VERSION 1
+
+/* error codes */
+#define B2GPU_OK 0
+#define B2GPU_E_INVALID (-1)   /* bad argument / misuse (reference: panic!/b2_assert) */
+#define B2GPU_E_NO_DEVICE (-2) /* no CUDA device: there is no CPU fallback */
+#define B2GPU_E_CUDA (-3)      /* CUDA runtime error, see b2gpu_last_error */
+#define B2GPU_E_CAPACITY (-4)  /* a device-side capacity was exceeded */
+#define B2GPU_E_UNSUPPORTED (-5) /* feature outside the hot-path scope (joints, TOI, sensors' GJK) */
+#define B2GPU_E_LOCKED (-6)    /* world is locked (reference: is_locked() panic) */
+
+/* body types: src/b2_body.rs B2bodyType */
+#define B2GPU_STATIC_BODY 0
+#define B2GPU_KINEMATIC_BODY 1
+#define B2GPU_DYNAMIC_BODY 2
+
+/* BodyFlags bits: src/b2_body.rs:209-221 */
+#define B2GPU_BODY_ISLAND 0x0001u
+#define B2GPU_BODY_AWAKE 0x0002u
+#define B2GPU_BODY_AUTO_SLEEP 0x0004u
+#define B2GPU_BODY_BULLET 0x0008u
+#define B2GPU_BODY_FIXED_ROTATION 0x0010u
+#define B2GPU_BODY_ENABLED 0x0020u
+#define B2GPU_BODY_TOI 0x0040u
+
+/* ContactFlags bits: src/b2_contact.rs:283-305 */
+#define B2GPU_CONTACT_ISLAND 0x0001u
+#define B2GPU_CONTACT_TOUCHING 0x0002u
+#define B2GPU_CONTACT_ENABLED 0x0004u
+#define B2GPU_CONTACT_FILTER 0x0008u
+
+/* shape types: src/b2_shape.rs:25-31 */
+#define B2GPU_SHAPE_CIRCLE 0
+#define B2GPU_SHAPE_EDGE 1
+#define B2GPU_SHAPE_POLYGON 2
+#define B2GPU_SHAPE_CHAIN 3
+
+/* manifold types: src/b2_collision.rs:63-67 */
+#define B2GPU_MANIFOLD_CIRCLES 0
+#define B2GPU_MANIFOLD_FACE_A 1
+#define B2GPU_MANIFOLD_FACE_B 2
+
+/* world flags */
+#define B2GPU_WORLD_ALLOW_SLEEP 0x01u   /* m_allow_sleep      (b2_world.rs(private):43) */
+#define B2GPU_WORLD_WARM_STARTING 0x02u /* m_warm_starting    (:37) */
+#define B2GPU_WORLD_NEW_CONTACTS 0x04u  /* m_new_contacts     (:46) */
+#define B2GPU_WORLD_CLEAR_FORCES 0x08u  /* m_clear_forces     (:48) */
+#define B2GPU_WORLD_BLOCK_SOLVE 0x10u   /* G_BLOCK_SOLVE      (src/b2_contact.rs:25) */
+
+#define B2GPU_NULL (-1)
+#define B2GPU_MAX_POLYGON_VERTICES 8
+
+/* ---------------------------------------------------------------- records */
+
+/* B2body (src/b2_body.rs) — the fields the step reads or writes. 128 bytes. */
+typedef struct b2gpu_body_rec {
+  int32_t type;
+  uint32_t flags;
+  float xf_px, xf_py, xf_qs, xf_qc;                 /* m_xf */
+  float lc_x, lc_y, c0_x, c0_y, c_x, c_y, a0, a;    /* m_sweep (alpha0 == 0 outside TOI) */
+  float vx, vy, w;                                  /* m_linear_velocity, m_angular_velocity */
+  float fx, fy, torque;                             /* m_force, m_torque */
+  float mass, inv_mass, inertia, inv_inertia;       /* m_mass, m_inv_mass, m_i, m_inv_i */
+  float linear_damping, angular_damping, gravity_scale, sleep_time;
+  int32_t fixture_head;                             /* newest fixture (m_fixture_list head) or -1 */
+  int32_t fixture_count;
+  int32_t reserved[2];
+} b2gpu_body_rec;
+
+/* B2fixture (src/b2_fixture.rs). 48 bytes. */
+typedef struct b2gpu_fixture_rec {
+  int32_t body;
+  int32_t next;        /* next older fixture of the same body, or -1 */
+  int32_t shape_type;  /* B2GPU_SHAPE_* of the fixture's shape (chain keeps its own type) */
+  int32_t shape_first; /* first child-shape record */
+  int32_t child_count; /* get_child_count(): 1, or edges of a chain */
+  int32_t proxy_first; /* first proxy record, -1 when the body is disabled */
+  float density, friction, restitution, restitution_threshold;
+  uint16_t category_bits, mask_bits; /* B2filter (src/b2_fixture.rs:30) */
+  int16_t group_index;
+  uint16_t is_sensor;
+} b2gpu_fixture_rec;
+
+/* One collision child: a circle, a polygon, or one edge (an edge shape, or child
+ * `i` of a chain materialised as in b2_chain_shape.rs(private):59-79). 160 bytes. */
+typedef struct b2gpu_shape_rec {
+  int32_t type;      /* CIRCLE, EDGE or POLYGON */
+  float radius;      /* m_radius */
+  int32_t count;     /* polygon vertex count */
+  int32_t one_sided; /* edge: m_one_sided */
+  float cx, cy;      /* polygon m_centroid / circle m_p */
+  float v[16];       /* polygon m_vertices (x,y)*8 ; edge: v0,v1,v2,v3 */
+  float n[16];       /* polygon m_normals */
+  int32_t reserved[2];
+} b2gpu_shape_rec;
+
+/* B2fixtureProxy (src/b2_fixture.rs). 32 bytes. */
+typedef struct b2gpu_proxy_rec {
+  int32_t fixture;
+  int32_t child_index;
+  int32_t proxy_id; /* tree node id */
+  int32_t reserved;
+  float aabb[4];    /* tight (swept) AABB lower.x lower.y upper.x upper.y */
+} b2gpu_proxy_rec;
+
+/* B2treeNode (src/b2_dynamic_tree.rs:11-32). 40 bytes. */
+typedef struct b2gpu_tree_node_rec {
+  float aabb[4];   /* fat AABB */
+  int32_t parent;  /* parent, or next free node when height == -1 */
+  int32_t child1, child2;
+  int32_t height;  /* leaf = 0, free = -1 */
+  int32_t proxy;   /* user data: index into proxies, -1 for internal nodes */
+  int32_t moved;
+} b2gpu_tree_node_rec;
+
+/* B2manifold (src/b2_collision.rs:104-114). 64 bytes. */
+typedef struct b2gpu_manifold_point {
+  float lp_x, lp_y;       /* local_point */
+  float normal_impulse, tangent_impulse;
+  uint32_t id;            /* B2contactFeature: index_a | index_b<<8 | type_a<<16 | type_b<<24 */
+} b2gpu_manifold_point;
+
+typedef struct b2gpu_manifold {
+  b2gpu_manifold_point points[2];
+  float ln_x, ln_y; /* local_normal */
+  float lp_x, lp_y; /* local_point */
+  int32_t type;
+  int32_t point_count;
+} b2gpu_manifold;
+
+/* B2contact (src/b2_contact.rs). 104 bytes. Array order = creation order
+ * (world contact list reversed); per-body edge lists follow from it. */
+typedef struct b2gpu_contact_rec {
+  int32_t fixture_a, fixture_b;
+  int32_t index_a, index_b; /* child indices */
+  uint32_t flags;
+  float friction, restitution, restitution_threshold, tangent_speed;
+  int32_t reserved;
+  b2gpu_manifold manifold;
+} b2gpu_contact_rec;
+
+/* World-level scalars: B2world + B2broadPhase + B2dynamicTree bookkeeping. */
+typedef struct b2gpu_world_rec {
+  float gravity_x, gravity_y;
+  float inv_dt0;        /* m_inv_dt0 */
+  uint32_t flags;       /* B2GPU_WORLD_* */
+  int32_t tree_root;    /* m_root */
+  int32_t tree_free_list;
+  int32_t tree_node_count;
+  int32_t tree_node_capacity;
+  int32_t tree_insertion_count;
+  int32_t proxy_count;  /* B2broadPhase::m_proxy_count */
+  int32_t reserved[2];
+} b2gpu_world_rec;
+
+typedef struct b2gpu_snapshot_sizes {
+  int32_t body_count, fixture_count, shape_count, proxy_count;
+  int32_t node_count; /* == tree_node_capacity: the whole pool incl. free nodes */
+  int32_t contact_count, move_count;
+  int32_t reserved;
+} b2gpu_snapshot_sizes;
+
+/* Full step state.  Arrays are caller-owned.  For download the caller allocates
+ * at least the sizes reported by *_snapshot_sizes and passes capacities in `n`. */
+typedef struct b2gpu_snapshot {
+  b2gpu_world_rec world;
+  b2gpu_snapshot_sizes n;
+  b2gpu_body_rec* bodies;         /* creation order; world body list = reverse */
+  b2gpu_fixture_rec* fixtures;    /* creation order */
+  b2gpu_shape_rec* shapes;
+  b2gpu_proxy_rec* proxies;
+  b2gpu_tree_node_rec* nodes;
+  b2gpu_contact_rec* contacts;    /* creation order; world contact list = reverse */
+  int32_t* move_buffer;           /* B2broadPhase::m_move_buffer (proxy ids, -1 = nulled) */
+} b2gpu_snapshot;
+
+/* Counters of the last step of one world (parity quick-check + roofline inputs). */
+typedef struct b2gpu_step_stats {
+  int32_t status;        /* 0 or B2GPU_E_CAPACITY / B2GPU_E_UNSUPPORTED raised on device */
+  int32_t contacts;      /* live contacts after the step */
+  int32_t touching;      /* contacts with TOUCHING after collide */
+  int32_t destroyed;     /* contacts destroyed in collide */
+  int32_t islands;
+  int32_t island_bodies; /* sum of island sizes (static bodies counted per island) */
+  int32_t island_contacts;
+  int32_t moved;         /* proxies re-inserted (move buffer length) */
+  int32_t pairs;         /* pair buffer length in update_pairs */
+  int32_t created;       /* contacts created by add_pair */
+  int32_t awake_bodies;
+  int32_t solver_levels; /* depth of the exact-order wavefront schedule of the velocity pass */
+  int32_t reserved[4];
+} b2gpu_step_stats;
+
+/* --------------------------------------------------------------- definitions */
+
+/* B2bodyDef (src/b2_body.rs:39-58) */
+typedef struct b2gpu_body_def {
+  int32_t type;
+  float position_x, position_y, angle;
+  float linear_velocity_x, linear_velocity_y, angular_velocity;
+  float linear_damping, angular_damping;
+  int32_t allow_sleep, awake, fixed_rotation, bullet, enabled;
+  float gravity_scale;
+} b2gpu_body_def;
+
+/* B2fixtureDef (src/b2_fixture.rs:44-57) */
+typedef struct b2gpu_fixture_def {
+  float friction, restitution, restitution_threshold, density;
+  int32_t is_sensor;
+  uint16_t category_bits, mask_bits;
+  int16_t group_index;
+  uint16_t reserved;
+} b2gpu_fixture_def;
+
+/* A shape as user code builds it (B2circleShape / B2edgeShape / B2polygonShape /
+ * B2chainShape).  Polygons carry already-computed hull data; use
+ * b2gpu_polygon_set / b2gpu_polygon_set_as_box to fill them. */
+typedef struct b2gpu_shape_def {
+  int32_t type;
+  float radius;
+  /* circle */
+  float p_x, p_y;
+  /* edge */
+  float v0[2], v1[2], v2[2], v3[2];
+  int32_t one_sided;
+  /* polygon */
+  int32_t count;
+  float centroid[2];
+  float vertices[2 * B2GPU_MAX_POLYGON_VERTICES];
+  float normals[2 * B2GPU_MAX_POLYGON_VERTICES];
+  /* chain: caller-owned vertex array (x,y)*chain_count, plus ghost vertices */
+  const float* chain_vertices;
+  int32_t chain_count;
+  float chain_prev[2], chain_next[2];
+} b2gpu_shape_def;
+
+typedef struct b2gpu_mass_data {
+  float mass, center_x, center_y, inertia;
+} b2gpu_mass_data;
+
+/* Device-side capacities of one world of a batch. 0 = derive from the prototype. */
+typedef struct b2gpu_caps {
+  int32_t max_bodies, max_fixtures, max_shapes, max_proxies, max_contacts, max_pairs;
+  int32_t reserved[2];
+} b2gpu_caps;
+
+typedef struct b2gpu_ctx b2gpu_ctx;
+typedef struct b2gpu_world b2gpu_world;
+typedef struct b2gpu_batch b2gpu_batch;
+
+/* ------------------------------------------------------------------ library */
+int b2gpu_abi_version(void);
+const char* b2gpu_last_error(void);
+/* Number of CUDA devices visible, or a negative error code. */
+int b2gpu_device_count(void);
+/* One context per device; creates the streams.  `stream` may be a caller's
+ * cudaStream_t (e.g. torch's current stream) or NULL for a private stream. */
+int b2gpu_init(int device, void* stream, b2gpu_ctx** out);
+void b2gpu_shutdown(b2gpu_ctx* ctx);
+int b2gpu_sync(b2gpu_ctx* ctx);
+void* b2gpu_stream(b2gpu_ctx* ctx);
+/* Total kernel launches issued by this context so far (bench `gpu_launches`). */
+int64_t b2gpu_launch_count(b2gpu_ctx* ctx);
+
+/* ----------------------------------------------- shapes (setup-time geometry) */
+/* B2polygonShape::set_as_box (b2_polygon_shape.rs(private):15-27) */
+int b2gpu_polygon_set_as_box(b2gpu_shape_def* s, float hx, float hy);
+/* B2polygonShape::set_as_box_angle (:29-57) */
+int b2gpu_polygon_set_as_box_angle(b2gpu_shape_def* s, float hx, float hy, float cx, float cy, float angle);
+/* B2polygonShape::set (:96-211): weld, gift-wrap hull, normals, centroid */
+int b2gpu_polygon_set(b2gpu_shape_def* s, const float* vertices_xy, int count);
+/* B2shapeDynTrait::compute_mass for circle/edge/polygon/chain */
+int b2gpu_shape_compute_mass(const b2gpu_shape_def* s, float density, b2gpu_mass_data* out);
+
+/* ------------------------------------------- single world (B2world mirror) */
+/* B2world::new(gravity) (src/b2_world.rs:22; private :26-56).  continuous_physics
+ * is fixed to false (TOI is out of scope, BASELINE.json north_star). */
+int b2gpu_world_create(b2gpu_ctx* ctx, float gravity_x, float gravity_y, b2gpu_world** out);
+void b2gpu_world_destroy(b2gpu_world* w);
+/* B2world::create_body (private :83-98). Returns the body index (>= 0). */
+int b2gpu_world_create_body(b2gpu_world* w, const b2gpu_body_def* def);
+/* B2body::create_fixture (b2_body.rs(private):155-200). Returns the fixture index. */
+int b2gpu_body_create_fixture(b2gpu_world* w, int body, const b2gpu_fixture_def* def, const b2gpu_shape_def* shape);
+/* B2body::set_transform (b2_body.rs(private):418-444) */
+int b2gpu_body_set_transform(b2gpu_world* w, int body, float px, float py, float angle);
+/* B2body::set_linear_velocity / set_angular_velocity (src/b2_body.rs) */
+int b2gpu_body_set_linear_velocity(b2gpu_world* w, int body, float vx, float vy);
+int b2gpu_body_set_angular_velocity(b2gpu_world* w, int body, float w_);
+/* B2body::apply_force_to_center(force, wake) */
+int b2gpu_body_apply_force_to_center(b2gpu_world* w, int body, float fx, float fy, int wake);
+/* B2world::set_allow_sleeping / set_warm_starting / set_continuous_physics */
+int b2gpu_world_set_allow_sleeping(b2gpu_world* w, int flag);
+int b2gpu_world_set_warm_starting(b2gpu_world* w, int flag);
+int b2gpu_world_set_continuous_physics(b2gpu_world* w, int flag); /* flag != 0 -> B2GPU_E_UNSUPPORTED */
+/* G_BLOCK_SOLVE (src/b2_contact.rs:25) */
+int b2gpu_world_set_block_solve(b2gpu_world* w, int flag);
+/* B2world::step (src/b2_world.rs:98; private :903-959) */
+int b2gpu_world_step(b2gpu_world* w, float dt, int velocity_iterations, int position_iterations);
+/* B2world::get_body_count / get_contact_count / get_proxy_count */
+int b2gpu_world_get_body_count(b2gpu_world* w);
+int b2gpu_world_get_contact_count(b2gpu_world* w);
+/* Body getters (B2body::get_position/get_angle/get_linear_velocity/...): copies the record. */
+int b2gpu_world_get_body(b2gpu_world* w, int body, b2gpu_body_rec* out);
+int b2gpu_world_get_stats(b2gpu_world* w, b2gpu_step_stats* out);
+/* Full step state in/out (teacher-forced parity; checkpoint/resume). */
+int b2gpu_world_snapshot_sizes(b2gpu_world* w, b2gpu_snapshot_sizes* out);
+int b2gpu_world_download(b2gpu_world* w, b2gpu_snapshot* out);
+int b2gpu_world_upload(b2gpu_world* w, const b2gpu_snapshot* in);
+
+/* ---------------------------------------- batched independent worlds (RL-style) */
+/* n_worlds replicas of `proto`, one CTA per world per step. */
+int b2gpu_batch_create(b2gpu_ctx* ctx, const b2gpu_snapshot* proto, int n_worlds, const b2gpu_caps* caps, b2gpu_batch** out);
+void b2gpu_batch_destroy(b2gpu_batch* b);
+int b2gpu_batch_world_count(b2gpu_batch* b);
+/* Asynchronous on the context stream: `steps` consecutive B2world::step calls on every world. */
+int b2gpu_batch_step(b2gpu_batch* b, float dt, int velocity_iterations, int position_iterations, int steps);
+int b2gpu_batch_upload_world(b2gpu_batch* b, int world, const b2gpu_snapshot* in);
+int b2gpu_batch_snapshot_sizes(b2gpu_batch* b, int world, b2gpu_snapshot_sizes* out);
+int b2gpu_batch_download_world(b2gpu_batch* b, int world, b2gpu_snapshot* out);
+int b2gpu_batch_get_stats(b2gpu_batch* b, int first_world, int count, b2gpu_step_stats* out);
+/* Per-body force/torque of every world for the next step (B2body::apply_force_to_center /
+ * apply_torque without wake): host array [n_worlds][body_count][3], pinned or pageable. */
+int b2gpu_batch_set_forces(b2gpu_batch* b, const float* host_fxfyt, int first_world, int count);
+/* Linear velocity of one body index in every world (B2body::set_linear_velocity). */
+int b2gpu_batch_set_linear_velocity(b2gpu_batch* b, int body, const float* host_vxvy, int first_world, int count);
+/* Body state of every world after the last step: host array [count][body_count][8] =
+ * (c.x, c.y, a, v.x, v.y, w, xf.p.x, xf.p.y) — what get_world_center/get_angle/
+ * get_linear_velocity/get_angular_velocity/get_position return. */
+int b2gpu_batch_get_body_state(b2gpu_batch* b, float* host_out, int first_world, int count);
+/* Device pointers for zero-copy use from torch (size in bytes returned through *bytes). */
+void* b2gpu_batch_body_state_device(b2gpu_batch* b, int64_t* bytes);
+void* b2gpu_batch_forces_device(b2gpu_batch* b, int64_t* bytes);
+/* One end-to-end step through HOST buffers: H2D forces, `steps` steps, D2H body state, synchronous. */
+int b2gpu_batch_step_host(b2gpu_batch* b, const float* host_forces, float* host_state_out, float dt,
+                          int velocity_iterations, int position_iterations, int steps);
+/* Algorithmic bytes of the last step summed over all worlds (SURVEY.md §8d formula). */
+int64_t b2gpu_batch_algorithmic_bytes(b2gpu_batch* b);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B2GPU_H */

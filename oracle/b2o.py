@@ -1,0 +1,209 @@
+"""TEST INFRASTRUCTURE — ctypes wrapper of the CPU oracle (oracle/libb2o.so).
+
+Only tests/, bench.py's cpu_baseline / --impl reference leg and __graft_entry__.smoke()
+may import this module.  PARITY UNPINNED beyond the reference's own four tests.
+The class/method names mirror the reference API (B2world::create_body, B2body::create_fixture,
+B2world::step, ...) so scene recipes run unchanged on the oracle and on the GPU engine.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+from box2d_rs_b200 import abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_LIB = None
+
+
+def build(force=False):
+    so = os.path.join(_HERE, "libb2o.so")
+    srcs = [os.path.join(_HERE, f) for f in os.listdir(_HERE) if f.endswith((".cpp", ".hpp"))]
+    srcs.append(os.path.join(_HERE, "..", "include", "b2gpu.h"))
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["make", "-C", _HERE, "-s"])
+    return so
+
+
+def lib():
+    global _LIB
+    if _LIB is None:
+        so = os.path.join(_HERE, "libb2o.so")
+        if not os.path.exists(so):
+            build()
+        L = C.CDLL(so)
+        L.b2o_world_create.restype = C.c_void_p
+        L.b2o_world_create.argtypes = [C.c_float, C.c_float]
+        L.b2o_world_clone.restype = C.c_void_p
+        L.b2o_world_clone.argtypes = [C.c_void_p]
+        L.b2o_world_destroy.argtypes = [C.c_void_p]
+        L.b2o_create_body.argtypes = [C.c_void_p, C.POINTER(abi.BodyDef)]
+        L.b2o_create_fixture.argtypes = [C.c_void_p, C.c_int, C.POINTER(abi.FixtureDef), C.POINTER(abi.ShapeDef)]
+        L.b2o_set_transform.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float]
+        L.b2o_set_linear_velocity.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float]
+        L.b2o_set_angular_velocity.argtypes = [C.c_void_p, C.c_int, C.c_float]
+        L.b2o_apply_force_to_center.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_int]
+        for f in ("b2o_set_allow_sleeping", "b2o_set_warm_starting", "b2o_set_block_solve", "b2o_set_collect_levels"):
+            getattr(L, f).argtypes = [C.c_void_p, C.c_int]
+        L.b2o_step.argtypes = [C.c_void_p, C.c_float, C.c_int, C.c_int]
+        L.b2o_body_count.argtypes = [C.c_void_p]
+        L.b2o_contact_count.argtypes = [C.c_void_p]
+        L.b2o_get_profile.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        L.b2o_get_stats.argtypes = [C.c_void_p, C.c_void_p]
+        L.b2o_snapshot_sizes.argtypes = [C.c_void_p, C.POINTER(abi.SnapshotSizes)]
+        L.b2o_snapshot_export.argtypes = [C.c_void_p, C.POINTER(abi.SnapshotC)]
+        L.b2o_get_body_state.argtypes = [C.c_void_p, C.c_void_p]
+        L.b2o_run_worlds_mt.restype = C.c_double
+        L.b2o_run_worlds_mt.argtypes = [C.POINTER(C.c_void_p), C.c_int, C.c_int, C.c_float, C.c_int, C.c_int, C.c_int]
+        L.b2o_polygon_set_as_box.argtypes = [C.POINTER(abi.ShapeDef), C.c_float, C.c_float]
+        L.b2o_polygon_set_as_box_angle.argtypes = [C.POINTER(abi.ShapeDef), C.c_float, C.c_float, C.c_float, C.c_float,
+                                                   C.c_float]
+        L.b2o_polygon_set.argtypes = [C.POINTER(abi.ShapeDef), C.POINTER(C.c_float), C.c_int]
+        L.b2o_shape_compute_mass.argtypes = [C.POINTER(abi.ShapeDef), C.c_float, C.POINTER(abi.MassData)]
+        L.b2o_sweep_get_transform.argtypes = [C.POINTER(C.c_float), C.c_float, C.POINTER(C.c_float)]
+        _LIB = L
+    return _LIB
+
+
+class Shapes:
+    """Shape factory with the reference's method names (B2polygonShape::set_as_box, ::set, ...)."""
+
+    @staticmethod
+    def polygon_box(hx, hy, center=None, angle=0.0):
+        s = abi.ShapeDef()
+        if center is None:
+            lib().b2o_polygon_set_as_box(C.byref(s), hx, hy)
+        else:
+            lib().b2o_polygon_set_as_box_angle(C.byref(s), hx, hy, center[0], center[1], angle)
+        return s
+
+    @staticmethod
+    def polygon(vertices):
+        s = abi.ShapeDef()
+        flat = (C.c_float * (2 * len(vertices)))(*[c for v in vertices for c in v])
+        rc = lib().b2o_polygon_set(C.byref(s), flat, len(vertices))
+        if rc != 0:
+            raise ValueError("degenerate polygon")
+        return s
+
+    circle = staticmethod(abi.circle_shape)
+    edge_two_sided = staticmethod(abi.edge_two_sided)
+    edge_one_sided = staticmethod(abi.edge_one_sided)
+    chain = staticmethod(abi.chain_shape)
+
+    @staticmethod
+    def compute_mass(shape, density):
+        md = abi.MassData()
+        lib().b2o_shape_compute_mass(C.byref(shape), density, C.byref(md))
+        return md
+
+
+class B2body:
+    def __init__(self, world, index):
+        self.world, self.index = world, index
+
+    def create_fixture(self, fixture_def, shape):
+        return lib().b2o_create_fixture(self.world.h, self.index, C.byref(fixture_def), C.byref(shape))
+
+    def create_fixture_by_shape(self, shape, density):
+        return self.create_fixture(abi.FixtureDef(density=density), shape)
+
+    def set_transform(self, position, angle):
+        lib().b2o_set_transform(self.world.h, self.index, position[0], position[1], angle)
+
+    def set_linear_velocity(self, v):
+        lib().b2o_set_linear_velocity(self.world.h, self.index, v[0], v[1])
+
+    def set_angular_velocity(self, w):
+        lib().b2o_set_angular_velocity(self.world.h, self.index, w)
+
+    def apply_force_to_center(self, f, wake=True):
+        lib().b2o_apply_force_to_center(self.world.h, self.index, f[0], f[1], int(wake))
+
+    def _rec(self):
+        return self.world.snapshot().bodies[self.index]
+
+    def get_position(self):
+        r = self._rec()
+        return float(r["xf"][0]), float(r["xf"][1])
+
+    def get_angle(self):
+        return float(self._rec()["a"])
+
+
+class B2world:
+    shapes = Shapes
+
+    def __init__(self, gravity, _handle=None):
+        self.h = C.c_void_p(_handle if _handle is not None else lib().b2o_world_create(gravity[0], gravity[1]))
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().b2o_world_destroy(self.h)
+            self.h = None
+
+    def clone(self):
+        return B2world(None, _handle=lib().b2o_world_clone(self.h))
+
+    def create_body(self, body_def):
+        return B2body(self, lib().b2o_create_body(self.h, C.byref(body_def)))
+
+    def body(self, index):
+        return B2body(self, index)
+
+    def set_allow_sleeping(self, flag):
+        lib().b2o_set_allow_sleeping(self.h, int(flag))
+
+    def set_warm_starting(self, flag):
+        lib().b2o_set_warm_starting(self.h, int(flag))
+
+    def set_continuous_physics(self, flag):
+        if flag:
+            raise NotImplementedError("TOI sub-stepping is out of scope (BASELINE.json north_star)")
+
+    def set_block_solve(self, flag):
+        lib().b2o_set_block_solve(self.h, int(flag))
+
+    def set_collect_levels(self, flag):
+        lib().b2o_set_collect_levels(self.h, int(flag))
+
+    def step(self, dt, velocity_iterations, position_iterations):
+        lib().b2o_step(self.h, dt, velocity_iterations, position_iterations)
+
+    def get_body_count(self):
+        return lib().b2o_body_count(self.h)
+
+    def get_contact_count(self):
+        return lib().b2o_contact_count(self.h)
+
+    def get_profile(self):
+        out = (C.c_double * 7)()
+        lib().b2o_get_profile(self.h, out)
+        return dict(zip(("step", "collide", "solve", "solve_init", "solve_velocity", "solve_position", "broadphase"),
+                        list(out)))
+
+    def get_stats(self):
+        out = np.zeros(1, abi.STATS_DTYPE)
+        lib().b2o_get_stats(self.h, out.ctypes.data)
+        return out[0]
+
+    def snapshot(self):
+        n = abi.SnapshotSizes()
+        lib().b2o_snapshot_sizes(self.h, C.byref(n))
+        snap = abi.Snapshot(n)
+        c = snap.as_c()
+        rc = lib().b2o_snapshot_export(self.h, C.byref(c))
+        assert rc == 0
+        return snap.finish(c)
+
+    def body_state(self):
+        out = np.zeros((self.get_body_count(), 8), np.float32)
+        lib().b2o_get_body_state(self.h, out.ctypes.data)
+        return out
+
+
+def run_worlds_mt(worlds, steps, dt, vi, pi, threads):
+    """CPU baseline: one world per host thread. Returns wall seconds."""
+    arr = (C.c_void_p * len(worlds))(*[w.h for w in worlds])
+    return lib().b2o_run_worlds_mt(arr, len(worlds), steps, dt, vi, pi, threads)

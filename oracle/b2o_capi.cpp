@@ -1,0 +1,299 @@
+// TEST INFRASTRUCTURE — C API of the CPU oracle for ctypes (tests/, bench.py cpu_baseline /
+// --impl reference, __graft_entry__.smoke only).  Never linked into the product.
+// PARITY UNPINNED beyond the reference's own tests (see b2o_math.hpp).
+#include <atomic>
+#include <cstring>
+#include <thread>
+#include <vector>
+
+#include "../include/b2gpu.h"
+#include "b2o_world.hpp"
+
+using namespace b2o;
+
+static Shape shape_from_def(const b2gpu_shape_def* d) {
+  Shape s;
+  s.type = d->type;
+  s.radius = d->radius;
+  s.p = Vec2(d->p_x, d->p_y);
+  s.v0 = Vec2(d->v0[0], d->v0[1]);
+  s.v1 = Vec2(d->v1[0], d->v1[1]);
+  s.v2 = Vec2(d->v2[0], d->v2[1]);
+  s.v3 = Vec2(d->v3[0], d->v3[1]);
+  s.one_sided = d->one_sided != 0;
+  s.count = d->count;
+  s.centroid = Vec2(d->centroid[0], d->centroid[1]);
+  for (int i = 0; i < MAX_POLYGON_VERTICES; ++i) {
+    s.vertices[i] = Vec2(d->vertices[2 * i], d->vertices[2 * i + 1]);
+    s.normals[i] = Vec2(d->normals[2 * i], d->normals[2 * i + 1]);
+  }
+  if (d->type == E_CHAIN) {
+    for (int i = 0; i < d->chain_count; ++i) s.chain.push_back(Vec2(d->chain_vertices[2 * i], d->chain_vertices[2 * i + 1]));
+    s.chain_prev = Vec2(d->chain_prev[0], d->chain_prev[1]);
+    s.chain_next = Vec2(d->chain_next[0], d->chain_next[1]);
+  }
+  return s;
+}
+static void shape_to_def(const Shape& s, b2gpu_shape_def* d) {
+  d->type = s.type;
+  d->radius = s.radius;
+  d->p_x = s.p.x; d->p_y = s.p.y;
+  d->count = s.count;
+  d->centroid[0] = s.centroid.x; d->centroid[1] = s.centroid.y;
+  for (int i = 0; i < MAX_POLYGON_VERTICES; ++i) {
+    d->vertices[2 * i] = s.vertices[i].x; d->vertices[2 * i + 1] = s.vertices[i].y;
+    d->normals[2 * i] = s.normals[i].x; d->normals[2 * i + 1] = s.normals[i].y;
+  }
+}
+
+extern "C" {
+
+// ---- shapes (restated setup geometry, used to pin collision_test.rs)
+int b2o_polygon_set_as_box(b2gpu_shape_def* d, float hx, float hy) {
+  Shape s; polygon_set_as_box(s, hx, hy); shape_to_def(s, d); return 0;
+}
+int b2o_polygon_set_as_box_angle(b2gpu_shape_def* d, float hx, float hy, float cx, float cy, float angle) {
+  Shape s; polygon_set_as_box_angle(s, hx, hy, Vec2(cx, cy), angle); shape_to_def(s, d); return 0;
+}
+int b2o_polygon_set(b2gpu_shape_def* d, const float* xy, int count) {
+  std::vector<Vec2> v;
+  for (int i = 0; i < count; ++i) v.push_back(Vec2(xy[2 * i], xy[2 * i + 1]));
+  Shape s; bool ok = polygon_set(s, v.data(), count); shape_to_def(s, d); return ok ? 0 : -1;
+}
+int b2o_shape_compute_mass(const b2gpu_shape_def* d, float density, b2gpu_mass_data* out) {
+  Shape s = shape_from_def(d);
+  MassData md; shape_compute_mass(s, md, density);
+  out->mass = md.mass; out->center_x = md.center.x; out->center_y = md.center.y; out->inertia = md.i;
+  return 0;
+}
+// tests/math_test.rs:25-49 — sweep endpoints
+void b2o_sweep_get_transform(const float* sweep8 /*lc c0 c a0 a*/, float beta, float* xf4) {
+  Vec2 lc(sweep8[0], sweep8[1]), c0(sweep8[2], sweep8[3]), c(sweep8[4], sweep8[5]);
+  float a0 = sweep8[6], a = sweep8[7];
+  Vec2 p = (1.0f - beta) * c0 + beta * c;  // src/b2_math.rs:762-769
+  float angle = (1.0f - beta) * a0 + beta * a;
+  Rot q(angle);
+  p -= b2_mul_rot(q, lc);
+  xf4[0] = p.x; xf4[1] = p.y; xf4[2] = q.s; xf4[3] = q.c;
+}
+
+// ---- world
+void* b2o_world_create(float gx, float gy) { return new World(Vec2(gx, gy)); }
+void b2o_world_destroy(void* w) { delete (World*)w; }
+void* b2o_world_clone(void* w) { return new World(*(World*)w); }
+int b2o_create_body(void* w, const b2gpu_body_def* d) {
+  BodyDef bd;
+  bd.type = d->type;
+  bd.position = Vec2(d->position_x, d->position_y);
+  bd.angle = d->angle;
+  bd.linear_velocity = Vec2(d->linear_velocity_x, d->linear_velocity_y);
+  bd.angular_velocity = d->angular_velocity;
+  bd.linear_damping = d->linear_damping;
+  bd.angular_damping = d->angular_damping;
+  bd.allow_sleep = d->allow_sleep; bd.awake = d->awake; bd.fixed_rotation = d->fixed_rotation;
+  bd.bullet = d->bullet; bd.enabled = d->enabled;
+  bd.gravity_scale = d->gravity_scale;
+  return ((World*)w)->create_body(bd);
+}
+int b2o_create_fixture(void* w, int body, const b2gpu_fixture_def* d, const b2gpu_shape_def* sd) {
+  FixtureDef fd;
+  fd.friction = d->friction; fd.restitution = d->restitution; fd.restitution_threshold = d->restitution_threshold;
+  fd.density = d->density; fd.is_sensor = d->is_sensor != 0;
+  fd.filter.category_bits = d->category_bits; fd.filter.mask_bits = d->mask_bits; fd.filter.group_index = d->group_index;
+  return ((World*)w)->create_fixture(body, fd, shape_from_def(sd));
+}
+void b2o_set_transform(void* w, int body, float px, float py, float angle) { ((World*)w)->set_transform(body, Vec2(px, py), angle); }
+void b2o_set_linear_velocity(void* w, int body, float vx, float vy) { ((World*)w)->set_linear_velocity(body, Vec2(vx, vy)); }
+void b2o_set_angular_velocity(void* w, int body, float av) { ((World*)w)->set_angular_velocity(body, av); }
+void b2o_apply_force_to_center(void* w, int body, float fx, float fy, int wake) { ((World*)w)->apply_force_to_center(body, Vec2(fx, fy), wake != 0); }
+void b2o_set_allow_sleeping(void* w, int f) {  // b2_world.rs(private):340-353
+  World* W = (World*)w;
+  if ((f != 0) == W->allow_sleep) return;
+  W->allow_sleep = f != 0;
+  if (!W->allow_sleep)
+    for (int b = W->body_list; b != -1; b = W->bodies[b].next) W->set_awake(b, true);
+}
+void b2o_set_warm_starting(void* w, int f) { ((World*)w)->warm_starting = f != 0; }
+void b2o_set_block_solve(void* w, int f) { ((World*)w)->block_solve = f != 0; }
+void b2o_set_collect_levels(void* w, int f) { ((World*)w)->collect_levels = f != 0; }
+void b2o_step(void* w, float dt, int vi, int pi) { ((World*)w)->step(dt, vi, pi); }
+int b2o_body_count(void* w) { return (int)((World*)w)->bodies.size(); }
+int b2o_contact_count(void* w) { return ((World*)w)->contact_count; }
+void b2o_get_profile(void* w, double* out7) {
+  const Profile& p = ((World*)w)->profile;
+  out7[0] = p.step; out7[1] = p.collide; out7[2] = p.solve; out7[3] = p.solve_init; out7[4] = p.solve_velocity;
+  out7[5] = p.solve_position; out7[6] = p.broadphase;
+}
+void b2o_get_stats(void* w, b2gpu_step_stats* out) {
+  const StepStats& s = ((World*)w)->stats;
+  std::memset(out, 0, sizeof(*out));
+  out->contacts = s.contacts; out->touching = s.touching; out->destroyed = s.destroyed; out->islands = s.islands;
+  out->island_bodies = s.island_bodies; out->island_contacts = s.island_contacts; out->moved = s.moved; out->pairs = s.pairs;
+  out->created = s.created; out->awake_bodies = s.awake_bodies; out->solver_levels = s.solver_levels;
+}
+
+// ---- snapshot export in the b2gpu.h format
+static int total_shapes(const World& W) {
+  int n = 0;
+  for (auto& f : W.fixtures) n += f.shape.child_count();
+  return n;
+}
+void b2o_snapshot_sizes(void* w, b2gpu_snapshot_sizes* n) {
+  const World& W = *(World*)w;
+  n->body_count = (int)W.bodies.size();
+  n->fixture_count = (int)W.fixtures.size();
+  n->shape_count = total_shapes(W);
+  n->proxy_count = (int)W.proxies.size();
+  n->node_count = W.broad_phase.tree.node_capacity;
+  n->contact_count = W.contact_count;
+  n->move_count = (int)W.broad_phase.move_buffer.size();
+  n->reserved = 0;
+}
+static void fill_shape_rec(const Shape& s, b2gpu_shape_rec* r) {
+  std::memset(r, 0, sizeof(*r));
+  r->type = s.type;
+  r->radius = s.radius;
+  if (s.type == E_CIRCLE) { r->cx = s.p.x; r->cy = s.p.y; r->v[0] = s.p.x; r->v[1] = s.p.y; }
+  else if (s.type == E_EDGE) {
+    r->one_sided = s.one_sided ? 1 : 0;
+    r->v[0] = s.v0.x; r->v[1] = s.v0.y; r->v[2] = s.v1.x; r->v[3] = s.v1.y;
+    r->v[4] = s.v2.x; r->v[5] = s.v2.y; r->v[6] = s.v3.x; r->v[7] = s.v3.y;
+  } else {
+    r->count = s.count;
+    r->cx = s.centroid.x; r->cy = s.centroid.y;
+    for (int i = 0; i < MAX_POLYGON_VERTICES; ++i) {
+      r->v[2 * i] = s.vertices[i].x; r->v[2 * i + 1] = s.vertices[i].y;
+      r->n[2 * i] = s.normals[i].x; r->n[2 * i + 1] = s.normals[i].y;
+    }
+  }
+}
+int b2o_snapshot_export(void* w, b2gpu_snapshot* out) {
+  World& W = *(World*)w;
+  b2gpu_snapshot_sizes need;
+  b2o_snapshot_sizes(w, &need);
+  if (out->n.body_count < need.body_count || out->n.fixture_count < need.fixture_count ||
+      out->n.shape_count < need.shape_count || out->n.proxy_count < need.proxy_count ||
+      out->n.node_count < need.node_count || out->n.contact_count < need.contact_count ||
+      out->n.move_count < need.move_count)
+    return -1;
+  out->n = need;
+  b2gpu_world_rec& wr = out->world;
+  std::memset(&wr, 0, sizeof(wr));
+  wr.gravity_x = W.gravity.x; wr.gravity_y = W.gravity.y;
+  wr.inv_dt0 = W.inv_dt0;
+  wr.flags = (W.allow_sleep ? B2GPU_WORLD_ALLOW_SLEEP : 0) | (W.warm_starting ? B2GPU_WORLD_WARM_STARTING : 0) |
+             (W.new_contacts ? B2GPU_WORLD_NEW_CONTACTS : 0) | (W.clear_forces_flag ? B2GPU_WORLD_CLEAR_FORCES : 0) |
+             (W.block_solve ? B2GPU_WORLD_BLOCK_SOLVE : 0);
+  const DynamicTree& T = W.broad_phase.tree;
+  wr.tree_root = T.root; wr.tree_free_list = T.free_list; wr.tree_node_count = T.node_count;
+  wr.tree_node_capacity = T.node_capacity; wr.tree_insertion_count = T.insertion_count;
+  wr.proxy_count = W.broad_phase.proxy_count;
+  for (size_t i = 0; i < W.bodies.size(); ++i) {
+    const Body& b = W.bodies[i];
+    b2gpu_body_rec& r = out->bodies[i];
+    std::memset(&r, 0, sizeof(r));
+    r.type = b.type; r.flags = b.flags;
+    r.xf_px = b.xf.p.x; r.xf_py = b.xf.p.y; r.xf_qs = b.xf.q.s; r.xf_qc = b.xf.q.c;
+    r.lc_x = b.sweep.local_center.x; r.lc_y = b.sweep.local_center.y;
+    r.c0_x = b.sweep.c0.x; r.c0_y = b.sweep.c0.y; r.c_x = b.sweep.c.x; r.c_y = b.sweep.c.y;
+    r.a0 = b.sweep.a0; r.a = b.sweep.a;
+    r.vx = b.linear_velocity.x; r.vy = b.linear_velocity.y; r.w = b.angular_velocity;
+    r.fx = b.force.x; r.fy = b.force.y; r.torque = b.torque;
+    r.mass = b.mass; r.inv_mass = b.inv_mass; r.inertia = b.i; r.inv_inertia = b.inv_i;
+    r.linear_damping = b.linear_damping; r.angular_damping = b.angular_damping; r.gravity_scale = b.gravity_scale;
+    r.sleep_time = b.sleep_time;
+    r.fixture_head = b.fixture_list; r.fixture_count = b.fixture_count;
+  }
+  int si = 0;
+  for (size_t i = 0; i < W.fixtures.size(); ++i) {
+    const Fixture& f = W.fixtures[i];
+    b2gpu_fixture_rec& r = out->fixtures[i];
+    std::memset(&r, 0, sizeof(r));
+    r.body = f.body; r.next = f.next; r.shape_type = f.shape.type; r.shape_first = si;
+    r.child_count = f.shape.child_count(); r.proxy_first = f.proxy_count > 0 ? f.proxy_first : -1;
+    r.density = f.density; r.friction = f.friction; r.restitution = f.restitution;
+    r.restitution_threshold = f.restitution_threshold;
+    r.category_bits = f.filter.category_bits; r.mask_bits = f.filter.mask_bits; r.group_index = f.filter.group_index;
+    r.is_sensor = f.is_sensor ? 1 : 0;
+    if (f.shape.type == E_CHAIN) {
+      for (int c = 0; c < r.child_count; ++c) {
+        Shape e; chain_get_child_edge(f.shape, e, c);
+        fill_shape_rec(e, &out->shapes[si++]);
+      }
+    } else {
+      fill_shape_rec(f.shape, &out->shapes[si++]);
+    }
+  }
+  for (size_t i = 0; i < W.proxies.size(); ++i) {
+    const FixtureProxy& p = W.proxies[i];
+    b2gpu_proxy_rec& r = out->proxies[i];
+    r.fixture = p.fixture; r.child_index = p.child_index; r.proxy_id = p.proxy_id; r.reserved = 0;
+    r.aabb[0] = p.aabb.lower.x; r.aabb[1] = p.aabb.lower.y; r.aabb[2] = p.aabb.upper.x; r.aabb[3] = p.aabb.upper.y;
+  }
+  for (int i = 0; i < T.node_capacity; ++i) {
+    const TreeNode& nd = T.nodes[i];
+    b2gpu_tree_node_rec& r = out->nodes[i];
+    r.aabb[0] = nd.aabb.lower.x; r.aabb[1] = nd.aabb.lower.y; r.aabb[2] = nd.aabb.upper.x; r.aabb[3] = nd.aabb.upper.y;
+    r.parent = nd.parent; r.child1 = nd.child1; r.child2 = nd.child2; r.height = nd.height;
+    r.proxy = nd.user_data; r.moved = nd.moved ? 1 : 0;
+  }
+  {
+    std::vector<int> order;
+    for (int c = W.contact_list; c != -1; c = W.contacts[c].next) order.push_back(c);
+    int k = 0;
+    for (auto it = order.rbegin(); it != order.rend(); ++it, ++k) {
+      const Contact& c = W.contacts[*it];
+      b2gpu_contact_rec& r = out->contacts[k];
+      std::memset(&r, 0, sizeof(r));
+      r.fixture_a = c.fixture_a; r.fixture_b = c.fixture_b; r.index_a = c.index_a; r.index_b = c.index_b;
+      r.flags = c.flags;
+      r.friction = c.friction; r.restitution = c.restitution; r.restitution_threshold = c.restitution_threshold;
+      r.tangent_speed = c.tangent_speed;
+      const Manifold& m = c.manifold;
+      for (int j = 0; j < 2; ++j) {
+        r.manifold.points[j].lp_x = m.points[j].local_point.x; r.manifold.points[j].lp_y = m.points[j].local_point.y;
+        r.manifold.points[j].normal_impulse = m.points[j].normal_impulse;
+        r.manifold.points[j].tangent_impulse = m.points[j].tangent_impulse;
+        r.manifold.points[j].id = m.points[j].id.key();
+      }
+      r.manifold.ln_x = m.local_normal.x; r.manifold.ln_y = m.local_normal.y;
+      r.manifold.lp_x = m.local_point.x; r.manifold.lp_y = m.local_point.y;
+      r.manifold.type = m.type; r.manifold.point_count = m.point_count;
+    }
+  }
+  for (size_t i = 0; i < W.broad_phase.move_buffer.size(); ++i) out->move_buffer[i] = W.broad_phase.move_buffer[i];
+  return 0;
+}
+
+// Compact per-body state [body][8] = c.x c.y a v.x v.y w xf.p.x xf.p.y (b2gpu_batch_get_body_state layout)
+void b2o_get_body_state(void* w, float* out) {
+  const World& W = *(World*)w;
+  for (size_t i = 0; i < W.bodies.size(); ++i) {
+    const Body& b = W.bodies[i];
+    float* o = out + 8 * i;
+    o[0] = b.sweep.c.x; o[1] = b.sweep.c.y; o[2] = b.sweep.a; o[3] = b.linear_velocity.x; o[4] = b.linear_velocity.y;
+    o[5] = b.angular_velocity; o[6] = b.xf.p.x; o[7] = b.xf.p.y;
+  }
+}
+
+// ---- CPU baseline: one world per host thread. Returns seconds of wall time.
+double b2o_run_worlds_mt(void** worlds, int n_worlds, int steps, float dt, int vi, int pi, int threads) {
+  if (threads < 1) threads = 1;
+  std::atomic<int> next(0);
+  double t0 = now_ms();
+  std::vector<std::thread> pool;
+  for (int t = 0; t < threads; ++t)
+    pool.emplace_back([&]() {
+      for (;;) {
+        int i = next.fetch_add(1);
+        if (i >= n_worlds) break;
+        World* W = (World*)worlds[i];
+        for (int s = 0; s < steps; ++s) W->step(dt, vi, pi);
+      }
+    });
+  for (auto& th : pool) th.join();
+  return (now_ms() - t0) * 1e-3;
+}
+int b2o_hardware_threads() { return (int)std::thread::hardware_concurrency(); }
+
+}  // extern "C"

@@ -1,0 +1,1073 @@
+// TEST INFRASTRUCTURE — CPU oracle (see b2o_math.hpp header). PARITY UNPINNED beyond the
+// reference's own tests (tests/test.rs, world_test.rs, collision_test.rs, math_test.rs).
+//
+// b2o_world.hpp — restates the step path of box2d-rs with index-based storage:
+//   src/private/dynamics/b2_world.rs (step :903-959, solve :356-531, create_body :83-98)
+//   src/private/dynamics/b2_body.rs, src/b2_body.rs (set_awake, synchronize_*)
+//   src/private/dynamics/b2_fixture.rs (create_proxies, synchronize)
+//   src/private/dynamics/b2_contact_manager.rs, b2_contact.rs, b2_contact_registers.rs
+//   src/private/dynamics/b2_island_private.rs, b2_contact_solver_private.rs
+// Intrusive lists are kept as real push_front linked lists through indices so the
+// iteration orders of SURVEY.md §3.4 hold by construction.
+#pragma once
+#include <algorithm>
+#include <chrono>
+#include <vector>
+
+#include "b2o_collision.hpp"
+#include "b2o_tree.hpp"
+
+namespace b2o {
+
+enum BodyType { STATIC_BODY = 0, KINEMATIC_BODY = 1, DYNAMIC_BODY = 2 };
+enum : uint32_t {  // src/b2_body.rs:209-221
+  BF_ISLAND = 0x0001, BF_AWAKE = 0x0002, BF_AUTO_SLEEP = 0x0004, BF_BULLET = 0x0008,
+  BF_FIXED_ROTATION = 0x0010, BF_ENABLED = 0x0020, BF_TOI = 0x0040
+};
+enum : uint32_t {  // src/b2_contact.rs:283-305
+  CF_ISLAND = 0x0001, CF_TOUCHING = 0x0002, CF_ENABLED = 0x0004, CF_FILTER = 0x0008
+};
+
+struct BodyDef {  // src/b2_body.rs:39-58
+  int type = STATIC_BODY;
+  Vec2 position;
+  float angle = 0.0f;
+  Vec2 linear_velocity;
+  float angular_velocity = 0.0f, linear_damping = 0.0f, angular_damping = 0.0f;
+  bool allow_sleep = true, awake = true, fixed_rotation = false, bullet = false, enabled = true;
+  float gravity_scale = 1.0f;
+};
+struct Filter {
+  uint16_t category_bits = 0x0001, mask_bits = 0xFFFF;
+  int16_t group_index = 0;
+};
+struct FixtureDef {  // src/b2_fixture.rs:44-57
+  float friction = 0.2f, restitution = 0.0f, restitution_threshold = 1.0f * LENGTH_UNITS_PER_METER, density = 0.0f;
+  bool is_sensor = false;
+  Filter filter;
+};
+
+struct Body {
+  int type = STATIC_BODY;
+  uint32_t flags = 0;
+  int island_index = -1;
+  Transform xf;
+  Sweep sweep;
+  Vec2 linear_velocity;
+  float angular_velocity = 0.0f;
+  Vec2 force;
+  float torque = 0.0f;
+  int prev = -1, next = -1;        // world body list
+  int fixture_list = -1;            // head = newest
+  int fixture_count = 0;
+  int contact_list = -1;            // head edge id (2*contact + side)
+  float mass = 0.0f, inv_mass = 0.0f, i = 0.0f, inv_i = 0.0f;
+  float linear_damping = 0.0f, angular_damping = 0.0f, gravity_scale = 1.0f, sleep_time = 0.0f;
+};
+struct FixtureProxy {
+  AABB aabb;
+  int fixture = -1, child_index = 0, proxy_id = -1;
+};
+struct Fixture {
+  int body = -1, next = -1;
+  Shape shape;
+  float density = 0.0f, friction = 0.0f, restitution = 0.0f, restitution_threshold = 0.0f;
+  Filter filter;
+  bool is_sensor = false;
+  int proxy_first = -1, proxy_count = 0;  // into World::proxies
+};
+struct ContactEdge {
+  int other = -1, prev = -1, next = -1;
+};
+struct Contact {
+  bool alive = false;
+  uint32_t flags = 0;
+  int prev = -1, next = -1;  // world contact list
+  ContactEdge node_a, node_b;
+  int fixture_a = -1, fixture_b = -1, index_a = 0, index_b = 0;
+  Manifold manifold;
+  float friction = 0.0f, restitution = 0.0f, restitution_threshold = 0.0f, tangent_speed = 0.0f;
+};
+
+struct TimeStep {  // src/b2_time_step.rs
+  float dt = 0.0f, inv_dt = 0.0f, dt_ratio = 0.0f;
+  int velocity_iterations = 0, position_iterations = 0;
+  bool warm_starting = false;
+};
+struct Profile {  // src/b2_time_step.rs:5-15 (ms)
+  double step = 0, collide = 0, solve = 0, solve_init = 0, solve_velocity = 0, solve_position = 0, broadphase = 0;
+};
+struct StepStats {
+  int contacts = 0, touching = 0, destroyed = 0, islands = 0, island_bodies = 0, island_contacts = 0, moved = 0, pairs = 0,
+      created = 0, awake_bodies = 0, solver_levels = 0;
+};
+
+// src/private/dynamics/b2_contact_solver.rs:11-119
+struct VelocityConstraintPoint {
+  Vec2 r_a, r_b;
+  float normal_impulse = 0, tangent_impulse = 0, normal_mass = 0, tangent_mass = 0, velocity_bias = 0;
+};
+struct ContactVelocityConstraint {
+  VelocityConstraintPoint points[MAX_MANIFOLD_POINTS];
+  Vec2 normal;
+  Mat22 normal_mass, k;
+  int index_a = 0, index_b = 0;
+  float inv_mass_a = 0, inv_mass_b = 0, inv_ia = 0, inv_ib = 0, friction = 0, restitution = 0, threshold = 0, tangent_speed = 0;
+  int point_count = 0, contact_index = 0;
+};
+struct ContactPositionConstraint {
+  Vec2 local_points[MAX_MANIFOLD_POINTS];
+  Vec2 local_normal, local_point;
+  int index_a = 0, index_b = 0;
+  float inv_mass_a = 0, inv_mass_b = 0;
+  Vec2 local_center_a, local_center_b;
+  float inv_ia = 0, inv_ib = 0;
+  int type = 0;
+  float radius_a = 0, radius_b = 0;
+  int point_count = 0;
+};
+struct Position { Vec2 c; float a = 0; };
+struct Velocity { Vec2 v; float w = 0; };
+
+inline double now_ms() {
+  return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+struct World {
+  // b2_world.rs(private):26-56
+  Vec2 gravity;
+  bool warm_starting = true, continuous_physics = false /* TOI out of scope */, allow_sleep = true;
+  bool new_contacts = false, locked = false, clear_forces_flag = true, step_complete = true;
+  bool block_solve = true;  // G_BLOCK_SOLVE
+  float inv_dt0 = 0.0f;
+  std::vector<Body> bodies;        // index = creation order (no destroy_body in scope)
+  int body_list = -1;              // head = newest
+  std::vector<Fixture> fixtures;   // creation order
+  std::vector<FixtureProxy> proxies;
+  std::vector<Contact> contacts;   // slots
+  std::vector<int> contact_free;
+  int contact_list = -1, contact_count = 0;
+  BroadPhase broad_phase;
+  Profile profile;
+  StepStats stats;
+  bool collect_levels = false;     // compute the wavefront depth statistic (diagnostic only)
+
+  explicit World(Vec2 g) : gravity(g) {}
+
+  // ---------------------------------------------------------------- bodies
+  int create_body(const BodyDef& bd) {  // b2_world.rs(private):83-98 ; b2_body.rs(private):15-90
+    Body b;
+    if (bd.bullet) b.flags |= BF_BULLET;
+    if (bd.fixed_rotation) b.flags |= BF_FIXED_ROTATION;
+    if (bd.allow_sleep) b.flags |= BF_AUTO_SLEEP;
+    if (bd.awake && bd.type != STATIC_BODY) b.flags |= BF_AWAKE;
+    if (bd.enabled) b.flags |= BF_ENABLED;
+    b.xf.p = bd.position;
+    b.xf.q = Rot(bd.angle);
+    b.sweep.local_center.set_zero();
+    b.sweep.c0 = b.xf.p;
+    b.sweep.c = b.xf.p;
+    b.sweep.a0 = bd.angle;
+    b.sweep.a = bd.angle;
+    b.linear_velocity = bd.linear_velocity;
+    b.angular_velocity = bd.angular_velocity;
+    b.linear_damping = bd.linear_damping;
+    b.angular_damping = bd.angular_damping;
+    b.gravity_scale = bd.gravity_scale;
+    b.type = bd.type;
+    int id = (int)bodies.size();
+    b.next = body_list;  // push_front
+    if (body_list != -1) bodies[body_list].prev = id;
+    bodies.push_back(b);
+    body_list = id;
+    return id;
+  }
+  void set_awake(int bi, bool flag) {  // src/b2_body.rs:783-801
+    Body& b = bodies[bi];
+    if (b.type == STATIC_BODY) return;
+    if (flag) {
+      b.flags |= BF_AWAKE;
+      b.sleep_time = 0.0f;
+    } else {
+      b.flags &= ~BF_AWAKE;
+      b.sleep_time = 0.0f;
+      b.linear_velocity.set_zero();
+      b.angular_velocity = 0.0f;
+      b.force.set_zero();
+      b.torque = 0.0f;
+    }
+  }
+  void synchronize_transform(Body& b) {  // src/b2_body.rs:974-977
+    b.xf.q.set(b.sweep.a);
+    b.xf.p = b.sweep.c - b2_mul_rot(b.xf.q, b.sweep.local_center);
+  }
+  void reset_mass_data(int bi) {  // b2_body.rs(private):292-350
+    Body& b = bodies[bi];
+    b.mass = 0.0f; b.inv_mass = 0.0f; b.i = 0.0f; b.inv_i = 0.0f;
+    b.sweep.local_center.set_zero();
+    if (b.type == STATIC_BODY || b.type == KINEMATIC_BODY) {
+      b.sweep.c0 = b.xf.p;
+      b.sweep.c = b.xf.p;
+      b.sweep.a0 = b.sweep.a;
+      return;
+    }
+    Vec2 local_center(0.0f, 0.0f);
+    for (int f = b.fixture_list; f != -1; f = fixtures[f].next) {
+      const Fixture& fx = fixtures[f];
+      if (fx.density == 0.0f) continue;
+      MassData md;
+      shape_compute_mass(fx.shape, md, fx.density);
+      b.mass += md.mass;
+      local_center += md.mass * md.center;
+      b.i += md.i;
+    }
+    if (b.mass > 0.0f) {
+      b.inv_mass = 1.0f / b.mass;
+      local_center *= b.inv_mass;
+    }
+    if (b.i > 0.0f && !(b.flags & BF_FIXED_ROTATION)) {
+      b.i -= b.mass * b2_dot(local_center, local_center);
+      b.inv_i = 1.0f / b.i;
+    } else {
+      b.i = 0.0f;
+      b.inv_i = 0.0f;
+    }
+    Vec2 old_center = b.sweep.c;
+    b.sweep.local_center = local_center;
+    b.sweep.c0 = b2_mul_xf(b.xf, b.sweep.local_center);
+    b.sweep.c = b.sweep.c0;
+    b.linear_velocity += b2_cross_sv(b.angular_velocity, b.sweep.c - old_center);
+  }
+  int create_fixture(int bi, const FixtureDef& def, const Shape& shape) {  // b2_body.rs(private):155-200
+    Fixture fx;
+    fx.friction = def.friction;
+    fx.restitution = def.restitution;
+    fx.restitution_threshold = def.restitution_threshold;
+    fx.body = bi;
+    fx.filter = def.filter;
+    fx.is_sensor = def.is_sensor;
+    fx.shape = shape;
+    fx.density = def.density;
+    int fi = (int)fixtures.size();
+    fixtures.push_back(fx);
+    Body& b = bodies[bi];
+    if (b.flags & BF_ENABLED) create_proxies(fi, b.xf);
+    fixtures[fi].next = b.fixture_list;  // push_front
+    b.fixture_list = fi;
+    b.fixture_count += 1;
+    if (fixtures[fi].density > 0.0f) reset_mass_data(bi);
+    new_contacts = true;
+    return fi;
+  }
+  void create_proxies(int fi, const Transform& xf) {  // b2_fixture.rs(private):114-132
+    Fixture& fx = fixtures[fi];
+    fx.proxy_count = fx.shape.child_count();
+    fx.proxy_first = (int)proxies.size();
+    for (int i = 0; i < fx.proxy_count; ++i) {
+      FixtureProxy p;
+      shape_compute_aabb(fx.shape, p.aabb, xf, i);
+      int pi = (int)proxies.size();
+      p.proxy_id = broad_phase.create_proxy(p.aabb, pi);
+      p.fixture = fi;
+      p.child_index = i;
+      proxies.push_back(p);
+    }
+  }
+  void fixture_synchronize(int fi, const Transform& xf1, const Transform& xf2) {  // b2_fixture.rs(private):147-173
+    Fixture& fx = fixtures[fi];
+    if (fx.proxy_count == 0) return;
+    for (int i = 0; i < fx.proxy_count; ++i) {
+      FixtureProxy& p = proxies[fx.proxy_first + i];
+      AABB aabb1, aabb2;
+      shape_compute_aabb(fx.shape, aabb1, xf1, p.child_index);
+      shape_compute_aabb(fx.shape, aabb2, xf2, p.child_index);
+      p.aabb.combine_two(aabb1, aabb2);
+      Vec2 displacement = aabb2.get_center() - aabb1.get_center();
+      broad_phase.move_proxy(p.proxy_id, p.aabb, displacement);
+    }
+  }
+  void synchronize_fixtures(int bi) {  // b2_body.rs(private):455-475
+    Body& b = bodies[bi];
+    if (b.flags & BF_AWAKE) {
+      Transform xf1;
+      xf1.q.set(b.sweep.a0);
+      xf1.p = b.sweep.c0 - b2_mul_rot(xf1.q, b.sweep.local_center);
+      for (int f = b.fixture_list; f != -1; f = fixtures[f].next) fixture_synchronize(f, xf1, b.xf);
+    } else {
+      for (int f = b.fixture_list; f != -1; f = fixtures[f].next) fixture_synchronize(f, b.xf, b.xf);
+    }
+  }
+  void set_transform(int bi, Vec2 position, float angle) {  // b2_body.rs(private):418-444
+    Body& b = bodies[bi];
+    b.xf.q.set(angle);
+    b.xf.p = position;
+    b.sweep.c = b2_mul_xf(b.xf, b.sweep.local_center);
+    b.sweep.a = angle;
+    b.sweep.c0 = b.sweep.c;
+    b.sweep.a0 = angle;
+    for (int f = b.fixture_list; f != -1; f = fixtures[f].next) fixture_synchronize(f, b.xf, b.xf);
+    new_contacts = true;
+  }
+  void set_linear_velocity(int bi, Vec2 v) {  // src/b2_body.rs set_linear_velocity
+    Body& b = bodies[bi];
+    if (b.type == STATIC_BODY) return;
+    if (b2_dot(v, v) > 0.0f) set_awake(bi, true);
+    b.linear_velocity = v;
+  }
+  void set_angular_velocity(int bi, float w) {
+    Body& b = bodies[bi];
+    if (b.type == STATIC_BODY) return;
+    if (w * w > 0.0f) set_awake(bi, true);
+    b.angular_velocity = w;
+  }
+  void apply_force_to_center(int bi, Vec2 f, bool wake) {  // src/b2_body.rs apply_force_to_center
+    Body& b = bodies[bi];
+    if (b.type != DYNAMIC_BODY) return;
+    if (wake && !(b.flags & BF_AWAKE)) set_awake(bi, true);
+    if (b.flags & BF_AWAKE) b.force += f;
+  }
+  bool body_should_collide(int self_, int other) const {  // b2_body.rs(private):391-416 (no joints in scope)
+    if (bodies[self_].type != DYNAMIC_BODY && bodies[other].type != DYNAMIC_BODY) return false;
+    return true;
+  }
+  bool filter_should_collide(int fa, int fb) const {  // b2_world_callbacks.rs(private):6-18
+    const Filter& a = fixtures[fa].filter;
+    const Filter& b = fixtures[fb].filter;
+    if (a.group_index == b.group_index && a.group_index != 0) return a.group_index > 0;
+    return (a.mask_bits & b.category_bits) != 0 && (a.category_bits & b.mask_bits) != 0;
+  }
+
+  // -------------------------------------------------------------- contacts
+  ContactEdge& edge(int e) { return (e & 1) ? contacts[e >> 1].node_b : contacts[e >> 1].node_a; }
+  static bool type_pair_registered(int t1, int t2, bool& primary) {  // b2_contact_registers.rs:67-103
+    // primary pairs: (circle,circle) (polygon,circle) (polygon,polygon) (edge,circle) (edge,polygon)
+    //                (chain,circle) (chain,polygon)
+    auto is_primary = [](int a, int b) {
+      return (a == E_CIRCLE && b == E_CIRCLE) || (a == E_POLYGON && b == E_CIRCLE) || (a == E_POLYGON && b == E_POLYGON) ||
+             (a == E_EDGE && b == E_CIRCLE) || (a == E_EDGE && b == E_POLYGON) || (a == E_CHAIN && b == E_CIRCLE) ||
+             (a == E_CHAIN && b == E_POLYGON);
+    };
+    if (is_primary(t1, t2)) { primary = true; return true; }
+    if (is_primary(t2, t1)) { primary = false; return true; }
+    return false;
+  }
+  void add_pair(int proxy_a, int proxy_b) {  // b2_contact_manager.rs(private):178-302
+    int fixture_a = proxies[proxy_a].fixture, fixture_b = proxies[proxy_b].fixture;
+    int index_a = proxies[proxy_a].child_index, index_b = proxies[proxy_b].child_index;
+    int body_a = fixtures[fixture_a].body, body_b = fixtures[fixture_b].body;
+    if (body_a == body_b) return;
+    for (int e = bodies[body_b].contact_list; e != -1; e = edge(e).next) {
+      if (edge(e).other == body_a) {
+        const Contact& c = contacts[e >> 1];
+        if (c.fixture_a == fixture_a && c.fixture_b == fixture_b && c.index_a == index_a && c.index_b == index_b) return;
+        if (c.fixture_a == fixture_b && c.fixture_b == fixture_a && c.index_a == index_b && c.index_b == index_a) return;
+      }
+    }
+    if (!body_should_collide(body_b, body_a)) return;
+    if (!filter_should_collide(fixture_a, fixture_b)) return;
+    // B2contact::create — b2_contact.rs(private):11-31
+    bool primary = true;
+    bool ok = type_pair_registered(fixtures[fixture_a].shape.type, fixtures[fixture_b].shape.type, primary);
+    assert(ok && "unregistered shape pair: the reference panics here (unwrap)");
+    (void)ok;
+    if (!primary) { std::swap(fixture_a, fixture_b); std::swap(index_a, index_b); }
+    int ci;
+    if (!contact_free.empty()) { ci = contact_free.back(); contact_free.pop_back(); }
+    else { ci = (int)contacts.size(); contacts.emplace_back(); }
+    Contact& c = contacts[ci];
+    c = Contact();
+    c.alive = true;
+    c.flags = CF_ENABLED;  // b2_contact.rs(private):48-99
+    c.fixture_a = fixture_a; c.fixture_b = fixture_b; c.index_a = index_a; c.index_b = index_b;
+    c.friction = sqrtf(fixtures[fixture_a].friction * fixtures[fixture_b].friction);
+    c.restitution = fixtures[fixture_a].restitution > fixtures[fixture_b].restitution ? fixtures[fixture_a].restitution
+                                                                                       : fixtures[fixture_b].restitution;
+    c.restitution_threshold = fixtures[fixture_a].restitution_threshold < fixtures[fixture_b].restitution_threshold
+                                  ? fixtures[fixture_a].restitution_threshold
+                                  : fixtures[fixture_b].restitution_threshold;
+    body_a = fixtures[fixture_a].body;
+    body_b = fixtures[fixture_b].body;
+    // world list push_front
+    c.prev = -1;
+    c.next = contact_list;
+    if (contact_list != -1) contacts[contact_list].prev = ci;
+    contact_list = ci;
+    // body A edge list push_front
+    c.node_a.other = body_b;
+    c.node_a.prev = -1;
+    c.node_a.next = bodies[body_a].contact_list;
+    if (bodies[body_a].contact_list != -1) edge(bodies[body_a].contact_list).prev = 2 * ci;
+    bodies[body_a].contact_list = 2 * ci;
+    // body B
+    c.node_b.other = body_a;
+    c.node_b.prev = -1;
+    c.node_b.next = bodies[body_b].contact_list;
+    if (bodies[body_b].contact_list != -1) edge(bodies[body_b].contact_list).prev = 2 * ci + 1;
+    bodies[body_b].contact_list = 2 * ci + 1;
+    ++contact_count;
+    ++stats.created;
+  }
+  void destroy_contact(int ci) {  // b2_contact_manager.rs(private):24-78 ; b2_contact.rs(private):33-46
+    Contact& c = contacts[ci];
+    int body_a = fixtures[c.fixture_a].body, body_b = fixtures[c.fixture_b].body;
+    if (c.prev != -1) contacts[c.prev].next = c.next;
+    if (c.next != -1) contacts[c.next].prev = c.prev;
+    if (contact_list == ci) contact_list = c.next;
+    if (c.node_a.prev != -1) edge(c.node_a.prev).next = c.node_a.next;
+    if (c.node_a.next != -1) edge(c.node_a.next).prev = c.node_a.prev;
+    if (bodies[body_a].contact_list == 2 * ci) bodies[body_a].contact_list = c.node_a.next;
+    if (c.node_b.prev != -1) edge(c.node_b.prev).next = c.node_b.next;
+    if (c.node_b.next != -1) edge(c.node_b.next).prev = c.node_b.prev;
+    if (bodies[body_b].contact_list == 2 * ci + 1) bodies[body_b].contact_list = c.node_b.next;
+    if (c.manifold.point_count > 0 && !fixtures[c.fixture_a].is_sensor && !fixtures[c.fixture_b].is_sensor) {
+      set_awake(body_a, true);
+      set_awake(body_b, true);
+    }
+    c.alive = false;
+    contact_free.push_back(ci);
+    --contact_count;
+    ++stats.destroyed;
+  }
+  void evaluate(const Contact& c, Manifold& m, const Transform& xf_a, const Transform& xf_b) {  // contacts/*.rs:45-56
+    const Shape& sa = fixtures[c.fixture_a].shape;
+    const Shape& sb = fixtures[c.fixture_b].shape;
+    Shape edge_tmp;
+    const Shape* a = &sa;
+    if (sa.type == E_CHAIN) { chain_get_child_edge(sa, edge_tmp, c.index_a); a = &edge_tmp; }
+    if (a->type == E_CIRCLE && sb.type == E_CIRCLE) collide_circles(m, *a, xf_a, sb, xf_b);
+    else if (a->type == E_POLYGON && sb.type == E_CIRCLE) collide_polygon_and_circle(m, *a, xf_a, sb, xf_b);
+    else if (a->type == E_POLYGON && sb.type == E_POLYGON) collide_polygons(m, *a, xf_a, sb, xf_b);
+    else if (a->type == E_EDGE && sb.type == E_CIRCLE) collide_edge_and_circle(m, *a, xf_a, sb, xf_b);
+    else if (a->type == E_EDGE && sb.type == E_POLYGON) collide_edge_and_polygon(m, *a, xf_a, sb, xf_b);
+    else assert(false);
+  }
+  void contact_update(int ci) {  // b2_contact.rs(private):103-218
+    Contact& c = contacts[ci];
+    c.flags |= CF_ENABLED;
+    Manifold old_manifold = c.manifold;
+    bool was_touching = (c.flags & CF_TOUCHING) != 0;
+    bool sensor = fixtures[c.fixture_a].is_sensor || fixtures[c.fixture_b].is_sensor;
+    int body_a = fixtures[c.fixture_a].body, body_b = fixtures[c.fixture_b].body;
+    const Transform xf_a = bodies[body_a].xf, xf_b = bodies[body_b].xf;
+    bool touching;
+    if (sensor) {
+      assert(false && "sensor overlap (GJK) is out of scope (SURVEY.md §8f)");
+      touching = false;
+      c.manifold.point_count = 0;
+    } else {
+      Manifold nm;
+      evaluate(c, nm, xf_a, xf_b);
+      c.manifold = nm;
+      touching = c.manifold.point_count > 0;
+      for (int i = 0; i < c.manifold.point_count; ++i) {
+        ManifoldPoint& mp2 = c.manifold.points[i];
+        mp2.normal_impulse = 0.0f;
+        mp2.tangent_impulse = 0.0f;
+        for (int j = 0; j < old_manifold.point_count; ++j) {
+          const ManifoldPoint& mp1 = old_manifold.points[j];
+          if (mp1.id == mp2.id) {
+            mp2.normal_impulse = mp1.normal_impulse;
+            mp2.tangent_impulse = mp1.tangent_impulse;
+            break;
+          }
+        }
+      }
+      if (touching != was_touching) {
+        set_awake(body_a, true);
+        set_awake(body_b, true);
+      }
+    }
+    if (touching) c.flags |= CF_TOUCHING; else c.flags &= ~CF_TOUCHING;
+  }
+  void collide() {  // b2_contact_manager.rs(private):83-171 — destroys AFTER the loop (box2d-rs deviation)
+    std::vector<int> to_destroy;
+    for (int ci = contact_list; ci != -1; ci = contacts[ci].next) {
+      Contact& c = contacts[ci];
+      int body_a = fixtures[c.fixture_a].body, body_b = fixtures[c.fixture_b].body;
+      if (c.flags & CF_FILTER) {
+        if (!body_should_collide(body_b, body_a)) { to_destroy.push_back(ci); continue; }
+        if (!filter_should_collide(c.fixture_a, c.fixture_b)) { to_destroy.push_back(ci); continue; }
+        c.flags &= ~CF_FILTER;
+      }
+      bool active_a = (bodies[body_a].flags & BF_AWAKE) && bodies[body_a].type != STATIC_BODY;
+      bool active_b = (bodies[body_b].flags & BF_AWAKE) && bodies[body_b].type != STATIC_BODY;
+      if (!active_a && !active_b) continue;
+      int proxy_id_a = proxies[fixtures[c.fixture_a].proxy_first + c.index_a].proxy_id;
+      int proxy_id_b = proxies[fixtures[c.fixture_b].proxy_first + c.index_b].proxy_id;
+      if (!broad_phase.test_overlap(proxy_id_a, proxy_id_b)) { to_destroy.push_back(ci); continue; }
+      contact_update(ci);
+    }
+    for (int ci : to_destroy) destroy_contact(ci);
+  }
+  void find_new_contacts() {  // :173-176
+    stats.moved += (int)broad_phase.move_buffer.size();
+    broad_phase.update_pairs([this](int pa, int pb) { add_pair(pa, pb); });
+    stats.pairs += (int)broad_phase.pair_buffer.size();
+  }
+
+  // ---------------------------------------------------------------- island
+  struct Island {
+    std::vector<int> bodies, contacts;
+    std::vector<Position> positions;
+    std::vector<Velocity> velocities;
+    void clear() { bodies.clear(); contacts.clear(); }
+  };
+  std::vector<ContactVelocityConstraint> vcs;
+  std::vector<ContactPositionConstraint> pcs;
+
+  void solver_new(const Island& is, const TimeStep& step) {  // b2_contact_solver_private.rs:20-110
+    size_t count = is.contacts.size();
+    vcs.assign(count, ContactVelocityConstraint());
+    pcs.assign(count, ContactPositionConstraint());
+    for (size_t i = 0; i < count; ++i) {
+      const Contact& contact = contacts[is.contacts[i]];
+      const Fixture& fa = fixtures[contact.fixture_a];
+      const Fixture& fb = fixtures[contact.fixture_b];
+      float radius_a = fa.shape.radius, radius_b = fb.shape.radius;
+      const Body& body_a = bodies[fa.body];
+      const Body& body_b = bodies[fb.body];
+      const Manifold& manifold = contact.manifold;
+      int point_count = manifold.point_count;
+      ContactVelocityConstraint& vc = vcs[i];
+      vc.friction = contact.friction;
+      vc.restitution = contact.restitution;
+      vc.threshold = contact.restitution_threshold;
+      vc.tangent_speed = contact.tangent_speed;
+      vc.index_a = body_a.island_index;
+      vc.index_b = body_b.island_index;
+      vc.inv_mass_a = body_a.inv_mass;
+      vc.inv_mass_b = body_b.inv_mass;
+      vc.inv_ia = body_a.inv_i;
+      vc.inv_ib = body_b.inv_i;
+      vc.contact_index = (int)i;
+      vc.point_count = point_count;
+      vc.k.set_zero();
+      vc.normal_mass.set_zero();
+      ContactPositionConstraint& pc = pcs[i];
+      pc.index_a = body_a.island_index;
+      pc.index_b = body_b.island_index;
+      pc.inv_mass_a = body_a.inv_mass;
+      pc.inv_mass_b = body_b.inv_mass;
+      pc.local_center_a = body_a.sweep.local_center;
+      pc.local_center_b = body_b.sweep.local_center;
+      pc.inv_ia = body_a.inv_i;
+      pc.inv_ib = body_b.inv_i;
+      pc.local_normal = manifold.local_normal;
+      pc.local_point = manifold.local_point;
+      pc.point_count = point_count;
+      pc.radius_a = radius_a;
+      pc.radius_b = radius_b;
+      pc.type = manifold.type;
+      for (int j = 0; j < point_count; ++j) {
+        const ManifoldPoint& cp = manifold.points[j];
+        VelocityConstraintPoint& vcp = vc.points[j];
+        if (step.warm_starting) {
+          vcp.normal_impulse = step.dt_ratio * cp.normal_impulse;
+          vcp.tangent_impulse = step.dt_ratio * cp.tangent_impulse;
+        } else {
+          vcp.normal_impulse = 0.0f;
+          vcp.tangent_impulse = 0.0f;
+        }
+        vcp.r_a.set_zero();
+        vcp.r_b.set_zero();
+        vcp.normal_mass = 0.0f;
+        vcp.tangent_mass = 0.0f;
+        vcp.velocity_bias = 0.0f;
+        pc.local_points[j] = cp.local_point;
+      }
+    }
+  }
+  void initialize_velocity_constraints(const Island& is) {  // :113-226
+    for (size_t i = 0; i < is.contacts.size(); ++i) {
+      ContactVelocityConstraint& vc = vcs[i];
+      ContactPositionConstraint& pc = pcs[i];
+      float radius_a = pc.radius_a, radius_b = pc.radius_b;
+      const Manifold& manifold = contacts[is.contacts[vc.contact_index]].manifold;
+      int index_a = vc.index_a, index_b = vc.index_b;
+      float m_a = vc.inv_mass_a, m_b = vc.inv_mass_b, i_a = vc.inv_ia, i_b = vc.inv_ib;
+      Vec2 local_center_a = pc.local_center_a, local_center_b = pc.local_center_b;
+      Vec2 c_a = is.positions[index_a].c;
+      float a_a = is.positions[index_a].a;
+      Vec2 v_a = is.velocities[index_a].v;
+      float w_a = is.velocities[index_a].w;
+      Vec2 c_b = is.positions[index_b].c;
+      float a_b = is.positions[index_b].a;
+      Vec2 v_b = is.velocities[index_b].v;
+      float w_b = is.velocities[index_b].w;
+      Transform xf_a, xf_b;
+      xf_a.q.set(a_a);
+      xf_b.q.set(a_b);
+      xf_a.p = c_a - b2_mul_rot(xf_a.q, local_center_a);
+      xf_b.p = c_b - b2_mul_rot(xf_b.q, local_center_b);
+      WorldManifold wm;
+      world_manifold_initialize(wm, manifold, xf_a, radius_a, xf_b, radius_b);
+      vc.normal = wm.normal;
+      int point_count = vc.point_count;
+      for (int j = 0; j < point_count; ++j) {
+        VelocityConstraintPoint& vcp = vc.points[j];
+        vcp.r_a = wm.points[j] - c_a;
+        vcp.r_b = wm.points[j] - c_b;
+        float rn_a = b2_cross(vcp.r_a, vc.normal);
+        float rn_b = b2_cross(vcp.r_b, vc.normal);
+        float k_normal = m_a + m_b + i_a * rn_a * rn_a + i_b * rn_b * rn_b;
+        vcp.normal_mass = k_normal > 0.0f ? 1.0f / k_normal : 0.0f;
+        Vec2 tangent = b2_cross_vs(vc.normal, 1.0f);
+        float rt_a = b2_cross(vcp.r_a, tangent);
+        float rt_b = b2_cross(vcp.r_b, tangent);
+        float k_tangent = m_a + m_b + i_a * rt_a * rt_a + i_b * rt_b * rt_b;
+        vcp.tangent_mass = k_tangent > 0.0f ? 1.0f / k_tangent : 0.0f;
+        vcp.velocity_bias = 0.0f;
+        float v_rel = b2_dot(vc.normal, v_b + b2_cross_sv(w_b, vcp.r_b) - v_a - b2_cross_sv(w_a, vcp.r_a));
+        if (v_rel < -vc.threshold) vcp.velocity_bias = -vc.restitution * v_rel;
+      }
+      if (vc.point_count == 2 && block_solve) {
+        const VelocityConstraintPoint& vcp1 = vc.points[0];
+        const VelocityConstraintPoint& vcp2 = vc.points[1];
+        float rn1_a = b2_cross(vcp1.r_a, vc.normal);
+        float rn1_b = b2_cross(vcp1.r_b, vc.normal);
+        float rn2_a = b2_cross(vcp2.r_a, vc.normal);
+        float rn2_b = b2_cross(vcp2.r_b, vc.normal);
+        float k11 = m_a + m_b + i_a * rn1_a * rn1_a + i_b * rn1_b * rn1_b;
+        float k22 = m_a + m_b + i_a * rn2_a * rn2_a + i_b * rn2_b * rn2_b;
+        float k12 = m_a + m_b + i_a * rn1_a * rn2_a + i_b * rn1_b * rn2_b;
+        const float k_max_condition_number = 1000.0f;
+        if (k11 * k11 < k_max_condition_number * (k11 * k22 - k12 * k12)) {
+          vc.k.ex.set(k11, k12);
+          vc.k.ey.set(k12, k22);
+          vc.normal_mass = vc.k.get_inverse();
+        } else {
+          vc.point_count = 1;
+        }
+      }
+    }
+  }
+  void warm_start(Island& is) {  // :228-266
+    for (auto& vc : vcs) {
+      int index_a = vc.index_a, index_b = vc.index_b;
+      float m_a = vc.inv_mass_a, i_a = vc.inv_ia, m_b = vc.inv_mass_b, i_b = vc.inv_ib;
+      int point_count = vc.point_count;
+      Vec2 v_a = is.velocities[index_a].v;
+      float w_a = is.velocities[index_a].w;
+      Vec2 v_b = is.velocities[index_b].v;
+      float w_b = is.velocities[index_b].w;
+      Vec2 normal = vc.normal;
+      Vec2 tangent = b2_cross_vs(normal, 1.0f);
+      for (int j = 0; j < point_count; ++j) {
+        const VelocityConstraintPoint& vcp = vc.points[j];
+        Vec2 p = vcp.normal_impulse * normal + vcp.tangent_impulse * tangent;
+        w_a -= i_a * b2_cross(vcp.r_a, p);
+        v_a -= m_a * p;
+        w_b += i_b * b2_cross(vcp.r_b, p);
+        v_b += m_b * p;
+      }
+      is.velocities[index_a].v = v_a;
+      is.velocities[index_a].w = w_a;
+      is.velocities[index_b].v = v_b;
+      is.velocities[index_b].w = w_b;
+    }
+  }
+  void solve_velocity_constraints(Island& is) {  // :268-583
+    for (auto& vc : vcs) {
+      int index_a = vc.index_a, index_b = vc.index_b;
+      float m_a = vc.inv_mass_a, i_a = vc.inv_ia, m_b = vc.inv_mass_b, i_b = vc.inv_ib;
+      int point_count = vc.point_count;
+      Vec2 v_a = is.velocities[index_a].v;
+      float w_a = is.velocities[index_a].w;
+      Vec2 v_b = is.velocities[index_b].v;
+      float w_b = is.velocities[index_b].w;
+      Vec2 normal = vc.normal;
+      Vec2 tangent = b2_cross_vs(normal, 1.0f);
+      float friction = vc.friction;
+      for (int j = 0; j < point_count; ++j) {
+        VelocityConstraintPoint& vcp = vc.points[j];
+        Vec2 dv = v_b + b2_cross_sv(w_b, vcp.r_b) - v_a - b2_cross_sv(w_a, vcp.r_a);
+        float vt = b2_dot(dv, tangent) - vc.tangent_speed;
+        float lambda = vcp.tangent_mass * (-vt);
+        float max_friction = friction * vcp.normal_impulse;
+        float new_impulse = b2_clamp(vcp.tangent_impulse + lambda, -max_friction, max_friction);
+        lambda = new_impulse - vcp.tangent_impulse;
+        vcp.tangent_impulse = new_impulse;
+        Vec2 p = lambda * tangent;
+        v_a -= m_a * p;
+        w_a -= i_a * b2_cross(vcp.r_a, p);
+        v_b += m_b * p;
+        w_b += i_b * b2_cross(vcp.r_b, p);
+      }
+      if (point_count == 1 || block_solve == false) {
+        for (int j = 0; j < point_count; ++j) {
+          VelocityConstraintPoint& vcp = vc.points[j];
+          Vec2 dv = v_b + b2_cross_sv(w_b, vcp.r_b) - v_a - b2_cross_sv(w_a, vcp.r_a);
+          float vn = b2_dot(dv, normal);
+          float lambda = -vcp.normal_mass * (vn - vcp.velocity_bias);
+          float new_impulse = b2_max(vcp.normal_impulse + lambda, 0.0f);
+          lambda = new_impulse - vcp.normal_impulse;
+          vcp.normal_impulse = new_impulse;
+          Vec2 p = lambda * normal;
+          v_a -= m_a * p;
+          w_a -= i_a * b2_cross(vcp.r_a, p);
+          v_b += m_b * p;
+          w_b += i_b * b2_cross(vcp.r_b, p);
+        }
+      } else {
+        VelocityConstraintPoint& cp1 = vc.points[0];
+        VelocityConstraintPoint& cp2 = vc.points[1];
+        Vec2 a(cp1.normal_impulse, cp2.normal_impulse);
+        Vec2 dv1 = v_b + b2_cross_sv(w_b, cp1.r_b) - v_a - b2_cross_sv(w_a, cp1.r_a);
+        Vec2 dv2 = v_b + b2_cross_sv(w_b, cp2.r_b) - v_a - b2_cross_sv(w_a, cp2.r_a);
+        float vn1 = b2_dot(dv1, normal);
+        float vn2 = b2_dot(dv2, normal);
+        Vec2 b(vn1 - cp1.velocity_bias, vn2 - cp2.velocity_bias);
+        b -= b2_mul(vc.k, a);
+        for (;;) {
+          Vec2 x = -b2_mul(vc.normal_mass, b);
+          if (x.x >= 0.0f && x.y >= 0.0f) {
+            Vec2 d = x - a;
+            Vec2 p1 = d.x * normal, p2 = d.y * normal;
+            v_a -= m_a * (p1 + p2);
+            w_a -= i_a * (b2_cross(cp1.r_a, p1) + b2_cross(cp2.r_a, p2));
+            v_b += m_b * (p1 + p2);
+            w_b += i_b * (b2_cross(cp1.r_b, p1) + b2_cross(cp2.r_b, p2));
+            cp1.normal_impulse = x.x;
+            cp2.normal_impulse = x.y;
+            break;
+          }
+          x.x = -cp1.normal_mass * b.x;
+          x.y = 0.0f;
+          vn1 = 0.0f;
+          vn2 = vc.k.ex.y * x.x + b.y;
+          if (x.x >= 0.0f && vn2 >= 0.0f) {
+            Vec2 d = x - a;
+            Vec2 p1 = d.x * normal, p2 = d.y * normal;
+            v_a -= m_a * (p1 + p2);
+            w_a -= i_a * (b2_cross(cp1.r_a, p1) + b2_cross(cp2.r_a, p2));
+            v_b += m_b * (p1 + p2);
+            w_b += i_b * (b2_cross(cp1.r_b, p1) + b2_cross(cp2.r_b, p2));
+            cp1.normal_impulse = x.x;
+            cp2.normal_impulse = x.y;
+            break;
+          }
+          x.x = 0.0f;
+          x.y = -cp2.normal_mass * b.y;
+          vn1 = vc.k.ey.x * x.y + b.x;
+          vn2 = 0.0f;
+          if (x.y >= 0.0f && vn1 >= 0.0f) {
+            Vec2 d = x - a;
+            Vec2 p1 = d.x * normal, p2 = d.y * normal;
+            v_a -= m_a * (p1 + p2);
+            w_a -= i_a * (b2_cross(cp1.r_a, p1) + b2_cross(cp2.r_a, p2));
+            v_b += m_b * (p1 + p2);
+            w_b += i_b * (b2_cross(cp1.r_b, p1) + b2_cross(cp2.r_b, p2));
+            cp1.normal_impulse = x.x;
+            cp2.normal_impulse = x.y;
+            break;
+          }
+          x.x = 0.0f;
+          x.y = 0.0f;
+          vn1 = b.x;
+          vn2 = b.y;
+          if (vn1 >= 0.0f && vn2 >= 0.0f) {
+            Vec2 d = x - a;
+            Vec2 p1 = d.x * normal, p2 = d.y * normal;
+            v_a -= m_a * (p1 + p2);
+            w_a -= i_a * (b2_cross(cp1.r_a, p1) + b2_cross(cp2.r_a, p2));
+            v_b += m_b * (p1 + p2);
+            w_b += i_b * (b2_cross(cp1.r_b, p1) + b2_cross(cp2.r_b, p2));
+            cp1.normal_impulse = x.x;
+            cp2.normal_impulse = x.y;
+            break;
+          }
+          break;
+        }
+      }
+      is.velocities[index_a].v = v_a;
+      is.velocities[index_a].w = w_a;
+      is.velocities[index_b].v = v_b;
+      is.velocities[index_b].w = w_b;
+    }
+  }
+  void store_impulses(const Island& is) {  // :585-598
+    for (auto& vc : vcs) {
+      Manifold& manifold = contacts[is.contacts[vc.contact_index]].manifold;
+      for (int j = 0; j < vc.point_count; ++j) {
+        manifold.points[j].normal_impulse = vc.points[j].normal_impulse;
+        manifold.points[j].tangent_impulse = vc.points[j].tangent_impulse;
+      }
+    }
+  }
+  bool solve_position_constraints(Island& is) {  // :600-730
+    float min_separation = 0.0f;
+    for (auto& pc : pcs) {
+      int index_a = pc.index_a, index_b = pc.index_b;
+      Vec2 local_center_a = pc.local_center_a;
+      float m_a = pc.inv_mass_a, i_a = pc.inv_ia;
+      Vec2 local_center_b = pc.local_center_b;
+      float m_b = pc.inv_mass_b, i_b = pc.inv_ib;
+      int point_count = pc.point_count;
+      Vec2 c_a = is.positions[index_a].c;
+      float a_a = is.positions[index_a].a;
+      Vec2 c_b = is.positions[index_b].c;
+      float a_b = is.positions[index_b].a;
+      for (int j = 0; j < point_count; ++j) {
+        Transform xf_a, xf_b;
+        xf_a.q.set(a_a);
+        xf_b.q.set(a_b);
+        xf_a.p = c_a - b2_mul_rot(xf_a.q, local_center_a);
+        xf_b.p = c_b - b2_mul_rot(xf_b.q, local_center_b);
+        Vec2 normal, point;
+        float separation;
+        switch (pc.type) {
+          case E_CIRCLES: {
+            Vec2 point_a = b2_mul_xf(xf_a, pc.local_point);
+            Vec2 point_b = b2_mul_xf(xf_b, pc.local_points[0]);
+            normal = point_b - point_a;
+            normal.normalize();
+            point = 0.5f * (point_a + point_b);
+            separation = b2_dot(point_b - point_a, normal) - pc.radius_a - pc.radius_b;
+          } break;
+          case E_FACE_A: {
+            normal = b2_mul_rot(xf_a.q, pc.local_normal);
+            Vec2 plane_point = b2_mul_xf(xf_a, pc.local_point);
+            Vec2 clip_point = b2_mul_xf(xf_b, pc.local_points[j]);
+            separation = b2_dot(clip_point - plane_point, normal) - pc.radius_a - pc.radius_b;
+            point = clip_point;
+          } break;
+          default: {
+            normal = b2_mul_rot(xf_b.q, pc.local_normal);
+            Vec2 plane_point = b2_mul_xf(xf_b, pc.local_point);
+            Vec2 clip_point = b2_mul_xf(xf_a, pc.local_points[j]);
+            separation = b2_dot(clip_point - plane_point, normal) - pc.radius_a - pc.radius_b;
+            point = clip_point;
+            normal = -normal;
+          } break;
+        }
+        Vec2 r_a = point - c_a, r_b = point - c_b;
+        min_separation = b2_min(min_separation, separation);
+        float c = b2_clamp(BAUMGARTE * (separation + LINEAR_SLOP), -MAX_LINEAR_CORRECTION, 0.0f);
+        float rn_a = b2_cross(r_a, normal);
+        float rn_b = b2_cross(r_b, normal);
+        float k = m_a + m_b + i_a * rn_a * rn_a + i_b * rn_b * rn_b;
+        float impulse = k > 0.0f ? -c / k : 0.0f;
+        Vec2 p = impulse * normal;
+        c_a -= m_a * p;
+        a_a -= i_a * b2_cross(r_a, p);
+        c_b += m_b * p;
+        a_b += i_b * b2_cross(r_b, p);
+      }
+      is.positions[index_a].c = c_a;
+      is.positions[index_a].a = a_a;
+      is.positions[index_b].c = c_b;
+      is.positions[index_b].a = a_b;
+    }
+    return min_separation >= -3.0f * LINEAR_SLOP;
+  }
+
+  // Diagnostic (not part of the reference): depth of the dependency DAG of one in-order
+  // sweep over the island's constraints, where only bodies with non-zero inverse mass or
+  // inertia create dependencies.
+  int wavefront_depth(const Island& is, int sweeps) const {
+    std::vector<int> last(is.bodies.size(), 0);
+    int depth = 0;
+    for (int s = 0; s < sweeps; ++s)
+      for (auto& vc : vcs) {
+        bool dyn_a = vc.inv_mass_a != 0.0f || vc.inv_ia != 0.0f;
+        bool dyn_b = vc.inv_mass_b != 0.0f || vc.inv_ib != 0.0f;
+        int l = 0;
+        if (dyn_a) l = std::max(l, last[vc.index_a]);
+        if (dyn_b) l = std::max(l, last[vc.index_b]);
+        ++l;
+        if (dyn_a) last[vc.index_a] = l;
+        if (dyn_b) last[vc.index_b] = l;
+        depth = std::max(depth, l);
+      }
+    return depth;
+  }
+
+  void island_solve(Island& is, const TimeStep& step) {  // b2_island_private.rs:129-328
+    double t0 = now_ms();
+    float h = step.dt;
+    is.positions.resize(is.bodies.size());
+    is.velocities.resize(is.bodies.size());
+    for (size_t i = 0; i < is.bodies.size(); ++i) {
+      Body& b = bodies[is.bodies[i]];
+      Vec2 c = b.sweep.c;
+      float a = b.sweep.a;
+      Vec2 v = b.linear_velocity;
+      float w = b.angular_velocity;
+      b.sweep.c0 = b.sweep.c;
+      b.sweep.a0 = b.sweep.a;
+      if (b.type == DYNAMIC_BODY) {
+        v += (h * b.inv_mass) * ((b.gravity_scale * b.mass) * gravity + b.force);
+        w += h * b.inv_i * b.torque;
+        v *= 1.0f / (1.0f + h * b.linear_damping);
+        w *= 1.0f / (1.0f + h * b.angular_damping);
+      }
+      is.positions[i].c = c;
+      is.positions[i].a = a;
+      is.velocities[i].v = v;
+      is.velocities[i].w = w;
+    }
+    solver_new(is, step);
+    initialize_velocity_constraints(is);
+    if (step.warm_starting) warm_start(is);
+    if (collect_levels) stats.solver_levels = std::max(stats.solver_levels, wavefront_depth(is, step.velocity_iterations));
+    double t1 = now_ms();
+    profile.solve_init += t1 - t0;
+    for (int it = 0; it < step.velocity_iterations; ++it) solve_velocity_constraints(is);
+    store_impulses(is);
+    double t2 = now_ms();
+    profile.solve_velocity += t2 - t1;
+    for (size_t i = 0; i < is.bodies.size(); ++i) {
+      Vec2 c = is.positions[i].c;
+      float a = is.positions[i].a;
+      Vec2 v = is.velocities[i].v;
+      float w = is.velocities[i].w;
+      Vec2 translation = h * v;
+      if (b2_dot(translation, translation) > MAX_TRANSLATION_SQUARED) {
+        float ratio = MAX_TRANSLATION / translation.length();
+        v *= ratio;
+      }
+      float rotation = h * w;
+      if (rotation * rotation > MAX_ROTATION_SQUARED) {
+        float ratio = MAX_ROTATION / fabsf(rotation);
+        w *= ratio;
+      }
+      c += h * v;
+      a += h * w;
+      is.positions[i].c = c;
+      is.positions[i].a = a;
+      is.velocities[i].v = v;
+      is.velocities[i].w = w;
+    }
+    bool position_solved = false;
+    for (int it = 0; it < step.position_iterations; ++it) {
+      bool contacts_okay = solve_position_constraints(is);
+      if (contacts_okay) { position_solved = true; break; }
+    }
+    for (size_t i = 0; i < is.bodies.size(); ++i) {
+      Body& body = bodies[is.bodies[i]];
+      body.sweep.c = is.positions[i].c;
+      body.sweep.a = is.positions[i].a;
+      body.linear_velocity = is.velocities[i].v;
+      body.angular_velocity = is.velocities[i].w;
+      synchronize_transform(body);
+    }
+    profile.solve_position += now_ms() - t2;
+    if (allow_sleep) {
+      float min_sleep_time = MAX_FLOAT;
+      const float lin_tol_sqr = LINEAR_SLEEP_TOLERANCE * LINEAR_SLEEP_TOLERANCE;
+      const float ang_tol_sqr = ANGULAR_SLEEP_TOLERANCE * ANGULAR_SLEEP_TOLERANCE;
+      for (int bi : is.bodies) {
+        Body& b = bodies[bi];
+        if (b.type == STATIC_BODY) continue;
+        if (!(b.flags & BF_AUTO_SLEEP) || b.angular_velocity * b.angular_velocity > ang_tol_sqr ||
+            b2_dot(b.linear_velocity, b.linear_velocity) > lin_tol_sqr) {
+          b.sleep_time = 0.0f;
+          min_sleep_time = 0.0f;
+        } else {
+          b.sleep_time += h;
+          min_sleep_time = b2_min(min_sleep_time, b.sleep_time);
+        }
+      }
+      if (min_sleep_time >= TIME_TO_SLEEP && position_solved)
+        for (int bi : is.bodies) set_awake(bi, false);
+    }
+  }
+
+  void solve(const TimeStep& step) {  // b2_world.rs(private):356-531
+    profile.solve_init = profile.solve_velocity = profile.solve_position = 0.0;
+    Island island;
+    for (int b = body_list; b != -1; b = bodies[b].next) bodies[b].flags &= ~BF_ISLAND;
+    for (int c = contact_list; c != -1; c = contacts[c].next) contacts[c].flags &= ~CF_ISLAND;
+    std::vector<int> stack;
+    stack.reserve(bodies.size());
+    for (int seed = body_list; seed != -1; seed = bodies[seed].next) {
+      {
+        const Body& s = bodies[seed];
+        if (s.flags & BF_ISLAND) continue;
+        if (!(s.flags & BF_AWAKE) || !(s.flags & BF_ENABLED)) continue;
+        if (s.type == STATIC_BODY) continue;
+      }
+      island.clear();
+      stack.clear();
+      stack.push_back(seed);
+      bodies[seed].flags |= BF_ISLAND;
+      while (!stack.empty()) {
+        int bi = stack.back();
+        stack.pop_back();
+        bodies[bi].island_index = (int)island.bodies.size();  // b2_island.rs:52-55
+        island.bodies.push_back(bi);
+        if (bodies[bi].type == STATIC_BODY) continue;
+        bodies[bi].flags |= BF_AWAKE;
+        for (int e = bodies[bi].contact_list; e != -1; e = edge(e).next) {
+          Contact& contact = contacts[e >> 1];
+          if (contact.flags & CF_ISLAND) continue;
+          if (!(contact.flags & CF_ENABLED) || !(contact.flags & CF_TOUCHING)) continue;
+          if (fixtures[contact.fixture_a].is_sensor || fixtures[contact.fixture_b].is_sensor) continue;
+          island.contacts.push_back(e >> 1);
+          contact.flags |= CF_ISLAND;
+          int other = edge(e).other;
+          if (bodies[other].flags & BF_ISLAND) continue;
+          stack.push_back(other);
+          bodies[other].flags |= BF_ISLAND;
+        }
+      }
+      island_solve(island, step);
+      ++stats.islands;
+      stats.island_bodies += (int)island.bodies.size();
+      stats.island_contacts += (int)island.contacts.size();
+      for (int bi : island.bodies)
+        if (bodies[bi].type == STATIC_BODY) bodies[bi].flags &= ~BF_ISLAND;
+    }
+    double t0 = now_ms();
+    for (int b = body_list; b != -1; b = bodies[b].next) {
+      if (!(bodies[b].flags & BF_ISLAND)) continue;
+      if (bodies[b].type == STATIC_BODY) continue;
+      synchronize_fixtures(b);
+    }
+    find_new_contacts();
+    profile.broadphase = now_ms() - t0;
+  }
+
+  void step(float dt, int velocity_iterations, int position_iterations) {  // b2_world.rs(private):903-959
+    double ts = now_ms();
+    stats = StepStats();
+    if (new_contacts) {
+      find_new_contacts();
+      new_contacts = false;
+    }
+    locked = true;
+    TimeStep st;
+    st.dt = dt;
+    st.velocity_iterations = velocity_iterations;
+    st.position_iterations = position_iterations;
+    st.inv_dt = dt > 0.0f ? 1.0f / dt : 0.0f;
+    st.dt_ratio = inv_dt0 * dt;
+    st.warm_starting = warm_starting;
+    {
+      double t = now_ms();
+      collide();
+      profile.collide = now_ms() - t;
+    }
+    for (int c = contact_list; c != -1; c = contacts[c].next)
+      if (contacts[c].flags & CF_TOUCHING) ++stats.touching;
+    if (step_complete && st.dt > 0.0f) {
+      double t = now_ms();
+      solve(st);
+      profile.solve = now_ms() - t;
+    }
+    // continuous physics (solve_toi) is out of scope and disabled in both engines
+    if (st.dt > 0.0f) inv_dt0 = st.inv_dt;
+    if (clear_forces_flag)
+      for (int b = body_list; b != -1; b = bodies[b].next) {
+        bodies[b].force.set_zero();
+        bodies[b].torque = 0.0f;
+      }
+    locked = false;
+    stats.contacts = contact_count;
+    for (auto& b : bodies)
+      if (b.flags & BF_AWAKE) ++stats.awake_bodies;
+    profile.step = now_ms() - ts;
+  }
+};
+
+}  // namespace b2o
