@@ -1,0 +1,86 @@
+"""Batched independent worlds (RL-style) on one GPU: thin mirror of the b2gpu_batch_* C ABI."""
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+from .lib import check, load
+
+
+class Context:
+    """One per device (b2gpu_init).  `stream` may be a raw cudaStream_t (e.g. torch's)."""
+
+    def __init__(self, device=0, stream=None, lib_path=None):
+        self.L = load(lib_path)
+        self.h = C.c_void_p()
+        check(self.L, self.L.b2gpu_init(device, C.c_void_p(stream) if stream else None, C.byref(self.h)))
+
+    def sync(self):
+        check(self.L, self.L.b2gpu_sync(self.h))
+
+    def launch_count(self):
+        return int(self.L.b2gpu_launch_count(self.h))
+
+    def stream(self):
+        return self.L.b2gpu_stream(self.h)
+
+    def close(self):
+        if self.h:
+            self.L.b2gpu_shutdown(self.h)
+            self.h = C.c_void_p()
+
+
+class Batch:
+    def __init__(self, ctx, proto, n_worlds, max_contacts=0, max_pairs=0, lane_block=0):
+        """proto: abi.Snapshot of the prototype world (from B2world.snapshot())."""
+        self.ctx, self.L = ctx, ctx.L
+        caps = abi.Caps()
+        caps.max_contacts, caps.max_pairs = max_contacts, max_pairs
+        caps.reserved[0] = lane_block
+        self.h = C.c_void_p()
+        c = proto.as_c()
+        self._keep = proto
+        check(self.L, self.L.b2gpu_batch_create(ctx.h, C.byref(c), n_worlds, C.byref(caps), C.byref(self.h)))
+        self.n_worlds = n_worlds
+        self.body_count = proto.n.body_count
+
+    def close(self):
+        if self.h:
+            self.L.b2gpu_batch_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def step(self, dt, velocity_iterations, position_iterations, steps=1):
+        check(self.L, self.L.b2gpu_batch_step(self.h, dt, velocity_iterations, position_iterations, steps))
+
+    def upload_world(self, world, snap):
+        c = snap.as_c()
+        check(self.L, self.L.b2gpu_batch_upload_world(self.h, world, C.byref(c)))
+
+    def download_world(self, world):
+        n = abi.SnapshotSizes()
+        check(self.L, self.L.b2gpu_batch_snapshot_sizes(self.h, world, C.byref(n)))
+        snap = abi.Snapshot(n)
+        c = snap.as_c()
+        check(self.L, self.L.b2gpu_batch_download_world(self.h, world, C.byref(c)))
+        return snap.finish(c)
+
+    def stats(self, first=0, count=None):
+        count = self.n_worlds - first if count is None else count
+        out = np.zeros(count, abi.STATS_DTYPE)
+        check(self.L, self.L.b2gpu_batch_get_stats(self.h, first, count, out.ctypes.data))
+        return out
+
+    def body_state(self, first=0, count=None):
+        count = self.n_worlds - first if count is None else count
+        out = np.zeros((count, self.body_count, 8), np.float32)
+        check(self.L, self.L.b2gpu_batch_get_body_state(self.h, out.ctypes.data, first, count))
+        return out
+
+    def set_forces(self, forces, first=0):
+        f = np.ascontiguousarray(forces, np.float32)
+        assert f.shape[1:] == (self.body_count, 3)
+        check(self.L, self.L.b2gpu_batch_set_forces(self.h, f.ctypes.data, first, f.shape[0]))
+
+    def set_linear_velocity(self, body, vxvy, first=0):
+        v = np.ascontiguousarray(vxvy, np.float32)
+        check(self.L, self.L.b2gpu_batch_set_linear_velocity(self.h, body, v.ctypes.data, first, v.shape[0]))

@@ -1,0 +1,168 @@
+// b2g_api.cu — extern "C" entry points of include/b2gpu.h (context + batched worlds).
+// No exception or C++ type crosses this boundary; every failure is an error code plus
+// b2gpu_last_error().  Without a CUDA device every call that needs one returns
+// B2GPU_E_NO_DEVICE: there is no CPU fallback in the product library.
+#include <string.h>
+
+#include <new>
+
+#include "b2g_runtime.h"
+#if !defined(B2G_HOSTSIM)
+#include <cuda_runtime.h>
+#endif
+
+using namespace b2g;
+
+struct b2gpu_ctx {
+  Ctx c;
+};
+struct b2gpu_batch {
+  BatchHost* h;
+  b2gpu_ctx* ctx;
+};
+
+#define GUARD_BEGIN try {
+#define GUARD_END                                   \
+  }                                                 \
+  catch (const std::bad_alloc&) {                   \
+    set_error("out of host memory");                \
+    return B2GPU_E_INVALID;                         \
+  }                                                 \
+  catch (...) {                                     \
+    set_error("unexpected C++ exception");          \
+    return B2GPU_E_INVALID;                         \
+  }
+
+extern "C" {
+
+int b2gpu_abi_version(void) { return B2GPU_ABI_VERSION; }
+const char* b2gpu_last_error(void) { return last_error(); }
+
+int b2gpu_device_count(void) {
+#if defined(B2G_HOSTSIM)
+  return 1;
+#else
+  int n = 0;
+  cudaError_t e = cudaGetDeviceCount(&n);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_error(std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e));
+    return B2GPU_E_NO_DEVICE;
+  }
+  return n;
+#endif
+}
+
+int b2gpu_init(int device, void* stream, b2gpu_ctx** out) {
+  GUARD_BEGIN
+  if (!out) { set_error("b2gpu_init: out is NULL"); return B2GPU_E_INVALID; }
+  *out = nullptr;
+#if !defined(B2G_HOSTSIM)
+  int n = b2gpu_device_count();
+  if (n <= 0) { if (n == 0) set_error("no CUDA device visible (there is no CPU fallback)"); return B2GPU_E_NO_DEVICE; }
+  if (device < 0 || device >= n) { set_error("b2gpu_init: bad device index"); return B2GPU_E_INVALID; }
+  cudaError_t e = cudaSetDevice(device);
+  if (e != cudaSuccess) { set_error(std::string("cudaSetDevice: ") + cudaGetErrorString(e)); return B2GPU_E_CUDA; }
+#endif
+  b2gpu_ctx* c = new b2gpu_ctx();
+  c->c.device = device;
+  c->c.stream = stream;
+  c->c.own_stream = false;
+#if !defined(B2G_HOSTSIM)
+  if (!stream) {
+    cudaStream_t s;
+    e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete c; set_error(std::string("cudaStreamCreate: ") + cudaGetErrorString(e)); return B2GPU_E_CUDA; }
+    c->c.stream = (void*)s;
+    c->c.own_stream = true;
+  }
+#endif
+  *out = c;
+  return 0;
+  GUARD_END
+}
+void b2gpu_shutdown(b2gpu_ctx* ctx) {
+  if (!ctx) return;
+#if !defined(B2G_HOSTSIM)
+  if (ctx->c.own_stream && ctx->c.stream) cudaStreamDestroy((cudaStream_t)ctx->c.stream);
+#endif
+  delete ctx;
+}
+int b2gpu_sync(b2gpu_ctx* ctx) {
+  if (!ctx) { set_error("b2gpu_sync: ctx is NULL"); return B2GPU_E_INVALID; }
+  return ctx_sync(&ctx->c);
+}
+void* b2gpu_stream(b2gpu_ctx* ctx) { return ctx ? ctx->c.stream : nullptr; }
+int64_t b2gpu_launch_count(b2gpu_ctx* ctx) { return ctx ? ctx->c.launches : 0; }
+
+int b2gpu_batch_create(b2gpu_ctx* ctx, const b2gpu_snapshot* proto, int n_worlds, const b2gpu_caps* caps, b2gpu_batch** out) {
+  GUARD_BEGIN
+  if (!ctx || !out) { set_error("b2gpu_batch_create: bad argument"); return B2GPU_E_INVALID; }
+  *out = nullptr;
+  BatchHost* h = nullptr;
+  int lane_block = caps ? caps->reserved[0] : 0;  // 0 = automatic (32 for >= 32 worlds, else 1)
+  int rc = batch_create(&ctx->c, proto, n_worlds, caps, lane_block, &h);
+  if (rc) return rc;
+  b2gpu_batch* b = new b2gpu_batch();
+  b->h = h;
+  b->ctx = ctx;
+  *out = b;
+  return 0;
+  GUARD_END
+}
+void b2gpu_batch_destroy(b2gpu_batch* b) {
+  if (!b) return;
+  batch_destroy(b->h);
+  delete b;
+}
+int b2gpu_batch_world_count(b2gpu_batch* b) { return b ? b->h->B.n_worlds : B2GPU_E_INVALID; }
+int b2gpu_batch_step(b2gpu_batch* b, float dt, int vi, int pi, int steps) {
+  GUARD_BEGIN
+  if (!b) { set_error("b2gpu_batch_step: batch is NULL"); return B2GPU_E_INVALID; }
+  return batch_step(b->h, dt, vi, pi, steps);
+  GUARD_END
+}
+int b2gpu_batch_upload_world(b2gpu_batch* b, int world, const b2gpu_snapshot* in) {
+  GUARD_BEGIN
+  if (!b) { set_error("batch is NULL"); return B2GPU_E_INVALID; }
+  return batch_upload_world(b->h, world, in);
+  GUARD_END
+}
+int b2gpu_batch_snapshot_sizes(b2gpu_batch* b, int world, b2gpu_snapshot_sizes* out) {
+  GUARD_BEGIN
+  if (!b) { set_error("batch is NULL"); return B2GPU_E_INVALID; }
+  return batch_snapshot_sizes(b->h, world, out);
+  GUARD_END
+}
+int b2gpu_batch_download_world(b2gpu_batch* b, int world, b2gpu_snapshot* out) {
+  GUARD_BEGIN
+  if (!b) { set_error("batch is NULL"); return B2GPU_E_INVALID; }
+  return batch_download_world(b->h, world, out);
+  GUARD_END
+}
+int b2gpu_batch_get_stats(b2gpu_batch* b, int first, int count, b2gpu_step_stats* out) {
+  GUARD_BEGIN
+  if (!b) { set_error("batch is NULL"); return B2GPU_E_INVALID; }
+  return batch_get_stats(b->h, first, count, out);
+  GUARD_END
+}
+int b2gpu_batch_set_forces(b2gpu_batch* b, const float* host, int first, int count) {
+  GUARD_BEGIN
+  if (!b) { set_error("batch is NULL"); return B2GPU_E_INVALID; }
+  return batch_set_forces(b->h, host, first, count);
+  GUARD_END
+}
+int b2gpu_batch_set_linear_velocity(b2gpu_batch* b, int body, const float* host_vxvy, int first, int count) {
+  GUARD_BEGIN
+  if (!b) { set_error("batch is NULL"); return B2GPU_E_INVALID; }
+  return batch_set_linear_velocity(b->h, body, host_vxvy, first, count);
+  GUARD_END
+}
+int b2gpu_batch_get_body_state(b2gpu_batch* b, float* host_out, int first, int count) {
+  GUARD_BEGIN
+  if (!b) { set_error("batch is NULL"); return B2GPU_E_INVALID; }
+  return batch_get_body_state(b->h, host_out, first, count);
+  GUARD_END
+}
+
+}  // extern "C"

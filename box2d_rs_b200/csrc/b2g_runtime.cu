@@ -1,0 +1,668 @@
+// b2g_runtime.cu — batch management and the step launch sequence (see b2g_runtime.h).
+#include "b2g_runtime.h"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+
+#if !defined(B2G_HOSTSIM)
+#include <cuda_runtime.h>
+#endif
+
+namespace b2g {
+
+static thread_local std::string g_error;
+const char* last_error() { return g_error.c_str(); }
+void set_error(const std::string& s) { g_error = s; }
+
+// ------------------------------------------------------------------ device abstraction
+#if defined(B2G_HOSTSIM)
+static int dev_alloc(void** p, size_t bytes) { *p = calloc(1, bytes ? bytes : 1); return *p ? 0 : B2GPU_E_CUDA; }
+static void dev_free(void* p) { free(p); }
+static int dev_h2d(Ctx*, void* d, const void* h, size_t n) { memcpy(d, h, n); return 0; }
+static int dev_d2h(Ctx*, void* h, const void* d, size_t n) { memcpy(h, d, n); return 0; }
+static int dev_zero(Ctx*, void* d, size_t n) { memset(d, 0, n); return 0; }
+int ctx_sync(Ctx*) { return 0; }
+template <class K> static int launch(Ctx* ctx, const K& k, int n, int /*block*/) {
+  for (int t = 0; t < n; ++t) k(t);
+  ctx->launches++;
+  return 0;
+}
+#else
+static int cuda_fail(cudaError_t e, const char* what) {
+  set_error(std::string(what) + ": " + cudaGetErrorString(e));
+  return B2GPU_E_CUDA;
+}
+#define CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return cuda_fail(e_, #x); } while (0)
+static int dev_alloc(void** p, size_t bytes) {
+  CU(cudaMalloc(p, bytes ? bytes : 16));
+  CU(cudaMemset(*p, 0, bytes ? bytes : 16));
+  return 0;
+}
+static void dev_free(void* p) { cudaFree(p); }
+static int dev_h2d(Ctx* c, void* d, const void* h, size_t n) {
+  CU(cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, (cudaStream_t)c->stream));
+  CU(cudaStreamSynchronize((cudaStream_t)c->stream));
+  return 0;
+}
+static int dev_d2h(Ctx* c, void* h, const void* d, size_t n) {
+  CU(cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, (cudaStream_t)c->stream));
+  CU(cudaStreamSynchronize((cudaStream_t)c->stream));
+  return 0;
+}
+static int dev_zero(Ctx* c, void* d, size_t n) {
+  CU(cudaMemsetAsync(d, 0, n, (cudaStream_t)c->stream));
+  return 0;
+}
+int ctx_sync(Ctx* c) {
+  CU(cudaStreamSynchronize((cudaStream_t)c->stream));
+  return 0;
+}
+template <class K> __global__ void stage_kernel(const K k, int n) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) k(t);
+}
+template <class K> static int launch(Ctx* ctx, const K& k, int n, int block) {
+  if (n <= 0) return 0;
+  int grid = (n + block - 1) / block;
+  stage_kernel<K><<<grid, block, 0, (cudaStream_t)ctx->stream>>>(k, n);
+  ctx->launches++;
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+  return 0;
+}
+#endif
+
+#define RC(x) do { int rc_ = (x); if (rc_ != 0) return rc_; } while (0)
+
+// ------------------------------------------------------------------ layout movers (4-byte words)
+struct MoveK {
+  int* dev;        // device array (blocked world-minor), elements of E words
+  int* compact;    // compact one-world array [N][E]
+  int N, E, mode;  // mode 0: compact -> world `w`; 1: world `w` -> compact; 2: compact -> every world
+  int LB, lb_shift, n_wblocks, w;
+  B2G_HD void operator()(int tid) const {
+    const int k = tid % E, e = tid / E;
+    if (mode == 2) {
+      const int i = (e >> lb_shift) % N;
+      dev[tid] = compact[i * E + k];
+    } else {
+      const int wb = w >> lb_shift, wl = w & (LB - 1);
+      const int idx = (wb * N + e) * LB + wl;
+      if (mode == 0) dev[idx * E + k] = compact[e * E + k];
+      else compact[e * E + k] = dev[idx * E + k];
+    }
+  }
+};
+
+struct ArrRef {
+  void* dev;
+  void* host;
+  int E, N;
+};
+static std::vector<ArrRef> array_table(BatchHost* bh, WorldImage& im) {
+  Batch& B = bh->B;
+  std::vector<ArrRef> t;
+  auto add = [&](void* dev, void* host, int bytes, int N) { ArrRef r = {dev, host, bytes / 4, N}; t.push_back(r); };
+  add(B.ws, im.ws.data(), 4, WS_COUNT);
+  add(B.b_flags, im.b_flags.data(), 4, B.NB);
+  add(B.b_xf, im.b_xf.data(), 16, B.NB);
+  add(B.b_pos, im.b_pos.data(), 16, B.NB);
+  add(B.b_pos0, im.b_pos0.data(), 16, B.NB);
+  add(B.b_vel, im.b_vel.data(), 16, B.NB);
+  add(B.b_mass, im.b_mass.data(), 16, B.NB);
+  add(B.b_force, im.b_force.data(), 16, B.NB);
+  add(B.b_misc, im.b_misc.data(), 16, B.NB);
+  add(B.n_aabb, im.n_aabb.data(), 16, B.NN);
+  add(B.n_link, im.n_link.data(), 16, B.NN);
+  add(B.n_moved, im.n_moved.data(), 4, B.NN);
+  add(B.p_aabb, im.p_aabb.data(), 16, B.NP);
+  add(B.move_buf, im.move_buf.data(), 4, B.NMOVE);
+  add(B.c_fix, im.c_fix.data(), 16, B.NC);
+  add(B.c_flags, im.c_flags.data(), 4, B.NC);
+  add(B.c_mat, im.c_mat.data(), 16, B.NC);
+  add(B.c_m0, im.c_m0.data(), 16, B.NC);
+  add(B.c_m1, im.c_m1.data(), 16, B.NC);
+  add(B.c_m2, im.c_m2.data(), 16, B.NC);
+  add(B.c_m3, im.c_m3.data(), 16, B.NC);
+  add(bh->b_chead, im.b_chead.data(), 4, B.NB);
+  add(bh->c_next, im.c_next.data(), 8, B.NC);
+  return t;
+}
+static void image_alloc(const Batch& B, WorldImage& im) {
+  im.ws.assign(WS_COUNT, 0);
+  im.b_flags.assign(B.NB, 0);
+  float4 z4 = make_float4(0, 0, 0, 0);
+  im.b_xf.assign(B.NB, z4); im.b_pos.assign(B.NB, z4); im.b_pos0.assign(B.NB, z4); im.b_vel.assign(B.NB, z4);
+  im.b_mass.assign(B.NB, z4); im.b_force.assign(B.NB, z4); im.b_misc.assign(B.NB, z4);
+  im.n_aabb.assign(B.NN, z4);
+  im.n_link.assign(B.NN, make_int4(-1, -1, -1, -1));
+  im.n_moved.assign(B.NN, 0);
+  im.p_aabb.assign(B.NP, z4);
+  im.move_buf.assign(B.NMOVE, -1);
+  im.c_fix.assign(B.NC, make_int4(0, 0, 0, 0));
+  im.c_flags.assign(B.NC, 0);
+  im.c_mat.assign(B.NC, z4); im.c_m0.assign(B.NC, z4); im.c_m1.assign(B.NC, z4); im.c_m2.assign(B.NC, z4);
+  im.c_m3.assign(B.NC, make_int4(0, 0, 0, 0));
+  im.b_chead.assign(B.NB, -1);
+  im.c_next.assign(B.NC, make_int2(-1, -1));
+}
+
+static int fbits(float f) { int i; memcpy(&i, &f, 4); return i; }
+static float bitsf(int i) { float f; memcpy(&f, &i, 4); return f; }
+
+// snapshot -> image
+static int image_pack(const BatchHost* bh, const b2gpu_snapshot* s, WorldImage& im) {
+  const Batch& B = bh->B;
+  image_alloc(B, im);
+  if (s->n.node_count > B.NN || s->n.contact_count > B.NC || s->n.move_count > B.NMOVE) {
+    set_error("snapshot exceeds the batch capacities (tree nodes / contacts / move buffer)");
+    return B2GPU_E_CAPACITY;
+  }
+  const b2gpu_world_rec& w = s->world;
+  im.ws[WS_GRAVITY_X] = fbits(w.gravity_x);
+  im.ws[WS_GRAVITY_Y] = fbits(w.gravity_y);
+  im.ws[WS_INV_DT0] = fbits(w.inv_dt0);
+  im.ws[WS_FLAGS] = (int)w.flags;
+  im.ws[WS_TREE_ROOT] = w.tree_root;
+  im.ws[WS_TREE_FREE] = w.tree_free_list;
+  im.ws[WS_TREE_COUNT] = w.tree_node_count;
+  im.ws[WS_TREE_CAP] = w.tree_node_capacity;
+  im.ws[WS_TREE_INSERTIONS] = w.tree_insertion_count;
+  im.ws[WS_PROXY_COUNT] = w.proxy_count;
+  im.ws[WS_CONTACT_COUNT] = s->n.contact_count;
+  im.ws[WS_MOVE_COUNT] = s->n.move_count;
+  im.ws[WS_TOPO_DIRTY] = 1;
+  for (int i = 0; i < B.NB; ++i) {
+    const b2gpu_body_rec& b = s->bodies[i];
+    im.b_flags[i] = (int)(b.flags & 0xffffu) | (b.type << 16);
+    im.b_xf[i] = make_float4(b.xf_px, b.xf_py, b.xf_qs, b.xf_qc);
+    im.b_pos[i] = make_float4(b.c_x, b.c_y, b.a, b.sleep_time);
+    im.b_pos0[i] = make_float4(b.c0_x, b.c0_y, b.a0, 0.0f);
+    im.b_vel[i] = make_float4(b.vx, b.vy, b.w, 0.0f);
+    im.b_mass[i] = make_float4(b.inv_mass, b.inv_inertia, b.lc_x, b.lc_y);
+    im.b_force[i] = make_float4(b.fx, b.fy, b.torque, b.gravity_scale);
+    im.b_misc[i] = make_float4(b.mass, b.inertia, b.linear_damping, b.angular_damping);
+  }
+  for (int i = 0; i < s->n.node_count; ++i) {
+    const b2gpu_tree_node_rec& n = s->nodes[i];
+    im.n_aabb[i] = make_float4(n.aabb[0], n.aabb[1], n.aabb[2], n.aabb[3]);
+    im.n_link[i] = make_int4(n.parent, n.child1, n.child2, n.height);
+    im.n_moved[i] = n.moved;
+  }
+  for (int i = 0; i < B.NP; ++i) {
+    const float* a = s->proxies[i].aabb;
+    im.p_aabb[i] = make_float4(a[0], a[1], a[2], a[3]);
+  }
+  for (int i = 0; i < s->n.move_count; ++i) im.move_buf[i] = s->move_buffer[i];
+  for (int i = 0; i < s->n.contact_count; ++i) {
+    const b2gpu_contact_rec& c = s->contacts[i];
+    if (c.fixture_a < 0 || c.fixture_a >= B.NF || c.fixture_b < 0 || c.fixture_b >= B.NF) {
+      set_error("contact references an unknown fixture");
+      return B2GPU_E_INVALID;
+    }
+    im.c_fix[i] = make_int4(c.fixture_a, c.fixture_b, c.index_a, c.index_b);
+    im.c_flags[i] = (int)(c.flags & 0xffu);
+    im.c_mat[i] = make_float4(c.friction, c.restitution, c.restitution_threshold, c.tangent_speed);
+    const b2gpu_manifold& m = c.manifold;
+    im.c_m0[i] = make_float4(m.points[0].lp_x, m.points[0].lp_y, m.points[0].normal_impulse, m.points[0].tangent_impulse);
+    im.c_m1[i] = make_float4(m.points[1].lp_x, m.points[1].lp_y, m.points[1].normal_impulse, m.points[1].tangent_impulse);
+    im.c_m2[i] = make_float4(m.ln_x, m.ln_y, m.lp_x, m.lp_y);
+    im.c_m3[i] = make_int4((int)m.points[0].id, (int)m.points[1].id, m.type, m.point_count);
+    // push_front on both bodies' edge lists
+    const int ba = bh->topo.fixtures[c.fixture_a].body, bb = bh->topo.fixtures[c.fixture_b].body;
+    im.c_next[i] = make_int2(im.b_chead[ba], 0);
+    im.b_chead[ba] = 2 * i;
+    im.c_next[i].y = im.b_chead[bb];
+    im.b_chead[bb] = 2 * i + 1;
+  }
+  return 0;
+}
+
+// image -> snapshot (caller-provided capacities in out->n)
+static int image_unpack(const BatchHost* bh, const WorldImage& im, b2gpu_snapshot* out) {
+  const Batch& B = bh->B;
+  const Topology& T = bh->topo;
+  b2gpu_snapshot_sizes need;
+  need.body_count = B.NB; need.fixture_count = B.NF; need.shape_count = B.NS; need.proxy_count = B.NP;
+  need.node_count = im.ws[WS_TREE_CAP]; need.contact_count = im.ws[WS_CONTACT_COUNT]; need.move_count = im.ws[WS_MOVE_COUNT];
+  need.reserved = 0;
+  if (out->n.body_count < need.body_count || out->n.fixture_count < need.fixture_count || out->n.shape_count < need.shape_count ||
+      out->n.proxy_count < need.proxy_count || out->n.node_count < need.node_count ||
+      out->n.contact_count < need.contact_count || out->n.move_count < need.move_count) {
+    set_error("download buffers smaller than snapshot_sizes");
+    return B2GPU_E_INVALID;
+  }
+  out->n = need;
+  b2gpu_world_rec& w = out->world;
+  memset(&w, 0, sizeof(w));
+  w.gravity_x = bitsf(im.ws[WS_GRAVITY_X]); w.gravity_y = bitsf(im.ws[WS_GRAVITY_Y]);
+  w.inv_dt0 = bitsf(im.ws[WS_INV_DT0]);
+  w.flags = (uint32_t)im.ws[WS_FLAGS];
+  w.tree_root = im.ws[WS_TREE_ROOT]; w.tree_free_list = im.ws[WS_TREE_FREE]; w.tree_node_count = im.ws[WS_TREE_COUNT];
+  w.tree_node_capacity = im.ws[WS_TREE_CAP]; w.tree_insertion_count = im.ws[WS_TREE_INSERTIONS];
+  w.proxy_count = im.ws[WS_PROXY_COUNT];
+  for (int i = 0; i < B.NB; ++i) {
+    b2gpu_body_rec& b = out->bodies[i];
+    b = T.bodies[i];
+    b.type = (im.b_flags[i] >> 16) & 0xff;
+    b.flags = (uint32_t)(im.b_flags[i] & 0xffff);
+    b.xf_px = im.b_xf[i].x; b.xf_py = im.b_xf[i].y; b.xf_qs = im.b_xf[i].z; b.xf_qc = im.b_xf[i].w;
+    b.c_x = im.b_pos[i].x; b.c_y = im.b_pos[i].y; b.a = im.b_pos[i].z; b.sleep_time = im.b_pos[i].w;
+    b.c0_x = im.b_pos0[i].x; b.c0_y = im.b_pos0[i].y; b.a0 = im.b_pos0[i].z;
+    b.vx = im.b_vel[i].x; b.vy = im.b_vel[i].y; b.w = im.b_vel[i].z;
+    b.inv_mass = im.b_mass[i].x; b.inv_inertia = im.b_mass[i].y; b.lc_x = im.b_mass[i].z; b.lc_y = im.b_mass[i].w;
+    b.fx = im.b_force[i].x; b.fy = im.b_force[i].y; b.torque = im.b_force[i].z; b.gravity_scale = im.b_force[i].w;
+    b.mass = im.b_misc[i].x; b.inertia = im.b_misc[i].y; b.linear_damping = im.b_misc[i].z; b.angular_damping = im.b_misc[i].w;
+  }
+  memcpy(out->fixtures, T.fixtures.data(), sizeof(b2gpu_fixture_rec) * B.NF);
+  memcpy(out->shapes, T.shapes.data(), sizeof(b2gpu_shape_rec) * B.NS);
+  for (int i = 0; i < B.NP; ++i) {
+    out->proxies[i] = T.proxies[i];
+    out->proxies[i].aabb[0] = im.p_aabb[i].x; out->proxies[i].aabb[1] = im.p_aabb[i].y;
+    out->proxies[i].aabb[2] = im.p_aabb[i].z; out->proxies[i].aabb[3] = im.p_aabb[i].w;
+  }
+  for (int i = 0; i < need.node_count; ++i) {
+    b2gpu_tree_node_rec& n = out->nodes[i];
+    n.aabb[0] = im.n_aabb[i].x; n.aabb[1] = im.n_aabb[i].y; n.aabb[2] = im.n_aabb[i].z; n.aabb[3] = im.n_aabb[i].w;
+    n.parent = im.n_link[i].x; n.child1 = im.n_link[i].y; n.child2 = im.n_link[i].z; n.height = im.n_link[i].w;
+    n.proxy = (n.height == 0 && i < (int)T.node_proxy.size()) ? T.node_proxy[i] : -1;
+    n.moved = im.n_moved[i];
+  }
+  for (int i = 0; i < need.contact_count; ++i) {
+    b2gpu_contact_rec& c = out->contacts[i];
+    memset(&c, 0, sizeof(c));
+    c.fixture_a = im.c_fix[i].x; c.fixture_b = im.c_fix[i].y; c.index_a = im.c_fix[i].z; c.index_b = im.c_fix[i].w;
+    c.flags = (uint32_t)(im.c_flags[i] & 0xff);
+    c.friction = im.c_mat[i].x; c.restitution = im.c_mat[i].y; c.restitution_threshold = im.c_mat[i].z; c.tangent_speed = im.c_mat[i].w;
+    b2gpu_manifold& m = c.manifold;
+    m.points[0].lp_x = im.c_m0[i].x; m.points[0].lp_y = im.c_m0[i].y;
+    m.points[0].normal_impulse = im.c_m0[i].z; m.points[0].tangent_impulse = im.c_m0[i].w;
+    m.points[1].lp_x = im.c_m1[i].x; m.points[1].lp_y = im.c_m1[i].y;
+    m.points[1].normal_impulse = im.c_m1[i].z; m.points[1].tangent_impulse = im.c_m1[i].w;
+    m.points[0].id = (uint32_t)im.c_m3[i].x; m.points[1].id = (uint32_t)im.c_m3[i].y;
+    m.ln_x = im.c_m2[i].x; m.ln_y = im.c_m2[i].y; m.lp_x = im.c_m2[i].z; m.lp_y = im.c_m2[i].w;
+    m.type = im.c_m3[i].z; m.point_count = im.c_m3[i].w;
+  }
+  for (int i = 0; i < need.move_count; ++i) out->move_buffer[i] = im.move_buf[i];
+  return 0;
+}
+
+static int topology_build(const b2gpu_snapshot* s, Topology& T) {
+  const b2gpu_snapshot_sizes& n = s->n;
+  T.bodies.assign(s->bodies, s->bodies + n.body_count);
+  T.fixtures.assign(s->fixtures, s->fixtures + n.fixture_count);
+  T.shapes.assign(s->shapes, s->shapes + n.shape_count);
+  T.proxies.assign(s->proxies, s->proxies + n.proxy_count);
+  T.proxy_s.resize(n.proxy_count);
+  T.node_proxy.assign(std::max(n.node_count, 1), -1);
+  for (int p = 0; p < n.proxy_count; ++p) {
+    const b2gpu_proxy_rec& pr = T.proxies[p];
+    if (pr.fixture < 0 || pr.fixture >= n.fixture_count || pr.proxy_id < 0 || pr.proxy_id >= n.node_count) {
+      set_error("proxy record out of range");
+      return B2GPU_E_INVALID;
+    }
+    T.proxy_s[p] = make_int4(pr.fixture, pr.child_index, pr.proxy_id, T.fixtures[pr.fixture].body);
+    T.node_proxy[pr.proxy_id] = p;
+  }
+  for (int f = 0; f < n.fixture_count; ++f) {
+    const b2gpu_fixture_rec& fx = T.fixtures[f];
+    if (fx.body < 0 || fx.body >= n.body_count || fx.shape_first < 0 || fx.shape_first + fx.child_count > n.shape_count) {
+      set_error("fixture record out of range");
+      return B2GPU_E_INVALID;
+    }
+    if (fx.proxy_first >= 0 && fx.proxy_first + fx.child_count > n.proxy_count) {
+      set_error("fixture proxies out of range");
+      return B2GPU_E_INVALID;
+    }
+  }
+  // synchronize order: body list newest first, each body's fixtures newest first, children ascending
+  T.sync_order.clear();
+  for (int b = n.body_count - 1; b >= 0; --b)
+    for (int f = T.bodies[b].fixture_head; f != -1; f = T.fixtures[f].next) {
+      if (f < 0 || f >= n.fixture_count) { set_error("fixture list corrupt"); return B2GPU_E_INVALID; }
+      if (T.fixtures[f].proxy_first < 0) continue;
+      for (int c = 0; c < T.fixtures[f].child_count; ++c) T.sync_order.push_back(T.fixtures[f].proxy_first + c);
+    }
+  if ((int)T.sync_order.size() != n.proxy_count) {
+    set_error("proxy table does not match the fixture lists");
+    return B2GPU_E_INVALID;
+  }
+  return 0;
+}
+
+static bool topology_matches(const Topology& T, const b2gpu_snapshot* s) {
+  const b2gpu_snapshot_sizes& n = s->n;
+  if (n.body_count != (int)T.bodies.size() || n.fixture_count != (int)T.fixtures.size() ||
+      n.shape_count != (int)T.shapes.size() || n.proxy_count != (int)T.proxies.size())
+    return false;
+  if (n.fixture_count && memcmp(s->fixtures, T.fixtures.data(), sizeof(b2gpu_fixture_rec) * n.fixture_count)) return false;
+  if (n.shape_count && memcmp(s->shapes, T.shapes.data(), sizeof(b2gpu_shape_rec) * n.shape_count)) return false;
+  for (int p = 0; p < n.proxy_count; ++p)
+    if (s->proxies[p].fixture != T.proxies[p].fixture || s->proxies[p].child_index != T.proxies[p].child_index ||
+        s->proxies[p].proxy_id != T.proxies[p].proxy_id)
+      return false;
+  for (int b = 0; b < n.body_count; ++b)
+    if (s->bodies[b].type != T.bodies[b].type || s->bodies[b].fixture_head != T.bodies[b].fixture_head) return false;
+  return true;
+}
+
+template <class T> static int alloc_arr(BatchHost* bh, T** p, long long count) {
+  void* v = nullptr;
+  RC(dev_alloc(&v, (size_t)count * sizeof(T)));
+  bh->allocs.push_back(v);
+  bh->total_bytes += count * (long long)sizeof(T);
+  *p = (T*)v;
+  return 0;
+}
+
+static int move_array(BatchHost* bh, const ArrRef& a, int mode, int world) {
+  Batch& B = bh->B;
+  const size_t bytes = (size_t)a.N * a.E * 4;
+  if (bytes > bh->stage_bytes) { set_error("staging buffer too small"); return B2GPU_E_INVALID; }
+  MoveK k;
+  k.dev = (int*)a.dev; k.compact = (int*)bh->stage_dev; k.N = a.N; k.E = a.E; k.mode = mode;
+  k.LB = B.LB; k.lb_shift = B.lb_shift; k.n_wblocks = B.n_wblocks; k.w = world;
+  if (mode == 1) {
+    RC(launch(bh->ctx, k, a.N * a.E, 256));
+    RC(dev_d2h(bh->ctx, a.host, bh->stage_dev, bytes));
+  } else {
+    RC(dev_h2d(bh->ctx, bh->stage_dev, a.host, bytes));
+    const long long n = mode == 2 ? (long long)B.n_wblocks * a.N * B.LB * a.E : (long long)a.N * a.E;
+    if (n > 0x7fffffffLL) { set_error("array too large for 32-bit indexing"); return B2GPU_E_CAPACITY; }
+    RC(launch(bh->ctx, k, (int)n, 256));
+    RC(ctx_sync(bh->ctx));
+  }
+  return 0;
+}
+
+int batch_create(Ctx* ctx, const b2gpu_snapshot* proto, int n_worlds, const b2gpu_caps* caps, int lane_block, BatchHost** out) {
+  if (!ctx || !proto || n_worlds < 1 || !out) { set_error("batch_create: bad argument"); return B2GPU_E_INVALID; }
+  BatchHost* bh = new BatchHost();
+  bh->ctx = ctx;
+  int rc = topology_build(proto, bh->topo);
+  if (rc) { delete bh; return rc; }
+  Batch& B = bh->B;
+  memset(&B, 0, sizeof(B));
+  B.n_worlds = n_worlds;
+  B.LB = lane_block > 0 ? lane_block : (n_worlds >= 32 ? 32 : 1);
+  if (B.LB & (B.LB - 1)) { set_error("lane block must be a power of two"); delete bh; return B2GPU_E_INVALID; }
+  B.lb_shift = 0;
+  while ((1 << B.lb_shift) < B.LB) ++B.lb_shift;
+  B.n_wblocks = (n_worlds + B.LB - 1) / B.LB;
+  const b2gpu_snapshot_sizes& n = proto->n;
+  B.NB = n.body_count; B.NF = n.fixture_count; B.NS = n.shape_count; B.NP = n.proxy_count;
+  if (B.NB < 1 || B.NP < 0) { set_error("empty world"); delete bh; return B2GPU_E_INVALID; }
+  B.NN = std::max(n.node_count, 16);
+  int want_contacts = std::max(n.contact_count * 2, B.NP * 4 + 64);
+  if (caps && caps->max_contacts > 0) want_contacts = std::max(caps->max_contacts, n.contact_count);
+  B.NC = want_contacts;
+  B.NPAIR = (caps && caps->max_pairs > 0) ? caps->max_pairs : std::max(B.NC, 8 * B.NP + 64);
+  B.NMOVE = std::max(2 * B.NP, n.move_count) + 16;
+  B.NIB = B.NB + B.NC;
+  if (B.NP < 1) B.NP = 0;
+  const long long W = (long long)B.n_wblocks * B.LB;
+  if (W * B.NC * VC_Q > 0x7fffffffLL || W * B.NIB > 0x7fffffffLL) {
+    set_error("batch too large for 32-bit element indexing");
+    delete bh;
+    return B2GPU_E_CAPACITY;
+  }
+#define AL(ptr, count) do { rc = alloc_arr(bh, &ptr, (count)); if (rc) { batch_destroy(bh); return rc; } } while (0)
+  // shared topology
+  b2gpu_fixture_rec* d_fix; b2gpu_shape_rec* d_shape; int4* d_ps; int* d_so; int* d_np;
+  AL(d_fix, std::max(B.NF, 1)); AL(d_shape, std::max(B.NS, 1)); AL(d_ps, std::max(B.NP, 1)); AL(d_so, std::max(B.NP, 1));
+  AL(d_np, (long long)bh->topo.node_proxy.size());
+  B.fixtures = d_fix; B.shapes = d_shape; B.proxy_s = d_ps; B.sync_order = d_so; B.node_proxy = d_np;
+  const int NPa = std::max(B.NP, 1);
+  AL(B.ws, W * WS_COUNT);
+  AL(B.b_flags, W * B.NB); AL(B.b_xf, W * B.NB); AL(B.b_pos, W * B.NB); AL(B.b_pos0, W * B.NB); AL(B.b_vel, W * B.NB);
+  AL(B.b_mass, W * B.NB); AL(B.b_force, W * B.NB); AL(B.b_misc, W * B.NB); AL(B.b_rot, W * B.NB);
+  AL(B.n_aabb, W * B.NN); AL(B.n_link, W * B.NN); AL(B.n_moved, W * B.NN);
+  AL(B.p_aabb, W * NPa); AL(B.p_fat, W * NPa); AL(B.p_move, W * NPa);
+  AL(B.move_buf, W * B.NMOVE); AL(B.pair_buf, W * B.NPAIR);
+  AL(B.c_fix, W * B.NC); AL(B.c_flags, W * B.NC); AL(B.c_mat, W * B.NC);
+  AL(B.c_m0, W * B.NC); AL(B.c_m1, W * B.NC); AL(B.c_m2, W * B.NC); AL(B.c_m3, W * B.NC);
+  AL(B.isl_body, W * B.NIB); AL(B.isl_contact, W * B.NC); AL(B.isl_range, W * B.NB); AL(B.isl_flags, W * B.NB);
+  AL(B.c_isl, W * B.NC); AL(B.vc, W * B.NC * VC_Q);
+  AL(bh->b_wake, W * B.NB); AL(bh->b_chead, W * B.NB); AL(bh->c_next, W * B.NC); AL(bh->stack, W * B.NB);
+  AL(bh->state_dev, (long long)n_worlds * B.NB * 8);
+  AL(bh->forces_dev, (long long)n_worlds * B.NB * 3);
+  bh->stage_bytes = 16 * (size_t)std::max(std::max(B.NB, B.NN), std::max(std::max(B.NC, B.NMOVE), (int)WS_COUNT));
+  {
+    void* v = nullptr;
+    rc = dev_alloc(&v, bh->stage_bytes);
+    if (rc) { batch_destroy(bh); return rc; }
+    bh->stage_dev = v;
+    bh->allocs.push_back(v);
+  }
+#undef AL
+  const Topology& T = bh->topo;
+#define UP(dst, vec) do { if (!(vec).empty()) { rc = dev_h2d(ctx, (void*)(dst), (vec).data(), (vec).size() * sizeof((vec)[0])); if (rc) { batch_destroy(bh); return rc; } } } while (0)
+  UP(d_fix, T.fixtures); UP(d_shape, T.shapes); UP(d_ps, T.proxy_s); UP(d_so, T.sync_order); UP(d_np, T.node_proxy);
+#undef UP
+  WorldImage im;
+  rc = image_pack(bh, proto, im);
+  if (rc) { batch_destroy(bh); return rc; }
+  std::vector<ArrRef> tab = array_table(bh, im);
+  for (const ArrRef& a : tab) {
+    rc = move_array(bh, a, 2, 0);
+    if (rc) { batch_destroy(bh); return rc; }
+  }
+  bh->pre_step_needed = true;
+  *out = bh;
+  return 0;
+}
+
+void batch_destroy(BatchHost* bh) {
+  if (!bh) return;
+  for (void* p : bh->allocs) dev_free(p);
+  delete bh;
+}
+
+int batch_upload_world(BatchHost* bh, int world, const b2gpu_snapshot* in) {
+  if (!bh || !in || world < 0 || world >= bh->B.n_worlds) { set_error("upload_world: bad argument"); return B2GPU_E_INVALID; }
+  if (!topology_matches(bh->topo, in)) {
+    set_error("upload_world: snapshot topology (fixtures/shapes/proxies/body types) differs from the batch prototype");
+    return B2GPU_E_INVALID;
+  }
+  WorldImage im;
+  RC(image_pack(bh, in, im));
+  std::vector<ArrRef> tab = array_table(bh, im);
+  for (const ArrRef& a : tab) RC(move_array(bh, a, 0, world));
+  bh->pre_step_needed = true;
+  return 0;
+}
+
+static int image_fetch(BatchHost* bh, int world, WorldImage& im) {
+  image_alloc(bh->B, im);
+  std::vector<ArrRef> tab = array_table(bh, im);
+  for (const ArrRef& a : tab) RC(move_array(bh, a, 1, world));
+  return 0;
+}
+
+int batch_snapshot_sizes(BatchHost* bh, int world, b2gpu_snapshot_sizes* out) {
+  if (!bh || !out || world < 0 || world >= bh->B.n_worlds) { set_error("snapshot_sizes: bad argument"); return B2GPU_E_INVALID; }
+  WorldImage im;
+  image_alloc(bh->B, im);
+  ArrRef a = {bh->B.ws, im.ws.data(), 1, WS_COUNT};
+  RC(move_array(bh, a, 1, world));
+  out->body_count = bh->B.NB; out->fixture_count = bh->B.NF; out->shape_count = bh->B.NS; out->proxy_count = bh->B.NP;
+  out->node_count = im.ws[WS_TREE_CAP]; out->contact_count = im.ws[WS_CONTACT_COUNT]; out->move_count = im.ws[WS_MOVE_COUNT];
+  out->reserved = 0;
+  return 0;
+}
+
+int batch_download_world(BatchHost* bh, int world, b2gpu_snapshot* out) {
+  if (!bh || !out || world < 0 || world >= bh->B.n_worlds) { set_error("download_world: bad argument"); return B2GPU_E_INVALID; }
+  WorldImage im;
+  RC(image_fetch(bh, world, im));
+  return image_unpack(bh, im, out);
+}
+
+// ------------------------------------------------------------------ step
+int batch_step(BatchHost* bh, float dt, int vi, int pi, int steps) {
+  if (!bh || steps < 0 || vi < 0 || pi < 0) { set_error("batch_step: bad argument"); return B2GPU_E_INVALID; }
+  Batch& B = bh->B;
+  Ctx* ctx = bh->ctx;
+  StepParams sp;
+  sp.dt = dt;
+  sp.inv_dt = dt > 0.0f ? 1.0f / dt : 0.0f;
+  sp.velocity_iterations = vi;
+  sp.position_iterations = pi;
+  bh->last_sp = sp;
+  const int W = B.n_wblocks * B.LB;
+  const int ordered_block = 32;
+  for (int s = 0; s < steps; ++s) {
+    {
+      TreePairsK k = {B, bh->b_chead, bh->c_next, sp, 1};
+      RC(launch(ctx, k, W, ordered_block));
+    }
+    {
+      CollideK k = {B, bh->b_wake};
+      RC(launch(ctx, k, W * B.NC, 128));
+    }
+    {
+      SerialAK k = {B, bh->b_wake, bh->b_chead, bh->c_next, bh->stack, sp};
+      RC(launch(ctx, k, W, ordered_block));
+    }
+    if (dt > 0.0f) {
+      { IntegrateK k = {B, sp}; RC(launch(ctx, k, W * B.NIB, 128)); }
+      { SolverInitK k = {B, sp}; RC(launch(ctx, k, W * B.NC, 128)); }
+      { VelocityK k = {B, sp}; RC(launch(ctx, k, W, ordered_block)); }
+      { PostVelocityK k = {B, sp}; RC(launch(ctx, k, W * B.NIB, 128)); }
+      { PositionK k = {B, sp}; RC(launch(ctx, k, W, ordered_block)); }
+      { FinalizeK k = {B, sp}; RC(launch(ctx, k, W * B.NIB, 128)); }
+      { SleepK k = {B}; RC(launch(ctx, k, W, ordered_block)); }
+      if (B.NP > 0) { SyncFixturesK k = {B}; RC(launch(ctx, k, W * B.NP, 128)); }
+    }
+    {
+      TreePairsK k = {B, bh->b_chead, bh->c_next, sp, 0};
+      RC(launch(ctx, k, W, ordered_block));
+    }
+    { BodyEndK k = {B}; RC(launch(ctx, k, W * B.NB, 128)); }
+  }
+  bh->pre_step_needed = false;
+  return 0;
+}
+
+// touching / awake counters on demand: one thread per world
+struct StatsK {
+  Batch B;
+  B2G_HD void operator()(int w) const {
+    if (w >= B.n_worlds) return;
+    WIdx x = widx(B, w);
+    Ws ws = ws_of(B, x);
+    int touching = 0, awake = 0;
+    const int cc = ws[WS_CONTACT_COUNT];
+    for (int c = 0; c < cc; ++c) touching += (B.c_flags[x.at(B.NC, c)] & B2GPU_CONTACT_TOUCHING) ? 1 : 0;
+    for (int b = 0; b < B.NB; ++b) awake += (B.b_flags[x.at(B.NB, b)] & B2GPU_BODY_AWAKE) ? 1 : 0;
+    ws[WS_ST_TOUCHING] = touching;
+    ws[WS_ST_AWAKE] = awake;
+    ws[WS_ST_CONTACTS] = cc;
+  }
+};
+
+int batch_get_stats(BatchHost* bh, int first, int count, b2gpu_step_stats* out) {
+  if (!bh || !out || first < 0 || count < 0 || first + count > bh->B.n_worlds) { set_error("get_stats: bad argument"); return B2GPU_E_INVALID; }
+  Batch& B = bh->B;
+  const int W = B.n_wblocks * B.LB;
+  { StatsK k = {B}; RC(launch(bh->ctx, k, W, 32)); }
+  std::vector<int> all((size_t)W * WS_COUNT);
+  RC(dev_d2h(bh->ctx, all.data(), B.ws, all.size() * 4));
+  for (int i = 0; i < count; ++i) {
+    const int w = first + i;
+    const int wb = w >> B.lb_shift, wl = w & (B.LB - 1);
+    auto get = [&](int slot) { return all[((size_t)wb * WS_COUNT + slot) * B.LB + wl]; };
+    b2gpu_step_stats& s = out[i];
+    memset(&s, 0, sizeof(s));
+    s.status = get(WS_STATUS);
+    s.contacts = get(WS_ST_CONTACTS); s.touching = get(WS_ST_TOUCHING); s.destroyed = get(WS_ST_DESTROYED);
+    s.islands = get(WS_ST_ISLANDS); s.island_bodies = get(WS_ST_ISL_BODIES); s.island_contacts = get(WS_ST_ISL_CONTACTS);
+    s.moved = get(WS_ST_MOVED); s.pairs = get(WS_ST_PAIRS); s.created = get(WS_ST_CREATED); s.awake_bodies = get(WS_ST_AWAKE);
+    s.solver_levels = get(WS_ST_LEVELS);
+  }
+  return 0;
+}
+
+// body state gather / force scatter: flat over bodies
+struct StateGatherK {
+  Batch B;
+  float* out;  // [n_worlds][NB][8]
+  B2G_HD void operator()(int tid) const {
+    int w, b;
+    if (!flat_decode(B, tid, B.NB, w, b)) return;
+    WIdx x = widx(B, w);
+    const int bi = x.at(B.NB, b);
+    const float4 pos = B.b_pos[bi], vel = B.b_vel[bi], xf = B.b_xf[bi];
+    float* o = out + ((size_t)w * B.NB + b) * 8;
+    o[0] = pos.x; o[1] = pos.y; o[2] = pos.z; o[3] = vel.x; o[4] = vel.y; o[5] = vel.z; o[6] = xf.x; o[7] = xf.y;
+  }
+};
+struct ForceScatterK {
+  Batch B;
+  const float* in;  // [count][NB][3] for worlds first..first+count
+  int first, count;
+  B2G_HD void operator()(int tid) const {
+    int w, b;
+    if (!flat_decode(B, tid, B.NB, w, b)) return;
+    if (w < first || w >= first + count) return;
+    WIdx x = widx(B, w);
+    const int bi = x.at(B.NB, b);
+    const int bf = B.b_flags[bi];
+    // B2body::apply_force / apply_torque with wake=false: only awake dynamic bodies accumulate
+    if (body_type(bf) != B2GPU_DYNAMIC_BODY || !(bf & B2GPU_BODY_AWAKE)) return;
+    const float* f = in + ((size_t)(w - first) * B.NB + b) * 3;
+    float4 fo = B.b_force[bi];
+    fo.x += f[0]; fo.y += f[1]; fo.z += f[2];
+    B.b_force[bi] = fo;
+  }
+};
+struct VelScatterK {
+  Batch B;
+  const float* in;  // [count][2]
+  int body, first, count;
+  B2G_HD void operator()(int i) const {
+    if (i >= count) return;
+    const int w = first + i;
+    WIdx x = widx(B, w);
+    const int bi = x.at(B.NB, body);
+    const int bf = B.b_flags[bi];
+    if (body_type(bf) == B2GPU_STATIC_BODY) return;  // B2body::set_linear_velocity
+    const float vx = in[2 * i], vy = in[2 * i + 1];
+    if (vx * vx + vy * vy > 0.0f) {
+      B.b_flags[bi] = bf | B2GPU_BODY_AWAKE;
+      B.b_pos[bi].w = 0.0f;
+    }
+    float4 v = B.b_vel[bi];
+    v.x = vx; v.y = vy;
+    B.b_vel[bi] = v;
+  }
+};
+
+int batch_get_body_state(BatchHost* bh, float* host_out, int first, int count) {
+  if (!bh || !host_out || first < 0 || count < 0 || first + count > bh->B.n_worlds) { set_error("get_body_state: bad argument"); return B2GPU_E_INVALID; }
+  Batch& B = bh->B;
+  { StateGatherK k = {B, bh->state_dev}; RC(launch(bh->ctx, k, B.n_wblocks * B.LB * B.NB, 128)); }
+  RC(dev_d2h(bh->ctx, host_out, bh->state_dev + (size_t)first * B.NB * 8, (size_t)count * B.NB * 8 * 4));
+  return 0;
+}
+int batch_set_forces(BatchHost* bh, const float* host, int first, int count) {
+  if (!bh || !host || first < 0 || count < 0 || first + count > bh->B.n_worlds) { set_error("set_forces: bad argument"); return B2GPU_E_INVALID; }
+  Batch& B = bh->B;
+  RC(dev_h2d(bh->ctx, bh->forces_dev, host, (size_t)count * B.NB * 3 * 4));
+  { ForceScatterK k = {B, bh->forces_dev, first, count}; RC(launch(bh->ctx, k, B.n_wblocks * B.LB * B.NB, 128)); }
+  return 0;
+}
+int batch_set_linear_velocity(BatchHost* bh, int body, const float* host_vxvy, int first, int count) {
+  if (!bh || !host_vxvy || body < 0 || body >= bh->B.NB || first < 0 || count < 0 || first + count > bh->B.n_worlds) {
+    set_error("set_linear_velocity: bad argument");
+    return B2GPU_E_INVALID;
+  }
+  RC(dev_h2d(bh->ctx, bh->forces_dev, host_vxvy, (size_t)count * 2 * 4));
+  { VelScatterK k = {bh->B, bh->forces_dev, body, first, count}; RC(launch(bh->ctx, k, count, 128)); }
+  return 0;
+}
+
+}  // namespace b2g

@@ -1,0 +1,71 @@
+// b2g_runtime.h — host-side management of a batch: allocation, (de)serialisation between the
+// C-ABI snapshot records (include/b2gpu.h) and the blocked world-minor device layout, and the
+// per-step launch sequence.  Compiled by nvcc for the product library (libb2gpu.so); the same
+// text is compiled by g++ with -DB2G_HOSTSIM into the test-only host simulator (tests/hostsim),
+// where a "launch" is a plain loop over thread ids.  The product never links the simulator.
+#pragma once
+#include <string>
+#include <vector>
+
+#include "b2g_step.h"
+
+namespace b2g {
+
+struct Ctx {
+  int device = 0;
+  void* stream = nullptr;  // cudaStream_t
+  bool own_stream = false;
+  long long launches = 0;
+};
+
+// One world in compact SoA form (host): the unit of upload/download.
+struct WorldImage {
+  std::vector<int> ws, b_flags, n_moved, move_buf, c_flags, b_chead;
+  std::vector<float4> b_xf, b_pos, b_pos0, b_vel, b_mass, b_force, b_misc, n_aabb, p_aabb, c_mat, c_m0, c_m1, c_m2;
+  std::vector<int4> n_link, c_fix, c_m3;
+  std::vector<int2> c_next;
+};
+
+struct Topology {  // shared by every world of a batch (host copies kept for validation/download)
+  std::vector<b2gpu_body_rec> bodies;  // static fields only are authoritative (type, fixture_head, fixture_count)
+  std::vector<b2gpu_fixture_rec> fixtures;
+  std::vector<b2gpu_shape_rec> shapes;
+  std::vector<b2gpu_proxy_rec> proxies;
+  std::vector<int4> proxy_s;
+  std::vector<int> sync_order, node_proxy;
+};
+
+struct BatchHost {
+  Ctx* ctx = nullptr;
+  Batch B;          // device pointers + dims
+  Topology topo;
+  std::vector<void*> allocs;
+  int* b_wake = nullptr;
+  int* b_chead = nullptr;
+  int2* c_next = nullptr;
+  int* stack = nullptr;
+  float* state_dev = nullptr;    // [n_worlds][NB][8] gather buffer
+  float* forces_dev = nullptr;   // [n_worlds][NB][3]
+  void* stage_dev = nullptr;     // staging for single-world upload/download
+  size_t stage_bytes = 0;
+  bool pre_step_needed = true;   // some world may carry m_new_contacts / a non-empty move buffer
+  long long total_bytes = 0;
+  StepParams last_sp{};
+};
+
+const char* last_error();
+void set_error(const std::string& s);
+
+int batch_create(Ctx* ctx, const b2gpu_snapshot* proto, int n_worlds, const b2gpu_caps* caps, int lane_block, BatchHost** out);
+void batch_destroy(BatchHost* b);
+int batch_upload_world(BatchHost* b, int world, const b2gpu_snapshot* in);
+int batch_snapshot_sizes(BatchHost* b, int world, b2gpu_snapshot_sizes* out);
+int batch_download_world(BatchHost* b, int world, b2gpu_snapshot* out);
+int batch_step(BatchHost* b, float dt, int vi, int pi, int steps);
+int batch_get_stats(BatchHost* b, int first, int count, b2gpu_step_stats* out);
+int batch_get_body_state(BatchHost* b, float* host_out, int first, int count);
+int batch_set_forces(BatchHost* b, const float* host, int first, int count);
+int batch_set_linear_velocity(BatchHost* b, int body, const float* host_vxvy, int first, int count);
+int ctx_sync(Ctx* ctx);
+
+}  // namespace b2g
