@@ -24,6 +24,17 @@ class Context:
     def stream(self):
         return self.L.b2gpu_stream(self.h)
 
+    def set_profiling(self, on):
+        check(self.L, self.L.b2gpu_set_profiling(self.h, int(on)))
+
+    def stage_times(self):
+        """{stage name: (milliseconds, launches)} accumulated since set_profiling(True)."""
+        n = self.L.b2gpu_stage_count()
+        ms = np.zeros(n, np.float64)
+        cnt = np.zeros(n, np.int64)
+        check(self.L, self.L.b2gpu_get_stage_times(self.h, ms.ctypes.data, cnt.ctypes.data, n))
+        return {self.L.b2gpu_stage_name(i).decode(): (float(ms[i]), int(cnt[i])) for i in range(n)}
+
     def close(self):
         if self.h:
             self.L.b2gpu_shutdown(self.h)
@@ -75,6 +86,15 @@ class Batch:
         out = np.zeros((count, self.body_count, 8), np.float32)
         check(self.L, self.L.b2gpu_batch_get_body_state(self.h, out.ctypes.data, first, count))
         return out
+
+    def step_host(self, forces, state_out, dt, velocity_iterations, position_iterations, steps=1):
+        """End-to-end step through HOST buffers: H2D forces, step(s), D2H body state (synchronous)."""
+        fp = forces.ctypes.data if forces is not None else None
+        check(self.L, self.L.b2gpu_batch_step_host(self.h, fp, state_out.ctypes.data, dt, velocity_iterations,
+                                                   position_iterations, steps))
+
+    def algorithmic_bytes(self):
+        return int(self.L.b2gpu_batch_algorithmic_bytes(self.h))
 
     def set_forces(self, forces, first=0):
         f = np.ascontiguousarray(forces, np.float32)

@@ -13,9 +13,6 @@
 
 using namespace b2g;
 
-struct b2gpu_ctx {
-  Ctx c;
-};
 struct b2gpu_batch {
   BatchHost* h;
   b2gpu_ctx* ctx;
@@ -162,6 +159,56 @@ int b2gpu_batch_get_body_state(b2gpu_batch* b, float* host_out, int first, int c
   GUARD_BEGIN
   if (!b) { set_error("batch is NULL"); return B2GPU_E_INVALID; }
   return batch_get_body_state(b->h, host_out, first, count);
+  GUARD_END
+}
+
+void* b2gpu_batch_body_state_device(b2gpu_batch* b, int64_t* bytes) {
+  if (!b) return nullptr;
+  if (bytes) *bytes = (int64_t)b->h->B.n_worlds * b->h->B.NB * 8 * 4;
+  return b->h->state_dev;
+}
+void* b2gpu_batch_forces_device(b2gpu_batch* b, int64_t* bytes) {
+  if (!b) return nullptr;
+  if (bytes) *bytes = (int64_t)b->h->B.n_worlds * b->h->B.NB * 3 * 4;
+  return b->h->forces_dev;
+}
+int b2gpu_batch_step_host(b2gpu_batch* b, const float* host_forces, float* host_state_out, float dt, int vi, int pi, int steps) {
+  GUARD_BEGIN
+  if (!b) { set_error("batch is NULL"); return B2GPU_E_INVALID; }
+  int rc = 0;
+  if (host_forces) rc = batch_set_forces(b->h, host_forces, 0, b->h->B.n_worlds);
+  if (!rc) rc = batch_step(b->h, dt, vi, pi, steps);
+  if (!rc && host_state_out) rc = batch_get_body_state(b->h, host_state_out, 0, b->h->B.n_worlds);
+  if (!rc && !host_state_out) rc = ctx_sync(&b->ctx->c);
+  return rc;
+  GUARD_END
+}
+int64_t b2gpu_batch_algorithmic_bytes(b2gpu_batch* b) { return b ? batch_algorithmic_bytes(b->h) : -1; }
+static const char* k_stage_names[STAGE_COUNT] = {"pre_step_pairs", "collide", "island", "integrate", "solver_init", "velocity",
+                                                  "post_velocity", "position", "finalize", "sleep", "sync_fixtures",
+                                                  "tree_pairs", "body_end", "other"};
+int b2gpu_stage_count(void) { return STAGE_COUNT; }
+const char* b2gpu_stage_name(int stage) { return stage >= 0 && stage < STAGE_COUNT ? k_stage_names[stage] : ""; }
+int b2gpu_set_profiling(b2gpu_ctx* ctx, int on) {
+  if (!ctx) { set_error("ctx is NULL"); return B2GPU_E_INVALID; }
+  int rc = ctx_collect_profile(&ctx->c);
+  ctx->c.profiling = on != 0;
+  for (int i = 0; i < STAGE_COUNT; ++i) { ctx->c.stage_ms[i] = 0.0; ctx->c.stage_launches[i] = 0; }
+  return rc;
+}
+int b2gpu_get_stage_times(b2gpu_ctx* ctx, double* ms_out, int64_t* launches_out, int n) {
+  if (!ctx || !ms_out || n < 0) { set_error("get_stage_times: bad argument"); return B2GPU_E_INVALID; }
+  int rc = ctx_collect_profile(&ctx->c);
+  for (int i = 0; i < n && i < STAGE_COUNT; ++i) {
+    ms_out[i] = ctx->c.stage_ms[i];
+    if (launches_out) launches_out[i] = ctx->c.stage_launches[i];
+  }
+  return rc;
+}
+int b2gpu_debug_sincos(b2gpu_ctx* ctx, const float* host_in, float* host_sin, float* host_cos, int n) {
+  GUARD_BEGIN
+  if (!ctx) { set_error("ctx is NULL"); return B2GPU_E_INVALID; }
+  return debug_sincos(&ctx->c, host_in, host_sin, host_cos, n);
   GUARD_END
 }
 

@@ -17,6 +17,8 @@ static thread_local std::string g_error;
 const char* last_error() { return g_error.c_str(); }
 void set_error(const std::string& s) { g_error = s; }
 
+#define RC(x) do { int rc_ = (x); if (rc_ != 0) return rc_; } while (0)
+
 // ------------------------------------------------------------------ device abstraction
 #if defined(B2G_HOSTSIM)
 static int dev_alloc(void** p, size_t bytes) { *p = calloc(1, bytes ? bytes : 1); return *p ? 0 : B2GPU_E_CUDA; }
@@ -25,11 +27,13 @@ static int dev_h2d(Ctx*, void* d, const void* h, size_t n) { memcpy(d, h, n); re
 static int dev_d2h(Ctx*, void* h, const void* d, size_t n) { memcpy(h, d, n); return 0; }
 static int dev_zero(Ctx*, void* d, size_t n) { memset(d, 0, n); return 0; }
 int ctx_sync(Ctx*) { return 0; }
-template <class K> static int launch(Ctx* ctx, const K& k, int n, int /*block*/) {
+template <class K> static int launch(Ctx* ctx, const K& k, int n, int /*block*/, int stage = STAGE_OTHER) {
   for (int t = 0; t < n; ++t) k(t);
   ctx->launches++;
+  ctx->stage_launches[stage] += 1;
   return 0;
 }
+int ctx_collect_profile(Ctx*) { return 0; }
 #else
 static int cuda_fail(cudaError_t e, const char* what) {
   set_error(std::string(what) + ": " + cudaGetErrorString(e));
@@ -64,18 +68,43 @@ template <class K> __global__ void stage_kernel(const K k, int n) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < n) k(t);
 }
-template <class K> static int launch(Ctx* ctx, const K& k, int n, int block) {
+static int prof_event(Ctx* ctx, cudaEvent_t* ev) {
+  if (!ctx->ev_free.empty()) { *ev = (cudaEvent_t)ctx->ev_free.back(); ctx->ev_free.pop_back(); }
+  else CU(cudaEventCreate(ev));
+  CU(cudaEventRecord(*ev, (cudaStream_t)ctx->stream));
+  return 0;
+}
+template <class K> static int launch(Ctx* ctx, const K& k, int n, int block, int stage = STAGE_OTHER) {
   if (n <= 0) return 0;
   int grid = (n + block - 1) / block;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  if (ctx->profiling) RC(prof_event(ctx, &e0));
   stage_kernel<K><<<grid, block, 0, (cudaStream_t)ctx->stream>>>(k, n);
+  if (ctx->profiling) {
+    RC(prof_event(ctx, &e1));
+    ProfSpan sp = {stage, (void*)e0, (void*)e1};
+    ctx->ev_pending.push_back(sp);
+  }
   ctx->launches++;
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
   return 0;
 }
+int ctx_collect_profile(Ctx* ctx) {
+  CU(cudaStreamSynchronize((cudaStream_t)ctx->stream));
+  for (const ProfSpan& sp : ctx->ev_pending) {
+    float ms = 0.0f;
+    CU(cudaEventElapsedTime(&ms, (cudaEvent_t)sp.e0, (cudaEvent_t)sp.e1));
+    ctx->stage_ms[sp.stage] += ms;
+    ctx->stage_launches[sp.stage] += 1;
+    ctx->ev_free.push_back(sp.e0);
+    ctx->ev_free.push_back(sp.e1);
+  }
+  ctx->ev_pending.clear();
+  return 0;
+}
 #endif
 
-#define RC(x) do { int rc_ = (x); if (rc_ != 0) return rc_; } while (0)
 
 // ------------------------------------------------------------------ layout movers (4-byte words)
 struct MoveK {
@@ -396,7 +425,7 @@ int batch_create(Ctx* ctx, const b2gpu_snapshot* proto, int n_worlds, const b2gp
   B.NB = n.body_count; B.NF = n.fixture_count; B.NS = n.shape_count; B.NP = n.proxy_count;
   if (B.NB < 1 || B.NP < 0) { set_error("empty world"); delete bh; return B2GPU_E_INVALID; }
   B.NN = std::max(n.node_count, 16);
-  int want_contacts = std::max(n.contact_count * 2, B.NP * 4 + 64);
+  int want_contacts = std::max(n.contact_count * 2, B.NP * 10 + 64);
   if (caps && caps->max_contacts > 0) want_contacts = std::max(caps->max_contacts, n.contact_count);
   B.NC = want_contacts;
   B.NPAIR = (caps && caps->max_pairs > 0) ? caps->max_pairs : std::max(B.NC, 8 * B.NP + 64);
@@ -517,31 +546,31 @@ int batch_step(BatchHost* bh, float dt, int vi, int pi, int steps) {
   for (int s = 0; s < steps; ++s) {
     {
       TreePairsK k = {B, bh->b_chead, bh->c_next, sp, 1};
-      RC(launch(ctx, k, W, ordered_block));
+      RC(launch(ctx, k, W, ordered_block, STAGE_PRE));
     }
     {
       CollideK k = {B, bh->b_wake};
-      RC(launch(ctx, k, W * B.NC, 128));
+      RC(launch(ctx, k, W * B.NC, 128, STAGE_COLLIDE));
     }
     {
       SerialAK k = {B, bh->b_wake, bh->b_chead, bh->c_next, bh->stack, sp};
-      RC(launch(ctx, k, W, ordered_block));
+      RC(launch(ctx, k, W, ordered_block, STAGE_ISLAND));
     }
     if (dt > 0.0f) {
-      { IntegrateK k = {B, sp}; RC(launch(ctx, k, W * B.NIB, 128)); }
-      { SolverInitK k = {B, sp}; RC(launch(ctx, k, W * B.NC, 128)); }
-      { VelocityK k = {B, sp}; RC(launch(ctx, k, W, ordered_block)); }
-      { PostVelocityK k = {B, sp}; RC(launch(ctx, k, W * B.NIB, 128)); }
-      { PositionK k = {B, sp}; RC(launch(ctx, k, W, ordered_block)); }
-      { FinalizeK k = {B, sp}; RC(launch(ctx, k, W * B.NIB, 128)); }
-      { SleepK k = {B}; RC(launch(ctx, k, W, ordered_block)); }
-      if (B.NP > 0) { SyncFixturesK k = {B}; RC(launch(ctx, k, W * B.NP, 128)); }
+      { IntegrateK k = {B, sp}; RC(launch(ctx, k, W * B.NIB, 128, STAGE_INTEGRATE)); }
+      { SolverInitK k = {B, sp}; RC(launch(ctx, k, W * B.NC, 128, STAGE_SOLVER_INIT)); }
+      { VelocityK k = {B, sp}; RC(launch(ctx, k, W, ordered_block, STAGE_VELOCITY)); }
+      { PostVelocityK k = {B, sp}; RC(launch(ctx, k, W * B.NIB, 128, STAGE_POST_VELOCITY)); }
+      { PositionK k = {B, sp}; RC(launch(ctx, k, W, ordered_block, STAGE_POSITION)); }
+      { FinalizeK k = {B, sp}; RC(launch(ctx, k, W * B.NIB, 128, STAGE_FINALIZE)); }
+      { SleepK k = {B}; RC(launch(ctx, k, W, ordered_block, STAGE_SLEEP)); }
+      if (B.NP > 0) { SyncFixturesK k = {B}; RC(launch(ctx, k, W * B.NP, 128, STAGE_SYNC_FIXTURES)); }
     }
     {
       TreePairsK k = {B, bh->b_chead, bh->c_next, sp, 0};
-      RC(launch(ctx, k, W, ordered_block));
+      RC(launch(ctx, k, W, ordered_block, STAGE_TREE_PAIRS));
     }
-    { BodyEndK k = {B}; RC(launch(ctx, k, W * B.NB, 128)); }
+    { BodyEndK k = {B}; RC(launch(ctx, k, W * B.NB, 128, STAGE_BODY_END)); }
   }
   bh->pre_step_needed = false;
   return 0;
@@ -663,6 +692,38 @@ int batch_set_linear_velocity(BatchHost* bh, int body, const float* host_vxvy, i
   RC(dev_h2d(bh->ctx, bh->forces_dev, host_vxvy, (size_t)count * 2 * 4));
   { VelScatterK k = {bh->B, bh->forces_dev, body, first, count}; RC(launch(bh->ctx, k, count, 128)); }
   return 0;
+}
+
+// sin/cos of an array of angles on the device (diagnostic: pins rot_from_angle against libm)
+struct SinCosK {
+  const float* in;
+  float* s;
+  float* c;
+  B2G_HD void operator()(int i) const { sincos_ref(in[i], &s[i], &c[i]); }
+};
+int debug_sincos(Ctx* ctx, const float* host_in, float* host_sin, float* host_cos, int n) {
+  if (!ctx || !host_in || !host_sin || !host_cos || n < 0) { set_error("debug_sincos: bad argument"); return B2GPU_E_INVALID; }
+  void* d = nullptr;
+  RC(dev_alloc(&d, (size_t)n * 12));
+  float* din = (float*)d;
+  int rc = dev_h2d(ctx, din, host_in, (size_t)n * 4);
+  if (!rc) { SinCosK k = {din, din + n, din + 2 * (size_t)n}; rc = launch(ctx, k, n, 256); }
+  if (!rc) rc = dev_d2h(ctx, host_sin, din + n, (size_t)n * 4);
+  if (!rc) rc = dev_d2h(ctx, host_cos, din + 2 * (size_t)n, (size_t)n * 4);
+  dev_free(d);
+  return rc;
+}
+
+// compulsory HBM traffic of the last step, summed over all worlds
+long long batch_algorithmic_bytes(BatchHost* bh) {
+  if (!bh) return -1;
+  Batch& B = bh->B;
+  std::vector<b2gpu_step_stats> st(B.n_worlds);
+  if (batch_get_stats(bh, 0, B.n_worlds, st.data())) return -1;
+  long long total = 0;
+  for (const b2gpu_step_stats& s : st)
+    total += 116LL * s.awake_bodies + 36LL * B.NP + 16LL * s.moved + 272LL * s.contacts + 168LL * s.created;
+  return total;
 }
 
 }  // namespace b2g

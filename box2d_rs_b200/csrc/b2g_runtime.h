@@ -11,12 +11,27 @@
 
 namespace b2g {
 
+// stages of one step, in launch order (profiling / ncu names)
+enum {
+  STAGE_PRE = 0, STAGE_COLLIDE, STAGE_ISLAND, STAGE_INTEGRATE, STAGE_SOLVER_INIT, STAGE_VELOCITY, STAGE_POST_VELOCITY,
+  STAGE_POSITION, STAGE_FINALIZE, STAGE_SLEEP, STAGE_SYNC_FIXTURES, STAGE_TREE_PAIRS, STAGE_BODY_END, STAGE_OTHER, STAGE_COUNT
+};
+struct ProfSpan {
+  int stage;
+  void *e0, *e1;  // cudaEvent_t
+};
 struct Ctx {
   int device = 0;
   void* stream = nullptr;  // cudaStream_t
   bool own_stream = false;
   long long launches = 0;
+  bool profiling = false;  // record a CUDA event pair around every launch
+  std::vector<void*> ev_free;
+  std::vector<ProfSpan> ev_pending;
+  double stage_ms[STAGE_COUNT] = {0};
+  long long stage_launches[STAGE_COUNT] = {0};
 };
+int ctx_collect_profile(Ctx* ctx);
 
 // One world in compact SoA form (host): the unit of upload/download.
 struct WorldImage {
@@ -67,5 +82,11 @@ int batch_get_body_state(BatchHost* b, float* host_out, int first, int count);
 int batch_set_forces(BatchHost* b, const float* host, int first, int count);
 int batch_set_linear_velocity(BatchHost* b, int body, const float* host_vxvy, int first, int count);
 int ctx_sync(Ctx* ctx);
+int debug_sincos(Ctx* ctx, const float* host_in, float* host_sin, float* host_cos, int n);
+long long batch_algorithmic_bytes(BatchHost* b);
 
 }  // namespace b2g
+
+struct b2gpu_ctx {
+  b2g::Ctx c;
+};

@@ -1,0 +1,847 @@
+// b2g_world.cu — host-side mirror of the reference's world-building API behind the C ABI:
+// B2world::new/create_body, B2body::create_fixture/set_transform/set_*_velocity/apply_force,
+// B2polygonShape::set/set_as_box, compute_mass.  This is setup-time bookkeeping (SURVEY.md §2:
+// "API stays on host, only mirrored into SoA"): it produces the snapshot that the device engine
+// steps.  Stepping itself always runs on the GPU (a one-world batch); nothing here simulates.
+//
+// Reference: src/private/dynamics/b2_world.rs:26-98, b2_body.rs(private):15-90,155-200,292-350,
+// 418-444, b2_fixture.rs(private):40-173, b2_polygon_shape.rs(private):15-211,314-390,
+// b2_circle_shape.rs(private):79-86, b2_edge_shape.rs(private):126-132, b2_chain_shape.rs(private):59-79,135-141,
+// b2_dynamic_tree.rs(private):81-168, b2_broad_phase.rs(private):33-75.
+#include <string.h>
+
+#include <new>
+#include <vector>
+
+#include "b2g_runtime.h"
+
+using namespace b2g;
+
+namespace {
+
+// user shapes are kept per fixture for reset_mass_data (compute_mass needs the whole shape)
+struct WorldDefs {
+  std::vector<b2gpu_shape_def> shape_defs;
+  std::vector<std::vector<float>> chain_storage;
+};
+
+struct HostWorld {
+  b2gpu_world_rec world;
+  std::vector<b2gpu_body_rec> bodies;
+  std::vector<b2gpu_fixture_rec> fixtures;
+  std::vector<b2gpu_shape_rec> shapes;
+  std::vector<b2gpu_proxy_rec> proxies;
+  std::vector<b2gpu_contact_rec> contacts;
+  std::vector<int> move_buffer;
+  // replica tree on the host (stride-1 arrays driven by the same Tree code as the device)
+  std::vector<float4> n_aabb;
+  std::vector<int4> n_link;
+  std::vector<int> n_moved, n_proxy;
+  int ws[WS_COUNT];
+  int status = 0;
+};
+
+void tree_reserve(HostWorld& w, int cap) {
+  w.n_aabb.resize(cap, make_float4(0, 0, 0, 0));
+  w.n_link.resize(cap, make_int4(-1, -1, -1, -1));
+  w.n_moved.resize(cap, 0);
+  w.n_proxy.resize(cap, -1);
+}
+Tree host_tree(HostWorld& w) {
+  Tree t;
+  t.aabb = w.n_aabb.data();
+  t.link = w.n_link.data();
+  t.moved = w.n_moved.data();
+  t.stride = 1;
+  t.ws = w.ws;
+  t.ws_stride = 1;
+  t.phys_cap = (int)w.n_aabb.size();
+  t.status = &w.status;
+  return t;
+}
+void host_world_init(HostWorld& w, float gx, float gy) {
+  memset(&w.world, 0, sizeof(w.world));
+  w.world.gravity_x = gx;
+  w.world.gravity_y = gy;
+  w.world.inv_dt0 = 0.0f;
+  // b2_world.rs(private):37-48: warm starting, sleep, auto clear forces on; continuous physics is
+  // outside the hot-path scope and fixed off.  G_BLOCK_SOLVE defaults to true.
+  w.world.flags = B2GPU_WORLD_ALLOW_SLEEP | B2GPU_WORLD_WARM_STARTING | B2GPU_WORLD_CLEAR_FORCES | B2GPU_WORLD_BLOCK_SOLVE;
+  memset(w.ws, 0, sizeof(w.ws));
+  // B2dynamicTree::new (b2_dynamic_tree.rs(private):7-32): pool of 16 chained free nodes
+  tree_reserve(w, 16);
+  for (int i = 0; i < 15; ++i) w.n_link[i] = make_int4(i + 1, -1, -1, -1);
+  w.n_link[15] = make_int4(-1, -1, -1, -1);
+  w.ws[WS_TREE_ROOT] = -1;
+  w.ws[WS_TREE_FREE] = 0;
+  w.ws[WS_TREE_COUNT] = 0;
+  w.ws[WS_TREE_CAP] = 16;
+  w.ws[WS_TREE_INSERTIONS] = 0;
+}
+
+Xf body_xf(const b2gpu_body_rec& b) {
+  Xf xf;
+  xf.p = v2(b.xf_px, b.xf_py);
+  xf.q.s = b.xf_qs;
+  xf.q.c = b.xf_qc;
+  return xf;
+}
+
+// B2broadPhase::create_proxy -> B2dynamicTree::create_proxy; grows the pool like allocate_node.
+int bp_create_proxy(HostWorld& w, const Box& aabb, int proxy_index) {
+  if (w.ws[WS_TREE_FREE] == -1) tree_reserve(w, w.ws[WS_TREE_CAP] * 2);
+  Tree t = host_tree(w);
+  Box fat;
+  fat.lo = aabb.lo - v2(B2G_AABB_EXTENSION, B2G_AABB_EXTENSION);
+  fat.hi = aabb.hi + v2(B2G_AABB_EXTENSION, B2G_AABB_EXTENSION);
+  // the leaf itself may exhaust the pool and its parent needs one more node
+  int id = t.allocate_node();
+  if (id < 0) return id;
+  t.setA(id, fat);
+  t.moved[id] = 1;
+  if (w.ws[WS_TREE_FREE] == -1) {
+    tree_reserve(w, w.ws[WS_TREE_CAP] * 2);
+    t = host_tree(w);
+  }
+  t.insert_leaf(id);
+  w.n_proxy[id] = proxy_index;
+  w.world.proxy_count += 1;
+  w.move_buffer.push_back(id);
+  return id;
+}
+// B2broadPhase::move_proxy -> B2dynamicTree::move_proxy (:109-168)
+void bp_move_proxy(HostWorld& w, int id, const Box& aabb, V2 displacement) {
+  Tree t = host_tree(w);
+  const V2 r = v2(B2G_AABB_EXTENSION, B2G_AABB_EXTENSION);
+  Box fat;
+  fat.lo = aabb.lo - r;
+  fat.hi = aabb.hi + r;
+  const V2 d = B2G_AABB_MULTIPLIER * displacement;
+  if (d.x < 0.0f) fat.lo.x += d.x; else fat.hi.x += d.x;
+  if (d.y < 0.0f) fat.lo.y += d.y; else fat.hi.y += d.y;
+  const Box tree_box = t.A(id);
+  if (box_contains(tree_box, aabb)) {
+    Box huge;
+    huge.lo = fat.lo - 4.0f * r;
+    huge.hi = fat.hi + 4.0f * r;
+    if (box_contains(huge, tree_box)) return;
+  }
+  t.remove_leaf(id);
+  t.setA(id, fat);
+  t.insert_leaf(id);
+  t.moved[id] = 1;
+  w.move_buffer.push_back(id);
+}
+
+void fill_child_shape(b2gpu_shape_rec& r, const b2gpu_shape_def* s, int child) {
+  memset(&r, 0, sizeof(r));
+  r.radius = s->radius;
+  if (s->type == B2GPU_SHAPE_CIRCLE) {
+    r.type = B2GPU_SHAPE_CIRCLE;
+    r.cx = s->p_x; r.cy = s->p_y;
+    r.v[0] = s->p_x; r.v[1] = s->p_y;
+  } else if (s->type == B2GPU_SHAPE_EDGE) {
+    r.type = B2GPU_SHAPE_EDGE;
+    r.one_sided = s->one_sided ? 1 : 0;
+    r.v[0] = s->v0[0]; r.v[1] = s->v0[1]; r.v[2] = s->v1[0]; r.v[3] = s->v1[1];
+    r.v[4] = s->v2[0]; r.v[5] = s->v2[1]; r.v[6] = s->v3[0]; r.v[7] = s->v3[1];
+  } else if (s->type == B2GPU_SHAPE_POLYGON) {
+    r.type = B2GPU_SHAPE_POLYGON;
+    r.count = s->count;
+    r.cx = s->centroid[0]; r.cy = s->centroid[1];
+    memcpy(r.v, s->vertices, sizeof(r.v));
+    memcpy(r.n, s->normals, sizeof(r.n));
+  } else {
+    // B2chainShape::get_child_edge (b2_chain_shape.rs(private):59-79): one-sided edge with ghost vertices
+    const float* cv = s->chain_vertices;
+    const int n = s->chain_count;
+    r.type = B2GPU_SHAPE_EDGE;
+    r.one_sided = 1;
+    r.v[2] = cv[2 * child]; r.v[3] = cv[2 * child + 1];
+    r.v[4] = cv[2 * (child + 1)]; r.v[5] = cv[2 * (child + 1) + 1];
+    if (child > 0) { r.v[0] = cv[2 * (child - 1)]; r.v[1] = cv[2 * (child - 1) + 1]; }
+    else { r.v[0] = s->chain_prev[0]; r.v[1] = s->chain_prev[1]; }
+    if (child < n - 2) { r.v[6] = cv[2 * (child + 2)]; r.v[7] = cv[2 * (child + 2) + 1]; }
+    else { r.v[6] = s->chain_next[0]; r.v[7] = s->chain_next[1]; }
+  }
+}
+
+void polygon_box(b2gpu_shape_def* s, float hx, float hy) {
+  s->type = B2GPU_SHAPE_POLYGON;
+  s->radius = B2G_POLYGON_RADIUS;
+  s->count = 4;
+  const float vx[4] = {-hx, hx, hx, -hx}, vy[4] = {-hy, -hy, hy, hy};
+  const float nx[4] = {0.0f, 1.0f, 0.0f, -1.0f}, ny[4] = {-1.0f, 0.0f, 1.0f, 0.0f};
+  memset(s->vertices, 0, sizeof(s->vertices));
+  memset(s->normals, 0, sizeof(s->normals));
+  for (int i = 0; i < 4; ++i) {
+    s->vertices[2 * i] = vx[i]; s->vertices[2 * i + 1] = vy[i];
+    s->normals[2 * i] = nx[i]; s->normals[2 * i + 1] = ny[i];
+  }
+  s->centroid[0] = 0.0f;
+  s->centroid[1] = 0.0f;
+}
+
+int shape_mass(const b2gpu_shape_def* s, float density, b2gpu_mass_data* md) {
+  switch (s->type) {
+    case B2GPU_SHAPE_CIRCLE: {
+      md->mass = density * B2G_PI * s->radius * s->radius;
+      md->center_x = s->p_x;
+      md->center_y = s->p_y;
+      md->inertia = md->mass * (0.5f * s->radius * s->radius + (s->p_x * s->p_x + s->p_y * s->p_y));
+      return 0;
+    }
+    case B2GPU_SHAPE_EDGE: {
+      md->mass = 0.0f;
+      md->center_x = 0.5f * (s->v1[0] + s->v2[0]);
+      md->center_y = 0.5f * (s->v1[1] + s->v2[1]);
+      md->inertia = 0.0f;
+      return 0;
+    }
+    case B2GPU_SHAPE_CHAIN: {
+      md->mass = 0.0f; md->center_x = 0.0f; md->center_y = 0.0f; md->inertia = 0.0f;
+      return 0;
+    }
+    case B2GPU_SHAPE_POLYGON: {
+      if (s->count < 3 || s->count > B2G_MAX_POLY) { set_error("polygon vertex count out of range"); return B2GPU_E_INVALID; }
+      V2 center = v2(0.0f, 0.0f);
+      float area = 0.0f, inert = 0.0f;
+      const V2 ref = v2(s->vertices[0], s->vertices[1]);
+      const float k_inv3 = 1.0f / 3.0f;
+      for (int i = 0; i < s->count; ++i) {
+        const int j = i + 1 < s->count ? i + 1 : 0;
+        const V2 e1 = v2(s->vertices[2 * i], s->vertices[2 * i + 1]) - ref;
+        const V2 e2 = v2(s->vertices[2 * j], s->vertices[2 * j + 1]) - ref;
+        const float d = cross(e1, e2);
+        const float tri = 0.5f * d;
+        area += tri;
+        center = center + (tri * k_inv3) * (e1 + e2);
+        const float intx2 = e1.x * e1.x + e2.x * e1.x + e2.x * e2.x;
+        const float inty2 = e1.y * e1.y + e2.y * e1.y + e2.y * e2.y;
+        inert += (0.25f * k_inv3 * d) * (intx2 + inty2);
+      }
+      md->mass = density * area;
+      if (!(area > B2G_EPSILON)) { set_error("degenerate polygon (zero area)"); return B2GPU_E_INVALID; }
+      center = (1.0f / area) * center;
+      const V2 c = center + ref;
+      md->center_x = c.x;
+      md->center_y = c.y;
+      md->inertia = density * inert;
+      md->inertia += md->mass * (dot(c, c) - dot(center, center));
+      return 0;
+    }
+  }
+  set_error("unknown shape type");
+  return B2GPU_E_INVALID;
+}
+
+}  // namespace
+
+struct b2gpu_world {
+  b2gpu_ctx* ctx = nullptr;
+  HostWorld h;
+  WorldDefs defs;
+  BatchHost* dev = nullptr;
+  bool host_dirty = true;   // host edits not on the device yet
+  bool topo_dirty = true;   // bodies/fixtures changed: the device batch must be rebuilt
+  bool dev_newer = false;   // the device holds the authoritative state
+};
+
+namespace {
+
+void fill_snapshot(b2gpu_world* W, b2gpu_snapshot* s, std::vector<b2gpu_tree_node_rec>& nodes) {
+  HostWorld& h = W->h;
+  h.world.tree_root = h.ws[WS_TREE_ROOT];
+  h.world.tree_free_list = h.ws[WS_TREE_FREE];
+  h.world.tree_node_count = h.ws[WS_TREE_COUNT];
+  h.world.tree_node_capacity = h.ws[WS_TREE_CAP];
+  h.world.tree_insertion_count = h.ws[WS_TREE_INSERTIONS];
+  const int cap = h.ws[WS_TREE_CAP];
+  nodes.resize(cap);
+  for (int i = 0; i < cap; ++i) {
+    b2gpu_tree_node_rec& n = nodes[i];
+    n.aabb[0] = h.n_aabb[i].x; n.aabb[1] = h.n_aabb[i].y; n.aabb[2] = h.n_aabb[i].z; n.aabb[3] = h.n_aabb[i].w;
+    n.parent = h.n_link[i].x; n.child1 = h.n_link[i].y; n.child2 = h.n_link[i].z; n.height = h.n_link[i].w;
+    n.proxy = n.height == 0 ? h.n_proxy[i] : -1;
+    n.moved = h.n_moved[i];
+  }
+  s->world = h.world;
+  s->n.body_count = (int)h.bodies.size(); s->n.fixture_count = (int)h.fixtures.size();
+  s->n.shape_count = (int)h.shapes.size(); s->n.proxy_count = (int)h.proxies.size();
+  s->n.node_count = cap; s->n.contact_count = (int)h.contacts.size(); s->n.move_count = (int)h.move_buffer.size();
+  s->n.reserved = 0;
+  s->bodies = h.bodies.data(); s->fixtures = h.fixtures.data(); s->shapes = h.shapes.data();
+  s->proxies = h.proxies.data(); s->nodes = nodes.data(); s->contacts = h.contacts.data();
+  s->move_buffer = h.move_buffer.data();
+}
+
+// Pull the device state back into the host mirror before the host reads or edits it.
+int ensure_host(b2gpu_world* W) {
+  if (!W->dev_newer) return 0;
+  HostWorld& h = W->h;
+  b2gpu_snapshot_sizes n;
+  int rc = batch_snapshot_sizes(W->dev, 0, &n);
+  if (rc) return rc;
+  std::vector<b2gpu_tree_node_rec> nodes(std::max(n.node_count, 1));
+  h.contacts.resize(std::max(n.contact_count, 1));
+  h.move_buffer.resize(std::max(n.move_count, 1));
+  b2gpu_snapshot s;
+  memset(&s, 0, sizeof(s));
+  s.n = n;
+  s.n.contact_count = (int)h.contacts.size();
+  s.n.move_count = (int)h.move_buffer.size();
+  s.n.node_count = (int)nodes.size();
+  s.bodies = h.bodies.data(); s.fixtures = h.fixtures.data(); s.shapes = h.shapes.data(); s.proxies = h.proxies.data();
+  s.nodes = nodes.data(); s.contacts = h.contacts.data(); s.move_buffer = h.move_buffer.data();
+  rc = batch_download_world(W->dev, 0, &s);
+  if (rc) return rc;
+  h.contacts.resize(s.n.contact_count);
+  h.move_buffer.resize(s.n.move_count);
+  h.world = s.world;
+  h.ws[WS_TREE_ROOT] = s.world.tree_root; h.ws[WS_TREE_FREE] = s.world.tree_free_list;
+  h.ws[WS_TREE_COUNT] = s.world.tree_node_count; h.ws[WS_TREE_CAP] = s.world.tree_node_capacity;
+  h.ws[WS_TREE_INSERTIONS] = s.world.tree_insertion_count;
+  if ((int)h.n_aabb.size() < s.n.node_count) tree_reserve(h, s.n.node_count);
+  for (int i = 0; i < s.n.node_count; ++i) {
+    const b2gpu_tree_node_rec& nd = nodes[i];
+    h.n_aabb[i] = make_float4(nd.aabb[0], nd.aabb[1], nd.aabb[2], nd.aabb[3]);
+    h.n_link[i] = make_int4(nd.parent, nd.child1, nd.child2, nd.height);
+    h.n_moved[i] = nd.moved;
+  }
+  W->dev_newer = false;
+  return 0;
+}
+
+int check_body(b2gpu_world* W, int body) {
+  if (!W) { set_error("world is NULL"); return B2GPU_E_INVALID; }
+  if (body < 0 || body >= (int)W->h.bodies.size()) { set_error("body index out of range"); return B2GPU_E_INVALID; }
+  return 0;
+}
+
+void set_awake(b2gpu_body_rec& b, bool flag) {  // src/b2_body.rs:783-801
+  if (b.type == B2GPU_STATIC_BODY) return;
+  if (flag) {
+    b.flags |= B2GPU_BODY_AWAKE;
+    b.sleep_time = 0.0f;
+  } else {
+    b.flags &= ~B2GPU_BODY_AWAKE;
+    b.sleep_time = 0.0f;
+    b.vx = b.vy = b.w = 0.0f;
+    b.fx = b.fy = b.torque = 0.0f;
+  }
+}
+
+int fixture_mass(const HostWorld& h, const std::vector<b2gpu_shape_def>& defs, int f, b2gpu_mass_data* md) {
+  return shape_mass(&defs[f], h.fixtures[f].density, md);
+}
+
+}  // namespace
+
+static WorldDefs* defs_of(b2gpu_world* W, bool) { return &W->defs; }
+
+static int reset_mass_data(b2gpu_world* W, int bi) {  // b2_body.rs(private):292-350
+  HostWorld& h = W->h;
+  WorldDefs* D = defs_of(W, true);
+  b2gpu_body_rec& b = h.bodies[bi];
+  b.mass = 0.0f; b.inv_mass = 0.0f; b.inertia = 0.0f; b.inv_inertia = 0.0f;
+  b.lc_x = 0.0f; b.lc_y = 0.0f;
+  if (b.type == B2GPU_STATIC_BODY || b.type == B2GPU_KINEMATIC_BODY) {
+    b.c0_x = b.xf_px; b.c0_y = b.xf_py;
+    b.c_x = b.xf_px; b.c_y = b.xf_py;
+    b.a0 = b.a;
+    return 0;
+  }
+  V2 local_center = v2(0.0f, 0.0f);
+  for (int f = b.fixture_head; f != -1; f = h.fixtures[f].next) {
+    if (h.fixtures[f].density == 0.0f) continue;
+    b2gpu_mass_data md;
+    int rc = fixture_mass(h, D->shape_defs, f, &md);
+    if (rc) return rc;
+    b.mass += md.mass;
+    local_center = local_center + md.mass * v2(md.center_x, md.center_y);
+    b.inertia += md.inertia;
+  }
+  if (b.mass > 0.0f) {
+    b.inv_mass = 1.0f / b.mass;
+    local_center = b.inv_mass * local_center;
+  }
+  if (b.inertia > 0.0f && !(b.flags & B2GPU_BODY_FIXED_ROTATION)) {
+    b.inertia -= b.mass * dot(local_center, local_center);
+    b.inv_inertia = 1.0f / b.inertia;
+  } else {
+    b.inertia = 0.0f;
+    b.inv_inertia = 0.0f;
+  }
+  const V2 old_center = v2(b.c_x, b.c_y);
+  b.lc_x = local_center.x; b.lc_y = local_center.y;
+  const V2 c0 = xf_mul(body_xf(b), local_center);
+  b.c0_x = c0.x; b.c0_y = c0.y;
+  b.c_x = c0.x; b.c_y = c0.y;
+  const V2 dv = cross_sv(b.w, c0 - old_center);
+  b.vx += dv.x;
+  b.vy += dv.y;
+  return 0;
+}
+
+// B2fixture::synchronize for every proxy of a fixture (b2_fixture.rs(private):147-173)
+static void fixture_synchronize(HostWorld& h, int f, const Xf& xf1, const Xf& xf2) {
+  const b2gpu_fixture_rec& fx = h.fixtures[f];
+  if (fx.proxy_first < 0) return;
+  for (int i = 0; i < fx.child_count; ++i) {
+    b2gpu_proxy_rec& p = h.proxies[fx.proxy_first + i];
+    const b2gpu_shape_rec* sh = &h.shapes[fx.shape_first + p.child_index];
+    const Box a1 = shape_aabb(sh, xf1), a2 = shape_aabb(sh, xf2);
+    const Box u = box_union(a1, a2);
+    p.aabb[0] = u.lo.x; p.aabb[1] = u.lo.y; p.aabb[2] = u.hi.x; p.aabb[3] = u.hi.y;
+    bp_move_proxy(h, p.proxy_id, u, box_center(a2) - box_center(a1));
+  }
+}
+
+#define GUARD_BEGIN try {
+#define GUARD_END                                                                       \
+  }                                                                                     \
+  catch (const std::bad_alloc&) { set_error("out of host memory"); return B2GPU_E_INVALID; } \
+  catch (...) { set_error("unexpected C++ exception"); return B2GPU_E_INVALID; }
+
+extern "C" {
+
+int b2gpu_polygon_set_as_box(b2gpu_shape_def* s, float hx, float hy) {
+  if (!s) { set_error("shape is NULL"); return B2GPU_E_INVALID; }
+  polygon_box(s, hx, hy);
+  return 0;
+}
+int b2gpu_polygon_set_as_box_angle(b2gpu_shape_def* s, float hx, float hy, float cx, float cy, float angle) {
+  if (!s) { set_error("shape is NULL"); return B2GPU_E_INVALID; }
+  polygon_box(s, hx, hy);
+  s->centroid[0] = cx;
+  s->centroid[1] = cy;
+  Xf xf;
+  xf.p = v2(cx, cy);
+  xf.q = rot_from_angle(angle);
+  for (int i = 0; i < 4; ++i) {
+    const V2 v = xf_mul(xf, v2(s->vertices[2 * i], s->vertices[2 * i + 1]));
+    const V2 n = rot_mul(xf.q, v2(s->normals[2 * i], s->normals[2 * i + 1]));
+    s->vertices[2 * i] = v.x; s->vertices[2 * i + 1] = v.y;
+    s->normals[2 * i] = n.x; s->normals[2 * i + 1] = n.y;
+  }
+  return 0;
+}
+int b2gpu_polygon_set(b2gpu_shape_def* s, const float* xy, int count) {
+  if (!s || !xy) { set_error("polygon_set: NULL argument"); return B2GPU_E_INVALID; }
+  if (count < 3 || count > B2G_MAX_POLY) {  // the reference asserts 3 <= count <= 8
+    set_error("polygon_set: vertex count must be in [3, 8]");
+    return B2GPU_E_INVALID;
+  }
+  V2 ps[B2G_MAX_POLY];
+  int n = 0;
+  const float weld = (0.5f * B2G_LINEAR_SLOP) * (0.5f * B2G_LINEAR_SLOP);
+  for (int i = 0; i < count; ++i) {  // weld close vertices
+    const V2 v = v2(xy[2 * i], xy[2 * i + 1]);
+    bool unique = true;
+    for (int j = 0; j < n; ++j)
+      if (dist_sq(v, ps[j]) < weld) { unique = false; break; }
+    if (unique) ps[n++] = v;
+  }
+  if (n < 3) { set_error("polygon_set: degenerate polygon"); return B2GPU_E_INVALID; }
+  int i0 = 0;  // right-most point, lowest on ties
+  float x0 = ps[0].x;
+  for (int i = 1; i < n; ++i) {
+    const float x = ps[i].x;
+    if (x > x0 || (x == x0 && ps[i].y < ps[i0].y)) { i0 = i; x0 = x; }
+  }
+  int hull[B2G_MAX_POLY];
+  int m = 0, ih = i0;
+  for (;;) {  // gift wrapping
+    if (m >= B2G_MAX_POLY) { set_error("polygon_set: hull overflow"); return B2GPU_E_INVALID; }
+    hull[m] = ih;
+    int ie = 0;
+    for (int j = 1; j < n; ++j) {
+      if (ie == ih) { ie = j; continue; }
+      const V2 r = ps[ie] - ps[hull[m]];
+      const V2 v = ps[j] - ps[hull[m]];
+      const float c = cross(r, v);
+      if (c < 0.0f) ie = j;
+      if (c == 0.0f && dot(v, v) > dot(r, r)) ie = j;
+    }
+    ++m;
+    ih = ie;
+    if (ie == i0) break;
+  }
+  if (m < 3) { set_error("polygon_set: degenerate polygon"); return B2GPU_E_INVALID; }
+  s->type = B2GPU_SHAPE_POLYGON;
+  s->radius = B2G_POLYGON_RADIUS;
+  s->count = m;
+  memset(s->vertices, 0, sizeof(s->vertices));
+  memset(s->normals, 0, sizeof(s->normals));
+  V2 vs[B2G_MAX_POLY];
+  for (int i = 0; i < m; ++i) {
+    vs[i] = ps[hull[i]];
+    s->vertices[2 * i] = vs[i].x;
+    s->vertices[2 * i + 1] = vs[i].y;
+  }
+  for (int i = 0; i < m; ++i) {
+    const int i2 = i + 1 < m ? i + 1 : 0;
+    V2 nrm = cross_vs(vs[i2] - vs[i], 1.0f);
+    normalize(nrm);
+    s->normals[2 * i] = nrm.x;
+    s->normals[2 * i + 1] = nrm.y;
+  }
+  // compute_centroid (:59-94)
+  V2 c = v2(0.0f, 0.0f);
+  float area = 0.0f;
+  const V2 origin = vs[0];
+  const float inv3 = 1.0f / 3.0f;
+  for (int i = 0; i < m; ++i) {
+    const V2 p1 = vs[0] - origin, p2 = vs[i] - origin, p3 = (i + 1 < m ? vs[i + 1] : vs[0]) - origin;
+    const V2 e1 = p2 - p1, e2 = p3 - p1;
+    const float tri = 0.5f * cross(e1, e2);
+    area += tri;
+    c = c + (tri * inv3) * (p1 + p2 + p3);
+  }
+  if (!(area > B2G_EPSILON)) { set_error("polygon_set: zero area"); return B2GPU_E_INVALID; }
+  c = (1.0f / area) * c + origin;
+  s->centroid[0] = c.x;
+  s->centroid[1] = c.y;
+  return 0;
+}
+int b2gpu_shape_compute_mass(const b2gpu_shape_def* s, float density, b2gpu_mass_data* out) {
+  if (!s || !out) { set_error("compute_mass: NULL argument"); return B2GPU_E_INVALID; }
+  return shape_mass(s, density, out);
+}
+
+int b2gpu_world_create(b2gpu_ctx* ctx, float gx, float gy, b2gpu_world** out) {
+  GUARD_BEGIN
+  if (!ctx || !out) { set_error("world_create: bad argument"); return B2GPU_E_INVALID; }
+  b2gpu_world* W = new b2gpu_world();
+  W->ctx = ctx;
+  host_world_init(W->h, gx, gy);
+  *out = W;
+  return 0;
+  GUARD_END
+}
+void b2gpu_world_destroy(b2gpu_world* W) {
+  if (!W) return;
+  if (W->dev) batch_destroy(W->dev);
+  delete W;
+}
+
+int b2gpu_world_create_body(b2gpu_world* W, const b2gpu_body_def* d) {
+  GUARD_BEGIN
+  if (!W || !d) { set_error("create_body: bad argument"); return B2GPU_E_INVALID; }
+  int rc = ensure_host(W);
+  if (rc) return rc;
+  b2gpu_body_rec b;
+  memset(&b, 0, sizeof(b));
+  b.type = d->type;
+  if (d->bullet) b.flags |= B2GPU_BODY_BULLET;
+  if (d->fixed_rotation) b.flags |= B2GPU_BODY_FIXED_ROTATION;
+  if (d->allow_sleep) b.flags |= B2GPU_BODY_AUTO_SLEEP;
+  if (d->awake && d->type != B2GPU_STATIC_BODY) b.flags |= B2GPU_BODY_AWAKE;
+  if (d->enabled) b.flags |= B2GPU_BODY_ENABLED;
+  const Rot q = rot_from_angle(d->angle);
+  b.xf_px = d->position_x; b.xf_py = d->position_y; b.xf_qs = q.s; b.xf_qc = q.c;
+  b.c0_x = b.c_x = d->position_x;
+  b.c0_y = b.c_y = d->position_y;
+  b.a0 = b.a = d->angle;
+  b.vx = d->linear_velocity_x; b.vy = d->linear_velocity_y; b.w = d->angular_velocity;
+  b.linear_damping = d->linear_damping; b.angular_damping = d->angular_damping; b.gravity_scale = d->gravity_scale;
+  b.fixture_head = -1;
+  W->h.bodies.push_back(b);
+  W->host_dirty = W->topo_dirty = true;
+  return (int)W->h.bodies.size() - 1;
+  GUARD_END
+}
+
+int b2gpu_body_create_fixture(b2gpu_world* W, int body, const b2gpu_fixture_def* def, const b2gpu_shape_def* shape) {
+  GUARD_BEGIN
+  int rc = check_body(W, body);
+  if (rc) return rc;
+  if (!def || !shape) { set_error("create_fixture: NULL argument"); return B2GPU_E_INVALID; }
+  if (shape->type < 0 || shape->type > B2GPU_SHAPE_CHAIN) { set_error("create_fixture: unknown shape type"); return B2GPU_E_INVALID; }
+  if (shape->type == B2GPU_SHAPE_CHAIN && (shape->chain_count < 2 || !shape->chain_vertices)) { set_error("create_fixture: chain needs >= 2 vertices"); return B2GPU_E_INVALID; }
+  if (shape->type == B2GPU_SHAPE_POLYGON && (shape->count < 3 || shape->count > B2G_MAX_POLY)) { set_error("create_fixture: polygon vertex count"); return B2GPU_E_INVALID; }
+  rc = ensure_host(W);
+  if (rc) return rc;
+  HostWorld& h = W->h;
+  WorldDefs* D = defs_of(W, true);
+  if (D->shape_defs.size() != h.fixtures.size()) {
+    set_error("create_fixture: fixtures cannot be added to a world restored with b2gpu_world_upload");
+    return B2GPU_E_UNSUPPORTED;
+  }
+  b2gpu_fixture_rec fx;
+  memset(&fx, 0, sizeof(fx));
+  fx.body = body;
+  fx.next = -1;
+  fx.shape_type = shape->type;
+  fx.shape_first = (int)h.shapes.size();
+  fx.child_count = shape->type == B2GPU_SHAPE_CHAIN ? shape->chain_count - 1 : 1;
+  fx.proxy_first = -1;
+  fx.density = def->density; fx.friction = def->friction; fx.restitution = def->restitution;
+  fx.restitution_threshold = def->restitution_threshold;
+  fx.category_bits = def->category_bits; fx.mask_bits = def->mask_bits; fx.group_index = def->group_index;
+  fx.is_sensor = def->is_sensor ? 1 : 0;
+  for (int c = 0; c < fx.child_count; ++c) {
+    b2gpu_shape_rec r;
+    fill_child_shape(r, shape, c);
+    h.shapes.push_back(r);
+  }
+  const int fi = (int)h.fixtures.size();
+  h.fixtures.push_back(fx);
+  // keep the user's shape for compute_mass (chains own a copy of their vertices)
+  b2gpu_shape_def keep = *shape;
+  if (shape->type == B2GPU_SHAPE_CHAIN) {
+    D->chain_storage.emplace_back(shape->chain_vertices, shape->chain_vertices + 2 * shape->chain_count);
+    keep.chain_vertices = D->chain_storage.back().data();
+  }
+  D->shape_defs.resize(fi + 1);
+  D->shape_defs[fi] = keep;
+  b2gpu_body_rec& b = h.bodies[body];
+  if (b.flags & B2GPU_BODY_ENABLED) {  // B2fixture::create_proxies with the body's current transform
+    h.fixtures[fi].proxy_first = (int)h.proxies.size();
+    const Xf xf = body_xf(b);
+    for (int c = 0; c < fx.child_count; ++c) {
+      const Box a = shape_aabb(&h.shapes[fx.shape_first + c], xf);
+      b2gpu_proxy_rec p;
+      memset(&p, 0, sizeof(p));
+      p.fixture = fi;
+      p.child_index = c;
+      p.aabb[0] = a.lo.x; p.aabb[1] = a.lo.y; p.aabb[2] = a.hi.x; p.aabb[3] = a.hi.y;
+      const int pi = (int)h.proxies.size();
+      p.proxy_id = bp_create_proxy(h, a, pi);
+      if (p.proxy_id < 0) { set_error("tree allocation failed"); return B2GPU_E_CAPACITY; }
+      h.proxies.push_back(p);
+    }
+  }
+  h.fixtures[fi].next = b.fixture_head;  // push_front
+  b.fixture_head = fi;
+  b.fixture_count += 1;
+  if (h.fixtures[fi].density > 0.0f) {
+    rc = reset_mass_data(W, body);
+    if (rc) return rc;
+  }
+  h.world.flags |= B2GPU_WORLD_NEW_CONTACTS;
+  W->host_dirty = W->topo_dirty = true;
+  return fi;
+  GUARD_END
+}
+
+int b2gpu_body_set_transform(b2gpu_world* W, int body, float px, float py, float angle) {
+  GUARD_BEGIN
+  int rc = check_body(W, body);
+  if (rc) return rc;
+  rc = ensure_host(W);
+  if (rc) return rc;
+  HostWorld& h = W->h;
+  b2gpu_body_rec& b = h.bodies[body];
+  const Rot q = rot_from_angle(angle);
+  b.xf_qs = q.s; b.xf_qc = q.c; b.xf_px = px; b.xf_py = py;
+  const Xf xf = body_xf(b);
+  const V2 c = xf_mul(xf, v2(b.lc_x, b.lc_y));
+  b.c_x = c.x; b.c_y = c.y; b.a = angle;
+  b.c0_x = c.x; b.c0_y = c.y; b.a0 = angle;
+  for (int f = b.fixture_head; f != -1; f = h.fixtures[f].next) fixture_synchronize(h, f, xf, xf);
+  h.world.flags |= B2GPU_WORLD_NEW_CONTACTS;
+  W->host_dirty = true;
+  return 0;
+  GUARD_END
+}
+int b2gpu_body_set_linear_velocity(b2gpu_world* W, int body, float vx, float vy) {
+  GUARD_BEGIN
+  int rc = check_body(W, body);
+  if (rc) return rc;
+  rc = ensure_host(W);
+  if (rc) return rc;
+  b2gpu_body_rec& b = W->h.bodies[body];
+  if (b.type == B2GPU_STATIC_BODY) return 0;
+  if (vx * vx + vy * vy > 0.0f) set_awake(b, true);
+  b.vx = vx; b.vy = vy;
+  W->host_dirty = true;
+  return 0;
+  GUARD_END
+}
+int b2gpu_body_set_angular_velocity(b2gpu_world* W, int body, float w_) {
+  GUARD_BEGIN
+  int rc = check_body(W, body);
+  if (rc) return rc;
+  rc = ensure_host(W);
+  if (rc) return rc;
+  b2gpu_body_rec& b = W->h.bodies[body];
+  if (b.type == B2GPU_STATIC_BODY) return 0;
+  if (w_ * w_ > 0.0f) set_awake(b, true);
+  b.w = w_;
+  W->host_dirty = true;
+  return 0;
+  GUARD_END
+}
+int b2gpu_body_apply_force_to_center(b2gpu_world* W, int body, float fx, float fy, int wake) {
+  GUARD_BEGIN
+  int rc = check_body(W, body);
+  if (rc) return rc;
+  rc = ensure_host(W);
+  if (rc) return rc;
+  b2gpu_body_rec& b = W->h.bodies[body];
+  if (b.type != B2GPU_DYNAMIC_BODY) return 0;
+  if (wake && !(b.flags & B2GPU_BODY_AWAKE)) set_awake(b, true);
+  if (b.flags & B2GPU_BODY_AWAKE) { b.fx += fx; b.fy += fy; }
+  W->host_dirty = true;
+  return 0;
+  GUARD_END
+}
+static int set_world_flag(b2gpu_world* W, uint32_t bit, int flag) {
+  if (!W) { set_error("world is NULL"); return B2GPU_E_INVALID; }
+  int rc = ensure_host(W);
+  if (rc) return rc;
+  if (flag) W->h.world.flags |= bit; else W->h.world.flags &= ~bit;
+  W->host_dirty = true;
+  return 0;
+}
+int b2gpu_world_set_allow_sleeping(b2gpu_world* W, int flag) {  // b2_world.rs(private):340-353
+  GUARD_BEGIN
+  if (!W) { set_error("world is NULL"); return B2GPU_E_INVALID; }
+  int rc = ensure_host(W);
+  if (rc) return rc;
+  const bool cur = (W->h.world.flags & B2GPU_WORLD_ALLOW_SLEEP) != 0;
+  if ((flag != 0) == cur) return 0;
+  rc = set_world_flag(W, B2GPU_WORLD_ALLOW_SLEEP, flag);
+  if (rc) return rc;
+  if (!flag)
+    for (auto& b : W->h.bodies) set_awake(b, true);
+  return 0;
+  GUARD_END
+}
+int b2gpu_world_set_warm_starting(b2gpu_world* W, int flag) { return set_world_flag(W, B2GPU_WORLD_WARM_STARTING, flag); }
+int b2gpu_world_set_block_solve(b2gpu_world* W, int flag) { return set_world_flag(W, B2GPU_WORLD_BLOCK_SOLVE, flag); }
+int b2gpu_world_set_continuous_physics(b2gpu_world* W, int flag) {
+  if (!W) { set_error("world is NULL"); return B2GPU_E_INVALID; }
+  if (flag) { set_error("continuous physics (TOI sub-stepping) is outside the hot-path scope"); return B2GPU_E_UNSUPPORTED; }
+  return 0;
+}
+
+int b2gpu_world_step(b2gpu_world* W, float dt, int vi, int pi) {
+  GUARD_BEGIN
+  if (!W) { set_error("world is NULL"); return B2GPU_E_INVALID; }
+  if (W->h.bodies.empty()) { set_error("world has no bodies"); return B2GPU_E_INVALID; }
+  int rc;
+  if (!W->dev || W->topo_dirty) {
+    rc = ensure_host(W);
+    if (rc) return rc;
+    if (W->dev) { batch_destroy(W->dev); W->dev = nullptr; }
+    b2gpu_snapshot s;
+    std::vector<b2gpu_tree_node_rec> nodes;
+    fill_snapshot(W, &s, nodes);
+    rc = batch_create(&W->ctx->c, &s, 1, nullptr, 1, &W->dev);
+    if (rc) return rc;
+  } else if (W->host_dirty) {
+    b2gpu_snapshot s;
+    std::vector<b2gpu_tree_node_rec> nodes;
+    fill_snapshot(W, &s, nodes);
+    rc = batch_upload_world(W->dev, 0, &s);
+    if (rc) return rc;
+  }
+  W->host_dirty = W->topo_dirty = false;
+  rc = batch_step(W->dev, dt, vi, pi, 1);
+  if (rc) return rc;
+  W->dev_newer = true;
+  return 0;
+  GUARD_END
+}
+
+int b2gpu_world_get_body_count(b2gpu_world* W) { return W ? (int)W->h.bodies.size() : B2GPU_E_INVALID; }
+int b2gpu_world_get_contact_count(b2gpu_world* W) {
+  GUARD_BEGIN
+  if (!W) { set_error("world is NULL"); return B2GPU_E_INVALID; }
+  int rc = ensure_host(W);
+  if (rc) return rc;
+  return (int)W->h.contacts.size();
+  GUARD_END
+}
+int b2gpu_world_get_body(b2gpu_world* W, int body, b2gpu_body_rec* out) {
+  GUARD_BEGIN
+  int rc = check_body(W, body);
+  if (rc) return rc;
+  if (!out) { set_error("out is NULL"); return B2GPU_E_INVALID; }
+  rc = ensure_host(W);
+  if (rc) return rc;
+  *out = W->h.bodies[body];
+  return 0;
+  GUARD_END
+}
+int b2gpu_world_get_stats(b2gpu_world* W, b2gpu_step_stats* out) {
+  GUARD_BEGIN
+  if (!W || !out) { set_error("get_stats: bad argument"); return B2GPU_E_INVALID; }
+  if (!W->dev) { memset(out, 0, sizeof(*out)); return 0; }
+  return batch_get_stats(W->dev, 0, 1, out);
+  GUARD_END
+}
+int b2gpu_world_snapshot_sizes(b2gpu_world* W, b2gpu_snapshot_sizes* out) {
+  GUARD_BEGIN
+  if (!W || !out) { set_error("snapshot_sizes: bad argument"); return B2GPU_E_INVALID; }
+  int rc = ensure_host(W);
+  if (rc) return rc;
+  const HostWorld& h = W->h;
+  out->body_count = (int)h.bodies.size(); out->fixture_count = (int)h.fixtures.size(); out->shape_count = (int)h.shapes.size();
+  out->proxy_count = (int)h.proxies.size(); out->node_count = h.ws[WS_TREE_CAP]; out->contact_count = (int)h.contacts.size();
+  out->move_count = (int)h.move_buffer.size(); out->reserved = 0;
+  return 0;
+  GUARD_END
+}
+int b2gpu_world_download(b2gpu_world* W, b2gpu_snapshot* out) {
+  GUARD_BEGIN
+  if (!W || !out) { set_error("download: bad argument"); return B2GPU_E_INVALID; }
+  int rc = ensure_host(W);
+  if (rc) return rc;
+  b2gpu_snapshot s;
+  std::vector<b2gpu_tree_node_rec> nodes;
+  fill_snapshot(W, &s, nodes);
+  if (out->n.body_count < s.n.body_count || out->n.fixture_count < s.n.fixture_count || out->n.shape_count < s.n.shape_count ||
+      out->n.proxy_count < s.n.proxy_count || out->n.node_count < s.n.node_count || out->n.contact_count < s.n.contact_count ||
+      out->n.move_count < s.n.move_count) {
+    set_error("download buffers smaller than snapshot_sizes");
+    return B2GPU_E_INVALID;
+  }
+  out->world = s.world;
+  out->n = s.n;
+  memcpy(out->bodies, s.bodies, sizeof(b2gpu_body_rec) * s.n.body_count);
+  memcpy(out->fixtures, s.fixtures, sizeof(b2gpu_fixture_rec) * s.n.fixture_count);
+  memcpy(out->shapes, s.shapes, sizeof(b2gpu_shape_rec) * s.n.shape_count);
+  memcpy(out->proxies, s.proxies, sizeof(b2gpu_proxy_rec) * s.n.proxy_count);
+  memcpy(out->nodes, s.nodes, sizeof(b2gpu_tree_node_rec) * s.n.node_count);
+  memcpy(out->contacts, s.contacts, sizeof(b2gpu_contact_rec) * s.n.contact_count);
+  memcpy(out->move_buffer, s.move_buffer, sizeof(int32_t) * s.n.move_count);
+  return 0;
+  GUARD_END
+}
+int b2gpu_world_upload(b2gpu_world* W, const b2gpu_snapshot* in) {
+  GUARD_BEGIN
+  if (!W || !in) { set_error("upload: bad argument"); return B2GPU_E_INVALID; }
+  HostWorld& h = W->h;
+  const b2gpu_snapshot_sizes& n = in->n;
+  if (n.body_count < 1 || n.node_count < 1) { set_error("upload: empty snapshot"); return B2GPU_E_INVALID; }
+  h.world = in->world;
+  h.bodies.assign(in->bodies, in->bodies + n.body_count);
+  h.fixtures.assign(in->fixtures, in->fixtures + n.fixture_count);
+  h.shapes.assign(in->shapes, in->shapes + n.shape_count);
+  h.proxies.assign(in->proxies, in->proxies + n.proxy_count);
+  h.contacts.assign(in->contacts, in->contacts + n.contact_count);
+  h.move_buffer.assign(in->move_buffer, in->move_buffer + n.move_count);
+  h.n_aabb.clear(); h.n_link.clear(); h.n_moved.clear(); h.n_proxy.clear();
+  tree_reserve(h, n.node_count);
+  for (int i = 0; i < n.node_count; ++i) {
+    const b2gpu_tree_node_rec& nd = in->nodes[i];
+    h.n_aabb[i] = make_float4(nd.aabb[0], nd.aabb[1], nd.aabb[2], nd.aabb[3]);
+    h.n_link[i] = make_int4(nd.parent, nd.child1, nd.child2, nd.height);
+    h.n_moved[i] = nd.moved;
+    h.n_proxy[i] = nd.proxy;
+  }
+  h.ws[WS_TREE_ROOT] = in->world.tree_root; h.ws[WS_TREE_FREE] = in->world.tree_free_list;
+  h.ws[WS_TREE_COUNT] = in->world.tree_node_count; h.ws[WS_TREE_CAP] = in->world.tree_node_capacity;
+  h.ws[WS_TREE_INSERTIONS] = in->world.tree_insertion_count;
+  W->defs.shape_defs.clear();
+  W->defs.chain_storage.clear();
+  W->dev_newer = false;
+  W->host_dirty = W->topo_dirty = true;
+  return 0;
+  GUARD_END
+}
+
+}  // extern "C"

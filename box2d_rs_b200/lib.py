@@ -74,6 +74,11 @@ def load(path=None):
         "b2gpu_batch_forces_device": (vp, [vp, C.POINTER(i64)]),
         "b2gpu_batch_step_host": (i32, [vp, vp, vp, f32, i32, i32, i32]),
         "b2gpu_batch_algorithmic_bytes": (i64, [vp]),
+        "b2gpu_debug_sincos": (i32, [vp, vp, vp, vp, i32]),
+        "b2gpu_stage_count": (i32, []),
+        "b2gpu_stage_name": (C.c_char_p, [i32]),
+        "b2gpu_set_profiling": (i32, [vp, i32]),
+        "b2gpu_get_stage_times": (i32, [vp, vp, vp, i32]),
     }
     missing = []
     for name, (res, args) in sig.items():

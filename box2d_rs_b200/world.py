@@ -1,0 +1,158 @@
+"""Mirror of the reference's world-building API (B2world / B2body / shapes) on top of the C ABI.
+
+Method names and argument meaning follow box2d-rs (src/b2_world.rs, src/b2_body.rs, src/shapes/*):
+B2world::new(gravity), create_body(&B2bodyDef), B2body::create_fixture(&B2fixtureDef),
+create_fixture_by_shape(shape, density), set_transform, set_linear_velocity, B2world::step(dt,
+velocity_iterations, position_iterations), set_allow_sleeping, set_warm_starting ...
+Scene recipes written against this API (box2d_rs_b200/scenes.py) run unchanged on the GPU engine.
+Stepping happens on the GPU only; on a machine without one, step() raises B2gpuError(NO_DEVICE).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+from .batch import Batch, Context
+from .lib import check
+
+
+class Shapes:
+    """Shape factory: B2polygonShape::set_as_box / set_as_box_angle / set, B2circleShape, B2edgeShape, B2chainShape."""
+
+    def __init__(self, L):
+        self.L = L
+
+    def polygon_box(self, hx, hy, center=None, angle=0.0):
+        s = abi.ShapeDef()
+        if center is None:
+            check(self.L, self.L.b2gpu_polygon_set_as_box(C.byref(s), hx, hy))
+        else:
+            check(self.L, self.L.b2gpu_polygon_set_as_box_angle(C.byref(s), hx, hy, center[0], center[1], angle))
+        return s
+
+    def polygon(self, vertices):
+        s = abi.ShapeDef()
+        flat = (C.c_float * (2 * len(vertices)))(*[c for v in vertices for c in v])
+        check(self.L, self.L.b2gpu_polygon_set(C.byref(s), flat, len(vertices)))
+        return s
+
+    circle = staticmethod(abi.circle_shape)
+    edge_two_sided = staticmethod(abi.edge_two_sided)
+    edge_one_sided = staticmethod(abi.edge_one_sided)
+    chain = staticmethod(abi.chain_shape)
+
+    def compute_mass(self, shape, density):
+        md = abi.MassData()
+        check(self.L, self.L.b2gpu_shape_compute_mass(C.byref(shape), density, C.byref(md)))
+        return md
+
+
+class B2body:
+    def __init__(self, world, index):
+        self.world, self.index = world, index
+
+    def create_fixture(self, fixture_def, shape):
+        w = self.world
+        return check(w.L, w.L.b2gpu_body_create_fixture(w.h, self.index, C.byref(fixture_def), C.byref(shape)))
+
+    def create_fixture_by_shape(self, shape, density):
+        return self.create_fixture(abi.FixtureDef(density=density), shape)
+
+    def set_transform(self, position, angle):
+        w = self.world
+        check(w.L, w.L.b2gpu_body_set_transform(w.h, self.index, position[0], position[1], angle))
+
+    def set_linear_velocity(self, v):
+        w = self.world
+        check(w.L, w.L.b2gpu_body_set_linear_velocity(w.h, self.index, v[0], v[1]))
+
+    def set_angular_velocity(self, omega):
+        w = self.world
+        check(w.L, w.L.b2gpu_body_set_angular_velocity(w.h, self.index, omega))
+
+    def apply_force_to_center(self, f, wake=True):
+        w = self.world
+        check(w.L, w.L.b2gpu_body_apply_force_to_center(w.h, self.index, f[0], f[1], int(wake)))
+
+    def _rec(self):
+        w = self.world
+        out = np.zeros(1, abi.BODY_DTYPE)
+        check(w.L, w.L.b2gpu_world_get_body(w.h, self.index, out.ctypes.data))
+        return out[0]
+
+    def get_position(self):
+        r = self._rec()
+        return float(r["xf"][0]), float(r["xf"][1])
+
+    def get_angle(self):
+        return float(self._rec()["a"])
+
+    def get_linear_velocity(self):
+        r = self._rec()
+        return float(r["v"][0]), float(r["v"][1])
+
+    def is_awake(self):
+        return bool(int(self._rec()["flags"]) & abi.BODY_AWAKE)
+
+
+class B2world:
+    def __init__(self, gravity, ctx=None, device=0, lib_path=None):
+        self.ctx = ctx or Context(device, lib_path=lib_path)
+        self.L = self.ctx.L
+        self.shapes = Shapes(self.L)
+        self.h = C.c_void_p()
+        check(self.L, self.L.b2gpu_world_create(self.ctx.h, gravity[0], gravity[1], C.byref(self.h)))
+
+    def close(self):
+        if self.h:
+            self.L.b2gpu_world_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def create_body(self, body_def):
+        return B2body(self, check(self.L, self.L.b2gpu_world_create_body(self.h, C.byref(body_def))))
+
+    def body(self, index):
+        return B2body(self, index)
+
+    def set_allow_sleeping(self, flag):
+        check(self.L, self.L.b2gpu_world_set_allow_sleeping(self.h, int(flag)))
+
+    def set_warm_starting(self, flag):
+        check(self.L, self.L.b2gpu_world_set_warm_starting(self.h, int(flag)))
+
+    def set_continuous_physics(self, flag):
+        check(self.L, self.L.b2gpu_world_set_continuous_physics(self.h, int(flag)))
+
+    def set_block_solve(self, flag):
+        check(self.L, self.L.b2gpu_world_set_block_solve(self.h, int(flag)))
+
+    def step(self, dt, velocity_iterations, position_iterations):
+        check(self.L, self.L.b2gpu_world_step(self.h, dt, velocity_iterations, position_iterations))
+
+    def get_body_count(self):
+        return check(self.L, self.L.b2gpu_world_get_body_count(self.h))
+
+    def get_contact_count(self):
+        return check(self.L, self.L.b2gpu_world_get_contact_count(self.h))
+
+    def get_stats(self):
+        out = np.zeros(1, abi.STATS_DTYPE)
+        check(self.L, self.L.b2gpu_world_get_stats(self.h, out.ctypes.data))
+        return out[0]
+
+    def snapshot(self):
+        """Full step state (b2gpu_world_download) as abi.Snapshot."""
+        n = abi.SnapshotSizes()
+        check(self.L, self.L.b2gpu_world_snapshot_sizes(self.h, C.byref(n)))
+        snap = abi.Snapshot(n)
+        c = snap.as_c()
+        check(self.L, self.L.b2gpu_world_download(self.h, C.byref(c)))
+        return snap.finish(c)
+
+    def upload(self, snap):
+        c = snap.as_c()
+        check(self.L, self.L.b2gpu_world_upload(self.h, C.byref(c)))
+
+    def batch(self, n_worlds, **kw):
+        """n_worlds replicas of this world's current state, one CTA lane per world (b2gpu_batch_create)."""
+        return Batch(self.ctx, self.snapshot(), n_worlds, **kw)

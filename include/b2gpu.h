@@ -273,7 +273,7 @@ typedef struct b2gpu_mass_data {
 /* Device-side capacities of one world of a batch. 0 = derive from the prototype. */
 typedef struct b2gpu_caps {
   int32_t max_bodies, max_fixtures, max_shapes, max_proxies, max_contacts, max_pairs;
-  int32_t reserved[2];
+  int32_t reserved[2]; /* reserved[0]: worlds per memory block (power of two; 0 = 32 for >= 32 worlds, else 1) */
 } b2gpu_caps;
 
 typedef struct b2gpu_ctx b2gpu_ctx;
@@ -367,6 +367,18 @@ int b2gpu_batch_step_host(b2gpu_batch* b, const float* host_forces, float* host_
                           int velocity_iterations, int position_iterations, int steps);
 /* Algorithmic bytes of the last step summed over all worlds (SURVEY.md §8d formula). */
 int64_t b2gpu_batch_algorithmic_bytes(b2gpu_batch* b);
+
+/* Per-stage device timing (bench.py roofline): when on, every kernel launch of the context is
+ * bracketed by a CUDA event pair on the context's stream.  get_stage_times synchronises and returns
+ * the accumulated milliseconds and launch counts per stage since profiling was switched on. */
+int b2gpu_stage_count(void);
+const char* b2gpu_stage_name(int stage);
+int b2gpu_set_profiling(b2gpu_ctx* ctx, int on);
+int b2gpu_get_stage_times(b2gpu_ctx* ctx, double* ms_out, int64_t* launches_out, int n);
+
+/* Diagnostic: sin/cos of n angles evaluated by the device's B2Rot::set path (src/b2_math.rs:372-376),
+ * host buffers in and out.  Used by the tests to pin the device trigonometry against libm. */
+int b2gpu_debug_sincos(b2gpu_ctx* ctx, const float* host_in, float* host_sin, float* host_cos, int n);
 
 #ifdef __cplusplus
 }

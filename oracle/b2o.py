@@ -62,6 +62,8 @@ def lib():
         L.b2o_polygon_set.argtypes = [C.POINTER(abi.ShapeDef), C.POINTER(C.c_float), C.c_int]
         L.b2o_shape_compute_mass.argtypes = [C.POINTER(abi.ShapeDef), C.c_float, C.POINTER(abi.MassData)]
         L.b2o_sweep_get_transform.argtypes = [C.POINTER(C.c_float), C.c_float, C.POINTER(C.c_float)]
+        L.b2o_sincosf.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.b2o_hardware_threads.restype = C.c_int
         _LIB = L
     return _LIB
 
@@ -207,3 +209,16 @@ def run_worlds_mt(worlds, steps, dt, vi, pi, threads):
     """CPU baseline: one world per host thread. Returns wall seconds."""
     arr = (C.c_void_p * len(worlds))(*[w.h for w in worlds])
     return lib().b2o_run_worlds_mt(arr, len(worlds), steps, dt, vi, pi, threads)
+
+
+def sincosf(angles):
+    """glibc sinf/cosf of a float32 array (reference for the device trigonometry)."""
+    a = np.ascontiguousarray(angles, np.float32)
+    s = np.empty_like(a)
+    c = np.empty_like(a)
+    lib().b2o_sincosf(a.ctypes.data, s.ctypes.data, c.ctypes.data, a.size)
+    return s, c
+
+
+def hardware_threads():
+    return int(lib().b2o_hardware_threads())

@@ -294,6 +294,11 @@ double b2o_run_worlds_mt(void** worlds, int n_worlds, int steps, float dt, int v
   for (auto& th : pool) th.join();
   return (now_ms() - t0) * 1e-3;
 }
+// libm sinf/cosf of an array (what f32::sin / f32::cos lower to on linux-gnu): reference for the
+// device trigonometry tests.
+void b2o_sincosf(const float* in, float* s, float* c, int n) {
+  for (int i = 0; i < n; ++i) { s[i] = sinf(in[i]); c[i] = cosf(in[i]); }
+}
 int b2o_hardware_threads() { return (int)std::thread::hardware_concurrency(); }
 
 }  // extern "C"

@@ -86,7 +86,7 @@ def compare_snapshots(ref, got, rtol=0.0, atol=0.0, what="", check_tree=True, bo
     return bad
 
 
-STAT_FIELDS = ("contacts", "touching", "destroyed", "islands", "island_bodies", "island_contacts", "moved", "pairs",
+STAT_FIELDS = ("status", "contacts", "touching", "destroyed", "islands", "island_bodies", "island_contacts", "moved", "pairs",
                "created", "awake_bodies")
 
 
