@@ -42,12 +42,13 @@ class Context:
 
 
 class Batch:
-    def __init__(self, ctx, proto, n_worlds, max_contacts=0, max_pairs=0, lane_block=0):
+    def __init__(self, ctx, proto, n_worlds, max_contacts=0, max_pairs=0, lane_block=0, generic_solver=False):
         """proto: abi.Snapshot of the prototype world (from B2world.snapshot())."""
         self.ctx, self.L = ctx, ctx.L
         caps = abi.Caps()
         caps.max_contacts, caps.max_pairs = max_contacts, max_pairs
         caps.reserved[0] = lane_block
+        caps.reserved[1] = 1 if generic_solver else 0
         self.h = C.c_void_p()
         c = proto.as_c()
         self._keep = proto

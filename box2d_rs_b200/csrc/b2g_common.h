@@ -45,7 +45,7 @@ enum {
 };
 
 // velocity-constraint record: VC_Q float4 per island contact
-enum { VC_Q = 10 };
+enum { VC_Q = 9, PC_Q = 6 };
 
 struct Batch {
   int n_worlds, LB, lb_shift, n_wblocks;
@@ -93,7 +93,8 @@ struct Batch {
   int4* isl_range;           // [NB] per island: body_first, body_end, contact_first, contact_end
   int* isl_flags;            // [NB] per island: bit0 = position solved
   int* c_isl;                // [NC] island index of each island contact slot
-  float4* vc;                // [NC * VC_Q] velocity/position constraint records
+  float4* vc;                // [NC * VC_Q] velocity constraint records
+  float4* pc;                // [NC * PC_Q] position constraint records
   int* c_tmp;                // [NC] scratch (destroy compaction, ordered fix-up)
 };
 

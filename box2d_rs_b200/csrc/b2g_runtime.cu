@@ -9,6 +9,8 @@
 
 #if !defined(B2G_HOSTSIM)
 #include <cuda_runtime.h>
+
+#include "b2g_solver_smem.cuh"
 #endif
 
 namespace b2g {
@@ -74,21 +76,31 @@ static int prof_event(Ctx* ctx, cudaEvent_t* ev) {
   CU(cudaEventRecord(*ev, (cudaStream_t)ctx->stream));
   return 0;
 }
+struct LaunchScope {  // brackets one launch with profiling events and checks the launch status
+  Ctx* ctx;
+  int stage;
+  cudaEvent_t e0 = nullptr;
+  int begin() { return ctx->profiling ? prof_event(ctx, &e0) : 0; }
+  int end() {
+    if (ctx->profiling) {
+      cudaEvent_t e1 = nullptr;
+      RC(prof_event(ctx, &e1));
+      ProfSpan sp = {stage, (void*)e0, (void*)e1};
+      ctx->ev_pending.push_back(sp);
+    }
+    ctx->launches++;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
+    return 0;
+  }
+};
 template <class K> static int launch(Ctx* ctx, const K& k, int n, int block, int stage = STAGE_OTHER) {
   if (n <= 0) return 0;
   int grid = (n + block - 1) / block;
-  cudaEvent_t e0 = nullptr, e1 = nullptr;
-  if (ctx->profiling) RC(prof_event(ctx, &e0));
+  LaunchScope ls = {ctx, stage};
+  RC(ls.begin());
   stage_kernel<K><<<grid, block, 0, (cudaStream_t)ctx->stream>>>(k, n);
-  if (ctx->profiling) {
-    RC(prof_event(ctx, &e1));
-    ProfSpan sp = {stage, (void*)e0, (void*)e1};
-    ctx->ev_pending.push_back(sp);
-  }
-  ctx->launches++;
-  cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return cuda_fail(e, "kernel launch");
-  return 0;
+  return ls.end();
 }
 int ctx_collect_profile(Ctx* ctx) {
   CU(cudaStreamSynchronize((cudaStream_t)ctx->stream));
@@ -454,7 +466,7 @@ int batch_create(Ctx* ctx, const b2gpu_snapshot* proto, int n_worlds, const b2gp
   AL(B.c_fix, W * B.NC); AL(B.c_flags, W * B.NC); AL(B.c_mat, W * B.NC);
   AL(B.c_m0, W * B.NC); AL(B.c_m1, W * B.NC); AL(B.c_m2, W * B.NC); AL(B.c_m3, W * B.NC);
   AL(B.isl_body, W * B.NIB); AL(B.isl_contact, W * B.NC); AL(B.isl_range, W * B.NB); AL(B.isl_flags, W * B.NB);
-  AL(B.c_isl, W * B.NC); AL(B.vc, W * B.NC * VC_Q);
+  AL(B.c_isl, W * B.NC); AL(B.vc, W * B.NC * VC_Q); AL(B.pc, W * B.NC * PC_Q);
   AL(bh->b_wake, W * B.NB); AL(bh->b_chead, W * B.NB); AL(bh->c_next, W * B.NC); AL(bh->stack, W * B.NB);
   AL(bh->state_dev, (long long)n_worlds * B.NB * 8);
   AL(bh->forces_dev, (long long)n_worlds * B.NB * 3);
@@ -480,6 +492,20 @@ int batch_create(Ctx* ctx, const b2gpu_snapshot* proto, int n_worlds, const b2gp
     if (rc) { batch_destroy(bh); return rc; }
   }
   bh->pre_step_needed = true;
+#if !defined(B2G_HOSTSIM)
+  // shared-memory Gauss-Seidel stages: batches in 32-world memory blocks whose bodies fit one SM
+  bh->smem_solver = false;
+  if (B.LB == 32 && !(caps && caps->reserved[1] == 1)) {
+    int max_optin = 0;
+    CU(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
+    const size_t need = std::max(velocity_smem_bytes(B.NB), position_smem_bytes(B.NB));
+    if (need <= (size_t)max_optin) {
+      CU(cudaFuncSetAttribute(velocity_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)velocity_smem_bytes(B.NB)));
+      CU(cudaFuncSetAttribute(position_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)position_smem_bytes(B.NB)));
+      bh->smem_solver = true;
+    }
+  }
+#endif
   *out = bh;
   return 0;
 }
@@ -559,8 +585,24 @@ int batch_step(BatchHost* bh, float dt, int vi, int pi, int steps) {
     if (dt > 0.0f) {
       { IntegrateK k = {B, sp}; RC(launch(ctx, k, W * B.NIB, 128, STAGE_INTEGRATE)); }
       { SolverInitK k = {B, sp}; RC(launch(ctx, k, W * B.NC, 128, STAGE_SOLVER_INIT)); }
+#if !defined(B2G_HOSTSIM)
+      if (bh->smem_solver) {
+        LaunchScope ls = {ctx, STAGE_VELOCITY};
+        RC(ls.begin());
+        velocity_smem_kernel<<<B.n_wblocks, 32, velocity_smem_bytes(B.NB), (cudaStream_t)ctx->stream>>>(B, sp);
+        RC(ls.end());
+      } else
+#endif
       { VelocityK k = {B, sp}; RC(launch(ctx, k, W, ordered_block, STAGE_VELOCITY)); }
       { PostVelocityK k = {B, sp}; RC(launch(ctx, k, W * B.NIB, 128, STAGE_POST_VELOCITY)); }
+#if !defined(B2G_HOSTSIM)
+      if (bh->smem_solver) {
+        LaunchScope ls = {ctx, STAGE_POSITION};
+        RC(ls.begin());
+        position_smem_kernel<<<B.n_wblocks, 32, position_smem_bytes(B.NB), (cudaStream_t)ctx->stream>>>(B, sp);
+        RC(ls.end());
+      } else
+#endif
       { PositionK k = {B, sp}; RC(launch(ctx, k, W, ordered_block, STAGE_POSITION)); }
       { FinalizeK k = {B, sp}; RC(launch(ctx, k, W * B.NIB, 128, STAGE_FINALIZE)); }
       { SleepK k = {B}; RC(launch(ctx, k, W, ordered_block, STAGE_SLEEP)); }
@@ -663,6 +705,7 @@ struct VelScatterK {
     if (vx * vx + vy * vy > 0.0f) {
       B.b_flags[bi] = bf | B2GPU_BODY_AWAKE;
       B.b_pos[bi].w = 0.0f;
+      if (!(bf & B2GPU_BODY_AWAKE)) ws_of(B, x)[WS_TOPO_DIRTY] = 1;
     }
     float4 v = B.b_vel[bi];
     v.x = vx; v.y = vy;

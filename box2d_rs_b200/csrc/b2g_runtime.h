@@ -63,6 +63,7 @@ struct BatchHost {
   float* forces_dev = nullptr;   // [n_worlds][NB][3]
   void* stage_dev = nullptr;     // staging for single-world upload/download
   size_t stage_bytes = 0;
+  bool smem_solver = false;      // shared-memory Gauss-Seidel kernels in use (b2g_solver_smem.cuh)
   bool pre_step_needed = true;   // some world may carry m_new_contacts / a non-empty move buffer
   long long total_bytes = 0;
   StepParams last_sp{};

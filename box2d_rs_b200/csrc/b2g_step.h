@@ -124,6 +124,7 @@ B2G_HD void collide_one(const Batch& B, const WIdx& x, const Ws& ws, int c, int*
     return;
   }
   // ---- B2contact::update
+  if (!(flags & B2GPU_CONTACT_ENABLED)) ws[WS_TOPO_DIRTY] = 1;
   flags |= B2GPU_CONTACT_ENABLED;
   const bool was_touching = (flags & B2GPU_CONTACT_TOUCHING) != 0;
   bool touching = false;
@@ -285,10 +286,24 @@ struct SerialAK {
       ws[WS_TOPO_DIRTY] = 1;
       rebuild_contact_lists(B, x, b_chead, c_next, cc);
     }
-    ws[WS_ISL_COUNT] = 0;
-    ws[WS_ISL_BODIES] = 0;
-    ws[WS_ISL_CONTACTS] = 0;
-    if (!(sp.dt > 0.0f)) return;
+    if (!(sp.dt > 0.0f)) {
+      ws[WS_ISL_COUNT] = 0;
+      ws[WS_ISL_BODIES] = 0;
+      ws[WS_ISL_CONTACTS] = 0;
+      ws[WS_TOPO_DIRTY] = 1;
+      return;
+    }
+    // Island cache: the DFS below is a pure function of the body list (types, AWAKE/ENABLED flags), the
+    // per-body contact edge lists and the contacts' ENABLED/TOUCHING flags.  Every stage that changes one
+    // of those raises WS_TOPO_DIRTY; when nothing changed since the previous step, last step's island
+    // order (and the ISLAND flags it left behind) is exactly what the reference would rebuild.
+    if (!ws[WS_TOPO_DIRTY]) {
+      ws[WS_ST_ISLANDS] = ws[WS_ISL_COUNT];
+      ws[WS_ST_ISL_BODIES] = ws[WS_ISL_BODIES];
+      ws[WS_ST_ISL_CONTACTS] = ws[WS_ISL_CONTACTS];
+      return;
+    }
+    bool dirty_next = false;
     // (4) islands: b2_world.rs(private):376-507.  Seeds newest body first, LIFO stack, each body's
     //     edge list newest first.
     for (int b = 0; b < B.NB; ++b) B.b_flags[x.at(B.NB, b)] &= ~B2GPU_BODY_ISLAND;
@@ -310,6 +325,7 @@ struct SerialAK {
         const int bi = x.at(B.NB, b);
         const int bf = B.b_flags[bi];
         if (body_type(bf) == B2GPU_STATIC_BODY) continue;
+        if (!(bf & B2GPU_BODY_AWAKE)) dirty_next = true;  // a sleeper joined: it is a seed candidate next step
         B.b_flags[bi] = bf | B2GPU_BODY_AWAKE;
         for (int e = b_chead[bi]; e != -1;) {
           const int c = e >> 1, side = e & 1;
@@ -336,7 +352,6 @@ struct SerialAK {
         }
       }
       B.isl_range[x.at(B.NB, nisl)] = make_int4(body_first, nb, contact_first, nc);
-      B.isl_flags[x.at(B.NB, nisl)] = 0;
       ++nisl;
       for (int k = body_first; k < nb; ++k) {  // static bodies may join other islands (:500-506)
         const int bi = x.at(B.NB, B.isl_body[x.at(B.NIB, k)]);
@@ -350,7 +365,7 @@ struct SerialAK {
     ws[WS_ST_ISLANDS] = nisl;
     ws[WS_ST_ISL_BODIES] = nb;
     ws[WS_ST_ISL_CONTACTS] = nc;
-    ws[WS_TOPO_DIRTY] = 0;
+    ws[WS_TOPO_DIRTY] = dirty_next ? 1 : 0;
   }
 };
 
@@ -389,13 +404,18 @@ struct IntegrateK {
   }
 };
 
-// velocity/position constraint record, VC_Q float4 per island contact:
+// Constraint streams written by SolverInitK, one record per island contact slot k; records of one
+// world block are contiguous (k-major), so the ordered stages stream them.
+// velocity record, VC_Q float4:
 //  0: rA0.xy rB0.xy      1: rA1.xy rB1.xy       2: normal.xy friction tangent_speed
 //  3: nMass0 tMass0 bias0 nMass1     4: tMass1 bias1 K11 K12     5: K22 NM11 NM12 NM22
 //  6: nImp0 tImp0 nImp1 tImp1 (mutable)   7: mA iA mB iB
 //  8: (int) bodyA bodyB (vc_points | pc_points<<8 | manifold type<<16) contact
-//  9: lcA.xy lcB.xy      (position pass also reads the manifold and radii through `contact`)
+// position record, PC_Q float4:
+//  0: mA iA mB iB   1: lcA.xy lcB.xy   2: local_point0.xy local_point1.xy   3: local_normal.xy local_point.xy
+//  4: radiusA radiusB (int)bodyA (int)bodyB      5: (int) pc_points | type<<8, island, -, -
 B2G_HD int vc_at(const Batch& B, const WIdx& x, int k, int q) { return x.at(B.NC * VC_Q, k * VC_Q + q); }
+B2G_HD int pc_at(const Batch& B, const WIdx& x, int k, int q) { return x.at(B.NC * PC_Q, k * PC_Q + q); }
 
 // B2contactSolver::new + initialize_velocity_constraints (b2_contact_solver_private.rs:20-226): flat.
 struct SolverInitK {
@@ -493,7 +513,12 @@ struct SolverInitK {
     B.vc[vc_at(B, x, k, 6)] = make_float4(ni[0], ti[0], ni[1], ti[1]);
     B.vc[vc_at(B, x, k, 7)] = make_float4(m_a, i_a, m_b, i_b);
     B.vc[vc_at(B, x, k, 8)] = make_float4(i2f(ba), i2f(bb), i2f(vc_points | (point_count << 8) | (m3.z << 16)), i2f(c));
-    B.vc[vc_at(B, x, k, 9)] = make_float4(msa.z, msa.w, msb.z, msb.w);
+    B.pc[pc_at(B, x, k, 0)] = make_float4(m_a, i_a, m_b, i_b);
+    B.pc[pc_at(B, x, k, 1)] = make_float4(msa.z, msa.w, msb.z, msb.w);
+    B.pc[pc_at(B, x, k, 2)] = make_float4(m0.x, m0.y, m1.x, m1.y);
+    B.pc[pc_at(B, x, k, 3)] = m2;
+    B.pc[pc_at(B, x, k, 4)] = make_float4(radius_a, radius_b, i2f(ba), i2f(bb));
+    B.pc[pc_at(B, x, k, 5)] = make_float4(i2f(point_count | (m3.z << 8)), i2f(B.c_isl[x.at(B.NC, k)]), 0.0f, 0.0f);
   }
 };
 
@@ -686,6 +711,10 @@ struct PostVelocityK {
     if (!flat_decode(B, tid, B.NIB, w, k)) return;
     WIdx x = widx(B, w);
     Ws ws = ws_of(B, x);
+    if (k < ws[WS_ISL_COUNT]) {
+      const int4 rg = B.isl_range[x.at(B.NB, k)];
+      B.isl_flags[x.at(B.NB, k)] = (rg.z == rg.w && sp.position_iterations > 0) ? 1 : 0;
+    }
     if (k < ws[WS_ISL_CONTACTS]) {
       const float4 q8 = B.vc[vc_at(B, x, k, 8)];
       const int vc_points = f2i(q8.z) & 0xff, c = f2i(q8.w);
@@ -736,10 +765,11 @@ struct PosState {
   float a_a, a_b;
   Rot q_a, q_b;
 };
-B2G_HD float solve_position_one(PosState& s, const float4 q7, const float4 q9, const float4 m0, const float4 m1, const float4 m2,
+B2G_HD float solve_position_one(PosState& s, const float4 q7, const float4 q9, const float4 lps, const float4 m2,
                                 int type, int pc_points, float radius_a, float radius_b, float min_separation) {
   const float m_a = q7.x, i_a = q7.y, m_b = q7.z, i_b = q7.w;
   const V2 lc_a = v2(q9.x, q9.y), lc_b = v2(q9.z, q9.w);
+  const float4 m0 = make_float4(lps.x, lps.y, 0.0f, 0.0f), m1 = make_float4(lps.z, lps.w, 0.0f, 0.0f);
   for (int j = 0; j < pc_points; ++j) {
     Xf xf_a, xf_b;
     xf_a.q = s.q_a;
@@ -787,6 +817,9 @@ B2G_HD float solve_position_one(PosState& s, const float4 q7, const float4 q9, c
 }
 
 // Ordered stage C (one thread per world), generic form: position iterations with per-island early exit.
+// Islands are contiguous runs of the constraint stream; a solved island is skipped in later sweeps
+// (the reference leaves its loop, b2_island_private.rs:257-274).  Islands without contacts were
+// marked solved by PostVelocityK.
 struct PositionK {
   Batch B;
   StepParams sp;
@@ -794,37 +827,43 @@ struct PositionK {
     if (w >= B.n_worlds) return;
     WIdx x = widx(B, w);
     Ws ws = ws_of(B, x);
-    const int nisl = ws[WS_ISL_COUNT];
+    const int nc = ws[WS_ISL_CONTACTS];
     for (int it = 0; it < sp.position_iterations; ++it) {
       bool all_solved = true;
-      for (int isl = 0; isl < nisl; ++isl) {
-        if (B.isl_flags[x.at(B.NB, isl)] & 1) continue;
-        const int4 rg = B.isl_range[x.at(B.NB, isl)];
-        float min_separation = 0.0f;
-        for (int k = rg.z; k < rg.w; ++k) {
-          const float4 q8 = B.vc[vc_at(B, x, k, 8)];
-          const int ba = f2i(q8.x), bb = f2i(q8.y), packed = f2i(q8.z), c = f2i(q8.w);
-          const int pc_points = (packed >> 8) & 0xff, type = (packed >> 16) & 0xff;
-          const int bai = x.at(B.NB, ba), bbi = x.at(B.NB, bb), ci = x.at(B.NC, c);
-          const int4 fx = B.c_fix[ci];
-          const float radius_a = B.shapes[B.fixtures[fx.x].shape_first].radius;
-          const float radius_b = B.shapes[B.fixtures[fx.y].shape_first].radius;
-          float4 pa = B.b_pos[bai], pb = B.b_pos[bbi];
-          float4 ra = B.b_rot[bai], rb = B.b_rot[bbi];
-          PosState s;
-          s.c_a = v2(pa.x, pa.y); s.a_a = pa.z; s.q_a.s = ra.x; s.q_a.c = ra.y;
-          s.c_b = v2(pb.x, pb.y); s.a_b = pb.z; s.q_b.s = rb.x; s.q_b.c = rb.y;
-          min_separation = solve_position_one(s, B.vc[vc_at(B, x, k, 7)], B.vc[vc_at(B, x, k, 9)], B.c_m0[ci], B.c_m1[ci],
-                                              B.c_m2[ci], type, pc_points, radius_a, radius_b, min_separation);
-          pa.x = s.c_a.x; pa.y = s.c_a.y; pa.z = s.a_a;
-          pb.x = s.c_b.x; pb.y = s.c_b.y; pb.z = s.a_b;
-          ra.x = s.q_a.s; ra.y = s.q_a.c;
-          rb.x = s.q_b.s; rb.y = s.q_b.c;
-          B.b_pos[bai] = pa; B.b_rot[bai] = ra;
-          B.b_pos[bbi] = pb; B.b_rot[bbi] = rb;
+      int cur = -1;
+      bool skip = false;
+      float min_separation = 0.0f;
+      for (int k = 0; k < nc; ++k) {
+        const float4 p5 = B.pc[pc_at(B, x, k, 5)];
+        const int isl = f2i(p5.y);
+        if (isl != cur) {
+          if (cur >= 0 && !skip) {
+            if (min_separation >= -3.0f * B2G_LINEAR_SLOP) B.isl_flags[x.at(B.NB, cur)] |= 1; else all_solved = false;
+          }
+          cur = isl;
+          skip = (B.isl_flags[x.at(B.NB, cur)] & 1) != 0;
+          min_separation = 0.0f;
         }
-        if (min_separation >= -3.0f * B2G_LINEAR_SLOP) B.isl_flags[x.at(B.NB, isl)] |= 1;
-        else all_solved = false;
+        if (skip) continue;
+        const float4 p4 = B.pc[pc_at(B, x, k, 4)];
+        const int ba = f2i(p4.z), bb = f2i(p4.w), packed = f2i(p5.x);
+        const int bai = x.at(B.NB, ba), bbi = x.at(B.NB, bb);
+        float4 pa = B.b_pos[bai], pb = B.b_pos[bbi];
+        float4 ra = B.b_rot[bai], rb = B.b_rot[bbi];
+        PosState s;
+        s.c_a = v2(pa.x, pa.y); s.a_a = pa.z; s.q_a.s = ra.x; s.q_a.c = ra.y;
+        s.c_b = v2(pb.x, pb.y); s.a_b = pb.z; s.q_b.s = rb.x; s.q_b.c = rb.y;
+        min_separation = solve_position_one(s, B.pc[pc_at(B, x, k, 0)], B.pc[pc_at(B, x, k, 1)], B.pc[pc_at(B, x, k, 2)],
+                                            B.pc[pc_at(B, x, k, 3)], (packed >> 8) & 0xff, packed & 0xff, p4.x, p4.y, min_separation);
+        pa.x = s.c_a.x; pa.y = s.c_a.y; pa.z = s.a_a;
+        pb.x = s.c_b.x; pb.y = s.c_b.y; pb.z = s.a_b;
+        ra.x = s.q_a.s; ra.y = s.q_a.c;
+        rb.x = s.q_b.s; rb.y = s.q_b.c;
+        B.b_pos[bai] = pa; B.b_rot[bai] = ra;
+        B.b_pos[bbi] = pb; B.b_rot[bbi] = rb;
+      }
+      if (cur >= 0 && !skip) {
+        if (min_separation >= -3.0f * B2G_LINEAR_SLOP) B.isl_flags[x.at(B.NB, cur)] |= 1; else all_solved = false;
       }
       if (all_solved) break;
     }

@@ -273,7 +273,9 @@ typedef struct b2gpu_mass_data {
 /* Device-side capacities of one world of a batch. 0 = derive from the prototype. */
 typedef struct b2gpu_caps {
   int32_t max_bodies, max_fixtures, max_shapes, max_proxies, max_contacts, max_pairs;
-  int32_t reserved[2]; /* reserved[0]: worlds per memory block (power of two; 0 = 32 for >= 32 worlds, else 1) */
+  int32_t reserved[2]; /* reserved[0]: worlds per memory block (power of two; 0 = 32 for >= 32 worlds, else 1);
+                          reserved[1]: 1 = use the generic global-memory solver stages even when the
+                          shared-memory ones apply (diagnostics) */
 } b2gpu_caps;
 
 typedef struct b2gpu_ctx b2gpu_ctx;

@@ -110,6 +110,25 @@ def test_batch_of_different_worlds(n_worlds, lane_block, ctx):
     wg.close()
 
 
+@pytest.mark.parametrize("name,steps", [("hello_world", 90), ("mixed300", 260), ("addpair2000", 120), ("pile400", 120)])
+def test_batch_replicas_shared_memory_solver(name, steps, ctx):
+    """32-world memory blocks run the shared-memory Gauss-Seidel kernels (resident ring for tiny islands,
+    streaming ring otherwise, many islands per world): replicas must match the oracle bit for bit."""
+    from box2d_rs_b200 import scenes
+    wo, wg, _ = _pair(name, ctx)
+    batch = wg.batch(40)
+    for i in range(steps):
+        batch.step(scenes.DT, 8, 3)
+        wo.step(scenes.DT, 8, 3)
+        if i % 20 == 19 or i == steps - 1:
+            for w in (0, 39):
+                bad = parity.compare_snapshots(wo.snapshot(), batch.download_world(w)) + \
+                    parity.compare_stats(wo.get_stats(), batch.stats()[w])
+                assert bad == [], "step %d world %d: %s" % (i, w, bad[:6])
+    batch.close()
+    wg.close()
+
+
 def test_full_size_batch_properties(ctx):
     """BASELINE config 3 at full size (4096 Pyramid worlds): size-independent properties — replicas stay
     bit-identical to each other and to the oracle; a world pushed by an external force diverges alone."""
