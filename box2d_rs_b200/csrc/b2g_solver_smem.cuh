@@ -29,16 +29,38 @@ template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile(
 constexpr int VEL_RING = 8;  // stages of the velocity constraint ring
 constexpr int POS_RING = 8;
 
-inline size_t velocity_smem_bytes(int NB) { return (size_t)NB * 3 * 32 * 4 + (size_t)VEL_RING * VC_Q * 32 * 16; }
-inline size_t position_smem_bytes(int NB) { return (size_t)NB * 5 * 32 * 4 + (size_t)POS_RING * PC_Q * 32 * 16; }
+inline size_t velocity_smem_bytes(int NB) { return (size_t)NB * 32 * 16 + (size_t)VEL_RING * VC_Q * 32 * 16; }
+inline size_t position_smem_bytes(int NB) { return (size_t)NB * 32 * (16 + 8) + (size_t)POS_RING * PC_Q * 32 * 16; }
+
+struct VcRegs {  // one velocity constraint of one world, in registers
+  float4 q0, q1, q2, q3, q4, q5, q6, q7;
+  int ba, bb, cnt;
+};
+__device__ __forceinline__ VcRegs vc_load(const float4* st) {
+  VcRegs r;
+  r.q0 = st[0 * 32]; r.q1 = st[1 * 32]; r.q2 = st[2 * 32]; r.q3 = st[3 * 32];
+  r.q4 = st[4 * 32]; r.q5 = st[5 * 32]; r.q6 = st[6 * 32]; r.q7 = st[7 * 32];
+  const float4 q8 = st[8 * 32];
+  r.ba = __float_as_int(q8.x);
+  r.bb = __float_as_int(q8.y);
+  r.cnt = __float_as_int(q8.z) & 0xff;
+  return r;
+}
 
 // ------------------------------------------------------------------------------------------
 // warm start + velocity iterations.  grid = world blocks, block = 32 lanes (one world each).
+//
+// The loop is software-pipelined by hand: while constraint p is being solved (a ~60-deep chain of
+// dependent fp32 operations), the rows of constraint p+1 are read from the ring into registers and
+// the velocities of its two bodies are read from shared memory.  Those velocity reads can be stale
+// for a body that constraint p is about to update — which, in the reference's DFS contact order, is
+// the usual case — so after the solve the fresh values are forwarded from registers (two compares
+// and selects instead of a store -> load round trip through shared memory on the dependent chain).
 // ------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(32) velocity_smem_kernel(const Batch B, const StepParams sp) {
   extern __shared__ float4 smem4[];
-  float4* ring = smem4;                                        // [VEL_RING][VC_Q][32]
-  float* vel = (float*)(smem4 + VEL_RING * VC_Q * 32);         // [NB][3][32]
+  float4* ring = smem4;                      // [VEL_RING][VC_Q][32]
+  float4* vel = smem4 + VEL_RING * VC_Q * 32;  // [NB][32]: v.x v.y w -
   const int lane = threadIdx.x;
   const int wb = blockIdx.x;
   const int w = wb * 32 + lane;
@@ -52,87 +74,137 @@ __global__ void __launch_bounds__(32) velocity_smem_kernel(const Batch B, const 
   const bool block = (wflags & B2GPU_WORLD_BLOCK_SOLVE) != 0;
   const int ncm = __reduce_max_sync(0xffffffffu, nc);
   if (ncm == 0) return;
-  // stage body velocities (coalesced float4 reads, conflict-free scalar smem writes)
-  if (live) {
-    for (int b = 0; b < B.NB; ++b) {
-      const float4 v = B.b_vel[x.at(B.NB, b)];
-      vel[(b * 3 + 0) * 32 + lane] = v.x;
-      vel[(b * 3 + 1) * 32 + lane] = v.y;
-      vel[(b * 3 + 2) * 32 + lane] = v.z;
-    }
-  }
+  if (live)
+    for (int b = 0; b < B.NB; ++b) vel[b * 32 + lane] = B.b_vel[x.at(B.NB, b)];
   const float4* src = B.vc + (size_t)wb * B.NC * VC_Q * 32 + lane;  // + (k * VC_Q + q) * 32
-  const int sweeps = 1 + sp.velocity_iterations;                   // sweep 0 = warm start
+  float4* q6_out = B.vc + (size_t)wb * B.NC * VC_Q * 32 + 6 * 32 + lane;
+  const int sweeps = 1 + sp.velocity_iterations;  // sweep 0 = warm start
   const int total = sweeps * ncm;
-  const bool resident = ncm <= VEL_RING;  // the whole stream fits: load once, iterate in shared memory
-  auto fetch = [&](int pos) {              // stage constraint (pos % ncm) of sweep (pos / ncm)
-    if (pos < total) {
-      const int k = pos % ncm;
-      if (k < nc) {
-        float4* dst = ring + (size_t)((resident ? k : pos % VEL_RING) * VC_Q) * 32 + lane;
-        const float4* s = src + (size_t)k * VC_Q * 32;
+  float4* vl = vel + lane;
+  float4* rl = ring + lane;
+
+  if (ncm <= VEL_RING) {
+    // ---- resident form: the whole stream fits the ring; load once, iterate in shared memory
+    for (int k = 0; k < ncm; ++k) {
 #pragma unroll
-        for (int q = 0; q < VC_Q; ++q) cp_async16(dst + q * 32, s + q * 32);
-      }
+      for (int q = 0; q < VC_Q; ++q) cp_async16(rl + (k * VC_Q + q) * 32, src + (size_t)(k * VC_Q + q) * 32);
     }
     cp_async_commit();
-  };
-  const int prologue = resident ? ncm : VEL_RING - 1;
-  for (int p = 0; p < VEL_RING - 1; ++p) {
-    if (resident) { if (p < ncm) fetch(p); else cp_async_commit(); }
-    else fetch(p);
-  }
-  if (resident && ncm == VEL_RING) fetch(VEL_RING - 1);
-  (void)prologue;
-  int k = 0, sweep = 0;
-  for (int pos = 0; pos < total; ++pos) {
-    if (resident) cp_async_wait<0>(); else cp_async_wait<VEL_RING - 2>();
-    if (!resident) fetch(pos + VEL_RING - 1);
-    if (k < nc && (sweep > 0 || warm)) {
-      float4* st = ring + (size_t)((resident ? k : pos % VEL_RING) * VC_Q) * 32 + lane;
-      const float4 q8 = st[8 * 32];
-      const int ba = __float_as_int(q8.x), bb = __float_as_int(q8.y), vc_points = __float_as_int(q8.z) & 0xff;
-      if (vc_points > 0) {
+    cp_async_wait<0>();
+    for (int sweep = 0; sweep < sweeps; ++sweep) {
+      if (sweep == 0 && !__any_sync(0xffffffffu, warm)) continue;
+      for (int k = 0; k < ncm; ++k) {
+        if (k >= nc || (sweep == 0 && !warm)) continue;
+        float4* st = rl + (k * VC_Q) * 32;
+        VcRegs c = vc_load(st);
+        if (c.cnt == 0) continue;
+        const float4 va = vl[c.ba * 32], vb = vl[c.bb * 32];
         VelState s;
-        s.v_a = v2(vel[(ba * 3 + 0) * 32 + lane], vel[(ba * 3 + 1) * 32 + lane]);
-        s.w_a = vel[(ba * 3 + 2) * 32 + lane];
-        s.v_b = v2(vel[(bb * 3 + 0) * 32 + lane], vel[(bb * 3 + 1) * 32 + lane]);
-        s.w_b = vel[(bb * 3 + 2) * 32 + lane];
-        const float4 q0 = st[0 * 32], q1 = st[1 * 32], q2 = st[2 * 32], q7 = st[7 * 32];
-        float4 q6 = st[6 * 32];
+        s.v_a = v2(va.x, va.y); s.w_a = va.z;
+        s.v_b = v2(vb.x, vb.y); s.w_b = vb.z;
         if (sweep == 0) {
-          warm_start_one(s, q0, q1, q2, q6, q7, vc_points);
+          warm_start_one(s, c.q0, c.q1, c.q2, c.q6, c.q7, c.cnt);
         } else {
-          const float4 q3 = st[3 * 32], q4 = st[4 * 32], q5 = st[5 * 32];
-          solve_velocity_one(s, q0, q1, q2, q3, q4, q5, q6, q7, vc_points, block);
-          if (resident) st[6 * 32] = q6;
-          if (!resident || sweep == sweeps - 1) B.vc[vc_at(B, x, k, 6)] = q6;
+          solve_velocity_one(s, c.q0, c.q1, c.q2, c.q3, c.q4, c.q5, c.q6, c.q7, c.cnt, block);
+          st[6 * 32] = c.q6;
+          if (sweep == sweeps - 1) q6_out[(size_t)k * VC_Q * 32] = c.q6;
         }
-        vel[(ba * 3 + 0) * 32 + lane] = s.v_a.x;
-        vel[(ba * 3 + 1) * 32 + lane] = s.v_a.y;
-        vel[(ba * 3 + 2) * 32 + lane] = s.w_a;
-        vel[(bb * 3 + 0) * 32 + lane] = s.v_b.x;
-        vel[(bb * 3 + 1) * 32 + lane] = s.v_b.y;
-        vel[(bb * 3 + 2) * 32 + lane] = s.w_b;
+        vl[c.ba * 32] = make_float4(s.v_a.x, s.v_a.y, s.w_a, 0.0f);
+        vl[c.bb * 32] = make_float4(s.v_b.x, s.v_b.y, s.w_b, 0.0f);
       }
     }
-    if (++k == ncm) { k = 0; ++sweep; }
+  } else {
+    // ---- streaming form: ring of VEL_RING stages, constraint p lives in stage p % VEL_RING
+    int fk = 0;                 // next constraint index to fetch (wraps at ncm)
+    int fpos = 0;               // its flattened position
+    const float4* fsrc = src;
+    auto fetch = [&]() {
+      if (fpos < total) {
+        float4* dst = rl + ((fpos & (VEL_RING - 1)) * VC_Q) * 32;
+#pragma unroll
+        for (int q = 0; q < VC_Q; ++q) cp_async16(dst + q * 32, fsrc + q * 32);
+        fsrc += VC_Q * 32;
+        if (++fk == ncm) { fk = 0; fsrc = src; }
+      }
+      ++fpos;
+      cp_async_commit();
+    };
+#pragma unroll
+    for (int p = 0; p < VEL_RING; ++p) fetch();  // positions 0 .. RING-1 in flight
+    cp_async_wait<VEL_RING - 1>();                 // position 0 landed
+    VcRegs cur = vc_load(rl);
+    int k = 0, sweep = 0;
+    bool act = (k < nc) && warm && cur.cnt > 0;
+    if (!act) { cur.ba = 0; cur.bb = 0; }
+    float4 va = vl[cur.ba * 32], vb = vl[cur.bb * 32];
+    for (int pos = 0; pos < total; ++pos) {
+      // -- prefetch position pos+1 into registers (its stage landed: at most RING-2 younger groups pending)
+      int nk = k + 1, nsweep = sweep;
+      if (nk == ncm) { nk = 0; ++nsweep; }
+      cp_async_wait<VEL_RING - 2>();
+      VcRegs nxt = vc_load(rl + (((pos + 1) & (VEL_RING - 1)) * VC_Q) * 32);
+      bool nact = (pos + 1 < total) && (nk < nc) && (nsweep > 0 || warm) && nxt.cnt > 0;
+      if (!nact) { nxt.ba = 0; nxt.bb = 0; }
+      float4 nva = vl[nxt.ba * 32], nvb = vl[nxt.bb * 32];
+      // the stage of position pos is free now (cur is in registers): refill it with position pos + RING
+      fetch();
+      // -- solve position pos
+      if (act) {
+        VelState s;
+        s.v_a = v2(va.x, va.y); s.w_a = va.z;
+        s.v_b = v2(vb.x, vb.y); s.w_b = vb.z;
+        if (sweep == 0) {
+          warm_start_one(s, cur.q0, cur.q1, cur.q2, cur.q6, cur.q7, cur.cnt);
+        } else {
+          if (__all_sync(__activemask(), cur.cnt == 2 && block))
+            solve_velocity_one(s, cur.q0, cur.q1, cur.q2, cur.q3, cur.q4, cur.q5, cur.q6, cur.q7, 2, true);
+          else
+            solve_velocity_one(s, cur.q0, cur.q1, cur.q2, cur.q3, cur.q4, cur.q5, cur.q6, cur.q7, cur.cnt, block);
+          q6_out[(size_t)k * VC_Q * 32] = cur.q6;
+        }
+        va = make_float4(s.v_a.x, s.v_a.y, s.w_a, 0.0f);
+        vb = make_float4(s.v_b.x, s.v_b.y, s.w_b, 0.0f);
+        vl[cur.ba * 32] = va;
+        vl[cur.bb * 32] = vb;
+        // -- forward the fresh velocities to the next constraint where it shares a body with this one
+        if (nxt.ba == cur.ba) nva = va; else if (nxt.ba == cur.bb) nva = vb;
+        if (nxt.bb == cur.ba) nvb = va; else if (nxt.bb == cur.bb) nvb = vb;
+      }
+      cur = nxt; act = nact; va = nva; vb = nvb; k = nk; sweep = nsweep;
+    }
+    cp_async_wait<0>();
   }
-  cp_async_wait<0>();
-  if (live) {
-    for (int b = 0; b < B.NB; ++b)
-      B.b_vel[x.at(B.NB, b)] = make_float4(vel[(b * 3 + 0) * 32 + lane], vel[(b * 3 + 1) * 32 + lane],
-                                           vel[(b * 3 + 2) * 32 + lane], 0.0f);
-  }
+  __syncwarp();
+  if (live)
+    for (int b = 0; b < B.NB; ++b) B.b_vel[x.at(B.NB, b)] = vel[b * 32 + lane];
 }
 
 // ------------------------------------------------------------------------------------------
-// position iterations with per-island early exit.  Same CTA shape; bodies carry (c.x, c.y, a, sin a, cos a).
+// position iterations with per-island early exit.  Same CTA shape and the same software pipeline;
+// bodies carry (c.x, c.y, a) and the cached rotation (sin a, cos a), see solve_position_one.
 // ------------------------------------------------------------------------------------------
+struct PcRegs {
+  float4 p0, p1, p2, p3;
+  float ra, rb;
+  int ba, bb, cnt, type, isl;
+};
+__device__ __forceinline__ PcRegs pc_load(const float4* st) {
+  PcRegs r;
+  r.p0 = st[0 * 32]; r.p1 = st[1 * 32]; r.p2 = st[2 * 32]; r.p3 = st[3 * 32];
+  const float4 p4 = st[4 * 32], p5 = st[5 * 32];
+  r.ra = p4.x; r.rb = p4.y;
+  r.ba = __float_as_int(p4.z); r.bb = __float_as_int(p4.w);
+  const int packed = __float_as_int(p5.x);
+  r.cnt = packed & 0xff; r.type = (packed >> 8) & 0xff;
+  r.isl = __float_as_int(p5.y);
+  return r;
+}
+
 __global__ void __launch_bounds__(32) position_smem_kernel(const Batch B, const StepParams sp) {
   extern __shared__ float4 smem4[];
-  float4* ring = smem4;                                        // [POS_RING][PC_Q][32]
-  float* pos = (float*)(smem4 + POS_RING * PC_Q * 32);         // [NB][5][32]
+  float4* ring = smem4;                                   // [POS_RING][PC_Q][32]
+  float4* pos = smem4 + POS_RING * PC_Q * 32;             // [NB][32]: c.x c.y a -
+  float2* rot = (float2*)(pos + (size_t)B.NB * 32);       // [NB][32]: sin a, cos a
   const int lane = threadIdx.x;
   const int wb = blockIdx.x;
   const int w = wb * 32 + lane;
@@ -147,105 +219,102 @@ __global__ void __launch_bounds__(32) position_smem_kernel(const Batch B, const 
     for (int b = 0; b < B.NB; ++b) {
       const float4 p = B.b_pos[x.at(B.NB, b)];
       const float4 r = B.b_rot[x.at(B.NB, b)];
-      pos[(b * 5 + 0) * 32 + lane] = p.x;
-      pos[(b * 5 + 1) * 32 + lane] = p.y;
-      pos[(b * 5 + 2) * 32 + lane] = p.z;
-      pos[(b * 5 + 3) * 32 + lane] = r.x;
-      pos[(b * 5 + 4) * 32 + lane] = r.y;
+      pos[b * 32 + lane] = p;
+      rot[b * 32 + lane] = make_float2(r.x, r.y);
     }
   }
   const float4* src = B.pc + (size_t)wb * B.NC * PC_Q * 32 + lane;
   const int total = sp.position_iterations * ncm;
+  float4* pl = pos + lane;
+  float2* ql = rot + lane;
+  float4* rl = ring + lane;
   const bool resident = ncm <= POS_RING;
-  auto fetch = [&](int p) {
-    if (p < total) {
-      const int k = p % ncm;
-      if (k < nc) {
-        float4* dst = ring + (size_t)((resident ? k : p % POS_RING) * PC_Q) * 32 + lane;
-        const float4* s = src + (size_t)k * PC_Q * 32;
+  int fk = 0, fpos = 0;
+  const float4* fsrc = src;
+  auto fetch = [&]() {
+    if (fpos < total && !(resident && fpos >= ncm)) {
+      float4* dst = rl + ((resident ? fk : (fpos & (POS_RING - 1))) * PC_Q) * 32;
 #pragma unroll
-        for (int q = 0; q < PC_Q; ++q) cp_async16(dst + q * 32, s + q * 32);
-      }
+      for (int q = 0; q < PC_Q; ++q) cp_async16(dst + q * 32, fsrc + q * 32);
+      fsrc += PC_Q * 32;
+      if (++fk == ncm) { fk = 0; fsrc = src; }
     }
+    ++fpos;
     cp_async_commit();
   };
-  for (int p = 0; p < POS_RING - 1; ++p) {
-    if (resident) { if (p < ncm) fetch(p); else cp_async_commit(); }
-    else fetch(p);
-  }
-  if (resident && ncm == POS_RING) fetch(POS_RING - 1);
+#pragma unroll
+  for (int p = 0; p < POS_RING; ++p) fetch();
+  if (resident) cp_async_wait<0>(); else cp_async_wait<POS_RING - 1>();
+  PcRegs cur = pc_load(rl);
   int k = 0;
-  int cur = -1;
+  bool act = k < nc;
+  if (!act) { cur.ba = 0; cur.bb = 0; }
+  float4 pa = pl[cur.ba * 32], pb = pl[cur.bb * 32];
+  float2 qa = ql[cur.ba * 32], qb = ql[cur.bb * 32];
+  int isl = -1;
   bool skip = false, all_solved = true, done = !live || nc == 0;
   float min_separation = 0.0f;
   for (int p = 0; p < total; ++p) {
-    if (resident) cp_async_wait<0>(); else cp_async_wait<POS_RING - 2>();
-    if (!resident) fetch(p + POS_RING - 1);
-    if (k < nc && !done) {
-      const float4* st = ring + (size_t)((resident ? k : p % POS_RING) * PC_Q) * 32 + lane;
-      const float4 p5 = st[5 * 32];
-      const int isl = __float_as_int(p5.y);
-      if (isl != cur) {
-        if (cur >= 0 && !skip) {
-          if (min_separation >= -3.0f * B2G_LINEAR_SLOP) B.isl_flags[x.at(B.NB, cur)] |= 1; else all_solved = false;
+    int nk = k + 1;
+    if (nk == ncm) nk = 0;
+    if (!resident) cp_async_wait<POS_RING - 2>();
+    PcRegs nxt = pc_load(rl + ((resident ? nk : ((p + 1) & (POS_RING - 1))) * PC_Q) * 32);
+    const bool nact = (p + 1 < total) && (nk < nc);
+    if (!nact) { nxt.ba = 0; nxt.bb = 0; }
+    float4 npa = pl[nxt.ba * 32], npb = pl[nxt.bb * 32];
+    float2 nqa = ql[nxt.ba * 32], nqb = ql[nxt.bb * 32];
+    if (!resident) fetch();
+    if (act && !done) {
+      if (cur.isl != isl) {  // island boundary: close the previous island, open the next
+        if (isl >= 0 && !skip) {
+          if (min_separation >= -3.0f * B2G_LINEAR_SLOP) B.isl_flags[x.at(B.NB, isl)] |= 1; else all_solved = false;
         }
-        cur = isl;
-        skip = (B.isl_flags[x.at(B.NB, cur)] & 1) != 0;
+        isl = cur.isl;
+        skip = (B.isl_flags[x.at(B.NB, isl)] & 1) != 0;
         min_separation = 0.0f;
       }
       if (!skip) {
-        const float4 p4 = st[4 * 32];
-        const int ba = __float_as_int(p4.z), bb = __float_as_int(p4.w), packed = __float_as_int(p5.x);
         PosState s;
-        s.c_a = v2(pos[(ba * 5 + 0) * 32 + lane], pos[(ba * 5 + 1) * 32 + lane]);
-        s.a_a = pos[(ba * 5 + 2) * 32 + lane];
-        s.q_a.s = pos[(ba * 5 + 3) * 32 + lane];
-        s.q_a.c = pos[(ba * 5 + 4) * 32 + lane];
-        s.c_b = v2(pos[(bb * 5 + 0) * 32 + lane], pos[(bb * 5 + 1) * 32 + lane]);
-        s.a_b = pos[(bb * 5 + 2) * 32 + lane];
-        s.q_b.s = pos[(bb * 5 + 3) * 32 + lane];
-        s.q_b.c = pos[(bb * 5 + 4) * 32 + lane];
-        min_separation = solve_position_one(s, st[0 * 32], st[1 * 32], st[2 * 32], st[3 * 32], (packed >> 8) & 0xff,
-                                            packed & 0xff, p4.x, p4.y, min_separation);
-        pos[(ba * 5 + 0) * 32 + lane] = s.c_a.x;
-        pos[(ba * 5 + 1) * 32 + lane] = s.c_a.y;
-        pos[(ba * 5 + 2) * 32 + lane] = s.a_a;
-        pos[(ba * 5 + 3) * 32 + lane] = s.q_a.s;
-        pos[(ba * 5 + 4) * 32 + lane] = s.q_a.c;
-        pos[(bb * 5 + 0) * 32 + lane] = s.c_b.x;
-        pos[(bb * 5 + 1) * 32 + lane] = s.c_b.y;
-        pos[(bb * 5 + 2) * 32 + lane] = s.a_b;
-        pos[(bb * 5 + 3) * 32 + lane] = s.q_b.s;
-        pos[(bb * 5 + 4) * 32 + lane] = s.q_b.c;
+        s.c_a = v2(pa.x, pa.y); s.a_a = pa.z; s.q_a.s = qa.x; s.q_a.c = qa.y;
+        s.c_b = v2(pb.x, pb.y); s.a_b = pb.z; s.q_b.s = qb.x; s.q_b.c = qb.y;
+        min_separation = solve_position_one(s, cur.p0, cur.p1, cur.p2, cur.p3, cur.type, cur.cnt, cur.ra, cur.rb, min_separation);
+        pa = make_float4(s.c_a.x, s.c_a.y, s.a_a, 0.0f);
+        pb = make_float4(s.c_b.x, s.c_b.y, s.a_b, 0.0f);
+        qa = make_float2(s.q_a.s, s.q_a.c);
+        qb = make_float2(s.q_b.s, s.q_b.c);
+        pl[cur.ba * 32] = pa; ql[cur.ba * 32] = qa;
+        pl[cur.bb * 32] = pb; ql[cur.bb * 32] = qb;
+        if (nxt.ba == cur.ba) { npa = pa; nqa = qa; } else if (nxt.ba == cur.bb) { npa = pb; nqa = qb; }
+        if (nxt.bb == cur.ba) { npb = pa; nqb = qa; } else if (nxt.bb == cur.bb) { npb = pb; nqb = qb; }
       }
     }
-    if (++k == ncm) {  // end of a sweep: close the last island, test the early exit of this world
-      k = 0;
+    if (nk == 0) {  // end of a sweep: close the last island, test the early exit of this world
       if (!done) {
-        if (cur >= 0 && !skip) {
-          if (min_separation >= -3.0f * B2G_LINEAR_SLOP) B.isl_flags[x.at(B.NB, cur)] |= 1; else all_solved = false;
+        if (isl >= 0 && !skip) {
+          if (min_separation >= -3.0f * B2G_LINEAR_SLOP) B.isl_flags[x.at(B.NB, isl)] |= 1; else all_solved = false;
         }
         if (all_solved) done = true;
-        cur = -1;
+        isl = -1;
         skip = false;
         all_solved = true;
         min_separation = 0.0f;
       }
       if (__all_sync(0xffffffffu, done)) break;
     }
+    cur = nxt; act = nact; pa = npa; pb = npb; qa = nqa; qb = nqb; k = nk;
   }
   cp_async_wait<0>();
+  __syncwarp();
   if (live && nc > 0) {
     for (int b = 0; b < B.NB; ++b) {
       const int bi = x.at(B.NB, b);
-      float4 p = B.b_pos[bi];
+      const float4 p = pos[b * 32 + lane];
+      const float2 q = rot[b * 32 + lane];
+      float4 op = B.b_pos[bi];
       float4 r = B.b_rot[bi];
-      p.x = pos[(b * 5 + 0) * 32 + lane];
-      p.y = pos[(b * 5 + 1) * 32 + lane];
-      p.z = pos[(b * 5 + 2) * 32 + lane];
-      r.x = pos[(b * 5 + 3) * 32 + lane];
-      r.y = pos[(b * 5 + 4) * 32 + lane];
-      B.b_pos[bi] = p;
+      op.x = p.x; op.y = p.y; op.z = p.z;
+      r.x = q.x; r.y = q.y;
+      B.b_pos[bi] = op;
       B.b_rot[bi] = r;
     }
   }

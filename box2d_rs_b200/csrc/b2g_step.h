@@ -594,41 +594,28 @@ B2G_HD void solve_velocity_one(VelState& s, const float4 q0, const float4 q1, co
       w_b += i_b * cross(rb1, p);
     }
   } else {
-    // block solver (:352-576): K = [k11 k12; k12 k22], normal_mass = K^-1
+    // block solver (:352-576): K = [k11 k12; k12 k22], normal_mass = K^-1.  The reference tries the four
+    // LCP cases in order and takes the first that satisfies its conditions; the candidates are evaluated
+    // branch-free here and selected in the same priority order (identical arithmetic per case).
     const float k11 = q4.z, k12 = q4.w, k22 = q5.x, n11 = q5.y, n12 = q5.z, n22 = q5.w;
     const V2 a = v2(q6.x, q6.z);
     const V2 dv1 = v_b + cross_sv(w_b, rb0) - v_a - cross_sv(w_a, ra0);
     const V2 dv2 = v_b + cross_sv(w_b, rb1) - v_a - cross_sv(w_a, ra1);
-    float vn1 = dot(dv1, normal);
-    float vn2 = dot(dv2, normal);
+    const float vn1 = dot(dv1, normal);
+    const float vn2 = dot(dv2, normal);
     V2 b = v2(vn1 - q3.z, vn2 - q4.y);
     b = b - v2(k11 * a.x + k12 * a.y, k12 * a.x + k22 * a.y);
+    const V2 x1 = -v2(n11 * b.x + n12 * b.y, n12 * b.x + n22 * b.y);  // case 1: both points active
+    const bool ok1 = x1.x >= 0.0f && x1.y >= 0.0f;
+    const float x2 = -q3.x * b.x;                                       // case 2: point 1 active
+    const bool ok2 = x2 >= 0.0f && (k12 * x2 + b.y) >= 0.0f;
+    const float x3 = -q3.w * b.y;                                       // case 3: point 2 active
+    const bool ok3 = x3 >= 0.0f && (k12 * x3 + b.x) >= 0.0f;
+    const bool ok4 = b.x >= 0.0f && b.y >= 0.0f;                        // case 4: none active
     V2 xs;
-    bool found = false;
-    {  // case 1: both active
-      xs = -v2(n11 * b.x + n12 * b.y, n12 * b.x + n22 * b.y);
-      if (xs.x >= 0.0f && xs.y >= 0.0f) found = true;
-    }
-    if (!found) {  // case 2: x1 active
-      xs.x = -q3.x * b.x;
-      xs.y = 0.0f;
-      vn2 = k12 * xs.x + b.y;
-      if (xs.x >= 0.0f && vn2 >= 0.0f) found = true;
-    }
-    if (!found) {  // case 3: x2 active
-      xs.x = 0.0f;
-      xs.y = -q3.w * b.y;
-      vn1 = k12 * xs.y + b.x;
-      if (xs.y >= 0.0f && vn1 >= 0.0f) found = true;
-    }
-    if (!found) {  // case 4: none active
-      xs.x = 0.0f;
-      xs.y = 0.0f;
-      vn1 = b.x;
-      vn2 = b.y;
-      if (vn1 >= 0.0f && vn2 >= 0.0f) found = true;
-    }
-    if (found) {
+    xs.x = ok1 ? x1.x : (ok2 ? x2 : 0.0f);
+    xs.y = ok1 ? x1.y : (ok2 ? 0.0f : (ok3 ? x3 : 0.0f));
+    if (ok1 || ok2 || ok3 || ok4) {
       const V2 d = xs - a;
       const V2 p1 = d.x * normal, p2 = d.y * normal;
       v_a = v_a - m_a * (p1 + p2);
