@@ -53,11 +53,13 @@ struct Batch {
   int NN;                    // tree node pool (physical capacity)
   int NC, NPAIR, NMOVE;      // capacities: contacts, pair buffer, move buffer
   int NIB;                   // island body list capacity (NB + NC: static bodies repeat per island)
+  int NMW;                   // words of the per-world moved-proxy bitmap ((NP + 31) / 32)
   // ---- shared topology
   const b2gpu_fixture_rec* fixtures;
   const b2gpu_shape_rec* shapes;
   const int4* proxy_s;       // {fixture, child index, tree node id, body}
   const int* sync_order;     // proxies in synchronize_fixtures order (bodies newest first, fixtures newest first)
+  const int* sync_rank;      // inverse of sync_order
   const int* node_proxy;     // tree node id -> proxy index (-1 for internal / unused nodes)
   // ---- per world (blocked world-minor)
   int* ws;                   // [WS_COUNT]
@@ -85,7 +87,7 @@ struct Batch {
   // ---- per-step scratch
   float4* b_rot;             // sin(a) cos(a) of the running angle (position pass cache), spare, spare
   float4* p_fat;             // new fat AABB of a proxy that must be re-inserted
-  int* p_move;               // 1 when the proxy left its fat box
+  int* p_move;               // [NMW] bitmap over synchronize ranks: proxies that left their fat box
   int* adj_off;              // [NB+1] CSR of eligible contacts per body (newest first)
   int* adj;                  // [2*NC]
   int* isl_body;             // [NIB] island body order
@@ -119,6 +121,13 @@ B2G_HD float i2f(int i) {
 B2G_HD int f2i(float f) { return (int)f2u(f); }
 
 B2G_HD int body_type(int flags) { return (flags >> 16) & 0xff; }
+B2G_HD int lowest_bit(unsigned v) {
+#if defined(__CUDA_ARCH__)
+  return __ffs((int)v) - 1;
+#else
+  return __builtin_ctz(v);
+#endif
+}
 
 struct StepParams {
   float dt, inv_dt;

@@ -1,0 +1,33 @@
+// b2g_island_layout.h — shared-memory carve-up of the island DFS kernel (b2g_island_smem.cuh).
+#pragma once
+#include <stddef.h>
+
+namespace b2g {
+
+struct IslandSmemLayout {
+  int NB, ECAP;
+  size_t off_chead, off_stack, off_bflag, off_enext, off_ebody, off_eorig, off_eisl, total;
+};
+inline IslandSmemLayout island_smem_layout(int NB, size_t budget) {
+  IslandSmemLayout L;
+  L.NB = NB;
+  const size_t per_body = 32 * (2 + 2 + 1), per_edge = 32 * (4 + 4 + 2 + 1);
+  const size_t fixed = (size_t)NB * per_body + 256;
+  long long ecap = budget > fixed ? (long long)((budget - fixed) / per_edge) : 0;
+  ecap = (ecap / 4) * 4;
+  if (ecap > 32760) ecap = 32760;
+  L.ECAP = (int)ecap;
+  size_t o = 0;
+  auto take = [&](size_t bytes) { size_t r = o; o += (bytes + 15) / 16 * 16; return r; };
+  L.off_enext = take((size_t)L.ECAP * 32 * 4);
+  L.off_ebody = take((size_t)L.ECAP * 32 * 4);
+  L.off_eorig = take((size_t)L.ECAP * 32 * 2);
+  L.off_chead = take((size_t)NB * 32 * 2);
+  L.off_stack = take((size_t)NB * 32 * 2);
+  L.off_eisl = take((size_t)L.ECAP * 32);
+  L.off_bflag = take((size_t)NB * 32);
+  L.total = o;
+  return L;
+}
+
+}  // namespace b2g

@@ -10,6 +10,7 @@
 #if !defined(B2G_HOSTSIM)
 #include <cuda_runtime.h>
 
+#include "b2g_island_smem.cuh"
 #include "b2g_solver_smem.cuh"
 #endif
 
@@ -367,6 +368,9 @@ static int topology_build(const b2gpu_snapshot* s, Topology& T) {
       if (T.fixtures[f].proxy_first < 0) continue;
       for (int c = 0; c < T.fixtures[f].child_count; ++c) T.sync_order.push_back(T.fixtures[f].proxy_first + c);
     }
+  T.sync_rank.assign(std::max(n.proxy_count, 1), 0);
+  for (size_t r = 0; r < T.sync_order.size(); ++r)
+    if (T.sync_order[r] >= 0 && T.sync_order[r] < n.proxy_count) T.sync_rank[T.sync_order[r]] = (int)r;
   if ((int)T.sync_order.size() != n.proxy_count) {
     set_error("proxy table does not match the fixture lists");
     return B2GPU_E_INVALID;
@@ -443,6 +447,7 @@ int batch_create(Ctx* ctx, const b2gpu_snapshot* proto, int n_worlds, const b2gp
   B.NPAIR = (caps && caps->max_pairs > 0) ? caps->max_pairs : std::max(B.NC, 8 * B.NP + 64);
   B.NMOVE = std::max(2 * B.NP, n.move_count) + 16;
   B.NIB = B.NB + B.NC;
+  B.NMW = std::max((B.NP + 31) / 32, 1);
   if (B.NP < 1) B.NP = 0;
   const long long W = (long long)B.n_wblocks * B.LB;
   if (W * B.NC * VC_Q > 0x7fffffffLL || W * B.NIB > 0x7fffffffLL) {
@@ -452,16 +457,17 @@ int batch_create(Ctx* ctx, const b2gpu_snapshot* proto, int n_worlds, const b2gp
   }
 #define AL(ptr, count) do { rc = alloc_arr(bh, &ptr, (count)); if (rc) { batch_destroy(bh); return rc; } } while (0)
   // shared topology
-  b2gpu_fixture_rec* d_fix; b2gpu_shape_rec* d_shape; int4* d_ps; int* d_so; int* d_np;
+  b2gpu_fixture_rec* d_fix; b2gpu_shape_rec* d_shape; int4* d_ps; int* d_so; int* d_np; int* d_sr;
   AL(d_fix, std::max(B.NF, 1)); AL(d_shape, std::max(B.NS, 1)); AL(d_ps, std::max(B.NP, 1)); AL(d_so, std::max(B.NP, 1));
   AL(d_np, (long long)bh->topo.node_proxy.size());
-  B.fixtures = d_fix; B.shapes = d_shape; B.proxy_s = d_ps; B.sync_order = d_so; B.node_proxy = d_np;
+  AL(d_sr, std::max(B.NP, 1));
+  B.fixtures = d_fix; B.shapes = d_shape; B.proxy_s = d_ps; B.sync_order = d_so; B.node_proxy = d_np; B.sync_rank = d_sr;
   const int NPa = std::max(B.NP, 1);
   AL(B.ws, W * WS_COUNT);
   AL(B.b_flags, W * B.NB); AL(B.b_xf, W * B.NB); AL(B.b_pos, W * B.NB); AL(B.b_pos0, W * B.NB); AL(B.b_vel, W * B.NB);
   AL(B.b_mass, W * B.NB); AL(B.b_force, W * B.NB); AL(B.b_misc, W * B.NB); AL(B.b_rot, W * B.NB);
   AL(B.n_aabb, W * B.NN); AL(B.n_link, W * B.NN); AL(B.n_moved, W * B.NN);
-  AL(B.p_aabb, W * NPa); AL(B.p_fat, W * NPa); AL(B.p_move, W * NPa);
+  AL(B.p_aabb, W * NPa); AL(B.p_fat, W * NPa); AL(B.p_move, W * B.NMW);
   AL(B.move_buf, W * B.NMOVE); AL(B.pair_buf, W * B.NPAIR);
   AL(B.c_fix, W * B.NC); AL(B.c_flags, W * B.NC); AL(B.c_mat, W * B.NC);
   AL(B.c_m0, W * B.NC); AL(B.c_m1, W * B.NC); AL(B.c_m2, W * B.NC); AL(B.c_m3, W * B.NC);
@@ -481,7 +487,7 @@ int batch_create(Ctx* ctx, const b2gpu_snapshot* proto, int n_worlds, const b2gp
 #undef AL
   const Topology& T = bh->topo;
 #define UP(dst, vec) do { if (!(vec).empty()) { rc = dev_h2d(ctx, (void*)(dst), (vec).data(), (vec).size() * sizeof((vec)[0])); if (rc) { batch_destroy(bh); return rc; } } } while (0)
-  UP(d_fix, T.fixtures); UP(d_shape, T.shapes); UP(d_ps, T.proxy_s); UP(d_so, T.sync_order); UP(d_np, T.node_proxy);
+  UP(d_fix, T.fixtures); UP(d_shape, T.shapes); UP(d_ps, T.proxy_s); UP(d_so, T.sync_order); UP(d_np, T.node_proxy); UP(d_sr, T.sync_rank);
 #undef UP
   WorldImage im;
   rc = image_pack(bh, proto, im);
@@ -503,6 +509,11 @@ int batch_create(Ctx* ctx, const b2gpu_snapshot* proto, int n_worlds, const b2gp
       CU(cudaFuncSetAttribute(velocity_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)velocity_smem_bytes(B.NB)));
       CU(cudaFuncSetAttribute(position_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)position_smem_bytes(B.NB)));
       bh->smem_solver = true;
+    }
+    bh->island_layout = island_smem_layout(B.NB, (size_t)max_optin - 1024);
+    if (B.NB < 32768 && B.NC < 65536 && bh->island_layout.ECAP >= 64) {
+      CU(cudaFuncSetAttribute(island_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bh->island_layout.total));
+      bh->smem_island = true;
     }
   }
 #endif
@@ -580,6 +591,14 @@ int batch_step(BatchHost* bh, float dt, int vi, int pi, int steps) {
     }
     {
       SerialAK k = {B, bh->b_wake, bh->b_chead, bh->c_next, bh->stack, sp};
+#if !defined(B2G_HOSTSIM)
+      if (bh->smem_island) {
+        LaunchScope ls = {ctx, STAGE_ISLAND};
+        RC(ls.begin());
+        island_smem_kernel<<<B.n_wblocks, 32, bh->island_layout.total, (cudaStream_t)ctx->stream>>>(k, bh->island_layout);
+        RC(ls.end());
+      } else
+#endif
       RC(launch(ctx, k, W, ordered_block, STAGE_ISLAND));
     }
     if (dt > 0.0f) {

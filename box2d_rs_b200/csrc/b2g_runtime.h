@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "b2g_step.h"
+#include "b2g_island_layout.h"
 
 namespace b2g {
 
@@ -47,7 +48,7 @@ struct Topology {  // shared by every world of a batch (host copies kept for val
   std::vector<b2gpu_shape_rec> shapes;
   std::vector<b2gpu_proxy_rec> proxies;
   std::vector<int4> proxy_s;
-  std::vector<int> sync_order, node_proxy;
+  std::vector<int> sync_order, sync_rank, node_proxy;
 };
 
 struct BatchHost {
@@ -63,6 +64,8 @@ struct BatchHost {
   float* forces_dev = nullptr;   // [n_worlds][NB][3]
   void* stage_dev = nullptr;     // staging for single-world upload/download
   size_t stage_bytes = 0;
+  bool smem_island = false;      // shared-memory island DFS in use (b2g_island_smem.cuh)
+  IslandSmemLayout island_layout;
   bool smem_solver = false;      // shared-memory Gauss-Seidel kernels in use (b2g_solver_smem.cuh)
   bool pre_step_needed = true;   // some world may carry m_new_contacts / a non-empty move buffer
   long long total_bytes = 0;

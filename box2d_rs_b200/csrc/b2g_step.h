@@ -220,6 +220,10 @@ struct SerialAK {
     if (w >= B.n_worlds) return;
     WIdx x = widx(B, w);
     Ws ws = ws_of(B, x);
+    if (prologue(x, ws)) islands_global(x, ws);
+  }
+  // Collide fix-up, wake merge, contact destruction.  Returns true when the island order must be rebuilt.
+  B2G_HD bool prologue(const WIdx& x, const Ws& ws) const {
     int cc = ws[WS_CONTACT_COUNT];
     // (1) A sleeping body was woken inside collide: contacts later in list order (older) that were
     //     skipped as inactive may have become active.  Replay the list newest-first with the
@@ -291,7 +295,7 @@ struct SerialAK {
       ws[WS_ISL_BODIES] = 0;
       ws[WS_ISL_CONTACTS] = 0;
       ws[WS_TOPO_DIRTY] = 1;
-      return;
+      return false;
     }
     // Island cache: the DFS below is a pure function of the body list (types, AWAKE/ENABLED flags), the
     // per-body contact edge lists and the contacts' ENABLED/TOUCHING flags.  Every stage that changes one
@@ -301,8 +305,13 @@ struct SerialAK {
       ws[WS_ST_ISLANDS] = ws[WS_ISL_COUNT];
       ws[WS_ST_ISL_BODIES] = ws[WS_ISL_BODIES];
       ws[WS_ST_ISL_CONTACTS] = ws[WS_ISL_CONTACTS];
-      return;
+      return false;
     }
+    return true;
+  }
+  // (4) islands from global memory (any world size): b2_world.rs(private):376-507.
+  B2G_HD void islands_global(const WIdx& x, const Ws& ws) const {
+    const int cc = ws[WS_CONTACT_COUNT];
     bool dirty_next = false;
     // (4) islands: b2_world.rs(private):376-507.  Seeds newest body first, LIFO stack, each body's
     //     edge list newest first.
@@ -973,7 +982,10 @@ struct SyncFixturesK {
       if (box_contains(huge, tree_box)) return;
     }
     B.p_fat[x.at(B.NP, p)] = make_float4(fat.lo.x, fat.lo.y, fat.hi.x, fat.hi.y);
-    B.p_move[x.at(B.NP, p)] = 1;
+    // mark the proxy in the world's move bitmap at its rank in synchronize order, so the ordered stage
+    // visits exactly the moved proxies, in the reference's order, without scanning all of them
+    const int r = B.sync_rank[p];
+    B2G_ATOMIC_OR(&B.p_move[x.at(B.NMW, r >> 5)], 1 << (r & 31));
     B2G_ATOMIC_ADD(&ws[WS_EV_MOVED], 1);
   }
 };
@@ -1115,18 +1127,22 @@ struct TreePairsK {
       if (ws[WS_EV_MOVED]) {
         Tree t = tree_of(B, x, ws);
         int mc = ws[WS_MOVE_COUNT];
-        for (int j = 0; j < B.NP; ++j) {
-          const int p = B.sync_order[j];
-          const int pi = x.at(B.NP, p);
-          if (!B.p_move[pi]) continue;
-          B.p_move[pi] = 0;
-          const int node = B.proxy_s[p].z;
-          t.remove_leaf(node);
-          t.aabb[node * t.stride] = B.p_fat[pi];
-          t.insert_leaf(node);
-          t.moved[node * t.stride] = 1;
-          if (mc >= B.NMOVE) { ws[WS_STATUS] = B2GPU_E_CAPACITY; break; }
-          B.move_buf[x.at(B.NMOVE, mc++)] = node;
+        for (int wi = 0; wi < B.NMW; ++wi) {
+          unsigned bits = (unsigned)B.p_move[x.at(B.NMW, wi)];
+          if (!bits) continue;
+          B.p_move[x.at(B.NMW, wi)] = 0;
+          while (bits) {
+            const int bit = lowest_bit(bits);
+            bits &= bits - 1;
+            const int p = B.sync_order[wi * 32 + bit];
+            const int node = B.proxy_s[p].z;
+            t.remove_leaf(node);
+            t.aabb[node * t.stride] = B.p_fat[x.at(B.NP, p)];
+            t.insert_leaf(node);
+            t.moved[node * t.stride] = 1;
+            if (mc >= B.NMOVE) { ws[WS_STATUS] = B2GPU_E_CAPACITY; break; }
+            B.move_buf[x.at(B.NMOVE, mc++)] = node;
+          }
         }
         ws[WS_MOVE_COUNT] = mc;
         ws[WS_EV_MOVED] = 0;
