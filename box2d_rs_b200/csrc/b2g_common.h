@@ -37,6 +37,7 @@ enum {
   WS_EV_DESTROY,   // contacts flagged for destruction this step
   WS_EV_MOVED,     // proxies that left their fat box this step
   WS_TOPO_DIRTY,   // island order must be rebuilt
+  WS_ISL_VALID,    // island arrays describe the last dt > 0 step of this world
   WS_STATUS,
   // stats of the last step (b2gpu_step_stats order from `contacts` on)
   WS_ST_CONTACTS, WS_ST_TOUCHING, WS_ST_DESTROYED, WS_ST_ISLANDS, WS_ST_ISL_BODIES, WS_ST_ISL_CONTACTS,

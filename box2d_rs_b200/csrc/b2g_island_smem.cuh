@@ -22,8 +22,10 @@ __global__ void __launch_bounds__(32) island_smem_kernel(const SerialAK K, const
   uint16_t* eorig = (uint16_t*)(smem_raw + L.off_eorig);   // [ECAP][32] contact index
   uint16_t* chead = (uint16_t*)(smem_raw + L.off_chead);   // [NB][32] newest eligible edge (2e + side) or 0xffff
   uint16_t* stack = (uint16_t*)(smem_raw + L.off_stack);   // [NB][32]
+  uint16_t* smark = (uint16_t*)(smem_raw + L.off_smark);   // [NB][32] static bodies: 1 + island that holds them
   uint8_t* eisl = (uint8_t*)(smem_raw + L.off_eisl);       // [ECAP][32] 1 = already in an island
   uint8_t* bflag = (uint8_t*)(smem_raw + L.off_bflag);     // [NB][32] bit0 ISLAND bit1 AWAKE bit2 ENABLED bit3 static
+  uint32_t* fxb = (uint32_t*)(smem_raw + L.off_fxb);       // [fxb_count] fixture -> body | sensor << 31
   const int lane = threadIdx.x;
   const int wb = blockIdx.x;
   const int w = wb * 32 + lane;
@@ -36,39 +38,60 @@ __global__ void __launch_bounds__(32) island_smem_kernel(const SerialAK K, const
   if (!__any_sync(0xffffffffu, need)) return;
   const int cc = need ? ws[WS_CONTACT_COUNT] : 0;
   const int NB = B.NB;
+  for (int f = lane; f < L.fxb_count; f += 32)
+    fxb[f] = (uint32_t)B.fixtures[f].body | (B.fixtures[f].is_sensor ? 0x80000000u : 0u);
+  __syncwarp();
+  auto fix_word = [&](int f) -> uint32_t {
+    if (L.fxb_count) return fxb[f];
+    return (uint32_t)B.fixtures[f].body | (B.fixtures[f].is_sensor ? 0x80000000u : 0u);
+  };
   // ---- stage: body flags, eligible contacts with per-body edge lists (ascending contact index +
-  //      push_front == newest first)
+  //      push_front == newest first).  Global reads are issued eight at a time.
   if (need) {
-    for (int b = 0; b < NB; ++b) {
-      const int f = B.b_flags[x.at(NB, b)];
-      bflag[b * 32 + lane] = (uint8_t)(((f & B2GPU_BODY_AWAKE) ? 2 : 0) | ((f & B2GPU_BODY_ENABLED) ? 4 : 0) |
-                                       (body_type(f) == B2GPU_STATIC_BODY ? 8 : 0));
-      chead[b * 32 + lane] = 0xffffu;
+    for (int b0 = 0; b0 < NB; b0 += 8) {
+      int f[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) f[j] = b0 + j < NB ? B.b_flags[x.at(NB, b0 + j)] : 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (b0 + j >= NB) break;
+        bflag[(b0 + j) * 32 + lane] = (uint8_t)(((f[j] & B2GPU_BODY_AWAKE) ? 2 : 0) | ((f[j] & B2GPU_BODY_ENABLED) ? 4 : 0) |
+                                                (body_type(f[j]) == B2GPU_STATIC_BODY ? 8 : 0));
+        chead[(b0 + j) * 32 + lane] = 0xffffu;
+        smark[(b0 + j) * 32 + lane] = 0;
+      }
     }
   }
   int ne = 0;
   bool overflow = false;
   if (need) {
-#pragma unroll 4
-    for (int c = 0; c < cc; ++c) {
-      const int ci = x.at(B.NC, c);
-      const int cf = B.c_flags[ci];
-      const int4 fx = B.c_fix[ci];
-      const b2gpu_fixture_rec& fa = B.fixtures[fx.x];
-      const b2gpu_fixture_rec& fb = B.fixtures[fx.y];
-      const bool eligible = (cf & B2GPU_CONTACT_ENABLED) && (cf & B2GPU_CONTACT_TOUCHING) && !fa.is_sensor && !fb.is_sensor;
-      if (!eligible) continue;
-      if (ne >= L.ECAP) { overflow = true; break; }
-      const int ba = fa.body, bb = fb.body;
-      const uint32_t na = chead[ba * 32 + lane];
-      chead[ba * 32 + lane] = (uint16_t)(2 * ne);
-      const uint32_t nb_ = chead[bb * 32 + lane];   // after the A push: a self pair is impossible (add_pair rejects it)
-      chead[bb * 32 + lane] = (uint16_t)(2 * ne + 1);
-      enext[ne * 32 + lane] = na | (nb_ << 16);
-      ebody[ne * 32 + lane] = (uint32_t)ba | ((uint32_t)bb << 16);
-      eorig[ne * 32 + lane] = (uint16_t)c;
-      eisl[ne * 32 + lane] = 0;
-      ++ne;
+    for (int c0 = 0; c0 < cc && !overflow; c0 += 8) {
+      int cf[8];
+      int4 fx[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int ci = x.at(B.NC, c0 + j < cc ? c0 + j : cc - 1);
+        cf[j] = B.c_flags[ci];
+        fx[j] = B.c_fix[ci];
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        if (c0 + j >= cc) break;
+        if (!(cf[j] & B2GPU_CONTACT_ENABLED) || !(cf[j] & B2GPU_CONTACT_TOUCHING)) continue;
+        const uint32_t wa = fix_word(fx[j].x), wbq = fix_word(fx[j].y);
+        if ((wa | wbq) & 0x80000000u) continue;  // sensors never join an island
+        if (ne >= L.ECAP) { overflow = true; break; }
+        const int ba = (int)wa, bb = (int)wbq;
+        const uint32_t na = chead[ba * 32 + lane];
+        chead[ba * 32 + lane] = (uint16_t)(2 * ne);
+        const uint32_t nb_ = chead[bb * 32 + lane];  // after the A push; a self pair is impossible (add_pair rejects it)
+        chead[bb * 32 + lane] = (uint16_t)(2 * ne + 1);
+        enext[ne * 32 + lane] = na | (nb_ << 16);
+        ebody[ne * 32 + lane] = (uint32_t)ba | ((uint32_t)bb << 16);
+        eorig[ne * 32 + lane] = (uint16_t)(c0 + j);
+        eisl[ne * 32 + lane] = 0;
+        ++ne;
+      }
     }
   }
   if (overflow) {  // graph does not fit: this world takes the global-memory path
@@ -106,38 +129,31 @@ __global__ void __launch_bounds__(32) island_smem_kernel(const SerialAK K, const
         const uint32_t bod = ebody[ei * 32 + lane];
         const int other = side ? (int)(bod & 0xffffu) : (int)(bod >> 16);
         const uint32_t of = bflag[other * 32 + lane];
-        if (of & 1) continue;
+        if (of & 8) {  // static: joins every island that touches it, once (flag un-set after each island, :500-506)
+          if (smark[other * 32 + lane] == (uint16_t)(nisl + 1)) continue;
+          smark[other * 32 + lane] = (uint16_t)(nisl + 1);
+        } else {
+          if (of & 1) continue;
+          bflag[other * 32 + lane] = (uint8_t)(of | 1);
+        }
         stack[(sp_++) * 32 + lane] = (uint16_t)other;
-        bflag[other * 32 + lane] = (uint8_t)(of | 1);
       }
     }
     B.isl_range[x.at(NB, nisl)] = make_int4(body_first, nbod, contact_first, ncon);
     ++nisl;
-    for (int k = body_first; k < nbod; ++k) {  // static bodies may join other islands
-      const int b = B.isl_body[x.at(B.NIB, k)];
-      const uint32_t bf = bflag[b * 32 + lane];
-      if (bf & 8) bflag[b * 32 + lane] = (uint8_t)(bf & ~1u);
-    }
   }
-  // ---- write the ISLAND / AWAKE flags back
-  for (int b = 0; b < NB; ++b) {
-    const int bi = x.at(NB, b);
-    const uint32_t bf = bflag[b * 32 + lane];
-    int f = B.b_flags[bi] & ~(B2GPU_BODY_ISLAND | B2GPU_BODY_AWAKE);
-    f |= ((bf & 1) ? B2GPU_BODY_ISLAND : 0) | ((bf & 2) ? B2GPU_BODY_AWAKE : 0);
-    B.b_flags[bi] = f;
-  }
-  {
-    int e = 0;
-#pragma unroll 4
-    for (int c = 0; c < cc; ++c) {
-      const int ci = x.at(B.NC, c);
-      int cf = B.c_flags[ci] & ~B2GPU_CONTACT_ISLAND;
-      if (e < ne && eorig[e * 32 + lane] == (uint16_t)c) {
-        if (eisl[e * 32 + lane]) cf |= B2GPU_CONTACT_ISLAND;
-        ++e;
-      }
-      B.c_flags[ci] = cf;
+  // ---- write the ISLAND / AWAKE flags of the bodies back (contacts: see ContactIslandFlagsK)
+  for (int b0 = 0; b0 < NB; b0 += 8) {
+    int f[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) f[j] = b0 + j < NB ? B.b_flags[x.at(NB, b0 + j)] : 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      if (b0 + j >= NB) break;
+      const uint32_t bf = bflag[(b0 + j) * 32 + lane];
+      const int nf = (f[j] & ~(B2GPU_BODY_ISLAND | B2GPU_BODY_AWAKE)) | ((bf & 1) ? B2GPU_BODY_ISLAND : 0) |
+                     ((bf & 2) ? B2GPU_BODY_AWAKE : 0);
+      if (nf != f[j]) B.b_flags[x.at(NB, b0 + j)] = nf;
     }
   }
   ws[WS_ISL_COUNT] = nisl;
@@ -147,6 +163,7 @@ __global__ void __launch_bounds__(32) island_smem_kernel(const SerialAK K, const
   ws[WS_ST_ISL_BODIES] = nbod;
   ws[WS_ST_ISL_CONTACTS] = ncon;
   ws[WS_TOPO_DIRTY] = dirty_next ? 1 : 0;
+  ws[WS_ISL_VALID] = 1;
 }
 
 }  // namespace b2g

@@ -510,7 +510,7 @@ int batch_create(Ctx* ctx, const b2gpu_snapshot* proto, int n_worlds, const b2gp
       CU(cudaFuncSetAttribute(position_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)position_smem_bytes(B.NB)));
       bh->smem_solver = true;
     }
-    bh->island_layout = island_smem_layout(B.NB, (size_t)max_optin - 1024);
+    bh->island_layout = island_smem_layout(B.NB, B.NF, (size_t)max_optin - 1024);
     if (B.NB < 32768 && B.NC < 65536 && bh->island_layout.ECAP >= 64) {
       CU(cudaFuncSetAttribute(island_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bh->island_layout.total));
       bh->smem_island = true;
@@ -542,6 +542,11 @@ int batch_upload_world(BatchHost* bh, int world, const b2gpu_snapshot* in) {
 }
 
 static int image_fetch(BatchHost* bh, int world, WorldImage& im) {
+  if (bh->smem_island && bh->stepped) {  // materialise the contacts' ISLAND bits (see ContactIslandFlagsK)
+    const int n = bh->B.n_wblocks * bh->B.LB * bh->B.NC;
+    { ContactIslandFlagsK k = {bh->B, 0}; RC(launch(bh->ctx, k, n, 128)); }
+    { ContactIslandFlagsK k = {bh->B, 1}; RC(launch(bh->ctx, k, n, 128)); }
+  }
   image_alloc(bh->B, im);
   std::vector<ArrRef> tab = array_table(bh, im);
   for (const ArrRef& a : tab) RC(move_array(bh, a, 1, world));
@@ -634,6 +639,7 @@ int batch_step(BatchHost* bh, float dt, int vi, int pi, int steps) {
     { BodyEndK k = {B}; RC(launch(ctx, k, W * B.NB, 128, STAGE_BODY_END)); }
   }
   bh->pre_step_needed = false;
+  if (steps > 0 && dt > 0.0f) bh->stepped = true;
   return 0;
 }
 

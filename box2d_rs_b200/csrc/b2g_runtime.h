@@ -67,6 +67,7 @@ struct BatchHost {
   bool smem_island = false;      // shared-memory island DFS in use (b2g_island_smem.cuh)
   IslandSmemLayout island_layout;
   bool smem_solver = false;      // shared-memory Gauss-Seidel kernels in use (b2g_solver_smem.cuh)
+  bool stepped = false;          // at least one dt > 0 step ran: island arrays are meaningful
   bool pre_step_needed = true;   // some world may carry m_new_contacts / a non-empty move buffer
   long long total_bytes = 0;
   StepParams last_sp{};

@@ -290,13 +290,7 @@ struct SerialAK {
       ws[WS_TOPO_DIRTY] = 1;
       rebuild_contact_lists(B, x, b_chead, c_next, cc);
     }
-    if (!(sp.dt > 0.0f)) {
-      ws[WS_ISL_COUNT] = 0;
-      ws[WS_ISL_BODIES] = 0;
-      ws[WS_ISL_CONTACTS] = 0;
-      ws[WS_TOPO_DIRTY] = 1;
-      return false;
-    }
+    if (!(sp.dt > 0.0f)) return false;  // collide only: islands (and their flags) stay as the last solve left them
     // Island cache: the DFS below is a pure function of the body list (types, AWAKE/ENABLED flags), the
     // per-body contact edge lists and the contacts' ENABLED/TOUCHING flags.  Every stage that changes one
     // of those raises WS_TOPO_DIRTY; when nothing changed since the previous step, last step's island
@@ -375,6 +369,7 @@ struct SerialAK {
     ws[WS_ST_ISL_BODIES] = nb;
     ws[WS_ST_ISL_CONTACTS] = nc;
     ws[WS_TOPO_DIRTY] = dirty_next ? 1 : 0;
+    ws[WS_ISL_VALID] = 1;
   }
 };
 
@@ -984,8 +979,8 @@ struct SyncFixturesK {
     B.p_fat[x.at(B.NP, p)] = make_float4(fat.lo.x, fat.lo.y, fat.hi.x, fat.hi.y);
     // mark the proxy in the world's move bitmap at its rank in synchronize order, so the ordered stage
     // visits exactly the moved proxies, in the reference's order, without scanning all of them
-    const int r = B.sync_rank[p];
-    B2G_ATOMIC_OR(&B.p_move[x.at(B.NMW, r >> 5)], 1 << (r & 31));
+    const int rank = B.sync_rank[p];
+    B2G_ATOMIC_OR(&B.p_move[x.at(B.NMW, rank >> 5)], 1 << (rank & 31));
     B2G_ATOMIC_ADD(&ws[WS_EV_MOVED], 1);
   }
 };
@@ -1151,6 +1146,26 @@ struct TreePairsK {
       ws[WS_INV_DT0] = f2i(sp.inv_dt);
     }
     ws[WS_ST_CONTACTS] = ws[WS_CONTACT_COUNT];
+  }
+};
+
+// The ISLAND bit of contacts is only consumed by the island DFS itself, so the shared-memory DFS keeps it
+// in shared memory; before a snapshot leaves the device this stage makes the bit match what the reference
+// would hold after the same step: set exactly on the contacts of the current island order.
+struct ContactIslandFlagsK {  // flat over contact slots
+  Batch B;
+  int phase;  // 0: clear every live contact's bit, 1: set it on island contacts
+  B2G_HD void operator()(int tid) const {
+    int w, c;
+    if (!flat_decode(B, tid, B.NC, w, c)) return;
+    WIdx x = widx(B, w);
+    Ws ws = ws_of(B, x);
+    if (!ws[WS_ISL_VALID]) return;
+    if (phase == 0) {
+      if (c < ws[WS_CONTACT_COUNT]) B.c_flags[x.at(B.NC, c)] &= ~B2GPU_CONTACT_ISLAND;
+    } else if (c < ws[WS_ISL_CONTACTS]) {
+      B.c_flags[x.at(B.NC, B.isl_contact[x.at(B.NC, c)])] |= B2GPU_CONTACT_ISLAND;
+    }
   }
 };
 
