@@ -132,35 +132,36 @@ __global__ void __launch_bounds__(32) velocity_smem_kernel(const Batch B, const 
 #pragma unroll
     for (int p = 0; p < VEL_RING; ++p) fetch();  // positions 0 .. RING-1 in flight
     cp_async_wait<VEL_RING - 1>();                 // position 0 landed
-    VcRegs cur = vc_load(rl);
-    int k = 0, sweep = 0;
-    bool act = (k < nc) && warm && cur.cnt > 0;
-    if (!act) { cur.ba = 0; cur.bb = 0; }
-    float4 va = vl[cur.ba * 32], vb = vl[cur.bb * 32];
-    for (int pos = 0; pos < total; ++pos) {
+    // Two register sets (A, B) alternate as "current" and "next": the loop body handles two positions
+    // so that the hand-over between them is pure register renaming.
+    VcRegs ca = vc_load(rl), cb;
+    int k = 0, sweep = 0, pos = 0;
+    bool acta = (k < nc) && warm && ca.cnt > 0, actb = false;
+    if (!acta) { ca.ba = 0; ca.bb = 0; }
+    float4 vaa = vl[ca.ba * 32], vab = vl[ca.bb * 32], vba, vbb;
+    auto half_step = [&](VcRegs& cur, bool act, float4& va, float4& vb, VcRegs& nxt, bool& nact, float4& nva, float4& nvb) {
       // -- prefetch position pos+1 into registers (its stage landed: at most RING-2 younger groups pending)
-      int nk = k + 1, nsweep = sweep;
-      if (nk == ncm) { nk = 0; ++nsweep; }
+      const int kc = k, sc = sweep;
+      if (++k == ncm) { k = 0; ++sweep; }
       cp_async_wait<VEL_RING - 2>();
-      VcRegs nxt = vc_load(rl + (((pos + 1) & (VEL_RING - 1)) * VC_Q) * 32);
-      bool nact = (pos + 1 < total) && (nk < nc) && (nsweep > 0 || warm) && nxt.cnt > 0;
+      nxt = vc_load(rl + (((pos + 1) & (VEL_RING - 1)) * VC_Q) * 32);
+      nact = (pos + 1 < total) && (k < nc) && (sweep > 0 || warm) && nxt.cnt > 0;
       if (!nact) { nxt.ba = 0; nxt.bb = 0; }
-      float4 nva = vl[nxt.ba * 32], nvb = vl[nxt.bb * 32];
-      // the stage of position pos is free now (cur is in registers): refill it with position pos + RING
-      fetch();
-      // -- solve position pos
+      nva = vl[nxt.ba * 32];
+      nvb = vl[nxt.bb * 32];
+      fetch();  // the stage of position pos is free now (cur is in registers): refill it with position pos + RING
       if (act) {
         VelState s;
         s.v_a = v2(va.x, va.y); s.w_a = va.z;
         s.v_b = v2(vb.x, vb.y); s.w_b = vb.z;
-        if (sweep == 0) {
+        if (sc == 0) {
           warm_start_one(s, cur.q0, cur.q1, cur.q2, cur.q6, cur.q7, cur.cnt);
         } else {
           if (__all_sync(__activemask(), cur.cnt == 2 && block))
             solve_velocity_one(s, cur.q0, cur.q1, cur.q2, cur.q3, cur.q4, cur.q5, cur.q6, cur.q7, 2, true);
           else
             solve_velocity_one(s, cur.q0, cur.q1, cur.q2, cur.q3, cur.q4, cur.q5, cur.q6, cur.q7, cur.cnt, block);
-          q6_out[(size_t)k * VC_Q * 32] = cur.q6;
+          q6_out[(size_t)kc * VC_Q * 32] = cur.q6;
         }
         va = make_float4(s.v_a.x, s.v_a.y, s.w_a, 0.0f);
         vb = make_float4(s.v_b.x, s.v_b.y, s.w_b, 0.0f);
@@ -170,7 +171,11 @@ __global__ void __launch_bounds__(32) velocity_smem_kernel(const Batch B, const 
         if (nxt.ba == cur.ba) nva = va; else if (nxt.ba == cur.bb) nva = vb;
         if (nxt.bb == cur.ba) nvb = va; else if (nxt.bb == cur.bb) nvb = vb;
       }
-      cur = nxt; act = nact; va = nva; vb = nvb; k = nk; sweep = nsweep;
+      ++pos;
+    };
+    while (pos < total) {
+      half_step(ca, acta, vaa, vab, cb, actb, vba, vbb);
+      half_step(cb, actb, vba, vbb, ca, acta, vaa, vab);
     }
     cp_async_wait<0>();
   }
@@ -245,24 +250,24 @@ __global__ void __launch_bounds__(32) position_smem_kernel(const Batch B, const 
 #pragma unroll
   for (int p = 0; p < POS_RING; ++p) fetch();
   if (resident) cp_async_wait<0>(); else cp_async_wait<POS_RING - 1>();
-  PcRegs cur = pc_load(rl);
-  int k = 0;
-  bool act = k < nc;
-  if (!act) { cur.ba = 0; cur.bb = 0; }
-  float4 pa = pl[cur.ba * 32], pb = pl[cur.bb * 32];
-  float2 qa = ql[cur.ba * 32], qb = ql[cur.bb * 32];
+  PcRegs ca = pc_load(rl), cb;
+  int k = 0, p = 0;
+  bool acta = k < nc, actb = false;
+  if (!acta) { ca.ba = 0; ca.bb = 0; }
+  float4 paa = pl[ca.ba * 32], pab = pl[ca.bb * 32], pba, pbb;
+  float2 qaa = ql[ca.ba * 32], qab = ql[ca.bb * 32], qba, qbb;
   int isl = -1;
-  bool skip = false, all_solved = true, done = !live || nc == 0;
+  bool skip = false, all_solved = true, done = !live || nc == 0, stop = false;
   float min_separation = 0.0f;
-  for (int p = 0; p < total; ++p) {
-    int nk = k + 1;
-    if (nk == ncm) nk = 0;
+  auto half_step = [&](PcRegs& cur, bool act, float4& pa, float4& pb, float2& qa, float2& qb, PcRegs& nxt, bool& nact,
+                       float4& npa, float4& npb, float2& nqa, float2& nqb) {
+    if (++k == ncm) k = 0;
     if (!resident) cp_async_wait<POS_RING - 2>();
-    PcRegs nxt = pc_load(rl + ((resident ? nk : ((p + 1) & (POS_RING - 1))) * PC_Q) * 32);
-    const bool nact = (p + 1 < total) && (nk < nc);
+    nxt = pc_load(rl + ((resident ? k : ((p + 1) & (POS_RING - 1))) * PC_Q) * 32);
+    nact = (p + 1 < total) && (k < nc);
     if (!nact) { nxt.ba = 0; nxt.bb = 0; }
-    float4 npa = pl[nxt.ba * 32], npb = pl[nxt.bb * 32];
-    float2 nqa = ql[nxt.ba * 32], nqb = ql[nxt.bb * 32];
+    npa = pl[nxt.ba * 32]; npb = pl[nxt.bb * 32];
+    nqa = ql[nxt.ba * 32]; nqb = ql[nxt.bb * 32];
     if (!resident) fetch();
     if (act && !done) {
       if (cur.isl != isl) {  // island boundary: close the previous island, open the next
@@ -288,7 +293,7 @@ __global__ void __launch_bounds__(32) position_smem_kernel(const Batch B, const 
         if (nxt.bb == cur.ba) { npb = pa; nqb = qa; } else if (nxt.bb == cur.bb) { npb = pb; nqb = qb; }
       }
     }
-    if (nk == 0) {  // end of a sweep: close the last island, test the early exit of this world
+    if (k == 0) {  // end of a sweep: close the last island, test the early exit of this world
       if (!done) {
         if (isl >= 0 && !skip) {
           if (min_separation >= -3.0f * B2G_LINEAR_SLOP) B.isl_flags[x.at(B.NB, isl)] |= 1; else all_solved = false;
@@ -299,9 +304,14 @@ __global__ void __launch_bounds__(32) position_smem_kernel(const Batch B, const 
         all_solved = true;
         min_separation = 0.0f;
       }
-      if (__all_sync(0xffffffffu, done)) break;
+      if (__all_sync(0xffffffffu, done)) stop = true;
     }
-    cur = nxt; act = nact; pa = npa; pb = npb; qa = nqa; qb = nqb; k = nk;
+    ++p;
+  };
+  while (p < total && !stop) {
+    half_step(ca, acta, paa, pab, qaa, qab, cb, actb, pba, pbb, qba, qbb);
+    if (p >= total || stop) break;
+    half_step(cb, actb, pba, pbb, qba, qbb, ca, acta, paa, pab, qaa, qab);
   }
   cp_async_wait<0>();
   __syncwarp();
