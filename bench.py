@@ -36,10 +36,9 @@ SEED = 0xB2D + 3
 
 
 def perturbation(n_worlds, rank):
-    rng = np.random.default_rng(SEED + 1000 * rank)
-    v = np.zeros((n_worlds, 2), np.float32)
-    v[:, 0] = rng.uniform(-0.5, 0.5, n_worlds).astype(np.float32)
-    return v
+    """Initial velocity of each world's top box: a function of the global world index (sharding.py)."""
+    from box2d_rs_b200 import sharding
+    return sharding.perturbation(rank * n_worlds, n_worlds, SEED)
 
 
 class ClockSampler(threading.Thread):
@@ -229,12 +228,13 @@ def run_ours(args, rank, world_size, local_rank):
            "ms_per_step": 1e3 * e2e_s / args.steps}
 
     # ---- validation gather over NCCL (outside the timed regions): per-rank digest of the body state
-    digest = torch.from_numpy(batch.body_state().astype(np.float64).sum(axis=(1, 2))[:8].copy()).cuda()
+    from box2d_rs_b200 import sharding
+    digests = sharding.world_digests(batch.body_state())
     gathered = None
     if dist is not None:
-        out = [torch.zeros_like(digest) for _ in range(world_size)]
-        dist.all_gather(out, digest)
-        gathered = [float(o.sum().item()) for o in out]
+        per_rank = sharding.allgather_digests(dist, digests, device="cuda")
+        gathered = {"worlds": int(sum(len(d) for d in per_rank)), "finite": bool(all(np.isfinite(d).all() for d in per_rank)),
+                    "per_rank_sum": [float(d.sum()) for d in per_rank]}
 
     cpu_baseline = None
     if rank == 0 and world_size == 1 and not args.no_cpu:
