@@ -154,10 +154,10 @@ def run_ours(args, rank, world_size, local_rank):
         torch.cuda.synchronize()
 
     # ---- device-resident throughput
-    batch.step(scenes.DT, scenes.VEL_ITERS, scenes.POS_ITERS, args.warmup)
-    barrier()
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank)  # samples while the device is under this load (warm-up + timed region)
     sampler.start()
+    batch.step(scenes.DT, scenes.VEL_ITERS, scenes.POS_ITERS, max(args.warmup, 60))
+    barrier()
     launches0 = ctx.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(stream):
@@ -199,8 +199,15 @@ def run_ours(args, rank, world_size, local_rank):
     stage_alg = {"velocity": 176 * isl_contacts + 48 * isl_bodies, "position": 144 * isl_contacts + 56 * isl_bodies}
     top_alg = stage_alg.get(top, alg_bytes_step)
     achieved = top_alg / (stage_ms[top] * 1e-3) / 1e9
+    traffic = None
+    try:  # DRAM bytes per launch of that kernel from the committed ncu --set full capture of this configuration
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        if tr.get("worlds") == n_worlds:
+            traffic = tr.get(top)
+    except Exception:
+        pass
     roofline = {"bound": "hbm", "kernel": top, "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "peak_source": peak_src, "algorithmic_bytes_per_launch": top_alg,
+                "traffic": traffic, "peak_source": peak_src, "algorithmic_bytes_per_launch": top_alg,
                 "kernel_ms_per_launch": stage_ms[top],
                 "whole_step": {"algorithmic_bytes": alg_bytes_step, "achieved": alg_bytes_step / (ms_per_step * 1e-3) / 1e9,
                                "frac": alg_bytes_step / (ms_per_step * 1e-3) / 1e9 / peak},
