@@ -119,7 +119,7 @@ def run_reference(args, rank):
         "e2e": {"value": value, "unit": "body-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    OUT.emit(json.dumps(line))
 
 
 def run_ours(args, rank, world_size, local_rank):
@@ -269,10 +269,34 @@ def run_ours(args, rank, world_size, local_rank):
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
             "clocks": clocks, "validation_allgather": gathered,
         }
-        print(json.dumps(line), flush=True)
+        OUT.emit(json.dumps(line))
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+class StdoutToStderr:
+    """Everything libraries print to fd 1 (e.g. NCCL's version banner) goes to stderr; the JSON line is
+    written to the real stdout through `emit`."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.real = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def emit(self, text):
+        sys.stdout.flush()
+        os.write(self.real, (text + "\n").encode())
+
+    def __exit__(self, *exc):
+        sys.stdout.flush()
+        os.dup2(self.real, 1)
+        os.close(self.real)
+        return False
+
+
+OUT = None
 
 
 def main():
@@ -297,10 +321,12 @@ def main():
             if not os.path.exists(__graft_entry__.SO):
                 raise
             print("bench.py: build skipped (%s)" % e, file=sys.stderr)
-    if args.impl == "reference":
-        run_reference(args, rank)
-    else:
-        run_ours(args, rank, world_size, local_rank)
+    global OUT
+    with StdoutToStderr() as OUT:
+        if args.impl == "reference":
+            run_reference(args, rank)
+        else:
+            run_ours(args, rank, world_size, local_rank)
 
 
 if __name__ == "__main__":
