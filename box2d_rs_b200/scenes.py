@@ -147,3 +147,51 @@ def add_pair(world, n=20000, seed=0xB2D + 5):
     box.set_linear_velocity((100.0, 0.0))
     bodies.append(box)
     return bodies
+
+
+def variety(world, seed=0xB2D + 9):
+    """Edge-case scene for the parity tests: a chain-shape bowl (one-sided edges with ghost vertices), a
+    kinematic paddle, restitution, collision filtering by group and by category/mask, polygons of 3..8
+    vertices, circles, a multi-fixture body, a fixed-rotation body, damping and gravity scale."""
+    rng = SplitMix64(seed)
+    ground = world.create_body(BodyDef())
+    bowl = [(-12.0, 8.0), (-10.0, 1.0), (-5.0, 0.0), (0.0, -0.5), (5.0, 0.0), (10.0, 1.0), (12.0, 8.0)]
+    bowl = [(x, y) for x, y in reversed(bowl)]  # counter-clockwise so the solid side faces the inside
+    ground.create_fixture(FixtureDef(friction=0.6), world.shapes.chain(bowl, (13.0, 9.0), (-13.0, 9.0)))
+    paddle = world.create_body(BodyDef(type=abi.KINEMATIC_BODY, position=(-6.0, 3.0), angle=0.3,
+                                       linear_velocity=(1.5, 0.0), angular_velocity=0.7))
+    paddle.create_fixture_by_shape(world.shapes.polygon_box(2.0, 0.2), 0.0)
+    bodies = []
+    for k in range(60):
+        px = f32(-8.0 + 16.0 * ((k * 7) % 60) / 60.0 + rng.uniform(-0.1, 0.1))
+        py = f32(4.0 + 0.9 * (k // 6) + rng.uniform(-0.1, 0.1))
+        kind = k % 6
+        bd = BodyDef(type=abi.DYNAMIC_BODY, position=(px, py), angle=f32(rng.uniform(-3.0, 3.0)))
+        if kind == 4:
+            bd.fixed_rotation = 1
+        if kind == 5:
+            bd.linear_damping, bd.angular_damping, bd.gravity_scale = 0.3, 0.2, 0.5
+        b = world.create_body(bd)
+        fd = FixtureDef(density=1.0 + 0.5 * kind, friction=0.1 * (1 + kind), restitution=0.0)
+        if kind == 0:
+            fd.restitution = 0.6
+            shape = world.shapes.circle(0.3 + 0.02 * (k % 5))
+        elif kind == 1:
+            nv = 3 + (k // 6) % 6
+            shape = world.shapes.polygon([(0.45 * math.cos(2 * math.pi * i / nv), 0.35 * math.sin(2 * math.pi * i / nv))
+                                          for i in range(nv)])
+        elif kind == 2:
+            fd.group_index = -3  # never collide with each other
+            shape = world.shapes.polygon_box(0.3, 0.5)
+        elif kind == 3:
+            fd.category_bits, fd.mask_bits = 0x0004, 0xFFFB  # ignore their own category
+            shape = world.shapes.circle(0.35)
+        elif kind == 4:
+            shape = world.shapes.polygon_box(0.4, 0.4, (0.1, -0.05), 0.4)
+        else:
+            shape = world.shapes.polygon_box(0.5, 0.2)
+        b.create_fixture(fd, shape)
+        if kind == 5:  # second fixture: multi-fixture mass data, two proxies per body
+            b.create_fixture(FixtureDef(density=2.0, friction=0.4), world.shapes.circle(0.2, (0.45, 0.0)))
+        bodies.append(b)
+    return bodies

@@ -23,6 +23,7 @@ CASES = {
     "mixed300": ("mixed300", (1, 50, 150, 300)),
     "pile400": ("pile400", (1, 50, 150)),
     "addpair2000": ("addpair2000", (1, 40, 120)),
+    "variety": ("variety", (1, 60, 200, 400)),
 }
 
 

@@ -110,7 +110,7 @@ def test_batch_of_different_worlds(n_worlds, lane_block, ctx):
     wg.close()
 
 
-@pytest.mark.parametrize("name,steps", [("hello_world", 90), ("mixed300", 260), ("addpair2000", 120), ("pile400", 120)])
+@pytest.mark.parametrize("name,steps", [("hello_world", 90), ("mixed300", 260), ("addpair2000", 120), ("pile400", 120), ("variety", 400)])
 def test_batch_replicas_shared_memory_solver(name, steps, ctx):
     """32-world memory blocks run the shared-memory Gauss-Seidel kernels (resident ring for tiny islands,
     streaming ring otherwise, many islands per world): replicas must match the oracle bit for bit."""
@@ -153,7 +153,7 @@ def test_full_size_batch_properties(ctx):
     wg.close()
 
 
-@pytest.mark.parametrize("name", ["pyramid", "mixed300", "pile400", "addpair2000", "hello_world"])
+@pytest.mark.parametrize("name", ["pyramid", "mixed300", "pile400", "addpair2000", "hello_world", "variety"])
 def test_gpu_matches_golden(name, ctx):
     """The committed fixtures (tests/golden, produced by the oracle) reproduced by the CUDA path, in a
     40-world batch (shared-memory solver and island kernels), bit for bit."""
@@ -183,4 +183,23 @@ def test_gpu_matches_golden(name, ctx):
         else:
             assert np.array_equal(g[k], v), k
     batch.close()
+    wg.close()
+
+
+@pytest.mark.parametrize("warm,block,sleep", [(False, True, True), (True, False, True), (False, False, False)])
+def test_world_flags(warm, block, sleep, ctx):
+    """set_warm_starting / G_BLOCK_SOLVE / set_allow_sleeping, plus a dt = 0 step (collide only) in between."""
+    from box2d_rs_b200 import scenes
+    wo, wg, _ = _pair("variety", ctx)
+    for w in (wo, wg):
+        w.set_warm_starting(warm)
+        w.set_block_solve(block)
+        w.set_allow_sleeping(sleep)
+    for i in range(150):
+        dt = 0.0 if i in (40, 41, 90) else scenes.DT
+        wo.step(dt, 8, 3)
+        wg.step(dt, 8, 3)
+        if i % 30 == 29 or i in (40, 41, 42):
+            bad = parity.compare_snapshots(wo.snapshot(), wg.snapshot()) + parity.compare_stats(wo.get_stats(), wg.get_stats())
+            assert bad == [], "step %d: %s" % (i, bad[:6])
     wg.close()

@@ -182,3 +182,22 @@ def test_simulator_matches_golden(name, ctx):
             assert np.array_equal(g[k], v), k
     batch.close()
     wg.close()
+
+
+@pytest.mark.parametrize("warm,block,sleep", [(False, True, True), (True, False, True), (False, False, False)])
+def test_world_flags(warm, block, sleep, ctx):
+    """set_warm_starting / G_BLOCK_SOLVE / set_allow_sleeping, plus a dt = 0 step (collide only) in between."""
+    from box2d_rs_b200 import scenes
+    wo, wg, _ = _pair("variety", ctx)
+    for w in (wo, wg):
+        w.set_warm_starting(warm)
+        w.set_block_solve(block)
+        w.set_allow_sleeping(sleep)
+    for i in range(150):
+        dt = 0.0 if i in (40, 41, 90) else scenes.DT
+        wo.step(dt, 8, 3)
+        wg.step(dt, 8, 3)
+        if i % 30 == 29 or i in (40, 41, 42):
+            bad = parity.compare_snapshots(wo.snapshot(), wg.snapshot()) + parity.compare_stats(wo.get_stats(), wg.get_stats())
+            assert bad == [], "step %d: %s" % (i, bad[:6])
+    wg.close()
