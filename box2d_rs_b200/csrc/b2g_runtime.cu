@@ -617,7 +617,7 @@ int batch_step(BatchHost* bh, float dt, int vi, int pi, int steps) {
         RC(ls.end());
       } else
 #endif
-      { VelocityK k = {B, sp}; RC(launch(ctx, k, W, ordered_block, STAGE_VELOCITY)); }
+      { VelocityK k = {B, sp}; RC(launch(ctx, k, W * B.NB, 64, STAGE_VELOCITY)); }
       { PostVelocityK k = {B, sp}; RC(launch(ctx, k, W * B.NIB, 128, STAGE_POST_VELOCITY)); }
 #if !defined(B2G_HOSTSIM)
       if (bh->smem_solver) {
@@ -627,9 +627,9 @@ int batch_step(BatchHost* bh, float dt, int vi, int pi, int steps) {
         RC(ls.end());
       } else
 #endif
-      { PositionK k = {B, sp}; RC(launch(ctx, k, W, ordered_block, STAGE_POSITION)); }
+      { PositionK k = {B, sp}; RC(launch(ctx, k, W * B.NB, 64, STAGE_POSITION)); }
       { FinalizeK k = {B, sp}; RC(launch(ctx, k, W * B.NIB, 128, STAGE_FINALIZE)); }
-      { SleepK k = {B}; RC(launch(ctx, k, W, ordered_block, STAGE_SLEEP)); }
+      { SleepK k = {B}; RC(launch(ctx, k, W * B.NB, 128, STAGE_SLEEP)); }
       if (B.NP > 0) { SyncFixturesK k = {B}; RC(launch(ctx, k, W * B.NP, 128, STAGE_SYNC_FIXTURES)); }
     }
     {

@@ -655,19 +655,23 @@ B2G_HD void warm_start_one(VelState& s, const float4 q0, const float4 q1, const 
   }
 }
 
-// Ordered stage B (one thread per world), generic global-memory form: warm start + velocity iterations.
+// Ordered stage B, generic global-memory form: warm start + velocity iterations, one thread per island
+// (islands share no dynamic body, so they are independent; inside an island the reference order is kept).
 struct VelocityK {
   Batch B;
   StepParams sp;
-  B2G_HD void operator()(int w) const {
-    if (w >= B.n_worlds) return;
+  B2G_HD void operator()(int tid) const {
+    int w, isl;
+    if (!flat_decode(B, tid, B.NB, w, isl)) return;
     WIdx x = widx(B, w);
     Ws ws = ws_of(B, x);
-    const int nc = ws[WS_ISL_CONTACTS];
+    if (isl >= ws[WS_ISL_COUNT]) return;
+    const int4 rg = B.isl_range[x.at(B.NB, isl)];
+    if (rg.z == rg.w) return;
     const bool warm = (ws[WS_FLAGS] & B2GPU_WORLD_WARM_STARTING) != 0;
     const bool block = (ws[WS_FLAGS] & B2GPU_WORLD_BLOCK_SOLVE) != 0;
     for (int it = warm ? -1 : 0; it < sp.velocity_iterations; ++it) {
-      for (int k = 0; k < nc; ++k) {
+      for (int k = rg.z; k < rg.w; ++k) {
         const float4 q8 = B.vc[vc_at(B, x, k, 8)];
         const int ba = f2i(q8.x), bb = f2i(q8.y), vc_points = f2i(q8.z) & 0xff;
         if (vc_points == 0) continue;
@@ -686,8 +690,9 @@ struct VelocityK {
           solve_velocity_one(s, q0, q1, q2, q3, q4, q5, q6, q7, vc_points, block);
           B.vc[vc_at(B, x, k, 6)] = q6;
         }
-        B.b_vel[bai] = make_float4(s.v_a.x, s.v_a.y, s.w_a, 0.0f);
-        B.b_vel[bbi] = make_float4(s.v_b.x, s.v_b.y, s.w_b, 0.0f);
+        // a static / kinematic body may sit in several islands: its velocity never changes, leave it alone
+        if (q7.x != 0.0f || q7.y != 0.0f) B.b_vel[bai] = make_float4(s.v_a.x, s.v_a.y, s.w_a, 0.0f);
+        if (q7.z != 0.0f || q7.w != 0.0f) B.b_vel[bbi] = make_float4(s.v_b.x, s.v_b.y, s.w_b, 0.0f);
       }
     }
   }
@@ -807,36 +812,25 @@ B2G_HD float solve_position_one(PosState& s, const float4 q7, const float4 q9, c
   return min_separation;
 }
 
-// Ordered stage C (one thread per world), generic form: position iterations with per-island early exit.
-// Islands are contiguous runs of the constraint stream; a solved island is skipped in later sweeps
-// (the reference leaves its loop, b2_island_private.rs:257-274).  Islands without contacts were
-// marked solved by PostVelocityK.
+// Ordered stage C, generic form: position iterations of one island per thread, with the reference's early
+// exit (b2_island_private.rs:257-274).  Islands without contacts were marked solved by PostVelocityK.
 struct PositionK {
   Batch B;
   StepParams sp;
-  B2G_HD void operator()(int w) const {
-    if (w >= B.n_worlds) return;
+  B2G_HD void operator()(int tid) const {
+    int w, isl;
+    if (!flat_decode(B, tid, B.NB, w, isl)) return;
     WIdx x = widx(B, w);
     Ws ws = ws_of(B, x);
-    const int nc = ws[WS_ISL_CONTACTS];
+    if (isl >= ws[WS_ISL_COUNT]) return;
+    const int4 rg = B.isl_range[x.at(B.NB, isl)];
+    if (rg.z == rg.w) return;
     for (int it = 0; it < sp.position_iterations; ++it) {
-      bool all_solved = true;
-      int cur = -1;
-      bool skip = false;
       float min_separation = 0.0f;
-      for (int k = 0; k < nc; ++k) {
+      for (int k = rg.z; k < rg.w; ++k) {
         const float4 p5 = B.pc[pc_at(B, x, k, 5)];
-        const int isl = f2i(p5.y);
-        if (isl != cur) {
-          if (cur >= 0 && !skip) {
-            if (min_separation >= -3.0f * B2G_LINEAR_SLOP) B.isl_flags[x.at(B.NB, cur)] |= 1; else all_solved = false;
-          }
-          cur = isl;
-          skip = (B.isl_flags[x.at(B.NB, cur)] & 1) != 0;
-          min_separation = 0.0f;
-        }
-        if (skip) continue;
         const float4 p4 = B.pc[pc_at(B, x, k, 4)];
+        const float4 p0 = B.pc[pc_at(B, x, k, 0)];
         const int ba = f2i(p4.z), bb = f2i(p4.w), packed = f2i(p5.x);
         const int bai = x.at(B.NB, ba), bbi = x.at(B.NB, bb);
         float4 pa = B.b_pos[bai], pb = B.b_pos[bbi];
@@ -844,19 +838,23 @@ struct PositionK {
         PosState s;
         s.c_a = v2(pa.x, pa.y); s.a_a = pa.z; s.q_a.s = ra.x; s.q_a.c = ra.y;
         s.c_b = v2(pb.x, pb.y); s.a_b = pb.z; s.q_b.s = rb.x; s.q_b.c = rb.y;
-        min_separation = solve_position_one(s, B.pc[pc_at(B, x, k, 0)], B.pc[pc_at(B, x, k, 1)], B.pc[pc_at(B, x, k, 2)],
+        min_separation = solve_position_one(s, p0, B.pc[pc_at(B, x, k, 1)], B.pc[pc_at(B, x, k, 2)],
                                             B.pc[pc_at(B, x, k, 3)], (packed >> 8) & 0xff, packed & 0xff, p4.x, p4.y, min_separation);
-        pa.x = s.c_a.x; pa.y = s.c_a.y; pa.z = s.a_a;
-        pb.x = s.c_b.x; pb.y = s.c_b.y; pb.z = s.a_b;
-        ra.x = s.q_a.s; ra.y = s.q_a.c;
-        rb.x = s.q_b.s; rb.y = s.q_b.c;
-        B.b_pos[bai] = pa; B.b_rot[bai] = ra;
-        B.b_pos[bbi] = pb; B.b_rot[bbi] = rb;
+        if (p0.x != 0.0f || p0.y != 0.0f) {  // immovable bodies are shared between islands: never written
+          pa.x = s.c_a.x; pa.y = s.c_a.y; pa.z = s.a_a;
+          ra.x = s.q_a.s; ra.y = s.q_a.c;
+          B.b_pos[bai] = pa; B.b_rot[bai] = ra;
+        }
+        if (p0.z != 0.0f || p0.w != 0.0f) {
+          pb.x = s.c_b.x; pb.y = s.c_b.y; pb.z = s.a_b;
+          rb.x = s.q_b.s; rb.y = s.q_b.c;
+          B.b_pos[bbi] = pb; B.b_rot[bbi] = rb;
+        }
       }
-      if (cur >= 0 && !skip) {
-        if (min_separation >= -3.0f * B2G_LINEAR_SLOP) B.isl_flags[x.at(B.NB, cur)] |= 1; else all_solved = false;
+      if (min_separation >= -3.0f * B2G_LINEAR_SLOP) {
+        B.isl_flags[x.at(B.NB, isl)] |= 1;
+        break;
       }
-      if (all_solved) break;
     }
   }
 };
@@ -896,37 +894,36 @@ struct FinalizeK {
   }
 };
 
-// Island-wide sleep decision (:319-327): one thread per world.
+// Island-wide sleep decision (:319-327): one thread per island.
 struct SleepK {
   Batch B;
-  B2G_HD void operator()(int w) const {
-    if (w >= B.n_worlds) return;
+  B2G_HD void operator()(int tid) const {
+    int w, isl;
+    if (!flat_decode(B, tid, B.NB, w, isl)) return;
     WIdx x = widx(B, w);
     Ws ws = ws_of(B, x);
     if (!(ws[WS_FLAGS] & B2GPU_WORLD_ALLOW_SLEEP)) return;
-    const int nisl = ws[WS_ISL_COUNT];
-    for (int isl = 0; isl < nisl; ++isl) {
-      const int4 rg = B.isl_range[x.at(B.NB, isl)];
-      float min_sleep_time = B2G_MAX_FLOAT;
-      for (int k = rg.x; k < rg.y; ++k) {
+    if (isl >= ws[WS_ISL_COUNT]) return;
+    const int4 rg = B.isl_range[x.at(B.NB, isl)];
+    float min_sleep_time = B2G_MAX_FLOAT;
+    for (int k = rg.x; k < rg.y; ++k) {
+      const int bi = x.at(B.NB, B.isl_body[x.at(B.NIB, k)]);
+      if (body_type(B.b_flags[bi]) == B2GPU_STATIC_BODY) continue;
+      min_sleep_time = fmin_sel(min_sleep_time, B.b_pos[bi].w);
+    }
+    if (min_sleep_time >= B2G_TIME_TO_SLEEP && (B.isl_flags[x.at(B.NB, isl)] & 1)) {
+      for (int k = rg.x; k < rg.y; ++k) {  // set_awake(false), src/b2_body.rs:783-801
         const int bi = x.at(B.NB, B.isl_body[x.at(B.NIB, k)]);
-        if (body_type(B.b_flags[bi]) == B2GPU_STATIC_BODY) continue;
-        min_sleep_time = fmin_sel(min_sleep_time, B.b_pos[bi].w);
+        const int bf = B.b_flags[bi];
+        if (body_type(bf) == B2GPU_STATIC_BODY) continue;
+        B.b_flags[bi] = bf & ~B2GPU_BODY_AWAKE;
+        B.b_pos[bi].w = 0.0f;
+        B.b_vel[bi] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+        float4 fo = B.b_force[bi];
+        fo.x = 0.0f; fo.y = 0.0f; fo.z = 0.0f;
+        B.b_force[bi] = fo;
       }
-      if (min_sleep_time >= B2G_TIME_TO_SLEEP && (B.isl_flags[x.at(B.NB, isl)] & 1)) {
-        for (int k = rg.x; k < rg.y; ++k) {  // set_awake(false), src/b2_body.rs:783-801
-          const int bi = x.at(B.NB, B.isl_body[x.at(B.NIB, k)]);
-          const int bf = B.b_flags[bi];
-          if (body_type(bf) == B2GPU_STATIC_BODY) continue;
-          B.b_flags[bi] = bf & ~B2GPU_BODY_AWAKE;
-          B.b_pos[bi].w = 0.0f;
-          B.b_vel[bi] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-          float4 fo = B.b_force[bi];
-          fo.x = 0.0f; fo.y = 0.0f; fo.z = 0.0f;
-          B.b_force[bi] = fo;
-        }
-        ws[WS_TOPO_DIRTY] = 1;
-      }
+      ws[WS_TOPO_DIRTY] = 1;
     }
   }
 };
