@@ -215,20 +215,6 @@ B2G_HD void sincos_ref(float y, float* sp, float* cp) {
   *sp = sc_poly(xs, x2, neg, n);
   *cp = sc_poly(xs, x2, neg, n ^ 1);
 }
-// B2Rot::set.  The common case |a| < pi/4 (bodies of a resting pile) is evaluated without branches:
-// both polynomials, then the "tiny argument returns (a, 1)" rule of sinf/cosf as a select.
-B2G_HD Rot rot_from_angle(float a) {
-  Rot q;
-  if (abstop12(a) < abstop12(0x1.921FB6p-1f)) {
-    const double x = (double)a, x2 = x * x;
-    const float ps = sc_poly(x, x2, 0, 0), pc = sc_poly(x, x2, 0, 1);
-    const bool tiny = abstop12(a) < abstop12(0x1p-12f);
-    q.s = tiny ? a : ps;
-    q.c = tiny ? 1.0f : pc;
-  } else {
-    sincos_ref(a, &q.s, &q.c);
-  }
-  return q;
-}
+B2G_HD Rot rot_from_angle(float a) { Rot q; sincos_ref(a, &q.s, &q.c); return q; }
 
 }  // namespace b2g

@@ -157,7 +157,10 @@ __global__ void __launch_bounds__(32) velocity_smem_kernel(const Batch B, const 
         if (sc == 0) {
           warm_start_one(s, cur.q0, cur.q1, cur.q2, cur.q6, cur.q7, cur.cnt);
         } else {
-          solve_velocity_one(s, cur.q0, cur.q1, cur.q2, cur.q3, cur.q4, cur.q5, cur.q6, cur.q7, cur.cnt, block);
+          if (__all_sync(__activemask(), cur.cnt == 2 && block))
+            solve_velocity_one(s, cur.q0, cur.q1, cur.q2, cur.q3, cur.q4, cur.q5, cur.q6, cur.q7, 2, true);
+          else
+            solve_velocity_one(s, cur.q0, cur.q1, cur.q2, cur.q3, cur.q4, cur.q5, cur.q6, cur.q7, cur.cnt, block);
           q6_out[(size_t)kc * VC_Q * 32] = cur.q6;
         }
         va = make_float4(s.v_a.x, s.v_a.y, s.w_a, 0.0f);

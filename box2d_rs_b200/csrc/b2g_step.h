@@ -754,78 +754,61 @@ struct PostVelocityK {
 
 // One position constraint (b2_contact_solver_private.rs:600-730).  The reference rebuilds both
 // transforms (sin/cos) for every manifold point from the running angles; sin/cos are pure
-// functions of the angle, so the values are cached per body (b_rot) and carried with the position:
-// a body's rotation is evaluated once per correction instead of once per point that reads it
-// (and never in the velocity stage) — bit-identical, fewer evaluations, off the next point's chain.
+// functions of the angle, so they are cached per body (b_rot) and recomputed only when a
+// correction actually changed the angle — bit-identical, far fewer evaluations.
 struct PosState {
   V2 c_a, c_b;
   float a_a, a_b;
   Rot q_a, q_b;
 };
-// One manifold point.  FACE_A and FACE_B are the same computation with the two bodies' roles exchanged
-// (and the normal negated at the end), so they share one branch-free path: the operands are selected,
-// the arithmetic is the reference's.
-B2G_HD float solve_position_point(PosState& s, float m_a, float i_a, float m_b, float i_b, V2 lc_a, V2 lc_b, V2 local_normal,
-                                  V2 local_point, V2 pt, int type, float radius_a, float radius_b, float min_separation) {
-  V2 normal, point;
-  float separation;
-  if (type == B2GPU_MANIFOLD_CIRCLES) {
+B2G_HD float solve_position_one(PosState& s, const float4 q7, const float4 q9, const float4 lps, const float4 m2,
+                                int type, int pc_points, float radius_a, float radius_b, float min_separation) {
+  const float m_a = q7.x, i_a = q7.y, m_b = q7.z, i_b = q7.w;
+  const V2 lc_a = v2(q9.x, q9.y), lc_b = v2(q9.z, q9.w);
+  const float4 m0 = make_float4(lps.x, lps.y, 0.0f, 0.0f), m1 = make_float4(lps.z, lps.w, 0.0f, 0.0f);
+  for (int j = 0; j < pc_points; ++j) {
     Xf xf_a, xf_b;
     xf_a.q = s.q_a;
     xf_b.q = s.q_b;
     xf_a.p = s.c_a - rot_mul(xf_a.q, lc_a);
     xf_b.p = s.c_b - rot_mul(xf_b.q, lc_b);
-    const V2 point_a = xf_mul(xf_a, local_point);
-    const V2 point_b = xf_mul(xf_b, pt);
-    normal = point_b - point_a;
-    normalize(normal);
-    point = 0.5f * (point_a + point_b);
-    separation = dot(point_b - point_a, normal) - radius_a - radius_b;
-  } else {
-    const bool face_b = type == B2GPU_MANIFOLD_FACE_B;
-    Xf xf_r, xf_i;  // reference body (owns the plane), incident body (owns the clip point)
-    xf_r.q.s = face_b ? s.q_b.s : s.q_a.s;
-    xf_r.q.c = face_b ? s.q_b.c : s.q_a.c;
-    xf_i.q.s = face_b ? s.q_a.s : s.q_b.s;
-    xf_i.q.c = face_b ? s.q_a.c : s.q_b.c;
-    const V2 c_r = v2(face_b ? s.c_b.x : s.c_a.x, face_b ? s.c_b.y : s.c_a.y);
-    const V2 c_i = v2(face_b ? s.c_a.x : s.c_b.x, face_b ? s.c_a.y : s.c_b.y);
-    const V2 lc_r = v2(face_b ? lc_b.x : lc_a.x, face_b ? lc_b.y : lc_a.y);
-    const V2 lc_i = v2(face_b ? lc_a.x : lc_b.x, face_b ? lc_a.y : lc_b.y);
-    xf_r.p = c_r - rot_mul(xf_r.q, lc_r);
-    xf_i.p = c_i - rot_mul(xf_i.q, lc_i);
-    normal = rot_mul(xf_r.q, local_normal);
-    const V2 plane_point = xf_mul(xf_r, local_point);
-    const V2 clip_point = xf_mul(xf_i, pt);
-    separation = dot(clip_point - plane_point, normal) - radius_a - radius_b;
-    point = clip_point;
-    if (face_b) normal = -normal;
+    V2 normal, point;
+    float separation;
+    if (type == B2GPU_MANIFOLD_CIRCLES) {
+      const V2 point_a = xf_mul(xf_a, v2(m2.z, m2.w));
+      const V2 point_b = xf_mul(xf_b, v2(m0.x, m0.y));
+      normal = point_b - point_a;
+      normalize(normal);
+      point = 0.5f * (point_a + point_b);
+      separation = dot(point_b - point_a, normal) - radius_a - radius_b;
+    } else if (type == B2GPU_MANIFOLD_FACE_A) {
+      normal = rot_mul(xf_a.q, v2(m2.x, m2.y));
+      const V2 plane_point = xf_mul(xf_a, v2(m2.z, m2.w));
+      const V2 clip_point = xf_mul(xf_b, j == 0 ? v2(m0.x, m0.y) : v2(m1.x, m1.y));
+      separation = dot(clip_point - plane_point, normal) - radius_a - radius_b;
+      point = clip_point;
+    } else {
+      normal = rot_mul(xf_b.q, v2(m2.x, m2.y));
+      const V2 plane_point = xf_mul(xf_b, v2(m2.z, m2.w));
+      const V2 clip_point = xf_mul(xf_a, j == 0 ? v2(m0.x, m0.y) : v2(m1.x, m1.y));
+      separation = dot(clip_point - plane_point, normal) - radius_a - radius_b;
+      point = clip_point;
+      normal = -normal;
+    }
+    const V2 r_a = point - s.c_a, r_b = point - s.c_b;
+    min_separation = fmin_sel(min_separation, separation);
+    const float cc = fclamp_sel(B2G_BAUMGARTE * (separation + B2G_LINEAR_SLOP), -B2G_MAX_LINEAR_CORRECTION, 0.0f);
+    const float rn_a = cross(r_a, normal), rn_b = cross(r_b, normal);
+    const float kk = m_a + m_b + i_a * rn_a * rn_a + i_b * rn_b * rn_b;
+    const float impulse = kk > 0.0f ? -cc / kk : 0.0f;
+    const V2 p = impulse * normal;
+    s.c_a = s.c_a - m_a * p;
+    const float na = s.a_a - i_a * cross(r_a, p);
+    s.c_b = s.c_b + m_b * p;
+    const float nb = s.a_b + i_b * cross(r_b, p);
+    if (f2u(na) != f2u(s.a_a)) { s.a_a = na; s.q_a = rot_from_angle(na); }
+    if (f2u(nb) != f2u(s.a_b)) { s.a_b = nb; s.q_b = rot_from_angle(nb); }
   }
-  const V2 r_a = point - s.c_a, r_b = point - s.c_b;
-  min_separation = fmin_sel(min_separation, separation);
-  const float cc = fclamp_sel(B2G_BAUMGARTE * (separation + B2G_LINEAR_SLOP), -B2G_MAX_LINEAR_CORRECTION, 0.0f);
-  const float rn_a = cross(r_a, normal), rn_b = cross(r_b, normal);
-  const float kk = m_a + m_b + i_a * rn_a * rn_a + i_b * rn_b * rn_b;
-  const float impulse = kk > 0.0f ? -cc / kk : 0.0f;
-  const V2 p = impulse * normal;
-  s.c_a = s.c_a - m_a * p;
-  s.a_a = s.a_a - i_a * cross(r_a, p);
-  s.c_b = s.c_b + m_b * p;
-  s.a_b = s.a_b + i_b * cross(r_b, p);
-  // sin/cos are pure functions of the angle: recomputing them here is what the reference does at the top
-  // of the next point that touches the body (and nearly every correction changes the angle's bits)
-  s.q_a = rot_from_angle(s.a_a);
-  s.q_b = rot_from_angle(s.a_b);
-  return min_separation;
-}
-B2G_HD float solve_position_one(PosState& s, const float4 q7, const float4 q9, const float4 lps, const float4 m2,
-                                int type, int pc_points, float radius_a, float radius_b, float min_separation) {
-  const V2 lc_a = v2(q9.x, q9.y), lc_b = v2(q9.z, q9.w);
-  min_separation = solve_position_point(s, q7.x, q7.y, q7.z, q7.w, lc_a, lc_b, v2(m2.x, m2.y), v2(m2.z, m2.w), v2(lps.x, lps.y),
-                                        type, radius_a, radius_b, min_separation);
-  if (pc_points > 1)
-    min_separation = solve_position_point(s, q7.x, q7.y, q7.z, q7.w, lc_a, lc_b, v2(m2.x, m2.y), v2(m2.z, m2.w),
-                                          v2(lps.z, lps.w), type, radius_a, radius_b, min_separation);
   return min_separation;
 }
 
