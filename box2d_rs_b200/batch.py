@@ -42,13 +42,14 @@ class Context:
 
 
 class Batch:
-    def __init__(self, ctx, proto, n_worlds, max_contacts=0, max_pairs=0, lane_block=0, generic_solver=False):
+    def __init__(self, ctx, proto, n_worlds, max_contacts=0, max_pairs=0, lane_block=0, generic_solver=False, solver=None):
         """proto: abi.Snapshot of the prototype world (from B2world.snapshot())."""
         self.ctx, self.L = ctx, ctx.L
         caps = abi.Caps()
         caps.max_contacts, caps.max_pairs = max_contacts, max_pairs
         caps.reserved[0] = lane_block
-        caps.reserved[1] = 1 if generic_solver else 0
+        # solver: None = best available, 'generic' = global-memory stages, 'lane' = one lane per world (no level schedule)
+        caps.reserved[1] = 1 if (generic_solver or solver == 'generic') else (2 if solver == 'lane' else 0)
         self.h = C.c_void_p()
         c = proto.as_c()
         self._keep = proto

@@ -38,6 +38,7 @@ enum {
   WS_EV_MOVED,     // proxies that left their fat box this step
   WS_TOPO_DIRTY,   // island order must be rebuilt
   WS_ISL_VALID,    // island arrays describe the last dt > 0 step of this world
+  WS_SCHED_ROUNDS, // rounds of the level schedule of the island contacts (-1: none, solve in list order)
   WS_STATUS,
   // stats of the last step (b2gpu_step_stats order from `contacts` on)
   WS_ST_CONTACTS, WS_ST_TOUCHING, WS_ST_DESTROYED, WS_ST_ISLANDS, WS_ST_ISL_BODIES, WS_ST_ISL_CONTACTS,
@@ -47,6 +48,8 @@ enum {
 
 // velocity-constraint record: VC_Q float4 per island contact
 enum { VC_Q = 9, PC_Q = 6 };
+// lanes that cooperate on one world in the level-scheduled Gauss-Seidel kernels
+enum { SCHED_G = 2, SCHED_MIN_ROUNDS = 6 };
 
 struct Batch {
   int n_worlds, LB, lb_shift, n_wblocks;
@@ -98,7 +101,7 @@ struct Batch {
   int* c_isl;                // [NC] island index of each island contact slot
   float4* vc;                // [NC * VC_Q] velocity constraint records
   float4* pc;                // [NC * PC_Q] position constraint records
-  int* c_tmp;                // [NC] scratch (destroy compaction, ordered fix-up)
+  int* sched;                // [NC * SCHED_G] level schedule: round r, slot g -> island contact k or -1
 };
 
 struct WIdx {  // index helper of one thread's world

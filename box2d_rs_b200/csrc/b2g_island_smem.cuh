@@ -26,6 +26,7 @@ __global__ void __launch_bounds__(32) island_smem_kernel(const SerialAK K, const
   uint8_t* eisl = (uint8_t*)(smem_raw + L.off_eisl);       // [ECAP][32] 1 = already in an island
   uint8_t* bflag = (uint8_t*)(smem_raw + L.off_bflag);     // [NB][32] bit0 ISLAND bit1 AWAKE bit2 ENABLED bit3 static
   uint32_t* fxb = (uint32_t*)(smem_raw + L.off_fxb);       // [fxb_count] fixture -> body | sensor << 31
+  uint16_t* korder = (uint16_t*)(smem_raw + L.off_korder); // [ECAP][32] island contact slot k -> eligible edge
   const int lane = threadIdx.x;
   const int wb = blockIdx.x;
   const int w = wb * 32 + lane;
@@ -50,13 +51,19 @@ __global__ void __launch_bounds__(32) island_smem_kernel(const SerialAK K, const
   if (need) {
     for (int b0 = 0; b0 < NB; b0 += 8) {
       int f[8];
+      float4 ms[8];
 #pragma unroll
-      for (int j = 0; j < 8; ++j) f[j] = b0 + j < NB ? B.b_flags[x.at(NB, b0 + j)] : 0;
+      for (int j = 0; j < 8; ++j) {
+        f[j] = b0 + j < NB ? B.b_flags[x.at(NB, b0 + j)] : 0;
+        ms[j] = b0 + j < NB ? B.b_mass[x.at(NB, b0 + j)] : make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      }
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         if (b0 + j >= NB) break;
+        // bit4: the solver can change this body's velocity/position (non-zero inverse mass or inertia)
         bflag[(b0 + j) * 32 + lane] = (uint8_t)(((f[j] & B2GPU_BODY_AWAKE) ? 2 : 0) | ((f[j] & B2GPU_BODY_ENABLED) ? 4 : 0) |
-                                                (body_type(f[j]) == B2GPU_STATIC_BODY ? 8 : 0));
+                                                (body_type(f[j]) == B2GPU_STATIC_BODY ? 8 : 0) |
+                                                ((ms[j].x != 0.0f || ms[j].y != 0.0f) ? 16 : 0));
         chead[(b0 + j) * 32 + lane] = 0xffffu;
         smark[(b0 + j) * 32 + lane] = 0;
       }
@@ -125,6 +132,7 @@ __global__ void __launch_bounds__(32) island_smem_kernel(const SerialAK K, const
         eisl[ei * 32 + lane] = 1;
         B.isl_contact[x.at(B.NC, ncon)] = eorig[ei * 32 + lane];
         B.c_isl[x.at(B.NC, ncon)] = nisl;
+        korder[ncon * 32 + lane] = (uint16_t)ei;
         ++ncon;
         const uint32_t bod = ebody[ei * 32 + lane];
         const int other = side ? (int)(bod & 0xffffu) : (int)(bod >> 16);
@@ -155,6 +163,36 @@ __global__ void __launch_bounds__(32) island_smem_kernel(const SerialAK K, const
                      ((bf & 2) ? B2GPU_BODY_AWAKE : 0);
       if (nf != f[j]) B.b_flags[x.at(NB, b0 + j)] = nf;
     }
+  }
+  // ---- level schedule of the island contacts for the multi-lane Gauss-Seidel kernels.
+  // Two constraints that share no movable body commute exactly, so a sweep in list order equals a sweep
+  // in "rounds": constraint k goes to the first round after the rounds of the earlier constraints that
+  // touch one of its movable bodies, SCHED_G constraints per round at most (list scheduling).  Every
+  // body still sees its constraints in the reference's order.
+  {
+    uint16_t* lastround = stack;                 // [NB][32] 1 + round of the last constraint on the body
+    uint8_t* fill = (uint8_t*)enext;             // [ECAP][32] slots used per round (rounds <= constraints)
+    for (int b = 0; b < NB; ++b) lastround[b * 32 + lane] = 0;
+    for (int r = 0; r < ncon + SCHED_MIN_ROUNDS; ++r) fill[r * 32 + lane] = 0;
+    int rounds = 0;
+    for (int k = 0; k < ncon; ++k) {
+      const uint32_t bod = ebody[korder[k * 32 + lane] * 32 + lane];
+      const int ba = (int)(bod & 0xffffu), bb = (int)(bod >> 16);
+      const bool mva = (bflag[ba * 32 + lane] & 16) != 0, mvb = (bflag[bb * 32 + lane] & 16) != 0;
+      int r = 0;
+      if (mva) r = lastround[ba * 32 + lane];
+      if (mvb) { const int rb = lastround[bb * 32 + lane]; r = rb > r ? rb : r; }
+      while (fill[r * 32 + lane] >= SCHED_G) ++r;
+      const int slot = fill[r * 32 + lane]++;
+      B.sched[x.at(B.NC * SCHED_G, r * SCHED_G + slot)] = k;
+      if (mva) lastround[ba * 32 + lane] = (uint16_t)(r + 1);
+      if (mvb) lastround[bb * 32 + lane] = (uint16_t)(r + 1);
+      rounds = r + 1 > rounds ? r + 1 : rounds;
+    }
+    if (ncon > 0 && rounds < SCHED_MIN_ROUNDS) rounds = SCHED_MIN_ROUNDS;  // keeps a constraint's re-read behind its write
+    for (int r = 0; r < rounds; ++r)
+      for (int slot = fill[r * 32 + lane]; slot < SCHED_G; ++slot) B.sched[x.at(B.NC * SCHED_G, r * SCHED_G + slot)] = -1;
+    ws[WS_SCHED_ROUNDS] = rounds;
   }
   ws[WS_ISL_COUNT] = nisl;
   ws[WS_ISL_BODIES] = nbod;

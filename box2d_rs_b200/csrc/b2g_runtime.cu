@@ -472,7 +472,7 @@ int batch_create(Ctx* ctx, const b2gpu_snapshot* proto, int n_worlds, const b2gp
   AL(B.c_fix, W * B.NC); AL(B.c_flags, W * B.NC); AL(B.c_mat, W * B.NC);
   AL(B.c_m0, W * B.NC); AL(B.c_m1, W * B.NC); AL(B.c_m2, W * B.NC); AL(B.c_m3, W * B.NC);
   AL(B.isl_body, W * B.NIB); AL(B.isl_contact, W * B.NC); AL(B.isl_range, W * B.NB); AL(B.isl_flags, W * B.NB);
-  AL(B.c_isl, W * B.NC); AL(B.vc, W * B.NC * VC_Q); AL(B.pc, W * B.NC * PC_Q);
+  AL(B.c_isl, W * B.NC); AL(B.vc, W * B.NC * VC_Q); AL(B.pc, W * B.NC * PC_Q); AL(B.sched, W * B.NC * SCHED_G);
   AL(bh->b_wake, W * B.NB); AL(bh->b_chead, W * B.NB); AL(bh->c_next, W * B.NC); AL(bh->stack, W * B.NB);
   AL(bh->state_dev, (long long)n_worlds * B.NB * 8);
   AL(bh->forces_dev, (long long)n_worlds * B.NB * 3);
@@ -509,6 +509,12 @@ int batch_create(Ctx* ctx, const b2gpu_snapshot* proto, int n_worlds, const b2gp
       CU(cudaFuncSetAttribute(velocity_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)velocity_smem_bytes(B.NB)));
       CU(cudaFuncSetAttribute(position_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)position_smem_bytes(B.NB)));
       bh->smem_solver = true;
+    }
+    const size_t need_ml = std::max(velocity_ml_smem_bytes(B.NB), position_ml_smem_bytes(B.NB));
+    if (bh->smem_solver && need_ml <= (size_t)max_optin && !(caps && caps->reserved[1] == 2)) {
+      CU(cudaFuncSetAttribute(velocity_ml_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)velocity_ml_smem_bytes(B.NB)));
+      CU(cudaFuncSetAttribute(position_ml_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)position_ml_smem_bytes(B.NB)));
+      bh->ml_solver = true;
     }
     bh->island_layout = island_smem_layout(B.NB, B.NF, (size_t)max_optin - 1024);
     if (B.NB < 32768 && B.NC < 65536 && bh->island_layout.ECAP >= 64) {
@@ -610,7 +616,12 @@ int batch_step(BatchHost* bh, float dt, int vi, int pi, int steps) {
       { IntegrateK k = {B, sp}; RC(launch(ctx, k, W * B.NIB, 128, STAGE_INTEGRATE)); }
       { SolverInitK k = {B, sp}; RC(launch(ctx, k, W * B.NC, 128, STAGE_SOLVER_INIT)); }
 #if !defined(B2G_HOSTSIM)
-      if (bh->smem_solver) {
+      if (bh->ml_solver) {
+        LaunchScope ls = {ctx, STAGE_VELOCITY};
+        RC(ls.begin());
+        velocity_ml_kernel<<<B.n_wblocks * SCHED_G, 32, velocity_ml_smem_bytes(B.NB), (cudaStream_t)ctx->stream>>>(B, sp);
+        RC(ls.end());
+      } else if (bh->smem_solver) {
         LaunchScope ls = {ctx, STAGE_VELOCITY};
         RC(ls.begin());
         velocity_smem_kernel<<<B.n_wblocks, 32, velocity_smem_bytes(B.NB), (cudaStream_t)ctx->stream>>>(B, sp);
@@ -620,7 +631,12 @@ int batch_step(BatchHost* bh, float dt, int vi, int pi, int steps) {
       { VelocityK k = {B, sp}; RC(launch(ctx, k, W * B.NB, 64, STAGE_VELOCITY)); }
       { PostVelocityK k = {B, sp}; RC(launch(ctx, k, W * B.NIB, 128, STAGE_POST_VELOCITY)); }
 #if !defined(B2G_HOSTSIM)
-      if (bh->smem_solver) {
+      if (bh->ml_solver) {
+        LaunchScope ls = {ctx, STAGE_POSITION};
+        RC(ls.begin());
+        position_ml_kernel<<<B.n_wblocks * SCHED_G, 32, position_ml_smem_bytes(B.NB), (cudaStream_t)ctx->stream>>>(B, sp);
+        RC(ls.end());
+      } else if (bh->smem_solver) {
         LaunchScope ls = {ctx, STAGE_POSITION};
         RC(ls.begin());
         position_smem_kernel<<<B.n_wblocks, 32, position_smem_bytes(B.NB), (cudaStream_t)ctx->stream>>>(B, sp);

@@ -330,4 +330,247 @@ __global__ void __launch_bounds__(32) position_smem_kernel(const Batch B, const 
   }
 }
 
+
+// ==========================================================================================
+// Level-scheduled Gauss-Seidel kernels: SCHED_G lanes cooperate on one world.
+//
+// The island kernel packs each world's island contacts into rounds of at most SCHED_G constraints that
+// share no movable body (b2g_island_smem.cuh).  Constraints of one round commute exactly, so the G
+// lanes of a world solve them concurrently; rounds are separated by __syncwarp().  A CTA is one warp =
+// 32 / SCHED_G worlds; the worlds of a 32-world memory block are spread over SCHED_G CTAs.  Per world
+// the dependent chain shrinks from "constraints per sweep" to "rounds per sweep" (Pyramid: 400 -> 296).
+// Body state lives in shared memory as [body][world] rows, each
+// lane streams the records of its own constraints through a private cp.async ring.
+// Worlds without a schedule (WS_SCHED_ROUNDS == -1) are solved by lane 0 in list order.
+// ==========================================================================================
+constexpr int ML_WPC = 32 / SCHED_G;  // worlds per CTA
+constexpr int ML_RING = 4;
+
+inline size_t velocity_ml_smem_bytes(int NB) { return (size_t)NB * ML_WPC * 16 + (size_t)ML_RING * VC_Q * 32 * 16; }
+inline size_t position_ml_smem_bytes(int NB) { return (size_t)NB * ML_WPC * (16 + 8 + 4) + (size_t)ML_RING * PC_Q * 32 * 16; }
+
+// [body][world] rows: the lanes of one slot g read one contiguous row segment each, conflict-free
+__device__ __forceinline__ int ml_col(int body, int wq) { return body * ML_WPC + wq; }
+
+// island contact handled by lane slot g of a world in round r (or -1)
+__device__ __forceinline__ int ml_item(const int* sched_w, int rounds, int nc, int r, int g) {
+  if (rounds < 0) return (g == 0 && r < nc) ? r : -1;  // no schedule: list order on lane 0
+  return r < rounds ? sched_w[(size_t)(r * SCHED_G + g) * 32] : -1;
+}
+
+__global__ void __launch_bounds__(32) velocity_ml_kernel(const Batch B, const StepParams sp) {
+  extern __shared__ float4 smem4[];
+  float4* ring = smem4;                          // [ML_RING][VC_Q][32] one private column per lane
+  float4* vel = smem4 + ML_RING * VC_Q * 32;     // [NB][ML_WPC] swizzled
+  const int lane = threadIdx.x;
+  const int g = lane / ML_WPC, wq = lane % ML_WPC;
+  const int wb = blockIdx.x / SCHED_G;
+  const int wl = (blockIdx.x % SCHED_G) * ML_WPC + wq;
+  const int w = wb * 32 + wl;
+  const bool live = w < B.n_worlds;
+  WIdx x;
+  x.wb = wb; x.wl = wl; x.LB = 32;
+  Ws ws = ws_of(B, x);
+  const int nc = live ? ws[WS_ISL_CONTACTS] : 0;
+  const int rounds_w = live ? ws[WS_SCHED_ROUNDS] : 0;
+  const int wflags = live ? ws[WS_FLAGS] : 0;
+  const bool warm = (wflags & B2GPU_WORLD_WARM_STARTING) != 0;
+  const bool block = (wflags & B2GPU_WORLD_BLOCK_SOLVE) != 0;
+  int rlen = nc == 0 ? 0 : (rounds_w < 0 ? (nc < SCHED_MIN_ROUNDS ? SCHED_MIN_ROUNDS : nc) : rounds_w);
+  const int rm = __reduce_max_sync(0xffffffffu, rlen);
+  if (rm == 0) return;
+  if (live)
+    for (int b = g; b < B.NB; b += SCHED_G) vel[ml_col(b, wq)] = B.b_vel[x.at(B.NB, b)];
+  __syncwarp();
+  const int* sched_w = B.sched + (size_t)wb * B.NC * SCHED_G * 32 + wl;
+  const float4* src = B.vc + (size_t)wb * B.NC * VC_Q * 32 + wl;
+  float4* rl = ring + lane;
+  const int sweeps = 1 + sp.velocity_iterations;
+  const int total = sweeps * rm;
+  // fetch pipeline: position p = sweep * rm + round; its record lands in ring stage p % ML_RING
+  int fr = 0, fpos = 0;
+  auto fetch = [&]() {
+    if (fpos < total) {
+      const int k = ml_item(sched_w, rounds_w, nc, fr, g);
+      if (k >= 0) {
+        float4* dst = rl + ((fpos & (ML_RING - 1)) * VC_Q) * 32;
+        const float4* s = src + (size_t)k * VC_Q * 32;
+#pragma unroll
+        for (int q = 0; q < VC_Q; ++q) cp_async16(dst + q * 32, s + q * 32);
+      }
+      if (++fr == rm) fr = 0;
+    }
+    ++fpos;
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int p = 0; p < ML_RING - 1; ++p) fetch();
+  int r = 0, sweep = 0;
+  for (int pos = 0; pos < total; ++pos) {
+    cp_async_wait<ML_RING - 2>();
+    const int k = ml_item(sched_w, rounds_w, nc, r, g);
+    const bool act = k >= 0 && (sweep > 0 || warm);
+    VcRegs c;
+    float4 va, vb;
+    if (act) {
+      c = vc_load(rl + ((pos & (ML_RING - 1)) * VC_Q) * 32);
+      va = vel[ml_col(c.ba, wq)];
+      vb = vel[ml_col(c.bb, wq)];
+    }
+    fetch();  // stage (pos - 1) % RING is free: refill it with position pos + RING - 1
+    if (act && c.cnt > 0) {
+      VelState s;
+      s.v_a = v2(va.x, va.y); s.w_a = va.z;
+      s.v_b = v2(vb.x, vb.y); s.w_b = vb.z;
+      if (sweep == 0) {
+        warm_start_one(s, c.q0, c.q1, c.q2, c.q6, c.q7, c.cnt);
+      } else {
+        solve_velocity_one(s, c.q0, c.q1, c.q2, c.q3, c.q4, c.q5, c.q6, c.q7, c.cnt, block);
+        B.vc[vc_at(B, x, k, 6)] = c.q6;
+      }
+      // immovable bodies (zero inverse mass and inertia) can be shared by the constraints of a round: never written
+      if (c.q7.x != 0.0f || c.q7.y != 0.0f) vel[ml_col(c.ba, wq)] = make_float4(s.v_a.x, s.v_a.y, s.w_a, 0.0f);
+      if (c.q7.z != 0.0f || c.q7.w != 0.0f) vel[ml_col(c.bb, wq)] = make_float4(s.v_b.x, s.v_b.y, s.w_b, 0.0f);
+    }
+    __syncwarp();
+    if (++r == rm) { r = 0; ++sweep; }
+  }
+  cp_async_wait<0>();
+  __syncwarp();
+  if (live)
+    for (int b = g; b < B.NB; b += SCHED_G) B.b_vel[x.at(B.NB, b)] = vel[ml_col(b, wq)];
+}
+
+// Position iterations, level-scheduled.  Per-island state of a sweep lives in a shared-memory table:
+// the most negative separation seen (as float bits: for negative floats larger bits = more negative, so
+// the lanes merge their contributions with atomicMax), or ML_SOLVED once the island passed the
+// reference's exit test min_separation >= -3 * linear_slop (b2_island_private.rs:257-274).
+constexpr unsigned ML_SOLVED = 0xffffffffu;
+
+__global__ void __launch_bounds__(32) position_ml_kernel(const Batch B, const StepParams sp) {
+  extern __shared__ float4 smem4[];
+  float4* ring = smem4;                                   // [ML_RING][PC_Q][32]
+  float4* pos = smem4 + ML_RING * PC_Q * 32;              // [NB][ML_WPC]: c.x c.y a -
+  float2* rot = (float2*)(pos + (size_t)B.NB * ML_WPC);   // [NB][ML_WPC]: sin a, cos a
+  unsigned* tab = (unsigned*)(rot + (size_t)B.NB * ML_WPC);  // [NB][ML_WPC] per island (see above)
+  const int lane = threadIdx.x;
+  const int g = lane / ML_WPC, wq = lane % ML_WPC;
+  const int wb = blockIdx.x / SCHED_G;
+  const int wl = (blockIdx.x % SCHED_G) * ML_WPC + wq;
+  const int w = wb * 32 + wl;
+  const bool live = w < B.n_worlds;
+  WIdx x;
+  x.wb = wb; x.wl = wl; x.LB = 32;
+  Ws ws = ws_of(B, x);
+  const int nc = live ? ws[WS_ISL_CONTACTS] : 0;
+  const int nisl = live ? ws[WS_ISL_COUNT] : 0;
+  const int rounds_w = live ? ws[WS_SCHED_ROUNDS] : 0;
+  int rlen = nc == 0 ? 0 : (rounds_w < 0 ? (nc < SCHED_MIN_ROUNDS ? SCHED_MIN_ROUNDS : nc) : rounds_w);
+  const int rm = __reduce_max_sync(0xffffffffu, rlen);
+  if (rm == 0 || sp.position_iterations <= 0) return;
+  if (live) {
+    for (int b = g; b < B.NB; b += SCHED_G) {
+      const float4 p = B.b_pos[x.at(B.NB, b)];
+      const float4 r = B.b_rot[x.at(B.NB, b)];
+      pos[ml_col(b, wq)] = p;
+      rot[ml_col(b, wq)] = make_float2(r.x, r.y);
+    }
+    for (int i = g; i < nisl; i += SCHED_G) tab[ml_col(i, wq)] = (B.isl_flags[x.at(B.NB, i)] & 1) ? ML_SOLVED : 0u;
+  }
+  __syncwarp();
+  const int* sched_w = B.sched + (size_t)wb * B.NC * SCHED_G * 32 + wl;
+  const float4* src = B.pc + (size_t)wb * B.NC * PC_Q * 32 + wl;
+  float4* rl = ring + lane;
+  const int total = sp.position_iterations * rm;
+  int fr = 0, fpos = 0;
+  auto fetch = [&]() {
+    if (fpos < total) {
+      const int k = ml_item(sched_w, rounds_w, nc, fr, g);
+      if (k >= 0) {
+        float4* dst = rl + ((fpos & (ML_RING - 1)) * PC_Q) * 32;
+        const float4* s = src + (size_t)k * PC_Q * 32;
+#pragma unroll
+        for (int q = 0; q < PC_Q; ++q) cp_async16(dst + q * 32, s + q * 32);
+      }
+      if (++fr == rm) fr = 0;
+    }
+    ++fpos;
+    cp_async_commit();
+  };
+#pragma unroll
+  for (int p = 0; p < ML_RING - 1; ++p) fetch();
+  int r = 0;
+  bool done = !live || nc == 0;
+  for (int p = 0; p < total; ++p) {
+    cp_async_wait<ML_RING - 2>();
+    const int k = ml_item(sched_w, rounds_w, nc, r, g);
+    const bool act = k >= 0 && !done;
+    PcRegs c;
+    float4 pa, pb;
+    float2 qa, qb;
+    bool solve = false;
+    if (act) {
+      c = pc_load(rl + ((p & (ML_RING - 1)) * PC_Q) * 32);
+      solve = tab[ml_col(c.isl, wq)] != ML_SOLVED;
+      pa = pos[ml_col(c.ba, wq)]; pb = pos[ml_col(c.bb, wq)];
+      qa = rot[ml_col(c.ba, wq)]; qb = rot[ml_col(c.bb, wq)];
+    }
+    fetch();
+    if (solve) {
+      PosState s;
+      s.c_a = v2(pa.x, pa.y); s.a_a = pa.z; s.q_a.s = qa.x; s.q_a.c = qa.y;
+      s.c_b = v2(pb.x, pb.y); s.a_b = pb.z; s.q_b.s = qb.x; s.q_b.c = qb.y;
+      const float ms = solve_position_one(s, c.p0, c.p1, c.p2, c.p3, c.type, c.cnt, c.ra, c.rb, 0.0f);
+      if (ms < 0.0f) atomicMax(&tab[ml_col(c.isl, wq)], __float_as_uint(ms));
+      if (c.p0.x != 0.0f || c.p0.y != 0.0f) {  // immovable bodies may be shared inside a round: never written
+        pos[ml_col(c.ba, wq)] = make_float4(s.c_a.x, s.c_a.y, s.a_a, 0.0f);
+        rot[ml_col(c.ba, wq)] = make_float2(s.q_a.s, s.q_a.c);
+      }
+      if (c.p0.z != 0.0f || c.p0.w != 0.0f) {
+        pos[ml_col(c.bb, wq)] = make_float4(s.c_b.x, s.c_b.y, s.a_b, 0.0f);
+        rot[ml_col(c.bb, wq)] = make_float2(s.q_b.s, s.q_b.c);
+      }
+    }
+    __syncwarp();
+    if (++r == rm) {  // end of a sweep: per island exit test, then the early exit of the whole world
+      r = 0;
+      bool open_left = false;
+      if (!done) {
+        for (int i = g; i < nisl; i += SCHED_G) {
+          const unsigned m = tab[ml_col(i, wq)];
+          if (m == ML_SOLVED) continue;
+          const float min_separation = m == 0u ? 0.0f : __uint_as_float(m);
+          if (min_separation >= -3.0f * B2G_LINEAR_SLOP) tab[ml_col(i, wq)] = ML_SOLVED;
+          else { tab[ml_col(i, wq)] = 0u; open_left = true; }
+        }
+      }
+      // a world is finished when none of its lanes still holds an unsolved island
+      const unsigned open_mask = __ballot_sync(0xffffffffu, open_left);
+      bool world_open = false;
+#pragma unroll
+      for (int gg = 0; gg < SCHED_G; ++gg) world_open = world_open || ((open_mask >> (gg * ML_WPC + wq)) & 1u);
+      if (!world_open) done = true;
+      __syncwarp();
+      if (__all_sync(0xffffffffu, done)) break;
+    }
+  }
+  cp_async_wait<0>();
+  __syncwarp();
+  if (live && nc > 0) {
+    for (int b = g; b < B.NB; b += SCHED_G) {
+      const int bi = x.at(B.NB, b);
+      const float4 p = pos[ml_col(b, wq)];
+      const float2 q = rot[ml_col(b, wq)];
+      float4 op = B.b_pos[bi];
+      float4 rr = B.b_rot[bi];
+      op.x = p.x; op.y = p.y; op.z = p.z;
+      rr.x = q.x; rr.y = q.y;
+      B.b_pos[bi] = op;
+      B.b_rot[bi] = rr;
+    }
+    for (int i = g; i < nisl; i += SCHED_G)
+      if (tab[ml_col(i, wq)] == ML_SOLVED) B.isl_flags[x.at(B.NB, i)] |= 1;
+  }
+}
+
 }  // namespace b2g

@@ -370,6 +370,7 @@ struct SerialAK {
     ws[WS_ST_ISL_CONTACTS] = nc;
     ws[WS_TOPO_DIRTY] = dirty_next ? 1 : 0;
     ws[WS_ISL_VALID] = 1;
+    ws[WS_SCHED_ROUNDS] = -1;  // no level schedule from this path: the solver stages keep list order
   }
 };
 

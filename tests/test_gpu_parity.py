@@ -129,6 +129,23 @@ def test_batch_replicas_shared_memory_solver(name, steps, ctx):
     wg.close()
 
 
+@pytest.mark.parametrize("solver", ["lane", "generic"])
+@pytest.mark.parametrize("name,steps", [("mixed300", 200), ("variety", 300)])
+def test_alternative_solver_kernels(name, steps, solver, ctx):
+    """The one-lane-per-world shared-memory kernels and the generic global-memory stages stay available
+    (worlds too large for the level-scheduled kernels): same bits as the oracle."""
+    from box2d_rs_b200 import scenes
+    wo, wg, _ = _pair(name, ctx)
+    batch = wg.batch(34, solver=solver)
+    for i in range(steps):
+        batch.step(scenes.DT, 8, 3)
+        wo.step(scenes.DT, 8, 3)
+    bad = parity.compare_snapshots(wo.snapshot(), batch.download_world(33)) + parity.compare_stats(wo.get_stats(), batch.stats()[33])
+    assert bad == [], bad[:6]
+    batch.close()
+    wg.close()
+
+
 def test_full_size_batch_properties(ctx):
     """BASELINE config 3 at full size (4096 Pyramid worlds): size-independent properties — replicas stay
     bit-identical to each other and to the oracle; a world pushed by an external force diverges alone."""
