@@ -387,28 +387,34 @@ __global__ void __launch_bounds__(32) velocity_ml_kernel(const Batch B, const St
   float4* rl = ring + lane;
   const int sweeps = 1 + sp.velocity_iterations;
   const int total = sweeps * rm;
-  // fetch pipeline: position p = sweep * rm + round; its record lands in ring stage p % ML_RING
-  int fr = 0, fpos = 0;
-  auto fetch = [&]() {
-    if (fpos < total) {
-      const int k = ml_item(sched_w, rounds_w, nc, fr, g);
-      if (k >= 0) {
-        float4* dst = rl + ((fpos & (ML_RING - 1)) * VC_Q) * 32;
-        const float4* s = src + (size_t)k * VC_Q * 32;
+  // Item queue: the schedule entry of round r + ML_RING is read from global memory while round r is
+  // solved, so neither the solve (needs item r) nor the record fetch (needs item r + ML_RING - 1) ever
+  // waits for it.  kq[i] = island contact of position pos + i.
+  int kq[ML_RING + 1];
+  int qr = 0;  // round of the next schedule entry to read
+  auto next_item = [&](int at_pos) {
+    const int k = at_pos < total ? ml_item(sched_w, rounds_w, nc, qr, g) : -1;
+    if (++qr == rm) qr = 0;
+    return k;
+  };
 #pragma unroll
-        for (int q = 0; q < VC_Q; ++q) cp_async16(dst + q * 32, s + q * 32);
-      }
-      if (++fr == rm) fr = 0;
+  for (int i = 0; i <= ML_RING; ++i) kq[i] = next_item(i);
+  // record fetch: position p lands in ring stage p % ML_RING
+  auto fetch = [&](int at_pos, int k) {
+    if (k >= 0) {
+      float4* dst = rl + ((at_pos & (ML_RING - 1)) * VC_Q) * 32;
+      const float4* s = src + (size_t)k * VC_Q * 32;
+#pragma unroll
+      for (int q = 0; q < VC_Q; ++q) cp_async16(dst + q * 32, s + q * 32);
     }
-    ++fpos;
     cp_async_commit();
   };
 #pragma unroll
-  for (int p = 0; p < ML_RING - 1; ++p) fetch();
-  int r = 0, sweep = 0;
+  for (int p = 0; p < ML_RING - 1; ++p) fetch(p, kq[p]);
+  int sweep = 0, r = 0;
   for (int pos = 0; pos < total; ++pos) {
     cp_async_wait<ML_RING - 2>();
-    const int k = ml_item(sched_w, rounds_w, nc, r, g);
+    const int k = kq[0];
     const bool act = k >= 0 && (sweep > 0 || warm);
     VcRegs c;
     float4 va, vb;
@@ -417,7 +423,10 @@ __global__ void __launch_bounds__(32) velocity_ml_kernel(const Batch B, const St
       va = vel[ml_col(c.ba, wq)];
       vb = vel[ml_col(c.bb, wq)];
     }
-    fetch();  // stage (pos - 1) % RING is free: refill it with position pos + RING - 1
+    fetch(pos + ML_RING - 1, kq[ML_RING - 1]);  // stage (pos - 1) % RING is free again
+#pragma unroll
+    for (int i = 0; i < ML_RING; ++i) kq[i] = kq[i + 1];
+    kq[ML_RING] = next_item(pos + ML_RING + 1);
     if (act && c.cnt > 0) {
       VelState s;
       s.v_a = v2(va.x, va.y); s.w_a = va.z;
@@ -482,28 +491,31 @@ __global__ void __launch_bounds__(32) position_ml_kernel(const Batch B, const St
   const float4* src = B.pc + (size_t)wb * B.NC * PC_Q * 32 + wl;
   float4* rl = ring + lane;
   const int total = sp.position_iterations * rm;
-  int fr = 0, fpos = 0;
-  auto fetch = [&]() {
-    if (fpos < total) {
-      const int k = ml_item(sched_w, rounds_w, nc, fr, g);
-      if (k >= 0) {
-        float4* dst = rl + ((fpos & (ML_RING - 1)) * PC_Q) * 32;
-        const float4* s = src + (size_t)k * PC_Q * 32;
+  int kq[ML_RING + 1];  // item queue, see velocity_ml_kernel
+  int qr = 0;
+  auto next_item = [&](int at_pos) {
+    const int k = at_pos < total ? ml_item(sched_w, rounds_w, nc, qr, g) : -1;
+    if (++qr == rm) qr = 0;
+    return k;
+  };
 #pragma unroll
-        for (int q = 0; q < PC_Q; ++q) cp_async16(dst + q * 32, s + q * 32);
-      }
-      if (++fr == rm) fr = 0;
+  for (int i = 0; i <= ML_RING; ++i) kq[i] = next_item(i);
+  auto fetch = [&](int at_pos, int k) {
+    if (k >= 0) {
+      float4* dst = rl + ((at_pos & (ML_RING - 1)) * PC_Q) * 32;
+      const float4* s = src + (size_t)k * PC_Q * 32;
+#pragma unroll
+      for (int q = 0; q < PC_Q; ++q) cp_async16(dst + q * 32, s + q * 32);
     }
-    ++fpos;
     cp_async_commit();
   };
 #pragma unroll
-  for (int p = 0; p < ML_RING - 1; ++p) fetch();
+  for (int p = 0; p < ML_RING - 1; ++p) fetch(p, kq[p]);
   int r = 0;
   bool done = !live || nc == 0;
   for (int p = 0; p < total; ++p) {
     cp_async_wait<ML_RING - 2>();
-    const int k = ml_item(sched_w, rounds_w, nc, r, g);
+    const int k = kq[0];
     const bool act = k >= 0 && !done;
     PcRegs c;
     float4 pa, pb;
@@ -515,7 +527,10 @@ __global__ void __launch_bounds__(32) position_ml_kernel(const Batch B, const St
       pa = pos[ml_col(c.ba, wq)]; pb = pos[ml_col(c.bb, wq)];
       qa = rot[ml_col(c.ba, wq)]; qb = rot[ml_col(c.bb, wq)];
     }
-    fetch();
+    fetch(p + ML_RING - 1, kq[ML_RING - 1]);
+#pragma unroll
+    for (int i = 0; i < ML_RING; ++i) kq[i] = kq[i + 1];
+    kq[ML_RING] = next_item(p + ML_RING + 1);
     if (solve) {
       PosState s;
       s.c_a = v2(pa.x, pa.y); s.a_a = pa.z; s.q_a.s = qa.x; s.q_a.c = qa.y;
