@@ -23,6 +23,10 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src)
   unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src) : "memory");
 }
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"(s), "l"(gmem_src) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
@@ -332,7 +336,9 @@ __global__ void __launch_bounds__(32) position_smem_kernel(const Batch B, const 
 
 
 // ==========================================================================================
-// Level-scheduled Gauss-Seidel kernels: SCHED_G lanes cooperate on one world.
+// Level-scheduled Gauss-Seidel: SCHED_G lanes cooperate on one world (used for the position stage; the
+// velocity stage measured faster in the one-lane-per-world form above, whose register forwarding
+// removes every shared-memory round trip from the chain — see profiles/).
 //
 // The island kernel packs each world's island contacts into rounds of at most SCHED_G constraints that
 // share no movable body (b2g_island_smem.cuh).  Constraints of one round commute exactly, so the G
@@ -346,8 +352,7 @@ __global__ void __launch_bounds__(32) position_smem_kernel(const Batch B, const 
 constexpr int ML_WPC = 32 / SCHED_G;  // worlds per CTA
 constexpr int ML_RING = 4;
 
-inline size_t velocity_ml_smem_bytes(int NB) { return (size_t)NB * ML_WPC * 16 + (size_t)ML_RING * VC_Q * 32 * 16; }
-inline size_t position_ml_smem_bytes(int NB) { return (size_t)NB * ML_WPC * (16 + 8 + 4) + (size_t)ML_RING * PC_Q * 32 * 16; }
+inline size_t position_ml_smem_bytes(int NB) { return (size_t)NB * ML_WPC * (16 + 8 + 4) + (size_t)ML_RING * PC_Q * 32 * 16 + 8 * 32 * 4; }
 
 // [body][world] rows: the lanes of one slot g read one contiguous row segment each, conflict-free
 __device__ __forceinline__ int ml_col(int body, int wq) { return body * ML_WPC + wq; }
@@ -356,98 +361,6 @@ __device__ __forceinline__ int ml_col(int body, int wq) { return body * ML_WPC +
 __device__ __forceinline__ int ml_item(const int* sched_w, int rounds, int nc, int r, int g) {
   if (rounds < 0) return (g == 0 && r < nc) ? r : -1;  // no schedule: list order on lane 0
   return r < rounds ? sched_w[(size_t)(r * SCHED_G + g) * 32] : -1;
-}
-
-__global__ void __launch_bounds__(32) velocity_ml_kernel(const Batch B, const StepParams sp) {
-  extern __shared__ float4 smem4[];
-  float4* ring = smem4;                          // [ML_RING][VC_Q][32] one private column per lane
-  float4* vel = smem4 + ML_RING * VC_Q * 32;     // [NB][ML_WPC] swizzled
-  const int lane = threadIdx.x;
-  const int g = lane / ML_WPC, wq = lane % ML_WPC;
-  const int wb = blockIdx.x / SCHED_G;
-  const int wl = (blockIdx.x % SCHED_G) * ML_WPC + wq;
-  const int w = wb * 32 + wl;
-  const bool live = w < B.n_worlds;
-  WIdx x;
-  x.wb = wb; x.wl = wl; x.LB = 32;
-  Ws ws = ws_of(B, x);
-  const int nc = live ? ws[WS_ISL_CONTACTS] : 0;
-  const int rounds_w = live ? ws[WS_SCHED_ROUNDS] : 0;
-  const int wflags = live ? ws[WS_FLAGS] : 0;
-  const bool warm = (wflags & B2GPU_WORLD_WARM_STARTING) != 0;
-  const bool block = (wflags & B2GPU_WORLD_BLOCK_SOLVE) != 0;
-  int rlen = nc == 0 ? 0 : (rounds_w < 0 ? (nc < SCHED_MIN_ROUNDS ? SCHED_MIN_ROUNDS : nc) : rounds_w);
-  const int rm = __reduce_max_sync(0xffffffffu, rlen);
-  if (rm == 0) return;
-  if (live)
-    for (int b = g; b < B.NB; b += SCHED_G) vel[ml_col(b, wq)] = B.b_vel[x.at(B.NB, b)];
-  __syncwarp();
-  const int* sched_w = B.sched + (size_t)wb * B.NC * SCHED_G * 32 + wl;
-  const float4* src = B.vc + (size_t)wb * B.NC * VC_Q * 32 + wl;
-  float4* rl = ring + lane;
-  const int sweeps = 1 + sp.velocity_iterations;
-  const int total = sweeps * rm;
-  // Item queue: the schedule entry of round r + ML_RING is read from global memory while round r is
-  // solved, so neither the solve (needs item r) nor the record fetch (needs item r + ML_RING - 1) ever
-  // waits for it.  kq[i] = island contact of position pos + i.
-  int kq[ML_RING + 1];
-  int qr = 0;  // round of the next schedule entry to read
-  auto next_item = [&](int at_pos) {
-    const int k = at_pos < total ? ml_item(sched_w, rounds_w, nc, qr, g) : -1;
-    if (++qr == rm) qr = 0;
-    return k;
-  };
-#pragma unroll
-  for (int i = 0; i <= ML_RING; ++i) kq[i] = next_item(i);
-  // record fetch: position p lands in ring stage p % ML_RING
-  auto fetch = [&](int at_pos, int k) {
-    if (k >= 0) {
-      float4* dst = rl + ((at_pos & (ML_RING - 1)) * VC_Q) * 32;
-      const float4* s = src + (size_t)k * VC_Q * 32;
-#pragma unroll
-      for (int q = 0; q < VC_Q; ++q) cp_async16(dst + q * 32, s + q * 32);
-    }
-    cp_async_commit();
-  };
-#pragma unroll
-  for (int p = 0; p < ML_RING - 1; ++p) fetch(p, kq[p]);
-  int sweep = 0, r = 0;
-  for (int pos = 0; pos < total; ++pos) {
-    cp_async_wait<ML_RING - 2>();
-    const int k = kq[0];
-    const bool act = k >= 0 && (sweep > 0 || warm);
-    VcRegs c;
-    float4 va, vb;
-    if (act) {
-      c = vc_load(rl + ((pos & (ML_RING - 1)) * VC_Q) * 32);
-      va = vel[ml_col(c.ba, wq)];
-      vb = vel[ml_col(c.bb, wq)];
-    }
-    fetch(pos + ML_RING - 1, kq[ML_RING - 1]);  // stage (pos - 1) % RING is free again
-#pragma unroll
-    for (int i = 0; i < ML_RING; ++i) kq[i] = kq[i + 1];
-    kq[ML_RING] = next_item(pos + ML_RING + 1);
-    if (act && c.cnt > 0) {
-      VelState s;
-      s.v_a = v2(va.x, va.y); s.w_a = va.z;
-      s.v_b = v2(vb.x, vb.y); s.w_b = vb.z;
-      if (sweep == 0) {
-        warm_start_one(s, c.q0, c.q1, c.q2, c.q6, c.q7, c.cnt);
-      } else {
-        solve_velocity_one(s, c.q0, c.q1, c.q2, c.q3, c.q4, c.q5, c.q6, c.q7, c.cnt, block);
-        B.vc[vc_at(B, x, k, 6)] = c.q6;
-      }
-      // immovable bodies (zero inverse mass and inertia) can be shared by the constraints of a round: never written
-      if (c.q7.x != 0.0f || c.q7.y != 0.0f) vel[ml_col(c.ba, wq)] = make_float4(s.v_a.x, s.v_a.y, s.w_a, 0.0f);
-      if (c.q7.z != 0.0f || c.q7.w != 0.0f) vel[ml_col(c.bb, wq)] = make_float4(s.v_b.x, s.v_b.y, s.w_b, 0.0f);
-    }
-    __syncwarp();
-    if (++r == rm) { r = 0; ++sweep; }
-  }
-  cp_async_wait<0>();
-  __syncwarp();
-  if (live)
-    for (int b = g; b < B.NB; b += SCHED_G) B.b_vel[x.at(B.NB, b)] = vel[ml_col(b, wq)];
 }
 
 // Position iterations, level-scheduled.  Per-island state of a sweep lives in a shared-memory table:
@@ -491,15 +404,21 @@ __global__ void __launch_bounds__(32) position_ml_kernel(const Batch B, const St
   const float4* src = B.pc + (size_t)wb * B.NC * PC_Q * 32 + wl;
   float4* rl = ring + lane;
   const int total = sp.position_iterations * rm;
-  int kq[ML_RING + 1];  // item queue, see velocity_ml_kernel
-  int qr = 0;
-  auto next_item = [&](int at_pos) {
-    const int k = at_pos < total ? ml_item(sched_w, rounds_w, nc, qr, g) : -1;
-    if (++qr == rm) qr = 0;
-    return k;
+  // Schedule entries travel through a small shared-memory queue filled by 4-byte cp.async copies that
+  // ride in the same commit groups as the record fetches, ML_AHEAD rounds before they are needed, so no
+  // register ever waits on a global load of the schedule (the record stream evicts it from L2).
+  constexpr int ML_AHEAD = 4, ML_Q = 8;
+  int* iq = (int*)(tab + (size_t)B.NB * ML_WPC) + lane;  // [ML_Q][32]
+  const bool have_sched = rounds_w >= 0;
+  auto item_now = [&](int at_pos, int rr) -> int {  // entry of position at_pos (round rr) once it has landed
+    if (at_pos >= total) return -1;
+    if (!have_sched) return (g == 0 && rr < nc) ? rr : -1;
+    return rr < rounds_w ? iq[(at_pos & (ML_Q - 1)) * 32] : -1;
   };
-#pragma unroll
-  for (int i = 0; i <= ML_RING; ++i) kq[i] = next_item(i);
+  auto item_request = [&](int at_pos, int rr) {       // start the copy of the entry of position at_pos
+    if (have_sched && at_pos < total && rr < rounds_w)
+      cp_async4(&iq[(at_pos & (ML_Q - 1)) * 32], sched_w + (size_t)(rr * SCHED_G + g) * 32);
+  };
   auto fetch = [&](int at_pos, int k) {
     if (k >= 0) {
       float4* dst = rl + ((at_pos & (ML_RING - 1)) * PC_Q) * 32;
@@ -507,30 +426,47 @@ __global__ void __launch_bounds__(32) position_ml_kernel(const Batch B, const St
 #pragma unroll
       for (int q = 0; q < PC_Q; ++q) cp_async16(dst + q * 32, s + q * 32);
     }
-    cp_async_commit();
   };
-#pragma unroll
-  for (int p = 0; p < ML_RING - 1; ++p) fetch(p, kq[p]);
+  // prologue: entries of positions 0 .. RING-2+AHEAD, then the records of positions 0 .. RING-2
+  int rq = 0;  // round of the next entry to request
+  for (int i = 0; i < ML_RING - 1 + ML_AHEAD; ++i) { item_request(i, rq); if (++rq == rm) rq = 0; }
+  cp_async_commit();
+  cp_async_wait<0>();
+  int rf = 0;  // round of the next record to fetch
+  for (int i = 0; i < ML_RING - 1; ++i) { fetch(i, item_now(i, rf)); cp_async_commit(); if (++rf == rm) rf = 0; }
   int r = 0;
   bool done = !live || nc == 0;
+  // software pipeline: the record of the next round is read into registers while this round is solved
+  cp_async_wait<ML_RING - 2>();
+  PcRegs cn;
+  int kn = item_now(0, 0);
+  if (kn >= 0) cn = pc_load(rl);
   for (int p = 0; p < total; ++p) {
-    cp_async_wait<ML_RING - 2>();
-    const int k = kq[0];
+    const int k = kn;
+    PcRegs c = cn;
     const bool act = k >= 0 && !done;
-    PcRegs c;
     float4 pa, pb;
     float2 qa, qb;
     bool solve = false;
     if (act) {
-      c = pc_load(rl + ((p & (ML_RING - 1)) * PC_Q) * 32);
       solve = tab[ml_col(c.isl, wq)] != ML_SOLVED;
       pa = pos[ml_col(c.ba, wq)]; pb = pos[ml_col(c.bb, wq)];
       qa = rot[ml_col(c.ba, wq)]; qb = rot[ml_col(c.bb, wq)];
     }
-    fetch(p + ML_RING - 1, kq[ML_RING - 1]);
-#pragma unroll
-    for (int i = 0; i < ML_RING; ++i) kq[i] = kq[i + 1];
-    kq[ML_RING] = next_item(p + ML_RING + 1);
+    // refill: record of position p + RING - 1 (its entry landed AHEAD rounds ago), entry of position p + RING - 1 + AHEAD
+    fetch(p + ML_RING - 1, item_now(p + ML_RING - 1, rf));
+    if (++rf == rm) rf = 0;
+    item_request(p + ML_RING - 1 + ML_AHEAD, rq);
+    if (++rq == rm) rq = 0;
+    cp_async_commit();
+    // next round's record into registers (group of position p + 1 is complete when <= RING-2 groups are pending)
+    cp_async_wait<ML_RING - 2>();
+    {
+      int rn = r + 1;
+      if (rn == rm) rn = 0;
+      kn = item_now(p + 1, rn);
+      if (kn >= 0) cn = pc_load(rl + (((p + 1) & (ML_RING - 1)) * PC_Q) * 32);
+    }
     if (solve) {
       PosState s;
       s.c_a = v2(pa.x, pa.y); s.a_a = pa.z; s.q_a.s = qa.x; s.q_a.c = qa.y;
