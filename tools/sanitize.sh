@@ -20,5 +20,5 @@ for name, build, g in (("pyramid", scenes.pyramid, (0.0, -10.0)), ("variety", sc
 PY
 for tool in memcheck racecheck; do
   echo "==== compute-sanitizer --tool $tool"
-  timeout 900 compute-sanitizer --tool $tool --print-limit 20 python /tmp/b2g_sanitize_case.py 2>&1 | tail -25
+  timeout 900 compute-sanitizer --tool $tool --print-limit 200 python /tmp/b2g_sanitize_case.py 2>&1 | tail -60
 done
