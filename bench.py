@@ -140,7 +140,7 @@ def run_ours(args, rank, world_size, local_rank):
     wg = world.B2world((0.0, -10.0), ctx=ctx)
     scenes.pyramid(wg)
     wg.set_allow_sleeping(False)
-    batch = wg.batch(n_worlds, max_contacts=args.max_contacts)
+    batch = wg.batch(n_worlds, max_contacts=args.max_contacts, solver=args.solver)
     batch.set_linear_velocity(211, perturbation(n_worlds, rank))
     batch.step(scenes.DT, scenes.VEL_ITERS, scenes.POS_ITERS, PREROLL)
     ctx.sync()
@@ -308,6 +308,7 @@ def main():
     ap.add_argument("--worlds", type=int, default=4096, help="worlds per GPU")
     ap.add_argument("--max-contacts", type=int, default=1024)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--solver", default=None, help="diagnostic: lane | generic | levels (default: best measured)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

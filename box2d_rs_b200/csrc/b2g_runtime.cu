@@ -513,6 +513,8 @@ int batch_create(Ctx* ctx, const b2gpu_snapshot* proto, int n_worlds, const b2gp
     const size_t need_ml = position_ml_smem_bytes(B.NB);
     if (bh->smem_solver && need_ml <= (size_t)max_optin && !(caps && caps->reserved[1] == 2)) {
       CU(cudaFuncSetAttribute(position_ml_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)position_ml_smem_bytes(B.NB)));
+      CU(cudaFuncSetAttribute(velocity_ml_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)velocity_ml_smem_bytes(B.NB)));
+      bh->ml_velocity = caps && caps->reserved[1] == 3;
       bh->ml_solver = true;
     }
     bh->island_layout = island_smem_layout(B.NB, B.NF, (size_t)max_optin - 1024);
@@ -615,7 +617,12 @@ int batch_step(BatchHost* bh, float dt, int vi, int pi, int steps) {
       { IntegrateK k = {B, sp}; RC(launch(ctx, k, W * B.NIB, 128, STAGE_INTEGRATE)); }
       { SolverInitK k = {B, sp}; RC(launch(ctx, k, W * B.NC, 128, STAGE_SOLVER_INIT)); }
 #if !defined(B2G_HOSTSIM)
-      if (bh->smem_solver) {
+      if (bh->ml_solver && bh->ml_velocity) {
+        LaunchScope ls = {ctx, STAGE_VELOCITY};
+        RC(ls.begin());
+        velocity_ml_kernel<<<B.n_wblocks * SCHED_G, 32, velocity_ml_smem_bytes(B.NB), (cudaStream_t)ctx->stream>>>(B, sp);
+        RC(ls.end());
+      } else if (bh->smem_solver) {
         LaunchScope ls = {ctx, STAGE_VELOCITY};
         RC(ls.begin());
         velocity_smem_kernel<<<B.n_wblocks, 32, velocity_smem_bytes(B.NB), (cudaStream_t)ctx->stream>>>(B, sp);

@@ -524,4 +524,113 @@ __global__ void __launch_bounds__(32) position_ml_kernel(const Batch B, const St
   }
 }
 
+// Warm start + velocity iterations, level-scheduled: the same round structure and pipeline as
+// position_ml_kernel (schedule queue in shared memory, next round's record read into registers while
+// the current round is solved).
+inline size_t velocity_ml_smem_bytes(int NB) { return (size_t)NB * ML_WPC * 16 + (size_t)ML_RING * VC_Q * 32 * 16 + 8 * 32 * 4; }
+
+__global__ void __launch_bounds__(32) velocity_ml_kernel(const Batch B, const StepParams sp) {
+  extern __shared__ float4 smem4[];
+  float4* ring = smem4;                          // [ML_RING][VC_Q][32] one private column per lane
+  float4* vel = smem4 + ML_RING * VC_Q * 32;     // [NB][ML_WPC]
+  const int lane = threadIdx.x;
+  const int g = lane / ML_WPC, wq = lane % ML_WPC;
+  const int wb = blockIdx.x / SCHED_G;
+  const int wl = (blockIdx.x % SCHED_G) * ML_WPC + wq;
+  const int w = wb * 32 + wl;
+  const bool live = w < B.n_worlds;
+  WIdx x;
+  x.wb = wb; x.wl = wl; x.LB = 32;
+  Ws ws = ws_of(B, x);
+  const int nc = live ? ws[WS_ISL_CONTACTS] : 0;
+  const int rounds_w = live ? ws[WS_SCHED_ROUNDS] : 0;
+  const int wflags = live ? ws[WS_FLAGS] : 0;
+  const bool warm = (wflags & B2GPU_WORLD_WARM_STARTING) != 0;
+  const bool block = (wflags & B2GPU_WORLD_BLOCK_SOLVE) != 0;
+  int rlen = nc == 0 ? 0 : (rounds_w < 0 ? (nc < SCHED_MIN_ROUNDS ? SCHED_MIN_ROUNDS : nc) : rounds_w);
+  const int rm = __reduce_max_sync(0xffffffffu, rlen);
+  if (rm == 0) return;
+  if (live)
+    for (int b = g; b < B.NB; b += SCHED_G) vel[ml_col(b, wq)] = B.b_vel[x.at(B.NB, b)];
+  __syncwarp();
+  const int* sched_w = B.sched + (size_t)wb * B.NC * SCHED_G * 32 + wl;
+  const float4* src = B.vc + (size_t)wb * B.NC * VC_Q * 32 + wl;
+  float4* q6_out = B.vc + (size_t)wb * B.NC * VC_Q * 32 + 6 * 32 + wl;
+  float4* rl = ring + lane;
+  const int sweeps = 1 + sp.velocity_iterations;  // sweep 0 = warm start
+  const int total = sweeps * rm;
+  constexpr int ML_AHEAD = 4, ML_Q = 8;
+  int* iq = (int*)(vel + (size_t)B.NB * ML_WPC) + lane;  // [ML_Q][32] schedule queue
+  const bool have_sched = rounds_w >= 0;
+  auto item_now = [&](int at_pos, int rr) -> int {
+    if (at_pos >= total) return -1;
+    if (!have_sched) return (g == 0 && rr < nc) ? rr : -1;
+    return rr < rounds_w ? iq[(at_pos & (ML_Q - 1)) * 32] : -1;
+  };
+  auto item_request = [&](int at_pos, int rr) {
+    if (have_sched && at_pos < total && rr < rounds_w)
+      cp_async4(&iq[(at_pos & (ML_Q - 1)) * 32], sched_w + (size_t)(rr * SCHED_G + g) * 32);
+  };
+  auto fetch = [&](int at_pos, int k) {
+    if (k >= 0) {
+      float4* dst = rl + ((at_pos & (ML_RING - 1)) * VC_Q) * 32;
+      const float4* s = src + (size_t)k * VC_Q * 32;
+#pragma unroll
+      for (int q = 0; q < VC_Q; ++q) cp_async16(dst + q * 32, s + q * 32);
+    }
+  };
+  int rq = 0, rf = 0;
+  for (int i = 0; i < ML_RING - 1 + ML_AHEAD; ++i) { item_request(i, rq); if (++rq == rm) rq = 0; }
+  cp_async_commit();
+  cp_async_wait<0>();
+  for (int i = 0; i < ML_RING - 1; ++i) { fetch(i, item_now(i, rf)); cp_async_commit(); if (++rf == rm) rf = 0; }
+  cp_async_wait<ML_RING - 2>();
+  VcRegs cn;
+  int kn = item_now(0, 0);
+  if (kn >= 0) cn = vc_load(rl);
+  int r = 0, sweep = 0;
+  for (int pos = 0; pos < total; ++pos) {
+    const int k = kn;
+    VcRegs c = cn;
+    const bool act = k >= 0 && (sweep > 0 || warm) && c.cnt > 0;
+    float4 va, vb;
+    if (act) {
+      va = vel[ml_col(c.ba, wq)];
+      vb = vel[ml_col(c.bb, wq)];
+    }
+    fetch(pos + ML_RING - 1, item_now(pos + ML_RING - 1, rf));
+    if (++rf == rm) rf = 0;
+    item_request(pos + ML_RING - 1 + ML_AHEAD, rq);
+    if (++rq == rm) rq = 0;
+    cp_async_commit();
+    cp_async_wait<ML_RING - 2>();
+    {
+      int rn = r + 1;
+      if (rn == rm) rn = 0;
+      kn = item_now(pos + 1, rn);
+      if (kn >= 0) cn = vc_load(rl + (((pos + 1) & (ML_RING - 1)) * VC_Q) * 32);
+    }
+    if (act) {
+      VelState s;
+      s.v_a = v2(va.x, va.y); s.w_a = va.z;
+      s.v_b = v2(vb.x, vb.y); s.w_b = vb.z;
+      if (sweep == 0) {
+        warm_start_one(s, c.q0, c.q1, c.q2, c.q6, c.q7, c.cnt);
+      } else {
+        solve_velocity_one(s, c.q0, c.q1, c.q2, c.q3, c.q4, c.q5, c.q6, c.q7, c.cnt, block);
+        q6_out[(size_t)k * VC_Q * 32] = c.q6;
+      }
+      // immovable bodies (zero inverse mass and inertia) can be shared by the constraints of a round: never written
+      if (c.q7.x != 0.0f || c.q7.y != 0.0f) vel[ml_col(c.ba, wq)] = make_float4(s.v_a.x, s.v_a.y, s.w_a, 0.0f);
+      if (c.q7.z != 0.0f || c.q7.w != 0.0f) vel[ml_col(c.bb, wq)] = make_float4(s.v_b.x, s.v_b.y, s.w_b, 0.0f);
+    }
+    __syncwarp();
+    if (++r == rm) { r = 0; ++sweep; }
+  }
+  cp_async_wait<0>();
+  __syncwarp();
+  if (live)
+    for (int b = g; b < B.NB; b += SCHED_G) B.b_vel[x.at(B.NB, b)] = vel[ml_col(b, wq)];
+}
+
 }  // namespace b2g
