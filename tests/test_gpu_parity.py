@@ -220,3 +220,25 @@ def test_world_flags(warm, block, sleep, ctx):
             bad = parity.compare_snapshots(wo.snapshot(), wg.snapshot()) + parity.compare_stats(wo.get_stats(), wg.get_stats())
             assert bad == [], "step %d: %s" % (i, bad[:6])
     wg.close()
+
+
+@pytest.mark.parametrize("allow_sleep", [True, False])
+def test_config1_pyramid_1000_steps(allow_sleep, ctx):
+    """BASELINE configs[0]: testbed Pyramid, 1000 steps, dt = 1/60, 8/3 iterations, continuous off —
+    free-running in a 64-world batch, compared with the oracle every 100 steps, bit for bit."""
+    from box2d_rs_b200 import scenes
+    wo, wg, _ = _pair("pyramid", ctx)
+    wo.set_allow_sleeping(allow_sleep)
+    wg.set_allow_sleeping(allow_sleep)
+    batch = wg.batch(64, max_contacts=1024)
+    for i in range(10):
+        batch.step(scenes.DT, 8, 3, 100)
+        for _ in range(100):
+            wo.step(scenes.DT, 8, 3)
+        bad = parity.compare_snapshots(wo.snapshot(), batch.download_world(63)) + \
+            parity.compare_stats(wo.get_stats(), batch.stats()[63])
+        assert bad == [], "step %d: %s" % (100 * (i + 1), bad[:6])
+    state = batch.body_state()
+    assert (state.view(np.uint32) == state[0].view(np.uint32)[None]).all()
+    batch.close()
+    wg.close()
