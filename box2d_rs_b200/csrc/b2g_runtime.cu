@@ -506,7 +506,9 @@ int batch_create(Ctx* ctx, const b2gpu_snapshot* proto, int n_worlds, const b2gp
     CU(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
     const size_t need = std::max(velocity_smem_bytes(B.NB), position_smem_bytes(B.NB));
     if (need <= (size_t)max_optin) {
-      CU(cudaFuncSetAttribute(velocity_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)velocity_smem_bytes(B.NB)));
+      CU(cudaFuncSetAttribute(velocity_smem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)velocity_smem_bytes(B.NB)));
+      CU(cudaFuncSetAttribute(velocity_smem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)velocity_smem_bytes(B.NB)));
+      bh->tma_ring = caps && caps->reserved[1] == 4;
       CU(cudaFuncSetAttribute(position_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)position_smem_bytes(B.NB)));
       bh->smem_solver = true;
     }
@@ -625,7 +627,10 @@ int batch_step(BatchHost* bh, float dt, int vi, int pi, int steps) {
       } else if (bh->smem_solver) {
         LaunchScope ls = {ctx, STAGE_VELOCITY};
         RC(ls.begin());
-        velocity_smem_kernel<<<B.n_wblocks, 32, velocity_smem_bytes(B.NB), (cudaStream_t)ctx->stream>>>(B, sp);
+        if (bh->tma_ring)
+          velocity_smem_kernel<true><<<B.n_wblocks, 32, velocity_smem_bytes(B.NB), (cudaStream_t)ctx->stream>>>(B, sp);
+        else
+          velocity_smem_kernel<false><<<B.n_wblocks, 32, velocity_smem_bytes(B.NB), (cudaStream_t)ctx->stream>>>(B, sp);
         RC(ls.end());
       } else
 #endif

@@ -30,10 +30,36 @@ __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gmem_src) 
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::: "memory"); }
 template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N) : "memory"); }
 
+// TMA 1-D bulk copy (cp.async.bulk, SASS UBLKCP) completing on an mbarrier: one elected lane moves a whole
+// constraint record of the 32-world block (VC_Q rows x 512 B, contiguous in HBM) into a ring stage.
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"((unsigned)__cvta_generic_to_shared(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void* smem_dst, const void* gmem_src, unsigned bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(
+                   (unsigned)__cvta_generic_to_shared(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"((unsigned)__cvta_generic_to_shared(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
+  unsigned done = 0;
+  const unsigned addr = (unsigned)__cvta_generic_to_shared(bar);
+  while (!done) {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(done)
+                 : "r"(addr), "r"(parity)
+                 : "memory");
+  }
+}
+
 constexpr int VEL_RING = 8;  // stages of the velocity constraint ring
 constexpr int POS_RING = 8;
 
-inline size_t velocity_smem_bytes(int NB) { return (size_t)NB * 32 * 16 + (size_t)VEL_RING * VC_Q * 32 * 16; }
+inline size_t velocity_smem_bytes(int NB) { return (size_t)NB * 32 * 16 + (size_t)VEL_RING * VC_Q * 32 * 16 + VEL_RING * 8; }
 inline size_t position_smem_bytes(int NB) { return (size_t)NB * 32 * (16 + 8) + (size_t)POS_RING * PC_Q * 32 * 16; }
 
 struct VcRegs {  // one velocity constraint of one world, in registers
@@ -61,10 +87,12 @@ __device__ __forceinline__ VcRegs vc_load(const float4* st) {
 // the usual case — so after the solve the fresh values are forwarded from registers (two compares
 // and selects instead of a store -> load round trip through shared memory on the dependent chain).
 // ------------------------------------------------------------------------------------------
+template <bool USE_TMA>
 __global__ void __launch_bounds__(32) velocity_smem_kernel(const Batch B, const StepParams sp) {
   extern __shared__ float4 smem4[];
   float4* ring = smem4;                      // [VEL_RING][VC_Q][32]
   float4* vel = smem4 + VEL_RING * VC_Q * 32;  // [NB][32]: v.x v.y w -
+  uint64_t* bars = (uint64_t*)(vel + (size_t)B.NB * 32);  // [VEL_RING] one mbarrier per ring stage (TMA form)
   const int lane = threadIdx.x;
   const int wb = blockIdx.x;
   const int w = wb * 32 + lane;
@@ -122,20 +150,48 @@ __global__ void __launch_bounds__(32) velocity_smem_kernel(const Batch B, const 
     int fk = 0;                 // next constraint index to fetch (wraps at ncm)
     int fpos = 0;               // its flattened position
     const float4* fsrc = src;
+    const float4* fsrc_block = B.vc + (size_t)wb * B.NC * VC_Q * 32;  // the block's records (all 32 lanes)
+    if (USE_TMA) {
+      if (lane == 0)
+        for (int st = 0; st < VEL_RING; ++st) mbar_init(&bars[st], 1);
+      asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory");
+      __syncwarp();
+    }
     auto fetch = [&]() {
       if (fpos < total) {
-        float4* dst = rl + ((fpos & (VEL_RING - 1)) * VC_Q) * 32;
+        if (USE_TMA) {
+          __syncwarp();  // every lane has copied this stage's previous record into registers
+          if (lane == 0) {
+            const int st = fpos & (VEL_RING - 1);
+            // the impulses of this record were last written by ordinary stores of all 32 lanes: order them
+            // before the async-proxy read
+            asm volatile("fence.proxy.async.global;\n" ::: "memory");
+            mbar_expect_tx(&bars[st], VC_Q * 32 * 16);
+            bulk_copy_g2s(ring + (size_t)st * VC_Q * 32, fsrc_block + (size_t)fk * VC_Q * 32, VC_Q * 32 * 16, &bars[st]);
+          }
+        } else {
+          float4* dst = rl + ((fpos & (VEL_RING - 1)) * VC_Q) * 32;
 #pragma unroll
-        for (int q = 0; q < VC_Q; ++q) cp_async16(dst + q * 32, fsrc + q * 32);
-        fsrc += VC_Q * 32;
+          for (int q = 0; q < VC_Q; ++q) cp_async16(dst + q * 32, fsrc + q * 32);
+          fsrc += VC_Q * 32;
+        }
         if (++fk == ncm) { fk = 0; fsrc = src; }
       }
       ++fpos;
-      cp_async_commit();
+      if (!USE_TMA) cp_async_commit();
+    };
+    auto landed = [&](int at_pos, int pending_ok) {  // the record of position at_pos is in its stage
+      if (USE_TMA) {
+        if (at_pos < total) mbar_wait(&bars[at_pos & (VEL_RING - 1)], (unsigned)(at_pos / VEL_RING) & 1u);
+      } else if (pending_ok == VEL_RING - 1) {
+        cp_async_wait<VEL_RING - 1>();
+      } else {
+        cp_async_wait<VEL_RING - 2>();
+      }
     };
 #pragma unroll
     for (int p = 0; p < VEL_RING; ++p) fetch();  // positions 0 .. RING-1 in flight
-    cp_async_wait<VEL_RING - 1>();                 // position 0 landed
+    landed(0, VEL_RING - 1);
     // Two register sets (A, B) alternate as "current" and "next": the loop body handles two positions
     // so that the hand-over between them is pure register renaming.
     VcRegs ca = vc_load(rl), cb;
@@ -147,7 +203,7 @@ __global__ void __launch_bounds__(32) velocity_smem_kernel(const Batch B, const 
       // -- prefetch position pos+1 into registers (its stage landed: at most RING-2 younger groups pending)
       const int kc = k, sc = sweep;
       if (++k == ncm) { k = 0; ++sweep; }
-      cp_async_wait<VEL_RING - 2>();
+      landed(pos + 1, VEL_RING - 2);
       nxt = vc_load(rl + (((pos + 1) & (VEL_RING - 1)) * VC_Q) * 32);
       nact = (pos + 1 < total) && (k < nc) && (sweep > 0 || warm) && nxt.cnt > 0;
       if (!nact) { nxt.ba = 0; nxt.bb = 0; }
