@@ -441,10 +441,12 @@ int batch_create(Ctx* ctx, const b2gpu_snapshot* proto, int n_worlds, const b2gp
   B.NB = n.body_count; B.NF = n.fixture_count; B.NS = n.shape_count; B.NP = n.proxy_count;
   if (B.NB < 1 || B.NP < 0) { set_error("empty world"); delete bh; return B2GPU_E_INVALID; }
   B.NN = std::max(n.node_count, 16);
-  int want_contacts = std::max(n.contact_count * 2, B.NP * 10 + 64);
+  // broadphase stress scenes (AddPair) reach ~30 contacts per body: a single world gets generous room,
+  // batches (thousands of replicas) default to 10 per proxy; b2gpu_caps.max_contacts overrides both
+  int want_contacts = std::max(n.contact_count * 2, B.NP * (n_worlds == 1 ? 40 : 10) + 64);
   if (caps && caps->max_contacts > 0) want_contacts = std::max(caps->max_contacts, n.contact_count);
   B.NC = want_contacts;
-  B.NPAIR = (caps && caps->max_pairs > 0) ? caps->max_pairs : std::max(B.NC, 8 * B.NP + 64);
+  B.NPAIR = 1;  // pairs are handed to add_pair as the tree query reports them: no pair buffer (b2g_step.h update_pairs)
   B.NMOVE = std::max(2 * B.NP, n.move_count) + 16;
   B.NIB = B.NB + B.NC;
   B.NMW = std::max((B.NP + 31) / 32, 1);

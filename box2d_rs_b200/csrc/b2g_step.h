@@ -1069,21 +1069,20 @@ B2G_HD void update_pairs(const Batch& B, const WIdx& x, const Ws& ws, int* b_che
       if (!box_overlap(t.A(id), fat)) continue;
       const int4 l = t.L(id);
       if (l.y == -1) {
-        // b2_broad_phase_query_callback (b2_broad_phase.rs(private):86-111)
+        // b2_broad_phase_query_callback (b2_broad_phase.rs(private):86-111).  The reference appends the
+        // pair to m_pair_buffer and calls add_pair for the whole buffer afterwards; add_pair changes
+        // neither the tree nor the moved flags, so calling it here, in the same order, is equivalent and
+        // needs no pair buffer (whose size is unbounded: every moved proxy re-reports all its overlaps).
         if (id == q) continue;
         if (t.moved[id * t.stride] && id > q) continue;
-        if (np >= B.NPAIR) { ws[WS_STATUS] = B2GPU_E_CAPACITY; continue; }
-        B.pair_buf[x.at(B.NPAIR, np++)] = make_int2(imin(id, q), imax(id, q));
+        ++np;
+        add_pair(B, x, ws, b_chead, c_next, B.node_proxy[imin(id, q)], B.node_proxy[imax(id, q)]);
       } else {
         if (sp_ + 2 > B2G_QUERY_STACK) { ws[WS_STATUS] = B2GPU_E_CAPACITY; continue; }
         stack[sp_++] = l.y;
         stack[sp_++] = l.z;
       }
     }
-  }
-  for (int i = 0; i < np; ++i) {
-    const int2 pr = B.pair_buf[x.at(B.NPAIR, i)];
-    add_pair(B, x, ws, b_chead, c_next, B.node_proxy[pr.x], B.node_proxy[pr.y]);
   }
   for (int i = 0; i < mc; ++i) {
     const int q = B.move_buf[x.at(B.NMOVE, i)];

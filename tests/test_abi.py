@@ -81,3 +81,13 @@ def test_argument_errors_are_codes_not_crashes(built):
     tri = (C.c_float * 4)(0.0, 0.0, 1.0, 0.0)
     assert L.b2gpu_polygon_set(C.byref(s), tri, 2) == abi.E_INVALID  # the reference asserts 3 <= count <= 8
     assert L.b2gpu_world_set_continuous_physics(None, 1) == abi.E_INVALID
+
+
+def test_rust_ffi_lists_every_symbol():
+    """rust/ffi.rs (the extern "C" block a box2d-rs maintainer adds; not buildable here: no Rust toolchain)
+    declares exactly the functions of include/b2gpu.h."""
+    text = open(os.path.join(ROOT, "rust", "ffi.rs")).read()
+    block = text[text.index('extern "C" {'):]
+    block = block[:block.index("\n}\n")]
+    rust = sorted(set(re.findall(r"pub fn (b2gpu_[a-z0-9_]+)\s*\(", block)))
+    assert rust == _declared_symbols()
