@@ -262,19 +262,31 @@ struct DynamicTree {
   }
   // src/b2_dynamic_tree.rs:239-267 — explicit stack, pushes child1 then child2 (child2 popped first)
   template <class F> void query(F&& callback, const AABB& aabb) const {
-    std::vector<int> stack;
-    stack.push_back(root);
-    while (!stack.empty()) {
-      int id = stack.back();
-      stack.pop_back();
+    // B2growableStack<i32, 256>: inline storage, heap only beyond 256 entries (src/b2_growable_stack.rs)
+    int inline_stack[256];
+    std::vector<int> heap_stack;
+    int* stack = inline_stack;
+    int capacity = 256, count = 0;
+    auto push = [&](int v) {
+      if (count == capacity) {
+        heap_stack.assign(stack, stack + count);
+        heap_stack.resize((size_t)capacity * 2);
+        stack = heap_stack.data();
+        capacity *= 2;
+      }
+      stack[count++] = v;
+    };
+    push(root);
+    while (count > 0) {
+      int id = stack[--count];
       if (id == NULL_NODE) continue;
       const TreeNode& node = nodes[id];
       if (b2_test_overlap(node.aabb, aabb)) {
         if (node.is_leaf()) {
           if (!callback(id)) return;
         } else {
-          stack.push_back(node.child1);
-          stack.push_back(node.child2);
+          push(node.child1);
+          push(node.child2);
         }
       }
     }
