@@ -31,7 +31,7 @@ namespace b2g {
 enum {
   WS_GRAVITY_X = 0, WS_GRAVITY_Y, WS_INV_DT0, WS_FLAGS,
   WS_TREE_ROOT, WS_TREE_FREE, WS_TREE_COUNT, WS_TREE_CAP, WS_TREE_INSERTIONS, WS_PROXY_COUNT,
-  WS_CONTACT_COUNT, WS_MOVE_COUNT, WS_PAIR_COUNT,
+  WS_CONTACT_COUNT, WS_MOVE_COUNT,
   WS_ISL_COUNT, WS_ISL_BODIES, WS_ISL_CONTACTS,
   WS_EV_WAKE,      // collide woke a sleeping body (needs the ordered fix-up pass)
   WS_EV_DESTROY,   // contacts flagged for destruction this step
@@ -55,7 +55,7 @@ struct Batch {
   int n_worlds, LB, lb_shift, n_wblocks;
   int NB, NF, NS, NP;        // bodies, fixtures, child shapes, proxies (exact, shared topology)
   int NN;                    // tree node pool (physical capacity)
-  int NC, NPAIR, NMOVE;      // capacities: contacts, pair buffer, move buffer
+  int NC, NMOVE;             // capacities: contacts, move buffer
   int NIB;                   // island body list capacity (NB + NC: static bodies repeat per island)
   int NMW;                   // words of the per-world moved-proxy bitmap ((NP + 31) / 32)
   // ---- shared topology
@@ -80,7 +80,6 @@ struct Batch {
   int* n_moved;
   float4* p_aabb;            // proxy tight AABB
   int* move_buf;
-  int2* pair_buf;
   int4* c_fix;               // fixture_a fixture_b index_a index_b
   int* c_flags;
   float4* c_mat;             // friction restitution threshold tangent_speed

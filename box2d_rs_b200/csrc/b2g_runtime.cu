@@ -446,7 +446,6 @@ int batch_create(Ctx* ctx, const b2gpu_snapshot* proto, int n_worlds, const b2gp
   int want_contacts = std::max(n.contact_count * 2, B.NP * (n_worlds == 1 ? 40 : 10) + 64);
   if (caps && caps->max_contacts > 0) want_contacts = std::max(caps->max_contacts, n.contact_count);
   B.NC = want_contacts;
-  B.NPAIR = 1;  // pairs are handed to add_pair as the tree query reports them: no pair buffer (b2g_step.h update_pairs)
   B.NMOVE = std::max(2 * B.NP, n.move_count) + 16;
   B.NIB = B.NB + B.NC;
   B.NMW = std::max((B.NP + 31) / 32, 1);
@@ -470,7 +469,7 @@ int batch_create(Ctx* ctx, const b2gpu_snapshot* proto, int n_worlds, const b2gp
   AL(B.b_mass, W * B.NB); AL(B.b_force, W * B.NB); AL(B.b_misc, W * B.NB); AL(B.b_rot, W * B.NB);
   AL(B.n_aabb, W * B.NN); AL(B.n_link, W * B.NN); AL(B.n_moved, W * B.NN);
   AL(B.p_aabb, W * NPa); AL(B.p_fat, W * NPa); AL(B.p_move, W * B.NMW);
-  AL(B.move_buf, W * B.NMOVE); AL(B.pair_buf, W * B.NPAIR);
+  AL(B.move_buf, W * B.NMOVE);
   AL(B.c_fix, W * B.NC); AL(B.c_flags, W * B.NC); AL(B.c_mat, W * B.NC);
   AL(B.c_m0, W * B.NC); AL(B.c_m1, W * B.NC); AL(B.c_m2, W * B.NC); AL(B.c_m3, W * B.NC);
   AL(B.isl_body, W * B.NIB); AL(B.isl_contact, W * B.NC); AL(B.isl_range, W * B.NB); AL(B.isl_flags, W * B.NB);
@@ -487,6 +486,11 @@ int batch_create(Ctx* ctx, const b2gpu_snapshot* proto, int n_worlds, const b2gp
     bh->allocs.push_back(v);
   }
 #undef AL
+#if !defined(B2G_HOSTSIM)
+  // allocations are zero-filled by cudaMemset on the default stream; the context stream may be a
+  // non-blocking one, so finish the fills before anything is copied into the buffers
+  CU(cudaDeviceSynchronize());
+#endif
   const Topology& T = bh->topo;
 #define UP(dst, vec) do { if (!(vec).empty()) { rc = dev_h2d(ctx, (void*)(dst), (vec).data(), (vec).size() * sizeof((vec)[0])); if (rc) { batch_destroy(bh); return rc; } } } while (0)
   UP(d_fix, T.fixtures); UP(d_shape, T.shapes); UP(d_ps, T.proxy_s); UP(d_so, T.sync_order); UP(d_np, T.node_proxy); UP(d_sr, T.sync_rank);

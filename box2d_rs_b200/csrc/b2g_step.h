@@ -1091,7 +1091,6 @@ B2G_HD void update_pairs(const Batch& B, const WIdx& x, const Ws& ws, int* b_che
   }
   ws[WS_ST_MOVED] += mc;
   ws[WS_ST_PAIRS] += np;
-  ws[WS_PAIR_COUNT] = np;
   ws[WS_MOVE_COUNT] = 0;
 }
 

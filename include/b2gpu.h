@@ -216,7 +216,7 @@ typedef struct b2gpu_step_stats {
   int32_t island_bodies; /* sum of island sizes (static bodies counted per island) */
   int32_t island_contacts;
   int32_t moved;         /* proxies re-inserted (move buffer length) */
-  int32_t pairs;         /* pair buffer length in update_pairs */
+  int32_t pairs;         /* pairs reported by update_pairs (the reference's pair buffer length) */
   int32_t created;       /* contacts created by add_pair */
   int32_t awake_bodies;
   int32_t solver_levels; /* depth of the exact-order wavefront schedule of the velocity pass */
@@ -272,7 +272,9 @@ typedef struct b2gpu_mass_data {
 
 /* Device-side capacities of one world of a batch. 0 = derive from the prototype. */
 typedef struct b2gpu_caps {
-  int32_t max_bodies, max_fixtures, max_shapes, max_proxies, max_contacts, max_pairs;
+  int32_t max_bodies, max_fixtures, max_shapes, max_proxies; /* reserved: topology is fixed by the prototype */
+  int32_t max_contacts; /* contacts per world (default: 10 per proxy for batches, 40 for a single world) */
+  int32_t max_pairs;    /* ignored: pairs are handed to add_pair as the tree query reports them, no pair buffer */
   int32_t reserved[2]; /* reserved[0]: worlds per memory block (power of two; 0 = 32 for >= 32 worlds, else 1);
                           reserved[1]: 1 = use the generic global-memory solver stages even when the
                           shared-memory ones apply (diagnostics) */
