@@ -45,7 +45,9 @@ static int cuda_fail(cudaError_t e, const char* what) {
 #define CU(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) return cuda_fail(e_, #x); } while (0)
 static int dev_alloc(void** p, size_t bytes) {
   CU(cudaMalloc(p, bytes ? bytes : 16));
+  // zero-fill on the default stream and finish it here: the context stream may be a non-blocking one
   CU(cudaMemset(*p, 0, bytes ? bytes : 16));
+  CU(cudaStreamSynchronize(0));
   return 0;
 }
 static void dev_free(void* p) { cudaFree(p); }
@@ -486,11 +488,6 @@ int batch_create(Ctx* ctx, const b2gpu_snapshot* proto, int n_worlds, const b2gp
     bh->allocs.push_back(v);
   }
 #undef AL
-#if !defined(B2G_HOSTSIM)
-  // allocations are zero-filled by cudaMemset on the default stream; the context stream may be a
-  // non-blocking one, so finish the fills before anything is copied into the buffers
-  CU(cudaDeviceSynchronize());
-#endif
   const Topology& T = bh->topo;
 #define UP(dst, vec) do { if (!(vec).empty()) { rc = dev_h2d(ctx, (void*)(dst), (vec).data(), (vec).size() * sizeof((vec)[0])); if (rc) { batch_destroy(bh); return rc; } } } while (0)
   UP(d_fix, T.fixtures); UP(d_shape, T.shapes); UP(d_ps, T.proxy_s); UP(d_so, T.sync_order); UP(d_np, T.node_proxy); UP(d_sr, T.sync_rank);
