@@ -1,0 +1,163 @@
+#!/usr/bin/env python
+"""Differential fuzzing of the device stages (host simulator build by default, --gpu for the CUDA path) against
+the CPU oracle: random scenes (polygons of 3..8 vertices, circles, edges, chains, kinematic / fixed-rotation /
+multi-fixture bodies, filters, restitution, damping, random world flags and iteration counts, dt = 0 steps,
+mid-run set_transform / set_linear_velocity edits), stepped freely and compared bit for bit.
+
+  python tools/fuzz_parity.py --seeds 200 [--gpu] [--batch]
+"""
+import argparse
+import math
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+from box2d_rs_b200 import abi, scenes  # noqa: E402
+from box2d_rs_b200.abi import BodyDef, FixtureDef  # noqa: E402
+
+
+def build(world, rng):
+    f32 = scenes.f32
+    ground = world.create_body(BodyDef())
+    kind = rng.integers(0, 3)
+    if kind == 0:
+        ground.create_fixture_by_shape(world.shapes.edge_two_sided((-15.0, 0.0), (15.0, 0.0)), 0.0)
+        ground.create_fixture_by_shape(world.shapes.edge_two_sided((-15.0, 0.0), (-15.0, 12.0)), 0.0)
+        ground.create_fixture_by_shape(world.shapes.edge_two_sided((15.0, 0.0), (15.0, 12.0)), 0.0)
+    elif kind == 1:
+        pts = [(15.0, 10.0), (12.0, 1.0), (4.0, f32(rng.uniform(-1, 1))), (-4.0, f32(rng.uniform(-1, 1))), (-12.0, 1.0), (-15.0, 10.0)]
+        ground.create_fixture(FixtureDef(friction=f32(rng.uniform(0, 1))), world.shapes.chain(pts, (16.0, 11.0), (-16.0, 11.0)))
+    else:
+        ground.create_fixture_by_shape(world.shapes.polygon_box(16.0, 0.5, (0.0, -0.5), f32(rng.uniform(-0.1, 0.1))), 0.0)
+        ground.create_fixture_by_shape(world.shapes.circle(2.0, (f32(rng.uniform(-5, 5)), 0.0)), 0.0)
+    n = int(rng.integers(2, 40))
+    for k in range(n):
+        t = rng.integers(0, 10)
+        bd = BodyDef(type=abi.DYNAMIC_BODY, position=(f32(rng.uniform(-10, 10)), f32(rng.uniform(0.5, 14))),
+                     angle=f32(rng.uniform(-4, 4)), linear_velocity=(f32(rng.uniform(-3, 3)), f32(rng.uniform(-3, 3))),
+                     angular_velocity=f32(rng.uniform(-2, 2)))
+        if t == 0:
+            bd.type = abi.KINEMATIC_BODY
+        if t == 1:
+            bd.fixed_rotation = 1
+        if t == 2:
+            bd.linear_damping, bd.angular_damping = f32(rng.uniform(0, 1)), f32(rng.uniform(0, 1))
+        if t == 3:
+            bd.gravity_scale = f32(rng.uniform(-0.5, 2))
+        if t == 4:
+            bd.allow_sleep = 0
+        if t == 5:
+            bd.awake = 0
+        b = world.create_body(bd)
+        for _ in range(1 + int(rng.integers(0, 3) == 0)):
+            fd = FixtureDef(density=f32(rng.uniform(0.2, 4)) if bd.type == abi.DYNAMIC_BODY else 0.0,
+                            friction=f32(rng.uniform(0, 1)), restitution=f32(rng.uniform(0, 0.8)) if rng.integers(0, 3) == 0 else 0.0)
+            r = rng.integers(0, 8)
+            if r == 0:
+                fd.group_index = int(rng.integers(-2, 3))
+            if r == 1:
+                fd.category_bits, fd.mask_bits = int(1 << rng.integers(0, 3)), int(0xFFFF ^ (1 << rng.integers(0, 3)))
+            s = rng.integers(0, 4)
+            if s == 0:
+                shape = world.shapes.circle(f32(rng.uniform(0.1, 0.6)), (f32(rng.uniform(-0.3, 0.3)), f32(rng.uniform(-0.3, 0.3))))
+            elif s == 1:
+                shape = world.shapes.polygon_box(f32(rng.uniform(0.1, 0.8)), f32(rng.uniform(0.1, 0.8)))
+            elif s == 2:
+                shape = world.shapes.polygon_box(f32(rng.uniform(0.1, 0.6)), f32(rng.uniform(0.1, 0.6)),
+                                                 (f32(rng.uniform(-0.3, 0.3)), f32(rng.uniform(-0.3, 0.3))), f32(rng.uniform(-3, 3)))
+            else:
+                nv = int(rng.integers(3, 9))
+                rad = rng.uniform(0.2, 0.7)
+                ang = np.sort(rng.uniform(0, 2 * math.pi, nv))
+                shape = world.shapes.polygon([(f32(rad * math.cos(a)), f32(rad * math.sin(a) * rng.uniform(0.5, 1.0))) for a in ang])
+            b.create_fixture(fd, shape)
+    return n + 1
+
+
+def run_seed(seed, make_world, steps, batch_mode):
+    import parity
+    from oracle import b2o
+    rng = np.random.default_rng(seed)
+    g = (0.0, f32v(rng.uniform(-12, 0)))
+    wo = b2o.B2world(g)
+    wg = make_world(g)
+    state = rng.bit_generator.state
+    try:
+        nb = build(wo, rng)
+    except ValueError:
+        wg.close()
+        return "skip"
+    rng.bit_generator.state = state
+    build(wg, rng)
+    flags = (bool(rng.integers(0, 4)), bool(rng.integers(0, 4)), bool(rng.integers(0, 4)))
+    for w in (wo, wg):
+        w.set_warm_starting(flags[0]); w.set_block_solve(flags[1]); w.set_allow_sleeping(flags[2])
+    vi, pi = int(rng.integers(1, 10)), int(rng.integers(0, 5))
+    bad = parity.compare_snapshots(wo.snapshot(), wg.snapshot())
+    if bad:
+        return "setup: %s" % bad[:3]
+    stepper = wg
+    batch = None
+    if batch_mode:
+        batch = wg.batch(int(rng.integers(33, 70)))
+    for i in range(steps):
+        dt = 0.0 if rng.integers(0, 40) == 0 else scenes.DT
+        ev = rng.integers(0, 30)
+        if batch is None and ev == 0:
+            b = int(rng.integers(1, nb))
+            p, a = (f32v(rng.uniform(-8, 8)), f32v(rng.uniform(1, 10))), f32v(rng.uniform(-3, 3))
+            wo.body(b).set_transform(p, a); wg.body(b).set_transform(p, a)
+        if batch is None and ev == 1:
+            b = int(rng.integers(1, nb))
+            v = (f32v(rng.uniform(-6, 6)), f32v(rng.uniform(-6, 6)))
+            wo.body(b).set_linear_velocity(v); wg.body(b).set_linear_velocity(v)
+        wo.step(dt, vi, pi)
+        if batch is None:
+            wg.step(dt, vi, pi)
+        else:
+            batch.step(dt, vi, pi)
+        if i % 16 == 15 or i == steps - 1:
+            got = wg.snapshot() if batch is None else batch.download_world(batch.n_worlds - 1)
+            st = wg.get_stats() if batch is None else batch.stats()[batch.n_worlds - 1]
+            bad = parity.compare_snapshots(wo.snapshot(), got) + parity.compare_stats(wo.get_stats(), st)
+            if bad:
+                return "step %d (vi=%d pi=%d flags=%s): %s" % (i, vi, pi, flags, bad[:4])
+    if batch is not None:
+        batch.close()
+    wg.close()
+    return None
+
+
+def f32v(x):
+    return float(np.float32(x))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--seeds", type=int, default=100)
+    ap.add_argument("--first", type=int, default=0)
+    ap.add_argument("--steps", type=int, default=160)
+    ap.add_argument("--gpu", action="store_true")
+    ap.add_argument("--batch", action="store_true")
+    args = ap.parse_args()
+    from box2d_rs_b200 import batch as batch_mod, world
+    lib_path = None if args.gpu else os.path.join(ROOT, "tests", "hostsim", "libb2gpu_hostsim.so")
+    ctx = batch_mod.Context(0, lib_path=lib_path)
+    fails = 0
+    for seed in range(args.first, args.first + args.seeds):
+        r = run_seed(seed, lambda g: world.B2world(g, ctx=ctx), args.steps, args.batch)
+        if r not in (None, "skip"):
+            fails += 1
+            print("seed %d: %s" % (seed, r), flush=True)
+    print("fuzz: %d seeds, %d failures (%s%s)" % (args.seeds, fails, "gpu" if args.gpu else "host simulator",
+                                                   ", batch" if args.batch else ""))
+    sys.exit(1 if fails else 0)
+
+
+if __name__ == "__main__":
+    main()
