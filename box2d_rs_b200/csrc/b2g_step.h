@@ -257,6 +257,15 @@ struct SerialAK {
     // (3) destroy flagged contacts after the loop (box2d-rs deviation, b2_contact_manager.rs(private):164-170),
     //     keeping the survivors in creation order.
     if (ws[WS_EV_DESTROY]) {
+      if (!(sp.dt > 0.0f) && ws[WS_ISL_VALID]) {
+        // collide-only step: the islands are not rebuilt, so the contacts' ISLAND bits (materialised lazily
+        // from the island order, see ContactIslandFlagsK) must be baked in before the compaction below
+        // shifts contact indices; afterwards the stale island order no longer describes the flags
+        for (int c = 0; c < cc; ++c) B.c_flags[x.at(B.NC, c)] &= ~B2GPU_CONTACT_ISLAND;
+        const int nic = ws[WS_ISL_CONTACTS];
+        for (int k = 0; k < nic; ++k) B.c_flags[x.at(B.NC, B.isl_contact[x.at(B.NC, k)])] |= B2GPU_CONTACT_ISLAND;
+        ws[WS_ISL_VALID] = 0;
+      }
       int out = 0;
       for (int c = 0; c < cc; ++c) {
         const int ci = x.at(B.NC, c);
