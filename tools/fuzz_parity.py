@@ -53,9 +53,16 @@ def build(world, rng):
             bd.allow_sleep = 0
         if t == 5:
             bd.awake = 0
+        if t == 6 and rng.integers(0, 3) == 0:
+            bd.enabled = 0  # no proxies: the fixture never collides
+        if t == 7:  # fast spinner / fast mover: rotation and translation clamps, sin/cos range reduction
+            bd.angular_velocity = f32(rng.uniform(-120, 120))
+            bd.linear_velocity = (f32(rng.uniform(-150, 150)), f32(rng.uniform(-50, 150)))
+            bd.angle = f32(rng.uniform(-200, 200))
         b = world.create_body(bd)
         for _ in range(1 + int(rng.integers(0, 3) == 0)):
-            fd = FixtureDef(density=f32(rng.uniform(0.2, 4)) if bd.type == abi.DYNAMIC_BODY else 0.0,
+            zero_mass = bd.type == abi.DYNAMIC_BODY and rng.integers(0, 25) == 0  # dynamic body nothing can push
+            fd = FixtureDef(density=f32(rng.uniform(0.2, 4)) if (bd.type == abi.DYNAMIC_BODY and not zero_mass) else 0.0,
                             friction=f32(rng.uniform(0, 1)), restitution=f32(rng.uniform(0, 0.8)) if rng.integers(0, 3) == 0 else 0.0)
             r = rng.integers(0, 8)
             if r == 0:
