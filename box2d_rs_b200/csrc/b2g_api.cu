@@ -175,12 +175,7 @@ void* b2gpu_batch_forces_device(b2gpu_batch* b, int64_t* bytes) {
 int b2gpu_batch_step_host(b2gpu_batch* b, const float* host_forces, float* host_state_out, float dt, int vi, int pi, int steps) {
   GUARD_BEGIN
   if (!b) { set_error("batch is NULL"); return B2GPU_E_INVALID; }
-  int rc = 0;
-  if (host_forces) rc = batch_set_forces(b->h, host_forces, 0, b->h->B.n_worlds);
-  if (!rc) rc = batch_step(b->h, dt, vi, pi, steps);
-  if (!rc && host_state_out) rc = batch_get_body_state(b->h, host_state_out, 0, b->h->B.n_worlds);
-  if (!rc && !host_state_out) rc = ctx_sync(&b->ctx->c);
-  return rc;
+  return batch_step_host(b->h, host_forces, host_state_out, dt, vi, pi, steps);
   GUARD_END
 }
 int64_t b2gpu_batch_algorithmic_bytes(b2gpu_batch* b) { return b ? batch_algorithmic_bytes(b->h) : -1; }

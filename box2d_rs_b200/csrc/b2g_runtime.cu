@@ -535,6 +535,15 @@ int batch_create(Ctx* ctx, const b2gpu_snapshot* proto, int n_worlds, const b2gp
 
 void batch_destroy(BatchHost* bh) {
   if (!bh) return;
+#if !defined(B2G_HOSTSIM)
+  if (bh->copy_stream) {
+    cudaStreamSynchronize((cudaStream_t)bh->copy_stream);
+    cudaEventDestroy((cudaEvent_t)bh->ev_entry);
+    cudaEventDestroy((cudaEvent_t)bh->ev_forces);
+    cudaEventDestroy((cudaEvent_t)bh->ev_state);
+    cudaStreamDestroy((cudaStream_t)bh->copy_stream);
+  }
+#endif
   for (void* p : bh->allocs) dev_free(p);
   delete bh;
 }
@@ -585,7 +594,16 @@ int batch_download_world(BatchHost* bh, int world, b2gpu_snapshot* out) {
 }
 
 // ------------------------------------------------------------------ step
-int batch_step(BatchHost* bh, float dt, int vi, int pi, int steps) {
+// Optional cross-stream dependencies of one batch_step call (used by batch_step_host to overlap the host
+// copies with the stages that neither read the forces nor change the body state).
+struct StepHooks {
+  void* wait_before_island = nullptr;  // cudaEvent_t: the island stage of the first step waits for it
+  void* record_state_final = nullptr;  // cudaEvent_t: recorded once the last step's body state is final
+};
+static int batch_step_impl(BatchHost* bh, float dt, int vi, int pi, int steps, const StepHooks* hooks);
+int batch_step(BatchHost* bh, float dt, int vi, int pi, int steps) { return batch_step_impl(bh, dt, vi, pi, steps, nullptr); }
+
+static int batch_step_impl(BatchHost* bh, float dt, int vi, int pi, int steps, const StepHooks* hooks) {
   if (!bh || steps < 0 || vi < 0 || pi < 0) { set_error("batch_step: bad argument"); return B2GPU_E_INVALID; }
   Batch& B = bh->B;
   Ctx* ctx = bh->ctx;
@@ -609,6 +627,8 @@ int batch_step(BatchHost* bh, float dt, int vi, int pi, int steps) {
     {
       SerialAK k = {B, bh->b_wake, bh->b_chead, bh->c_next, bh->stack, sp};
 #if !defined(B2G_HOSTSIM)
+      if (hooks && hooks->wait_before_island && s == 0)
+        CU(cudaStreamWaitEvent((cudaStream_t)ctx->stream, (cudaEvent_t)hooks->wait_before_island, 0));
       if (bh->smem_island) {
         LaunchScope ls = {ctx, STAGE_ISLAND};
         RC(ls.begin());
@@ -655,6 +675,12 @@ int batch_step(BatchHost* bh, float dt, int vi, int pi, int steps) {
       { PositionK k = {B, sp}; RC(launch(ctx, k, W * B.NB, 64, STAGE_POSITION)); }
       { FinalizeK k = {B, sp}; RC(launch(ctx, k, W * B.NIB, 128, STAGE_FINALIZE)); }
       { SleepK k = {B}; RC(launch(ctx, k, W * B.NB, 128, STAGE_SLEEP)); }
+#if !defined(B2G_HOSTSIM)
+      // positions, velocities and transforms are final from here on (the remaining stages only touch the
+      // broadphase, the contact set and the forces)
+      if (hooks && hooks->record_state_final && s == steps - 1)
+        CU(cudaEventRecord((cudaEvent_t)hooks->record_state_final, (cudaStream_t)ctx->stream));
+#endif
       if (B.NP > 0) { SyncFixturesK k = {B}; RC(launch(ctx, k, W * B.NP, 128, STAGE_SYNC_FIXTURES)); }
     }
     {
@@ -785,6 +811,68 @@ int batch_set_linear_velocity(BatchHost* bh, int body, const float* host_vxvy, i
   RC(dev_h2d(bh->ctx, bh->forces_dev, host_vxvy, (size_t)count * 2 * 4));
   { VelScatterK k = {bh->B, bh->forces_dev, body, first, count}; RC(launch(bh->ctx, k, count, 128)); }
   return 0;
+}
+
+// One end-to-end call through HOST buffers: forces H2D, `steps` steps, body state D2H.  The copies run on
+// a second stream: the force upload overlaps the pre-step pair pass and collide (neither reads forces),
+// the state download overlaps fixture synchronisation, tree updates and pair reporting (none of which
+// changes body state).  Synchronous: returns when the state is in `host_state_out`.
+int batch_step_host(BatchHost* bh, const float* host_forces, float* host_state_out, float dt, int vi, int pi, int steps) {
+  if (!bh || steps < 0) { set_error("batch_step_host: bad argument"); return B2GPU_E_INVALID; }
+  Batch& B = bh->B;
+  Ctx* ctx = bh->ctx;
+#if defined(B2G_HOSTSIM)
+  if (host_forces) RC(batch_set_forces(bh, host_forces, 0, B.n_worlds));
+  RC(batch_step(bh, dt, vi, pi, steps));
+  if (host_state_out) RC(batch_get_body_state(bh, host_state_out, 0, B.n_worlds));
+  return 0;
+#else
+  if (steps == 0 || !(dt > 0.0f) || ctx->profiling) {  // no overlap window: plain sequence
+    if (host_forces) RC(batch_set_forces(bh, host_forces, 0, B.n_worlds));
+    RC(batch_step(bh, dt, vi, pi, steps));
+    if (host_state_out) RC(batch_get_body_state(bh, host_state_out, 0, B.n_worlds));
+    else RC(ctx_sync(ctx));
+    return 0;
+  }
+  if (!bh->copy_stream) {
+    cudaStream_t cs;
+    CU(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+    bh->copy_stream = (void*)cs;
+    cudaEvent_t e;
+    CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); bh->ev_entry = (void*)e;
+    CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); bh->ev_forces = (void*)e;
+    CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); bh->ev_state = (void*)e;
+  }
+  cudaStream_t main_s = (cudaStream_t)ctx->stream, copy_s = (cudaStream_t)bh->copy_stream;
+  const int n_flat = B.n_wblocks * B.LB * B.NB;
+  StepHooks hooks;
+  CU(cudaEventRecord((cudaEvent_t)bh->ev_entry, main_s));
+  CU(cudaStreamWaitEvent(copy_s, (cudaEvent_t)bh->ev_entry, 0));
+  if (host_forces) {
+    CU(cudaMemcpyAsync(bh->forces_dev, host_forces, (size_t)B.n_worlds * B.NB * 3 * 4, cudaMemcpyHostToDevice, copy_s));
+    ctx->stream = (void*)copy_s;
+    ForceScatterK k = {B, bh->forces_dev, 0, B.n_worlds};
+    int rc = launch(ctx, k, n_flat, 128);
+    ctx->stream = (void*)main_s;
+    RC(rc);
+    CU(cudaEventRecord((cudaEvent_t)bh->ev_forces, copy_s));
+    hooks.wait_before_island = bh->ev_forces;
+  }
+  if (host_state_out) hooks.record_state_final = bh->ev_state;
+  RC(batch_step_impl(bh, dt, vi, pi, steps, &hooks));
+  if (host_state_out) {
+    CU(cudaStreamWaitEvent(copy_s, (cudaEvent_t)bh->ev_state, 0));
+    ctx->stream = (void*)copy_s;
+    StateGatherK k = {B, bh->state_dev};
+    int rc = launch(ctx, k, n_flat, 128);
+    ctx->stream = (void*)main_s;
+    RC(rc);
+    CU(cudaMemcpyAsync(host_state_out, bh->state_dev, (size_t)B.n_worlds * B.NB * 8 * 4, cudaMemcpyDeviceToHost, copy_s));
+  }
+  CU(cudaStreamSynchronize(copy_s));
+  CU(cudaStreamSynchronize(main_s));
+  return 0;
+#endif
 }
 
 // sin/cos of an array of angles on the device (diagnostic: pins rot_from_angle against libm)

@@ -70,6 +70,10 @@ struct BatchHost {
   bool ml_velocity = false;      // velocity stage also level-scheduled (experiment switch)
   bool ml_solver = false;        // level-scheduled multi-lane Gauss-Seidel kernels in use
   bool smem_solver = false;      // shared-memory Gauss-Seidel kernels in use (b2g_solver_smem.cuh)
+  void* copy_stream = nullptr;   // second stream + events of batch_step_host (created on first use)
+  void* ev_entry = nullptr;
+  void* ev_forces = nullptr;
+  void* ev_state = nullptr;
   bool stepped = false;          // at least one dt > 0 step ran: island arrays are meaningful
   bool pre_step_needed = true;   // some world may carry m_new_contacts / a non-empty move buffer
   long long total_bytes = 0;
@@ -85,6 +89,7 @@ int batch_upload_world(BatchHost* b, int world, const b2gpu_snapshot* in);
 int batch_snapshot_sizes(BatchHost* b, int world, b2gpu_snapshot_sizes* out);
 int batch_download_world(BatchHost* b, int world, b2gpu_snapshot* out);
 int batch_step(BatchHost* b, float dt, int vi, int pi, int steps);
+int batch_step_host(BatchHost* b, const float* host_forces, float* host_state_out, float dt, int vi, int pi, int steps);
 int batch_get_stats(BatchHost* b, int first, int count, b2gpu_step_stats* out);
 int batch_get_body_state(BatchHost* b, float* host_out, int first, int count);
 int batch_set_forces(BatchHost* b, const float* host, int first, int count);

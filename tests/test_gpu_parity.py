@@ -261,3 +261,30 @@ def test_differential_fuzz(first, count, batch_mode, ctx):
         if r not in (None, "skip"):
             fails.append((seed, r))
     assert fails == []
+
+
+def test_step_host_overlapped_copies_match_plain_calls(ctx):
+    """b2gpu_batch_step_host overlaps the force upload and the state download with stages that do not touch
+    them; its results must equal set_forces + step + get_body_state, and the oracle."""
+    from box2d_rs_b200 import scenes
+    wo, wg, _ = _pair("pyramid", ctx)
+    n = 64
+    a = wg.batch(n, max_contacts=1024)
+    b = wg.batch(n, max_contacts=1024)
+    rng = np.random.default_rng(5)
+    state = np.zeros((n, a.body_count, 8), np.float32)
+    for i in range(40):
+        forces = np.zeros((n, a.body_count, 3), np.float32)
+        forces[:, 2:, 0] = rng.uniform(-30.0, 30.0, (n, a.body_count - 2)).astype(np.float32)
+        a.step_host(forces, state, scenes.DT, 8, 3, 1)
+        b.set_forces(forces)
+        b.step(scenes.DT, 8, 3)
+        assert np.array_equal(state.view(np.uint32), b.body_state().view(np.uint32)), "step %d" % i
+        for k in range(2, a.body_count):
+            wo.body(k).apply_force_to_center((float(forces[n - 1, k, 0]), 0.0), wake=False)
+        wo.step(scenes.DT, 8, 3)
+    assert np.array_equal(state[n - 1].view(np.uint32), wo.body_state().view(np.uint32))
+    assert parity.compare_snapshots(wo.snapshot(), a.download_world(n - 1)) == []
+    a.close()
+    b.close()
+    wg.close()
