@@ -31,7 +31,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 DYNAMIC_BODIES = 210
-PREROLL = 150
+PREROLL = 400
 SEED = 0xB2D + 3
 
 
