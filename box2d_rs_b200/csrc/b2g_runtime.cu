@@ -36,6 +36,7 @@ template <class K> static int launch(Ctx* ctx, const K& k, int n, int /*block*/,
   ctx->stage_launches[stage] += 1;
   return 0;
 }
+template <class K> static int launch_occ(Ctx* ctx, const K& k, int n, int stage) { return launch(ctx, k, n, 128, stage); }
 int ctx_collect_profile(Ctx*) { return 0; }
 #else
 static int cuda_fail(cudaError_t e, const char* what) {
@@ -103,6 +104,18 @@ template <class K> static int launch(Ctx* ctx, const K& k, int n, int block, int
   LaunchScope ls = {ctx, stage};
   RC(ls.begin());
   stage_kernel<K><<<grid, block, 0, (cudaStream_t)ctx->stream>>>(k, n);
+  return ls.end();
+}
+// Latency-bound flat stages (narrowphase): cap registers so that 8 blocks of 128 threads fit an SM.
+template <class K> __global__ void __launch_bounds__(128, 8) stage_kernel_occ(const K k, int n) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < n) k(t);
+}
+template <class K> static int launch_occ(Ctx* ctx, const K& k, int n, int stage) {
+  if (n <= 0) return 0;
+  LaunchScope ls = {ctx, stage};
+  RC(ls.begin());
+  stage_kernel_occ<K><<<(n + 127) / 128, 128, 0, (cudaStream_t)ctx->stream>>>(k, n);
   return ls.end();
 }
 int ctx_collect_profile(Ctx* ctx) {
@@ -622,7 +635,7 @@ static int batch_step_impl(BatchHost* bh, float dt, int vi, int pi, int steps, c
     }
     {
       CollideK k = {B, bh->b_wake};
-      RC(launch(ctx, k, W * B.NC, 128, STAGE_COLLIDE));
+      RC(launch_occ(ctx, k, W * B.NC, STAGE_COLLIDE));
     }
     {
       SerialAK k = {B, bh->b_wake, bh->b_chead, bh->c_next, bh->stack, sp};
