@@ -53,6 +53,7 @@ enum { SCHED_G = 2, SCHED_MIN_ROUNDS = 6 };
 
 struct Batch {
   int n_worlds, LB, lb_shift, n_wblocks;
+  int wb_first, wb_count;    // window of world blocks a launch works on (stream groups); default: all
   int NB, NF, NS, NP;        // bodies, fixtures, child shapes, proxies (exact, shared topology)
   int NN;                    // tree node pool (physical capacity)
   int NC, NMOVE;             // capacities: contacts, move buffer

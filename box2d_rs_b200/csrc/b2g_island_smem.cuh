@@ -28,7 +28,7 @@ __global__ void __launch_bounds__(32) island_smem_kernel(const SerialAK K, const
   uint32_t* fxb = (uint32_t*)(smem_raw + L.off_fxb);       // [fxb_count] fixture -> body | sensor << 31
   uint16_t* korder = (uint16_t*)(smem_raw + L.off_korder); // [ECAP][32] island contact slot k -> eligible edge
   const int lane = threadIdx.x;
-  const int wb = blockIdx.x;
+  const int wb = blockIdx.x + B.wb_first;
   const int w = wb * 32 + lane;
   const bool live = w < B.n_worlds;
   WIdx x;

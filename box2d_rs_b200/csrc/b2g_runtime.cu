@@ -452,6 +452,8 @@ int batch_create(Ctx* ctx, const b2gpu_snapshot* proto, int n_worlds, const b2gp
   B.lb_shift = 0;
   while ((1 << B.lb_shift) < B.LB) ++B.lb_shift;
   B.n_wblocks = (n_worlds + B.LB - 1) / B.LB;
+  B.wb_first = 0;
+  B.wb_count = B.n_wblocks;
   const b2gpu_snapshot_sizes& n = proto->n;
   B.NB = n.body_count; B.NF = n.fixture_count; B.NS = n.shape_count; B.NP = n.proxy_count;
   if (B.NB < 1 || B.NP < 0) { set_error("empty world"); delete bh; return B2GPU_E_INVALID; }
@@ -525,6 +527,7 @@ int batch_create(Ctx* ctx, const b2gpu_snapshot* proto, int n_worlds, const b2gp
       CU(cudaFuncSetAttribute(velocity_smem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)velocity_smem_bytes(B.NB)));
       CU(cudaFuncSetAttribute(velocity_smem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)velocity_smem_bytes(B.NB)));
       bh->tma_ring = caps && caps->reserved[1] == 4;
+      if (caps && caps->reserved[1] == 5) bh->stream_groups = 1;
       CU(cudaFuncSetAttribute(position_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)position_smem_bytes(B.NB)));
       bh->smem_solver = true;
     }
@@ -549,13 +552,13 @@ int batch_create(Ctx* ctx, const b2gpu_snapshot* proto, int n_worlds, const b2gp
 void batch_destroy(BatchHost* bh) {
   if (!bh) return;
 #if !defined(B2G_HOSTSIM)
-  if (bh->copy_stream) {
-    cudaStreamSynchronize((cudaStream_t)bh->copy_stream);
-    cudaEventDestroy((cudaEvent_t)bh->ev_entry);
-    cudaEventDestroy((cudaEvent_t)bh->ev_forces);
-    cudaEventDestroy((cudaEvent_t)bh->ev_state);
-    cudaStreamDestroy((cudaStream_t)bh->copy_stream);
+  for (StreamGroup& sg : bh->groups) {
+    cudaStreamSynchronize((cudaStream_t)sg.stream);
+    cudaEventDestroy((cudaEvent_t)sg.ev_init);
+    cudaEventDestroy((cudaEvent_t)sg.ev_done);
+    cudaStreamDestroy((cudaStream_t)sg.stream);
   }
+  if (bh->ev_entry) cudaEventDestroy((cudaEvent_t)bh->ev_entry);
 #endif
   for (void* p : bh->allocs) dev_free(p);
   delete bh;
@@ -607,145 +610,6 @@ int batch_download_world(BatchHost* bh, int world, b2gpu_snapshot* out) {
 }
 
 // ------------------------------------------------------------------ step
-// Optional cross-stream dependencies of one batch_step call (used by batch_step_host to overlap the host
-// copies with the stages that neither read the forces nor change the body state).
-struct StepHooks {
-  void* wait_before_island = nullptr;  // cudaEvent_t: the island stage of the first step waits for it
-  void* record_state_final = nullptr;  // cudaEvent_t: recorded once the last step's body state is final
-};
-static int batch_step_impl(BatchHost* bh, float dt, int vi, int pi, int steps, const StepHooks* hooks);
-int batch_step(BatchHost* bh, float dt, int vi, int pi, int steps) { return batch_step_impl(bh, dt, vi, pi, steps, nullptr); }
-
-static int batch_step_impl(BatchHost* bh, float dt, int vi, int pi, int steps, const StepHooks* hooks) {
-  if (!bh || steps < 0 || vi < 0 || pi < 0) { set_error("batch_step: bad argument"); return B2GPU_E_INVALID; }
-  Batch& B = bh->B;
-  Ctx* ctx = bh->ctx;
-  StepParams sp;
-  sp.dt = dt;
-  sp.inv_dt = dt > 0.0f ? 1.0f / dt : 0.0f;
-  sp.velocity_iterations = vi;
-  sp.position_iterations = pi;
-  bh->last_sp = sp;
-  const int W = B.n_wblocks * B.LB;
-  const int ordered_block = 32;
-  for (int s = 0; s < steps; ++s) {
-    {
-      TreePairsK k = {B, bh->b_chead, bh->c_next, sp, 1};
-      RC(launch(ctx, k, W, ordered_block, STAGE_PRE));
-    }
-    {
-      CollideK k = {B, bh->b_wake};
-      RC(launch_occ(ctx, k, W * B.NC, STAGE_COLLIDE));
-    }
-    {
-      SerialAK k = {B, bh->b_wake, bh->b_chead, bh->c_next, bh->stack, sp};
-#if !defined(B2G_HOSTSIM)
-      if (hooks && hooks->wait_before_island && s == 0)
-        CU(cudaStreamWaitEvent((cudaStream_t)ctx->stream, (cudaEvent_t)hooks->wait_before_island, 0));
-      if (bh->smem_island) {
-        LaunchScope ls = {ctx, STAGE_ISLAND};
-        RC(ls.begin());
-        island_smem_kernel<<<B.n_wblocks, 32, bh->island_layout.total, (cudaStream_t)ctx->stream>>>(k, bh->island_layout);
-        RC(ls.end());
-      } else
-#endif
-      RC(launch(ctx, k, W, ordered_block, STAGE_ISLAND));
-    }
-    if (dt > 0.0f) {
-      { IntegrateK k = {B, sp}; RC(launch(ctx, k, W * B.NIB, 128, STAGE_INTEGRATE)); }
-      { SolverInitK k = {B, sp}; RC(launch(ctx, k, W * B.NC, 128, STAGE_SOLVER_INIT)); }
-#if !defined(B2G_HOSTSIM)
-      if (bh->ml_solver && bh->ml_velocity) {
-        LaunchScope ls = {ctx, STAGE_VELOCITY};
-        RC(ls.begin());
-        velocity_ml_kernel<<<B.n_wblocks * SCHED_G, 32, velocity_ml_smem_bytes(B.NB), (cudaStream_t)ctx->stream>>>(B, sp);
-        RC(ls.end());
-      } else if (bh->smem_solver) {
-        LaunchScope ls = {ctx, STAGE_VELOCITY};
-        RC(ls.begin());
-        if (bh->tma_ring)
-          velocity_smem_kernel<true><<<B.n_wblocks, 32, velocity_smem_bytes(B.NB), (cudaStream_t)ctx->stream>>>(B, sp);
-        else
-          velocity_smem_kernel<false><<<B.n_wblocks, 32, velocity_smem_bytes(B.NB), (cudaStream_t)ctx->stream>>>(B, sp);
-        RC(ls.end());
-      } else
-#endif
-      { VelocityK k = {B, sp}; RC(launch(ctx, k, W * B.NB, 64, STAGE_VELOCITY)); }
-      { PostVelocityK k = {B, sp}; RC(launch(ctx, k, W * B.NIB, 128, STAGE_POST_VELOCITY)); }
-#if !defined(B2G_HOSTSIM)
-      if (bh->ml_solver) {
-        LaunchScope ls = {ctx, STAGE_POSITION};
-        RC(ls.begin());
-        position_ml_kernel<<<B.n_wblocks * SCHED_G, 32, position_ml_smem_bytes(B.NB), (cudaStream_t)ctx->stream>>>(B, sp);
-        RC(ls.end());
-      } else if (bh->smem_solver) {
-        LaunchScope ls = {ctx, STAGE_POSITION};
-        RC(ls.begin());
-        position_smem_kernel<<<B.n_wblocks, 32, position_smem_bytes(B.NB), (cudaStream_t)ctx->stream>>>(B, sp);
-        RC(ls.end());
-      } else
-#endif
-      { PositionK k = {B, sp}; RC(launch(ctx, k, W * B.NB, 64, STAGE_POSITION)); }
-      { FinalizeK k = {B, sp}; RC(launch(ctx, k, W * B.NIB, 128, STAGE_FINALIZE)); }
-      { SleepK k = {B}; RC(launch(ctx, k, W * B.NB, 128, STAGE_SLEEP)); }
-#if !defined(B2G_HOSTSIM)
-      // positions, velocities and transforms are final from here on (the remaining stages only touch the
-      // broadphase, the contact set and the forces)
-      if (hooks && hooks->record_state_final && s == steps - 1)
-        CU(cudaEventRecord((cudaEvent_t)hooks->record_state_final, (cudaStream_t)ctx->stream));
-#endif
-      if (B.NP > 0) { SyncFixturesK k = {B}; RC(launch(ctx, k, W * B.NP, 128, STAGE_SYNC_FIXTURES)); }
-    }
-    {
-      TreePairsK k = {B, bh->b_chead, bh->c_next, sp, 0};
-      RC(launch(ctx, k, W, ordered_block, STAGE_TREE_PAIRS));
-    }
-    { BodyEndK k = {B}; RC(launch(ctx, k, W * B.NB, 128, STAGE_BODY_END)); }
-  }
-  bh->pre_step_needed = false;
-  if (steps > 0 && dt > 0.0f) bh->stepped = true;
-  return 0;
-}
-
-// touching / awake counters on demand: one thread per world
-struct StatsK {
-  Batch B;
-  B2G_HD void operator()(int w) const {
-    if (w >= B.n_worlds) return;
-    WIdx x = widx(B, w);
-    Ws ws = ws_of(B, x);
-    int touching = 0, awake = 0;
-    const int cc = ws[WS_CONTACT_COUNT];
-    for (int c = 0; c < cc; ++c) touching += (B.c_flags[x.at(B.NC, c)] & B2GPU_CONTACT_TOUCHING) ? 1 : 0;
-    for (int b = 0; b < B.NB; ++b) awake += (B.b_flags[x.at(B.NB, b)] & B2GPU_BODY_AWAKE) ? 1 : 0;
-    ws[WS_ST_TOUCHING] = touching;
-    ws[WS_ST_AWAKE] = awake;
-    ws[WS_ST_CONTACTS] = cc;
-  }
-};
-
-int batch_get_stats(BatchHost* bh, int first, int count, b2gpu_step_stats* out) {
-  if (!bh || !out || first < 0 || count < 0 || first + count > bh->B.n_worlds) { set_error("get_stats: bad argument"); return B2GPU_E_INVALID; }
-  Batch& B = bh->B;
-  const int W = B.n_wblocks * B.LB;
-  { StatsK k = {B}; RC(launch(bh->ctx, k, W, 32)); }
-  std::vector<int> all((size_t)W * WS_COUNT);
-  RC(dev_d2h(bh->ctx, all.data(), B.ws, all.size() * 4));
-  for (int i = 0; i < count; ++i) {
-    const int w = first + i;
-    const int wb = w >> B.lb_shift, wl = w & (B.LB - 1);
-    auto get = [&](int slot) { return all[((size_t)wb * WS_COUNT + slot) * B.LB + wl]; };
-    b2gpu_step_stats& s = out[i];
-    memset(&s, 0, sizeof(s));
-    s.status = get(WS_STATUS);
-    s.contacts = get(WS_ST_CONTACTS); s.touching = get(WS_ST_TOUCHING); s.destroyed = get(WS_ST_DESTROYED);
-    s.islands = get(WS_ST_ISLANDS); s.island_bodies = get(WS_ST_ISL_BODIES); s.island_contacts = get(WS_ST_ISL_CONTACTS);
-    s.moved = get(WS_ST_MOVED); s.pairs = get(WS_ST_PAIRS); s.created = get(WS_ST_CREATED); s.awake_bodies = get(WS_ST_AWAKE);
-    s.solver_levels = get(WS_ST_LEVELS);
-  }
-  return 0;
-}
-
 // body state gather / force scatter: flat over bodies
 struct StateGatherK {
   Batch B;
@@ -802,6 +666,240 @@ struct VelScatterK {
   }
 };
 
+// All stages of `steps` consecutive steps for the world-block window of Bw, on ctx->stream.
+// `init_done` (optional cudaEvent_t) is recorded after the solver set-up stage of the first step: the
+// next stream group starts behind it, so the groups run staggered (one group's flat stages overlap the
+// other groups' latency-bound Gauss-Seidel kernels instead of all groups doing the same stage at once).
+static int step_window(BatchHost* bh, const Batch& Bw, const StepParams& sp, int steps, void* init_done) {
+  Ctx* ctx = bh->ctx;
+  const Batch& B = Bw;
+  const int W = B.wb_count * B.LB;
+  const int ordered_block = 32;
+  const float dt = sp.dt;
+  for (int s = 0; s < steps; ++s) {
+    {
+      TreePairsK k = {B, bh->b_chead, bh->c_next, sp, 1};
+      RC(launch(ctx, k, W, ordered_block, STAGE_PRE));
+    }
+    {
+      CollideK k = {B, bh->b_wake};
+      RC(launch_occ(ctx, k, W * B.NC, STAGE_COLLIDE));
+    }
+    {
+      SerialAK k = {B, bh->b_wake, bh->b_chead, bh->c_next, bh->stack, sp};
+#if !defined(B2G_HOSTSIM)
+      if (bh->smem_island) {
+        LaunchScope ls = {ctx, STAGE_ISLAND};
+        RC(ls.begin());
+        island_smem_kernel<<<B.wb_count, 32, bh->island_layout.total, (cudaStream_t)ctx->stream>>>(k, bh->island_layout);
+        RC(ls.end());
+      } else
+#endif
+      RC(launch(ctx, k, W, ordered_block, STAGE_ISLAND));
+    }
+    if (dt > 0.0f) {
+      { IntegrateK k = {B, sp}; RC(launch(ctx, k, W * B.NIB, 128, STAGE_INTEGRATE)); }
+      { SolverInitK k = {B, sp}; RC(launch(ctx, k, W * B.NC, 128, STAGE_SOLVER_INIT)); }
+#if !defined(B2G_HOSTSIM)
+      if (init_done && s == 0) CU(cudaEventRecord((cudaEvent_t)init_done, (cudaStream_t)ctx->stream));
+      if (bh->ml_solver && bh->ml_velocity) {
+        LaunchScope ls = {ctx, STAGE_VELOCITY};
+        RC(ls.begin());
+        velocity_ml_kernel<<<B.wb_count * SCHED_G, 32, velocity_ml_smem_bytes(B.NB), (cudaStream_t)ctx->stream>>>(B, sp);
+        RC(ls.end());
+      } else if (bh->smem_solver) {
+        LaunchScope ls = {ctx, STAGE_VELOCITY};
+        RC(ls.begin());
+        if (bh->tma_ring)
+          velocity_smem_kernel<true><<<B.wb_count, 32, velocity_smem_bytes(B.NB), (cudaStream_t)ctx->stream>>>(B, sp);
+        else
+          velocity_smem_kernel<false><<<B.wb_count, 32, velocity_smem_bytes(B.NB), (cudaStream_t)ctx->stream>>>(B, sp);
+        RC(ls.end());
+      } else
+#endif
+      { VelocityK k = {B, sp}; RC(launch(ctx, k, W * B.NB, 64, STAGE_VELOCITY)); }
+      { PostVelocityK k = {B, sp}; RC(launch(ctx, k, W * B.NIB, 128, STAGE_POST_VELOCITY)); }
+#if !defined(B2G_HOSTSIM)
+      if (bh->ml_solver) {
+        LaunchScope ls = {ctx, STAGE_POSITION};
+        RC(ls.begin());
+        position_ml_kernel<<<B.wb_count * SCHED_G, 32, position_ml_smem_bytes(B.NB), (cudaStream_t)ctx->stream>>>(B, sp);
+        RC(ls.end());
+      } else if (bh->smem_solver) {
+        LaunchScope ls = {ctx, STAGE_POSITION};
+        RC(ls.begin());
+        position_smem_kernel<<<B.wb_count, 32, position_smem_bytes(B.NB), (cudaStream_t)ctx->stream>>>(B, sp);
+        RC(ls.end());
+      } else
+#endif
+      { PositionK k = {B, sp}; RC(launch(ctx, k, W * B.NB, 64, STAGE_POSITION)); }
+      { FinalizeK k = {B, sp}; RC(launch(ctx, k, W * B.NIB, 128, STAGE_FINALIZE)); }
+      { SleepK k = {B}; RC(launch(ctx, k, W * B.NB, 128, STAGE_SLEEP)); }
+      if (B.NP > 0) { SyncFixturesK k = {B}; RC(launch(ctx, k, W * B.NP, 128, STAGE_SYNC_FIXTURES)); }
+    }
+#if !defined(B2G_HOSTSIM)
+    else if (init_done && s == 0) CU(cudaEventRecord((cudaEvent_t)init_done, (cudaStream_t)ctx->stream));
+#endif
+    {
+      TreePairsK k = {B, bh->b_chead, bh->c_next, sp, 0};
+      RC(launch(ctx, k, W, ordered_block, STAGE_TREE_PAIRS));
+    }
+    { BodyEndK k = {B}; RC(launch(ctx, k, W * B.NB, 128, STAGE_BODY_END)); }
+  }
+  return 0;
+}
+
+static StepParams make_params(float dt, int vi, int pi) {
+  StepParams sp;
+  sp.dt = dt;
+  sp.inv_dt = dt > 0.0f ? 1.0f / dt : 0.0f;
+  sp.velocity_iterations = vi;
+  sp.position_iterations = pi;
+  return sp;
+}
+
+#if !defined(B2G_HOSTSIM)
+// Stream groups: the world blocks of a batch are split into a few windows, each an independent in-order
+// pipeline on its own stream (worlds never interact).  Created on first use.
+static int ensure_groups(BatchHost* bh) {
+  if (!bh->groups.empty()) return 0;
+  const Batch& B = bh->B;
+  int ng = (B.LB == 32 && B.n_wblocks >= 16 && bh->stream_groups != 1) ? (bh->stream_groups > 1 ? bh->stream_groups : 4) : 1;
+  if (ng > B.n_wblocks) ng = B.n_wblocks;
+  for (int g = 0; g < ng; ++g) {
+    StreamGroup sg;
+    sg.wb_first = (int)((long long)B.n_wblocks * g / ng);
+    sg.wb_count = (int)((long long)B.n_wblocks * (g + 1) / ng) - sg.wb_first;
+    cudaStream_t st;
+    CU(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    sg.stream = (void*)st;
+    cudaEvent_t e;
+    CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); sg.ev_init = (void*)e;
+    CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); sg.ev_done = (void*)e;
+    bh->groups.push_back(sg);
+  }
+  cudaEvent_t e;
+  CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+  bh->ev_entry = (void*)e;
+  return 0;
+}
+#endif
+
+// Runs `steps` steps; optional host buffers: forces are uploaded before the first step, the body state
+// is downloaded after the last.  With stream groups every group moves its own slice of the host buffers
+// on its own stream, so the copies of one group overlap the kernels of the others.
+static int run_steps(BatchHost* bh, float dt, int vi, int pi, int steps, const float* host_forces, float* host_state_out) {
+  if (!bh || steps < 0 || vi < 0 || pi < 0) { set_error("batch_step: bad argument"); return B2GPU_E_INVALID; }
+  Batch& B = bh->B;
+  Ctx* ctx = bh->ctx;
+  const StepParams sp = make_params(dt, vi, pi);
+  bh->last_sp = sp;
+  Batch all = B;
+  all.wb_first = 0;
+  all.wb_count = B.n_wblocks;
+#if defined(B2G_HOSTSIM)
+  if (host_forces) RC(batch_set_forces(bh, host_forces, 0, B.n_worlds));
+  RC(step_window(bh, all, sp, steps, nullptr));
+  if (host_state_out) RC(batch_get_body_state(bh, host_state_out, 0, B.n_worlds));
+#else
+  RC(ensure_groups(bh));
+  const bool grouped = bh->groups.size() > 1 && !ctx->profiling && steps > 0;
+  if (!grouped) {
+    if (host_forces) RC(batch_set_forces(bh, host_forces, 0, B.n_worlds));
+    RC(step_window(bh, all, sp, steps, nullptr));
+    if (host_state_out) RC(batch_get_body_state(bh, host_state_out, 0, B.n_worlds));
+  } else {
+    cudaStream_t main_s = (cudaStream_t)ctx->stream;
+    CU(cudaEventRecord((cudaEvent_t)bh->ev_entry, main_s));
+    int rc = 0;
+    for (size_t g = 0; g < bh->groups.size() && !rc; ++g) {
+      StreamGroup& sg = bh->groups[g];
+      cudaStream_t gs = (cudaStream_t)sg.stream;
+      Batch Bw = B;
+      Bw.wb_first = sg.wb_first;
+      Bw.wb_count = sg.wb_count;
+      const int w0 = sg.wb_first * B.LB;
+      const int wn = std::min(B.n_worlds, (sg.wb_first + sg.wb_count) * B.LB) - w0;
+      CU(cudaStreamWaitEvent(gs, (cudaEvent_t)bh->ev_entry, 0));
+      ctx->stream = (void*)gs;
+      if (host_forces && wn > 0) {
+        const size_t off = (size_t)w0 * B.NB * 3;
+        cudaError_t e = cudaMemcpyAsync(bh->forces_dev + off, host_forces + off, (size_t)wn * B.NB * 3 * 4, cudaMemcpyHostToDevice, gs);
+        if (e != cudaSuccess) { ctx->stream = (void*)main_s; return cuda_fail(e, "cudaMemcpyAsync(forces)"); }
+        ForceScatterK k = {Bw, bh->forces_dev + off, w0, wn};
+        rc = launch(ctx, k, sg.wb_count * B.LB * B.NB, 128);
+      }
+      // stagger: start behind the previous group's solver set-up of its first step
+      if (!rc && g > 0) {
+        cudaError_t e = cudaStreamWaitEvent(gs, (cudaEvent_t)bh->groups[g - 1].ev_init, 0);
+        if (e != cudaSuccess) { ctx->stream = (void*)main_s; return cuda_fail(e, "cudaStreamWaitEvent"); }
+      }
+      if (!rc) rc = step_window(bh, Bw, sp, steps, sg.ev_init);
+      if (!rc && host_state_out && wn > 0) {
+        StateGatherK k = {Bw, bh->state_dev};
+        rc = launch(ctx, k, sg.wb_count * B.LB * B.NB, 128);
+        if (!rc) {
+          const size_t off = (size_t)w0 * B.NB * 8;
+          cudaError_t e = cudaMemcpyAsync(host_state_out + off, bh->state_dev + off, (size_t)wn * B.NB * 8 * 4, cudaMemcpyDeviceToHost, gs);
+          if (e != cudaSuccess) { ctx->stream = (void*)main_s; return cuda_fail(e, "cudaMemcpyAsync(state)"); }
+        }
+      }
+      ctx->stream = (void*)main_s;
+      if (!rc) {
+        CU(cudaEventRecord((cudaEvent_t)sg.ev_done, gs));
+        CU(cudaStreamWaitEvent(main_s, (cudaEvent_t)sg.ev_done, 0));
+      }
+    }
+    RC(rc);
+    if (host_state_out) CU(cudaStreamSynchronize(main_s));
+  }
+#endif
+  bh->pre_step_needed = false;
+  if (steps > 0 && dt > 0.0f) bh->stepped = true;
+  return 0;
+}
+
+int batch_step(BatchHost* bh, float dt, int vi, int pi, int steps) { return run_steps(bh, dt, vi, pi, steps, nullptr, nullptr); }
+
+// touching / awake counters on demand: one thread per world
+struct StatsK {
+  Batch B;
+  B2G_HD void operator()(int w) const {
+    if (w >= B.n_worlds) return;
+    WIdx x = widx(B, w);
+    Ws ws = ws_of(B, x);
+    int touching = 0, awake = 0;
+    const int cc = ws[WS_CONTACT_COUNT];
+    for (int c = 0; c < cc; ++c) touching += (B.c_flags[x.at(B.NC, c)] & B2GPU_CONTACT_TOUCHING) ? 1 : 0;
+    for (int b = 0; b < B.NB; ++b) awake += (B.b_flags[x.at(B.NB, b)] & B2GPU_BODY_AWAKE) ? 1 : 0;
+    ws[WS_ST_TOUCHING] = touching;
+    ws[WS_ST_AWAKE] = awake;
+    ws[WS_ST_CONTACTS] = cc;
+  }
+};
+
+int batch_get_stats(BatchHost* bh, int first, int count, b2gpu_step_stats* out) {
+  if (!bh || !out || first < 0 || count < 0 || first + count > bh->B.n_worlds) { set_error("get_stats: bad argument"); return B2GPU_E_INVALID; }
+  Batch& B = bh->B;
+  const int W = B.n_wblocks * B.LB;
+  { StatsK k = {B}; RC(launch(bh->ctx, k, W, 32)); }
+  std::vector<int> all((size_t)W * WS_COUNT);
+  RC(dev_d2h(bh->ctx, all.data(), B.ws, all.size() * 4));
+  for (int i = 0; i < count; ++i) {
+    const int w = first + i;
+    const int wb = w >> B.lb_shift, wl = w & (B.LB - 1);
+    auto get = [&](int slot) { return all[((size_t)wb * WS_COUNT + slot) * B.LB + wl]; };
+    b2gpu_step_stats& s = out[i];
+    memset(&s, 0, sizeof(s));
+    s.status = get(WS_STATUS);
+    s.contacts = get(WS_ST_CONTACTS); s.touching = get(WS_ST_TOUCHING); s.destroyed = get(WS_ST_DESTROYED);
+    s.islands = get(WS_ST_ISLANDS); s.island_bodies = get(WS_ST_ISL_BODIES); s.island_contacts = get(WS_ST_ISL_CONTACTS);
+    s.moved = get(WS_ST_MOVED); s.pairs = get(WS_ST_PAIRS); s.created = get(WS_ST_CREATED); s.awake_bodies = get(WS_ST_AWAKE);
+    s.solver_levels = get(WS_ST_LEVELS);
+  }
+  return 0;
+}
+
 int batch_get_body_state(BatchHost* bh, float* host_out, int first, int count) {
   if (!bh || !host_out || first < 0 || count < 0 || first + count > bh->B.n_worlds) { set_error("get_body_state: bad argument"); return B2GPU_E_INVALID; }
   Batch& B = bh->B;
@@ -826,66 +924,12 @@ int batch_set_linear_velocity(BatchHost* bh, int body, const float* host_vxvy, i
   return 0;
 }
 
-// One end-to-end call through HOST buffers: forces H2D, `steps` steps, body state D2H.  The copies run on
-// a second stream: the force upload overlaps the pre-step pair pass and collide (neither reads forces),
-// the state download overlaps fixture synchronisation, tree updates and pair reporting (none of which
-// changes body state).  Synchronous: returns when the state is in `host_state_out`.
+// One end-to-end call through HOST buffers: forces H2D, `steps` steps, body state D2H.  Synchronous:
+// returns when the state is in `host_state_out`.
 int batch_step_host(BatchHost* bh, const float* host_forces, float* host_state_out, float dt, int vi, int pi, int steps) {
-  if (!bh || steps < 0) { set_error("batch_step_host: bad argument"); return B2GPU_E_INVALID; }
-  Batch& B = bh->B;
-  Ctx* ctx = bh->ctx;
-#if defined(B2G_HOSTSIM)
-  if (host_forces) RC(batch_set_forces(bh, host_forces, 0, B.n_worlds));
-  RC(batch_step(bh, dt, vi, pi, steps));
-  if (host_state_out) RC(batch_get_body_state(bh, host_state_out, 0, B.n_worlds));
+  RC(run_steps(bh, dt, vi, pi, steps, host_forces, host_state_out));
+  if (!host_state_out) RC(ctx_sync(bh->ctx));
   return 0;
-#else
-  if (steps == 0 || !(dt > 0.0f) || ctx->profiling) {  // no overlap window: plain sequence
-    if (host_forces) RC(batch_set_forces(bh, host_forces, 0, B.n_worlds));
-    RC(batch_step(bh, dt, vi, pi, steps));
-    if (host_state_out) RC(batch_get_body_state(bh, host_state_out, 0, B.n_worlds));
-    else RC(ctx_sync(ctx));
-    return 0;
-  }
-  if (!bh->copy_stream) {
-    cudaStream_t cs;
-    CU(cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
-    bh->copy_stream = (void*)cs;
-    cudaEvent_t e;
-    CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); bh->ev_entry = (void*)e;
-    CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); bh->ev_forces = (void*)e;
-    CU(cudaEventCreateWithFlags(&e, cudaEventDisableTiming)); bh->ev_state = (void*)e;
-  }
-  cudaStream_t main_s = (cudaStream_t)ctx->stream, copy_s = (cudaStream_t)bh->copy_stream;
-  const int n_flat = B.n_wblocks * B.LB * B.NB;
-  StepHooks hooks;
-  CU(cudaEventRecord((cudaEvent_t)bh->ev_entry, main_s));
-  CU(cudaStreamWaitEvent(copy_s, (cudaEvent_t)bh->ev_entry, 0));
-  if (host_forces) {
-    CU(cudaMemcpyAsync(bh->forces_dev, host_forces, (size_t)B.n_worlds * B.NB * 3 * 4, cudaMemcpyHostToDevice, copy_s));
-    ctx->stream = (void*)copy_s;
-    ForceScatterK k = {B, bh->forces_dev, 0, B.n_worlds};
-    int rc = launch(ctx, k, n_flat, 128);
-    ctx->stream = (void*)main_s;
-    RC(rc);
-    CU(cudaEventRecord((cudaEvent_t)bh->ev_forces, copy_s));
-    hooks.wait_before_island = bh->ev_forces;
-  }
-  if (host_state_out) hooks.record_state_final = bh->ev_state;
-  RC(batch_step_impl(bh, dt, vi, pi, steps, &hooks));
-  if (host_state_out) {
-    CU(cudaStreamWaitEvent(copy_s, (cudaEvent_t)bh->ev_state, 0));
-    ctx->stream = (void*)copy_s;
-    StateGatherK k = {B, bh->state_dev};
-    int rc = launch(ctx, k, n_flat, 128);
-    ctx->stream = (void*)main_s;
-    RC(rc);
-    CU(cudaMemcpyAsync(host_state_out, bh->state_dev, (size_t)B.n_worlds * B.NB * 8 * 4, cudaMemcpyDeviceToHost, copy_s));
-  }
-  CU(cudaStreamSynchronize(copy_s));
-  CU(cudaStreamSynchronize(main_s));
-  return 0;
-#endif
 }
 
 // sin/cos of an array of angles on the device (diagnostic: pins rot_from_angle against libm)

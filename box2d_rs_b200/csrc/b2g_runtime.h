@@ -51,6 +51,13 @@ struct Topology {  // shared by every world of a batch (host copies kept for val
   std::vector<int> sync_order, sync_rank, node_proxy;
 };
 
+struct StreamGroup {
+  int wb_first = 0, wb_count = 0;
+  void* stream = nullptr;   // cudaStream_t
+  void* ev_init = nullptr;  // cudaEvent_t: solver set-up of the first step issued (stagger point)
+  void* ev_done = nullptr;  // cudaEvent_t: all work of the call issued on this stream
+};
+
 struct BatchHost {
   Ctx* ctx = nullptr;
   Batch B;          // device pointers + dims
@@ -70,10 +77,9 @@ struct BatchHost {
   bool ml_velocity = false;      // velocity stage also level-scheduled (experiment switch)
   bool ml_solver = false;        // level-scheduled multi-lane Gauss-Seidel kernels in use
   bool smem_solver = false;      // shared-memory Gauss-Seidel kernels in use (b2g_solver_smem.cuh)
-  void* copy_stream = nullptr;   // second stream + events of batch_step_host (created on first use)
-  void* ev_entry = nullptr;
-  void* ev_forces = nullptr;
-  void* ev_state = nullptr;
+  std::vector<StreamGroup> groups;  // independent pipelines over windows of world blocks (created on first use)
+  void* ev_entry = nullptr;         // cudaEvent_t: fork point on the context stream
+  int stream_groups = 0;            // 0 = automatic (4 for batches of >= 16 world blocks), 1 = single stream
   bool stepped = false;          // at least one dt > 0 step ran: island arrays are meaningful
   bool pre_step_needed = true;   // some world may carry m_new_contacts / a non-empty move buffer
   long long total_bytes = 0;

@@ -94,7 +94,7 @@ __global__ void __launch_bounds__(32) velocity_smem_kernel(const Batch B, const 
   float4* vel = smem4 + VEL_RING * VC_Q * 32;  // [NB][32]: v.x v.y w -
   uint64_t* bars = (uint64_t*)(vel + (size_t)B.NB * 32);  // [VEL_RING] one mbarrier per ring stage (TMA form)
   const int lane = threadIdx.x;
-  const int wb = blockIdx.x;
+  const int wb = blockIdx.x + B.wb_first;
   const int w = wb * 32 + lane;
   const bool live = w < B.n_worlds;
   WIdx x;
@@ -271,7 +271,7 @@ __global__ void __launch_bounds__(32) position_smem_kernel(const Batch B, const 
   float4* pos = smem4 + POS_RING * PC_Q * 32;             // [NB][32]: c.x c.y a -
   float2* rot = (float2*)(pos + (size_t)B.NB * 32);       // [NB][32]: sin a, cos a
   const int lane = threadIdx.x;
-  const int wb = blockIdx.x;
+  const int wb = blockIdx.x + B.wb_first;
   const int w = wb * 32 + lane;
   const bool live = w < B.n_worlds;
   WIdx x;
@@ -433,7 +433,7 @@ __global__ void __launch_bounds__(32) position_ml_kernel(const Batch B, const St
   unsigned* tab = (unsigned*)(rot + (size_t)B.NB * ML_WPC);  // [NB][ML_WPC] per island (see above)
   const int lane = threadIdx.x;
   const int g = lane / ML_WPC, wq = lane % ML_WPC;
-  const int wb = blockIdx.x / SCHED_G;
+  const int wb = blockIdx.x / SCHED_G + B.wb_first;
   const int wl = (blockIdx.x % SCHED_G) * ML_WPC + wq;
   const int w = wb * 32 + wl;
   const bool live = w < B.n_worlds;
@@ -591,7 +591,7 @@ __global__ void __launch_bounds__(32) velocity_ml_kernel(const Batch B, const St
   float4* vel = smem4 + ML_RING * VC_Q * 32;     // [NB][ML_WPC]
   const int lane = threadIdx.x;
   const int g = lane / ML_WPC, wq = lane % ML_WPC;
-  const int wb = blockIdx.x / SCHED_G;
+  const int wb = blockIdx.x / SCHED_G + B.wb_first;
   const int wl = (blockIdx.x % SCHED_G) * ML_WPC + wq;
   const int w = wb * 32 + wl;
   const bool live = w < B.n_worlds;

@@ -51,9 +51,9 @@ B2G_HD bool flat_decode(const Batch& B, int tid, int N, int& w, int& i) {
   int wl = tid & (B.LB - 1);
   int rest = tid >> B.lb_shift;
   i = rest % N;
-  int wb = rest / N;
+  int wb = rest / N + B.wb_first;
   w = (wb << B.lb_shift) + wl;
-  return wb < B.n_wblocks && w < B.n_worlds;
+  return wb < B.wb_first + B.wb_count && w < B.n_worlds;
 }
 
 B2G_HD Xf load_xf(const Batch& B, const WIdx& x, int b) {
@@ -216,7 +216,8 @@ struct SerialAK {
   int2* c_next;   // per contact: next older edge of body A / body B
   int* stack;     // [NB] DFS stack
   StepParams sp;
-  B2G_HD void operator()(int w) const {
+  B2G_HD void operator()(int tid) const {
+    const int w = tid + (B.wb_first << B.lb_shift);
     if (w >= B.n_worlds) return;
     WIdx x = widx(B, w);
     Ws ws = ws_of(B, x);
@@ -1111,7 +1112,8 @@ struct TreePairsK {
   int2* c_next;
   StepParams sp;
   int pre_step;  // 1: the find_new_contacts call at the top of step (m_new_contacts), no tree moves
-  B2G_HD void operator()(int w) const {
+  B2G_HD void operator()(int tid) const {
+    const int w = tid + (B.wb_first << B.lb_shift);
     if (w >= B.n_worlds) return;
     WIdx x = widx(B, w);
     Ws ws = ws_of(B, x);
