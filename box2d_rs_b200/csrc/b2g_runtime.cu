@@ -528,6 +528,7 @@ int batch_create(Ctx* ctx, const b2gpu_snapshot* proto, int n_worlds, const b2gp
       CU(cudaFuncSetAttribute(velocity_smem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)velocity_smem_bytes(B.NB)));
       bh->tma_ring = caps && caps->reserved[1] == 4;
       if (caps && caps->reserved[1] == 5) bh->stream_groups = 1;
+      if (caps && caps->reserved[1] == 6) bh->use_graphs = false;
       CU(cudaFuncSetAttribute(position_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)position_smem_bytes(B.NB)));
       bh->smem_solver = true;
     }
@@ -559,6 +560,7 @@ void batch_destroy(BatchHost* bh) {
     cudaStreamDestroy((cudaStream_t)sg.stream);
   }
   if (bh->ev_entry) cudaEventDestroy((cudaEvent_t)bh->ev_entry);
+  for (StepGraph& g : bh->graphs) cudaGraphExecDestroy((cudaGraphExec_t)g.exec);
 #endif
   for (void* p : bh->allocs) dev_free(p);
   delete bh;
@@ -785,15 +787,11 @@ static int ensure_groups(BatchHost* bh) {
 }
 #endif
 
-// Runs `steps` steps; optional host buffers: forces are uploaded before the first step, the body state
-// is downloaded after the last.  With stream groups every group moves its own slice of the host buffers
-// on its own stream, so the copies of one group overlap the kernels of the others.
-static int run_steps(BatchHost* bh, float dt, int vi, int pi, int steps, const float* host_forces, float* host_state_out) {
-  if (!bh || steps < 0 || vi < 0 || pi < 0) { set_error("batch_step: bad argument"); return B2GPU_E_INVALID; }
+// Enqueues `steps` steps (and the optional host copies) on the context stream / the stream groups.
+// Pure enqueue: no host synchronisation, so the same code runs under stream capture.
+static int enqueue_steps(BatchHost* bh, const StepParams& sp, int steps, const float* host_forces, float* host_state_out) {
   Batch& B = bh->B;
   Ctx* ctx = bh->ctx;
-  const StepParams sp = make_params(dt, vi, pi);
-  bh->last_sp = sp;
   Batch all = B;
   all.wb_first = 0;
   all.wb_count = B.n_wblocks;
@@ -801,58 +799,129 @@ static int run_steps(BatchHost* bh, float dt, int vi, int pi, int steps, const f
   if (host_forces) RC(batch_set_forces(bh, host_forces, 0, B.n_worlds));
   RC(step_window(bh, all, sp, steps, nullptr));
   if (host_state_out) RC(batch_get_body_state(bh, host_state_out, 0, B.n_worlds));
+  return 0;
 #else
-  RC(ensure_groups(bh));
+  cudaStream_t main_s = (cudaStream_t)ctx->stream;
   const bool grouped = bh->groups.size() > 1 && !ctx->profiling && steps > 0;
   if (!grouped) {
-    if (host_forces) RC(batch_set_forces(bh, host_forces, 0, B.n_worlds));
+    if (host_forces) {
+      CU(cudaMemcpyAsync(bh->forces_dev, host_forces, (size_t)B.n_worlds * B.NB * 3 * 4, cudaMemcpyHostToDevice, main_s));
+      ForceScatterK k = {all, bh->forces_dev, 0, B.n_worlds};
+      RC(launch(ctx, k, B.n_wblocks * B.LB * B.NB, 128));
+    }
     RC(step_window(bh, all, sp, steps, nullptr));
-    if (host_state_out) RC(batch_get_body_state(bh, host_state_out, 0, B.n_worlds));
-  } else {
-    cudaStream_t main_s = (cudaStream_t)ctx->stream;
-    CU(cudaEventRecord((cudaEvent_t)bh->ev_entry, main_s));
-    int rc = 0;
-    for (size_t g = 0; g < bh->groups.size() && !rc; ++g) {
-      StreamGroup& sg = bh->groups[g];
-      cudaStream_t gs = (cudaStream_t)sg.stream;
-      Batch Bw = B;
-      Bw.wb_first = sg.wb_first;
-      Bw.wb_count = sg.wb_count;
-      const int w0 = sg.wb_first * B.LB;
-      const int wn = std::min(B.n_worlds, (sg.wb_first + sg.wb_count) * B.LB) - w0;
-      CU(cudaStreamWaitEvent(gs, (cudaEvent_t)bh->ev_entry, 0));
-      ctx->stream = (void*)gs;
-      if (host_forces && wn > 0) {
-        const size_t off = (size_t)w0 * B.NB * 3;
-        cudaError_t e = cudaMemcpyAsync(bh->forces_dev + off, host_forces + off, (size_t)wn * B.NB * 3 * 4, cudaMemcpyHostToDevice, gs);
-        if (e != cudaSuccess) { ctx->stream = (void*)main_s; return cuda_fail(e, "cudaMemcpyAsync(forces)"); }
-        ForceScatterK k = {Bw, bh->forces_dev + off, w0, wn};
-        rc = launch(ctx, k, sg.wb_count * B.LB * B.NB, 128);
-      }
-      // stagger: start behind the previous group's solver set-up of its first step
-      if (!rc && g > 0) {
-        cudaError_t e = cudaStreamWaitEvent(gs, (cudaEvent_t)bh->groups[g - 1].ev_init, 0);
-        if (e != cudaSuccess) { ctx->stream = (void*)main_s; return cuda_fail(e, "cudaStreamWaitEvent"); }
-      }
-      if (!rc) rc = step_window(bh, Bw, sp, steps, sg.ev_init);
-      if (!rc && host_state_out && wn > 0) {
-        StateGatherK k = {Bw, bh->state_dev};
-        rc = launch(ctx, k, sg.wb_count * B.LB * B.NB, 128);
-        if (!rc) {
-          const size_t off = (size_t)w0 * B.NB * 8;
-          cudaError_t e = cudaMemcpyAsync(host_state_out + off, bh->state_dev + off, (size_t)wn * B.NB * 8 * 4, cudaMemcpyDeviceToHost, gs);
-          if (e != cudaSuccess) { ctx->stream = (void*)main_s; return cuda_fail(e, "cudaMemcpyAsync(state)"); }
-        }
-      }
-      ctx->stream = (void*)main_s;
+    if (host_state_out) {
+      StateGatherK k = {all, bh->state_dev};
+      RC(launch(ctx, k, B.n_wblocks * B.LB * B.NB, 128));
+      CU(cudaMemcpyAsync(host_state_out, bh->state_dev, (size_t)B.n_worlds * B.NB * 8 * 4, cudaMemcpyDeviceToHost, main_s));
+    }
+    return 0;
+  }
+  CU(cudaEventRecord((cudaEvent_t)bh->ev_entry, main_s));
+  int rc = 0;
+  for (size_t g = 0; g < bh->groups.size() && !rc; ++g) {
+    StreamGroup& sg = bh->groups[g];
+    cudaStream_t gs = (cudaStream_t)sg.stream;
+    Batch Bw = B;
+    Bw.wb_first = sg.wb_first;
+    Bw.wb_count = sg.wb_count;
+    const int w0 = sg.wb_first * B.LB;
+    const int wn = std::min(B.n_worlds, (sg.wb_first + sg.wb_count) * B.LB) - w0;
+    CU(cudaStreamWaitEvent(gs, (cudaEvent_t)bh->ev_entry, 0));
+    ctx->stream = (void*)gs;
+    if (host_forces && wn > 0) {
+      const size_t off = (size_t)w0 * B.NB * 3;
+      cudaError_t e = cudaMemcpyAsync(bh->forces_dev + off, host_forces + off, (size_t)wn * B.NB * 3 * 4, cudaMemcpyHostToDevice, gs);
+      if (e != cudaSuccess) { ctx->stream = (void*)main_s; return cuda_fail(e, "cudaMemcpyAsync(forces)"); }
+      ForceScatterK k = {Bw, bh->forces_dev + off, w0, wn};
+      rc = launch(ctx, k, sg.wb_count * B.LB * B.NB, 128);
+    }
+    // stagger: start behind the previous group's solver set-up of its first step
+    if (!rc && g > 0) {
+      cudaError_t e = cudaStreamWaitEvent(gs, (cudaEvent_t)bh->groups[g - 1].ev_init, 0);
+      if (e != cudaSuccess) { ctx->stream = (void*)main_s; return cuda_fail(e, "cudaStreamWaitEvent"); }
+    }
+    if (!rc) rc = step_window(bh, Bw, sp, steps, sg.ev_init);
+    if (!rc && host_state_out && wn > 0) {
+      StateGatherK k = {Bw, bh->state_dev};
+      rc = launch(ctx, k, sg.wb_count * B.LB * B.NB, 128);
       if (!rc) {
-        CU(cudaEventRecord((cudaEvent_t)sg.ev_done, gs));
-        CU(cudaStreamWaitEvent(main_s, (cudaEvent_t)sg.ev_done, 0));
+        const size_t off = (size_t)w0 * B.NB * 8;
+        cudaError_t e = cudaMemcpyAsync(host_state_out + off, bh->state_dev + off, (size_t)wn * B.NB * 8 * 4, cudaMemcpyDeviceToHost, gs);
+        if (e != cudaSuccess) { ctx->stream = (void*)main_s; return cuda_fail(e, "cudaMemcpyAsync(state)"); }
       }
     }
-    RC(rc);
-    if (host_state_out) CU(cudaStreamSynchronize(main_s));
+    ctx->stream = (void*)main_s;
+    if (!rc) {
+      CU(cudaEventRecord((cudaEvent_t)sg.ev_done, gs));
+      CU(cudaStreamWaitEvent(main_s, (cudaEvent_t)sg.ev_done, 0));
+    }
   }
+  return rc;
+#endif
+}
+
+#if !defined(B2G_HOSTSIM)
+static bool host_pointer_capturable(const void* p) {  // memcpy nodes need page-locked host memory
+  if (!p) return true;
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+#endif
+
+// Runs `steps` steps; optional host buffers: forces are uploaded before the first step, the body state is
+// downloaded after the last.  The enqueue sequence of a call signature (dt, iterations, steps, host
+// pointers) is captured once into a CUDA graph and replayed afterwards: a step is 13 launches per stream
+// group, and at a few milliseconds per step the launch overhead of the host would otherwise show.
+static int run_steps(BatchHost* bh, float dt, int vi, int pi, int steps, const float* host_forces, float* host_state_out) {
+  if (!bh || steps < 0 || vi < 0 || pi < 0) { set_error("batch_step: bad argument"); return B2GPU_E_INVALID; }
+  Ctx* ctx = bh->ctx;
+  const StepParams sp = make_params(dt, vi, pi);
+  bh->last_sp = sp;
+#if defined(B2G_HOSTSIM)
+  RC(enqueue_steps(bh, sp, steps, host_forces, host_state_out));
+#else
+  RC(ensure_groups(bh));
+  cudaStream_t main_s = (cudaStream_t)ctx->stream;
+  const bool use_graph = bh->use_graphs && !ctx->profiling && steps > 0 && host_pointer_capturable(host_forces) &&
+                         host_pointer_capturable(host_state_out);
+  if (!use_graph) {
+    RC(enqueue_steps(bh, sp, steps, host_forces, host_state_out));
+  } else {
+    StepGraph* hit = nullptr;
+    for (StepGraph& sgph : bh->graphs)
+      if (sgph.dt == dt && sgph.vi == vi && sgph.pi == pi && sgph.steps == steps && sgph.forces == (const void*)host_forces &&
+          sgph.state == (void*)host_state_out)
+        hit = &sgph;
+    if (!hit) {
+      const long long launches_before = ctx->launches;
+      CU(cudaStreamBeginCapture(main_s, cudaStreamCaptureModeThreadLocal));
+      int rc = enqueue_steps(bh, sp, steps, host_forces, host_state_out);
+      cudaGraph_t graph = nullptr;
+      cudaError_t e = cudaStreamEndCapture(main_s, &graph);
+      if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+      if (e != cudaSuccess) return cuda_fail(e, "cudaStreamEndCapture");
+      cudaGraphExec_t exec = nullptr;
+      e = cudaGraphInstantiate(&exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (e != cudaSuccess) return cuda_fail(e, "cudaGraphInstantiate");
+      if (bh->graphs.size() >= 8) {  // small cache: drop the oldest signature
+        cudaGraphExecDestroy((cudaGraphExec_t)bh->graphs.front().exec);
+        bh->graphs.erase(bh->graphs.begin());
+      }
+      StepGraph ng;
+      ng.dt = dt; ng.vi = vi; ng.pi = pi; ng.steps = steps; ng.forces = host_forces; ng.state = host_state_out;
+      ng.exec = (void*)exec;
+      ng.launches = ctx->launches - launches_before;
+      ctx->launches = launches_before;  // capture issued nothing; replays are counted below
+      bh->graphs.push_back(ng);
+      hit = &bh->graphs.back();
+    }
+    CU(cudaGraphLaunch((cudaGraphExec_t)hit->exec, main_s));
+    ctx->launches += hit->launches;
+  }
+  if (host_state_out) CU(cudaStreamSynchronize(main_s));
 #endif
   bh->pre_step_needed = false;
   if (steps > 0 && dt > 0.0f) bh->stepped = true;

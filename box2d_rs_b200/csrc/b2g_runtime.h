@@ -58,6 +58,15 @@ struct StreamGroup {
   void* ev_done = nullptr;  // cudaEvent_t: all work of the call issued on this stream
 };
 
+struct StepGraph {  // instantiated CUDA graph of one run_steps call signature
+  float dt = 0.0f;
+  int vi = 0, pi = 0, steps = 0;
+  const void* forces = nullptr;
+  void* state = nullptr;
+  void* exec = nullptr;  // cudaGraphExec_t
+  long long launches = 0;
+};
+
 struct BatchHost {
   Ctx* ctx = nullptr;
   Batch B;          // device pointers + dims
@@ -79,6 +88,8 @@ struct BatchHost {
   bool smem_solver = false;      // shared-memory Gauss-Seidel kernels in use (b2g_solver_smem.cuh)
   std::vector<StreamGroup> groups;  // independent pipelines over windows of world blocks (created on first use)
   void* ev_entry = nullptr;         // cudaEvent_t: fork point on the context stream
+  std::vector<StepGraph> graphs;    // CUDA graphs per call signature (see run_steps)
+  bool use_graphs = true;
   int stream_groups = 0;            // 0 = automatic (4 for batches of >= 16 world blocks), 1 = single stream
   bool stepped = false;          // at least one dt > 0 step ran: island arrays are meaningful
   bool pre_step_needed = true;   // some world may carry m_new_contacts / a non-empty move buffer
