@@ -157,6 +157,8 @@ def run_ours(args, rank, world_size, local_rank):
     sampler = ClockSampler(local_rank)  # samples while the device is under this load (warm-up + timed region)
     sampler.start()
     batch.step(scenes.DT, scenes.VEL_ITERS, scenes.POS_ITERS, max(args.warmup, 60))
+    # one untimed call with the timed call's signature: the library captures a CUDA graph per signature
+    batch.step(scenes.DT, scenes.VEL_ITERS, scenes.POS_ITERS, args.steps)
     barrier()
     launches0 = ctx.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
