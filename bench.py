@@ -48,7 +48,7 @@ class ClockSampler(threading.Thread):
 
     def __init__(self, index):
         super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.rows, self.stop_flag, self.interval = index, [], False, 0.2
 
     def run(self):
         while not self.stop_flag:
@@ -60,7 +60,7 @@ class ClockSampler(threading.Thread):
                     self.rows.append(parts)
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(self.interval)
 
     def summary(self):
         self.stop_flag = True
