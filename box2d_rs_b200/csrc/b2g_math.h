@@ -41,6 +41,23 @@ namespace b2g {
 #define B2G_MAX_POLY 8
 
 B2G_HD float fmin_sel(float a, float b) { return a < b ? a : b; }  // b2_min
+// Branch-free select that stays one: the mask is opaque to the optimiser, so (a & m) | (b & ~m) is not
+// turned back into a select and from there into a branch (a branch ends a scheduling region on the
+// latency-bound chains of the Gauss-Seidel kernels).
+B2G_HD int sel_mask(bool c) {
+  int m = c ? -1 : 0;
+#if defined(__CUDA_ARCH__)
+  asm("" : "+r"(m));
+#endif
+  return m;
+}
+B2G_HD float msel(int m, float a, float b) {
+#if defined(__CUDA_ARCH__)
+  return __int_as_float((__float_as_int(a) & m) | (__float_as_int(b) & ~m));
+#else
+  return m ? a : b;
+#endif
+}
 B2G_HD float fmax_sel(float a, float b) { return a > b ? a : b; }  // b2_max
 B2G_HD float fclamp_sel(float a, float lo, float hi) { return fmax_sel(lo, fmin_sel(a, hi)); }
 B2G_HD int imin(int a, int b) { return a < b ? a : b; }

@@ -526,7 +526,9 @@ int batch_create(Ctx* ctx, const b2gpu_snapshot* proto, int n_worlds, const b2gp
     if (need <= (size_t)max_optin) {
       CU(cudaFuncSetAttribute(velocity_smem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)velocity_smem_bytes(B.NB)));
       CU(cudaFuncSetAttribute(velocity_smem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)velocity_smem_bytes(B.NB)));
+      CU(cudaFuncSetAttribute(velocity_sl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)velocity_smem_bytes(B.NB)));
       bh->tma_ring = caps && caps->reserved[1] == 4;
+      bh->pipelined_velocity = caps && caps->reserved[1] == 7;
       if (caps && caps->reserved[1] == 5) bh->stream_groups = 1;
       if (caps && caps->reserved[1] == 6) bh->use_graphs = false;
       CU(cudaFuncSetAttribute(position_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)position_smem_bytes(B.NB)));
@@ -712,7 +714,9 @@ static int step_window(BatchHost* bh, const Batch& Bw, const StepParams& sp, int
       } else if (bh->smem_solver) {
         LaunchScope ls = {ctx, STAGE_VELOCITY};
         RC(ls.begin());
-        if (bh->tma_ring)
+        if (!bh->tma_ring && !bh->pipelined_velocity)
+          velocity_sl_kernel<<<B.wb_count, 32, velocity_smem_bytes(B.NB), (cudaStream_t)ctx->stream>>>(B, sp);
+        else if (bh->tma_ring)
           velocity_smem_kernel<true><<<B.wb_count, 32, velocity_smem_bytes(B.NB), (cudaStream_t)ctx->stream>>>(B, sp);
         else
           velocity_smem_kernel<false><<<B.wb_count, 32, velocity_smem_bytes(B.NB), (cudaStream_t)ctx->stream>>>(B, sp);

@@ -83,6 +83,7 @@ struct BatchHost {
   bool smem_island = false;      // shared-memory island DFS in use (b2g_island_smem.cuh)
   IslandSmemLayout island_layout;
   bool tma_ring = false;         // velocity ring filled by cp.async.bulk + mbarrier instead of cp.async
+  bool pipelined_velocity = false;  // diagnostic: the branchy pipelined velocity kernel instead of the straight-line one
   bool ml_velocity = false;      // velocity stage also level-scheduled (experiment switch)
   bool ml_solver = false;        // level-scheduled multi-lane Gauss-Seidel kernels in use
   bool smem_solver = false;      // shared-memory Gauss-Seidel kernels in use (b2g_solver_smem.cuh)

@@ -16,6 +16,7 @@
 // write-back.  Results are bit-identical to the generic stages in b2g_step.h (same device functions).
 #pragma once
 #include "b2g_step.h"
+#include <type_traits>
 
 namespace b2g {
 
@@ -59,7 +60,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
 constexpr int VEL_RING = 8;  // stages of the velocity constraint ring
 constexpr int POS_RING = 8;
 
-inline size_t velocity_smem_bytes(int NB) { return (size_t)NB * 32 * 16 + (size_t)VEL_RING * VC_Q * 32 * 16 + VEL_RING * 8; }
+inline size_t velocity_smem_bytes(int NB) { return (size_t)(NB + 1) * 32 * 16 + (size_t)VEL_RING * VC_Q * 32 * 16 + VEL_RING * 8; }
 inline size_t position_smem_bytes(int NB) { return (size_t)NB * 32 * (16 + 8) + (size_t)POS_RING * PC_Q * 32 * 16; }
 
 struct VcRegs {  // one velocity constraint of one world, in registers
@@ -77,6 +78,40 @@ __device__ __forceinline__ VcRegs vc_load(const float4* st) {
   return r;
 }
 
+// Resident form of the velocity stage: the whole constraint stream of the block fits the ring; load it once
+// and iterate in shared memory (small islands).
+__device__ __forceinline__ void velocity_resident(float4* rl, float4* vl, const float4* src, float4* q6_out, int nc, int ncm,
+                                                  bool warm, bool block, int sweeps) {
+  for (int k = 0; k < ncm; ++k) {
+#pragma unroll
+    for (int q = 0; q < VC_Q; ++q) cp_async16(rl + (k * VC_Q + q) * 32, src + (size_t)(k * VC_Q + q) * 32);
+  }
+  cp_async_commit();
+  cp_async_wait<0>();
+  for (int sweep = 0; sweep < sweeps; ++sweep) {
+    if (sweep == 0 && !__any_sync(0xffffffffu, warm)) continue;
+    for (int k = 0; k < ncm; ++k) {
+      if (k >= nc || (sweep == 0 && !warm)) continue;
+      float4* st = rl + (k * VC_Q) * 32;
+      VcRegs c = vc_load(st);
+      if (c.cnt == 0) continue;
+      const float4 va = vl[c.ba * 32], vb = vl[c.bb * 32];
+      VelState s;
+      s.v_a = v2(va.x, va.y); s.w_a = va.z;
+      s.v_b = v2(vb.x, vb.y); s.w_b = vb.z;
+      if (sweep == 0) {
+        warm_start_one(s, c.q0, c.q1, c.q2, c.q6, c.q7, c.cnt);
+      } else {
+        solve_velocity_one(s, c.q0, c.q1, c.q2, c.q3, c.q4, c.q5, c.q6, c.q7, c.cnt, block);
+        st[6 * 32] = c.q6;
+        if (sweep == sweeps - 1) q6_out[(size_t)k * VC_Q * 32] = c.q6;
+      }
+      vl[c.ba * 32] = make_float4(s.v_a.x, s.v_a.y, s.w_a, 0.0f);
+      vl[c.bb * 32] = make_float4(s.v_b.x, s.v_b.y, s.w_b, 0.0f);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------
 // warm start + velocity iterations.  grid = world blocks, block = 32 lanes (one world each).
 //
@@ -92,7 +127,7 @@ __global__ void __launch_bounds__(32) velocity_smem_kernel(const Batch B, const 
   extern __shared__ float4 smem4[];
   float4* ring = smem4;                      // [VEL_RING][VC_Q][32]
   float4* vel = smem4 + VEL_RING * VC_Q * 32;  // [NB][32]: v.x v.y w -
-  uint64_t* bars = (uint64_t*)(vel + (size_t)B.NB * 32);  // [VEL_RING] one mbarrier per ring stage (TMA form)
+  uint64_t* bars = (uint64_t*)(vel + (size_t)(B.NB + 1) * 32);  // [VEL_RING] one mbarrier per ring stage (TMA form)
   const int lane = threadIdx.x;
   const int wb = blockIdx.x + B.wb_first;
   const int w = wb * 32 + lane;
@@ -116,35 +151,7 @@ __global__ void __launch_bounds__(32) velocity_smem_kernel(const Batch B, const 
   float4* rl = ring + lane;
 
   if (ncm <= VEL_RING) {
-    // ---- resident form: the whole stream fits the ring; load once, iterate in shared memory
-    for (int k = 0; k < ncm; ++k) {
-#pragma unroll
-      for (int q = 0; q < VC_Q; ++q) cp_async16(rl + (k * VC_Q + q) * 32, src + (size_t)(k * VC_Q + q) * 32);
-    }
-    cp_async_commit();
-    cp_async_wait<0>();
-    for (int sweep = 0; sweep < sweeps; ++sweep) {
-      if (sweep == 0 && !__any_sync(0xffffffffu, warm)) continue;
-      for (int k = 0; k < ncm; ++k) {
-        if (k >= nc || (sweep == 0 && !warm)) continue;
-        float4* st = rl + (k * VC_Q) * 32;
-        VcRegs c = vc_load(st);
-        if (c.cnt == 0) continue;
-        const float4 va = vl[c.ba * 32], vb = vl[c.bb * 32];
-        VelState s;
-        s.v_a = v2(va.x, va.y); s.w_a = va.z;
-        s.v_b = v2(vb.x, vb.y); s.w_b = vb.z;
-        if (sweep == 0) {
-          warm_start_one(s, c.q0, c.q1, c.q2, c.q6, c.q7, c.cnt);
-        } else {
-          solve_velocity_one(s, c.q0, c.q1, c.q2, c.q3, c.q4, c.q5, c.q6, c.q7, c.cnt, block);
-          st[6 * 32] = c.q6;
-          if (sweep == sweeps - 1) q6_out[(size_t)k * VC_Q * 32] = c.q6;
-        }
-        vl[c.ba * 32] = make_float4(s.v_a.x, s.v_a.y, s.w_a, 0.0f);
-        vl[c.bb * 32] = make_float4(s.v_b.x, s.v_b.y, s.w_b, 0.0f);
-      }
-    }
+    velocity_resident(rl, vl, src, q6_out, nc, ncm, warm, block, sweeps);
   } else {
     // ---- streaming form: ring of VEL_RING stages, constraint p lives in stage p % VEL_RING
     int fk = 0;                 // next constraint index to fetch (wraps at ncm)
@@ -237,6 +244,160 @@ __global__ void __launch_bounds__(32) velocity_smem_kernel(const Batch B, const 
       half_step(ca, acta, vaa, vab, cb, actb, vba, vbb);
       half_step(cb, actb, vba, vbb, ca, acta, vaa, vab);
     }
+    cp_async_wait<0>();
+  }
+  __syncwarp();
+  if (live)
+    for (int b = 0; b < B.NB; ++b) B.b_vel[x.at(B.NB, b)] = vel[b * 32 + lane];
+}
+
+// ------------------------------------------------------------------------------------------
+// Straight-line form of the same stage (the default).  The pipelined loop above spends 40 % of a visit in
+// bookkeeping around the arithmetic (ncu source page, round 1: 92 of 280 instructions at 3 cycles each:
+// convergence barriers of five data-dependent branches, the ring refill, register forwarding), none of which
+// can overlap the dependent fp32 chain because every branch ends a scheduling region.  Here one visit is ONE
+// basic block: the refill is unconditional (the stream wraps, so reading ahead past the end is harmless), an
+// inactive visit (world with fewer constraints, empty manifold, no warm start) runs the same arithmetic on a
+// scratch row instead of being predicated, selects are kept from becoming branches (sel_mask), the warm-start
+// sweep has its own loop, and the choice between the two-point block solver and the general path is a warp
+// vote taken one visit ahead.  ptxas can
+// then fill the issue slots the chain leaves empty with the next visit's loads.
+// ------------------------------------------------------------------------------------------
+static_assert(VC_Q == 9, "cp_async_record copies nine rows");
+__device__ __forceinline__ void cp_async_record(float4* smem_dst, const float4* gmem_src) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile(
+      "cp.async.cg.shared.global [%0], [%1], 16;\n"
+      "cp.async.cg.shared.global [%0+512], [%1+512], 16;\n"
+      "cp.async.cg.shared.global [%0+1024], [%1+1024], 16;\n"
+      "cp.async.cg.shared.global [%0+1536], [%1+1536], 16;\n"
+      "cp.async.cg.shared.global [%0+2048], [%1+2048], 16;\n"
+      "cp.async.cg.shared.global [%0+2560], [%1+2560], 16;\n"
+      "cp.async.cg.shared.global [%0+3072], [%1+3072], 16;\n"
+      "cp.async.cg.shared.global [%0+3584], [%1+3584], 16;\n"
+      "cp.async.cg.shared.global [%0+4096], [%1+4096], 16;\n"
+      "cp.async.commit_group;\n" ::"r"(s),
+      "l"(gmem_src)
+      : "memory");
+}
+
+__global__ void __launch_bounds__(32) velocity_sl_kernel(const Batch B, const StepParams sp) {
+  extern __shared__ float4 smem4[];
+  float4* ring = smem4;                        // [VEL_RING][VC_Q][32]
+  float4* vel = smem4 + VEL_RING * VC_Q * 32;  // [NB][32]: v.x v.y w -
+  const int lane = threadIdx.x;
+  const int wb = blockIdx.x + B.wb_first;
+  const int w = wb * 32 + lane;
+  const bool live = w < B.n_worlds;
+  WIdx x;
+  x.wb = wb; x.wl = lane; x.LB = 32;
+  Ws ws = ws_of(B, x);
+  const int nc = live ? ws[WS_ISL_CONTACTS] : 0;
+  const int wflags = live ? ws[WS_FLAGS] : 0;
+  const bool warm = (wflags & B2GPU_WORLD_WARM_STARTING) != 0;
+  const bool block = (wflags & B2GPU_WORLD_BLOCK_SOLVE) != 0;
+  const int ncm = __reduce_max_sync(0xffffffffu, nc);
+  if (ncm == 0) return;
+  if (live)
+    for (int b = 0; b < B.NB; ++b) vel[b * 32 + lane] = B.b_vel[x.at(B.NB, b)];
+  const float4* src = B.vc + (size_t)wb * B.NC * VC_Q * 32 + lane;  // + (k * VC_Q + q) * 32
+  float4* q6_out = B.vc + (size_t)wb * B.NC * VC_Q * 32 + 6 * 32 + lane;
+  float4* vl = vel + lane;
+  float4* rl = ring + lane;
+  if (ncm <= VEL_RING) {
+    velocity_resident(rl, vl, src, q6_out, nc, ncm, warm, block, 1 + sp.velocity_iterations);
+  } else {
+    const int n_warm = __any_sync(0xffffffffu, warm) ? ncm : 0;  // positions of the warm-start sweep
+    const int total = n_warm + sp.velocity_iterations * ncm;
+    int fk = 0;
+    const float4* fsrc = src;
+    auto fetch = [&](int p) {  // next record of the (wrapping) stream -> stage p % RING
+      cp_async_record(rl + ((p & (VEL_RING - 1)) * VC_Q) * 32, fsrc);
+      const bool wrap = (fk + 1 == ncm);
+      fk = wrap ? 0 : fk + 1;
+      fsrc = wrap ? src : fsrc + VC_Q * 32;
+    };
+#pragma unroll
+    for (int p = 0; p < VEL_RING; ++p) fetch(p);
+    cp_async_wait<VEL_RING - 1>();
+    // An inactive visit (world with fewer constraints, empty manifold, warm-start sweep of a world without
+    // warm starting) runs the same arithmetic on row NB of the velocity array, a scratch row no body owns, so
+    // the visit needs no predicate: its loads, stores and forwards only ever touch that row, and the impulses
+    // it writes belong to a record nobody reads (k >= nc, or zero points).
+    const int scratch = B.NB;
+    VcRegs ca = vc_load(rl), cb;
+    int k = 0, pos = 0;
+    const bool act0 = nc > 0 && ca.cnt > 0 && (warm || n_warm == 0);
+    bool fa = __all_sync(0xffffffffu, !act0 || (ca.cnt == 2 && block)), fb = false;
+    if (!act0) { ca.ba = scratch; ca.bb = scratch; }
+    float4 vaa = vl[ca.ba * 32], vab = vl[ca.bb * 32], vba = vaa, vbb = vab;
+    cb = ca;
+    auto half = [&](auto WARM, auto FAST, VcRegs& cur, float4& va, float4& vb, VcRegs& nxt, bool& nfast, float4& nva,
+                    float4& nvb) {
+      // -- position pos+1: rows from its ring stage and the velocities of its two bodies, into the other register set
+      const int kc = k;
+      k = (k + 1 == ncm) ? 0 : k + 1;
+      cp_async_wait<VEL_RING - 2>();
+      nxt = vc_load(rl + (((pos + 1) & (VEL_RING - 1)) * VC_Q) * 32);
+      const bool nact = (k < nc) && nxt.cnt > 0 && (warm || pos + 1 >= n_warm);
+      nfast = __all_sync(0xffffffffu, !nact || (nxt.cnt == 2 && block));
+      nxt.ba = nact ? nxt.ba : scratch;
+      nxt.bb = nact ? nxt.bb : scratch;
+      nva = vl[nxt.ba * 32];
+      nvb = vl[nxt.bb * 32];
+      fetch(pos);  // this position's stage is free (cur is in registers): refill it with position pos + RING
+      // -- position pos: the reference's arithmetic
+      VelState s;
+      s.v_a = v2(va.x, va.y); s.w_a = va.z;
+      s.v_b = v2(vb.x, vb.y); s.w_b = vb.z;
+      if (decltype(WARM)::value) {
+        warm_start_one(s, cur.q0, cur.q1, cur.q2, cur.q6, cur.q7, decltype(FAST)::value ? 2 : cur.cnt);
+      } else {
+        float4 q6 = cur.q6;
+        if (decltype(FAST)::value)
+          solve_velocity_one(s, cur.q0, cur.q1, cur.q2, cur.q3, cur.q4, cur.q5, q6, cur.q7, 2, true);
+        else
+          solve_velocity_one(s, cur.q0, cur.q1, cur.q2, cur.q3, cur.q4, cur.q5, q6, cur.q7, cur.cnt, block);
+        q6_out[(size_t)kc * VC_Q * 32] = q6;
+      }
+      // the fourth component is carried so that its register stays owned by this value (a scratch reuse would
+      // wait for the shared-memory load that also writes it)
+      va = make_float4(s.v_a.x, s.v_a.y, s.w_a, va.w);
+      vb = make_float4(s.v_b.x, s.v_b.y, s.w_b, vb.w);
+      vl[cur.ba * 32] = va;
+      vl[cur.bb * 32] = vb;
+      // -- forward the fresh velocities to the next constraint where it shares a body with this one (the loads
+      //    above were issued before these stores)
+      const int maa = sel_mask(nxt.ba == cur.ba), mab = sel_mask(nxt.ba == cur.bb);
+      const int mba = sel_mask(nxt.bb == cur.ba), mbb = sel_mask(nxt.bb == cur.bb);
+      nva.x = msel(maa, va.x, msel(mab, vb.x, nva.x));
+      nva.y = msel(maa, va.y, msel(mab, vb.y, nva.y));
+      nva.z = msel(maa, va.z, msel(mab, vb.z, nva.z));
+      nvb.x = msel(mba, va.x, msel(mbb, vb.x, nvb.x));
+      nvb.y = msel(mba, va.y, msel(mbb, vb.y, nvb.y));
+      nvb.z = msel(mba, va.z, msel(mbb, vb.z, nvb.z));
+      ++pos;
+    };
+    auto step_ab = [&](auto WARM) {
+      if (fa) half(WARM, std::true_type{}, ca, vaa, vab, cb, fb, vba, vbb);
+      else half(WARM, std::false_type{}, ca, vaa, vab, cb, fb, vba, vbb);
+    };
+    auto step_ba = [&](auto WARM) {
+      if (fb) half(WARM, std::true_type{}, cb, vba, vbb, ca, fa, vaa, vab);
+      else half(WARM, std::false_type{}, cb, vba, vbb, ca, fa, vaa, vab);
+    };
+    auto run_to = [&](auto WARM, const int end) {
+      while (pos + 2 <= end) {
+        step_ab(WARM);
+        step_ba(WARM);
+      }
+      if (pos < end) {  // odd count: one more visit, then the register sets swap roles
+        step_ab(WARM);
+        ca = cb; fa = fb; vaa = vba; vab = vbb;
+      }
+    };
+    run_to(std::true_type{}, n_warm);
+    run_to(std::false_type{}, total);
     cp_async_wait<0>();
   }
   __syncwarp();

@@ -630,15 +630,20 @@ B2G_HD void solve_velocity_one(VelState& s, const float4 q0, const float4 q1, co
     V2 xs;
     xs.x = ok1 ? x1.x : (ok2 ? x2 : 0.0f);
     xs.y = ok1 ? x1.y : (ok2 ? 0.0f : (ok3 ? x3 : 0.0f));
-    if (ok1 || ok2 || ok3 || ok4) {
+    {  // "no solution, give up" (:570) leaves everything untouched: select, do not branch
+      const int any = sel_mask(ok1 || ok2 || ok3 || ok4);
       const V2 d = xs - a;
       const V2 p1 = d.x * normal, p2 = d.y * normal;
-      v_a = v_a - m_a * (p1 + p2);
-      w_a -= i_a * (cross(ra0, p1) + cross(ra1, p2));
-      v_b = v_b + m_b * (p1 + p2);
-      w_b += i_b * (cross(rb0, p1) + cross(rb1, p2));
-      q6.x = xs.x;
-      q6.z = xs.y;
+      const V2 nv_a = v_a - m_a * (p1 + p2);
+      const float nw_a = w_a - i_a * (cross(ra0, p1) + cross(ra1, p2));
+      const V2 nv_b = v_b + m_b * (p1 + p2);
+      const float nw_b = w_b + i_b * (cross(rb0, p1) + cross(rb1, p2));
+      v_a = v2(msel(any, nv_a.x, v_a.x), msel(any, nv_a.y, v_a.y));
+      w_a = msel(any, nw_a, w_a);
+      v_b = v2(msel(any, nv_b.x, v_b.x), msel(any, nv_b.y, v_b.y));
+      w_b = msel(any, nw_b, w_b);
+      q6.x = msel(any, xs.x, q6.x);
+      q6.z = msel(any, xs.y, q6.z);
     }
   }
   s.v_a = v_a; s.v_b = v_b; s.w_a = w_a; s.w_b = w_b;
