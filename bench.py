@@ -272,6 +272,7 @@ def run_ours(args, rank, world_size, local_rank):
             "clocks": clocks, "validation_allgather": gathered,
         }
         OUT.emit(json.dumps(line))
+    batch.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

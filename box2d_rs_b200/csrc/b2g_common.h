@@ -102,6 +102,7 @@ struct Batch {
   float4* vc;                // [NC * VC_Q] velocity constraint records
   float4* pc;                // [NC * PC_Q] position constraint records
   int* sched;                // [NC * SCHED_G] level schedule: round r, slot g -> island contact k or -1
+  unsigned long long* timeline;  // diagnostic (B2GPU_TIMELINE): [0] = entries used, [1] = capacity, then {kind<<32|cta, t0, t1} per CTA
 };
 
 struct WIdx {  // index helper of one thread's world

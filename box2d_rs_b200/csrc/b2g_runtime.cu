@@ -1,5 +1,6 @@
 // b2g_runtime.cu — batch management and the step launch sequence (see b2g_runtime.h).
 #include "b2g_runtime.h"
+#include <cstdlib>
 
 #include <stdio.h>
 #include <stdlib.h>
@@ -529,6 +530,21 @@ int batch_create(Ctx* ctx, const b2gpu_snapshot* proto, int n_worlds, const b2gp
       CU(cudaFuncSetAttribute(velocity_sl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)velocity_smem_bytes(B.NB)));
       bh->tma_ring = caps && caps->reserved[1] == 4;
       bh->pipelined_velocity = caps && caps->reserved[1] == 7;
+      bh->ws_velocity = caps && caps->reserved[1] == 8 && velocity_ws_smem_bytes(B.NB) <= (size_t)max_optin;
+      if (bh->ws_velocity)
+        CU(cudaFuncSetAttribute(velocity_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)velocity_ws_smem_bytes(B.NB)));
+      if (const char* e = getenv("B2GPU_TIMELINE")) {  // diagnostic: per-CTA start/end of the Gauss-Seidel kernels
+        const size_t cap = 600000;
+        unsigned long long* t = nullptr;
+        rc = alloc_arr(bh, &t, 2 + cap * 3);
+        if (rc) { batch_destroy(bh); return rc; }
+        const unsigned long long head[2] = {0ull, (unsigned long long)cap};
+        rc = dev_h2d(ctx, t, head, sizeof(head));
+        if (rc) { batch_destroy(bh); return rc; }
+        bh->B.timeline = t;
+        bh->timeline_path = e;
+      }
+      if (const char* e = getenv("B2GPU_STREAM_GROUPS")) bh->stream_groups = atoi(e);  // tuning experiments
       if (caps && caps->reserved[1] == 5) bh->stream_groups = 1;
       if (caps && caps->reserved[1] == 6) bh->use_graphs = false;
       CU(cudaFuncSetAttribute(position_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)position_smem_bytes(B.NB)));
@@ -563,6 +579,17 @@ void batch_destroy(BatchHost* bh) {
   }
   if (bh->ev_entry) cudaEventDestroy((cudaEvent_t)bh->ev_entry);
   for (StepGraph& g : bh->graphs) cudaGraphExecDestroy((cudaGraphExec_t)g.exec);
+#endif
+#if !defined(B2G_HOSTSIM)
+  if (bh->B.timeline && !bh->timeline_path.empty()) {
+    unsigned long long head[2] = {0, 0};
+    cudaDeviceSynchronize();
+    cudaMemcpy(head, bh->B.timeline, sizeof(head), cudaMemcpyDeviceToHost);
+    const size_t n = (size_t)std::min(head[0], head[1]);
+    std::vector<unsigned long long> rows(n * 3);
+    if (n) cudaMemcpy(rows.data(), bh->B.timeline + 2, n * 3 * 8, cudaMemcpyDeviceToHost);
+    if (FILE* f = fopen(bh->timeline_path.c_str(), "wb")) { fwrite(rows.data(), 8, rows.size(), f); fclose(f); }
+  }
 #endif
   for (void* p : bh->allocs) dev_free(p);
   delete bh;
@@ -714,7 +741,9 @@ static int step_window(BatchHost* bh, const Batch& Bw, const StepParams& sp, int
       } else if (bh->smem_solver) {
         LaunchScope ls = {ctx, STAGE_VELOCITY};
         RC(ls.begin());
-        if (!bh->tma_ring && !bh->pipelined_velocity)
+        if (bh->ws_velocity)
+          velocity_ws_kernel<<<B.wb_count, 64, velocity_ws_smem_bytes(B.NB), (cudaStream_t)ctx->stream>>>(B, sp);
+        else if (!bh->tma_ring && !bh->pipelined_velocity)
           velocity_sl_kernel<<<B.wb_count, 32, velocity_smem_bytes(B.NB), (cudaStream_t)ctx->stream>>>(B, sp);
         else if (bh->tma_ring)
           velocity_smem_kernel<true><<<B.wb_count, 32, velocity_smem_bytes(B.NB), (cudaStream_t)ctx->stream>>>(B, sp);

@@ -69,7 +69,7 @@ struct StepGraph {  // instantiated CUDA graph of one run_steps call signature
 
 struct BatchHost {
   Ctx* ctx = nullptr;
-  Batch B;          // device pointers + dims
+  Batch B = {};     // device pointers + dims
   Topology topo;
   std::vector<void*> allocs;
   int* b_wake = nullptr;
@@ -83,6 +83,8 @@ struct BatchHost {
   bool smem_island = false;      // shared-memory island DFS in use (b2g_island_smem.cuh)
   IslandSmemLayout island_layout;
   bool tma_ring = false;         // velocity ring filled by cp.async.bulk + mbarrier instead of cp.async
+  std::string timeline_path;        // diagnostic: where batch_destroy writes the Gauss-Seidel CTA timeline
+  bool ws_velocity = false;         // diagnostic: straight-line velocity kernel with a producer warp (measured slower)
   bool pipelined_velocity = false;  // diagnostic: the branchy pipelined velocity kernel instead of the straight-line one
   bool ml_velocity = false;      // velocity stage also level-scheduled (experiment switch)
   bool ml_solver = false;        // level-scheduled multi-lane Gauss-Seidel kernels in use

@@ -57,6 +57,25 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, unsigned parity) {
   }
 }
 
+
+// Diagnostic timeline (env B2GPU_TIMELINE=<file>): every CTA of the two Gauss-Seidel kernels records its start
+// and end on the global nanosecond timer, so the overlap of the stream groups can be reconstructed.
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void timeline_record(const Batch& B, int kind, unsigned long long t0) {
+  if (B.timeline && threadIdx.x == 0) {
+    const unsigned long long slot = atomicAdd(B.timeline, 1ull);
+    if (slot < B.timeline[1]) {
+      B.timeline[2 + slot * 3] = ((unsigned long long)kind << 32) | (unsigned)(blockIdx.x + (B.wb_first << 8));
+      B.timeline[3 + slot * 3] = t0;
+      B.timeline[4 + slot * 3] = global_ns();
+    }
+  }
+}
+
 constexpr int VEL_RING = 8;  // stages of the velocity constraint ring
 constexpr int POS_RING = 8;
 
@@ -283,6 +302,7 @@ __device__ __forceinline__ void cp_async_record(float4* smem_dst, const float4* 
 
 __global__ void __launch_bounds__(32) velocity_sl_kernel(const Batch B, const StepParams sp) {
   extern __shared__ float4 smem4[];
+  const unsigned long long t_start = B.timeline ? global_ns() : 0ull;
   float4* ring = smem4;                        // [VEL_RING][VC_Q][32]
   float4* vel = smem4 + VEL_RING * VC_Q * 32;  // [NB][32]: v.x v.y w -
   const int lane = threadIdx.x;
@@ -403,6 +423,202 @@ __global__ void __launch_bounds__(32) velocity_sl_kernel(const Batch B, const St
   __syncwarp();
   if (live)
     for (int b = 0; b < B.NB; ++b) B.b_vel[x.at(B.NB, b)] = vel[b * 32 + lane];
+  timeline_record(B, 1, t_start);
+}
+
+// ------------------------------------------------------------------------------------------
+// Warp-specialised form of the straight-line kernel (experiment, solver='producer'; measured 8 % slower than
+// velocity_sl_kernel: what the solving warp saves in copy instructions it pays back in barrier tests and in
+// the shared-memory flags that replace the warp vote): a second warp of the CTA does nothing
+// but keep the ring full, so the solving warp issues no copy instruction at all.  Hand-over per ring stage
+// through two mbarriers: `full` (the 32 producer lanes' cp.async copies of a record have landed:
+// cp.async.mbarrier.arrive.noinc) and `empty` (the 32 solving lanes have the record in registers).  The
+// solving warp tests `full` two visits ahead with a non-blocking test_wait whose predicate is consumed at
+// the end of the visit, so the barrier's latency is off the chain; the producer sleeps in try_wait.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ bool mbar_test(unsigned bar, unsigned parity) {
+  unsigned ok;
+  asm volatile("{\n.reg .pred p;\nmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+               : "=r"(ok)
+               : "r"(bar), "r"(parity)
+               : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_spin(unsigned bar, unsigned parity) {
+  unsigned done = 0;
+  while (!done) {
+    asm volatile("{\n.reg .pred p;\nmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\nselp.u32 %0, 1, 0, p;\n}\n"
+                 : "=r"(done)
+                 : "r"(bar), "r"(parity)
+                 : "memory");
+  }
+}
+__device__ __forceinline__ void mbar_arrive(unsigned bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];\n" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void cp_async_record_signal(float4* smem_dst, const float4* gmem_src, unsigned bar) {
+  const unsigned s = smem_u32(smem_dst);
+  asm volatile(
+      "cp.async.cg.shared.global [%0], [%1], 16;\n"
+      "cp.async.cg.shared.global [%0+512], [%1+512], 16;\n"
+      "cp.async.cg.shared.global [%0+1024], [%1+1024], 16;\n"
+      "cp.async.cg.shared.global [%0+1536], [%1+1536], 16;\n"
+      "cp.async.cg.shared.global [%0+2048], [%1+2048], 16;\n"
+      "cp.async.cg.shared.global [%0+2560], [%1+2560], 16;\n"
+      "cp.async.cg.shared.global [%0+3072], [%1+3072], 16;\n"
+      "cp.async.cg.shared.global [%0+3584], [%1+3584], 16;\n"
+      "cp.async.cg.shared.global [%0+4096], [%1+4096], 16;\n"
+      "cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%2];\n" ::"r"(s),
+      "l"(gmem_src), "r"(bar)
+      : "memory");
+}
+
+inline size_t velocity_ws_smem_bytes(int NB) { return velocity_smem_bytes(NB) + 2 * VEL_RING * 8 + 32; }
+
+__global__ void __launch_bounds__(64) velocity_ws_kernel(const Batch B, const StepParams sp) {
+  extern __shared__ float4 smem4[];
+  const unsigned long long t_start = B.timeline ? global_ns() : 0ull;
+  float4* ring = smem4;                        // [VEL_RING][VC_Q][32]
+  float4* vel = smem4 + VEL_RING * VC_Q * 32;  // [NB + 1][32]: v.x v.y w -; row NB is scratch
+  uint64_t* bars = (uint64_t*)(vel + (size_t)(B.NB + 1) * 32);  // full[RING], empty[RING]
+  const int lane = threadIdx.x & 31;
+  const int role = threadIdx.x >> 5;  // 0: solver, 1: producer
+  const int wb = blockIdx.x + B.wb_first;
+  const int w = wb * 32 + lane;
+  const bool live = w < B.n_worlds;
+  WIdx x;
+  x.wb = wb; x.wl = lane; x.LB = 32;
+  Ws ws = ws_of(B, x);
+  const int nc = live ? ws[WS_ISL_CONTACTS] : 0;
+  const int wflags = live ? ws[WS_FLAGS] : 0;
+  const bool warm = (wflags & B2GPU_WORLD_WARM_STARTING) != 0;
+  const bool block = (wflags & B2GPU_WORLD_BLOCK_SOLVE) != 0;
+  const int ncm = __reduce_max_sync(0xffffffffu, nc);
+  if (ncm == 0) return;
+  if (live)  // both warps share the load of the velocity rows
+    for (int b = role; b < B.NB; b += 2) vel[b * 32 + lane] = B.b_vel[x.at(B.NB, b)];
+  const float4* src = B.vc + (size_t)wb * B.NC * VC_Q * 32 + lane;  // + (k * VC_Q + q) * 32
+  float4* q6_out = B.vc + (size_t)wb * B.NC * VC_Q * 32 + 6 * 32 + lane;
+  float4* vl = vel + lane;
+  float4* rl = ring + lane;
+  const bool streaming = ncm > VEL_RING;
+  const int n_warm = __any_sync(0xffffffffu, warm) ? ncm : 0;  // positions of the warm-start sweep
+  const int total = n_warm + sp.velocity_iterations * ncm;
+  const unsigned full0 = smem_u32(bars), empty0 = smem_u32(bars + VEL_RING);
+  // "some lane needs the general path at position p" flags, slot p % 4: written (benign same-value race) one
+  // visit ahead by the solving warp, which runs in lockstep, and cleared two visits before reuse.  A warp
+  // vote would do, but inside the role branch it costs a convergence check that splits the visit's block.
+  volatile int* gflag = (volatile int*)(bars + 2 * VEL_RING);
+  if (streaming && threadIdx.x == 0) {
+    for (int st = 0; st < VEL_RING; ++st) { mbar_init(&bars[st], 32); mbar_init(&bars[VEL_RING + st], 32); }
+    for (int i = 0; i < 4; ++i) gflag[i] = 0;
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+  }
+  __syncthreads();
+  if (!streaming) {
+    if (role == 0) velocity_resident(rl, vl, src, q6_out, nc, ncm, warm, block, 1 + sp.velocity_iterations);
+  } else if (role == 1) {
+    // ---- producer: position p -> stage p % RING, as soon as the solver has released the stage's previous
+    //      record; two positions past the end so that the solver's look-ahead test always completes
+    int fk = 0;
+    const float4* fsrc = src;
+    for (int p = 0; p < total + 2; ++p) {
+      const int st = p & (VEL_RING - 1);
+      if (p >= VEL_RING) mbar_spin(empty0 + st * 8, (unsigned)((p / VEL_RING) - 1) & 1u);
+      cp_async_record_signal(rl + (st * VC_Q) * 32, fsrc, full0 + st * 8);
+      const bool wrap = (fk + 1 == ncm);
+      fk = wrap ? 0 : fk + 1;
+      fsrc = wrap ? src : fsrc + VC_Q * 32;
+    }
+    asm volatile("cp.async.wait_all;\n" ::: "memory");
+  } else {
+    // ---- solver (see velocity_sl_kernel for the structure of a visit)
+    const int scratch = B.NB;
+    mbar_spin(full0, 0u);
+    mbar_spin(full0 + 8, 0u);
+    VcRegs ca = vc_load(rl), cb;
+    int k = 0, pos = 0;
+    const bool act0 = nc > 0 && ca.cnt > 0 && (warm || n_warm == 0);
+    if (act0 && !(ca.cnt == 2 && block)) gflag[0] = 1;
+    __syncwarp();
+    bool fa = gflag[0] == 0, fb = false;
+    if (!act0) { ca.ba = scratch; ca.bb = scratch; }
+    float4 vaa = vl[ca.ba * 32], vab = vl[ca.bb * 32], vba = vaa, vbb = vab;
+    cb = ca;
+    auto half = [&](auto WARM, auto FAST, VcRegs& cur, float4& va, float4& vb, VcRegs& nxt, bool& nfast, float4& nva,
+                    float4& nvb) {
+      // -- look-ahead: has the record of position pos+2 landed?  (consumed at the end of this visit)
+      const bool ahead = mbar_test(full0 + ((pos + 2) & (VEL_RING - 1)) * 8, (unsigned)((pos + 2) / VEL_RING) & 1u);
+      // -- position pos+1 (known to have landed): rows and body velocities into the other register set
+      const int kc = k;
+      k = (k + 1 == ncm) ? 0 : k + 1;
+      nxt = vc_load(rl + (((pos + 1) & (VEL_RING - 1)) * VC_Q) * 32);
+      const bool nact = (k < nc) && nxt.cnt > 0 && (warm || pos + 1 >= n_warm);
+      gflag[(nact && !(nxt.cnt == 2 && block)) ? ((pos + 1) & 3) : 4] = 1;  // slot 4: nobody reads it
+      gflag[(pos + 3) & 3] = 0;
+      nfast = gflag[(pos + 1) & 3] == 0;
+      nxt.ba = nact ? nxt.ba : scratch;
+      nxt.bb = nact ? nxt.bb : scratch;
+      nva = vl[nxt.ba * 32];
+      nvb = vl[nxt.bb * 32];
+      // -- position pos: the reference's arithmetic
+      VelState s;
+      s.v_a = v2(va.x, va.y); s.w_a = va.z;
+      s.v_b = v2(vb.x, vb.y); s.w_b = vb.z;
+      if (decltype(WARM)::value) {
+        warm_start_one(s, cur.q0, cur.q1, cur.q2, cur.q6, cur.q7, decltype(FAST)::value ? 2 : cur.cnt);
+      } else {
+        float4 q6 = cur.q6;
+        if (decltype(FAST)::value)
+          solve_velocity_one(s, cur.q0, cur.q1, cur.q2, cur.q3, cur.q4, cur.q5, q6, cur.q7, 2, true);
+        else
+          solve_velocity_one(s, cur.q0, cur.q1, cur.q2, cur.q3, cur.q4, cur.q5, q6, cur.q7, cur.cnt, block);
+        q6_out[(size_t)kc * VC_Q * 32] = q6;
+      }
+      va = make_float4(s.v_a.x, s.v_a.y, s.w_a, va.w);
+      vb = make_float4(s.v_b.x, s.v_b.y, s.w_b, vb.w);
+      vl[cur.ba * 32] = va;
+      vl[cur.bb * 32] = vb;
+      const int maa = sel_mask(nxt.ba == cur.ba), mab = sel_mask(nxt.ba == cur.bb);
+      const int mba = sel_mask(nxt.bb == cur.ba), mbb = sel_mask(nxt.bb == cur.bb);
+      nva.x = msel(maa, va.x, msel(mab, vb.x, nva.x));
+      nva.y = msel(maa, va.y, msel(mab, vb.y, nva.y));
+      nva.z = msel(maa, va.z, msel(mab, vb.z, nva.z));
+      nvb.x = msel(mba, va.x, msel(mbb, vb.x, nvb.x));
+      nvb.y = msel(mba, va.y, msel(mbb, vb.y, nvb.y));
+      nvb.z = msel(mba, va.z, msel(mbb, vb.z, nvb.z));
+      // -- this position's stage is free (its rows were consumed above; the impulses written here are ordered
+      //    before the producer's re-read of the record by the release/acquire pair on the barrier)
+      mbar_arrive(empty0 + (pos & (VEL_RING - 1)) * 8);
+      if (!ahead) mbar_spin(full0 + ((pos + 2) & (VEL_RING - 1)) * 8, (unsigned)((pos + 2) / VEL_RING) & 1u);
+      ++pos;
+    };
+    auto step_ab = [&](auto WARM) {
+      if (fa) half(WARM, std::true_type{}, ca, vaa, vab, cb, fb, vba, vbb);
+      else half(WARM, std::false_type{}, ca, vaa, vab, cb, fb, vba, vbb);
+    };
+    auto step_ba = [&](auto WARM) {
+      if (fb) half(WARM, std::true_type{}, cb, vba, vbb, ca, fa, vaa, vab);
+      else half(WARM, std::false_type{}, cb, vba, vbb, ca, fa, vaa, vab);
+    };
+    auto run_to = [&](auto WARM, const int end) {
+      while (pos + 2 <= end) {
+        step_ab(WARM);
+        step_ba(WARM);
+      }
+      if (pos < end) {  // odd count: one more visit, then the register sets swap roles
+        step_ab(WARM);
+        ca = cb; fa = fb; vaa = vba; vab = vbb;
+      }
+    };
+    run_to(std::true_type{}, n_warm);
+    run_to(std::false_type{}, total);
+  }
+  __syncthreads();
+  if (live)
+    for (int b = role; b < B.NB; b += 2) B.b_vel[x.at(B.NB, b)] = vel[b * 32 + lane];
+  timeline_record(B, 1, t_start);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -588,6 +804,7 @@ constexpr unsigned ML_SOLVED = 0xffffffffu;
 
 __global__ void __launch_bounds__(32) position_ml_kernel(const Batch B, const StepParams sp) {
   extern __shared__ float4 smem4[];
+  const unsigned long long t_start = B.timeline ? global_ns() : 0ull;
   float4* ring = smem4;                                   // [ML_RING][PC_Q][32]
   float4* pos = smem4 + ML_RING * PC_Q * 32;              // [NB][ML_WPC]: c.x c.y a -
   float2* rot = (float2*)(pos + (size_t)B.NB * ML_WPC);   // [NB][ML_WPC]: sin a, cos a
@@ -739,6 +956,7 @@ __global__ void __launch_bounds__(32) position_ml_kernel(const Batch B, const St
     for (int i = g; i < nisl; i += SCHED_G)
       if (tab[ml_col(i, wq)] == ML_SOLVED) B.isl_flags[x.at(B.NB, i)] |= 1;
   }
+  timeline_record(B, 2, t_start);
 }
 
 // Warm start + velocity iterations, level-scheduled: the same round structure and pipeline as
