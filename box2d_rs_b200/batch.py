@@ -49,7 +49,7 @@ class Batch:
         caps.max_contacts, caps.max_pairs = max_contacts, max_pairs
         caps.reserved[0] = lane_block
         # solver: None = best available, 'generic' = global-memory stages, 'lane' = one lane per world (no level schedule)
-        caps.reserved[1] = 1 if (generic_solver or solver == 'generic') else (2 if solver == 'lane' else (3 if solver == 'levels' else (4 if solver == 'tma' else (5 if solver == 'one_stream' else (6 if solver == 'no_graph' else (7 if solver == 'pipelined' else (8 if solver == 'producer' else 0)))))))
+        caps.reserved[1] = 1 if (generic_solver or solver == 'generic') else (2 if solver == 'lane' else (3 if solver == 'levels' else (4 if solver == 'tma' else (5 if solver == 'one_stream' else (6 if solver == 'no_graph' else (7 if solver == 'pipelined' else (8 if solver == 'producer' else (9 if solver == 'ml_position' else 0))))))))
         self.h = C.c_void_p()
         c = proto.as_c()
         self._keep = proto

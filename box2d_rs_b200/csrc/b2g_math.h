@@ -234,4 +234,39 @@ B2G_HD void sincos_ref(float y, float* sp, float* cp) {
 }
 B2G_HD Rot rot_from_angle(float a) { Rot q; sincos_ref(a, &q.s, &q.c); return q; }
 
+// Branch-free form of sincos_ref for |y| < 120 (abstop12(y) < abstop12(120.0f)): the medium-range reduction
+// with n = 0 is the identity, so it also serves the small range; both polynomials are evaluated once and
+// swapped / negated by selects.  Bit-identical to sincos_ref on its whole domain (tests/test_abi.py runs the
+// exhaustive comparison of tools/sincos_mid_check.cpp on a stride; the full 2^31 sweep was run once).
+B2G_HD bool sincos_mid_domain(float y) { return abstop12(y) < abstop12(120.0f); }
+B2G_HD void sincos_mid(float y, float* sp, float* cp) {
+  const double x0 = (double)y;
+  const double r = x0 * 0x1.45F306DC9C883p+23;
+  const int n = ((int32_t)r + 0x800000) >> 24;
+  const double x = fma(-(double)n, 0x1.921FB54442D18p0, x0);
+  const bool flip = ((n & 3) == 1 || (n & 3) == 2);
+  const double xs = flip ? -x : x;  // x * -1.0 is exact
+  const double x2 = x * x;
+  const double S1 = -0x1.555545995a603p-3, S2 = 0x1.1107605230bc4p-7, S3 = -0x1.994eb3774cf24p-13;
+  const double C0 = 0x1p0, C1 = -0x1.ffffffd0c621cp-2, C2 = 0x1.55553e1068f19p-5, C3 = -0x1.6c087e89a359dp-10,
+               C4 = 0x1.99343027bf8c3p-16;
+  const double x3 = xs * x2;
+  const double s1 = fma(x2, S3, S2);
+  const double x7 = x3 * x2;
+  const double sa = fma(x3, S1, xs);
+  const float sn = (float)fma(x7, s1, sa);
+  const double x4 = x2 * x2;
+  const double c2 = fma(x2, C4, C3);
+  const double c1 = fma(x2, C1, C0);
+  const double x6 = x4 * x2;
+  const double ca = fma(x4, C2, c1);
+  const float cpos = (float)fma(x6, c2, ca);
+  const float cs = (n & 2) ? -cpos : cpos;  // negated coefficients give the exactly negated value
+  const bool odd = (n & 1) != 0;
+  const bool tiny = abstop12(y) < abstop12(0x1p-12f);
+  const float so = odd ? cs : sn, co = odd ? sn : cs;
+  *sp = tiny ? y : so;
+  *cp = tiny ? 1.0f : co;
+}
+
 }  // namespace b2g

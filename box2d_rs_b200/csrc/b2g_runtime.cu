@@ -549,6 +549,11 @@ int batch_create(Ctx* ctx, const b2gpu_snapshot* proto, int n_worlds, const b2gp
       if (caps && caps->reserved[1] == 6) bh->use_graphs = false;
       CU(cudaFuncSetAttribute(position_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)position_smem_bytes(B.NB)));
       bh->smem_solver = true;
+      // straight-line position kernel: the default where its tables fit (diagnostic switches 2, 3, 9 keep the others)
+      bh->sl_position = position_sl_smem_bytes(B.NB) <= (size_t)max_optin &&
+                        !(caps && (caps->reserved[1] == 2 || caps->reserved[1] == 3 || caps->reserved[1] == 9));
+      if (bh->sl_position)
+        CU(cudaFuncSetAttribute(position_sl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)position_sl_smem_bytes(B.NB)));
     }
     const size_t need_ml = position_ml_smem_bytes(B.NB);
     if (bh->smem_solver && need_ml <= (size_t)max_optin && !(caps && caps->reserved[1] == 2)) {
@@ -755,7 +760,12 @@ static int step_window(BatchHost* bh, const Batch& Bw, const StepParams& sp, int
       { VelocityK k = {B, sp}; RC(launch(ctx, k, W * B.NB, 64, STAGE_VELOCITY)); }
       { PostVelocityK k = {B, sp}; RC(launch(ctx, k, W * B.NIB, 128, STAGE_POST_VELOCITY)); }
 #if !defined(B2G_HOSTSIM)
-      if (bh->ml_solver) {
+      if (bh->sl_position) {
+        LaunchScope ls = {ctx, STAGE_POSITION};
+        RC(ls.begin());
+        position_sl_kernel<<<B.wb_count, 32, position_sl_smem_bytes(B.NB), (cudaStream_t)ctx->stream>>>(B, sp);
+        RC(ls.end());
+      } else if (bh->ml_solver) {
         LaunchScope ls = {ctx, STAGE_POSITION};
         RC(ls.begin());
         position_ml_kernel<<<B.wb_count * SCHED_G, 32, position_ml_smem_bytes(B.NB), (cudaStream_t)ctx->stream>>>(B, sp);

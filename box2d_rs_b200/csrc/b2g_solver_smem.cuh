@@ -768,6 +768,197 @@ __global__ void __launch_bounds__(32) position_smem_kernel(const Batch B, const 
 }
 
 
+// ------------------------------------------------------------------------------------------
+// Straight-line position stage (the default for batches): one lane per world like velocity_sl_kernel, one
+// visit = one basic block.  Face manifolds with two points (the vote taken one visit ahead says whether all
+// active lanes have one) go through solve_position_face2: selects instead of the face-type branches, and an
+// unconditional branch-free rotation refresh.  Island bookkeeping is arithmetic: the running minimum
+// separation is closed into a per-island byte table in shared memory at the island's last constraint
+// (address-selected store: a visit that closes nothing writes a scratch entry), solved islands and finished
+// worlds run on the scratch body row.  A sweep starts with a fresh prologue, so the early exit of
+// b2_island_private.rs:257-274 is evaluated once per sweep, outside the visits.
+// ------------------------------------------------------------------------------------------
+static_assert(PC_Q == 6, "cp_async_prec copies six rows");
+__device__ __forceinline__ void cp_async_prec(float4* smem_dst, const float4* gmem_src) {
+  const unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile(
+      "cp.async.cg.shared.global [%0], [%1], 16;\n"
+      "cp.async.cg.shared.global [%0+512], [%1+512], 16;\n"
+      "cp.async.cg.shared.global [%0+1024], [%1+1024], 16;\n"
+      "cp.async.cg.shared.global [%0+1536], [%1+1536], 16;\n"
+      "cp.async.cg.shared.global [%0+2048], [%1+2048], 16;\n"
+      "cp.async.cg.shared.global [%0+2560], [%1+2560], 16;\n"
+      "cp.async.commit_group;\n" ::"r"(s),
+      "l"(gmem_src)
+      : "memory");
+}
+
+inline size_t position_sl_smem_bytes(int NB) {
+  return (size_t)POS_RING * PC_Q * 32 * 16 + (size_t)(NB + 1) * 32 * (16 + 8) + (size_t)(NB + 1) * 32;
+}
+
+__global__ void __launch_bounds__(32) position_sl_kernel(const Batch B, const StepParams sp) {
+  extern __shared__ float4 smem4[];
+  const unsigned long long t_start = B.timeline ? global_ns() : 0ull;
+  float4* ring = smem4;                                          // [POS_RING][PC_Q][32]
+  float4* pos = smem4 + POS_RING * PC_Q * 32;                    // [NB + 1][32]: c.x c.y a -; row NB is scratch
+  float2* rot = (float2*)(pos + (size_t)(B.NB + 1) * 32);        // [NB + 1][32]: sin a, cos a
+  unsigned char* tab = (unsigned char*)(rot + (size_t)(B.NB + 1) * 32);  // [NB + 1][32]: island solved; row NB is scratch
+  const int lane = threadIdx.x;
+  const int wb = blockIdx.x + B.wb_first;
+  const int w = wb * 32 + lane;
+  const bool live = w < B.n_worlds;
+  WIdx x;
+  x.wb = wb; x.wl = lane; x.LB = 32;
+  Ws ws = ws_of(B, x);
+  const int nc = live ? ws[WS_ISL_CONTACTS] : 0;
+  const int nisl = live ? ws[WS_ISL_COUNT] : 0;
+  const int ncm = __reduce_max_sync(0xffffffffu, nc);
+  if (ncm == 0 || sp.position_iterations <= 0) return;
+  if (live) {
+    for (int b = 0; b < B.NB; ++b) {
+      const float4 p = B.b_pos[x.at(B.NB, b)];
+      const float4 r = B.b_rot[x.at(B.NB, b)];
+      pos[b * 32 + lane] = p;
+      rot[b * 32 + lane] = make_float2(r.x, r.y);
+    }
+    for (int i = 0; i < nisl; ++i) tab[i * 32 + lane] = (unsigned char)(B.isl_flags[x.at(B.NB, i)] & 1);
+  }
+  pos[B.NB * 32 + lane] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  rot[B.NB * 32 + lane] = make_float2(0.0f, 1.0f);
+  tab[B.NB * 32 + lane] = 0;
+  const float4* src = B.pc + (size_t)wb * B.NC * PC_Q * 32 + lane;
+  float4* pl = pos + lane;
+  float2* ql = rot + lane;
+  unsigned char* tl = tab + lane;
+  float4* rl = ring + lane;
+  const int scratch = B.NB;
+  int fk = 0;
+  const float4* fsrc = src;
+  auto fetch = [&](int p) {  // next record of the (wrapping) stream -> stage p % RING
+    cp_async_prec(rl + ((p & (POS_RING - 1)) * PC_Q) * 32, fsrc);
+    const bool wrap = (fk + 1 == ncm);
+    fk = wrap ? 0 : fk + 1;
+    fsrc = wrap ? src : fsrc + PC_Q * 32;
+  };
+#pragma unroll
+  for (int p = 0; p < POS_RING; ++p) fetch(p);
+  PcRegs ca, cb;
+  bool acta = false, actb = false, fa = true, fb = true;
+  float4 paa, pab, pba, pbb;
+  float2 qaa, qab, qba, qbb;
+  int k = 0, p = 0;
+  bool done = !live || nc == 0, all_solved = true;
+  float min_separation = 0.0f;
+  // activity of the constraint at stream index kk whose record is r: its island is still open in this sweep
+  auto prepare = [&](PcRegs& r, int kk, bool& act, bool& fast, float4& pa, float4& pb, float2& qa, float2& qb) {
+    const bool in = kk < nc;
+    const int isl = in ? r.isl : scratch;
+    act = in && !done && tl[isl * 32] == 0;
+    fast = __all_sync(0xffffffffu, !act || (r.type != B2GPU_MANIFOLD_CIRCLES && r.cnt == 2));
+    r.ba = act ? r.ba : scratch;
+    r.bb = act ? r.bb : scratch;
+    r.cnt = act ? r.cnt : 0;
+    r.isl = isl;
+    pa = pl[r.ba * 32]; pb = pl[r.bb * 32];
+    qa = ql[r.ba * 32]; qb = ql[r.bb * 32];
+  };
+  auto half = [&](auto FAST, PcRegs& cur, const bool act, float4& pa, float4& pb, float2& qa, float2& qb, PcRegs& nxt,
+                  bool& nact, bool& nfast, float4& npa, float4& npb, float2& nqa, float2& nqb) {
+    // -- position p+1 into the other register set (at the end of a sweep this is discarded: the next sweep
+    //    starts from its own prologue, after the island table and `done` are final)
+    const int kc = k;
+    k = (k + 1 == ncm) ? 0 : k + 1;
+    cp_async_wait<POS_RING - 2>();
+    nxt = pc_load(rl + (((p + 1) & (POS_RING - 1)) * PC_Q) * 32);
+    prepare(nxt, k, nact, nfast, npa, npb, nqa, nqb);
+    fetch(p);  // this position's stage is free (cur is in registers): refill it with position p + RING
+    // -- position p: the reference's arithmetic
+    PosState s;
+    s.c_a = v2(pa.x, pa.y); s.a_a = pa.z; s.q_a.s = qa.x; s.q_a.c = qa.y;
+    s.c_b = v2(pb.x, pb.y); s.a_b = pb.z; s.q_b.s = qb.x; s.q_b.c = qb.y;
+    float ms;
+    if (decltype(FAST)::value) {
+      const PosState s0 = s;
+      bool wide;
+      ms = solve_position_face2(s, cur.p0, cur.p1, cur.p2, cur.p3, cur.type == B2GPU_MANIFOLD_FACE_A, cur.ra, cur.rb, min_separation, wide);
+      if (__any_sync(0xffffffffu, wide)) {  // never in practice: an angle beyond +-120 rad
+        s = s0;
+        ms = solve_position_one(s, cur.p0, cur.p1, cur.p2, cur.p3, cur.type, cur.cnt, cur.ra, cur.rb, min_separation);
+      }
+    } else {
+      ms = solve_position_one(s, cur.p0, cur.p1, cur.p2, cur.p3, cur.type, cur.cnt, cur.ra, cur.rb, min_separation);
+    }
+    pa = make_float4(s.c_a.x, s.c_a.y, s.a_a, pa.w);
+    pb = make_float4(s.c_b.x, s.c_b.y, s.a_b, pb.w);
+    qa = make_float2(s.q_a.s, s.q_a.c);
+    qb = make_float2(s.q_b.s, s.q_b.c);
+    pl[cur.ba * 32] = pa; ql[cur.ba * 32] = qa;
+    pl[cur.bb * 32] = pb; ql[cur.bb * 32] = qb;
+    // -- forward the fresh state to the next constraint where it shares a body with this one
+    const int maa = sel_mask(nxt.ba == cur.ba), mab = sel_mask(nxt.ba == cur.bb);
+    const int mba = sel_mask(nxt.bb == cur.ba), mbb = sel_mask(nxt.bb == cur.bb);
+    npa.x = msel(maa, pa.x, msel(mab, pb.x, npa.x));
+    npa.y = msel(maa, pa.y, msel(mab, pb.y, npa.y));
+    npa.z = msel(maa, pa.z, msel(mab, pb.z, npa.z));
+    nqa.x = msel(maa, qa.x, msel(mab, qb.x, nqa.x));
+    nqa.y = msel(maa, qa.y, msel(mab, qb.y, nqa.y));
+    npb.x = msel(mba, pa.x, msel(mbb, pb.x, npb.x));
+    npb.y = msel(mba, pa.y, msel(mbb, pb.y, npb.y));
+    npb.z = msel(mba, pa.z, msel(mbb, pb.z, npb.z));
+    nqb.x = msel(mba, qa.x, msel(mbb, qb.x, nqb.x));
+    nqb.y = msel(mba, qa.y, msel(mbb, qb.y, nqb.y));
+    // -- island bookkeeping: close the island at its last constraint
+    const bool last = act && ((kc + 1 == nc) || (nxt.isl != cur.isl));
+    min_separation = act ? ms : min_separation;
+    const bool solved = min_separation >= -3.0f * B2G_LINEAR_SLOP;
+    tl[(last ? cur.isl : scratch) * 32] = (unsigned char)(solved ? 1 : 0);
+    all_solved = all_solved && (!last || solved);
+    min_separation = last ? 0.0f : min_separation;
+    ++p;
+  };
+  auto step_ab = [&]() {
+    if (fa) half(std::true_type{}, ca, acta, paa, pab, qaa, qab, cb, actb, fb, pba, pbb, qba, qbb);
+    else half(std::false_type{}, ca, acta, paa, pab, qaa, qab, cb, actb, fb, pba, pbb, qba, qbb);
+  };
+  auto step_ba = [&]() {
+    if (fb) half(std::true_type{}, cb, actb, pba, pbb, qba, qbb, ca, acta, fa, paa, pab, qaa, qab);
+    else half(std::false_type{}, cb, actb, pba, pbb, qba, qbb, ca, acta, fa, paa, pab, qaa, qab);
+  };
+  for (int sweep = 0; sweep < sp.position_iterations; ++sweep) {
+    // prologue of the sweep: position p (stream index 0) from its ring stage
+    k = 0;
+    cp_async_wait<POS_RING - 1>();
+    ca = pc_load(rl + ((p & (POS_RING - 1)) * PC_Q) * 32);
+    prepare(ca, 0, acta, fa, paa, pab, qaa, qab);
+    int i = 0;
+    for (; i + 2 <= ncm; i += 2) {
+      step_ab();
+      step_ba();
+    }
+    if (i < ncm) step_ab();
+    // end of the sweep: a world is finished when every island passed the exit test
+    if (!done && all_solved) done = true;
+    all_solved = true;
+    min_separation = 0.0f;
+    if (__all_sync(0xffffffffu, done)) break;
+  }
+  cp_async_wait<0>();
+  __syncwarp();
+  if (live && nc > 0) {
+    // the rows carry the fourth component of b_pos (sleep time) through unchanged; of b_rot only the running
+    // rotation (first two components) is written, so neither store needs a read
+    for (int b = 0; b < B.NB; ++b) {
+      const int bi = x.at(B.NB, b);
+      B.b_pos[bi] = pos[b * 32 + lane];
+      *reinterpret_cast<float2*>(&B.b_rot[bi]) = rot[b * 32 + lane];
+    }
+    for (int i = 0; i < nisl; ++i)
+      if (tab[i * 32 + lane]) B.isl_flags[x.at(B.NB, i)] = 1;  // bit 0 is the only bit of the word
+  }
+  timeline_record(B, 2, t_start);
+}
+
 // ==========================================================================================
 // Level-scheduled Gauss-Seidel: SCHED_G lanes cooperate on one world (used for the position stage; the
 // velocity stage measured faster in the one-lane-per-world form above, whose register forwarding

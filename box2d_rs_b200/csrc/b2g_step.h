@@ -828,6 +828,59 @@ B2G_HD float solve_position_one(PosState& s, const float4 q7, const float4 q9, c
   return min_separation;
 }
 
+// Straight-line form of solve_position_one for the common case, a face manifold with two points.  FACE_A and
+// FACE_B differ only in which body carries the reference face, so the (rotation, origin) pair of the
+// reference body and of the incident body are selected (sel_mask: a select that cannot become a branch) and
+// the arithmetic is shared, operation for operation as in solve_position_one.  The rotations are refreshed
+// unconditionally with the branch-free sincos_mid: b_rot always holds rot_from_angle of the running angle, so
+// an unchanged angle reproduces the same sine and cosine bits.  An angle outside sincos_mid's domain sets
+// `wide`: the result is then invalid and the caller redoes the constraint with solve_position_one.
+B2G_HD float solve_position_face2(PosState& s, const float4 q7, const float4 q9, const float4 lps, const float4 m2,
+                                  bool face_a, float radius_a, float radius_b, float min_separation, bool& wide) {
+  const float m_a = q7.x, i_a = q7.y, m_b = q7.z, i_b = q7.w;
+  const V2 lc_a = v2(q9.x, q9.y), lc_b = v2(q9.z, q9.w);
+  const int fa = sel_mask(face_a);
+  wide = false;
+  const int sign = fa ? 0 : (int)0x80000000u;  // FACE_B reports the negated normal
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int j = 0; j < 2; ++j) {
+    const V2 mj = j == 0 ? v2(lps.x, lps.y) : v2(lps.z, lps.w);
+    Xf xf_a, xf_b;
+    xf_a.q = s.q_a;
+    xf_b.q = s.q_b;
+    xf_a.p = s.c_a - rot_mul(xf_a.q, lc_a);
+    xf_b.p = s.c_b - rot_mul(xf_b.q, lc_b);
+    Xf xr, xi;  // reference-face body, incident body
+    xr.q.s = msel(fa, xf_a.q.s, xf_b.q.s); xr.q.c = msel(fa, xf_a.q.c, xf_b.q.c);
+    xr.p.x = msel(fa, xf_a.p.x, xf_b.p.x); xr.p.y = msel(fa, xf_a.p.y, xf_b.p.y);
+    xi.q.s = msel(fa, xf_b.q.s, xf_a.q.s); xi.q.c = msel(fa, xf_b.q.c, xf_a.q.c);
+    xi.p.x = msel(fa, xf_b.p.x, xf_a.p.x); xi.p.y = msel(fa, xf_b.p.y, xf_a.p.y);
+    V2 normal = rot_mul(xr.q, v2(m2.x, m2.y));
+    const V2 plane_point = xf_mul(xr, v2(m2.z, m2.w));
+    const V2 clip_point = xf_mul(xi, mj);
+    const float separation = dot(clip_point - plane_point, normal) - radius_a - radius_b;
+    const V2 point = clip_point;
+    normal = v2(i2f(f2i(normal.x) ^ sign), i2f(f2i(normal.y) ^ sign));
+    const V2 r_a = point - s.c_a, r_b = point - s.c_b;
+    min_separation = fmin_sel(min_separation, separation);
+    const float cc = fclamp_sel(B2G_BAUMGARTE * (separation + B2G_LINEAR_SLOP), -B2G_MAX_LINEAR_CORRECTION, 0.0f);
+    const float rn_a = cross(r_a, normal), rn_b = cross(r_b, normal);
+    const float kk = m_a + m_b + i_a * rn_a * rn_a + i_b * rn_b * rn_b;
+    const float impulse = kk > 0.0f ? -cc / kk : 0.0f;
+    const V2 p = impulse * normal;
+    s.c_a = s.c_a - m_a * p;
+    s.a_a = s.a_a - i_a * cross(r_a, p);
+    s.c_b = s.c_b + m_b * p;
+    s.a_b = s.a_b + i_b * cross(r_b, p);
+    sincos_mid(s.a_a, &s.q_a.s, &s.q_a.c);
+    sincos_mid(s.a_b, &s.q_b.s, &s.q_b.c);
+    wide = wide || !(sincos_mid_domain(s.a_a) && sincos_mid_domain(s.a_b));
+  }
+  return min_separation;
+}
+
 // Ordered stage C, generic form: position iterations of one island per thread, with the reference's early
 // exit (b2_island_private.rs:257-274).  Islands without contacts were marked solved by PostVelocityK.
 struct PositionK {
