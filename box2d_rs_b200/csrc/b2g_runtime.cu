@@ -809,7 +809,7 @@ static StepParams make_params(float dt, int vi, int pi) {
 static int ensure_groups(BatchHost* bh) {
   if (!bh->groups.empty()) return 0;
   const Batch& B = bh->B;
-  int ng = (B.LB == 32 && B.n_wblocks >= 16 && bh->stream_groups != 1) ? (bh->stream_groups > 1 ? bh->stream_groups : 4) : 1;
+  int ng = (B.LB == 32 && B.n_wblocks >= 16 && bh->stream_groups != 1) ? (bh->stream_groups > 1 ? bh->stream_groups : (B.n_wblocks >= 64 ? 8 : 4)) : 1;
   if (ng > B.n_wblocks) ng = B.n_wblocks;
   for (int g = 0; g < ng; ++g) {
     StreamGroup sg;

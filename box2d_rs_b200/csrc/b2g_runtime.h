@@ -94,7 +94,7 @@ struct BatchHost {
   void* ev_entry = nullptr;         // cudaEvent_t: fork point on the context stream
   std::vector<StepGraph> graphs;    // CUDA graphs per call signature (see run_steps)
   bool use_graphs = true;
-  int stream_groups = 0;            // 0 = automatic (4 for batches of >= 16 world blocks), 1 = single stream
+  int stream_groups = 0;            // 0 = automatic (4 for batches of >= 16 world blocks, 8 for >= 64), 1 = single stream
   bool stepped = false;          // at least one dt > 0 step ran: island arrays are meaningful
   bool pre_step_needed = true;   // some world may carry m_new_contacts / a non-empty move buffer
   long long total_bytes = 0;
