@@ -48,8 +48,14 @@ class Batch:
         caps = abi.Caps()
         caps.max_contacts, caps.max_pairs = max_contacts, max_pairs
         caps.reserved[0] = lane_block
-        # solver: None = best available, 'generic' = global-memory stages, 'lane' = one lane per world (no level schedule)
-        caps.reserved[1] = 1 if (generic_solver or solver == 'generic') else (2 if solver == 'lane' else (3 if solver == 'levels' else (4 if solver == 'tma' else (5 if solver == 'one_stream' else (6 if solver == 'no_graph' else (7 if solver == 'pipelined' else (8 if solver == 'producer' else (9 if solver == 'ml_position' else 0))))))))
+        # solver (diagnostic switch, b2gpu_caps.reserved[1]): None = default kernels (straight-line velocity and
+        # position, 8 stream groups, CUDA graphs); 'generic' = global-memory stages; 'lane' = branchy pipelined
+        # one-lane position kernel; 'levels' = level-scheduled velocity + position; 'tma' = TMA-fed velocity ring;
+        # 'one_stream' = no stream groups; 'no_graph' = no CUDA graphs; 'pipelined' = branchy velocity kernel only;
+        # 'producer' = straight-line velocity kernel with a producer warp; 'ml_position' = level-scheduled position
+        codes = {None: 0, 'generic': 1, 'lane': 2, 'levels': 3, 'tma': 4, 'one_stream': 5, 'no_graph': 6, 'pipelined': 7,
+                 'producer': 8, 'ml_position': 9}
+        caps.reserved[1] = 1 if generic_solver else codes[solver]
         self.h = C.c_void_p()
         c = proto.as_c()
         self._keep = proto

@@ -276,8 +276,11 @@ typedef struct b2gpu_caps {
   int32_t max_contacts; /* contacts per world (default: 10 per proxy for batches, 40 for a single world) */
   int32_t max_pairs;    /* ignored: pairs are handed to add_pair as the tree query reports them, no pair buffer */
   int32_t reserved[2]; /* reserved[0]: worlds per memory block (power of two; 0 = 32 for >= 32 worlds, else 1);
-                          reserved[1]: 1 = use the generic global-memory solver stages even when the
-                          shared-memory ones apply (diagnostics) */
+                          reserved[1]: diagnostic switch, 0 = default kernels.  1 generic global-memory solver
+                          stages, 2 branchy one-lane position kernel, 3 level-scheduled velocity + position,
+                          4 TMA-fed velocity ring, 5 one stream (no stream groups), 6 no CUDA graphs, 7 branchy
+                          velocity kernel only, 8 velocity kernel with a producer warp, 9 level-scheduled
+                          position kernel (all bit-identical; profiles/r01_ncu_summary.md has their timings) */
 } b2gpu_caps;
 
 typedef struct b2gpu_ctx b2gpu_ctx;
