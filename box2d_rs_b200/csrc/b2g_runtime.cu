@@ -560,6 +560,9 @@ int batch_create(Ctx* ctx, const b2gpu_snapshot* proto, int n_worlds, const b2gp
       CU(cudaFuncSetAttribute(position_ml_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)position_ml_smem_bytes(B.NB)));
       CU(cudaFuncSetAttribute(velocity_ml_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)velocity_ml_smem_bytes(B.NB)));
       bh->ml_velocity = caps && caps->reserved[1] == 3;
+      bh->ml2_velocity = caps && caps->reserved[1] == 10 && velocity_ml2_smem_bytes(B.NB) <= (size_t)max_optin;
+      if (bh->ml2_velocity)
+        CU(cudaFuncSetAttribute(velocity_ml2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)velocity_ml2_smem_bytes(B.NB)));
       bh->ml_solver = true;
     }
     bh->island_layout = island_smem_layout(B.NB, B.NF, (size_t)max_optin - 1024);
@@ -738,7 +741,12 @@ static int step_window(BatchHost* bh, const Batch& Bw, const StepParams& sp, int
       { SolverInitK k = {B, sp}; RC(launch(ctx, k, W * B.NC, 128, STAGE_SOLVER_INIT)); }
 #if !defined(B2G_HOSTSIM)
       if (init_done && s == 0) CU(cudaEventRecord((cudaEvent_t)init_done, (cudaStream_t)ctx->stream));
-      if (bh->ml_solver && bh->ml_velocity) {
+      if (bh->ml_solver && bh->ml2_velocity) {
+        LaunchScope ls = {ctx, STAGE_VELOCITY};
+        RC(ls.begin());
+        velocity_ml2_kernel<<<B.wb_count * SCHED_G, 32, velocity_ml2_smem_bytes(B.NB), (cudaStream_t)ctx->stream>>>(B, sp);
+        RC(ls.end());
+      } else if (bh->ml_solver && bh->ml_velocity) {
         LaunchScope ls = {ctx, STAGE_VELOCITY};
         RC(ls.begin());
         velocity_ml_kernel<<<B.wb_count * SCHED_G, 32, velocity_ml_smem_bytes(B.NB), (cudaStream_t)ctx->stream>>>(B, sp);

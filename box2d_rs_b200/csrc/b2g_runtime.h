@@ -84,6 +84,7 @@ struct BatchHost {
   IslandSmemLayout island_layout;
   bool tma_ring = false;         // velocity ring filled by cp.async.bulk + mbarrier instead of cp.async
   std::string timeline_path;        // diagnostic: where batch_destroy writes the Gauss-Seidel CTA timeline
+  bool ml2_velocity = false;        // experiment: straight-line level-scheduled velocity kernel (two lanes per world)
   bool sl_position = false;         // straight-line position kernel (default for batches)
   bool ws_velocity = false;         // diagnostic: straight-line velocity kernel with a producer warp (measured slower)
   bool pipelined_velocity = false;  // diagnostic: the branchy pipelined velocity kernel instead of the straight-line one

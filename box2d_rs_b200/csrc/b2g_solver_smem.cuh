@@ -1259,4 +1259,155 @@ __global__ void __launch_bounds__(32) velocity_ml_kernel(const Batch B, const St
     for (int b = g; b < B.NB; b += SCHED_G) B.b_vel[x.at(B.NB, b)] = vel[ml_col(b, wq)];
 }
 
+
+// ------------------------------------------------------------------------------------------
+// Level-scheduled velocity stage, straight-line form (experiment, solver='levels2').  Two lanes per world
+// solve the (at most two) constraints of a round of the island kernel's schedule concurrently; a round is one
+// basic block per lane (scratch rows for empty slots and immovable bodies, unconditional refills with clamped
+// addresses, vote one round ahead), body velocities travel between the two lanes through shared memory with
+// one __syncwarp() per round.  Fewer rounds than constraints (Pyramid 296 vs 400), but every round pays the
+// store -> barrier -> load round trip that register forwarding avoids in velocity_sl_kernel.
+// ------------------------------------------------------------------------------------------
+inline size_t velocity_ml2_smem_bytes(int NB) {
+  return (size_t)(NB + SCHED_G) * ML_WPC * 16 + (size_t)ML_RING * VC_Q * 32 * 16 + 8 * 32 * 4;
+}
+__device__ __forceinline__ void st_global_v4_if(float4* p, float4 v, bool on) {
+  asm volatile("{\n.reg .pred q;\nsetp.ne.s32 q, %5, 0;\n@q st.global.v4.f32 [%0], {%1, %2, %3, %4};\n}\n" ::"l"(p), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w), "r"((int)on)
+               : "memory");
+}
+
+__global__ void __launch_bounds__(32) velocity_ml2_kernel(const Batch B, const StepParams sp) {
+  extern __shared__ float4 smem4[];
+  const unsigned long long t_start = B.timeline ? global_ns() : 0ull;
+  float4* ring = smem4;                          // [ML_RING][VC_Q][32] one private column per lane
+  float4* vel = smem4 + ML_RING * VC_Q * 32;     // [NB + SCHED_G][ML_WPC]; rows NB + g are lane slot g's scratch
+  const int lane = threadIdx.x;
+  const int g = lane / ML_WPC, wq = lane % ML_WPC;
+  const int wb = blockIdx.x / SCHED_G + B.wb_first;
+  const int wl = (blockIdx.x % SCHED_G) * ML_WPC + wq;
+  const int w = wb * 32 + wl;
+  const bool live = w < B.n_worlds;
+  WIdx x;
+  x.wb = wb; x.wl = wl; x.LB = 32;
+  Ws ws = ws_of(B, x);
+  const int nc = live ? ws[WS_ISL_CONTACTS] : 0;
+  const int rounds_w = live ? ws[WS_SCHED_ROUNDS] : 0;
+  const int wflags = live ? ws[WS_FLAGS] : 0;
+  const bool warm = (wflags & B2GPU_WORLD_WARM_STARTING) != 0;
+  const bool block = (wflags & B2GPU_WORLD_BLOCK_SOLVE) != 0;
+  const bool have_sched = rounds_w >= 0;
+  const int rlen = nc == 0 ? 0 : (have_sched ? rounds_w : nc);  // rounds of this world (list order: one per contact)
+  const int rm = __reduce_max_sync(0xffffffffu, rlen);
+  if (rm == 0) return;
+  if (live)
+    for (int b = g; b < B.NB; b += SCHED_G) vel[ml_col(b, wq)] = B.b_vel[x.at(B.NB, b)];
+  const int scratch = B.NB + g;
+  vel[ml_col(scratch, wq)] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  __syncwarp();
+  const int* sched_w = B.sched + (size_t)wb * B.NC * SCHED_G * 32 + wl;
+  const float4* src = B.vc + (size_t)wb * B.NC * VC_Q * 32 + wl;
+  float4* q6_out = B.vc + (size_t)wb * B.NC * VC_Q * 32 + 6 * 32 + wl;
+  float4* rl = ring + lane;
+  float4* vcol = vel + wq;                       // + body * ML_WPC
+  constexpr int AHEAD = 4, QN = 8;
+  int* iq = (int*)(vel + (size_t)(B.NB + SCHED_G) * ML_WPC) + lane;  // [QN][32] schedule queue
+  const int n_warm = __any_sync(0xffffffffu, warm) ? rm : 0;
+  const int total = n_warm + sp.velocity_iterations * rm;
+  // entry of the position whose round is rr (landed in the queue): island contact index or -1
+  auto item_now = [&](int at_pos, int rr) -> int {
+    const int q = iq[(at_pos & (QN - 1)) * 32];
+    const int listed = (g == 0 && rr < nc) ? rr : -1;
+    return have_sched ? (rr < rounds_w ? q : -1) : listed;
+  };
+  auto item_request = [&](int at_pos, int rr) {  // unconditional: a round past the end re-reads round 0
+    const int r2 = (have_sched && rr < rounds_w) ? rr : 0;
+    cp_async4(&iq[(at_pos & (QN - 1)) * 32], sched_w + (size_t)(r2 * SCHED_G + g) * 32);
+  };
+  auto fetch = [&](int at_pos, int k) {          // unconditional: an empty slot re-reads record 0
+    cp_async_record(rl + ((at_pos & (ML_RING - 1)) * VC_Q) * 32, src + (size_t)(k < 0 ? 0 : k) * VC_Q * 32);
+  };
+  auto next_round = [&](int rr) { return rr + 1 == rm ? 0 : rr + 1; };
+  int rq = 0, rf = 0;
+  for (int i = 0; i < ML_RING - 1 + AHEAD; ++i) { item_request(i, rq); rq = next_round(rq); }
+  cp_async_commit();
+  cp_async_wait<0>();
+  // cp.async groups alternate record / entry from here on (the record copy commits its own group)
+  for (int i = 0; i < ML_RING - 1; ++i) { fetch(i, item_now(i, rf)); rf = next_round(rf); cp_async_commit(); }
+  cp_async_wait<2 * (ML_RING - 1) - 2>();  // record 0
+  int r = 0, pos = 0;
+  int ka = item_now(0, 0), kb = -1;
+  VcRegs ca = vc_load(rl), cb;
+  bool acta = ka >= 0 && ca.cnt > 0 && (warm || n_warm == 0), actb = false;
+  bool fa = __all_sync(0xffffffffu, !acta || (ca.cnt == 2 && block)), fb = true;
+  ca.ba = acta ? ca.ba : scratch;
+  ca.bb = acta ? ca.bb : scratch;
+  cb = ca;
+  auto round = [&](auto WARM, auto FAST, VcRegs& c, const int kc, const bool act, VcRegs& cn, int& kn, bool& nact, bool& nfast) {
+    // -- this round's bodies (the barrier of the previous round made the partner lane's stores visible)
+    const float4 va = vcol[c.ba * ML_WPC], vb = vcol[c.bb * ML_WPC];
+    // -- refill: record of position pos + RING - 1 (its entry landed AHEAD rounds ago), entry of pos + RING - 1 + AHEAD
+    fetch(pos + ML_RING - 1, item_now(pos + ML_RING - 1, rf));
+    rf = next_round(rf);
+    item_request(pos + ML_RING - 1 + AHEAD, rq);
+    rq = next_round(rq);
+    cp_async_commit();
+    // -- next round's record into the other register set: 2 (RING - 1) - 1 groups are younger than it
+    cp_async_wait<2 * (ML_RING - 1) - 1>();
+    r = next_round(r);
+    kn = item_now(pos + 1, r);
+    cn = vc_load(rl + (((pos + 1) & (ML_RING - 1)) * VC_Q) * 32);
+    nact = kn >= 0 && cn.cnt > 0 && (warm || pos + 1 >= n_warm);
+    nfast = __all_sync(0xffffffffu, !nact || (cn.cnt == 2 && block));
+    cn.ba = nact ? cn.ba : scratch;
+    cn.bb = nact ? cn.bb : scratch;
+    // -- the reference's arithmetic
+    VelState s;
+    s.v_a = v2(va.x, va.y); s.w_a = va.z;
+    s.v_b = v2(vb.x, vb.y); s.w_b = vb.z;
+    if (decltype(WARM)::value) {
+      warm_start_one(s, c.q0, c.q1, c.q2, c.q6, c.q7, decltype(FAST)::value ? 2 : c.cnt);
+    } else {
+      float4 q6 = c.q6;
+      if (decltype(FAST)::value)
+        solve_velocity_one(s, c.q0, c.q1, c.q2, c.q3, c.q4, c.q5, q6, c.q7, 2, true);
+      else
+        solve_velocity_one(s, c.q0, c.q1, c.q2, c.q3, c.q4, c.q5, q6, c.q7, c.cnt, block);
+      st_global_v4_if(q6_out + (size_t)(kc < 0 ? 0 : kc) * VC_Q * 32, q6, act);
+    }
+    // immovable bodies (zero inverse mass and inertia) can be shared by the constraints of a round: never written
+    const int sa = (c.q7.x != 0.0f || c.q7.y != 0.0f) ? c.ba : scratch;
+    const int sb = (c.q7.z != 0.0f || c.q7.w != 0.0f) ? c.bb : scratch;
+    vcol[sa * ML_WPC] = make_float4(s.v_a.x, s.v_a.y, s.w_a, va.w);
+    vcol[sb * ML_WPC] = make_float4(s.v_b.x, s.v_b.y, s.w_b, vb.w);
+    __syncwarp();
+    ++pos;
+  };
+  auto step_ab = [&](auto WARM) {
+    if (fa) round(WARM, std::true_type{}, ca, ka, acta, cb, kb, actb, fb);
+    else round(WARM, std::false_type{}, ca, ka, acta, cb, kb, actb, fb);
+  };
+  auto step_ba = [&](auto WARM) {
+    if (fb) round(WARM, std::true_type{}, cb, kb, actb, ca, ka, acta, fa);
+    else round(WARM, std::false_type{}, cb, kb, actb, ca, ka, acta, fa);
+  };
+  auto run_to = [&](auto WARM, const int end) {
+    while (pos + 2 <= end) {
+      step_ab(WARM);
+      step_ba(WARM);
+    }
+    if (pos < end) {  // odd count: one more round, then the register sets swap roles
+      step_ab(WARM);
+      ca = cb; ka = kb; acta = actb; fa = fb;
+    }
+  };
+  run_to(std::true_type{}, n_warm);
+  run_to(std::false_type{}, total);
+  cp_async_wait<0>();
+  __syncwarp();
+  if (live)
+    for (int b = g; b < B.NB; b += SCHED_G) B.b_vel[x.at(B.NB, b)] = vel[ml_col(b, wq)];
+  timeline_record(B, 1, t_start);
+}
+
 }  // namespace b2g

@@ -280,7 +280,7 @@ typedef struct b2gpu_caps {
                           stages, 2 branchy one-lane position kernel, 3 level-scheduled velocity + position,
                           4 TMA-fed velocity ring, 5 one stream (no stream groups), 6 no CUDA graphs, 7 branchy
                           velocity kernel only, 8 velocity kernel with a producer warp, 9 level-scheduled
-                          position kernel (all bit-identical; profiles/r01_ncu_summary.md has their timings) */
+                          position kernel, 10 straight-line level-scheduled velocity kernel (all bit-identical; profiles/r01_ncu_summary.md has their timings) */
 } b2gpu_caps;
 
 typedef struct b2gpu_ctx b2gpu_ctx;
