@@ -19,6 +19,7 @@
 #pragma once
 #include "b2g_common.h"
 #include "b2g_narrow.h"
+#include "b2g_distance.h"
 #include "b2g_tree.h"
 
 #if defined(__CUDA_ARCH__)
@@ -129,8 +130,8 @@ B2G_HD void collide_one(const Batch& B, const WIdx& x, const Ws& ws, int c, int*
   const bool was_touching = (flags & B2GPU_CONTACT_TOUCHING) != 0;
   bool touching = false;
   if (fa.is_sensor || fb.is_sensor) {
-    // sensor overlap needs GJK (b2_distance.rs) — outside the hot-path scope
-    ws[WS_STATUS] = B2GPU_E_UNSUPPORTED;
+    // sensors don't generate manifolds; touching = GJK overlap of the two child shapes (b2_contact.rs(private):149-163)
+    touching = test_overlap_shapes(&B.shapes[fa.shape_first + fx.z], &B.shapes[fb.shape_first + fx.w], load_xf(B, x, ba), load_xf(B, x, bb));
     int4 m3 = B.c_m3[ci];
     m3.w = 0;
     B.c_m3[ci] = m3;

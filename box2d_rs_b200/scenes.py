@@ -195,3 +195,42 @@ def variety(world, seed=0xB2D + 9):
             b.create_fixture(FixtureDef(density=2.0, friction=0.4), world.shapes.circle(0.2, (0.45, 0.0)))
         bodies.append(b)
     return bodies
+
+
+def sensors(world, seed=0xB2D + 11):
+    """Sensor fixtures of every shape kind (b2_contact.rs(private):149-163: touching = GJK overlap, no
+    manifold, no response): a circular and a polygonal sensor zone on the ground body, a one-sided chain
+    sensor, a sensor edge, and dynamic bodies that carry a sensor halo next to their solid fixture, raining
+    through the zones onto a floor."""
+    rng = SplitMix64(seed)
+    ground = world.create_body(BodyDef())
+    ground.create_fixture_by_shape(world.shapes.edge_two_sided((-12.0, 0.0), (12.0, 0.0)), 0.0)
+    ground.create_fixture(FixtureDef(is_sensor=1), world.shapes.circle(2.0, (-5.0, 4.0)))
+    ground.create_fixture(FixtureDef(is_sensor=1), world.shapes.polygon_box(2.5, 1.0, (4.0, 3.0), 0.35))
+    ground.create_fixture(FixtureDef(is_sensor=1), world.shapes.edge_two_sided((-3.0, 6.0), (3.0, 7.0)))
+    ground.create_fixture(FixtureDef(is_sensor=1),
+                          world.shapes.chain([(9.0, 2.0), (7.0, 2.5), (5.5, 4.5), (6.0, 7.0)], (10.0, 2.0), (6.5, 8.0)))
+    mover = world.create_body(BodyDef(type=abi.KINEMATIC_BODY, position=(-8.0, 2.0), linear_velocity=(2.0, 0.3),
+                                      angular_velocity=-0.9))
+    mover.create_fixture(FixtureDef(is_sensor=1), world.shapes.polygon([(-1.2, -0.4), (1.0, -0.6), (1.4, 0.5), (-0.2, 0.9)]))
+    bodies = []
+    for k in range(48):
+        px = f32(-9.0 + 18.0 * ((k * 11) % 48) / 48.0 + rng.uniform(-0.15, 0.15))
+        py = f32(5.0 + 0.8 * (k // 8) + rng.uniform(-0.1, 0.1))
+        b = world.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(px, py), angle=f32(rng.uniform(-3.0, 3.0))))
+        kind = k % 4
+        if kind == 0:
+            b.create_fixture(FixtureDef(density=1.0, friction=0.3), world.shapes.circle(0.3))
+        elif kind == 1:
+            b.create_fixture(FixtureDef(density=1.0, friction=0.3), world.shapes.polygon_box(0.35, 0.25))
+        elif kind == 2:  # solid core + sensor halo on the same body
+            b.create_fixture(FixtureDef(density=2.0, friction=0.5), world.shapes.polygon_box(0.25, 0.25))
+            b.create_fixture(FixtureDef(density=0.0, is_sensor=1), world.shapes.circle(0.7))
+        else:            # a body made only of a sensor polygon next to a small solid circle
+            b.create_fixture(FixtureDef(density=1.5, friction=0.2), world.shapes.circle(0.2, (0.0, -0.2)))
+            nv = 3 + (k // 4) % 5
+            b.create_fixture(FixtureDef(density=0.0, is_sensor=1),
+                             world.shapes.polygon([(0.6 * math.cos(2 * math.pi * i / nv), 0.45 * math.sin(2 * math.pi * i / nv) + 0.3)
+                                                   for i in range(nv)]))
+        bodies.append(b)
+    return bodies

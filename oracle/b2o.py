@@ -63,6 +63,10 @@ def lib():
         L.b2o_shape_compute_mass.argtypes = [C.POINTER(abi.ShapeDef), C.c_float, C.POINTER(abi.MassData)]
         L.b2o_sweep_get_transform.argtypes = [C.POINTER(C.c_float), C.c_float, C.POINTER(C.c_float)]
         L.b2o_sincosf.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
+        L.b2o_shape_distance.argtypes = [C.POINTER(abi.ShapeDef), C.c_int, C.c_void_p, C.POINTER(abi.ShapeDef), C.c_int,
+                                         C.c_void_p, C.c_int, C.c_void_p]
+        L.b2o_test_overlap_shapes.argtypes = [C.POINTER(abi.ShapeDef), C.c_int, C.c_void_p, C.POINTER(abi.ShapeDef), C.c_int,
+                                              C.c_void_p]
         L.b2o_hardware_threads.restype = C.c_int
         _LIB = L
     return _LIB
@@ -222,3 +226,21 @@ def sincosf(angles):
 
 def hardware_threads():
     return int(lib().b2o_hardware_threads())
+
+
+def shape_distance(shape_a, xf_a, shape_b, xf_b, use_radii=True, index_a=0, index_b=0):
+    """b2_distance_fn (GJK) between two shapes under (x, y, angle) transforms: (point_a, point_b, distance, iterations)."""
+    import numpy as np
+    xa = np.asarray(xf_a, np.float32)
+    xb = np.asarray(xf_b, np.float32)
+    out = np.zeros(5, np.float32)
+    it = lib().b2o_shape_distance(C.byref(shape_a), index_a, xa.ctypes.data, C.byref(shape_b), index_b, xb.ctypes.data,
+                                  1 if use_radii else 0, out.ctypes.data)
+    return (float(out[0]), float(out[1])), (float(out[2]), float(out[3])), float(out[4]), it
+
+
+def test_overlap_shapes(shape_a, xf_a, shape_b, xf_b, index_a=0, index_b=0):
+    import numpy as np
+    xa = np.asarray(xf_a, np.float32)
+    xb = np.asarray(xf_b, np.float32)
+    return bool(lib().b2o_test_overlap_shapes(C.byref(shape_a), index_a, xa.ctypes.data, C.byref(shape_b), index_b, xb.ctypes.data))

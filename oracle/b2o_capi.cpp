@@ -66,6 +66,30 @@ int b2o_shape_compute_mass(const b2gpu_shape_def* d, float density, b2gpu_mass_d
   out->mass = md.mass; out->center_x = md.center.x; out->center_y = md.center.y; out->inertia = md.i;
   return 0;
 }
+// b2_distance_fn between two shapes' children under (p.x, p.y, angle) transforms: out5 = point_a, point_b, distance
+int b2o_shape_distance(const b2gpu_shape_def* da, int index_a, const float* xa3, const b2gpu_shape_def* db, int index_b,
+                       const float* xb3, int use_radii, float* out5) {
+  Shape a = shape_from_def(da), b = shape_from_def(db);
+  DistanceProxy pa, pb;
+  proxy_set_shape(pa, a, index_a);
+  proxy_set_shape(pb, b, index_b);
+  Transform ta, tb;
+  ta.p = Vec2(xa3[0], xa3[1]); ta.q.set(xa3[2]);
+  tb.p = Vec2(xb3[0], xb3[1]); tb.q.set(xb3[2]);
+  SimplexCache cache;
+  DistanceOutput o;
+  b2_distance(o, cache, pa, ta, pb, tb, use_radii != 0);
+  out5[0] = o.point_a.x; out5[1] = o.point_a.y; out5[2] = o.point_b.x; out5[3] = o.point_b.y; out5[4] = o.distance;
+  return o.iterations;
+}
+int b2o_test_overlap_shapes(const b2gpu_shape_def* da, int index_a, const float* xa3, const b2gpu_shape_def* db, int index_b,
+                            const float* xb3) {
+  Shape a = shape_from_def(da), b = shape_from_def(db);
+  Transform ta, tb;
+  ta.p = Vec2(xa3[0], xa3[1]); ta.q.set(xa3[2]);
+  tb.p = Vec2(xb3[0], xb3[1]); tb.q.set(xb3[2]);
+  return b2_test_overlap_shapes(a, index_a, b, index_b, ta, tb) ? 1 : 0;
+}
 // tests/math_test.rs:25-49 — sweep endpoints
 void b2o_sweep_get_transform(const float* sweep8 /*lc c0 c a0 a*/, float beta, float* xf4) {
   Vec2 lc(sweep8[0], sweep8[1]), c0(sweep8[2], sweep8[3]), c(sweep8[4], sweep8[5]);

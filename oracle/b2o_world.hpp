@@ -15,6 +15,7 @@
 #include <vector>
 
 #include "b2o_collision.hpp"
+#include "b2o_distance.hpp"
 #include "b2o_tree.hpp"
 
 namespace b2o {
@@ -450,9 +451,8 @@ struct World {
     int body_a = fixtures[c.fixture_a].body, body_b = fixtures[c.fixture_b].body;
     const Transform xf_a = bodies[body_a].xf, xf_b = bodies[body_b].xf;
     bool touching;
-    if (sensor) {
-      assert(false && "sensor overlap (GJK) is out of scope (SURVEY.md §8f)");
-      touching = false;
+    if (sensor) {  // b2_contact.rs(private):149-163: GJK overlap, sensors don't generate manifolds
+      touching = b2_test_overlap_shapes(fixtures[c.fixture_a].shape, c.index_a, fixtures[c.fixture_b].shape, c.index_b, xf_a, xf_b);
       c.manifold.point_count = 0;
     } else {
       Manifold nm;

@@ -36,4 +36,5 @@ SCENES = {
     "pile400": (lambda s, w: s.pile(w, n=400, width=12.0), (0.0, -10.0), 200),
     "addpair2000": (lambda s, w: s.add_pair(w, n=2000), (0.0, 0.0), 150),
     "variety": (lambda s, w: s.variety(w), (0.0, -10.0), 400),
+    "sensors": (lambda s, w: s.sensors(w), (0.0, -10.0), 300),
 }

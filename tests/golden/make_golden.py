@@ -24,6 +24,7 @@ CASES = {
     "pile400": ("pile400", (1, 50, 150)),
     "addpair2000": ("addpair2000", (1, 40, 120)),
     "variety": ("variety", (1, 60, 200, 400)),
+    "sensors": ("sensors", (1, 60, 150, 300)),
 }
 
 
@@ -51,7 +52,10 @@ def main():
     from conftest import SCENES
     from box2d_rs_b200 import scenes
     from oracle import b2o
+    only = sys.argv[1:]  # optional: regenerate only the named cases (a new scene must not rewrite the old pins)
     for name, (key, steps) in CASES.items():
+        if only and name not in only:
+            continue
         recipe, gravity, _ = SCENES[key]
         w = b2o.B2world(gravity)
         recipe(scenes, w)

@@ -110,7 +110,7 @@ def test_batch_of_different_worlds(n_worlds, lane_block, ctx):
     wg.close()
 
 
-@pytest.mark.parametrize("name,steps", [("hello_world", 90), ("mixed300", 260), ("addpair2000", 120), ("pile400", 120), ("variety", 400)])
+@pytest.mark.parametrize("name,steps", [("hello_world", 90), ("mixed300", 260), ("addpair2000", 120), ("pile400", 120), ("variety", 400), ("sensors", 300)])
 def test_batch_replicas_shared_memory_solver(name, steps, ctx):
     """32-world memory blocks run the shared-memory Gauss-Seidel kernels (resident ring for tiny islands,
     streaming ring otherwise, many islands per world): replicas must match the oracle bit for bit."""
@@ -130,7 +130,7 @@ def test_batch_replicas_shared_memory_solver(name, steps, ctx):
 
 
 @pytest.mark.parametrize("solver", ["lane", "generic", "levels", "tma", "pipelined", "producer", "ml_position", "levels2"])
-@pytest.mark.parametrize("name,steps", [("mixed300", 200), ("variety", 300)])
+@pytest.mark.parametrize("name,steps", [("mixed300", 200), ("variety", 300), ("sensors", 200)])
 def test_alternative_solver_kernels(name, steps, solver, ctx):
     """The one-lane-per-world shared-memory kernels and the generic global-memory stages stay available
     (worlds too large for the level-scheduled kernels): same bits as the oracle."""
@@ -170,7 +170,7 @@ def test_full_size_batch_properties(ctx):
     wg.close()
 
 
-@pytest.mark.parametrize("name", ["pyramid", "mixed300", "pile400", "addpair2000", "hello_world", "variety"])
+@pytest.mark.parametrize("name", ["pyramid", "mixed300", "pile400", "addpair2000", "hello_world", "variety", "sensors"])
 def test_gpu_matches_golden(name, ctx):
     """The committed fixtures (tests/golden, produced by the oracle) reproduced by the CUDA path, in a
     40-world batch (shared-memory solver and island kernels), bit for bit."""

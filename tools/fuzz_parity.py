@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Differential fuzzing of the device stages (host simulator build by default, --gpu for the CUDA path) against
 the CPU oracle: random scenes (polygons of 3..8 vertices, circles, edges, chains, kinematic / fixed-rotation /
-multi-fixture bodies, filters, restitution, damping, random world flags and iteration counts, dt = 0 steps,
+multi-fixture bodies, sensors, filters, restitution, damping, random world flags and iteration counts, dt = 0 steps,
 mid-run set_transform / set_linear_velocity edits), stepped freely and compared bit for bit.
 
   python tools/fuzz_parity.py --seeds 200 [--gpu] [--batch]
@@ -69,6 +69,8 @@ def build(world, rng):
                 fd.group_index = int(rng.integers(-2, 3))
             if r == 1:
                 fd.category_bits, fd.mask_bits = int(1 << rng.integers(0, 3)), int(0xFFFF ^ (1 << rng.integers(0, 3)))
+            if r == 2:
+                fd.is_sensor = 1  # touching by GJK overlap, no manifold, no response
             s = rng.integers(0, 4)
             if s == 0:
                 shape = world.shapes.circle(f32(rng.uniform(0.1, 0.6)), (f32(rng.uniform(-0.3, 0.3)), f32(rng.uniform(-0.3, 0.3))))
