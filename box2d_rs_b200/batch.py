@@ -53,9 +53,10 @@ class Batch:
         # one-lane position kernel; 'levels' = level-scheduled velocity + position; 'tma' = TMA-fed velocity ring;
         # 'one_stream' = no stream groups; 'no_graph' = no CUDA graphs; 'pipelined' = branchy velocity kernel only;
         # 'producer' = straight-line velocity kernel with a producer warp; 'ml_position' = level-scheduled position;
-        # 'levels2' = straight-line level-scheduled velocity kernel (two lanes per world)
+        # 'levels2' = straight-line level-scheduled velocity kernel (two lanes per world);
+        # 'large' = large-world mode (exactly one world: data-parallel broadphase / islands, b2g_large.h)
         codes = {None: 0, 'generic': 1, 'lane': 2, 'levels': 3, 'tma': 4, 'one_stream': 5, 'no_graph': 6, 'pipelined': 7,
-                 'producer': 8, 'ml_position': 9, 'levels2': 10}
+                 'producer': 8, 'ml_position': 9, 'levels2': 10, 'large': 11}
         caps.reserved[1] = 1 if generic_solver else codes[solver]
         self.h = C.c_void_p()
         c = proto.as_c()

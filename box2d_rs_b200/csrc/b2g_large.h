@@ -1,0 +1,766 @@
+// b2g_large.h — data-parallel forms of the ordered stages for ONE large world (LB = 1, configs 2/4/5 of
+// BASELINE.json: 10k–100k bodies).  b2g_step.h runs the order-dependent parts of a step as one thread per
+// world, which is the right shape for thousands of small worlds and hopeless for one world of 100k bodies
+// (558 ms of tree maintenance + 58 ms of island DFS per step, profiles/r01_single_world_*.json).  The stages
+// here produce the same results from flat kernels plus scans and sorts:
+//
+//  * broadphase ("set-exact", SURVEY H1 option ii): move_proxy's keep-or-refatten decision stays the flat
+//    SyncFixturesK; the moved proxies are compacted into the move buffer in synchronize order; an LBVH
+//    (Morton order of the fat-box centres, Karras construction, bottom-up refit) is rebuilt over all proxies;
+//    every moved proxy queries it (one thread per query, count -> scan -> emit) under the reference's pair
+//    rule (b2_broad_phase.rs(private):86-111: skip self, skip a moved partner with the larger id);
+//    add_pair's tests (b2_contact_manager.rs(private):178-302) run flat over the candidate pairs and the
+//    survivors are appended by a prefix sum.  The pair SET and the created contact SET are the reference's;
+//    the creation ORDER inside one update_pairs call is (move-buffer order, LBVH traversal order) instead of
+//    (move-buffer order, reference-tree traversal order), because the reference's order is a function of its
+//    incrementally balanced tree, whose maintenance is sequential.  The replica tree is not maintained in
+//    this mode (its leaf boxes are; the internal nodes are refitted on download).
+//  * contact destruction: flag -> scan -> stable compaction (same order of survivors as the reference list).
+//  * per-body contact edge lists (push_front lists = each body's contacts by descending index): rebuilt by one
+//    radix sort of (body, edge) keys whenever the contact set changed.
+//  * islands (b2_world.rs(private):376-507): connected components by a lock-free union-find over the eligible
+//    contacts give each island's member set, its seed (the newest awake body: the reference's seed loop runs
+//    newest first) and its body / contact counts; a prefix sum in seed order lays out the island arrays; then
+//    ONE THREAD PER ISLAND runs the reference's LIFO traversal from its seed, so every island's contact order —
+//    the Gauss-Seidel order — is exactly the reference's.  Static bodies never propagate an island and are
+//    not listed (they only needed their rotation cached, done flat by LwStaticRotK).
+//
+// Every functor is B2G_HD and is stepped by the test-only host simulator as well (tests/hostsim).
+#pragma once
+#include "b2g_step.h"
+
+#if defined(__CUDA_ARCH__)
+#define B2G_ATOMIC_MAX(p, v) atomicMax((p), (v))
+#define B2G_ATOMIC_CAS(p, c, v) atomicCAS((p), (c), (v))
+#define B2G_FENCE() __threadfence()
+#define B2G_VLOAD(p) (*(volatile const int*)(p))
+#else
+#define B2G_ATOMIC_MAX(p, v) (*(p) = (*(p) > (v) ? *(p) : (v)))
+#define B2G_FENCE()
+#define B2G_VLOAD(p) (*(p))
+static inline int b2g_host_cas(int* p, int c, int v) { int o = *p; if (o == c) *p = v; return o; }
+#define B2G_ATOMIC_CAS(p, c, v) b2g_host_cas((p), (c), (v))
+#endif
+
+namespace b2g {
+
+typedef unsigned long long u64;
+
+struct Large {  // device scratch of the large-world mode
+  // sort keys (LBVH Morton keys, edge-list keys)
+  u64* keys;      // [NK]
+  u64* keys_alt;  // [NK]
+  // LBVH over the NP proxies: internal nodes 0..n-2 (0 = root), leaves by sorted position
+  float4* lb_box;  // [NP] boxes of internal nodes
+  int2* lb_child;  // [NP] children: >= 0 internal node, < 0 leaf at sorted position ~c
+  int* lb_parent;  // [2 NP] parent of internal node i at [i], of the leaf at sorted position s at [NP + s]
+  int* lb_flag;    // [NP] refit arrival counters
+  int* lb_leaf;    // [NP] tree node id (= proxy id of the reference) of the leaf at sorted position s
+  // pair finding
+  int* q_cnt;      // [NMOVE + 1] candidates per moved proxy; moved-word popcounts
+  int* q_off;      // [NMOVE + 1]
+  int2* cand;      // [NCAND] candidate pairs (query node id, other node id)
+  int* cand_flag;  // [NCAND + 1] 1 = add_pair creates a contact
+  int* cand_pos;   // [NCAND + 1]
+  int4* cand_fix;  // [NCAND] (fixture_a, fixture_b, index_a, index_b) after the register-order swap
+  int NCAND;
+  // islands
+  int* uf_parent;  // [NB]
+  int* cnt_b;      // [NB] per root: non-static bodies
+  int* cnt_c;      // [NB] per root: eligible contacts
+  int* seed;       // [NB] per root: newest awake, enabled, non-static member or -1
+  u64* pk_in;      // [NB + 1] islands in seed order: 1 << 44 | bodies << 24 | contacts
+  u64* pk_out;     // [NB + 1]
+  int* isl_seed;   // [NB]
+  // destroy compaction
+  int* keep_flag;  // [NC + 1]
+  int* keep_pos;   // [NC + 1]
+};
+
+B2G_HD Box lw_box(const float4* a, int i) { return load_box(a, i); }
+
+// ------------------------------------------------------------------------------------------
+// union-find (lock-free hooking by atomicCAS, path halving; the larger index becomes the root)
+// ------------------------------------------------------------------------------------------
+B2G_HD int uf_find(int* parent, int x) {
+  for (;;) {
+    const int p = B2G_VLOAD(&parent[x]);
+    if (p == x) return x;
+    const int gp = B2G_VLOAD(&parent[p]);
+    if (gp != p) parent[x] = gp;  // only ever points further up: safe under concurrent unions
+    x = p;
+  }
+}
+B2G_HD void uf_union(int* parent, int a, int b) {
+  for (;;) {
+    a = uf_find(parent, a);
+    b = uf_find(parent, b);
+    if (a == b) return;
+    if (a < b) { const int t = a; a = b; b = t; }
+    if (B2G_ATOMIC_CAS(&parent[b], b, a) == b) return;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// prologue: wake merge, contact destruction
+// ------------------------------------------------------------------------------------------
+struct LwStatsResetK {  // one thread: what TreePairsK(pre_step) does before the optional find_new_contacts
+  Batch B;
+  B2G_HD void operator()(int) const {
+    for (int s = WS_ST_CONTACTS; s <= WS_ST_LEVELS; ++s) B.ws[s] = 0;
+  }
+};
+
+struct LwClearNewContactsK {  // one thread
+  Batch B;
+  B2G_HD void operator()(int) const { B.ws[WS_FLAGS] &= ~B2GPU_WORLD_NEW_CONTACTS; }
+};
+
+struct LwWakeFixupK {  // one thread, only when collide woke a sleeping body (SerialAK::prologue part 1)
+  Batch B;
+  int* b_wake;
+  B2G_HD void operator()(int) const {
+    WIdx x = widx(B, 0);
+    Ws ws = ws_of(B, x);
+    if (!ws[WS_EV_WAKE]) return;
+    const int cc = ws[WS_CONTACT_COUNT];
+    for (int b = 0; b < B.NB; ++b) b_wake[b] = 0;
+    for (int c = cc - 1; c >= 0; --c) {
+      const int flags = B.c_flags[c];
+      if (flags & CF_SKIPPED) {
+        collide_one(B, x, ws, c, b_wake, true);
+      } else if (flags & CF_WOKE) {
+        const int4 fx = B.c_fix[c];
+        const int ba = B.fixtures[fx.x].body, bb = B.fixtures[fx.y].body;
+        if (body_type(B.b_flags[ba]) != B2GPU_STATIC_BODY) b_wake[ba] = 1;
+        if (body_type(B.b_flags[bb]) != B2GPU_STATIC_BODY) b_wake[bb] = 1;
+      }
+    }
+    ws[WS_EV_WAKE] = 0;
+  }
+};
+
+struct LwWakeMergeK {  // flat over bodies: set_awake(true) for every body collide marked
+  Batch B;
+  int* b_wake;
+  B2G_HD void operator()(int b) const {
+    if (b >= B.NB || !b_wake[b]) return;
+    b_wake[b] = 0;
+    const int f = B.b_flags[b];
+    if (body_type(f) == B2GPU_STATIC_BODY) return;
+    B.b_flags[b] = f | B2GPU_BODY_AWAKE;
+    B.b_pos[b].w = 0.0f;
+  }
+};
+
+struct LwDestroyFlagK {  // flat over cc + 1 contact slots
+  Batch B;
+  Large L;
+  int cc;
+  B2G_HD void operator()(int c) const {
+    if (c > cc) return;
+    if (c == cc) { L.keep_flag[c] = 0; return; }
+    const int flags = B.c_flags[c];
+    const bool gone = (flags & CF_DESTROY) != 0;
+    L.keep_flag[c] = gone ? 0 : 1;
+    if (!gone) return;
+    const int4 fx = B.c_fix[c];
+    const b2gpu_fixture_rec& fa = B.fixtures[fx.x];
+    const b2gpu_fixture_rec& fb = B.fixtures[fx.y];
+    if (B.c_m3[c].w > 0 && !fa.is_sensor && !fb.is_sensor) {  // b2_contact.rs(private):39-45
+      const int bs[2] = {fa.body, fb.body};
+      for (int s = 0; s < 2; ++s) {
+        const int b = bs[s];
+        if (body_type(B.b_flags[b]) == B2GPU_STATIC_BODY) continue;
+        B2G_ATOMIC_OR(&B.b_flags[b], B2GPU_BODY_AWAKE);
+        B.b_pos[b].w = 0.0f;
+      }
+    }
+  }
+};
+
+// Stable compaction through the (not yet written) velocity-constraint stream as scratch:
+// sections of NC float4 each: fix, mat, m0, m1, m2, m3, flags.
+struct LwCompactK {
+  Batch B;
+  Large L;
+  int n;      // phase 0: old contact count; phase 1: new contact count
+  int phase;  // 0: survivors -> scratch at their new index; 1: scratch -> contact arrays
+  B2G_HD void operator()(int c) const {
+    if (c >= n) return;
+    float4* t = B.vc;
+    const size_t NC = (size_t)B.NC;
+    if (phase == 0) {
+      if (!L.keep_flag[c]) return;
+      const size_t k = (size_t)L.keep_pos[c];
+      const int4 fx = B.c_fix[c], m3 = B.c_m3[c];
+      t[k] = make_float4(i2f(fx.x), i2f(fx.y), i2f(fx.z), i2f(fx.w));
+      t[NC + k] = B.c_mat[c];
+      t[2 * NC + k] = B.c_m0[c];
+      t[3 * NC + k] = B.c_m1[c];
+      t[4 * NC + k] = B.c_m2[c];
+      t[5 * NC + k] = make_float4(i2f(m3.x), i2f(m3.y), i2f(m3.z), i2f(m3.w));
+      ((int*)(t + 6 * NC))[k] = B.c_flags[c];
+    } else {
+      const size_t k = (size_t)c;
+      const float4 fx = t[k], m3 = t[5 * NC + k];
+      B.c_fix[c] = make_int4(f2i(fx.x), f2i(fx.y), f2i(fx.z), f2i(fx.w));
+      B.c_mat[c] = t[NC + k];
+      B.c_m0[c] = t[2 * NC + k];
+      B.c_m1[c] = t[3 * NC + k];
+      B.c_m2[c] = t[4 * NC + k];
+      B.c_m3[c] = make_int4(f2i(m3.x), f2i(m3.y), f2i(m3.z), f2i(m3.w));
+      B.c_flags[c] = ((const int*)(t + 6 * NC))[k];
+    }
+  }
+};
+
+struct LwDestroyFinishK {  // one thread
+  Batch B;
+  StepParams sp;
+  int old_cc, new_cc;
+  B2G_HD void operator()(int) const {
+    int* ws = B.ws;
+    ws[WS_ST_DESTROYED] += old_cc - new_cc;
+    ws[WS_CONTACT_COUNT] = new_cc;
+    ws[WS_EV_DESTROY] = 0;
+    ws[WS_TOPO_DIRTY] = 1;
+    if (!(sp.dt > 0.0f)) ws[WS_ISL_VALID] = 0;  // collide-only step: the island order no longer describes the contacts
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+// per-body contact edge lists from a sort of (body, edge) keys
+// ------------------------------------------------------------------------------------------
+struct LwEdgeKeysK {  // flat over max(2 cc, NB): keys of the 2 cc edges; heads reset
+  Batch B;
+  Large L;
+  int* b_chead;
+  int cc, edge_bits;
+  B2G_HD void operator()(int t) const {
+    if (t < B.NB) b_chead[t] = -1;
+    if (t >= 2 * cc) return;
+    const int c = t >> 1;
+    const int4 fx = B.c_fix[c];
+    const int body = (t & 1) ? B.fixtures[fx.y].body : B.fixtures[fx.x].body;
+    L.keys[t] = ((u64)(unsigned)body << edge_bits) | (u64)(unsigned)t;
+  }
+};
+struct LwEdgeLinkK {  // flat over the 2 cc sorted keys: each body's edges ascending -> next = the older neighbour
+  Batch B;
+  Large L;
+  int* b_chead;
+  int2* c_next;
+  int n, edge_bits;
+  B2G_HD void operator()(int i) const {
+    if (i >= n) return;
+    const u64 k = L.keys_alt[i];
+    const u64 mask = ((u64)1 << edge_bits) - 1;
+    const int e = (int)(k & mask);
+    const u64 body = k >> edge_bits;
+    int prev = -1;
+    if (i > 0) {
+      const u64 kp = L.keys_alt[i - 1];
+      if ((kp >> edge_bits) == body) prev = (int)(kp & mask);
+    }
+    int* nx = (int*)&c_next[e >> 1];
+    nx[e & 1] = prev;
+    if (i == n - 1 || (L.keys_alt[i + 1] >> edge_bits) != body) b_chead[(int)body] = e;
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+// islands
+// ------------------------------------------------------------------------------------------
+B2G_HD bool lw_contact_eligible(const Batch& B, int c, int& ba, int& bb) {
+  const int cf = B.c_flags[c];
+  if (!(cf & B2GPU_CONTACT_ENABLED) || !(cf & B2GPU_CONTACT_TOUCHING)) return false;
+  const int4 fx = B.c_fix[c];
+  const b2gpu_fixture_rec& fa = B.fixtures[fx.x];
+  const b2gpu_fixture_rec& fb = B.fixtures[fx.y];
+  if (fa.is_sensor || fb.is_sensor) return false;
+  ba = fa.body;
+  bb = fb.body;
+  return true;
+}
+
+struct LwIslInitK {  // flat over max(NB, cc)
+  Batch B;
+  Large L;
+  int cc;
+  B2G_HD void operator()(int t) const {
+    if (t < B.NB) {
+      L.uf_parent[t] = t;
+      L.cnt_b[t] = 0;
+      L.cnt_c[t] = 0;
+      L.seed[t] = -1;
+      B.b_flags[t] &= ~B2GPU_BODY_ISLAND;
+    }
+    if (t < cc) B.c_flags[t] &= ~B2GPU_CONTACT_ISLAND;
+  }
+};
+struct LwUnionK {  // flat over contacts
+  Batch B;
+  Large L;
+  int cc;
+  B2G_HD void operator()(int c) const {
+    if (c >= cc) return;
+    int ba, bb;
+    if (!lw_contact_eligible(B, c, ba, bb)) return;
+    if (body_type(B.b_flags[ba]) == B2GPU_STATIC_BODY || body_type(B.b_flags[bb]) == B2GPU_STATIC_BODY) return;
+    uf_union(L.uf_parent, ba, bb);
+  }
+};
+struct LwCountK {  // flat over max(NB, cc): sizes and seed of every component, at its root
+  Batch B;
+  Large L;
+  int cc;
+  B2G_HD void operator()(int t) const {
+    if (t < B.NB) {
+      const int f = B.b_flags[t];
+      if (body_type(f) != B2GPU_STATIC_BODY) {
+        const int r = uf_find(L.uf_parent, t);
+        B2G_ATOMIC_ADD(&L.cnt_b[r], 1);
+        if ((f & B2GPU_BODY_AWAKE) && (f & B2GPU_BODY_ENABLED)) B2G_ATOMIC_MAX(&L.seed[r], t);
+      }
+    }
+    if (t < cc) {
+      int ba, bb;
+      if (lw_contact_eligible(B, t, ba, bb)) {
+        const int m = body_type(B.b_flags[ba]) != B2GPU_STATIC_BODY ? ba : bb;
+        if (body_type(B.b_flags[m]) != B2GPU_STATIC_BODY) B2G_ATOMIC_ADD(&L.cnt_c[uf_find(L.uf_parent, m)], 1);
+      }
+    }
+  }
+};
+enum { LW_PK_ISL = 44, LW_PK_BODY = 24 };
+struct LwSeedPackK {  // flat over NB + 1, newest body first: one entry per island at its seed
+  Batch B;
+  Large L;
+  B2G_HD void operator()(int i) const {
+    if (i > B.NB) return;
+    u64 v = 0;
+    if (i < B.NB) {
+      const int b = B.NB - 1 - i;
+      if (body_type(B.b_flags[b]) != B2GPU_STATIC_BODY) {
+        const int r = uf_find(L.uf_parent, b);
+        L.uf_parent[b] = r;
+        if (L.seed[r] == b) v = ((u64)1 << LW_PK_ISL) | ((u64)L.cnt_b[r] << LW_PK_BODY) | (u64)L.cnt_c[r];
+      }
+    }
+    L.pk_in[i] = v;
+  }
+};
+struct LwRangeK {  // flat over NB + 1
+  Batch B;
+  Large L;
+  B2G_HD void operator()(int i) const {
+    if (i > B.NB) return;
+    const u64 o = L.pk_out[i];
+    const int isl = (int)(o >> LW_PK_ISL), bf = (int)((o >> LW_PK_BODY) & 0xfffff), cf = (int)(o & 0xffffff);
+    if (i == B.NB) {
+      int* ws = B.ws;
+      ws[WS_ISL_COUNT] = isl; ws[WS_ISL_BODIES] = bf; ws[WS_ISL_CONTACTS] = cf;
+      ws[WS_ST_ISLANDS] = isl; ws[WS_ST_ISL_BODIES] = bf; ws[WS_ST_ISL_CONTACTS] = cf;
+      ws[WS_TOPO_DIRTY] = 0;  // the island traversal raises it again when a sleeper joined
+      ws[WS_ISL_VALID] = 1;
+      ws[WS_SCHED_ROUNDS] = -1;
+      return;
+    }
+    if (!(L.pk_in[i] >> LW_PK_ISL)) return;
+    const int b = B.NB - 1 - i;
+    const int r = L.uf_parent[b];
+    B.isl_range[isl] = make_int4(bf, bf + L.cnt_b[r], cf, cf + L.cnt_c[r]);
+    L.isl_seed[isl] = b;
+  }
+};
+struct LwDfsK {  // one thread per island: the reference's traversal from the island's seed
+  Batch B;
+  Large L;
+  int* b_chead;
+  int2* c_next;
+  int* stack;  // [NB]: island i uses the slots of its body range
+  int n_islands;
+  B2G_HD void operator()(int isl) const {
+    if (isl >= n_islands) return;
+    const int4 rg = B.isl_range[isl];
+    int* st = stack + rg.x;
+    int nb = rg.x, nc = rg.z, sp_ = 0;
+    const int seed = L.isl_seed[isl];
+    st[sp_++] = seed;
+    B.b_flags[seed] |= B2GPU_BODY_ISLAND;
+    bool dirty_next = false;
+    while (sp_ > 0) {
+      const int b = st[--sp_];
+      B.isl_body[nb++] = b;
+      const int bf = B.b_flags[b];
+      if (!(bf & B2GPU_BODY_AWAKE)) dirty_next = true;  // a sleeper joined: it is a seed candidate next step
+      B.b_flags[b] = bf | B2GPU_BODY_AWAKE;
+      for (int e = b_chead[b]; e != -1;) {
+        const int c = e >> 1, side = e & 1;
+        const int2 nx = c_next[c];
+        e = side ? nx.y : nx.x;
+        const int cf = B.c_flags[c];
+        if (cf & B2GPU_CONTACT_ISLAND) continue;
+        if (!(cf & B2GPU_CONTACT_ENABLED) || !(cf & B2GPU_CONTACT_TOUCHING)) continue;
+        const int4 fx = B.c_fix[c];
+        const b2gpu_fixture_rec& fa = B.fixtures[fx.x];
+        const b2gpu_fixture_rec& fb = B.fixtures[fx.y];
+        if (fa.is_sensor || fb.is_sensor) continue;
+        B.isl_contact[nc] = c;
+        B.c_isl[nc] = isl;
+        ++nc;
+        B.c_flags[c] = cf | B2GPU_CONTACT_ISLAND;
+        const int other = side ? fa.body : fb.body;
+        const int of = B.b_flags[other];
+        if (body_type(of) == B2GPU_STATIC_BODY) continue;  // never propagates; not listed in this mode
+        if (of & B2GPU_BODY_ISLAND) continue;
+        st[sp_++] = other;
+        B.b_flags[other] = of | B2GPU_BODY_ISLAND;
+      }
+    }
+    if (nb != rg.y || nc != rg.w) B.ws[WS_STATUS] = B2GPU_E_INTERNAL;
+    if (dirty_next) B.ws[WS_TOPO_DIRTY] = 1;
+  }
+};
+struct LwIslCachedK {  // one thread: nothing the island order depends on changed
+  Batch B;
+  B2G_HD void operator()(int) const {
+    int* ws = B.ws;
+    ws[WS_ST_ISLANDS] = ws[WS_ISL_COUNT];
+    ws[WS_ST_ISL_BODIES] = ws[WS_ISL_BODIES];
+    ws[WS_ST_ISL_CONTACTS] = ws[WS_ISL_CONTACTS];
+  }
+};
+struct LwStaticRotK {  // flat over bodies: what IntegrateK does for the static members of an island
+  Batch B;
+  B2G_HD void operator()(int b) const {
+    if (b >= B.NB || body_type(B.b_flags[b]) != B2GPU_STATIC_BODY) return;
+    const float4 pos = B.b_pos[b];
+    B.b_pos0[b] = make_float4(pos.x, pos.y, pos.z, 0.0f);
+    const Rot q = rot_from_angle(pos.z);
+    B.b_rot[b] = make_float4(q.s, q.c, q.s, q.c);
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+// broadphase: move buffer, LBVH, pair queries, add_pair
+// ------------------------------------------------------------------------------------------
+B2G_HD int popcount32(unsigned v) {
+#if defined(__CUDA_ARCH__)
+  return __popc(v);
+#else
+  return __builtin_popcount(v);
+#endif
+}
+struct LwMoveCountK {  // flat over NMW + 1 bitmap words
+  Batch B;
+  Large L;
+  B2G_HD void operator()(int w) const {
+    if (w > B.NMW) return;
+    L.q_cnt[w] = w < B.NMW ? popcount32((unsigned)B.p_move[w]) : 0;
+  }
+};
+struct LwMoveEmitK {  // flat over bitmap words: re-fattened proxies enter the move buffer in synchronize order
+  Batch B;
+  Large L;
+  int base;  // move count before this step's moves
+  B2G_HD void operator()(int w) const {
+    if (w >= B.NMW) return;
+    unsigned bits = (unsigned)B.p_move[w];
+    if (!bits) return;
+    B.p_move[w] = 0;
+    int at = base + L.q_off[w];
+    while (bits) {
+      const int bit = lowest_bit(bits);
+      bits &= bits - 1;
+      const int p = B.sync_order[w * 32 + bit];
+      const int node = B.proxy_s[p].z;
+      B.n_aabb[node] = B.p_fat[p];
+      B.n_moved[node] = 1;
+      if (at < B.NMOVE) B.move_buf[at] = node;
+      ++at;
+    }
+  }
+};
+struct LwMoveFinishK {  // one thread
+  Batch B;
+  int mc;
+  B2G_HD void operator()(int) const {
+    B.ws[WS_MOVE_COUNT] = mc;
+    B.ws[WS_EV_MOVED] = 0;
+  }
+};
+
+B2G_HD unsigned lw_spread16(unsigned v) {  // 16 bits -> even bit positions
+  v &= 0xffffu;
+  v = (v | (v << 8)) & 0x00ff00ffu;
+  v = (v | (v << 4)) & 0x0f0f0f0fu;
+  v = (v | (v << 2)) & 0x33333333u;
+  v = (v | (v << 1)) & 0x55555555u;
+  return v;
+}
+struct LwMortonK {  // flat over proxies: key = Morton code of the fat-box centre (1/32 m cells, +-1024 m) << 32 | proxy
+  Batch B;
+  Large L;
+  B2G_HD void operator()(int p) const {
+    if (p >= B.NP) return;
+    const float4 a = B.n_aabb[B.proxy_s[p].z];
+    const float cx = 0.5f * (a.x + a.z), cy = 0.5f * (a.y + a.w);
+    float fx = cx * 32.0f + 32768.0f, fy = cy * 32.0f + 32768.0f;
+    fx = fx > 0.0f ? fx : 0.0f;  // also maps NaN to cell 0
+    fy = fy > 0.0f ? fy : 0.0f;
+    const unsigned qx = fx < 65535.0f ? (unsigned)fx : 65535u, qy = fy < 65535.0f ? (unsigned)fy : 65535u;
+    const unsigned code = lw_spread16(qx) | (lw_spread16(qy) << 1);
+    L.keys[p] = ((u64)code << 32) | (u64)(unsigned)p;
+  }
+};
+B2G_HD int lw_clz64(u64 v) {
+#if defined(__CUDA_ARCH__)
+  return __clzll((long long)v);
+#else
+  return v ? __builtin_clzll(v) : 64;
+#endif
+}
+B2G_HD int lw_delta(const u64* k, int n, int i, int j) {
+  if (j < 0 || j >= n) return -1;
+  return lw_clz64(k[i] ^ k[j]);  // keys are unique (proxy index in the low word)
+}
+struct LwKarrasK {  // flat over n: internal node i < n - 1 (Karras 2012), leaf table
+  Batch B;
+  Large L;
+  int n;
+  B2G_HD void operator()(int i) const {
+    if (i >= n) return;
+    const u64* k = L.keys_alt;
+    L.lb_leaf[i] = B.proxy_s[(int)(k[i] & 0xffffffffu)].z;
+    if (i >= n - 1) return;
+    L.lb_flag[i] = 0;
+    const int d = lw_delta(k, n, i, i + 1) - lw_delta(k, n, i, i - 1) >= 0 ? 1 : -1;
+    const int dmin = lw_delta(k, n, i, i - d);
+    int lmax = 2;
+    while (lw_delta(k, n, i, i + lmax * d) > dmin) lmax *= 2;
+    int l = 0;
+    for (int t = lmax >> 1; t >= 1; t >>= 1)
+      if (lw_delta(k, n, i, i + (l + t) * d) > dmin) l += t;
+    const int j = i + l * d;
+    const int dnode = lw_delta(k, n, i, j);
+    int s = 0;
+    for (int t = l;;) {
+      t = (t + 1) >> 1;
+      if (lw_delta(k, n, i, i + (s + t) * d) > dnode) s += t;
+      if (t <= 1) break;
+    }
+    const int gamma = i + s * d + (d < 0 ? d : 0);
+    const int lo = i < j ? i : j, hi = i < j ? j : i;
+    int2 ch;
+    if (lo == gamma) { ch.x = ~gamma; L.lb_parent[B.NP + gamma] = i; } else { ch.x = gamma; L.lb_parent[gamma] = i; }
+    if (hi == gamma + 1) { ch.y = ~(gamma + 1); L.lb_parent[B.NP + gamma + 1] = i; } else { ch.y = gamma + 1; L.lb_parent[gamma + 1] = i; }
+    L.lb_child[i] = ch;
+    if (i == 0) L.lb_parent[0] = -1;
+  }
+};
+B2G_HD float4 lw_child_box(const Batch& B, const Large& L, int c) { return c >= 0 ? L.lb_box[c] : B.n_aabb[L.lb_leaf[~c]]; }
+struct LwRefitK {  // flat over leaves: the second thread to arrive at a node computes its box
+  Batch B;
+  Large L;
+  int n;
+  B2G_HD void operator()(int s) const {
+    if (s >= n || n < 2) return;
+    int node = L.lb_parent[B.NP + s];
+    while (node != -1) {
+      B2G_FENCE();
+      if (B2G_ATOMIC_ADD(&L.lb_flag[node], 1) == 0) return;
+      B2G_FENCE();
+      const int2 ch = L.lb_child[node];
+      const float4 a = lw_child_box(B, L, ch.x), b = lw_child_box(B, L, ch.y);
+      L.lb_box[node] = make_float4(a.x < b.x ? a.x : b.x, a.y < b.y ? a.y : b.y, a.z > b.z ? a.z : b.z, a.w > b.w ? a.w : b.w);
+      node = L.lb_parent[node];
+    }
+  }
+};
+B2G_HD bool lw_overlap(const float4 a, const Box& q) {  // b2_test_overlap(AABB), src/b2_collision.rs:355-368
+  Box b;
+  b.lo = v2(a.x, a.y);
+  b.hi = v2(a.z, a.w);
+  return box_overlap(b, q);
+}
+enum { LW_STACK = 128 };
+// One thread per move-buffer entry; emit = 0 counts, 1 writes the candidate pairs.  use_tree = 1 walks the
+// uploaded replica of the reference's tree instead of the LBVH (child2 first, b2_dynamic_tree.rs:239-267): the
+// find_new_contacts call at the top of a step (m_new_contacts) always follows an upload, whose tree is current,
+// and its contacts enter an island in the same step — so there the reference's creation order is kept exactly.
+struct LwQueryK {
+  Batch B;
+  Large L;
+  int mc, n, emit, use_tree;
+  B2G_HD void operator()(int i) const {
+    if (i > mc) return;
+    if (i == mc) { if (!emit) L.q_cnt[i] = 0; return; }
+    const int q = B.move_buf[i];
+    int count = 0;
+    int2* out = emit ? L.cand + L.q_off[i] : nullptr;
+    const int room = emit ? L.NCAND - L.q_off[i] : 0;
+    if (q != -1 && n > 0) {
+      const Box qb = lw_box(B.n_aabb, q);
+      int stack[LW_STACK];
+      int sp_ = 0;
+      if (use_tree) {
+        stack[sp_++] = B.ws[WS_TREE_ROOT];
+        while (sp_ > 0) {
+          const int id = stack[--sp_];
+          if (id == -1) continue;
+          if (!lw_overlap(B.n_aabb[id], qb)) continue;
+          const int4 l = B.n_link[id];
+          if (l.y == -1) {
+            if (id == q) continue;
+            if (B.n_moved[id] && id > q) continue;
+            if (emit && count < room) out[count] = make_int2(q, id);
+            ++count;
+          } else {
+            if (sp_ + 2 > LW_STACK) { B.ws[WS_STATUS] = B2GPU_E_CAPACITY; continue; }
+            stack[sp_++] = l.y;
+            stack[sp_++] = l.z;
+          }
+        }
+      } else {
+        stack[sp_++] = n > 1 ? 0 : ~0;
+        while (sp_ > 0) {
+          const int c = stack[--sp_];
+          if (c < 0) {
+            // b2_broad_phase_query_callback (b2_broad_phase.rs(private):86-111)
+            const int id = L.lb_leaf[~c];
+            if (id == q) continue;
+            if (!lw_overlap(B.n_aabb[id], qb)) continue;
+            if (B.n_moved[id] && id > q) continue;
+            if (emit && count < room) out[count] = make_int2(q, id);
+            ++count;
+          } else {
+            if (!lw_overlap(L.lb_box[c], qb)) continue;
+            const int2 ch = L.lb_child[c];
+            if (sp_ + 2 > LW_STACK) { B.ws[WS_STATUS] = B2GPU_E_CAPACITY; continue; }
+            stack[sp_++] = ch.y;
+            stack[sp_++] = ch.x;
+          }
+        }
+      }
+    }
+    if (!emit) L.q_cnt[i] = count;
+  }
+};
+struct LwAddPairK {  // flat over candidates (+1 tail): the tests of add_pair, no side effects
+  Batch B;
+  Large L;
+  int* b_chead;
+  int2* c_next;
+  int n;
+  B2G_HD void operator()(int j) const {
+    if (j > n) return;
+    if (j == n) { L.cand_flag[j] = 0; return; }
+    L.cand_flag[j] = 0;
+    const int2 pr = L.cand[j];
+    const int proxy_a = B.node_proxy[imin(pr.x, pr.y)], proxy_b = B.node_proxy[imax(pr.x, pr.y)];
+    const int4 pa = B.proxy_s[proxy_a], pb = B.proxy_s[proxy_b];
+    int fixture_a = pa.x, fixture_b = pb.x, index_a = pa.y, index_b = pb.y;
+    const int body_a = pa.w, body_b = pb.w;
+    if (body_a == body_b) return;
+    // a contact between the two fixtures is on both bodies' edge lists: walk the list of the movable one when
+    // the other is static (the ground's list holds every resting contact of the world)
+    const int fb_ = B.b_flags[body_b], fa_ = B.b_flags[body_a];
+    const int walk = (body_type(fb_) == B2GPU_STATIC_BODY && body_type(fa_) != B2GPU_STATIC_BODY) ? body_a : body_b;
+    for (int e = b_chead[walk]; e != -1;) {
+      const int c = e >> 1, side = e & 1;
+      const int2 nx = c_next[c];
+      e = side ? nx.y : nx.x;
+      const int4 fx = B.c_fix[c];
+      if (fx.x == fixture_a && fx.y == fixture_b && fx.z == index_a && fx.w == index_b) return;
+      if (fx.x == fixture_b && fx.y == fixture_a && fx.z == index_b && fx.w == index_a) return;
+    }
+    if (!body_should_collide(fb_, fa_)) return;
+    const b2gpu_fixture_rec* fa = &B.fixtures[fixture_a];
+    const b2gpu_fixture_rec* fb = &B.fixtures[fixture_b];
+    if (!filter_should_collide(*fa, *fb)) return;
+    if (!type_pair_primary(fa->shape_type, fb->shape_type)) {
+      if (!type_pair_primary(fb->shape_type, fa->shape_type)) {
+        B.ws[WS_STATUS] = B2GPU_E_UNSUPPORTED;  // the reference panics (unwrap on an unregistered pair)
+        return;
+      }
+      int t = fixture_a; fixture_a = fixture_b; fixture_b = t;
+      t = index_a; index_a = index_b; index_b = t;
+    }
+    L.cand_fix[j] = make_int4(fixture_a, fixture_b, index_a, index_b);
+    L.cand_flag[j] = 1;
+  }
+};
+struct LwCreateK {  // flat over candidates: B2contact::create at contact index cc0 + rank among the survivors
+  Batch B;
+  Large L;
+  int n, cc0;
+  B2G_HD void operator()(int j) const {
+    if (j >= n || !L.cand_flag[j]) return;
+    const int c = cc0 + L.cand_pos[j];
+    if (c >= B.NC) return;
+    const int4 fx = L.cand_fix[j];
+    const b2gpu_fixture_rec* fa = &B.fixtures[fx.x];
+    const b2gpu_fixture_rec* fb = &B.fixtures[fx.y];
+    B.c_fix[c] = fx;
+    B.c_flags[c] = B2GPU_CONTACT_ENABLED;
+    B.c_mat[c] = make_float4(sqrtf(fa->friction * fb->friction),
+                             fa->restitution > fb->restitution ? fa->restitution : fb->restitution,
+                             fa->restitution_threshold < fb->restitution_threshold ? fa->restitution_threshold
+                                                                                   : fb->restitution_threshold,
+                             0.0f);
+    B.c_m0[c] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    B.c_m1[c] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    B.c_m2[c] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+    B.c_m3[c] = make_int4(0, 0, 0, 0);
+  }
+};
+struct LwClearMovedK {  // flat over the move buffer
+  Batch B;
+  int mc;
+  B2G_HD void operator()(int i) const {
+    if (i >= mc) return;
+    const int q = B.move_buf[i];
+    if (q != -1) B.n_moved[q] = 0;
+  }
+};
+struct LwPairsFinishK {  // one thread
+  Batch B;
+  int mc, n_cand, created, status;
+  B2G_HD void operator()(int) const {
+    int* ws = B.ws;
+    ws[WS_CONTACT_COUNT] += created;
+    ws[WS_ST_CREATED] += created;
+    ws[WS_ST_MOVED] += mc;
+    ws[WS_ST_PAIRS] += n_cand;
+    ws[WS_MOVE_COUNT] = 0;
+    if (status) ws[WS_STATUS] = status;
+  }
+};
+struct LwStatsK {  // touching / awake counters on demand: phase 0 one thread (reset), phase 1 flat over max(cc, NB)
+  Batch B;
+  int cc, phase;
+  B2G_HD void operator()(int t) const {
+    int* ws = B.ws;
+    if (phase == 0) {
+      ws[WS_ST_TOUCHING] = 0;
+      ws[WS_ST_AWAKE] = 0;
+      ws[WS_ST_CONTACTS] = cc;
+      return;
+    }
+    if (t < cc && (B.c_flags[t] & B2GPU_CONTACT_TOUCHING)) B2G_ATOMIC_ADD(&ws[WS_ST_TOUCHING], 1);
+    if (t < B.NB && (B.b_flags[t] & B2GPU_BODY_AWAKE)) B2G_ATOMIC_ADD(&ws[WS_ST_AWAKE], 1);
+  }
+};
+struct LwStepEndK {  // one thread: the tail of TreePairsK
+  Batch B;
+  StepParams sp;
+  B2G_HD void operator()(int) const {
+    int* ws = B.ws;
+    if (sp.dt > 0.0f) ws[WS_INV_DT0] = f2i(sp.inv_dt);
+    ws[WS_ST_CONTACTS] = ws[WS_CONTACT_COUNT];
+  }
+};
+
+}  // namespace b2g

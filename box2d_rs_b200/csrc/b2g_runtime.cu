@@ -10,6 +10,7 @@
 
 #if !defined(B2G_HOSTSIM)
 #include <cuda_runtime.h>
+#include <cub/cub.cuh>
 
 #include "b2g_island_smem.cuh"
 #include "b2g_solver_smem.cuh"
@@ -22,6 +23,9 @@ const char* last_error() { return g_error.c_str(); }
 void set_error(const std::string& s) { g_error = s; }
 
 #define RC(x) do { int rc_ = (x); if (rc_ != 0) return rc_; } while (0)
+
+static int large_alloc(BatchHost* bh);
+static void large_free(BatchHost* bh);
 
 // ------------------------------------------------------------------ device abstraction
 #if defined(B2G_HOSTSIM)
@@ -517,6 +521,12 @@ int batch_create(Ctx* ctx, const b2gpu_snapshot* proto, int n_worlds, const b2gp
     if (rc) { batch_destroy(bh); return rc; }
   }
   bh->pre_step_needed = true;
+  if (caps && caps->reserved[1] == 11) {  // large-world mode: one world, data-parallel ordered stages (b2g_large.h)
+    if (n_worlds != 1 || B.LB != 1) { set_error("large-world mode needs a batch of exactly one world"); batch_destroy(bh); return B2GPU_E_INVALID; }
+    rc = large_alloc(bh);
+    if (rc) { batch_destroy(bh); return rc; }
+    bh->large = true;
+  }
 #if !defined(B2G_HOSTSIM)
   // shared-memory Gauss-Seidel stages: batches in 32-world memory blocks whose bodies fit one SM
   bh->smem_solver = false;
@@ -599,6 +609,7 @@ void batch_destroy(BatchHost* bh) {
     if (FILE* f = fopen(bh->timeline_path.c_str(), "wb")) { fwrite(rows.data(), 8, rows.size(), f); fclose(f); }
   }
 #endif
+  large_free(bh);
   for (void* p : bh->allocs) dev_free(p);
   delete bh;
 }
@@ -626,6 +637,30 @@ static int image_fetch(BatchHost* bh, int world, WorldImage& im) {
   image_alloc(bh->B, im);
   std::vector<ArrRef> tab = array_table(bh, im);
   for (const ArrRef& a : tab) RC(move_array(bh, a, 1, world));
+  if (bh->large) {
+    // large-world mode does not maintain the replica tree: the leaf boxes are current, the topology is the
+    // one last uploaded.  Refit the internal boxes (children before parents) so the snapshot carries a valid
+    // bounding hierarchy for whoever continues from it (host-side proxy creation, the exact mode).
+    const int root = im.ws[WS_TREE_ROOT];
+    if (root >= 0) {
+      std::vector<int> order, st;
+      st.push_back(root);
+      while (!st.empty()) {
+        const int i = st.back();
+        st.pop_back();
+        const int4 l = im.n_link[i];
+        if (l.y == -1) continue;
+        order.push_back(i);
+        st.push_back(l.y);
+        st.push_back(l.z);
+      }
+      for (size_t k = order.size(); k-- > 0;) {
+        const int i = order[k];
+        const float4 a = im.n_aabb[im.n_link[i].y], b = im.n_aabb[im.n_link[i].z];
+        im.n_aabb[i] = make_float4(std::min(a.x, b.x), std::min(a.y, b.y), std::max(a.z, b.z), std::max(a.w, b.w));
+      }
+    }
+  }
   return 0;
 }
 
@@ -802,6 +837,239 @@ static int step_window(BatchHost* bh, const Batch& Bw, const StepParams& sp, int
   return 0;
 }
 
+// ------------------------------------------------------------------ large-world mode (b2g_large.h)
+// Host-driven: the world's scalar slots are read back at a few points of the step (a 4-byte-scale copy and
+// a stream synchronisation each), so every launch is sized by the live counts and stages with nothing to do
+// are skipped.  Scans and sorts are CUB device primitives (std:: algorithms in the host simulator).
+#if defined(B2G_HOSTSIM)
+static int lw_scan_int(BatchHost*, const int* in, int* out, int n, int) {
+  int acc = 0;
+  for (int i = 0; i < n; ++i) { const int v = in[i]; out[i] = acc; acc += v; }
+  return 0;
+}
+static int lw_scan_u64(BatchHost*, const u64* in, u64* out, int n, int) {
+  u64 acc = 0;
+  for (int i = 0; i < n; ++i) { const u64 v = in[i]; out[i] = acc; acc += v; }
+  return 0;
+}
+static int lw_sort_keys(BatchHost*, const u64* in, u64* out, int n, int, int) {
+  std::copy(in, in + n, out);
+  std::sort(out, out + n);
+  return 0;
+}
+static int lw_read(BatchHost* bh, const void* dev, int words) { memcpy(bh->lw_host, dev, (size_t)words * 4); return 0; }
+#else
+static int lw_scan_int(BatchHost* bh, const int* in, int* out, int n, int stage) {
+  if (n <= 0) return 0;
+  LaunchScope ls = {bh->ctx, stage};
+  RC(ls.begin());
+  size_t bytes = bh->lw_tmp_bytes;
+  CU(cub::DeviceScan::ExclusiveSum(bh->lw_tmp, bytes, in, out, n, (cudaStream_t)bh->ctx->stream));
+  return ls.end();
+}
+static int lw_scan_u64(BatchHost* bh, const u64* in, u64* out, int n, int stage) {
+  if (n <= 0) return 0;
+  LaunchScope ls = {bh->ctx, stage};
+  RC(ls.begin());
+  size_t bytes = bh->lw_tmp_bytes;
+  CU(cub::DeviceScan::ExclusiveSum(bh->lw_tmp, bytes, in, out, n, (cudaStream_t)bh->ctx->stream));
+  return ls.end();
+}
+static int lw_sort_keys(BatchHost* bh, const u64* in, u64* out, int n, int end_bit, int stage) {
+  if (n <= 0) return 0;
+  LaunchScope ls = {bh->ctx, stage};
+  RC(ls.begin());
+  size_t bytes = bh->lw_tmp_bytes;
+  CU(cub::DeviceRadixSort::SortKeys(bh->lw_tmp, bytes, in, out, n, 0, end_bit, (cudaStream_t)bh->ctx->stream));
+  return ls.end();
+}
+static int lw_read(BatchHost* bh, const void* dev, int words) {
+  CU(cudaMemcpyAsync(bh->lw_host, dev, (size_t)words * 4, cudaMemcpyDeviceToHost, (cudaStream_t)bh->ctx->stream));
+  CU(cudaStreamSynchronize((cudaStream_t)bh->ctx->stream));
+  return 0;
+}
+#endif
+static int ceil_log2(long long v) { int b = 0; while ((1LL << b) < v) ++b; return b; }
+
+static int large_alloc(BatchHost* bh) {
+  Batch& B = bh->B;
+  Large& L = bh->L;
+  if (B.NB >= (1 << 20) || B.NC >= (1 << 24) || B.NP < 1) {
+    set_error("large-world mode: needs 1 <= proxies, bodies < 2^20, contact capacity < 2^24");
+    return B2GPU_E_CAPACITY;
+  }
+  bh->lw_edge_bits = ceil_log2(2LL * B.NC);
+  bh->lw_body_bits = ceil_log2(B.NB);
+  bh->lw_keys = std::max<long long>(2LL * B.NC, B.NP) + 1;
+  L.NCAND = 2 * B.NC + B.NP;
+  int rc = 0;
+#define AL(ptr, count) do { rc = alloc_arr(bh, &ptr, (count)); if (rc) return rc; } while (0)
+  AL(L.keys, bh->lw_keys); AL(L.keys_alt, bh->lw_keys);
+  AL(L.lb_box, B.NP); AL(L.lb_child, B.NP); AL(L.lb_parent, 2LL * B.NP); AL(L.lb_flag, B.NP); AL(L.lb_leaf, B.NP);
+  const long long nq = std::max(B.NMOVE, B.NMW) + 1;
+  AL(L.q_cnt, nq); AL(L.q_off, nq);
+  AL(L.cand, L.NCAND); AL(L.cand_flag, L.NCAND + 1LL); AL(L.cand_pos, L.NCAND + 1LL); AL(L.cand_fix, L.NCAND);
+  AL(L.uf_parent, B.NB); AL(L.cnt_b, B.NB); AL(L.cnt_c, B.NB); AL(L.seed, B.NB); AL(L.isl_seed, B.NB);
+  AL(L.pk_in, B.NB + 1LL); AL(L.pk_out, B.NB + 1LL);
+  AL(L.keep_flag, B.NC + 1LL); AL(L.keep_pos, B.NC + 1LL);
+#undef AL
+#if defined(B2G_HOSTSIM)
+  bh->lw_host = (int*)calloc(WS_COUNT + 16, 4);
+#else
+  CU(cudaMallocHost((void**)&bh->lw_host, (WS_COUNT + 16) * 4));
+  size_t need = 0, b = 0;
+  CU(cub::DeviceScan::ExclusiveSum(nullptr, b, (const int*)nullptr, (int*)nullptr, L.NCAND + 1));
+  need = std::max(need, b);
+  CU(cub::DeviceScan::ExclusiveSum(nullptr, b, (const u64*)nullptr, (u64*)nullptr, B.NB + 1));
+  need = std::max(need, b);
+  CU(cub::DeviceRadixSort::SortKeys(nullptr, b, (const u64*)nullptr, (u64*)nullptr, (int)bh->lw_keys, 0, 64));
+  need = std::max(need, b);
+  void* v = nullptr;
+  RC(dev_alloc(&v, need + 256));
+  bh->allocs.push_back(v);
+  bh->lw_tmp = v;
+  bh->lw_tmp_bytes = need + 256;
+#endif
+  return 0;
+}
+static void large_free(BatchHost* bh) {
+  if (!bh->lw_host) return;
+#if defined(B2G_HOSTSIM)
+  free(bh->lw_host);
+#else
+  cudaFreeHost(bh->lw_host);
+#endif
+  bh->lw_host = nullptr;
+}
+
+// per-body contact edge lists from scratch (after the contact set changed)
+static int lw_rebuild_lists(BatchHost* bh, int cc, int stage) {
+  Ctx* ctx = bh->ctx;
+  const Batch& B = bh->B;
+  { LwEdgeKeysK k = {B, bh->L, bh->b_chead, cc, bh->lw_edge_bits}; RC(launch(ctx, k, std::max(2 * cc, B.NB), 256, stage)); }
+  if (cc == 0) return 0;
+  RC(lw_sort_keys(bh, bh->L.keys, bh->L.keys_alt, 2 * cc, bh->lw_edge_bits + bh->lw_body_bits, stage));
+  { LwEdgeLinkK k = {B, bh->L, bh->b_chead, bh->c_next, 2 * cc, bh->lw_edge_bits}; RC(launch(ctx, k, 2 * cc, 256, stage)); }
+  return 0;
+}
+
+// B2broadPhase::update_pairs + add_pair over the current move buffer (mc entries, cc contacts before)
+static int lw_update_pairs(BatchHost* bh, int mc, int cc, int stage, int use_tree) {
+  Ctx* ctx = bh->ctx;
+  const Batch& B = bh->B;
+  const Large& L = bh->L;
+  if (mc <= 0) return 0;
+  const int n = B.NP;
+  if (!use_tree) {
+    { LwMortonK k = {B, L}; RC(launch(ctx, k, n, 256, stage)); }
+    RC(lw_sort_keys(bh, L.keys, L.keys_alt, n, 64, stage));
+    { LwKarrasK k = {B, L, n}; RC(launch(ctx, k, n, 128, stage)); }
+    { LwRefitK k = {B, L, n}; RC(launch(ctx, k, n, 128, stage)); }
+  }
+  { LwQueryK k = {B, L, mc, n, 0, use_tree}; RC(launch(ctx, k, mc + 1, 64, stage)); }
+  RC(lw_scan_int(bh, L.q_cnt, L.q_off, mc + 1, stage));
+  RC(lw_read(bh, L.q_off + mc, 1));
+  int n_cand = bh->lw_host[0], status = 0;
+  if (n_cand > L.NCAND) { n_cand = L.NCAND; status = B2GPU_E_CAPACITY; }
+  int created = 0;
+  if (n_cand > 0) {
+    { LwQueryK k = {B, L, mc, n, 1, use_tree}; RC(launch(ctx, k, mc, 64, stage)); }
+    { LwAddPairK k = {B, L, bh->b_chead, bh->c_next, n_cand}; RC(launch(ctx, k, n_cand + 1, 128, stage)); }
+    RC(lw_scan_int(bh, L.cand_flag, L.cand_pos, n_cand + 1, stage));
+    RC(lw_read(bh, L.cand_pos + n_cand, 1));
+    created = bh->lw_host[0];
+    if (cc + created > B.NC) { created = B.NC - cc; status = B2GPU_E_CAPACITY; }
+    if (created > 0) { LwCreateK k = {B, L, n_cand, cc}; RC(launch(ctx, k, n_cand, 128, stage)); }
+  }
+  { LwClearMovedK k = {B, mc}; RC(launch(ctx, k, mc, 256, stage)); }
+  { LwPairsFinishK k = {B, mc, n_cand, created, status}; RC(launch(ctx, k, 1, 32, stage)); }
+  if (created > 0) RC(lw_rebuild_lists(bh, cc + created, stage));
+  return 0;
+}
+
+static int step_large(BatchHost* bh, const StepParams& sp, int steps) {
+  Ctx* ctx = bh->ctx;
+  const Batch& B = bh->B;
+  const Large& L = bh->L;
+  int* hw = bh->lw_host;
+  const float dt = sp.dt;
+  for (int s = 0; s < steps; ++s) {
+    // ---- top of step: stats, find_new_contacts when m_new_contacts (b2_world.rs(private):912-915)
+    { LwStatsResetK k = {B}; RC(launch(ctx, k, 1, 32, STAGE_PRE)); }
+    RC(lw_read(bh, B.ws, WS_COUNT));
+    int cc = hw[WS_CONTACT_COUNT];
+    if (hw[WS_FLAGS] & B2GPU_WORLD_NEW_CONTACTS) {
+      const int mc = hw[WS_MOVE_COUNT];
+      RC(lw_update_pairs(bh, mc, cc, STAGE_PRE, 1));
+      { LwClearNewContactsK k = {B}; RC(launch(ctx, k, 1, 32, STAGE_PRE)); }
+      RC(lw_read(bh, B.ws, WS_COUNT));
+      cc = hw[WS_CONTACT_COUNT];
+    }
+    // ---- collide
+    { CollideK k = {B, bh->b_wake}; RC(launch_occ(ctx, k, cc, STAGE_COLLIDE)); }
+    RC(lw_read(bh, B.ws, WS_COUNT));
+    if (hw[WS_EV_WAKE]) {
+      { LwWakeFixupK k = {B, bh->b_wake}; RC(launch(ctx, k, 1, 32, STAGE_ISLAND)); }
+      RC(lw_read(bh, B.ws, WS_COUNT));
+    }
+    if (hw[WS_TOPO_DIRTY]) { LwWakeMergeK k = {B, bh->b_wake}; RC(launch(ctx, k, B.NB, 256, STAGE_ISLAND)); }
+    bool dirty = hw[WS_TOPO_DIRTY] != 0;
+    if (hw[WS_EV_DESTROY]) {
+      const int new_cc = cc - hw[WS_EV_DESTROY];
+      { LwDestroyFlagK k = {B, L, cc}; RC(launch(ctx, k, cc + 1, 256, STAGE_ISLAND)); }
+      RC(lw_scan_int(bh, L.keep_flag, L.keep_pos, cc + 1, STAGE_ISLAND));
+      { LwCompactK k = {B, L, cc, 0}; RC(launch(ctx, k, cc, 256, STAGE_ISLAND)); }
+      { LwCompactK k = {B, L, new_cc, 1}; RC(launch(ctx, k, new_cc, 256, STAGE_ISLAND)); }
+      { LwDestroyFinishK k = {B, sp, cc, new_cc}; RC(launch(ctx, k, 1, 32, STAGE_ISLAND)); }
+      cc = new_cc;
+      RC(lw_rebuild_lists(bh, cc, STAGE_ISLAND));
+      dirty = true;
+    }
+    if (dt > 0.0f) {
+      // ---- islands
+      if (dirty) {
+        const int nbc = std::max(B.NB, cc);
+        { LwIslInitK k = {B, L, cc}; RC(launch(ctx, k, nbc, 256, STAGE_ISLAND)); }
+        { LwUnionK k = {B, L, cc}; RC(launch(ctx, k, cc, 256, STAGE_ISLAND)); }
+        { LwCountK k = {B, L, cc}; RC(launch(ctx, k, nbc, 256, STAGE_ISLAND)); }
+        { LwSeedPackK k = {B, L}; RC(launch(ctx, k, B.NB + 1, 256, STAGE_ISLAND)); }
+        RC(lw_scan_u64(bh, L.pk_in, L.pk_out, B.NB + 1, STAGE_ISLAND));
+        { LwRangeK k = {B, L}; RC(launch(ctx, k, B.NB + 1, 256, STAGE_ISLAND)); }
+        RC(lw_read(bh, B.ws, WS_COUNT));
+        { LwDfsK k = {B, L, bh->b_chead, bh->c_next, bh->stack, hw[WS_ISL_COUNT]}; RC(launch(ctx, k, hw[WS_ISL_COUNT], 64, STAGE_ISLAND)); }
+      } else {
+        LwIslCachedK k = {B};
+        RC(launch(ctx, k, 1, 32, STAGE_ISLAND));
+      }
+      const int ni = hw[WS_ISL_COUNT], nib = hw[WS_ISL_BODIES], nic = hw[WS_ISL_CONTACTS];
+      { LwStaticRotK k = {B}; RC(launch(ctx, k, B.NB, 256, STAGE_INTEGRATE)); }
+      { IntegrateK k = {B, sp}; RC(launch(ctx, k, nib, 128, STAGE_INTEGRATE)); }
+      { SolverInitK k = {B, sp}; RC(launch(ctx, k, nic, 128, STAGE_SOLVER_INIT)); }
+      { VelocityK k = {B, sp}; RC(launch(ctx, k, ni, 64, STAGE_VELOCITY)); }
+      { PostVelocityK k = {B, sp}; RC(launch(ctx, k, std::max(std::max(ni, nib), nic), 128, STAGE_POST_VELOCITY)); }
+      { PositionK k = {B, sp}; RC(launch(ctx, k, ni, 64, STAGE_POSITION)); }
+      { FinalizeK k = {B, sp}; RC(launch(ctx, k, nib, 128, STAGE_FINALIZE)); }
+      { SleepK k = {B}; RC(launch(ctx, k, ni, 128, STAGE_SLEEP)); }
+      { SyncFixturesK k = {B}; RC(launch(ctx, k, B.NP, 128, STAGE_SYNC_FIXTURES)); }
+      // ---- find_new_contacts
+      RC(lw_read(bh, B.ws, WS_COUNT));
+      int mc = hw[WS_MOVE_COUNT];
+      if (hw[WS_EV_MOVED]) {
+        { LwMoveCountK k = {B, L}; RC(launch(ctx, k, B.NMW + 1, 256, STAGE_TREE_PAIRS)); }
+        RC(lw_scan_int(bh, L.q_cnt, L.q_off, B.NMW + 1, STAGE_TREE_PAIRS));
+        { LwMoveEmitK k = {B, L, mc}; RC(launch(ctx, k, B.NMW, 128, STAGE_TREE_PAIRS)); }
+        mc += hw[WS_EV_MOVED];
+        if (mc > B.NMOVE) { set_error("move buffer capacity exceeded"); return B2GPU_E_CAPACITY; }
+        { LwMoveFinishK k = {B, mc}; RC(launch(ctx, k, 1, 32, STAGE_TREE_PAIRS)); }
+      }
+      RC(lw_update_pairs(bh, mc, cc, STAGE_TREE_PAIRS, 0));
+    }
+    { LwStepEndK k = {B, sp}; RC(launch(ctx, k, 1, 32, STAGE_TREE_PAIRS)); }
+    { BodyEndK k = {B}; RC(launch(ctx, k, B.NB, 128, STAGE_BODY_END)); }
+  }
+  return 0;
+}
+
 static StepParams make_params(float dt, int vi, int pi) {
   StepParams sp;
   sp.dt = dt;
@@ -848,19 +1116,21 @@ static int enqueue_steps(BatchHost* bh, const StepParams& sp, int steps, const f
   all.wb_count = B.n_wblocks;
 #if defined(B2G_HOSTSIM)
   if (host_forces) RC(batch_set_forces(bh, host_forces, 0, B.n_worlds));
-  RC(step_window(bh, all, sp, steps, nullptr));
+  if (bh->large) RC(step_large(bh, sp, steps));
+  else RC(step_window(bh, all, sp, steps, nullptr));
   if (host_state_out) RC(batch_get_body_state(bh, host_state_out, 0, B.n_worlds));
   return 0;
 #else
   cudaStream_t main_s = (cudaStream_t)ctx->stream;
-  const bool grouped = bh->groups.size() > 1 && !ctx->profiling && steps > 0;
+  const bool grouped = bh->groups.size() > 1 && !ctx->profiling && steps > 0 && !bh->large;
   if (!grouped) {
     if (host_forces) {
       CU(cudaMemcpyAsync(bh->forces_dev, host_forces, (size_t)B.n_worlds * B.NB * 3 * 4, cudaMemcpyHostToDevice, main_s));
       ForceScatterK k = {all, bh->forces_dev, 0, B.n_worlds};
       RC(launch(ctx, k, B.n_wblocks * B.LB * B.NB, 128));
     }
-    RC(step_window(bh, all, sp, steps, nullptr));
+    if (bh->large) RC(step_large(bh, sp, steps));
+    else RC(step_window(bh, all, sp, steps, nullptr));
     if (host_state_out) {
       StateGatherK k = {all, bh->state_dev};
       RC(launch(ctx, k, B.n_wblocks * B.LB * B.NB, 128));
@@ -935,7 +1205,7 @@ static int run_steps(BatchHost* bh, float dt, int vi, int pi, int steps, const f
 #else
   RC(ensure_groups(bh));
   cudaStream_t main_s = (cudaStream_t)ctx->stream;
-  const bool use_graph = bh->use_graphs && !ctx->profiling && steps > 0 && host_pointer_capturable(host_forces) &&
+  const bool use_graph = bh->use_graphs && !bh->large && !ctx->profiling && steps > 0 && host_pointer_capturable(host_forces) &&
                          host_pointer_capturable(host_state_out);
   if (!use_graph) {
     RC(enqueue_steps(bh, sp, steps, host_forces, host_state_out));
@@ -1002,7 +1272,15 @@ int batch_get_stats(BatchHost* bh, int first, int count, b2gpu_step_stats* out) 
   if (!bh || !out || first < 0 || count < 0 || first + count > bh->B.n_worlds) { set_error("get_stats: bad argument"); return B2GPU_E_INVALID; }
   Batch& B = bh->B;
   const int W = B.n_wblocks * B.LB;
-  { StatsK k = {B}; RC(launch(bh->ctx, k, W, 32)); }
+  if (bh->large) {  // one world of 10^5 contacts: count flat
+    RC(lw_read(bh, B.ws, WS_COUNT));
+    const int cc = bh->lw_host[WS_CONTACT_COUNT];
+    { LwStatsK k = {B, cc, 0}; RC(launch(bh->ctx, k, 1, 32)); }
+    { LwStatsK k = {B, cc, 1}; RC(launch(bh->ctx, k, std::max(cc, B.NB), 256)); }
+  } else {
+    StatsK k = {B};
+    RC(launch(bh->ctx, k, W, 32));
+  }
   std::vector<int> all((size_t)W * WS_COUNT);
   RC(dev_d2h(bh->ctx, all.data(), B.ws, all.size() * 4));
   for (int i = 0; i < count; ++i) {

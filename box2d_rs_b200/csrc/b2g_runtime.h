@@ -8,6 +8,7 @@
 #include <vector>
 
 #include "b2g_step.h"
+#include "b2g_large.h"
 #include "b2g_island_layout.h"
 
 namespace b2g {
@@ -100,6 +101,14 @@ struct BatchHost {
   bool pre_step_needed = true;   // some world may carry m_new_contacts / a non-empty move buffer
   long long total_bytes = 0;
   StepParams last_sp{};
+  // large-world mode (b2g_large.h): one world, flat stages + scans + sorts, host-driven control flow
+  bool large = false;
+  Large L = {};
+  int* lw_host = nullptr;        // pinned readback buffer (world scalars, scan totals)
+  void* lw_tmp = nullptr;        // scan / sort temporary storage
+  size_t lw_tmp_bytes = 0;
+  int lw_edge_bits = 0, lw_body_bits = 0;
+  long long lw_keys = 0;         // capacity of the key buffers
 };
 
 const char* last_error();

@@ -245,6 +245,7 @@ struct b2gpu_world {
   bool host_dirty = true;   // host edits not on the device yet
   bool topo_dirty = true;   // bodies/fixtures changed: the device batch must be rebuilt
   bool dev_newer = false;   // the device holds the authoritative state
+  bool large = false;       // step with the data-parallel large-world stages (b2g_large.h)
 };
 
 namespace {
@@ -711,6 +712,15 @@ int b2gpu_world_set_allow_sleeping(b2gpu_world* W, int flag) {  // b2_world.rs(p
 }
 int b2gpu_world_set_warm_starting(b2gpu_world* W, int flag) { return set_world_flag(W, B2GPU_WORLD_WARM_STARTING, flag); }
 int b2gpu_world_set_block_solve(b2gpu_world* W, int flag) { return set_world_flag(W, B2GPU_WORLD_BLOCK_SOLVE, flag); }
+int b2gpu_world_set_large_mode(b2gpu_world* W, int flag) {
+  if (!W) { set_error("world is NULL"); return B2GPU_E_INVALID; }
+  if ((flag != 0) == W->large) return 0;
+  int rc = ensure_host(W);  // bring the state back before the device batch is rebuilt in the other mode
+  if (rc) return rc;
+  W->large = flag != 0;
+  W->topo_dirty = true;
+  return 0;
+}
 int b2gpu_world_set_continuous_physics(b2gpu_world* W, int flag) {
   if (!W) { set_error("world is NULL"); return B2GPU_E_INVALID; }
   if (flag) { set_error("continuous physics (TOI sub-stepping) is outside the hot-path scope"); return B2GPU_E_UNSUPPORTED; }
@@ -729,7 +739,10 @@ int b2gpu_world_step(b2gpu_world* W, float dt, int vi, int pi) {
     b2gpu_snapshot s;
     std::vector<b2gpu_tree_node_rec> nodes;
     fill_snapshot(W, &s, nodes);
-    rc = batch_create(&W->ctx->c, &s, 1, nullptr, 1, &W->dev);
+    b2gpu_caps caps;
+    memset(&caps, 0, sizeof(caps));
+    caps.reserved[1] = W->large ? 11 : 0;
+    rc = batch_create(&W->ctx->c, &s, 1, &caps, 1, &W->dev);
     if (rc) return rc;
   } else if (W->host_dirty) {
     b2gpu_snapshot s;

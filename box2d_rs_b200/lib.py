@@ -51,6 +51,7 @@ def load(path=None):
         "b2gpu_world_set_warm_starting": (i32, [vp, i32]),
         "b2gpu_world_set_continuous_physics": (i32, [vp, i32]),
         "b2gpu_world_set_block_solve": (i32, [vp, i32]),
+        "b2gpu_world_set_large_mode": (i32, [vp, i32]),
         "b2gpu_world_step": (i32, [vp, f32, i32, i32]),
         "b2gpu_world_get_body_count": (i32, [vp]),
         "b2gpu_world_get_contact_count": (i32, [vp]),

@@ -126,6 +126,11 @@ class B2world:
     def set_block_solve(self, flag):
         check(self.L, self.L.b2gpu_world_set_block_solve(self.h, int(flag)))
 
+    def set_large_mode(self, flag):
+        """Data-parallel ordered stages for one large world (b2gpu_world_set_large_mode): same step semantics,
+        contacts created in one update_pairs call are appended in LBVH order instead of reference-tree order."""
+        check(self.L, self.L.b2gpu_world_set_large_mode(self.h, int(flag)))
+
     def step(self, dt, velocity_iterations, position_iterations):
         check(self.L, self.L.b2gpu_world_step(self.h, dt, velocity_iterations, position_iterations))
 

@@ -40,6 +40,7 @@ extern "C" {
 #define B2GPU_E_CAPACITY (-4)  /* a device-side capacity was exceeded */
 #define B2GPU_E_UNSUPPORTED (-5) /* feature outside the hot-path scope (joints, TOI) */
 #define B2GPU_E_LOCKED (-6)    /* world is locked (reference: is_locked() panic) */
+#define B2GPU_E_INTERNAL (-7)  /* a device-side consistency check failed (a bug: please report) */
 
 /* body types: src/b2_body.rs B2bodyType */
 #define B2GPU_STATIC_BODY 0
@@ -280,7 +281,8 @@ typedef struct b2gpu_caps {
                           stages, 2 branchy one-lane position kernel, 3 level-scheduled velocity + position,
                           4 TMA-fed velocity ring, 5 one stream (no stream groups), 6 no CUDA graphs, 7 branchy
                           velocity kernel only, 8 velocity kernel with a producer warp, 9 level-scheduled
-                          position kernel, 10 straight-line level-scheduled velocity kernel (all bit-identical; profiles/r01_ncu_summary.md has their timings) */
+                          position kernel, 10 straight-line level-scheduled velocity kernel (all bit-identical; profiles/r01_ncu_summary.md has their timings);
+                          11 large-world mode (one world only; see b2gpu_world_set_large_mode) */
 } b2gpu_caps;
 
 typedef struct b2gpu_ctx b2gpu_ctx;
@@ -333,6 +335,15 @@ int b2gpu_world_set_warm_starting(b2gpu_world* w, int flag);
 int b2gpu_world_set_continuous_physics(b2gpu_world* w, int flag); /* flag != 0 -> B2GPU_E_UNSUPPORTED */
 /* G_BLOCK_SOLVE (src/b2_contact.rs:25) */
 int b2gpu_world_set_block_solve(b2gpu_world* w, int flag);
+/* Large-world mode for ONE world of 10^4..10^6 bodies (no reference counterpart: the reference steps a world
+ * on one thread).  flag != 0: the order-dependent stages of the step run data-parallel (LBVH pair finding with
+ * prefix-sum compaction, parallel contact destruction, union-find islands with one thread per island keeping
+ * the reference's traversal and Gauss-Seidel order).  Every step is the reference's step of the same state —
+ * the pair set, the created and destroyed contact sets and all body / manifold values are identical — but
+ * contacts created within one update_pairs call are appended in LBVH order instead of the order of the
+ * reference's incrementally balanced tree, so free-running trajectories may diverge from the reference after
+ * a step that creates several contacts on one body (SURVEY.md H1 option ii).  Default 0: exact replica tree. */
+int b2gpu_world_set_large_mode(b2gpu_world* w, int flag);
 /* B2world::step (src/b2_world.rs:98; private :903-959) */
 int b2gpu_world_step(b2gpu_world* w, float dt, int velocity_iterations, int position_iterations);
 /* B2world::get_body_count / get_contact_count / get_proxy_count */

@@ -135,6 +135,7 @@ extern "C" {
     pub fn b2gpu_world_set_warm_starting(w: *mut b2gpu_world, flag: c_int) -> c_int;
     pub fn b2gpu_world_set_continuous_physics(w: *mut b2gpu_world, flag: c_int) -> c_int;
     pub fn b2gpu_world_set_block_solve(w: *mut b2gpu_world, flag: c_int) -> c_int;
+    pub fn b2gpu_world_set_large_mode(w: *mut b2gpu_world, flag: c_int) -> c_int;
     pub fn b2gpu_world_step(w: *mut b2gpu_world, dt: c_float, velocity_iterations: c_int, position_iterations: c_int) -> c_int;
     pub fn b2gpu_world_get_body_count(w: *mut b2gpu_world) -> c_int;
     pub fn b2gpu_world_get_contact_count(w: *mut b2gpu_world) -> c_int;

@@ -288,3 +288,53 @@ def test_step_host_overlapped_copies_match_plain_calls(ctx):
     a.close()
     b.close()
     wg.close()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# large-world mode (b2g_large.h): data-parallel broadphase / destruction / islands for one big world
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name,every", [("pyramid", 3), ("mixed300", 3), ("pile400", 2), ("variety", 2), ("sensors", 3),
+                                        ("addpair2000", 5)])
+def test_large_mode_teacher_forced(name, every, ctx):
+    """Every step of the large-world mode is the oracle's step of the same state: upload S_n, step both once,
+    compare everything bit for bit (contacts created in that step as a set: they are appended in LBVH order)."""
+    from box2d_rs_b200 import scenes
+    wo, wg, steps = _pair(name, ctx)
+    bt = wg.batch(1, lane_block=1, solver='large')
+    for i in range(steps):
+        if i % every == 0:
+            bt.upload_world(0, wo.snapshot())
+            wo.step(scenes.DT, 8, 3)
+            bt.step(scenes.DT, 8, 3)
+            bad = parity.compare_large_step(wo.snapshot(), bt.download_world(0), wo.get_stats(), bt.stats()[0])
+            assert bad == [], "step %d: %s" % (i, bad[:6])
+        else:
+            wo.step(scenes.DT, 8, 3)
+    bt.close()
+    wg.close()
+
+
+@pytest.mark.parametrize("name,n_steps", [("pile400", 200), ("addpair2000", 150), ("mixed300", 200)])
+def test_large_mode_free_running_is_deterministic(name, n_steps, ctx):
+    """Free-running, the large-world mode on the GPU (atomics, union-find hooking, refit arrival order, CUB
+    scans and sorts) and its sequential host simulation (test infrastructure) produce the same bits."""
+    from box2d_rs_b200 import batch as batch_mod, scenes, world
+    from conftest import HOSTSIM_SO
+    recipe, gravity, _ = SCENES[name]
+    hctx = batch_mod.Context(0, lib_path=HOSTSIM_SO)
+    ws = []
+    for c in (ctx, hctx):
+        w = world.B2world(gravity, ctx=c)
+        recipe(scenes, w)
+        w.set_large_mode(True)
+        ws.append(w)
+    for i in range(n_steps):
+        for w in ws:
+            w.step(scenes.DT, 8, 3)
+        if i % 50 == 49 or i == n_steps - 1:
+            bad = parity.compare_snapshots(ws[1].snapshot(), ws[0].snapshot()) + parity.compare_stats(ws[1].get_stats(), ws[0].get_stats())
+            assert bad == [], "step %d: %s" % (i, bad[:6])
+    assert int(ws[0].get_stats()["status"]) == 0
+    for w in ws:
+        w.close()
+    hctx.close()
