@@ -738,6 +738,137 @@ struct LwPairsFinishK {  // one thread
     if (status) ws[WS_STATUS] = status;
   }
 };
+// ------------------------------------------------------------------------------------------
+// Gauss-Seidel sweeps of one island per thread, software-pipelined for global memory: the island's chain of
+// constraints is sequential by definition, so the time of a sweep is (visits) x (latency of one visit).  The
+// generic VelocityK / PositionK pay two dependent memory round trips per visit (record, then the two bodies
+// the record names).  Here the record of visit k+2 and the bodies of visit k+1 are requested before visit k is
+// solved, and a body shared with the visit just solved is forwarded from registers (the prefetched copy is
+// stale by construction), so the arithmetic of visit k overlaps the loads of the next two.  Same functions,
+// same order, same bits as VelocityK / PositionK.
+// ------------------------------------------------------------------------------------------
+struct LwVcRec { float4 q0, q1, q2, q3, q4, q5, q6, q7, q8; };
+B2G_HD LwVcRec lw_load_vc(const float4* vc, int k) {
+  const float4* r = vc + (size_t)k * VC_Q;
+  LwVcRec o;
+  o.q0 = r[0]; o.q1 = r[1]; o.q2 = r[2]; o.q3 = r[3]; o.q4 = r[4]; o.q5 = r[5]; o.q6 = r[6]; o.q7 = r[7]; o.q8 = r[8];
+  return o;
+}
+struct LwVelocityK {
+  Batch B;
+  StepParams sp;
+  int n_islands;
+  B2G_HD void operator()(int isl) const {
+    if (isl >= n_islands) return;
+    const int4 rg = B.isl_range[isl];
+    if (rg.z == rg.w) return;
+    const bool warm = (B.ws[WS_FLAGS] & B2GPU_WORLD_WARM_STARTING) != 0;
+    const bool block = (B.ws[WS_FLAGS] & B2GPU_WORLD_BLOCK_SOLVE) != 0;
+    const int first = rg.z, n = rg.w - rg.z;
+    const int sweeps = sp.velocity_iterations + (warm ? 1 : 0);
+    if (sweeps == 0) return;
+    const long long total = (long long)n * sweeps;
+    // visit v -> constraint first + v % n of sweep v / n (sweep 0 is the warm start when enabled)
+    LwVcRec cur = lw_load_vc(B.vc, first);
+    LwVcRec nxt = lw_load_vc(B.vc, first + (1 % n));
+    int ba = f2i(cur.q8.x), bb = f2i(cur.q8.y);
+    float4 va = B.b_vel[ba], vb = B.b_vel[bb];
+    int k = 0, it = warm ? -1 : 0;
+    for (long long v = 0; v < total; ++v) {
+      // requests for the next two visits
+      int k2 = k + 2;
+      if (k2 >= n) k2 -= n;
+      if (k2 >= n) k2 -= n;
+      const LwVcRec nn = lw_load_vc(B.vc, first + k2);
+      const int nba = f2i(nxt.q8.x), nbb = f2i(nxt.q8.y);
+      float4 nva = B.b_vel[nba], nvb = B.b_vel[nbb];
+      // visit (it, k)
+      const int vc_points = f2i(cur.q8.z) & 0xff;
+      if (vc_points != 0) {
+        VelState s;
+        s.v_a = v2(va.x, va.y); s.w_a = va.z;
+        s.v_b = v2(vb.x, vb.y); s.w_b = vb.z;
+        if (it < 0) {
+          warm_start_one(s, cur.q0, cur.q1, cur.q2, cur.q6, cur.q7, vc_points);
+        } else {
+          solve_velocity_one(s, cur.q0, cur.q1, cur.q2, cur.q3, cur.q4, cur.q5, cur.q6, cur.q7, vc_points, block);
+          B.vc[(size_t)(first + k) * VC_Q + 6] = cur.q6;
+        }
+        // a static / kinematic body may sit in several islands: its velocity never changes, leave it alone
+        if (cur.q7.x != 0.0f || cur.q7.y != 0.0f) { va = make_float4(s.v_a.x, s.v_a.y, s.w_a, 0.0f); B.b_vel[ba] = va; }
+        if (cur.q7.z != 0.0f || cur.q7.w != 0.0f) { vb = make_float4(s.v_b.x, s.v_b.y, s.w_b, 0.0f); B.b_vel[bb] = vb; }
+      }
+      // forward what this visit wrote
+      if (nba == ba) nva = va; else if (nba == bb) nva = vb;
+      if (nbb == ba) nvb = va; else if (nbb == bb) nvb = vb;
+      // the record two visits ahead may be this very constraint (islands of one or two constraints): its
+      // accumulated impulses were just rewritten
+      LwVcRec n2 = nn;
+      if (k2 == k) n2.q6 = cur.q6;
+      if (n == 1) nxt.q6 = cur.q6;
+      cur = nxt;
+      nxt = n2;
+      ba = nba; bb = nbb; va = nva; vb = nvb;
+      if (++k == n) { k = 0; ++it; }
+    }
+  }
+};
+
+struct LwPcRec { float4 p0, p1, p2, p3, p4, p5; };
+B2G_HD LwPcRec lw_load_pc(const float4* pc, int k) {
+  const float4* r = pc + (size_t)k * PC_Q;
+  LwPcRec o;
+  o.p0 = r[0]; o.p1 = r[1]; o.p2 = r[2]; o.p3 = r[3]; o.p4 = r[4]; o.p5 = r[5];
+  return o;
+}
+struct LwPositionK {
+  Batch B;
+  StepParams sp;
+  int n_islands;
+  B2G_HD void operator()(int isl) const {
+    if (isl >= n_islands) return;
+    const int4 rg = B.isl_range[isl];
+    if (rg.z == rg.w) return;
+    const int first = rg.z, n = rg.w - rg.z;
+    for (int it = 0; it < sp.position_iterations; ++it) {
+      float min_separation = 0.0f;
+      LwPcRec cur = lw_load_pc(B.pc, first);
+      int ba = f2i(cur.p4.z), bb = f2i(cur.p4.w);
+      float4 pa = B.b_pos[ba], pb = B.b_pos[bb], ra = B.b_rot[ba], rb = B.b_rot[bb];
+      for (int k = 0; k < n; ++k) {
+        const int k1 = k + 1 < n ? k + 1 : k;
+        const LwPcRec nxt = lw_load_pc(B.pc, first + k1);
+        const int nba = f2i(nxt.p4.z), nbb = f2i(nxt.p4.w);
+        float4 npa = B.b_pos[nba], npb = B.b_pos[nbb], nra = B.b_rot[nba], nrb = B.b_rot[nbb];
+        const int packed = f2i(cur.p5.x);
+        PosState s;
+        s.c_a = v2(pa.x, pa.y); s.a_a = pa.z; s.q_a.s = ra.x; s.q_a.c = ra.y;
+        s.c_b = v2(pb.x, pb.y); s.a_b = pb.z; s.q_b.s = rb.x; s.q_b.c = rb.y;
+        min_separation = solve_position_one(s, cur.p0, cur.p1, cur.p2, cur.p3, (packed >> 8) & 0xff, packed & 0xff, cur.p4.x,
+                                            cur.p4.y, min_separation);
+        if (cur.p0.x != 0.0f || cur.p0.y != 0.0f) {  // immovable bodies are shared between islands: never written
+          pa.x = s.c_a.x; pa.y = s.c_a.y; pa.z = s.a_a;
+          ra.x = s.q_a.s; ra.y = s.q_a.c;
+          B.b_pos[ba] = pa; B.b_rot[ba] = ra;
+        }
+        if (cur.p0.z != 0.0f || cur.p0.w != 0.0f) {
+          pb.x = s.c_b.x; pb.y = s.c_b.y; pb.z = s.a_b;
+          rb.x = s.q_b.s; rb.y = s.q_b.c;
+          B.b_pos[bb] = pb; B.b_rot[bb] = rb;
+        }
+        if (nba == ba) { npa = pa; nra = ra; } else if (nba == bb) { npa = pb; nra = rb; }
+        if (nbb == ba) { npb = pa; nrb = ra; } else if (nbb == bb) { npb = pb; nrb = rb; }
+        cur = nxt;
+        ba = nba; bb = nbb; pa = npa; pb = npb; ra = nra; rb = nrb;
+      }
+      if (min_separation >= -3.0f * B2G_LINEAR_SLOP) {
+        B.isl_flags[isl] |= 1;
+        break;
+      }
+    }
+  }
+};
+
 struct LwStatsK {  // touching / awake counters on demand: phase 0 one thread (reset), phase 1 flat over max(cc, NB)
   Batch B;
   int cc, phase;

@@ -38,6 +38,9 @@ def main():
     ap.add_argument("--skip", type=int, default=5, help="untimed leading steps")
     ap.add_argument("--check", action="store_true", help="compare the final state with the oracle bit for bit")
     ap.add_argument("--no-gpu", action="store_true")
+    ap.add_argument("--large", action="store_true",
+                    help="large-world mode (b2gpu_world_set_large_mode): data-parallel broadphase / islands; --check then "
+                         "verifies one teacher-forced step from the oracle's final state (contacts created in it as a set)")
     args = ap.parse_args()
     from box2d_rs_b200 import scenes, world
     from oracle import b2o
@@ -69,6 +72,9 @@ def main():
         t0 = time.time()
         build(args.scene, wg, args.n)
         out["build_s_gpu_host_mirror"] = time.time() - t0
+        out["mode"] = "large" if args.large else "exact"
+        if args.large:
+            wg.set_large_mode(True)
         wg.ctx.set_profiling(True)
         t_gpu = 0.0
         for i in range(args.steps):
@@ -86,7 +92,17 @@ def main():
         out["gpu_over_cpu"] = out["cpu_ms_per_step"] / out["gpu_ms_per_step"]
         gs = wg.get_stats()
         out["gpu_status"] = int(gs["status"])
-        if args.check:
+        if args.check and args.large:
+            import parity
+            wg.upload(wo.snapshot())
+            wg.set_large_mode(True)
+            wo.step(scenes.DT, 8, 3)
+            wg.step(scenes.DT, 8, 3)
+            bad = parity.compare_large_step(wo.snapshot(), wg.snapshot(), wo.get_stats(), wg.get_stats())
+            out["teacher_forced_step_identical_to_oracle"] = not bad
+            if bad:
+                out["mismatch"] = bad[:4]
+        elif args.check:
             import parity
             bad = parity.compare_snapshots(wo.snapshot(), wg.snapshot())
             out["bit_identical_to_oracle"] = not bad
