@@ -16,8 +16,8 @@
 //    incrementally balanced tree, whose maintenance is sequential.  The replica tree is not maintained in
 //    this mode (its leaf boxes are; the internal nodes are refitted on download).
 //  * contact destruction: flag -> scan -> stable compaction (same order of survivors as the reference list).
-//  * per-body contact edge lists (push_front lists = each body's contacts by descending index): rebuilt by one
-//    radix sort of (body, edge) keys whenever the contact set changed.
+//  * per-body contact edge lists (push_front lists = each body's contacts by descending index): kept as contiguous
+//    rows (CSR), rebuilt by one radix sort of (body, edge) keys whenever the contact set changed.
 //  * islands (b2_world.rs(private):376-507): connected components by a lock-free union-find over the eligible
 //    contacts give each island's member set, its seed (the newest awake body: the reference's seed loop runs
 //    newest first) and its body / contact counts; a prefix sum in seed order lays out the island arrays; then
@@ -72,6 +72,12 @@ struct Large {  // device scratch of the large-world mode
   u64* pk_in;      // [NB + 1] islands in seed order: 1 << 44 | bodies << 24 | contacts
   u64* pk_out;     // [NB + 1]
   int* isl_seed;   // [NB]
+  int* state;      // [NB] island traversal: 0 unvisited, 1 on the stack, 2 listed
+  // per-body contact rows (CSR): the edges 2 c + side of a body, ascending = oldest first
+  int* adj;        // [2 NC] edge ids sorted by (body, edge)
+  int* adj_info;   // [2 NC] per row entry, refreshed when islands are rebuilt: other body | static << 30 | eligible << 31
+  int* row_start;  // [NB]
+  int* row_end;    // [NB]
   // destroy compaction
   int* keep_flag;  // [NC + 1]
   int* keep_pos;   // [NC + 1]
@@ -232,13 +238,12 @@ struct LwDestroyFinishK {  // one thread
 // ------------------------------------------------------------------------------------------
 // per-body contact edge lists from a sort of (body, edge) keys
 // ------------------------------------------------------------------------------------------
-struct LwEdgeKeysK {  // flat over max(2 cc, NB): keys of the 2 cc edges; heads reset
+struct LwEdgeKeysK {  // flat over max(2 cc, NB): keys of the 2 cc edges; rows reset
   Batch B;
   Large L;
-  int* b_chead;
   int cc, edge_bits;
   B2G_HD void operator()(int t) const {
-    if (t < B.NB) b_chead[t] = -1;
+    if (t < B.NB) { L.row_start[t] = 0; L.row_end[t] = 0; }
     if (t >= 2 * cc) return;
     const int c = t >> 1;
     const int4 fx = B.c_fix[c];
@@ -246,26 +251,18 @@ struct LwEdgeKeysK {  // flat over max(2 cc, NB): keys of the 2 cc edges; heads 
     L.keys[t] = ((u64)(unsigned)body << edge_bits) | (u64)(unsigned)t;
   }
 };
-struct LwEdgeLinkK {  // flat over the 2 cc sorted keys: each body's edges ascending -> next = the older neighbour
+struct LwEdgeRowsK {  // flat over the 2 cc sorted keys: one contiguous row of edges per body
   Batch B;
   Large L;
-  int* b_chead;
-  int2* c_next;
   int n, edge_bits;
   B2G_HD void operator()(int i) const {
     if (i >= n) return;
     const u64 k = L.keys_alt[i];
     const u64 mask = ((u64)1 << edge_bits) - 1;
-    const int e = (int)(k & mask);
     const u64 body = k >> edge_bits;
-    int prev = -1;
-    if (i > 0) {
-      const u64 kp = L.keys_alt[i - 1];
-      if ((kp >> edge_bits) == body) prev = (int)(kp & mask);
-    }
-    int* nx = (int*)&c_next[e >> 1];
-    nx[e & 1] = prev;
-    if (i == n - 1 || (L.keys_alt[i + 1] >> edge_bits) != body) b_chead[(int)body] = e;
+    L.adj[i] = (int)(k & mask);
+    if (i == 0 || (L.keys_alt[i - 1] >> edge_bits) != body) L.row_start[(int)body] = i;
+    if (i == n - 1 || (L.keys_alt[i + 1] >> edge_bits) != body) L.row_end[(int)body] = i + 1;
   }
 };
 
@@ -294,6 +291,7 @@ struct LwIslInitK {  // flat over max(NB, cc)
       L.cnt_b[t] = 0;
       L.cnt_c[t] = 0;
       L.seed[t] = -1;
+      L.state[t] = 0;
       B.b_flags[t] &= ~B2GPU_BODY_ISLAND;
     }
     if (t < cc) B.c_flags[t] &= ~B2GPU_CONTACT_ISLAND;
@@ -374,11 +372,31 @@ struct LwRangeK {  // flat over NB + 1
     L.isl_seed[isl] = b;
   }
 };
-struct LwDfsK {  // one thread per island: the reference's traversal from the island's seed
+struct LwAdjInfoK {  // flat over the 2 cc row entries: what the traversal needs to know about each edge
   Batch B;
   Large L;
-  int* b_chead;
-  int2* c_next;
+  int n;
+  B2G_HD void operator()(int i) const {
+    if (i >= n) return;
+    const int e = L.adj[i];
+    int ba, bb;
+    int info = 0;
+    if (lw_contact_eligible(B, e >> 1, ba, bb)) {
+      const int other = (e & 1) ? ba : bb;
+      info = other | (int)0x80000000u | (body_type(B.b_flags[other]) == B2GPU_STATIC_BODY ? 0x40000000 : 0);
+    }
+    L.adj_info[i] = info;
+  }
+};
+// One thread per island: the reference's traversal from the island's seed (LIFO stack, every unvisited
+// neighbour pushed when a body is listed, each body's edges newest first).  Works on the contact rows: a row is
+// contiguous, so the loads of one listed body are independent of each other (a linked list would chain them),
+// and they are requested four edges at a time.  "Contact already in the island" needs no contact flag: an
+// eligible contact was added when the first of its two movable bodies was listed, so it is skipped exactly when
+// the other body is already listed (state 2).  Body / contact ISLAND flags are set flat afterwards.
+struct LwDfsK {
+  Batch B;
+  Large L;
   int* stack;  // [NB]: island i uses the slots of its body range
   int n_islands;
   B2G_HD void operator()(int isl) const {
@@ -388,39 +406,60 @@ struct LwDfsK {  // one thread per island: the reference's traversal from the is
     int nb = rg.x, nc = rg.z, sp_ = 0;
     const int seed = L.isl_seed[isl];
     st[sp_++] = seed;
-    B.b_flags[seed] |= B2GPU_BODY_ISLAND;
-    bool dirty_next = false;
+    L.state[seed] = 1;
     while (sp_ > 0) {
       const int b = st[--sp_];
       B.isl_body[nb++] = b;
-      const int bf = B.b_flags[b];
-      if (!(bf & B2GPU_BODY_AWAKE)) dirty_next = true;  // a sleeper joined: it is a seed candidate next step
-      B.b_flags[b] = bf | B2GPU_BODY_AWAKE;
-      for (int e = b_chead[b]; e != -1;) {
-        const int c = e >> 1, side = e & 1;
-        const int2 nx = c_next[c];
-        e = side ? nx.y : nx.x;
-        const int cf = B.c_flags[c];
-        if (cf & B2GPU_CONTACT_ISLAND) continue;
-        if (!(cf & B2GPU_CONTACT_ENABLED) || !(cf & B2GPU_CONTACT_TOUCHING)) continue;
-        const int4 fx = B.c_fix[c];
-        const b2gpu_fixture_rec& fa = B.fixtures[fx.x];
-        const b2gpu_fixture_rec& fb = B.fixtures[fx.y];
-        if (fa.is_sensor || fb.is_sensor) continue;
-        B.isl_contact[nc] = c;
-        B.c_isl[nc] = isl;
-        ++nc;
-        B.c_flags[c] = cf | B2GPU_CONTACT_ISLAND;
-        const int other = side ? fa.body : fb.body;
-        const int of = B.b_flags[other];
-        if (body_type(of) == B2GPU_STATIC_BODY) continue;  // never propagates; not listed in this mode
-        if (of & B2GPU_BODY_ISLAND) continue;
-        st[sp_++] = other;
-        B.b_flags[other] = of | B2GPU_BODY_ISLAND;
+      L.state[b] = 2;
+      const int r0 = L.row_start[b], r1 = L.row_end[b];
+      for (int i = r1 - 1; i >= r0; i -= 4) {
+        int e[4], info[4], sv[4];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int j = 0; j < 4; ++j) {
+          const bool in = i - j >= r0;
+          e[j] = in ? L.adj[i - j] : 0;
+          info[j] = in ? L.adj_info[i - j] : 0;
+        }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int j = 0; j < 4; ++j) sv[j] = (info[j] < 0 && !(info[j] & 0x40000000)) ? L.state[info[j] & 0x3fffffff] : 0;
+        int pushed[4] = {-1, -1, -1, -1};
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+        for (int j = 0; j < 4; ++j) {
+          if (info[j] >= 0) continue;  // not eligible (or padding)
+          const int other = info[j] & 0x3fffffff;
+          const bool is_static = (info[j] & 0x40000000) != 0;
+          if (!is_static && sv[j] == 2) continue;  // added when `other` was listed
+          B.isl_contact[nc] = e[j] >> 1;
+          B.c_isl[nc] = isl;
+          ++nc;
+          if (is_static || sv[j] != 0) continue;  // static bodies never propagate; not listed in this mode
+          if (other == pushed[0] || other == pushed[1] || other == pushed[2]) continue;  // pushed by an earlier edge of this group
+          pushed[j] = other;
+          st[sp_++] = other;
+          L.state[other] = 1;
+        }
       }
     }
     if (nb != rg.y || nc != rg.w) B.ws[WS_STATUS] = B2GPU_E_INTERNAL;
-    if (dirty_next) B.ws[WS_TOPO_DIRTY] = 1;
+  }
+};
+struct LwIslFlagsK {  // flat over max(island bodies, island contacts): what the traversal leaves on bodies and contacts
+  Batch B;
+  int nib, nic;
+  B2G_HD void operator()(int k) const {
+    if (k < nib) {
+      const int b = B.isl_body[k];
+      const int bf = B.b_flags[b];
+      if (!(bf & B2GPU_BODY_AWAKE)) B.ws[WS_TOPO_DIRTY] = 1;  // a sleeper joined: it is a seed candidate next step
+      B.b_flags[b] = bf | B2GPU_BODY_ISLAND | B2GPU_BODY_AWAKE;
+    }
+    if (k < nic) B.c_flags[B.isl_contact[k]] |= B2GPU_CONTACT_ISLAND;
   }
 };
 struct LwIslCachedK {  // one thread: nothing the island order depends on changed
@@ -560,7 +599,13 @@ struct LwKarrasK {  // flat over n: internal node i < n - 1 (Karras 2012), leaf 
     if (i == 0) L.lb_parent[0] = -1;
   }
 };
-B2G_HD float4 lw_child_box(const Batch& B, const Large& L, int c) { return c >= 0 ? L.lb_box[c] : B.n_aabb[L.lb_leaf[~c]]; }
+B2G_HD float4 lw_ldcg(const float4* p) {
+#if defined(__CUDA_ARCH__)
+  return __ldcg(p);
+#else
+  return *p;
+#endif
+}
 struct LwRefitK {  // flat over leaves: the second thread to arrive at a node computes its box
   Batch B;
   Large L;
@@ -573,7 +618,10 @@ struct LwRefitK {  // flat over leaves: the second thread to arrive at a node co
       if (B2G_ATOMIC_ADD(&L.lb_flag[node], 1) == 0) return;
       B2G_FENCE();
       const int2 ch = L.lb_child[node];
-      const float4 a = lw_child_box(B, L, ch.x), b = lw_child_box(B, L, ch.y);
+      // boxes of internal children were written by other threads of this launch: read them past L1 (a line
+      // fetched earlier for a neighbouring node may hold a stale copy)
+      const float4 a = ch.x >= 0 ? lw_ldcg(&L.lb_box[ch.x]) : B.n_aabb[L.lb_leaf[~ch.x]];
+      const float4 b = ch.y >= 0 ? lw_ldcg(&L.lb_box[ch.y]) : B.n_aabb[L.lb_leaf[~ch.y]];
       L.lb_box[node] = make_float4(a.x < b.x ? a.x : b.x, a.y < b.y ? a.y : b.y, a.z > b.z ? a.z : b.z, a.w > b.w ? a.w : b.w);
       node = L.lb_parent[node];
     }
@@ -651,8 +699,6 @@ struct LwQueryK {
 struct LwAddPairK {  // flat over candidates (+1 tail): the tests of add_pair, no side effects
   Batch B;
   Large L;
-  int* b_chead;
-  int2* c_next;
   int n;
   B2G_HD void operator()(int j) const {
     if (j > n) return;
@@ -664,15 +710,12 @@ struct LwAddPairK {  // flat over candidates (+1 tail): the tests of add_pair, n
     int fixture_a = pa.x, fixture_b = pb.x, index_a = pa.y, index_b = pb.y;
     const int body_a = pa.w, body_b = pb.w;
     if (body_a == body_b) return;
-    // a contact between the two fixtures is on both bodies' edge lists: walk the list of the movable one when
-    // the other is static (the ground's list holds every resting contact of the world)
+    // a contact between the two fixtures is in both bodies' contact rows: scan the row of the movable one when
+    // the other is static (the ground's row holds every resting contact of the world)
     const int fb_ = B.b_flags[body_b], fa_ = B.b_flags[body_a];
     const int walk = (body_type(fb_) == B2GPU_STATIC_BODY && body_type(fa_) != B2GPU_STATIC_BODY) ? body_a : body_b;
-    for (int e = b_chead[walk]; e != -1;) {
-      const int c = e >> 1, side = e & 1;
-      const int2 nx = c_next[c];
-      e = side ? nx.y : nx.x;
-      const int4 fx = B.c_fix[c];
+    for (int i = L.row_start[walk], i1 = L.row_end[walk]; i < i1; ++i) {
+      const int4 fx = B.c_fix[L.adj[i] >> 1];
       if (fx.x == fixture_a && fx.y == fixture_b && fx.z == index_a && fx.w == index_b) return;
       if (fx.x == fixture_b && fx.y == fixture_a && fx.z == index_b && fx.w == index_a) return;
     }

@@ -912,6 +912,7 @@ static int large_alloc(BatchHost* bh) {
   AL(L.uf_parent, B.NB); AL(L.cnt_b, B.NB); AL(L.cnt_c, B.NB); AL(L.seed, B.NB); AL(L.isl_seed, B.NB);
   AL(L.pk_in, B.NB + 1LL); AL(L.pk_out, B.NB + 1LL);
   AL(L.keep_flag, B.NC + 1LL); AL(L.keep_pos, B.NC + 1LL);
+  AL(L.state, B.NB); AL(L.adj, 2LL * B.NC); AL(L.adj_info, 2LL * B.NC); AL(L.row_start, B.NB); AL(L.row_end, B.NB);
 #undef AL
 #if defined(B2G_HOSTSIM)
   bh->lw_host = (int*)calloc(WS_COUNT + 16, 4);
@@ -946,10 +947,10 @@ static void large_free(BatchHost* bh) {
 static int lw_rebuild_lists(BatchHost* bh, int cc, int stage) {
   Ctx* ctx = bh->ctx;
   const Batch& B = bh->B;
-  { LwEdgeKeysK k = {B, bh->L, bh->b_chead, cc, bh->lw_edge_bits}; RC(launch(ctx, k, std::max(2 * cc, B.NB), 256, stage)); }
+  { LwEdgeKeysK k = {B, bh->L, cc, bh->lw_edge_bits}; RC(launch(ctx, k, std::max(2 * cc, B.NB), 256, stage)); }
   if (cc == 0) return 0;
   RC(lw_sort_keys(bh, bh->L.keys, bh->L.keys_alt, 2 * cc, bh->lw_edge_bits + bh->lw_body_bits, stage));
-  { LwEdgeLinkK k = {B, bh->L, bh->b_chead, bh->c_next, 2 * cc, bh->lw_edge_bits}; RC(launch(ctx, k, 2 * cc, 256, stage)); }
+  { LwEdgeRowsK k = {B, bh->L, 2 * cc, bh->lw_edge_bits}; RC(launch(ctx, k, 2 * cc, 256, stage)); }
   return 0;
 }
 
@@ -974,7 +975,7 @@ static int lw_update_pairs(BatchHost* bh, int mc, int cc, int stage, int use_tre
   int created = 0;
   if (n_cand > 0) {
     { LwQueryK k = {B, L, mc, n, 1, use_tree}; RC(launch(ctx, k, mc, 64, stage)); }
-    { LwAddPairK k = {B, L, bh->b_chead, bh->c_next, n_cand}; RC(launch(ctx, k, n_cand + 1, 128, stage)); }
+    { LwAddPairK k = {B, L, n_cand}; RC(launch(ctx, k, n_cand + 1, 128, stage)); }
     RC(lw_scan_int(bh, L.cand_flag, L.cand_pos, n_cand + 1, stage));
     RC(lw_read(bh, L.cand_pos + n_cand, 1));
     created = bh->lw_host[0];
@@ -998,6 +999,7 @@ static int step_large(BatchHost* bh, const StepParams& sp, int steps) {
     { LwStatsResetK k = {B}; RC(launch(ctx, k, 1, 32, STAGE_PRE)); }
     RC(lw_read(bh, B.ws, WS_COUNT));
     int cc = hw[WS_CONTACT_COUNT];
+    if (bh->pre_step_needed && s == 0) RC(lw_rebuild_lists(bh, cc, STAGE_PRE));  // first step after an upload: contact rows
     if (hw[WS_FLAGS] & B2GPU_WORLD_NEW_CONTACTS) {
       const int mc = hw[WS_MOVE_COUNT];
       RC(lw_update_pairs(bh, mc, cc, STAGE_PRE, 1));
@@ -1036,7 +1038,9 @@ static int step_large(BatchHost* bh, const StepParams& sp, int steps) {
         RC(lw_scan_u64(bh, L.pk_in, L.pk_out, B.NB + 1, STAGE_ISLAND));
         { LwRangeK k = {B, L}; RC(launch(ctx, k, B.NB + 1, 256, STAGE_ISLAND)); }
         RC(lw_read(bh, B.ws, WS_COUNT));
-        { LwDfsK k = {B, L, bh->b_chead, bh->c_next, bh->stack, hw[WS_ISL_COUNT]}; RC(launch(ctx, k, hw[WS_ISL_COUNT], 64, STAGE_ISLAND)); }
+        { LwAdjInfoK k = {B, L, 2 * cc}; RC(launch(ctx, k, 2 * cc, 256, STAGE_ISLAND)); }
+        { LwDfsK k = {B, L, bh->stack, hw[WS_ISL_COUNT]}; RC(launch(ctx, k, hw[WS_ISL_COUNT], 32, STAGE_ISLAND)); }
+        { LwIslFlagsK k = {B, hw[WS_ISL_BODIES], hw[WS_ISL_CONTACTS]}; RC(launch(ctx, k, std::max(hw[WS_ISL_BODIES], hw[WS_ISL_CONTACTS]), 256, STAGE_ISLAND)); }
       } else {
         LwIslCachedK k = {B};
         RC(launch(ctx, k, 1, 32, STAGE_ISLAND));
