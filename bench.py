@@ -122,6 +122,63 @@ def run_reference(args, rank):
     OUT.emit(json.dumps(line))
 
 
+def single_world_leg(ctx):
+    """The second half of BASELINE.json's metric: ms/step of ONE large world (configs[3] pile-100k, configs[4]
+    AddPair-20k) in the large-world mode (b2gpu_world_set_large_mode), next to the oracle on one host thread
+    (the reference steps a world on one thread by construction).  Bounded: a few dozen steps from t = 0, both
+    engines over the same steps.  Wall clock around step + sync: the mode is host-driven (scalar readbacks)."""
+    from box2d_rs_b200 import scenes, world
+    from oracle import b2o  # measured CPU arm
+    out = {"mode": "large-world (data-parallel broadphase / destruction / islands; exact Gauss-Seidel order per island)",
+           "cpu": "C++ oracle restating box2d-rs, 1 thread"}
+    cases = [("addpair20k", lambda w: scenes.add_pair(w, n=20000), (0.0, 0.0), 5, 40),
+             ("pile100k", lambda w: scenes.pile(w, n=100000), (0.0, -10.0), 3, 12)]
+    for name, recipe, gravity, skip, steps in cases:
+        try:
+            wo = b2o.B2world(gravity)
+            recipe(wo)
+            t_cpu = 0.0
+            for i in range(steps):
+                t0 = time.perf_counter()
+                wo.step(scenes.DT, scenes.VEL_ITERS, scenes.POS_ITERS)
+                if i >= skip:
+                    t_cpu += time.perf_counter() - t0
+            so = wo.get_stats()
+            del wo
+            wg = world.B2world(gravity, ctx=ctx)
+            recipe(wg)
+            wg.set_large_mode(True)
+            t_gpu = 0.0
+            for i in range(steps):
+                t0 = time.perf_counter()
+                wg.step(scenes.DT, scenes.VEL_ITERS, scenes.POS_ITERS)
+                ctx.sync()
+                if i >= skip:
+                    t_gpu += time.perf_counter() - t0
+            sg = wg.get_stats()
+            n_prof = 4  # stage split from a few further steps with an event pair around every launch (not timed above)
+            ctx.set_profiling(True)
+            for _ in range(n_prof):
+                wg.step(scenes.DT, scenes.VEL_ITERS, scenes.POS_ITERS)
+            stages = ctx.stage_times()
+            ctx.set_profiling(False)
+            n_t = steps - skip
+            out[name] = {"ms_per_step": 1e3 * t_gpu / n_t, "cpu_ms_per_step": 1e3 * t_cpu / n_t,
+                         "speedup_vs_cpu_thread": t_cpu / t_gpu, "steps": "%d-%d from t=0" % (skip, steps - 1),
+                         "contacts": int(sg["contacts"]), "touching": int(sg["touching"]), "islands": int(sg["islands"]),
+                         "status": int(sg["status"]),
+                         "same_counts_as_oracle": bool(int(sg["contacts"]) == int(so["contacts"]) and int(sg["touching"]) == int(so["touching"])),
+                         "stage_ms_next_%d_steps" % n_prof: {k: round(v[0] / n_prof, 4) for k, v in stages.items() if v[1] > 0}}
+            wg.close()
+        except Exception as e:  # never lose the main line over the secondary leg
+            out[name] = {"error": "%s: %s" % (type(e).__name__, e)}
+            try:
+                ctx.set_profiling(False)
+            except Exception:
+                pass
+    return out
+
+
 def run_ours(args, rank, world_size, local_rank):
     import torch
     from box2d_rs_b200 import scenes, world
@@ -255,6 +312,10 @@ def run_ours(args, rank, world_size, local_rank):
         cpu_baseline = {"value": cv, "unit": "body-steps/s", "cores": threads, "kind": "port",
                         "sample": "%d Pyramid worlds x %d steps x 3 repeats, one world per host thread (C++ oracle "
                                   "restating box2d-rs; %.1f s of CPU work)" % (n_sample, inner, sum(secs) * threads)}
+    single_world = None
+    if rank == 0 and world_size == 1 and not args.no_single_world:
+        batch.close()
+        single_world = single_world_leg(ctx)
     if rank == 0:
         line = {
             "metric": "body-steps/s, batched Pyramid worlds", "value": value, "unit": "body-steps/s",
@@ -269,7 +330,7 @@ def run_ours(args, rank, world_size, local_rank):
                        "contacts_per_world": float(st["contacts"].mean()), "touching_per_world": float(st["touching"].mean()),
                        "parallelism": "worlds sharded by index, no data-path collective"},
             "roofline": roofline, "cpu_baseline": cpu_baseline, "e2e": e2e, "gpu_launches": int(launches),
-            "clocks": clocks, "validation_allgather": gathered,
+            "clocks": clocks, "validation_allgather": gathered, "single_world": single_world,
         }
         OUT.emit(json.dumps(line))
     batch.close()
@@ -311,6 +372,7 @@ def main():
     ap.add_argument("--worlds", type=int, default=4096, help="worlds per GPU")
     ap.add_argument("--max-contacts", type=int, default=1024)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-single-world", action="store_true", help="skip the single-large-world leg (ms/step of one world)")
     ap.add_argument("--solver", default=None, help="diagnostic: lane | generic | levels (default: best measured)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
