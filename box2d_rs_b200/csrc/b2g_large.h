@@ -31,11 +31,13 @@
 
 #if defined(__CUDA_ARCH__)
 #define B2G_ATOMIC_MAX(p, v) atomicMax((p), (v))
+#define B2G_ATOMIC_MIN(p, v) atomicMin((p), (v))
 #define B2G_ATOMIC_CAS(p, c, v) atomicCAS((p), (c), (v))
 #define B2G_FENCE() __threadfence()
 #define B2G_VLOAD(p) (*(volatile const int*)(p))
 #else
 #define B2G_ATOMIC_MAX(p, v) (*(p) = (*(p) > (v) ? *(p) : (v)))
+#define B2G_ATOMIC_MIN(p, v) (*(p) = (*(p) < (v) ? *(p) : (v)))
 #define B2G_FENCE()
 #define B2G_VLOAD(p) (*(p))
 static inline int b2g_host_cas(int* p, int c, int v) { int o = *p; if (o == c) *p = v; return o; }
@@ -64,6 +66,8 @@ struct Large {  // device scratch of the large-world mode
   int* cand_pos;   // [NCAND + 1]
   int4* cand_fix;  // [NCAND] (fixture_a, fixture_b, index_a, index_b) after the register-order swap
   int NCAND;
+  int4* vc_idx;    // [NC] per island contact slot: (body A, body B, velocity points, -), see LwVelocity4K
+  int* first_idx;  // [NN] first move-buffer index of a tree node (host edits can buffer a proxy more than once)
   // islands
   int* uf_parent;  // [NB]
   int* cnt_b;      // [NB] per root: non-static bodies
@@ -75,7 +79,9 @@ struct Large {  // device scratch of the large-world mode
   int* state;      // [NB] island traversal: 0 unvisited, 1 on the stack, 2 listed
   // per-body contact rows (CSR): the edges 2 c + side of a body, ascending = oldest first
   int* adj;        // [2 NC] edge ids sorted by (body, edge)
-  int* adj_info;   // [2 NC] per row entry, refreshed when islands are rebuilt: other body | static << 30 | eligible << 31
+  int2* eadj;      // [2 NC] the ELIGIBLE row entries only (enabled, touching, no sensor), refreshed when islands are
+                   // rebuilt: (edge, other body | static << 30 | 1 << 31), same order
+  int2* erow;      // [NB] begin / end of a body's eligible entries in eadj
   int* row_start;  // [NB]
   int* row_end;    // [NB]
   // destroy compaction
@@ -372,26 +378,34 @@ struct LwRangeK {  // flat over NB + 1
     L.isl_seed[isl] = b;
   }
 };
-struct LwAdjInfoK {  // flat over the 2 cc row entries: what the traversal needs to know about each edge
+struct LwAdjInfoK {  // flat over the 2 cc row entries (+1 tail): which edges the traversal may follow
   Batch B;
   Large L;
   int n;
   B2G_HD void operator()(int i) const {
-    if (i >= n) return;
-    const int e = L.adj[i];
+    if (i > n) return;
     int ba, bb;
-    int info = 0;
-    if (lw_contact_eligible(B, e >> 1, ba, bb)) {
-      const int other = (e & 1) ? ba : bb;
-      info = other | (int)0x80000000u | (body_type(B.b_flags[other]) == B2GPU_STATIC_BODY ? 0x40000000 : 0);
-    }
-    L.adj_info[i] = info;
+    L.cand_flag[i] = (i < n && lw_contact_eligible(B, L.adj[i] >> 1, ba, bb)) ? 1 : 0;
+  }
+};
+struct LwAdjCompactK {  // flat over max(2 cc, NB): eligible entries packed in row order; per-body ranges
+  Batch B;
+  Large L;
+  int n;
+  B2G_HD void operator()(int i) const {
+    if (i < B.NB) L.erow[i] = make_int2(L.cand_pos[L.row_start[i]], L.cand_pos[L.row_end[i]]);
+    if (i >= n || !L.cand_flag[i]) return;
+    const int e = L.adj[i];
+    const int4 fx = B.c_fix[e >> 1];
+    const int other = (e & 1) ? B.fixtures[fx.x].body : B.fixtures[fx.y].body;
+    L.eadj[L.cand_pos[i]] = make_int2(e, other | (int)0x80000000u | (body_type(B.b_flags[other]) == B2GPU_STATIC_BODY ? 0x40000000 : 0));
   }
 };
 // One thread per island: the reference's traversal from the island's seed (LIFO stack, every unvisited
-// neighbour pushed when a body is listed, each body's edges newest first).  Works on the contact rows: a row is
-// contiguous, so the loads of one listed body are independent of each other (a linked list would chain them),
-// and they are requested four edges at a time.  "Contact already in the island" needs no contact flag: an
+// neighbour pushed when a body is listed, each body's edges newest first).  Works on the rows of ELIGIBLE
+// edges: a row is contiguous, so the loads of one listed body are independent of each other (a linked list would
+// chain them), they are requested four edges at a time, and the many non-touching contacts of a crowded body
+// (AddPair: ~60 per circle) cost nothing.  "Contact already in the island" needs no contact flag: an
 // eligible contact was added when the first of its two movable bodies was listed, so it is skipped exactly when
 // the other body is already listed (state 2).  Body / contact ISLAND flags are set flat afterwards.
 struct LwDfsK {
@@ -411,16 +425,17 @@ struct LwDfsK {
       const int b = st[--sp_];
       B.isl_body[nb++] = b;
       L.state[b] = 2;
-      const int r0 = L.row_start[b], r1 = L.row_end[b];
+      const int2 row = L.erow[b];
+      const int r0 = row.x, r1 = row.y;
       for (int i = r1 - 1; i >= r0; i -= 4) {
         int e[4], info[4], sv[4];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
         for (int j = 0; j < 4; ++j) {
-          const bool in = i - j >= r0;
-          e[j] = in ? L.adj[i - j] : 0;
-          info[j] = in ? L.adj_info[i - j] : 0;
+          const int2 ent = i - j >= r0 ? L.eadj[i - j] : make_int2(0, 0);
+          e[j] = ent.x;
+          info[j] = ent.y;
         }
 #if defined(__CUDA_ARCH__)
 #pragma unroll
@@ -633,6 +648,22 @@ B2G_HD bool lw_overlap(const float4 a, const Box& q) {  // b2_test_overlap(AABB)
   b.hi = v2(a.z, a.w);
   return box_overlap(b, q);
 }
+// A proxy edited twice on the host (created, then set_transform) sits twice in the move buffer; the reference
+// queries it twice and add_pair rejects the second round of pairs because the first round's contacts exist by
+// then.  Flat add_pair sees only the contacts that existed before the call, so the repeated queries are marked
+// (their pairs still count as reported) and create nothing.  phase 0: reset, phase 1: first index per node.
+struct LwMoveFirstK {
+  Batch B;
+  Large L;
+  int mc, phase;
+  B2G_HD void operator()(int i) const {
+    if (i >= mc) return;
+    const int q = B.move_buf[i];
+    if (q == -1) return;
+    if (phase == 0) L.first_idx[q] = 0x7fffffff;
+    else B2G_ATOMIC_MIN(&L.first_idx[q], i);
+  }
+};
 enum { LW_STACK = 128 };
 // One thread per move-buffer entry; emit = 0 counts, 1 writes the candidate pairs.  use_tree = 1 walks the
 // uploaded replica of the reference's tree instead of the LBVH (child2 first, b2_dynamic_tree.rs:239-267): the
@@ -654,6 +685,7 @@ struct LwQueryK {
       int stack[LW_STACK];
       int sp_ = 0;
       if (use_tree) {
+        const int qq = L.first_idx[q] != i ? ~q : q;  // repeated entry: report, never create
         stack[sp_++] = B.ws[WS_TREE_ROOT];
         while (sp_ > 0) {
           const int id = stack[--sp_];
@@ -663,7 +695,7 @@ struct LwQueryK {
           if (l.y == -1) {
             if (id == q) continue;
             if (B.n_moved[id] && id > q) continue;
-            if (emit && count < room) out[count] = make_int2(q, id);
+            if (emit && count < room) out[count] = make_int2(qq, id);
             ++count;
           } else {
             if (sp_ + 2 > LW_STACK) { B.ws[WS_STATUS] = B2GPU_E_CAPACITY; continue; }
@@ -705,6 +737,7 @@ struct LwAddPairK {  // flat over candidates (+1 tail): the tests of add_pair, n
     if (j == n) { L.cand_flag[j] = 0; return; }
     L.cand_flag[j] = 0;
     const int2 pr = L.cand[j];
+    if (pr.x < 0) return;  // reported by a repeated move-buffer entry (see LwMoveFirstK)
     const int proxy_a = B.node_proxy[imin(pr.x, pr.y)], proxy_b = B.node_proxy[imax(pr.x, pr.y)];
     const int4 pa = B.proxy_s[proxy_a], pb = B.proxy_s[proxy_b];
     int fixture_a = pa.x, fixture_b = pb.x, index_a = pa.y, index_b = pb.y;
@@ -853,6 +886,122 @@ struct LwVelocityK {
       nxt = n2;
       ba = nba; bb = nbb; va = nva; vb = nvb;
       if (++k == n) { k = 0; ++it; }
+    }
+  }
+};
+
+// Deeper pipeline for the velocity sweeps (the longest chain of a large world).  In LwVelocityK the prefetched
+// record and bodies are handed from "next" to "current" by register moves, and a move of a register whose load
+// is still in flight stalls — so the effective prefetch distance is one visit of arithmetic (~300 cycles), less
+// than an L2 round trip.  Here four register sets rotate through an unrolled loop (no moves): at visit v the
+// body indices of visit v+3 are requested (from a compact index array, 16 B per constraint), the record and
+// the two bodies of visit v+2 are requested, visit v is solved, and its results are forwarded into the two
+// body sets already in flight.  Same functions, same order, same bits.
+struct LwVcIdxK {  // flat over island contacts: (body A, body B, velocity points, -) next to the constraint stream
+  Batch B;
+  Large L;
+  int n;
+  B2G_HD void operator()(int k) const {
+    if (k >= n) return;
+    const float4 q8 = B.vc[(size_t)k * VC_Q + 8];
+    L.vc_idx[k] = make_int4(f2i(q8.x), f2i(q8.y), f2i(q8.z) & 0xff, 0);
+  }
+};
+struct LwVelocity4K {
+  Batch B;
+  Large L;
+  StepParams sp;
+  int n_islands;
+  B2G_HD void operator()(int isl) const {
+    if (isl >= n_islands) return;
+    const int4 rg = B.isl_range[isl];
+    if (rg.z == rg.w) return;
+    const bool warm = (B.ws[WS_FLAGS] & B2GPU_WORLD_WARM_STARTING) != 0;
+    const bool block = (B.ws[WS_FLAGS] & B2GPU_WORLD_BLOCK_SOLVE) != 0;
+    const int first = rg.z, n = rg.w - rg.z;
+    const int sweeps = sp.velocity_iterations + (warm ? 1 : 0);
+    if (sweeps == 0) return;
+    if (n < 4) {  // the rotation assumes a constraint is not in flight twice: tiny islands take the plain loop
+      for (int it = warm ? -1 : 0; it < sp.velocity_iterations; ++it) {
+        for (int k = rg.z; k < rg.w; ++k) {
+          const int4 ix = L.vc_idx[k];
+          if (ix.z == 0) continue;
+          const float4 va = B.b_vel[ix.x], vb = B.b_vel[ix.y];
+          VelState s;
+          s.v_a = v2(va.x, va.y); s.w_a = va.z;
+          s.v_b = v2(vb.x, vb.y); s.w_b = vb.z;
+          LwVcRec r = lw_load_vc(B.vc, k);
+          if (it < 0) {
+            warm_start_one(s, r.q0, r.q1, r.q2, r.q6, r.q7, ix.z);
+          } else {
+            solve_velocity_one(s, r.q0, r.q1, r.q2, r.q3, r.q4, r.q5, r.q6, r.q7, ix.z, block);
+            B.vc[(size_t)k * VC_Q + 6] = r.q6;
+          }
+          if (r.q7.x != 0.0f || r.q7.y != 0.0f) B.b_vel[ix.x] = make_float4(s.v_a.x, s.v_a.y, s.w_a, 0.0f);
+          if (r.q7.z != 0.0f || r.q7.w != 0.0f) B.b_vel[ix.y] = make_float4(s.v_b.x, s.v_b.y, s.w_b, 0.0f);
+        }
+      }
+      return;
+    }
+    const long long total = (long long)n * sweeps;
+    int4 ix[4];
+    float4 q0[4], q1[4], q2[4], q3[4], q4[4], q5[4], q6[4], q7[4], va[4], vb[4];
+    // prologue: indices of visits 0..2, records and bodies of visits 0..1
+    ix[0] = L.vc_idx[first];
+    ix[1] = L.vc_idx[first + 1];
+    ix[2] = L.vc_idx[first + 2];
+    ix[3] = make_int4(0, 0, 0, 0);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < 2; ++j) {
+      const float4* r = B.vc + (size_t)(first + j) * VC_Q;
+      q0[j] = r[0]; q1[j] = r[1]; q2[j] = r[2]; q3[j] = r[3]; q4[j] = r[4]; q5[j] = r[5]; q6[j] = r[6]; q7[j] = r[7];
+      va[j] = B.b_vel[ix[j].x];
+      vb[j] = B.b_vel[ix[j].y];
+    }
+    int k = 0, k2 = 2, k3 = 3 % n, it = warm ? -1 : 0;
+    for (long long v = 0; v < total; v += 4) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+      for (int j = 0; j < 4; ++j) {
+        if (v + j < total) {
+          const int j2 = (j + 2) & 3, j3 = (j + 3) & 3, j1 = (j + 1) & 3;
+          // requests: indices of visit v+3, record and bodies of visit v+2
+          ix[j3] = L.vc_idx[first + k3];
+          {
+            const float4* r = B.vc + (size_t)(first + k2) * VC_Q;
+            q0[j2] = r[0]; q1[j2] = r[1]; q2[j2] = r[2]; q3[j2] = r[3]; q4[j2] = r[4]; q5[j2] = r[5]; q6[j2] = r[6]; q7[j2] = r[7];
+            va[j2] = B.b_vel[ix[j2].x];
+            vb[j2] = B.b_vel[ix[j2].y];
+          }
+          // visit (it, k) on set j
+          const int ba = ix[j].x, bb = ix[j].y, vc_points = ix[j].z;
+          if (vc_points != 0) {
+            VelState s;
+            s.v_a = v2(va[j].x, va[j].y); s.w_a = va[j].z;
+            s.v_b = v2(vb[j].x, vb[j].y); s.w_b = vb[j].z;
+            if (it < 0) {
+              warm_start_one(s, q0[j], q1[j], q2[j], q6[j], q7[j], vc_points);
+            } else {
+              solve_velocity_one(s, q0[j], q1[j], q2[j], q3[j], q4[j], q5[j], q6[j], q7[j], vc_points, block);
+              B.vc[(size_t)(first + k) * VC_Q + 6] = q6[j];
+            }
+            // a static / kinematic body may sit in several islands: its velocity never changes, leave it alone
+            if (q7[j].x != 0.0f || q7[j].y != 0.0f) { va[j] = make_float4(s.v_a.x, s.v_a.y, s.w_a, 0.0f); B.b_vel[ba] = va[j]; }
+            if (q7[j].z != 0.0f || q7[j].w != 0.0f) { vb[j] = make_float4(s.v_b.x, s.v_b.y, s.w_b, 0.0f); B.b_vel[bb] = vb[j]; }
+          }
+          // forward into the two body sets in flight (requested before this visit's stores)
+          if (ix[j1].x == ba) va[j1] = va[j]; else if (ix[j1].x == bb) va[j1] = vb[j];
+          if (ix[j1].y == ba) vb[j1] = va[j]; else if (ix[j1].y == bb) vb[j1] = vb[j];
+          if (ix[j2].x == ba) va[j2] = va[j]; else if (ix[j2].x == bb) va[j2] = vb[j];
+          if (ix[j2].y == ba) vb[j2] = va[j]; else if (ix[j2].y == bb) vb[j2] = vb[j];
+          if (++k == n) { k = 0; ++it; }
+          if (++k2 == n) k2 = 0;
+          if (++k3 == n) k3 = 0;
+        }
+      }
     }
   }
 };

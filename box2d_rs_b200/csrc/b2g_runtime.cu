@@ -526,6 +526,7 @@ int batch_create(Ctx* ctx, const b2gpu_snapshot* proto, int n_worlds, const b2gp
     rc = large_alloc(bh);
     if (rc) { batch_destroy(bh); return rc; }
     bh->large = true;
+    if (const char* e = getenv("B2GPU_LW_VELOCITY")) bh->lw_deep_velocity = atoi(e) != 1;  // 1 = distance-1 pipeline (diagnostic)
   }
 #if !defined(B2G_HOSTSIM)
   // shared-memory Gauss-Seidel stages: batches in 32-world memory blocks whose bodies fit one SM
@@ -912,7 +913,8 @@ static int large_alloc(BatchHost* bh) {
   AL(L.uf_parent, B.NB); AL(L.cnt_b, B.NB); AL(L.cnt_c, B.NB); AL(L.seed, B.NB); AL(L.isl_seed, B.NB);
   AL(L.pk_in, B.NB + 1LL); AL(L.pk_out, B.NB + 1LL);
   AL(L.keep_flag, B.NC + 1LL); AL(L.keep_pos, B.NC + 1LL);
-  AL(L.state, B.NB); AL(L.adj, 2LL * B.NC); AL(L.adj_info, 2LL * B.NC); AL(L.row_start, B.NB); AL(L.row_end, B.NB);
+  AL(L.first_idx, B.NN); AL(L.vc_idx, B.NC);
+  AL(L.state, B.NB); AL(L.adj, 2LL * B.NC); AL(L.eadj, 2LL * B.NC); AL(L.erow, B.NB); AL(L.row_start, B.NB); AL(L.row_end, B.NB);
 #undef AL
 #if defined(B2G_HOSTSIM)
   bh->lw_host = (int*)calloc(WS_COUNT + 16, 4);
@@ -966,6 +968,10 @@ static int lw_update_pairs(BatchHost* bh, int mc, int cc, int stage, int use_tre
     RC(lw_sort_keys(bh, L.keys, L.keys_alt, n, 64, stage));
     { LwKarrasK k = {B, L, n}; RC(launch(ctx, k, n, 128, stage)); }
     { LwRefitK k = {B, L, n}; RC(launch(ctx, k, n, 128, stage)); }
+  }
+  if (use_tree) {
+    { LwMoveFirstK k = {B, L, mc, 0}; RC(launch(ctx, k, mc, 256, stage)); }
+    { LwMoveFirstK k = {B, L, mc, 1}; RC(launch(ctx, k, mc, 256, stage)); }
   }
   { LwQueryK k = {B, L, mc, n, 0, use_tree}; RC(launch(ctx, k, mc + 1, 64, stage)); }
   RC(lw_scan_int(bh, L.q_cnt, L.q_off, mc + 1, stage));
@@ -1038,7 +1044,9 @@ static int step_large(BatchHost* bh, const StepParams& sp, int steps) {
         RC(lw_scan_u64(bh, L.pk_in, L.pk_out, B.NB + 1, STAGE_ISLAND));
         { LwRangeK k = {B, L}; RC(launch(ctx, k, B.NB + 1, 256, STAGE_ISLAND)); }
         RC(lw_read(bh, B.ws, WS_COUNT));
-        { LwAdjInfoK k = {B, L, 2 * cc}; RC(launch(ctx, k, 2 * cc, 256, STAGE_ISLAND)); }
+        { LwAdjInfoK k = {B, L, 2 * cc}; RC(launch(ctx, k, 2 * cc + 1, 256, STAGE_ISLAND)); }
+        RC(lw_scan_int(bh, L.cand_flag, L.cand_pos, 2 * cc + 1, STAGE_ISLAND));
+        { LwAdjCompactK k = {B, L, 2 * cc}; RC(launch(ctx, k, std::max(2 * cc, B.NB), 256, STAGE_ISLAND)); }
         { LwDfsK k = {B, L, bh->stack, hw[WS_ISL_COUNT]}; RC(launch(ctx, k, hw[WS_ISL_COUNT], 32, STAGE_ISLAND)); }
         { LwIslFlagsK k = {B, hw[WS_ISL_BODIES], hw[WS_ISL_CONTACTS]}; RC(launch(ctx, k, std::max(hw[WS_ISL_BODIES], hw[WS_ISL_CONTACTS]), 256, STAGE_ISLAND)); }
       } else {
@@ -1049,7 +1057,13 @@ static int step_large(BatchHost* bh, const StepParams& sp, int steps) {
       { LwStaticRotK k = {B}; RC(launch(ctx, k, B.NB, 256, STAGE_INTEGRATE)); }
       { IntegrateK k = {B, sp}; RC(launch(ctx, k, nib, 128, STAGE_INTEGRATE)); }
       { SolverInitK k = {B, sp}; RC(launch(ctx, k, nic, 128, STAGE_SOLVER_INIT)); }
-      { LwVelocityK k = {B, sp, ni}; RC(launch(ctx, k, ni, 32, STAGE_VELOCITY)); }
+      if (bh->lw_deep_velocity) {
+        { LwVcIdxK k = {B, L, nic}; RC(launch(ctx, k, nic, 256, STAGE_SOLVER_INIT)); }
+        { LwVelocity4K k = {B, L, sp, ni}; RC(launch(ctx, k, ni, 32, STAGE_VELOCITY)); }
+      } else {
+        LwVelocityK k = {B, sp, ni};
+        RC(launch(ctx, k, ni, 32, STAGE_VELOCITY));
+      }
       { PostVelocityK k = {B, sp}; RC(launch(ctx, k, std::max(std::max(ni, nib), nic), 128, STAGE_POST_VELOCITY)); }
       { LwPositionK k = {B, sp, ni}; RC(launch(ctx, k, ni, 32, STAGE_POSITION)); }
       { FinalizeK k = {B, sp}; RC(launch(ctx, k, nib, 128, STAGE_FINALIZE)); }

@@ -109,6 +109,7 @@ struct BatchHost {
   size_t lw_tmp_bytes = 0;
   int lw_edge_bits = 0, lw_body_bits = 0;
   long long lw_keys = 0;         // capacity of the key buffers
+  bool lw_deep_velocity = true;  // LwVelocity4K (rotating register sets) instead of LwVelocityK
 };
 
 const char* last_error();

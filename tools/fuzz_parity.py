@@ -4,7 +4,10 @@ the CPU oracle: random scenes (polygons of 3..8 vertices, circles, edges, chains
 multi-fixture bodies, sensors, filters, restitution, damping, random world flags and iteration counts, dt = 0 steps,
 mid-run set_transform / set_linear_velocity edits), stepped freely and compared bit for bit.
 
-  python tools/fuzz_parity.py --seeds 200 [--gpu] [--batch]
+  python tools/fuzz_parity.py --seeds 200 [--gpu] [--batch] [--large]
+
+--large: the large-world mode (b2g_large.h), teacher-forced: every step starts from the oracle's state and must
+reproduce the oracle's step (contacts created in that step compared as a set).
 """
 import argparse
 import math
@@ -88,7 +91,7 @@ def build(world, rng):
     return n + 1
 
 
-def run_seed(seed, make_world, steps, batch_mode):
+def run_seed(seed, make_world, steps, batch_mode, large=False):
     import parity
     from oracle import b2o
     rng = np.random.default_rng(seed)
@@ -114,6 +117,24 @@ def run_seed(seed, make_world, steps, batch_mode):
     batch = None
     if batch_mode:
         batch = wg.batch(int(rng.integers(33, 70)))
+    if large:
+        bt = wg.batch(1, lane_block=1, solver='large')
+        for i in range(steps):
+            dt = 0.0 if rng.integers(0, 40) == 0 else scenes.DT
+            ev = rng.integers(0, 30)
+            if ev == 0:
+                wo.body(int(rng.integers(1, nb))).set_transform((f32v(rng.uniform(-8, 8)), f32v(rng.uniform(1, 10))), f32v(rng.uniform(-3, 3)))
+            if ev == 1:
+                wo.body(int(rng.integers(1, nb))).set_linear_velocity((f32v(rng.uniform(-6, 6)), f32v(rng.uniform(-6, 6))))
+            bt.upload_world(0, wo.snapshot())
+            wo.step(dt, vi, pi)
+            bt.step(dt, vi, pi)
+            bad = parity.compare_large_step(wo.snapshot(), bt.download_world(0), wo.get_stats(), bt.stats()[0])
+            if bad:
+                return "large, step %d (dt=%g vi=%d pi=%d flags=%s): %s" % (i, dt, vi, pi, flags, bad[:4])
+        bt.close()
+        wg.close()
+        return None
     for i in range(steps):
         dt = 0.0 if rng.integers(0, 40) == 0 else scenes.DT
         ev = rng.integers(0, 30)
@@ -153,18 +174,19 @@ def main():
     ap.add_argument("--steps", type=int, default=160)
     ap.add_argument("--gpu", action="store_true")
     ap.add_argument("--batch", action="store_true")
+    ap.add_argument("--large", action="store_true")
     args = ap.parse_args()
     from box2d_rs_b200 import batch as batch_mod, world
     lib_path = None if args.gpu else os.path.join(ROOT, "tests", "hostsim", "libb2gpu_hostsim.so")
     ctx = batch_mod.Context(0, lib_path=lib_path)
     fails = 0
     for seed in range(args.first, args.first + args.seeds):
-        r = run_seed(seed, lambda g: world.B2world(g, ctx=ctx), args.steps, args.batch)
+        r = run_seed(seed, lambda g: world.B2world(g, ctx=ctx), args.steps, args.batch, args.large)
         if r not in (None, "skip"):
             fails += 1
             print("seed %d: %s" % (seed, r), flush=True)
     print("fuzz: %d seeds, %d failures (%s%s)" % (args.seeds, fails, "gpu" if args.gpu else "host simulator",
-                                                   ", batch" if args.batch else ""))
+                                                   ", batch" if args.batch else ", large-world mode teacher-forced" if args.large else ""))
     sys.exit(1 if fails else 0)
 
 
