@@ -30,13 +30,11 @@
 #include "b2g_step.h"
 
 #if defined(__CUDA_ARCH__)
-#define B2G_ATOMIC_MAX(p, v) atomicMax((p), (v))
 #define B2G_ATOMIC_MIN(p, v) atomicMin((p), (v))
 #define B2G_ATOMIC_CAS(p, c, v) atomicCAS((p), (c), (v))
 #define B2G_FENCE() __threadfence()
 #define B2G_VLOAD(p) (*(volatile const int*)(p))
 #else
-#define B2G_ATOMIC_MAX(p, v) (*(p) = (*(p) > (v) ? *(p) : (v)))
 #define B2G_ATOMIC_MIN(p, v) (*(p) = (*(p) < (v) ? *(p) : (v)))
 #define B2G_FENCE()
 #define B2G_VLOAD(p) (*(p))
@@ -76,6 +74,7 @@ struct Large {  // device scratch of the large-world mode
   u64* pk_in;      // [NB + 1] islands in seed order: 1 << 44 | bodies << 24 | contacts
   u64* pk_out;     // [NB + 1]
   int* isl_seed;   // [NB]
+  int* wake_idx;   // [NB + 1] collide wake-up cascade (LwWakeK); [NB] = another round needed
   int* state;      // [NB] island traversal: 0 unvisited, 1 on the stack, 2 listed
   // per-body contact rows (CSR): the edges 2 c + side of a body, ascending = oldest first
   int* adj;        // [2 NC] edge ids sorted by (body, edge)
@@ -128,27 +127,46 @@ struct LwClearNewContactsK {  // one thread
   B2G_HD void operator()(int) const { B.ws[WS_FLAGS] &= ~B2GPU_WORLD_NEW_CONTACTS; }
 };
 
-struct LwWakeFixupK {  // one thread, only when collide woke a sleeping body (SerialAK::prologue part 1)
+// Wake-up cascade inside collide (only when the flat narrowphase woke a sleeping body).  The reference's loop
+// visits contacts newest first; a contact it skipped as inactive in the flat pass must be evaluated after all
+// iff one of its bodies is woken by a contact with a LARGER index.  wake_idx[b] = largest index of a contact
+// whose touching state changed on body b.  Rounds of a flat kernel evaluate every skipped contact c with
+// wake_idx[body] > c; an evaluation that changes touching raises wake_idx and asks for another round.  The
+// fixpoint is the reference's result: by induction over descending c, "woken by then" only ever depends on
+// contacts above c.  phase 0: reset (flat over bodies), 1: seed from the flat pass (flat over contacts),
+// 2: one round (flat over contacts), 3: done (one thread).
+struct LwWakeK {
   Batch B;
+  Large L;
   int* b_wake;
-  B2G_HD void operator()(int) const {
+  int cc, phase;
+  B2G_HD void operator()(int t) const {
+    if (phase == 0) {
+      if (t < B.NB) L.wake_idx[t] = -1;
+      if (t == 0) L.wake_idx[B.NB] = 0;  // "another round" flag
+      return;
+    }
+    if (phase == 3) { B.ws[WS_EV_WAKE] = 0; L.wake_idx[B.NB] = 0; return; }
+    if (t >= cc) return;
+    const int flags = B.c_flags[t];
+    if (phase == 1) {
+      if (!(flags & CF_WOKE)) return;
+      const int4 fx = B.c_fix[t];
+      const int ba = B.fixtures[fx.x].body, bb = B.fixtures[fx.y].body;
+      if (body_type(B.b_flags[ba]) != B2GPU_STATIC_BODY) B2G_ATOMIC_MAX(&L.wake_idx[ba], t);
+      if (body_type(B.b_flags[bb]) != B2GPU_STATIC_BODY) B2G_ATOMIC_MAX(&L.wake_idx[bb], t);
+      return;
+    }
+    if (!(flags & CF_SKIPPED)) return;
+    const int4 fx = B.c_fix[t];
+    const int ba = B.fixtures[fx.x].body, bb = B.fixtures[fx.y].body;
+    const bool wa = body_type(B.b_flags[ba]) != B2GPU_STATIC_BODY && L.wake_idx[ba] > t;
+    const bool wb = body_type(B.b_flags[bb]) != B2GPU_STATIC_BODY && L.wake_idx[bb] > t;
+    if (!wa && !wb) return;
     WIdx x = widx(B, 0);
     Ws ws = ws_of(B, x);
-    if (!ws[WS_EV_WAKE]) return;
-    const int cc = ws[WS_CONTACT_COUNT];
-    for (int b = 0; b < B.NB; ++b) b_wake[b] = 0;
-    for (int c = cc - 1; c >= 0; --c) {
-      const int flags = B.c_flags[c];
-      if (flags & CF_SKIPPED) {
-        collide_one(B, x, ws, c, b_wake, true);
-      } else if (flags & CF_WOKE) {
-        const int4 fx = B.c_fix[c];
-        const int ba = B.fixtures[fx.x].body, bb = B.fixtures[fx.y].body;
-        if (body_type(B.b_flags[ba]) != B2GPU_STATIC_BODY) b_wake[ba] = 1;
-        if (body_type(B.b_flags[bb]) != B2GPU_STATIC_BODY) b_wake[bb] = 1;
-      }
-    }
-    ws[WS_EV_WAKE] = 0;
+    collide_one(B, x, ws, t, b_wake, true, L.wake_idx);
+    if (B.c_flags[t] & CF_WOKE) L.wake_idx[B.NB] = 1;
   }
 };
 
@@ -897,14 +915,14 @@ struct LwVelocityK {
 // body indices of visit v+3 are requested (from a compact index array, 16 B per constraint), the record and
 // the two bodies of visit v+2 are requested, visit v is solved, and its results are forwarded into the two
 // body sets already in flight.  Same functions, same order, same bits.
-struct LwVcIdxK {  // flat over island contacts: (body A, body B, velocity points, -) next to the constraint stream
+struct LwVcIdxK {  // flat over island contacts: (body A, body B, velocity points, position points | type << 8)
   Batch B;
   Large L;
   int n;
   B2G_HD void operator()(int k) const {
     if (k >= n) return;
     const float4 q8 = B.vc[(size_t)k * VC_Q + 8];
-    L.vc_idx[k] = make_int4(f2i(q8.x), f2i(q8.y), f2i(q8.z) & 0xff, 0);
+    L.vc_idx[k] = make_int4(f2i(q8.x), f2i(q8.y), f2i(q8.z) & 0xff, f2i(B.pc[(size_t)k * PC_Q + 5].x));
   }
 };
 struct LwVelocity4K {
@@ -1056,6 +1074,86 @@ struct LwPositionK {
       if (min_separation >= -3.0f * B2G_LINEAR_SLOP) {
         B.isl_flags[isl] |= 1;
         break;
+      }
+    }
+  }
+};
+
+// The position sweeps with the same rotating register sets as LwVelocity4K (the position records are
+// immutable, so any island size takes this path); the reference's early exit is evaluated at every sweep end.
+struct LwPosition4K {
+  Batch B;
+  Large L;
+  StepParams sp;
+  int n_islands;
+  B2G_HD void operator()(int isl) const {
+    if (isl >= n_islands) return;
+    const int4 rg = B.isl_range[isl];
+    if (rg.z == rg.w || sp.position_iterations <= 0) return;
+    const int first = rg.z, n = rg.w - rg.z;
+    const long long total = (long long)n * sp.position_iterations;
+    int4 ix[4];
+    float4 p0[4], p1[4], p2[4], p3[4], p4[4], pa[4], pb[4], ra[4], rb[4];
+    ix[0] = L.vc_idx[first];
+    ix[1] = L.vc_idx[first + 1 % n];
+    ix[2] = L.vc_idx[first + 2 % n];
+    ix[3] = make_int4(0, 0, 0, 0);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < 2; ++j) {
+      const float4* r = B.pc + (size_t)(first + j % n) * PC_Q;
+      p0[j] = r[0]; p1[j] = r[1]; p2[j] = r[2]; p3[j] = r[3]; p4[j] = r[4];
+      pa[j] = B.b_pos[ix[j].x]; ra[j] = B.b_rot[ix[j].x];
+      pb[j] = B.b_pos[ix[j].y]; rb[j] = B.b_rot[ix[j].y];
+    }
+    int k = 0, k2 = 2 % n, k3 = 3 % n;
+    float min_separation = 0.0f;
+    for (long long v = 0; v < total; v += 4) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+      for (int j = 0; j < 4; ++j) {
+        if (v + j < total) {
+          const int j2 = (j + 2) & 3, j3 = (j + 3) & 3, j1 = (j + 1) & 3;
+          ix[j3] = L.vc_idx[first + k3];
+          {
+            const float4* r = B.pc + (size_t)(first + k2) * PC_Q;
+            p0[j2] = r[0]; p1[j2] = r[1]; p2[j2] = r[2]; p3[j2] = r[3]; p4[j2] = r[4];
+            pa[j2] = B.b_pos[ix[j2].x]; ra[j2] = B.b_rot[ix[j2].x];
+            pb[j2] = B.b_pos[ix[j2].y]; rb[j2] = B.b_rot[ix[j2].y];
+          }
+          const int ba = ix[j].x, bb = ix[j].y, packed = ix[j].w;
+          PosState s;
+          s.c_a = v2(pa[j].x, pa[j].y); s.a_a = pa[j].z; s.q_a.s = ra[j].x; s.q_a.c = ra[j].y;
+          s.c_b = v2(pb[j].x, pb[j].y); s.a_b = pb[j].z; s.q_b.s = rb[j].x; s.q_b.c = rb[j].y;
+          min_separation = solve_position_one(s, p0[j], p1[j], p2[j], p3[j], (packed >> 8) & 0xff, packed & 0xff, p4[j].x,
+                                              p4[j].y, min_separation);
+          if (p0[j].x != 0.0f || p0[j].y != 0.0f) {  // immovable bodies are shared between islands: never written
+            pa[j].x = s.c_a.x; pa[j].y = s.c_a.y; pa[j].z = s.a_a;
+            ra[j].x = s.q_a.s; ra[j].y = s.q_a.c;
+            B.b_pos[ba] = pa[j]; B.b_rot[ba] = ra[j];
+          }
+          if (p0[j].z != 0.0f || p0[j].w != 0.0f) {
+            pb[j].x = s.c_b.x; pb[j].y = s.c_b.y; pb[j].z = s.a_b;
+            rb[j].x = s.q_b.s; rb[j].y = s.q_b.c;
+            B.b_pos[bb] = pb[j]; B.b_rot[bb] = rb[j];
+          }
+          if (ix[j1].x == ba) { pa[j1] = pa[j]; ra[j1] = ra[j]; } else if (ix[j1].x == bb) { pa[j1] = pb[j]; ra[j1] = rb[j]; }
+          if (ix[j1].y == ba) { pb[j1] = pa[j]; rb[j1] = ra[j]; } else if (ix[j1].y == bb) { pb[j1] = pb[j]; rb[j1] = rb[j]; }
+          if (ix[j2].x == ba) { pa[j2] = pa[j]; ra[j2] = ra[j]; } else if (ix[j2].x == bb) { pa[j2] = pb[j]; ra[j2] = rb[j]; }
+          if (ix[j2].y == ba) { pb[j2] = pa[j]; rb[j2] = ra[j]; } else if (ix[j2].y == bb) { pb[j2] = pb[j]; rb[j2] = rb[j]; }
+          if (++k2 == n) k2 = 0;
+          if (++k3 == n) k3 = 0;
+          if (++k == n) {  // end of a sweep: b2_island_private.rs:257-274
+            k = 0;
+            if (min_separation >= -3.0f * B2G_LINEAR_SLOP) {
+              B.isl_flags[isl] |= 1;
+              return;
+            }
+            min_separation = 0.0f;
+          }
+        }
       }
     }
   }

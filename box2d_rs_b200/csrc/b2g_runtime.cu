@@ -914,6 +914,7 @@ static int large_alloc(BatchHost* bh) {
   AL(L.pk_in, B.NB + 1LL); AL(L.pk_out, B.NB + 1LL);
   AL(L.keep_flag, B.NC + 1LL); AL(L.keep_pos, B.NC + 1LL);
   AL(L.first_idx, B.NN); AL(L.vc_idx, B.NC);
+  AL(L.wake_idx, B.NB + 1LL);
   AL(L.state, B.NB); AL(L.adj, 2LL * B.NC); AL(L.eadj, 2LL * B.NC); AL(L.erow, B.NB); AL(L.row_start, B.NB); AL(L.row_end, B.NB);
 #undef AL
 #if defined(B2G_HOSTSIM)
@@ -1017,7 +1018,15 @@ static int step_large(BatchHost* bh, const StepParams& sp, int steps) {
     { CollideK k = {B, bh->b_wake}; RC(launch_occ(ctx, k, cc, STAGE_COLLIDE)); }
     RC(lw_read(bh, B.ws, WS_COUNT));
     if (hw[WS_EV_WAKE]) {
-      { LwWakeFixupK k = {B, bh->b_wake}; RC(launch(ctx, k, 1, 32, STAGE_ISLAND)); }
+      { LwWakeK k = {B, L, bh->b_wake, cc, 0}; RC(launch(ctx, k, B.NB, 256, STAGE_ISLAND)); }
+      { LwWakeK k = {B, L, bh->b_wake, cc, 1}; RC(launch(ctx, k, cc, 256, STAGE_ISLAND)); }
+      for (int round = 0; round <= cc; ++round) {
+        { LwWakeK k = {B, L, bh->b_wake, cc, 2}; RC(launch_occ(ctx, k, cc, STAGE_ISLAND)); }
+        RC(lw_read(bh, L.wake_idx + B.NB, 1));
+        if (!hw[0]) break;
+        { LwWakeK k = {B, L, bh->b_wake, cc, 3}; RC(launch(ctx, k, 1, 32, STAGE_ISLAND)); }
+      }
+      { LwWakeK k = {B, L, bh->b_wake, cc, 3}; RC(launch(ctx, k, 1, 32, STAGE_ISLAND)); }
       RC(lw_read(bh, B.ws, WS_COUNT));
     }
     if (hw[WS_TOPO_DIRTY]) { LwWakeMergeK k = {B, bh->b_wake}; RC(launch(ctx, k, B.NB, 256, STAGE_ISLAND)); }
@@ -1065,7 +1074,13 @@ static int step_large(BatchHost* bh, const StepParams& sp, int steps) {
         RC(launch(ctx, k, ni, 32, STAGE_VELOCITY));
       }
       { PostVelocityK k = {B, sp}; RC(launch(ctx, k, std::max(std::max(ni, nib), nic), 128, STAGE_POST_VELOCITY)); }
-      { LwPositionK k = {B, sp, ni}; RC(launch(ctx, k, ni, 32, STAGE_POSITION)); }
+      if (bh->lw_deep_velocity) {
+        LwPosition4K k = {B, L, sp, ni};
+        RC(launch(ctx, k, ni, 32, STAGE_POSITION));
+      } else {
+        LwPositionK k = {B, sp, ni};
+        RC(launch(ctx, k, ni, 32, STAGE_POSITION));
+      }
       { FinalizeK k = {B, sp}; RC(launch(ctx, k, nib, 128, STAGE_FINALIZE)); }
       { SleepK k = {B}; RC(launch(ctx, k, ni, 128, STAGE_SLEEP)); }
       { SyncFixturesK k = {B}; RC(launch(ctx, k, B.NP, 128, STAGE_SYNC_FIXTURES)); }

@@ -25,9 +25,11 @@
 #if defined(__CUDA_ARCH__)
 #define B2G_ATOMIC_ADD(p, v) atomicAdd((p), (v))
 #define B2G_ATOMIC_OR(p, v) atomicOr((p), (v))
+#define B2G_ATOMIC_MAX(p, v) atomicMax((p), (v))
 #else
 #define B2G_ATOMIC_ADD(p, v) (*(p) += (v))
 #define B2G_ATOMIC_OR(p, v) (*(p) |= (v))
+#define B2G_ATOMIC_MAX(p, v) (*(p) = (*(p) > (v) ? *(p) : (v)))
 #endif
 
 namespace b2g {
@@ -86,7 +88,10 @@ B2G_HD bool body_should_collide(int flags_a, int flags_b) {  // b2_body.rs(priva
 // Wake-ups are recorded in b_wake marks (merged after the pass) so the flat pass never races
 // with the activity test of another contact.
 // ------------------------------------------------------------------------------------------
-B2G_HD void collide_one(const Batch& B, const WIdx& x, const Ws& ws, int c, int* b_wake, bool ordered_pass) {
+// `wake_idx` (large-world mode, b2g_large.h): when given, the ordered pass is evaluated out of order — a body
+// counts as woken "by then" when a contact with a larger index (visited earlier by the reference's newest-first
+// loop) woke it, and wake-ups are recorded as the largest such index.
+B2G_HD void collide_one(const Batch& B, const WIdx& x, const Ws& ws, int c, int* b_wake, bool ordered_pass, int* wake_idx = nullptr) {
   const int ci = x.at(B.NC, c);
   int flags = B.c_flags[ci];
   const int4 fx = B.c_fix[ci];
@@ -107,7 +112,10 @@ B2G_HD void collide_one(const Batch& B, const WIdx& x, const Ws& ws, int c, int*
     }
   }
   bool awake_a = (bfa & B2GPU_BODY_AWAKE) != 0, awake_b = (bfb & B2GPU_BODY_AWAKE) != 0;
-  if (ordered_pass) {
+  if (ordered_pass && wake_idx) {
+    awake_a = awake_a || wake_idx[bai] > c;
+    awake_b = awake_b || wake_idx[bbi] > c;
+  } else if (ordered_pass) {
     awake_a = awake_a || b_wake[bai] != 0;
     awake_b = awake_b || b_wake[bbi] != 0;
   }
@@ -158,10 +166,12 @@ B2G_HD void collide_one(const Batch& B, const WIdx& x, const Ws& ws, int c, int*
       if (body_type(bfa) != B2GPU_STATIC_BODY) {
         b_wake[bai] = 1;
         if (!awake_a) ws[WS_EV_WAKE] = 1;
+        if (wake_idx) B2G_ATOMIC_MAX(&wake_idx[bai], c);
       }
       if (body_type(bfb) != B2GPU_STATIC_BODY) {
         b_wake[bbi] = 1;
         if (!awake_b) ws[WS_EV_WAKE] = 1;
+        if (wake_idx) B2G_ATOMIC_MAX(&wake_idx[bbi], c);
       }
       ws[WS_TOPO_DIRTY] = 1;
     }

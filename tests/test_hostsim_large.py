@@ -124,3 +124,49 @@ def test_large_mode_world_api_and_tree_refit(ctx):
     assert int(wg.get_stats()["status"]) == 0
     for w in runs:
         w.close()
+
+
+def test_large_mode_wake_cascade_through_touching_changes(ctx):
+    """Sleeping boxes teleported apart while asleep (set_transform does not wake): when a ball then touches the
+    first one, every stale TOUCHING flag down the former stack flips in ONE collide call, each flip waking the
+    next body — the cascade the reference resolves by its newest-first loop order (LwWakeK's fixpoint rounds)."""
+    from box2d_rs_b200 import abi, scenes, world
+    from oracle import b2o
+
+    def build(w):
+        ground = w.create_body(abi.BodyDef())
+        ground.create_fixture_by_shape(w.shapes.edge_two_sided((-30.0, 0.0), (30.0, 0.0)), 0.0)
+        box = w.shapes.polygon_box(0.5, 0.5)
+        for i in range(7):
+            b = w.create_body(abi.BodyDef(type=abi.DYNAMIC_BODY, position=(0.0, 0.51 + 1.02 * i)))
+            b.create_fixture_by_shape(box, 1.0)
+        ball = w.create_body(abi.BodyDef(type=abi.DYNAMIC_BODY, position=(-15.0, 3.0), allow_sleep=0, gravity_scale=0.0))
+        ball.create_fixture_by_shape(w.shapes.circle(0.4), 2.0)
+
+    wo = b2o.B2world((0.0, -10.0))
+    build(wo)
+    wg = world.B2world((0.0, -10.0), ctx=ctx)
+    build(wg)
+    bt = wg.batch(1, lane_block=1, solver='large')
+    woke_in_one_step = 0
+    for i in range(240):
+        if i == 200:
+            assert int(wo.get_stats()["awake_bodies"]) <= 1
+            # lift the sleeping boxes 1..6 slightly apart (their fat boxes still overlap, so the contacts survive and
+            # keep a stale TOUCHING flag); the ball is put right on top of the uppermost one
+            for k in range(1, 7):
+                wo.body(1 + k).set_transform((0.0, 0.51 + 1.02 * k + 0.03 * k), 0.0)
+            wo.body(8).set_transform((0.0, 0.51 + 1.02 * 6 + 0.18 + 0.5 + 0.39), 0.0)
+        if i >= 198:
+            before = int(wo.get_stats()["awake_bodies"])
+            bt.upload_world(0, wo.snapshot())
+            wo.step(scenes.DT, 8, 3)
+            bt.step(scenes.DT, 8, 3)
+            bad = parity.compare_large_step(wo.snapshot(), bt.download_world(0), wo.get_stats(), bt.stats()[0])
+            assert bad == [], "step %d: %s" % (i, bad[:6])
+            woke_in_one_step = max(woke_in_one_step, int(wo.get_stats()["awake_bodies"]) - before)
+        else:
+            wo.step(scenes.DT, 8, 3)
+    assert woke_in_one_step >= 4, woke_in_one_step  # the cascade really happened
+    bt.close()
+    wg.close()
