@@ -1024,6 +1024,114 @@ struct LwVelocity4K {
   }
 };
 
+// Straighter form of LwVelocity4K (diagnostic switch B2GPU_LW_VELOCITY=3): the warm-start sweep is its own
+// pipelined loop, the main loop runs whole groups of four visits without a bounds test, immovable bodies are
+// "written" to a scratch slot instead of being skipped, and island contacts are assumed to carry at least one
+// point (touching contacts always do).
+template <bool WARM>
+B2G_HD void lw_velocity_run(const Batch& B, const Large& L, int first, int n, int sweeps, bool block) {
+  const long long total = (long long)n * sweeps;
+  int4 ix[4];
+  float4 q0[4], q1[4], q2[4], q3[4], q4[4], q5[4], q6[4], q7[4], va[4], vb[4];
+  ix[0] = L.vc_idx[first];
+  ix[1] = L.vc_idx[first + 1];
+  ix[2] = L.vc_idx[first + 2];
+  ix[3] = make_int4(0, 0, 0, 0);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+  for (int j = 0; j < 2; ++j) {
+    const float4* r = B.vc + (size_t)(first + j) * VC_Q;
+    q0[j] = r[0]; q1[j] = r[1]; q2[j] = r[2]; q6[j] = r[6]; q7[j] = r[7];
+    if (!WARM) { q3[j] = r[3]; q4[j] = r[4]; q5[j] = r[5]; }
+    va[j] = B.b_vel[ix[j].x];
+    vb[j] = B.b_vel[ix[j].y];
+  }
+  int k = 0, k2 = 2, k3 = 3;
+  float4* scratch = (float4*)L.pk_out;  // not in use during the solver stages
+  long long v = 0;
+  for (; v + 4 <= total; v += 4) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < 4; ++j) {
+      const int j2 = (j + 2) & 3, j3 = (j + 3) & 3, j1 = (j + 1) & 3;
+      ix[j3] = L.vc_idx[first + k3];
+      {
+        const float4* r = B.vc + (size_t)(first + k2) * VC_Q;
+        q0[j2] = r[0]; q1[j2] = r[1]; q2[j2] = r[2]; q6[j2] = r[6]; q7[j2] = r[7];
+        if (!WARM) { q3[j2] = r[3]; q4[j2] = r[4]; q5[j2] = r[5]; }
+        va[j2] = B.b_vel[ix[j2].x];
+        vb[j2] = B.b_vel[ix[j2].y];
+      }
+      const int ba = ix[j].x, bb = ix[j].y, vc_points = ix[j].z;
+      VelState s;
+      s.v_a = v2(va[j].x, va[j].y); s.w_a = va[j].z;
+      s.v_b = v2(vb[j].x, vb[j].y); s.w_b = vb[j].z;
+      if (WARM) {
+        warm_start_one(s, q0[j], q1[j], q2[j], q6[j], q7[j], vc_points);
+      } else {
+        solve_velocity_one(s, q0[j], q1[j], q2[j], q3[j], q4[j], q5[j], q6[j], q7[j], vc_points, block);
+        B.vc[(size_t)(first + k) * VC_Q + 6] = q6[j];
+      }
+      // a static / kinematic body may sit in several islands: its velocity never changes — the result of the
+      // arithmetic on it (inverse mass 0) is its old value, which is stored to a scratch slot instead
+      const bool mov_a = q7[j].x != 0.0f || q7[j].y != 0.0f, mov_b = q7[j].z != 0.0f || q7[j].w != 0.0f;
+      const float4 na = make_float4(s.v_a.x, s.v_a.y, s.w_a, 0.0f), nb = make_float4(s.v_b.x, s.v_b.y, s.w_b, 0.0f);
+      va[j] = mov_a ? na : va[j];
+      vb[j] = mov_b ? nb : vb[j];
+      *(mov_a ? &B.b_vel[ba] : scratch) = va[j];
+      *(mov_b ? &B.b_vel[bb] : scratch + 1) = vb[j];
+      if (ix[j1].x == ba) va[j1] = va[j]; else if (ix[j1].x == bb) va[j1] = vb[j];
+      if (ix[j1].y == ba) vb[j1] = va[j]; else if (ix[j1].y == bb) vb[j1] = vb[j];
+      if (ix[j2].x == ba) va[j2] = va[j]; else if (ix[j2].x == bb) va[j2] = vb[j];
+      if (ix[j2].y == ba) vb[j2] = va[j]; else if (ix[j2].y == bb) vb[j2] = vb[j];
+      if (++k == n) k = 0;
+      if (++k2 == n) k2 = 0;
+      if (++k3 == n) k3 = 0;
+    }
+  }
+  for (; v < total; ++v) {  // at most three visits left: every store above went to memory, plain loads are current
+    const int kk = first + k;
+    const int4 ixx = L.vc_idx[kk];
+    const float4 a = B.b_vel[ixx.x], b = B.b_vel[ixx.y];
+    VelState s;
+    s.v_a = v2(a.x, a.y); s.w_a = a.z;
+    s.v_b = v2(b.x, b.y); s.w_b = b.z;
+    LwVcRec r = lw_load_vc(B.vc, kk);
+    if (WARM) {
+      warm_start_one(s, r.q0, r.q1, r.q2, r.q6, r.q7, ixx.z);
+    } else {
+      solve_velocity_one(s, r.q0, r.q1, r.q2, r.q3, r.q4, r.q5, r.q6, r.q7, ixx.z, block);
+      B.vc[(size_t)kk * VC_Q + 6] = r.q6;
+    }
+    if (r.q7.x != 0.0f || r.q7.y != 0.0f) B.b_vel[ixx.x] = make_float4(s.v_a.x, s.v_a.y, s.w_a, 0.0f);
+    if (r.q7.z != 0.0f || r.q7.w != 0.0f) B.b_vel[ixx.y] = make_float4(s.v_b.x, s.v_b.y, s.w_b, 0.0f);
+    if (++k == n) k = 0;
+  }
+}
+struct LwVelocity5K {
+  Batch B;
+  Large L;
+  StepParams sp;
+  int n_islands;
+  B2G_HD void operator()(int isl) const {
+    if (isl >= n_islands) return;
+    const int4 rg = B.isl_range[isl];
+    if (rg.z == rg.w) return;
+    const bool warm = (B.ws[WS_FLAGS] & B2GPU_WORLD_WARM_STARTING) != 0;
+    const bool block = (B.ws[WS_FLAGS] & B2GPU_WORLD_BLOCK_SOLVE) != 0;
+    const int first = rg.z, n = rg.w - rg.z;
+    if (n < 4) {
+      LwVelocity4K small = {B, L, sp, n_islands};
+      small(isl);
+      return;
+    }
+    if (warm) lw_velocity_run<true>(B, L, first, n, 1, block);
+    if (sp.velocity_iterations > 0) lw_velocity_run<false>(B, L, first, n, sp.velocity_iterations, block);
+  }
+};
+
 struct LwPcRec { float4 p0, p1, p2, p3, p4, p5; };
 B2G_HD LwPcRec lw_load_pc(const float4* pc, int k) {
   const float4* r = pc + (size_t)k * PC_Q;

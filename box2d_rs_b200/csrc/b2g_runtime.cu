@@ -526,7 +526,7 @@ int batch_create(Ctx* ctx, const b2gpu_snapshot* proto, int n_worlds, const b2gp
     rc = large_alloc(bh);
     if (rc) { batch_destroy(bh); return rc; }
     bh->large = true;
-    if (const char* e = getenv("B2GPU_LW_VELOCITY")) bh->lw_deep_velocity = atoi(e) != 1;  // 1 = distance-1 pipeline (diagnostic)
+    if (const char* e = getenv("B2GPU_LW_VELOCITY")) bh->lw_velocity_variant = atoi(e);  // diagnostic, see step_large
   }
 #if !defined(B2G_HOSTSIM)
   // shared-memory Gauss-Seidel stages: batches in 32-world memory blocks whose bodies fit one SM
@@ -1066,21 +1066,15 @@ static int step_large(BatchHost* bh, const StepParams& sp, int steps) {
       { LwStaticRotK k = {B}; RC(launch(ctx, k, B.NB, 256, STAGE_INTEGRATE)); }
       { IntegrateK k = {B, sp}; RC(launch(ctx, k, nib, 128, STAGE_INTEGRATE)); }
       { SolverInitK k = {B, sp}; RC(launch(ctx, k, nic, 128, STAGE_SOLVER_INIT)); }
-      if (bh->lw_deep_velocity) {
-        { LwVcIdxK k = {B, L, nic}; RC(launch(ctx, k, nic, 256, STAGE_SOLVER_INIT)); }
-        { LwVelocity4K k = {B, L, sp, ni}; RC(launch(ctx, k, ni, 32, STAGE_VELOCITY)); }
-      } else {
-        LwVelocityK k = {B, sp, ni};
-        RC(launch(ctx, k, ni, 32, STAGE_VELOCITY));
-      }
+      // default: the distance-1 pipelines (measured fastest: the sweeps are bound by dependent issue, not by memory
+      // latency); B2GPU_LW_VELOCITY = 2 / 3 / 4 select the rotating-register experiments (profiles/r01_large_world.md)
+      if (bh->lw_velocity_variant >= 2) { LwVcIdxK k = {B, L, nic}; RC(launch(ctx, k, nic, 256, STAGE_SOLVER_INIT)); }
+      if (bh->lw_velocity_variant == 3) { LwVelocity5K k = {B, L, sp, ni}; RC(launch(ctx, k, ni, 32, STAGE_VELOCITY)); }
+      else if (bh->lw_velocity_variant == 2) { LwVelocity4K k = {B, L, sp, ni}; RC(launch(ctx, k, ni, 32, STAGE_VELOCITY)); }
+      else { LwVelocityK k = {B, sp, ni}; RC(launch(ctx, k, ni, 32, STAGE_VELOCITY)); }
       { PostVelocityK k = {B, sp}; RC(launch(ctx, k, std::max(std::max(ni, nib), nic), 128, STAGE_POST_VELOCITY)); }
-      if (bh->lw_deep_velocity) {
-        LwPosition4K k = {B, L, sp, ni};
-        RC(launch(ctx, k, ni, 32, STAGE_POSITION));
-      } else {
-        LwPositionK k = {B, sp, ni};
-        RC(launch(ctx, k, ni, 32, STAGE_POSITION));
-      }
+      if (bh->lw_velocity_variant == 4) { LwPosition4K k = {B, L, sp, ni}; RC(launch(ctx, k, ni, 32, STAGE_POSITION)); }
+      else { LwPositionK k = {B, sp, ni}; RC(launch(ctx, k, ni, 32, STAGE_POSITION)); }
       { FinalizeK k = {B, sp}; RC(launch(ctx, k, nib, 128, STAGE_FINALIZE)); }
       { SleepK k = {B}; RC(launch(ctx, k, ni, 128, STAGE_SLEEP)); }
       { SyncFixturesK k = {B}; RC(launch(ctx, k, B.NP, 128, STAGE_SYNC_FIXTURES)); }

@@ -109,7 +109,7 @@ struct BatchHost {
   size_t lw_tmp_bytes = 0;
   int lw_edge_bits = 0, lw_body_bits = 0;
   long long lw_keys = 0;         // capacity of the key buffers
-  bool lw_deep_velocity = true;  // LwVelocity4K (rotating register sets) instead of LwVelocityK
+  int lw_velocity_variant = 0;   // diagnostic: 2 LwVelocity4K, 3 LwVelocity5K, 4 LwPosition4K (default: distance-1 pipelines)
 };
 
 const char* last_error();

@@ -38,6 +38,7 @@ def main():
     ap.add_argument("--skip", type=int, default=5, help="untimed leading steps")
     ap.add_argument("--check", action="store_true", help="compare the final state with the oracle bit for bit")
     ap.add_argument("--no-gpu", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true", help="skip the oracle (profiling runs)")
     ap.add_argument("--large", action="store_true",
                     help="large-world mode (b2gpu_world_set_large_mode): data-parallel broadphase / islands; --check then "
                          "verifies one teacher-forced step from the oracle's final state (contacts created in it as a set)")
@@ -52,7 +53,7 @@ def main():
     out["build_s_oracle"] = time.time() - t0
     prof = {}
     t_cpu = 0.0
-    for i in range(args.steps):
+    for i in range(0 if args.no_cpu else args.steps):
         t0 = time.perf_counter()
         wo.step(scenes.DT, 8, 3)
         dt = time.perf_counter() - t0
@@ -89,7 +90,7 @@ def main():
         stages = wg.ctx.stage_times()
         out["gpu_ms_per_step"] = 1e3 * t_gpu / n_t
         out["gpu_stage_ms"] = {k: v[0] / n_t for k, v in stages.items() if v[1] > 0}
-        out["gpu_over_cpu"] = out["cpu_ms_per_step"] / out["gpu_ms_per_step"]
+        out["gpu_over_cpu"] = out["cpu_ms_per_step"] / out["gpu_ms_per_step"] if not args.no_cpu else None
         gs = wg.get_stats()
         out["gpu_status"] = int(gs["status"])
         if args.check and args.large:
