@@ -1068,10 +1068,15 @@ B2G_HD void lw_velocity_run(const Batch& B, const Large& L, int first, int n, in
       VelState s;
       s.v_a = v2(va[j].x, va[j].y); s.w_a = va[j].z;
       s.v_b = v2(vb[j].x, vb[j].y); s.w_b = vb[j].z;
+      // one dispatch on the constraint's shape (known three visits ahead), then straight-line arithmetic: with
+      // constant point count / block flag the branches inside the solve functions fold away
       if (WARM) {
-        warm_start_one(s, q0[j], q1[j], q2[j], q6[j], q7[j], vc_points);
+        if (vc_points == 1) warm_start_one(s, q0[j], q1[j], q2[j], q6[j], q7[j], 1);
+        else warm_start_one(s, q0[j], q1[j], q2[j], q6[j], q7[j], 2);
       } else {
-        solve_velocity_one(s, q0[j], q1[j], q2[j], q3[j], q4[j], q5[j], q6[j], q7[j], vc_points, block);
+        if (vc_points == 1) solve_velocity_one(s, q0[j], q1[j], q2[j], q3[j], q4[j], q5[j], q6[j], q7[j], 1, false);
+        else if (block) solve_velocity_one(s, q0[j], q1[j], q2[j], q3[j], q4[j], q5[j], q6[j], q7[j], 2, true);
+        else solve_velocity_one(s, q0[j], q1[j], q2[j], q3[j], q4[j], q5[j], q6[j], q7[j], 2, false);
         B.vc[(size_t)(first + k) * VC_Q + 6] = q6[j];
       }
       // a static / kinematic body may sit in several islands: its velocity never changes — the result of the
@@ -1262,6 +1267,126 @@ struct LwPosition4K {
             min_separation = 0.0f;
           }
         }
+      }
+    }
+  }
+};
+
+// Position sweeps in the straighter form (see lw_velocity_run): one pipelined pass per sweep (groups of four
+// visits without a bounds test, at most three plain visits at the end), immovable bodies stored to a scratch
+// slot, the reference's early exit evaluated between sweeps.
+B2G_HD float lw_position_visit_plain(const Batch& B, const Large& L, int kk, float min_separation) {
+  const int4 ixx = L.vc_idx[kk];
+  const float4* r = B.pc + (size_t)kk * PC_Q;
+  const float4 p0 = r[0];
+  float4 pa = B.b_pos[ixx.x], pb = B.b_pos[ixx.y], ra = B.b_rot[ixx.x], rb = B.b_rot[ixx.y];
+  PosState s;
+  s.c_a = v2(pa.x, pa.y); s.a_a = pa.z; s.q_a.s = ra.x; s.q_a.c = ra.y;
+  s.c_b = v2(pb.x, pb.y); s.a_b = pb.z; s.q_b.s = rb.x; s.q_b.c = rb.y;
+  const float4 p4 = r[4];
+  min_separation = solve_position_one(s, p0, r[1], r[2], r[3], (ixx.w >> 8) & 0xff, ixx.w & 0xff, p4.x, p4.y, min_separation);
+  if (p0.x != 0.0f || p0.y != 0.0f) {
+    pa.x = s.c_a.x; pa.y = s.c_a.y; pa.z = s.a_a; ra.x = s.q_a.s; ra.y = s.q_a.c;
+    B.b_pos[ixx.x] = pa; B.b_rot[ixx.x] = ra;
+  }
+  if (p0.z != 0.0f || p0.w != 0.0f) {
+    pb.x = s.c_b.x; pb.y = s.c_b.y; pb.z = s.a_b; rb.x = s.q_b.s; rb.y = s.q_b.c;
+    B.b_pos[ixx.y] = pb; B.b_rot[ixx.y] = rb;
+  }
+  return min_separation;
+}
+B2G_HD float lw_position_sweep(const Batch& B, const Large& L, int first, int n) {
+  float min_separation = 0.0f;
+  int v = 0;
+  if (n >= 8) {
+    int4 ix[4];
+    float4 p0[4], p1[4], p2[4], p3[4], p4[4], pa[4], pb[4], ra[4], rb[4];
+    ix[0] = L.vc_idx[first];
+    ix[1] = L.vc_idx[first + 1];
+    ix[2] = L.vc_idx[first + 2];
+    ix[3] = make_int4(0, 0, 0, 0);
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+    for (int j = 0; j < 2; ++j) {
+      const float4* r = B.pc + (size_t)(first + j) * PC_Q;
+      p0[j] = r[0]; p1[j] = r[1]; p2[j] = r[2]; p3[j] = r[3]; p4[j] = r[4];
+      pa[j] = B.b_pos[ix[j].x]; ra[j] = B.b_rot[ix[j].x];
+      pb[j] = B.b_pos[ix[j].y]; rb[j] = B.b_rot[ix[j].y];
+    }
+    float4* scratch = (float4*)L.pk_out;  // not in use during the solver stages
+    int k = 0, k2 = 2, k3 = 3;
+    for (; v + 4 <= n; v += 4) {
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+      for (int j = 0; j < 4; ++j) {
+        const int j2 = (j + 2) & 3, j3 = (j + 3) & 3, j1 = (j + 1) & 3;
+        ix[j3] = L.vc_idx[first + k3];
+        {
+          const float4* r = B.pc + (size_t)(first + k2) * PC_Q;
+          p0[j2] = r[0]; p1[j2] = r[1]; p2[j2] = r[2]; p3[j2] = r[3]; p4[j2] = r[4];
+          pa[j2] = B.b_pos[ix[j2].x]; ra[j2] = B.b_rot[ix[j2].x];
+          pb[j2] = B.b_pos[ix[j2].y]; rb[j2] = B.b_rot[ix[j2].y];
+        }
+        const int ba = ix[j].x, bb = ix[j].y, packed = ix[j].w;
+        PosState s;
+        s.c_a = v2(pa[j].x, pa[j].y); s.a_a = pa[j].z; s.q_a.s = ra[j].x; s.q_a.c = ra[j].y;
+        s.c_b = v2(pb[j].x, pb[j].y); s.a_b = pb[j].z; s.q_b.s = rb[j].x; s.q_b.c = rb[j].y;
+        const int type = (packed >> 8) & 0xff, pts = packed & 0xff;
+        if (type != B2GPU_MANIFOLD_CIRCLES && pts == 2) {
+          // the branch-free two-point face form of the batch kernels (solve_position_face2: selects instead of the
+          // face-type branches, unconditional sincos_mid refresh); an angle outside its domain redoes the visit
+          const PosState s0 = s;
+          bool wide;
+          const float ms = solve_position_face2(s, p0[j], p1[j], p2[j], p3[j], type == B2GPU_MANIFOLD_FACE_A, p4[j].x, p4[j].y,
+                                                min_separation, wide);
+          if (wide) {
+            s = s0;
+            min_separation = solve_position_one(s, p0[j], p1[j], p2[j], p3[j], type, pts, p4[j].x, p4[j].y, min_separation);
+          } else {
+            min_separation = ms;
+          }
+        } else if (type == B2GPU_MANIFOLD_CIRCLES) {
+          min_separation = solve_position_one(s, p0[j], p1[j], p2[j], p3[j], B2GPU_MANIFOLD_CIRCLES, pts, p4[j].x, p4[j].y, min_separation);
+        } else {
+          min_separation = solve_position_one(s, p0[j], p1[j], p2[j], p3[j], type, pts, p4[j].x, p4[j].y, min_separation);
+        }
+        // immovable bodies (inverse mass and inertia 0) come out of the arithmetic unchanged and are shared between
+        // islands: their value goes to a scratch slot
+        const bool mov_a = p0[j].x != 0.0f || p0[j].y != 0.0f, mov_b = p0[j].z != 0.0f || p0[j].w != 0.0f;
+        if (mov_a) { pa[j].x = s.c_a.x; pa[j].y = s.c_a.y; pa[j].z = s.a_a; ra[j].x = s.q_a.s; ra[j].y = s.q_a.c; }
+        if (mov_b) { pb[j].x = s.c_b.x; pb[j].y = s.c_b.y; pb[j].z = s.a_b; rb[j].x = s.q_b.s; rb[j].y = s.q_b.c; }
+        *(mov_a ? &B.b_pos[ba] : scratch) = pa[j];
+        *(mov_a ? &B.b_rot[ba] : scratch + 1) = ra[j];
+        *(mov_b ? &B.b_pos[bb] : scratch + 2) = pb[j];
+        *(mov_b ? &B.b_rot[bb] : scratch + 3) = rb[j];
+        if (ix[j1].x == ba) { pa[j1] = pa[j]; ra[j1] = ra[j]; } else if (ix[j1].x == bb) { pa[j1] = pb[j]; ra[j1] = rb[j]; }
+        if (ix[j1].y == ba) { pb[j1] = pa[j]; rb[j1] = ra[j]; } else if (ix[j1].y == bb) { pb[j1] = pb[j]; rb[j1] = rb[j]; }
+        if (ix[j2].x == ba) { pa[j2] = pa[j]; ra[j2] = ra[j]; } else if (ix[j2].x == bb) { pa[j2] = pb[j]; ra[j2] = rb[j]; }
+        if (ix[j2].y == ba) { pb[j2] = pa[j]; rb[j2] = ra[j]; } else if (ix[j2].y == bb) { pb[j2] = pb[j]; rb[j2] = rb[j]; }
+        if (++k == n) k = 0;
+        if (++k2 == n) k2 = 0;
+        if (++k3 == n) k3 = 0;
+      }
+    }
+  }
+  for (; v < n; ++v) min_separation = lw_position_visit_plain(B, L, first + v, min_separation);
+  return min_separation;
+}
+struct LwPosition5K {
+  Batch B;
+  Large L;
+  StepParams sp;
+  int n_islands;
+  B2G_HD void operator()(int isl) const {
+    if (isl >= n_islands) return;
+    const int4 rg = B.isl_range[isl];
+    if (rg.z == rg.w) return;
+    for (int it = 0; it < sp.position_iterations; ++it) {
+      if (lw_position_sweep(B, L, rg.z, rg.w - rg.z) >= -3.0f * B2G_LINEAR_SLOP) {  // b2_island_private.rs:257-274
+        B.isl_flags[isl] |= 1;
+        break;
       }
     }
   }

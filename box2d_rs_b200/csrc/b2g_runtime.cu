@@ -1066,15 +1066,17 @@ static int step_large(BatchHost* bh, const StepParams& sp, int steps) {
       { LwStaticRotK k = {B}; RC(launch(ctx, k, B.NB, 256, STAGE_INTEGRATE)); }
       { IntegrateK k = {B, sp}; RC(launch(ctx, k, nib, 128, STAGE_INTEGRATE)); }
       { SolverInitK k = {B, sp}; RC(launch(ctx, k, nic, 128, STAGE_SOLVER_INIT)); }
-      // default: the distance-1 pipelines (measured fastest: the sweeps are bound by dependent issue, not by memory
-      // latency); B2GPU_LW_VELOCITY = 2 / 3 / 4 select the rotating-register experiments (profiles/r01_large_world.md)
-      if (bh->lw_velocity_variant >= 2) { LwVcIdxK k = {B, L, nic}; RC(launch(ctx, k, nic, 256, STAGE_SOLVER_INIT)); }
-      if (bh->lw_velocity_variant == 3) { LwVelocity5K k = {B, L, sp, ni}; RC(launch(ctx, k, ni, 32, STAGE_VELOCITY)); }
-      else if (bh->lw_velocity_variant == 2) { LwVelocity4K k = {B, L, sp, ni}; RC(launch(ctx, k, ni, 32, STAGE_VELOCITY)); }
-      else { LwVelocityK k = {B, sp, ni}; RC(launch(ctx, k, ni, 32, STAGE_VELOCITY)); }
+      // default: the straight rotating-register sweeps (LwVelocity5K / LwPosition5K).  B2GPU_LW_VELOCITY selects the
+      // other forms for comparison: 1 distance-1 pipelines, 2 LwVelocity4K, 4 LwPosition4K (profiles/r01_large_world.md)
+      const int gs = bh->lw_velocity_variant;
+      if (gs != 1) { LwVcIdxK k = {B, L, nic}; RC(launch(ctx, k, nic, 256, STAGE_SOLVER_INIT)); }
+      if (gs == 1 || gs == 4) { LwVelocityK k = {B, sp, ni}; RC(launch(ctx, k, ni, 32, STAGE_VELOCITY)); }
+      else if (gs == 2) { LwVelocity4K k = {B, L, sp, ni}; RC(launch(ctx, k, ni, 32, STAGE_VELOCITY)); }
+      else { LwVelocity5K k = {B, L, sp, ni}; RC(launch(ctx, k, ni, 32, STAGE_VELOCITY)); }
       { PostVelocityK k = {B, sp}; RC(launch(ctx, k, std::max(std::max(ni, nib), nic), 128, STAGE_POST_VELOCITY)); }
-      if (bh->lw_velocity_variant == 4) { LwPosition4K k = {B, L, sp, ni}; RC(launch(ctx, k, ni, 32, STAGE_POSITION)); }
-      else { LwPositionK k = {B, sp, ni}; RC(launch(ctx, k, ni, 32, STAGE_POSITION)); }
+      if (gs == 4) { LwPosition4K k = {B, L, sp, ni}; RC(launch(ctx, k, ni, 32, STAGE_POSITION)); }
+      else if (gs == 1 || gs == 2 || gs == 3) { LwPositionK k = {B, sp, ni}; RC(launch(ctx, k, ni, 32, STAGE_POSITION)); }
+      else { LwPosition5K k = {B, L, sp, ni}; RC(launch(ctx, k, ni, 32, STAGE_POSITION)); }
       { FinalizeK k = {B, sp}; RC(launch(ctx, k, nib, 128, STAGE_FINALIZE)); }
       { SleepK k = {B}; RC(launch(ctx, k, ni, 128, STAGE_SLEEP)); }
       { SyncFixturesK k = {B}; RC(launch(ctx, k, B.NP, 128, STAGE_SYNC_FIXTURES)); }
