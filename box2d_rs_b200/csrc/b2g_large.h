@@ -64,6 +64,7 @@ struct Large {  // device scratch of the large-world mode
   int* cand_pos;   // [NCAND + 1]
   int4* cand_fix;  // [NCAND] (fixture_a, fixture_b, index_a, index_b) after the register-order swap
   int NCAND;
+  float4* scratch4; // [16] store target for bodies that must not be written (immovable: shared between islands)
   int4* vc_idx;    // [NC] per island contact slot: (body A, body B, velocity points, -), see LwVelocity4K
   int* first_idx;  // [NN] first move-buffer index of a tree node (host edits can buffer a proxy more than once)
   // islands
@@ -1048,14 +1049,25 @@ B2G_HD void lw_velocity_run(const Batch& B, const Large& L, int first, int n, in
     vb[j] = B.b_vel[ix[j].y];
   }
   int k = 0, k2 = 2, k3 = 3;
-  float4* scratch = (float4*)L.pk_out;  // not in use during the solver stages
+  float4* scratch = L.scratch4;  // where the "results" of immovable bodies go
+  // results of the two previous visits, for forwarding at the point of USE.  (Forwarding into the register sets
+  // still in flight — as LwVelocity4K does — makes every select wait for the load it patches: ncu showed 37 % of
+  // the samples on those selects, stall_long_scoreboard.)  Body -1 matches nothing.
+  int h1a = -1, h1b = -1, h2a = -1, h2b = -1;
+  float4 r1a = make_float4(0, 0, 0, 0), r1b = r1a, r2a = r1a, r2b = r1a;
   long long v = 0;
   for (; v + 4 <= total; v += 4) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
     for (int j = 0; j < 4; ++j) {
-      const int j2 = (j + 2) & 3, j3 = (j + 3) & 3, j1 = (j + 1) & 3;
+      const int j2 = (j + 2) & 3, j3 = (j + 3) & 3;
+      // inputs of this visit: requested two visits ago, so possibly older than the last two visits' results
+      const int ba = ix[j].x, bb = ix[j].y, vc_points = ix[j].z;
+      float4 a = va[j], b = vb[j];
+      a = ba == h1a ? r1a : ba == h1b ? r1b : ba == h2a ? r2a : ba == h2b ? r2b : a;
+      b = bb == h1a ? r1a : bb == h1b ? r1b : bb == h2a ? r2a : bb == h2b ? r2b : b;
+      // requests: indices of visit v+3, record and bodies of visit v+2
       ix[j3] = L.vc_idx[first + k3];
       {
         const float4* r = B.vc + (size_t)(first + k2) * VC_Q;
@@ -1064,33 +1076,24 @@ B2G_HD void lw_velocity_run(const Batch& B, const Large& L, int first, int n, in
         va[j2] = B.b_vel[ix[j2].x];
         vb[j2] = B.b_vel[ix[j2].y];
       }
-      const int ba = ix[j].x, bb = ix[j].y, vc_points = ix[j].z;
       VelState s;
-      s.v_a = v2(va[j].x, va[j].y); s.w_a = va[j].z;
-      s.v_b = v2(vb[j].x, vb[j].y); s.w_b = vb[j].z;
-      // one dispatch on the constraint's shape (known three visits ahead), then straight-line arithmetic: with
-      // constant point count / block flag the branches inside the solve functions fold away
+      s.v_a = v2(a.x, a.y); s.w_a = a.z;
+      s.v_b = v2(b.x, b.y); s.w_b = b.z;
       if (WARM) {
-        if (vc_points == 1) warm_start_one(s, q0[j], q1[j], q2[j], q6[j], q7[j], 1);
-        else warm_start_one(s, q0[j], q1[j], q2[j], q6[j], q7[j], 2);
+        warm_start_one(s, q0[j], q1[j], q2[j], q6[j], q7[j], vc_points);
       } else {
-        if (vc_points == 1) solve_velocity_one(s, q0[j], q1[j], q2[j], q3[j], q4[j], q5[j], q6[j], q7[j], 1, false);
-        else if (block) solve_velocity_one(s, q0[j], q1[j], q2[j], q3[j], q4[j], q5[j], q6[j], q7[j], 2, true);
-        else solve_velocity_one(s, q0[j], q1[j], q2[j], q3[j], q4[j], q5[j], q6[j], q7[j], 2, false);
+        solve_velocity_one(s, q0[j], q1[j], q2[j], q3[j], q4[j], q5[j], q6[j], q7[j], vc_points, block);
         B.vc[(size_t)(first + k) * VC_Q + 6] = q6[j];
       }
       // a static / kinematic body may sit in several islands: its velocity never changes — the result of the
       // arithmetic on it (inverse mass 0) is its old value, which is stored to a scratch slot instead
       const bool mov_a = q7[j].x != 0.0f || q7[j].y != 0.0f, mov_b = q7[j].z != 0.0f || q7[j].w != 0.0f;
-      const float4 na = make_float4(s.v_a.x, s.v_a.y, s.w_a, 0.0f), nb = make_float4(s.v_b.x, s.v_b.y, s.w_b, 0.0f);
-      va[j] = mov_a ? na : va[j];
-      vb[j] = mov_b ? nb : vb[j];
-      *(mov_a ? &B.b_vel[ba] : scratch) = va[j];
-      *(mov_b ? &B.b_vel[bb] : scratch + 1) = vb[j];
-      if (ix[j1].x == ba) va[j1] = va[j]; else if (ix[j1].x == bb) va[j1] = vb[j];
-      if (ix[j1].y == ba) vb[j1] = va[j]; else if (ix[j1].y == bb) vb[j1] = vb[j];
-      if (ix[j2].x == ba) va[j2] = va[j]; else if (ix[j2].x == bb) va[j2] = vb[j];
-      if (ix[j2].y == ba) vb[j2] = va[j]; else if (ix[j2].y == bb) vb[j2] = vb[j];
+      const float4 na = mov_a ? make_float4(s.v_a.x, s.v_a.y, s.w_a, 0.0f) : a;
+      const float4 nb = mov_b ? make_float4(s.v_b.x, s.v_b.y, s.w_b, 0.0f) : b;
+      *(mov_a ? &B.b_vel[ba] : scratch) = na;
+      *(mov_b ? &B.b_vel[bb] : scratch + 1) = nb;
+      h2a = h1a; h2b = h1b; r2a = r1a; r2b = r1b;
+      h1a = ba; h1b = bb; r1a = na; r1b = nb;
       if (++k == n) k = 0;
       if (++k2 == n) k2 = 0;
       if (++k3 == n) k3 = 0;
@@ -1314,7 +1317,7 @@ B2G_HD float lw_position_sweep(const Batch& B, const Large& L, int first, int n)
       pa[j] = B.b_pos[ix[j].x]; ra[j] = B.b_rot[ix[j].x];
       pb[j] = B.b_pos[ix[j].y]; rb[j] = B.b_rot[ix[j].y];
     }
-    float4* scratch = (float4*)L.pk_out;  // not in use during the solver stages
+    float4* scratch = L.scratch4;  // where the "results" of immovable bodies go
     int k = 0, k2 = 2, k3 = 3;
     for (; v + 4 <= n; v += 4) {
 #if defined(__CUDA_ARCH__)
@@ -1385,6 +1388,72 @@ struct LwPosition5K {
     if (rg.z == rg.w) return;
     for (int it = 0; it < sp.position_iterations; ++it) {
       if (lw_position_sweep(B, L, rg.z, rg.w - rg.z) >= -3.0f * B2G_LINEAR_SLOP) {  // b2_island_private.rs:257-274
+        B.isl_flags[isl] |= 1;
+        break;
+      }
+    }
+  }
+};
+
+// Position sweeps, final form: two register sets alternate through a loop unrolled by two (no moves of registers
+// whose loads are in flight), the next visit's record and bodies are requested at the start of a visit, and the
+// bodies the previous visit wrote are forwarded at the point of use.  One inlined copy of solve_position_one per
+// set keeps the loop inside the instruction cache (the four-set forms above measured slower: stall_no_inst).
+struct LwPosSet { float4 p0, p1, p2, p3, p4, pa, pb, ra, rb; int4 ix; };
+B2G_HD void lw_pos_request(const Batch& B, const Large& L, int kk, LwPosSet& t) {
+  t.ix = L.vc_idx[kk];
+  const float4* r = B.pc + (size_t)kk * PC_Q;
+  t.p0 = r[0]; t.p1 = r[1]; t.p2 = r[2]; t.p3 = r[3]; t.p4 = r[4];
+  t.pa = B.b_pos[t.ix.x]; t.ra = B.b_rot[t.ix.x];
+  t.pb = B.b_pos[t.ix.y]; t.rb = B.b_rot[t.ix.y];
+}
+struct LwPosHist { int a, b; float4 pa, ra, pb, rb; };
+B2G_HD float lw_pos_visit(const Batch& B, float4* scratch, const LwPosSet& t, LwPosHist& h, float min_separation) {
+  const int ba = t.ix.x, bb = t.ix.y, packed = t.ix.w;
+  float4 pa = t.pa, ra = t.ra, pb = t.pb, rb = t.rb;
+  if (ba == h.a) { pa = h.pa; ra = h.ra; } else if (ba == h.b) { pa = h.pb; ra = h.rb; }
+  if (bb == h.a) { pb = h.pa; rb = h.ra; } else if (bb == h.b) { pb = h.pb; rb = h.rb; }
+  PosState s;
+  s.c_a = v2(pa.x, pa.y); s.a_a = pa.z; s.q_a.s = ra.x; s.q_a.c = ra.y;
+  s.c_b = v2(pb.x, pb.y); s.a_b = pb.z; s.q_b.s = rb.x; s.q_b.c = rb.y;
+  min_separation = solve_position_one(s, t.p0, t.p1, t.p2, t.p3, (packed >> 8) & 0xff, packed & 0xff, t.p4.x, t.p4.y, min_separation);
+  const bool mov_a = t.p0.x != 0.0f || t.p0.y != 0.0f, mov_b = t.p0.z != 0.0f || t.p0.w != 0.0f;
+  if (mov_a) { pa.x = s.c_a.x; pa.y = s.c_a.y; pa.z = s.a_a; ra.x = s.q_a.s; ra.y = s.q_a.c; }
+  if (mov_b) { pb.x = s.c_b.x; pb.y = s.c_b.y; pb.z = s.a_b; rb.x = s.q_b.s; rb.y = s.q_b.c; }
+  *(mov_a ? &B.b_pos[ba] : scratch) = pa;
+  *(mov_a ? &B.b_rot[ba] : scratch + 1) = ra;
+  *(mov_b ? &B.b_pos[bb] : scratch + 2) = pb;
+  *(mov_b ? &B.b_rot[bb] : scratch + 3) = rb;
+  h.a = ba; h.b = bb; h.pa = pa; h.ra = ra; h.pb = pb; h.rb = rb;
+  return min_separation;
+}
+struct LwPosition6K {
+  Batch B;
+  Large L;
+  StepParams sp;
+  int n_islands;
+  B2G_HD void operator()(int isl) const {
+    if (isl >= n_islands) return;
+    const int4 rg = B.isl_range[isl];
+    if (rg.z == rg.w) return;
+    const int first = rg.z, n = rg.w - rg.z;
+    float4* scratch = L.scratch4 + 4;  // where the "results" of immovable bodies go
+    for (int it = 0; it < sp.position_iterations; ++it) {
+      float min_separation = 0.0f;
+      LwPosHist h;
+      h.a = -1; h.b = -1;
+      h.pa = h.ra = h.pb = h.rb = make_float4(0, 0, 0, 0);
+      LwPosSet s0, s1;
+      lw_pos_request(B, L, first, s0);
+      int k = 0;
+      for (; k + 2 <= n; k += 2) {
+        lw_pos_request(B, L, first + k + 1, s1);
+        min_separation = lw_pos_visit(B, scratch, s0, h, min_separation);
+        lw_pos_request(B, L, first + (k + 2 < n ? k + 2 : k + 1), s0);
+        min_separation = lw_pos_visit(B, scratch, s1, h, min_separation);
+      }
+      if (k < n) min_separation = lw_pos_visit(B, scratch, s0, h, min_separation);
+      if (min_separation >= -3.0f * B2G_LINEAR_SLOP) {  // b2_island_private.rs:257-274
         B.isl_flags[isl] |= 1;
         break;
       }

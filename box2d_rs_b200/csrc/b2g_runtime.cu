@@ -913,7 +913,7 @@ static int large_alloc(BatchHost* bh) {
   AL(L.uf_parent, B.NB); AL(L.cnt_b, B.NB); AL(L.cnt_c, B.NB); AL(L.seed, B.NB); AL(L.isl_seed, B.NB);
   AL(L.pk_in, B.NB + 1LL); AL(L.pk_out, B.NB + 1LL);
   AL(L.keep_flag, B.NC + 1LL); AL(L.keep_pos, B.NC + 1LL);
-  AL(L.first_idx, B.NN); AL(L.vc_idx, B.NC);
+  AL(L.first_idx, B.NN); AL(L.vc_idx, B.NC); AL(L.scratch4, 16);
   AL(L.wake_idx, B.NB + 1LL);
   AL(L.state, B.NB); AL(L.adj, 2LL * B.NC); AL(L.eadj, 2LL * B.NC); AL(L.erow, B.NB); AL(L.row_start, B.NB); AL(L.row_end, B.NB);
 #undef AL
@@ -1066,8 +1066,10 @@ static int step_large(BatchHost* bh, const StepParams& sp, int steps) {
       { LwStaticRotK k = {B}; RC(launch(ctx, k, B.NB, 256, STAGE_INTEGRATE)); }
       { IntegrateK k = {B, sp}; RC(launch(ctx, k, nib, 128, STAGE_INTEGRATE)); }
       { SolverInitK k = {B, sp}; RC(launch(ctx, k, nic, 128, STAGE_SOLVER_INIT)); }
-      // default: the straight rotating-register sweeps (LwVelocity5K / LwPosition5K).  B2GPU_LW_VELOCITY selects the
-      // other forms for comparison: 1 distance-1 pipelines, 2 LwVelocity4K, 4 LwPosition4K (profiles/r01_large_world.md)
+      // default: LwVelocity5K (four rotating register sets, forwarding at the point of use) + LwPosition6K (two
+      // alternating sets).  B2GPU_LW_VELOCITY selects the other forms for comparison: 1 distance-1 pipelines with
+      // register moves, 2 LwVelocity4K, 3 LwVelocity5K + LwPositionK, 4 LwPosition4K, 5 LwPosition5K
+      // (profiles/r01_large_world.md)
       const int gs = bh->lw_velocity_variant;
       if (gs != 1) { LwVcIdxK k = {B, L, nic}; RC(launch(ctx, k, nic, 256, STAGE_SOLVER_INIT)); }
       if (gs == 1 || gs == 4) { LwVelocityK k = {B, sp, ni}; RC(launch(ctx, k, ni, 32, STAGE_VELOCITY)); }
@@ -1076,7 +1078,8 @@ static int step_large(BatchHost* bh, const StepParams& sp, int steps) {
       { PostVelocityK k = {B, sp}; RC(launch(ctx, k, std::max(std::max(ni, nib), nic), 128, STAGE_POST_VELOCITY)); }
       if (gs == 4) { LwPosition4K k = {B, L, sp, ni}; RC(launch(ctx, k, ni, 32, STAGE_POSITION)); }
       else if (gs == 1 || gs == 2 || gs == 3) { LwPositionK k = {B, sp, ni}; RC(launch(ctx, k, ni, 32, STAGE_POSITION)); }
-      else { LwPosition5K k = {B, L, sp, ni}; RC(launch(ctx, k, ni, 32, STAGE_POSITION)); }
+      else if (gs == 5) { LwPosition5K k = {B, L, sp, ni}; RC(launch(ctx, k, ni, 32, STAGE_POSITION)); }
+      else { LwPosition6K k = {B, L, sp, ni}; RC(launch(ctx, k, ni, 32, STAGE_POSITION)); }
       { FinalizeK k = {B, sp}; RC(launch(ctx, k, nib, 128, STAGE_FINALIZE)); }
       { SleepK k = {B}; RC(launch(ctx, k, ni, 128, STAGE_SLEEP)); }
       { SyncFixturesK k = {B}; RC(launch(ctx, k, B.NP, 128, STAGE_SYNC_FIXTURES)); }
