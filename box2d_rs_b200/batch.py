@@ -54,9 +54,10 @@ class Batch:
         # 'one_stream' = no stream groups; 'no_graph' = no CUDA graphs; 'pipelined' = branchy velocity kernel only;
         # 'producer' = straight-line velocity kernel with a producer warp; 'ml_position' = level-scheduled position;
         # 'levels2' = straight-line level-scheduled velocity kernel (two lanes per world);
-        # 'large' = large-world mode (exactly one world: data-parallel broadphase / islands, b2g_large.h)
+        # 'large' = large-world mode (exactly one world: data-parallel broadphase / islands, b2g_large.h);
+        # 'large_exact' = large-world mode that keeps the replica tree (reference contact order, bit-identical free-running)
         codes = {None: 0, 'generic': 1, 'lane': 2, 'levels': 3, 'tma': 4, 'one_stream': 5, 'no_graph': 6, 'pipelined': 7,
-                 'producer': 8, 'ml_position': 9, 'levels2': 10, 'large': 11}
+                 'producer': 8, 'ml_position': 9, 'levels2': 10, 'large': 11, 'large_exact': 12}
         caps.reserved[1] = 1 if generic_solver else codes[solver]
         self.h = C.c_void_p()
         c = proto.as_c()

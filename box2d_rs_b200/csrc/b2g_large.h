@@ -565,6 +565,41 @@ struct LwMoveFinishK {  // one thread
   }
 };
 
+// Exact-order variant of the mode (b2gpu_world_set_large_mode(w, 2)): the replica of the reference's tree IS
+// maintained — one thread re-inserts the moved proxies in synchronize order, exactly as TreePairsK does — and
+// every query walks that tree, so contacts are created in the reference's order and free-running state stays
+// bit-identical to the reference.  Everything else of the mode is unchanged.  The price is the sequential
+// re-insertion: fine while few proxies move per step (AddPair: hundreds), slow when most of a 100k world moves.
+struct LwTreeMoveK {  // one thread
+  Batch B;
+  B2G_HD void operator()(int) const {
+    WIdx x = widx(B, 0);
+    Ws ws = ws_of(B, x);
+    if (!ws[WS_EV_MOVED]) return;
+    Tree t = tree_of(B, x, ws);
+    int mc = ws[WS_MOVE_COUNT];
+    for (int wi = 0; wi < B.NMW; ++wi) {
+      unsigned bits = (unsigned)B.p_move[wi];
+      if (!bits) continue;
+      B.p_move[wi] = 0;
+      while (bits) {
+        const int bit = lowest_bit(bits);
+        bits &= bits - 1;
+        const int p = B.sync_order[wi * 32 + bit];
+        const int node = B.proxy_s[p].z;
+        t.remove_leaf(node);
+        t.aabb[node] = B.p_fat[p];
+        t.insert_leaf(node);
+        t.moved[node] = 1;
+        if (mc >= B.NMOVE) { ws[WS_STATUS] = B2GPU_E_CAPACITY; break; }
+        B.move_buf[mc++] = node;
+      }
+    }
+    ws[WS_MOVE_COUNT] = mc;
+    ws[WS_EV_MOVED] = 0;
+  }
+};
+
 B2G_HD unsigned lw_spread16(unsigned v) {  // 16 bits -> even bit positions
   v &= 0xffffu;
   v = (v | (v << 8)) & 0x00ff00ffu;
@@ -1037,7 +1072,7 @@ B2G_HD void lw_velocity_run(const Batch& B, const Large& L, int first, int n, in
   ix[0] = L.vc_idx[first];
   ix[1] = L.vc_idx[first + 1];
   ix[2] = L.vc_idx[first + 2];
-  ix[3] = make_int4(0, 0, 0, 0);
+  ix[3] = L.vc_idx[first + 3];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
@@ -1048,7 +1083,7 @@ B2G_HD void lw_velocity_run(const Batch& B, const Large& L, int first, int n, in
     va[j] = B.b_vel[ix[j].x];
     vb[j] = B.b_vel[ix[j].y];
   }
-  int k = 0, k2 = 2, k3 = 3;
+  int k = 0, k2 = 2, k4 = 4 % n;
   float4* scratch = L.scratch4;  // where the "results" of immovable bodies go
   // results of the two previous visits, for forwarding at the point of USE.  (Forwarding into the register sets
   // still in flight — as LwVelocity4K does — makes every select wait for the load it patches: ncu showed 37 % of
@@ -1061,14 +1096,16 @@ B2G_HD void lw_velocity_run(const Batch& B, const Large& L, int first, int n, in
 #pragma unroll
 #endif
     for (int j = 0; j < 4; ++j) {
-      const int j2 = (j + 2) & 3, j3 = (j + 3) & 3;
+      const int j2 = (j + 2) & 3;
       // inputs of this visit: requested two visits ago, so possibly older than the last two visits' results
       const int ba = ix[j].x, bb = ix[j].y, vc_points = ix[j].z;
+      // requests: the indices of visit v+4 take this visit's slot (they are needed two visits from now, to request
+      // the bodies of visit v+4: an index that is still in flight when its bodies are requested stalls the warp —
+      // ncu, second build); the record and the bodies of visit v+2
+      ix[j] = L.vc_idx[first + k4];
       float4 a = va[j], b = vb[j];
       a = ba == h1a ? r1a : ba == h1b ? r1b : ba == h2a ? r2a : ba == h2b ? r2b : a;
       b = bb == h1a ? r1a : bb == h1b ? r1b : bb == h2a ? r2a : bb == h2b ? r2b : b;
-      // requests: indices of visit v+3, record and bodies of visit v+2
-      ix[j3] = L.vc_idx[first + k3];
       {
         const float4* r = B.vc + (size_t)(first + k2) * VC_Q;
         q0[j2] = r[0]; q1[j2] = r[1]; q2[j2] = r[2]; q6[j2] = r[6]; q7[j2] = r[7];
@@ -1096,7 +1133,7 @@ B2G_HD void lw_velocity_run(const Batch& B, const Large& L, int first, int n, in
       h1a = ba; h1b = bb; r1a = na; r1b = nb;
       if (++k == n) k = 0;
       if (++k2 == n) k2 = 0;
-      if (++k3 == n) k3 = 0;
+      if (++k4 == n) k4 = 0;
     }
   }
   for (; v < total; ++v) {  // at most three visits left: every store above went to memory, plain loads are current
@@ -1400,16 +1437,18 @@ struct LwPosition5K {
 // bodies the previous visit wrote are forwarded at the point of use.  One inlined copy of solve_position_one per
 // set keeps the loop inside the instruction cache (the four-set forms above measured slower: stall_no_inst).
 struct LwPosSet { float4 p0, p1, p2, p3, p4, pa, pb, ra, rb; int4 ix; };
-B2G_HD void lw_pos_request(const Batch& B, const Large& L, int kk, LwPosSet& t) {
-  t.ix = L.vc_idx[kk];
+B2G_HD void lw_pos_request(const Batch& B, const Large& L, int kk, LwPosSet& t) {  // t.ix was loaded a visit earlier
   const float4* r = B.pc + (size_t)kk * PC_Q;
   t.p0 = r[0]; t.p1 = r[1]; t.p2 = r[2]; t.p3 = r[3]; t.p4 = r[4];
   t.pa = B.b_pos[t.ix.x]; t.ra = B.b_rot[t.ix.x];
   t.pb = B.b_pos[t.ix.y]; t.rb = B.b_rot[t.ix.y];
 }
 struct LwPosHist { int a, b; float4 pa, ra, pb, rb; };
-B2G_HD float lw_pos_visit(const Batch& B, float4* scratch, const LwPosSet& t, LwPosHist& h, float min_separation) {
+// One visit on set t; afterwards t.ix holds the indices of constraint `next_ix` (this set's next use, two visits
+// from now), requested before the arithmetic so they have landed when that visit's bodies are requested.
+B2G_HD float lw_pos_visit(const Batch& B, const Large& L, float4* scratch, LwPosSet& t, int next_ix, LwPosHist& h, float min_separation) {
   const int ba = t.ix.x, bb = t.ix.y, packed = t.ix.w;
+  t.ix = L.vc_idx[next_ix];
   float4 pa = t.pa, ra = t.ra, pb = t.pb, rb = t.rb;
   if (ba == h.a) { pa = h.pa; ra = h.ra; } else if (ba == h.b) { pa = h.pb; ra = h.rb; }
   if (bb == h.a) { pb = h.pa; rb = h.ra; } else if (bb == h.b) { pb = h.pb; rb = h.rb; }
@@ -1444,15 +1483,19 @@ struct LwPosition6K {
       h.a = -1; h.b = -1;
       h.pa = h.ra = h.pb = h.rb = make_float4(0, 0, 0, 0);
       LwPosSet s0, s1;
+      const int last = first + n - 1;
+      s0.ix = L.vc_idx[first];
+      s1.ix = L.vc_idx[first + 1 <= last ? first + 1 : last];
       lw_pos_request(B, L, first, s0);
       int k = 0;
       for (; k + 2 <= n; k += 2) {
-        lw_pos_request(B, L, first + k + 1, s1);
-        min_separation = lw_pos_visit(B, scratch, s0, h, min_separation);
-        lw_pos_request(B, L, first + (k + 2 < n ? k + 2 : k + 1), s0);
-        min_separation = lw_pos_visit(B, scratch, s1, h, min_separation);
+        const int c1 = first + k + 1, c2 = first + k + 2 <= last ? first + k + 2 : last, c3 = first + k + 3 <= last ? first + k + 3 : last;
+        lw_pos_request(B, L, c1, s1);
+        min_separation = lw_pos_visit(B, L, scratch, s0, c2, h, min_separation);
+        lw_pos_request(B, L, c2, s0);
+        min_separation = lw_pos_visit(B, L, scratch, s1, c3, h, min_separation);
       }
-      if (k < n) min_separation = lw_pos_visit(B, scratch, s0, h, min_separation);
+      if (k < n) min_separation = lw_pos_visit(B, L, scratch, s0, last, h, min_separation);
       if (min_separation >= -3.0f * B2G_LINEAR_SLOP) {  // b2_island_private.rs:257-274
         B.isl_flags[isl] |= 1;
         break;

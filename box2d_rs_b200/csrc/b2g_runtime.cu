@@ -521,11 +521,12 @@ int batch_create(Ctx* ctx, const b2gpu_snapshot* proto, int n_worlds, const b2gp
     if (rc) { batch_destroy(bh); return rc; }
   }
   bh->pre_step_needed = true;
-  if (caps && caps->reserved[1] == 11) {  // large-world mode: one world, data-parallel ordered stages (b2g_large.h)
+  if (caps && (caps->reserved[1] == 11 || caps->reserved[1] == 12)) {  // large-world mode (12: with the exact replica tree): one world, data-parallel ordered stages (b2g_large.h)
     if (n_worlds != 1 || B.LB != 1) { set_error("large-world mode needs a batch of exactly one world"); batch_destroy(bh); return B2GPU_E_INVALID; }
     rc = large_alloc(bh);
     if (rc) { batch_destroy(bh); return rc; }
     bh->large = true;
+    bh->lw_exact_tree = caps->reserved[1] == 12;
     if (const char* e = getenv("B2GPU_LW_VELOCITY")) bh->lw_velocity_variant = atoi(e);  // diagnostic, see step_large
   }
 #if !defined(B2G_HOSTSIM)
@@ -638,7 +639,7 @@ static int image_fetch(BatchHost* bh, int world, WorldImage& im) {
   image_alloc(bh->B, im);
   std::vector<ArrRef> tab = array_table(bh, im);
   for (const ArrRef& a : tab) RC(move_array(bh, a, 1, world));
-  if (bh->large) {
+  if (bh->large && !bh->lw_exact_tree) {
     // large-world mode does not maintain the replica tree: the leaf boxes are current, the topology is the
     // one last uploaded.  Refit the internal boxes (children before parents) so the snapshot carries a valid
     // bounding hierarchy for whoever continues from it (host-side proxy creation, the exact mode).
@@ -1086,7 +1087,11 @@ static int step_large(BatchHost* bh, const StepParams& sp, int steps) {
       // ---- find_new_contacts
       RC(lw_read(bh, B.ws, WS_COUNT));
       int mc = hw[WS_MOVE_COUNT];
-      if (hw[WS_EV_MOVED]) {
+      if (hw[WS_EV_MOVED] && bh->lw_exact_tree) {
+        { LwTreeMoveK k = {B}; RC(launch(ctx, k, 1, 32, STAGE_TREE_PAIRS)); }
+        mc += hw[WS_EV_MOVED];
+        if (mc > B.NMOVE) { set_error("move buffer capacity exceeded"); return B2GPU_E_CAPACITY; }
+      } else if (hw[WS_EV_MOVED]) {
         { LwMoveCountK k = {B, L}; RC(launch(ctx, k, B.NMW + 1, 256, STAGE_TREE_PAIRS)); }
         RC(lw_scan_int(bh, L.q_cnt, L.q_off, B.NMW + 1, STAGE_TREE_PAIRS));
         { LwMoveEmitK k = {B, L, mc}; RC(launch(ctx, k, B.NMW, 128, STAGE_TREE_PAIRS)); }
@@ -1094,7 +1099,7 @@ static int step_large(BatchHost* bh, const StepParams& sp, int steps) {
         if (mc > B.NMOVE) { set_error("move buffer capacity exceeded"); return B2GPU_E_CAPACITY; }
         { LwMoveFinishK k = {B, mc}; RC(launch(ctx, k, 1, 32, STAGE_TREE_PAIRS)); }
       }
-      RC(lw_update_pairs(bh, mc, cc, STAGE_TREE_PAIRS, 0));
+      RC(lw_update_pairs(bh, mc, cc, STAGE_TREE_PAIRS, bh->lw_exact_tree ? 1 : 0));
     }
     { LwStepEndK k = {B, sp}; RC(launch(ctx, k, 1, 32, STAGE_TREE_PAIRS)); }
     { BodyEndK k = {B}; RC(launch(ctx, k, B.NB, 128, STAGE_BODY_END)); }

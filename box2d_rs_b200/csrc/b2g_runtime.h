@@ -103,6 +103,7 @@ struct BatchHost {
   StepParams last_sp{};
   // large-world mode (b2g_large.h): one world, flat stages + scans + sorts, host-driven control flow
   bool large = false;
+  bool lw_exact_tree = false;    // large-world mode that keeps the replica tree (sequential re-insertion, reference contact order)
   Large L = {};
   int* lw_host = nullptr;        // pinned readback buffer (world scalars, scan totals)
   void* lw_tmp = nullptr;        // scan / sort temporary storage

@@ -245,7 +245,7 @@ struct b2gpu_world {
   bool host_dirty = true;   // host edits not on the device yet
   bool topo_dirty = true;   // bodies/fixtures changed: the device batch must be rebuilt
   bool dev_newer = false;   // the device holds the authoritative state
-  bool large = false;       // step with the data-parallel large-world stages (b2g_large.h)
+  int large = 0;            // 1: data-parallel large-world stages (b2g_large.h); 2: the same with the exact replica tree
 };
 
 namespace {
@@ -714,10 +714,11 @@ int b2gpu_world_set_warm_starting(b2gpu_world* W, int flag) { return set_world_f
 int b2gpu_world_set_block_solve(b2gpu_world* W, int flag) { return set_world_flag(W, B2GPU_WORLD_BLOCK_SOLVE, flag); }
 int b2gpu_world_set_large_mode(b2gpu_world* W, int flag) {
   if (!W) { set_error("world is NULL"); return B2GPU_E_INVALID; }
-  if ((flag != 0) == W->large) return 0;
+  if (flag < 0 || flag > 2) { set_error("large mode: 0, 1 or 2"); return B2GPU_E_INVALID; }
+  if (flag == W->large) return 0;
   int rc = ensure_host(W);  // bring the state back before the device batch is rebuilt in the other mode
   if (rc) return rc;
-  W->large = flag != 0;
+  W->large = flag;
   W->topo_dirty = true;
   return 0;
 }
@@ -741,7 +742,7 @@ int b2gpu_world_step(b2gpu_world* W, float dt, int vi, int pi) {
     fill_snapshot(W, &s, nodes);
     b2gpu_caps caps;
     memset(&caps, 0, sizeof(caps));
-    caps.reserved[1] = W->large ? 11 : 0;
+    caps.reserved[1] = W->large == 1 ? 11 : W->large == 2 ? 12 : 0;
     rc = batch_create(&W->ctx->c, &s, 1, &caps, 1, &W->dev);
     if (rc) return rc;
   } else if (W->host_dirty) {

@@ -128,7 +128,8 @@ class B2world:
 
     def set_large_mode(self, flag):
         """Data-parallel ordered stages for one large world (b2gpu_world_set_large_mode): same step semantics,
-        contacts created in one update_pairs call are appended in LBVH order instead of reference-tree order."""
+        contacts created in one update_pairs call are appended in LBVH order instead of reference-tree order.
+        flag = 2 keeps the replica tree (sequential re-insertion): reference contact order, bit-identical free-running."""
         check(self.L, self.L.b2gpu_world_set_large_mode(self.h, int(flag)))
 
     def step(self, dt, velocity_iterations, position_iterations):

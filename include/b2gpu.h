@@ -282,7 +282,7 @@ typedef struct b2gpu_caps {
                           4 TMA-fed velocity ring, 5 one stream (no stream groups), 6 no CUDA graphs, 7 branchy
                           velocity kernel only, 8 velocity kernel with a producer warp, 9 level-scheduled
                           position kernel, 10 straight-line level-scheduled velocity kernel (all bit-identical; profiles/r01_ncu_summary.md has their timings);
-                          11 large-world mode (one world only; see b2gpu_world_set_large_mode) */
+                          11 / 12 large-world mode (one world only; see b2gpu_world_set_large_mode flag 1 / 2) */
 } b2gpu_caps;
 
 typedef struct b2gpu_ctx b2gpu_ctx;
@@ -342,7 +342,11 @@ int b2gpu_world_set_block_solve(b2gpu_world* w, int flag);
  * the pair set, the created and destroyed contact sets and all body / manifold values are identical — but
  * contacts created within one update_pairs call are appended in LBVH order instead of the order of the
  * reference's incrementally balanced tree, so free-running trajectories may diverge from the reference after
- * a step that creates several contacts on one body (SURVEY.md H1 option ii).  Default 0: exact replica tree. */
+ * a step that creates several contacts on one body (SURVEY.md H1 option ii).
+ * flag == 2: the same data-parallel stages, but the replica of the reference's tree is kept (one thread re-inserts
+ * the moved proxies in order) and every query walks it: contacts are created in the reference's order and
+ * free-running state stays bit-identical to the reference; costs the sequential re-insertion when many proxies move.
+ * Default 0: exact replica tree, ordered stages one thread per world. */
 int b2gpu_world_set_large_mode(b2gpu_world* w, int flag);
 /* B2world::step (src/b2_world.rs:98; private :903-959) */
 int b2gpu_world_step(b2gpu_world* w, float dt, int velocity_iterations, int position_iterations);

@@ -338,3 +338,20 @@ def test_large_mode_free_running_is_deterministic(name, n_steps, ctx):
     for w in ws:
         w.close()
     hctx.close()
+
+
+@pytest.mark.parametrize("name", ["pyramid", "mixed300", "pile400", "addpair2000", "variety", "sensors"])
+def test_large_mode_exact_order_free_running(name, ctx):
+    """Large-world mode with the replica tree kept (flag 2): free-running, the whole snapshot — tree included —
+    is bit-identical to the oracle."""
+    from box2d_rs_b200 import scenes
+    wo, wg, steps = _pair(name, ctx)
+    wg.set_large_mode(2)
+    for i in range(steps):
+        wo.step(scenes.DT, 8, 3)
+        wg.step(scenes.DT, 8, 3)
+        if i < 2 or i % 50 == 49 or i == steps - 1:
+            bad = parity.compare_snapshots(wo.snapshot(), wg.snapshot()) + \
+                [b for b in parity.compare_stats(wo.get_stats(), wg.get_stats()) if "island_bodies" not in b]
+            assert bad == [], "step %d: %s" % (i, bad[:6])
+    wg.close()

@@ -170,3 +170,21 @@ def test_large_mode_wake_cascade_through_touching_changes(ctx):
     assert woke_in_one_step >= 4, woke_in_one_step  # the cascade really happened
     bt.close()
     wg.close()
+
+
+@pytest.mark.parametrize("name", list(SCENES))
+def test_large_mode_exact_order_free_running(name, ctx):
+    """b2gpu_world_set_large_mode(w, 2): the data-parallel stages with the replica tree kept (sequential
+    re-insertion, queries on that tree) create contacts in the reference's order, so the whole snapshot — tree
+    included — stays bit-identical to the oracle free-running, like the exact mode."""
+    from box2d_rs_b200 import scenes
+    wo, wg, steps = _pair(name, ctx)
+    wg.set_large_mode(2)
+    for i in range(steps):
+        wo.step(scenes.DT, 8, 3)
+        wg.step(scenes.DT, 8, 3)
+        if i < 2 or i % 40 == 39 or i == steps - 1:
+            bad = parity.compare_snapshots(wo.snapshot(), wg.snapshot()) + \
+                [b for b in parity.compare_stats(wo.get_stats(), wg.get_stats()) if "island_bodies" not in b]
+            assert bad == [], "step %d: %s" % (i, bad[:6])
+    wg.close()
