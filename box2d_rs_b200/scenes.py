@@ -234,3 +234,33 @@ def sensors(world, seed=0xB2D + 11):
                                                    for i in range(nv)]))
         bodies.append(b)
     return bodies
+
+
+def terrain(world, n=160, segments=1200, seed=0xB2D + 13):
+    """Chain shapes at scale: ONE chain fixture of `segments` one-sided edges with ghost
+    vertices (a rolling height field, 0.5 m per edge: `segments` proxies, child-edge materialisation per
+    contact, b2_chain_shape.rs(private):59-79) plus a closed chain loop as an obstacle; circles and polygons
+    of every archetype rain on it, roll downhill and pile up in the valleys."""
+    rng = SplitMix64(seed)
+    ground = world.create_body(BodyDef())
+    half = 0.25 * segments
+    pts = []
+    for i in range(segments + 1):
+        x = half - 0.5 * i  # right to left: the solid side of a one-sided chain is on the right of its direction
+        y = 3.0 * math.sin(0.045 * x) + 1.2 * math.sin(0.31 * x + 1.0) + 0.02 * abs(x)
+        pts.append((f32(x), f32(y)))
+    ground.create_fixture(FixtureDef(friction=0.6), world.shapes.chain(pts, (f32(half + 0.5), pts[0][1]), (f32(-half - 0.5), pts[-1][1])))
+    loop = [(f32(2.0 * math.cos(2 * math.pi * i / 12)), f32(9.0 + 1.0 * math.sin(2 * math.pi * i / 12))) for i in range(12)]
+    ground.create_fixture(FixtureDef(friction=0.4), world.shapes.chain(loop, (0.0, 0.0), (0.0, 0.0), loop=True))
+    shapes = [world.shapes.circle(0.35), world.shapes.polygon_box(0.4, 0.3), world.shapes.circle(0.2),
+              world.shapes.polygon([(-0.4, -0.3), (0.4, -0.3), (0.0, 0.45)]),
+              world.shapes.polygon([(f32(0.4 * math.cos(2 * math.pi * i / 8)), f32(0.4 * math.sin(2 * math.pi * i / 8))) for i in range(8)])]
+    bodies = []
+    for k in range(n):
+        px = f32(-0.2 * segments + 0.4 * segments * ((k * 37) % n) / n + rng.uniform(-0.3, 0.3))
+        py = f32(12.0 + 1.1 * (k % 7) + rng.uniform(-0.2, 0.2))
+        b = world.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(px, py), angle=f32(rng.uniform(-3.0, 3.0)),
+                                      linear_velocity=(f32(rng.uniform(-2.0, 2.0)), 0.0)))
+        b.create_fixture(FixtureDef(density=1.0, friction=0.4, restitution=0.1 if k % 5 == 0 else 0.0), shapes[int(rng.next() % 5)])
+        bodies.append(b)
+    return bodies

@@ -37,4 +37,5 @@ SCENES = {
     "addpair2000": (lambda s, w: s.add_pair(w, n=2000), (0.0, 0.0), 150),
     "variety": (lambda s, w: s.variety(w), (0.0, -10.0), 400),
     "sensors": (lambda s, w: s.sensors(w), (0.0, -10.0), 300),
+    "terrain": (lambda s, w: s.terrain(w), (0.0, -10.0), 260),
 }

@@ -25,6 +25,7 @@ CASES = {
     "addpair2000": ("addpair2000", (1, 40, 120)),
     "variety": ("variety", (1, 60, 200, 400)),
     "sensors": ("sensors", (1, 60, 150, 300)),
+    "terrain": ("terrain", (1, 80, 160, 260)),
 }
 
 

@@ -170,7 +170,7 @@ def test_full_size_batch_properties(ctx):
     wg.close()
 
 
-@pytest.mark.parametrize("name", ["pyramid", "mixed300", "pile400", "addpair2000", "hello_world", "variety", "sensors"])
+@pytest.mark.parametrize("name", ["pyramid", "mixed300", "pile400", "addpair2000", "hello_world", "variety", "sensors", "terrain"])
 def test_gpu_matches_golden(name, ctx):
     """The committed fixtures (tests/golden, produced by the oracle) reproduced by the CUDA path, in a
     40-world batch (shared-memory solver and island kernels), bit for bit."""
@@ -294,7 +294,7 @@ def test_step_host_overlapped_copies_match_plain_calls(ctx):
 # large-world mode (b2g_large.h): data-parallel broadphase / destruction / islands for one big world
 # ---------------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("name,every", [("pyramid", 3), ("mixed300", 3), ("pile400", 2), ("variety", 2), ("sensors", 3),
-                                        ("addpair2000", 5)])
+                                        ("addpair2000", 5), ("terrain", 3)])
 def test_large_mode_teacher_forced(name, every, ctx):
     """Every step of the large-world mode is the oracle's step of the same state: upload S_n, step both once,
     compare everything bit for bit (contacts created in that step as a set: they are appended in LBVH order)."""
@@ -340,7 +340,7 @@ def test_large_mode_free_running_is_deterministic(name, n_steps, ctx):
     hctx.close()
 
 
-@pytest.mark.parametrize("name", ["pyramid", "mixed300", "pile400", "addpair2000", "variety", "sensors"])
+@pytest.mark.parametrize("name", ["pyramid", "mixed300", "pile400", "addpair2000", "variety", "sensors", "terrain"])
 def test_large_mode_exact_order_free_running(name, ctx):
     """Large-world mode with the replica tree kept (flag 2): free-running, the whole snapshot — tree included —
     is bit-identical to the oracle."""

@@ -41,7 +41,7 @@ def teacher_forced(wo, bt, steps, every, world_index=0):
 
 
 @pytest.mark.parametrize("name,every", [("hello_world", 1), ("pyramid", 2), ("mixed300", 2), ("pile400", 2), ("variety", 1),
-                                        ("sensors", 1), ("addpair2000", 3)])
+                                        ("sensors", 1), ("addpair2000", 3), ("terrain", 2)])
 def test_large_mode_teacher_forced(name, every, ctx):
     wo, wg, steps = _pair(name, ctx)
     bt = wg.batch(1, lane_block=1, solver='large')

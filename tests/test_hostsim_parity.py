@@ -155,7 +155,7 @@ def test_forces_and_velocity_inputs(ctx):
     wg.close()
 
 
-@pytest.mark.parametrize("name", ["pyramid", "mixed300"])
+@pytest.mark.parametrize("name", ["pyramid", "mixed300", "terrain"])
 def test_simulator_matches_golden(name, ctx):
     import sys
     sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))

@@ -116,7 +116,7 @@ def test_restated_sincos_matches_libm_on_host(b2o):
     ctx.close()
 
 
-@pytest.mark.parametrize("name", ["pyramid", "hello_world", "mixed300", "pile400", "addpair2000", "variety", "sensors"])
+@pytest.mark.parametrize("name", ["pyramid", "hello_world", "mixed300", "pile400", "addpair2000", "variety", "sensors", "terrain"])
 def test_oracle_matches_golden(name, b2o):
     """The committed fixtures (tests/golden/make_golden.py) pin the oracle's trajectories bit for bit."""
     import sys
