@@ -130,7 +130,11 @@ def single_world_leg(ctx):
     from box2d_rs_b200 import scenes, world
     from oracle import b2o  # measured CPU arm
     out = {"mode": "large-world (data-parallel broadphase / destruction / islands; exact Gauss-Seidel order per island)",
-           "cpu": "C++ oracle restating box2d-rs, 1 thread"}
+           "cpu": "C++ oracle restating box2d-rs, 1 thread",
+           "note": "free-running: contacts created in one update_pairs call are appended in LBVH order, so after many steps the "
+                   "trajectory (and the contact counts) differ from the oracle's, as two valid Box2D runs do; every single step "
+                   "is the oracle's step of the same state (tests: test_large_mode_teacher_forced); "
+                   "b2gpu_world_set_large_mode(w, 2) keeps the reference order at the price of sequential tree updates"}
     cases = [("addpair20k", lambda w: scenes.add_pair(w, n=20000), (0.0, 0.0), 5, 40),
              ("pile100k", lambda w: scenes.pile(w, n=100000), (0.0, -10.0), 3, 12)]
     for name, recipe, gravity, skip, steps in cases:

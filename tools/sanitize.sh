@@ -19,6 +19,19 @@ for name, build, g in (("pyramid", scenes.pyramid, (0.0, -10.0)), ("variety", sc
     w.close()
 PY
 for tool in memcheck racecheck; do
+  [ "${1:-}" = "large" ] && break
   echo "==== compute-sanitizer --tool $tool"
   timeout 900 compute-sanitizer --tool $tool --print-limit 200 python /tmp/b2g_sanitize_case.py 2>&1 | tail -60
 done
+
+# large-world mode (b2g_large.h): global-memory kernels only, so memcheck + initcheck (racecheck covers shared memory).
+# Run alone with:  bash tools/sanitize.sh large
+if [ "${1:-}" = "large" ] || [ "${1:-}" = "all" ]; then
+  for tool in memcheck initcheck; do
+    for sc in "pile 400 40 1" "addpair 1500 60 1" "variety 0 120 2"; do
+      set -- $sc
+      echo "==== compute-sanitizer --tool $tool  large-world mode $4: $1 n=$2 steps=$3"
+      timeout 600 compute-sanitizer --tool $tool --print-limit 50 python tools/large_smoke.py --scene $1 --n $2 --steps $3 --mode $4 2>&1 | tail -8
+    done
+  done
+fi
