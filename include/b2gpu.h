@@ -361,6 +361,31 @@ int b2gpu_world_snapshot_sizes(b2gpu_world* w, b2gpu_snapshot_sizes* out);
 int b2gpu_world_download(b2gpu_world* w, b2gpu_snapshot* out);
 int b2gpu_world_upload(b2gpu_world* w, const b2gpu_snapshot* in);
 
+/* ------------------------------------------------------------ world queries
+ * B2world::ray_cast (src/private/dynamics/b2_world.rs:1015-1049) with the "closest hit" callback
+ * `|fixture, point, normal, fraction| fraction`, and B2world::query_aabb (:969-980) with a callback that
+ * always continues, for n rays / boxes at once on the device: one thread per query walks the broadphase tree
+ * (b2_dynamic_tree.rs:239-347; the LBVH in large-world mode 1) and runs the reference's shape ray casts
+ * (b2_circle_shape.rs(private):26-62, b2_edge_shape.rs(private):39-102, b2_polygon_shape.rs(private):226-290,
+ * b2_chain_shape.rs(private):86-108).  State = the world after its last step (or as built). */
+typedef struct b2gpu_ray_hit {
+  int32_t fixture;     /* -1: the ray hit nothing */
+  int32_t child_index;
+  float fraction;      /* output.fraction of the closest hit */
+  float point_x, point_y;   /* (1 - fraction) * p1 + fraction * p2 */
+  float normal_x, normal_y;
+  int32_t reserved;
+} b2gpu_ray_hit;
+/* p1p2: host array [n][4] = p1.x p1.y p2.x p2.y (p1 != p2, the reference asserts it); out: host array [n]. */
+int b2gpu_world_ray_cast_closest(b2gpu_world* w, const float* p1p2, int n, b2gpu_ray_hit* out);
+/* aabbs: host array [n][4] = lower.x lower.y upper.x upper.y; counts[n] = proxies whose fat AABB overlaps box i
+ * (may exceed max_hits: then only the first max_hits are stored); hits: host array [n][max_hits][2] =
+ * (fixture, child index) in the order the reference's tree query reports them (LBVH order in large-world mode 1). */
+int b2gpu_world_query_aabb(b2gpu_world* w, const float* aabbs, int n, int max_hits, int32_t* counts, int32_t* hits);
+/* The same for every world of a batch: rays [n_worlds][rays_per_world][4], out [n_worlds][rays_per_world]
+ * (an RL-style range sensor: one launch for all worlds). */
+int b2gpu_batch_ray_cast_closest(b2gpu_batch* b, const float* p1p2, int rays_per_world, b2gpu_ray_hit* out);
+
 /* ---------------------------------------- batched independent worlds (RL-style) */
 /* n_worlds replicas of `proto`, one CTA per world per step. */
 int b2gpu_batch_create(b2gpu_ctx* ctx, const b2gpu_snapshot* proto, int n_worlds, const b2gpu_caps* caps, b2gpu_batch** out);

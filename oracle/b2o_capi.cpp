@@ -8,6 +8,7 @@
 
 #include "../include/b2gpu.h"
 #include "b2o_world.hpp"
+#include "b2o_query.hpp"
 
 using namespace b2o;
 
@@ -154,6 +155,35 @@ void b2o_get_stats(void* w, b2gpu_step_stats* out) {
   out->contacts = s.contacts; out->touching = s.touching; out->destroyed = s.destroyed; out->islands = s.islands;
   out->island_bodies = s.island_bodies; out->island_contacts = s.island_contacts; out->moved = s.moved; out->pairs = s.pairs;
   out->created = s.created; out->awake_bodies = s.awake_bodies; out->solver_levels = s.solver_levels;
+}
+
+// ---- world queries (b2o_query.hpp): same record layout as b2gpu_ray_hit / b2gpu_world_query_aabb
+void b2o_ray_cast_closest(void* w, const float* p1p2, int n, b2gpu_ray_hit* out) {
+  const World& W = *(World*)w;
+  for (int i = 0; i < n; ++i) {
+    RayHit h = world_ray_cast_closest(W, Vec2(p1p2[4 * i], p1p2[4 * i + 1]), Vec2(p1p2[4 * i + 2], p1p2[4 * i + 3]));
+    std::memset(&out[i], 0, sizeof(out[i]));
+    out[i].fixture = h.fixture;
+    out[i].child_index = h.child;
+    out[i].fraction = h.fraction;
+    out[i].point_x = h.point.x; out[i].point_y = h.point.y;
+    out[i].normal_x = h.normal.x; out[i].normal_y = h.normal.y;
+  }
+}
+void b2o_query_aabb(void* w, const float* boxes, int n, int max_hits, int* counts, int* hits) {
+  const World& W = *(World*)w;
+  for (int i = 0; i < n; ++i) {
+    AABB box;
+    box.lower = Vec2(boxes[4 * i], boxes[4 * i + 1]);
+    box.upper = Vec2(boxes[4 * i + 2], boxes[4 * i + 3]);
+    std::vector<std::pair<int, int>> found;
+    world_query_aabb(W, box, found);
+    counts[i] = (int)found.size();
+    for (int k = 0; k < (int)found.size() && k < max_hits; ++k) {
+      hits[((size_t)i * max_hits + k) * 2] = found[k].first;
+      hits[((size_t)i * max_hits + k) * 2 + 1] = found[k].second;
+    }
+  }
 }
 
 // ---- snapshot export in the b2gpu.h format
