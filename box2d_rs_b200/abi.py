@@ -249,3 +249,8 @@ def chain_shape(vertices, prev_vertex, next_vertex, loop=False):
     s.chain_prev[0], s.chain_prev[1] = prev_vertex
     s.chain_next[0], s.chain_next[1] = next_vertex
     return s
+
+
+# b2gpu_ray_hit (include/b2gpu.h)
+RAY_HIT_DTYPE = np.dtype([("fixture", np.int32), ("child_index", np.int32), ("fraction", np.float32), ("point", np.float32, 2),
+                          ("normal", np.float32, 2), ("reserved", np.int32)])

@@ -104,6 +104,14 @@ class Batch:
         check(self.L, self.L.b2gpu_batch_step_host(self.h, fp, state_out.ctypes.data, dt, velocity_iterations,
                                                    position_iterations, steps))
 
+    def ray_cast_closest(self, p1p2):
+        """Closest-hit ray casts in every world: p1p2 [n_worlds][rays][4] -> abi.RAY_HIT_DTYPE [n_worlds][rays]."""
+        rays = np.ascontiguousarray(p1p2, np.float32)
+        assert rays.ndim == 3 and rays.shape[0] == self.n_worlds and rays.shape[2] == 4
+        out = np.zeros(rays.shape[:2], abi.RAY_HIT_DTYPE)
+        check(self.L, self.L.b2gpu_batch_ray_cast_closest(self.h, rays.ctypes.data, rays.shape[1], out.ctypes.data))
+        return out
+
     def algorithmic_bytes(self):
         return int(self.L.b2gpu_batch_algorithmic_bytes(self.h))
 

@@ -25,6 +25,7 @@ void set_error(const std::string& s) { g_error = s; }
 #define RC(x) do { int rc_ = (x); if (rc_ != 0) return rc_; } while (0)
 
 static int large_alloc(BatchHost* bh);
+static int lw_build_lbvh(BatchHost* bh, int stage);
 static void large_free(BatchHost* bh);
 
 // ------------------------------------------------------------------ device abstraction
@@ -958,6 +959,19 @@ static int lw_rebuild_lists(BatchHost* bh, int cc, int stage) {
   return 0;
 }
 
+// LBVH over the fat boxes of all proxies: Morton keys, radix sort, Karras construction, bottom-up refit
+static int lw_build_lbvh(BatchHost* bh, int stage) {
+  Ctx* ctx = bh->ctx;
+  const Batch& B = bh->B;
+  const Large& L = bh->L;
+  const int n = B.NP;
+  { LwMortonK k = {B, L}; RC(launch(ctx, k, n, 256, stage)); }
+  RC(lw_sort_keys(bh, L.keys, L.keys_alt, n, 64, stage));
+  { LwKarrasK k = {B, L, n}; RC(launch(ctx, k, n, 128, stage)); }
+  { LwRefitK k = {B, L, n}; RC(launch(ctx, k, n, 128, stage)); }
+  return 0;
+}
+
 // B2broadPhase::update_pairs + add_pair over the current move buffer (mc entries, cc contacts before)
 static int lw_update_pairs(BatchHost* bh, int mc, int cc, int stage, int use_tree) {
   Ctx* ctx = bh->ctx;
@@ -965,12 +979,7 @@ static int lw_update_pairs(BatchHost* bh, int mc, int cc, int stage, int use_tre
   const Large& L = bh->L;
   if (mc <= 0) return 0;
   const int n = B.NP;
-  if (!use_tree) {
-    { LwMortonK k = {B, L}; RC(launch(ctx, k, n, 256, stage)); }
-    RC(lw_sort_keys(bh, L.keys, L.keys_alt, n, 64, stage));
-    { LwKarrasK k = {B, L, n}; RC(launch(ctx, k, n, 128, stage)); }
-    { LwRefitK k = {B, L, n}; RC(launch(ctx, k, n, 128, stage)); }
-  }
+  if (!use_tree) RC(lw_build_lbvh(bh, stage));
   if (use_tree) {
     { LwMoveFirstK k = {B, L, mc, 0}; RC(launch(ctx, k, mc, 256, stage)); }
     { LwMoveFirstK k = {B, L, mc, 1}; RC(launch(ctx, k, mc, 256, stage)); }
@@ -1104,6 +1113,66 @@ static int step_large(BatchHost* bh, const StepParams& sp, int steps) {
     { LwStepEndK k = {B, sp}; RC(launch(ctx, k, 1, 32, STAGE_TREE_PAIRS)); }
     { BodyEndK k = {B}; RC(launch(ctx, k, B.NB, 128, STAGE_BODY_END)); }
   }
+  return 0;
+}
+
+// ------------------------------------------------------------------ world queries (b2g_query.h)
+struct DevTmp {  // device scratch of one call
+  std::vector<void*> p;
+  ~DevTmp() { for (void* v : p) dev_free(v); }
+  template <class T> int get(T** out, size_t count) {
+    void* v = nullptr;
+    int rc = dev_alloc(&v, std::max<size_t>(count, 1) * sizeof(T));
+    if (rc) return rc;
+    p.push_back(v);
+    *out = (T*)v;
+    return 0;
+  }
+};
+static int query_prepare(BatchHost* bh, int& use_lbvh) {
+  use_lbvh = bh->large && !bh->lw_exact_tree;  // the replica tree is current in every other mode
+  if (use_lbvh && bh->B.NP > 0) RC(lw_build_lbvh(bh, STAGE_OTHER));
+  return 0;
+}
+int batch_ray_cast_closest(BatchHost* bh, const float* host_rays, int rays_per_world, b2gpu_ray_hit* host_out) {
+  if (!bh || !host_rays || !host_out || rays_per_world < 0) { set_error("ray_cast: bad argument"); return B2GPU_E_INVALID; }
+  const Batch& B = bh->B;
+  const long long total = (long long)B.n_worlds * rays_per_world;
+  if (total == 0) return 0;
+  if (total > 0x7fffffffLL) { set_error("ray_cast: too many rays"); return B2GPU_E_CAPACITY; }
+  for (long long i = 0; i < total; ++i)
+    if (host_rays[4 * i] == host_rays[4 * i + 2] && host_rays[4 * i + 1] == host_rays[4 * i + 3]) {
+      set_error("ray_cast: p1 == p2 (the reference asserts length_squared > 0)");
+      return B2GPU_E_INVALID;
+    }
+  DevTmp tmp;
+  float* d_rays = nullptr;
+  b2gpu_ray_hit* d_out = nullptr;
+  RC(tmp.get(&d_rays, (size_t)total * 4));
+  RC(tmp.get(&d_out, (size_t)total));
+  RC(dev_h2d(bh->ctx, d_rays, host_rays, (size_t)total * 16));
+  int use_lbvh = 0;
+  RC(query_prepare(bh, use_lbvh));
+  { RayCastK k = {B, bh->L, d_rays, d_out, rays_per_world, use_lbvh, B.NP}; RC(launch(bh->ctx, k, (int)total, 64)); }
+  RC(dev_d2h(bh->ctx, host_out, d_out, (size_t)total * sizeof(b2gpu_ray_hit)));
+  return 0;
+}
+int batch_query_aabb(BatchHost* bh, const float* host_boxes, int n, int max_hits, int* host_counts, int* host_hits) {
+  if (!bh || !host_boxes || !host_counts || n < 0 || max_hits < 0 || (max_hits > 0 && !host_hits)) { set_error("query_aabb: bad argument"); return B2GPU_E_INVALID; }
+  if (bh->B.n_worlds != 1) { set_error("query_aabb: one world at a time"); return B2GPU_E_INVALID; }
+  if (n == 0) return 0;
+  DevTmp tmp;
+  float* d_boxes = nullptr;
+  int *d_counts = nullptr, *d_hits = nullptr;
+  RC(tmp.get(&d_boxes, (size_t)n * 4));
+  RC(tmp.get(&d_counts, (size_t)n));
+  RC(tmp.get(&d_hits, (size_t)n * max_hits * 2));
+  RC(dev_h2d(bh->ctx, d_boxes, host_boxes, (size_t)n * 16));
+  int use_lbvh = 0;
+  RC(query_prepare(bh, use_lbvh));
+  { QueryAabbK k = {bh->B, bh->L, d_boxes, d_counts, d_hits, n, max_hits, use_lbvh, bh->B.NP}; RC(launch(bh->ctx, k, n, 64)); }
+  RC(dev_d2h(bh->ctx, host_counts, d_counts, (size_t)n * 4));
+  if (max_hits > 0) RC(dev_d2h(bh->ctx, host_hits, d_hits, (size_t)n * max_hits * 8));
   return 0;
 }
 

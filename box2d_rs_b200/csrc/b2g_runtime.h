@@ -9,6 +9,7 @@
 
 #include "b2g_step.h"
 #include "b2g_large.h"
+#include "b2g_query.h"
 #include "b2g_island_layout.h"
 
 namespace b2g {
@@ -128,6 +129,8 @@ int batch_get_stats(BatchHost* b, int first, int count, b2gpu_step_stats* out);
 int batch_get_body_state(BatchHost* b, float* host_out, int first, int count);
 int batch_set_forces(BatchHost* b, const float* host, int first, int count);
 int batch_set_linear_velocity(BatchHost* b, int body, const float* host_vxvy, int first, int count);
+int batch_ray_cast_closest(BatchHost* b, const float* host_rays, int rays_per_world, b2gpu_ray_hit* host_out);
+int batch_query_aabb(BatchHost* b, const float* host_boxes, int n, int max_hits, int* host_counts, int* host_hits);
 int ctx_sync(Ctx* ctx);
 int debug_sincos(Ctx* ctx, const float* host_in, float* host_sin, float* host_cos, int n);
 long long batch_algorithmic_bytes(BatchHost* b);

@@ -728,9 +728,8 @@ int b2gpu_world_set_continuous_physics(b2gpu_world* W, int flag) {
   return 0;
 }
 
-int b2gpu_world_step(b2gpu_world* W, float dt, int vi, int pi) {
-  GUARD_BEGIN
-  if (!W) { set_error("world is NULL"); return B2GPU_E_INVALID; }
+// The device batch of a world, created / refreshed from the host mirror when the user edited the world.
+static int ensure_device(b2gpu_world* W) {
   if (W->h.bodies.empty()) { set_error("world has no bodies"); return B2GPU_E_INVALID; }
   int rc;
   if (!W->dev || W->topo_dirty) {
@@ -753,10 +752,35 @@ int b2gpu_world_step(b2gpu_world* W, float dt, int vi, int pi) {
     if (rc) return rc;
   }
   W->host_dirty = W->topo_dirty = false;
+  return 0;
+}
+
+int b2gpu_world_step(b2gpu_world* W, float dt, int vi, int pi) {
+  GUARD_BEGIN
+  if (!W) { set_error("world is NULL"); return B2GPU_E_INVALID; }
+  int rc = ensure_device(W);
+  if (rc) return rc;
   rc = batch_step(W->dev, dt, vi, pi, 1);
   if (rc) return rc;
   W->dev_newer = true;
   return 0;
+  GUARD_END
+}
+
+int b2gpu_world_ray_cast_closest(b2gpu_world* W, const float* p1p2, int n, b2gpu_ray_hit* out) {
+  GUARD_BEGIN
+  if (!W) { set_error("world is NULL"); return B2GPU_E_INVALID; }
+  int rc = ensure_device(W);
+  if (rc) return rc;
+  return batch_ray_cast_closest(W->dev, p1p2, n, out);
+  GUARD_END
+}
+int b2gpu_world_query_aabb(b2gpu_world* W, const float* aabbs, int n, int max_hits, int32_t* counts, int32_t* hits) {
+  GUARD_BEGIN
+  if (!W) { set_error("world is NULL"); return B2GPU_E_INVALID; }
+  int rc = ensure_device(W);
+  if (rc) return rc;
+  return batch_query_aabb(W->dev, aabbs, n, max_hits, counts, hits);
   GUARD_END
 }
 

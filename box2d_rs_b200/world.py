@@ -159,6 +159,23 @@ class B2world:
         c = snap.as_c()
         check(self.L, self.L.b2gpu_world_upload(self.h, C.byref(c)))
 
+    def ray_cast_closest(self, p1p2):
+        """B2world::ray_cast with the closest-hit callback for an [n][4] array of rays (p1.x p1.y p2.x p2.y).
+        Returns a structured array (abi.RAY_HIT_DTYPE); fixture == -1 where nothing was hit."""
+        rays = np.ascontiguousarray(p1p2, np.float32).reshape(-1, 4)
+        out = np.zeros(rays.shape[0], abi.RAY_HIT_DTYPE)
+        check(self.L, self.L.b2gpu_world_ray_cast_closest(self.h, rays.ctypes.data, rays.shape[0], out.ctypes.data))
+        return out
+
+    def query_aabb(self, aabbs, max_hits=64):
+        """B2world::query_aabb for an [n][4] array of boxes: list of [(fixture, child), ...] per box, report order."""
+        boxes = np.ascontiguousarray(aabbs, np.float32).reshape(-1, 4)
+        counts = np.zeros(boxes.shape[0], np.int32)
+        hits = np.zeros((boxes.shape[0], max(max_hits, 1), 2), np.int32)
+        check(self.L, self.L.b2gpu_world_query_aabb(self.h, boxes.ctypes.data, boxes.shape[0], max_hits, counts.ctypes.data,
+                                                    hits.ctypes.data))
+        return [[(int(f), int(c)) for f, c in hits[i, :min(int(counts[i]), max_hits)]] for i in range(boxes.shape[0])], counts
+
     def batch(self, n_worlds, **kw):
         """n_worlds replicas of this world's current state, one CTA lane per world (b2gpu_batch_create)."""
         return Batch(self.ctx, self.snapshot(), n_worlds, **kw)

@@ -51,6 +51,8 @@ def lib():
         L.b2o_contact_count.argtypes = [C.c_void_p]
         L.b2o_get_profile.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         L.b2o_get_stats.argtypes = [C.c_void_p, C.c_void_p]
+        L.b2o_ray_cast_closest.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
+        L.b2o_query_aabb.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.b2o_snapshot_sizes.argtypes = [C.c_void_p, C.POINTER(abi.SnapshotSizes)]
         L.b2o_snapshot_export.argtypes = [C.c_void_p, C.POINTER(abi.SnapshotC)]
         L.b2o_get_body_state.argtypes = [C.c_void_p, C.c_void_p]
@@ -193,6 +195,19 @@ class B2world:
         out = np.zeros(1, abi.STATS_DTYPE)
         lib().b2o_get_stats(self.h, out.ctypes.data)
         return out[0]
+
+    def ray_cast_closest(self, p1p2):
+        rays = np.ascontiguousarray(p1p2, np.float32).reshape(-1, 4)
+        out = np.zeros(rays.shape[0], abi.RAY_HIT_DTYPE)
+        lib().b2o_ray_cast_closest(self.h, rays.ctypes.data, rays.shape[0], out.ctypes.data)
+        return out
+
+    def query_aabb(self, aabbs, max_hits=64):
+        boxes = np.ascontiguousarray(aabbs, np.float32).reshape(-1, 4)
+        counts = np.zeros(boxes.shape[0], np.int32)
+        hits = np.zeros((boxes.shape[0], max(max_hits, 1), 2), np.int32)
+        lib().b2o_query_aabb(self.h, boxes.ctypes.data, boxes.shape[0], max_hits, counts.ctypes.data, hits.ctypes.data)
+        return [[(int(f), int(c)) for f, c in hits[i, :min(int(counts[i]), max_hits)]] for i in range(boxes.shape[0])], counts
 
     def snapshot(self):
         n = abi.SnapshotSizes()

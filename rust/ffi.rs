@@ -110,6 +110,18 @@ pub struct b2gpu_caps {
     pub max_pairs: i32, pub reserved: [i32; 2],
 }
 
+/// b2gpu_ray_hit (include/b2gpu.h): closest hit of one ray, fixture == -1 when nothing was hit.
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct b2gpu_ray_hit {
+    pub fixture: i32,
+    pub child_index: i32,
+    pub fraction: c_float,
+    pub point: [c_float; 2],
+    pub normal: [c_float; 2],
+    pub reserved: i32,
+}
+
 extern "C" {
     pub fn b2gpu_abi_version() -> c_int;
     pub fn b2gpu_last_error() -> *const c_char;
@@ -136,6 +148,9 @@ extern "C" {
     pub fn b2gpu_world_set_continuous_physics(w: *mut b2gpu_world, flag: c_int) -> c_int;
     pub fn b2gpu_world_set_block_solve(w: *mut b2gpu_world, flag: c_int) -> c_int;
     pub fn b2gpu_world_set_large_mode(w: *mut b2gpu_world, flag: c_int) -> c_int;
+    pub fn b2gpu_world_ray_cast_closest(w: *mut b2gpu_world, p1p2: *const c_float, n: c_int, out: *mut b2gpu_ray_hit) -> c_int;
+    pub fn b2gpu_world_query_aabb(w: *mut b2gpu_world, aabbs: *const c_float, n: c_int, max_hits: c_int, counts: *mut i32, hits: *mut i32) -> c_int;
+    pub fn b2gpu_batch_ray_cast_closest(b: *mut b2gpu_batch, p1p2: *const c_float, rays_per_world: c_int, out: *mut b2gpu_ray_hit) -> c_int;
     pub fn b2gpu_world_step(w: *mut b2gpu_world, dt: c_float, velocity_iterations: c_int, position_iterations: c_int) -> c_int;
     pub fn b2gpu_world_get_body_count(w: *mut b2gpu_world) -> c_int;
     pub fn b2gpu_world_get_contact_count(w: *mut b2gpu_world) -> c_int;
