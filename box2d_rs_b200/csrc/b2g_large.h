@@ -1085,27 +1085,30 @@ B2G_HD void lw_velocity_run(const Batch& B, const Large& L, int first, int n, in
   }
   int k = 0, k2 = 2, k4 = 4 % n;
   float4* scratch = L.scratch4;  // where the "results" of immovable bodies go
-  // results of the two previous visits, for forwarding at the point of USE.  (Forwarding into the register sets
-  // still in flight — as LwVelocity4K does — makes every select wait for the load it patches: ncu showed 37 % of
-  // the samples on those selects, stall_long_scoreboard.)  Body -1 matches nothing.
-  int h1a = -1, h1b = -1, h2a = -1, h2b = -1;
-  float4 r1a = make_float4(0, 0, 0, 0), r1b = r1a, r2a = r1a, r2b = r1a;
+  // Forwarding at the point of USE: the results of a visit stay in its register set (va / vb), the bodies it
+  // touched in hba / hbb; a visit patches its own inputs from the sets of the two previous visits before the set
+  // of visit v-2 is reused for the requests of visit v+2.  (Forwarding INTO the sets still in flight — as
+  // LwVelocity4K does — makes every select wait for the load it patches: ncu showed 37 % of the samples there;
+  // keeping the history in separate registers instead cost ~25 moves per visit.)  Body -1 matches nothing.
+  int hba[4] = {-1, -1, -1, -1}, hbb[4] = {-1, -1, -1, -1};
   long long v = 0;
   for (; v + 4 <= total; v += 4) {
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
     for (int j = 0; j < 4; ++j) {
-      const int j2 = (j + 2) & 3;
+      const int j2 = (j + 2) & 3, j3 = (j + 3) & 3;
       // inputs of this visit: requested two visits ago, so possibly older than the last two visits' results
       const int ba = ix[j].x, bb = ix[j].y, vc_points = ix[j].z;
+      float4 a = va[j], b = vb[j];
+      a = ba == hba[j3] ? va[j3] : ba == hbb[j3] ? vb[j3] : ba == hba[j2] ? va[j2] : ba == hbb[j2] ? vb[j2] : a;
+      b = bb == hba[j3] ? va[j3] : bb == hbb[j3] ? vb[j3] : bb == hba[j2] ? va[j2] : bb == hbb[j2] ? vb[j2] : b;
+      hba[j] = ba;
+      hbb[j] = bb;
       // requests: the indices of visit v+4 take this visit's slot (they are needed two visits from now, to request
       // the bodies of visit v+4: an index that is still in flight when its bodies are requested stalls the warp —
-      // ncu, second build); the record and the bodies of visit v+2
+      // ncu, second build); the record and the bodies of visit v+2 take the set of visit v-2
       ix[j] = L.vc_idx[first + k4];
-      float4 a = va[j], b = vb[j];
-      a = ba == h1a ? r1a : ba == h1b ? r1b : ba == h2a ? r2a : ba == h2b ? r2b : a;
-      b = bb == h1a ? r1a : bb == h1b ? r1b : bb == h2a ? r2a : bb == h2b ? r2b : b;
       {
         const float4* r = B.vc + (size_t)(first + k2) * VC_Q;
         q0[j2] = r[0]; q1[j2] = r[1]; q2[j2] = r[2]; q6[j2] = r[6]; q7[j2] = r[7];
@@ -1125,12 +1128,10 @@ B2G_HD void lw_velocity_run(const Batch& B, const Large& L, int first, int n, in
       // a static / kinematic body may sit in several islands: its velocity never changes — the result of the
       // arithmetic on it (inverse mass 0) is its old value, which is stored to a scratch slot instead
       const bool mov_a = q7[j].x != 0.0f || q7[j].y != 0.0f, mov_b = q7[j].z != 0.0f || q7[j].w != 0.0f;
-      const float4 na = mov_a ? make_float4(s.v_a.x, s.v_a.y, s.w_a, 0.0f) : a;
-      const float4 nb = mov_b ? make_float4(s.v_b.x, s.v_b.y, s.w_b, 0.0f) : b;
-      *(mov_a ? &B.b_vel[ba] : scratch) = na;
-      *(mov_b ? &B.b_vel[bb] : scratch + 1) = nb;
-      h2a = h1a; h2b = h1b; r2a = r1a; r2b = r1b;
-      h1a = ba; h1b = bb; r1a = na; r1b = nb;
+      va[j] = mov_a ? make_float4(s.v_a.x, s.v_a.y, s.w_a, 0.0f) : a;
+      vb[j] = mov_b ? make_float4(s.v_b.x, s.v_b.y, s.w_b, 0.0f) : b;
+      *(mov_a ? &B.b_vel[ba] : scratch) = va[j];
+      *(mov_b ? &B.b_vel[bb] : scratch + 1) = vb[j];
       if (++k == n) k = 0;
       if (++k2 == n) k2 = 0;
       if (++k4 == n) k4 = 0;
@@ -1436,34 +1437,40 @@ struct LwPosition5K {
 // whose loads are in flight), the next visit's record and bodies are requested at the start of a visit, and the
 // bodies the previous visit wrote are forwarded at the point of use.  One inlined copy of solve_position_one per
 // set keeps the loop inside the instruction cache (the four-set forms above measured slower: stall_no_inst).
-struct LwPosSet { float4 p0, p1, p2, p3, p4, pa, pb, ra, rb; int4 ix; };
+struct LwPosSet { float4 p0, p1, p2, p3, p4, pa, pb, ra, rb; int4 ix; int hba, hbb; };
 B2G_HD void lw_pos_request(const Batch& B, const Large& L, int kk, LwPosSet& t) {  // t.ix was loaded a visit earlier
   const float4* r = B.pc + (size_t)kk * PC_Q;
   t.p0 = r[0]; t.p1 = r[1]; t.p2 = r[2]; t.p3 = r[3]; t.p4 = r[4];
   t.pa = B.b_pos[t.ix.x]; t.ra = B.b_rot[t.ix.x];
   t.pb = B.b_pos[t.ix.y]; t.rb = B.b_rot[t.ix.y];
 }
-struct LwPosHist { int a, b; float4 pa, ra, pb, rb; };
-// One visit on set t; afterwards t.ix holds the indices of constraint `next_ix` (this set's next use, two visits
-// from now), requested before the arithmetic so they have landed when that visit's bodies are requested.
-B2G_HD float lw_pos_visit(const Batch& B, const Large& L, float4* scratch, LwPosSet& t, int next_ix, LwPosHist& h, float min_separation) {
+// One visit on set t.  The other set o holds the previous visit's results (o.pa .. o.rb of bodies o.hba / o.hbb):
+// they are forwarded into this visit's inputs first; then o is reused for the request of the next visit
+// (constraint `next_k`, whose indices o.ix were requested a visit ago), and t.ix is requested for constraint
+// `next_ix` (this set's next use, two visits from now); then the arithmetic; the results stay in t.
+B2G_HD float lw_pos_visit(const Batch& B, const Large& L, float4* scratch, LwPosSet& t, LwPosSet& o, int next_k, int next_ix,
+                          float min_separation) {
   const int ba = t.ix.x, bb = t.ix.y, packed = t.ix.w;
-  t.ix = L.vc_idx[next_ix];
   float4 pa = t.pa, ra = t.ra, pb = t.pb, rb = t.rb;
-  if (ba == h.a) { pa = h.pa; ra = h.ra; } else if (ba == h.b) { pa = h.pb; ra = h.rb; }
-  if (bb == h.a) { pb = h.pa; rb = h.ra; } else if (bb == h.b) { pb = h.pb; rb = h.rb; }
+  if (ba == o.hba) { pa = o.pa; ra = o.ra; } else if (ba == o.hbb) { pa = o.pb; ra = o.rb; }
+  if (bb == o.hba) { pb = o.pa; rb = o.ra; } else if (bb == o.hbb) { pb = o.pb; rb = o.rb; }
+  const float4 p0 = t.p0, p1 = t.p1, p2 = t.p2, p3 = t.p3, p4 = t.p4;
+  t.hba = ba;
+  t.hbb = bb;
+  t.ix = L.vc_idx[next_ix];
+  if (next_k >= 0) lw_pos_request(B, L, next_k, o);
   PosState s;
   s.c_a = v2(pa.x, pa.y); s.a_a = pa.z; s.q_a.s = ra.x; s.q_a.c = ra.y;
   s.c_b = v2(pb.x, pb.y); s.a_b = pb.z; s.q_b.s = rb.x; s.q_b.c = rb.y;
-  min_separation = solve_position_one(s, t.p0, t.p1, t.p2, t.p3, (packed >> 8) & 0xff, packed & 0xff, t.p4.x, t.p4.y, min_separation);
-  const bool mov_a = t.p0.x != 0.0f || t.p0.y != 0.0f, mov_b = t.p0.z != 0.0f || t.p0.w != 0.0f;
+  min_separation = solve_position_one(s, p0, p1, p2, p3, (packed >> 8) & 0xff, packed & 0xff, p4.x, p4.y, min_separation);
+  const bool mov_a = p0.x != 0.0f || p0.y != 0.0f, mov_b = p0.z != 0.0f || p0.w != 0.0f;
   if (mov_a) { pa.x = s.c_a.x; pa.y = s.c_a.y; pa.z = s.a_a; ra.x = s.q_a.s; ra.y = s.q_a.c; }
   if (mov_b) { pb.x = s.c_b.x; pb.y = s.c_b.y; pb.z = s.a_b; rb.x = s.q_b.s; rb.y = s.q_b.c; }
   *(mov_a ? &B.b_pos[ba] : scratch) = pa;
   *(mov_a ? &B.b_rot[ba] : scratch + 1) = ra;
   *(mov_b ? &B.b_pos[bb] : scratch + 2) = pb;
   *(mov_b ? &B.b_rot[bb] : scratch + 3) = rb;
-  h.a = ba; h.b = bb; h.pa = pa; h.ra = ra; h.pb = pb; h.rb = rb;
+  t.pa = pa; t.ra = ra; t.pb = pb; t.rb = rb;
   return min_separation;
 }
 struct LwPosition6K {
@@ -1479,23 +1486,20 @@ struct LwPosition6K {
     float4* scratch = L.scratch4 + 4;  // where the "results" of immovable bodies go
     for (int it = 0; it < sp.position_iterations; ++it) {
       float min_separation = 0.0f;
-      LwPosHist h;
-      h.a = -1; h.b = -1;
-      h.pa = h.ra = h.pb = h.rb = make_float4(0, 0, 0, 0);
       LwPosSet s0, s1;
       const int last = first + n - 1;
       s0.ix = L.vc_idx[first];
       s1.ix = L.vc_idx[first + 1 <= last ? first + 1 : last];
+      s1.hba = -1; s1.hbb = -1;
+      s1.pa = s1.ra = s1.pb = s1.rb = make_float4(0, 0, 0, 0);
       lw_pos_request(B, L, first, s0);
       int k = 0;
       for (; k + 2 <= n; k += 2) {
         const int c1 = first + k + 1, c2 = first + k + 2 <= last ? first + k + 2 : last, c3 = first + k + 3 <= last ? first + k + 3 : last;
-        lw_pos_request(B, L, c1, s1);
-        min_separation = lw_pos_visit(B, L, scratch, s0, c2, h, min_separation);
-        lw_pos_request(B, L, c2, s0);
-        min_separation = lw_pos_visit(B, L, scratch, s1, c3, h, min_separation);
+        min_separation = lw_pos_visit(B, L, scratch, s0, s1, c1, c2, min_separation);
+        min_separation = lw_pos_visit(B, L, scratch, s1, s0, c2, c3, min_separation);
       }
-      if (k < n) min_separation = lw_pos_visit(B, L, scratch, s0, last, h, min_separation);
+      if (k < n) min_separation = lw_pos_visit(B, L, scratch, s0, s1, -1, last, min_separation);
       if (min_separation >= -3.0f * B2G_LINEAR_SLOP) {  // b2_island_private.rs:257-274
         B.isl_flags[isl] |= 1;
         break;
