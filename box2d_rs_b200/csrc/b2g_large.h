@@ -1178,6 +1178,126 @@ struct LwVelocity5K {
   }
 };
 
+// ------------------------------------------------------------------------------------------
+// Velocity sweeps through a cp.async shared-memory ring (experiment, B2GPU_LW_VELOCITY=7).  Prefetching into
+// registers cannot take the global-memory round trip off the chain (six scoreboard slots alias the loads in
+// flight: profiles/r01_large_world.md), so here — as in the batch kernels — the constraint records are copied by
+// cp.async into a per-thread ring eight visits ahead and the two bodies two visits ahead (their indices come
+// from the record already in the ring); a visit reads its record and bodies with shared-memory loads and patches
+// the bodies from the results of the last three visits, which covers every store the asynchronous copy may or
+// may not have seen.  Same functions, same order, same bits.  In the host simulator a copy is a plain assignment.
+// ------------------------------------------------------------------------------------------
+#if defined(__CUDA_ARCH__)
+#define LW_CP16(dst, src) asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory")
+#define LW_CP_COMMIT() asm volatile("cp.async.commit_group;\n" ::: "memory")
+#define LW_CP_WAIT1() asm volatile("cp.async.wait_group 1;\n" ::: "memory")
+#define LW_CP_WAIT0() asm volatile("cp.async.wait_group 0;\n" ::: "memory")
+#else
+#define LW_CP16(dst, src) (*(float4*)(dst) = *(const float4*)(src))
+#define LW_CP_COMMIT()
+#define LW_CP_WAIT1()
+#define LW_CP_WAIT0()
+#endif
+enum { LW_RING = 8, LW_BRING = 4 };
+template <bool WARM>
+B2G_HD void lw_velocity_ring(const Batch& B, int first, int n, int sweeps, bool block, float4* ring, float4* bod, int stride,
+                             float4* scratch) {
+  const long long total = (long long)n * sweeps;
+  int kf = 0;  // constraint whose record is fetched next
+  for (int p = 0; p < LW_RING; ++p) {
+    const float4* r = B.vc + (size_t)(first + kf) * VC_Q;
+    for (int q = 0; q < VC_Q; ++q) LW_CP16(ring + (p * VC_Q + q) * stride, r + q);
+    if (++kf == n) kf = 0;
+  }
+  LW_CP_COMMIT();
+  LW_CP_WAIT0();
+  for (int p = 0; p < 2; ++p) {
+    const float4 q8 = ring[(p * VC_Q + 8) * stride];
+    LW_CP16(bod + (p * 2) * stride, &B.b_vel[f2i(q8.x)]);
+    LW_CP16(bod + (p * 2 + 1) * stride, &B.b_vel[f2i(q8.y)]);
+  }
+  LW_CP_COMMIT();
+  LW_CP_WAIT0();
+  LW_CP_COMMIT();  // an empty group, so that "all but the newest group" below always means "two visits back"
+  int h1a = -1, h1b = -1, h2a = -1, h2b = -1, h3a = -1, h3b = -1;
+  float4 r1a = make_float4(0, 0, 0, 0), r1b = r1a, r2a = r1a, r2b = r1a, r3a = r1a, r3b = r1a;
+  int k = 0;
+  for (long long v = 0; v < total; ++v) {
+    const int slot = (int)(v & (LW_RING - 1)), bs = (int)(v & (LW_BRING - 1));
+    LW_CP_WAIT1();
+    const float4* rs = ring + (slot * VC_Q) * stride;
+    const float4 q0 = rs[0], q1 = rs[stride], q2 = rs[2 * stride], q3 = rs[3 * stride], q4 = rs[4 * stride], q5 = rs[5 * stride];
+    float4 q6 = rs[6 * stride];
+    const float4 q7 = rs[7 * stride], q8 = rs[8 * stride];
+    float4 a = bod[(bs * 2) * stride], b = bod[(bs * 2 + 1) * stride];
+    const int ba = f2i(q8.x), bb = f2i(q8.y), vc_points = f2i(q8.z) & 0xff;
+    a = ba == h1a ? r1a : ba == h1b ? r1b : ba == h2a ? r2a : ba == h2b ? r2b : ba == h3a ? r3a : ba == h3b ? r3b : a;
+    b = bb == h1a ? r1a : bb == h1b ? r1b : bb == h2a ? r2a : bb == h2b ? r2b : bb == h3a ? r3a : bb == h3b ? r3b : b;
+    {  // refill this slot with the record eight visits ahead; request the bodies of the visit two ahead
+      const float4* r = B.vc + (size_t)(first + kf) * VC_Q;
+      for (int q = 0; q < VC_Q; ++q) LW_CP16(ring + (slot * VC_Q + q) * stride, r + q);
+      if (++kf == n) kf = 0;
+      const int s2 = (int)((v + 2) & (LW_RING - 1)), b2 = (int)((v + 2) & (LW_BRING - 1));
+      const float4 n8 = ring[(s2 * VC_Q + 8) * stride];
+      LW_CP16(bod + (b2 * 2) * stride, &B.b_vel[f2i(n8.x)]);
+      LW_CP16(bod + (b2 * 2 + 1) * stride, &B.b_vel[f2i(n8.y)]);
+      LW_CP_COMMIT();
+    }
+    VelState s;
+    s.v_a = v2(a.x, a.y); s.w_a = a.z;
+    s.v_b = v2(b.x, b.y); s.w_b = b.z;
+    if (WARM) {
+      warm_start_one(s, q0, q1, q2, q6, q7, vc_points);
+    } else {
+      solve_velocity_one(s, q0, q1, q2, q3, q4, q5, q6, q7, vc_points, block);
+      B.vc[(size_t)(first + k) * VC_Q + 6] = q6;
+    }
+    const bool mov_a = q7.x != 0.0f || q7.y != 0.0f, mov_b = q7.z != 0.0f || q7.w != 0.0f;
+    const float4 na = mov_a ? make_float4(s.v_a.x, s.v_a.y, s.w_a, 0.0f) : a;
+    const float4 nb = mov_b ? make_float4(s.v_b.x, s.v_b.y, s.w_b, 0.0f) : b;
+    *(mov_a ? &B.b_vel[ba] : scratch) = na;
+    *(mov_b ? &B.b_vel[bb] : scratch + 1) = nb;
+    h3a = h2a; h3b = h2b; r3a = r2a; r3b = r2b;
+    h2a = h1a; h2b = h1b; r2a = r1a; r2b = r1b;
+    h1a = ba; h1b = bb; r1a = na; r1b = nb;
+    if (++k == n) k = 0;
+  }
+  LW_CP_WAIT0();
+}
+struct LwVelocity7K {
+  Batch B;
+  Large L;
+  StepParams sp;
+  int n_islands;
+  B2G_HD void operator()(int isl) const {
+#if defined(__CUDA_ARCH__)
+    __shared__ float4 ring_s[LW_RING * VC_Q * 32];
+    __shared__ float4 bod_s[LW_BRING * 2 * 32];
+    float4* ring = ring_s + (threadIdx.x & 31);
+    float4* bod = bod_s + (threadIdx.x & 31);
+    const int stride = 32;
+#else
+    float4 ring_s[LW_RING * VC_Q], bod_s[LW_BRING * 2];
+    float4* ring = ring_s;
+    float4* bod = bod_s;
+    const int stride = 1;
+#endif
+    if (isl >= n_islands) return;
+    const int4 rg = B.isl_range[isl];
+    if (rg.z == rg.w) return;
+    const bool warm = (B.ws[WS_FLAGS] & B2GPU_WORLD_WARM_STARTING) != 0;
+    const bool block = (B.ws[WS_FLAGS] & B2GPU_WORLD_BLOCK_SOLVE) != 0;
+    const int first = rg.z, n = rg.w - rg.z;
+    if (n < 2 * LW_RING) {  // a record must not be in the ring while its impulses are rewritten: small islands take the register form
+      LwVelocity5K small = {B, L, sp, n_islands};
+      small(isl);
+      return;
+    }
+    if (warm) lw_velocity_ring<true>(B, first, n, 1, block, ring, bod, stride, L.scratch4 + 8);
+    if (sp.velocity_iterations > 0) lw_velocity_ring<false>(B, first, n, sp.velocity_iterations, block, ring, bod, stride, L.scratch4 + 8);
+  }
+};
+
 struct LwPcRec { float4 p0, p1, p2, p3, p4, p5; };
 B2G_HD LwPcRec lw_load_pc(const float4* pc, int k) {
   const float4* r = pc + (size_t)k * PC_Q;
@@ -1501,6 +1621,113 @@ struct LwPosition6K {
       }
       if (k < n) min_separation = lw_pos_visit(B, L, scratch, s0, s1, -1, last, min_separation);
       if (min_separation >= -3.0f * B2G_LINEAR_SLOP) {  // b2_island_private.rs:257-274
+        B.isl_flags[isl] |= 1;
+        break;
+      }
+    }
+  }
+};
+
+// Position sweeps through the same kind of cp.async ring (experiment, B2GPU_LW_VELOCITY=7): records (6 rows)
+// eight visits ahead, the two bodies' position and rotation rows two visits ahead, results of the last three
+// visits forwarded at the point of use.  One pipeline start per sweep (the early exit sits between sweeps).
+B2G_HD float lw_position_ring_sweep(const Batch& B, int first, int n, float4* ring, float4* bod, int stride, float4* scratch) {
+  int kf = 0;
+  for (int p = 0; p < LW_RING; ++p) {
+    const float4* r = B.pc + (size_t)(first + kf) * PC_Q;
+    for (int q = 0; q < PC_Q; ++q) LW_CP16(ring + (p * PC_Q + q) * stride, r + q);
+    if (++kf == n) kf = 0;
+  }
+  LW_CP_COMMIT();
+  LW_CP_WAIT0();
+  for (int p = 0; p < 2; ++p) {
+    const float4 p4 = ring[(p * PC_Q + 4) * stride];
+    const int ba = f2i(p4.z), bb = f2i(p4.w);
+    LW_CP16(bod + (p * 4) * stride, &B.b_pos[ba]);
+    LW_CP16(bod + (p * 4 + 1) * stride, &B.b_rot[ba]);
+    LW_CP16(bod + (p * 4 + 2) * stride, &B.b_pos[bb]);
+    LW_CP16(bod + (p * 4 + 3) * stride, &B.b_rot[bb]);
+  }
+  LW_CP_COMMIT();
+  LW_CP_WAIT0();
+  LW_CP_COMMIT();
+  int h1a = -1, h1b = -1, h2a = -1, h2b = -1, h3a = -1, h3b = -1;
+  const float4 z = make_float4(0, 0, 0, 0);
+  float4 c1a = z, c1b = z, c2a = z, c2b = z, c3a = z, c3b = z, t1a = z, t1b = z, t2a = z, t2b = z, t3a = z, t3b = z;
+  float min_separation = 0.0f;
+  for (int v = 0; v < n; ++v) {
+    const int slot = v & (LW_RING - 1), bs = v & (LW_BRING - 1);
+    LW_CP_WAIT1();
+    const float4* rs = ring + (slot * PC_Q) * stride;
+    const float4 p0 = rs[0], p1 = rs[stride], p2 = rs[2 * stride], p3 = rs[3 * stride], p4 = rs[4 * stride], p5 = rs[5 * stride];
+    float4 pa = bod[(bs * 4) * stride], ra = bod[(bs * 4 + 1) * stride], pb = bod[(bs * 4 + 2) * stride], rb = bod[(bs * 4 + 3) * stride];
+    const int ba = f2i(p4.z), bb = f2i(p4.w), packed = f2i(p5.x);
+    if (ba == h1a) { pa = c1a; ra = t1a; } else if (ba == h1b) { pa = c1b; ra = t1b; }
+    else if (ba == h2a) { pa = c2a; ra = t2a; } else if (ba == h2b) { pa = c2b; ra = t2b; }
+    else if (ba == h3a) { pa = c3a; ra = t3a; } else if (ba == h3b) { pa = c3b; ra = t3b; }
+    if (bb == h1a) { pb = c1a; rb = t1a; } else if (bb == h1b) { pb = c1b; rb = t1b; }
+    else if (bb == h2a) { pb = c2a; rb = t2a; } else if (bb == h2b) { pb = c2b; rb = t2b; }
+    else if (bb == h3a) { pb = c3a; rb = t3a; } else if (bb == h3b) { pb = c3b; rb = t3b; }
+    {
+      const float4* r = B.pc + (size_t)(first + kf) * PC_Q;
+      for (int q = 0; q < PC_Q; ++q) LW_CP16(ring + (slot * PC_Q + q) * stride, r + q);
+      if (++kf == n) kf = 0;
+      const int s2 = (v + 2) & (LW_RING - 1), b2 = (v + 2) & (LW_BRING - 1);
+      const float4 n4 = ring[(s2 * PC_Q + 4) * stride];
+      const int na = f2i(n4.z), nb = f2i(n4.w);
+      LW_CP16(bod + (b2 * 4) * stride, &B.b_pos[na]);
+      LW_CP16(bod + (b2 * 4 + 1) * stride, &B.b_rot[na]);
+      LW_CP16(bod + (b2 * 4 + 2) * stride, &B.b_pos[nb]);
+      LW_CP16(bod + (b2 * 4 + 3) * stride, &B.b_rot[nb]);
+      LW_CP_COMMIT();
+    }
+    PosState s;
+    s.c_a = v2(pa.x, pa.y); s.a_a = pa.z; s.q_a.s = ra.x; s.q_a.c = ra.y;
+    s.c_b = v2(pb.x, pb.y); s.a_b = pb.z; s.q_b.s = rb.x; s.q_b.c = rb.y;
+    min_separation = solve_position_one(s, p0, p1, p2, p3, (packed >> 8) & 0xff, packed & 0xff, p4.x, p4.y, min_separation);
+    const bool mov_a = p0.x != 0.0f || p0.y != 0.0f, mov_b = p0.z != 0.0f || p0.w != 0.0f;
+    if (mov_a) { pa.x = s.c_a.x; pa.y = s.c_a.y; pa.z = s.a_a; ra.x = s.q_a.s; ra.y = s.q_a.c; }
+    if (mov_b) { pb.x = s.c_b.x; pb.y = s.c_b.y; pb.z = s.a_b; rb.x = s.q_b.s; rb.y = s.q_b.c; }
+    *(mov_a ? &B.b_pos[ba] : scratch) = pa;
+    *(mov_a ? &B.b_rot[ba] : scratch + 1) = ra;
+    *(mov_b ? &B.b_pos[bb] : scratch + 2) = pb;
+    *(mov_b ? &B.b_rot[bb] : scratch + 3) = rb;
+    h3a = h2a; h3b = h2b; c3a = c2a; c3b = c2b; t3a = t2a; t3b = t2b;
+    h2a = h1a; h2b = h1b; c2a = c1a; c2b = c1b; t2a = t1a; t2b = t1b;
+    h1a = ba; h1b = bb; c1a = pa; c1b = pb; t1a = ra; t1b = rb;
+  }
+  LW_CP_WAIT0();
+  return min_separation;
+}
+struct LwPosition7K {
+  Batch B;
+  Large L;
+  StepParams sp;
+  int n_islands;
+  B2G_HD void operator()(int isl) const {
+#if defined(__CUDA_ARCH__)
+    __shared__ float4 ring_s[LW_RING * PC_Q * 32];
+    __shared__ float4 bod_s[LW_BRING * 4 * 32];
+    float4* ring = ring_s + (threadIdx.x & 31);
+    float4* bod = bod_s + (threadIdx.x & 31);
+    const int stride = 32;
+#else
+    float4 ring_s[LW_RING * PC_Q], bod_s[LW_BRING * 4];
+    float4* ring = ring_s;
+    float4* bod = bod_s;
+    const int stride = 1;
+#endif
+    if (isl >= n_islands) return;
+    const int4 rg = B.isl_range[isl];
+    if (rg.z == rg.w) return;
+    const int first = rg.z, n = rg.w - rg.z;
+    if (n < 2 * LW_RING) {
+      LwPosition6K small = {B, L, sp, n_islands};
+      small(isl);
+      return;
+    }
+    for (int it = 0; it < sp.position_iterations; ++it) {
+      if (lw_position_ring_sweep(B, first, n, ring, bod, stride, L.scratch4 + 12) >= -3.0f * B2G_LINEAR_SLOP) {  // b2_island_private.rs:257-274
         B.isl_flags[isl] |= 1;
         break;
       }
