@@ -1199,6 +1199,63 @@ struct LwVelocity5K {
 #define LW_CP_WAIT0()
 #endif
 enum { LW_RING = 8, LW_BRING = 4 };
+// One register set of the ring form: a record, the two bodies (patched), and what the visit left behind.
+struct LwVset {
+  float4 q0, q1, q2, q3, q4, q5, q6, q7;
+  float4 a, b;   // body velocities: inputs before the solve, results after it
+  int ba, bb, pts;
+};
+// Two register sets alternate (visit v in `cur`, visit v+1 prepared in `nxt`): no register moves, and the results
+// of visit v-1 are still in `nxt` when the bodies of visit v+1 are patched.  Per visit: (1) the record of visit
+// v+1 is read from the ring (it landed long ago), (2) the copies for the bodies of visit v+1 and for the record of
+// visit v+8 are issued, (3) visit v is solved and stored, (4) the copies are awaited (issued a whole visit ago) and
+// the bodies of visit v+1 are read and patched with the results of visits v and v-1: the asynchronous copy of a
+// body was issued before visit v stored and possibly before visit v-1's store became visible to it.
+template <bool WARM>
+B2G_HD void lw_ring_visit(const Batch& B, int first, int n, bool block, float4* ring, float4* bod, int stride, float4* scratch,
+                          LwVset& cur, LwVset& nxt, long long v, int& k, int& kf) {
+  const int slot = (int)(v & (LW_RING - 1)), s1 = (int)((v + 1) & (LW_RING - 1)), b1 = (int)((v + 1) & (LW_BRING - 1));
+  // (1) record of the next visit; the bodies the previous visit (whose results are in nxt.a / nxt.b) touched
+  const int pa_ = nxt.ba, pb_ = nxt.bb;
+  const float4 pra = nxt.a, prb = nxt.b;
+  const float4* rs = ring + (s1 * VC_Q) * stride;
+  nxt.q0 = rs[0]; nxt.q1 = rs[stride]; nxt.q2 = rs[2 * stride]; nxt.q6 = rs[6 * stride]; nxt.q7 = rs[7 * stride];
+  if (!WARM) { nxt.q3 = rs[3 * stride]; nxt.q4 = rs[4 * stride]; nxt.q5 = rs[5 * stride]; }
+  const float4 n8 = rs[8 * stride];
+  nxt.ba = f2i(n8.x); nxt.bb = f2i(n8.y); nxt.pts = f2i(n8.z) & 0xff;
+  // (2) copies: bodies of the next visit, record eight visits ahead into the slot this visit's record came from
+  LW_CP16(bod + (b1 * 2) * stride, &B.b_vel[nxt.ba]);
+  LW_CP16(bod + (b1 * 2 + 1) * stride, &B.b_vel[nxt.bb]);
+  {
+    const float4* r = B.vc + (size_t)(first + kf) * VC_Q;
+    for (int q = 0; q < VC_Q; ++q) LW_CP16(ring + (slot * VC_Q + q) * stride, r + q);
+    if (++kf == n) kf = 0;
+  }
+  LW_CP_COMMIT();
+  // (3) this visit
+  VelState s;
+  s.v_a = v2(cur.a.x, cur.a.y); s.w_a = cur.a.z;
+  s.v_b = v2(cur.b.x, cur.b.y); s.w_b = cur.b.z;
+  if (WARM) {
+    warm_start_one(s, cur.q0, cur.q1, cur.q2, cur.q6, cur.q7, cur.pts);
+  } else {
+    solve_velocity_one(s, cur.q0, cur.q1, cur.q2, cur.q3, cur.q4, cur.q5, cur.q6, cur.q7, cur.pts, block);
+    B.vc[(size_t)(first + k) * VC_Q + 6] = cur.q6;
+  }
+  const bool mov_a = cur.q7.x != 0.0f || cur.q7.y != 0.0f, mov_b = cur.q7.z != 0.0f || cur.q7.w != 0.0f;
+  if (mov_a) cur.a = make_float4(s.v_a.x, s.v_a.y, s.w_a, 0.0f);
+  if (mov_b) cur.b = make_float4(s.v_b.x, s.v_b.y, s.w_b, 0.0f);
+  *(mov_a ? &B.b_vel[cur.ba] : scratch) = cur.a;
+  *(mov_b ? &B.b_vel[cur.bb] : scratch + 1) = cur.b;
+  if (++k == n) k = 0;
+  // (4) bodies of the next visit
+  LW_CP_WAIT0();
+  float4 a = bod[(b1 * 2) * stride], b = bod[(b1 * 2 + 1) * stride];
+  a = nxt.ba == cur.ba ? cur.a : nxt.ba == cur.bb ? cur.b : nxt.ba == pa_ ? pra : nxt.ba == pb_ ? prb : a;
+  b = nxt.bb == cur.ba ? cur.a : nxt.bb == cur.bb ? cur.b : nxt.bb == pa_ ? pra : nxt.bb == pb_ ? prb : b;
+  nxt.a = a;
+  nxt.b = b;
+}
 template <bool WARM>
 B2G_HD void lw_velocity_ring(const Batch& B, int first, int n, int sweeps, bool block, float4* ring, float4* bod, int stride,
                              float4* scratch) {
@@ -1211,57 +1268,25 @@ B2G_HD void lw_velocity_ring(const Batch& B, int first, int n, int sweeps, bool 
   }
   LW_CP_COMMIT();
   LW_CP_WAIT0();
-  for (int p = 0; p < 2; ++p) {
-    const float4 q8 = ring[(p * VC_Q + 8) * stride];
-    LW_CP16(bod + (p * 2) * stride, &B.b_vel[f2i(q8.x)]);
-    LW_CP16(bod + (p * 2 + 1) * stride, &B.b_vel[f2i(q8.y)]);
+  LwVset A, Bs;
+  {  // visit 0 into A, straight from memory (nothing was written yet)
+    const float4* rs = ring;
+    A.q0 = rs[0]; A.q1 = rs[stride]; A.q2 = rs[2 * stride]; A.q3 = rs[3 * stride]; A.q4 = rs[4 * stride]; A.q5 = rs[5 * stride];
+    A.q6 = rs[6 * stride]; A.q7 = rs[7 * stride];
+    const float4 q8 = rs[8 * stride];
+    A.ba = f2i(q8.x); A.bb = f2i(q8.y); A.pts = f2i(q8.z) & 0xff;
+    A.a = B.b_vel[A.ba];
+    A.b = B.b_vel[A.bb];
   }
-  LW_CP_COMMIT();
-  LW_CP_WAIT0();
-  LW_CP_COMMIT();  // an empty group, so that "all but the newest group" below always means "two visits back"
-  int h1a = -1, h1b = -1, h2a = -1, h2b = -1, h3a = -1, h3b = -1;
-  float4 r1a = make_float4(0, 0, 0, 0), r1b = r1a, r2a = r1a, r2b = r1a, r3a = r1a, r3b = r1a;
+  Bs = A;
+  Bs.ba = -1; Bs.bb = -1;  // "previous visit": none
   int k = 0;
-  for (long long v = 0; v < total; ++v) {
-    const int slot = (int)(v & (LW_RING - 1)), bs = (int)(v & (LW_BRING - 1));
-    LW_CP_WAIT1();
-    const float4* rs = ring + (slot * VC_Q) * stride;
-    const float4 q0 = rs[0], q1 = rs[stride], q2 = rs[2 * stride], q3 = rs[3 * stride], q4 = rs[4 * stride], q5 = rs[5 * stride];
-    float4 q6 = rs[6 * stride];
-    const float4 q7 = rs[7 * stride], q8 = rs[8 * stride];
-    float4 a = bod[(bs * 2) * stride], b = bod[(bs * 2 + 1) * stride];
-    const int ba = f2i(q8.x), bb = f2i(q8.y), vc_points = f2i(q8.z) & 0xff;
-    a = ba == h1a ? r1a : ba == h1b ? r1b : ba == h2a ? r2a : ba == h2b ? r2b : ba == h3a ? r3a : ba == h3b ? r3b : a;
-    b = bb == h1a ? r1a : bb == h1b ? r1b : bb == h2a ? r2a : bb == h2b ? r2b : bb == h3a ? r3a : bb == h3b ? r3b : b;
-    {  // refill this slot with the record eight visits ahead; request the bodies of the visit two ahead
-      const float4* r = B.vc + (size_t)(first + kf) * VC_Q;
-      for (int q = 0; q < VC_Q; ++q) LW_CP16(ring + (slot * VC_Q + q) * stride, r + q);
-      if (++kf == n) kf = 0;
-      const int s2 = (int)((v + 2) & (LW_RING - 1)), b2 = (int)((v + 2) & (LW_BRING - 1));
-      const float4 n8 = ring[(s2 * VC_Q + 8) * stride];
-      LW_CP16(bod + (b2 * 2) * stride, &B.b_vel[f2i(n8.x)]);
-      LW_CP16(bod + (b2 * 2 + 1) * stride, &B.b_vel[f2i(n8.y)]);
-      LW_CP_COMMIT();
-    }
-    VelState s;
-    s.v_a = v2(a.x, a.y); s.w_a = a.z;
-    s.v_b = v2(b.x, b.y); s.w_b = b.z;
-    if (WARM) {
-      warm_start_one(s, q0, q1, q2, q6, q7, vc_points);
-    } else {
-      solve_velocity_one(s, q0, q1, q2, q3, q4, q5, q6, q7, vc_points, block);
-      B.vc[(size_t)(first + k) * VC_Q + 6] = q6;
-    }
-    const bool mov_a = q7.x != 0.0f || q7.y != 0.0f, mov_b = q7.z != 0.0f || q7.w != 0.0f;
-    const float4 na = mov_a ? make_float4(s.v_a.x, s.v_a.y, s.w_a, 0.0f) : a;
-    const float4 nb = mov_b ? make_float4(s.v_b.x, s.v_b.y, s.w_b, 0.0f) : b;
-    *(mov_a ? &B.b_vel[ba] : scratch) = na;
-    *(mov_b ? &B.b_vel[bb] : scratch + 1) = nb;
-    h3a = h2a; h3b = h2b; r3a = r2a; r3b = r2b;
-    h2a = h1a; h2b = h1b; r2a = r1a; r2b = r1b;
-    h1a = ba; h1b = bb; r1a = na; r1b = nb;
-    if (++k == n) k = 0;
+  long long v = 0;
+  for (; v + 2 <= total; v += 2) {
+    lw_ring_visit<WARM>(B, first, n, block, ring, bod, stride, scratch, A, Bs, v, k, kf);
+    lw_ring_visit<WARM>(B, first, n, block, ring, bod, stride, scratch, Bs, A, v + 1, k, kf);
   }
+  if (v < total) lw_ring_visit<WARM>(B, first, n, block, ring, bod, stride, scratch, A, Bs, v, k, kf);
   LW_CP_WAIT0();
 }
 struct LwVelocity7K {
