@@ -1199,7 +1199,74 @@ struct LwVelocity5K {
 #define LW_CP_WAIT0()
 #endif
 enum { LW_RING = 8, LW_BRING = 4 };
-// One register set of the ring form: a record, the two bodies (patched), and what the visit left behind.
+template <bool WARM>
+B2G_HD void lw_velocity_ring(const Batch& B, int first, int n, int sweeps, bool block, float4* ring, float4* bod, int stride,
+                             float4* scratch) {
+  const long long total = (long long)n * sweeps;
+  int kf = 0;  // constraint whose record is fetched next
+  for (int p = 0; p < LW_RING; ++p) {
+    const float4* r = B.vc + (size_t)(first + kf) * VC_Q;
+    for (int q = 0; q < VC_Q; ++q) LW_CP16(ring + (p * VC_Q + q) * stride, r + q);
+    if (++kf == n) kf = 0;
+  }
+  LW_CP_COMMIT();
+  LW_CP_WAIT0();
+  for (int p = 0; p < 2; ++p) {
+    const float4 q8 = ring[(p * VC_Q + 8) * stride];
+    LW_CP16(bod + (p * 2) * stride, &B.b_vel[f2i(q8.x)]);
+    LW_CP16(bod + (p * 2 + 1) * stride, &B.b_vel[f2i(q8.y)]);
+  }
+  LW_CP_COMMIT();
+  LW_CP_WAIT0();
+  LW_CP_COMMIT();  // an empty group, so that "all but the newest group" below always means "two visits back"
+  int h1a = -1, h1b = -1, h2a = -1, h2b = -1, h3a = -1, h3b = -1;
+  float4 r1a = make_float4(0, 0, 0, 0), r1b = r1a, r2a = r1a, r2b = r1a, r3a = r1a, r3b = r1a;
+  int k = 0;
+  for (long long v = 0; v < total; ++v) {
+    const int slot = (int)(v & (LW_RING - 1)), bs = (int)(v & (LW_BRING - 1));
+    LW_CP_WAIT1();
+    const float4* rs = ring + (slot * VC_Q) * stride;
+    const float4 q0 = rs[0], q1 = rs[stride], q2 = rs[2 * stride], q3 = rs[3 * stride], q4 = rs[4 * stride], q5 = rs[5 * stride];
+    float4 q6 = rs[6 * stride];
+    const float4 q7 = rs[7 * stride], q8 = rs[8 * stride];
+    float4 a = bod[(bs * 2) * stride], b = bod[(bs * 2 + 1) * stride];
+    const int ba = f2i(q8.x), bb = f2i(q8.y), vc_points = f2i(q8.z) & 0xff;
+    a = ba == h1a ? r1a : ba == h1b ? r1b : ba == h2a ? r2a : ba == h2b ? r2b : ba == h3a ? r3a : ba == h3b ? r3b : a;
+    b = bb == h1a ? r1a : bb == h1b ? r1b : bb == h2a ? r2a : bb == h2b ? r2b : bb == h3a ? r3a : bb == h3b ? r3b : b;
+    {  // refill this slot with the record eight visits ahead; request the bodies of the visit two ahead
+      const float4* r = B.vc + (size_t)(first + kf) * VC_Q;
+      for (int q = 0; q < VC_Q; ++q) LW_CP16(ring + (slot * VC_Q + q) * stride, r + q);
+      if (++kf == n) kf = 0;
+      const int s2 = (int)((v + 2) & (LW_RING - 1)), b2 = (int)((v + 2) & (LW_BRING - 1));
+      const float4 n8 = ring[(s2 * VC_Q + 8) * stride];
+      LW_CP16(bod + (b2 * 2) * stride, &B.b_vel[f2i(n8.x)]);
+      LW_CP16(bod + (b2 * 2 + 1) * stride, &B.b_vel[f2i(n8.y)]);
+      LW_CP_COMMIT();
+    }
+    VelState s;
+    s.v_a = v2(a.x, a.y); s.w_a = a.z;
+    s.v_b = v2(b.x, b.y); s.w_b = b.z;
+    if (WARM) {
+      warm_start_one(s, q0, q1, q2, q6, q7, vc_points);
+    } else {
+      solve_velocity_one(s, q0, q1, q2, q3, q4, q5, q6, q7, vc_points, block);
+      B.vc[(size_t)(first + k) * VC_Q + 6] = q6;
+    }
+    const bool mov_a = q7.x != 0.0f || q7.y != 0.0f, mov_b = q7.z != 0.0f || q7.w != 0.0f;
+    const float4 na = mov_a ? make_float4(s.v_a.x, s.v_a.y, s.w_a, 0.0f) : a;
+    const float4 nb = mov_b ? make_float4(s.v_b.x, s.v_b.y, s.w_b, 0.0f) : b;
+    *(mov_a ? &B.b_vel[ba] : scratch) = na;
+    *(mov_b ? &B.b_vel[bb] : scratch + 1) = nb;
+    h3a = h2a; h3b = h2b; r3a = r2a; r3b = r2b;
+    h2a = h1a; h2b = h1b; r2a = r1a; r2b = r1b;
+    h1a = ba; h1b = bb; r1a = na; r1b = nb;
+    if (++k == n) k = 0;
+  }
+  LW_CP_WAIT0();
+}
+// Alternating-set form of the ring sweep (experiment, B2GPU_LW_VELOCITY=9; measured SLOWER than the form above:
+// 14.4 vs 9.7 ms on AddPair-20k — with the bodies requested only one visit ahead the wait at the end of a short
+// visit is exposed).  One register set of the ring form: a record, the two bodies (patched), and what the visit left behind.
 struct LwVset {
   float4 q0, q1, q2, q3, q4, q5, q6, q7;
   float4 a, b;   // body velocities: inputs before the solve, results after it
@@ -1257,7 +1324,7 @@ B2G_HD void lw_ring_visit(const Batch& B, int first, int n, bool block, float4* 
   nxt.b = b;
 }
 template <bool WARM>
-B2G_HD void lw_velocity_ring(const Batch& B, int first, int n, int sweeps, bool block, float4* ring, float4* bod, int stride,
+B2G_HD void lw_velocity_ring_alt(const Batch& B, int first, int n, int sweeps, bool block, float4* ring, float4* bod, int stride,
                              float4* scratch) {
   const long long total = (long long)n * sweeps;
   int kf = 0;  // constraint whose record is fetched next
@@ -1320,6 +1387,40 @@ struct LwVelocity7K {
     }
     if (warm) lw_velocity_ring<true>(B, first, n, 1, block, ring, bod, stride, L.scratch4 + 8);
     if (sp.velocity_iterations > 0) lw_velocity_ring<false>(B, first, n, sp.velocity_iterations, block, ring, bod, stride, L.scratch4 + 8);
+  }
+};
+
+struct LwVelocity9K {
+  Batch B;
+  Large L;
+  StepParams sp;
+  int n_islands;
+  B2G_HD void operator()(int isl) const {
+#if defined(__CUDA_ARCH__)
+    __shared__ float4 ring_s[LW_RING * VC_Q * 32];
+    __shared__ float4 bod_s[LW_BRING * 2 * 32];
+    float4* ring = ring_s + (threadIdx.x & 31);
+    float4* bod = bod_s + (threadIdx.x & 31);
+    const int stride = 32;
+#else
+    float4 ring_s[LW_RING * VC_Q], bod_s[LW_BRING * 2];
+    float4* ring = ring_s;
+    float4* bod = bod_s;
+    const int stride = 1;
+#endif
+    if (isl >= n_islands) return;
+    const int4 rg = B.isl_range[isl];
+    if (rg.z == rg.w) return;
+    const bool warm = (B.ws[WS_FLAGS] & B2GPU_WORLD_WARM_STARTING) != 0;
+    const bool block = (B.ws[WS_FLAGS] & B2GPU_WORLD_BLOCK_SOLVE) != 0;
+    const int first = rg.z, n = rg.w - rg.z;
+    if (n < 2 * LW_RING) {  // a record must not be in the ring while its impulses are rewritten: small islands take the register form
+      LwVelocity5K small = {B, L, sp, n_islands};
+      small(isl);
+      return;
+    }
+    if (warm) lw_velocity_ring_alt<true>(B, first, n, 1, block, ring, bod, stride, L.scratch4 + 8);
+    if (sp.velocity_iterations > 0) lw_velocity_ring_alt<false>(B, first, n, sp.velocity_iterations, block, ring, bod, stride, L.scratch4 + 8);
   }
 };
 

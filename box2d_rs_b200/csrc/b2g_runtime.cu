@@ -1076,21 +1076,23 @@ static int step_large(BatchHost* bh, const StepParams& sp, int steps) {
       { LwStaticRotK k = {B}; RC(launch(ctx, k, B.NB, 256, STAGE_INTEGRATE)); }
       { IntegrateK k = {B, sp}; RC(launch(ctx, k, nib, 128, STAGE_INTEGRATE)); }
       { SolverInitK k = {B, sp}; RC(launch(ctx, k, nic, 128, STAGE_SOLVER_INIT)); }
-      // default: LwVelocity5K (four rotating register sets, forwarding at the point of use) + LwPosition6K (two
-      // alternating sets).  B2GPU_LW_VELOCITY selects the other forms for comparison: 1 distance-1 pipelines with
-      // register moves, 2 LwVelocity4K, 3 LwVelocity5K + LwPositionK, 4 LwPosition4K, 5 LwPosition5K
-      // (profiles/r01_large_world.md)
+      // default: LwVelocity7K (records and bodies staged through a cp.async shared-memory ring; islands under 16
+      // contacts take LwVelocity5K) + LwPosition6K (two alternating register sets).  B2GPU_LW_VELOCITY selects the
+      // other forms for comparison (profiles/r01_large_world.md): 1 distance-1 pipelines with register moves,
+      // 2 LwVelocity4K, 3 LwVelocity5K + LwPositionK, 4 LwPosition4K, 5 LwVelocity5K + LwPosition5K,
+      // 6 LwVelocity5K + LwPosition6K, 8 LwVelocity7K + LwPosition7K (ring), 9 LwVelocity9K (alternating ring)
       const int gs = bh->lw_velocity_variant;
       if (gs != 1) { LwVcIdxK k = {B, L, nic}; RC(launch(ctx, k, nic, 256, STAGE_SOLVER_INIT)); }
       if (gs == 1 || gs == 4) { LwVelocityK k = {B, sp, ni}; RC(launch(ctx, k, ni, 32, STAGE_VELOCITY)); }
       else if (gs == 2) { LwVelocity4K k = {B, L, sp, ni}; RC(launch(ctx, k, ni, 32, STAGE_VELOCITY)); }
-      else if (gs == 7) { LwVelocity7K k = {B, L, sp, ni}; RC(launch(ctx, k, ni, 32, STAGE_VELOCITY)); }
-      else { LwVelocity5K k = {B, L, sp, ni}; RC(launch(ctx, k, ni, 32, STAGE_VELOCITY)); }
+      else if (gs == 3 || gs == 5 || gs == 6) { LwVelocity5K k = {B, L, sp, ni}; RC(launch(ctx, k, ni, 32, STAGE_VELOCITY)); }
+      else if (gs == 9) { LwVelocity9K k = {B, L, sp, ni}; RC(launch(ctx, k, ni, 32, STAGE_VELOCITY)); }
+      else { LwVelocity7K k = {B, L, sp, ni}; RC(launch(ctx, k, ni, 32, STAGE_VELOCITY)); }
       { PostVelocityK k = {B, sp}; RC(launch(ctx, k, std::max(std::max(ni, nib), nic), 128, STAGE_POST_VELOCITY)); }
       if (gs == 4) { LwPosition4K k = {B, L, sp, ni}; RC(launch(ctx, k, ni, 32, STAGE_POSITION)); }
       else if (gs == 1 || gs == 2 || gs == 3) { LwPositionK k = {B, sp, ni}; RC(launch(ctx, k, ni, 32, STAGE_POSITION)); }
       else if (gs == 5) { LwPosition5K k = {B, L, sp, ni}; RC(launch(ctx, k, ni, 32, STAGE_POSITION)); }
-      else if (gs == 7 || gs == 8) { LwPosition7K k = {B, L, sp, ni}; RC(launch(ctx, k, ni, 32, STAGE_POSITION)); }
+      else if (gs == 8) { LwPosition7K k = {B, L, sp, ni}; RC(launch(ctx, k, ni, 32, STAGE_POSITION)); }
       else { LwPosition6K k = {B, L, sp, ni}; RC(launch(ctx, k, ni, 32, STAGE_POSITION)); }
       { FinalizeK k = {B, sp}; RC(launch(ctx, k, nib, 128, STAGE_FINALIZE)); }
       { SleepK k = {B}; RC(launch(ctx, k, ni, 128, STAGE_SLEEP)); }

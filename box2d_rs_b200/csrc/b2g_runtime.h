@@ -111,8 +111,7 @@ struct BatchHost {
   size_t lw_tmp_bytes = 0;
   int lw_edge_bits = 0, lw_body_bits = 0;
   long long lw_keys = 0;         // capacity of the key buffers
-  int lw_velocity_variant = 0;   // diagnostic (B2GPU_LW_VELOCITY): 0 default (LwVelocity5K + LwPosition5K), 1 distance-1 pipelines,
-                                 // 2 LwVelocity4K, 3 LwVelocity5K + LwPositionK, 4 LwPosition4K
+  int lw_velocity_variant = 0;   // diagnostic (B2GPU_LW_VELOCITY): 0 default (LwVelocity7K + LwPosition6K); others see step_large
 };
 
 const char* last_error();
