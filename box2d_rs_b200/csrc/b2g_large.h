@@ -1200,7 +1200,7 @@ struct LwVelocity5K {
 #endif
 enum { LW_RING = 8, LW_BRING = 4 };
 template <bool WARM>
-B2G_HD void lw_velocity_ring(const Batch& B, int first, int n, int sweeps, bool block, float4* ring, float4* bod, float4* hist, int stride,
+B2G_HD void lw_velocity_ring(const Batch& B, int first, int n, int sweeps, bool block, float4* ring, float4* bod, int stride,
                              float4* scratch) {
   const long long total = (long long)n * sweeps;
   int kf = 0;  // constraint whose record is fetched next
@@ -1219,11 +1219,8 @@ B2G_HD void lw_velocity_ring(const Batch& B, int first, int n, int sweeps, bool 
   LW_CP_COMMIT();
   LW_CP_WAIT0();
   LW_CP_COMMIT();  // an empty group, so that "all but the newest group" below always means "two visits back"
-  // results of the previous visit in registers (the usual forward: consecutive constraints of a DFS-ordered
-  // island share a body); results of the two visits before it in a small shared-memory history, read only when
-  // one of their bodies comes up again (a rarely taken branch instead of 24 selects and 18 moves per visit)
   int h1a = -1, h1b = -1, h2a = -1, h2b = -1, h3a = -1, h3b = -1;
-  float4 r1a = make_float4(0, 0, 0, 0), r1b = r1a;
+  float4 r1a = make_float4(0, 0, 0, 0), r1b = r1a, r2a = r1a, r2b = r1a, r3a = r1a, r3b = r1a;
   int k = 0;
   for (long long v = 0; v < total; ++v) {
     const int slot = (int)(v & (LW_RING - 1)), bs = (int)(v & (LW_BRING - 1));
@@ -1234,16 +1231,8 @@ B2G_HD void lw_velocity_ring(const Batch& B, int first, int n, int sweeps, bool 
     const float4 q7 = rs[7 * stride], q8 = rs[8 * stride];
     float4 a = bod[(bs * 2) * stride], b = bod[(bs * 2 + 1) * stride];
     const int ba = f2i(q8.x), bb = f2i(q8.y), vc_points = f2i(q8.z) & 0xff;
-    const int hs2 = (int)((v + 3) & 3), hs3 = (int)((v + 2) & 3);  // history slots of visits v-1 (unused: registers), v-2, v-3
-    if (ba == h2a || ba == h2b || ba == h3a || ba == h3b || bb == h2a || bb == h2b || bb == h3a || bb == h3b) {
-      const float4 r2a = hist[((int)((v + 2) & 3) * 2) * stride], r2b = hist[((int)((v + 2) & 3) * 2 + 1) * stride];
-      const float4 r3a = hist[((int)((v + 1) & 3) * 2) * stride], r3b = hist[((int)((v + 1) & 3) * 2 + 1) * stride];
-      a = ba == h2a ? r2a : ba == h2b ? r2b : ba == h3a ? r3a : ba == h3b ? r3b : a;
-      b = bb == h2a ? r2a : bb == h2b ? r2b : bb == h3a ? r3a : bb == h3b ? r3b : b;
-    }
-    (void)hs2; (void)hs3;
-    a = ba == h1a ? r1a : ba == h1b ? r1b : a;
-    b = bb == h1a ? r1a : bb == h1b ? r1b : b;
+    a = ba == h1a ? r1a : ba == h1b ? r1b : ba == h2a ? r2a : ba == h2b ? r2b : ba == h3a ? r3a : ba == h3b ? r3b : a;
+    b = bb == h1a ? r1a : bb == h1b ? r1b : bb == h2a ? r2a : bb == h2b ? r2b : bb == h3a ? r3a : bb == h3b ? r3b : b;
     {  // refill this slot with the record eight visits ahead; request the bodies of the visit two ahead
       const float4* r = B.vc + (size_t)(first + kf) * VC_Q;
       for (int q = 0; q < VC_Q; ++q) LW_CP16(ring + (slot * VC_Q + q) * stride, r + q);
@@ -1268,10 +1257,8 @@ B2G_HD void lw_velocity_ring(const Batch& B, int first, int n, int sweeps, bool 
     const float4 nb = mov_b ? make_float4(s.v_b.x, s.v_b.y, s.w_b, 0.0f) : b;
     *(mov_a ? &B.b_vel[ba] : scratch) = na;
     *(mov_b ? &B.b_vel[bb] : scratch + 1) = nb;
-    hist[((int)(v & 3) * 2) * stride] = na;  // visit v's results: slot v & 3 (read as v-2 / v-3 two and three visits on)
-    hist[((int)(v & 3) * 2 + 1) * stride] = nb;
-    h3a = h2a; h3b = h2b;
-    h2a = h1a; h2b = h1b;
+    h3a = h2a; h3b = h2b; r3a = r2a; r3b = r2b;
+    h2a = h1a; h2b = h1b; r2a = r1a; r2b = r1b;
     h1a = ba; h1b = bb; r1a = na; r1b = nb;
     if (++k == n) k = 0;
   }
@@ -1378,16 +1365,13 @@ struct LwVelocity7K {
 #if defined(__CUDA_ARCH__)
     __shared__ float4 ring_s[LW_RING * VC_Q * 32];
     __shared__ float4 bod_s[LW_BRING * 2 * 32];
-    __shared__ float4 hist_s[4 * 2 * 32];
     float4* ring = ring_s + (threadIdx.x & 31);
     float4* bod = bod_s + (threadIdx.x & 31);
-    float4* hist = hist_s + (threadIdx.x & 31);
     const int stride = 32;
 #else
-    float4 ring_s[LW_RING * VC_Q], bod_s[LW_BRING * 2], hist_s[4 * 2];
+    float4 ring_s[LW_RING * VC_Q], bod_s[LW_BRING * 2];
     float4* ring = ring_s;
     float4* bod = bod_s;
-    float4* hist = hist_s;
     const int stride = 1;
 #endif
     if (isl >= n_islands) return;
@@ -1401,8 +1385,8 @@ struct LwVelocity7K {
       small(isl);
       return;
     }
-    if (warm) lw_velocity_ring<true>(B, first, n, 1, block, ring, bod, hist, stride, L.scratch4 + 8);
-    if (sp.velocity_iterations > 0) lw_velocity_ring<false>(B, first, n, sp.velocity_iterations, block, ring, bod, hist, stride, L.scratch4 + 8);
+    if (warm) lw_velocity_ring<true>(B, first, n, 1, block, ring, bod, stride, L.scratch4 + 8);
+    if (sp.velocity_iterations > 0) lw_velocity_ring<false>(B, first, n, sp.velocity_iterations, block, ring, bod, stride, L.scratch4 + 8);
   }
 };
 
