@@ -1199,6 +1199,57 @@ struct LwVelocity5K {
 #define LW_CP_WAIT0()
 #endif
 enum { LW_RING = 8, LW_BRING = 4 };
+struct LwHist { int a, b; float ax, ay, az, bx, by, bz; };  // bodies a visit touched and what it left in them
+// One visit of the ring form.  `out` still holds the results of visit v-3 when the visit starts and receives this
+// visit's results; h1 / h2 are visits v-1 / v-2.  The three history slots rotate through a loop unrolled by three,
+// so nothing is moved (ncu, fourth capture: the shuffle of a three-level history was ≈30 of ≈70 moves per visit).
+template <bool WARM>
+B2G_HD void lw_ring_visit(const Batch& B, int first, int n, bool block, float4* ring, float4* bod, int stride, float4* scratch,
+                          LwHist& out, const LwHist& h1, const LwHist& h2, long long v, int& k, int& kf) {
+  const int slot = (int)(v & (LW_RING - 1)), bs = (int)(v & (LW_BRING - 1));
+  LW_CP_WAIT1();
+  const float4* rs = ring + (slot * VC_Q) * stride;
+  const float4 q0 = rs[0], q1 = rs[stride], q2 = rs[2 * stride], q3 = rs[3 * stride], q4 = rs[4 * stride], q5 = rs[5 * stride];
+  float4 q6 = rs[6 * stride];
+  const float4 q7 = rs[7 * stride], q8 = rs[8 * stride];
+  const float4 la = bod[(bs * 2) * stride], lb = bod[(bs * 2 + 1) * stride];
+  const int ba = f2i(q8.x), bb = f2i(q8.y), vc_points = f2i(q8.z) & 0xff;
+  float ax = la.x, ay = la.y, az = la.z, bx = lb.x, by = lb.y, bz = lb.z;
+  if (ba == h1.a) { ax = h1.ax; ay = h1.ay; az = h1.az; } else if (ba == h1.b) { ax = h1.bx; ay = h1.by; az = h1.bz; }
+  else if (ba == h2.a) { ax = h2.ax; ay = h2.ay; az = h2.az; } else if (ba == h2.b) { ax = h2.bx; ay = h2.by; az = h2.bz; }
+  else if (ba == out.a) { ax = out.ax; ay = out.ay; az = out.az; } else if (ba == out.b) { ax = out.bx; ay = out.by; az = out.bz; }
+  if (bb == h1.a) { bx = h1.ax; by = h1.ay; bz = h1.az; } else if (bb == h1.b) { bx = h1.bx; by = h1.by; bz = h1.bz; }
+  else if (bb == h2.a) { bx = h2.ax; by = h2.ay; bz = h2.az; } else if (bb == h2.b) { bx = h2.bx; by = h2.by; bz = h2.bz; }
+  else if (bb == out.a) { bx = out.ax; by = out.ay; bz = out.az; } else if (bb == out.b) { bx = out.bx; by = out.by; bz = out.bz; }
+  {  // refill this slot with the record eight visits ahead; request the bodies of the visit two ahead
+    const float4* r = B.vc + (size_t)(first + kf) * VC_Q;
+    for (int q = 0; q < VC_Q; ++q) LW_CP16(ring + (slot * VC_Q + q) * stride, r + q);
+    if (++kf == n) kf = 0;
+    const int s2 = (int)((v + 2) & (LW_RING - 1)), b2 = (int)((v + 2) & (LW_BRING - 1));
+    const float4 n8 = ring[(s2 * VC_Q + 8) * stride];
+    LW_CP16(bod + (b2 * 2) * stride, &B.b_vel[f2i(n8.x)]);
+    LW_CP16(bod + (b2 * 2 + 1) * stride, &B.b_vel[f2i(n8.y)]);
+    LW_CP_COMMIT();
+  }
+  VelState s;
+  s.v_a = v2(ax, ay); s.w_a = az;
+  s.v_b = v2(bx, by); s.w_b = bz;
+  if (WARM) {
+    warm_start_one(s, q0, q1, q2, q6, q7, vc_points);
+  } else {
+    solve_velocity_one(s, q0, q1, q2, q3, q4, q5, q6, q7, vc_points, block);
+    B.vc[(size_t)(first + k) * VC_Q + 6] = q6;
+  }
+  // a static / kinematic body may sit in several islands: its velocity never changes — the result of the arithmetic
+  // on it (inverse mass 0) is its old value, which is stored to a scratch slot instead
+  const bool mov_a = q7.x != 0.0f || q7.y != 0.0f, mov_b = q7.z != 0.0f || q7.w != 0.0f;
+  out.a = ba; out.b = bb;
+  out.ax = mov_a ? s.v_a.x : ax; out.ay = mov_a ? s.v_a.y : ay; out.az = mov_a ? s.w_a : az;
+  out.bx = mov_b ? s.v_b.x : bx; out.by = mov_b ? s.v_b.y : by; out.bz = mov_b ? s.w_b : bz;
+  *(mov_a ? &B.b_vel[ba] : scratch) = make_float4(out.ax, out.ay, out.az, 0.0f);
+  *(mov_b ? &B.b_vel[bb] : scratch + 1) = make_float4(out.bx, out.by, out.bz, 0.0f);
+  if (++k == n) k = 0;
+}
 template <bool WARM>
 B2G_HD void lw_velocity_ring(const Batch& B, int first, int n, int sweeps, bool block, float4* ring, float4* bod, int stride,
                              float4* scratch) {
@@ -1218,50 +1269,22 @@ B2G_HD void lw_velocity_ring(const Batch& B, int first, int n, int sweeps, bool 
   }
   LW_CP_COMMIT();
   LW_CP_WAIT0();
-  LW_CP_COMMIT();  // an empty group, so that "all but the newest group" below always means "two visits back"
-  int h1a = -1, h1b = -1, h2a = -1, h2b = -1, h3a = -1, h3b = -1;
-  float4 r1a = make_float4(0, 0, 0, 0), r1b = r1a, r2a = r1a, r2b = r1a, r3a = r1a, r3b = r1a;
+  LW_CP_COMMIT();  // an empty group, so that "all but the newest group" in a visit always means "two visits back"
+  LwHist H0, H1, H2;
+  H0.a = H0.b = H1.a = H1.b = H2.a = H2.b = -1;  // body -1 matches nothing
+  H0.ax = H0.ay = H0.az = H0.bx = H0.by = H0.bz = 0.0f;
+  H1 = H0;
+  H2 = H0;
+  H1.a = H1.b = H2.a = H2.b = -1;
   int k = 0;
-  for (long long v = 0; v < total; ++v) {
-    const int slot = (int)(v & (LW_RING - 1)), bs = (int)(v & (LW_BRING - 1));
-    LW_CP_WAIT1();
-    const float4* rs = ring + (slot * VC_Q) * stride;
-    const float4 q0 = rs[0], q1 = rs[stride], q2 = rs[2 * stride], q3 = rs[3 * stride], q4 = rs[4 * stride], q5 = rs[5 * stride];
-    float4 q6 = rs[6 * stride];
-    const float4 q7 = rs[7 * stride], q8 = rs[8 * stride];
-    float4 a = bod[(bs * 2) * stride], b = bod[(bs * 2 + 1) * stride];
-    const int ba = f2i(q8.x), bb = f2i(q8.y), vc_points = f2i(q8.z) & 0xff;
-    a = ba == h1a ? r1a : ba == h1b ? r1b : ba == h2a ? r2a : ba == h2b ? r2b : ba == h3a ? r3a : ba == h3b ? r3b : a;
-    b = bb == h1a ? r1a : bb == h1b ? r1b : bb == h2a ? r2a : bb == h2b ? r2b : bb == h3a ? r3a : bb == h3b ? r3b : b;
-    {  // refill this slot with the record eight visits ahead; request the bodies of the visit two ahead
-      const float4* r = B.vc + (size_t)(first + kf) * VC_Q;
-      for (int q = 0; q < VC_Q; ++q) LW_CP16(ring + (slot * VC_Q + q) * stride, r + q);
-      if (++kf == n) kf = 0;
-      const int s2 = (int)((v + 2) & (LW_RING - 1)), b2 = (int)((v + 2) & (LW_BRING - 1));
-      const float4 n8 = ring[(s2 * VC_Q + 8) * stride];
-      LW_CP16(bod + (b2 * 2) * stride, &B.b_vel[f2i(n8.x)]);
-      LW_CP16(bod + (b2 * 2 + 1) * stride, &B.b_vel[f2i(n8.y)]);
-      LW_CP_COMMIT();
-    }
-    VelState s;
-    s.v_a = v2(a.x, a.y); s.w_a = a.z;
-    s.v_b = v2(b.x, b.y); s.w_b = b.z;
-    if (WARM) {
-      warm_start_one(s, q0, q1, q2, q6, q7, vc_points);
-    } else {
-      solve_velocity_one(s, q0, q1, q2, q3, q4, q5, q6, q7, vc_points, block);
-      B.vc[(size_t)(first + k) * VC_Q + 6] = q6;
-    }
-    const bool mov_a = q7.x != 0.0f || q7.y != 0.0f, mov_b = q7.z != 0.0f || q7.w != 0.0f;
-    const float4 na = mov_a ? make_float4(s.v_a.x, s.v_a.y, s.w_a, 0.0f) : a;
-    const float4 nb = mov_b ? make_float4(s.v_b.x, s.v_b.y, s.w_b, 0.0f) : b;
-    *(mov_a ? &B.b_vel[ba] : scratch) = na;
-    *(mov_b ? &B.b_vel[bb] : scratch + 1) = nb;
-    h3a = h2a; h3b = h2b; r3a = r2a; r3b = r2b;
-    h2a = h1a; h2b = h1b; r2a = r1a; r2b = r1b;
-    h1a = ba; h1b = bb; r1a = na; r1b = nb;
-    if (++k == n) k = 0;
+  long long v = 0;
+  for (; v + 3 <= total; v += 3) {  // before a group: H2 = visit v-1, H1 = v-2, H0 = v-3
+    lw_ring_visit<WARM>(B, first, n, block, ring, bod, stride, scratch, H0, H2, H1, v, k, kf);
+    lw_ring_visit<WARM>(B, first, n, block, ring, bod, stride, scratch, H1, H0, H2, v + 1, k, kf);
+    lw_ring_visit<WARM>(B, first, n, block, ring, bod, stride, scratch, H2, H1, H0, v + 2, k, kf);
   }
+  if (v < total) { lw_ring_visit<WARM>(B, first, n, block, ring, bod, stride, scratch, H0, H2, H1, v, k, kf); ++v; }
+  if (v < total) lw_ring_visit<WARM>(B, first, n, block, ring, bod, stride, scratch, H1, H0, H2, v, k, kf);
   LW_CP_WAIT0();
 }
 // Alternating-set form of the ring sweep (experiment, B2GPU_LW_VELOCITY=9; measured SLOWER than the form above:
@@ -1279,8 +1302,8 @@ struct LwVset {
 // the bodies of visit v+1 are read and patched with the results of visits v and v-1: the asynchronous copy of a
 // body was issued before visit v stored and possibly before visit v-1's store became visible to it.
 template <bool WARM>
-B2G_HD void lw_ring_visit(const Batch& B, int first, int n, bool block, float4* ring, float4* bod, int stride, float4* scratch,
-                          LwVset& cur, LwVset& nxt, long long v, int& k, int& kf) {
+B2G_HD void lw_ring_visit_alt(const Batch& B, int first, int n, bool block, float4* ring, float4* bod, int stride, float4* scratch,
+                              LwVset& cur, LwVset& nxt, long long v, int& k, int& kf) {
   const int slot = (int)(v & (LW_RING - 1)), s1 = (int)((v + 1) & (LW_RING - 1)), b1 = (int)((v + 1) & (LW_BRING - 1));
   // (1) record of the next visit; the bodies the previous visit (whose results are in nxt.a / nxt.b) touched
   const int pa_ = nxt.ba, pb_ = nxt.bb;
@@ -1350,10 +1373,10 @@ B2G_HD void lw_velocity_ring_alt(const Batch& B, int first, int n, int sweeps, b
   int k = 0;
   long long v = 0;
   for (; v + 2 <= total; v += 2) {
-    lw_ring_visit<WARM>(B, first, n, block, ring, bod, stride, scratch, A, Bs, v, k, kf);
-    lw_ring_visit<WARM>(B, first, n, block, ring, bod, stride, scratch, Bs, A, v + 1, k, kf);
+    lw_ring_visit_alt<WARM>(B, first, n, block, ring, bod, stride, scratch, A, Bs, v, k, kf);
+    lw_ring_visit_alt<WARM>(B, first, n, block, ring, bod, stride, scratch, Bs, A, v + 1, k, kf);
   }
-  if (v < total) lw_ring_visit<WARM>(B, first, n, block, ring, bod, stride, scratch, A, Bs, v, k, kf);
+  if (v < total) lw_ring_visit_alt<WARM>(B, first, n, block, ring, bod, stride, scratch, A, Bs, v, k, kf);
   LW_CP_WAIT0();
 }
 struct LwVelocity7K {
