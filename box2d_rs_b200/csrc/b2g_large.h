@@ -59,6 +59,7 @@ struct Large {  // device scratch of the large-world mode
   // pair finding
   int* q_cnt;      // [NMOVE + 1] candidates per moved proxy; moved-word popcounts
   int* q_off;      // [NMOVE + 1]
+  int* q_local;    // [NMOVE][LW_QLOCAL] the first candidates of each query, kept by the counting pass
   int2* cand;      // [NCAND] candidate pairs (query node id, other node id)
   int* cand_flag;  // [NCAND + 1] 1 = add_pair creates a contact
   int* cand_pos;   // [NCAND + 1]
@@ -718,7 +719,7 @@ struct LwMoveFirstK {
     else B2G_ATOMIC_MIN(&L.first_idx[q], i);
   }
 };
-enum { LW_STACK = 128 };
+enum { LW_STACK = 128, LW_QLOCAL = 24 };
 // One thread per move-buffer entry; emit = 0 counts, 1 writes the candidate pairs.  use_tree = 1 walks the
 // uploaded replica of the reference's tree instead of the LBVH (child2 first, b2_dynamic_tree.rs:239-267): the
 // find_new_contacts call at the top of a step (m_new_contacts) always follows an upload, whose tree is current,
@@ -734,6 +735,16 @@ struct LwQueryK {
     int count = 0;
     int2* out = emit ? L.cand + L.q_off[i] : nullptr;
     const int room = emit ? L.NCAND - L.q_off[i] : 0;
+    int* local = L.q_local + (size_t)i * LW_QLOCAL;
+    if (emit && q != -1) {
+      // the counting pass kept the first LW_QLOCAL candidates: a query that fits needs no second walk
+      const int cnt = L.q_off[i + 1] - L.q_off[i];
+      if (cnt <= LW_QLOCAL) {
+        const int qq = (use_tree && L.first_idx[q] != i) ? ~q : q;  // repeated move-buffer entry: report, never create
+        for (int k = 0; k < cnt && k < room; ++k) out[k] = make_int2(qq, local[k]);
+        return;
+      }
+    }
     if (q != -1 && n > 0) {
       const Box qb = lw_box(B.n_aabb, q);
       int stack[LW_STACK];
@@ -749,7 +760,8 @@ struct LwQueryK {
           if (l.y == -1) {
             if (id == q) continue;
             if (B.n_moved[id] && id > q) continue;
-            if (emit && count < room) out[count] = make_int2(qq, id);
+            if (emit) { if (count < room) out[count] = make_int2(qq, id); }
+            else if (count < LW_QLOCAL) local[count] = id;
             ++count;
           } else {
             if (sp_ + 2 > LW_STACK) { B.ws[WS_STATUS] = B2GPU_E_CAPACITY; continue; }
@@ -767,7 +779,8 @@ struct LwQueryK {
             if (id == q) continue;
             if (!lw_overlap(B.n_aabb[id], qb)) continue;
             if (B.n_moved[id] && id > q) continue;
-            if (emit && count < room) out[count] = make_int2(q, id);
+            if (emit) { if (count < room) out[count] = make_int2(q, id); }
+            else if (count < LW_QLOCAL) local[count] = id;
             ++count;
           } else {
             if (!lw_overlap(L.lb_box[c], qb)) continue;

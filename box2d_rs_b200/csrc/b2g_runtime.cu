@@ -613,6 +613,7 @@ void batch_destroy(BatchHost* bh) {
   }
 #endif
   large_free(bh);
+  if (bh->query_buf) dev_free(bh->query_buf);
   for (void* p : bh->allocs) dev_free(p);
   delete bh;
 }
@@ -910,7 +911,7 @@ static int large_alloc(BatchHost* bh) {
   AL(L.keys, bh->lw_keys); AL(L.keys_alt, bh->lw_keys);
   AL(L.lb_box, B.NP); AL(L.lb_child, B.NP); AL(L.lb_parent, 2LL * B.NP); AL(L.lb_flag, B.NP); AL(L.lb_leaf, B.NP);
   const long long nq = std::max(B.NMOVE, B.NMW) + 1;
-  AL(L.q_cnt, nq); AL(L.q_off, nq);
+  AL(L.q_cnt, nq); AL(L.q_off, nq); AL(L.q_local, (long long)B.NMOVE * LW_QLOCAL);
   AL(L.cand, L.NCAND); AL(L.cand_flag, L.NCAND + 1LL); AL(L.cand_pos, L.NCAND + 1LL); AL(L.cand_fix, L.NCAND);
   AL(L.uf_parent, B.NB); AL(L.cnt_b, B.NB); AL(L.cnt_c, B.NB); AL(L.seed, B.NB); AL(L.isl_seed, B.NB);
   AL(L.pk_in, B.NB + 1LL); AL(L.pk_out, B.NB + 1LL);
@@ -1121,18 +1122,26 @@ static int step_large(BatchHost* bh, const StepParams& sp, int steps) {
 }
 
 // ------------------------------------------------------------------ world queries (b2g_query.h)
-struct DevTmp {  // device scratch of one call
-  std::vector<void*> p;
-  ~DevTmp() { for (void* v : p) dev_free(v); }
-  template <class T> int get(T** out, size_t count) {
+// Device scratch of the query calls: one buffer per batch, grown on demand and kept (a cudaMalloc / cudaFree pair
+// per call cost more than the ray casts of a small world).
+static int query_scratch(BatchHost* bh, size_t bytes, char** out) {
+  if (bytes > bh->query_bytes) {
+    if (bh->query_buf) {
+      RC(ctx_sync(bh->ctx));
+      dev_free(bh->query_buf);
+      bh->query_buf = nullptr;
+      bh->query_bytes = 0;
+    }
     void* v = nullptr;
-    int rc = dev_alloc(&v, std::max<size_t>(count, 1) * sizeof(T));
-    if (rc) return rc;
-    p.push_back(v);
-    *out = (T*)v;
-    return 0;
+    const size_t want = bytes + bytes / 2 + 4096;
+    RC(dev_alloc(&v, want));
+    bh->query_buf = v;
+    bh->query_bytes = want;
   }
-};
+  *out = (char*)bh->query_buf;
+  return 0;
+}
+static size_t align256(size_t n) { return (n + 255) & ~(size_t)255; }
 static int query_prepare(BatchHost* bh, int& use_lbvh) {
   use_lbvh = bh->large && !bh->lw_exact_tree;  // the replica tree is current in every other mode
   if (use_lbvh && bh->B.NP > 0) RC(lw_build_lbvh(bh, STAGE_OTHER));
@@ -1149,11 +1158,11 @@ int batch_ray_cast_closest(BatchHost* bh, const float* host_rays, int rays_per_w
       set_error("ray_cast: p1 == p2 (the reference asserts length_squared > 0)");
       return B2GPU_E_INVALID;
     }
-  DevTmp tmp;
-  float* d_rays = nullptr;
-  b2gpu_ray_hit* d_out = nullptr;
-  RC(tmp.get(&d_rays, (size_t)total * 4));
-  RC(tmp.get(&d_out, (size_t)total));
+  char* base = nullptr;
+  const size_t rays_bytes = align256((size_t)total * 16);
+  RC(query_scratch(bh, rays_bytes + (size_t)total * sizeof(b2gpu_ray_hit), &base));
+  float* d_rays = (float*)base;
+  b2gpu_ray_hit* d_out = (b2gpu_ray_hit*)(base + rays_bytes);
   RC(dev_h2d(bh->ctx, d_rays, host_rays, (size_t)total * 16));
   int use_lbvh = 0;
   RC(query_prepare(bh, use_lbvh));
@@ -1165,12 +1174,12 @@ int batch_query_aabb(BatchHost* bh, const float* host_boxes, int n, int max_hits
   if (!bh || !host_boxes || !host_counts || n < 0 || max_hits < 0 || (max_hits > 0 && !host_hits)) { set_error("query_aabb: bad argument"); return B2GPU_E_INVALID; }
   if (bh->B.n_worlds != 1) { set_error("query_aabb: one world at a time"); return B2GPU_E_INVALID; }
   if (n == 0) return 0;
-  DevTmp tmp;
-  float* d_boxes = nullptr;
-  int *d_counts = nullptr, *d_hits = nullptr;
-  RC(tmp.get(&d_boxes, (size_t)n * 4));
-  RC(tmp.get(&d_counts, (size_t)n));
-  RC(tmp.get(&d_hits, (size_t)n * max_hits * 2));
+  char* base = nullptr;
+  const size_t boxes_bytes = align256((size_t)n * 16), counts_bytes = align256((size_t)n * 4);
+  RC(query_scratch(bh, boxes_bytes + counts_bytes + (size_t)n * max_hits * 8 + 16, &base));
+  float* d_boxes = (float*)base;
+  int* d_counts = (int*)(base + boxes_bytes);
+  int* d_hits = (int*)(base + boxes_bytes + counts_bytes);
   RC(dev_h2d(bh->ctx, d_boxes, host_boxes, (size_t)n * 16));
   int use_lbvh = 0;
   RC(query_prepare(bh, use_lbvh));

@@ -111,6 +111,8 @@ struct BatchHost {
   size_t lw_tmp_bytes = 0;
   int lw_edge_bits = 0, lw_body_bits = 0;
   long long lw_keys = 0;         // capacity of the key buffers
+  void* query_buf = nullptr;     // device scratch of the world-query calls (grown on demand)
+  size_t query_bytes = 0;
   int lw_velocity_variant = 0;   // diagnostic (B2GPU_LW_VELOCITY): 0 default (LwVelocity7K + LwPosition6K); others see step_large
 };
 
