@@ -9,7 +9,7 @@ import numpy as np
 
 ABI_VERSION = 1
 
-OK, E_INVALID, E_NO_DEVICE, E_CUDA, E_CAPACITY, E_UNSUPPORTED, E_LOCKED, E_INTERNAL = 0, -1, -2, -3, -4, -5, -6, -7
+OK, E_INVALID, E_NO_DEVICE, E_CUDA, E_CAPACITY, E_UNSUPPORTED, E_LOCKED, E_INTERNAL, E_IO = 0, -1, -2, -3, -4, -5, -6, -7, -8
 
 STATIC_BODY, KINEMATIC_BODY, DYNAMIC_BODY = 0, 1, 2
 BODY_ISLAND, BODY_AWAKE, BODY_AUTO_SLEEP, BODY_BULLET, BODY_FIXED_ROTATION, BODY_ENABLED, BODY_TOI = (

@@ -86,6 +86,15 @@ class Batch:
         check(self.L, self.L.b2gpu_batch_download_world(self.h, world, C.byref(c)))
         return snap.finish(c)
 
+    def save_checkpoint(self, world, path):
+        """One world of the batch to a snapshot file (b2gpu_snapshot_save)."""
+        from . import checkpoint
+        checkpoint.save(self.download_world(world), path, self.L)
+
+    def load_checkpoint(self, world, path):
+        from . import checkpoint
+        self.upload_world(world, checkpoint.load(path, self.L))
+
     def stats(self, first=0, count=None):
         count = self.n_worlds - first if count is None else count
         out = np.zeros(count, abi.STATS_DTYPE)

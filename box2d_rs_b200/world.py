@@ -159,6 +159,16 @@ class B2world:
         c = snap.as_c()
         check(self.L, self.L.b2gpu_world_upload(self.h, C.byref(c)))
 
+    def save_checkpoint(self, path):
+        """Full step state to a snapshot file (b2gpu_snapshot_save); see checkpoint.py."""
+        from . import checkpoint
+        checkpoint.save(self.snapshot(), path, self.L)
+
+    def load_checkpoint(self, path):
+        """Resume from a snapshot file: the next step continues the saved run bit for bit."""
+        from . import checkpoint
+        self.upload(checkpoint.load(path, self.L))
+
     def ray_cast_closest(self, p1p2):
         """B2world::ray_cast with the closest-hit callback for an [n][4] array of rays (p1.x p1.y p2.x p2.y).
         Returns a structured array (abi.RAY_HIT_DTYPE); fixture == -1 where nothing was hit."""

@@ -41,6 +41,7 @@ extern "C" {
 #define B2GPU_E_UNSUPPORTED (-5) /* feature outside the hot-path scope (joints, TOI) */
 #define B2GPU_E_LOCKED (-6)    /* world is locked (reference: is_locked() panic) */
 #define B2GPU_E_INTERNAL (-7)  /* a device-side consistency check failed (a bug: please report) */
+#define B2GPU_E_IO (-8)        /* a checkpoint file could not be opened, read or written */
 
 /* body types: src/b2_body.rs B2bodyType */
 #define B2GPU_STATIC_BODY 0
@@ -360,6 +361,28 @@ int b2gpu_world_get_stats(b2gpu_world* w, b2gpu_step_stats* out);
 int b2gpu_world_snapshot_sizes(b2gpu_world* w, b2gpu_snapshot_sizes* out);
 int b2gpu_world_download(b2gpu_world* w, b2gpu_snapshot* out);
 int b2gpu_world_upload(b2gpu_world* w, const b2gpu_snapshot* in);
+
+/* Checkpoint / resume: a snapshot on disk.  The reference's serde support
+ * (src/serialize/serialize_b2_world.rs:133-178) saves the world *definition*; a
+ * world rebuilt from it has no contacts, no warm-start impulses and a fresh tree,
+ * so it does not continue the saved run.  A snapshot file carries the whole step
+ * state, and upload + step after load is bit-identical to the uninterrupted run.
+ * Host-only calls (no device needed).  File: checksummed header + the seven
+ * tables of b2gpu_snapshot as declared above, little-endian
+ * (box2d_rs_b200/csrc/b2g_checkpoint.cu).
+ *   validate:   every index of `s` stays inside its table (B2GPU_E_INVALID if not);
+ *               save and load run it, so a corrupt file never reaches the device.
+ *   save:       writes `path`.tmp, then renames it to `path`.
+ *   file_sizes: table sizes of a file, for allocating the arrays.
+ *   load:       `out->n` = capacities of the caller's arrays on entry, table sizes
+ *               on return; B2GPU_E_CAPACITY if an array is too small, B2GPU_E_IO if
+ *               the file cannot be opened, B2GPU_E_INVALID if it is not a snapshot,
+ *               truncated or fails a checksum, B2GPU_E_UNSUPPORTED for another
+ *               file or ABI version. */
+int b2gpu_snapshot_validate(const b2gpu_snapshot* s);
+int b2gpu_snapshot_save(const b2gpu_snapshot* s, const char* path);
+int b2gpu_snapshot_file_sizes(const char* path, b2gpu_snapshot_sizes* out);
+int b2gpu_snapshot_load(const char* path, b2gpu_snapshot* out);
 
 /* ------------------------------------------------------------ world queries
  * B2world::ray_cast (src/private/dynamics/b2_world.rs:1015-1049) with the "closest hit" callback

@@ -159,6 +159,12 @@ extern "C" {
     pub fn b2gpu_world_snapshot_sizes(w: *mut b2gpu_world, out: *mut b2gpu_snapshot_sizes) -> c_int;
     pub fn b2gpu_world_download(w: *mut b2gpu_world, out: *mut b2gpu_snapshot) -> c_int;
     pub fn b2gpu_world_upload(w: *mut b2gpu_world, snap: *const b2gpu_snapshot) -> c_int;
+    // checkpoint / resume (host-only): the whole step state on disk, where the crate's serde support
+    // (src/serialize/serialize_b2_world.rs) saves definitions only
+    pub fn b2gpu_snapshot_validate(s: *const b2gpu_snapshot) -> c_int;
+    pub fn b2gpu_snapshot_save(s: *const b2gpu_snapshot, path: *const c_char) -> c_int;
+    pub fn b2gpu_snapshot_file_sizes(path: *const c_char, out: *mut b2gpu_snapshot_sizes) -> c_int;
+    pub fn b2gpu_snapshot_load(path: *const c_char, out: *mut b2gpu_snapshot) -> c_int;
     pub fn b2gpu_batch_create(ctx: *mut b2gpu_ctx, proto: *const b2gpu_snapshot, n_worlds: c_int, caps: *const b2gpu_caps, out: *mut *mut b2gpu_batch) -> c_int;
     pub fn b2gpu_batch_destroy(b: *mut b2gpu_batch);
     pub fn b2gpu_batch_world_count(b: *mut b2gpu_batch) -> c_int;
