@@ -446,6 +446,7 @@ static int move_array(BatchHost* bh, const ArrRef& a, int mode, int world) {
 
 int batch_create(Ctx* ctx, const b2gpu_snapshot* proto, int n_worlds, const b2gpu_caps* caps, int lane_block, BatchHost** out) {
   if (!ctx || !proto || n_worlds < 1 || !out) { set_error("batch_create: bad argument"); return B2GPU_E_INVALID; }
+  RC(b2gpu_snapshot_validate(proto));
   BatchHost* bh = new BatchHost();
   bh->ctx = ctx;
   int rc = topology_build(proto, bh->topo);
@@ -620,6 +621,7 @@ void batch_destroy(BatchHost* bh) {
 
 int batch_upload_world(BatchHost* bh, int world, const b2gpu_snapshot* in) {
   if (!bh || !in || world < 0 || world >= bh->B.n_worlds) { set_error("upload_world: bad argument"); return B2GPU_E_INVALID; }
+  RC(b2gpu_snapshot_validate(in));  // every index inside its table: a damaged snapshot must not reach the kernels
   if (!topology_matches(bh->topo, in)) {
     set_error("upload_world: snapshot topology (fixtures/shapes/proxies/body types) differs from the batch prototype");
     return B2GPU_E_INVALID;
@@ -1230,6 +1232,7 @@ static int ensure_groups(BatchHost* bh) {
 static int enqueue_steps(BatchHost* bh, const StepParams& sp, int steps, const float* host_forces, float* host_state_out) {
   Batch& B = bh->B;
   Ctx* ctx = bh->ctx;
+  (void)ctx;
   Batch all = B;
   all.wb_first = 0;
   all.wb_count = B.n_wblocks;
@@ -1317,6 +1320,7 @@ static bool host_pointer_capturable(const void* p) {  // memcpy nodes need page-
 static int run_steps(BatchHost* bh, float dt, int vi, int pi, int steps, const float* host_forces, float* host_state_out) {
   if (!bh || steps < 0 || vi < 0 || pi < 0) { set_error("batch_step: bad argument"); return B2GPU_E_INVALID; }
   Ctx* ctx = bh->ctx;
+  (void)ctx;
   const StepParams sp = make_params(dt, vi, pi);
   bh->last_sp = sp;
 #if defined(B2G_HOSTSIM)

@@ -855,6 +855,7 @@ int b2gpu_world_upload(b2gpu_world* W, const b2gpu_snapshot* in) {
   HostWorld& h = W->h;
   const b2gpu_snapshot_sizes& n = in->n;
   if (n.body_count < 1 || n.node_count < 1) { set_error("upload: empty snapshot"); return B2GPU_E_INVALID; }
+  { int rc = b2gpu_snapshot_validate(in); if (rc) return rc; }
   h.world = in->world;
   h.bodies.assign(in->bodies, in->bodies + n.body_count);
   h.fixtures.assign(in->fixtures, in->fixtures + n.fixture_count);

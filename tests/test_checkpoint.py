@@ -179,3 +179,27 @@ def test_gpu_resume_is_bit_identical(built, tmp_path):
         b.close()
         w2.close()
         wg.close()
+
+
+def test_committed_file_still_loads(built):
+    """Format stability: the version-1 file committed under tests/golden/ (make_checkpoint_golden.py) loads, agrees
+    with the golden fixture of the same scene at step 30, and resumed for 30 steps reaches its step-60 record."""
+    import sys
+    from conftest import ROOT
+    from box2d_rs_b200 import batch, checkpoint, scenes, world
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import make_golden
+    g = np.load(os.path.join(ROOT, "tests", "golden", "hello_world.npz"))
+    snap = checkpoint.load(os.path.join(ROOT, "tests", "golden", "hello_world_step30.b2snap"))
+    assert np.array_equal(make_golden.contact_table(snap), g["contacts_30"])
+    ctx = batch.Context(0, lib_path=HOSTSIM_SO)
+    wg = world.B2world((0.0, -10.0), ctx=ctx)
+    wg.upload(snap)
+    b = wg.batch(1, lane_block=1)
+    assert np.array_equal(b.body_state()[0].view(np.uint32), g["state_30"].view(np.uint32))
+    b.step(scenes.DT, scenes.VEL_ITERS, scenes.POS_ITERS, steps=30)
+    assert np.array_equal(b.body_state()[0].view(np.uint32), g["state_60"].view(np.uint32))
+    assert np.array_equal(make_golden.contact_table(b.download_world(0)), g["contacts_60"])
+    b.close()
+    wg.close()
+    ctx.close()
