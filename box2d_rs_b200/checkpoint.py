@@ -37,3 +37,25 @@ def load(path, L=None):
     c = snap.as_c()
     check(L, L.b2gpu_snapshot_load(os.fsencode(path), C.byref(c)))
     return snap.finish(c)
+
+
+# ---- batches: one snapshot file per world, named by GLOBAL world index, so a run sharded over N ranks
+# (sharding.world_range) can be resumed over M ranks: each rank reads the files of the worlds it owns now.
+def world_path(directory, global_world):
+    return os.path.join(os.fspath(directory), "world_%08d.b2snap" % global_world)
+
+
+def save_batch(batch, directory, first_global_world=0):
+    """Every world of this rank's batch to `directory`; `first_global_world` = sharding.world_range(...)[0].
+    Ranks write disjoint files, so no coordination is needed beyond a barrier before anybody reads."""
+    os.makedirs(directory, exist_ok=True)
+    for w in range(batch.n_worlds):
+        save(batch.download_world(w), world_path(directory, first_global_world + w), batch.L)
+    return batch.n_worlds
+
+
+def load_batch(batch, directory, first_global_world=0):
+    """Restore every world of this rank's batch from the files of its global world indices."""
+    for w in range(batch.n_worlds):
+        batch.upload_world(w, load(world_path(directory, first_global_world + w), batch.L))
+    return batch.n_worlds

@@ -203,3 +203,40 @@ def test_committed_file_still_loads(built):
     b.close()
     wg.close()
     ctx.close()
+
+
+def test_sharded_batch_resumes_under_another_world_size(built, tmp_path):
+    """7 perturbed Pyramid worlds stepped as 2 shards, saved per global world index, resumed as 3 shards: every
+    world ends where the same world of one unsharded batch ends (worlds are the only unit that shards)."""
+    from box2d_rs_b200 import batch, checkpoint, scenes, sharding, world
+    ctx = batch.Context(0, lib_path=HOSTSIM_SO)
+    wg = world.B2world((0.0, -10.0), ctx=ctx)
+    scenes.pyramid(wg)
+    total, seed = 7, 2864
+
+    def make(first, end):
+        b = wg.batch(end - first, lane_block=2, max_contacts=800)
+        v = sharding.perturbation(first, end - first, seed)
+        b.set_linear_velocity(211, v)
+        return b
+
+    whole = make(0, total)
+    whole.step(scenes.DT, 8, 3, steps=50)
+    for rank in range(2):
+        first, end = sharding.world_range(total, rank, 2)
+        b = make(first, end)
+        b.step(scenes.DT, 8, 3, steps=20)
+        assert checkpoint.save_batch(b, tmp_path / "ckpt", first) == end - first
+        b.close()
+    assert len(os.listdir(tmp_path / "ckpt")) == total
+    for rank in range(3):
+        first, end = sharding.world_range(total, rank, 3)
+        b = wg.batch(end - first, lane_block=1, max_contacts=800)
+        checkpoint.load_batch(b, tmp_path / "ckpt", first)
+        b.step(scenes.DT, 8, 3, steps=30)
+        for w in range(end - first):
+            assert parity.compare_snapshots(whole.download_world(first + w), b.download_world(w)) == [], (rank, w)
+        b.close()
+    whole.close()
+    wg.close()
+    ctx.close()
