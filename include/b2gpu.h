@@ -357,7 +357,8 @@ int b2gpu_world_get_contact_count(b2gpu_world* w);
 /* Body getters (B2body::get_position/get_angle/get_linear_velocity/...): copies the record. */
 int b2gpu_world_get_body(b2gpu_world* w, int body, b2gpu_body_rec* out);
 int b2gpu_world_get_stats(b2gpu_world* w, b2gpu_step_stats* out);
-/* Full step state in/out (teacher-forced parity; checkpoint/resume). */
+/* Full step state in/out (teacher-forced parity; checkpoint/resume).  Upload (here, per batch world and at batch
+ * creation) runs b2gpu_snapshot_validate first: an index outside its table is B2GPU_E_INVALID, never a device fault. */
 int b2gpu_world_snapshot_sizes(b2gpu_world* w, b2gpu_snapshot_sizes* out);
 int b2gpu_world_download(b2gpu_world* w, b2gpu_snapshot* out);
 int b2gpu_world_upload(b2gpu_world* w, const b2gpu_snapshot* in);
