@@ -121,6 +121,18 @@ class Batch:
         check(self.L, self.L.b2gpu_batch_ray_cast_closest(self.h, rays.ctypes.data, rays.shape[1], out.ctypes.data))
         return out
 
+    def query_aabb(self, aabbs, max_hits=64):
+        """B2world::query_aabb in every world: aabbs [n_worlds][boxes][4] -> (hits [n_worlds][boxes][max_hits][2] of
+        (fixture, child) in report order, counts [n_worlds][boxes]; counts may exceed max_hits: hits are truncated, and
+        entries past min(count, max_hits) of a box are unspecified)."""
+        boxes = np.ascontiguousarray(aabbs, np.float32)
+        assert boxes.ndim == 3 and boxes.shape[0] == self.n_worlds and boxes.shape[2] == 4
+        counts = np.zeros(boxes.shape[:2], np.int32)
+        hits = np.full(boxes.shape[:2] + (max(max_hits, 1), 2), -1, np.int32)
+        check(self.L, self.L.b2gpu_batch_query_aabb(self.h, boxes.ctypes.data, boxes.shape[1], max_hits, counts.ctypes.data,
+                                                     hits.ctypes.data))
+        return hits, counts
+
     def algorithmic_bytes(self):
         return int(self.L.b2gpu_batch_algorithmic_bytes(self.h))
 

@@ -119,6 +119,12 @@ int b2gpu_batch_step(b2gpu_batch* b, float dt, int vi, int pi, int steps) {
   return batch_step(b->h, dt, vi, pi, steps);
   GUARD_END
 }
+int b2gpu_batch_query_aabb(b2gpu_batch* b, const float* aabbs, int boxes_per_world, int max_hits, int32_t* counts, int32_t* hits) {
+  GUARD_BEGIN
+  if (!b) { set_error("b2gpu_batch_query_aabb: batch is NULL"); return B2GPU_E_INVALID; }
+  return batch_query_aabb_per_world(b->h, aabbs, boxes_per_world, max_hits, counts, hits);
+  GUARD_END
+}
 int b2gpu_batch_ray_cast_closest(b2gpu_batch* b, const float* p1p2, int rays_per_world, b2gpu_ray_hit* out) {
   GUARD_BEGIN
   if (!b) { set_error("b2gpu_batch_ray_cast_closest: batch is NULL"); return B2GPU_E_INVALID; }

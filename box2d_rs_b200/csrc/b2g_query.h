@@ -186,16 +186,17 @@ struct RayCastK {  // flat over (world, ray): tid = world * rays + r (any LB)
   }
 };
 
-struct QueryAabbK {  // flat over boxes of one world (world 0)
+struct QueryAabbK {  // flat over boxes: all of world 0 (per_world == 0), or per_world boxes of every world of a batch
   Batch B;
   Large L;
   const float* boxes;  // [n][4]
   int* counts;         // [n]
   int* hits;           // [n][max_hits][2]
   int n, max_hits, use_lbvh, n_leaves;
+  int per_world;       // 0: every box queries world 0; k > 0: box i queries world i / k
   B2G_HD void operator()(int i) const {
     if (i >= n) return;
-    WIdx x = widx(B, 0);
+    WIdx x = widx(B, per_world > 0 ? i / per_world : 0);
     Ws ws = ws_of(B, x);
     Box q;
     q.lo = v2(boxes[4 * i], boxes[4 * i + 1]);

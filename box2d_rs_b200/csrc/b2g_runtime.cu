@@ -1172,10 +1172,11 @@ int batch_ray_cast_closest(BatchHost* bh, const float* host_rays, int rays_per_w
   RC(dev_d2h(bh->ctx, host_out, d_out, (size_t)total * sizeof(b2gpu_ray_hit)));
   return 0;
 }
-int batch_query_aabb(BatchHost* bh, const float* host_boxes, int n, int max_hits, int* host_counts, int* host_hits) {
-  if (!bh || !host_boxes || !host_counts || n < 0 || max_hits < 0 || (max_hits > 0 && !host_hits)) { set_error("query_aabb: bad argument"); return B2GPU_E_INVALID; }
-  if (bh->B.n_worlds != 1) { set_error("query_aabb: one world at a time"); return B2GPU_E_INVALID; }
+// per_world == 0: `n` boxes against the single world of `bh`; per_world > 0: per_world boxes for every world of the
+// batch, boxes [n_worlds][per_world][4], n = n_worlds * per_world.
+static int query_aabb_impl(BatchHost* bh, const float* host_boxes, int n, int per_world, int max_hits, int* host_counts, int* host_hits) {
   if (n == 0) return 0;
+  if ((long long)n * (max_hits > 0 ? max_hits : 1) > 0x3fffffffLL) { set_error("query_aabb: too many boxes x hits"); return B2GPU_E_CAPACITY; }
   char* base = nullptr;
   const size_t boxes_bytes = align256((size_t)n * 16), counts_bytes = align256((size_t)n * 4);
   RC(query_scratch(bh, boxes_bytes + counts_bytes + (size_t)n * max_hits * 8 + 16, &base));
@@ -1185,10 +1186,22 @@ int batch_query_aabb(BatchHost* bh, const float* host_boxes, int n, int max_hits
   RC(dev_h2d(bh->ctx, d_boxes, host_boxes, (size_t)n * 16));
   int use_lbvh = 0;
   RC(query_prepare(bh, use_lbvh));
-  { QueryAabbK k = {bh->B, bh->L, d_boxes, d_counts, d_hits, n, max_hits, use_lbvh, bh->B.NP}; RC(launch(bh->ctx, k, n, 64)); }
+  { QueryAabbK k = {bh->B, bh->L, d_boxes, d_counts, d_hits, n, max_hits, use_lbvh, bh->B.NP, per_world}; RC(launch(bh->ctx, k, n, 64)); }
   RC(dev_d2h(bh->ctx, host_counts, d_counts, (size_t)n * 4));
   if (max_hits > 0) RC(dev_d2h(bh->ctx, host_hits, d_hits, (size_t)n * max_hits * 8));
   return 0;
+}
+int batch_query_aabb(BatchHost* bh, const float* host_boxes, int n, int max_hits, int* host_counts, int* host_hits) {
+  if (!bh || !host_boxes || !host_counts || n < 0 || max_hits < 0 || (max_hits > 0 && !host_hits)) { set_error("query_aabb: bad argument"); return B2GPU_E_INVALID; }
+  if (bh->B.n_worlds != 1) { set_error("query_aabb: one world at a time (use b2gpu_batch_query_aabb for a batch)"); return B2GPU_E_INVALID; }
+  return query_aabb_impl(bh, host_boxes, n, 0, max_hits, host_counts, host_hits);
+}
+int batch_query_aabb_per_world(BatchHost* bh, const float* host_boxes, int boxes_per_world, int max_hits, int* host_counts, int* host_hits) {
+  if (!bh || !host_boxes || !host_counts || boxes_per_world < 0 || max_hits < 0 || (max_hits > 0 && !host_hits)) { set_error("batch_query_aabb: bad argument"); return B2GPU_E_INVALID; }
+  const long long total = (long long)bh->B.n_worlds * boxes_per_world;
+  if (total > 0x7fffffffLL) { set_error("batch_query_aabb: too many boxes"); return B2GPU_E_CAPACITY; }
+  if (boxes_per_world == 0) return 0;
+  return query_aabb_impl(bh, host_boxes, (int)total, boxes_per_world, max_hits, host_counts, host_hits);
 }
 
 static StepParams make_params(float dt, int vi, int pi) {

@@ -67,6 +67,7 @@ def load(path=None):
         "b2gpu_world_ray_cast_closest": (i32, [vp, vp, i32, vp]),
         "b2gpu_world_query_aabb": (i32, [vp, vp, i32, i32, vp, vp]),
         "b2gpu_batch_ray_cast_closest": (i32, [vp, vp, i32, vp]),
+        "b2gpu_batch_query_aabb": (i32, [vp, vp, i32, i32, vp, vp]),
         "b2gpu_batch_create": (i32, [vp, C.POINTER(abi.SnapshotC), i32, C.POINTER(abi.Caps), C.POINTER(vp)]),
         "b2gpu_batch_destroy": (None, [vp]),
         "b2gpu_batch_world_count": (i32, [vp]),

@@ -409,6 +409,10 @@ int b2gpu_world_query_aabb(b2gpu_world* w, const float* aabbs, int n, int max_hi
 /* The same for every world of a batch: rays [n_worlds][rays_per_world][4], out [n_worlds][rays_per_world]
  * (an RL-style range sensor: one launch for all worlds). */
 int b2gpu_batch_ray_cast_closest(b2gpu_batch* b, const float* p1p2, int rays_per_world, b2gpu_ray_hit* out);
+/* B2world::query_aabb for every world of a batch (an RL-style region sensor): aabbs [n_worlds][boxes_per_world][4],
+ * counts [n_worlds][boxes_per_world], hits [n_worlds][boxes_per_world][max_hits][2]; per box as
+ * b2gpu_world_query_aabb (report order of the reference's tree query, true count returned, hits truncated). */
+int b2gpu_batch_query_aabb(b2gpu_batch* b, const float* aabbs, int boxes_per_world, int max_hits, int32_t* counts, int32_t* hits);
 
 /* ---------------------------------------- batched independent worlds (RL-style) */
 /* n_worlds replicas of `proto`, one CTA per world per step. */

@@ -151,6 +151,7 @@ extern "C" {
     pub fn b2gpu_world_ray_cast_closest(w: *mut b2gpu_world, p1p2: *const c_float, n: c_int, out: *mut b2gpu_ray_hit) -> c_int;
     pub fn b2gpu_world_query_aabb(w: *mut b2gpu_world, aabbs: *const c_float, n: c_int, max_hits: c_int, counts: *mut i32, hits: *mut i32) -> c_int;
     pub fn b2gpu_batch_ray_cast_closest(b: *mut b2gpu_batch, p1p2: *const c_float, rays_per_world: c_int, out: *mut b2gpu_ray_hit) -> c_int;
+    pub fn b2gpu_batch_query_aabb(b: *mut b2gpu_batch, aabbs: *const f32, boxes_per_world: c_int, max_hits: c_int, counts: *mut i32, hits: *mut i32) -> c_int;
     pub fn b2gpu_world_step(w: *mut b2gpu_world, dt: c_float, velocity_iterations: c_int, position_iterations: c_int) -> c_int;
     pub fn b2gpu_world_get_body_count(w: *mut b2gpu_world) -> c_int;
     pub fn b2gpu_world_get_contact_count(w: *mut b2gpu_world) -> c_int;

@@ -158,3 +158,62 @@ def test_queries_gpu(name, mode, built):
         run_scene(name, c, mode)
     finally:
         c.close()
+
+
+def _batch_query_aabb_case(ctx, lane_block):
+    """b2gpu_batch_query_aabb: different boxes in every world of a batch (one world perturbed), each world's
+    answer == the oracle's query_aabb of that world: counts, and (fixture, child) in the reference's report order;
+    truncation at max_hits keeps the true count."""
+    from box2d_rs_b200 import abi, lib, scenes, world
+    from oracle import b2o
+    wo = b2o.B2world((0.0, -10.0))
+    scenes.pyramid(wo)
+    wg = world.B2world((0.0, -10.0), ctx=ctx)
+    scenes.pyramid(wg)
+    n_worlds, per_world = 6, 60
+    bt = wg.batch(n_worlds, lane_block=lane_block, max_contacts=800)
+    o2 = wo.clone()
+    o2.body(211).set_transform((2.0, 26.0), 0.4)
+    bt.upload_world(4, o2.snapshot())
+    for _ in range(30):
+        bt.step(scenes.DT, 8, 3)
+        wo.step(scenes.DT, 8, 3)
+        o2.step(scenes.DT, 8, 3)
+    boxes = np.stack([make_queries(50 + w, per_world, np.array((-15, -1)), np.array((15, 28)))[1] for w in range(n_worlds)])
+    hits, counts = bt.query_aabb(boxes, max_hits=128)
+    total = 0
+    for w in range(n_worlds):
+        ref_hits, ref_counts = (o2 if w == 4 else wo).query_aabb(boxes[w], 128)
+        assert np.array_equal(ref_counts, counts[w]), w
+        for i in range(per_world):
+            assert [tuple(int(v) for v in h) for h in hits[w, i, :counts[w, i]]] == ref_hits[i], (w, i)
+        total += int(ref_counts.sum())
+    assert total > 500 and counts.max() > 6
+    small_hits, small_counts = bt.query_aabb(boxes, max_hits=3)
+    assert np.array_equal(small_counts, counts)
+    keep = np.arange(3)[None, None, :] < np.minimum(counts, 3)[:, :, None]  # entries past a box's count are unspecified
+    assert np.array_equal(small_hits[keep], hits[:, :, :3][keep])
+    # no boxes: nothing to do; NULL batch: error code
+    assert bt.L.b2gpu_batch_query_aabb(bt.h, boxes.ctypes.data, 0, 4, counts.ctypes.data, hits.ctypes.data) == 0
+    assert bt.L.b2gpu_batch_query_aabb(None, boxes.ctypes.data, 1, 4, counts.ctypes.data, hits.ctypes.data) == abi.E_INVALID
+    # the one-world call refuses a batch and says where to go
+    with pytest.raises(lib.B2gpuError):
+        lib.check(bt.L, bt.L.b2gpu_batch_query_aabb(bt.h, boxes.ctypes.data, -1, 4, counts.ctypes.data, hits.ctypes.data))
+    bt.close()
+    wg.close()
+
+
+@pytest.mark.parametrize("lane_block", [1, 4, 32])
+def test_batch_query_aabb(lane_block, hctx):
+    _batch_query_aabb_case(hctx, lane_block)
+
+
+@pytest.mark.gpu
+def test_batch_query_aabb_gpu(built):
+    from box2d_rs_b200 import batch
+    c = batch.Context(0)
+    try:
+        _batch_query_aabb_case(c, 32)
+        _batch_query_aabb_case(c, 1)
+    finally:
+        c.close()
