@@ -251,6 +251,12 @@ def chain_shape(vertices, prev_vertex, next_vertex, loop=False):
     return s
 
 
+# b2gpu_contact_event (include/b2gpu.h)
+EVENT_BEGIN_CONTACT, EVENT_END_CONTACT = 1, 2
+CONTACT_EVENT_DTYPE = np.dtype([("type", np.int32), ("fixture_a", np.int32), ("index_a", np.int32), ("fixture_b", np.int32),
+                                ("index_b", np.int32), ("reserved", np.int32, 3)])
+assert CONTACT_EVENT_DTYPE.itemsize == 32
+
 # b2gpu_ray_hit (include/b2gpu.h)
 RAY_HIT_DTYPE = np.dtype([("fixture", np.int32), ("child_index", np.int32), ("fraction", np.float32), ("point", np.float32, 2),
                           ("normal", np.float32, 2), ("reserved", np.int32)])

@@ -159,6 +159,14 @@ class B2world:
         c = snap.as_c()
         check(self.L, self.L.b2gpu_world_upload(self.h, C.byref(c)))
 
+    def step_with_events(self, dt, velocity_iterations, position_iterations):
+        """One step plus the begin_contact / end_contact events the reference's listener would have received during
+        it, in firing order (b2gpu_contact_events; abi.CONTACT_EVENT_DTYPE).  Costs two snapshot downloads."""
+        before = self.snapshot()
+        self.step(dt, velocity_iterations, position_iterations)
+        after = self.snapshot()
+        return contact_events(self.L, before, after, int(self.get_stats()["destroyed"]))
+
     def save_checkpoint(self, path):
         """Full step state to a snapshot file (b2gpu_snapshot_save); see checkpoint.py."""
         from . import checkpoint
@@ -189,3 +197,12 @@ class B2world:
     def batch(self, n_worlds, **kw):
         """n_worlds replicas of this world's current state, one CTA lane per world (b2gpu_batch_create)."""
         return Batch(self.ctx, self.snapshot(), n_worlds, **kw)
+
+
+def contact_events(L, before, after, destroyed=-1):
+    """b2gpu_contact_events on two abi.Snapshot objects -> structured array of abi.CONTACT_EVENT_DTYPE."""
+    cb, ca = before.as_c(), after.as_c()
+    n = check(L, L.b2gpu_contact_events(C.byref(cb), C.byref(ca), destroyed, None, 0))
+    out = np.zeros(max(n, 1), abi.CONTACT_EVENT_DTYPE)
+    check(L, L.b2gpu_contact_events(C.byref(cb), C.byref(ca), destroyed, out.ctypes.data, n))
+    return out[:n]

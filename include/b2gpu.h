@@ -385,6 +385,24 @@ int b2gpu_snapshot_save(const b2gpu_snapshot* s, const char* path);
 int b2gpu_snapshot_file_sizes(const char* path, b2gpu_snapshot_sizes* out);
 int b2gpu_snapshot_load(const char* path, b2gpu_snapshot* out);
 
+/* Contact listener events for a device-resident step.  B2contactListener::begin_contact / end_contact
+ * (src/b2_world_callbacks.rs:68-104) fire inside the reference's step (b2_contact.rs(private):201-211 from the
+ * collide loop, b2_contact_manager.rs(private):24-49 for destroyed contacts); here they are derived on the host
+ * from the snapshots taken before and after a step and returned in the reference's firing order, for replay to a
+ * listener once the step has finished (pre_solve / post_solve mutations are out of scope).
+ * `destroyed` = b2gpu_step_stats.destroyed of that step, or -1 to infer it.  Returns the number of events (it may
+ * exceed `capacity`; `out` then holds the first `capacity`) or a negative error.  Host-only.
+ * (box2d_rs_b200/csrc/b2g_events.cu) */
+#define B2GPU_EVENT_BEGIN_CONTACT 1
+#define B2GPU_EVENT_END_CONTACT 2
+typedef struct b2gpu_contact_event {
+  int32_t type;
+  int32_t fixture_a, index_a, fixture_b, index_b; /* as in b2gpu_contact_rec */
+  int32_t reserved[3];
+} b2gpu_contact_event;
+int b2gpu_contact_events(const b2gpu_snapshot* before, const b2gpu_snapshot* after, int destroyed,
+                         b2gpu_contact_event* out, int capacity);
+
 /* ------------------------------------------------------------ world queries
  * B2world::ray_cast (src/private/dynamics/b2_world.rs:1015-1049) with the "closest hit" callback
  * `|fixture, point, normal, fraction| fraction`, and B2world::query_aabb (:969-980) with a callback that

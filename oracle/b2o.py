@@ -51,6 +51,8 @@ def lib():
         L.b2o_contact_count.argtypes = [C.c_void_p]
         L.b2o_get_profile.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         L.b2o_get_stats.argtypes = [C.c_void_p, C.c_void_p]
+        L.b2o_get_events.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.b2o_get_events.restype = C.c_int
         L.b2o_ray_cast_closest.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.b2o_query_aabb.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.b2o_snapshot_sizes.argtypes = [C.c_void_p, C.POINTER(abi.SnapshotSizes)]
@@ -208,6 +210,14 @@ class B2world:
         hits = np.zeros((boxes.shape[0], max(max_hits, 1), 2), np.int32)
         lib().b2o_query_aabb(self.h, boxes.ctypes.data, boxes.shape[0], max_hits, counts.ctypes.data, hits.ctypes.data)
         return [[(int(f), int(c)) for f, c in hits[i, :min(int(counts[i]), max_hits)]] for i in range(boxes.shape[0])], counts
+
+    def contact_events(self):
+        """begin_contact (1) / end_contact (2) events of the last step in the reference's firing order:
+        int32 [n][5] = (type, fixture_a, index_a, fixture_b, index_b)."""
+        n = lib().b2o_get_events(self.h, None, 0)
+        out = np.zeros((max(n, 1), 5), np.int32)
+        lib().b2o_get_events(self.h, out.ctypes.data, n)
+        return out[:n]
 
     def snapshot(self):
         n = abi.SnapshotSizes()

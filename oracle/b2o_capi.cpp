@@ -149,6 +149,16 @@ void b2o_get_profile(void* w, double* out7) {
   out7[0] = p.step; out7[1] = p.collide; out7[2] = p.solve; out7[3] = p.solve_init; out7[4] = p.solve_velocity;
   out7[5] = p.solve_position; out7[6] = p.broadphase;
 }
+// begin/end contact events of the last step in firing order: out = [cap][5] (type, fixture_a, index_a, fixture_b,
+// index_b); returns the number of events (may exceed cap).
+int b2o_get_events(void* w, int32_t* out, int cap) {
+  const std::vector<ContactEvent>& ev = ((World*)w)->events;
+  for (size_t i = 0; i < ev.size() && (int)i < cap; ++i) {
+    out[5 * i] = ev[i].type; out[5 * i + 1] = ev[i].fixture_a; out[5 * i + 2] = ev[i].index_a;
+    out[5 * i + 3] = ev[i].fixture_b; out[5 * i + 4] = ev[i].index_b;
+  }
+  return (int)ev.size();
+}
 void b2o_get_stats(void* w, b2gpu_step_stats* out) {
   const StepStats& s = ((World*)w)->stats;
   std::memset(out, 0, sizeof(*out));

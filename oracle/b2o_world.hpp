@@ -98,6 +98,12 @@ struct TimeStep {  // src/b2_time_step.rs
 struct Profile {  // src/b2_time_step.rs:5-15 (ms)
   double step = 0, collide = 0, solve = 0, solve_init = 0, solve_velocity = 0, solve_position = 0, broadphase = 0;
 };
+// B2contactListener::begin_contact / end_contact (src/b2_world_callbacks.rs:68-104) as the reference would fire them
+// during one step, recorded in firing order (test infrastructure for b2gpu_contact_events).
+struct ContactEvent {
+  int type;  // 1 = begin_contact, 2 = end_contact
+  int fixture_a, index_a, fixture_b, index_b;
+};
 struct StepStats {
   int contacts = 0, touching = 0, destroyed = 0, islands = 0, island_bodies = 0, island_contacts = 0, moved = 0, pairs = 0,
       created = 0, awake_bodies = 0, solver_levels = 0;
@@ -408,8 +414,10 @@ struct World {
     ++contact_count;
     ++stats.created;
   }
+  std::vector<ContactEvent> events;  // cleared at the top of step()
   void destroy_contact(int ci) {  // b2_contact_manager.rs(private):24-78 ; b2_contact.rs(private):33-46
     Contact& c = contacts[ci];
+    if (c.flags & CF_TOUCHING) events.push_back({2, c.fixture_a, c.index_a, c.fixture_b, c.index_b});  // :44-49 end_contact
     int body_a = fixtures[c.fixture_a].body, body_b = fixtures[c.fixture_b].body;
     if (c.prev != -1) contacts[c.prev].next = c.next;
     if (c.next != -1) contacts[c.next].prev = c.prev;
@@ -478,6 +486,8 @@ struct World {
       }
     }
     if (touching) c.flags |= CF_TOUCHING; else c.flags &= ~CF_TOUCHING;
+    if (!was_touching && touching) events.push_back({1, c.fixture_a, c.index_a, c.fixture_b, c.index_b});  // :205-207
+    if (was_touching && !touching) events.push_back({2, c.fixture_a, c.index_a, c.fixture_b, c.index_b});  // :209-211
   }
   void collide() {  // b2_contact_manager.rs(private):83-171 — destroys AFTER the loop (box2d-rs deviation)
     std::vector<int> to_destroy;
@@ -1031,6 +1041,7 @@ struct World {
   void step(float dt, int velocity_iterations, int position_iterations) {  // b2_world.rs(private):903-959
     double ts = now_ms();
     stats = StepStats();
+    events.clear();
     if (new_contacts) {
       find_new_contacts();
       new_contacts = false;

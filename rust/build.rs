@@ -5,7 +5,7 @@ use std::process::Command;
 
 fn main() {
     let out = std::env::var("OUT_DIR").unwrap();
-    let sources = ["b2g_api.cu", "b2g_runtime.cu", "b2g_world.cu", "b2g_checkpoint.cu"];
+    let sources = ["b2g_api.cu", "b2g_runtime.cu", "b2g_world.cu", "b2g_checkpoint.cu", "b2g_events.cu"];
     let mut cmd = Command::new(std::env::var("NVCC").unwrap_or_else(|_| "nvcc".into()));
     // --fmad=false is mandatory: rustc never contracts a*b+c, and pair sets are downstream of the solver.
     cmd.args([

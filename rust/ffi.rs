@@ -122,6 +122,18 @@ pub struct b2gpu_ray_hit {
     pub reserved: i32,
 }
 
+/// b2gpu_contact_event (include/b2gpu.h): one begin_contact (1) / end_contact (2) of a step, in firing order.
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct b2gpu_contact_event {
+    pub type_: i32,
+    pub fixture_a: i32,
+    pub index_a: i32,
+    pub fixture_b: i32,
+    pub index_b: i32,
+    pub reserved: [i32; 3],
+}
+
 extern "C" {
     pub fn b2gpu_abi_version() -> c_int;
     pub fn b2gpu_last_error() -> *const c_char;
@@ -162,6 +174,7 @@ extern "C" {
     pub fn b2gpu_world_upload(w: *mut b2gpu_world, snap: *const b2gpu_snapshot) -> c_int;
     // checkpoint / resume (host-only): the whole step state on disk, where the crate's serde support
     // (src/serialize/serialize_b2_world.rs) saves definitions only
+    pub fn b2gpu_contact_events(before: *const b2gpu_snapshot, after: *const b2gpu_snapshot, destroyed: c_int, out: *mut b2gpu_contact_event, capacity: c_int) -> c_int;
     pub fn b2gpu_snapshot_validate(s: *const b2gpu_snapshot) -> c_int;
     pub fn b2gpu_snapshot_save(s: *const b2gpu_snapshot, path: *const c_char) -> c_int;
     pub fn b2gpu_snapshot_file_sizes(path: *const c_char, out: *mut b2gpu_snapshot_sizes) -> c_int;
