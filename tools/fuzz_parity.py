@@ -91,7 +91,7 @@ def build(world, rng):
     return n + 1
 
 
-def run_seed(seed, make_world, steps, batch_mode, large=False):
+def run_seed(seed, make_world, steps, batch_mode, large=False, events=False):
     import parity
     from oracle import b2o
     rng = np.random.default_rng(seed)
@@ -147,7 +147,14 @@ def run_seed(seed, make_world, steps, batch_mode, large=False):
             v = (f32v(rng.uniform(-6, 6)), f32v(rng.uniform(-6, 6)))
             wo.body(b).set_linear_velocity(v); wg.body(b).set_linear_velocity(v)
         wo.step(dt, vi, pi)
-        if batch is None:
+        if batch is None and events:  # begin / end contact events of every step, in the reference's firing order
+            ev_g = wg.step_with_events(dt, vi, pi)
+            ev_o = wo.contact_events()
+            tab = np.stack([ev_g[k] for k in ("type", "fixture_a", "index_a", "fixture_b", "index_b")], 1) if len(ev_g) else np.zeros((0, 5), np.int32)
+            if not np.array_equal(tab, ev_o):
+                return "events, step %d: %s vs %s" % (i, tab[:4].tolist(), ev_o[:4].tolist())
+            run_seed.event_total = getattr(run_seed, "event_total", 0) + len(ev_o)
+        elif batch is None:
             wg.step(dt, vi, pi)
         else:
             batch.step(dt, vi, pi)
@@ -175,18 +182,20 @@ def main():
     ap.add_argument("--gpu", action="store_true")
     ap.add_argument("--batch", action="store_true")
     ap.add_argument("--large", action="store_true")
+    ap.add_argument("--events", action="store_true", help="also compare b2gpu_contact_events with the oracle's listener log every step")
     args = ap.parse_args()
     from box2d_rs_b200 import batch as batch_mod, world
     lib_path = None if args.gpu else os.path.join(ROOT, "tests", "hostsim", "libb2gpu_hostsim.so")
     ctx = batch_mod.Context(0, lib_path=lib_path)
     fails = 0
     for seed in range(args.first, args.first + args.seeds):
-        r = run_seed(seed, lambda g: world.B2world(g, ctx=ctx), args.steps, args.batch, args.large)
+        r = run_seed(seed, lambda g: world.B2world(g, ctx=ctx), args.steps, args.batch, args.large, args.events)
         if r not in (None, "skip"):
             fails += 1
             print("seed %d: %s" % (seed, r), flush=True)
-    print("fuzz: %d seeds, %d failures (%s%s)" % (args.seeds, fails, "gpu" if args.gpu else "host simulator",
-                                                   ", batch" if args.batch else ", large-world mode teacher-forced" if args.large else ""))
+    print("fuzz: %d seeds, %d failures (%s%s%s)" % (args.seeds, fails, "gpu" if args.gpu else "host simulator",
+                                                     ", batch" if args.batch else ", large-world mode teacher-forced" if args.large else "",
+                                                     ", %d contact events compared" % getattr(run_seed, "event_total", 0) if args.events else ""))
     sys.exit(1 if fails else 0)
 
 
