@@ -688,6 +688,87 @@ int b2gpu_body_apply_force_to_center(b2gpu_world* W, int body, float fx, float f
   return 0;
   GUARD_END
 }
+// The rest of B2body's force / impulse API (src/b2_body.rs:869-972): host-side edits of the body record between
+// steps, like apply_force_to_center above.  Expression shapes follow the reference operation for operation.
+static int dynamic_body_for_apply(b2gpu_world* W, int body, int wake, b2gpu_body_rec** out) {
+  *out = nullptr;
+  int rc = check_body(W, body);
+  if (rc) return rc;
+  rc = ensure_host(W);
+  if (rc) return rc;
+  b2gpu_body_rec& b = W->h.bodies[body];
+  if (b.type != B2GPU_DYNAMIC_BODY) return 0;
+  if (wake && !(b.flags & B2GPU_BODY_AWAKE)) set_awake(b, true);
+  W->host_dirty = true;
+  if (b.flags & B2GPU_BODY_AWAKE) *out = &b;  // a sleeping body accumulates nothing
+  return 0;
+}
+int b2gpu_body_apply_force(b2gpu_world* W, int body, float fx, float fy, float px, float py, int wake) {  // :869-888
+  GUARD_BEGIN
+  b2gpu_body_rec* b;
+  int rc = dynamic_body_for_apply(W, body, wake, &b);
+  if (rc || !b) return rc;
+  b->fx += fx; b->fy += fy;
+  const float rx = px - b->c_x, ry = py - b->c_y;
+  const float t1 = rx * fy, t2 = ry * fx;
+  b->torque += t1 - t2;
+  return 0;
+  GUARD_END
+}
+int b2gpu_body_apply_torque(b2gpu_world* W, int body, float torque, int wake) {  // :905-918
+  GUARD_BEGIN
+  b2gpu_body_rec* b;
+  int rc = dynamic_body_for_apply(W, body, wake, &b);
+  if (rc || !b) return rc;
+  b->torque += torque;
+  return 0;
+  GUARD_END
+}
+int b2gpu_body_apply_linear_impulse(b2gpu_world* W, int body, float ix, float iy, float px, float py, int wake) {  // :920-939
+  GUARD_BEGIN
+  b2gpu_body_rec* b;
+  int rc = dynamic_body_for_apply(W, body, wake, &b);
+  if (rc || !b) return rc;
+  const float dvx = b->inv_mass * ix, dvy = b->inv_mass * iy;
+  b->vx += dvx; b->vy += dvy;
+  const float rx = px - b->c_x, ry = py - b->c_y;
+  const float t1 = rx * iy, t2 = ry * ix;
+  const float dw = b->inv_inertia * (t1 - t2);
+  b->w += dw;
+  return 0;
+  GUARD_END
+}
+int b2gpu_body_apply_linear_impulse_to_center(b2gpu_world* W, int body, float ix, float iy, int wake) {  // :941-957
+  GUARD_BEGIN
+  b2gpu_body_rec* b;
+  int rc = dynamic_body_for_apply(W, body, wake, &b);
+  if (rc || !b) return rc;
+  const float dvx = b->inv_mass * ix, dvy = b->inv_mass * iy;
+  b->vx += dvx; b->vy += dvy;
+  return 0;
+  GUARD_END
+}
+int b2gpu_body_apply_angular_impulse(b2gpu_world* W, int body, float impulse, int wake) {  // :959-972
+  GUARD_BEGIN
+  b2gpu_body_rec* b;
+  int rc = dynamic_body_for_apply(W, body, wake, &b);
+  if (rc || !b) return rc;
+  const float dw = b->inv_inertia * impulse;
+  b->w += dw;
+  return 0;
+  GUARD_END
+}
+int b2gpu_body_set_awake(b2gpu_world* W, int body, int flag) {  // src/b2_body.rs:783-801
+  GUARD_BEGIN
+  int rc = check_body(W, body);
+  if (rc) return rc;
+  rc = ensure_host(W);
+  if (rc) return rc;
+  set_awake(W->h.bodies[body], flag != 0);
+  W->host_dirty = true;
+  return 0;
+  GUARD_END
+}
 static int set_world_flag(b2gpu_world* W, uint32_t bit, int flag) {
   if (!W) { set_error("world is NULL"); return B2GPU_E_INVALID; }
   int rc = ensure_host(W);

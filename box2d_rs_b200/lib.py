@@ -47,6 +47,12 @@ def load(path=None):
         "b2gpu_body_set_linear_velocity": (i32, [vp, i32, f32, f32]),
         "b2gpu_body_set_angular_velocity": (i32, [vp, i32, f32]),
         "b2gpu_body_apply_force_to_center": (i32, [vp, i32, f32, f32, i32]),
+        "b2gpu_body_apply_force": (i32, [vp, i32, f32, f32, f32, f32, i32]),
+        "b2gpu_body_apply_torque": (i32, [vp, i32, f32, i32]),
+        "b2gpu_body_apply_linear_impulse": (i32, [vp, i32, f32, f32, f32, f32, i32]),
+        "b2gpu_body_apply_linear_impulse_to_center": (i32, [vp, i32, f32, f32, i32]),
+        "b2gpu_body_apply_angular_impulse": (i32, [vp, i32, f32, i32]),
+        "b2gpu_body_set_awake": (i32, [vp, i32, i32]),
         "b2gpu_world_set_allow_sleeping": (i32, [vp, i32]),
         "b2gpu_world_set_warm_starting": (i32, [vp, i32]),
         "b2gpu_world_set_continuous_physics": (i32, [vp, i32]),

@@ -74,6 +74,30 @@ class B2body:
         w = self.world
         check(w.L, w.L.b2gpu_body_apply_force_to_center(w.h, self.index, f[0], f[1], int(wake)))
 
+    def apply_force(self, f, point, wake=True):
+        w = self.world
+        check(w.L, w.L.b2gpu_body_apply_force(w.h, self.index, f[0], f[1], point[0], point[1], int(wake)))
+
+    def apply_torque(self, torque, wake=True):
+        w = self.world
+        check(w.L, w.L.b2gpu_body_apply_torque(w.h, self.index, torque, int(wake)))
+
+    def apply_linear_impulse(self, impulse, point, wake=True):
+        w = self.world
+        check(w.L, w.L.b2gpu_body_apply_linear_impulse(w.h, self.index, impulse[0], impulse[1], point[0], point[1], int(wake)))
+
+    def apply_linear_impulse_to_center(self, impulse, wake=True):
+        w = self.world
+        check(w.L, w.L.b2gpu_body_apply_linear_impulse_to_center(w.h, self.index, impulse[0], impulse[1], int(wake)))
+
+    def apply_angular_impulse(self, impulse, wake=True):
+        w = self.world
+        check(w.L, w.L.b2gpu_body_apply_angular_impulse(w.h, self.index, impulse, int(wake)))
+
+    def set_awake(self, flag):
+        w = self.world
+        check(w.L, w.L.b2gpu_body_set_awake(w.h, self.index, int(flag)))
+
     def _rec(self):
         w = self.world
         out = np.zeros(1, abi.BODY_DTYPE)

@@ -330,6 +330,15 @@ int b2gpu_body_set_linear_velocity(b2gpu_world* w, int body, float vx, float vy)
 int b2gpu_body_set_angular_velocity(b2gpu_world* w, int body, float w_);
 /* B2body::apply_force_to_center(force, wake) */
 int b2gpu_body_apply_force_to_center(b2gpu_world* w, int body, float fx, float fy, int wake);
+/* B2body::apply_force / apply_torque / apply_linear_impulse / apply_linear_impulse_to_center /
+ * apply_angular_impulse (src/b2_body.rs:869-972) and set_awake (:783-801): only dynamic bodies react, `wake` wakes a
+ * sleeping body first, a body that stays asleep accumulates nothing; points are world points. */
+int b2gpu_body_apply_force(b2gpu_world* w, int body, float fx, float fy, float point_x, float point_y, int wake);
+int b2gpu_body_apply_torque(b2gpu_world* w, int body, float torque, int wake);
+int b2gpu_body_apply_linear_impulse(b2gpu_world* w, int body, float ix, float iy, float point_x, float point_y, int wake);
+int b2gpu_body_apply_linear_impulse_to_center(b2gpu_world* w, int body, float ix, float iy, int wake);
+int b2gpu_body_apply_angular_impulse(b2gpu_world* w, int body, float impulse, int wake);
+int b2gpu_body_set_awake(b2gpu_world* w, int body, int flag);
 /* B2world::set_allow_sleeping / set_warm_starting / set_continuous_physics */
 int b2gpu_world_set_allow_sleeping(b2gpu_world* w, int flag);
 int b2gpu_world_set_warm_starting(b2gpu_world* w, int flag);

@@ -44,6 +44,12 @@ def lib():
         L.b2o_set_linear_velocity.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float]
         L.b2o_set_angular_velocity.argtypes = [C.c_void_p, C.c_int, C.c_float]
         L.b2o_apply_force_to_center.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_int]
+        L.b2o_apply_force.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int]
+        L.b2o_apply_linear_impulse.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float, C.c_float, C.c_int]
+        L.b2o_apply_linear_impulse_to_center.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_int]
+        L.b2o_apply_torque.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_int]
+        L.b2o_apply_angular_impulse.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_int]
+        L.b2o_body_set_awake.argtypes = [C.c_void_p, C.c_int, C.c_int]
         for f in ("b2o_set_allow_sleeping", "b2o_set_warm_starting", "b2o_set_block_solve", "b2o_set_collect_levels"):
             getattr(L, f).argtypes = [C.c_void_p, C.c_int]
         L.b2o_step.argtypes = [C.c_void_p, C.c_float, C.c_int, C.c_int]
@@ -130,6 +136,24 @@ class B2body:
 
     def apply_force_to_center(self, f, wake=True):
         lib().b2o_apply_force_to_center(self.world.h, self.index, f[0], f[1], int(wake))
+
+    def apply_force(self, f, point, wake=True):
+        lib().b2o_apply_force(self.world.h, self.index, f[0], f[1], point[0], point[1], int(wake))
+
+    def apply_torque(self, torque, wake=True):
+        lib().b2o_apply_torque(self.world.h, self.index, torque, int(wake))
+
+    def apply_linear_impulse(self, impulse, point, wake=True):
+        lib().b2o_apply_linear_impulse(self.world.h, self.index, impulse[0], impulse[1], point[0], point[1], int(wake))
+
+    def apply_linear_impulse_to_center(self, impulse, wake=True):
+        lib().b2o_apply_linear_impulse_to_center(self.world.h, self.index, impulse[0], impulse[1], int(wake))
+
+    def apply_angular_impulse(self, impulse, wake=True):
+        lib().b2o_apply_angular_impulse(self.world.h, self.index, impulse, int(wake))
+
+    def set_awake(self, flag):
+        lib().b2o_body_set_awake(self.world.h, self.index, int(flag))
 
     def _rec(self):
         return self.world.snapshot().bodies[self.index]

@@ -131,6 +131,12 @@ void b2o_set_transform(void* w, int body, float px, float py, float angle) { ((W
 void b2o_set_linear_velocity(void* w, int body, float vx, float vy) { ((World*)w)->set_linear_velocity(body, Vec2(vx, vy)); }
 void b2o_set_angular_velocity(void* w, int body, float av) { ((World*)w)->set_angular_velocity(body, av); }
 void b2o_apply_force_to_center(void* w, int body, float fx, float fy, int wake) { ((World*)w)->apply_force_to_center(body, Vec2(fx, fy), wake != 0); }
+void b2o_apply_force(void* w, int body, float fx, float fy, float px, float py, int wake) { ((World*)w)->apply_force(body, Vec2(fx, fy), Vec2(px, py), wake != 0); }
+void b2o_apply_torque(void* w, int body, float t, int wake) { ((World*)w)->apply_torque(body, t, wake != 0); }
+void b2o_apply_linear_impulse(void* w, int body, float ix, float iy, float px, float py, int wake) { ((World*)w)->apply_linear_impulse(body, Vec2(ix, iy), Vec2(px, py), wake != 0); }
+void b2o_apply_linear_impulse_to_center(void* w, int body, float ix, float iy, int wake) { ((World*)w)->apply_linear_impulse_to_center(body, Vec2(ix, iy), wake != 0); }
+void b2o_apply_angular_impulse(void* w, int body, float i, int wake) { ((World*)w)->apply_angular_impulse(body, i, wake != 0); }
+void b2o_body_set_awake(void* w, int body, int flag) { ((World*)w)->set_awake(body, flag != 0); }
 void b2o_set_allow_sleeping(void* w, int f) {  // b2_world.rs(private):340-353
   World* W = (World*)w;
   if ((f != 0) == W->allow_sleep) return;

@@ -333,6 +333,43 @@ struct World {
     if (wake && !(b.flags & BF_AWAKE)) set_awake(bi, true);
     if (b.flags & BF_AWAKE) b.force += f;
   }
+  // src/b2_body.rs:869-972 — the rest of the force / impulse API (inline module of B2body)
+  void apply_force(int bi, Vec2 f, Vec2 point, bool wake) {  // :869-888
+    Body& b = bodies[bi];
+    if (b.type != DYNAMIC_BODY) return;
+    if (wake && !(b.flags & BF_AWAKE)) set_awake(bi, true);
+    if (b.flags & BF_AWAKE) {
+      b.force += f;
+      b.torque += b2_cross(point - b.sweep.c, f);
+    }
+  }
+  void apply_torque(int bi, float torque, bool wake) {  // :905-918
+    Body& b = bodies[bi];
+    if (b.type != DYNAMIC_BODY) return;
+    if (wake && !(b.flags & BF_AWAKE)) set_awake(bi, true);
+    if (b.flags & BF_AWAKE) b.torque += torque;
+  }
+  void apply_linear_impulse(int bi, Vec2 impulse, Vec2 point, bool wake) {  // :920-939
+    Body& b = bodies[bi];
+    if (b.type != DYNAMIC_BODY) return;
+    if (wake && !(b.flags & BF_AWAKE)) set_awake(bi, true);
+    if (b.flags & BF_AWAKE) {
+      b.linear_velocity += b.inv_mass * impulse;
+      b.angular_velocity += b.inv_i * b2_cross(point - b.sweep.c, impulse);
+    }
+  }
+  void apply_linear_impulse_to_center(int bi, Vec2 impulse, bool wake) {  // :941-957
+    Body& b = bodies[bi];
+    if (b.type != DYNAMIC_BODY) return;
+    if (wake && !(b.flags & BF_AWAKE)) set_awake(bi, true);
+    if (b.flags & BF_AWAKE) b.linear_velocity += b.inv_mass * impulse;
+  }
+  void apply_angular_impulse(int bi, float impulse, bool wake) {  // :959-972
+    Body& b = bodies[bi];
+    if (b.type != DYNAMIC_BODY) return;
+    if (wake && !(b.flags & BF_AWAKE)) set_awake(bi, true);
+    if (b.flags & BF_AWAKE) b.angular_velocity += b.inv_i * impulse;
+  }
   bool body_should_collide(int self_, int other) const {  // b2_body.rs(private):391-416 (no joints in scope)
     if (bodies[self_].type != DYNAMIC_BODY && bodies[other].type != DYNAMIC_BODY) return false;
     return true;

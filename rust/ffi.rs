@@ -155,6 +155,12 @@ extern "C" {
     pub fn b2gpu_body_set_linear_velocity(w: *mut b2gpu_world, body: c_int, vx: c_float, vy: c_float) -> c_int;
     pub fn b2gpu_body_set_angular_velocity(w: *mut b2gpu_world, body: c_int, w_: c_float) -> c_int;
     pub fn b2gpu_body_apply_force_to_center(w: *mut b2gpu_world, body: c_int, fx: c_float, fy: c_float, wake: c_int) -> c_int;
+    pub fn b2gpu_body_apply_force(w: *mut b2gpu_world, body: c_int, fx: c_float, fy: c_float, point_x: c_float, point_y: c_float, wake: c_int) -> c_int;
+    pub fn b2gpu_body_apply_torque(w: *mut b2gpu_world, body: c_int, torque: c_float, wake: c_int) -> c_int;
+    pub fn b2gpu_body_apply_linear_impulse(w: *mut b2gpu_world, body: c_int, ix: c_float, iy: c_float, point_x: c_float, point_y: c_float, wake: c_int) -> c_int;
+    pub fn b2gpu_body_apply_linear_impulse_to_center(w: *mut b2gpu_world, body: c_int, ix: c_float, iy: c_float, wake: c_int) -> c_int;
+    pub fn b2gpu_body_apply_angular_impulse(w: *mut b2gpu_world, body: c_int, impulse: c_float, wake: c_int) -> c_int;
+    pub fn b2gpu_body_set_awake(w: *mut b2gpu_world, body: c_int, flag: c_int) -> c_int;
     pub fn b2gpu_world_set_allow_sleeping(w: *mut b2gpu_world, flag: c_int) -> c_int;
     pub fn b2gpu_world_set_warm_starting(w: *mut b2gpu_world, flag: c_int) -> c_int;
     pub fn b2gpu_world_set_continuous_physics(w: *mut b2gpu_world, flag: c_int) -> c_int;

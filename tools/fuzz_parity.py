@@ -2,7 +2,7 @@
 """Differential fuzzing of the device stages (host simulator build by default, --gpu for the CUDA path) against
 the CPU oracle: random scenes (polygons of 3..8 vertices, circles, edges, chains, kinematic / fixed-rotation /
 multi-fixture bodies, sensors, filters, restitution, damping, random world flags and iteration counts, dt = 0 steps,
-mid-run set_transform / set_linear_velocity edits), stepped freely and compared bit for bit.
+mid-run set_transform / set_linear_velocity / apply_force / apply_torque / apply_*_impulse / set_awake edits), stepped freely and compared bit for bit.
 
   python tools/fuzz_parity.py --seeds 200 [--gpu] [--batch] [--large]
 
@@ -146,6 +146,20 @@ def run_seed(seed, make_world, steps, batch_mode, large=False, events=False):
             b = int(rng.integers(1, nb))
             v = (f32v(rng.uniform(-6, 6)), f32v(rng.uniform(-6, 6)))
             wo.body(b).set_linear_velocity(v); wg.body(b).set_linear_velocity(v)
+        if batch is None and 2 <= ev <= 7:  # the rest of B2body's force / impulse API, sleeping bodies included
+            b = int(rng.integers(1, nb))
+            vec = (f32v(rng.uniform(-40, 40)), f32v(rng.uniform(-40, 40)))
+            pt = (f32v(rng.uniform(-8, 8)), f32v(rng.uniform(0, 10)))
+            sc = f32v(rng.uniform(-20, 20))
+            wake = bool(rng.integers(0, 3))
+            for w in (wo, wg):
+                bd = w.body(b)
+                if ev == 2: bd.apply_force(vec, pt, wake)
+                elif ev == 3: bd.apply_torque(sc, wake)
+                elif ev == 4: bd.apply_linear_impulse((vec[0] * 0.1, vec[1] * 0.1), pt, wake)
+                elif ev == 5: bd.apply_linear_impulse_to_center((vec[0] * 0.1, vec[1] * 0.1), wake)
+                elif ev == 6: bd.apply_angular_impulse(sc * 0.05, wake)
+                else: bd.set_awake(wake)
         wo.step(dt, vi, pi)
         if batch is None and events:  # begin / end contact events of every step, in the reference's firing order
             ev_g = wg.step_with_events(dt, vi, pi)
