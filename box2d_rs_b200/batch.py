@@ -86,6 +86,15 @@ class Batch:
         check(self.L, self.L.b2gpu_batch_download_world(self.h, world, C.byref(c)))
         return snap.finish(c)
 
+    def step_with_events(self, dt, velocity_iterations, position_iterations, worlds):
+        """One step of the whole batch plus, for the listed worlds, the begin_contact / end_contact events of that step
+        in the reference's firing order (b2gpu_contact_events): {world: abi.CONTACT_EVENT_DTYPE array}.  Costs two
+        snapshot downloads per listed world — meant for the few worlds somebody is watching, not for all of them."""
+        from .world import contact_events
+        before = {w: self.download_world(w) for w in worlds}
+        self.step(dt, velocity_iterations, position_iterations)
+        return {w: contact_events(self.L, before[w], self.download_world(w), int(self.stats(w, 1)[0]["destroyed"])) for w in worlds}
+
     def save_checkpoint(self, world, path):
         """One world of the batch to a snapshot file (b2gpu_snapshot_save)."""
         from . import checkpoint

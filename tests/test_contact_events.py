@@ -101,3 +101,30 @@ def test_truncation_and_errors(built):
     assert L.b2gpu_contact_events(C.byref(cb), C.byref(ca), 10 ** 6, out.ctypes.data, 2) == abi.E_INVALID
     # identical snapshots: no events
     assert len(world.contact_events(L, after, after)) == 0
+
+
+def test_batch_step_with_events(built):
+    """Events of selected worlds of a batch (one of them perturbed) == the oracle's listener log of that world."""
+    from box2d_rs_b200 import batch, scenes, world
+    from oracle import b2o
+    ctx = batch.Context(0, lib_path=HOSTSIM_SO)
+    wo = b2o.B2world((0.0, -10.0))
+    scenes.pyramid(wo)
+    wg = world.B2world((0.0, -10.0), ctx=ctx)
+    scenes.pyramid(wg)
+    bt = wg.batch(6, lane_block=4, max_contacts=800)
+    o2 = wo.clone()
+    o2.body(211).set_transform((2.0, 26.0), 0.4)
+    bt.upload_world(5, o2.snapshot())
+    total = {0: 0, 5: 0}
+    for i in range(70):
+        wo.step(scenes.DT, 8, 3)
+        o2.step(scenes.DT, 8, 3)
+        got = bt.step_with_events(scenes.DT, 8, 3, [0, 5])
+        for w, o in ((0, wo), (5, o2)):
+            assert np.array_equal(_table(got[w]), o.contact_events()), (i, w)
+            total[w] += len(got[w])
+    assert total[0] > 300 and total[5] != total[0]
+    bt.close()
+    wg.close()
+    ctx.close()
