@@ -251,7 +251,10 @@ int b2gpu_snapshot_load(const char* path, b2gpu_snapshot* out) {
   Table t[7];
   tables_of(&staged, t);
   uint64_t total = 0;
-  for (int i = 0; i < 7; ++i) total += t[i].bytes;
+  for (int i = 0; i < 7; ++i) {
+    total += t[i].bytes;
+    if (t[i].bytes && !t[i].ptr) { fclose(f); return fail(B2GPU_E_INVALID, "snapshot_load: a table of the file is not empty but the caller's array pointer is NULL"); }
+  }
   if (total != h.payload_bytes) { fclose(f); return fail(B2GPU_E_INVALID, "checkpoint: payload size does not match the table sizes"); }
   std::vector<unsigned char> buf(total ? total : 1);
   size_t got = fread(buf.data(), 1, total, f);

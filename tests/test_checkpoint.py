@@ -113,6 +113,11 @@ def test_rejects_bad_files(built, tmp_path):
     c = small.as_c()
     assert L.b2gpu_snapshot_load(os.fsencode(good), C.byref(c)) == abi.E_CAPACITY
     assert small.bodies[0]["type"] == 0 and c.n.body_count == 1  # untouched
+    # big enough capacities but a NULL array: an error code, not a crash
+    roomy = abi.Snapshot(checkpoint.file_sizes(good))
+    c = roomy.as_c()
+    c.bodies = None
+    assert L.b2gpu_snapshot_load(os.fsencode(good), C.byref(c)) == abi.E_INVALID
 
 
 def test_validate_catches_out_of_range_indices(built, tmp_path):
