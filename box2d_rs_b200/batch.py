@@ -74,6 +74,16 @@ class Batch:
     def step(self, dt, velocity_iterations, position_iterations, steps=1):
         check(self.L, self.L.b2gpu_batch_step(self.h, dt, velocity_iterations, position_iterations, steps))
 
+    def reset(self, snap):
+        """Every world back to the state of `snap` (b2gpu_batch_reset: an RL-style reset of all environments)."""
+        c = snap.as_c()
+        check(self.L, self.L.b2gpu_batch_reset(self.h, C.byref(c)))
+
+    def check_status(self):
+        """Synchronises and raises B2gpuError if a world failed on the device (capacity overflow, unsupported shape
+        pair).  step() is asynchronous and cannot report it; step_host / body_state / download_world do."""
+        check(self.L, self.L.b2gpu_batch_status(self.h))
+
     def upload_world(self, world, snap):
         c = snap.as_c()
         check(self.L, self.L.b2gpu_batch_upload_world(self.h, world, C.byref(c)))

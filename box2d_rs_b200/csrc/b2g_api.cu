@@ -146,7 +146,25 @@ int b2gpu_batch_snapshot_sizes(b2gpu_batch* b, int world, b2gpu_snapshot_sizes* 
 int b2gpu_batch_download_world(b2gpu_batch* b, int world, b2gpu_snapshot* out) {
   GUARD_BEGIN
   if (!b) { set_error("batch is NULL"); return B2GPU_E_INVALID; }
-  return batch_download_world(b->h, world, out);
+  int rc = batch_download_world(b->h, world, out);
+  if (rc) return rc;
+  return batch_last_download_status(b->h);  // buffers are filled; a failed world reports its device status
+  GUARD_END
+}
+int b2gpu_batch_reset(b2gpu_batch* b, const b2gpu_snapshot* in) {
+  GUARD_BEGIN
+  if (!b) { set_error("batch is NULL"); return B2GPU_E_INVALID; }
+  return batch_reset(b->h, in);
+  GUARD_END
+}
+int b2gpu_batch_status(b2gpu_batch* b) {
+  GUARD_BEGIN
+  if (!b) { set_error("batch is NULL"); return B2GPU_E_INVALID; }
+  int st = 0;
+  int rc = batch_status(b->h, &st);
+  if (rc) return rc;
+  if (st) set_error("a world of the batch failed on the device (see b2gpu_step_stats.status per world)");
+  return st;
   GUARD_END
 }
 int b2gpu_batch_get_stats(b2gpu_batch* b, int first, int count, b2gpu_step_stats* out) {

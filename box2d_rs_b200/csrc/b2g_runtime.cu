@@ -24,6 +24,7 @@ void set_error(const std::string& s) { g_error = s; }
 
 #define RC(x) do { int rc_ = (x); if (rc_ != 0) return rc_; } while (0)
 
+static int status_error(int st);
 static int large_alloc(BatchHost* bh);
 static int lw_build_lbvh(BatchHost* bh, int stage);
 static void large_free(BatchHost* bh);
@@ -501,6 +502,12 @@ int batch_create(Ctx* ctx, const b2gpu_snapshot* proto, int n_worlds, const b2gp
   AL(bh->b_wake, W * B.NB); AL(bh->b_chead, W * B.NB); AL(bh->c_next, W * B.NC); AL(bh->stack, W * B.NB);
   AL(bh->state_dev, (long long)n_worlds * B.NB * 8);
   AL(bh->forces_dev, (long long)n_worlds * B.NB * 3);
+  AL(bh->status_dev, 4);
+#if defined(B2G_HOSTSIM)
+  bh->status_host = (int*)calloc(4, 4);
+#else
+  { cudaError_t e_ = cudaMallocHost((void**)&bh->status_host, 16); if (e_ != cudaSuccess) { batch_destroy(bh); return cuda_fail(e_, "cudaMallocHost(status)"); } bh->status_host[0] = 0; }
+#endif
   bh->stage_bytes = 16 * (size_t)std::max(std::max(B.NB, B.NN), std::max(std::max(B.NC, B.NMOVE), (int)WS_COUNT));
   {
     void* v = nullptr;
@@ -614,6 +621,11 @@ void batch_destroy(BatchHost* bh) {
   }
 #endif
   large_free(bh);
+#if defined(B2G_HOSTSIM)
+  free(bh->status_host);
+#else
+  if (bh->status_host) cudaFreeHost(bh->status_host);
+#endif
   if (bh->query_buf) dev_free(bh->query_buf);
   for (void* p : bh->allocs) dev_free(p);
   delete bh;
@@ -631,6 +643,28 @@ int batch_upload_world(BatchHost* bh, int world, const b2gpu_snapshot* in) {
   std::vector<ArrRef> tab = array_table(bh, im);
   for (const ArrRef& a : tab) RC(move_array(bh, a, 0, world));
   bh->pre_step_needed = true;
+  RC(dev_zero(bh->ctx, bh->status_dev, 4));  // recomputed from the worlds' own (sticky) status words on the next check
+  return 0;
+}
+
+// Every world of the batch back to the state of `in` (an RL-style reset of all environments): the same broadcast
+// batch_create performs for the prototype.
+int batch_reset(BatchHost* bh, const b2gpu_snapshot* in) {
+  if (!bh || !in) { set_error("batch_reset: bad argument"); return B2GPU_E_INVALID; }
+  RC(b2gpu_snapshot_validate(in));
+  if (!topology_matches(bh->topo, in)) {
+    set_error("batch_reset: snapshot topology (fixtures/shapes/proxies/body types) differs from the batch prototype");
+    return B2GPU_E_INVALID;
+  }
+  if (bh->large) { set_error("batch_reset: use upload_world for the single world of the large-world mode"); return B2GPU_E_INVALID; }
+  WorldImage im;
+  RC(image_pack(bh, in, im));
+  RC(ctx_sync(bh->ctx));
+  std::vector<ArrRef> tab = array_table(bh, im);
+  for (const ArrRef& a : tab) RC(move_array(bh, a, 2, 0));
+  bh->pre_step_needed = true;
+  bh->stepped = false;
+  RC(dev_zero(bh->ctx, bh->status_dev, 4));
   return 0;
 }
 
@@ -643,6 +677,7 @@ static int image_fetch(BatchHost* bh, int world, WorldImage& im) {
   image_alloc(bh->B, im);
   std::vector<ArrRef> tab = array_table(bh, im);
   for (const ArrRef& a : tab) RC(move_array(bh, a, 1, world));
+  bh->last_fetch_status = im.ws[WS_STATUS];
   if (bh->large && !bh->lw_exact_tree) {
     // large-world mode does not maintain the replica tree: the leaf boxes are current, the topology is the
     // one last uploaded.  Refit the internal boxes (children before parents) so the snapshot carries a valid
@@ -688,6 +723,9 @@ int batch_download_world(BatchHost* bh, int world, b2gpu_snapshot* out) {
   RC(image_fetch(bh, world, im));
   return image_unpack(bh, im, out);
 }
+// Error code of the world last downloaded (its sticky WS_STATUS), 0 if it is healthy: the buffers of the download
+// are filled either way, so a failed world can still be inspected.
+int batch_last_download_status(BatchHost* bh) { return bh ? status_error(bh->last_fetch_status) : B2GPU_E_INVALID; }
 
 // ------------------------------------------------------------------ step
 // body state gather / force scatter: flat over bodies
@@ -745,6 +783,28 @@ struct VelScatterK {
     B.b_vel[bi] = v;
   }
 };
+
+// Device-side failures (contact table / move buffer / island list full, unregistered shape pair, query stack
+// overflow) are recorded per world in WS_STATUS and stay set; this reduces them to one word so that every call that
+// already synchronises can return the first failure instead of 0 (the word is the most negative code of any world).
+struct StatusK {
+  Batch B;
+  int* out;
+  B2G_HD void operator()(int w) const {
+    if (w >= B.n_worlds) return;
+    WIdx x = widx(B, w);
+    const int st = ws_of(B, x)[WS_STATUS];
+    if (st < 0) B2G_ATOMIC_MIN(out, st);
+  }
+};
+static int status_error(int st) {
+  if (st == 0) return 0;
+  set_error(st == B2GPU_E_CAPACITY ? "a world ran out of device capacity during a step (contact table, move buffer or island list full: "
+                                     "raise b2gpu_caps.max_contacts); its state is no longer the reference's"
+            : st == B2GPU_E_UNSUPPORTED ? "a world hit an unsupported case on the device (unregistered shape pair, e.g. edge against edge)"
+                                        : "a world raised an internal device status");
+  return st;
+}
 
 // All stages of `steps` consecutive steps for the world-block window of Bw, on ctx->stream.
 // `init_done` (optional cudaEvent_t) is recorded after the solver set-up stage of the first step: the
@@ -1253,7 +1313,7 @@ static int enqueue_steps(BatchHost* bh, const StepParams& sp, int steps, const f
   if (host_forces) RC(batch_set_forces(bh, host_forces, 0, B.n_worlds));
   if (bh->large) RC(step_large(bh, sp, steps));
   else RC(step_window(bh, all, sp, steps, nullptr));
-  if (host_state_out) RC(batch_get_body_state(bh, host_state_out, 0, B.n_worlds));
+  if (host_state_out) return batch_get_body_state(bh, host_state_out, 0, B.n_worlds);
   return 0;
 #else
   cudaStream_t main_s = (cudaStream_t)ctx->stream;
@@ -1270,6 +1330,8 @@ static int enqueue_steps(BatchHost* bh, const StepParams& sp, int steps, const f
       StateGatherK k = {all, bh->state_dev};
       RC(launch(ctx, k, B.n_wblocks * B.LB * B.NB, 128));
       CU(cudaMemcpyAsync(host_state_out, bh->state_dev, (size_t)B.n_worlds * B.NB * 8 * 4, cudaMemcpyDeviceToHost, main_s));
+      { StatusK k = {all, bh->status_dev}; RC(launch(ctx, k, B.n_worlds, 128)); }
+      CU(cudaMemcpyAsync(bh->status_host, bh->status_dev, 4, cudaMemcpyDeviceToHost, main_s));
     }
     return 0;
   }
@@ -1312,6 +1374,10 @@ static int enqueue_steps(BatchHost* bh, const StepParams& sp, int steps, const f
       CU(cudaEventRecord((cudaEvent_t)sg.ev_done, gs));
       CU(cudaStreamWaitEvent(main_s, (cudaEvent_t)sg.ev_done, 0));
     }
+  }
+  if (!rc && host_state_out) {
+    { StatusK k = {all, bh->status_dev}; RC(launch(ctx, k, B.n_worlds, 128)); }
+    CU(cudaMemcpyAsync(bh->status_host, bh->status_dev, 4, cudaMemcpyDeviceToHost, main_s));
   }
   return rc;
 #endif
@@ -1382,6 +1448,9 @@ static int run_steps(BatchHost* bh, float dt, int vi, int pi, int steps, const f
 #endif
   bh->pre_step_needed = false;
   if (steps > 0 && dt > 0.0f) bh->stepped = true;
+#if !defined(B2G_HOSTSIM)
+  if (host_state_out) return status_error(*bh->status_host);
+#endif
   return 0;
 }
 
@@ -1434,12 +1503,25 @@ int batch_get_stats(BatchHost* bh, int first, int count, b2gpu_step_stats* out) 
   return 0;
 }
 
+// Most negative WS_STATUS of any world of the batch (0: none).  Synchronises.
+int batch_status(BatchHost* bh, int* out) {
+  if (!bh || !out) { set_error("batch_status: bad argument"); return B2GPU_E_INVALID; }
+  Batch all = bh->B;
+  all.wb_first = 0;
+  all.wb_count = bh->B.n_wblocks;
+  { StatusK k = {all, bh->status_dev}; RC(launch(bh->ctx, k, all.n_worlds, 128)); }
+  RC(dev_d2h(bh->ctx, bh->status_host, bh->status_dev, 4));
+  *out = *bh->status_host;
+  return 0;
+}
 int batch_get_body_state(BatchHost* bh, float* host_out, int first, int count) {
   if (!bh || !host_out || first < 0 || count < 0 || first + count > bh->B.n_worlds) { set_error("get_body_state: bad argument"); return B2GPU_E_INVALID; }
   Batch& B = bh->B;
   { StateGatherK k = {B, bh->state_dev}; RC(launch(bh->ctx, k, B.n_wblocks * B.LB * B.NB, 128)); }
   RC(dev_d2h(bh->ctx, host_out, bh->state_dev + (size_t)first * B.NB * 8, (size_t)count * B.NB * 8 * 4));
-  return 0;
+  int st = 0;
+  RC(batch_status(bh, &st));
+  return status_error(st);
 }
 int batch_set_forces(BatchHost* bh, const float* host, int first, int count) {
   if (!bh || !host || first < 0 || count < 0 || first + count > bh->B.n_worlds) { set_error("set_forces: bad argument"); return B2GPU_E_INVALID; }

@@ -80,6 +80,9 @@ struct BatchHost {
   int* stack = nullptr;
   float* state_dev = nullptr;    // [n_worlds][NB][8] gather buffer
   float* forces_dev = nullptr;   // [n_worlds][NB][3]
+  int* status_dev = nullptr;     // reduced WS_STATUS of the batch (StatusK)
+  int* status_host = nullptr;    // pinned copy of it
+  int last_fetch_status = 0;     // WS_STATUS of the world last fetched by image_fetch
   void* stage_dev = nullptr;     // staging for single-world upload/download
   size_t stage_bytes = 0;
   bool smem_island = false;      // shared-memory island DFS in use (b2g_island_smem.cuh)
@@ -122,6 +125,9 @@ void set_error(const std::string& s);
 int batch_create(Ctx* ctx, const b2gpu_snapshot* proto, int n_worlds, const b2gpu_caps* caps, int lane_block, BatchHost** out);
 void batch_destroy(BatchHost* b);
 int batch_upload_world(BatchHost* b, int world, const b2gpu_snapshot* in);
+int batch_reset(BatchHost* b, const b2gpu_snapshot* in);
+int batch_status(BatchHost* b, int* out);
+int batch_last_download_status(BatchHost* b);
 int batch_snapshot_sizes(BatchHost* b, int world, b2gpu_snapshot_sizes* out);
 int batch_download_world(BatchHost* b, int world, b2gpu_snapshot* out);
 int batch_step(BatchHost* b, float dt, int vi, int pi, int steps);

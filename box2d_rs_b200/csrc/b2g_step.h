@@ -26,10 +26,12 @@
 #define B2G_ATOMIC_ADD(p, v) atomicAdd((p), (v))
 #define B2G_ATOMIC_OR(p, v) atomicOr((p), (v))
 #define B2G_ATOMIC_MAX(p, v) atomicMax((p), (v))
+#define B2G_ATOMIC_MIN(p, v) atomicMin((p), (v))
 #else
 #define B2G_ATOMIC_ADD(p, v) (*(p) += (v))
 #define B2G_ATOMIC_OR(p, v) (*(p) |= (v))
 #define B2G_ATOMIC_MAX(p, v) (*(p) = (*(p) > (v) ? *(p) : (v)))
+#define B2G_ATOMIC_MIN(p, v) (*(p) = (*(p) < (v) ? *(p) : (v)))
 #endif
 
 namespace b2g {

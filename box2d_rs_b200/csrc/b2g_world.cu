@@ -310,7 +310,9 @@ int ensure_host(b2gpu_world* W) {
     h.n_moved[i] = nd.moved;
   }
   W->dev_newer = false;
-  return 0;
+  // a world that overflowed a device table during a step (B2GPU_E_CAPACITY) or met an unregistered shape pair is no
+  // longer the reference's world: every call that reads the state back reports it instead of returning 0
+  return batch_last_download_status(W->dev);
 }
 
 int check_body(b2gpu_world* W, int body) {

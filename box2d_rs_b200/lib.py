@@ -83,6 +83,8 @@ def load(path=None):
         "b2gpu_batch_snapshot_sizes": (i32, [vp, i32, C.POINTER(abi.SnapshotSizes)]),
         "b2gpu_batch_download_world": (i32, [vp, i32, C.POINTER(abi.SnapshotC)]),
         "b2gpu_batch_get_stats": (i32, [vp, i32, i32, vp]),
+        "b2gpu_batch_reset": (i32, [vp, C.POINTER(abi.SnapshotC)]),
+        "b2gpu_batch_status": (i32, [vp]),
         "b2gpu_batch_set_forces": (i32, [vp, vp, i32, i32]),
         "b2gpu_batch_set_linear_velocity": (i32, [vp, i32, vp, i32, i32]),
         "b2gpu_batch_get_body_state": (i32, [vp, vp, i32, i32]),

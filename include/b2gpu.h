@@ -452,6 +452,17 @@ int b2gpu_batch_upload_world(b2gpu_batch* b, int world, const b2gpu_snapshot* in
 int b2gpu_batch_snapshot_sizes(b2gpu_batch* b, int world, b2gpu_snapshot_sizes* out);
 int b2gpu_batch_download_world(b2gpu_batch* b, int world, b2gpu_snapshot* out);
 int b2gpu_batch_get_stats(b2gpu_batch* b, int first_world, int count, b2gpu_step_stats* out);
+/* Every world of the batch back to the state of `in` (same topology as the prototype): an RL-style reset of all
+ * environments, the broadcast b2gpu_batch_create performs.  Synchronous. */
+int b2gpu_batch_reset(b2gpu_batch* b, const b2gpu_snapshot* in);
+/* Device-side failures.  The reference grows its tables; a batch has fixed capacities (b2gpu_caps), so a step can
+ * overflow the contact table, the move buffer or an island list (B2GPU_E_CAPACITY), or meet an unregistered shape
+ * pair where the reference panics (B2GPU_E_UNSUPPORTED).  The failure is recorded per world (b2gpu_step_stats.status),
+ * stays set until that world is uploaded again, and is RETURNED by every call that synchronises anyway:
+ * b2gpu_batch_step_host, b2gpu_batch_get_body_state, b2gpu_batch_download_world (buffers are still filled), and by
+ * the b2gpu_world_* calls that read state back.  b2gpu_batch_step / b2gpu_world_step are asynchronous and return
+ * before the device has run: poll b2gpu_batch_status (synchronises; 0 or the most negative status of any world). */
+int b2gpu_batch_status(b2gpu_batch* b);
 /* Per-body force/torque of every world for the next step (B2body::apply_force_to_center /
  * apply_torque without wake): host array [n_worlds][body_count][3], pinned or pageable. */
 int b2gpu_batch_set_forces(b2gpu_batch* b, const float* host_fxfyt, int first_world, int count);

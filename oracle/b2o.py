@@ -52,6 +52,8 @@ def lib():
         L.b2o_body_set_awake.argtypes = [C.c_void_p, C.c_int, C.c_int]
         for f in ("b2o_set_allow_sleeping", "b2o_set_warm_starting", "b2o_set_block_solve", "b2o_set_collect_levels"):
             getattr(L, f).argtypes = [C.c_void_p, C.c_int]
+        L.b2o_set_collect_dag.argtypes = [C.c_void_p, C.c_int, C.c_double]
+        L.b2o_get_dag_stats.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         L.b2o_step.argtypes = [C.c_void_p, C.c_float, C.c_int, C.c_int]
         L.b2o_body_count.argtypes = [C.c_void_p]
         L.b2o_contact_count.argtypes = [C.c_void_p]
@@ -201,6 +203,18 @@ class B2world:
 
     def set_collect_levels(self, flag):
         lib().b2o_set_collect_levels(self.h, int(flag))
+
+    def set_collect_dag(self, flag, handover=2.0):
+        lib().b2o_set_collect_dag(self.h, int(flag), float(handover))
+
+    def dag_stats(self):
+        """Largest island of the last step: dependency-DAG depth of the exact-order velocity sweeps and the simulated
+        makespan (in visits) of the chunked dataflow schedule for 256 / 1024 / 4096 / 16384 workers."""
+        out = (C.c_double * 10)()
+        lib().b2o_get_dag_stats(self.h, out)
+        keys = ("contacts", "bodies", "sweeps", "depth", "depth_one_sweep", "handover", "makespan_256", "makespan_1024",
+                "makespan_4096", "makespan_16384")
+        return dict(zip(keys, list(out)))
 
     def step(self, dt, velocity_iterations, position_iterations):
         lib().b2o_step(self.h, dt, velocity_iterations, position_iterations)

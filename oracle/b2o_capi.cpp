@@ -2,7 +2,9 @@
 // --impl reference, __graft_entry__.smoke only).  Never linked into the product.
 // PARITY UNPINNED beyond the reference's own tests (see b2o_math.hpp).
 #include <atomic>
+#include <condition_variable>
 #include <cstring>
+#include <mutex>
 #include <thread>
 #include <vector>
 
@@ -147,6 +149,14 @@ void b2o_set_allow_sleeping(void* w, int f) {  // b2_world.rs(private):340-353
 void b2o_set_warm_starting(void* w, int f) { ((World*)w)->warm_starting = f != 0; }
 void b2o_set_block_solve(void* w, int f) { ((World*)w)->block_solve = f != 0; }
 void b2o_set_collect_levels(void* w, int f) { ((World*)w)->collect_levels = f != 0; }
+// largest island of the last step: out10 = contacts, bodies, sweeps, depth, depth of one sweep, handover, makespan x4
+void b2o_set_collect_dag(void* w, int f, double handover) { World* W = (World*)w; W->collect_dag = f != 0; W->collect_levels = W->collect_levels || f != 0; W->dag_handover = handover; }
+void b2o_get_dag_stats(void* w, double* out10) {
+  const World::DagStats& d = ((World*)w)->dag;
+  out10[0] = d.contacts; out10[1] = d.bodies; out10[2] = d.sweeps; out10[3] = d.depth; out10[4] = d.depth_one_sweep;
+  out10[5] = ((World*)w)->dag_handover;
+  for (int i = 0; i < 4; ++i) out10[6 + i] = d.makespan[i];
+}
 void b2o_step(void* w, float dt, int vi, int pi) { ((World*)w)->step(dt, vi, pi); }
 int b2o_body_count(void* w) { return (int)((World*)w)->bodies.size(); }
 int b2o_contact_count(void* w) { return ((World*)w)->contact_count; }
@@ -347,21 +357,72 @@ void b2o_get_body_state(void* w, float* out) {
 }
 
 // ---- CPU baseline: one world per host thread. Returns seconds of wall time.
-double b2o_run_worlds_mt(void** worlds, int n_worlds, int steps, float dt, int vi, int pi, int threads) {
-  if (threads < 1) threads = 1;
-  std::atomic<int> next(0);
-  double t0 = now_ms();
-  std::vector<std::thread> pool;
-  for (int t = 0; t < threads; ++t)
-    pool.emplace_back([&]() {
-      for (;;) {
-        int i = next.fetch_add(1);
-        if (i >= n_worlds) break;
+// A persistent pool (created on first use, reused by every call: the timed region contains no thread creation), worlds
+// dealt out statically round-robin so every thread steps the same number of worlds when n_worlds % threads == 0.
+namespace {
+struct Pool {
+  std::vector<std::thread> threads;
+  std::mutex m;
+  std::condition_variable cv_go, cv_done;
+  long generation = 0;
+  int pending = 0;
+  bool quit = false;
+  void** worlds = nullptr;
+  int n_worlds = 0, steps = 0, vi = 0, pi = 0;
+  float dt = 0.0f;
+  void worker(int t, int nt, long seen) {
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> lk(m);
+        cv_go.wait(lk, [&] { return quit || generation != seen; });
+        if (quit) return;
+        seen = generation;
+      }
+      for (int i = t; i < n_worlds; i += nt) {
         World* W = (World*)worlds[i];
         for (int s = 0; s < steps; ++s) W->step(dt, vi, pi);
       }
-    });
-  for (auto& th : pool) th.join();
+      {
+        std::lock_guard<std::mutex> lk(m);
+        if (--pending == 0) cv_done.notify_all();
+      }
+    }
+  }
+  void ensure(int nt) {
+    if ((int)threads.size() == nt) return;
+    shutdown();
+    quit = false;
+    const long gen = generation;
+    for (int t = 0; t < nt; ++t) threads.emplace_back([this, t, nt, gen] { worker(t, nt, gen); });
+  }
+  void shutdown() {
+    {
+      std::lock_guard<std::mutex> lk(m);
+      quit = true;
+    }
+    cv_go.notify_all();
+    for (auto& th : threads) th.join();
+    threads.clear();
+  }
+  ~Pool() { shutdown(); }
+};
+Pool g_pool;
+}  // namespace
+double b2o_run_worlds_mt(void** worlds, int n_worlds, int steps, float dt, int vi, int pi, int threads) {
+  if (threads < 1) threads = 1;
+  g_pool.ensure(threads);
+  double t0 = now_ms();
+  {
+    std::lock_guard<std::mutex> lk(g_pool.m);
+    g_pool.worlds = worlds; g_pool.n_worlds = n_worlds; g_pool.steps = steps; g_pool.dt = dt; g_pool.vi = vi; g_pool.pi = pi;
+    g_pool.pending = threads;
+    ++g_pool.generation;
+  }
+  g_pool.cv_go.notify_all();
+  {
+    std::unique_lock<std::mutex> lk(g_pool.m);
+    g_pool.cv_done.wait(lk, [&] { return g_pool.pending == 0; });
+  }
   return (now_ms() - t0) * 1e-3;
 }
 // libm sinf/cosf of an array (what f32::sin / f32::cos lower to on linux-gnu): reference for the

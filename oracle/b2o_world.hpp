@@ -158,6 +158,8 @@ struct World {
   Profile profile;
   StepStats stats;
   bool collect_levels = false;     // compute the wavefront depth statistic (diagnostic only)
+  bool collect_dag = false;        // also the largest island's DAG statistics (dag_collect)
+  double dag_handover = 2.0;
 
   explicit World(Vec2 g) : gravity(g) {}
 
@@ -929,6 +931,49 @@ struct World {
     return depth;
   }
 
+  // Diagnostic (not part of the reference): the same DAG for the largest island of the step, plus a simulation of
+  // the chunked dataflow schedule of the GPU's giant-island solver (b2g_large.h: the island's constraint list is cut
+  // into `workers` contiguous chunks, each worker walks its chunk in order sweep after sweep and waits for the
+  // previous visit of either body; one visit = 1 time unit, a hand-over between workers costs `handover` units).
+  struct DagStats {
+    int contacts = 0, bodies = 0, sweeps = 0, depth = 0, depth_one_sweep = 0;
+    double makespan[4] = {0, 0, 0, 0};  // workers = 256, 1024, 4096, 16384
+  };
+  DagStats dag;
+  void dag_collect(const Island& is, int sweeps, double handover) {
+    if ((int)vcs.size() <= dag.contacts) return;
+    dag = DagStats();
+    dag.contacts = (int)vcs.size();
+    dag.bodies = (int)is.bodies.size();
+    dag.sweeps = sweeps;
+    dag.depth = wavefront_depth(is, sweeps);
+    dag.depth_one_sweep = wavefront_depth(is, 1);
+    const int workers[4] = {256, 1024, 4096, 16384};
+    for (int wi = 0; wi < 4; ++wi) {
+      const int P = workers[wi];
+      const int chunk = ((int)vcs.size() + P - 1) / P;
+      std::vector<double> bfin(is.bodies.size(), 0.0), tfin(P, 0.0);
+      std::vector<int> bown(is.bodies.size(), -1);
+      double end = 0.0;
+      for (int s = 0; s < sweeps; ++s)
+        for (size_t k = 0; k < vcs.size(); ++k) {
+          const ContactVelocityConstraint& vc = vcs[k];
+          const int p = (int)k / chunk;
+          const bool dyn_a = vc.inv_mass_a != 0.0f || vc.inv_ia != 0.0f;
+          const bool dyn_b = vc.inv_mass_b != 0.0f || vc.inv_ib != 0.0f;
+          double start = tfin[p];
+          if (dyn_a) start = std::max(start, bfin[vc.index_a] + (bown[vc.index_a] != p && bown[vc.index_a] >= 0 ? handover : 0.0));
+          if (dyn_b) start = std::max(start, bfin[vc.index_b] + (bown[vc.index_b] != p && bown[vc.index_b] >= 0 ? handover : 0.0));
+          const double fin = start + 1.0;
+          tfin[p] = fin;
+          if (dyn_a) { bfin[vc.index_a] = fin; bown[vc.index_a] = p; }
+          if (dyn_b) { bfin[vc.index_b] = fin; bown[vc.index_b] = p; }
+          end = std::max(end, fin);
+        }
+      dag.makespan[wi] = end;
+    }
+  }
+
   void island_solve(Island& is, const TimeStep& step) {  // b2_island_private.rs:129-328
     double t0 = now_ms();
     float h = step.dt;
@@ -957,6 +1002,7 @@ struct World {
     initialize_velocity_constraints(is);
     if (step.warm_starting) warm_start(is);
     if (collect_levels) stats.solver_levels = std::max(stats.solver_levels, wavefront_depth(is, step.velocity_iterations));
+    if (collect_levels && collect_dag) dag_collect(is, step.velocity_iterations + (step.warm_starting ? 1 : 0), dag_handover);
     double t1 = now_ms();
     profile.solve_init += t1 - t0;
     for (int it = 0; it < step.velocity_iterations; ++it) solve_velocity_constraints(is);
@@ -1078,6 +1124,7 @@ struct World {
   void step(float dt, int velocity_iterations, int position_iterations) {  // b2_world.rs(private):903-959
     double ts = now_ms();
     stats = StepStats();
+    dag = DagStats();
     events.clear();
     if (new_contacts) {
       find_new_contacts();

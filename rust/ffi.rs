@@ -193,6 +193,8 @@ extern "C" {
     pub fn b2gpu_batch_snapshot_sizes(b: *mut b2gpu_batch, world: c_int, out: *mut b2gpu_snapshot_sizes) -> c_int;
     pub fn b2gpu_batch_download_world(b: *mut b2gpu_batch, world: c_int, out: *mut b2gpu_snapshot) -> c_int;
     pub fn b2gpu_batch_get_stats(b: *mut b2gpu_batch, first_world: c_int, count: c_int, out: *mut b2gpu_step_stats) -> c_int;
+    pub fn b2gpu_batch_reset(b: *mut b2gpu_batch, input: *const b2gpu_snapshot) -> c_int;
+    pub fn b2gpu_batch_status(b: *mut b2gpu_batch) -> c_int;
     pub fn b2gpu_batch_set_forces(b: *mut b2gpu_batch, host_fxfyt: *const c_float, first_world: c_int, count: c_int) -> c_int;
     pub fn b2gpu_batch_set_linear_velocity(b: *mut b2gpu_batch, body: c_int, host_vxvy: *const c_float, first_world: c_int, count: c_int) -> c_int;
     pub fn b2gpu_batch_get_body_state(b: *mut b2gpu_batch, host_out: *mut c_float, first_world: c_int, count: c_int) -> c_int;

@@ -1,0 +1,84 @@
+"""Device-side failures reach a return code (WS_STATUS used to be visible only through get_stats), and
+b2gpu_batch_reset puts every world of a batch back to a snapshot.  Host simulator here; the GPU forms are marked."""
+import numpy as np
+import pytest
+
+import parity
+from conftest import HOSTSIM_SO
+
+
+def _ctx(gpu):
+    from box2d_rs_b200 import batch
+    return batch.Context(0) if gpu else batch.Context(0, lib_path=HOSTSIM_SO)
+
+
+def _capacity_overflow(gpu):
+    from box2d_rs_b200 import abi, scenes, world
+    from box2d_rs_b200.lib import B2gpuError
+    ctx = _ctx(gpu)
+    wg = world.B2world((0.0, -10.0), ctx=ctx)
+    scenes.pyramid(wg)
+    b = wg.batch(32 if gpu else 3, max_contacts=100)  # the Pyramid creates 190 contacts before its first step: add_pair must overflow
+    state = np.zeros((b.n_worlds, b.body_count, 8), np.float32)
+    b.step(scenes.DT, 8, 3, 2)
+    with pytest.raises(B2gpuError) as e:
+        b.check_status()
+    assert e.value.code == abi.E_CAPACITY
+    with pytest.raises(B2gpuError) as e:
+        b.step_host(None, state, scenes.DT, 8, 3, 1)
+    assert e.value.code == abi.E_CAPACITY
+    with pytest.raises(B2gpuError) as e:
+        b.body_state()
+    assert e.value.code == abi.E_CAPACITY
+    with pytest.raises(B2gpuError) as e:
+        b.download_world(0)
+    assert e.value.code == abi.E_CAPACITY
+    assert (b.stats()["status"] == abi.E_CAPACITY).all()
+    # a reset clears the failure: the worlds are the prototype again
+    b.reset(wg.snapshot())
+    b.check_status()
+    b.close()
+    wg.close()
+    ctx.close()
+
+
+def _reset_equals_fresh(gpu):
+    from box2d_rs_b200 import scenes, world
+    from oracle import b2o
+    ctx = _ctx(gpu)
+    wg = world.B2world((0.0, -10.0), ctx=ctx)
+    scenes.pyramid(wg)
+    wo = b2o.B2world((0.0, -10.0))
+    scenes.pyramid(wo)
+    proto = wg.snapshot()
+    n = 33 if gpu else 5
+    b = wg.batch(n, max_contacts=800)
+    b.set_linear_velocity(211, np.tile(np.array([[0.4, 0.0]], np.float32), (n, 1)))
+    b.step(scenes.DT, 8, 3, 60)
+    b.reset(proto)
+    for _ in range(45):
+        b.step(scenes.DT, 8, 3)
+        wo.step(scenes.DT, 8, 3)
+    for w in (0, n - 1):
+        assert parity.compare_snapshots(wo.snapshot(), b.download_world(w)) == []
+    b.close()
+    wg.close()
+    ctx.close()
+
+
+def test_capacity_overflow_is_reported(built):
+    _capacity_overflow(False)
+
+
+def test_reset_equals_fresh_batch(built):
+    _reset_equals_fresh(False)
+
+
+@pytest.mark.gpu
+def test_capacity_overflow_is_reported_gpu(built):
+    _capacity_overflow(True)
+
+
+@pytest.mark.gpu
+def test_reset_equals_fresh_batch_gpu(built):
+    _reset_equals_fresh(True)
