@@ -12,9 +12,12 @@
 //   move_buffer — the seven tables of b2gpu_snapshot, records exactly as declared in include/b2gpu.h.
 // A reader rejects a file whose magic, version, endianness tag, record sizes or either checksum do not match, or
 // whose indices point outside their tables (b2gpu_snapshot_validate), before anything reaches the device.
+#include <fcntl.h>
 #include <stddef.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #include <new>
 #include <string>
@@ -113,8 +116,10 @@ int read_header(FILE* f, const char* path, FileHeader* h) {
 
 extern "C" {
 
-// Index consistency of a snapshot: every link stays inside its table.  Not a physics check — a snapshot that passes
-// cannot make upload or a step read outside the arrays.
+// Consistency of a snapshot: every link stays inside its table AND the linked structures are what the step assumes
+// (acyclic fixture lists owned by one body each, a tree whose internal nodes have two children pointing back and whose
+// leaves own a proxy, a free list covering the rest of the pool, move-buffer entries that are leaves).  Not a physics
+// check — a snapshot that passes cannot make upload or a step loop forever or read outside the arrays.
 int b2gpu_snapshot_validate(const b2gpu_snapshot* s) {
   if (!s) return fail(B2GPU_E_INVALID, "snapshot_validate: snapshot is NULL");
   const b2gpu_snapshot_sizes& n = s->n;
@@ -169,7 +174,79 @@ int b2gpu_snapshot_validate(const b2gpu_snapshot* s) {
   if (w.tree_root < -1 || w.tree_root >= nn || w.tree_free_list < -1 || w.tree_free_list >= nn || w.tree_node_capacity != nn ||
       w.tree_node_count < 0 || w.tree_node_count > nn || w.proxy_count < 0 || w.proxy_count > np)
     return fail(B2GPU_E_INVALID, "snapshot: world tree bookkeeping inconsistent with the node table");
+  GUARD_BEGIN
+  // ---- structure (range checks alone let cycles and dangling links through: a fixture list that loops makes the
+  //      host-side builders spin, a half-linked tree node makes the device read link[-1]).
+  // (1) every fixture sits on exactly one body's list, the list of its own body, and the counts agree
+  std::vector<unsigned char> seen_f((size_t)nf, 0);
+  for (int b = 0; b < nb; ++b) {
+    int count = 0;
+    for (int f = s->bodies[b].fixture_head; f != -1; f = s->fixtures[f].next) {
+      if (seen_f[f]) return fail(B2GPU_E_INVALID, "snapshot: fixture lists form a cycle or share fixture " + std::to_string(f));
+      seen_f[f] = 1;
+      if (s->fixtures[f].body != b) return fail(B2GPU_E_INVALID, "snapshot: fixture " + std::to_string(f) + " is on the list of another body");
+      ++count;
+    }
+    if (count != s->bodies[b].fixture_count) return fail(B2GPU_E_INVALID, "snapshot: fixture_count of body " + std::to_string(b) + " does not match its list");
+  }
+  for (int f = 0; f < nf; ++f)
+    if (!seen_f[f]) return fail(B2GPU_E_INVALID, "snapshot: fixture " + std::to_string(f) + " is on no body's list");
+  // (2) a fixture's proxies are its own, one per child, in child order
+  for (int f = 0; f < nf; ++f) {
+    const b2gpu_fixture_rec& fx = s->fixtures[f];
+    for (int c = 0; fx.proxy_first >= 0 && c < fx.child_count; ++c) {
+      const b2gpu_proxy_rec& p = s->proxies[fx.proxy_first + c];
+      if (p.fixture != f || p.child_index != c) return fail(B2GPU_E_INVALID, "snapshot: proxy table does not match fixture " + std::to_string(f));
+    }
+  }
+  for (int i = 0; i < n.contact_count; ++i)
+    if (s->fixtures[s->contacts[i].fixture_a].proxy_first < 0 || s->fixtures[s->contacts[i].fixture_b].proxy_first < 0)
+      return fail(B2GPU_E_INVALID, "snapshot: contact " + std::to_string(i) + " references a fixture without proxies");
+  // (3) the tree: walked from the root, every node once; internal nodes have two children that point back, leaves
+  //     carry a proxy that points back; as many nodes as the world record says
+  std::vector<unsigned char> state((size_t)nn, 0);  // 1 = internal node of the tree, 2 = leaf, 3 = on the free list
+  int in_tree = 0;
+  if (w.tree_root != -1) {
+    if (s->nodes[w.tree_root].parent != -1) return fail(B2GPU_E_INVALID, "snapshot: tree root has a parent");
+    std::vector<int> stack(1, w.tree_root);
+    while (!stack.empty()) {
+      const int i = stack.back();
+      stack.pop_back();
+      if (state[i]) return fail(B2GPU_E_INVALID, "snapshot: tree node " + std::to_string(i) + " is reachable twice (cycle)");
+      const b2gpu_tree_node_rec& d = s->nodes[i];
+      ++in_tree;
+      if (d.height < 0) return fail(B2GPU_E_INVALID, "snapshot: free node " + std::to_string(i) + " is linked into the tree");
+      if (d.child1 == -1) {
+        state[i] = 2;
+        if (d.child2 != -1 || d.height != 0) return fail(B2GPU_E_INVALID, "snapshot: tree leaf " + std::to_string(i) + " is half-linked");
+        if (d.proxy < 0 || s->proxies[d.proxy].proxy_id != i) return fail(B2GPU_E_INVALID, "snapshot: tree leaf " + std::to_string(i) + " has no proxy pointing back at it");
+      } else {
+        state[i] = 1;
+        if (d.child2 == -1 || d.child1 == d.child2 || d.height < 1) return fail(B2GPU_E_INVALID, "snapshot: internal tree node " + std::to_string(i) + " is half-linked");
+        if (s->nodes[d.child1].parent != i || s->nodes[d.child2].parent != i)
+          return fail(B2GPU_E_INVALID, "snapshot: a child of tree node " + std::to_string(i) + " does not point back");
+        stack.push_back(d.child1);
+        stack.push_back(d.child2);
+      }
+    }
+  }
+  if (in_tree != w.tree_node_count) return fail(B2GPU_E_INVALID, "snapshot: tree_node_count does not match the nodes reachable from the root");
+  int on_free = 0;
+  for (int i = w.tree_free_list; i != -1; i = s->nodes[i].parent) {
+    if (state[i]) return fail(B2GPU_E_INVALID, "snapshot: free list revisits node " + std::to_string(i));
+    state[i] = 3;
+    ++on_free;
+  }
+  if (on_free != nn - w.tree_node_count) return fail(B2GPU_E_INVALID, "snapshot: free list length does not match the node pool");
+  // (4) proxies and move-buffer entries name leaves of that tree
+  for (int i = 0; i < np; ++i) {
+    const int id = s->proxies[i].proxy_id;
+    if (id >= 0 && (state[id] != 2 || s->nodes[id].proxy != i)) return fail(B2GPU_E_INVALID, "snapshot: proxy " + std::to_string(i) + " does not own its tree leaf");
+  }
+  for (int i = 0; i < n.move_count; ++i)
+    if (s->move_buffer[i] != -1 && state[s->move_buffer[i]] != 2) return fail(B2GPU_E_INVALID, "snapshot: move buffer entry " + std::to_string(i) + " is not a tree leaf");
   return 0;
+  GUARD_END
 }
 
 // Writes `s` to `path` (through `path`.tmp + rename, so a crash mid-write never leaves a truncated checkpoint under
@@ -198,16 +275,28 @@ int b2gpu_snapshot_save(const b2gpu_snapshot* s, const char* path) {
   }
   h.payload_hash = hash;
   h.header_hash = fnv1a(&h, offsetof(FileHeader, header_hash));
-  std::string tmp = std::string(path) + ".tmp";
-  FILE* f = fopen(tmp.c_str(), "wb");
-  if (!f) return fail(B2GPU_E_IO, "snapshot_save: cannot create " + tmp);
+  // unique temporary name (two writers saving to the same path do not collide), data on stable storage before the
+  // rename and the directory entry after it: a crash never leaves a truncated file under the final name
+  std::string tmp = std::string(path) + ".XXXXXX.tmp";
+  const int fd = mkstemps(&tmp[0], 4);
+  if (fd < 0) return fail(B2GPU_E_IO, "snapshot_save: cannot create a temporary file next to " + std::string(path));
+  FILE* f = fdopen(fd, "wb");
+  if (!f) { close(fd); remove(tmp.c_str()); return fail(B2GPU_E_IO, "snapshot_save: cannot open " + tmp); }
   bool ok = fwrite(&h, 1, sizeof h, f) == sizeof h;
   for (int i = 0; ok && i < 7; ++i) ok = t[i].bytes == 0 || fwrite(t[i].ptr, 1, t[i].bytes, f) == t[i].bytes;
   ok = (fflush(f) == 0) && ok;
+  ok = (fsync(fileno(f)) == 0) && ok;
   ok = (fclose(f) == 0) && ok;
   if (!ok || rename(tmp.c_str(), path) != 0) {
     remove(tmp.c_str());
     return fail(B2GPU_E_IO, std::string("snapshot_save: write to ") + path + " failed");
+  }
+  {
+    std::string dir(path);
+    const size_t slash = dir.find_last_of('/');
+    dir = slash == std::string::npos ? "." : (slash == 0 ? "/" : dir.substr(0, slash));
+    const int dfd = open(dir.c_str(), O_RDONLY);
+    if (dfd >= 0) { fsync(dfd); close(dfd); }
   }
   return 0;
   GUARD_END

@@ -156,6 +156,57 @@ def test_validate_catches_out_of_range_indices(built, tmp_path):
         s.contacts[0]["manifold"]["point_count"] = 3
     broken(bad_manifold)
 
+    # structural damage that keeps every index in range: the step would loop forever or read link[-1]
+    broken(set_field("fixtures", 0, "next", 0))                       # fixture list cycle
+    broken(set_field("fixtures", 5, "body", 3))                       # fixture on the list of another body
+    broken(set_field("bodies", 4, "fixture_count", 2))                # count does not match the list
+
+    def internal(s):
+        return int(np.flatnonzero(s.nodes["height"] > 0)[3])
+
+    def leaf(s):
+        return int(np.flatnonzero((s.nodes["height"] == 0) & (s.nodes["proxy"] >= 0))[3])
+
+    def half_linked(s):
+        s.nodes[internal(s)]["child2"] = -1
+    broken(half_linked)
+
+    def self_cycle(s):
+        i = internal(s)
+        s.nodes[i]["child1"] = i
+    broken(self_cycle)
+
+    def leaf_without_proxy(s):
+        s.nodes[leaf(s)]["proxy"] = -1
+    broken(leaf_without_proxy)
+
+    def wrong_back_link(s):
+        i = internal(s)
+        s.nodes[int(s.nodes[i]["child1"])]["parent"] = -1
+    broken(wrong_back_link)
+
+    def move_buffer_names_internal_node(s):
+        assert len(s.move_buffer) > 0
+        s.move_buffer[0] = internal(s)
+
+    def with_moves(mutate):
+        o = _oracle("pyramid", 30)
+        o.body(211).set_transform((0.0, 30.0), 0.1)  # buffers a move
+        s = o.snapshot()
+        mutate(s)
+        with pytest.raises(lib.B2gpuError) as e:
+            checkpoint.validate(s)
+        assert e.value.code == abi.E_INVALID
+    with_moves(move_buffer_names_internal_node)
+
+    def bad_node_count(s):
+        s.world.tree_node_count += 1
+    broken(bad_node_count)
+
+    def proxy_of_other_fixture(s):
+        s.proxies[6]["fixture"] = 3
+    broken(proxy_of_other_fixture)
+
 
 @pytest.mark.gpu
 def test_gpu_resume_is_bit_identical(built, tmp_path):

@@ -355,3 +355,48 @@ def test_large_mode_exact_order_free_running(name, ctx):
                 [b for b in parity.compare_stats(wo.get_stats(), wg.get_stats()) if "island_bodies" not in b]
             assert bad == [], "step %d: %s" % (i, bad[:6])
     wg.close()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# BASELINE configs[1], [3], [4] at FULL size (10k mixed, 100k pile, AddPair-20k): teacher-forced single steps
+# ---------------------------------------------------------------------------------------------------------
+FULL_SIZE = {
+    # name: (recipe, gravity, oracle steps at which one teacher-forced GPU step is compared)
+    "mixed10k": (lambda s, w: s.mixed(w, n=10000), (0.0, -10.0), (0, 25, 60)),
+    "pile100k": (lambda s, w: s.pile(w, n=100000), (0.0, -10.0), (0, 12, 30)),
+    "addpair20k": (lambda s, w: s.add_pair(w, n=20000), (0.0, 0.0), (0, 26, 40)),
+}
+
+
+@pytest.mark.parametrize("mode", ["large", "large_exact"])
+@pytest.mark.parametrize("name", list(FULL_SIZE))
+def test_full_size_teacher_forced(name, mode, ctx):
+    """The oracle runs the full-size scene; at the listed steps its whole state S_n is uploaded, both engines step
+    once, and everything is compared bit for bit: in mode 1 the contacts created in that step as a set (LBVH
+    append order), in mode 2 (reference contact order) the complete snapshot including the replica tree."""
+    from box2d_rs_b200 import scenes, world
+    from oracle import b2o
+    recipe, gravity, at = FULL_SIZE[name]
+    wo = b2o.B2world(gravity)
+    recipe(scenes, wo)
+    wg = world.B2world(gravity, ctx=ctx)
+    recipe(scenes, wg)
+    assert parity.compare_snapshots(wo.snapshot(), wg.snapshot()) == []
+    bt = wg.batch(1, lane_block=1, solver=mode)
+    for i in range(max(at) + 1):
+        if i in at:
+            bt.upload_world(0, wo.snapshot())
+            wo.step(scenes.DT, 8, 3)
+            bt.step(scenes.DT, 8, 3)
+            got, so, sg = bt.download_world(0), wo.get_stats(), bt.stats()[0]
+            if mode == "large":
+                bad = parity.compare_large_step(wo.snapshot(), got, so, sg)
+            else:
+                bad = parity.compare_snapshots(wo.snapshot(), got) + \
+                    [b for b in parity.compare_stats(so, sg) if "island_bodies" not in b]
+            assert bad == [], "%s step %d: %s" % (name, i, bad[:6])
+        else:
+            wo.step(scenes.DT, 8, 3)
+    assert int(wo.get_stats()["contacts"]) > 1000
+    bt.close()
+    wg.close()
