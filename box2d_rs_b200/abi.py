@@ -7,7 +7,7 @@ import ctypes as C
 
 import numpy as np
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 
 OK, E_INVALID, E_NO_DEVICE, E_CUDA, E_CAPACITY, E_UNSUPPORTED, E_LOCKED, E_INTERNAL, E_IO = 0, -1, -2, -3, -4, -5, -6, -7, -8
 
@@ -20,6 +20,8 @@ MANIFOLD_CIRCLES, MANIFOLD_FACE_A, MANIFOLD_FACE_B = 0, 1, 2
 WORLD_ALLOW_SLEEP, WORLD_WARM_STARTING, WORLD_NEW_CONTACTS, WORLD_CLEAR_FORCES, WORLD_BLOCK_SOLVE = (
     0x01, 0x02, 0x04, 0x08, 0x10)
 MAX_POLYGON_VERTICES = 8
+JOINT_DISTANCE, JOINT_REVOLUTE = 1, 8  # B2jointType numbering (src/b2_joint.rs:46-58)
+JOINT_COLLIDE_CONNECTED, JOINT_ENABLE_LIMIT, JOINT_ENABLE_MOTOR = 0x1, 0x2, 0x4
 POLYGON_RADIUS = float(np.float32(2.0) * np.float32(0.005))  # src/b2_common.rs:48
 
 f32, i32, u32, u16, i16 = np.float32, np.int32, np.uint32, np.uint16, np.int16
@@ -60,6 +62,10 @@ CONTACT_DTYPE = np.dtype([
     ("friction", f32), ("restitution", f32), ("restitution_threshold", f32), ("tangent_speed", f32), ("reserved", i32),
     ("manifold", MANIFOLD_DTYPE),
 ], align=True)
+JOINT_DTYPE = np.dtype([
+    ("type", i32), ("body_a", i32), ("body_b", i32), ("flags", u32),
+    ("local_anchor_a", f32, 2), ("local_anchor_b", f32, 2), ("param", f32, 8), ("impulse", f32, 8),
+], align=True)
 STATS_DTYPE = np.dtype([
     ("status", i32), ("contacts", i32), ("touching", i32), ("destroyed", i32), ("islands", i32), ("island_bodies", i32),
     ("island_contacts", i32), ("moved", i32), ("pairs", i32), ("created", i32), ("awake_bodies", i32),
@@ -74,6 +80,7 @@ assert NODE_DTYPE.itemsize == 40
 assert MANIFOLD_DTYPE.itemsize == 64, MANIFOLD_DTYPE.itemsize
 assert CONTACT_DTYPE.itemsize == 104, CONTACT_DTYPE.itemsize
 assert STATS_DTYPE.itemsize == 64
+assert JOINT_DTYPE.itemsize == 96, JOINT_DTYPE.itemsize
 
 
 class WorldRec(C.Structure):
@@ -86,13 +93,13 @@ class WorldRec(C.Structure):
 class SnapshotSizes(C.Structure):
     _fields_ = [("body_count", C.c_int32), ("fixture_count", C.c_int32), ("shape_count", C.c_int32),
                 ("proxy_count", C.c_int32), ("node_count", C.c_int32), ("contact_count", C.c_int32),
-                ("move_count", C.c_int32), ("reserved", C.c_int32)]
+                ("move_count", C.c_int32), ("joint_count", C.c_int32)]
 
 
 class SnapshotC(C.Structure):
     _fields_ = [("world", WorldRec), ("n", SnapshotSizes), ("bodies", C.c_void_p), ("fixtures", C.c_void_p),
                 ("shapes", C.c_void_p), ("proxies", C.c_void_p), ("nodes", C.c_void_p), ("contacts", C.c_void_p),
-                ("move_buffer", C.c_void_p)]
+                ("move_buffer", C.c_void_p), ("joints", C.c_void_p)]
 
 
 class BodyDef(C.Structure):
@@ -147,6 +154,18 @@ class ShapeDef(C.Structure):
                 ("chain_prev", C.c_float * 2), ("chain_next", C.c_float * 2)]
 
 
+class JointDef(C.Structure):
+    """b2gpu_joint_def: B2revoluteJointDef / B2distanceJointDef as one plain struct (filled by
+    world.revolute_joint_def / world.distance_joint_def = the reference's Default + initialize)."""
+    _fields_ = [("type", C.c_int32), ("body_a", C.c_int32), ("body_b", C.c_int32), ("collide_connected", C.c_int32),
+                ("local_anchor_a", C.c_float * 2), ("local_anchor_b", C.c_float * 2),
+                ("reference_angle", C.c_float), ("lower_angle", C.c_float), ("upper_angle", C.c_float),
+                ("max_motor_torque", C.c_float), ("motor_speed", C.c_float),
+                ("enable_limit", C.c_int32), ("enable_motor", C.c_int32),
+                ("length", C.c_float), ("min_length", C.c_float), ("max_length", C.c_float),
+                ("stiffness", C.c_float), ("damping", C.c_float)]
+
+
 class MassData(C.Structure):
     _fields_ = [("mass", C.c_float), ("center_x", C.c_float), ("center_y", C.c_float), ("inertia", C.c_float)]
 
@@ -172,8 +191,9 @@ class Snapshot:
         self.nodes = np.zeros(max(n.node_count, 1), NODE_DTYPE)
         self.contacts = np.zeros(max(n.contact_count, 1), CONTACT_DTYPE)
         self.move_buffer = np.zeros(max(n.move_count, 1), np.int32)
+        self.joints = np.zeros(max(n.joint_count, 1), JOINT_DTYPE)
         self.n = SnapshotSizes(n.body_count, n.fixture_count, n.shape_count, n.proxy_count, n.node_count,
-                               n.contact_count, n.move_count, 0)
+                               n.contact_count, n.move_count, n.joint_count)
 
     def as_c(self):
         s = SnapshotC()
@@ -186,6 +206,7 @@ class Snapshot:
         s.nodes = self.nodes.ctypes.data
         s.contacts = self.contacts.ctypes.data
         s.move_buffer = self.move_buffer.ctypes.data
+        s.joints = self.joints.ctypes.data
         return s
 
     def finish(self, c):
@@ -200,6 +221,7 @@ class Snapshot:
         self.nodes = self.nodes[:n.node_count]
         self.contacts = self.contacts[:n.contact_count]
         self.move_buffer = self.move_buffer[:n.move_count]
+        self.joints = self.joints[:n.joint_count]
         return self
 
 

@@ -30,7 +30,7 @@ using namespace b2g;
 namespace {
 
 const char kMagic[8] = {'B', '2', 'G', 'P', 'U', 'S', 'N', 'P'};
-const uint32_t kFileVersion = 1;
+const uint32_t kFileVersion = 2;  // 2: joint table after the move buffer (a version-1 file is a version-2 file without joints)
 const uint32_t kEndianTag = 0x01020304u;
 
 struct FileHeader {
@@ -39,8 +39,7 @@ struct FileHeader {
   uint32_t abi_version;
   uint32_t endian_tag;
   uint32_t header_bytes;
-  uint32_t record_bytes[7];  // body, fixture, shape, proxy, node, contact, move-buffer entry
-  uint32_t reserved;
+  uint32_t record_bytes[8];  // body, fixture, shape, proxy, node, contact, move-buffer entry, joint (0 in version-1 files)
   b2gpu_world_rec world;
   b2gpu_snapshot_sizes n;
   uint64_t payload_bytes;
@@ -48,9 +47,10 @@ struct FileHeader {
   uint64_t header_hash;   // FNV-1a 64 over every header byte before this field
 };
 
-const uint32_t kRecordBytes[7] = {sizeof(b2gpu_body_rec),      sizeof(b2gpu_fixture_rec), sizeof(b2gpu_shape_rec),
-                                  sizeof(b2gpu_proxy_rec),     sizeof(b2gpu_tree_node_rec),
-                                  sizeof(b2gpu_contact_rec),   sizeof(int32_t)};
+const int kTables = 8;
+const uint32_t kRecordBytes[kTables] = {sizeof(b2gpu_body_rec),    sizeof(b2gpu_fixture_rec),   sizeof(b2gpu_shape_rec),
+                                        sizeof(b2gpu_proxy_rec),   sizeof(b2gpu_tree_node_rec), sizeof(b2gpu_contact_rec),
+                                        sizeof(int32_t),           sizeof(b2gpu_joint_rec)};
 
 uint64_t fnv1a(const void* p, size_t n, uint64_t h = 1469598103934665603ull) {
   const unsigned char* b = (const unsigned char*)p;
@@ -60,7 +60,7 @@ uint64_t fnv1a(const void* p, size_t n, uint64_t h = 1469598103934665603ull) {
 
 struct Table { const void* ptr; size_t bytes; };
 
-void tables_of(const b2gpu_snapshot* s, Table t[7]) {
+void tables_of(const b2gpu_snapshot* s, Table t[kTables]) {
   const b2gpu_snapshot_sizes& n = s->n;
   t[0] = {s->bodies, sizeof(b2gpu_body_rec) * (size_t)n.body_count};
   t[1] = {s->fixtures, sizeof(b2gpu_fixture_rec) * (size_t)n.fixture_count};
@@ -69,11 +69,12 @@ void tables_of(const b2gpu_snapshot* s, Table t[7]) {
   t[4] = {s->nodes, sizeof(b2gpu_tree_node_rec) * (size_t)n.node_count};
   t[5] = {s->contacts, sizeof(b2gpu_contact_rec) * (size_t)n.contact_count};
   t[6] = {s->move_buffer, sizeof(int32_t) * (size_t)n.move_count};
+  t[7] = {s->joints, sizeof(b2gpu_joint_rec) * (size_t)n.joint_count};
 }
 
 bool sizes_ok(const b2gpu_snapshot_sizes& n) {
   return n.body_count >= 0 && n.fixture_count >= 0 && n.shape_count >= 0 && n.proxy_count >= 0 && n.node_count >= 0 &&
-         n.contact_count >= 0 && n.move_count >= 0;
+         n.contact_count >= 0 && n.move_count >= 0 && n.joint_count >= 0;
 }
 
 int fail(int code, const std::string& msg) {
@@ -87,14 +88,17 @@ int read_header(FILE* f, const char* path, FileHeader* h) {
     return fail(B2GPU_E_INVALID, std::string("checkpoint: ") + path + " is shorter than a snapshot header");
   if (memcmp(h->magic, kMagic, 8) != 0) return fail(B2GPU_E_INVALID, std::string("checkpoint: ") + path + " is not a b2gpu snapshot file");
   if (h->endian_tag != kEndianTag) return fail(B2GPU_E_INVALID, "checkpoint: file was written with another byte order");
-  if (h->file_version != kFileVersion) return fail(B2GPU_E_UNSUPPORTED, "checkpoint: unknown file version " + std::to_string(h->file_version));
+  if (h->file_version != kFileVersion && h->file_version != 1) return fail(B2GPU_E_UNSUPPORTED, "checkpoint: unknown file version " + std::to_string(h->file_version));
   if (h->header_bytes != sizeof(FileHeader)) return fail(B2GPU_E_INVALID, "checkpoint: header size mismatch");
   if (h->header_hash != fnv1a(h, offsetof(FileHeader, header_hash))) return fail(B2GPU_E_INVALID, "checkpoint: header checksum mismatch (corrupt file)");
-  if (h->abi_version != B2GPU_ABI_VERSION)
+  // ABI 2 added the joint table and changed no other record: version-1 files (ABI 1, no joints) still load
+  if (h->abi_version != B2GPU_ABI_VERSION && !(h->abi_version == 1 && h->file_version == 1))
     return fail(B2GPU_E_UNSUPPORTED, "checkpoint: file carries ABI version " + std::to_string(h->abi_version) + ", this library is " +
                                          std::to_string(B2GPU_ABI_VERSION));
-  for (int i = 0; i < 7; ++i)
+  const int n_tables = h->file_version == 1 ? 7 : kTables;
+  for (int i = 0; i < n_tables; ++i)
     if (h->record_bytes[i] != kRecordBytes[i]) return fail(B2GPU_E_INVALID, "checkpoint: record layout differs from include/b2gpu.h");
+  if (h->file_version == 1 && (h->record_bytes[7] != 0 || h->n.joint_count != 0)) return fail(B2GPU_E_INVALID, "checkpoint: version-1 file with a joint table");
   if (!sizes_ok(h->n)) return fail(B2GPU_E_INVALID, "checkpoint: negative table size");
   return 0;
 }
@@ -124,9 +128,9 @@ int b2gpu_snapshot_validate(const b2gpu_snapshot* s) {
   if (!s) return fail(B2GPU_E_INVALID, "snapshot_validate: snapshot is NULL");
   const b2gpu_snapshot_sizes& n = s->n;
   if (!sizes_ok(n)) return fail(B2GPU_E_INVALID, "snapshot: negative table size");
-  Table t[7];
+  Table t[kTables];
   tables_of(s, t);
-  for (int i = 0; i < 7; ++i)
+  for (int i = 0; i < kTables; ++i)
     if (t[i].bytes && !t[i].ptr) return fail(B2GPU_E_INVALID, "snapshot: a non-empty table has a NULL pointer");
   const int nb = n.body_count, nf = n.fixture_count, ns = n.shape_count, np = n.proxy_count, nn = n.node_count;
   for (int i = 0; i < nb; ++i) {
@@ -170,6 +174,11 @@ int b2gpu_snapshot_validate(const b2gpu_snapshot* s) {
     CHECK_RANGE(c.manifold.type >= B2GPU_MANIFOLD_CIRCLES && c.manifold.type <= B2GPU_MANIFOLD_FACE_B, "manifold type", i);
   }
   for (int i = 0; i < n.move_count; ++i) CHECK_RANGE(s->move_buffer[i] >= -1 && s->move_buffer[i] < nn, "move buffer entry", i);
+  for (int i = 0; i < n.joint_count; ++i) {
+    const b2gpu_joint_rec& j = s->joints[i];
+    CHECK_RANGE(j.type == B2GPU_JOINT_REVOLUTE || j.type == B2GPU_JOINT_DISTANCE, "joint type", i);
+    CHECK_RANGE(j.body_a >= 0 && j.body_a < nb && j.body_b >= 0 && j.body_b < nb && j.body_a != j.body_b, "joint body", i);
+  }
   const b2gpu_world_rec& w = s->world;
   if (w.tree_root < -1 || w.tree_root >= nn || w.tree_free_list < -1 || w.tree_free_list >= nn || w.tree_node_capacity != nn ||
       w.tree_node_count < 0 || w.tree_node_count > nn || w.proxy_count < 0 || w.proxy_count > np)
@@ -256,7 +265,7 @@ int b2gpu_snapshot_save(const b2gpu_snapshot* s, const char* path) {
   if (!s || !path || !*path) return fail(B2GPU_E_INVALID, "snapshot_save: bad argument");
   int rc = b2gpu_snapshot_validate(s);
   if (rc) return rc;
-  Table t[7];
+  Table t[kTables];
   tables_of(s, t);
   FileHeader h;
   memset(&h, 0, sizeof h);
@@ -269,7 +278,7 @@ int b2gpu_snapshot_save(const b2gpu_snapshot* s, const char* path) {
   h.world = s->world;
   h.n = s->n;
   uint64_t hash = 1469598103934665603ull;
-  for (int i = 0; i < 7; ++i) {
+  for (int i = 0; i < kTables; ++i) {
     h.payload_bytes += t[i].bytes;
     hash = fnv1a(t[i].ptr, t[i].bytes, hash);
   }
@@ -283,7 +292,7 @@ int b2gpu_snapshot_save(const b2gpu_snapshot* s, const char* path) {
   FILE* f = fdopen(fd, "wb");
   if (!f) { close(fd); remove(tmp.c_str()); return fail(B2GPU_E_IO, "snapshot_save: cannot open " + tmp); }
   bool ok = fwrite(&h, 1, sizeof h, f) == sizeof h;
-  for (int i = 0; ok && i < 7; ++i) ok = t[i].bytes == 0 || fwrite(t[i].ptr, 1, t[i].bytes, f) == t[i].bytes;
+  for (int i = 0; ok && i < kTables; ++i) ok = t[i].bytes == 0 || fwrite(t[i].ptr, 1, t[i].bytes, f) == t[i].bytes;
   ok = (fflush(f) == 0) && ok;
   ok = (fsync(fileno(f)) == 0) && ok;
   ok = (fclose(f) == 0) && ok;
@@ -330,17 +339,17 @@ int b2gpu_snapshot_load(const char* path, b2gpu_snapshot* out) {
   const b2gpu_snapshot_sizes cap = out->n;
   if (h.n.body_count > cap.body_count || h.n.fixture_count > cap.fixture_count || h.n.shape_count > cap.shape_count ||
       h.n.proxy_count > cap.proxy_count || h.n.node_count > cap.node_count || h.n.contact_count > cap.contact_count ||
-      h.n.move_count > cap.move_count) {
+      h.n.move_count > cap.move_count || h.n.joint_count > cap.joint_count) {
     fclose(f);
     return fail(B2GPU_E_CAPACITY, "snapshot_load: caller arrays are smaller than the tables in the file (see b2gpu_snapshot_file_sizes)");
   }
   b2gpu_snapshot staged = *out;
   staged.world = h.world;
   staged.n = h.n;
-  Table t[7];
+  Table t[kTables];
   tables_of(&staged, t);
   uint64_t total = 0;
-  for (int i = 0; i < 7; ++i) {
+  for (int i = 0; i < kTables; ++i) {
     total += t[i].bytes;
     if (t[i].bytes && !t[i].ptr) { fclose(f); return fail(B2GPU_E_INVALID, "snapshot_load: a table of the file is not empty but the caller's array pointer is NULL"); }
   }
@@ -363,11 +372,12 @@ int b2gpu_snapshot_load(const char* path, b2gpu_snapshot* out) {
   view.proxies = (b2gpu_proxy_rec*)(base + off); off += t[3].bytes;
   view.nodes = (b2gpu_tree_node_rec*)(base + off); off += t[4].bytes;
   view.contacts = (b2gpu_contact_rec*)(base + off); off += t[5].bytes;
-  view.move_buffer = (int32_t*)(base + off);
+  view.move_buffer = (int32_t*)(base + off); off += t[6].bytes;
+  view.joints = (b2gpu_joint_rec*)(base + off);
   rc = b2gpu_snapshot_validate(&view);
   if (rc) return rc;
   off = 0;
-  for (int i = 0; i < 7; ++i) {
+  for (int i = 0; i < kTables; ++i) {
     if (t[i].bytes) memcpy(const_cast<void*>(t[i].ptr), base + off, t[i].bytes);
     off += t[i].bytes;
   }

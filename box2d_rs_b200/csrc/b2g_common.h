@@ -32,7 +32,7 @@ enum {
   WS_GRAVITY_X = 0, WS_GRAVITY_Y, WS_INV_DT0, WS_FLAGS,
   WS_TREE_ROOT, WS_TREE_FREE, WS_TREE_COUNT, WS_TREE_CAP, WS_TREE_INSERTIONS, WS_PROXY_COUNT,
   WS_CONTACT_COUNT, WS_MOVE_COUNT,
-  WS_ISL_COUNT, WS_ISL_BODIES, WS_ISL_CONTACTS,
+  WS_ISL_COUNT, WS_ISL_BODIES, WS_ISL_CONTACTS, WS_ISL_JOINTS,
   WS_EV_WAKE,      // collide woke a sleeping body (needs the ordered fix-up pass)
   WS_EV_DESTROY,   // contacts flagged for destruction this step
   WS_EV_MOVED,     // proxies that left their fat box this step
@@ -48,6 +48,8 @@ enum {
 
 // velocity-constraint record: VC_Q float4 per island contact
 enum { VC_Q = 9, PC_Q = 6 };
+// per-step joint scratch: JT_Q float4 per joint (see b2g_joint.h)
+enum { JT_Q = 4 };
 // lanes that cooperate on one world in the level-scheduled Gauss-Seidel kernels
 enum { SCHED_G = 2, SCHED_MIN_ROUNDS = 6 };
 
@@ -59,6 +61,7 @@ struct Batch {
   int NC, NMOVE;             // capacities: contacts, move buffer
   int NIB;                   // island body list capacity (NB + NC: static bodies repeat per island)
   int NMW;                   // words of the per-world moved-proxy bitmap ((NP + 31) / 32)
+  int NJ;                    // joints (exact, shared topology; 0 for most scenes)
   // ---- shared topology
   const b2gpu_fixture_rec* fixtures;
   const b2gpu_shape_rec* shapes;
@@ -66,6 +69,9 @@ struct Batch {
   const int* sync_order;     // proxies in synchronize_fixtures order (bodies newest first, fixtures newest first)
   const int* sync_rank;      // inverse of sync_order
   const int* node_proxy;     // tree node id -> proxy index (-1 for internal / unused nodes)
+  const b2gpu_joint_rec* joints;  // static part of the joint table: type, bodies, COLLIDE_CONNECTED, anchors, limits, lengths
+  const int* jadj_off;       // [NB+1] per body: its joint edges (2*joint + side) in the order the reference's list iterates (newest first)
+  const int* jadj;           // [2*NJ]
   // ---- per world (blocked world-minor)
   int* ws;                   // [WS_COUNT]
   int* b_flags;              // BodyFlags | type << 16
@@ -88,6 +94,8 @@ struct Batch {
   float4* c_m1;              // point1
   float4* c_m2;              // local_normal.xy local_point.xy
   int4* c_m3;                // id0 id1 type point_count
+  float4* j_s0;              // joint: impulse.x impulse.y motor_impulse lower_impulse   (distance: impulse - - lower)
+  float4* j_s1;              // joint: upper_impulse motor_speed max_motor_torque (int) ENABLE_LIMIT | ENABLE_MOTOR bits
   // ---- per-step scratch
   float4* b_rot;             // sin(a) cos(a) of the running angle (position pass cache), spare, spare
   float4* p_fat;             // new fat AABB of a proxy that must be re-inserted
@@ -99,6 +107,10 @@ struct Batch {
   int4* isl_range;           // [NB] per island: body_first, body_end, contact_first, contact_end
   int* isl_flags;            // [NB] per island: bit0 = position solved
   int* c_isl;                // [NC] island index of each island contact slot
+  int* isl_joint;            // [NJ] island joint order
+  int2* isl_jrange;          // [NB] per island: joint_first, joint_end
+  int* j_flag;               // [NJ] m_island_flag of the island DFS
+  float4* j_tmp;             // [NJ * JT_Q] per-step joint solver data (b2g_joint.h)
   float4* vc;                // [NC * VC_Q] velocity constraint records
   float4* pc;                // [NC * PC_Q] position constraint records
   int* sched;                // [NC * SCHED_G] level schedule: round r, slot g -> island contact k or -1

@@ -1,0 +1,372 @@
+// b2g_joint.h — joints inside the island solve: revolute and distance joints.
+//
+// Reference: B2jointTraitDyn::{init_velocity_constraints, solve_velocity_constraints, solve_position_constraints}
+// (src/b2_joint.rs:268-286) as driven by B2island::solve (src/private/dynamics/b2_island_private.rs:198-201 init after the
+// contact warm start, :207-215 joints BEFORE contacts in every velocity iteration, :257-274 joints AFTER contacts in every
+// position iteration, early exit only when both are within tolerance);
+//   revolute: src/private/dynamics/joints/b2_revolute_joint.rs:22-123 / :125-217 / :219-301
+//   distance: src/private/dynamics/joints/b2_distance_joint.rs:80-184 / :186-277 / :279-320
+// Expression shapes are kept operation for operation (one rounding per operation, no FMA), like the contact solver.
+//
+// Data: the static part of a joint (type, bodies, anchors, limits, lengths, COLLIDE_CONNECTED) is topology shared by the
+// worlds of a batch (Batch::joints); what the solver or the user changes per world lives in two float4 rows
+//   j_s0: impulse.x impulse.y motor_impulse lower_impulse     (distance: impulse, -, -, lower_impulse)
+//   j_s1: upper_impulse motor_speed max_motor_torque (int bits) ENABLE_LIMIT | ENABLE_MOTOR
+// and the per-step solver data (the reference's "solver temp" members) in JT_Q float4 rows of j_tmp:
+//   0: rA.xy rB.xy
+//   1: revolute K.ex.x K.ey.x K.ey.y axial_mass      | distance u.x u.y mass soft_mass
+//   2: revolute angle - - -                          | distance gamma bias current_length -
+//   3: mA iA mB iB
+// Joint visits are ordered work: they run in the island's joint order inside the per-island Gauss-Seidel stages
+// (VelocityK / PositionK); worlds with joints take the generic (global-memory) form of those stages.
+#pragma once
+#include "b2g_common.h"
+
+namespace b2g {
+
+#define B2G_ANGULAR_SLOP (2.0f / 180.0f * B2G_PI)            // src/b2_common.rs:43
+#define B2G_MAX_ANGULAR_CORRECTION (8.0f / 180.0f * B2G_PI)  // src/b2_common.rs:64
+
+B2G_HD int jt_at(const Batch& B, const WIdx& x, int j, int q) { return x.at(B.NJ * JT_Q, j * JT_Q + q); }
+
+// B2Mat22::solve (src/b2_math.rs:276-293) for the symmetric K = [ex.x ey.x; ey.x ey.y]
+B2G_HD V2 mat22_solve(float exx, float eyx, float exy, float eyy, V2 b) {
+  const float a11 = exx, a12 = eyx, a21 = exy, a22 = eyy;
+  float det = a11 * a22 - a12 * a21;
+  if (det != 0.0f) det = 1.0f / det;
+  return v2(det * (a22 * b.x - a12 * b.y), det * (a11 * b.y - a21 * b.x));
+}
+
+// Does a joint of `self_` prevent collision with `other`? (B2body::should_collide, b2_body.rs(private):400-413)
+B2G_HD bool joints_prevent_collision(const Batch& B, int self_, int other) {
+  if (B.NJ == 0) return false;
+  for (int e = B.jadj_off[self_]; e < B.jadj_off[self_ + 1]; ++e) {
+    const int je = B.jadj[e];
+    const b2gpu_joint_rec& jr = B.joints[je >> 1];
+    const int jn_other = (je & 1) ? jr.body_a : jr.body_b;
+    if (jn_other == other && !(jr.flags & B2GPU_JOINT_COLLIDE_CONNECTED)) return true;
+  }
+  return false;
+}
+
+// init_velocity_constraints of joint j: solver data into j_tmp, impulses scaled (or zeroed) in j_s0 / j_s1, the warm-start
+// impulse applied to the two bodies' velocities.
+B2G_HD void joint_init_velocity(const Batch& B, const WIdx& x, int j, bool warm_starting, float dt_ratio, float h) {
+  const b2gpu_joint_rec& jr = B.joints[j];
+  const int bai = x.at(B.NB, jr.body_a), bbi = x.at(B.NB, jr.body_b);
+  const float4 msa = B.b_mass[bai], msb = B.b_mass[bbi];
+  const float m_a = msa.x, i_a = msa.y, m_b = msb.x, i_b = msb.y;
+  const float4 pa = B.b_pos[bai], pb = B.b_pos[bbi];
+  const float4 ra4 = B.b_rot[bai], rb4 = B.b_rot[bbi];  // B2Rot::new(a) of the island body's angle (IntegrateK)
+  float4 va = B.b_vel[bai], vb = B.b_vel[bbi];
+  V2 v_a = v2(va.x, va.y), v_b = v2(vb.x, vb.y);
+  float w_a = va.z, w_b = vb.z;
+  const V2 c_a = v2(pa.x, pa.y), c_b = v2(pb.x, pb.y);
+  const float a_a = pa.z, a_b = pb.z;
+  Rot q_a, q_b;
+  q_a.s = ra4.x; q_a.c = ra4.y;
+  q_b.s = rb4.x; q_b.c = rb4.y;
+  const V2 r_a = rot_mul(q_a, v2(jr.local_anchor_a[0], jr.local_anchor_a[1]) - v2(msa.z, msa.w));
+  const V2 r_b = rot_mul(q_b, v2(jr.local_anchor_b[0], jr.local_anchor_b[1]) - v2(msb.z, msb.w));
+  const int ji = x.at(B.NJ, j);
+  float4 s0 = B.j_s0[ji], s1 = B.j_s1[ji];
+  const int jflags = f2i(s1.w);
+  float4 t1, t2 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+  if (jr.type == B2GPU_JOINT_REVOLUTE) {
+    const float kxx = m_a + m_b + r_a.y * r_a.y * i_a + r_b.y * r_b.y * i_b;
+    const float kyx = -r_a.y * r_a.x * i_a - r_b.y * r_b.x * i_b;
+    const float kyy = m_a + m_b + r_a.x * r_a.x * i_a + r_b.x * r_b.x * i_b;
+    float axial_mass = i_a + i_b;
+    bool fixed_rotation;
+    if (axial_mass > 0.0f) { axial_mass = 1.0f / axial_mass; fixed_rotation = false; }
+    else fixed_rotation = true;
+    t2.x = a_b - a_a - jr.param[0];
+    if (!(jflags & B2GPU_JOINT_ENABLE_LIMIT) || fixed_rotation) { s0.w = 0.0f; s1.x = 0.0f; }
+    if (!(jflags & B2GPU_JOINT_ENABLE_MOTOR) || fixed_rotation) s0.z = 0.0f;
+    if (warm_starting) {
+      s0.x *= dt_ratio; s0.y *= dt_ratio;
+      s0.z *= dt_ratio;
+      s0.w *= dt_ratio;
+      s1.x *= dt_ratio;
+      const float axial_impulse = s0.z + s0.w - s1.x;
+      const V2 p = v2(s0.x, s0.y);
+      v_a = v_a - m_a * p;
+      w_a -= i_a * (cross(r_a, p) + axial_impulse);
+      v_b = v_b + m_b * p;
+      w_b += i_b * (cross(r_b, p) + axial_impulse);
+    } else {
+      s0.x = 0.0f; s0.y = 0.0f; s0.z = 0.0f; s0.w = 0.0f; s1.x = 0.0f;
+    }
+    t1 = make_float4(kxx, kyx, kyy, axial_mass);
+  } else {  // distance
+    V2 u = c_b + r_b - c_a - r_a;
+    const float current_length = length(u);
+    if (current_length > B2G_LINEAR_SLOP) {
+      u = (1.0f / current_length) * u;
+    } else {
+      u = v2(0.0f, 0.0f);
+      s0.x = 0.0f; s0.w = 0.0f; s1.x = 0.0f;
+    }
+    const float cr_au = cross(r_a, u), cr_bu = cross(r_b, u);
+    float inv_mass = m_a + i_a * cr_au * cr_au + m_b + i_b * cr_bu * cr_bu;
+    const float mass = inv_mass != 0.0f ? 1.0f / inv_mass : 0.0f;
+    float soft_mass, gamma, bias;
+    const float length_ = jr.param[0], min_length = jr.param[1], max_length = jr.param[2], stiffness = jr.param[3], damping = jr.param[4];
+    if (stiffness > 0.0f && min_length < max_length) {
+      const float c = current_length - length_;
+      gamma = h * (damping + h * stiffness);
+      gamma = gamma != 0.0f ? 1.0f / gamma : 0.0f;
+      bias = c * h * stiffness * gamma;
+      inv_mass += gamma;
+      soft_mass = inv_mass != 0.0f ? 1.0f / inv_mass : 0.0f;
+    } else {
+      gamma = 0.0f;
+      bias = 0.0f;
+      soft_mass = mass;
+    }
+    if (warm_starting) {
+      s0.x *= dt_ratio;
+      s0.w *= dt_ratio;
+      s1.x *= dt_ratio;
+      const V2 p = (s0.x + s0.w - s1.x) * u;
+      v_a = v_a - m_a * p;
+      w_a -= i_a * cross(r_a, p);
+      v_b = v_b + m_b * p;
+      w_b += i_b * cross(r_b, p);
+    } else {
+      s0.x = 0.0f;
+    }
+    t1 = make_float4(u.x, u.y, mass, soft_mass);
+    t2 = make_float4(gamma, bias, current_length, 0.0f);
+  }
+  B.j_s0[ji] = s0;
+  B.j_s1[ji] = s1;
+  B.j_tmp[jt_at(B, x, j, 0)] = make_float4(r_a.x, r_a.y, r_b.x, r_b.y);
+  B.j_tmp[jt_at(B, x, j, 1)] = t1;
+  B.j_tmp[jt_at(B, x, j, 2)] = t2;
+  B.j_tmp[jt_at(B, x, j, 3)] = make_float4(m_a, i_a, m_b, i_b);
+  // an immovable body may sit in several islands: its velocity never changes, leave it alone
+  if (m_a != 0.0f || i_a != 0.0f) B.b_vel[bai] = make_float4(v_a.x, v_a.y, w_a, 0.0f);
+  if (m_b != 0.0f || i_b != 0.0f) B.b_vel[bbi] = make_float4(v_b.x, v_b.y, w_b, 0.0f);
+}
+
+B2G_HD void joint_solve_velocity(const Batch& B, const WIdx& x, int j, float h, float inv_dt) {
+  const b2gpu_joint_rec& jr = B.joints[j];
+  const int bai = x.at(B.NB, jr.body_a), bbi = x.at(B.NB, jr.body_b);
+  const float4 va = B.b_vel[bai], vb = B.b_vel[bbi];
+  V2 v_a = v2(va.x, va.y), v_b = v2(vb.x, vb.y);
+  float w_a = va.z, w_b = vb.z;
+  const float4 t0 = B.j_tmp[jt_at(B, x, j, 0)], t1 = B.j_tmp[jt_at(B, x, j, 1)], t2 = B.j_tmp[jt_at(B, x, j, 2)];
+  const float4 t3 = B.j_tmp[jt_at(B, x, j, 3)];
+  const float m_a = t3.x, i_a = t3.y, m_b = t3.z, i_b = t3.w;
+  const V2 r_a = v2(t0.x, t0.y), r_b = v2(t0.z, t0.w);
+  const int ji = x.at(B.NJ, j);
+  float4 s0 = B.j_s0[ji], s1 = B.j_s1[ji];
+  const int jflags = f2i(s1.w);
+  if (jr.type == B2GPU_JOINT_REVOLUTE) {
+    const float axial_mass = t1.w, angle = t2.x;
+    const bool fixed_rotation = i_a + i_b == 0.0f;
+    if ((jflags & B2GPU_JOINT_ENABLE_MOTOR) && fixed_rotation == false) {
+      const float cdot = w_b - w_a - s1.y;
+      float impulse = -axial_mass * cdot;
+      const float old_impulse = s0.z;
+      const float max_impulse = h * s1.z;
+      s0.z = fclamp_sel(s0.z + impulse, -max_impulse, max_impulse);
+      impulse = s0.z - old_impulse;
+      w_a -= i_a * impulse;
+      w_b += i_b * impulse;
+    }
+    if ((jflags & B2GPU_JOINT_ENABLE_LIMIT) && fixed_rotation == false) {
+      {  // lower limit
+        const float c = angle - jr.param[1];
+        const float cdot = w_b - w_a;
+        float impulse = -axial_mass * (cdot + fmax_sel(c, 0.0f) * inv_dt);
+        const float old_impulse = s0.w;
+        s0.w = fmax_sel(s0.w + impulse, 0.0f);
+        impulse = s0.w - old_impulse;
+        w_a -= i_a * impulse;
+        w_b += i_b * impulse;
+      }
+      {  // upper limit: signs flipped to keep c positive when the constraint is satisfied
+        const float c = jr.param[2] - angle;
+        const float cdot = w_a - w_b;
+        float impulse = -axial_mass * (cdot + fmax_sel(c, 0.0f) * inv_dt);
+        const float old_impulse = s1.x;
+        s1.x = fmax_sel(s1.x + impulse, 0.0f);
+        impulse = s1.x - old_impulse;
+        w_a += i_a * impulse;
+        w_b -= i_b * impulse;
+      }
+    }
+    {  // point-to-point constraint
+      const V2 cdot = v_b + cross_sv(w_b, r_b) - v_a - cross_sv(w_a, r_a);
+      const V2 impulse = mat22_solve(t1.x, t1.y, t1.y, t1.z, -cdot);
+      s0.x += impulse.x;
+      s0.y += impulse.y;
+      v_a = v_a - m_a * impulse;
+      w_a -= i_a * cross(r_a, impulse);
+      v_b = v_b + m_b * impulse;
+      w_b += i_b * cross(r_b, impulse);
+    }
+  } else {  // distance
+    const V2 u = v2(t1.x, t1.y);
+    const float mass = t1.z, soft_mass = t1.w, gamma = t2.x, bias_ = t2.y, current_length = t2.z;
+    const float min_length = jr.param[1], max_length = jr.param[2], stiffness = jr.param[3];
+    if (min_length < max_length) {
+      if (stiffness > 0.0f) {
+        const V2 vp_a = v_a + cross_sv(w_a, r_a);
+        const V2 vp_b = v_b + cross_sv(w_b, r_b);
+        const float cdot = dot(u, vp_b - vp_a);
+        const float impulse = -soft_mass * (cdot + bias_ + gamma * s0.x);
+        s0.x += impulse;
+        const V2 p = impulse * u;
+        v_a = v_a - m_a * p;
+        w_a -= i_a * cross(r_a, p);
+        v_b = v_b + m_b * p;
+        w_b += i_b * cross(r_b, p);
+      }
+      {  // lower
+        const float c = current_length - min_length;
+        const float bias = fmax_sel(0.0f, c) * inv_dt;
+        const V2 vp_a = v_a + cross_sv(w_a, r_a);
+        const V2 vp_b = v_b + cross_sv(w_b, r_b);
+        const float cdot = dot(u, vp_b - vp_a);
+        float impulse = -mass * (cdot + bias);
+        const float old_impulse = s0.w;
+        s0.w = fmax_sel(0.0f, s0.w + impulse);
+        impulse = s0.w - old_impulse;
+        const V2 p = impulse * u;
+        v_a = v_a - m_a * p;
+        w_a -= i_a * cross(r_a, p);
+        v_b = v_b + m_b * p;
+        w_b += i_b * cross(r_b, p);
+      }
+      {  // upper
+        const float c = max_length - current_length;
+        const float bias = fmax_sel(0.0f, c) * inv_dt;
+        const V2 vp_a = v_a + cross_sv(w_a, r_a);
+        const V2 vp_b = v_b + cross_sv(w_b, r_b);
+        const float cdot = dot(u, vp_a - vp_b);
+        float impulse = -mass * (cdot + bias);
+        const float old_impulse = s1.x;
+        s1.x = fmax_sel(0.0f, s1.x + impulse);
+        impulse = s1.x - old_impulse;
+        const V2 p = (-impulse) * u;
+        v_a = v_a - m_a * p;
+        w_a -= i_a * cross(r_a, p);
+        v_b = v_b + m_b * p;
+        w_b += i_b * cross(r_b, p);
+      }
+    } else {  // equal limits
+      const V2 vp_a = v_a + cross_sv(w_a, r_a);
+      const V2 vp_b = v_b + cross_sv(w_b, r_b);
+      const float cdot = dot(u, vp_b - vp_a);
+      const float impulse = -mass * cdot;
+      s0.x += impulse;
+      const V2 p = impulse * u;
+      v_a = v_a - m_a * p;
+      w_a -= i_a * cross(r_a, p);
+      v_b = v_b + m_b * p;
+      w_b += i_b * cross(r_b, p);
+    }
+  }
+  B.j_s0[ji] = s0;
+  B.j_s1[ji] = s1;
+  if (m_a != 0.0f || i_a != 0.0f) B.b_vel[bai] = make_float4(v_a.x, v_a.y, w_a, 0.0f);
+  if (m_b != 0.0f || i_b != 0.0f) B.b_vel[bbi] = make_float4(v_b.x, v_b.y, w_b, 0.0f);
+}
+
+// solve_position_constraints of joint j; returns "within tolerance".  b_rot caches B2Rot::new of the running angle (the
+// contact position solver relies on it), so it is refreshed whenever this joint changed an angle's bits.
+B2G_HD bool joint_solve_position(const Batch& B, const WIdx& x, int j) {
+  const b2gpu_joint_rec& jr = B.joints[j];
+  const int bai = x.at(B.NB, jr.body_a), bbi = x.at(B.NB, jr.body_b);
+  const float4 msa = B.b_mass[bai], msb = B.b_mass[bbi];
+  const float m_a = msa.x, i_a = msa.y, m_b = msb.x, i_b = msb.y;
+  float4 pa = B.b_pos[bai], pb = B.b_pos[bbi];
+  float4 ra4 = B.b_rot[bai], rb4 = B.b_rot[bbi];
+  V2 c_a = v2(pa.x, pa.y), c_b = v2(pb.x, pb.y);
+  float a_a = pa.z, a_b = pb.z;
+  Rot q_a, q_b;
+  q_a.s = ra4.x; q_a.c = ra4.y;
+  q_b.s = rb4.x; q_b.c = rb4.y;
+  const V2 la = v2(jr.local_anchor_a[0], jr.local_anchor_a[1]) - v2(msa.z, msa.w);
+  const V2 lb = v2(jr.local_anchor_b[0], jr.local_anchor_b[1]) - v2(msb.z, msb.w);
+  bool okay;
+  if (jr.type == B2GPU_JOINT_REVOLUTE) {
+    const float axial_mass = B.j_tmp[jt_at(B, x, j, 1)].w;
+    const int jflags = f2i(B.j_s1[x.at(B.NJ, j)].w);
+    float angular_error = 0.0f;
+    const bool fixed_rotation = i_a + i_b == 0.0f;
+    if ((jflags & B2GPU_JOINT_ENABLE_LIMIT) && fixed_rotation == false) {
+      const float lower = jr.param[1], upper = jr.param[2];
+      const float angle = a_b - a_a - jr.param[0];
+      float c = 0.0f;
+      if (fabsf(upper - lower) < 2.0f * B2G_ANGULAR_SLOP) {
+        c = fclamp_sel(angle - lower, -B2G_MAX_ANGULAR_CORRECTION, B2G_MAX_ANGULAR_CORRECTION);
+      } else if (angle <= lower) {
+        c = fclamp_sel(angle - lower + B2G_ANGULAR_SLOP, -B2G_MAX_ANGULAR_CORRECTION, 0.0f);
+      } else if (angle >= upper) {
+        c = fclamp_sel(angle - upper - B2G_ANGULAR_SLOP, 0.0f, B2G_MAX_ANGULAR_CORRECTION);
+      }
+      const float limit_impulse = -axial_mass * c;
+      const float na = a_a - i_a * limit_impulse, nb = a_b + i_b * limit_impulse;
+      if (f2u(na) != f2u(a_a)) { a_a = na; q_a = rot_from_angle(na); }
+      if (f2u(nb) != f2u(a_b)) { a_b = nb; q_b = rot_from_angle(nb); }
+      angular_error = fabsf(c);
+    }
+    const V2 r_a = rot_mul(q_a, la);
+    const V2 r_b = rot_mul(q_b, lb);
+    const V2 c = c_b + r_b - c_a - r_a;
+    const float position_error = length(c);
+    const float kxx = m_a + m_b + i_a * r_a.y * r_a.y + i_b * r_b.y * r_b.y;
+    const float kxy = -i_a * r_a.x * r_a.y - i_b * r_b.x * r_b.y;
+    const float kyy = m_a + m_b + i_a * r_a.x * r_a.x + i_b * r_b.x * r_b.x;
+    const V2 impulse = -mat22_solve(kxx, kxy, kxy, kyy, c);
+    c_a = c_a - m_a * impulse;
+    a_a -= i_a * cross(r_a, impulse);
+    c_b = c_b + m_b * impulse;
+    a_b += i_b * cross(r_b, impulse);
+    okay = position_error <= B2G_LINEAR_SLOP && angular_error <= B2G_ANGULAR_SLOP;
+  } else {  // distance
+    const float mass = B.j_tmp[jt_at(B, x, j, 1)].z;
+    const float min_length = jr.param[1], max_length = jr.param[2];
+    const V2 r_a = rot_mul(q_a, la);
+    const V2 r_b = rot_mul(q_b, lb);
+    V2 u = c_b + r_b - c_a - r_a;
+    const float len = normalize(u);
+    float c;
+    if (min_length == max_length) c = len - min_length;
+    else if (len < min_length) c = len - min_length;
+    else if (max_length < len) c = len - max_length;
+    else return true;  // positions untouched
+    const float impulse = -mass * c;
+    const V2 p = impulse * u;
+    c_a = c_a - m_a * p;
+    a_a -= i_a * cross(r_a, p);
+    c_b = c_b + m_b * p;
+    a_b += i_b * cross(r_b, p);
+    okay = fabsf(c) < B2G_LINEAR_SLOP;
+  }
+  if (m_a != 0.0f || i_a != 0.0f) {  // immovable bodies are shared between islands: never written
+    if (f2u(a_a) != f2u(pa.z)) {
+      const Rot q = rot_from_angle(a_a);
+      ra4.x = q.s; ra4.y = q.c;
+      B.b_rot[bai] = ra4;
+    }
+    pa.x = c_a.x; pa.y = c_a.y; pa.z = a_a;
+    B.b_pos[bai] = pa;
+  }
+  if (m_b != 0.0f || i_b != 0.0f) {
+    if (f2u(a_b) != f2u(pb.z)) {
+      const Rot q = rot_from_angle(a_b);
+      rb4.x = q.s; rb4.y = q.c;
+      B.b_rot[bbi] = rb4;
+    }
+    pb.x = c_b.x; pb.y = c_b.y; pb.z = a_b;
+    B.b_pos[bbi] = pb;
+  }
+  return okay;
+}
+
+}  // namespace b2g

@@ -193,6 +193,10 @@ static std::vector<ArrRef> array_table(BatchHost* bh, WorldImage& im) {
   add(B.c_m3, im.c_m3.data(), 16, B.NC);
   add(bh->b_chead, im.b_chead.data(), 4, B.NB);
   add(bh->c_next, im.c_next.data(), 8, B.NC);
+  if (B.NJ > 0) {
+    add(B.j_s0, im.j_s0.data(), 16, B.NJ);
+    add(B.j_s1, im.j_s1.data(), 16, B.NJ);
+  }
   return t;
 }
 static void image_alloc(const Batch& B, WorldImage& im) {
@@ -212,6 +216,8 @@ static void image_alloc(const Batch& B, WorldImage& im) {
   im.c_m3.assign(B.NC, make_int4(0, 0, 0, 0));
   im.b_chead.assign(B.NB, -1);
   im.c_next.assign(B.NC, make_int2(-1, -1));
+  im.j_s0.assign(std::max(B.NJ, 1), z4);
+  im.j_s1.assign(std::max(B.NJ, 1), z4);
 }
 
 static int fbits(float f) { int i; memcpy(&i, &f, 4); return i; }
@@ -261,6 +267,15 @@ static int image_pack(const BatchHost* bh, const b2gpu_snapshot* s, WorldImage& 
     im.p_aabb[i] = make_float4(a[0], a[1], a[2], a[3]);
   }
   for (int i = 0; i < s->n.move_count; ++i) im.move_buf[i] = s->move_buffer[i];
+  for (int i = 0; i < B.NJ; ++i) {
+    const b2gpu_joint_rec& j = s->joints[i];
+    // revolute: param 3 = max_motor_torque, 4 = motor_speed are per world (an RL action); distance joints keep
+    // everything static (their slots of j_s1 are unused)
+    im.j_s0[i] = make_float4(j.impulse[0], j.impulse[1], j.impulse[2], j.impulse[3]);
+    im.j_s1[i] = make_float4(j.impulse[4], j.type == B2GPU_JOINT_REVOLUTE ? j.param[4] : 0.0f,
+                             j.type == B2GPU_JOINT_REVOLUTE ? j.param[3] : 0.0f,
+                             bitsf((int)(j.flags & (B2GPU_JOINT_ENABLE_LIMIT | B2GPU_JOINT_ENABLE_MOTOR))));
+  }
   for (int i = 0; i < s->n.contact_count; ++i) {
     const b2gpu_contact_rec& c = s->contacts[i];
     if (c.fixture_a < 0 || c.fixture_a >= B.NF || c.fixture_b < 0 || c.fixture_b >= B.NF) {
@@ -292,7 +307,11 @@ static int image_unpack(const BatchHost* bh, const WorldImage& im, b2gpu_snapsho
   b2gpu_snapshot_sizes need;
   need.body_count = B.NB; need.fixture_count = B.NF; need.shape_count = B.NS; need.proxy_count = B.NP;
   need.node_count = im.ws[WS_TREE_CAP]; need.contact_count = im.ws[WS_CONTACT_COUNT]; need.move_count = im.ws[WS_MOVE_COUNT];
-  need.reserved = 0;
+  need.joint_count = B.NJ;
+  if (B.NJ > 0 && (out->n.joint_count < B.NJ || !out->joints)) {
+    set_error("download buffers smaller than snapshot_sizes (joints)");
+    return B2GPU_E_INVALID;
+  }
   if (out->n.body_count < need.body_count || out->n.fixture_count < need.fixture_count || out->n.shape_count < need.shape_count ||
       out->n.proxy_count < need.proxy_count || out->n.node_count < need.node_count ||
       out->n.contact_count < need.contact_count || out->n.move_count < need.move_count) {
@@ -351,6 +370,18 @@ static int image_unpack(const BatchHost* bh, const WorldImage& im, b2gpu_snapsho
     m.type = im.c_m3[i].z; m.point_count = im.c_m3[i].w;
   }
   for (int i = 0; i < need.move_count; ++i) out->move_buffer[i] = im.move_buf[i];
+  for (int i = 0; i < B.NJ; ++i) {
+    b2gpu_joint_rec& j = out->joints[i];
+    j = T.joints[i];
+    const float4 s0 = im.j_s0[i], s1 = im.j_s1[i];
+    j.impulse[0] = s0.x; j.impulse[1] = s0.y; j.impulse[2] = s0.z; j.impulse[3] = s0.w; j.impulse[4] = s1.x;
+    j.impulse[5] = j.impulse[6] = j.impulse[7] = 0.0f;
+    if (j.type == B2GPU_JOINT_REVOLUTE) {
+      j.param[4] = s1.y;
+      j.param[3] = s1.z;
+      j.flags = (j.flags & B2GPU_JOINT_COLLIDE_CONNECTED) | ((uint32_t)fbits(s1.w) & (B2GPU_JOINT_ENABLE_LIMIT | B2GPU_JOINT_ENABLE_MOTOR));
+    }
+  }
   return 0;
 }
 
@@ -380,6 +411,33 @@ static int topology_build(const b2gpu_snapshot* s, Topology& T) {
     if (fx.proxy_first >= 0 && fx.proxy_first + fx.child_count > n.proxy_count) {
       set_error("fixture proxies out of range");
       return B2GPU_E_INVALID;
+    }
+  }
+  // joints: static table + per-body joint lists.  create_joint pushes edge A on body A's list and then edge B on
+  // body B's (b2_world.rs(private):176-208); the lists are push_front lists, so a body iterates its edges by
+  // descending joint creation order.
+  T.joints.assign(s->joints, s->joints + (s->joints ? n.joint_count : 0));
+  if ((int)T.joints.size() != n.joint_count) { set_error("joint table missing"); return B2GPU_E_INVALID; }
+  T.jadj_off.assign(n.body_count + 1, 0);
+  T.jadj.assign(2 * (size_t)n.joint_count, 0);
+  for (const b2gpu_joint_rec& j : T.joints) {
+    if (j.type != B2GPU_JOINT_REVOLUTE && j.type != B2GPU_JOINT_DISTANCE) {
+      set_error("joint type outside the supported set (revolute, distance)");
+      return B2GPU_E_UNSUPPORTED;
+    }
+    if (j.body_a < 0 || j.body_a >= n.body_count || j.body_b < 0 || j.body_b >= n.body_count || j.body_a == j.body_b) {
+      set_error("joint record out of range");
+      return B2GPU_E_INVALID;
+    }
+    T.jadj_off[j.body_a + 1] += 1;
+    T.jadj_off[j.body_b + 1] += 1;
+  }
+  for (int b = 0; b < n.body_count; ++b) T.jadj_off[b + 1] += T.jadj_off[b];
+  {
+    std::vector<int> fill(T.jadj_off.begin(), T.jadj_off.end() - 1);
+    for (int j = n.joint_count - 1; j >= 0; --j) {  // newest joint first
+      T.jadj[fill[T.joints[j].body_a]++] = 2 * j;
+      T.jadj[fill[T.joints[j].body_b]++] = 2 * j + 1;
     }
   }
   // synchronize order: body list newest first, each body's fixtures newest first, children ascending
@@ -413,6 +471,16 @@ static bool topology_matches(const Topology& T, const b2gpu_snapshot* s) {
       return false;
   for (int b = 0; b < n.body_count; ++b)
     if (s->bodies[b].type != T.bodies[b].type || s->bodies[b].fixture_head != T.bodies[b].fixture_head) return false;
+  if (n.joint_count != (int)T.joints.size()) return false;
+  for (int j = 0; j < n.joint_count; ++j) {
+    const b2gpu_joint_rec &a = s->joints[j], &b = T.joints[j];
+    if (a.type != b.type || a.body_a != b.body_a || a.body_b != b.body_b ||
+        (a.flags & B2GPU_JOINT_COLLIDE_CONNECTED) != (b.flags & B2GPU_JOINT_COLLIDE_CONNECTED) ||
+        memcmp(a.local_anchor_a, b.local_anchor_a, 8) || memcmp(a.local_anchor_b, b.local_anchor_b, 8))
+      return false;
+    const int n_static = a.type == B2GPU_JOINT_REVOLUTE ? 3 : 5;  // revolute: motor torque / speed are per world
+    if (memcmp(a.param, b.param, 4 * n_static)) return false;
+  }
   return true;
 }
 
@@ -473,6 +541,7 @@ int batch_create(Ctx* ctx, const b2gpu_snapshot* proto, int n_worlds, const b2gp
   B.NC = want_contacts;
   B.NMOVE = std::max(2 * B.NP, n.move_count) + 16;
   B.NIB = B.NB + B.NC;
+  B.NJ = n.joint_count;
   B.NMW = std::max((B.NP + 31) / 32, 1);
   if (B.NP < 1) B.NP = 0;
   const long long W = (long long)B.n_wblocks * B.LB;
@@ -488,6 +557,9 @@ int batch_create(Ctx* ctx, const b2gpu_snapshot* proto, int n_worlds, const b2gp
   AL(d_np, (long long)bh->topo.node_proxy.size());
   AL(d_sr, std::max(B.NP, 1));
   B.fixtures = d_fix; B.shapes = d_shape; B.proxy_s = d_ps; B.sync_order = d_so; B.node_proxy = d_np; B.sync_rank = d_sr;
+  b2gpu_joint_rec* d_joints; int* d_joff; int* d_jadj;
+  AL(d_joints, std::max(B.NJ, 1)); AL(d_joff, B.NB + 1); AL(d_jadj, std::max(2 * B.NJ, 1));
+  B.joints = d_joints; B.jadj_off = d_joff; B.jadj = d_jadj;
   const int NPa = std::max(B.NP, 1);
   AL(B.ws, W * WS_COUNT);
   AL(B.b_flags, W * B.NB); AL(B.b_xf, W * B.NB); AL(B.b_pos, W * B.NB); AL(B.b_pos0, W * B.NB); AL(B.b_vel, W * B.NB);
@@ -499,6 +571,10 @@ int batch_create(Ctx* ctx, const b2gpu_snapshot* proto, int n_worlds, const b2gp
   AL(B.c_m0, W * B.NC); AL(B.c_m1, W * B.NC); AL(B.c_m2, W * B.NC); AL(B.c_m3, W * B.NC);
   AL(B.isl_body, W * B.NIB); AL(B.isl_contact, W * B.NC); AL(B.isl_range, W * B.NB); AL(B.isl_flags, W * B.NB);
   AL(B.c_isl, W * B.NC); AL(B.vc, W * B.NC * VC_Q); AL(B.pc, W * B.NC * PC_Q); AL(B.sched, W * B.NC * SCHED_G);
+  if (B.NJ > 0) {
+    AL(B.j_s0, W * B.NJ); AL(B.j_s1, W * B.NJ); AL(B.isl_joint, W * B.NJ); AL(B.isl_jrange, W * B.NB); AL(B.j_flag, W * B.NJ);
+    AL(B.j_tmp, W * B.NJ * JT_Q);
+  }
   AL(bh->b_wake, W * B.NB); AL(bh->b_chead, W * B.NB); AL(bh->c_next, W * B.NC); AL(bh->stack, W * B.NB);
   AL(bh->state_dev, (long long)n_worlds * B.NB * 8);
   AL(bh->forces_dev, (long long)n_worlds * B.NB * 3);
@@ -508,7 +584,7 @@ int batch_create(Ctx* ctx, const b2gpu_snapshot* proto, int n_worlds, const b2gp
 #else
   { cudaError_t e_ = cudaMallocHost((void**)&bh->status_host, 16); if (e_ != cudaSuccess) { batch_destroy(bh); return cuda_fail(e_, "cudaMallocHost(status)"); } bh->status_host[0] = 0; }
 #endif
-  bh->stage_bytes = 16 * (size_t)std::max(std::max(B.NB, B.NN), std::max(std::max(B.NC, B.NMOVE), (int)WS_COUNT));
+  bh->stage_bytes = 16 * (size_t)std::max(std::max(std::max(B.NB, B.NJ), B.NN), std::max(std::max(B.NC, B.NMOVE), (int)WS_COUNT));
   {
     void* v = nullptr;
     rc = dev_alloc(&v, bh->stage_bytes);
@@ -520,6 +596,7 @@ int batch_create(Ctx* ctx, const b2gpu_snapshot* proto, int n_worlds, const b2gp
   const Topology& T = bh->topo;
 #define UP(dst, vec) do { if (!(vec).empty()) { rc = dev_h2d(ctx, (void*)(dst), (vec).data(), (vec).size() * sizeof((vec)[0])); if (rc) { batch_destroy(bh); return rc; } } } while (0)
   UP(d_fix, T.fixtures); UP(d_shape, T.shapes); UP(d_ps, T.proxy_s); UP(d_so, T.sync_order); UP(d_np, T.node_proxy); UP(d_sr, T.sync_rank);
+  UP(d_joints, T.joints); UP(d_joff, T.jadj_off); UP(d_jadj, T.jadj);
 #undef UP
   WorldImage im;
   rc = image_pack(bh, proto, im);
@@ -532,6 +609,7 @@ int batch_create(Ctx* ctx, const b2gpu_snapshot* proto, int n_worlds, const b2gp
   bh->pre_step_needed = true;
   if (caps && (caps->reserved[1] == 11 || caps->reserved[1] == 12)) {  // large-world mode (12: with the exact replica tree): one world, data-parallel ordered stages (b2g_large.h)
     if (n_worlds != 1 || B.LB != 1) { set_error("large-world mode needs a batch of exactly one world"); batch_destroy(bh); return B2GPU_E_INVALID; }
+    if (B.NJ > 0) { set_error("joints are not supported in the large-world modes yet (use the default exact mode)"); batch_destroy(bh); return B2GPU_E_UNSUPPORTED; }
     rc = large_alloc(bh);
     if (rc) { batch_destroy(bh); return rc; }
     bh->large = true;
@@ -541,7 +619,8 @@ int batch_create(Ctx* ctx, const b2gpu_snapshot* proto, int n_worlds, const b2gp
 #if !defined(B2G_HOSTSIM)
   // shared-memory Gauss-Seidel stages: batches in 32-world memory blocks whose bodies fit one SM
   bh->smem_solver = false;
-  if (B.LB == 32 && !(caps && caps->reserved[1] == 1)) {
+  // worlds with joints take the generic per-island Gauss-Seidel stages (joint visits interleave with contact visits)
+  if (B.LB == 32 && !(caps && caps->reserved[1] == 1) && B.NJ == 0) {
     int max_optin = 0;
     CU(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
     const size_t need = std::max(velocity_smem_bytes(B.NB), position_smem_bytes(B.NB));
@@ -713,7 +792,7 @@ int batch_snapshot_sizes(BatchHost* bh, int world, b2gpu_snapshot_sizes* out) {
   RC(move_array(bh, a, 1, world));
   out->body_count = bh->B.NB; out->fixture_count = bh->B.NF; out->shape_count = bh->B.NS; out->proxy_count = bh->B.NP;
   out->node_count = im.ws[WS_TREE_CAP]; out->contact_count = im.ws[WS_CONTACT_COUNT]; out->move_count = im.ws[WS_MOVE_COUNT];
-  out->reserved = 0;
+  out->joint_count = bh->B.NJ;
   return 0;
 }
 

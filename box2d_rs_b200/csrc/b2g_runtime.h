@@ -39,7 +39,7 @@ int ctx_collect_profile(Ctx* ctx);
 // One world in compact SoA form (host): the unit of upload/download.
 struct WorldImage {
   std::vector<int> ws, b_flags, n_moved, move_buf, c_flags, b_chead;
-  std::vector<float4> b_xf, b_pos, b_pos0, b_vel, b_mass, b_force, b_misc, n_aabb, p_aabb, c_mat, c_m0, c_m1, c_m2;
+  std::vector<float4> b_xf, b_pos, b_pos0, b_vel, b_mass, b_force, b_misc, n_aabb, p_aabb, c_mat, c_m0, c_m1, c_m2, j_s0, j_s1;
   std::vector<int4> n_link, c_fix, c_m3;
   std::vector<int2> c_next;
 };
@@ -51,6 +51,8 @@ struct Topology {  // shared by every world of a batch (host copies kept for val
   std::vector<b2gpu_proxy_rec> proxies;
   std::vector<int4> proxy_s;
   std::vector<int> sync_order, sync_rank, node_proxy;
+  std::vector<b2gpu_joint_rec> joints;  // static fields authoritative (type, bodies, COLLIDE_CONNECTED, anchors, param 0-2 / 0-4)
+  std::vector<int> jadj_off, jadj;      // per body: joint edges in the reference's list order (newest first)
 };
 
 struct StreamGroup {

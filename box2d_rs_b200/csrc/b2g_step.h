@@ -21,6 +21,7 @@
 #include "b2g_narrow.h"
 #include "b2g_distance.h"
 #include "b2g_tree.h"
+#include "b2g_joint.h"
 
 #if defined(__CUDA_ARCH__)
 #define B2G_ATOMIC_ADD(p, v) atomicAdd((p), (v))
@@ -80,7 +81,7 @@ B2G_HD bool filter_should_collide(const b2gpu_fixture_rec& a, const b2gpu_fixtur
   if (a.group_index == b.group_index && a.group_index != 0) return a.group_index > 0;
   return (a.mask_bits & b.category_bits) != 0 && (a.category_bits & b.mask_bits) != 0;
 }
-B2G_HD bool body_should_collide(int flags_a, int flags_b) {  // b2_body.rs(private):391-416 (no joints in scope)
+B2G_HD bool body_should_collide(int flags_a, int flags_b) {  // b2_body.rs(private):391-398; the joint test (:400-413) is joints_prevent_collision
   return body_type(flags_a) == B2GPU_DYNAMIC_BODY || body_type(flags_b) == B2GPU_DYNAMIC_BODY;
 }
 
@@ -105,7 +106,7 @@ B2G_HD void collide_one(const Batch& B, const WIdx& x, const Ws& ws, int c, int*
   if (!ordered_pass) {
     flags &= ~CF_INTERNAL;
     if (flags & B2GPU_CONTACT_FILTER) {
-      if (!body_should_collide(bfb, bfa) || !filter_should_collide(fa, fb)) {
+      if (!body_should_collide(bfb, bfa) || joints_prevent_collision(B, bb, ba) || !filter_should_collide(fa, fb)) {
         B.c_flags[ci] = flags | CF_DESTROY;
         B2G_ATOMIC_ADD(&ws[WS_EV_DESTROY], 1);
         return;
@@ -334,13 +335,14 @@ struct SerialAK {
     //     edge list newest first.
     for (int b = 0; b < B.NB; ++b) B.b_flags[x.at(B.NB, b)] &= ~B2GPU_BODY_ISLAND;
     for (int c = 0; c < cc; ++c) B.c_flags[x.at(B.NC, c)] &= ~B2GPU_CONTACT_ISLAND;
-    int nisl = 0, nb = 0, nc = 0;
+    for (int j = 0; j < B.NJ; ++j) B.j_flag[x.at(B.NJ, j)] = 0;
+    int nisl = 0, nb = 0, nc = 0, nj = 0;
     for (int seed = B.NB - 1; seed >= 0; --seed) {
       const int sf = B.b_flags[x.at(B.NB, seed)];
       if (sf & B2GPU_BODY_ISLAND) continue;
       if (!(sf & B2GPU_BODY_AWAKE) || !(sf & B2GPU_BODY_ENABLED)) continue;
       if (body_type(sf) == B2GPU_STATIC_BODY) continue;
-      const int body_first = nb, contact_first = nc;
+      const int body_first = nb, contact_first = nc, joint_first = nj;
       int sp_ = 0;
       stack[x.at(B.NB, sp_++)] = seed;
       B.b_flags[x.at(B.NB, seed)] = sf | B2GPU_BODY_ISLAND;
@@ -376,8 +378,25 @@ struct SerialAK {
           stack[x.at(B.NB, sp_++)] = other;
           B.b_flags[oi] = of | B2GPU_BODY_ISLAND;
         }
+        // joints connected to this body (b2_world.rs(private):461-483), newest edge first
+        if (B.NJ > 0)
+          for (int q = B.jadj_off[b]; q < B.jadj_off[b + 1]; ++q) {
+            const int je = B.jadj[q], j = je >> 1;
+            const int ji = x.at(B.NJ, j);
+            if (B.j_flag[ji]) continue;
+            const int other = (je & 1) ? B.joints[j].body_a : B.joints[j].body_b;
+            const int oi = x.at(B.NB, other);
+            const int of = B.b_flags[oi];
+            if (!(of & B2GPU_BODY_ENABLED)) continue;  // don't simulate joints connected to disabled bodies
+            B.isl_joint[x.at(B.NJ, nj++)] = j;
+            B.j_flag[ji] = 1;
+            if (of & B2GPU_BODY_ISLAND) continue;
+            stack[x.at(B.NB, sp_++)] = other;
+            B.b_flags[oi] = of | B2GPU_BODY_ISLAND;
+          }
       }
       B.isl_range[x.at(B.NB, nisl)] = make_int4(body_first, nb, contact_first, nc);
+      if (B.NJ > 0) B.isl_jrange[x.at(B.NB, nisl)] = make_int2(joint_first, nj);
       ++nisl;
       for (int k = body_first; k < nb; ++k) {  // static bodies may join other islands (:500-506)
         const int bi = x.at(B.NB, B.isl_body[x.at(B.NIB, k)]);
@@ -388,6 +407,7 @@ struct SerialAK {
     ws[WS_ISL_COUNT] = nisl;
     ws[WS_ISL_BODIES] = nb;
     ws[WS_ISL_CONTACTS] = nc;
+    ws[WS_ISL_JOINTS] = nj;
     ws[WS_ST_ISLANDS] = nisl;
     ws[WS_ST_ISL_BODIES] = nb;
     ws[WS_ST_ISL_CONTACTS] = nc;
@@ -689,6 +709,32 @@ B2G_HD void warm_start_one(VelState& s, const float4 q0, const float4 q1, const 
 struct VelocityK {
   Batch B;
   StepParams sp;
+  // one pass over the island's contact constraints: the warm start (:228-266) or one velocity iteration (:268-583)
+  B2G_HD void contact_sweep(const WIdx& x, const int4 rg, bool warm_pass, bool block) const {
+    for (int k = rg.z; k < rg.w; ++k) {
+      const float4 q8 = B.vc[vc_at(B, x, k, 8)];
+      const int ba = f2i(q8.x), bb = f2i(q8.y), vc_points = f2i(q8.z) & 0xff;
+      if (vc_points == 0) continue;
+      const int bai = x.at(B.NB, ba), bbi = x.at(B.NB, bb);
+      const float4 va = B.b_vel[bai], vb = B.b_vel[bbi];
+      VelState s;
+      s.v_a = v2(va.x, va.y); s.w_a = va.z;
+      s.v_b = v2(vb.x, vb.y); s.w_b = vb.z;
+      const float4 q0 = B.vc[vc_at(B, x, k, 0)], q1 = B.vc[vc_at(B, x, k, 1)], q2 = B.vc[vc_at(B, x, k, 2)];
+      float4 q6 = B.vc[vc_at(B, x, k, 6)];
+      const float4 q7 = B.vc[vc_at(B, x, k, 7)];
+      if (warm_pass) {
+        warm_start_one(s, q0, q1, q2, q6, q7, vc_points);
+      } else {
+        const float4 q3 = B.vc[vc_at(B, x, k, 3)], q4 = B.vc[vc_at(B, x, k, 4)], q5 = B.vc[vc_at(B, x, k, 5)];
+        solve_velocity_one(s, q0, q1, q2, q3, q4, q5, q6, q7, vc_points, block);
+        B.vc[vc_at(B, x, k, 6)] = q6;
+      }
+      // a static / kinematic body may sit in several islands: its velocity never changes, leave it alone
+      if (q7.x != 0.0f || q7.y != 0.0f) B.b_vel[bai] = make_float4(s.v_a.x, s.v_a.y, s.w_a, 0.0f);
+      if (q7.z != 0.0f || q7.w != 0.0f) B.b_vel[bbi] = make_float4(s.v_b.x, s.v_b.y, s.w_b, 0.0f);
+    }
+  }
   B2G_HD void operator()(int tid) const {
     int w, isl;
     if (!flat_decode(B, tid, B.NB, w, isl)) return;
@@ -696,33 +742,19 @@ struct VelocityK {
     Ws ws = ws_of(B, x);
     if (isl >= ws[WS_ISL_COUNT]) return;
     const int4 rg = B.isl_range[x.at(B.NB, isl)];
-    if (rg.z == rg.w) return;
+    int2 jr = make_int2(0, 0);
+    if (B.NJ > 0) jr = B.isl_jrange[x.at(B.NB, isl)];
+    if (rg.z == rg.w && jr.x == jr.y) return;
     const bool warm = (ws[WS_FLAGS] & B2GPU_WORLD_WARM_STARTING) != 0;
     const bool block = (ws[WS_FLAGS] & B2GPU_WORLD_BLOCK_SOLVE) != 0;
-    for (int it = warm ? -1 : 0; it < sp.velocity_iterations; ++it) {
-      for (int k = rg.z; k < rg.w; ++k) {
-        const float4 q8 = B.vc[vc_at(B, x, k, 8)];
-        const int ba = f2i(q8.x), bb = f2i(q8.y), vc_points = f2i(q8.z) & 0xff;
-        if (vc_points == 0) continue;
-        const int bai = x.at(B.NB, ba), bbi = x.at(B.NB, bb);
-        const float4 va = B.b_vel[bai], vb = B.b_vel[bbi];
-        VelState s;
-        s.v_a = v2(va.x, va.y); s.w_a = va.z;
-        s.v_b = v2(vb.x, vb.y); s.w_b = vb.z;
-        const float4 q0 = B.vc[vc_at(B, x, k, 0)], q1 = B.vc[vc_at(B, x, k, 1)], q2 = B.vc[vc_at(B, x, k, 2)];
-        float4 q6 = B.vc[vc_at(B, x, k, 6)];
-        const float4 q7 = B.vc[vc_at(B, x, k, 7)];
-        if (it < 0) {
-          warm_start_one(s, q0, q1, q2, q6, q7, vc_points);
-        } else {
-          const float4 q3 = B.vc[vc_at(B, x, k, 3)], q4 = B.vc[vc_at(B, x, k, 4)], q5 = B.vc[vc_at(B, x, k, 5)];
-          solve_velocity_one(s, q0, q1, q2, q3, q4, q5, q6, q7, vc_points, block);
-          B.vc[vc_at(B, x, k, 6)] = q6;
-        }
-        // a static / kinematic body may sit in several islands: its velocity never changes, leave it alone
-        if (q7.x != 0.0f || q7.y != 0.0f) B.b_vel[bai] = make_float4(s.v_a.x, s.v_a.y, s.w_a, 0.0f);
-        if (q7.z != 0.0f || q7.w != 0.0f) B.b_vel[bbi] = make_float4(s.v_b.x, s.v_b.y, s.w_b, 0.0f);
-      }
+    // order of B2island::solve (b2_island_private.rs:193-215): contact warm start, every joint's
+    // init_velocity_constraints (which applies the joint's own warm start), then per iteration joints before contacts
+    if (warm) contact_sweep(x, rg, true, block);
+    const float dt_ratio = i2f(ws[WS_INV_DT0]) * sp.dt;
+    for (int q = jr.x; q < jr.y; ++q) joint_init_velocity(B, x, B.isl_joint[x.at(B.NJ, q)], warm, dt_ratio, sp.dt);
+    for (int it = 0; it < sp.velocity_iterations; ++it) {
+      for (int q = jr.x; q < jr.y; ++q) joint_solve_velocity(B, x, B.isl_joint[x.at(B.NJ, q)], sp.dt, sp.inv_dt);
+      contact_sweep(x, rg, false, block);
     }
   }
 };
@@ -738,7 +770,9 @@ struct PostVelocityK {
     Ws ws = ws_of(B, x);
     if (k < ws[WS_ISL_COUNT]) {
       const int4 rg = B.isl_range[x.at(B.NB, k)];
-      B.isl_flags[x.at(B.NB, k)] = (rg.z == rg.w && sp.position_iterations > 0) ? 1 : 0;
+      bool no_joints = true;
+      if (B.NJ > 0) { const int2 jr = B.isl_jrange[x.at(B.NB, k)]; no_joints = jr.x == jr.y; }
+      B.isl_flags[x.at(B.NB, k)] = (rg.z == rg.w && no_joints && sp.position_iterations > 0) ? 1 : 0;
     }
     if (k < ws[WS_ISL_CONTACTS]) {
       const float4 q8 = B.vc[vc_at(B, x, k, 8)];
@@ -906,7 +940,9 @@ struct PositionK {
     Ws ws = ws_of(B, x);
     if (isl >= ws[WS_ISL_COUNT]) return;
     const int4 rg = B.isl_range[x.at(B.NB, isl)];
-    if (rg.z == rg.w) return;
+    int2 jr = make_int2(0, 0);
+    if (B.NJ > 0) jr = B.isl_jrange[x.at(B.NB, isl)];
+    if (rg.z == rg.w && jr.x == jr.y) return;
     for (int it = 0; it < sp.position_iterations; ++it) {
       float min_separation = 0.0f;
       for (int k = rg.z; k < rg.w; ++k) {
@@ -933,7 +969,12 @@ struct PositionK {
           B.b_pos[bbi] = pb; B.b_rot[bbi] = rb;
         }
       }
-      if (min_separation >= -3.0f * B2G_LINEAR_SLOP) {
+      bool joints_okay = true;  // b2_island_private.rs:262-266: every joint is solved, none short-circuits
+      for (int q = jr.x; q < jr.y; ++q) {
+        const bool joint_okay = joint_solve_position(B, x, B.isl_joint[x.at(B.NJ, q)]);
+        joints_okay = joints_okay && joint_okay;
+      }
+      if (min_separation >= -3.0f * B2G_LINEAR_SLOP && joints_okay) {
         B.isl_flags[x.at(B.NB, isl)] |= 1;
         break;
       }
@@ -1100,6 +1141,7 @@ B2G_HD void add_pair(const Batch& B, const WIdx& x, const Ws& ws, int* b_chead, 
     if (fx.x == fixture_b && fx.y == fixture_a && fx.z == index_b && fx.w == index_a) return;
   }
   if (!body_should_collide(B.b_flags[x.at(B.NB, body_b)], B.b_flags[x.at(B.NB, body_a)])) return;
+  if (joints_prevent_collision(B, body_b, body_a)) return;
   const b2gpu_fixture_rec* fa = &B.fixtures[fixture_a];
   const b2gpu_fixture_rec* fb = &B.fixtures[fixture_b];
   if (!filter_should_collide(*fa, *fb)) return;

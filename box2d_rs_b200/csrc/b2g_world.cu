@@ -32,6 +32,7 @@ struct HostWorld {
   std::vector<b2gpu_shape_rec> shapes;
   std::vector<b2gpu_proxy_rec> proxies;
   std::vector<b2gpu_contact_rec> contacts;
+  std::vector<b2gpu_joint_rec> joints;  // creation order
   std::vector<int> move_buffer;
   // replica tree on the host (stride-1 arrays driven by the same Tree code as the device)
   std::vector<float4> n_aabb;
@@ -270,7 +271,8 @@ void fill_snapshot(b2gpu_world* W, b2gpu_snapshot* s, std::vector<b2gpu_tree_nod
   s->n.body_count = (int)h.bodies.size(); s->n.fixture_count = (int)h.fixtures.size();
   s->n.shape_count = (int)h.shapes.size(); s->n.proxy_count = (int)h.proxies.size();
   s->n.node_count = cap; s->n.contact_count = (int)h.contacts.size(); s->n.move_count = (int)h.move_buffer.size();
-  s->n.reserved = 0;
+  s->n.joint_count = (int)h.joints.size();
+  s->joints = h.joints.empty() ? nullptr : h.joints.data();
   s->bodies = h.bodies.data(); s->fixtures = h.fixtures.data(); s->shapes = h.shapes.data();
   s->proxies = h.proxies.data(); s->nodes = nodes.data(); s->contacts = h.contacts.data();
   s->move_buffer = h.move_buffer.data();
@@ -294,6 +296,8 @@ int ensure_host(b2gpu_world* W) {
   s.n.node_count = (int)nodes.size();
   s.bodies = h.bodies.data(); s.fixtures = h.fixtures.data(); s.shapes = h.shapes.data(); s.proxies = h.proxies.data();
   s.nodes = nodes.data(); s.contacts = h.contacts.data(); s.move_buffer = h.move_buffer.data();
+  s.n.joint_count = (int)h.joints.size();
+  s.joints = h.joints.empty() ? nullptr : h.joints.data();
   rc = batch_download_world(W->dev, 0, &s);
   if (rc) return rc;
   h.contacts.resize(s.n.contact_count);
@@ -771,6 +775,201 @@ int b2gpu_body_set_awake(b2gpu_world* W, int body, int flag) {  // src/b2_body.r
   return 0;
   GUARD_END
 }
+// ---------------------------------------------------------------- joints
+static V2 body_local_point(const b2gpu_body_rec& b, V2 world_point) { return xf_mul_t(body_xf(b), world_point); }  // src/b2_body.rs:728-730
+static void joint_def_defaults(b2gpu_joint_def* d, int type, int body_a, int body_b) {
+  memset(d, 0, sizeof(*d));
+  d->type = type; d->body_a = body_a; d->body_b = body_b;
+  d->length = 1.0f; d->min_length = 0.0f; d->max_length = B2G_MAX_FLOAT;  // B2distanceJointDef::default
+}
+int b2gpu_revolute_joint_def(b2gpu_world* W, b2gpu_joint_def* def, int body_a, int body_b, float ax, float ay) {
+  GUARD_BEGIN
+  int rc = check_body(W, body_a);
+  if (!rc) rc = check_body(W, body_b);
+  if (rc) return rc;
+  if (!def) { set_error("joint def is NULL"); return B2GPU_E_INVALID; }
+  rc = ensure_host(W);
+  if (rc) return rc;
+  joint_def_defaults(def, B2GPU_JOINT_REVOLUTE, body_a, body_b);
+  const b2gpu_body_rec &a = W->h.bodies[body_a], &b = W->h.bodies[body_b];
+  const V2 la = body_local_point(a, v2(ax, ay)), lb = body_local_point(b, v2(ax, ay));
+  def->local_anchor_a[0] = la.x; def->local_anchor_a[1] = la.y;
+  def->local_anchor_b[0] = lb.x; def->local_anchor_b[1] = lb.y;
+  def->reference_angle = b.a - a.a;
+  return 0;
+  GUARD_END
+}
+int b2gpu_distance_joint_def(b2gpu_world* W, b2gpu_joint_def* def, int body_a, int body_b, float a1x, float a1y, float a2x, float a2y) {
+  GUARD_BEGIN
+  int rc = check_body(W, body_a);
+  if (!rc) rc = check_body(W, body_b);
+  if (rc) return rc;
+  if (!def) { set_error("joint def is NULL"); return B2GPU_E_INVALID; }
+  rc = ensure_host(W);
+  if (rc) return rc;
+  joint_def_defaults(def, B2GPU_JOINT_DISTANCE, body_a, body_b);
+  const V2 la = body_local_point(W->h.bodies[body_a], v2(a1x, a1y)), lb = body_local_point(W->h.bodies[body_b], v2(a2x, a2y));
+  def->local_anchor_a[0] = la.x; def->local_anchor_a[1] = la.y;
+  def->local_anchor_b[0] = lb.x; def->local_anchor_b[1] = lb.y;
+  const V2 d = v2(a2x, a2y) - v2(a1x, a1y);
+  def->length = fmax_sel(length(d), B2G_LINEAR_SLOP);
+  def->min_length = def->length;
+  def->max_length = def->length;
+  return 0;
+  GUARD_END
+}
+int b2gpu_linear_stiffness(b2gpu_world* W, float frequency_hertz, float damping_ratio, int body_a, int body_b, float* stiffness,
+                           float* damping) {  // src/private/dynamics/b2_joint.rs:22-45
+  GUARD_BEGIN
+  int rc = check_body(W, body_a);
+  if (!rc) rc = check_body(W, body_b);
+  if (rc) return rc;
+  if (!stiffness || !damping) { set_error("linear_stiffness: NULL output"); return B2GPU_E_INVALID; }
+  rc = ensure_host(W);
+  if (rc) return rc;
+  const float mass_a = W->h.bodies[body_a].mass, mass_b = W->h.bodies[body_b].mass;
+  float mass;
+  if (mass_a > 0.0f && mass_b > 0.0f) mass = mass_a * mass_b / (mass_a + mass_b);
+  else if (mass_a > 0.0f) mass = mass_a;
+  else mass = mass_b;
+  const float omega = 2.0f * B2G_PI * frequency_hertz;
+  *stiffness = mass * omega * omega;
+  *damping = 2.0f * mass * damping_ratio * omega;
+  return 0;
+  GUARD_END
+}
+int b2gpu_world_create_joint(b2gpu_world* W, const b2gpu_joint_def* def) {  // b2_world.rs(private):156-262
+  GUARD_BEGIN
+  if (!W || !def) { set_error("create_joint: bad argument"); return B2GPU_E_INVALID; }
+  int rc = check_body(W, def->body_a);
+  if (!rc) rc = check_body(W, def->body_b);
+  if (rc) return rc;
+  if (def->body_a == def->body_b) { set_error("create_joint: body_a == body_b (the reference asserts)"); return B2GPU_E_INVALID; }
+  if (def->type != B2GPU_JOINT_REVOLUTE && def->type != B2GPU_JOINT_DISTANCE) {
+    set_error("create_joint: only revolute and distance joints are inside the accelerated path");
+    return B2GPU_E_UNSUPPORTED;
+  }
+  rc = ensure_host(W);
+  if (rc) return rc;
+  HostWorld& h = W->h;
+  b2gpu_joint_rec j;
+  memset(&j, 0, sizeof(j));
+  j.type = def->type; j.body_a = def->body_a; j.body_b = def->body_b;
+  j.flags = def->collide_connected ? B2GPU_JOINT_COLLIDE_CONNECTED : 0;
+  memcpy(j.local_anchor_a, def->local_anchor_a, 8);
+  memcpy(j.local_anchor_b, def->local_anchor_b, 8);
+  if (def->type == B2GPU_JOINT_REVOLUTE) {  // B2revoluteJoint::new (src/joints/b2_revolute_joint.rs:253-287)
+    j.param[0] = def->reference_angle; j.param[1] = def->lower_angle; j.param[2] = def->upper_angle;
+    j.param[3] = def->max_motor_torque; j.param[4] = def->motor_speed;
+    if (def->enable_limit) j.flags |= B2GPU_JOINT_ENABLE_LIMIT;
+    if (def->enable_motor) j.flags |= B2GPU_JOINT_ENABLE_MOTOR;
+  } else {  // b2_distance_joint_new (private b2_distance_joint.rs:43-78)
+    const float min_length = fmax_sel(def->min_length, B2G_LINEAR_SLOP);
+    j.param[0] = fmax_sel(def->length, B2G_LINEAR_SLOP);
+    j.param[1] = min_length;
+    j.param[2] = fmax_sel(def->max_length, min_length);
+    j.param[3] = def->stiffness; j.param[4] = def->damping;
+  }
+  h.joints.push_back(j);
+  if (!def->collide_connected) {  // flag the contacts between the two bodies for filtering
+    for (b2gpu_contact_rec& c : h.contacts) {
+      const int ba = h.fixtures[c.fixture_a].body, bb = h.fixtures[c.fixture_b].body;
+      if ((ba == def->body_a && bb == def->body_b) || (ba == def->body_b && bb == def->body_a)) c.flags |= B2GPU_CONTACT_FILTER;
+    }
+  }
+  W->host_dirty = W->topo_dirty = true;  // the joint table is batch topology
+  return (int)h.joints.size() - 1;  // creating a joint doesn't wake the bodies
+  GUARD_END
+}
+int b2gpu_world_get_joint_count(b2gpu_world* W) { return W ? (int)W->h.joints.size() : B2GPU_E_INVALID; }
+static int check_joint(b2gpu_world* W, int joint, int type) {
+  if (!W) { set_error("world is NULL"); return B2GPU_E_INVALID; }
+  if (joint < 0 || joint >= (int)W->h.joints.size()) { set_error("joint index out of range"); return B2GPU_E_INVALID; }
+  if (type && W->h.joints[joint].type != type) { set_error("joint is not of the type this call edits"); return B2GPU_E_INVALID; }
+  return 0;
+}
+int b2gpu_world_get_joint(b2gpu_world* W, int joint, b2gpu_joint_rec* out) {
+  GUARD_BEGIN
+  int rc = check_joint(W, joint, 0);
+  if (rc) return rc;
+  if (!out) { set_error("out is NULL"); return B2GPU_E_INVALID; }
+  rc = ensure_host(W);
+  if (rc) return rc;
+  *out = W->h.joints[joint];
+  return 0;
+  GUARD_END
+}
+// B2revoluteJoint setters (src/joints/b2_revolute_joint.rs:172-242): wake both bodies when the value changes
+static void joint_wake(b2gpu_world* W, const b2gpu_joint_rec& j) {
+  set_awake(W->h.bodies[j.body_a], true);
+  set_awake(W->h.bodies[j.body_b], true);
+}
+int b2gpu_joint_set_motor_speed(b2gpu_world* W, int joint, float speed) {
+  GUARD_BEGIN
+  int rc = check_joint(W, joint, B2GPU_JOINT_REVOLUTE);
+  if (!rc) rc = ensure_host(W);
+  if (rc) return rc;
+  b2gpu_joint_rec& j = W->h.joints[joint];
+  if (speed != j.param[4]) { joint_wake(W, j); j.param[4] = speed; W->host_dirty = true; }
+  return 0;
+  GUARD_END
+}
+int b2gpu_joint_set_max_motor_torque(b2gpu_world* W, int joint, float torque) {
+  GUARD_BEGIN
+  int rc = check_joint(W, joint, B2GPU_JOINT_REVOLUTE);
+  if (!rc) rc = ensure_host(W);
+  if (rc) return rc;
+  b2gpu_joint_rec& j = W->h.joints[joint];
+  if (torque != j.param[3]) { joint_wake(W, j); j.param[3] = torque; W->host_dirty = true; }
+  return 0;
+  GUARD_END
+}
+int b2gpu_joint_enable_motor(b2gpu_world* W, int joint, int flag) {
+  GUARD_BEGIN
+  int rc = check_joint(W, joint, B2GPU_JOINT_REVOLUTE);
+  if (!rc) rc = ensure_host(W);
+  if (rc) return rc;
+  b2gpu_joint_rec& j = W->h.joints[joint];
+  if ((flag != 0) != ((j.flags & B2GPU_JOINT_ENABLE_MOTOR) != 0)) {
+    joint_wake(W, j);
+    j.flags = flag ? (j.flags | B2GPU_JOINT_ENABLE_MOTOR) : (j.flags & ~B2GPU_JOINT_ENABLE_MOTOR);
+    W->host_dirty = true;
+  }
+  return 0;
+  GUARD_END
+}
+int b2gpu_joint_enable_limit(b2gpu_world* W, int joint, int flag) {
+  GUARD_BEGIN
+  int rc = check_joint(W, joint, B2GPU_JOINT_REVOLUTE);
+  if (!rc) rc = ensure_host(W);
+  if (rc) return rc;
+  b2gpu_joint_rec& j = W->h.joints[joint];
+  if ((flag != 0) != ((j.flags & B2GPU_JOINT_ENABLE_LIMIT) != 0)) {
+    joint_wake(W, j);
+    j.flags = flag ? (j.flags | B2GPU_JOINT_ENABLE_LIMIT) : (j.flags & ~B2GPU_JOINT_ENABLE_LIMIT);
+    j.impulse[3] = 0.0f; j.impulse[4] = 0.0f;
+    W->host_dirty = true;
+  }
+  return 0;
+  GUARD_END
+}
+int b2gpu_joint_set_limits(b2gpu_world* W, int joint, float lower, float upper) {
+  GUARD_BEGIN
+  int rc = check_joint(W, joint, B2GPU_JOINT_REVOLUTE);
+  if (!rc) rc = ensure_host(W);
+  if (rc) return rc;
+  if (!(lower <= upper)) { set_error("set_limits: lower > upper (the reference asserts)"); return B2GPU_E_INVALID; }
+  b2gpu_joint_rec& j = W->h.joints[joint];
+  if (lower != j.param[1] || upper != j.param[2]) {
+    joint_wake(W, j);
+    j.impulse[3] = 0.0f; j.impulse[4] = 0.0f;
+    j.param[1] = lower; j.param[2] = upper;
+    W->host_dirty = W->topo_dirty = true;  // the limits are static batch topology
+  }
+  return 0;
+  GUARD_END
+}
+
 static int set_world_flag(b2gpu_world* W, uint32_t bit, int flag) {
   if (!W) { set_error("world is NULL"); return B2GPU_E_INVALID; }
   int rc = ensure_host(W);
@@ -902,7 +1101,7 @@ int b2gpu_world_snapshot_sizes(b2gpu_world* W, b2gpu_snapshot_sizes* out) {
   const HostWorld& h = W->h;
   out->body_count = (int)h.bodies.size(); out->fixture_count = (int)h.fixtures.size(); out->shape_count = (int)h.shapes.size();
   out->proxy_count = (int)h.proxies.size(); out->node_count = h.ws[WS_TREE_CAP]; out->contact_count = (int)h.contacts.size();
-  out->move_count = (int)h.move_buffer.size(); out->reserved = 0;
+  out->move_count = (int)h.move_buffer.size(); out->joint_count = (int)h.joints.size();
   return 0;
   GUARD_END
 }
@@ -916,7 +1115,7 @@ int b2gpu_world_download(b2gpu_world* W, b2gpu_snapshot* out) {
   fill_snapshot(W, &s, nodes);
   if (out->n.body_count < s.n.body_count || out->n.fixture_count < s.n.fixture_count || out->n.shape_count < s.n.shape_count ||
       out->n.proxy_count < s.n.proxy_count || out->n.node_count < s.n.node_count || out->n.contact_count < s.n.contact_count ||
-      out->n.move_count < s.n.move_count) {
+      out->n.move_count < s.n.move_count || out->n.joint_count < s.n.joint_count || (s.n.joint_count > 0 && !out->joints)) {
     set_error("download buffers smaller than snapshot_sizes");
     return B2GPU_E_INVALID;
   }
@@ -929,6 +1128,7 @@ int b2gpu_world_download(b2gpu_world* W, b2gpu_snapshot* out) {
   memcpy(out->nodes, s.nodes, sizeof(b2gpu_tree_node_rec) * s.n.node_count);
   memcpy(out->contacts, s.contacts, sizeof(b2gpu_contact_rec) * s.n.contact_count);
   memcpy(out->move_buffer, s.move_buffer, sizeof(int32_t) * s.n.move_count);
+  if (s.n.joint_count > 0) memcpy(out->joints, s.joints, sizeof(b2gpu_joint_rec) * s.n.joint_count);
   return 0;
   GUARD_END
 }
@@ -946,6 +1146,7 @@ int b2gpu_world_upload(b2gpu_world* W, const b2gpu_snapshot* in) {
   h.proxies.assign(in->proxies, in->proxies + n.proxy_count);
   h.contacts.assign(in->contacts, in->contacts + n.contact_count);
   h.move_buffer.assign(in->move_buffer, in->move_buffer + n.move_count);
+  h.joints.assign(in->joints, in->joints + (in->joints ? n.joint_count : 0));
   h.n_aabb.clear(); h.n_link.clear(); h.n_moved.clear(); h.n_proxy.clear();
   tree_reserve(h, n.node_count);
   for (int i = 0; i < n.node_count; ++i) {

@@ -53,6 +53,17 @@ def load(path=None):
         "b2gpu_body_apply_linear_impulse_to_center": (i32, [vp, i32, f32, f32, i32]),
         "b2gpu_body_apply_angular_impulse": (i32, [vp, i32, f32, i32]),
         "b2gpu_body_set_awake": (i32, [vp, i32, i32]),
+        "b2gpu_revolute_joint_def": (i32, [vp, C.POINTER(abi.JointDef), i32, i32, f32, f32]),
+        "b2gpu_distance_joint_def": (i32, [vp, C.POINTER(abi.JointDef), i32, i32, f32, f32, f32, f32]),
+        "b2gpu_linear_stiffness": (i32, [vp, f32, f32, i32, i32, C.POINTER(f32), C.POINTER(f32)]),
+        "b2gpu_world_create_joint": (i32, [vp, C.POINTER(abi.JointDef)]),
+        "b2gpu_world_get_joint_count": (i32, [vp]),
+        "b2gpu_world_get_joint": (i32, [vp, i32, vp]),
+        "b2gpu_joint_set_motor_speed": (i32, [vp, i32, f32]),
+        "b2gpu_joint_set_max_motor_torque": (i32, [vp, i32, f32]),
+        "b2gpu_joint_enable_motor": (i32, [vp, i32, i32]),
+        "b2gpu_joint_enable_limit": (i32, [vp, i32, i32]),
+        "b2gpu_joint_set_limits": (i32, [vp, i32, f32, f32]),
         "b2gpu_world_set_allow_sleeping": (i32, [vp, i32]),
         "b2gpu_world_set_warm_starting": (i32, [vp, i32]),
         "b2gpu_world_set_continuous_physics": (i32, [vp, i32]),

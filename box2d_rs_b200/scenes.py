@@ -264,3 +264,122 @@ def terrain(world, n=160, segments=1200, seed=0xB2D + 13):
         b.create_fixture(FixtureDef(density=1.0, friction=0.4, restitution=0.1 if k % 5 == 0 else 0.0), shapes[int(rng.next() % 5)])
         bodies.append(b)
     return bodies
+
+
+# ------------------------------------------------------------------------------------------------------------
+# scenes with joints: the reference has no joint test, so these follow its testbed recipes
+# ------------------------------------------------------------------------------------------------------------
+def bridge(world, count=30, testbed_ground_body=True):
+    """examples/testbed/tests/bridge.rs:58-141: a plank bridge of `count` boxes chained by revolute joints between two
+    anchors on the ground body, two triangles and three circles dropped on it."""
+    if testbed_ground_body:
+        world.create_body(BodyDef())
+    ground = world.create_body(BodyDef())
+    ground.create_fixture_by_shape(world.shapes.edge_two_sided((-40.0, 0.0), (40.0, 0.0)), 0.0)
+    plank = world.shapes.polygon_box(0.5, 0.125)
+    prev = ground
+    for i in range(count):
+        body = world.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(f32(-14.5 + 1.0 * i), 5.0)))
+        body.create_fixture(FixtureDef(density=20.0, friction=0.2), plank)
+        world.create_joint(world.revolute_joint_def(prev, body, (f32(-15.0 + 1.0 * i), 5.0)))
+        prev = body
+    world.create_joint(world.revolute_joint_def(prev, ground, (f32(-15.0 + 1.0 * count), 5.0)))
+    tri = world.shapes.polygon([(-0.5, 0.0), (0.5, 0.0), (0.0, 1.5)])
+    for i in range(2):
+        b = world.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(f32(-8.0 + 8.0 * i), 12.0)))
+        b.create_fixture(FixtureDef(density=1.0), tri)
+    ball = world.shapes.circle(0.5)
+    for i in range(3):
+        b = world.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(f32(-6.0 + 6.0 * i), 10.0)))
+        b.create_fixture(FixtureDef(density=1.0), ball)
+
+
+def tumbler(world, n=200, seed=0xB2D + 21):
+    """examples/testbed/tests/tumbler.rs:62-97: a hollow box of four plank fixtures turned by a revolute-joint motor
+    (0.05 pi rad/s, torque 1e8) around a point of the ground body; the testbed drops one 0.125 box per step, here `n`
+    boxes start inside on a jittered grid (the step itself stays deterministic)."""
+    rng = SplitMix64(seed)
+    ground = world.create_body(BodyDef())
+    body = world.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(0.0, 10.0), allow_sleep=0))
+    for hx, hy, cx, cy in ((0.5, 10.0, 10.0, 0.0), (0.5, 10.0, -10.0, 0.0), (10.0, 0.5, 0.0, 10.0), (10.0, 0.5, 0.0, -10.0)):
+        body.create_fixture_by_shape(world.shapes.polygon_box(hx, hy, center=(cx, cy), angle=0.0), 5.0)
+    jd = world.revolute_joint_def(ground, body, (0.0, 10.0))
+    jd.local_anchor_a[0], jd.local_anchor_a[1] = 0.0, 10.0
+    jd.local_anchor_b[0], jd.local_anchor_b[1] = 0.0, 0.0
+    jd.reference_angle = 0.0
+    jd.motor_speed = f32(np.float32(0.05) * np.float32(math.pi))
+    jd.max_motor_torque = 1e8
+    jd.enable_motor = 1
+    joint = world.create_joint(jd)
+    small = world.shapes.polygon_box(0.125, 0.125)
+    cols = 20
+    for k in range(n):
+        px = f32(-4.0 + 0.4 * (k % cols) + rng.uniform(-0.05, 0.05))
+        py = f32(3.0 + 0.4 * (k // cols) + rng.uniform(-0.05, 0.05))
+        b = world.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(px, py)))
+        b.create_fixture_by_shape(small, 1.0)
+    return joint
+
+
+def joints_mix(world, seed=0xB2D + 23):
+    """Every joint branch of the step in one small scene: a rigid distance-joint pendulum, a soft distance joint
+    (b2_linear_stiffness, min < max: spring + lower + upper rows), a revolute chain with limits hanging from a static
+    anchor (examples/testbed/tests/chain.rs), a limited + motorised revolute arm, a joint with collide_connected, a
+    fixed-rotation body on a revolute joint, and loose boxes that collide with all of it."""
+    rng = SplitMix64(seed)
+    ground = world.create_body(BodyDef())
+    ground.create_fixture_by_shape(world.shapes.edge_two_sided((-30.0, 0.0), (30.0, 0.0)), 0.0)
+    ball = world.shapes.circle(0.4)
+    # rigid pendulum (equal limits)
+    p1 = world.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(-12.0, 8.0)))
+    p1.create_fixture(FixtureDef(density=1.0, friction=0.3), ball)
+    world.create_joint(world.distance_joint_def(ground, p1, (-15.0, 12.0), (-12.0, 8.0)))
+    # soft spring with slack between min and max length
+    p2 = world.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(-8.0, 9.0), angular_damping=0.1))
+    p2.create_fixture(FixtureDef(density=2.0, friction=0.3), world.shapes.polygon_box(0.5, 0.3))
+    jd = world.distance_joint_def(ground, p2, (-8.0, 13.0), (-8.0, 9.5))
+    jd.stiffness, jd.damping = world.linear_stiffness(2.0, 0.3, ground, p2)
+    jd.min_length = f32(jd.length - 1.0)
+    jd.max_length = f32(jd.length + 0.5)
+    world.create_joint(jd)
+    # revolute chain with limits (chain.rs: friction 0.2, density 20; here every joint is limited to +-0.6 rad)
+    link = world.shapes.polygon_box(0.6, 0.125)
+    prev = ground
+    y = 14.0
+    for i in range(12):
+        b = world.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(f32(0.5 + i * 1.0), y)))
+        b.create_fixture(FixtureDef(density=20.0, friction=0.2), link)
+        jd = world.revolute_joint_def(prev, b, (f32(i * 1.0), y))
+        if i > 0:
+            jd.enable_limit = 1
+            jd.lower_angle = -0.6
+            jd.upper_angle = 0.6
+        world.create_joint(jd)
+        prev = b
+    # motorised, limited arm; its two bodies may collide (collide_connected)
+    base = world.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(-3.0, 1.0)))
+    base.create_fixture(FixtureDef(density=5.0, friction=0.6), world.shapes.polygon_box(1.0, 1.0))
+    arm = world.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(-3.0, 3.5)))
+    arm.create_fixture(FixtureDef(density=1.0, friction=0.3), world.shapes.polygon_box(0.2, 1.5))
+    jd = world.revolute_joint_def(base, arm, (-3.0, 2.0))
+    jd.collide_connected = 1
+    jd.enable_limit, jd.lower_angle, jd.upper_angle = 1, -1.0, 0.8
+    jd.enable_motor, jd.motor_speed, jd.max_motor_torque = 1, 1.5, 40.0
+    motor = world.create_joint(jd)
+    # fixed-rotation body on a revolute joint with a very narrow limit range (the "equal limits" correction branch)
+    fr = world.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(6.0, 5.0), fixed_rotation=1))
+    fr.create_fixture(FixtureDef(density=1.0), world.shapes.polygon_box(0.4, 0.4))
+    nb = world.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(7.5, 5.0)))
+    nb.create_fixture(FixtureDef(density=1.0), world.shapes.polygon_box(0.9, 0.2))
+    jd = world.revolute_joint_def(fr, nb, (6.6, 5.0))
+    jd.enable_limit, jd.lower_angle, jd.upper_angle = 1, -0.01, 0.01
+    world.create_joint(jd)
+    world.create_joint(world.distance_joint_def(ground, fr, (6.0, 9.0), (6.0, 5.0)))
+    # loose bodies
+    box = world.shapes.polygon_box(0.35, 0.35)
+    for k in range(24):
+        px = f32(-10.0 + 0.9 * k + rng.uniform(-0.1, 0.1))
+        py = f32(16.0 + (k % 3) * 1.1 + rng.uniform(-0.1, 0.1))
+        b = world.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(px, py), angle=f32(rng.uniform(-1.0, 1.0))))
+        b.create_fixture(FixtureDef(density=1.0, friction=0.4), box if k % 2 else ball)
+    return motor

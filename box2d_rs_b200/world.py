@@ -119,6 +119,37 @@ class B2body:
         return bool(int(self._rec()["flags"]) & abi.BODY_AWAKE)
 
 
+class B2joint:
+    """B2revoluteJoint / B2distanceJoint handle (setters of src/joints/b2_revolute_joint.rs:172-242)."""
+
+    def __init__(self, world, index):
+        self.world, self.index = world, index
+
+    def set_motor_speed(self, speed):
+        check(self.world.L, self.world.L.b2gpu_joint_set_motor_speed(self.world.h, self.index, speed))
+
+    def set_max_motor_torque(self, torque):
+        check(self.world.L, self.world.L.b2gpu_joint_set_max_motor_torque(self.world.h, self.index, torque))
+
+    def enable_motor(self, flag):
+        check(self.world.L, self.world.L.b2gpu_joint_enable_motor(self.world.h, self.index, int(flag)))
+
+    def enable_limit(self, flag):
+        check(self.world.L, self.world.L.b2gpu_joint_enable_limit(self.world.h, self.index, int(flag)))
+
+    def set_limits(self, lower, upper):
+        check(self.world.L, self.world.L.b2gpu_joint_set_limits(self.world.h, self.index, lower, upper))
+
+    def record(self):
+        out = np.zeros(1, abi.JOINT_DTYPE)
+        check(self.world.L, self.world.L.b2gpu_world_get_joint(self.world.h, self.index, out.ctypes.data))
+        return out[0]
+
+
+def _body_index(b):
+    return b.index if hasattr(b, "index") else int(b)
+
+
 class B2world:
     def __init__(self, gravity, ctx=None, device=0, lib_path=None):
         self.ctx = ctx or Context(device, lib_path=lib_path)
@@ -137,6 +168,37 @@ class B2world:
 
     def body(self, index):
         return B2body(self, index)
+
+    def revolute_joint_def(self, body_a, body_b, anchor):
+        """B2revoluteJointDef::default() + initialize(body_a, body_b, anchor): edit the fields, then create_joint."""
+        d = abi.JointDef()
+        check(self.L, self.L.b2gpu_revolute_joint_def(self.h, C.byref(d), _body_index(body_a), _body_index(body_b),
+                                                      anchor[0], anchor[1]))
+        return d
+
+    def distance_joint_def(self, body_a, body_b, anchor_a, anchor_b):
+        """B2distanceJointDef::default() + initialize(b1, b2, anchor1, anchor2)."""
+        d = abi.JointDef()
+        check(self.L, self.L.b2gpu_distance_joint_def(self.h, C.byref(d), _body_index(body_a), _body_index(body_b),
+                                                      anchor_a[0], anchor_a[1], anchor_b[0], anchor_b[1]))
+        return d
+
+    def linear_stiffness(self, frequency_hertz, damping_ratio, body_a, body_b):
+        """b2_linear_stiffness: (stiffness, damping) of a soft distance joint."""
+        k, d = C.c_float(), C.c_float()
+        check(self.L, self.L.b2gpu_linear_stiffness(self.h, frequency_hertz, damping_ratio, _body_index(body_a),
+                                                    _body_index(body_b), C.byref(k), C.byref(d)))
+        return k.value, d.value
+
+    def create_joint(self, joint_def):
+        """B2world::create_joint (revolute and distance joints)."""
+        return B2joint(self, check(self.L, self.L.b2gpu_world_create_joint(self.h, C.byref(joint_def))))
+
+    def joint(self, index):
+        return B2joint(self, index)
+
+    def get_joint_count(self):
+        return check(self.L, self.L.b2gpu_world_get_joint_count(self.h))
 
     def set_allow_sleeping(self, flag):
         check(self.L, self.L.b2gpu_world_set_allow_sleeping(self.h, int(flag)))

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define B2GPU_ABI_VERSION 1
+#define B2GPU_ABI_VERSION 2 /* 2: joint table in the snapshot (b2gpu_joint_rec, b2gpu_snapshot.joints) */
 
 /* error codes */
 #define B2GPU_OK 0
@@ -38,7 +38,7 @@ extern "C" {
 #define B2GPU_E_NO_DEVICE (-2) /* no CUDA device: there is no CPU fallback */
 #define B2GPU_E_CUDA (-3)      /* CUDA runtime error, see b2gpu_last_error */
 #define B2GPU_E_CAPACITY (-4)  /* a device-side capacity was exceeded */
-#define B2GPU_E_UNSUPPORTED (-5) /* feature outside the hot-path scope (joints, TOI) */
+#define B2GPU_E_UNSUPPORTED (-5) /* feature outside the hot-path scope (TOI, joint types other than revolute / distance) */
 #define B2GPU_E_LOCKED (-6)    /* world is locked (reference: is_locked() panic) */
 #define B2GPU_E_INTERNAL (-7)  /* a device-side consistency check failed (a bug: please report) */
 #define B2GPU_E_IO (-8)        /* a checkpoint file could not be opened, read or written */
@@ -80,6 +80,14 @@ extern "C" {
 #define B2GPU_WORLD_NEW_CONTACTS 0x04u  /* m_new_contacts     (:46) */
 #define B2GPU_WORLD_CLEAR_FORCES 0x08u  /* m_clear_forces     (:48) */
 #define B2GPU_WORLD_BLOCK_SOLVE 0x10u   /* G_BLOCK_SOLVE      (src/b2_contact.rs:25) */
+
+/* joint types: B2jointType (src/b2_joint.rs:46-58), same numbering */
+#define B2GPU_JOINT_DISTANCE 1
+#define B2GPU_JOINT_REVOLUTE 8
+/* b2gpu_joint_rec.flags */
+#define B2GPU_JOINT_COLLIDE_CONNECTED 0x1u /* B2jointDef::collide_connected */
+#define B2GPU_JOINT_ENABLE_LIMIT 0x2u      /* revolute: m_enable_limit */
+#define B2GPU_JOINT_ENABLE_MOTOR 0x4u      /* revolute: m_enable_motor */
 
 #define B2GPU_NULL (-1)
 #define B2GPU_MAX_POLYGON_VERTICES 8
@@ -173,6 +181,23 @@ typedef struct b2gpu_contact_rec {
   b2gpu_manifold manifold;
 } b2gpu_contact_rec;
 
+/* B2joint + the derived joint (src/b2_joint.rs:160-180; revolute: src/joints/b2_revolute_joint.rs:104-136,
+ * distance: src/joints/b2_distance_joint.rs) — definition, user-settable parameters and the accumulated impulses
+ * the solver warm-starts from.  Array order = creation order; a body's joint list (push_front of edge A on body A,
+ * then edge B on body B, src/private/dynamics/b2_world.rs:176-208) follows from it.  96 bytes.
+ *   param[]  revolute: 0 reference_angle, 1 lower_angle, 2 upper_angle, 3 max_motor_torque, 4 motor_speed
+ *            distance: 0 length, 1 min_length, 2 max_length, 3 stiffness, 4 damping
+ *   impulse[] revolute: 0,1 m_impulse.xy, 2 m_motor_impulse, 3 m_lower_impulse, 4 m_upper_impulse
+ *            distance: 0 m_impulse, 3 m_lower_impulse, 4 m_upper_impulse */
+typedef struct b2gpu_joint_rec {
+  int32_t type;             /* B2GPU_JOINT_* */
+  int32_t body_a, body_b;
+  uint32_t flags;           /* B2GPU_JOINT_COLLIDE_CONNECTED | ENABLE_LIMIT | ENABLE_MOTOR */
+  float local_anchor_a[2], local_anchor_b[2];
+  float param[8];
+  float impulse[8];
+} b2gpu_joint_rec;
+
 /* World-level scalars: B2world + B2broadPhase + B2dynamicTree bookkeeping. */
 typedef struct b2gpu_world_rec {
   float gravity_x, gravity_y;
@@ -191,7 +216,7 @@ typedef struct b2gpu_snapshot_sizes {
   int32_t body_count, fixture_count, shape_count, proxy_count;
   int32_t node_count; /* == tree_node_capacity: the whole pool incl. free nodes */
   int32_t contact_count, move_count;
-  int32_t reserved;
+  int32_t joint_count;
 } b2gpu_snapshot_sizes;
 
 /* Full step state.  Arrays are caller-owned.  For download the caller allocates
@@ -206,6 +231,7 @@ typedef struct b2gpu_snapshot {
   b2gpu_tree_node_rec* nodes;
   b2gpu_contact_rec* contacts;    /* creation order; world contact list = reverse */
   int32_t* move_buffer;           /* B2broadPhase::m_move_buffer (proxy ids, -1 = nulled) */
+  b2gpu_joint_rec* joints;        /* creation order (ABI 2); may be NULL when n.joint_count == 0 */
 } b2gpu_snapshot;
 
 /* Counters of the last step of one world (parity quick-check + roofline inputs). */
@@ -271,6 +297,21 @@ typedef struct b2gpu_shape_def {
 typedef struct b2gpu_mass_data {
   float mass, center_x, center_y, inertia;
 } b2gpu_mass_data;
+
+/* B2revoluteJointDef / B2distanceJointDef (src/joints/b2_revolute_joint.rs:10-72, b2_distance_joint.rs:11-58) as one
+ * plain struct; fill it with b2gpu_revolute_joint_def / b2gpu_distance_joint_def (the reference's Default + initialize)
+ * and edit the fields before b2gpu_world_create_joint. */
+typedef struct b2gpu_joint_def {
+  int32_t type;
+  int32_t body_a, body_b;
+  int32_t collide_connected;
+  float local_anchor_a[2], local_anchor_b[2];
+  /* revolute */
+  float reference_angle, lower_angle, upper_angle, max_motor_torque, motor_speed;
+  int32_t enable_limit, enable_motor;
+  /* distance */
+  float length, min_length, max_length, stiffness, damping;
+} b2gpu_joint_def;
 
 /* Device-side capacities of one world of a batch. 0 = derive from the prototype. */
 typedef struct b2gpu_caps {
@@ -339,6 +380,29 @@ int b2gpu_body_apply_linear_impulse(b2gpu_world* w, int body, float ix, float iy
 int b2gpu_body_apply_linear_impulse_to_center(b2gpu_world* w, int body, float ix, float iy, int wake);
 int b2gpu_body_apply_angular_impulse(b2gpu_world* w, int body, float impulse, int wake);
 int b2gpu_body_set_awake(b2gpu_world* w, int body, int flag);
+/* Joints.  B2revoluteJointDef::default + ::initialize(body_a, body_b, anchor)
+ * (src/joints/b2_revolute_joint.rs:10-86): local anchors and reference angle from the bodies' current transforms. */
+int b2gpu_revolute_joint_def(b2gpu_world* w, b2gpu_joint_def* def, int body_a, int body_b, float anchor_x, float anchor_y);
+/* B2distanceJointDef::default + ::initialize(b1, b2, anchor1, anchor2) (private b2_distance_joint.rs:26-41):
+ * length = max(|anchor2 - anchor1|, linear slop), min_length = max_length = length. */
+int b2gpu_distance_joint_def(b2gpu_world* w, b2gpu_joint_def* def, int body_a, int body_b, float a1x, float a1y, float a2x, float a2y);
+/* b2_linear_stiffness (src/private/dynamics/b2_joint.rs:22-45): stiffness and damping of a soft distance joint. */
+int b2gpu_linear_stiffness(b2gpu_world* w, float frequency_hertz, float damping_ratio, int body_a, int body_b, float* stiffness,
+                           float* damping);
+/* B2world::create_joint (src/private/dynamics/b2_world.rs:156-262): returns the joint index (>= 0); contacts between
+ * the two bodies are flagged for filtering when collide_connected is false.  Does not wake the bodies.
+ * Joint types other than revolute and distance: B2GPU_E_UNSUPPORTED. */
+int b2gpu_world_create_joint(b2gpu_world* w, const b2gpu_joint_def* def);
+int b2gpu_world_get_joint_count(b2gpu_world* w);
+int b2gpu_world_get_joint(b2gpu_world* w, int joint, b2gpu_joint_rec* out);
+/* B2revoluteJoint::set_motor_speed / set_max_motor_torque / enable_motor / enable_limit / set_limits
+ * (src/joints/b2_revolute_joint.rs): wake both bodies when the value changes, as the reference does; enable_limit and
+ * set_limits also zero the limit impulses. */
+int b2gpu_joint_set_motor_speed(b2gpu_world* w, int joint, float speed);
+int b2gpu_joint_set_max_motor_torque(b2gpu_world* w, int joint, float torque);
+int b2gpu_joint_enable_motor(b2gpu_world* w, int joint, int flag);
+int b2gpu_joint_enable_limit(b2gpu_world* w, int joint, int flag);
+int b2gpu_joint_set_limits(b2gpu_world* w, int joint, float lower, float upper);
 /* B2world::set_allow_sleeping / set_warm_starting / set_continuous_physics */
 int b2gpu_world_set_allow_sleeping(b2gpu_world* w, int flag);
 int b2gpu_world_set_warm_starting(b2gpu_world* w, int flag);

@@ -52,6 +52,18 @@ def lib():
         L.b2o_body_set_awake.argtypes = [C.c_void_p, C.c_int, C.c_int]
         for f in ("b2o_set_allow_sleeping", "b2o_set_warm_starting", "b2o_set_block_solve", "b2o_set_collect_levels"):
             getattr(L, f).argtypes = [C.c_void_p, C.c_int]
+        L.b2o_revolute_joint_def.argtypes = [C.c_void_p, C.POINTER(abi.JointDef), C.c_int, C.c_int, C.c_float, C.c_float]
+        L.b2o_distance_joint_def.argtypes = [C.c_void_p, C.POINTER(abi.JointDef), C.c_int, C.c_int, C.c_float, C.c_float,
+                                             C.c_float, C.c_float]
+        L.b2o_linear_stiffness.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_int, C.POINTER(C.c_float),
+                                           C.POINTER(C.c_float)]
+        L.b2o_create_joint.argtypes = [C.c_void_p, C.POINTER(abi.JointDef)]
+        L.b2o_joint_count.argtypes = [C.c_void_p]
+        L.b2o_joint_set_motor_speed.argtypes = [C.c_void_p, C.c_int, C.c_float]
+        L.b2o_joint_set_max_motor_torque.argtypes = [C.c_void_p, C.c_int, C.c_float]
+        L.b2o_joint_enable_motor.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.b2o_joint_enable_limit.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.b2o_joint_set_limits.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float]
         L.b2o_set_collect_dag.argtypes = [C.c_void_p, C.c_int, C.c_double]
         L.b2o_get_dag_stats.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         L.b2o_step.argtypes = [C.c_void_p, C.c_float, C.c_int, C.c_int]
@@ -168,6 +180,32 @@ class B2body:
         return float(self._rec()["a"])
 
 
+class B2joint:
+    """B2revoluteJoint / B2distanceJoint handle (setters of src/joints/b2_revolute_joint.rs:172-242)."""
+
+    def __init__(self, world, index):
+        self.world, self.index = world, index
+
+    def set_motor_speed(self, speed):
+        lib().b2o_joint_set_motor_speed(self.world.h, self.index, speed)
+
+    def set_max_motor_torque(self, torque):
+        lib().b2o_joint_set_max_motor_torque(self.world.h, self.index, torque)
+
+    def enable_motor(self, flag):
+        lib().b2o_joint_enable_motor(self.world.h, self.index, int(flag))
+
+    def enable_limit(self, flag):
+        lib().b2o_joint_enable_limit(self.world.h, self.index, int(flag))
+
+    def set_limits(self, lower, upper):
+        lib().b2o_joint_set_limits(self.world.h, self.index, lower, upper)
+
+
+def _body_index(b):
+    return b.index if hasattr(b, "index") else int(b)
+
+
 class B2world:
     shapes = Shapes
 
@@ -187,6 +225,35 @@ class B2world:
 
     def body(self, index):
         return B2body(self, index)
+
+    def revolute_joint_def(self, body_a, body_b, anchor):
+        """B2revoluteJointDef::default() + initialize(body_a, body_b, anchor)."""
+        d = abi.JointDef()
+        lib().b2o_revolute_joint_def(self.h, C.byref(d), _body_index(body_a), _body_index(body_b), anchor[0], anchor[1])
+        return d
+
+    def distance_joint_def(self, body_a, body_b, anchor_a, anchor_b):
+        """B2distanceJointDef::default() + initialize(b1, b2, anchor1, anchor2)."""
+        d = abi.JointDef()
+        lib().b2o_distance_joint_def(self.h, C.byref(d), _body_index(body_a), _body_index(body_b), anchor_a[0], anchor_a[1],
+                                     anchor_b[0], anchor_b[1])
+        return d
+
+    def linear_stiffness(self, frequency_hertz, damping_ratio, body_a, body_b):
+        """b2_linear_stiffness: (stiffness, damping)."""
+        k, d = C.c_float(), C.c_float()
+        lib().b2o_linear_stiffness(self.h, frequency_hertz, damping_ratio, _body_index(body_a), _body_index(body_b),
+                                   C.byref(k), C.byref(d))
+        return k.value, d.value
+
+    def create_joint(self, joint_def):
+        return B2joint(self, lib().b2o_create_joint(self.h, C.byref(joint_def)))
+
+    def joint(self, index):
+        return B2joint(self, index)
+
+    def get_joint_count(self):
+        return lib().b2o_joint_count(self.h)
 
     def set_allow_sleeping(self, flag):
         lib().b2o_set_allow_sleeping(self.h, int(flag))

@@ -139,6 +139,46 @@ void b2o_apply_linear_impulse(void* w, int body, float ix, float iy, float px, f
 void b2o_apply_linear_impulse_to_center(void* w, int body, float ix, float iy, int wake) { ((World*)w)->apply_linear_impulse_to_center(body, Vec2(ix, iy), wake != 0); }
 void b2o_apply_angular_impulse(void* w, int body, float i, int wake) { ((World*)w)->apply_angular_impulse(body, i, wake != 0); }
 void b2o_body_set_awake(void* w, int body, int flag) { ((World*)w)->set_awake(body, flag != 0); }
+// ---- joints (b2gpu_joint_def in and out, so the scene recipes drive both engines)
+static void joint_def_out(const JointDef& d, b2gpu_joint_def* o) {
+  std::memset(o, 0, sizeof(*o));
+  o->type = d.type; o->body_a = d.body_a; o->body_b = d.body_b; o->collide_connected = d.collide_connected ? 1 : 0;
+  o->local_anchor_a[0] = d.local_anchor_a.x; o->local_anchor_a[1] = d.local_anchor_a.y;
+  o->local_anchor_b[0] = d.local_anchor_b.x; o->local_anchor_b[1] = d.local_anchor_b.y;
+  o->reference_angle = d.reference_angle; o->lower_angle = d.lower_angle; o->upper_angle = d.upper_angle;
+  o->max_motor_torque = d.max_motor_torque; o->motor_speed = d.motor_speed;
+  o->enable_limit = d.enable_limit ? 1 : 0; o->enable_motor = d.enable_motor ? 1 : 0;
+  o->length = d.length; o->min_length = d.min_length; o->max_length = d.max_length; o->stiffness = d.stiffness; o->damping = d.damping;
+}
+int b2o_revolute_joint_def(void* w, b2gpu_joint_def* def, int body_a, int body_b, float ax, float ay) {
+  joint_def_out(((World*)w)->revolute_joint_def(body_a, body_b, Vec2(ax, ay)), def);
+  return 0;
+}
+int b2o_distance_joint_def(void* w, b2gpu_joint_def* def, int body_a, int body_b, float a1x, float a1y, float a2x, float a2y) {
+  joint_def_out(((World*)w)->distance_joint_def(body_a, body_b, Vec2(a1x, a1y), Vec2(a2x, a2y)), def);
+  return 0;
+}
+int b2o_linear_stiffness(void* w, float hz, float ratio, int body_a, int body_b, float* stiffness, float* damping) {
+  ((World*)w)->linear_stiffness(*stiffness, *damping, hz, ratio, body_a, body_b);
+  return 0;
+}
+int b2o_create_joint(void* w, const b2gpu_joint_def* d) {
+  JointDef jd;
+  jd.type = d->type; jd.body_a = d->body_a; jd.body_b = d->body_b; jd.collide_connected = d->collide_connected != 0;
+  jd.local_anchor_a = Vec2(d->local_anchor_a[0], d->local_anchor_a[1]);
+  jd.local_anchor_b = Vec2(d->local_anchor_b[0], d->local_anchor_b[1]);
+  jd.reference_angle = d->reference_angle; jd.lower_angle = d->lower_angle; jd.upper_angle = d->upper_angle;
+  jd.max_motor_torque = d->max_motor_torque; jd.motor_speed = d->motor_speed;
+  jd.enable_limit = d->enable_limit != 0; jd.enable_motor = d->enable_motor != 0;
+  jd.length = d->length; jd.min_length = d->min_length; jd.max_length = d->max_length; jd.stiffness = d->stiffness; jd.damping = d->damping;
+  return ((World*)w)->create_joint(jd);
+}
+int b2o_joint_count(void* w) { return (int)((World*)w)->joints.size(); }
+void b2o_joint_set_motor_speed(void* w, int j, float v) { ((World*)w)->joint_set_motor_speed(j, v); }
+void b2o_joint_set_max_motor_torque(void* w, int j, float v) { ((World*)w)->joint_set_max_motor_torque(j, v); }
+void b2o_joint_enable_motor(void* w, int j, int f) { ((World*)w)->joint_enable_motor(j, f != 0); }
+void b2o_joint_enable_limit(void* w, int j, int f) { ((World*)w)->joint_enable_limit(j, f != 0); }
+void b2o_joint_set_limits(void* w, int j, float lo, float hi) { ((World*)w)->joint_set_limits(j, lo, hi); }
 void b2o_set_allow_sleeping(void* w, int f) {  // b2_world.rs(private):340-353
   World* W = (World*)w;
   if ((f != 0) == W->allow_sleep) return;
@@ -227,7 +267,7 @@ void b2o_snapshot_sizes(void* w, b2gpu_snapshot_sizes* n) {
   n->node_count = W.broad_phase.tree.node_capacity;
   n->contact_count = W.contact_count;
   n->move_count = (int)W.broad_phase.move_buffer.size();
-  n->reserved = 0;
+  n->joint_count = (int)W.joints.size();
 }
 static void fill_shape_rec(const Shape& s, b2gpu_shape_rec* r) {
   std::memset(r, 0, sizeof(*r));
@@ -254,9 +294,28 @@ int b2o_snapshot_export(void* w, b2gpu_snapshot* out) {
   if (out->n.body_count < need.body_count || out->n.fixture_count < need.fixture_count ||
       out->n.shape_count < need.shape_count || out->n.proxy_count < need.proxy_count ||
       out->n.node_count < need.node_count || out->n.contact_count < need.contact_count ||
-      out->n.move_count < need.move_count)
+      out->n.move_count < need.move_count || out->n.joint_count < need.joint_count || (need.joint_count > 0 && !out->joints))
     return -1;
   out->n = need;
+  for (size_t i = 0; i < W.joints.size(); ++i) {
+    const Joint& j = W.joints[i];
+    b2gpu_joint_rec& r = out->joints[i];
+    std::memset(&r, 0, sizeof(r));
+    r.type = j.type; r.body_a = j.body_a; r.body_b = j.body_b;
+    r.flags = (j.collide_connected ? B2GPU_JOINT_COLLIDE_CONNECTED : 0) | (j.enable_limit ? B2GPU_JOINT_ENABLE_LIMIT : 0) |
+              (j.enable_motor ? B2GPU_JOINT_ENABLE_MOTOR : 0);
+    r.local_anchor_a[0] = j.local_anchor_a.x; r.local_anchor_a[1] = j.local_anchor_a.y;
+    r.local_anchor_b[0] = j.local_anchor_b.x; r.local_anchor_b[1] = j.local_anchor_b.y;
+    if (j.type == J_REVOLUTE) {
+      r.param[0] = j.reference_angle; r.param[1] = j.lower_angle; r.param[2] = j.upper_angle;
+      r.param[3] = j.max_motor_torque; r.param[4] = j.motor_speed;
+      r.impulse[0] = j.impulse2.x; r.impulse[1] = j.impulse2.y; r.impulse[2] = j.motor_impulse;
+    } else {
+      r.param[0] = j.length; r.param[1] = j.min_length; r.param[2] = j.max_length; r.param[3] = j.stiffness; r.param[4] = j.damping;
+      r.impulse[0] = j.impulse;
+    }
+    r.impulse[3] = j.lower_impulse; r.impulse[4] = j.upper_impulse;
+  }
   b2gpu_world_rec& wr = out->world;
   std::memset(&wr, 0, sizeof(wr));
   wr.gravity_x = W.gravity.x; wr.gravity_y = W.gravity.y;

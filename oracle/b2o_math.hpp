@@ -24,6 +24,7 @@ constexpr float LINEAR_SLOP = 0.005f * LENGTH_UNITS_PER_METER;
 constexpr float ANGULAR_SLOP = 2.0f / 180.0f * PI;
 constexpr float POLYGON_RADIUS = 2.0f * LINEAR_SLOP;
 constexpr float MAX_LINEAR_CORRECTION = 0.2f * LENGTH_UNITS_PER_METER;
+constexpr float MAX_ANGULAR_CORRECTION = 8.0f / 180.0f * PI;  // src/b2_common.rs:64
 constexpr float MAX_TRANSLATION = 2.0f * LENGTH_UNITS_PER_METER;
 constexpr float MAX_TRANSLATION_SQUARED = MAX_TRANSLATION * MAX_TRANSLATION;
 constexpr float MAX_ROTATION = 0.5f * PI;
@@ -77,6 +78,13 @@ struct Mat22 {
     m.ex = Vec2(det * d, -det * c);
     m.ey = Vec2(-det * b, det * a);
     return m;
+  }
+  // :276-293 — solve A * x = b
+  Vec2 solve(Vec2 b) const {
+    float a11 = ex.x, a12 = ey.x, a21 = ex.y, a22 = ey.y;
+    float det = a11 * a22 - a12 * a21;
+    if (det != 0.0f) det = 1.0f / det;
+    return Vec2(det * (a22 * b.x - a12 * b.y), det * (a11 * b.y - a21 * b.x));
   }
 };
 

@@ -62,6 +62,7 @@ struct Body {
   int fixture_list = -1;            // head = newest
   int fixture_count = 0;
   int contact_list = -1;            // head edge id (2*contact + side)
+  std::vector<int> joint_edges;     // m_joint_list in push order (2*joint + side); the list iterates it in reverse
   float mass = 0.0f, inv_mass = 0.0f, i = 0.0f, inv_i = 0.0f;
   float linear_damping = 0.0f, angular_damping = 0.0f, gravity_scale = 1.0f, sleep_time = 0.0f;
 };
@@ -88,6 +89,38 @@ struct Contact {
   int fixture_a = -1, fixture_b = -1, index_a = 0, index_b = 0;
   Manifold manifold;
   float friction = 0.0f, restitution = 0.0f, restitution_threshold = 0.0f, tangent_speed = 0.0f;
+};
+
+// Joints: B2jointDef + B2revoluteJointDef / B2distanceJointDef as one plain struct
+// (src/b2_joint.rs:112-122, src/joints/b2_revolute_joint.rs:10-72, src/joints/b2_distance_joint.rs:11-58).
+enum JointType { J_DISTANCE = 1, J_REVOLUTE = 8 };  // B2jointType numbering (src/b2_joint.rs:46-58)
+struct JointDef {
+  int type = 0, body_a = -1, body_b = -1;
+  bool collide_connected = false;
+  Vec2 local_anchor_a, local_anchor_b;
+  float reference_angle = 0.0f, lower_angle = 0.0f, upper_angle = 0.0f, max_motor_torque = 0.0f, motor_speed = 0.0f;
+  bool enable_limit = false, enable_motor = false;
+  float length = 1.0f, min_length = 0.0f, max_length = MAX_FLOAT, stiffness = 0.0f, damping = 0.0f;
+};
+struct Joint {  // B2joint + B2revoluteJoint (src/joints/b2_revolute_joint.rs:104-136) / B2distanceJoint fields
+  int type = 0, body_a = -1, body_b = -1;
+  bool collide_connected = false, island_flag = false;
+  Vec2 local_anchor_a, local_anchor_b;
+  // revolute: solver shared
+  Vec2 impulse2;
+  float motor_impulse = 0.0f, lower_impulse = 0.0f, upper_impulse = 0.0f;
+  bool enable_motor = false, enable_limit = false;
+  float max_motor_torque = 0.0f, motor_speed = 0.0f, reference_angle = 0.0f, lower_angle = 0.0f, upper_angle = 0.0f;
+  // distance: solver shared
+  float length = 0.0f, min_length = 0.0f, max_length = 0.0f, stiffness = 0.0f, damping = 0.0f, impulse = 0.0f;
+  float gamma = 0.0f, bias = 0.0f, current_length = 0.0f, mass = 0.0f, soft_mass = 0.0f;
+  Vec2 u;
+  // solver temp
+  int index_a = 0, index_b = 0;
+  Vec2 r_a, r_b, local_center_a, local_center_b;
+  float inv_mass_a = 0.0f, inv_mass_b = 0.0f, inv_ia = 0.0f, inv_ib = 0.0f;
+  Mat22 k;
+  float angle = 0.0f, axial_mass = 0.0f;
 };
 
 struct TimeStep {  // src/b2_time_step.rs
@@ -372,9 +405,104 @@ struct World {
     if (wake && !(b.flags & BF_AWAKE)) set_awake(bi, true);
     if (b.flags & BF_AWAKE) b.angular_velocity += b.inv_i * impulse;
   }
-  bool body_should_collide(int self_, int other) const {  // b2_body.rs(private):391-416 (no joints in scope)
+  bool body_should_collide(int self_, int other) const {  // b2_body.rs(private):391-416
     if (bodies[self_].type != DYNAMIC_BODY && bodies[other].type != DYNAMIC_BODY) return false;
+    const std::vector<int>& je = bodies[self_].joint_edges;  // does a joint prevent collision?
+    for (size_t i = je.size(); i-- > 0;) {
+      const Joint& j = joints[je[i] >> 1];
+      const int jn_other = (je[i] & 1) ? j.body_a : j.body_b;
+      if (jn_other == other && !j.collide_connected) return false;
+    }
     return true;
+  }
+
+  // ---------------------------------------------------------------- joints
+  std::vector<Joint> joints;  // creation order
+  // B2revoluteJointDef::initialize (src/joints/b2_revolute_joint.rs:77-85)
+  JointDef revolute_joint_def(int body_a, int body_b, Vec2 anchor) const {
+    JointDef d;
+    d.type = J_REVOLUTE;
+    d.body_a = body_a; d.body_b = body_b;
+    d.local_anchor_a = b2_mul_t_xf(bodies[body_a].xf, anchor);  // get_local_point (src/b2_body.rs:728-730)
+    d.local_anchor_b = b2_mul_t_xf(bodies[body_b].xf, anchor);
+    d.reference_angle = bodies[body_b].sweep.a - bodies[body_a].sweep.a;
+    return d;
+  }
+  // b2_distance_joint_def_initialize (private b2_distance_joint.rs:26-41)
+  JointDef distance_joint_def(int b1, int b2, Vec2 anchor1, Vec2 anchor2) const {
+    JointDef d;
+    d.type = J_DISTANCE;
+    d.body_a = b1; d.body_b = b2;
+    d.local_anchor_a = b2_mul_t_xf(bodies[b1].xf, anchor1);
+    d.local_anchor_b = b2_mul_t_xf(bodies[b2].xf, anchor2);
+    Vec2 dd = anchor2 - anchor1;
+    d.length = b2_max(dd.length(), LINEAR_SLOP);
+    d.min_length = d.length;
+    d.max_length = d.length;
+    return d;
+  }
+  // b2_linear_stiffness (src/private/dynamics/b2_joint.rs:22-45)
+  void linear_stiffness(float& stiffness, float& damping, float frequency_hertz, float damping_ratio, int body_a, int body_b) const {
+    float mass_a = bodies[body_a].mass, mass_b = bodies[body_b].mass, mass;
+    if (mass_a > 0.0f && mass_b > 0.0f) mass = mass_a * mass_b / (mass_a + mass_b);
+    else if (mass_a > 0.0f) mass = mass_a;
+    else mass = mass_b;
+    float omega = 2.0f * PI * frequency_hertz;
+    stiffness = mass * omega * omega;
+    damping = 2.0f * mass * damping_ratio * omega;
+  }
+  int create_joint(const JointDef& def) {  // b2_world.rs(private):156-262
+    assert(def.body_a != def.body_b);
+    Joint j;
+    j.type = def.type; j.body_a = def.body_a; j.body_b = def.body_b; j.collide_connected = def.collide_connected;
+    j.local_anchor_a = def.local_anchor_a; j.local_anchor_b = def.local_anchor_b;
+    if (def.type == J_REVOLUTE) {  // B2revoluteJoint::new (src/joints/b2_revolute_joint.rs:253-287)
+      j.enable_motor = def.enable_motor; j.max_motor_torque = def.max_motor_torque; j.motor_speed = def.motor_speed;
+      j.enable_limit = def.enable_limit; j.reference_angle = def.reference_angle;
+      j.lower_angle = def.lower_angle; j.upper_angle = def.upper_angle;
+    } else if (def.type == J_DISTANCE) {  // b2_distance_joint_new (private b2_distance_joint.rs:43-78)
+      j.min_length = b2_max(def.min_length, LINEAR_SLOP);
+      j.length = b2_max(def.length, LINEAR_SLOP);
+      j.max_length = b2_max(def.max_length, j.min_length);
+      j.stiffness = def.stiffness; j.damping = def.damping;
+    } else {
+      assert(false && "joint type outside the oracle's scope");
+    }
+    int ji = (int)joints.size();
+    joints.push_back(j);
+    bodies[def.body_a].joint_edges.push_back(2 * ji);      // edge A on body A's list, then edge B on body B's
+    bodies[def.body_b].joint_edges.push_back(2 * ji + 1);
+    if (!def.collide_connected)  // flag the contacts between the two bodies for filtering
+      for (int e = bodies[def.body_b].contact_list; e != -1; e = edge(e).next)
+        if (edge(e).other == def.body_a) contacts[e >> 1].flags |= CF_FILTER;
+    return ji;  // creating a joint doesn't wake the bodies
+  }
+  // B2revoluteJoint setters (src/joints/b2_revolute_joint.rs:172-242)
+  void joint_set_motor_speed(int ji, float speed) {
+    Joint& j = joints[ji];
+    if (speed != j.motor_speed) { set_awake(j.body_a, true); set_awake(j.body_b, true); j.motor_speed = speed; }
+  }
+  void joint_set_max_motor_torque(int ji, float torque) {
+    Joint& j = joints[ji];
+    if (torque != j.max_motor_torque) { set_awake(j.body_a, true); set_awake(j.body_b, true); j.max_motor_torque = torque; }
+  }
+  void joint_enable_motor(int ji, bool flag) {
+    Joint& j = joints[ji];
+    if (flag != j.enable_motor) { set_awake(j.body_a, true); set_awake(j.body_b, true); j.enable_motor = flag; }
+  }
+  void joint_enable_limit(int ji, bool flag) {
+    Joint& j = joints[ji];
+    if (flag != j.enable_limit) {
+      set_awake(j.body_a, true); set_awake(j.body_b, true);
+      j.enable_limit = flag; j.lower_impulse = 0.0f; j.upper_impulse = 0.0f;
+    }
+  }
+  void joint_set_limits(int ji, float lower, float upper) {
+    Joint& j = joints[ji];
+    if (lower != j.lower_angle || upper != j.upper_angle) {
+      set_awake(j.body_a, true); set_awake(j.body_b, true);
+      j.lower_impulse = 0.0f; j.upper_impulse = 0.0f; j.lower_angle = lower; j.upper_angle = upper;
+    }
   }
   bool filter_should_collide(int fa, int fb) const {  // b2_world_callbacks.rs(private):6-18
     const Filter& a = fixtures[fa].filter;
@@ -556,10 +684,10 @@ struct World {
 
   // ---------------------------------------------------------------- island
   struct Island {
-    std::vector<int> bodies, contacts;
+    std::vector<int> bodies, contacts, joints;
     std::vector<Position> positions;
     std::vector<Velocity> velocities;
-    void clear() { bodies.clear(); contacts.clear(); }
+    void clear() { bodies.clear(); contacts.clear(); joints.clear(); }
   };
   std::vector<ContactVelocityConstraint> vcs;
   std::vector<ContactPositionConstraint> pcs;
@@ -910,6 +1038,292 @@ struct World {
     return min_separation >= -3.0f * LINEAR_SLOP;
   }
 
+  // -------------------------------------------------------------- joint solver
+  // B2jointTraitDyn::init_velocity_constraints / solve_velocity_constraints / solve_position_constraints
+  // (src/b2_joint.rs:268-286), dispatched on the joint type.
+  void joint_init_velocity_constraints(Joint& j, const TimeStep& step, Island& is) {
+    const Body& body_a = bodies[j.body_a];
+    const Body& body_b = bodies[j.body_b];
+    j.index_a = body_a.island_index;
+    j.index_b = body_b.island_index;
+    j.local_center_a = body_a.sweep.local_center;
+    j.local_center_b = body_b.sweep.local_center;
+    j.inv_mass_a = body_a.inv_mass;
+    j.inv_mass_b = body_b.inv_mass;
+    j.inv_ia = body_a.inv_i;
+    j.inv_ib = body_b.inv_i;
+    Vec2 c_a = is.positions[j.index_a].c;
+    float a_a = is.positions[j.index_a].a;
+    Vec2 v_a = is.velocities[j.index_a].v;
+    float w_a = is.velocities[j.index_a].w;
+    Vec2 c_b = is.positions[j.index_b].c;
+    float a_b = is.positions[j.index_b].a;
+    Vec2 v_b = is.velocities[j.index_b].v;
+    float w_b = is.velocities[j.index_b].w;
+    Rot q_a(a_a), q_b(a_b);
+    j.r_a = b2_mul_rot(q_a, j.local_anchor_a - j.local_center_a);
+    j.r_b = b2_mul_rot(q_b, j.local_anchor_b - j.local_center_b);
+    if (j.type == J_REVOLUTE) {  // private joints/b2_revolute_joint.rs:22-123
+      float m_a = j.inv_mass_a, m_b = j.inv_mass_b, i_a = j.inv_ia, i_b = j.inv_ib;
+      j.k.ex.x = m_a + m_b + j.r_a.y * j.r_a.y * i_a + j.r_b.y * j.r_b.y * i_b;
+      j.k.ey.x = -j.r_a.y * j.r_a.x * i_a - j.r_b.y * j.r_b.x * i_b;
+      j.k.ex.y = j.k.ey.x;
+      j.k.ey.y = m_a + m_b + j.r_a.x * j.r_a.x * i_a + j.r_b.x * j.r_b.x * i_b;
+      j.axial_mass = i_a + i_b;
+      bool fixed_rotation;
+      if (j.axial_mass > 0.0f) { j.axial_mass = 1.0f / j.axial_mass; fixed_rotation = false; }
+      else fixed_rotation = true;
+      j.angle = a_b - a_a - j.reference_angle;
+      if (j.enable_limit == false || fixed_rotation) { j.lower_impulse = 0.0f; j.upper_impulse = 0.0f; }
+      if (j.enable_motor == false || fixed_rotation) j.motor_impulse = 0.0f;
+      if (step.warm_starting) {
+        j.impulse2 *= step.dt_ratio;
+        j.motor_impulse *= step.dt_ratio;
+        j.lower_impulse *= step.dt_ratio;
+        j.upper_impulse *= step.dt_ratio;
+        float axial_impulse = j.motor_impulse + j.lower_impulse - j.upper_impulse;
+        Vec2 p(j.impulse2.x, j.impulse2.y);
+        v_a -= m_a * p;
+        w_a -= i_a * (b2_cross(j.r_a, p) + axial_impulse);
+        v_b += m_b * p;
+        w_b += i_b * (b2_cross(j.r_b, p) + axial_impulse);
+      } else {
+        j.impulse2.set_zero();
+        j.motor_impulse = 0.0f;
+        j.lower_impulse = 0.0f;
+        j.upper_impulse = 0.0f;
+      }
+    } else {  // distance: private joints/b2_distance_joint.rs:80-184
+      j.u = c_b + j.r_b - c_a - j.r_a;
+      j.current_length = j.u.length();
+      if (j.current_length > LINEAR_SLOP) {
+        j.u *= 1.0f / j.current_length;
+      } else {
+        j.u.set(0.0f, 0.0f);
+        j.mass = 0.0f;
+        j.impulse = 0.0f;
+        j.lower_impulse = 0.0f;
+        j.upper_impulse = 0.0f;
+      }
+      float cr_au = b2_cross(j.r_a, j.u), cr_bu = b2_cross(j.r_b, j.u);
+      float inv_mass = j.inv_mass_a + j.inv_ia * cr_au * cr_au + j.inv_mass_b + j.inv_ib * cr_bu * cr_bu;
+      j.mass = inv_mass != 0.0f ? 1.0f / inv_mass : 0.0f;
+      if (j.stiffness > 0.0f && j.min_length < j.max_length) {  // soft
+        float c = j.current_length - j.length;
+        float d = j.damping, k = j.stiffness, h = step.dt;
+        j.gamma = h * (d + h * k);
+        j.gamma = j.gamma != 0.0f ? 1.0f / j.gamma : 0.0f;
+        j.bias = c * h * k * j.gamma;
+        inv_mass += j.gamma;
+        j.soft_mass = inv_mass != 0.0f ? 1.0f / inv_mass : 0.0f;
+      } else {  // rigid
+        j.gamma = 0.0f;
+        j.bias = 0.0f;
+        j.soft_mass = j.mass;
+      }
+      if (step.warm_starting) {
+        j.impulse *= step.dt_ratio;
+        j.lower_impulse *= step.dt_ratio;
+        j.upper_impulse *= step.dt_ratio;
+        Vec2 p = (j.impulse + j.lower_impulse - j.upper_impulse) * j.u;
+        v_a -= j.inv_mass_a * p;
+        w_a -= j.inv_ia * b2_cross(j.r_a, p);
+        v_b += j.inv_mass_b * p;
+        w_b += j.inv_ib * b2_cross(j.r_b, p);
+      } else {
+        j.impulse = 0.0f;
+      }
+    }
+    is.velocities[j.index_a].v = v_a;
+    is.velocities[j.index_a].w = w_a;
+    is.velocities[j.index_b].v = v_b;
+    is.velocities[j.index_b].w = w_b;
+  }
+  void joint_solve_velocity_constraints(Joint& j, const TimeStep& step, Island& is) {
+    Vec2 v_a = is.velocities[j.index_a].v;
+    float w_a = is.velocities[j.index_a].w;
+    Vec2 v_b = is.velocities[j.index_b].v;
+    float w_b = is.velocities[j.index_b].w;
+    if (j.type == J_REVOLUTE) {  // private joints/b2_revolute_joint.rs:125-217
+      float m_a = j.inv_mass_a, m_b = j.inv_mass_b, i_a = j.inv_ia, i_b = j.inv_ib;
+      bool fixed_rotation = i_a + i_b == 0.0f;
+      if (j.enable_motor && fixed_rotation == false) {
+        float cdot = w_b - w_a - j.motor_speed;
+        float impulse = -j.axial_mass * cdot;
+        float old_impulse = j.motor_impulse;
+        float max_impulse = step.dt * j.max_motor_torque;
+        j.motor_impulse = b2_clamp(j.motor_impulse + impulse, -max_impulse, max_impulse);
+        impulse = j.motor_impulse - old_impulse;
+        w_a -= i_a * impulse;
+        w_b += i_b * impulse;
+      }
+      if (j.enable_limit && fixed_rotation == false) {
+        {  // lower limit
+          float c = j.angle - j.lower_angle;
+          float cdot = w_b - w_a;
+          float impulse = -j.axial_mass * (cdot + b2_max(c, 0.0f) * step.inv_dt);
+          float old_impulse = j.lower_impulse;
+          j.lower_impulse = b2_max(j.lower_impulse + impulse, 0.0f);
+          impulse = j.lower_impulse - old_impulse;
+          w_a -= i_a * impulse;
+          w_b += i_b * impulse;
+        }
+        {  // upper limit (signs flipped)
+          float c = j.upper_angle - j.angle;
+          float cdot = w_a - w_b;
+          float impulse = -j.axial_mass * (cdot + b2_max(c, 0.0f) * step.inv_dt);
+          float old_impulse = j.upper_impulse;
+          j.upper_impulse = b2_max(j.upper_impulse + impulse, 0.0f);
+          impulse = j.upper_impulse - old_impulse;
+          w_a += i_a * impulse;
+          w_b -= i_b * impulse;
+        }
+      }
+      {  // point-to-point constraint
+        Vec2 cdot = v_b + b2_cross_sv(w_b, j.r_b) - v_a - b2_cross_sv(w_a, j.r_a);
+        Vec2 impulse = j.k.solve(-cdot);
+        j.impulse2.x += impulse.x;
+        j.impulse2.y += impulse.y;
+        v_a -= m_a * impulse;
+        w_a -= i_a * b2_cross(j.r_a, impulse);
+        v_b += m_b * impulse;
+        w_b += i_b * b2_cross(j.r_b, impulse);
+      }
+    } else {  // distance: private joints/b2_distance_joint.rs:186-277
+      if (j.min_length < j.max_length) {
+        if (j.stiffness > 0.0f) {
+          Vec2 vp_a = v_a + b2_cross_sv(w_a, j.r_a);
+          Vec2 vp_b = v_b + b2_cross_sv(w_b, j.r_b);
+          float cdot = b2_dot(j.u, vp_b - vp_a);
+          float impulse = -j.soft_mass * (cdot + j.bias + j.gamma * j.impulse);
+          j.impulse += impulse;
+          Vec2 p = impulse * j.u;
+          v_a -= j.inv_mass_a * p;
+          w_a -= j.inv_ia * b2_cross(j.r_a, p);
+          v_b += j.inv_mass_b * p;
+          w_b += j.inv_ib * b2_cross(j.r_b, p);
+        }
+        {  // lower
+          float c = j.current_length - j.min_length;
+          float bias = b2_max(0.0f, c) * step.inv_dt;
+          Vec2 vp_a = v_a + b2_cross_sv(w_a, j.r_a);
+          Vec2 vp_b = v_b + b2_cross_sv(w_b, j.r_b);
+          float cdot = b2_dot(j.u, vp_b - vp_a);
+          float impulse = -j.mass * (cdot + bias);
+          float old_impulse = j.lower_impulse;
+          j.lower_impulse = b2_max(0.0f, j.lower_impulse + impulse);
+          impulse = j.lower_impulse - old_impulse;
+          Vec2 p = impulse * j.u;
+          v_a -= j.inv_mass_a * p;
+          w_a -= j.inv_ia * b2_cross(j.r_a, p);
+          v_b += j.inv_mass_b * p;
+          w_b += j.inv_ib * b2_cross(j.r_b, p);
+        }
+        {  // upper
+          float c = j.max_length - j.current_length;
+          float bias = b2_max(0.0f, c) * step.inv_dt;
+          Vec2 vp_a = v_a + b2_cross_sv(w_a, j.r_a);
+          Vec2 vp_b = v_b + b2_cross_sv(w_b, j.r_b);
+          float cdot = b2_dot(j.u, vp_a - vp_b);
+          float impulse = -j.mass * (cdot + bias);
+          float old_impulse = j.upper_impulse;
+          j.upper_impulse = b2_max(0.0f, j.upper_impulse + impulse);
+          impulse = j.upper_impulse - old_impulse;
+          Vec2 p = -impulse * j.u;
+          v_a -= j.inv_mass_a * p;
+          w_a -= j.inv_ia * b2_cross(j.r_a, p);
+          v_b += j.inv_mass_b * p;
+          w_b += j.inv_ib * b2_cross(j.r_b, p);
+        }
+      } else {  // equal limits
+        Vec2 vp_a = v_a + b2_cross_sv(w_a, j.r_a);
+        Vec2 vp_b = v_b + b2_cross_sv(w_b, j.r_b);
+        float cdot = b2_dot(j.u, vp_b - vp_a);
+        float impulse = -j.mass * cdot;
+        j.impulse += impulse;
+        Vec2 p = impulse * j.u;
+        v_a -= j.inv_mass_a * p;
+        w_a -= j.inv_ia * b2_cross(j.r_a, p);
+        v_b += j.inv_mass_b * p;
+        w_b += j.inv_ib * b2_cross(j.r_b, p);
+      }
+    }
+    is.velocities[j.index_a].v = v_a;
+    is.velocities[j.index_a].w = w_a;
+    is.velocities[j.index_b].v = v_b;
+    is.velocities[j.index_b].w = w_b;
+  }
+  bool joint_solve_position_constraints(Joint& j, Island& is) {
+    Vec2 c_a = is.positions[j.index_a].c;
+    float a_a = is.positions[j.index_a].a;
+    Vec2 c_b = is.positions[j.index_b].c;
+    float a_b = is.positions[j.index_b].a;
+    bool okay;
+    if (j.type == J_REVOLUTE) {  // private joints/b2_revolute_joint.rs:219-301
+      Rot q_a(a_a), q_b(a_b);
+      float angular_error = 0.0f, position_error;
+      bool fixed_rotation = j.inv_ia + j.inv_ib == 0.0f;
+      if (j.enable_limit && fixed_rotation == false) {
+        float angle = a_b - a_a - j.reference_angle;
+        float c = 0.0f;
+        if (fabsf(j.upper_angle - j.lower_angle) < 2.0f * ANGULAR_SLOP) {
+          c = b2_clamp(angle - j.lower_angle, -MAX_ANGULAR_CORRECTION, MAX_ANGULAR_CORRECTION);
+        } else if (angle <= j.lower_angle) {
+          c = b2_clamp(angle - j.lower_angle + ANGULAR_SLOP, -MAX_ANGULAR_CORRECTION, 0.0f);
+        } else if (angle >= j.upper_angle) {
+          c = b2_clamp(angle - j.upper_angle - ANGULAR_SLOP, 0.0f, MAX_ANGULAR_CORRECTION);
+        }
+        float limit_impulse = -j.axial_mass * c;
+        a_a -= j.inv_ia * limit_impulse;
+        a_b += j.inv_ib * limit_impulse;
+        angular_error = fabsf(c);
+      }
+      {
+        q_a.set(a_a);
+        q_b.set(a_b);
+        Vec2 r_a = b2_mul_rot(q_a, j.local_anchor_a - j.local_center_a);
+        Vec2 r_b = b2_mul_rot(q_b, j.local_anchor_b - j.local_center_b);
+        Vec2 c = c_b + r_b - c_a - r_a;
+        position_error = c.length();
+        float m_a = j.inv_mass_a, m_b = j.inv_mass_b, i_a = j.inv_ia, i_b = j.inv_ib;
+        Mat22 k;
+        k.ex.x = m_a + m_b + i_a * r_a.y * r_a.y + i_b * r_b.y * r_b.y;
+        k.ex.y = -i_a * r_a.x * r_a.y - i_b * r_b.x * r_b.y;
+        k.ey.x = k.ex.y;
+        k.ey.y = m_a + m_b + i_a * r_a.x * r_a.x + i_b * r_b.x * r_b.x;
+        Vec2 impulse = -k.solve(c);
+        c_a -= m_a * impulse;
+        a_a -= i_a * b2_cross(r_a, impulse);
+        c_b += m_b * impulse;
+        a_b += i_b * b2_cross(r_b, impulse);
+      }
+      okay = position_error <= LINEAR_SLOP && angular_error <= ANGULAR_SLOP;
+    } else {  // distance: private joints/b2_distance_joint.rs:279-320
+      Rot q_a(a_a), q_b(a_b);
+      Vec2 r_a = b2_mul_rot(q_a, j.local_anchor_a - j.local_center_a);
+      Vec2 r_b = b2_mul_rot(q_b, j.local_anchor_b - j.local_center_b);
+      Vec2 u = c_b + r_b - c_a - r_a;
+      float length = u.normalize();
+      float c;
+      if (j.min_length == j.max_length) c = length - j.min_length;
+      else if (length < j.min_length) c = length - j.min_length;
+      else if (j.max_length < length) c = length - j.max_length;
+      else return true;  // positions untouched
+      float impulse = -j.mass * c;
+      Vec2 p = impulse * u;
+      c_a -= j.inv_mass_a * p;
+      a_a -= j.inv_ia * b2_cross(r_a, p);
+      c_b += j.inv_mass_b * p;
+      a_b += j.inv_ib * b2_cross(r_b, p);
+      okay = fabsf(c) < LINEAR_SLOP;
+    }
+    is.positions[j.index_a].c = c_a;
+    is.positions[j.index_a].a = a_a;
+    is.positions[j.index_b].c = c_b;
+    is.positions[j.index_b].a = a_b;
+    return okay;
+  }
+
   // Diagnostic (not part of the reference): depth of the dependency DAG of one in-order
   // sweep over the island's constraints, where only bodies with non-zero inverse mass or
   // inertia create dependencies.
@@ -1001,11 +1415,15 @@ struct World {
     solver_new(is, step);
     initialize_velocity_constraints(is);
     if (step.warm_starting) warm_start(is);
+    for (int ji : is.joints) joint_init_velocity_constraints(joints[ji], step, is);  // b2_island_private.rs:198-201
     if (collect_levels) stats.solver_levels = std::max(stats.solver_levels, wavefront_depth(is, step.velocity_iterations));
     if (collect_levels && collect_dag) dag_collect(is, step.velocity_iterations + (step.warm_starting ? 1 : 0), dag_handover);
     double t1 = now_ms();
     profile.solve_init += t1 - t0;
-    for (int it = 0; it < step.velocity_iterations; ++it) solve_velocity_constraints(is);
+    for (int it = 0; it < step.velocity_iterations; ++it) {  // :207-215: joints first, then contacts
+      for (int ji : is.joints) joint_solve_velocity_constraints(joints[ji], step, is);
+      solve_velocity_constraints(is);
+    }
     store_impulses(is);
     double t2 = now_ms();
     profile.solve_velocity += t2 - t1;
@@ -1034,7 +1452,12 @@ struct World {
     bool position_solved = false;
     for (int it = 0; it < step.position_iterations; ++it) {
       bool contacts_okay = solve_position_constraints(is);
-      if (contacts_okay) { position_solved = true; break; }
+      bool joints_okay = true;  // :262-266
+      for (int ji : is.joints) {
+        bool joint_okay = joint_solve_position_constraints(joints[ji], is);
+        joints_okay = joints_okay && joint_okay;
+      }
+      if (contacts_okay && joints_okay) { position_solved = true; break; }
     }
     for (size_t i = 0; i < is.bodies.size(); ++i) {
       Body& body = bodies[is.bodies[i]];
@@ -1071,6 +1494,7 @@ struct World {
     Island island;
     for (int b = body_list; b != -1; b = bodies[b].next) bodies[b].flags &= ~BF_ISLAND;
     for (int c = contact_list; c != -1; c = contacts[c].next) contacts[c].flags &= ~CF_ISLAND;
+    for (Joint& j : joints) j.island_flag = false;
     std::vector<int> stack;
     stack.reserve(bodies.size());
     for (int seed = body_list; seed != -1; seed = bodies[seed].next) {
@@ -1099,6 +1523,19 @@ struct World {
           island.contacts.push_back(e >> 1);
           contact.flags |= CF_ISLAND;
           int other = edge(e).other;
+          if (bodies[other].flags & BF_ISLAND) continue;
+          stack.push_back(other);
+          bodies[other].flags |= BF_ISLAND;
+        }
+        // search all joints connected to this body (b2_world.rs(private):461-483), newest edge first
+        const std::vector<int>& je = bodies[bi].joint_edges;
+        for (size_t q = je.size(); q-- > 0;) {
+          Joint& joint = joints[je[q] >> 1];
+          if (joint.island_flag) continue;
+          int other = (je[q] & 1) ? joint.body_a : joint.body_b;
+          if (!(bodies[other].flags & BF_ENABLED)) continue;  // don't simulate joints connected to disabled bodies
+          island.joints.push_back(je[q] >> 1);
+          joint.island_flag = true;
           if (bodies[other].flags & BF_ISLAND) continue;
           stack.push_back(other);
           bodies[other].flags |= BF_ISLAND;

@@ -1,12 +1,12 @@
 //! src/private/gpu/ffi.rs — the crate's only `unsafe`: the `extern "C"` surface of libb2gpu.so
-//! (include/b2gpu.h, ABI version 1) and thin safe wrappers that turn error codes into `Result`.
+//! (include/b2gpu.h, ABI version 2) and thin safe wrappers that turn error codes into `Result`.
 //! NOT BUILT IN THIS REPOSITORY'S CI (no Rust toolchain in the image); kept in sync with the header by
 //! tests/test_abi.py::test_rust_ffi_lists_every_symbol.
 #![allow(non_camel_case_types, dead_code)]
 use std::ffi::CStr;
 use std::os::raw::{c_char, c_float, c_int, c_void};
 
-pub const B2GPU_ABI_VERSION: c_int = 1;
+pub const B2GPU_ABI_VERSION: c_int = 2;
 pub const B2GPU_E_INVALID: c_int = -1;
 pub const B2GPU_E_NO_DEVICE: c_int = -2;
 pub const B2GPU_E_CUDA: c_int = -3;
@@ -59,6 +59,20 @@ pub struct b2gpu_contact_rec {
     pub friction: f32, pub restitution: f32, pub restitution_threshold: f32, pub tangent_speed: f32, pub reserved: i32,
     pub manifold: b2gpu_manifold,
 }
+/// B2joint + B2revoluteJoint / B2distanceJoint: definition, parameters and accumulated impulses (96 bytes).
+#[repr(C)] #[derive(Clone, Copy, Default)]
+pub struct b2gpu_joint_rec {
+    pub type_: i32, pub body_a: i32, pub body_b: i32, pub flags: u32,
+    pub local_anchor_a: [f32; 2], pub local_anchor_b: [f32; 2], pub param: [f32; 8], pub impulse: [f32; 8],
+}
+#[repr(C)] #[derive(Clone, Copy, Default)]
+pub struct b2gpu_joint_def {
+    pub type_: i32, pub body_a: i32, pub body_b: i32, pub collide_connected: i32,
+    pub local_anchor_a: [f32; 2], pub local_anchor_b: [f32; 2],
+    pub reference_angle: f32, pub lower_angle: f32, pub upper_angle: f32, pub max_motor_torque: f32, pub motor_speed: f32,
+    pub enable_limit: i32, pub enable_motor: i32,
+    pub length: f32, pub min_length: f32, pub max_length: f32, pub stiffness: f32, pub damping: f32,
+}
 #[repr(C)] #[derive(Clone, Copy, Default)]
 pub struct b2gpu_world_rec {
     pub gravity_x: f32, pub gravity_y: f32, pub inv_dt0: f32, pub flags: u32,
@@ -68,7 +82,7 @@ pub struct b2gpu_world_rec {
 #[repr(C)] #[derive(Clone, Copy, Default)]
 pub struct b2gpu_snapshot_sizes {
     pub body_count: i32, pub fixture_count: i32, pub shape_count: i32, pub proxy_count: i32,
-    pub node_count: i32, pub contact_count: i32, pub move_count: i32, pub reserved: i32,
+    pub node_count: i32, pub contact_count: i32, pub move_count: i32, pub joint_count: i32,
 }
 #[repr(C)]
 pub struct b2gpu_snapshot {
@@ -76,6 +90,7 @@ pub struct b2gpu_snapshot {
     pub bodies: *mut b2gpu_body_rec, pub fixtures: *mut b2gpu_fixture_rec, pub shapes: *mut b2gpu_shape_rec,
     pub proxies: *mut b2gpu_proxy_rec, pub nodes: *mut b2gpu_tree_node_rec, pub contacts: *mut b2gpu_contact_rec,
     pub move_buffer: *mut i32,
+    pub joints: *mut b2gpu_joint_rec,
 }
 #[repr(C)] #[derive(Clone, Copy, Default)]
 pub struct b2gpu_step_stats {
@@ -161,6 +176,17 @@ extern "C" {
     pub fn b2gpu_body_apply_linear_impulse_to_center(w: *mut b2gpu_world, body: c_int, ix: c_float, iy: c_float, wake: c_int) -> c_int;
     pub fn b2gpu_body_apply_angular_impulse(w: *mut b2gpu_world, body: c_int, impulse: c_float, wake: c_int) -> c_int;
     pub fn b2gpu_body_set_awake(w: *mut b2gpu_world, body: c_int, flag: c_int) -> c_int;
+    pub fn b2gpu_revolute_joint_def(w: *mut b2gpu_world, def: *mut b2gpu_joint_def, body_a: c_int, body_b: c_int, anchor_x: c_float, anchor_y: c_float) -> c_int;
+    pub fn b2gpu_distance_joint_def(w: *mut b2gpu_world, def: *mut b2gpu_joint_def, body_a: c_int, body_b: c_int, a1x: c_float, a1y: c_float, a2x: c_float, a2y: c_float) -> c_int;
+    pub fn b2gpu_linear_stiffness(w: *mut b2gpu_world, frequency_hertz: c_float, damping_ratio: c_float, body_a: c_int, body_b: c_int, stiffness: *mut c_float, damping: *mut c_float) -> c_int;
+    pub fn b2gpu_world_create_joint(w: *mut b2gpu_world, def: *const b2gpu_joint_def) -> c_int;
+    pub fn b2gpu_world_get_joint_count(w: *mut b2gpu_world) -> c_int;
+    pub fn b2gpu_world_get_joint(w: *mut b2gpu_world, joint: c_int, out: *mut b2gpu_joint_rec) -> c_int;
+    pub fn b2gpu_joint_set_motor_speed(w: *mut b2gpu_world, joint: c_int, speed: c_float) -> c_int;
+    pub fn b2gpu_joint_set_max_motor_torque(w: *mut b2gpu_world, joint: c_int, torque: c_float) -> c_int;
+    pub fn b2gpu_joint_enable_motor(w: *mut b2gpu_world, joint: c_int, flag: c_int) -> c_int;
+    pub fn b2gpu_joint_enable_limit(w: *mut b2gpu_world, joint: c_int, flag: c_int) -> c_int;
+    pub fn b2gpu_joint_set_limits(w: *mut b2gpu_world, joint: c_int, lower: c_float, upper: c_float) -> c_int;
     pub fn b2gpu_world_set_allow_sleeping(w: *mut b2gpu_world, flag: c_int) -> c_int;
     pub fn b2gpu_world_set_warm_starting(w: *mut b2gpu_world, flag: c_int) -> c_int;
     pub fn b2gpu_world_set_continuous_physics(w: *mut b2gpu_world, flag: c_int) -> c_int;

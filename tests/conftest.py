@@ -39,3 +39,10 @@ SCENES = {
     "sensors": (lambda s, w: s.sensors(w), (0.0, -10.0), 300),
     "terrain": (lambda s, w: s.terrain(w), (0.0, -10.0), 260),
 }
+
+# scenes with joints (revolute / distance): the exact mode and batches; the large-world modes reject joints
+JOINT_SCENES = {
+    "bridge": (lambda s, w: s.bridge(w), (0.0, -10.0), 240),
+    "tumbler": (lambda s, w: s.tumbler(w, n=120), (0.0, -10.0), 240),
+    "joints_mix": (lambda s, w: s.joints_mix(w), (0.0, -10.0), 400),
+}

@@ -44,7 +44,7 @@ def compare_snapshots(ref, got, rtol=0.0, atol=0.0, what="", check_tree=True, bo
             bad.append("%s%s: %d float mismatches, first at %s: ref %r got %r" %
                        (what, name, int((~ok).sum()), idx, float(a[i0]), float(b[i0])))
 
-    for f in ("body_count", "fixture_count", "shape_count", "proxy_count", "node_count", "contact_count", "move_count"):
+    for f in ("body_count", "fixture_count", "shape_count", "proxy_count", "node_count", "contact_count", "move_count", "joint_count"):
         if getattr(ref.n, f) != getattr(got.n, f):
             bad.append("%ssizes.%s: %d vs %d" % (what, f, getattr(ref.n, f), getattr(got.n, f)))
     if bad:
@@ -71,6 +71,10 @@ def compare_snapshots(ref, got, rtol=0.0, atol=0.0, what="", check_tree=True, bo
             chk_int("nodes." + f, ref.nodes[f][live], got.nodes[f][live])
         chk_f("nodes.aabb", ref.nodes["aabb"][live], got.nodes["aabb"][live])
     chk_int("move_buffer", ref.move_buffer, got.move_buffer)
+    for f in ("type", "body_a", "body_b", "flags"):
+        chk_int("joints." + f, ref.joints[f], got.joints[f])
+    for f in ("local_anchor_a", "local_anchor_b", "param", "impulse"):
+        chk_f("joints." + f, ref.joints[f], got.joints[f])
     for f in ("fixture_a", "fixture_b", "index_a", "index_b", "flags"):
         chk_int("contacts." + f, ref.contacts[f], got.contacts[f])
     for f in ("friction", "restitution", "restitution_threshold", "tangent_speed"):

@@ -16,6 +16,10 @@ def _declared_symbols():
     return sorted(set(re.findall(r"\b(b2gpu_[a-z0-9_]+)\s*\(", text)))
 
 
+def abi_version_of_header():
+    return int(re.search(r"#define B2GPU_ABI_VERSION (\d+)", open(os.path.join(ROOT, "include", "b2gpu.h")).read()).group(1))
+
+
 def test_library_exports_every_declared_symbol(built):
     from box2d_rs_b200 import lib
     L = C.CDLL(lib.DEFAULT_SO)
@@ -26,7 +30,7 @@ def test_library_exports_every_declared_symbol(built):
     bound = lib.load()
     assert bound._b2gpu_missing == []
     assert sorted(set(names) - set(bound._b2gpu_declared)) == [], "lib.py does not bind every header symbol"
-    assert bound.b2gpu_abi_version() == 1
+    assert bound.b2gpu_abi_version() == abi_version_of_header() == 2
 
 
 def test_record_sizes_match_header(built):
@@ -37,7 +41,8 @@ def test_record_sizes_match_header(built):
     src = r'''
 #include <stdio.h>
 #include "b2gpu.h"
-int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(b2gpu_body_rec), sizeof(b2gpu_fixture_rec),
+int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n", sizeof(b2gpu_joint_rec), sizeof(b2gpu_joint_def),
+  sizeof(b2gpu_snapshot), sizeof(b2gpu_body_rec), sizeof(b2gpu_fixture_rec),
   sizeof(b2gpu_shape_rec), sizeof(b2gpu_proxy_rec), sizeof(b2gpu_tree_node_rec), sizeof(b2gpu_manifold), sizeof(b2gpu_contact_rec),
   sizeof(b2gpu_step_stats), sizeof(b2gpu_world_rec), sizeof(b2gpu_snapshot_sizes), sizeof(b2gpu_body_def), sizeof(b2gpu_fixture_def),
   sizeof(b2gpu_shape_def)); return 0; }
@@ -46,7 +51,7 @@ int main(void) { printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\n",
         open(os.path.join(d, "t.c"), "w").write(src)
         subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), "-o", os.path.join(d, "t"), os.path.join(d, "t.c")])
         sizes = [int(v) for v in subprocess.check_output([os.path.join(d, "t")]).split()]
-    mirror = [abi.BODY_DTYPE.itemsize, abi.FIXTURE_DTYPE.itemsize, abi.SHAPE_DTYPE.itemsize, abi.PROXY_DTYPE.itemsize,
+    mirror = [abi.JOINT_DTYPE.itemsize, C.sizeof(abi.JointDef), C.sizeof(abi.SnapshotC), abi.BODY_DTYPE.itemsize, abi.FIXTURE_DTYPE.itemsize, abi.SHAPE_DTYPE.itemsize, abi.PROXY_DTYPE.itemsize,
               abi.NODE_DTYPE.itemsize, abi.MANIFOLD_DTYPE.itemsize, abi.CONTACT_DTYPE.itemsize, abi.STATS_DTYPE.itemsize,
               C.sizeof(abi.WorldRec), C.sizeof(abi.SnapshotSizes), C.sizeof(abi.BodyDef), C.sizeof(abi.FixtureDef),
               C.sizeof(abi.ShapeDef)]

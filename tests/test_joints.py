@@ -1,0 +1,318 @@
+"""Joints inside the island solve: revolute and distance joints.
+
+The reference has NO joint test (tests/ only covers a falling box, begin_contact, polygon mass and sweeps), so the
+oracle's joint code is pinned by analytic known answers here and is otherwise a literal restatement of
+src/private/dynamics/joints/b2_{revolute,distance}_joint.rs ("parity unpinned" applies to it as to the rest).  The
+device stages (host simulator here, CUDA in the tests marked gpu) must equal the oracle bit for bit."""
+import math
+
+import numpy as np
+import pytest
+
+import parity
+from conftest import HOSTSIM_SO, JOINT_SCENES
+
+
+@pytest.fixture(scope="module")
+def hctx(built):
+    from box2d_rs_b200 import batch
+    c = batch.Context(0, lib_path=HOSTSIM_SO)
+    yield c
+    c.close()
+
+
+@pytest.fixture(scope="module")
+def gctx(built):
+    from box2d_rs_b200 import batch
+    c = batch.Context(0)
+    yield c
+    c.close()
+
+
+def _pair(name, ctx):
+    from box2d_rs_b200 import scenes, world
+    from oracle import b2o
+    recipe, gravity, steps = JOINT_SCENES[name]
+    wo = b2o.B2world(gravity)
+    ro = recipe(scenes, wo)
+    wg = world.B2world(gravity, ctx=ctx)
+    rg = recipe(scenes, wg)
+    return wo, wg, steps, ro, rg
+
+
+# ---------------------------------------------------------------------------------------------- oracle known answers
+def test_oracle_distance_joint_keeps_its_length(built):
+    from box2d_rs_b200 import abi, scenes
+    from box2d_rs_b200.abi import BodyDef
+    from oracle import b2o
+    w = b2o.B2world((0.0, -10.0))
+    ground = w.create_body(BodyDef())
+    bob = w.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(3.0, 5.0)))
+    bob.create_fixture_by_shape(w.shapes.circle(0.5), 1.0)
+    w.create_joint(w.distance_joint_def(ground, bob, (0.0, 5.0), (3.0, 5.0)))
+    lowest = 5.0
+    for _ in range(240):
+        w.step(scenes.DT, 8, 3)
+        c = w.snapshot().bodies[1]["c"]
+        assert abs(math.hypot(c[0], c[1] - 5.0) - 3.0) < 0.005  # within the linear slop
+        lowest = min(lowest, float(c[1]))
+    assert lowest < 2.2  # it really swung through the bottom (y = 2)
+
+
+def test_oracle_revolute_joint_pins_the_anchor_and_respects_limits(built):
+    from box2d_rs_b200 import abi, scenes
+    from box2d_rs_b200.abi import BodyDef
+    from oracle import b2o
+    w = b2o.B2world((0.0, -10.0))
+    ground = w.create_body(BodyDef())
+    arm = w.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(1.0, 4.0)))
+    arm.create_fixture_by_shape(w.shapes.polygon_box(1.0, 0.1), 1.0)
+    jd = w.revolute_joint_def(ground, arm, (0.0, 4.0))
+    jd.enable_limit, jd.lower_angle, jd.upper_angle = 1, -0.5, 0.25
+    w.create_joint(jd)
+    for _ in range(180):
+        w.step(scenes.DT, 8, 3)
+        b = w.snapshot().bodies[1]
+        # anchor of the arm (local (-1, 0)) stays on the ground anchor (0, 4)
+        ax = b["xf"][0] + b["xf"][3] * -1.0
+        ay = b["xf"][1] + b["xf"][2] * -1.0
+        assert math.hypot(ax, ay - 4.0) < 0.01
+        assert -0.5 - 0.05 <= b["a"] <= 0.25 + 0.05
+    assert abs(w.snapshot().bodies[1]["a"] + 0.5) < 0.04  # resting on the lower limit
+
+
+def test_oracle_revolute_motor_reaches_its_speed(built):
+    from box2d_rs_b200 import abi, scenes
+    from box2d_rs_b200.abi import BodyDef
+    from oracle import b2o
+    w = b2o.B2world((0.0, 0.0))
+    ground = w.create_body(BodyDef())
+    wheel = w.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(0.0, 0.0)))
+    wheel.create_fixture_by_shape(w.shapes.circle(1.0), 1.0)
+    jd = w.revolute_joint_def(ground, wheel, (0.0, 0.0))
+    jd.enable_motor, jd.motor_speed, jd.max_motor_torque = 1, 2.0, 1000.0
+    j = w.create_joint(jd)
+    for _ in range(30):
+        w.step(scenes.DT, 8, 3)
+    assert abs(w.snapshot().bodies[1]["w"] - 2.0) < 1e-4
+    j.set_motor_speed(-1.0)
+    for _ in range(30):
+        w.step(scenes.DT, 8, 3)
+    assert abs(w.snapshot().bodies[1]["w"] + 1.0) < 1e-4
+
+
+def test_oracle_joint_prevents_collision_unless_collide_connected(built):
+    from box2d_rs_b200 import abi, scenes
+    from box2d_rs_b200.abi import BodyDef
+    from oracle import b2o
+    counts = []
+    for collide in (0, 1):
+        w = b2o.B2world((0.0, 0.0))
+        a = w.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(0.0, 0.0)))
+        a.create_fixture_by_shape(w.shapes.polygon_box(1.0, 1.0), 1.0)
+        b = w.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(1.5, 0.0)))
+        b.create_fixture_by_shape(w.shapes.polygon_box(1.0, 1.0), 1.0)
+        jd = w.revolute_joint_def(a, b, (0.75, 0.0))
+        jd.collide_connected = collide
+        w.create_joint(jd)
+        w.step(scenes.DT, 8, 3)
+        counts.append(w.get_contact_count())
+    assert counts == [0, 1]
+
+
+# ---------------------------------------------------------------------------------------------- device stages vs oracle
+def _free_running(name, ctx, every):
+    from box2d_rs_b200 import scenes
+    wo, wg, steps, ro, rg = _pair(name, ctx)
+    assert parity.compare_snapshots(wo.snapshot(), wg.snapshot()) == []
+    assert wo.get_joint_count() == wg.get_joint_count() > 0
+    for i in range(steps):
+        if name == "joints_mix":  # user edits of the motorised arm mid-run (B2revoluteJoint setters)
+            if i == 150:
+                for m in (ro, rg):
+                    m.set_motor_speed(-2.0)
+            if i == 220:
+                for m in (ro, rg):
+                    m.enable_limit(False)
+                    m.set_max_motor_torque(15.0)
+            if i == 260:
+                for m in (ro, rg):
+                    m.enable_motor(False)
+                    m.enable_limit(True)
+                    m.set_limits(-0.5, 0.5)
+        wo.step(scenes.DT, 8, 3)
+        wg.step(scenes.DT, 8, 3)
+        if i < 3 or i % every == every - 1 or i == steps - 1:
+            bad = parity.compare_snapshots(wo.snapshot(), wg.snapshot()) + parity.compare_stats(wo.get_stats(), wg.get_stats())
+            assert bad == [], "%s step %d: %s" % (name, i, bad[:6])
+    assert np.abs(wo.snapshot().joints["impulse"]).max() > 0.0
+    wg.close()
+
+
+def _batched(name, ctx, n, lane_block):
+    """Replicas of a joint scene in one batch, some perturbed: every memory-block size gives the oracle's worlds; flags
+    (warm starting off, block solver off) and a sleeping world included."""
+    from box2d_rs_b200 import scenes
+    wo, wg, steps, _, _ = _pair(name, ctx)
+    bt = wg.batch(n, lane_block=lane_block)
+    picks = {0: wo.clone(), n - 1: wo.clone()}
+    picks[n - 1].body(wo.get_body_count() - 1).set_linear_velocity((0.7, -0.3))
+    picks[n - 1].set_warm_starting(False)
+    for w, o in picks.items():
+        bt.upload_world(w, o.snapshot())
+    for i in range(min(steps, 160)):
+        bt.step(scenes.DT, 8, 3)
+        for o in picks.values():
+            o.step(scenes.DT, 8, 3)
+        if i % 40 == 39:
+            for w, o in picks.items():
+                bad = parity.compare_snapshots(o.snapshot(), bt.download_world(w)) + parity.compare_stats(o.get_stats(), bt.stats()[w])
+                assert bad == [], "%s world %d step %d: %s" % (name, w, i, bad[:6])
+    bt.close()
+    wg.close()
+
+
+def _teacher_forced(name, ctx):
+    from box2d_rs_b200 import scenes
+    wo, wg, steps, _, _ = _pair(name, ctx)
+    bt = wg.batch(2, lane_block=1)
+    for i in range(min(steps, 150)):
+        if i % 5 == 0:
+            bt.upload_world(1, wo.snapshot())
+            wo.step(scenes.DT, 8, 3)
+            bt.step(scenes.DT, 8, 3)
+            bad = parity.compare_snapshots(wo.snapshot(), bt.download_world(1)) + parity.compare_stats(wo.get_stats(), bt.stats()[1])
+            assert bad == [], "%s step %d: %s" % (name, i, bad[:6])
+        else:
+            wo.step(scenes.DT, 8, 3)
+    bt.close()
+    wg.close()
+
+
+@pytest.mark.parametrize("name", list(JOINT_SCENES))
+def test_hostsim_free_running(name, hctx):
+    _free_running(name, hctx, 20)
+
+
+@pytest.mark.parametrize("name,lane_block", [("bridge", 1), ("tumbler", 4), ("joints_mix", 32)])
+def test_hostsim_batched(name, lane_block, hctx):
+    _batched(name, hctx, 5 if lane_block < 32 else 34, lane_block)
+
+
+@pytest.mark.parametrize("name", list(JOINT_SCENES))
+def test_hostsim_teacher_forced(name, hctx):
+    _teacher_forced(name, hctx)
+
+
+def test_sleeping_island_with_joints(hctx):
+    """Two boxes resting apart on the ground, tied by a distance joint, fall asleep as ONE island (the joint propagates
+    the island DFS); an impulse on one wakes both in the same step."""
+    from box2d_rs_b200 import abi, scenes, world
+    from box2d_rs_b200.abi import BodyDef, FixtureDef
+    from oracle import b2o
+
+    def build(w):
+        ground = w.create_body(BodyDef())
+        ground.create_fixture_by_shape(w.shapes.edge_two_sided((-20.0, 0.0), (20.0, 0.0)), 0.0)
+        boxes = []
+        for px in (-3.0, 3.0):
+            b = w.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(px, 0.51)))
+            b.create_fixture(FixtureDef(density=1.0, friction=0.5), w.shapes.polygon_box(0.5, 0.5))
+            boxes.append(b)
+        w.create_joint(w.distance_joint_def(boxes[0], boxes[1], (-3.0, 0.51), (3.0, 0.51)))
+    wo = b2o.B2world((0.0, -10.0))
+    build(wo)
+    wg = world.B2world((0.0, -10.0), ctx=hctx)
+    build(wg)
+    slept_at = None
+    for i in range(200):
+        wo.step(scenes.DT, 8, 3)
+        wg.step(scenes.DT, 8, 3)
+        bad = parity.compare_snapshots(wo.snapshot(), wg.snapshot()) + parity.compare_stats(wo.get_stats(), wg.get_stats())
+        assert bad == [], "step %d: %s" % (i, bad[:6])
+        if slept_at is None and int(wo.get_stats()["awake_bodies"]) == 0:
+            slept_at = i
+            assert int(wo.get_stats()["islands"]) == 1  # one island although the boxes do not touch
+            for w in (wo, wg):
+                w.body(1).apply_linear_impulse_to_center((0.0, 3.0), True)
+        elif slept_at is not None and i == slept_at + 1:
+            assert int(wo.get_stats()["awake_bodies"]) == 2  # the island DFS through the joint woke the other box
+    assert slept_at is not None
+    wg.close()
+
+
+def test_checkpoint_round_trip_with_joints(hctx, tmp_path):
+    from box2d_rs_b200 import checkpoint, scenes, world
+    wo, wg, _, _, _ = _pair("joints_mix", hctx)
+    for _ in range(60):
+        wo.step(scenes.DT, 8, 3)
+    snap = wo.snapshot()
+    path = str(tmp_path / "joints.b2snap")
+    checkpoint.save(snap, path, hctx.L)
+    back = checkpoint.load(path, hctx.L)
+    assert parity.compare_snapshots(snap, back) == []
+    w2 = world.B2world((0.0, -10.0), ctx=hctx)
+    w2.upload(back)
+    for _ in range(40):
+        wo.step(scenes.DT, 8, 3)
+        w2.step(scenes.DT, 8, 3)
+    assert parity.compare_snapshots(wo.snapshot(), w2.snapshot()) == []
+    w2.close()
+    wg.close()
+
+
+def test_validate_rejects_bad_joint_records(built):
+    from box2d_rs_b200 import abi, checkpoint, lib, scenes
+    from oracle import b2o
+
+    def broken(mutate):
+        w = b2o.B2world((0.0, -10.0))
+        scenes.bridge(w)
+        s = w.snapshot()
+        mutate(s)
+        with pytest.raises(lib.B2gpuError) as e:
+            checkpoint.validate(s)
+        assert e.value.code == abi.E_INVALID
+
+    def body_out_of_range(s):
+        s.joints[3]["body_b"] = len(s.bodies)
+
+    def same_body(s):
+        s.joints[3]["body_b"] = s.joints[3]["body_a"]
+
+    def unknown_type(s):
+        s.joints[0]["type"] = 5
+    broken(body_out_of_range)
+    broken(same_body)
+    broken(unknown_type)
+
+
+def test_large_modes_reject_joints(hctx):
+    from box2d_rs_b200 import abi, scenes, world
+    from box2d_rs_b200.lib import B2gpuError
+    wg = world.B2world((0.0, -10.0), ctx=hctx)
+    scenes.bridge(wg)
+    wg.set_large_mode(1)
+    with pytest.raises(B2gpuError) as e:
+        wg.step(scenes.DT, 8, 3)
+    assert e.value.code == abi.E_UNSUPPORTED
+    wg.close()
+
+
+# ---------------------------------------------------------------------------------------------- CUDA path
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(JOINT_SCENES))
+def test_gpu_free_running(name, gctx):
+    _free_running(name, gctx, 20)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,lane_block", [("bridge", 1), ("tumbler", 32), ("joints_mix", 32)])
+def test_gpu_batched(name, lane_block, gctx):
+    _batched(name, gctx, 5 if lane_block < 32 else 70, lane_block)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(JOINT_SCENES))
+def test_gpu_teacher_forced(name, gctx):
+    _teacher_forced(name, gctx)
