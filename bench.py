@@ -12,7 +12,7 @@ does the same work, and the timed steps follow an untimed 400-step pre-roll (set
 body-steps = 210 dynamic bodies x worlds x steps.
 
 ours:       value        = device-resident throughput (CUDA events on the launching stream, max over ranks)
-            e2e          = the same steps through b2gpu_batch_step_host with pinned HOST buffers: per step the
+            e2e          = the same steps through b2gpu_batch_step_host_dynamic with pinned HOST buffers: per step the
                            H2D of per-body forces and the D2H of the body state are inside the timed region
             run_from_t0  = the reference's own case (configs[0]: 1000 steps from t = 0: falling, settling,
                            settled) for the same 4096 worlds, device-resident, CPU arm beside it
@@ -285,17 +285,17 @@ class Arm:
     def e2e(self, steps, warmup):
         import torch
         s = self.scenes
-        nb = self.batch.body_count
-        forces = torch.zeros((self.n_worlds, nb, 3), dtype=torch.float32).pin_memory()
-        state = torch.zeros((self.n_worlds, nb, 8), dtype=torch.float32).pin_memory()
+        nd = len(self.batch.dynamic_bodies())  # compact I/O: the 210 dynamic boxes (5040 B of state per world)
+        forces = torch.zeros((self.n_worlds, nd, 3), dtype=torch.float32).pin_memory()
+        state = torch.zeros((self.n_worlds, nd, 6), dtype=torch.float32).pin_memory()
         f_np, s_np = forces.numpy(), state.numpy()
         for _ in range(max(warmup, 3)):
-            self.batch.step_host(f_np, s_np, s.DT, s.VEL_ITERS, s.POS_ITERS, 1)
+            self.batch.step_host_dynamic(f_np, s_np, s.DT, s.VEL_ITERS, s.POS_ITERS, 1)
             self.steps_done += 1
         self.barrier()
         t0 = time.perf_counter()
         for _ in range(steps):
-            self.batch.step_host(f_np, s_np, s.DT, s.VEL_ITERS, s.POS_ITERS, 1)
+            self.batch.step_host_dynamic(f_np, s_np, s.DT, s.VEL_ITERS, s.POS_ITERS, 1)
         self.barrier()
         sec = self.max_over_ranks(time.perf_counter() - t0)
         self.steps_done += steps
@@ -399,7 +399,8 @@ def run_ours(args, rank, world_size, local_rank):
     e2e_s, h2d, d2h = arm.e2e(args.steps, args.warmup)
     e2e = {"value": DYNAMIC_BODIES * total * args.steps / e2e_s, "unit": "body-steps/s",
            "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "ms_per_step": 1e3 * e2e_s / args.steps,
-           "bytes_are": "per rank (this rank's shard of %d worlds)" % arm.n_worlds}
+           "bytes_are": "per rank (this rank's shard of %d worlds)" % arm.n_worlds,
+           "layout": "b2gpu_batch_step_host_dynamic: per dynamic body 3 floats of force in, (c, a, v, w) = 6 floats out"}
 
     # ---- validation: sampled worlds against the oracle (every rank), digests of all worlds gathered over NCCL
     picks, ok = arm.validate()

@@ -48,16 +48,12 @@ class Batch:
         caps = abi.Caps()
         caps.max_contacts, caps.max_pairs = max_contacts, max_pairs
         caps.reserved[0] = lane_block
-        # solver (diagnostic switch, b2gpu_caps.reserved[1]): None = default kernels (straight-line velocity and
-        # position, 8 stream groups, CUDA graphs); 'generic' = global-memory stages; 'lane' = branchy pipelined
-        # one-lane position kernel; 'levels' = level-scheduled velocity + position; 'tma' = TMA-fed velocity ring;
-        # 'one_stream' = no stream groups; 'no_graph' = no CUDA graphs; 'pipelined' = branchy velocity kernel only;
-        # 'producer' = straight-line velocity kernel with a producer warp; 'ml_position' = level-scheduled position;
-        # 'levels2' = straight-line level-scheduled velocity kernel (two lanes per world);
-        # 'large' = large-world mode (exactly one world: data-parallel broadphase / islands, b2g_large.h);
-        # 'large_exact' = large-world mode that keeps the replica tree (reference contact order, bit-identical free-running)
-        codes = {None: 0, 'generic': 1, 'lane': 2, 'levels': 3, 'tma': 4, 'one_stream': 5, 'no_graph': 6, 'pipelined': 7,
-                 'producer': 8, 'ml_position': 9, 'levels2': 10, 'large': 11, 'large_exact': 12}
+        # solver (diagnostic switch, b2gpu_caps.reserved[1]): None = default kernels (straight-line velocity and position,
+        # 8 stream groups, CUDA graphs); 'generic' = global-memory stages; 'one_stream' = no stream groups; 'no_graph' = no
+        # CUDA graphs; 'large' = large-world mode (exactly one world: data-parallel broadphase / islands, b2g_large.h);
+        # 'large_exact' = large-world mode that keeps the replica tree (reference contact order, bit-identical free-running).
+        # (Round 1's rejected kernel variants — pipelined, TMA ring, producer warp, level-scheduled — were removed.)
+        codes = {None: 0, 'generic': 1, 'one_stream': 5, 'no_graph': 6, 'large': 11, 'large_exact': 12}
         caps.reserved[1] = 1 if generic_solver else codes[solver]
         self.h = C.c_void_p()
         c = proto.as_c()
@@ -131,6 +127,20 @@ class Batch:
         fp = forces.ctypes.data if forces is not None else None
         check(self.L, self.L.b2gpu_batch_step_host(self.h, fp, state_out.ctypes.data, dt, velocity_iterations,
                                                    position_iterations, steps))
+
+    def dynamic_bodies(self):
+        """Body indices of the prototype's dynamic bodies (the rows of the compact I/O arrays)."""
+        n = check(self.L, self.L.b2gpu_batch_dynamic_bodies(self.h, None, 0))
+        out = np.zeros(max(n, 1), np.int32)
+        check(self.L, self.L.b2gpu_batch_dynamic_bodies(self.h, out.ctypes.data, n))
+        return out[:n]
+
+    def step_host_dynamic(self, forces, state_out, dt, velocity_iterations, position_iterations, steps=1):
+        """step_host with compact I/O: forces [n_worlds][nd][3] (or None), state_out [n_worlds][nd][6] = c.x c.y a v.x v.y w
+        of the dynamic bodies only."""
+        fp = forces.ctypes.data if forces is not None else None
+        check(self.L, self.L.b2gpu_batch_step_host_dynamic(self.h, fp, state_out.ctypes.data, dt, velocity_iterations,
+                                                           position_iterations, steps))
 
     def ray_cast_closest(self, p1p2):
         """Closest-hit ray casts in every world: p1p2 [n_worlds][rays][4] -> abi.RAY_HIT_DTYPE [n_worlds][rays]."""

@@ -208,6 +208,18 @@ int b2gpu_batch_step_host(b2gpu_batch* b, const float* host_forces, float* host_
   return batch_step_host(b->h, host_forces, host_state_out, dt, vi, pi, steps);
   GUARD_END
 }
+int b2gpu_batch_step_host_dynamic(b2gpu_batch* b, const float* host_forces, float* host_state_out, float dt, int vi, int pi, int steps) {
+  GUARD_BEGIN
+  if (!b) { set_error("batch is NULL"); return B2GPU_E_INVALID; }
+  return batch_step_host_dynamic(b->h, host_forces, host_state_out, dt, vi, pi, steps);
+  GUARD_END
+}
+int b2gpu_batch_dynamic_bodies(b2gpu_batch* b, int32_t* out, int capacity) {
+  GUARD_BEGIN
+  if (!b) { set_error("batch is NULL"); return B2GPU_E_INVALID; }
+  return batch_dynamic_bodies(b->h, out, capacity);
+  GUARD_END
+}
 int64_t b2gpu_batch_algorithmic_bytes(b2gpu_batch* b) { return b ? batch_algorithmic_bytes(b->h) : -1; }
 static const char* k_stage_names[STAGE_COUNT] = {"pre_step_pairs", "collide", "island", "integrate", "solver_init", "velocity",
                                                   "post_velocity", "position", "finalize", "sleep", "sync_fixtures",

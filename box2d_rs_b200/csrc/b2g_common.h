@@ -50,8 +50,6 @@ enum {
 enum { VC_Q = 9, PC_Q = 6 };
 // per-step joint scratch: JT_Q float4 per joint (see b2g_joint.h)
 enum { JT_Q = 4 };
-// lanes that cooperate on one world in the level-scheduled Gauss-Seidel kernels
-enum { SCHED_G = 2, SCHED_MIN_ROUNDS = 6 };
 
 struct Batch {
   int n_worlds, LB, lb_shift, n_wblocks;
@@ -113,7 +111,6 @@ struct Batch {
   float4* j_tmp;             // [NJ * JT_Q] per-step joint solver data (b2g_joint.h)
   float4* vc;                // [NC * VC_Q] velocity constraint records
   float4* pc;                // [NC * PC_Q] position constraint records
-  int* sched;                // [NC * SCHED_G] level schedule: round r, slot g -> island contact k or -1
   unsigned long long* timeline;  // diagnostic (B2GPU_TIMELINE): [0] = entries used, [1] = capacity, then {kind<<32|cta, t0, t1} per CTA
 };
 

@@ -164,40 +164,8 @@ __global__ void __launch_bounds__(32) island_smem_kernel(const SerialAK K, const
       if (nf != f[j]) B.b_flags[x.at(NB, b0 + j)] = nf;
     }
   }
-  // ---- level schedule of the island contacts for the multi-lane Gauss-Seidel kernels.
-  // Two constraints that share no movable body commute exactly, so a sweep in list order equals a sweep
-  // in "rounds": constraint k goes to the first round after the rounds of the earlier constraints that
-  // touch one of its movable bodies, SCHED_G constraints per round at most (list scheduling).  Every
-  // body still sees its constraints in the reference's order.
-  {
-    // scratch reuses this lane's own columns of the DFS arrays (same element size: no lane ever touches
-    // another lane's bytes, whatever the divergence between worlds)
-    uint16_t* lastround = stack;                 // [NB][32] 1 + round of the last constraint on the body
-    uint32_t* fill = enext;                      // [ECAP][32] slots used per round (rounds <= constraints)
-    const int fill_rounds = ncon + SCHED_MIN_ROUNDS < L.ECAP ? ncon + SCHED_MIN_ROUNDS : L.ECAP;
-    for (int b = 0; b < NB; ++b) lastround[b * 32 + lane] = 0;
-    for (int r = 0; r < fill_rounds; ++r) fill[r * 32 + lane] = 0;
-    int rounds = 0;
-    for (int k = 0; k < ncon; ++k) {
-      const uint32_t bod = ebody[korder[k * 32 + lane] * 32 + lane];
-      const int ba = (int)(bod & 0xffffu), bb = (int)(bod >> 16);
-      const bool mva = (bflag[ba * 32 + lane] & 16) != 0, mvb = (bflag[bb * 32 + lane] & 16) != 0;
-      int r = 0;
-      if (mva) r = lastround[ba * 32 + lane];
-      if (mvb) { const int rb = lastround[bb * 32 + lane]; r = rb > r ? rb : r; }
-      while (fill[r * 32 + lane] >= (uint32_t)SCHED_G) ++r;  // r < ncon <= ECAP: at most one full round per earlier constraint
-      const int slot = (int)fill[r * 32 + lane]++;
-      B.sched[x.at(B.NC * SCHED_G, r * SCHED_G + slot)] = k;
-      if (mva) lastround[ba * 32 + lane] = (uint16_t)(r + 1);
-      if (mvb) lastround[bb * 32 + lane] = (uint16_t)(r + 1);
-      rounds = r + 1 > rounds ? r + 1 : rounds;
-    }
-    if (ncon > 0 && rounds < SCHED_MIN_ROUNDS) rounds = SCHED_MIN_ROUNDS;  // keeps a constraint's re-read behind its write
-    if (rounds > fill_rounds) rounds = fill_rounds;
-    for (int r = 0; r < rounds; ++r)
-      for (int slot = (int)fill[r * 32 + lane]; slot < SCHED_G; ++slot) B.sched[x.at(B.NC * SCHED_G, r * SCHED_G + slot)] = -1;
-    ws[WS_SCHED_ROUNDS] = rounds;
-  }
+  ws[WS_SCHED_ROUNDS] = -1;  // no level schedule: the Gauss-Seidel stages keep list order (round-1's level-scheduled
+                             // two-lane kernels measured slower and were removed, profiles/r01_ncu_summary.md)
   ws[WS_ISL_COUNT] = nisl;
   ws[WS_ISL_BODIES] = nbod;
   ws[WS_ISL_CONTACTS] = ncon;

@@ -897,73 +897,6 @@ B2G_HD LwVcRec lw_load_vc(const float4* vc, int k) {
   o.q0 = r[0]; o.q1 = r[1]; o.q2 = r[2]; o.q3 = r[3]; o.q4 = r[4]; o.q5 = r[5]; o.q6 = r[6]; o.q7 = r[7]; o.q8 = r[8];
   return o;
 }
-struct LwVelocityK {
-  Batch B;
-  StepParams sp;
-  int n_islands;
-  B2G_HD void operator()(int isl) const {
-    if (isl >= n_islands) return;
-    const int4 rg = B.isl_range[isl];
-    if (rg.z == rg.w) return;
-    const bool warm = (B.ws[WS_FLAGS] & B2GPU_WORLD_WARM_STARTING) != 0;
-    const bool block = (B.ws[WS_FLAGS] & B2GPU_WORLD_BLOCK_SOLVE) != 0;
-    const int first = rg.z, n = rg.w - rg.z;
-    const int sweeps = sp.velocity_iterations + (warm ? 1 : 0);
-    if (sweeps == 0) return;
-    const long long total = (long long)n * sweeps;
-    // visit v -> constraint first + v % n of sweep v / n (sweep 0 is the warm start when enabled)
-    LwVcRec cur = lw_load_vc(B.vc, first);
-    LwVcRec nxt = lw_load_vc(B.vc, first + (1 % n));
-    int ba = f2i(cur.q8.x), bb = f2i(cur.q8.y);
-    float4 va = B.b_vel[ba], vb = B.b_vel[bb];
-    int k = 0, it = warm ? -1 : 0;
-    for (long long v = 0; v < total; ++v) {
-      // requests for the next two visits
-      int k2 = k + 2;
-      if (k2 >= n) k2 -= n;
-      if (k2 >= n) k2 -= n;
-      const LwVcRec nn = lw_load_vc(B.vc, first + k2);
-      const int nba = f2i(nxt.q8.x), nbb = f2i(nxt.q8.y);
-      float4 nva = B.b_vel[nba], nvb = B.b_vel[nbb];
-      // visit (it, k)
-      const int vc_points = f2i(cur.q8.z) & 0xff;
-      if (vc_points != 0) {
-        VelState s;
-        s.v_a = v2(va.x, va.y); s.w_a = va.z;
-        s.v_b = v2(vb.x, vb.y); s.w_b = vb.z;
-        if (it < 0) {
-          warm_start_one(s, cur.q0, cur.q1, cur.q2, cur.q6, cur.q7, vc_points);
-        } else {
-          solve_velocity_one(s, cur.q0, cur.q1, cur.q2, cur.q3, cur.q4, cur.q5, cur.q6, cur.q7, vc_points, block);
-          B.vc[(size_t)(first + k) * VC_Q + 6] = cur.q6;
-        }
-        // a static / kinematic body may sit in several islands: its velocity never changes, leave it alone
-        if (cur.q7.x != 0.0f || cur.q7.y != 0.0f) { va = make_float4(s.v_a.x, s.v_a.y, s.w_a, 0.0f); B.b_vel[ba] = va; }
-        if (cur.q7.z != 0.0f || cur.q7.w != 0.0f) { vb = make_float4(s.v_b.x, s.v_b.y, s.w_b, 0.0f); B.b_vel[bb] = vb; }
-      }
-      // forward what this visit wrote
-      if (nba == ba) nva = va; else if (nba == bb) nva = vb;
-      if (nbb == ba) nvb = va; else if (nbb == bb) nvb = vb;
-      // the record two visits ahead may be this very constraint (islands of one or two constraints): its
-      // accumulated impulses were just rewritten
-      LwVcRec n2 = nn;
-      if (k2 == k) n2.q6 = cur.q6;
-      if (n == 1) nxt.q6 = cur.q6;
-      cur = nxt;
-      nxt = n2;
-      ba = nba; bb = nbb; va = nva; vb = nvb;
-      if (++k == n) { k = 0; ++it; }
-    }
-  }
-};
-
-// Deeper pipeline for the velocity sweeps (the longest chain of a large world).  In LwVelocityK the prefetched
-// record and bodies are handed from "next" to "current" by register moves, and a move of a register whose load
-// is still in flight stalls — so the effective prefetch distance is one visit of arithmetic (~300 cycles), less
-// than an L2 round trip.  Here four register sets rotate through an unrolled loop (no moves): at visit v the
-// body indices of visit v+3 are requested (from a compact index array, 16 B per constraint), the record and
-// the two bodies of visit v+2 are requested, visit v is solved, and its results are forwarded into the two
-// body sets already in flight.  Same functions, same order, same bits.
 struct LwVcIdxK {  // flat over island contacts: (body A, body B, velocity points, position points | type << 8)
   Batch B;
   Large L;
@@ -974,109 +907,6 @@ struct LwVcIdxK {  // flat over island contacts: (body A, body B, velocity point
     L.vc_idx[k] = make_int4(f2i(q8.x), f2i(q8.y), f2i(q8.z) & 0xff, f2i(B.pc[(size_t)k * PC_Q + 5].x));
   }
 };
-struct LwVelocity4K {
-  Batch B;
-  Large L;
-  StepParams sp;
-  int n_islands;
-  B2G_HD void operator()(int isl) const {
-    if (isl >= n_islands) return;
-    const int4 rg = B.isl_range[isl];
-    if (rg.z == rg.w) return;
-    const bool warm = (B.ws[WS_FLAGS] & B2GPU_WORLD_WARM_STARTING) != 0;
-    const bool block = (B.ws[WS_FLAGS] & B2GPU_WORLD_BLOCK_SOLVE) != 0;
-    const int first = rg.z, n = rg.w - rg.z;
-    const int sweeps = sp.velocity_iterations + (warm ? 1 : 0);
-    if (sweeps == 0) return;
-    if (n < 4) {  // the rotation assumes a constraint is not in flight twice: tiny islands take the plain loop
-      for (int it = warm ? -1 : 0; it < sp.velocity_iterations; ++it) {
-        for (int k = rg.z; k < rg.w; ++k) {
-          const int4 ix = L.vc_idx[k];
-          if (ix.z == 0) continue;
-          const float4 va = B.b_vel[ix.x], vb = B.b_vel[ix.y];
-          VelState s;
-          s.v_a = v2(va.x, va.y); s.w_a = va.z;
-          s.v_b = v2(vb.x, vb.y); s.w_b = vb.z;
-          LwVcRec r = lw_load_vc(B.vc, k);
-          if (it < 0) {
-            warm_start_one(s, r.q0, r.q1, r.q2, r.q6, r.q7, ix.z);
-          } else {
-            solve_velocity_one(s, r.q0, r.q1, r.q2, r.q3, r.q4, r.q5, r.q6, r.q7, ix.z, block);
-            B.vc[(size_t)k * VC_Q + 6] = r.q6;
-          }
-          if (r.q7.x != 0.0f || r.q7.y != 0.0f) B.b_vel[ix.x] = make_float4(s.v_a.x, s.v_a.y, s.w_a, 0.0f);
-          if (r.q7.z != 0.0f || r.q7.w != 0.0f) B.b_vel[ix.y] = make_float4(s.v_b.x, s.v_b.y, s.w_b, 0.0f);
-        }
-      }
-      return;
-    }
-    const long long total = (long long)n * sweeps;
-    int4 ix[4];
-    float4 q0[4], q1[4], q2[4], q3[4], q4[4], q5[4], q6[4], q7[4], va[4], vb[4];
-    // prologue: indices of visits 0..2, records and bodies of visits 0..1
-    ix[0] = L.vc_idx[first];
-    ix[1] = L.vc_idx[first + 1];
-    ix[2] = L.vc_idx[first + 2];
-    ix[3] = make_int4(0, 0, 0, 0);
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int j = 0; j < 2; ++j) {
-      const float4* r = B.vc + (size_t)(first + j) * VC_Q;
-      q0[j] = r[0]; q1[j] = r[1]; q2[j] = r[2]; q3[j] = r[3]; q4[j] = r[4]; q5[j] = r[5]; q6[j] = r[6]; q7[j] = r[7];
-      va[j] = B.b_vel[ix[j].x];
-      vb[j] = B.b_vel[ix[j].y];
-    }
-    int k = 0, k2 = 2, k3 = 3 % n, it = warm ? -1 : 0;
-    for (long long v = 0; v < total; v += 4) {
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-      for (int j = 0; j < 4; ++j) {
-        if (v + j < total) {
-          const int j2 = (j + 2) & 3, j3 = (j + 3) & 3, j1 = (j + 1) & 3;
-          // requests: indices of visit v+3, record and bodies of visit v+2
-          ix[j3] = L.vc_idx[first + k3];
-          {
-            const float4* r = B.vc + (size_t)(first + k2) * VC_Q;
-            q0[j2] = r[0]; q1[j2] = r[1]; q2[j2] = r[2]; q3[j2] = r[3]; q4[j2] = r[4]; q5[j2] = r[5]; q6[j2] = r[6]; q7[j2] = r[7];
-            va[j2] = B.b_vel[ix[j2].x];
-            vb[j2] = B.b_vel[ix[j2].y];
-          }
-          // visit (it, k) on set j
-          const int ba = ix[j].x, bb = ix[j].y, vc_points = ix[j].z;
-          if (vc_points != 0) {
-            VelState s;
-            s.v_a = v2(va[j].x, va[j].y); s.w_a = va[j].z;
-            s.v_b = v2(vb[j].x, vb[j].y); s.w_b = vb[j].z;
-            if (it < 0) {
-              warm_start_one(s, q0[j], q1[j], q2[j], q6[j], q7[j], vc_points);
-            } else {
-              solve_velocity_one(s, q0[j], q1[j], q2[j], q3[j], q4[j], q5[j], q6[j], q7[j], vc_points, block);
-              B.vc[(size_t)(first + k) * VC_Q + 6] = q6[j];
-            }
-            // a static / kinematic body may sit in several islands: its velocity never changes, leave it alone
-            if (q7[j].x != 0.0f || q7[j].y != 0.0f) { va[j] = make_float4(s.v_a.x, s.v_a.y, s.w_a, 0.0f); B.b_vel[ba] = va[j]; }
-            if (q7[j].z != 0.0f || q7[j].w != 0.0f) { vb[j] = make_float4(s.v_b.x, s.v_b.y, s.w_b, 0.0f); B.b_vel[bb] = vb[j]; }
-          }
-          // forward into the two body sets in flight (requested before this visit's stores)
-          if (ix[j1].x == ba) va[j1] = va[j]; else if (ix[j1].x == bb) va[j1] = vb[j];
-          if (ix[j1].y == ba) vb[j1] = va[j]; else if (ix[j1].y == bb) vb[j1] = vb[j];
-          if (ix[j2].x == ba) va[j2] = va[j]; else if (ix[j2].x == bb) va[j2] = vb[j];
-          if (ix[j2].y == ba) vb[j2] = va[j]; else if (ix[j2].y == bb) vb[j2] = vb[j];
-          if (++k == n) { k = 0; ++it; }
-          if (++k2 == n) k2 = 0;
-          if (++k3 == n) k3 = 0;
-        }
-      }
-    }
-  }
-};
-
-// Straighter form of LwVelocity4K (diagnostic switch B2GPU_LW_VELOCITY=3): the warm-start sweep is its own
-// pipelined loop, the main loop runs whole groups of four visits without a bounds test, immovable bodies are
-// "written" to a scratch slot instead of being skipped, and island contacts are assumed to carry at least one
-// point (touching contacts always do).
 template <bool WARM>
 B2G_HD void lw_velocity_run(const Batch& B, const Large& L, int first, int n, int sweeps, bool block) {
   const long long total = (long long)n * sweeps;
@@ -1181,9 +1011,26 @@ struct LwVelocity5K {
     const bool warm = (B.ws[WS_FLAGS] & B2GPU_WORLD_WARM_STARTING) != 0;
     const bool block = (B.ws[WS_FLAGS] & B2GPU_WORLD_BLOCK_SOLVE) != 0;
     const int first = rg.z, n = rg.w - rg.z;
-    if (n < 4) {
-      LwVelocity4K small = {B, L, sp, n_islands};
-      small(isl);
+    if (n < 4) {  // the pipeline assumes a constraint is not in flight twice: tiny islands take the plain loop
+      for (int it = warm ? -1 : 0; it < sp.velocity_iterations; ++it) {
+        for (int k = rg.z; k < rg.w; ++k) {
+          const int4 ix = L.vc_idx[k];
+          if (ix.z == 0) continue;
+          const float4 va = B.b_vel[ix.x], vb = B.b_vel[ix.y];
+          VelState s;
+          s.v_a = v2(va.x, va.y); s.w_a = va.z;
+          s.v_b = v2(vb.x, vb.y); s.w_b = vb.z;
+          LwVcRec r = lw_load_vc(B.vc, k);
+          if (it < 0) {
+            warm_start_one(s, r.q0, r.q1, r.q2, r.q6, r.q7, ix.z);
+          } else {
+            solve_velocity_one(s, r.q0, r.q1, r.q2, r.q3, r.q4, r.q5, r.q6, r.q7, ix.z, block);
+            B.vc[(size_t)k * VC_Q + 6] = r.q6;
+          }
+          if (r.q7.x != 0.0f || r.q7.y != 0.0f) B.b_vel[ix.x] = make_float4(s.v_a.x, s.v_a.y, s.w_a, 0.0f);
+          if (r.q7.z != 0.0f || r.q7.w != 0.0f) B.b_vel[ix.y] = make_float4(s.v_b.x, s.v_b.y, s.w_b, 0.0f);
+        }
+      }
       return;
     }
     if (warm) lw_velocity_run<true>(B, L, first, n, 1, block);
@@ -1300,98 +1147,6 @@ B2G_HD void lw_velocity_ring(const Batch& B, int first, int n, int sweeps, bool 
   if (v < total) lw_ring_visit<WARM>(B, first, n, block, ring, bod, stride, scratch, H1, H0, H2, v, k, kf);
   LW_CP_WAIT0();
 }
-// Alternating-set form of the ring sweep (experiment, B2GPU_LW_VELOCITY=9; measured SLOWER than the form above:
-// 14.4 vs 9.7 ms on AddPair-20k — with the bodies requested only one visit ahead the wait at the end of a short
-// visit is exposed).  One register set of the ring form: a record, the two bodies (patched), and what the visit left behind.
-struct LwVset {
-  float4 q0, q1, q2, q3, q4, q5, q6, q7;
-  float4 a, b;   // body velocities: inputs before the solve, results after it
-  int ba, bb, pts;
-};
-// Two register sets alternate (visit v in `cur`, visit v+1 prepared in `nxt`): no register moves, and the results
-// of visit v-1 are still in `nxt` when the bodies of visit v+1 are patched.  Per visit: (1) the record of visit
-// v+1 is read from the ring (it landed long ago), (2) the copies for the bodies of visit v+1 and for the record of
-// visit v+8 are issued, (3) visit v is solved and stored, (4) the copies are awaited (issued a whole visit ago) and
-// the bodies of visit v+1 are read and patched with the results of visits v and v-1: the asynchronous copy of a
-// body was issued before visit v stored and possibly before visit v-1's store became visible to it.
-template <bool WARM>
-B2G_HD void lw_ring_visit_alt(const Batch& B, int first, int n, bool block, float4* ring, float4* bod, int stride, float4* scratch,
-                              LwVset& cur, LwVset& nxt, long long v, int& k, int& kf) {
-  const int slot = (int)(v & (LW_RING - 1)), s1 = (int)((v + 1) & (LW_RING - 1)), b1 = (int)((v + 1) & (LW_BRING - 1));
-  // (1) record of the next visit; the bodies the previous visit (whose results are in nxt.a / nxt.b) touched
-  const int pa_ = nxt.ba, pb_ = nxt.bb;
-  const float4 pra = nxt.a, prb = nxt.b;
-  const float4* rs = ring + (s1 * VC_Q) * stride;
-  nxt.q0 = rs[0]; nxt.q1 = rs[stride]; nxt.q2 = rs[2 * stride]; nxt.q6 = rs[6 * stride]; nxt.q7 = rs[7 * stride];
-  if (!WARM) { nxt.q3 = rs[3 * stride]; nxt.q4 = rs[4 * stride]; nxt.q5 = rs[5 * stride]; }
-  const float4 n8 = rs[8 * stride];
-  nxt.ba = f2i(n8.x); nxt.bb = f2i(n8.y); nxt.pts = f2i(n8.z) & 0xff;
-  // (2) copies: bodies of the next visit, record eight visits ahead into the slot this visit's record came from
-  LW_CP16(bod + (b1 * 2) * stride, &B.b_vel[nxt.ba]);
-  LW_CP16(bod + (b1 * 2 + 1) * stride, &B.b_vel[nxt.bb]);
-  {
-    const float4* r = B.vc + (size_t)(first + kf) * VC_Q;
-    for (int q = 0; q < VC_Q; ++q) LW_CP16(ring + (slot * VC_Q + q) * stride, r + q);
-    if (++kf == n) kf = 0;
-  }
-  LW_CP_COMMIT();
-  // (3) this visit
-  VelState s;
-  s.v_a = v2(cur.a.x, cur.a.y); s.w_a = cur.a.z;
-  s.v_b = v2(cur.b.x, cur.b.y); s.w_b = cur.b.z;
-  if (WARM) {
-    warm_start_one(s, cur.q0, cur.q1, cur.q2, cur.q6, cur.q7, cur.pts);
-  } else {
-    solve_velocity_one(s, cur.q0, cur.q1, cur.q2, cur.q3, cur.q4, cur.q5, cur.q6, cur.q7, cur.pts, block);
-    B.vc[(size_t)(first + k) * VC_Q + 6] = cur.q6;
-  }
-  const bool mov_a = cur.q7.x != 0.0f || cur.q7.y != 0.0f, mov_b = cur.q7.z != 0.0f || cur.q7.w != 0.0f;
-  if (mov_a) cur.a = make_float4(s.v_a.x, s.v_a.y, s.w_a, 0.0f);
-  if (mov_b) cur.b = make_float4(s.v_b.x, s.v_b.y, s.w_b, 0.0f);
-  *(mov_a ? &B.b_vel[cur.ba] : scratch) = cur.a;
-  *(mov_b ? &B.b_vel[cur.bb] : scratch + 1) = cur.b;
-  if (++k == n) k = 0;
-  // (4) bodies of the next visit
-  LW_CP_WAIT0();
-  float4 a = bod[(b1 * 2) * stride], b = bod[(b1 * 2 + 1) * stride];
-  a = nxt.ba == cur.ba ? cur.a : nxt.ba == cur.bb ? cur.b : nxt.ba == pa_ ? pra : nxt.ba == pb_ ? prb : a;
-  b = nxt.bb == cur.ba ? cur.a : nxt.bb == cur.bb ? cur.b : nxt.bb == pa_ ? pra : nxt.bb == pb_ ? prb : b;
-  nxt.a = a;
-  nxt.b = b;
-}
-template <bool WARM>
-B2G_HD void lw_velocity_ring_alt(const Batch& B, int first, int n, int sweeps, bool block, float4* ring, float4* bod, int stride,
-                             float4* scratch) {
-  const long long total = (long long)n * sweeps;
-  int kf = 0;  // constraint whose record is fetched next
-  for (int p = 0; p < LW_RING; ++p) {
-    const float4* r = B.vc + (size_t)(first + kf) * VC_Q;
-    for (int q = 0; q < VC_Q; ++q) LW_CP16(ring + (p * VC_Q + q) * stride, r + q);
-    if (++kf == n) kf = 0;
-  }
-  LW_CP_COMMIT();
-  LW_CP_WAIT0();
-  LwVset A, Bs;
-  {  // visit 0 into A, straight from memory (nothing was written yet)
-    const float4* rs = ring;
-    A.q0 = rs[0]; A.q1 = rs[stride]; A.q2 = rs[2 * stride]; A.q3 = rs[3 * stride]; A.q4 = rs[4 * stride]; A.q5 = rs[5 * stride];
-    A.q6 = rs[6 * stride]; A.q7 = rs[7 * stride];
-    const float4 q8 = rs[8 * stride];
-    A.ba = f2i(q8.x); A.bb = f2i(q8.y); A.pts = f2i(q8.z) & 0xff;
-    A.a = B.b_vel[A.ba];
-    A.b = B.b_vel[A.bb];
-  }
-  Bs = A;
-  Bs.ba = -1; Bs.bb = -1;  // "previous visit": none
-  int k = 0;
-  long long v = 0;
-  for (; v + 2 <= total; v += 2) {
-    lw_ring_visit_alt<WARM>(B, first, n, block, ring, bod, stride, scratch, A, Bs, v, k, kf);
-    lw_ring_visit_alt<WARM>(B, first, n, block, ring, bod, stride, scratch, Bs, A, v + 1, k, kf);
-  }
-  if (v < total) lw_ring_visit_alt<WARM>(B, first, n, block, ring, bod, stride, scratch, A, Bs, v, k, kf);
-  LW_CP_WAIT0();
-}
 struct LwVelocity7K {
   Batch B;
   Large L;
@@ -1426,40 +1181,6 @@ struct LwVelocity7K {
   }
 };
 
-struct LwVelocity9K {
-  Batch B;
-  Large L;
-  StepParams sp;
-  int n_islands;
-  B2G_HD void operator()(int isl) const {
-#if defined(__CUDA_ARCH__)
-    __shared__ float4 ring_s[LW_RING * VC_Q * 32];
-    __shared__ float4 bod_s[LW_BRING * 2 * 32];
-    float4* ring = ring_s + (threadIdx.x & 31);
-    float4* bod = bod_s + (threadIdx.x & 31);
-    const int stride = 32;
-#else
-    float4 ring_s[LW_RING * VC_Q], bod_s[LW_BRING * 2];
-    float4* ring = ring_s;
-    float4* bod = bod_s;
-    const int stride = 1;
-#endif
-    if (isl >= n_islands) return;
-    const int4 rg = B.isl_range[isl];
-    if (rg.z == rg.w) return;
-    const bool warm = (B.ws[WS_FLAGS] & B2GPU_WORLD_WARM_STARTING) != 0;
-    const bool block = (B.ws[WS_FLAGS] & B2GPU_WORLD_BLOCK_SOLVE) != 0;
-    const int first = rg.z, n = rg.w - rg.z;
-    if (n < 2 * LW_RING) {  // a record must not be in the ring while its impulses are rewritten: small islands take the register form
-      LwVelocity5K small = {B, L, sp, n_islands};
-      small(isl);
-      return;
-    }
-    if (warm) lw_velocity_ring_alt<true>(B, first, n, 1, block, ring, bod, stride, L.scratch4 + 8);
-    if (sp.velocity_iterations > 0) lw_velocity_ring_alt<false>(B, first, n, sp.velocity_iterations, block, ring, bod, stride, L.scratch4 + 8);
-  }
-};
-
 struct LwPcRec { float4 p0, p1, p2, p3, p4, p5; };
 B2G_HD LwPcRec lw_load_pc(const float4* pc, int k) {
   const float4* r = pc + (size_t)k * PC_Q;
@@ -1467,258 +1188,6 @@ B2G_HD LwPcRec lw_load_pc(const float4* pc, int k) {
   o.p0 = r[0]; o.p1 = r[1]; o.p2 = r[2]; o.p3 = r[3]; o.p4 = r[4]; o.p5 = r[5];
   return o;
 }
-struct LwPositionK {
-  Batch B;
-  StepParams sp;
-  int n_islands;
-  B2G_HD void operator()(int isl) const {
-    if (isl >= n_islands) return;
-    const int4 rg = B.isl_range[isl];
-    if (rg.z == rg.w) return;
-    const int first = rg.z, n = rg.w - rg.z;
-    for (int it = 0; it < sp.position_iterations; ++it) {
-      float min_separation = 0.0f;
-      LwPcRec cur = lw_load_pc(B.pc, first);
-      int ba = f2i(cur.p4.z), bb = f2i(cur.p4.w);
-      float4 pa = B.b_pos[ba], pb = B.b_pos[bb], ra = B.b_rot[ba], rb = B.b_rot[bb];
-      for (int k = 0; k < n; ++k) {
-        const int k1 = k + 1 < n ? k + 1 : k;
-        const LwPcRec nxt = lw_load_pc(B.pc, first + k1);
-        const int nba = f2i(nxt.p4.z), nbb = f2i(nxt.p4.w);
-        float4 npa = B.b_pos[nba], npb = B.b_pos[nbb], nra = B.b_rot[nba], nrb = B.b_rot[nbb];
-        const int packed = f2i(cur.p5.x);
-        PosState s;
-        s.c_a = v2(pa.x, pa.y); s.a_a = pa.z; s.q_a.s = ra.x; s.q_a.c = ra.y;
-        s.c_b = v2(pb.x, pb.y); s.a_b = pb.z; s.q_b.s = rb.x; s.q_b.c = rb.y;
-        min_separation = solve_position_one(s, cur.p0, cur.p1, cur.p2, cur.p3, (packed >> 8) & 0xff, packed & 0xff, cur.p4.x,
-                                            cur.p4.y, min_separation);
-        if (cur.p0.x != 0.0f || cur.p0.y != 0.0f) {  // immovable bodies are shared between islands: never written
-          pa.x = s.c_a.x; pa.y = s.c_a.y; pa.z = s.a_a;
-          ra.x = s.q_a.s; ra.y = s.q_a.c;
-          B.b_pos[ba] = pa; B.b_rot[ba] = ra;
-        }
-        if (cur.p0.z != 0.0f || cur.p0.w != 0.0f) {
-          pb.x = s.c_b.x; pb.y = s.c_b.y; pb.z = s.a_b;
-          rb.x = s.q_b.s; rb.y = s.q_b.c;
-          B.b_pos[bb] = pb; B.b_rot[bb] = rb;
-        }
-        if (nba == ba) { npa = pa; nra = ra; } else if (nba == bb) { npa = pb; nra = rb; }
-        if (nbb == ba) { npb = pa; nrb = ra; } else if (nbb == bb) { npb = pb; nrb = rb; }
-        cur = nxt;
-        ba = nba; bb = nbb; pa = npa; pb = npb; ra = nra; rb = nrb;
-      }
-      if (min_separation >= -3.0f * B2G_LINEAR_SLOP) {
-        B.isl_flags[isl] |= 1;
-        break;
-      }
-    }
-  }
-};
-
-// The position sweeps with the same rotating register sets as LwVelocity4K (the position records are
-// immutable, so any island size takes this path); the reference's early exit is evaluated at every sweep end.
-struct LwPosition4K {
-  Batch B;
-  Large L;
-  StepParams sp;
-  int n_islands;
-  B2G_HD void operator()(int isl) const {
-    if (isl >= n_islands) return;
-    const int4 rg = B.isl_range[isl];
-    if (rg.z == rg.w || sp.position_iterations <= 0) return;
-    const int first = rg.z, n = rg.w - rg.z;
-    const long long total = (long long)n * sp.position_iterations;
-    int4 ix[4];
-    float4 p0[4], p1[4], p2[4], p3[4], p4[4], pa[4], pb[4], ra[4], rb[4];
-    ix[0] = L.vc_idx[first];
-    ix[1] = L.vc_idx[first + 1 % n];
-    ix[2] = L.vc_idx[first + 2 % n];
-    ix[3] = make_int4(0, 0, 0, 0);
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int j = 0; j < 2; ++j) {
-      const float4* r = B.pc + (size_t)(first + j % n) * PC_Q;
-      p0[j] = r[0]; p1[j] = r[1]; p2[j] = r[2]; p3[j] = r[3]; p4[j] = r[4];
-      pa[j] = B.b_pos[ix[j].x]; ra[j] = B.b_rot[ix[j].x];
-      pb[j] = B.b_pos[ix[j].y]; rb[j] = B.b_rot[ix[j].y];
-    }
-    int k = 0, k2 = 2 % n, k3 = 3 % n;
-    float min_separation = 0.0f;
-    for (long long v = 0; v < total; v += 4) {
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-      for (int j = 0; j < 4; ++j) {
-        if (v + j < total) {
-          const int j2 = (j + 2) & 3, j3 = (j + 3) & 3, j1 = (j + 1) & 3;
-          ix[j3] = L.vc_idx[first + k3];
-          {
-            const float4* r = B.pc + (size_t)(first + k2) * PC_Q;
-            p0[j2] = r[0]; p1[j2] = r[1]; p2[j2] = r[2]; p3[j2] = r[3]; p4[j2] = r[4];
-            pa[j2] = B.b_pos[ix[j2].x]; ra[j2] = B.b_rot[ix[j2].x];
-            pb[j2] = B.b_pos[ix[j2].y]; rb[j2] = B.b_rot[ix[j2].y];
-          }
-          const int ba = ix[j].x, bb = ix[j].y, packed = ix[j].w;
-          PosState s;
-          s.c_a = v2(pa[j].x, pa[j].y); s.a_a = pa[j].z; s.q_a.s = ra[j].x; s.q_a.c = ra[j].y;
-          s.c_b = v2(pb[j].x, pb[j].y); s.a_b = pb[j].z; s.q_b.s = rb[j].x; s.q_b.c = rb[j].y;
-          min_separation = solve_position_one(s, p0[j], p1[j], p2[j], p3[j], (packed >> 8) & 0xff, packed & 0xff, p4[j].x,
-                                              p4[j].y, min_separation);
-          if (p0[j].x != 0.0f || p0[j].y != 0.0f) {  // immovable bodies are shared between islands: never written
-            pa[j].x = s.c_a.x; pa[j].y = s.c_a.y; pa[j].z = s.a_a;
-            ra[j].x = s.q_a.s; ra[j].y = s.q_a.c;
-            B.b_pos[ba] = pa[j]; B.b_rot[ba] = ra[j];
-          }
-          if (p0[j].z != 0.0f || p0[j].w != 0.0f) {
-            pb[j].x = s.c_b.x; pb[j].y = s.c_b.y; pb[j].z = s.a_b;
-            rb[j].x = s.q_b.s; rb[j].y = s.q_b.c;
-            B.b_pos[bb] = pb[j]; B.b_rot[bb] = rb[j];
-          }
-          if (ix[j1].x == ba) { pa[j1] = pa[j]; ra[j1] = ra[j]; } else if (ix[j1].x == bb) { pa[j1] = pb[j]; ra[j1] = rb[j]; }
-          if (ix[j1].y == ba) { pb[j1] = pa[j]; rb[j1] = ra[j]; } else if (ix[j1].y == bb) { pb[j1] = pb[j]; rb[j1] = rb[j]; }
-          if (ix[j2].x == ba) { pa[j2] = pa[j]; ra[j2] = ra[j]; } else if (ix[j2].x == bb) { pa[j2] = pb[j]; ra[j2] = rb[j]; }
-          if (ix[j2].y == ba) { pb[j2] = pa[j]; rb[j2] = ra[j]; } else if (ix[j2].y == bb) { pb[j2] = pb[j]; rb[j2] = rb[j]; }
-          if (++k2 == n) k2 = 0;
-          if (++k3 == n) k3 = 0;
-          if (++k == n) {  // end of a sweep: b2_island_private.rs:257-274
-            k = 0;
-            if (min_separation >= -3.0f * B2G_LINEAR_SLOP) {
-              B.isl_flags[isl] |= 1;
-              return;
-            }
-            min_separation = 0.0f;
-          }
-        }
-      }
-    }
-  }
-};
-
-// Position sweeps in the straighter form (see lw_velocity_run): one pipelined pass per sweep (groups of four
-// visits without a bounds test, at most three plain visits at the end), immovable bodies stored to a scratch
-// slot, the reference's early exit evaluated between sweeps.
-B2G_HD float lw_position_visit_plain(const Batch& B, const Large& L, int kk, float min_separation) {
-  const int4 ixx = L.vc_idx[kk];
-  const float4* r = B.pc + (size_t)kk * PC_Q;
-  const float4 p0 = r[0];
-  float4 pa = B.b_pos[ixx.x], pb = B.b_pos[ixx.y], ra = B.b_rot[ixx.x], rb = B.b_rot[ixx.y];
-  PosState s;
-  s.c_a = v2(pa.x, pa.y); s.a_a = pa.z; s.q_a.s = ra.x; s.q_a.c = ra.y;
-  s.c_b = v2(pb.x, pb.y); s.a_b = pb.z; s.q_b.s = rb.x; s.q_b.c = rb.y;
-  const float4 p4 = r[4];
-  min_separation = solve_position_one(s, p0, r[1], r[2], r[3], (ixx.w >> 8) & 0xff, ixx.w & 0xff, p4.x, p4.y, min_separation);
-  if (p0.x != 0.0f || p0.y != 0.0f) {
-    pa.x = s.c_a.x; pa.y = s.c_a.y; pa.z = s.a_a; ra.x = s.q_a.s; ra.y = s.q_a.c;
-    B.b_pos[ixx.x] = pa; B.b_rot[ixx.x] = ra;
-  }
-  if (p0.z != 0.0f || p0.w != 0.0f) {
-    pb.x = s.c_b.x; pb.y = s.c_b.y; pb.z = s.a_b; rb.x = s.q_b.s; rb.y = s.q_b.c;
-    B.b_pos[ixx.y] = pb; B.b_rot[ixx.y] = rb;
-  }
-  return min_separation;
-}
-B2G_HD float lw_position_sweep(const Batch& B, const Large& L, int first, int n) {
-  float min_separation = 0.0f;
-  int v = 0;
-  if (n >= 8) {
-    int4 ix[4];
-    float4 p0[4], p1[4], p2[4], p3[4], p4[4], pa[4], pb[4], ra[4], rb[4];
-    ix[0] = L.vc_idx[first];
-    ix[1] = L.vc_idx[first + 1];
-    ix[2] = L.vc_idx[first + 2];
-    ix[3] = make_int4(0, 0, 0, 0);
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-    for (int j = 0; j < 2; ++j) {
-      const float4* r = B.pc + (size_t)(first + j) * PC_Q;
-      p0[j] = r[0]; p1[j] = r[1]; p2[j] = r[2]; p3[j] = r[3]; p4[j] = r[4];
-      pa[j] = B.b_pos[ix[j].x]; ra[j] = B.b_rot[ix[j].x];
-      pb[j] = B.b_pos[ix[j].y]; rb[j] = B.b_rot[ix[j].y];
-    }
-    float4* scratch = L.scratch4;  // where the "results" of immovable bodies go
-    int k = 0, k2 = 2, k3 = 3;
-    for (; v + 4 <= n; v += 4) {
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-      for (int j = 0; j < 4; ++j) {
-        const int j2 = (j + 2) & 3, j3 = (j + 3) & 3, j1 = (j + 1) & 3;
-        ix[j3] = L.vc_idx[first + k3];
-        {
-          const float4* r = B.pc + (size_t)(first + k2) * PC_Q;
-          p0[j2] = r[0]; p1[j2] = r[1]; p2[j2] = r[2]; p3[j2] = r[3]; p4[j2] = r[4];
-          pa[j2] = B.b_pos[ix[j2].x]; ra[j2] = B.b_rot[ix[j2].x];
-          pb[j2] = B.b_pos[ix[j2].y]; rb[j2] = B.b_rot[ix[j2].y];
-        }
-        const int ba = ix[j].x, bb = ix[j].y, packed = ix[j].w;
-        PosState s;
-        s.c_a = v2(pa[j].x, pa[j].y); s.a_a = pa[j].z; s.q_a.s = ra[j].x; s.q_a.c = ra[j].y;
-        s.c_b = v2(pb[j].x, pb[j].y); s.a_b = pb[j].z; s.q_b.s = rb[j].x; s.q_b.c = rb[j].y;
-        const int type = (packed >> 8) & 0xff, pts = packed & 0xff;
-        if (type != B2GPU_MANIFOLD_CIRCLES && pts == 2) {
-          // the branch-free two-point face form of the batch kernels (solve_position_face2: selects instead of the
-          // face-type branches, unconditional sincos_mid refresh); an angle outside its domain redoes the visit
-          const PosState s0 = s;
-          bool wide;
-          const float ms = solve_position_face2(s, p0[j], p1[j], p2[j], p3[j], type == B2GPU_MANIFOLD_FACE_A, p4[j].x, p4[j].y,
-                                                min_separation, wide);
-          if (wide) {
-            s = s0;
-            min_separation = solve_position_one(s, p0[j], p1[j], p2[j], p3[j], type, pts, p4[j].x, p4[j].y, min_separation);
-          } else {
-            min_separation = ms;
-          }
-        } else if (type == B2GPU_MANIFOLD_CIRCLES) {
-          min_separation = solve_position_one(s, p0[j], p1[j], p2[j], p3[j], B2GPU_MANIFOLD_CIRCLES, pts, p4[j].x, p4[j].y, min_separation);
-        } else {
-          min_separation = solve_position_one(s, p0[j], p1[j], p2[j], p3[j], type, pts, p4[j].x, p4[j].y, min_separation);
-        }
-        // immovable bodies (inverse mass and inertia 0) come out of the arithmetic unchanged and are shared between
-        // islands: their value goes to a scratch slot
-        const bool mov_a = p0[j].x != 0.0f || p0[j].y != 0.0f, mov_b = p0[j].z != 0.0f || p0[j].w != 0.0f;
-        if (mov_a) { pa[j].x = s.c_a.x; pa[j].y = s.c_a.y; pa[j].z = s.a_a; ra[j].x = s.q_a.s; ra[j].y = s.q_a.c; }
-        if (mov_b) { pb[j].x = s.c_b.x; pb[j].y = s.c_b.y; pb[j].z = s.a_b; rb[j].x = s.q_b.s; rb[j].y = s.q_b.c; }
-        *(mov_a ? &B.b_pos[ba] : scratch) = pa[j];
-        *(mov_a ? &B.b_rot[ba] : scratch + 1) = ra[j];
-        *(mov_b ? &B.b_pos[bb] : scratch + 2) = pb[j];
-        *(mov_b ? &B.b_rot[bb] : scratch + 3) = rb[j];
-        if (ix[j1].x == ba) { pa[j1] = pa[j]; ra[j1] = ra[j]; } else if (ix[j1].x == bb) { pa[j1] = pb[j]; ra[j1] = rb[j]; }
-        if (ix[j1].y == ba) { pb[j1] = pa[j]; rb[j1] = ra[j]; } else if (ix[j1].y == bb) { pb[j1] = pb[j]; rb[j1] = rb[j]; }
-        if (ix[j2].x == ba) { pa[j2] = pa[j]; ra[j2] = ra[j]; } else if (ix[j2].x == bb) { pa[j2] = pb[j]; ra[j2] = rb[j]; }
-        if (ix[j2].y == ba) { pb[j2] = pa[j]; rb[j2] = ra[j]; } else if (ix[j2].y == bb) { pb[j2] = pb[j]; rb[j2] = rb[j]; }
-        if (++k == n) k = 0;
-        if (++k2 == n) k2 = 0;
-        if (++k3 == n) k3 = 0;
-      }
-    }
-  }
-  for (; v < n; ++v) min_separation = lw_position_visit_plain(B, L, first + v, min_separation);
-  return min_separation;
-}
-struct LwPosition5K {
-  Batch B;
-  Large L;
-  StepParams sp;
-  int n_islands;
-  B2G_HD void operator()(int isl) const {
-    if (isl >= n_islands) return;
-    const int4 rg = B.isl_range[isl];
-    if (rg.z == rg.w) return;
-    for (int it = 0; it < sp.position_iterations; ++it) {
-      if (lw_position_sweep(B, L, rg.z, rg.w - rg.z) >= -3.0f * B2G_LINEAR_SLOP) {  // b2_island_private.rs:257-274
-        B.isl_flags[isl] |= 1;
-        break;
-      }
-    }
-  }
-};
-
-// Position sweeps, final form: two register sets alternate through a loop unrolled by two (no moves of registers
-// whose loads are in flight), the next visit's record and bodies are requested at the start of a visit, and the
-// bodies the previous visit wrote are forwarded at the point of use.  One inlined copy of solve_position_one per
-// set keeps the loop inside the instruction cache (the four-set forms above measured slower: stall_no_inst).
 struct LwPosSet { float4 p0, p1, p2, p3, p4, pa, pb, ra, rb; int4 ix; int hba, hbb; };
 B2G_HD void lw_pos_request(const Batch& B, const Large& L, int kk, LwPosSet& t) {  // t.ix was loaded a visit earlier
   const float4* r = B.pc + (size_t)kk * PC_Q;
@@ -1783,113 +1252,6 @@ struct LwPosition6K {
       }
       if (k < n) min_separation = lw_pos_visit(B, L, scratch, s0, s1, -1, last, min_separation);
       if (min_separation >= -3.0f * B2G_LINEAR_SLOP) {  // b2_island_private.rs:257-274
-        B.isl_flags[isl] |= 1;
-        break;
-      }
-    }
-  }
-};
-
-// Position sweeps through the same kind of cp.async ring (experiment, B2GPU_LW_VELOCITY=7): records (6 rows)
-// eight visits ahead, the two bodies' position and rotation rows two visits ahead, results of the last three
-// visits forwarded at the point of use.  One pipeline start per sweep (the early exit sits between sweeps).
-B2G_HD float lw_position_ring_sweep(const Batch& B, int first, int n, float4* ring, float4* bod, int stride, float4* scratch) {
-  int kf = 0;
-  for (int p = 0; p < LW_RING; ++p) {
-    const float4* r = B.pc + (size_t)(first + kf) * PC_Q;
-    for (int q = 0; q < PC_Q; ++q) LW_CP16(ring + (p * PC_Q + q) * stride, r + q);
-    if (++kf == n) kf = 0;
-  }
-  LW_CP_COMMIT();
-  LW_CP_WAIT0();
-  for (int p = 0; p < 2; ++p) {
-    const float4 p4 = ring[(p * PC_Q + 4) * stride];
-    const int ba = f2i(p4.z), bb = f2i(p4.w);
-    LW_CP16(bod + (p * 4) * stride, &B.b_pos[ba]);
-    LW_CP16(bod + (p * 4 + 1) * stride, &B.b_rot[ba]);
-    LW_CP16(bod + (p * 4 + 2) * stride, &B.b_pos[bb]);
-    LW_CP16(bod + (p * 4 + 3) * stride, &B.b_rot[bb]);
-  }
-  LW_CP_COMMIT();
-  LW_CP_WAIT0();
-  LW_CP_COMMIT();
-  int h1a = -1, h1b = -1, h2a = -1, h2b = -1, h3a = -1, h3b = -1;
-  const float4 z = make_float4(0, 0, 0, 0);
-  float4 c1a = z, c1b = z, c2a = z, c2b = z, c3a = z, c3b = z, t1a = z, t1b = z, t2a = z, t2b = z, t3a = z, t3b = z;
-  float min_separation = 0.0f;
-  for (int v = 0; v < n; ++v) {
-    const int slot = v & (LW_RING - 1), bs = v & (LW_BRING - 1);
-    LW_CP_WAIT1();
-    const float4* rs = ring + (slot * PC_Q) * stride;
-    const float4 p0 = rs[0], p1 = rs[stride], p2 = rs[2 * stride], p3 = rs[3 * stride], p4 = rs[4 * stride], p5 = rs[5 * stride];
-    float4 pa = bod[(bs * 4) * stride], ra = bod[(bs * 4 + 1) * stride], pb = bod[(bs * 4 + 2) * stride], rb = bod[(bs * 4 + 3) * stride];
-    const int ba = f2i(p4.z), bb = f2i(p4.w), packed = f2i(p5.x);
-    if (ba == h1a) { pa = c1a; ra = t1a; } else if (ba == h1b) { pa = c1b; ra = t1b; }
-    else if (ba == h2a) { pa = c2a; ra = t2a; } else if (ba == h2b) { pa = c2b; ra = t2b; }
-    else if (ba == h3a) { pa = c3a; ra = t3a; } else if (ba == h3b) { pa = c3b; ra = t3b; }
-    if (bb == h1a) { pb = c1a; rb = t1a; } else if (bb == h1b) { pb = c1b; rb = t1b; }
-    else if (bb == h2a) { pb = c2a; rb = t2a; } else if (bb == h2b) { pb = c2b; rb = t2b; }
-    else if (bb == h3a) { pb = c3a; rb = t3a; } else if (bb == h3b) { pb = c3b; rb = t3b; }
-    {
-      const float4* r = B.pc + (size_t)(first + kf) * PC_Q;
-      for (int q = 0; q < PC_Q; ++q) LW_CP16(ring + (slot * PC_Q + q) * stride, r + q);
-      if (++kf == n) kf = 0;
-      const int s2 = (v + 2) & (LW_RING - 1), b2 = (v + 2) & (LW_BRING - 1);
-      const float4 n4 = ring[(s2 * PC_Q + 4) * stride];
-      const int na = f2i(n4.z), nb = f2i(n4.w);
-      LW_CP16(bod + (b2 * 4) * stride, &B.b_pos[na]);
-      LW_CP16(bod + (b2 * 4 + 1) * stride, &B.b_rot[na]);
-      LW_CP16(bod + (b2 * 4 + 2) * stride, &B.b_pos[nb]);
-      LW_CP16(bod + (b2 * 4 + 3) * stride, &B.b_rot[nb]);
-      LW_CP_COMMIT();
-    }
-    PosState s;
-    s.c_a = v2(pa.x, pa.y); s.a_a = pa.z; s.q_a.s = ra.x; s.q_a.c = ra.y;
-    s.c_b = v2(pb.x, pb.y); s.a_b = pb.z; s.q_b.s = rb.x; s.q_b.c = rb.y;
-    min_separation = solve_position_one(s, p0, p1, p2, p3, (packed >> 8) & 0xff, packed & 0xff, p4.x, p4.y, min_separation);
-    const bool mov_a = p0.x != 0.0f || p0.y != 0.0f, mov_b = p0.z != 0.0f || p0.w != 0.0f;
-    if (mov_a) { pa.x = s.c_a.x; pa.y = s.c_a.y; pa.z = s.a_a; ra.x = s.q_a.s; ra.y = s.q_a.c; }
-    if (mov_b) { pb.x = s.c_b.x; pb.y = s.c_b.y; pb.z = s.a_b; rb.x = s.q_b.s; rb.y = s.q_b.c; }
-    *(mov_a ? &B.b_pos[ba] : scratch) = pa;
-    *(mov_a ? &B.b_rot[ba] : scratch + 1) = ra;
-    *(mov_b ? &B.b_pos[bb] : scratch + 2) = pb;
-    *(mov_b ? &B.b_rot[bb] : scratch + 3) = rb;
-    h3a = h2a; h3b = h2b; c3a = c2a; c3b = c2b; t3a = t2a; t3b = t2b;
-    h2a = h1a; h2b = h1b; c2a = c1a; c2b = c1b; t2a = t1a; t2b = t1b;
-    h1a = ba; h1b = bb; c1a = pa; c1b = pb; t1a = ra; t1b = rb;
-  }
-  LW_CP_WAIT0();
-  return min_separation;
-}
-struct LwPosition7K {
-  Batch B;
-  Large L;
-  StepParams sp;
-  int n_islands;
-  B2G_HD void operator()(int isl) const {
-#if defined(__CUDA_ARCH__)
-    __shared__ float4 ring_s[LW_RING * PC_Q * 32];
-    __shared__ float4 bod_s[LW_BRING * 4 * 32];
-    float4* ring = ring_s + (threadIdx.x & 31);
-    float4* bod = bod_s + (threadIdx.x & 31);
-    const int stride = 32;
-#else
-    float4 ring_s[LW_RING * PC_Q], bod_s[LW_BRING * 4];
-    float4* ring = ring_s;
-    float4* bod = bod_s;
-    const int stride = 1;
-#endif
-    if (isl >= n_islands) return;
-    const int4 rg = B.isl_range[isl];
-    if (rg.z == rg.w) return;
-    const int first = rg.z, n = rg.w - rg.z;
-    if (n < 2 * LW_RING) {
-      LwPosition6K small = {B, L, sp, n_islands};
-      small(isl);
-      return;
-    }
-    for (int it = 0; it < sp.position_iterations; ++it) {
-      if (lw_position_ring_sweep(B, first, n, ring, bod, stride, L.scratch4 + 12) >= -3.0f * B2G_LINEAR_SLOP) {  // b2_island_private.rs:257-274
         B.isl_flags[isl] |= 1;
         break;
       }

@@ -570,7 +570,7 @@ int batch_create(Ctx* ctx, const b2gpu_snapshot* proto, int n_worlds, const b2gp
   AL(B.c_fix, W * B.NC); AL(B.c_flags, W * B.NC); AL(B.c_mat, W * B.NC);
   AL(B.c_m0, W * B.NC); AL(B.c_m1, W * B.NC); AL(B.c_m2, W * B.NC); AL(B.c_m3, W * B.NC);
   AL(B.isl_body, W * B.NIB); AL(B.isl_contact, W * B.NC); AL(B.isl_range, W * B.NB); AL(B.isl_flags, W * B.NB);
-  AL(B.c_isl, W * B.NC); AL(B.vc, W * B.NC * VC_Q); AL(B.pc, W * B.NC * PC_Q); AL(B.sched, W * B.NC * SCHED_G);
+  AL(B.c_isl, W * B.NC); AL(B.vc, W * B.NC * VC_Q); AL(B.pc, W * B.NC * PC_Q);
   if (B.NJ > 0) {
     AL(B.j_s0, W * B.NJ); AL(B.j_s1, W * B.NJ); AL(B.isl_joint, W * B.NJ); AL(B.isl_jrange, W * B.NB); AL(B.j_flag, W * B.NJ);
     AL(B.j_tmp, W * B.NJ * JT_Q);
@@ -579,6 +579,14 @@ int batch_create(Ctx* ctx, const b2gpu_snapshot* proto, int n_worlds, const b2gp
   AL(bh->state_dev, (long long)n_worlds * B.NB * 8);
   AL(bh->forces_dev, (long long)n_worlds * B.NB * 3);
   AL(bh->status_dev, 4);
+  {
+    std::vector<int> dyn;
+    for (int b = 0; b < B.NB; ++b)
+      if (bh->topo.bodies[b].type == B2GPU_DYNAMIC_BODY) dyn.push_back(b);
+    bh->n_dyn = (int)dyn.size();
+    AL(bh->dyn_idx, std::max(bh->n_dyn, 1));
+    if (bh->n_dyn) { rc = dev_h2d(ctx, bh->dyn_idx, dyn.data(), dyn.size() * 4); if (rc) { batch_destroy(bh); return rc; } }
+  }
 #if defined(B2G_HOSTSIM)
   bh->status_host = (int*)calloc(4, 4);
 #else
@@ -614,7 +622,6 @@ int batch_create(Ctx* ctx, const b2gpu_snapshot* proto, int n_worlds, const b2gp
     if (rc) { batch_destroy(bh); return rc; }
     bh->large = true;
     bh->lw_exact_tree = caps->reserved[1] == 12;
-    if (const char* e = getenv("B2GPU_LW_VELOCITY")) bh->lw_velocity_variant = atoi(e);  // diagnostic, see step_large
   }
 #if !defined(B2G_HOSTSIM)
   // shared-memory Gauss-Seidel stages: batches in 32-world memory blocks whose bodies fit one SM
@@ -623,16 +630,11 @@ int batch_create(Ctx* ctx, const b2gpu_snapshot* proto, int n_worlds, const b2gp
   if (B.LB == 32 && !(caps && caps->reserved[1] == 1) && B.NJ == 0) {
     int max_optin = 0;
     CU(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
-    const size_t need = std::max(velocity_smem_bytes(B.NB), position_smem_bytes(B.NB));
+    const size_t need = std::max(velocity_smem_bytes(B.NB), position_sl_smem_bytes(B.NB));
     if (need <= (size_t)max_optin) {
-      CU(cudaFuncSetAttribute(velocity_smem_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)velocity_smem_bytes(B.NB)));
-      CU(cudaFuncSetAttribute(velocity_smem_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)velocity_smem_bytes(B.NB)));
       CU(cudaFuncSetAttribute(velocity_sl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)velocity_smem_bytes(B.NB)));
-      bh->tma_ring = caps && caps->reserved[1] == 4;
-      bh->pipelined_velocity = caps && caps->reserved[1] == 7;
-      bh->ws_velocity = caps && caps->reserved[1] == 8 && velocity_ws_smem_bytes(B.NB) <= (size_t)max_optin;
-      if (bh->ws_velocity)
-        CU(cudaFuncSetAttribute(velocity_ws_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)velocity_ws_smem_bytes(B.NB)));
+      CU(cudaFuncSetAttribute(position_sl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)position_sl_smem_bytes(B.NB)));
+      bh->smem_solver = true;
       if (const char* e = getenv("B2GPU_TIMELINE")) {  // diagnostic: per-CTA start/end of the Gauss-Seidel kernels
         const size_t cap = 600000;
         unsigned long long* t = nullptr;
@@ -644,27 +646,10 @@ int batch_create(Ctx* ctx, const b2gpu_snapshot* proto, int n_worlds, const b2gp
         bh->B.timeline = t;
         bh->timeline_path = e;
       }
-      if (const char* e = getenv("B2GPU_STREAM_GROUPS")) bh->stream_groups = atoi(e);  // tuning experiments
-      if (caps && caps->reserved[1] == 5) bh->stream_groups = 1;
-      if (caps && caps->reserved[1] == 6) bh->use_graphs = false;
-      CU(cudaFuncSetAttribute(position_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)position_smem_bytes(B.NB)));
-      bh->smem_solver = true;
-      // straight-line position kernel: the default where its tables fit (diagnostic switches 2, 3, 9 keep the others)
-      bh->sl_position = position_sl_smem_bytes(B.NB) <= (size_t)max_optin &&
-                        !(caps && (caps->reserved[1] == 2 || caps->reserved[1] == 3 || caps->reserved[1] == 9));
-      if (bh->sl_position)
-        CU(cudaFuncSetAttribute(position_sl_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)position_sl_smem_bytes(B.NB)));
     }
-    const size_t need_ml = position_ml_smem_bytes(B.NB);
-    if (bh->smem_solver && need_ml <= (size_t)max_optin && !(caps && caps->reserved[1] == 2)) {
-      CU(cudaFuncSetAttribute(position_ml_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)position_ml_smem_bytes(B.NB)));
-      CU(cudaFuncSetAttribute(velocity_ml_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)velocity_ml_smem_bytes(B.NB)));
-      bh->ml_velocity = caps && caps->reserved[1] == 3;
-      bh->ml2_velocity = caps && caps->reserved[1] == 10 && velocity_ml2_smem_bytes(B.NB) <= (size_t)max_optin;
-      if (bh->ml2_velocity)
-        CU(cudaFuncSetAttribute(velocity_ml2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)velocity_ml2_smem_bytes(B.NB)));
-      bh->ml_solver = true;
-    }
+    if (const char* e = getenv("B2GPU_STREAM_GROUPS")) bh->stream_groups = atoi(e);  // tuning experiments
+    if (caps && caps->reserved[1] == 5) bh->stream_groups = 1;
+    if (caps && caps->reserved[1] == 6) bh->use_graphs = false;
     bh->island_layout = island_smem_layout(B.NB, B.NF, (size_t)max_optin - 1024);
     if (B.NB < 32768 && B.NC < 65536 && bh->island_layout.ECAP >= 64) {
       CU(cudaFuncSetAttribute(island_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bh->island_layout.total));
@@ -840,6 +825,41 @@ struct ForceScatterK {
     B.b_force[bi] = fo;
   }
 };
+// Compact I/O (RL loops): only the prototype's DYNAMIC bodies, in body order — forces [n_worlds][nd][3] in, state
+// [n_worlds][nd][6] = (c.x, c.y, a, v.x, v.y, w) out (24 B per body: SURVEY §8e's 5040 B per Pyramid world).
+struct StateGatherDynK {
+  Batch B;
+  float* out;
+  const int* dyn;
+  int nd;
+  B2G_HD void operator()(int tid) const {
+    int w, j;
+    if (!flat_decode(B, tid, nd, w, j)) return;
+    WIdx x = widx(B, w);
+    const int bi = x.at(B.NB, dyn[j]);
+    const float4 pos = B.b_pos[bi], vel = B.b_vel[bi];
+    float* o = out + ((size_t)w * nd + j) * 6;
+    o[0] = pos.x; o[1] = pos.y; o[2] = pos.z; o[3] = vel.x; o[4] = vel.y; o[5] = vel.z;
+  }
+};
+struct ForceScatterDynK {
+  Batch B;
+  const float* in;  // [count][nd][3] for worlds first..first+count
+  const int* dyn;
+  int nd, first, count;
+  B2G_HD void operator()(int tid) const {
+    int w, j;
+    if (!flat_decode(B, tid, nd, w, j)) return;
+    if (w < first || w >= first + count) return;
+    WIdx x = widx(B, w);
+    const int bi = x.at(B.NB, dyn[j]);
+    if (!(B.b_flags[bi] & B2GPU_BODY_AWAKE)) return;  // apply_force / apply_torque with wake = false
+    const float* f = in + ((size_t)(w - first) * nd + j) * 3;
+    float4 fo = B.b_force[bi];
+    fo.x += f[0]; fo.y += f[1]; fo.z += f[2];
+    B.b_force[bi] = fo;
+  }
+};
 struct VelScatterK {
   Batch B;
   const float* in;  // [count][2]
@@ -921,47 +941,20 @@ static int step_window(BatchHost* bh, const Batch& Bw, const StepParams& sp, int
       { SolverInitK k = {B, sp}; RC(launch(ctx, k, W * B.NC, 128, STAGE_SOLVER_INIT)); }
 #if !defined(B2G_HOSTSIM)
       if (init_done && s == 0) CU(cudaEventRecord((cudaEvent_t)init_done, (cudaStream_t)ctx->stream));
-      if (bh->ml_solver && bh->ml2_velocity) {
+      if (bh->smem_solver) {
         LaunchScope ls = {ctx, STAGE_VELOCITY};
         RC(ls.begin());
-        velocity_ml2_kernel<<<B.wb_count * SCHED_G, 32, velocity_ml2_smem_bytes(B.NB), (cudaStream_t)ctx->stream>>>(B, sp);
-        RC(ls.end());
-      } else if (bh->ml_solver && bh->ml_velocity) {
-        LaunchScope ls = {ctx, STAGE_VELOCITY};
-        RC(ls.begin());
-        velocity_ml_kernel<<<B.wb_count * SCHED_G, 32, velocity_ml_smem_bytes(B.NB), (cudaStream_t)ctx->stream>>>(B, sp);
-        RC(ls.end());
-      } else if (bh->smem_solver) {
-        LaunchScope ls = {ctx, STAGE_VELOCITY};
-        RC(ls.begin());
-        if (bh->ws_velocity)
-          velocity_ws_kernel<<<B.wb_count, 64, velocity_ws_smem_bytes(B.NB), (cudaStream_t)ctx->stream>>>(B, sp);
-        else if (!bh->tma_ring && !bh->pipelined_velocity)
-          velocity_sl_kernel<<<B.wb_count, 32, velocity_smem_bytes(B.NB), (cudaStream_t)ctx->stream>>>(B, sp);
-        else if (bh->tma_ring)
-          velocity_smem_kernel<true><<<B.wb_count, 32, velocity_smem_bytes(B.NB), (cudaStream_t)ctx->stream>>>(B, sp);
-        else
-          velocity_smem_kernel<false><<<B.wb_count, 32, velocity_smem_bytes(B.NB), (cudaStream_t)ctx->stream>>>(B, sp);
+        velocity_sl_kernel<<<B.wb_count, 32, velocity_smem_bytes(B.NB), (cudaStream_t)ctx->stream>>>(B, sp);
         RC(ls.end());
       } else
 #endif
       { VelocityK k = {B, sp}; RC(launch(ctx, k, W * B.NB, 64, STAGE_VELOCITY)); }
       { PostVelocityK k = {B, sp}; RC(launch(ctx, k, W * B.NIB, 128, STAGE_POST_VELOCITY)); }
 #if !defined(B2G_HOSTSIM)
-      if (bh->sl_position) {
+      if (bh->smem_solver) {
         LaunchScope ls = {ctx, STAGE_POSITION};
         RC(ls.begin());
         position_sl_kernel<<<B.wb_count, 32, position_sl_smem_bytes(B.NB), (cudaStream_t)ctx->stream>>>(B, sp);
-        RC(ls.end());
-      } else if (bh->ml_solver) {
-        LaunchScope ls = {ctx, STAGE_POSITION};
-        RC(ls.begin());
-        position_ml_kernel<<<B.wb_count * SCHED_G, 32, position_ml_smem_bytes(B.NB), (cudaStream_t)ctx->stream>>>(B, sp);
-        RC(ls.end());
-      } else if (bh->smem_solver) {
-        LaunchScope ls = {ctx, STAGE_POSITION};
-        RC(ls.begin());
-        position_smem_kernel<<<B.wb_count, 32, position_smem_bytes(B.NB), (cudaStream_t)ctx->stream>>>(B, sp);
         RC(ls.end());
       } else
 #endif
@@ -1218,24 +1211,13 @@ static int step_large(BatchHost* bh, const StepParams& sp, int steps) {
       { LwStaticRotK k = {B}; RC(launch(ctx, k, B.NB, 256, STAGE_INTEGRATE)); }
       { IntegrateK k = {B, sp}; RC(launch(ctx, k, nib, 128, STAGE_INTEGRATE)); }
       { SolverInitK k = {B, sp}; RC(launch(ctx, k, nic, 128, STAGE_SOLVER_INIT)); }
-      // default: LwVelocity7K (records and bodies staged through a cp.async shared-memory ring; islands under 16
-      // contacts take LwVelocity5K) + LwPosition6K (two alternating register sets).  B2GPU_LW_VELOCITY selects the
-      // other forms for comparison (profiles/r01_large_world.md): 1 distance-1 pipelines with register moves,
-      // 2 LwVelocity4K, 3 LwVelocity5K + LwPositionK, 4 LwPosition4K, 5 LwVelocity5K + LwPosition5K,
-      // 6 LwVelocity5K + LwPosition6K, 8 LwVelocity7K + LwPosition7K (ring), 9 LwVelocity9K (alternating ring)
-      const int gs = bh->lw_velocity_variant;
-      if (gs != 1) { LwVcIdxK k = {B, L, nic}; RC(launch(ctx, k, nic, 256, STAGE_SOLVER_INIT)); }
-      if (gs == 1 || gs == 4) { LwVelocityK k = {B, sp, ni}; RC(launch(ctx, k, ni, 32, STAGE_VELOCITY)); }
-      else if (gs == 2) { LwVelocity4K k = {B, L, sp, ni}; RC(launch(ctx, k, ni, 32, STAGE_VELOCITY)); }
-      else if (gs == 3 || gs == 5 || gs == 6) { LwVelocity5K k = {B, L, sp, ni}; RC(launch(ctx, k, ni, 32, STAGE_VELOCITY)); }
-      else if (gs == 9) { LwVelocity9K k = {B, L, sp, ni}; RC(launch(ctx, k, ni, 32, STAGE_VELOCITY)); }
-      else { LwVelocity7K k = {B, L, sp, ni}; RC(launch(ctx, k, ni, 32, STAGE_VELOCITY)); }
+      // LwVelocity7K: records and bodies staged through a cp.async shared-memory ring (islands under 16 contacts take the
+      // register form LwVelocity5K); LwPosition6K: two alternating register sets.  The other forms round 1 measured
+      // (profiles/r01_large_world.md) were removed from the library.
+      { LwVcIdxK k = {B, L, nic}; RC(launch(ctx, k, nic, 256, STAGE_SOLVER_INIT)); }
+      { LwVelocity7K k = {B, L, sp, ni}; RC(launch(ctx, k, ni, 32, STAGE_VELOCITY)); }
       { PostVelocityK k = {B, sp}; RC(launch(ctx, k, std::max(std::max(ni, nib), nic), 128, STAGE_POST_VELOCITY)); }
-      if (gs == 4) { LwPosition4K k = {B, L, sp, ni}; RC(launch(ctx, k, ni, 32, STAGE_POSITION)); }
-      else if (gs == 1 || gs == 2 || gs == 3) { LwPositionK k = {B, sp, ni}; RC(launch(ctx, k, ni, 32, STAGE_POSITION)); }
-      else if (gs == 5) { LwPosition5K k = {B, L, sp, ni}; RC(launch(ctx, k, ni, 32, STAGE_POSITION)); }
-      else if (gs == 8) { LwPosition7K k = {B, L, sp, ni}; RC(launch(ctx, k, ni, 32, STAGE_POSITION)); }
-      else { LwPosition6K k = {B, L, sp, ni}; RC(launch(ctx, k, ni, 32, STAGE_POSITION)); }
+      { LwPosition6K k = {B, L, sp, ni}; RC(launch(ctx, k, ni, 32, STAGE_POSITION)); }
       { FinalizeK k = {B, sp}; RC(launch(ctx, k, nib, 128, STAGE_FINALIZE)); }
       { SleepK k = {B}; RC(launch(ctx, k, ni, 128, STAGE_SLEEP)); }
       { SyncFixturesK k = {B}; RC(launch(ctx, k, B.NP, 128, STAGE_SYNC_FIXTURES)); }
@@ -1381,7 +1363,7 @@ static int ensure_groups(BatchHost* bh) {
 
 // Enqueues `steps` steps (and the optional host copies) on the context stream / the stream groups.
 // Pure enqueue: no host synchronisation, so the same code runs under stream capture.
-static int enqueue_steps(BatchHost* bh, const StepParams& sp, int steps, const float* host_forces, float* host_state_out) {
+static int enqueue_steps(BatchHost* bh, const StepParams& sp, int steps, const float* host_forces, float* host_state_out, bool compact) {
   Batch& B = bh->B;
   Ctx* ctx = bh->ctx;
   (void)ctx;
@@ -1389,26 +1371,42 @@ static int enqueue_steps(BatchHost* bh, const StepParams& sp, int steps, const f
   all.wb_first = 0;
   all.wb_count = B.n_wblocks;
 #if defined(B2G_HOSTSIM)
-  if (host_forces) RC(batch_set_forces(bh, host_forces, 0, B.n_worlds));
+  if (host_forces) {
+    if (compact) {
+      memcpy(bh->forces_dev, host_forces, (size_t)B.n_worlds * bh->n_dyn * 3 * 4);
+      ForceScatterDynK k = {all, bh->forces_dev, bh->dyn_idx, bh->n_dyn, 0, B.n_worlds};
+      RC(launch(ctx, k, B.n_wblocks * B.LB * bh->n_dyn, 128));
+    } else RC(batch_set_forces(bh, host_forces, 0, B.n_worlds));
+  }
   if (bh->large) RC(step_large(bh, sp, steps));
   else RC(step_window(bh, all, sp, steps, nullptr));
+  if (host_state_out && compact) {
+    StateGatherDynK k = {all, bh->state_dev, bh->dyn_idx, bh->n_dyn};
+    RC(launch(ctx, k, B.n_wblocks * B.LB * bh->n_dyn, 128));
+    memcpy(host_state_out, bh->state_dev, (size_t)B.n_worlds * bh->n_dyn * 6 * 4);
+    int st = 0;
+    RC(batch_status(bh, &st));
+    return status_error(st);
+  }
   if (host_state_out) return batch_get_body_state(bh, host_state_out, 0, B.n_worlds);
   return 0;
 #else
+  const int fstride = compact ? bh->n_dyn * 3 : B.NB * 3, sstride = compact ? bh->n_dyn * 6 : B.NB * 8;
+  const int io_n = compact ? bh->n_dyn : B.NB;
   cudaStream_t main_s = (cudaStream_t)ctx->stream;
   const bool grouped = bh->groups.size() > 1 && !ctx->profiling && steps > 0 && !bh->large;
   if (!grouped) {
     if (host_forces) {
-      CU(cudaMemcpyAsync(bh->forces_dev, host_forces, (size_t)B.n_worlds * B.NB * 3 * 4, cudaMemcpyHostToDevice, main_s));
-      ForceScatterK k = {all, bh->forces_dev, 0, B.n_worlds};
-      RC(launch(ctx, k, B.n_wblocks * B.LB * B.NB, 128));
+      CU(cudaMemcpyAsync(bh->forces_dev, host_forces, (size_t)B.n_worlds * fstride * 4, cudaMemcpyHostToDevice, main_s));
+      if (compact) { ForceScatterDynK k = {all, bh->forces_dev, bh->dyn_idx, bh->n_dyn, 0, B.n_worlds}; RC(launch(ctx, k, B.n_wblocks * B.LB * io_n, 128)); }
+      else { ForceScatterK k = {all, bh->forces_dev, 0, B.n_worlds}; RC(launch(ctx, k, B.n_wblocks * B.LB * B.NB, 128)); }
     }
     if (bh->large) RC(step_large(bh, sp, steps));
     else RC(step_window(bh, all, sp, steps, nullptr));
     if (host_state_out) {
-      StateGatherK k = {all, bh->state_dev};
-      RC(launch(ctx, k, B.n_wblocks * B.LB * B.NB, 128));
-      CU(cudaMemcpyAsync(host_state_out, bh->state_dev, (size_t)B.n_worlds * B.NB * 8 * 4, cudaMemcpyDeviceToHost, main_s));
+      if (compact) { StateGatherDynK k = {all, bh->state_dev, bh->dyn_idx, bh->n_dyn}; RC(launch(ctx, k, B.n_wblocks * B.LB * io_n, 128)); }
+      else { StateGatherK k = {all, bh->state_dev}; RC(launch(ctx, k, B.n_wblocks * B.LB * B.NB, 128)); }
+      CU(cudaMemcpyAsync(host_state_out, bh->state_dev, (size_t)B.n_worlds * sstride * 4, cudaMemcpyDeviceToHost, main_s));
       { StatusK k = {all, bh->status_dev}; RC(launch(ctx, k, B.n_worlds, 128)); }
       CU(cudaMemcpyAsync(bh->status_host, bh->status_dev, 4, cudaMemcpyDeviceToHost, main_s));
     }
@@ -1427,11 +1425,11 @@ static int enqueue_steps(BatchHost* bh, const StepParams& sp, int steps, const f
     CU(cudaStreamWaitEvent(gs, (cudaEvent_t)bh->ev_entry, 0));
     ctx->stream = (void*)gs;
     if (host_forces && wn > 0) {
-      const size_t off = (size_t)w0 * B.NB * 3;
-      cudaError_t e = cudaMemcpyAsync(bh->forces_dev + off, host_forces + off, (size_t)wn * B.NB * 3 * 4, cudaMemcpyHostToDevice, gs);
+      const size_t off = (size_t)w0 * fstride;
+      cudaError_t e = cudaMemcpyAsync(bh->forces_dev + off, host_forces + off, (size_t)wn * fstride * 4, cudaMemcpyHostToDevice, gs);
       if (e != cudaSuccess) { ctx->stream = (void*)main_s; return cuda_fail(e, "cudaMemcpyAsync(forces)"); }
-      ForceScatterK k = {Bw, bh->forces_dev + off, w0, wn};
-      rc = launch(ctx, k, sg.wb_count * B.LB * B.NB, 128);
+      if (compact) { ForceScatterDynK k = {Bw, bh->forces_dev + off, bh->dyn_idx, bh->n_dyn, w0, wn}; rc = launch(ctx, k, sg.wb_count * B.LB * io_n, 128); }
+      else { ForceScatterK k = {Bw, bh->forces_dev + off, w0, wn}; rc = launch(ctx, k, sg.wb_count * B.LB * B.NB, 128); }
     }
     // stagger: start behind the previous group's solver set-up of its first step
     if (!rc && g > 0) {
@@ -1440,11 +1438,11 @@ static int enqueue_steps(BatchHost* bh, const StepParams& sp, int steps, const f
     }
     if (!rc) rc = step_window(bh, Bw, sp, steps, sg.ev_init);
     if (!rc && host_state_out && wn > 0) {
-      StateGatherK k = {Bw, bh->state_dev};
-      rc = launch(ctx, k, sg.wb_count * B.LB * B.NB, 128);
+      if (compact) { StateGatherDynK k = {Bw, bh->state_dev, bh->dyn_idx, bh->n_dyn}; rc = launch(ctx, k, sg.wb_count * B.LB * io_n, 128); }
+      else { StateGatherK k = {Bw, bh->state_dev}; rc = launch(ctx, k, sg.wb_count * B.LB * B.NB, 128); }
       if (!rc) {
-        const size_t off = (size_t)w0 * B.NB * 8;
-        cudaError_t e = cudaMemcpyAsync(host_state_out + off, bh->state_dev + off, (size_t)wn * B.NB * 8 * 4, cudaMemcpyDeviceToHost, gs);
+        const size_t off = (size_t)w0 * sstride;
+        cudaError_t e = cudaMemcpyAsync(host_state_out + off, bh->state_dev + off, (size_t)wn * sstride * 4, cudaMemcpyDeviceToHost, gs);
         if (e != cudaSuccess) { ctx->stream = (void*)main_s; return cuda_fail(e, "cudaMemcpyAsync(state)"); }
       }
     }
@@ -1475,31 +1473,32 @@ static bool host_pointer_capturable(const void* p) {  // memcpy nodes need page-
 // downloaded after the last.  The enqueue sequence of a call signature (dt, iterations, steps, host
 // pointers) is captured once into a CUDA graph and replayed afterwards: a step is 13 launches per stream
 // group, and at a few milliseconds per step the launch overhead of the host would otherwise show.
-static int run_steps(BatchHost* bh, float dt, int vi, int pi, int steps, const float* host_forces, float* host_state_out) {
+static int run_steps(BatchHost* bh, float dt, int vi, int pi, int steps, const float* host_forces, float* host_state_out, bool compact = false) {
   if (!bh || steps < 0 || vi < 0 || pi < 0) { set_error("batch_step: bad argument"); return B2GPU_E_INVALID; }
   Ctx* ctx = bh->ctx;
   (void)ctx;
   const StepParams sp = make_params(dt, vi, pi);
   bh->last_sp = sp;
 #if defined(B2G_HOSTSIM)
-  RC(enqueue_steps(bh, sp, steps, host_forces, host_state_out));
+  const int rc_sim = enqueue_steps(bh, sp, steps, host_forces, host_state_out, compact);
+  if (rc_sim && rc_sim != B2GPU_E_CAPACITY && rc_sim != B2GPU_E_UNSUPPORTED && rc_sim != B2GPU_E_INTERNAL) return rc_sim;
 #else
   RC(ensure_groups(bh));
   cudaStream_t main_s = (cudaStream_t)ctx->stream;
   const bool use_graph = bh->use_graphs && !bh->large && !ctx->profiling && steps > 0 && host_pointer_capturable(host_forces) &&
                          host_pointer_capturable(host_state_out);
   if (!use_graph) {
-    RC(enqueue_steps(bh, sp, steps, host_forces, host_state_out));
+    RC(enqueue_steps(bh, sp, steps, host_forces, host_state_out, compact));
   } else {
     StepGraph* hit = nullptr;
     for (StepGraph& sgph : bh->graphs)
       if (sgph.dt == dt && sgph.vi == vi && sgph.pi == pi && sgph.steps == steps && sgph.forces == (const void*)host_forces &&
-          sgph.state == (void*)host_state_out)
+          sgph.state == (void*)host_state_out && sgph.compact == compact)
         hit = &sgph;
     if (!hit) {
       const long long launches_before = ctx->launches;
       CU(cudaStreamBeginCapture(main_s, cudaStreamCaptureModeThreadLocal));
-      int rc = enqueue_steps(bh, sp, steps, host_forces, host_state_out);
+      int rc = enqueue_steps(bh, sp, steps, host_forces, host_state_out, compact);
       cudaGraph_t graph = nullptr;
       cudaError_t e = cudaStreamEndCapture(main_s, &graph);
       if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
@@ -1513,7 +1512,7 @@ static int run_steps(BatchHost* bh, float dt, int vi, int pi, int steps, const f
         bh->graphs.erase(bh->graphs.begin());
       }
       StepGraph ng;
-      ng.dt = dt; ng.vi = vi; ng.pi = pi; ng.steps = steps; ng.forces = host_forces; ng.state = host_state_out;
+      ng.dt = dt; ng.vi = vi; ng.pi = pi; ng.steps = steps; ng.forces = host_forces; ng.state = host_state_out; ng.compact = compact;
       ng.exec = (void*)exec;
       ng.launches = ctx->launches - launches_before;
       ctx->launches = launches_before;  // capture issued nothing; replays are counted below
@@ -1529,8 +1528,10 @@ static int run_steps(BatchHost* bh, float dt, int vi, int pi, int steps, const f
   if (steps > 0 && dt > 0.0f) bh->stepped = true;
 #if !defined(B2G_HOSTSIM)
   if (host_state_out) return status_error(*bh->status_host);
-#endif
   return 0;
+#else
+  return rc_sim;  // a device status raised by a world (the state was still written)
+#endif
 }
 
 int batch_step(BatchHost* bh, float dt, int vi, int pi, int steps) { return run_steps(bh, dt, vi, pi, steps, nullptr, nullptr); }
@@ -1625,6 +1626,20 @@ int batch_step_host(BatchHost* bh, const float* host_forces, float* host_state_o
   RC(run_steps(bh, dt, vi, pi, steps, host_forces, host_state_out));
   if (!host_state_out) RC(ctx_sync(bh->ctx));
   return 0;
+}
+
+int batch_step_host_dynamic(BatchHost* bh, const float* host_forces, float* host_state_out, float dt, int vi, int pi, int steps) {
+  if (!bh || bh->n_dyn <= 0) { set_error("step_host_dynamic: the prototype has no dynamic body"); return B2GPU_E_INVALID; }
+  RC(run_steps(bh, dt, vi, pi, steps, host_forces, host_state_out, true));
+  if (!host_state_out) RC(ctx_sync(bh->ctx));
+  return 0;
+}
+int batch_dynamic_bodies(BatchHost* bh, int* out, int capacity) {
+  if (!bh || capacity < 0 || (capacity > 0 && !out)) { set_error("dynamic_bodies: bad argument"); return B2GPU_E_INVALID; }
+  int n = 0;
+  for (int b = 0; b < bh->B.NB; ++b)
+    if (bh->topo.bodies[b].type == B2GPU_DYNAMIC_BODY) { if (n < capacity) out[n] = b; ++n; }
+  return n;
 }
 
 // sin/cos of an array of angles on the device (diagnostic: pins rot_from_angle against libm)

@@ -67,6 +67,7 @@ struct StepGraph {  // instantiated CUDA graph of one run_steps call signature
   int vi = 0, pi = 0, steps = 0;
   const void* forces = nullptr;
   void* state = nullptr;
+  bool compact = false;
   void* exec = nullptr;  // cudaGraphExec_t
   long long launches = 0;
 };
@@ -82,6 +83,8 @@ struct BatchHost {
   int* stack = nullptr;
   float* state_dev = nullptr;    // [n_worlds][NB][8] gather buffer
   float* forces_dev = nullptr;   // [n_worlds][NB][3]
+  int* dyn_idx = nullptr;        // [n_dyn] body indices of the prototype's dynamic bodies (compact I/O)
+  int n_dyn = 0;
   int* status_dev = nullptr;     // reduced WS_STATUS of the batch (StatusK)
   int* status_host = nullptr;    // pinned copy of it
   int last_fetch_status = 0;     // WS_STATUS of the world last fetched by image_fetch
@@ -89,15 +92,8 @@ struct BatchHost {
   size_t stage_bytes = 0;
   bool smem_island = false;      // shared-memory island DFS in use (b2g_island_smem.cuh)
   IslandSmemLayout island_layout;
-  bool tma_ring = false;         // velocity ring filled by cp.async.bulk + mbarrier instead of cp.async
   std::string timeline_path;        // diagnostic: where batch_destroy writes the Gauss-Seidel CTA timeline
-  bool ml2_velocity = false;        // experiment: straight-line level-scheduled velocity kernel (two lanes per world)
-  bool sl_position = false;         // straight-line position kernel (default for batches)
-  bool ws_velocity = false;         // diagnostic: straight-line velocity kernel with a producer warp (measured slower)
-  bool pipelined_velocity = false;  // diagnostic: the branchy pipelined velocity kernel instead of the straight-line one
-  bool ml_velocity = false;      // velocity stage also level-scheduled (experiment switch)
-  bool ml_solver = false;        // level-scheduled multi-lane Gauss-Seidel kernels in use
-  bool smem_solver = false;      // shared-memory Gauss-Seidel kernels in use (b2g_solver_smem.cuh)
+  bool smem_solver = false;      // straight-line shared-memory Gauss-Seidel kernels in use (b2g_solver_smem.cuh)
   std::vector<StreamGroup> groups;  // independent pipelines over windows of world blocks (created on first use)
   void* ev_entry = nullptr;         // cudaEvent_t: fork point on the context stream
   std::vector<StepGraph> graphs;    // CUDA graphs per call signature (see run_steps)
@@ -118,7 +114,6 @@ struct BatchHost {
   long long lw_keys = 0;         // capacity of the key buffers
   void* query_buf = nullptr;     // device scratch of the world-query calls (grown on demand)
   size_t query_bytes = 0;
-  int lw_velocity_variant = 0;   // diagnostic (B2GPU_LW_VELOCITY): 0 default (LwVelocity7K + LwPosition6K); others see step_large
 };
 
 const char* last_error();
@@ -135,6 +130,8 @@ int batch_download_world(BatchHost* b, int world, b2gpu_snapshot* out);
 int batch_step(BatchHost* b, float dt, int vi, int pi, int steps);
 int batch_step_host(BatchHost* b, const float* host_forces, float* host_state_out, float dt, int vi, int pi, int steps);
 int batch_get_stats(BatchHost* b, int first, int count, b2gpu_step_stats* out);
+int batch_step_host_dynamic(BatchHost* b, const float* host_forces, float* host_state_out, float dt, int vi, int pi, int steps);
+int batch_dynamic_bodies(BatchHost* b, int* out, int capacity);
 int batch_get_body_state(BatchHost* b, float* host_out, int first, int count);
 int batch_set_forces(BatchHost* b, const float* host, int first, int count);
 int batch_set_linear_velocity(BatchHost* b, int body, const float* host_vxvy, int first, int count);

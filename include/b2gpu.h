@@ -319,11 +319,8 @@ typedef struct b2gpu_caps {
   int32_t max_contacts; /* contacts per world (default: 10 per proxy for batches, 40 for a single world) */
   int32_t max_pairs;    /* ignored: pairs are handed to add_pair as the tree query reports them, no pair buffer */
   int32_t reserved[2]; /* reserved[0]: worlds per memory block (power of two; 0 = 32 for >= 32 worlds, else 1);
-                          reserved[1]: diagnostic switch, 0 = default kernels.  1 generic global-memory solver
-                          stages, 2 branchy one-lane position kernel, 3 level-scheduled velocity + position,
-                          4 TMA-fed velocity ring, 5 one stream (no stream groups), 6 no CUDA graphs, 7 branchy
-                          velocity kernel only, 8 velocity kernel with a producer warp, 9 level-scheduled
-                          position kernel, 10 straight-line level-scheduled velocity kernel (all bit-identical; profiles/r01_ncu_summary.md has their timings);
+                          reserved[1]: diagnostic switch, 0 = default kernels.  1 generic global-memory solver stages,
+                          5 one stream (no stream groups), 6 no CUDA graphs (all bit-identical);
                           11 / 12 large-world mode (one world only; see b2gpu_world_set_large_mode flag 1 / 2) */
 } b2gpu_caps;
 
@@ -542,6 +539,14 @@ void* b2gpu_batch_forces_device(b2gpu_batch* b, int64_t* bytes);
 /* One end-to-end step through HOST buffers: H2D forces, `steps` steps, D2H body state, synchronous. */
 int b2gpu_batch_step_host(b2gpu_batch* b, const float* host_forces, float* host_state_out, float dt,
                           int velocity_iterations, int position_iterations, int steps);
+/* The same round trip with compact I/O: only the prototype's DYNAMIC bodies, in body order (static bodies never move and
+ * ignore forces).  b2gpu_batch_dynamic_bodies returns their count nd (and fills up to `capacity` body indices);
+ * host_forces is [n_worlds][nd][3] (fx, fy, torque; may be NULL), host_state_out is [n_worlds][nd][6] =
+ * (c.x, c.y, a, v.x, v.y, w) — 24 B per body instead of 32 B for every body (xf.p follows from c, a and the local
+ * centre: src/b2_body.rs:974-977). */
+int b2gpu_batch_dynamic_bodies(b2gpu_batch* b, int32_t* out_body_indices, int capacity);
+int b2gpu_batch_step_host_dynamic(b2gpu_batch* b, const float* host_forces, float* host_state_out, float dt,
+                                  int velocity_iterations, int position_iterations, int steps);
 /* Algorithmic bytes of the last step summed over all worlds (SURVEY.md §8d formula). */
 int64_t b2gpu_batch_algorithmic_bytes(b2gpu_batch* b);
 

@@ -129,7 +129,7 @@ def test_batch_replicas_shared_memory_solver(name, steps, ctx):
     wg.close()
 
 
-@pytest.mark.parametrize("solver", ["lane", "generic", "levels", "tma", "pipelined", "producer", "ml_position", "levels2"])
+@pytest.mark.parametrize("solver", ["generic", "one_stream", "no_graph"])
 @pytest.mark.parametrize("name,steps", [("mixed300", 200), ("variety", 300), ("sensors", 200)])
 def test_alternative_solver_kernels(name, steps, solver, ctx):
     """The one-lane-per-world shared-memory kernels and the generic global-memory stages stay available

@@ -82,3 +82,37 @@ def test_capacity_overflow_is_reported_gpu(built):
 @pytest.mark.gpu
 def test_reset_equals_fresh_batch_gpu(built):
     _reset_equals_fresh(True)
+
+
+def _compact_io(gpu):
+    """b2gpu_batch_step_host_dynamic: dynamic bodies only, 6 floats each, equals the full-layout round trip."""
+    from box2d_rs_b200 import scenes, world
+    ctx = _ctx(gpu)
+    wg = world.B2world((0.0, -10.0), ctx=ctx)
+    scenes.pyramid(wg)
+    n = 40 if gpu else 3
+    a, b = wg.batch(n, max_contacts=800), wg.batch(n, max_contacts=800)
+    dyn = a.dynamic_bodies()
+    assert dyn.tolist() == list(range(2, 212))
+    rng = np.random.default_rng(3)
+    full = np.zeros((n, a.body_count, 8), np.float32)
+    comp = np.zeros((n, len(dyn), 6), np.float32)
+    for _ in range(12):
+        f = np.zeros((n, a.body_count, 3), np.float32)
+        f[:, 2:, :2] = rng.uniform(-20.0, 20.0, (n, 210, 2)).astype(np.float32)
+        a.step_host(f, full, scenes.DT, 8, 3, 1)
+        b.step_host_dynamic(np.ascontiguousarray(f[:, dyn]), comp, scenes.DT, 8, 3, 1)
+        assert np.array_equal(full[:, dyn, :6].view(np.uint32), comp.view(np.uint32))
+    a.close()
+    b.close()
+    wg.close()
+    ctx.close()
+
+
+def test_compact_io(built):
+    _compact_io(False)
+
+
+@pytest.mark.gpu
+def test_compact_io_gpu(built):
+    _compact_io(True)
