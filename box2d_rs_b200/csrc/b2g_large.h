@@ -50,6 +50,8 @@ struct Large {  // device scratch of the large-world mode
   // sort keys (LBVH Morton keys, edge-list keys)
   u64* keys;      // [NK]
   u64* keys_alt;  // [NK]
+  unsigned* sort_in;   // [2 NP] Morton codes, then proxy indices (32-bit key / value pairs of the LBVH sort)
+  unsigned* sort_out;  // [2 NP]
   // LBVH over the NP proxies: internal nodes 0..n-2 (0 = root), leaves by sorted position
   float4* lb_box;  // [NP] boxes of internal nodes
   int2* lb_child;  // [NP] children: >= 0 internal node, < 0 leaf at sorted position ~c
@@ -621,7 +623,18 @@ struct LwMortonK {  // flat over proxies: key = Morton code of the fat-box centr
     fy = fy > 0.0f ? fy : 0.0f;
     const unsigned qx = fx < 65535.0f ? (unsigned)fx : 65535u, qy = fy < 65535.0f ? (unsigned)fy : 65535u;
     const unsigned code = lw_spread16(qx) | (lw_spread16(qy) << 1);
-    L.keys[p] = ((u64)code << 32) | (u64)(unsigned)p;
+    // (code, proxy) as a 32-bit key / value pair: a stable 4-pass radix sort by code leaves equal codes in proxy order,
+    // i.e. the order of the unique 64-bit keys code << 32 | proxy that LwKeyPackK rebuilds (an 8-pass sort before)
+    L.sort_in[p] = code;
+    L.sort_in[B.NP + p] = (unsigned)p;
+  }
+};
+struct LwKeyPackK {  // flat over proxies: sorted (code, proxy) pairs -> unique 64-bit keys for the radix-tree construction
+  Batch B;
+  Large L;
+  B2G_HD void operator()(int i) const {
+    if (i >= B.NP) return;
+    L.keys_alt[i] = ((u64)L.sort_out[i] << 32) | (u64)L.sort_out[B.NP + i];
   }
 };
 B2G_HD int lw_clz64(u64 v) {
@@ -1270,8 +1283,8 @@ struct LwStatsK {  // touching / awake counters on demand: phase 0 one thread (r
       ws[WS_ST_CONTACTS] = cc;
       return;
     }
-    if (t < cc && (B.c_flags[t] & B2GPU_CONTACT_TOUCHING)) B2G_ATOMIC_ADD(&ws[WS_ST_TOUCHING], 1);
-    if (t < B.NB && (B.b_flags[t] & B2GPU_BODY_AWAKE)) B2G_ATOMIC_ADD(&ws[WS_ST_AWAKE], 1);
+    if (t < cc && (B.c_flags[t] & B2GPU_CONTACT_TOUCHING)) counter_inc(&ws[WS_ST_TOUCHING]);
+    if (t < B.NB && (B.b_flags[t] & B2GPU_BODY_AWAKE)) counter_inc(&ws[WS_ST_AWAKE]);
   }
 };
 struct LwStepEndK {  // one thread: the tail of TreePairsK

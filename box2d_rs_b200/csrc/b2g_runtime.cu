@@ -707,6 +707,7 @@ int batch_upload_world(BatchHost* bh, int world, const b2gpu_snapshot* in) {
   std::vector<ArrRef> tab = array_table(bh, im);
   for (const ArrRef& a : tab) RC(move_array(bh, a, 0, world));
   bh->pre_step_needed = true;
+  bh->lw_cc_valid = false;
   RC(dev_zero(bh->ctx, bh->status_dev, 4));  // recomputed from the worlds' own (sticky) status words on the next check
   return 0;
 }
@@ -995,8 +996,23 @@ static int lw_sort_keys(BatchHost*, const u64* in, u64* out, int n, int, int) {
   std::sort(out, out + n);
   return 0;
 }
+static int lw_sort_pairs32(BatchHost*, const unsigned* kin, unsigned* kout, const unsigned* vin, unsigned* vout, int n, int) {
+  std::vector<int> order(n);
+  for (int i = 0; i < n; ++i) order[i] = i;
+  std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return kin[a] < kin[b]; });
+  for (int i = 0; i < n; ++i) { kout[i] = kin[order[i]]; vout[i] = vin[order[i]]; }
+  return 0;
+}
 static int lw_read(BatchHost* bh, const void* dev, int words) { memcpy(bh->lw_host, dev, (size_t)words * 4); return 0; }
 #else
+static int lw_sort_pairs32(BatchHost* bh, const unsigned* kin, unsigned* kout, const unsigned* vin, unsigned* vout, int n, int stage) {
+  if (n <= 0) return 0;
+  LaunchScope ls = {bh->ctx, stage};
+  RC(ls.begin());
+  size_t bytes = bh->lw_tmp_bytes;
+  CU(cub::DeviceRadixSort::SortPairs(bh->lw_tmp, bytes, kin, kout, vin, vout, n, 0, 32, (cudaStream_t)bh->ctx->stream));
+  return ls.end();
+}
 static int lw_scan_int(BatchHost* bh, const int* in, int* out, int n, int stage) {
   if (n <= 0) return 0;
   LaunchScope ls = {bh->ctx, stage};
@@ -1042,7 +1058,7 @@ static int large_alloc(BatchHost* bh) {
   L.NCAND = 2 * B.NC + B.NP;
   int rc = 0;
 #define AL(ptr, count) do { rc = alloc_arr(bh, &ptr, (count)); if (rc) return rc; } while (0)
-  AL(L.keys, bh->lw_keys); AL(L.keys_alt, bh->lw_keys);
+  AL(L.keys, bh->lw_keys); AL(L.keys_alt, bh->lw_keys); AL(L.sort_in, 2LL * B.NP); AL(L.sort_out, 2LL * B.NP);
   AL(L.lb_box, B.NP); AL(L.lb_child, B.NP); AL(L.lb_parent, 2LL * B.NP); AL(L.lb_flag, B.NP); AL(L.lb_leaf, B.NP);
   const long long nq = std::max(B.NMOVE, B.NMW) + 1;
   AL(L.q_cnt, nq); AL(L.q_off, nq); AL(L.q_local, (long long)B.NMOVE * LW_QLOCAL);
@@ -1064,6 +1080,8 @@ static int large_alloc(BatchHost* bh) {
   CU(cub::DeviceScan::ExclusiveSum(nullptr, b, (const u64*)nullptr, (u64*)nullptr, B.NB + 1));
   need = std::max(need, b);
   CU(cub::DeviceRadixSort::SortKeys(nullptr, b, (const u64*)nullptr, (u64*)nullptr, (int)bh->lw_keys, 0, 64));
+  need = std::max(need, b);
+  CU(cub::DeviceRadixSort::SortPairs(nullptr, b, (const unsigned*)nullptr, (unsigned*)nullptr, (const unsigned*)nullptr, (unsigned*)nullptr, B.NP, 0, 32));
   need = std::max(need, b);
   void* v = nullptr;
   RC(dev_alloc(&v, need + 256));
@@ -1101,14 +1119,16 @@ static int lw_build_lbvh(BatchHost* bh, int stage) {
   const Large& L = bh->L;
   const int n = B.NP;
   { LwMortonK k = {B, L}; RC(launch(ctx, k, n, 256, stage)); }
-  RC(lw_sort_keys(bh, L.keys, L.keys_alt, n, 64, stage));
+  RC(lw_sort_pairs32(bh, L.sort_in, L.sort_out, L.sort_in + n, L.sort_out + n, n, stage));
+  { LwKeyPackK k = {B, L}; RC(launch(ctx, k, n, 256, stage)); }
   { LwKarrasK k = {B, L, n}; RC(launch(ctx, k, n, 128, stage)); }
   { LwRefitK k = {B, L, n}; RC(launch(ctx, k, n, 128, stage)); }
   return 0;
 }
 
 // B2broadPhase::update_pairs + add_pair over the current move buffer (mc entries, cc contacts before)
-static int lw_update_pairs(BatchHost* bh, int mc, int cc, int stage, int use_tree) {
+static int lw_update_pairs(BatchHost* bh, int mc, int cc, int stage, int use_tree, int* created_out = nullptr) {
+  if (created_out) *created_out = 0;
   Ctx* ctx = bh->ctx;
   const Batch& B = bh->B;
   const Large& L = bh->L;
@@ -1137,6 +1157,7 @@ static int lw_update_pairs(BatchHost* bh, int mc, int cc, int stage, int use_tre
   { LwClearMovedK k = {B, mc}; RC(launch(ctx, k, mc, 256, stage)); }
   { LwPairsFinishK k = {B, mc, n_cand, created, status}; RC(launch(ctx, k, 1, 32, stage)); }
   if (created > 0) RC(lw_rebuild_lists(bh, cc + created, stage));
+  if (created_out) *created_out = created;
   return 0;
 }
 
@@ -1149,8 +1170,12 @@ static int step_large(BatchHost* bh, const StepParams& sp, int steps) {
   for (int s = 0; s < steps; ++s) {
     // ---- top of step: stats, find_new_contacts when m_new_contacts (b2_world.rs(private):912-915)
     { LwStatsResetK k = {B}; RC(launch(ctx, k, 1, 32, STAGE_PRE)); }
-    RC(lw_read(bh, B.ws, WS_COUNT));
-    int cc = hw[WS_CONTACT_COUNT];
+    // the contact count is known on the host from the previous step of this call sequence (count after the
+    // destruction pass + contacts created): one read-back and stream synchronisation less per step
+    const bool know = bh->lw_cc_valid && !(bh->pre_step_needed && s == 0);
+    if (!know) RC(lw_read(bh, B.ws, WS_COUNT));
+    else hw[WS_FLAGS] &= ~B2GPU_WORLD_NEW_CONTACTS;
+    int cc = know ? bh->lw_cc : hw[WS_CONTACT_COUNT];
     if (bh->pre_step_needed && s == 0) RC(lw_rebuild_lists(bh, cc, STAGE_PRE));  // first step after an upload: contact rows
     if (hw[WS_FLAGS] & B2GPU_WORLD_NEW_CONTACTS) {
       const int mc = hw[WS_MOVE_COUNT];
@@ -1236,8 +1261,12 @@ static int step_large(BatchHost* bh, const StepParams& sp, int steps) {
         if (mc > B.NMOVE) { set_error("move buffer capacity exceeded"); return B2GPU_E_CAPACITY; }
         { LwMoveFinishK k = {B, mc}; RC(launch(ctx, k, 1, 32, STAGE_TREE_PAIRS)); }
       }
-      RC(lw_update_pairs(bh, mc, cc, STAGE_TREE_PAIRS, bh->lw_exact_tree ? 1 : 0));
+      int created = 0;
+      RC(lw_update_pairs(bh, mc, cc, STAGE_TREE_PAIRS, bh->lw_exact_tree ? 1 : 0, &created));
+      cc += created;
     }
+    bh->lw_cc = cc;
+    bh->lw_cc_valid = true;
     { LwStepEndK k = {B, sp}; RC(launch(ctx, k, 1, 32, STAGE_TREE_PAIRS)); }
     { BodyEndK k = {B}; RC(launch(ctx, k, B.NB, 128, STAGE_BODY_END)); }
   }

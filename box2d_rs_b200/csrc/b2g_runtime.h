@@ -108,6 +108,8 @@ struct BatchHost {
   bool lw_exact_tree = false;    // large-world mode that keeps the replica tree (sequential re-insertion, reference contact order)
   Large L = {};
   int* lw_host = nullptr;        // pinned readback buffer (world scalars, scan totals)
+  int lw_cc = 0;                 // contact count after the last large-mode step (host copy)
+  bool lw_cc_valid = false;
   void* lw_tmp = nullptr;        // scan / sort temporary storage
   size_t lw_tmp_bytes = 0;
   int lw_edge_bits = 0, lw_body_bits = 0;

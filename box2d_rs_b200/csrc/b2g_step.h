@@ -37,6 +37,19 @@
 
 namespace b2g {
 
+// ws counter += 1 from many threads.  In a single large world (LB = 1) every thread of a flat stage hits the SAME
+// word (100k proxies leaving their fat boxes in one step: ncu showed SyncFixturesK three times slower than on a
+// batch of nine times as many proxies), so lanes that target one address elect a leader that adds their count.
+B2G_HD void counter_inc(int* p) {
+#if defined(__CUDA_ARCH__)
+  const unsigned active = __activemask();
+  const unsigned peers = __match_any_sync(active, (unsigned long long)p);
+  if ((threadIdx.x & 31) == (unsigned)(__ffs((int)peers) - 1)) atomicAdd(p, __popc(peers));
+#else
+  *p += 1;
+#endif
+}
+
 // internal contact flag bits (never leave the device)
 enum { CF_DESTROY = 0x100, CF_SKIPPED = 0x200, CF_WOKE = 0x400, CF_INTERNAL = 0xff00 };
 
@@ -108,7 +121,7 @@ B2G_HD void collide_one(const Batch& B, const WIdx& x, const Ws& ws, int c, int*
     if (flags & B2GPU_CONTACT_FILTER) {
       if (!body_should_collide(bfb, bfa) || joints_prevent_collision(B, bb, ba) || !filter_should_collide(fa, fb)) {
         B.c_flags[ci] = flags | CF_DESTROY;
-        B2G_ATOMIC_ADD(&ws[WS_EV_DESTROY], 1);
+        counter_inc(&ws[WS_EV_DESTROY]);
         return;
       }
       flags &= ~B2GPU_CONTACT_FILTER;
@@ -132,7 +145,7 @@ B2G_HD void collide_one(const Batch& B, const WIdx& x, const Ws& ws, int c, int*
   const int node_a = B.proxy_s[fa.proxy_first + fx.z].z, node_b = B.proxy_s[fb.proxy_first + fx.w].z;
   if (!box_overlap(load_box(B.n_aabb, x.at(B.NN, node_a)), load_box(B.n_aabb, x.at(B.NN, node_b)))) {
     B.c_flags[ci] = flags | CF_DESTROY;
-    B2G_ATOMIC_ADD(&ws[WS_EV_DESTROY], 1);
+    counter_inc(&ws[WS_EV_DESTROY]);
     return;
   }
   // ---- B2contact::update
@@ -1101,7 +1114,7 @@ struct SyncFixturesK {
     // visits exactly the moved proxies, in the reference's order, without scanning all of them
     const int rank = B.sync_rank[p];
     B2G_ATOMIC_OR(&B.p_move[x.at(B.NMW, rank >> 5)], 1 << (rank & 31));
-    B2G_ATOMIC_ADD(&ws[WS_EV_MOVED], 1);
+    counter_inc(&ws[WS_EV_MOVED]);
   }
 };
 

@@ -66,6 +66,7 @@ def lib():
         L.b2o_joint_set_limits.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float]
         L.b2o_set_collect_dag.argtypes = [C.c_void_p, C.c_int, C.c_double]
         L.b2o_get_dag_stats.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
+        L.b2o_get_dag_cyclic.argtypes = [C.c_void_p, C.POINTER(C.c_double)]
         L.b2o_step.argtypes = [C.c_void_p, C.c_float, C.c_int, C.c_int]
         L.b2o_body_count.argtypes = [C.c_void_p]
         L.b2o_contact_count.argtypes = [C.c_void_p]
@@ -281,7 +282,12 @@ class B2world:
         lib().b2o_get_dag_stats(self.h, out)
         keys = ("contacts", "bodies", "sweeps", "depth", "depth_one_sweep", "handover", "makespan_256", "makespan_1024",
                 "makespan_4096", "makespan_16384")
-        return dict(zip(keys, list(out)))
+        d = dict(zip(keys, list(out)))
+        cyc = (C.c_double * 12)()
+        lib().b2o_get_dag_cyclic(self.h, cyc)
+        d["cyclic"] = {"chunk%d_workers%d" % (c, p): cyc[3 * i + j] for i, c in enumerate((1, 4, 16, 64))
+                       for j, p in enumerate((2048, 16384, 65536))}
+        return d
 
     def step(self, dt, velocity_iterations, position_iterations):
         lib().b2o_step(self.h, dt, velocity_iterations, position_iterations)

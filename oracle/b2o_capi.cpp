@@ -197,6 +197,11 @@ void b2o_get_dag_stats(void* w, double* out10) {
   out10[5] = ((World*)w)->dag_handover;
   for (int i = 0; i < 4; ++i) out10[6 + i] = d.makespan[i];
 }
+void b2o_get_dag_cyclic(void* w, double* out12) {
+  const World::DagStats& d = ((World*)w)->dag;
+  for (int i = 0; i < 4; ++i)
+    for (int j = 0; j < 3; ++j) out12[3 * i + j] = d.makespan_cyclic[i][j];
+}
 void b2o_step(void* w, float dt, int vi, int pi) { ((World*)w)->step(dt, vi, pi); }
 int b2o_body_count(void* w) { return (int)((World*)w)->bodies.size(); }
 int b2o_contact_count(void* w) { return ((World*)w)->contact_count; }

@@ -1352,6 +1352,9 @@ struct World {
   struct DagStats {
     int contacts = 0, bodies = 0, sweeps = 0, depth = 0, depth_one_sweep = 0;
     double makespan[4] = {0, 0, 0, 0};  // workers = 256, 1024, 4096, 16384
+    // cyclic schedule: chunks of `chunk` consecutive constraints dealt round-robin to `workers` threads (the dataflow
+    // solver's mapping): makespan_cyclic[i][j] for chunk = {1, 4, 16, 64}[i], workers = {2048, 16384, 65536}[j]
+    double makespan_cyclic[4][3] = {{0}};
   };
   DagStats dag;
   void dag_collect(const Island& is, int sweeps, double handover) {
@@ -1386,6 +1389,30 @@ struct World {
         }
       dag.makespan[wi] = end;
     }
+    const int chunks[4] = {1, 4, 16, 64}, nworkers[3] = {2048, 16384, 65536};
+    for (int ci = 0; ci < 4; ++ci)
+      for (int wi = 0; wi < 3; ++wi) {
+        const int c = chunks[ci], P = nworkers[wi];
+        std::vector<double> bfin(is.bodies.size(), 0.0), tfin(P, 0.0);
+        std::vector<int> bown(is.bodies.size(), -1);
+        double end = 0.0;
+        for (int s = 0; s < sweeps; ++s)
+          for (size_t k = 0; k < vcs.size(); ++k) {
+            const ContactVelocityConstraint& vc = vcs[k];
+            const int p = (int)((k / c) % P);
+            const bool dyn_a = vc.inv_mass_a != 0.0f || vc.inv_ia != 0.0f;
+            const bool dyn_b = vc.inv_mass_b != 0.0f || vc.inv_ib != 0.0f;
+            double start = tfin[p];
+            if (dyn_a) start = std::max(start, bfin[vc.index_a] + (bown[vc.index_a] != p && bown[vc.index_a] >= 0 ? handover : 0.0));
+            if (dyn_b) start = std::max(start, bfin[vc.index_b] + (bown[vc.index_b] != p && bown[vc.index_b] >= 0 ? handover : 0.0));
+            const double fin = start + 1.0;
+            tfin[p] = fin;
+            if (dyn_a) { bfin[vc.index_a] = fin; bown[vc.index_a] = p; }
+            if (dyn_b) { bfin[vc.index_b] = fin; bown[vc.index_b] = p; }
+            end = std::max(end, fin);
+          }
+        dag.makespan_cyclic[ci][wi] = end;
+      }
   }
 
   void island_solve(Island& is, const TimeStep& step) {  // b2_island_private.rs:129-328
