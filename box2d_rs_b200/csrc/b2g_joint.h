@@ -49,16 +49,32 @@ B2G_HD bool joints_prevent_collision(const Batch& B, int self_, int other) {
   return false;
 }
 
+// Where a joint visit reads and writes the running body state.  BodyStateGlobal: the per-world arrays in HBM (generic
+// stages, host simulator).  The shared-memory Gauss-Seidel kernels of b2g_solver_smem.cuh pass accessors over their
+// [body][lane] rows instead, so joint rows run inside velocity_sl_kernel / position_sl_kernel.
+struct BodyStateGlobal {
+  const Batch& B;
+  const WIdx& x;
+  B2G_HD float4 vel(int b) const { return B.b_vel[x.at(B.NB, b)]; }
+  B2G_HD void set_vel(int b, float4 v) const { B.b_vel[x.at(B.NB, b)] = v; }
+  B2G_HD float4 pos(int b) const { return B.b_pos[x.at(B.NB, b)]; }   // c.x c.y a sleep_time
+  B2G_HD void set_pos(int b, float4 p) const { B.b_pos[x.at(B.NB, b)] = p; }
+  B2G_HD Rot rot(int b) const { const float4 r = B.b_rot[x.at(B.NB, b)]; Rot q; q.s = r.x; q.c = r.y; return q; }
+  B2G_HD void set_rot(int b, Rot q) const { float4 r = B.b_rot[x.at(B.NB, b)]; r.x = q.s; r.y = q.c; B.b_rot[x.at(B.NB, b)] = r; }
+};
+
 // init_velocity_constraints of joint j: solver data into j_tmp, impulses scaled (or zeroed) in j_s0 / j_s1, the warm-start
 // impulse applied to the two bodies' velocities.
-B2G_HD void joint_init_velocity(const Batch& B, const WIdx& x, int j, bool warm_starting, float dt_ratio, float h) {
+template <class S>
+B2G_HD void joint_init_velocity(const Batch& B, const WIdx& x, const S& st, int j, bool warm_starting, float dt_ratio, float h) {
   const b2gpu_joint_rec& jr = B.joints[j];
   const int bai = x.at(B.NB, jr.body_a), bbi = x.at(B.NB, jr.body_b);
   const float4 msa = B.b_mass[bai], msb = B.b_mass[bbi];
   const float m_a = msa.x, i_a = msa.y, m_b = msb.x, i_b = msb.y;
-  const float4 pa = B.b_pos[bai], pb = B.b_pos[bbi];
-  const float4 ra4 = B.b_rot[bai], rb4 = B.b_rot[bbi];  // B2Rot::new(a) of the island body's angle (IntegrateK)
-  float4 va = B.b_vel[bai], vb = B.b_vel[bbi];
+  const float4 pa = st.pos(jr.body_a), pb = st.pos(jr.body_b);
+  const Rot rqa = st.rot(jr.body_a), rqb = st.rot(jr.body_b);  // B2Rot::new(a) of the island body's angle (IntegrateK)
+  const float4 ra4 = make_float4(rqa.s, rqa.c, 0.0f, 0.0f), rb4 = make_float4(rqb.s, rqb.c, 0.0f, 0.0f);
+  float4 va = st.vel(jr.body_a), vb = st.vel(jr.body_b);
   V2 v_a = v2(va.x, va.y), v_b = v2(vb.x, vb.y);
   float w_a = va.z, w_b = vb.z;
   const V2 c_a = v2(pa.x, pa.y), c_b = v2(pb.x, pb.y);
@@ -146,14 +162,14 @@ B2G_HD void joint_init_velocity(const Batch& B, const WIdx& x, int j, bool warm_
   B.j_tmp[jt_at(B, x, j, 2)] = t2;
   B.j_tmp[jt_at(B, x, j, 3)] = make_float4(m_a, i_a, m_b, i_b);
   // an immovable body may sit in several islands: its velocity never changes, leave it alone
-  if (m_a != 0.0f || i_a != 0.0f) B.b_vel[bai] = make_float4(v_a.x, v_a.y, w_a, 0.0f);
-  if (m_b != 0.0f || i_b != 0.0f) B.b_vel[bbi] = make_float4(v_b.x, v_b.y, w_b, 0.0f);
+  if (m_a != 0.0f || i_a != 0.0f) st.set_vel(jr.body_a, make_float4(v_a.x, v_a.y, w_a, 0.0f));
+  if (m_b != 0.0f || i_b != 0.0f) st.set_vel(jr.body_b, make_float4(v_b.x, v_b.y, w_b, 0.0f));
 }
 
-B2G_HD void joint_solve_velocity(const Batch& B, const WIdx& x, int j, float h, float inv_dt) {
+template <class S>
+B2G_HD void joint_solve_velocity(const Batch& B, const WIdx& x, const S& st, int j, float h, float inv_dt) {
   const b2gpu_joint_rec& jr = B.joints[j];
-  const int bai = x.at(B.NB, jr.body_a), bbi = x.at(B.NB, jr.body_b);
-  const float4 va = B.b_vel[bai], vb = B.b_vel[bbi];
+  const float4 va = st.vel(jr.body_a), vb = st.vel(jr.body_b);
   V2 v_a = v2(va.x, va.y), v_b = v2(vb.x, vb.y);
   float w_a = va.z, w_b = vb.z;
   const float4 t0 = B.j_tmp[jt_at(B, x, j, 0)], t1 = B.j_tmp[jt_at(B, x, j, 1)], t2 = B.j_tmp[jt_at(B, x, j, 2)];
@@ -272,24 +288,22 @@ B2G_HD void joint_solve_velocity(const Batch& B, const WIdx& x, int j, float h, 
   }
   B.j_s0[ji] = s0;
   B.j_s1[ji] = s1;
-  if (m_a != 0.0f || i_a != 0.0f) B.b_vel[bai] = make_float4(v_a.x, v_a.y, w_a, 0.0f);
-  if (m_b != 0.0f || i_b != 0.0f) B.b_vel[bbi] = make_float4(v_b.x, v_b.y, w_b, 0.0f);
+  if (m_a != 0.0f || i_a != 0.0f) st.set_vel(jr.body_a, make_float4(v_a.x, v_a.y, w_a, 0.0f));
+  if (m_b != 0.0f || i_b != 0.0f) st.set_vel(jr.body_b, make_float4(v_b.x, v_b.y, w_b, 0.0f));
 }
 
 // solve_position_constraints of joint j; returns "within tolerance".  b_rot caches B2Rot::new of the running angle (the
 // contact position solver relies on it), so it is refreshed whenever this joint changed an angle's bits.
-B2G_HD bool joint_solve_position(const Batch& B, const WIdx& x, int j) {
+template <class S>
+B2G_HD bool joint_solve_position(const Batch& B, const WIdx& x, const S& st, int j) {
   const b2gpu_joint_rec& jr = B.joints[j];
   const int bai = x.at(B.NB, jr.body_a), bbi = x.at(B.NB, jr.body_b);
   const float4 msa = B.b_mass[bai], msb = B.b_mass[bbi];
   const float m_a = msa.x, i_a = msa.y, m_b = msb.x, i_b = msb.y;
-  float4 pa = B.b_pos[bai], pb = B.b_pos[bbi];
-  float4 ra4 = B.b_rot[bai], rb4 = B.b_rot[bbi];
+  float4 pa = st.pos(jr.body_a), pb = st.pos(jr.body_b);
   V2 c_a = v2(pa.x, pa.y), c_b = v2(pb.x, pb.y);
   float a_a = pa.z, a_b = pb.z;
-  Rot q_a, q_b;
-  q_a.s = ra4.x; q_a.c = ra4.y;
-  q_b.s = rb4.x; q_b.c = rb4.y;
+  Rot q_a = st.rot(jr.body_a), q_b = st.rot(jr.body_b);
   const V2 la = v2(jr.local_anchor_a[0], jr.local_anchor_a[1]) - v2(msa.z, msa.w);
   const V2 lb = v2(jr.local_anchor_b[0], jr.local_anchor_b[1]) - v2(msb.z, msb.w);
   bool okay;
@@ -349,22 +363,14 @@ B2G_HD bool joint_solve_position(const Batch& B, const WIdx& x, int j) {
     okay = fabsf(c) < B2G_LINEAR_SLOP;
   }
   if (m_a != 0.0f || i_a != 0.0f) {  // immovable bodies are shared between islands: never written
-    if (f2u(a_a) != f2u(pa.z)) {
-      const Rot q = rot_from_angle(a_a);
-      ra4.x = q.s; ra4.y = q.c;
-      B.b_rot[bai] = ra4;
-    }
+    if (f2u(a_a) != f2u(pa.z)) st.set_rot(jr.body_a, rot_from_angle(a_a));
     pa.x = c_a.x; pa.y = c_a.y; pa.z = a_a;
-    B.b_pos[bai] = pa;
+    st.set_pos(jr.body_a, pa);
   }
   if (m_b != 0.0f || i_b != 0.0f) {
-    if (f2u(a_b) != f2u(pb.z)) {
-      const Rot q = rot_from_angle(a_b);
-      rb4.x = q.s; rb4.y = q.c;
-      B.b_rot[bbi] = rb4;
-    }
+    if (f2u(a_b) != f2u(pb.z)) st.set_rot(jr.body_b, rot_from_angle(a_b));
     pb.x = c_b.x; pb.y = c_b.y; pb.z = a_b;
-    B.b_pos[bbi] = pb;
+    st.set_pos(jr.body_b, pb);
   }
   return okay;
 }

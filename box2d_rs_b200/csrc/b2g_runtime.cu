@@ -626,8 +626,7 @@ int batch_create(Ctx* ctx, const b2gpu_snapshot* proto, int n_worlds, const b2gp
 #if !defined(B2G_HOSTSIM)
   // shared-memory Gauss-Seidel stages: batches in 32-world memory blocks whose bodies fit one SM
   bh->smem_solver = false;
-  // worlds with joints take the generic per-island Gauss-Seidel stages (joint visits interleave with contact visits)
-  if (B.LB == 32 && !(caps && caps->reserved[1] == 1) && B.NJ == 0) {
+  if (B.LB == 32 && !(caps && caps->reserved[1] == 1)) {
     int max_optin = 0;
     CU(cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, ctx->device));
     const size_t need = std::max(velocity_smem_bytes(B.NB), position_sl_smem_bytes(B.NB));
@@ -651,7 +650,8 @@ int batch_create(Ctx* ctx, const b2gpu_snapshot* proto, int n_worlds, const b2gp
     if (caps && caps->reserved[1] == 5) bh->stream_groups = 1;
     if (caps && caps->reserved[1] == 6) bh->use_graphs = false;
     bh->island_layout = island_smem_layout(B.NB, B.NF, (size_t)max_optin - 1024);
-    if (B.NB < 32768 && B.NC < 65536 && bh->island_layout.ECAP >= 64) {
+    // worlds with joints build their islands with the generic traversal (joint edges: SerialAK::islands_global)
+    if (B.NB < 32768 && B.NC < 65536 && bh->island_layout.ECAP >= 64 && B.NJ == 0) {
       CU(cudaFuncSetAttribute(island_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bh->island_layout.total));
       bh->smem_island = true;
     }

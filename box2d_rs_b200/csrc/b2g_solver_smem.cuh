@@ -55,6 +55,29 @@ constexpr int POS_RING = 8;
 inline size_t velocity_smem_bytes(int NB) { return (size_t)(NB + 1) * 32 * 16 + (size_t)VEL_RING * VC_Q * 32 * 16 + VEL_RING * 8; }
 inline size_t position_smem_bytes(int NB) { return (size_t)NB * 32 * (16 + 8) + (size_t)POS_RING * PC_Q * 32 * 16; }
 
+// Body-state accessors of the joint rows (b2g_joint.h) over this file's [body][lane] shared-memory rows.
+struct BodyStateVelSmem {  // velocity stage: velocities in shared memory, positions / rotations read-only in HBM
+  const Batch& B;
+  const WIdx& x;
+  float4* vl;  // this lane's column of the velocity rows
+  __device__ __forceinline__ float4 vel(int b) const { return vl[b * 32]; }
+  __device__ __forceinline__ void set_vel(int b, float4 v) const { vl[b * 32] = v; }
+  __device__ __forceinline__ float4 pos(int b) const { return B.b_pos[x.at(B.NB, b)]; }
+  __device__ __forceinline__ Rot rot(int b) const { const float4 r = B.b_rot[x.at(B.NB, b)]; Rot q; q.s = r.x; q.c = r.y; return q; }
+  __device__ __forceinline__ void set_pos(int, float4) const {}
+  __device__ __forceinline__ void set_rot(int, Rot) const {}
+};
+struct BodyStatePosSmem {  // position stage: positions and cached rotations in shared memory
+  float4* pl;
+  float2* ql;
+  __device__ __forceinline__ float4 vel(int) const { return make_float4(0.0f, 0.0f, 0.0f, 0.0f); }
+  __device__ __forceinline__ void set_vel(int, float4) const {}
+  __device__ __forceinline__ float4 pos(int b) const { return pl[b * 32]; }
+  __device__ __forceinline__ void set_pos(int b, float4 p) const { pl[b * 32] = p; }
+  __device__ __forceinline__ Rot rot(int b) const { const float2 r = ql[b * 32]; Rot q; q.s = r.x; q.c = r.y; return q; }
+  __device__ __forceinline__ void set_rot(int b, Rot q) const { ql[b * 32] = make_float2(q.s, q.c); }
+};
+
 struct VcRegs {  // one velocity constraint of one world, in registers
   float4 q0, q1, q2, q3, q4, q5, q6, q7;
   int ba, bb, cnt;
@@ -72,8 +95,10 @@ __device__ __forceinline__ VcRegs vc_load(const float4* st) {
 
 // Resident form of the velocity stage: the whole constraint stream of the block fits the ring; load it once
 // and iterate in shared memory (small islands).
+template <class JointInit, class JointSolve>
 __device__ __forceinline__ void velocity_resident(float4* rl, float4* vl, const float4* src, float4* q6_out, int nc, int ncm,
-                                                  bool warm, bool block, int sweeps) {
+                                                  bool warm, bool block, int sweeps, const JointInit& joint_init,
+                                                  const JointSolve& joint_solve) {
   for (int k = 0; k < ncm; ++k) {
 #pragma unroll
     for (int q = 0; q < VC_Q; ++q) cp_async16(rl + (k * VC_Q + q) * 32, src + (size_t)(k * VC_Q + q) * 32);
@@ -81,6 +106,9 @@ __device__ __forceinline__ void velocity_resident(float4* rl, float4* vl, const 
   cp_async_commit();
   cp_async_wait<0>();
   for (int sweep = 0; sweep < sweeps; ++sweep) {
+    // joints: init_velocity_constraints after the contact warm start, then before the contacts in every iteration
+    if (sweep == 1) joint_init();
+    if (sweep >= 1) joint_solve();
     if (sweep == 0 && !__any_sync(0xffffffffu, warm)) continue;
     for (int k = 0; k < ncm; ++k) {
       if (k >= nc || (sweep == 0 && !warm)) continue;
@@ -102,6 +130,7 @@ __device__ __forceinline__ void velocity_resident(float4* rl, float4* vl, const 
       vl[c.bb * 32] = make_float4(s.v_b.x, s.v_b.y, s.w_b, 0.0f);
     }
   }
+  if (sweeps == 1) joint_init();  // no velocity iterations: the joints' warm start still applies (b2_island_private.rs:198-201)
 }
 
 // ------------------------------------------------------------------------------------------
@@ -151,15 +180,27 @@ __global__ void __launch_bounds__(32) velocity_sl_kernel(const Batch B, const St
   const bool warm = (wflags & B2GPU_WORLD_WARM_STARTING) != 0;
   const bool block = (wflags & B2GPU_WORLD_BLOCK_SOLVE) != 0;
   const int ncm = __reduce_max_sync(0xffffffffu, nc);
-  if (ncm == 0) return;
+  // joints of this lane's world, all islands concatenated in island order: islands share no movable body, so one pass
+  // over the concatenation equals the reference's per-island passes
+  const int nj = (live && B.NJ > 0) ? ws[WS_ISL_JOINTS] : 0;
+  const int njm = B.NJ > 0 ? __reduce_max_sync(0xffffffffu, nj) : 0;
+  if (ncm == 0 && njm == 0) return;
   if (live)
     for (int b = 0; b < B.NB; ++b) vel[b * 32 + lane] = B.b_vel[x.at(B.NB, b)];
   const float4* src = B.vc + (size_t)wb * B.NC * VC_Q * 32 + lane;  // + (k * VC_Q + q) * 32
   float4* q6_out = B.vc + (size_t)wb * B.NC * VC_Q * 32 + 6 * 32 + lane;
   float4* vl = vel + lane;
   float4* rl = ring + lane;
+  const BodyStateVelSmem jst = {B, x, vl};
+  const float dt_ratio = live ? i2f(ws[WS_INV_DT0]) * sp.dt : 0.0f;
+  auto joint_init = [&]() {
+    for (int q = 0; q < nj; ++q) joint_init_velocity(B, x, jst, B.isl_joint[x.at(B.NJ, q)], warm, dt_ratio, sp.dt);
+  };
+  auto joint_solve = [&]() {
+    for (int q = 0; q < nj; ++q) joint_solve_velocity(B, x, jst, B.isl_joint[x.at(B.NJ, q)], sp.dt, sp.inv_dt);
+  };
   if (ncm <= VEL_RING) {
-    velocity_resident(rl, vl, src, q6_out, nc, ncm, warm, block, 1 + sp.velocity_iterations);
+    velocity_resident(rl, vl, src, q6_out, nc, ncm, warm, block, 1 + sp.velocity_iterations, joint_init, joint_solve);
   } else {
     const int n_warm = __any_sync(0xffffffffu, warm) ? ncm : 0;  // positions of the warm-start sweep
     const int total = n_warm + sp.velocity_iterations * ncm;
@@ -251,7 +292,19 @@ __global__ void __launch_bounds__(32) velocity_sl_kernel(const Batch B, const St
       }
     };
     run_to(std::true_type{}, n_warm);
-    run_to(std::false_type{}, total);
+    if (njm == 0) {
+      run_to(std::false_type{}, total);
+    } else {
+      // joint rows between the contact sweeps: they change velocities in the shared-memory rows, so the velocities the
+      // pipeline already holds for its current constraint are re-read afterwards
+      joint_init();
+      for (int it = 0; it < sp.velocity_iterations; ++it) {
+        joint_solve();
+        vaa = vl[ca.ba * 32];
+        vab = vl[ca.bb * 32];
+        run_to(std::false_type{}, n_warm + (it + 1) * ncm);
+      }
+    }
     cp_async_wait<0>();
   }
   __syncwarp();
@@ -307,7 +360,7 @@ __device__ __forceinline__ void cp_async_prec(float4* smem_dst, const float4* gm
 }
 
 inline size_t position_sl_smem_bytes(int NB) {
-  return (size_t)POS_RING * PC_Q * 32 * 16 + (size_t)(NB + 1) * 32 * (16 + 8) + (size_t)(NB + 1) * 32;
+  return (size_t)POS_RING * PC_Q * 32 * 16 + (size_t)(NB + 1) * 32 * (16 + 8) + 2 * (size_t)(NB + 1) * 32;
 }
 
 __global__ void __launch_bounds__(32) position_sl_kernel(const Batch B, const StepParams sp) {
@@ -317,6 +370,7 @@ __global__ void __launch_bounds__(32) position_sl_kernel(const Batch B, const St
   float4* pos = smem4 + POS_RING * PC_Q * 32;                    // [NB + 1][32]: c.x c.y a -; row NB is scratch
   float2* rot = (float2*)(pos + (size_t)(B.NB + 1) * 32);        // [NB + 1][32]: sin a, cos a
   unsigned char* tab = (unsigned char*)(rot + (size_t)(B.NB + 1) * 32);  // [NB + 1][32]: island solved; row NB is scratch
+  unsigned char* tab_prev = tab + (size_t)(B.NB + 1) * 32;               // [NB + 1][32]: the table before the current sweep (joints)
   const int lane = threadIdx.x;
   const int wb = blockIdx.x + B.wb_first;
   const int w = wb * 32 + lane;
@@ -327,7 +381,9 @@ __global__ void __launch_bounds__(32) position_sl_kernel(const Batch B, const St
   const int nc = live ? ws[WS_ISL_CONTACTS] : 0;
   const int nisl = live ? ws[WS_ISL_COUNT] : 0;
   const int ncm = __reduce_max_sync(0xffffffffu, nc);
-  if (ncm == 0 || sp.position_iterations <= 0) return;
+  const int nj = (live && B.NJ > 0) ? ws[WS_ISL_JOINTS] : 0;
+  const int njm = B.NJ > 0 ? __reduce_max_sync(0xffffffffu, nj) : 0;
+  if ((ncm == 0 && njm == 0) || sp.position_iterations <= 0) return;
   if (live) {
     for (int b = 0; b < B.NB; ++b) {
       const float4 p = B.b_pos[x.at(B.NB, b)];
@@ -354,14 +410,17 @@ __global__ void __launch_bounds__(32) position_sl_kernel(const Batch B, const St
     fk = wrap ? 0 : fk + 1;
     fsrc = wrap ? src : fsrc + PC_Q * 32;
   };
+  if (ncm > 0) {
 #pragma unroll
-  for (int p = 0; p < POS_RING; ++p) fetch(p);
+    for (int p = 0; p < POS_RING; ++p) fetch(p);
+  }
   PcRegs ca, cb;
   bool acta = false, actb = false, fa = true, fb = true;
   float4 paa, pab, pba, pbb;
   float2 qaa, qab, qba, qbb;
   int k = 0, p = 0;
-  bool done = !live || nc == 0, all_solved = true;
+  bool done = !live || (nc == 0 && nj == 0), all_solved = true;
+  const BodyStatePosSmem jst = {pl, ql};
   float min_separation = 0.0f;
   // activity of the constraint at stream index kk whose record is r: its island is still open in this sweep
   auto prepare = [&](PcRegs& r, int kk, bool& act, bool& fast, float4& pa, float4& pb, float2& qa, float2& qb) {
@@ -439,17 +498,40 @@ __global__ void __launch_bounds__(32) position_sl_kernel(const Batch B, const St
     else half(std::false_type{}, cb, actb, pba, pbb, qba, qbb, ca, acta, fa, paa, pab, qaa, qab);
   };
   for (int sweep = 0; sweep < sp.position_iterations; ++sweep) {
-    // prologue of the sweep: position p (stream index 0) from its ring stage
-    k = 0;
-    cp_async_wait<POS_RING - 1>();
-    ca = pc_load(rl + ((p & (POS_RING - 1)) * PC_Q) * 32);
-    prepare(ca, 0, acta, fa, paa, pab, qaa, qab);
-    int i = 0;
-    for (; i + 2 <= ncm; i += 2) {
-      step_ab();
-      step_ba();
+    if (njm > 0 && !done)
+      for (int i = 0; i < nisl; ++i) tab_prev[i * 32 + lane] = tl[i * 32];
+    if (ncm > 0) {
+      // prologue of the sweep: position p (stream index 0) from its ring stage
+      k = 0;
+      cp_async_wait<POS_RING - 1>();
+      ca = pc_load(rl + ((p & (POS_RING - 1)) * PC_Q) * 32);
+      prepare(ca, 0, acta, fa, paa, pab, qaa, qab);
+      int i = 0;
+      for (; i + 2 <= ncm; i += 2) {
+        step_ab();
+        step_ba();
+      }
+      if (i < ncm) step_ab();
     }
-    if (i < ncm) step_ab();
+    if (njm > 0 && !done) {
+      // joint rows after the contact rows (b2_island_private.rs:262-266), island by island: an island that was open at the
+      // start of this sweep solves all its joints; it is solved when its contacts passed (closed to 1 by this sweep, or it
+      // has none) AND every joint is within tolerance
+      all_solved = true;
+      for (int i = 0; i < nisl; ++i) {
+        if (tab_prev[i * 32 + lane] == 0) {
+          const int4 rg = B.isl_range[x.at(B.NB, i)];
+          const int2 jr = B.isl_jrange[x.at(B.NB, i)];
+          bool ok = tl[i * 32] != 0 || rg.z == rg.w;
+          for (int q = jr.x; q < jr.y; ++q) {
+            const bool joint_okay = joint_solve_position(B, x, jst, B.isl_joint[x.at(B.NJ, q)]);
+            ok = ok && joint_okay;
+          }
+          tl[i * 32] = (unsigned char)(ok ? 1 : 0);
+        }
+        all_solved = all_solved && tl[i * 32] != 0;
+      }
+    }
     // end of the sweep: a world is finished when every island passed the exit test
     if (!done && all_solved) done = true;
     all_solved = true;
@@ -458,7 +540,7 @@ __global__ void __launch_bounds__(32) position_sl_kernel(const Batch B, const St
   }
   cp_async_wait<0>();
   __syncwarp();
-  if (live && nc > 0) {
+  if (live && (nc > 0 || nj > 0)) {
     // the rows carry the fourth component of b_pos (sleep time) through unchanged; of b_rot only the running
     // rotation (first two components) is written, so neither store needs a read
     for (int b = 0; b < B.NB; ++b) {

@@ -764,9 +764,10 @@ struct VelocityK {
     // init_velocity_constraints (which applies the joint's own warm start), then per iteration joints before contacts
     if (warm) contact_sweep(x, rg, true, block);
     const float dt_ratio = i2f(ws[WS_INV_DT0]) * sp.dt;
-    for (int q = jr.x; q < jr.y; ++q) joint_init_velocity(B, x, B.isl_joint[x.at(B.NJ, q)], warm, dt_ratio, sp.dt);
+    const BodyStateGlobal st = {B, x};
+    for (int q = jr.x; q < jr.y; ++q) joint_init_velocity(B, x, st, B.isl_joint[x.at(B.NJ, q)], warm, dt_ratio, sp.dt);
     for (int it = 0; it < sp.velocity_iterations; ++it) {
-      for (int q = jr.x; q < jr.y; ++q) joint_solve_velocity(B, x, B.isl_joint[x.at(B.NJ, q)], sp.dt, sp.inv_dt);
+      for (int q = jr.x; q < jr.y; ++q) joint_solve_velocity(B, x, st, B.isl_joint[x.at(B.NJ, q)], sp.dt, sp.inv_dt);
       contact_sweep(x, rg, false, block);
     }
   }
@@ -984,7 +985,7 @@ struct PositionK {
       }
       bool joints_okay = true;  // b2_island_private.rs:262-266: every joint is solved, none short-circuits
       for (int q = jr.x; q < jr.y; ++q) {
-        const bool joint_okay = joint_solve_position(B, x, B.isl_joint[x.at(B.NJ, q)]);
+        const bool joint_okay = joint_solve_position(B, x, BodyStateGlobal{B, x}, B.isl_joint[x.at(B.NJ, q)]);
         joints_okay = joints_okay && joint_okay;
       }
       if (min_separation >= -3.0f * B2G_LINEAR_SLOP && joints_okay) {
