@@ -78,6 +78,9 @@ struct Large {  // device scratch of the large-world mode
   u64* pk_in;      // [NB + 1] islands in seed order: 1 << 44 | bodies << 24 | contacts
   u64* pk_out;     // [NB + 1]
   int* isl_seed;   // [NB]
+  int* cnt_j;      // [NB] per root: joints of the component (joints with an enabled other body)
+  int* pj_in;      // [NB + 1] joint counts in seed order
+  int* pj_out;     // [NB + 1]
   int* wake_idx;   // [NB + 1] collide wake-up cascade (LwWakeK); [NB] = another round needed
   int* state;      // [NB] island traversal: 0 unvisited, 1 on the stack, 2 listed
   // per-body contact rows (CSR): the edges 2 c + side of a body, ascending = oldest first
@@ -318,6 +321,7 @@ struct LwIslInitK {  // flat over max(NB, cc)
       L.uf_parent[t] = t;
       L.cnt_b[t] = 0;
       L.cnt_c[t] = 0;
+      if (B.NJ > 0) L.cnt_j[t] = 0;
       L.seed[t] = -1;
       L.state[t] = 0;
       B.b_flags[t] &= ~B2GPU_BODY_ISLAND;
@@ -330,6 +334,14 @@ struct LwUnionK {  // flat over contacts
   Large L;
   int cc;
   B2G_HD void operator()(int c) const {
+    if (c < B.NJ) {  // joints connect their two bodies like contacts do (b2_world.rs(private):461-483): static bodies do not
+                     // propagate, and a joint to a disabled body is not simulated
+      const b2gpu_joint_rec& jr = B.joints[c];
+      const int fa = B.b_flags[jr.body_a], fb = B.b_flags[jr.body_b];
+      if (body_type(fa) != B2GPU_STATIC_BODY && body_type(fb) != B2GPU_STATIC_BODY && (fa & B2GPU_BODY_ENABLED) &&
+          (fb & B2GPU_BODY_ENABLED))
+        uf_union(L.uf_parent, jr.body_a, jr.body_b);
+    }
     if (c >= cc) return;
     int ba, bb;
     if (!lw_contact_eligible(B, c, ba, bb)) return;
@@ -357,6 +369,14 @@ struct LwCountK {  // flat over max(NB, cc): sizes and seed of every component, 
         if (body_type(B.b_flags[m]) != B2GPU_STATIC_BODY) B2G_ATOMIC_ADD(&L.cnt_c[uf_find(L.uf_parent, m)], 1);
       }
     }
+    if (t < B.NJ) {  // a joint belongs to the island of its movable body (both movable: the same island)
+      const b2gpu_joint_rec& jr = B.joints[t];
+      const int fa = B.b_flags[jr.body_a], fb = B.b_flags[jr.body_b];
+      if ((fa & B2GPU_BODY_ENABLED) && (fb & B2GPU_BODY_ENABLED)) {
+        const int m = body_type(fa) != B2GPU_STATIC_BODY ? jr.body_a : jr.body_b;
+        if (body_type(B.b_flags[m]) != B2GPU_STATIC_BODY) B2G_ATOMIC_ADD(&L.cnt_j[uf_find(L.uf_parent, m)], 1);
+      }
+    }
   }
 };
 enum { LW_PK_ISL = 44, LW_PK_BODY = 24 };
@@ -371,9 +391,12 @@ struct LwSeedPackK {  // flat over NB + 1, newest body first: one entry per isla
       if (body_type(B.b_flags[b]) != B2GPU_STATIC_BODY) {
         const int r = uf_find(L.uf_parent, b);
         L.uf_parent[b] = r;
-        if (L.seed[r] == b) v = ((u64)1 << LW_PK_ISL) | ((u64)L.cnt_b[r] << LW_PK_BODY) | (u64)L.cnt_c[r];
-      }
-    }
+        if (L.seed[r] == b) {
+          v = ((u64)1 << LW_PK_ISL) | ((u64)L.cnt_b[r] << LW_PK_BODY) | (u64)L.cnt_c[r];
+          if (B.NJ > 0) L.pj_in[i] = L.cnt_j[r];
+        } else if (B.NJ > 0) L.pj_in[i] = 0;
+      } else if (B.NJ > 0) L.pj_in[i] = 0;
+    } else if (B.NJ > 0) L.pj_in[i] = 0;
     L.pk_in[i] = v;
   }
 };
@@ -391,12 +414,14 @@ struct LwRangeK {  // flat over NB + 1
       ws[WS_TOPO_DIRTY] = 0;  // the island traversal raises it again when a sleeper joined
       ws[WS_ISL_VALID] = 1;
       ws[WS_SCHED_ROUNDS] = -1;
+      ws[WS_ISL_JOINTS] = B.NJ > 0 ? L.pj_out[i] : 0;
       return;
     }
     if (!(L.pk_in[i] >> LW_PK_ISL)) return;
     const int b = B.NB - 1 - i;
     const int r = L.uf_parent[b];
     B.isl_range[isl] = make_int4(bf, bf + L.cnt_b[r], cf, cf + L.cnt_c[r]);
+    if (B.NJ > 0) B.isl_jrange[isl] = make_int2(L.pj_out[i], L.pj_out[i] + L.cnt_j[r]);
     L.isl_seed[isl] = b;
   }
 };
@@ -440,6 +465,7 @@ struct LwDfsK {
     const int4 rg = B.isl_range[isl];
     int* st = stack + rg.x;
     int nb = rg.x, nc = rg.z, sp_ = 0;
+    int nj = B.NJ > 0 ? B.isl_jrange[isl].x : 0;
     const int seed = L.isl_seed[isl];
     st[sp_++] = seed;
     L.state[seed] = 1;
@@ -482,8 +508,24 @@ struct LwDfsK {
           L.state[other] = 1;
         }
       }
+      // joints of this body, newest edge first (b2_world.rs(private):461-483).  "Already in the island" needs no joint
+      // flag either: a joint is added when the first of its movable bodies is listed
+      if (B.NJ > 0)
+        for (int q = B.jadj_off[b]; q < B.jadj_off[b + 1]; ++q) {
+          const int je = B.jadj[q], jn = je >> 1;
+          const int other = (je & 1) ? B.joints[jn].body_a : B.joints[jn].body_b;
+          const int of = B.b_flags[other];
+          if (!(of & B2GPU_BODY_ENABLED)) continue;
+          const bool is_static = body_type(of) == B2GPU_STATIC_BODY;
+          const int so = is_static ? 0 : L.state[other];
+          if (!is_static && so == 2) continue;
+          B.isl_joint[nj++] = jn;
+          if (is_static || so != 0) continue;
+          st[sp_++] = other;
+          L.state[other] = 1;
+        }
     }
-    if (nb != rg.y || nc != rg.w) B.ws[WS_STATUS] = B2GPU_E_INTERNAL;
+    if (nb != rg.y || nc != rg.w || (B.NJ > 0 && nj != B.isl_jrange[isl].y)) B.ws[WS_STATUS] = B2GPU_E_INTERNAL;
   }
 };
 struct LwIslFlagsK {  // flat over max(island bodies, island contacts): what the traversal leaves on bodies and contacts
@@ -833,6 +875,7 @@ struct LwAddPairK {  // flat over candidates (+1 tail): the tests of add_pair, n
       if (fx.x == fixture_b && fx.y == fixture_a && fx.z == index_b && fx.w == index_a) return;
     }
     if (!body_should_collide(fb_, fa_)) return;
+    if (joints_prevent_collision(B, body_b, body_a)) return;
     const b2gpu_fixture_rec* fa = &B.fixtures[fixture_a];
     const b2gpu_fixture_rec* fb = &B.fixtures[fixture_b];
     if (!filter_should_collide(*fa, *fb)) return;
@@ -1012,44 +1055,71 @@ B2G_HD void lw_velocity_run(const Batch& B, const Large& L, int first, int n, in
     if (++k == n) k = 0;
   }
 }
-struct LwVelocity5K {
-  Batch B;
-  Large L;
-  StepParams sp;
-  int n_islands;
-  B2G_HD void operator()(int isl) const {
-    if (isl >= n_islands) return;
-    const int4 rg = B.isl_range[isl];
-    if (rg.z == rg.w) return;
-    const bool warm = (B.ws[WS_FLAGS] & B2GPU_WORLD_WARM_STARTING) != 0;
-    const bool block = (B.ws[WS_FLAGS] & B2GPU_WORLD_BLOCK_SOLVE) != 0;
-    const int first = rg.z, n = rg.w - rg.z;
-    if (n < 4) {  // the pipeline assumes a constraint is not in flight twice: tiny islands take the plain loop
-      for (int it = warm ? -1 : 0; it < sp.velocity_iterations; ++it) {
-        for (int k = rg.z; k < rg.w; ++k) {
-          const int4 ix = L.vc_idx[k];
-          if (ix.z == 0) continue;
-          const float4 va = B.b_vel[ix.x], vb = B.b_vel[ix.y];
-          VelState s;
-          s.v_a = v2(va.x, va.y); s.w_a = va.z;
-          s.v_b = v2(vb.x, vb.y); s.w_b = vb.z;
-          LwVcRec r = lw_load_vc(B.vc, k);
-          if (it < 0) {
-            warm_start_one(s, r.q0, r.q1, r.q2, r.q6, r.q7, ix.z);
-          } else {
-            solve_velocity_one(s, r.q0, r.q1, r.q2, r.q3, r.q4, r.q5, r.q6, r.q7, ix.z, block);
-            B.vc[(size_t)k * VC_Q + 6] = r.q6;
-          }
-          if (r.q7.x != 0.0f || r.q7.y != 0.0f) B.b_vel[ix.x] = make_float4(s.v_a.x, s.v_a.y, s.w_a, 0.0f);
-          if (r.q7.z != 0.0f || r.q7.w != 0.0f) B.b_vel[ix.y] = make_float4(s.v_b.x, s.v_b.y, s.w_b, 0.0f);
+// `sweeps` passes of one kind (warm start, or velocity iterations) over the contact constraints [first, first + n) of an
+// island in the register-pipelined form; islands under four contacts take the plain loop.
+template <bool WARM>
+B2G_HD void lw_contact_sweeps_small(const Batch& B, const Large& L, int first, int n, int sweeps, bool block) {
+  if (n <= 0 || sweeps <= 0) return;
+  if (n < 4) {  // the pipeline assumes a constraint is not in flight twice
+    for (int it = 0; it < sweeps; ++it) {
+      for (int k = first; k < first + n; ++k) {
+        const int4 ix = L.vc_idx[k];
+        if (ix.z == 0) continue;
+        const float4 va = B.b_vel[ix.x], vb = B.b_vel[ix.y];
+        VelState s;
+        s.v_a = v2(va.x, va.y); s.w_a = va.z;
+        s.v_b = v2(vb.x, vb.y); s.w_b = vb.z;
+        LwVcRec r = lw_load_vc(B.vc, k);
+        if (WARM) {
+          warm_start_one(s, r.q0, r.q1, r.q2, r.q6, r.q7, ix.z);
+        } else {
+          solve_velocity_one(s, r.q0, r.q1, r.q2, r.q3, r.q4, r.q5, r.q6, r.q7, ix.z, block);
+          B.vc[(size_t)k * VC_Q + 6] = r.q6;
         }
+        if (r.q7.x != 0.0f || r.q7.y != 0.0f) B.b_vel[ix.x] = make_float4(s.v_a.x, s.v_a.y, s.w_a, 0.0f);
+        if (r.q7.z != 0.0f || r.q7.w != 0.0f) B.b_vel[ix.y] = make_float4(s.v_b.x, s.v_b.y, s.w_b, 0.0f);
       }
-      return;
     }
-    if (warm) lw_velocity_run<true>(B, L, first, n, 1, block);
-    if (sp.velocity_iterations > 0) lw_velocity_run<false>(B, L, first, n, sp.velocity_iterations, block);
+    return;
   }
-};
+  lw_velocity_run<WARM>(B, L, first, n, sweeps, block);
+}
+// Joint rows of island `isl` (large-world mode: LB = 1, body state in the plain arrays)
+B2G_HD void lw_joints_init(const Batch& B, int isl, bool warm, const StepParams& sp) {
+  if (B.NJ == 0) return;
+  const int2 jr = B.isl_jrange[isl];
+  WIdx x;
+  x.wb = 0; x.wl = 0; x.LB = 1;
+  const BodyStateGlobal st = {B, x};
+  const float dt_ratio = i2f(B.ws[WS_INV_DT0]) * sp.dt;
+  for (int q = jr.x; q < jr.y; ++q) joint_init_velocity(B, x, st, B.isl_joint[q], warm, dt_ratio, sp.dt);
+}
+B2G_HD void lw_joints_velocity(const Batch& B, int isl, const StepParams& sp) {
+  if (B.NJ == 0) return;
+  const int2 jr = B.isl_jrange[isl];
+  WIdx x;
+  x.wb = 0; x.wl = 0; x.LB = 1;
+  const BodyStateGlobal st = {B, x};
+  for (int q = jr.x; q < jr.y; ++q) joint_solve_velocity(B, x, st, B.isl_joint[q], sp.dt, sp.inv_dt);
+}
+B2G_HD bool lw_joints_position(const Batch& B, int isl) {
+  if (B.NJ == 0) return true;
+  const int2 jr = B.isl_jrange[isl];
+  WIdx x;
+  x.wb = 0; x.wl = 0; x.LB = 1;
+  const BodyStateGlobal st = {B, x};
+  bool ok = true;
+  for (int q = jr.x; q < jr.y; ++q) {
+    const bool joint_okay = joint_solve_position(B, x, st, B.isl_joint[q]);
+    ok = ok && joint_okay;
+  }
+  return ok;
+}
+B2G_HD bool lw_island_has_joints(const Batch& B, int isl) {
+  if (B.NJ == 0) return false;
+  const int2 jr = B.isl_jrange[isl];
+  return jr.x != jr.y;
+}
 
 // ------------------------------------------------------------------------------------------
 // Velocity sweeps through a cp.async shared-memory ring (experiment, B2GPU_LW_VELOCITY=7).  Prefetching into
@@ -1180,17 +1250,34 @@ struct LwVelocity7K {
 #endif
     if (isl >= n_islands) return;
     const int4 rg = B.isl_range[isl];
-    if (rg.z == rg.w) return;
+    const bool joints = lw_island_has_joints(B, isl);
+    if (rg.z == rg.w && !joints) return;
     const bool warm = (B.ws[WS_FLAGS] & B2GPU_WORLD_WARM_STARTING) != 0;
     const bool block = (B.ws[WS_FLAGS] & B2GPU_WORLD_BLOCK_SOLVE) != 0;
     const int first = rg.z, n = rg.w - rg.z;
-    if (n < 2 * LW_RING) {  // a record must not be in the ring while its impulses are rewritten: small islands take the register form
-      LwVelocity5K small = {B, L, sp, n_islands};
-      small(isl);
+    const bool small = n < 2 * LW_RING;  // a record must not be in the ring while its impulses are rewritten: small islands take the register form
+    if (!joints) {
+      if (small) {
+        if (warm) lw_contact_sweeps_small<true>(B, L, first, n, 1, block);
+        lw_contact_sweeps_small<false>(B, L, first, n, sp.velocity_iterations, block);
+      } else {
+        if (warm) lw_velocity_ring<true>(B, first, n, 1, block, ring, bod, stride, L.scratch4 + 8);
+        if (sp.velocity_iterations > 0) lw_velocity_ring<false>(B, first, n, sp.velocity_iterations, block, ring, bod, stride, L.scratch4 + 8);
+      }
       return;
     }
-    if (warm) lw_velocity_ring<true>(B, first, n, 1, block, ring, bod, stride, L.scratch4 + 8);
-    if (sp.velocity_iterations > 0) lw_velocity_ring<false>(B, first, n, sp.velocity_iterations, block, ring, bod, stride, L.scratch4 + 8);
+    // an island with joints (b2_island_private.rs:193-215): contact warm start, every joint's init_velocity_constraints,
+    // then per iteration the joint rows before the contact rows
+    if (warm) {
+      if (small) lw_contact_sweeps_small<true>(B, L, first, n, 1, block);
+      else lw_velocity_ring<true>(B, first, n, 1, block, ring, bod, stride, L.scratch4 + 8);
+    }
+    lw_joints_init(B, isl, warm, sp);
+    for (int it = 0; it < sp.velocity_iterations; ++it) {
+      lw_joints_velocity(B, isl, sp);
+      if (small) lw_contact_sweeps_small<false>(B, L, first, n, 1, block);
+      else lw_velocity_ring<false>(B, first, n, 1, block, ring, bod, stride, L.scratch4 + 8);
+    }
   }
 };
 
@@ -1245,26 +1332,30 @@ struct LwPosition6K {
   B2G_HD void operator()(int isl) const {
     if (isl >= n_islands) return;
     const int4 rg = B.isl_range[isl];
-    if (rg.z == rg.w) return;
+    const bool joints = lw_island_has_joints(B, isl);
+    if (rg.z == rg.w && !joints) return;
     const int first = rg.z, n = rg.w - rg.z;
     float4* scratch = L.scratch4 + 4;  // where the "results" of immovable bodies go
     for (int it = 0; it < sp.position_iterations; ++it) {
       float min_separation = 0.0f;
-      LwPosSet s0, s1;
-      const int last = first + n - 1;
-      s0.ix = L.vc_idx[first];
-      s1.ix = L.vc_idx[first + 1 <= last ? first + 1 : last];
-      s1.hba = -1; s1.hbb = -1;
-      s1.pa = s1.ra = s1.pb = s1.rb = make_float4(0, 0, 0, 0);
-      lw_pos_request(B, L, first, s0);
-      int k = 0;
-      for (; k + 2 <= n; k += 2) {
-        const int c1 = first + k + 1, c2 = first + k + 2 <= last ? first + k + 2 : last, c3 = first + k + 3 <= last ? first + k + 3 : last;
-        min_separation = lw_pos_visit(B, L, scratch, s0, s1, c1, c2, min_separation);
-        min_separation = lw_pos_visit(B, L, scratch, s1, s0, c2, c3, min_separation);
+      if (n > 0) {
+        LwPosSet s0, s1;
+        const int last = first + n - 1;
+        s0.ix = L.vc_idx[first];
+        s1.ix = L.vc_idx[first + 1 <= last ? first + 1 : last];
+        s1.hba = -1; s1.hbb = -1;
+        s1.pa = s1.ra = s1.pb = s1.rb = make_float4(0, 0, 0, 0);
+        lw_pos_request(B, L, first, s0);
+        int k = 0;
+        for (; k + 2 <= n; k += 2) {
+          const int c1 = first + k + 1, c2 = first + k + 2 <= last ? first + k + 2 : last, c3 = first + k + 3 <= last ? first + k + 3 : last;
+          min_separation = lw_pos_visit(B, L, scratch, s0, s1, c1, c2, min_separation);
+          min_separation = lw_pos_visit(B, L, scratch, s1, s0, c2, c3, min_separation);
+        }
+        if (k < n) min_separation = lw_pos_visit(B, L, scratch, s0, s1, -1, last, min_separation);
       }
-      if (k < n) min_separation = lw_pos_visit(B, L, scratch, s0, s1, -1, last, min_separation);
-      if (min_separation >= -3.0f * B2G_LINEAR_SLOP) {  // b2_island_private.rs:257-274
+      const bool joints_okay = !joints || lw_joints_position(B, isl);  // :262-266, after the contact rows
+      if (min_separation >= -3.0f * B2G_LINEAR_SLOP && joints_okay) {  // b2_island_private.rs:257-274
         B.isl_flags[isl] |= 1;
         break;
       }

@@ -617,7 +617,6 @@ int batch_create(Ctx* ctx, const b2gpu_snapshot* proto, int n_worlds, const b2gp
   bh->pre_step_needed = true;
   if (caps && (caps->reserved[1] == 11 || caps->reserved[1] == 12)) {  // large-world mode (12: with the exact replica tree): one world, data-parallel ordered stages (b2g_large.h)
     if (n_worlds != 1 || B.LB != 1) { set_error("large-world mode needs a batch of exactly one world"); batch_destroy(bh); return B2GPU_E_INVALID; }
-    if (B.NJ > 0) { set_error("joints are not supported in the large-world modes yet (use the default exact mode)"); batch_destroy(bh); return B2GPU_E_UNSUPPORTED; }
     rc = large_alloc(bh);
     if (rc) { batch_destroy(bh); return rc; }
     bh->large = true;
@@ -1064,6 +1063,7 @@ static int large_alloc(BatchHost* bh) {
   AL(L.q_cnt, nq); AL(L.q_off, nq); AL(L.q_local, (long long)B.NMOVE * LW_QLOCAL);
   AL(L.cand, L.NCAND); AL(L.cand_flag, L.NCAND + 1LL); AL(L.cand_pos, L.NCAND + 1LL); AL(L.cand_fix, L.NCAND);
   AL(L.uf_parent, B.NB); AL(L.cnt_b, B.NB); AL(L.cnt_c, B.NB); AL(L.seed, B.NB); AL(L.isl_seed, B.NB);
+  AL(L.cnt_j, B.NB); AL(L.pj_in, B.NB + 1LL); AL(L.pj_out, B.NB + 1LL);
   AL(L.pk_in, B.NB + 1LL); AL(L.pk_out, B.NB + 1LL);
   AL(L.keep_flag, B.NC + 1LL); AL(L.keep_pos, B.NC + 1LL);
   AL(L.first_idx, B.NN); AL(L.vc_idx, B.NC); AL(L.scratch4, 16);
@@ -1215,12 +1215,13 @@ static int step_large(BatchHost* bh, const StepParams& sp, int steps) {
     if (dt > 0.0f) {
       // ---- islands
       if (dirty) {
-        const int nbc = std::max(B.NB, cc);
+        const int nbc = std::max(std::max(B.NB, cc), B.NJ);
         { LwIslInitK k = {B, L, cc}; RC(launch(ctx, k, nbc, 256, STAGE_ISLAND)); }
-        { LwUnionK k = {B, L, cc}; RC(launch(ctx, k, cc, 256, STAGE_ISLAND)); }
+        { LwUnionK k = {B, L, cc}; RC(launch(ctx, k, std::max(cc, B.NJ), 256, STAGE_ISLAND)); }
         { LwCountK k = {B, L, cc}; RC(launch(ctx, k, nbc, 256, STAGE_ISLAND)); }
         { LwSeedPackK k = {B, L}; RC(launch(ctx, k, B.NB + 1, 256, STAGE_ISLAND)); }
         RC(lw_scan_u64(bh, L.pk_in, L.pk_out, B.NB + 1, STAGE_ISLAND));
+        if (B.NJ > 0) RC(lw_scan_int(bh, L.pj_in, L.pj_out, B.NB + 1, STAGE_ISLAND));
         { LwRangeK k = {B, L}; RC(launch(ctx, k, B.NB + 1, 256, STAGE_ISLAND)); }
         RC(lw_read(bh, B.ws, WS_COUNT));
         { LwAdjInfoK k = {B, L, 2 * cc}; RC(launch(ctx, k, 2 * cc + 1, 256, STAGE_ISLAND)); }

@@ -287,16 +287,48 @@ def test_validate_rejects_bad_joint_records(built):
     broken(unknown_type)
 
 
-def test_large_modes_reject_joints(hctx):
-    from box2d_rs_b200 import abi, scenes, world
-    from box2d_rs_b200.lib import B2gpuError
-    wg = world.B2world((0.0, -10.0), ctx=hctx)
-    scenes.bridge(wg)
-    wg.set_large_mode(1)
-    with pytest.raises(B2gpuError) as e:
-        wg.step(scenes.DT, 8, 3)
-    assert e.value.code == abi.E_UNSUPPORTED
+def _large_teacher_forced(name, ctx, every):
+    """Large-world mode 1 with joints: every step is the oracle's step of the same state (joint edges in the union-find
+    islands and in the per-island traversal, joint rows in the per-island sweeps)."""
+    from box2d_rs_b200 import scenes
+    wo, wg, steps, _, _ = _pair(name, ctx)
+    bt = wg.batch(1, lane_block=1, solver='large')
+    for i in range(min(steps, 200)):
+        if i % every == 0:
+            bt.upload_world(0, wo.snapshot())
+            wo.step(scenes.DT, 8, 3)
+            bt.step(scenes.DT, 8, 3)
+            bad = parity.compare_large_step(wo.snapshot(), bt.download_world(0), wo.get_stats(), bt.stats()[0])
+            assert bad == [], "%s step %d: %s" % (name, i, bad[:6])
+        else:
+            wo.step(scenes.DT, 8, 3)
+    bt.close()
     wg.close()
+
+
+def _large_exact_free_running(name, ctx):
+    """Large-world mode 2 (reference contact order) with joints: free-running state bit-identical to the oracle."""
+    from box2d_rs_b200 import scenes
+    wo, wg, steps, _, _ = _pair(name, ctx)
+    wg.set_large_mode(2)
+    for i in range(steps):
+        wo.step(scenes.DT, 8, 3)
+        wg.step(scenes.DT, 8, 3)
+        if i < 2 or i % 40 == 39 or i == steps - 1:
+            bad = parity.compare_snapshots(wo.snapshot(), wg.snapshot()) + \
+                [b for b in parity.compare_stats(wo.get_stats(), wg.get_stats()) if "island_bodies" not in b]
+            assert bad == [], "%s step %d: %s" % (name, i, bad[:6])
+    wg.close()
+
+
+@pytest.mark.parametrize("name,every", [("bridge", 3), ("tumbler", 4), ("joints_mix", 2)])
+def test_hostsim_large_mode_teacher_forced(name, every, hctx):
+    _large_teacher_forced(name, hctx, every)
+
+
+@pytest.mark.parametrize("name", list(JOINT_SCENES))
+def test_hostsim_large_exact_free_running(name, hctx):
+    _large_exact_free_running(name, hctx)
 
 
 # ---------------------------------------------------------------------------------------------- CUDA path
@@ -316,3 +348,15 @@ def test_gpu_batched(name, lane_block, gctx):
 @pytest.mark.parametrize("name", list(JOINT_SCENES))
 def test_gpu_teacher_forced(name, gctx):
     _teacher_forced(name, gctx)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,every", [("bridge", 3), ("tumbler", 4), ("joints_mix", 2)])
+def test_gpu_large_mode_teacher_forced(name, every, gctx):
+    _large_teacher_forced(name, gctx, every)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", list(JOINT_SCENES))
+def test_gpu_large_exact_free_running(name, gctx):
+    _large_exact_free_running(name, gctx)
