@@ -282,3 +282,9 @@ assert CONTACT_EVENT_DTYPE.itemsize == 32
 # b2gpu_ray_hit (include/b2gpu.h)
 RAY_HIT_DTYPE = np.dtype([("fixture", np.int32), ("child_index", np.int32), ("fraction", np.float32), ("point", np.float32, 2),
                           ("normal", np.float32, 2), ("reserved", np.int32)])
+
+# b2gpu_post_solve_event (include/b2gpu.h)
+POST_SOLVE_DTYPE = np.dtype([("fixture_a", np.int32), ("index_a", np.int32), ("fixture_b", np.int32), ("index_b", np.int32),
+                             ("count", np.int32), ("normal_impulses", np.float32, 2), ("tangent_impulses", np.float32, 2),
+                             ("reserved", np.int32, 3)])
+assert POST_SOLVE_DTYPE.itemsize == 48

@@ -101,6 +101,13 @@ class Batch:
         self.step(dt, velocity_iterations, position_iterations)
         return {w: contact_events(self.L, before[w], self.download_world(w), int(self.stats(w, 1)[0]["destroyed"])) for w in worlds}
 
+    def post_solve_events(self, world):
+        """post_solve reports of the last step of one world of the batch (b2gpu_batch_post_solve_events)."""
+        n = check(self.L, self.L.b2gpu_batch_post_solve_events(self.h, world, None, 0))
+        out = np.zeros(max(n, 1), abi.POST_SOLVE_DTYPE)
+        check(self.L, self.L.b2gpu_batch_post_solve_events(self.h, world, out.ctypes.data, n))
+        return out[:n]
+
     def save_checkpoint(self, world, path):
         """One world of the batch to a snapshot file (b2gpu_snapshot_save)."""
         from . import checkpoint

@@ -151,6 +151,12 @@ int b2gpu_batch_download_world(b2gpu_batch* b, int world, b2gpu_snapshot* out) {
   return batch_last_download_status(b->h);  // buffers are filled; a failed world reports its device status
   GUARD_END
 }
+int b2gpu_batch_post_solve_events(b2gpu_batch* b, int world, b2gpu_post_solve_event* out, int capacity) {
+  GUARD_BEGIN
+  if (!b) { set_error("batch is NULL"); return B2GPU_E_INVALID; }
+  return batch_post_solve_events(b->h, world, out, capacity);
+  GUARD_END
+}
 int b2gpu_batch_reset(b2gpu_batch* b, const b2gpu_snapshot* in) {
   GUARD_BEGIN
   if (!b) { set_error("batch is NULL"); return B2GPU_E_INVALID; }

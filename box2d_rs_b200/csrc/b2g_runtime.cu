@@ -1672,6 +1672,46 @@ int batch_dynamic_bodies(BatchHost* bh, int* out, int capacity) {
   return n;
 }
 
+// post_solve reports of the last step of one world: island contact slot k -> (fixtures, children, impulses)
+struct PostSolveGatherK {
+  Batch B;
+  b2gpu_post_solve_event* out;
+  int w;
+  B2G_HD void operator()(int k) const {
+    WIdx x = widx(B, w);
+    Ws ws = ws_of(B, x);
+    if (k >= ws[WS_ISL_CONTACTS]) return;
+    const float4 q6 = B.vc[vc_at(B, x, k, 6)], q8 = B.vc[vc_at(B, x, k, 8)];
+    const int4 fx = B.c_fix[x.at(B.NC, f2i(q8.w))];
+    b2gpu_post_solve_event e;
+    e.fixture_a = fx.x; e.fixture_b = fx.y; e.index_a = fx.z; e.index_b = fx.w;
+    e.count = f2i(q8.z) & 0xff;
+    e.normal_impulses[0] = e.count > 0 ? q6.x : 0.0f; e.tangent_impulses[0] = e.count > 0 ? q6.y : 0.0f;
+    e.normal_impulses[1] = e.count > 1 ? q6.z : 0.0f; e.tangent_impulses[1] = e.count > 1 ? q6.w : 0.0f;
+    e.reserved[0] = e.reserved[1] = e.reserved[2] = 0;
+    out[k] = e;
+  }
+};
+int batch_post_solve_events(BatchHost* bh, int world, b2gpu_post_solve_event* out, int capacity) {
+  if (!bh || world < 0 || world >= bh->B.n_worlds || capacity < 0 || (capacity > 0 && !out)) { set_error("post_solve_events: bad argument"); return B2GPU_E_INVALID; }
+  if (!bh->stepped) return 0;
+  Batch all = bh->B;
+  all.wb_first = 0;
+  all.wb_count = bh->B.n_wblocks;
+  WorldImage im;
+  image_alloc(bh->B, im);
+  ArrRef a = {bh->B.ws, im.ws.data(), 1, WS_COUNT};
+  RC(move_array(bh, a, 1, world));
+  if (!im.ws[WS_ISL_VALID]) return 0;  // the last step did not solve (dt = 0)
+  const int n = im.ws[WS_ISL_CONTACTS];
+  if (n == 0 || capacity == 0) return n;
+  char* base = nullptr;
+  RC(query_scratch(bh, (size_t)n * sizeof(b2gpu_post_solve_event), &base));
+  { PostSolveGatherK k = {all, (b2gpu_post_solve_event*)base, world}; RC(launch(bh->ctx, k, n, 128)); }
+  RC(dev_d2h(bh->ctx, out, base, (size_t)std::min(n, capacity) * sizeof(b2gpu_post_solve_event)));
+  return n;
+}
+
 // sin/cos of an array of angles on the device (diagnostic: pins rot_from_angle against libm)
 struct SinCosK {
   const float* in;

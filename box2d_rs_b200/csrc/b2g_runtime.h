@@ -126,6 +126,7 @@ void batch_destroy(BatchHost* b);
 int batch_upload_world(BatchHost* b, int world, const b2gpu_snapshot* in);
 int batch_reset(BatchHost* b, const b2gpu_snapshot* in);
 int batch_status(BatchHost* b, int* out);
+int batch_post_solve_events(BatchHost* b, int world, b2gpu_post_solve_event* out, int capacity);
 int batch_last_download_status(BatchHost* b);
 int batch_snapshot_sizes(BatchHost* b, int world, b2gpu_snapshot_sizes* out);
 int batch_download_world(BatchHost* b, int world, b2gpu_snapshot* out);

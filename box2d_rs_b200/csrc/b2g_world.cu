@@ -1066,6 +1066,13 @@ int b2gpu_world_query_aabb(b2gpu_world* W, const float* aabbs, int n, int max_hi
   GUARD_END
 }
 
+int b2gpu_world_post_solve_events(b2gpu_world* W, b2gpu_post_solve_event* out, int capacity) {
+  GUARD_BEGIN
+  if (!W) { set_error("world is NULL"); return B2GPU_E_INVALID; }
+  if (!W->dev || W->host_dirty || W->topo_dirty) return 0;  // edited since the last step: the device tables are about to be replaced
+  return batch_post_solve_events(W->dev, 0, out, capacity);
+  GUARD_END
+}
 int b2gpu_world_get_body_count(b2gpu_world* W) { return W ? (int)W->h.bodies.size() : B2GPU_E_INVALID; }
 int b2gpu_world_get_contact_count(b2gpu_world* W) {
   GUARD_BEGIN

@@ -81,6 +81,8 @@ def load(path=None):
         "b2gpu_snapshot_save": (i32, [C.POINTER(abi.SnapshotC), C.c_char_p]),
         "b2gpu_snapshot_file_sizes": (i32, [C.c_char_p, C.POINTER(abi.SnapshotSizes)]),
         "b2gpu_snapshot_load": (i32, [C.c_char_p, C.POINTER(abi.SnapshotC)]),
+        "b2gpu_world_post_solve_events": (i32, [vp, vp, i32]),
+        "b2gpu_batch_post_solve_events": (i32, [vp, i32, vp, i32]),
         "b2gpu_contact_events": (i32, [C.POINTER(abi.SnapshotC), C.POINTER(abi.SnapshotC), i32, vp, i32]),
         "b2gpu_world_ray_cast_closest": (i32, [vp, vp, i32, vp]),
         "b2gpu_world_query_aabb": (i32, [vp, vp, i32, i32, vp, vp]),

@@ -253,6 +253,13 @@ class B2world:
         after = self.snapshot()
         return contact_events(self.L, before, after, int(self.get_stats()["destroyed"]))
 
+    def post_solve_events(self):
+        """B2contactListener::post_solve reports of the last step in the reference's call order (abi.POST_SOLVE_DTYPE)."""
+        n = check(self.L, self.L.b2gpu_world_post_solve_events(self.h, None, 0))
+        out = np.zeros(max(n, 1), abi.POST_SOLVE_DTYPE)
+        check(self.L, self.L.b2gpu_world_post_solve_events(self.h, out.ctypes.data, n))
+        return out[:n]
+
     def save_checkpoint(self, path):
         """Full step state to a snapshot file (b2gpu_snapshot_save); see checkpoint.py."""
         from . import checkpoint

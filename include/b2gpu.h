@@ -473,6 +473,21 @@ typedef struct b2gpu_contact_event {
 int b2gpu_contact_events(const b2gpu_snapshot* before, const b2gpu_snapshot* after, int destroyed,
                          b2gpu_contact_event* out, int capacity);
 
+/* B2contactListener::post_solve (src/b2_world_callbacks.rs:94-103): the reference calls it from B2island::report
+ * (b2_island_private.rs:460-487) for every contact of every solved island, in island order, with the impulses of the
+ * contact's velocity constraint (`count` = the constraint's point count: 1 when the block solver dropped an
+ * ill-conditioned second point).  With the step on the device the reports of the LAST step are read back afterwards, in
+ * the reference's call order; returns their number (it may exceed `capacity`; `out` then holds the first `capacity`) or a
+ * negative error.  pre_solve stays out of scope (it may mutate the contact between narrowphase and solver). */
+typedef struct b2gpu_post_solve_event {
+  int32_t fixture_a, index_a, fixture_b, index_b; /* as in b2gpu_contact_rec */
+  int32_t count;
+  float normal_impulses[2], tangent_impulses[2];
+  int32_t reserved[3];
+} b2gpu_post_solve_event;
+int b2gpu_world_post_solve_events(b2gpu_world* w, b2gpu_post_solve_event* out, int capacity);
+int b2gpu_batch_post_solve_events(b2gpu_batch* b, int world, b2gpu_post_solve_event* out, int capacity);
+
 /* ------------------------------------------------------------ world queries
  * B2world::ray_cast (src/private/dynamics/b2_world.rs:1015-1049) with the "closest hit" callback
  * `|fixture, point, normal, fraction| fraction`, and B2world::query_aabb (:969-980) with a callback that

@@ -74,6 +74,8 @@ def lib():
         L.b2o_get_stats.argtypes = [C.c_void_p, C.c_void_p]
         L.b2o_get_events.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.b2o_get_events.restype = C.c_int
+        L.b2o_get_post_solve.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
+        L.b2o_get_post_solve.restype = C.c_int
         L.b2o_ray_cast_closest.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p]
         L.b2o_query_aabb.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p]
         L.b2o_snapshot_sizes.argtypes = [C.c_void_p, C.POINTER(abi.SnapshotSizes)]
@@ -328,6 +330,13 @@ class B2world:
         n = lib().b2o_get_events(self.h, None, 0)
         out = np.zeros((max(n, 1), 5), np.int32)
         lib().b2o_get_events(self.h, out.ctypes.data, n)
+        return out[:n]
+
+    def post_solve_events(self):
+        """post_solve reports of the last step (B2island::report order): abi.POST_SOLVE_DTYPE array."""
+        n = lib().b2o_get_post_solve(self.h, None, 0)
+        out = np.zeros(max(n, 1), abi.POST_SOLVE_DTYPE)
+        lib().b2o_get_post_solve(self.h, out.ctypes.data, n)
         return out[:n]
 
     def snapshot(self):

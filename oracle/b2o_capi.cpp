@@ -220,6 +220,17 @@ int b2o_get_events(void* w, int32_t* out, int cap) {
   }
   return (int)ev.size();
 }
+// post_solve reports of the last step in call order: out = b2gpu_post_solve_event[cap]; returns the number (may exceed cap)
+int b2o_get_post_solve(void* w, b2gpu_post_solve_event* out, int cap) {
+  const std::vector<PostSolveEvent>& ev = ((World*)w)->post_solve_events;
+  for (size_t i = 0; i < ev.size() && (int)i < cap; ++i) {
+    std::memset(&out[i], 0, sizeof(out[i]));
+    out[i].fixture_a = ev[i].fixture_a; out[i].index_a = ev[i].index_a; out[i].fixture_b = ev[i].fixture_b; out[i].index_b = ev[i].index_b;
+    out[i].count = ev[i].count;
+    for (int j = 0; j < 2; ++j) { out[i].normal_impulses[j] = ev[i].normal_impulses[j]; out[i].tangent_impulses[j] = ev[i].tangent_impulses[j]; }
+  }
+  return (int)ev.size();
+}
 void b2o_get_stats(void* w, b2gpu_step_stats* out) {
   const StepStats& s = ((World*)w)->stats;
   std::memset(out, 0, sizeof(*out));

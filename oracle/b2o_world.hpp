@@ -137,6 +137,12 @@ struct ContactEvent {
   int type;  // 1 = begin_contact, 2 = end_contact
   int fixture_a, index_a, fixture_b, index_b;
 };
+// B2contactListener::post_solve (src/b2_world_callbacks.rs:94-103) as B2island::report would call it
+// (b2_island_private.rs:460-487): per island, contacts in island order, the impulses of the velocity constraint.
+struct PostSolveEvent {
+  int fixture_a, index_a, fixture_b, index_b, count;
+  float normal_impulses[2], tangent_impulses[2];
+};
 struct StepStats {
   int contacts = 0, touching = 0, destroyed = 0, islands = 0, island_bodies = 0, island_contacts = 0, moved = 0, pairs = 0,
       created = 0, awake_bodies = 0, solver_levels = 0;
@@ -582,6 +588,7 @@ struct World {
     ++stats.created;
   }
   std::vector<ContactEvent> events;  // cleared at the top of step()
+  std::vector<PostSolveEvent> post_solve_events;  // likewise
   void destroy_contact(int ci) {  // b2_contact_manager.rs(private):24-78 ; b2_contact.rs(private):33-46
     Contact& c = contacts[ci];
     if (c.flags & CF_TOUCHING) events.push_back({2, c.fixture_a, c.index_a, c.fixture_b, c.index_b});  // :44-49 end_contact
@@ -1495,6 +1502,16 @@ struct World {
       synchronize_transform(body);
     }
     profile.solve_position += now_ms() - t2;
+    for (size_t i = 0; i < is.contacts.size(); ++i) {  // self_.report(&contact_solver.m_velocity_constraints)
+      const Contact& c = contacts[is.contacts[i]];
+      const ContactVelocityConstraint& vc = vcs[i];
+      PostSolveEvent e = {c.fixture_a, c.index_a, c.fixture_b, c.index_b, vc.point_count, {0.0f, 0.0f}, {0.0f, 0.0f}};
+      for (int j = 0; j < vc.point_count; ++j) {
+        e.normal_impulses[j] = vc.points[j].normal_impulse;
+        e.tangent_impulses[j] = vc.points[j].tangent_impulse;
+      }
+      post_solve_events.push_back(e);
+    }
     if (allow_sleep) {
       float min_sleep_time = MAX_FLOAT;
       const float lin_tol_sqr = LINEAR_SLEEP_TOLERANCE * LINEAR_SLEEP_TOLERANCE;
@@ -1590,6 +1607,7 @@ struct World {
     stats = StepStats();
     dag = DagStats();
     events.clear();
+    post_solve_events.clear();
     if (new_contacts) {
       find_new_contacts();
       new_contacts = false;

@@ -149,6 +149,14 @@ pub struct b2gpu_contact_event {
     pub reserved: [i32; 3],
 }
 
+/// b2gpu_post_solve_event (include/b2gpu.h): one B2contactListener::post_solve report of the last step.
+#[repr(C)]
+#[derive(Clone, Copy, Debug, Default)]
+pub struct b2gpu_post_solve_event {
+    pub fixture_a: i32, pub index_a: i32, pub fixture_b: i32, pub index_b: i32, pub count: i32,
+    pub normal_impulses: [c_float; 2], pub tangent_impulses: [c_float; 2], pub reserved: [i32; 3],
+}
+
 extern "C" {
     pub fn b2gpu_abi_version() -> c_int;
     pub fn b2gpu_last_error() -> *const c_char;
@@ -219,6 +227,8 @@ extern "C" {
     pub fn b2gpu_batch_snapshot_sizes(b: *mut b2gpu_batch, world: c_int, out: *mut b2gpu_snapshot_sizes) -> c_int;
     pub fn b2gpu_batch_download_world(b: *mut b2gpu_batch, world: c_int, out: *mut b2gpu_snapshot) -> c_int;
     pub fn b2gpu_batch_get_stats(b: *mut b2gpu_batch, first_world: c_int, count: c_int, out: *mut b2gpu_step_stats) -> c_int;
+    pub fn b2gpu_world_post_solve_events(w: *mut b2gpu_world, out: *mut b2gpu_post_solve_event, capacity: c_int) -> c_int;
+    pub fn b2gpu_batch_post_solve_events(b: *mut b2gpu_batch, world: c_int, out: *mut b2gpu_post_solve_event, capacity: c_int) -> c_int;
     pub fn b2gpu_batch_reset(b: *mut b2gpu_batch, input: *const b2gpu_snapshot) -> c_int;
     pub fn b2gpu_batch_status(b: *mut b2gpu_batch) -> c_int;
     pub fn b2gpu_batch_set_forces(b: *mut b2gpu_batch, host_fxfyt: *const c_float, first_world: c_int, count: c_int) -> c_int;

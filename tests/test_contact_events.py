@@ -128,3 +128,55 @@ def test_batch_step_with_events(built):
     bt.close()
     wg.close()
     ctx.close()
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# post_solve reports (B2island::report): fixtures, point count and impulses of every island contact, in call order
+# ---------------------------------------------------------------------------------------------------------------------
+def _post_solve(name, ctx, batch_mode, n=3, lane_block=1):
+    from box2d_rs_b200 import scenes, world
+    from oracle import b2o
+    from conftest import JOINT_SCENES
+    recipe, gravity, steps = {**SCENES, **JOINT_SCENES}[name]
+    wo = b2o.B2world(gravity)
+    recipe(scenes, wo)
+    wg = world.B2world(gravity, ctx=ctx)
+    recipe(scenes, wg)
+    bt = wg.batch(n, lane_block=lane_block) if batch_mode else None
+    seen = 0
+    for i in range(min(steps, 150)):
+        wo.step(scenes.DT, 8, 3)
+        if bt is not None:
+            bt.step(scenes.DT, 8, 3)
+        else:
+            wg.step(scenes.DT, 8, 3)
+        if i % 7 == 0 or i < 3:
+            ref = wo.post_solve_events()
+            got = bt.post_solve_events(n - 1) if bt is not None else wg.post_solve_events()
+            assert len(ref) == len(got), "step %d: %d vs %d reports" % (i, len(ref), len(got))
+            for f in ("fixture_a", "index_a", "fixture_b", "index_b", "count"):
+                assert np.array_equal(ref[f], got[f]), "step %d: %s" % (i, f)
+            for f in ("normal_impulses", "tangent_impulses"):
+                assert np.array_equal(ref[f].view(np.uint32), got[f].view(np.uint32)), "step %d: %s" % (i, f)
+            seen += len(ref)
+    assert seen > 0
+    if bt is not None:
+        bt.close()
+    wg.close()
+
+
+@pytest.mark.parametrize("name,batch_mode", [("pyramid", True), ("mixed300", False), ("variety", True), ("joints_mix", False)])
+def test_post_solve_reports_match_the_oracle(name, batch_mode, built):
+    from box2d_rs_b200 import batch
+    ctx = batch.Context(0, lib_path=HOSTSIM_SO)
+    _post_solve(name, ctx, batch_mode)
+    ctx.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name,batch_mode", [("pyramid", True), ("variety", False), ("joints_mix", True)])
+def test_post_solve_reports_match_the_oracle_gpu(name, batch_mode, built):
+    from box2d_rs_b200 import batch
+    ctx = batch.Context(0)
+    _post_solve(name, ctx, batch_mode, n=34, lane_block=0)  # 32-world memory blocks: the shared-memory kernels
+    ctx.close()
