@@ -135,6 +135,20 @@ class Batch:
         check(self.L, self.L.b2gpu_batch_step_host(self.h, fp, state_out.ctypes.data, dt, velocity_iterations,
                                                    position_iterations, steps))
 
+    def device_buffers(self):
+        """(forces pointer, forces bytes, state pointer, state bytes): raw device addresses of the staging buffers for zero-copy
+        consumers (e.g. torch tensors); see apply_device_forces / refresh_device_state."""
+        nf, ns = C.c_int64(), C.c_int64()
+        pf = self.L.b2gpu_batch_forces_device(self.h, C.byref(nf))
+        ps = self.L.b2gpu_batch_body_state_device(self.h, C.byref(ns))
+        return pf, nf.value, ps, ns.value
+
+    def apply_device_forces(self):
+        check(self.L, self.L.b2gpu_batch_apply_device_forces(self.h))
+
+    def refresh_device_state(self):
+        check(self.L, self.L.b2gpu_batch_refresh_device_state(self.h))
+
     def dynamic_bodies(self):
         """Body indices of the prototype's dynamic bodies (the rows of the compact I/O arrays)."""
         n = check(self.L, self.L.b2gpu_batch_dynamic_bodies(self.h, None, 0))

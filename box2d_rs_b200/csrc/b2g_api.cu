@@ -208,6 +208,18 @@ void* b2gpu_batch_forces_device(b2gpu_batch* b, int64_t* bytes) {
   if (bytes) *bytes = (int64_t)b->h->B.n_worlds * b->h->B.NB * 3 * 4;
   return b->h->forces_dev;
 }
+int b2gpu_batch_apply_device_forces(b2gpu_batch* b) {
+  GUARD_BEGIN
+  if (!b) { set_error("batch is NULL"); return B2GPU_E_INVALID; }
+  return batch_apply_device_forces(b->h);
+  GUARD_END
+}
+int b2gpu_batch_refresh_device_state(b2gpu_batch* b) {
+  GUARD_BEGIN
+  if (!b) { set_error("batch is NULL"); return B2GPU_E_INVALID; }
+  return batch_refresh_device_state(b->h);
+  GUARD_END
+}
 int b2gpu_batch_step_host(b2gpu_batch* b, const float* host_forces, float* host_state_out, float dt, int vi, int pi, int steps) {
   GUARD_BEGIN
   if (!b) { set_error("batch is NULL"); return B2GPU_E_INVALID; }

@@ -63,7 +63,8 @@ extern "C" int b2gpu_contact_events(const b2gpu_snapshot* before, const b2gpu_sn
     } else {  // infer: longest prefix of `after` that is a subsequence of `before`
       int k = 0;
       n_surv = 0;
-      while (n_surv < na) {
+      while (n_surv < na && n_surv < nb) {  // survivors <= min(before, after); best effort: pass the step's `destroyed` stat
+                                             // when a destroyed contact may have been re-created for the same fixture pair
         auto it = in_before.find(key_of(after->contacts[n_surv]));
         if (it == in_before.end() || it->second < k) break;
         k = it->second + 1;

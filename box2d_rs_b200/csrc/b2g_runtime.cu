@@ -579,6 +579,7 @@ int batch_create(Ctx* ctx, const b2gpu_snapshot* proto, int n_worlds, const b2gp
   AL(bh->state_dev, (long long)n_worlds * B.NB * 8);
   AL(bh->forces_dev, (long long)n_worlds * B.NB * 3);
   AL(bh->status_dev, 4);
+  AL(bh->vel_scratch, (long long)n_worlds * 2);
   {
     std::vector<int> dyn;
     for (int b = 0; b < B.NB; ++b)
@@ -1645,9 +1646,28 @@ int batch_set_linear_velocity(BatchHost* bh, int body, const float* host_vxvy, i
     set_error("set_linear_velocity: bad argument");
     return B2GPU_E_INVALID;
   }
-  RC(dev_h2d(bh->ctx, bh->forces_dev, host_vxvy, (size_t)count * 2 * 4));
-  { VelScatterK k = {bh->B, bh->forces_dev, body, first, count}; RC(launch(bh->ctx, k, count, 128)); }
+  RC(dev_h2d(bh->ctx, bh->vel_scratch, host_vxvy, (size_t)count * 2 * 4));  // its own scratch: forces_dev belongs to the caller
+  { VelScatterK k = {bh->B, bh->vel_scratch, body, first, count}; RC(launch(bh->ctx, k, count, 128)); }
   return 0;
+}
+// The device-pointer forms (zero-copy consumers, e.g. torch tensors over b2gpu_batch_forces_device /
+// b2gpu_batch_body_state_device): scatter the caller-written force buffer into the worlds / refresh the state buffer.
+// Asynchronous on the context stream.
+int batch_apply_device_forces(BatchHost* bh) {
+  if (!bh) { set_error("apply_device_forces: bad argument"); return B2GPU_E_INVALID; }
+  Batch all = bh->B;
+  all.wb_first = 0;
+  all.wb_count = bh->B.n_wblocks;
+  ForceScatterK k = {all, bh->forces_dev, 0, all.n_worlds};
+  return launch(bh->ctx, k, all.n_wblocks * all.LB * all.NB, 128);
+}
+int batch_refresh_device_state(BatchHost* bh) {
+  if (!bh) { set_error("refresh_device_state: bad argument"); return B2GPU_E_INVALID; }
+  Batch all = bh->B;
+  all.wb_first = 0;
+  all.wb_count = bh->B.n_wblocks;
+  StateGatherK k = {all, bh->state_dev};
+  return launch(bh->ctx, k, all.n_wblocks * all.LB * all.NB, 128);
 }
 
 // One end-to-end call through HOST buffers: forces H2D, `steps` steps, body state D2H.  Synchronous:

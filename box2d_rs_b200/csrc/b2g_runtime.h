@@ -83,6 +83,7 @@ struct BatchHost {
   int* stack = nullptr;
   float* state_dev = nullptr;    // [n_worlds][NB][8] gather buffer
   float* forces_dev = nullptr;   // [n_worlds][NB][3]
+  float* vel_scratch = nullptr;  // [n_worlds][2] staging of batch_set_linear_velocity
   int* dyn_idx = nullptr;        // [n_dyn] body indices of the prototype's dynamic bodies (compact I/O)
   int n_dyn = 0;
   int* status_dev = nullptr;     // reduced WS_STATUS of the batch (StatusK)
@@ -126,6 +127,8 @@ void batch_destroy(BatchHost* b);
 int batch_upload_world(BatchHost* b, int world, const b2gpu_snapshot* in);
 int batch_reset(BatchHost* b, const b2gpu_snapshot* in);
 int batch_status(BatchHost* b, int* out);
+int batch_apply_device_forces(BatchHost* b);
+int batch_refresh_device_state(BatchHost* b);
 int batch_post_solve_events(BatchHost* b, int world, b2gpu_post_solve_event* out, int capacity);
 int batch_last_download_status(BatchHost* b);
 int batch_snapshot_sizes(BatchHost* b, int world, b2gpu_snapshot_sizes* out);

@@ -103,6 +103,8 @@ def load(path=None):
         "b2gpu_batch_get_body_state": (i32, [vp, vp, i32, i32]),
         "b2gpu_batch_body_state_device": (vp, [vp, C.POINTER(i64)]),
         "b2gpu_batch_forces_device": (vp, [vp, C.POINTER(i64)]),
+        "b2gpu_batch_apply_device_forces": (i32, [vp]),
+        "b2gpu_batch_refresh_device_state": (i32, [vp]),
         "b2gpu_batch_step_host": (i32, [vp, vp, vp, f32, i32, i32, i32]),
         "b2gpu_batch_dynamic_bodies": (i32, [vp, vp, i32]),
         "b2gpu_batch_step_host_dynamic": (i32, [vp, vp, vp, f32, i32, i32, i32]),

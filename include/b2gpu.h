@@ -548,9 +548,16 @@ int b2gpu_batch_set_linear_velocity(b2gpu_batch* b, int body, const float* host_
  * (c.x, c.y, a, v.x, v.y, w, xf.p.x, xf.p.y) — what get_world_center/get_angle/
  * get_linear_velocity/get_angular_velocity/get_position return. */
 int b2gpu_batch_get_body_state(b2gpu_batch* b, float* host_out, int first_world, int count);
-/* Device pointers for zero-copy use from torch (size in bytes returned through *bytes). */
+/* Device buffers for zero-copy use from torch (size in bytes returned through *bytes): forces [n_worlds][body_count][3]
+ * written by the caller, state [n_worlds][body_count][8] as in b2gpu_batch_get_body_state.  They are STAGING buffers:
+ * b2gpu_batch_apply_device_forces adds the force buffer to the worlds (like b2gpu_batch_set_forces, without the host
+ * copy) and b2gpu_batch_refresh_device_state fills the state buffer from the worlds; both are asynchronous on the context
+ * stream, so  write forces -> apply -> b2gpu_batch_step -> refresh -> read state  needs no host synchronisation when the
+ * caller works on that stream (b2gpu_stream). */
 void* b2gpu_batch_body_state_device(b2gpu_batch* b, int64_t* bytes);
 void* b2gpu_batch_forces_device(b2gpu_batch* b, int64_t* bytes);
+int b2gpu_batch_apply_device_forces(b2gpu_batch* b);
+int b2gpu_batch_refresh_device_state(b2gpu_batch* b);
 /* One end-to-end step through HOST buffers: H2D forces, `steps` steps, D2H body state, synchronous. */
 int b2gpu_batch_step_host(b2gpu_batch* b, const float* host_forces, float* host_state_out, float dt,
                           int velocity_iterations, int position_iterations, int steps);

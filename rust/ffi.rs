@@ -236,6 +236,8 @@ extern "C" {
     pub fn b2gpu_batch_get_body_state(b: *mut b2gpu_batch, host_out: *mut c_float, first_world: c_int, count: c_int) -> c_int;
     pub fn b2gpu_batch_body_state_device(b: *mut b2gpu_batch, bytes: *mut i64) -> *mut c_void;
     pub fn b2gpu_batch_forces_device(b: *mut b2gpu_batch, bytes: *mut i64) -> *mut c_void;
+    pub fn b2gpu_batch_apply_device_forces(b: *mut b2gpu_batch) -> c_int;
+    pub fn b2gpu_batch_refresh_device_state(b: *mut b2gpu_batch) -> c_int;
     pub fn b2gpu_batch_step_host(b: *mut b2gpu_batch, host_forces: *const c_float, host_state_out: *mut c_float, dt: c_float,
                                  velocity_iterations: c_int, position_iterations: c_int, steps: c_int) -> c_int;
     pub fn b2gpu_batch_dynamic_bodies(b: *mut b2gpu_batch, out_body_indices: *mut i32, capacity: c_int) -> c_int;

@@ -116,3 +116,46 @@ def test_compact_io(built):
 @pytest.mark.gpu
 def test_compact_io_gpu(built):
     _compact_io(True)
+
+
+@pytest.mark.gpu
+def test_device_pointer_round_trip_gpu(built):
+    """Zero-copy path: forces written on the device into b2gpu_batch_forces_device, applied by
+    b2gpu_batch_apply_device_forces, state read from b2gpu_batch_body_state_device after refresh — equals the host-buffer path."""
+    import ctypes as C
+    import torch
+    from box2d_rs_b200 import scenes, world
+    ctx = _ctx(True)
+    wg = world.B2world((0.0, -10.0), ctx=ctx)
+    scenes.pyramid(wg)
+    n = 40
+    a, b = wg.batch(n, max_contacts=800), wg.batch(n, max_contacts=800)
+    pf, nf, ps, ns = b.device_buffers()
+    assert nf == n * a.body_count * 3 * 4 and ns == n * a.body_count * 8 * 4
+    rng = np.random.default_rng(11)
+    cudart = pytest.importorskip("cuda.cudart")  # cuda-python: a plain device-to-device copy by raw address
+    d2d = cudart.cudaMemcpyKind.cudaMemcpyDeviceToDevice
+
+    def copy(dst, src, nbytes):
+        (err,) = cudart.cudaMemcpy(dst, src, nbytes, d2d)
+        assert int(err) == 0, err
+    for _ in range(6):
+        f = np.zeros((n, a.body_count, 3), np.float32)
+        f[:, 2:, 0] = rng.uniform(-25.0, 25.0, (n, 210)).astype(np.float32)
+        a.set_forces(f)
+        a.step(scenes.DT, 8, 3)
+        ft = torch.from_numpy(f).cuda()
+        torch.cuda.synchronize()
+        # device-to-device copy of the forces into the library's buffer (what a torch policy would write in place)
+        copy(pf, ft.data_ptr(), nf)
+        b.apply_device_forces()
+        b.step(scenes.DT, 8, 3)
+        b.refresh_device_state()
+        ctx.sync()
+        out = torch.empty((n, a.body_count, 8), dtype=torch.float32, device="cuda")
+        copy(out.data_ptr(), ps, ns)
+        assert np.array_equal(out.cpu().numpy().view(np.uint32), a.body_state().view(np.uint32))
+    a.close()
+    b.close()
+    wg.close()
+    ctx.close()
