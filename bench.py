@@ -436,6 +436,8 @@ def run_ours(args, rank, world_size, local_rank):
         per_gpu = args.worlds
         arm = Arm(args, ctx, stream, dist, rank * per_gpu, per_gpu)
         arm.preroll()
+        for _ in range(3):
+            arm.step(PREROLL_CHUNK)  # the same ~0.5 s under load as before the main measurement
         arm.step(args.steps)
         ms_w = arm.timed_device(1, args.steps)
         es, _, _ = arm.e2e(args.steps, args.warmup)

@@ -17,8 +17,9 @@
 //   1: revolute K.ex.x K.ey.x K.ey.y axial_mass      | distance u.x u.y mass soft_mass
 //   2: revolute angle - - -                          | distance gamma bias current_length -
 //   3: mA iA mB iB
-// Joint visits are ordered work: they run in the island's joint order inside the per-island Gauss-Seidel stages
-// (VelocityK / PositionK); worlds with joints take the generic (global-memory) form of those stages.
+// Joint visits are ordered work: they run in the island's joint order inside every form of the Gauss-Seidel stages
+// (VelocityK / PositionK generic; velocity_sl_kernel / position_sl_kernel for batches, through an accessor over their
+// shared-memory rows; LwVelocity7K / LwPosition6K in the large-world modes).
 #pragma once
 #include "b2g_common.h"
 
