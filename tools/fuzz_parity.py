@@ -1,7 +1,8 @@
 #!/usr/bin/env python
 """Differential fuzzing of the device stages (host simulator build by default, --gpu for the CUDA path) against
 the CPU oracle: random scenes (polygons of 3..8 vertices, circles, edges, chains, kinematic / fixed-rotation /
-multi-fixture bodies, sensors, filters, restitution, damping, random world flags and iteration counts, dt = 0 steps,
+multi-fixture bodies, sensors, filters, restitution, damping, revolute / distance joints with limits, motors and springs,
+random world flags and iteration counts, dt = 0 steps,
 mid-run set_transform / set_linear_velocity / apply_force / apply_torque / apply_*_impulse / set_awake edits), stepped freely and compared bit for bit.
 
   python tools/fuzz_parity.py --seeds 200 [--gpu] [--batch] [--large]
@@ -88,6 +89,33 @@ def build(world, rng):
                 ang = np.sort(rng.uniform(0, 2 * math.pi, nv))
                 shape = world.shapes.polygon([(f32(rad * math.cos(a)), f32(rad * math.sin(a) * rng.uniform(0.5, 1.0))) for a in ang])
             b.create_fixture(fd, shape)
+    # joints (revolute / distance) between random bodies, the ground included: limits, motors, soft springs, slack ranges,
+    # collide_connected, degenerate pairs (kinematic or fixed-rotation bodies, anchors far from the bodies)
+    joints = []
+    if rng.integers(0, 5) < 3:
+        for _ in range(int(rng.integers(1, 9))):
+            a, b = int(rng.integers(0, n + 1)), int(rng.integers(0, n + 1))
+            if a == b:
+                continue
+            if rng.integers(0, 2) == 0:
+                jd = world.revolute_joint_def(a, b, (f32(rng.uniform(-10, 10)), f32(rng.uniform(0.5, 14))))
+                if rng.integers(0, 2) == 0:
+                    lo = f32(rng.uniform(-1.5, 0.2))
+                    jd.enable_limit, jd.lower_angle, jd.upper_angle = 1, lo, f32(lo + (0.0 if rng.integers(0, 5) == 0 else rng.uniform(0, 2)))
+                if rng.integers(0, 2) == 0:
+                    jd.enable_motor, jd.motor_speed, jd.max_motor_torque = 1, f32(rng.uniform(-3, 3)), f32(rng.uniform(0, 200))
+            else:
+                jd = world.distance_joint_def(a, b, (f32(rng.uniform(-10, 10)), f32(rng.uniform(0.5, 14))),
+                                              (f32(rng.uniform(-10, 10)), f32(rng.uniform(0.5, 14))))
+                r = rng.integers(0, 4)
+                if r == 0:
+                    jd.stiffness, jd.damping = world.linear_stiffness(f32(rng.uniform(0.5, 5)), f32(rng.uniform(0, 1)), a, b)
+                if r <= 1:
+                    jd.min_length = f32(max(jd.length - rng.uniform(0, 2), 0.0))
+                    jd.max_length = f32(jd.length + rng.uniform(0, 2))
+            jd.collide_connected = int(rng.integers(0, 2))
+            joints.append((world.create_joint(jd), jd.type))
+    world._fuzz_joints = joints
     return n + 1
 
 
@@ -116,7 +144,7 @@ def run_seed(seed, make_world, steps, batch_mode, large=False, events=False):
     stepper = wg
     batch = None
     if batch_mode:
-        batch = wg.batch(int(rng.integers(33, 70)))
+        batch = wg.batch(int(rng.integers(33, 70)), max_contacts=40 * nb + 256)  # the reference grows its tables; a batch cannot
     if large:
         bt = wg.batch(1, lane_block=1, solver='large')
         for i in range(steps):
@@ -128,6 +156,9 @@ def run_seed(seed, make_world, steps, batch_mode, large=False, events=False):
                 wo.body(int(rng.integers(1, nb))).set_linear_velocity((f32v(rng.uniform(-6, 6)), f32v(rng.uniform(-6, 6))))
             bt.upload_world(0, wo.snapshot())
             wo.step(dt, vi, pi)
+            if exploded(wo):
+                run_seed.exploded = getattr(run_seed, "exploded", 0) + 1
+                break
             bt.step(dt, vi, pi)
             bad = parity.compare_large_step(wo.snapshot(), bt.download_world(0), wo.get_stats(), bt.stats()[0])
             if bad:
@@ -146,6 +177,17 @@ def run_seed(seed, make_world, steps, batch_mode, large=False, events=False):
             b = int(rng.integers(1, nb))
             v = (f32v(rng.uniform(-6, 6)), f32v(rng.uniform(-6, 6)))
             wo.body(b).set_linear_velocity(v); wg.body(b).set_linear_velocity(v)
+        if batch is None and ev == 8 and wo._fuzz_joints:  # B2revoluteJoint setters mid-run
+            q = int(rng.integers(0, len(wo._fuzz_joints)))
+            if wo._fuzz_joints[q][1] == abi.JOINT_REVOLUTE:
+                op, val, flag = int(rng.integers(0, 5)), f32v(rng.uniform(-3, 3)), bool(rng.integers(0, 2))
+                for w in (wo, wg):
+                    j = w._fuzz_joints[q][0]
+                    if op == 0: j.set_motor_speed(val)
+                    elif op == 1: j.set_max_motor_torque(abs(val) * 50.0)
+                    elif op == 2: j.enable_motor(flag)
+                    elif op == 3: j.enable_limit(flag)
+                    else: j.set_limits(min(val, 0.0) - 0.3, max(val, 0.0) + 0.3)
         if batch is None and 2 <= ev <= 7:  # the rest of B2body's force / impulse API, sleeping bodies included
             b = int(rng.integers(1, nb))
             vec = (f32v(rng.uniform(-40, 40)), f32v(rng.uniform(-40, 40)))
@@ -161,6 +203,9 @@ def run_seed(seed, make_world, steps, batch_mode, large=False, events=False):
                 elif ev == 6: bd.apply_angular_impulse(sc * 0.05, wake)
                 else: bd.set_awake(wake)
         wo.step(dt, vi, pi)
+        if exploded(wo):
+            run_seed.exploded = getattr(run_seed, "exploded", 0) + 1
+            break
         if batch is None and events:  # begin / end contact events of every step, in the reference's firing order
             ev_g = wg.step_with_events(dt, vi, pi)
             ev_o = wo.contact_events()
@@ -188,6 +233,12 @@ def f32v(x):
     return float(np.float32(x))
 
 
+def exploded(world):
+    """Random joints can over-constrain a scene until velocities overflow: once the oracle's state holds inf / NaN the run is
+    over (0 * inf = NaN then reaches even static bodies in the reference, which the device never writes): not a parity case."""
+    return not np.isfinite(world.body_state()).all()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--seeds", type=int, default=100)
@@ -207,7 +258,8 @@ def main():
         if r not in (None, "skip"):
             fails += 1
             print("seed %d: %s" % (seed, r), flush=True)
-    print("fuzz: %d seeds, %d failures (%s%s%s)" % (args.seeds, fails, "gpu" if args.gpu else "host simulator",
+    print("fuzz: %d seeds, %d failures, %d runs ended early by a numerical explosion of the scene (%s%s%s)"
+          % (args.seeds, fails, getattr(run_seed, "exploded", 0), "gpu" if args.gpu else "host simulator",
                                                      ", batch" if args.batch else ", large-world mode teacher-forced" if args.large else "",
                                                      ", %d contact events compared" % getattr(run_seed, "event_total", 0) if args.events else ""))
     sys.exit(1 if fails else 0)
