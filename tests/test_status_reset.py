@@ -137,7 +137,12 @@ def test_device_pointer_round_trip_gpu(built):
     d2d = cudart.cudaMemcpyKind.cudaMemcpyDeviceToDevice
 
     def copy(dst, src, nbytes):
+        # a device-to-device cudaMemcpy runs on the legacy default stream and returns before it has finished; the context's
+        # stream is non-blocking, so the copy is ordered against the library's kernels by hand (a caller that works on
+        # b2gpu_stream needs none of this)
         (err,) = cudart.cudaMemcpy(dst, src, nbytes, d2d)
+        assert int(err) == 0, err
+        (err,) = cudart.cudaDeviceSynchronize()
         assert int(err) == 0, err
     for _ in range(6):
         f = np.zeros((n, a.body_count, 3), np.float32)
