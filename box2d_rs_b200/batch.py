@@ -80,6 +80,11 @@ class Batch:
         pair).  step() is asynchronous and cannot report it; step_host / body_state / download_world do."""
         check(self.L, self.L.b2gpu_batch_status(self.h))
 
+    def set_level_threshold(self, contacts):
+        """Large-world batches: islands with at least `contacts` contacts (no joints) are swept in dependency-level order by a
+        CTA (b2gpu_batch_set_level_threshold); 0 = library default (1024), negative = never."""
+        check(self.L, self.L.b2gpu_batch_set_level_threshold(self.h, int(contacts)))
+
     def upload_world(self, world, snap):
         c = snap.as_c()
         check(self.L, self.L.b2gpu_batch_upload_world(self.h, world, C.byref(c)))

@@ -173,6 +173,11 @@ int b2gpu_batch_status(b2gpu_batch* b) {
   return st;
   GUARD_END
 }
+int b2gpu_batch_set_level_threshold(b2gpu_batch* b, int contacts) {
+  if (!b) { set_error("batch is NULL"); return B2GPU_E_INVALID; }
+  b->h->lw_level_min = contacts == 0 ? (int)LW_LEVEL_MIN_DEFAULT : contacts;
+  return 0;
+}
 int b2gpu_batch_get_stats(b2gpu_batch* b, int first, int count, b2gpu_step_stats* out) {
   GUARD_BEGIN
   if (!b) { set_error("batch is NULL"); return B2GPU_E_INVALID; }

@@ -70,6 +70,16 @@ struct Large {  // device scratch of the large-world mode
   float4* scratch4; // [16] store target for bodies that must not be written (immovable: shared between islands)
   int4* vc_idx;    // [NC] per island contact slot: (body A, body B, velocity points, -), see LwVelocity4K
   int* first_idx;  // [NN] first move-buffer index of a tree node (host edits can buffer a proxy more than once)
+  // level schedule of giant islands (b2g_levels.h)
+  int* lv_meta;       // [4] [0] = giant islands chosen at the last island rebuild
+  int4* lv_info;      // [LW_MAXG] (island, first constraint, constraints, levels)
+  int* lv_isl_giant;  // [NB] per island: 1 = swept by the level-scheduled kernels
+  int* lv_last;       // [NB] per body: level after its latest constraint (build scratch)
+  int* lv_level;      // [NC] level of the constraint at island-order position k
+  int* lv_count;      // [NC + NB + 2] constraints per level (build scratch), at first + island + level
+  int* lv_start;      // [NC + NB + 2] first position of a level in lv_order, at first + island + level
+  int* lv_order;      // [NC] constraints in level order, per island at its contact range
+  int4* lv_ix;        // [NC] vc_idx of the constraint at each position of the level order (refreshed every step)
   // islands
   int* uf_parent;  // [NB]
   int* cnt_b;      // [NB] per root: non-static bodies
@@ -1248,7 +1258,7 @@ struct LwVelocity7K {
     float4* bod = bod_s;
     const int stride = 1;
 #endif
-    if (isl >= n_islands) return;
+    if (isl >= n_islands || L.lv_isl_giant[isl]) return;  // a giant island is swept by LwLevelVelocityK
     const int4 rg = B.isl_range[isl];
     const bool joints = lw_island_has_joints(B, isl);
     if (rg.z == rg.w && !joints) return;
@@ -1330,7 +1340,7 @@ struct LwPosition6K {
   StepParams sp;
   int n_islands;
   B2G_HD void operator()(int isl) const {
-    if (isl >= n_islands) return;
+    if (isl >= n_islands || L.lv_isl_giant[isl]) return;  // a giant island is swept by LwLevelPositionK
     const int4 rg = B.isl_range[isl];
     const bool joints = lw_island_has_joints(B, isl);
     if (rg.z == rg.w && !joints) return;

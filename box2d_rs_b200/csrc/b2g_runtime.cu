@@ -44,6 +44,13 @@ template <class K> static int launch(Ctx* ctx, const K& k, int n, int /*block*/,
   return 0;
 }
 template <class K> static int launch_occ(Ctx* ctx, const K& k, int n, int stage) { return launch(ctx, k, n, 128, stage); }
+// CTA functors k(cta, thread, threads): one thread per CTA here, so a barrier is the end of a loop
+template <class K> static int launch_cta(Ctx* ctx, const K& k, int n_cta, int /*threads*/, int stage) {
+  for (int g = 0; g < n_cta; ++g) k(g, 0, 1);
+  ctx->launches++;
+  ctx->stage_launches[stage] += 1;
+  return 0;
+}
 int ctx_collect_profile(Ctx*) { return 0; }
 #else
 static int cuda_fail(cudaError_t e, const char* what) {
@@ -123,6 +130,15 @@ template <class K> static int launch_occ(Ctx* ctx, const K& k, int n, int stage)
   LaunchScope ls = {ctx, stage};
   RC(ls.begin());
   stage_kernel_occ<K><<<(n + 127) / 128, 128, 0, (cudaStream_t)ctx->stream>>>(k, n);
+  return ls.end();
+}
+// CTA functors k(cta, thread, threads) that synchronise their threads (b2g_levels.h)
+template <class K> __global__ void cta_kernel(const K k) { k((int)blockIdx.x, (int)threadIdx.x, (int)blockDim.x); }
+template <class K> static int launch_cta(Ctx* ctx, const K& k, int n_cta, int threads, int stage) {
+  if (n_cta <= 0) return 0;
+  LaunchScope ls = {ctx, stage};
+  RC(ls.begin());
+  cta_kernel<K><<<n_cta, threads, 0, (cudaStream_t)ctx->stream>>>(k);
   return ls.end();
 }
 int ctx_collect_profile(Ctx* ctx) {
@@ -1069,6 +1085,8 @@ static int large_alloc(BatchHost* bh) {
   AL(L.keep_flag, B.NC + 1LL); AL(L.keep_pos, B.NC + 1LL);
   AL(L.first_idx, B.NN); AL(L.vc_idx, B.NC); AL(L.scratch4, 16);
   AL(L.wake_idx, B.NB + 1LL);
+  AL(L.lv_meta, 4); AL(L.lv_info, LW_MAXG); AL(L.lv_isl_giant, B.NB + 1LL); AL(L.lv_last, B.NB + 1LL); AL(L.lv_level, B.NC + 1LL);
+  AL(L.lv_count, (long long)B.NC + B.NB + 2); AL(L.lv_start, (long long)B.NC + B.NB + 2); AL(L.lv_order, B.NC + 1LL); AL(L.lv_ix, B.NC + 1LL);
   AL(L.state, B.NB); AL(L.adj, 2LL * B.NC); AL(L.eadj, 2LL * B.NC); AL(L.erow, B.NB); AL(L.row_start, B.NB); AL(L.row_end, B.NB);
 #undef AL
 #if defined(B2G_HOSTSIM)
@@ -1242,8 +1260,21 @@ static int step_large(BatchHost* bh, const StepParams& sp, int steps) {
       // register form LwVelocity5K); LwPosition6K: two alternating register sets.  The other forms round 1 measured
       // (profiles/r01_large_world.md) were removed from the library.
       { LwVcIdxK k = {B, L, nic}; RC(launch(ctx, k, nic, 256, STAGE_SOLVER_INIT)); }
+      // giant islands without joints (>= lw_level_min contacts): level schedule rebuilt with the islands, one CTA per island
+      // sweeps level by level (b2g_levels.h); every other island one thread
+      const bool levels = bh->lw_level_min > 0 && nic >= bh->lw_level_min;
+      if (dirty) {
+        { LwLevelResetK k = {L}; RC(launch(ctx, k, 1, 32, STAGE_ISLAND)); }
+        { LwGiantSelectK k = {B, L, ni, levels ? bh->lw_level_min : 0}; RC(launch(ctx, k, ni, 256, STAGE_ISLAND)); }
+        if (levels) { LwLevelBuildK k = {B, L}; RC(launch_cta(ctx, k, LW_MAXG, LW_LEVEL_BUILD_NT, STAGE_ISLAND)); }
+      }
+      if (levels) {
+        { LwLevelIdxK k = {B, L, nic}; RC(launch(ctx, k, nic, 256, STAGE_SOLVER_INIT)); }
+        { LwLevelVelocityK k = {B, L, sp}; RC(launch_cta(ctx, k, LW_MAXG, LW_LEVEL_NT, STAGE_VELOCITY)); }
+      }
       { LwVelocity7K k = {B, L, sp, ni}; RC(launch(ctx, k, ni, 32, STAGE_VELOCITY)); }
       { PostVelocityK k = {B, sp}; RC(launch(ctx, k, std::max(std::max(ni, nib), nic), 128, STAGE_POST_VELOCITY)); }
+      if (levels) { LwLevelPositionK k = {B, L, sp}; RC(launch_cta(ctx, k, LW_MAXG, LW_LEVEL_NT, STAGE_POSITION)); }
       { LwPosition6K k = {B, L, sp, ni}; RC(launch(ctx, k, ni, 32, STAGE_POSITION)); }
       { FinalizeK k = {B, sp}; RC(launch(ctx, k, nib, 128, STAGE_FINALIZE)); }
       { SleepK k = {B}; RC(launch(ctx, k, ni, 128, STAGE_SLEEP)); }

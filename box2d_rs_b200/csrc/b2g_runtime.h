@@ -8,7 +8,7 @@
 #include <vector>
 
 #include "b2g_step.h"
-#include "b2g_large.h"
+#include "b2g_levels.h"
 #include "b2g_query.h"
 #include "b2g_island_layout.h"
 
@@ -106,6 +106,7 @@ struct BatchHost {
   StepParams last_sp{};
   // large-world mode (b2g_large.h): one world, flat stages + scans + sorts, host-driven control flow
   bool large = false;
+  int lw_level_min = LW_LEVEL_MIN_DEFAULT;  // islands with at least this many contacts (no joints) are swept level by level by a CTA; <= 0: never
   bool lw_exact_tree = false;    // large-world mode that keeps the replica tree (sequential re-insertion, reference contact order)
   Large L = {};
   int* lw_host = nullptr;        // pinned readback buffer (world scalars, scan totals)

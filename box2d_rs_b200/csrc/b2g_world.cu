@@ -247,6 +247,7 @@ struct b2gpu_world {
   bool topo_dirty = true;   // bodies/fixtures changed: the device batch must be rebuilt
   bool dev_newer = false;   // the device holds the authoritative state
   int large = 0;            // 1: data-parallel large-world stages (b2g_large.h); 2: the same with the exact replica tree
+  int level_min = 0;        // b2gpu_world_set_level_threshold: 0 = the library default
 };
 
 namespace {
@@ -1004,6 +1005,12 @@ int b2gpu_world_set_large_mode(b2gpu_world* W, int flag) {
   W->topo_dirty = true;
   return 0;
 }
+int b2gpu_world_set_level_threshold(b2gpu_world* W, int contacts) {
+  if (!W) { set_error("world is NULL"); return B2GPU_E_INVALID; }
+  W->level_min = contacts;
+  if (W->dev) W->dev->lw_level_min = contacts == 0 ? (int)LW_LEVEL_MIN_DEFAULT : contacts;  // takes effect at the next island rebuild
+  return 0;
+}
 int b2gpu_world_set_continuous_physics(b2gpu_world* W, int flag) {
   if (!W) { set_error("world is NULL"); return B2GPU_E_INVALID; }
   if (flag) { set_error("continuous physics (TOI sub-stepping) is outside the hot-path scope"); return B2GPU_E_UNSUPPORTED; }
@@ -1026,6 +1033,7 @@ static int ensure_device(b2gpu_world* W) {
     caps.reserved[1] = W->large == 1 ? 11 : W->large == 2 ? 12 : 0;
     rc = batch_create(&W->ctx->c, &s, 1, &caps, 1, &W->dev);
     if (rc) return rc;
+    if (W->level_min != 0) W->dev->lw_level_min = W->level_min;
   } else if (W->host_dirty) {
     b2gpu_snapshot s;
     std::vector<b2gpu_tree_node_rec> nodes;

@@ -69,6 +69,7 @@ def load(path=None):
         "b2gpu_world_set_continuous_physics": (i32, [vp, i32]),
         "b2gpu_world_set_block_solve": (i32, [vp, i32]),
         "b2gpu_world_set_large_mode": (i32, [vp, i32]),
+        "b2gpu_world_set_level_threshold": (i32, [vp, i32]),
         "b2gpu_world_step": (i32, [vp, f32, i32, i32]),
         "b2gpu_world_get_body_count": (i32, [vp]),
         "b2gpu_world_get_contact_count": (i32, [vp]),
@@ -98,6 +99,7 @@ def load(path=None):
         "b2gpu_batch_get_stats": (i32, [vp, i32, i32, vp]),
         "b2gpu_batch_reset": (i32, [vp, C.POINTER(abi.SnapshotC)]),
         "b2gpu_batch_status": (i32, [vp]),
+        "b2gpu_batch_set_level_threshold": (i32, [vp, i32]),
         "b2gpu_batch_set_forces": (i32, [vp, vp, i32, i32]),
         "b2gpu_batch_set_linear_velocity": (i32, [vp, i32, vp, i32, i32]),
         "b2gpu_batch_get_body_state": (i32, [vp, vp, i32, i32]),

@@ -218,6 +218,11 @@ class B2world:
         flag = 2 keeps the replica tree (sequential re-insertion): reference contact order, bit-identical free-running."""
         check(self.L, self.L.b2gpu_world_set_large_mode(self.h, int(flag)))
 
+    def set_level_threshold(self, contacts):
+        """Large-world mode: islands with at least `contacts` contacts (and no joints) are swept by one CTA in dependency-level
+        order (b2gpu_world_set_level_threshold); 0 = library default (1024), negative = never."""
+        check(self.L, self.L.b2gpu_world_set_level_threshold(self.h, int(contacts)))
+
     def step(self, dt, velocity_iterations, position_iterations):
         check(self.L, self.L.b2gpu_world_step(self.h, dt, velocity_iterations, position_iterations))
 

@@ -247,7 +247,8 @@ typedef struct b2gpu_step_stats {
   int32_t pairs;         /* pairs reported by update_pairs (the reference's pair buffer length) */
   int32_t created;       /* contacts created by add_pair */
   int32_t awake_bodies;
-  int32_t solver_levels; /* depth of the exact-order wavefront schedule of the velocity pass */
+  int32_t solver_levels; /* large-world mode: dependency levels of one sweep, summed over the islands swept level by level
+                            (b2gpu_world_set_level_threshold); 0 when every island took the one-thread form */
   int32_t reserved[4];
 } b2gpu_step_stats;
 
@@ -419,6 +420,11 @@ int b2gpu_world_set_block_solve(b2gpu_world* w, int flag);
  * free-running state stays bit-identical to the reference; costs the sequential re-insertion when many proxies move.
  * Default 0: exact replica tree, ordered stages one thread per world. */
 int b2gpu_world_set_large_mode(b2gpu_world* w, int flag);
+/* Large-world mode, giant islands: an island with at least `contacts` contact constraints and no joints is swept by one
+ * CTA in dependency-level order instead of by one thread in list order (two constraints that share no movable body
+ * commute, so the results are the reference's bit for bit; levels are rebuilt with the islands).  0 = the library
+ * default (1024), negative = never.  Takes effect at the next island rebuild. */
+int b2gpu_world_set_level_threshold(b2gpu_world* w, int contacts);
 /* B2world::step (src/b2_world.rs:98; private :903-959) */
 int b2gpu_world_step(b2gpu_world* w, float dt, int velocity_iterations, int position_iterations);
 /* B2world::get_body_count / get_contact_count / get_proxy_count */
@@ -539,6 +545,8 @@ int b2gpu_batch_reset(b2gpu_batch* b, const b2gpu_snapshot* in);
  * the b2gpu_world_* calls that read state back.  b2gpu_batch_step / b2gpu_world_step are asynchronous and return
  * before the device has run: poll b2gpu_batch_status (synchronises; 0 or the most negative status of any world). */
 int b2gpu_batch_status(b2gpu_batch* b);
+/* b2gpu_world_set_level_threshold for a batch created in a large-world mode (b2gpu_caps.reserved[1] = 11 / 12). */
+int b2gpu_batch_set_level_threshold(b2gpu_batch* b, int contacts);
 /* Per-body force/torque of every world for the next step (B2body::apply_force_to_center /
  * apply_torque without wake): host array [n_worlds][body_count][3], pinned or pageable. */
 int b2gpu_batch_set_forces(b2gpu_batch* b, const float* host_fxfyt, int first_world, int count);

@@ -200,6 +200,7 @@ extern "C" {
     pub fn b2gpu_world_set_continuous_physics(w: *mut b2gpu_world, flag: c_int) -> c_int;
     pub fn b2gpu_world_set_block_solve(w: *mut b2gpu_world, flag: c_int) -> c_int;
     pub fn b2gpu_world_set_large_mode(w: *mut b2gpu_world, flag: c_int) -> c_int;
+    pub fn b2gpu_world_set_level_threshold(w: *mut b2gpu_world, contacts: c_int) -> c_int;
     pub fn b2gpu_world_ray_cast_closest(w: *mut b2gpu_world, p1p2: *const c_float, n: c_int, out: *mut b2gpu_ray_hit) -> c_int;
     pub fn b2gpu_world_query_aabb(w: *mut b2gpu_world, aabbs: *const c_float, n: c_int, max_hits: c_int, counts: *mut i32, hits: *mut i32) -> c_int;
     pub fn b2gpu_batch_ray_cast_closest(b: *mut b2gpu_batch, p1p2: *const c_float, rays_per_world: c_int, out: *mut b2gpu_ray_hit) -> c_int;
@@ -231,6 +232,7 @@ extern "C" {
     pub fn b2gpu_batch_post_solve_events(b: *mut b2gpu_batch, world: c_int, out: *mut b2gpu_post_solve_event, capacity: c_int) -> c_int;
     pub fn b2gpu_batch_reset(b: *mut b2gpu_batch, input: *const b2gpu_snapshot) -> c_int;
     pub fn b2gpu_batch_status(b: *mut b2gpu_batch) -> c_int;
+    pub fn b2gpu_batch_set_level_threshold(b: *mut b2gpu_batch, contacts: c_int) -> c_int;
     pub fn b2gpu_batch_set_forces(b: *mut b2gpu_batch, host_fxfyt: *const c_float, first_world: c_int, count: c_int) -> c_int;
     pub fn b2gpu_batch_set_linear_velocity(b: *mut b2gpu_batch, body: c_int, host_vxvy: *const c_float, first_world: c_int, count: c_int) -> c_int;
     pub fn b2gpu_batch_get_body_state(b: *mut b2gpu_batch, host_out: *mut c_float, first_world: c_int, count: c_int) -> c_int;

@@ -357,12 +357,56 @@ def test_large_mode_exact_order_free_running(name, ctx):
     wg.close()
 
 
+# ---- level-scheduled sweeps of giant islands (b2g_levels.h): one CTA per island, a barrier per dependency level
+@pytest.mark.parametrize("name,every", [("pyramid", 3), ("mixed300", 3), ("pile400", 2), ("variety", 2), ("addpair2000", 3), ("terrain", 3)])
+def test_level_scheduled_islands_teacher_forced(name, every, ctx):
+    from box2d_rs_b200 import scenes
+    wo, wg, steps = _pair(name, ctx)
+    bt = wg.batch(1, lane_block=1, solver='large')
+    bt.set_level_threshold(6)
+    levels = 0
+    for i in range(steps):
+        if i % every == 0:
+            bt.upload_world(0, wo.snapshot())
+            wo.step(scenes.DT, 8, 3)
+            bt.step(scenes.DT, 8, 3)
+            st = bt.stats()[0]
+            bad = parity.compare_large_step(wo.snapshot(), bt.download_world(0), wo.get_stats(), st)
+            assert bad == [], "step %d: %s" % (i, bad[:6])
+            levels = max(levels, int(st["solver_levels"]))
+        else:
+            wo.step(scenes.DT, 8, 3)
+    assert levels > 0
+    bt.close()
+    wg.close()
+
+
+@pytest.mark.parametrize("name", ["pyramid", "pile400", "mixed300", "variety"])
+def test_level_scheduled_islands_free_running(name, ctx):
+    """Mode 2 with every island of >= 4 contacts swept level by level: bit-identical to the oracle free-running."""
+    from box2d_rs_b200 import scenes
+    wo, wg, steps = _pair(name, ctx)
+    wg.set_large_mode(2)
+    wg.set_level_threshold(4)
+    levels = 0
+    for i in range(steps):
+        wo.step(scenes.DT, 8, 3)
+        wg.step(scenes.DT, 8, 3)
+        if i < 2 or i % 50 == 49 or i == steps - 1:
+            bad = parity.compare_snapshots(wo.snapshot(), wg.snapshot()) + \
+                [b for b in parity.compare_stats(wo.get_stats(), wg.get_stats()) if "island_bodies" not in b]
+            assert bad == [], "step %d: %s" % (i, bad[:6])
+            levels = max(levels, int(wg.get_stats()["solver_levels"]))
+    assert levels > 0
+    wg.close()
+
+
 # ---------------------------------------------------------------------------------------------------------
 # BASELINE configs[1], [3], [4] at FULL size (10k mixed, 100k pile, AddPair-20k): teacher-forced single steps
 # ---------------------------------------------------------------------------------------------------------
 FULL_SIZE = {
     # name: (recipe, gravity, oracle steps at which one teacher-forced GPU step is compared)
-    "mixed10k": (lambda s, w: s.mixed(w, n=10000), (0.0, -10.0), (0, 25, 60)),
+    "mixed10k": (lambda s, w: s.mixed(w, n=10000), (0.0, -10.0), (0, 25, 60, 125)),  # step 125: an island of > 1024 contacts (level-scheduled sweep)
     "pile100k": (lambda s, w: s.pile(w, n=100000), (0.0, -10.0), (0, 12, 30)),
     "addpair20k": (lambda s, w: s.add_pair(w, n=20000), (0.0, 0.0), (0, 26, 40)),
 }

@@ -28,16 +28,21 @@ def _pair(name, ctx):
 
 
 def teacher_forced(wo, bt, steps, every, world_index=0):
+    """Returns the largest b2gpu_step_stats.solver_levels seen (0: no island took the level-scheduled form)."""
     from box2d_rs_b200 import scenes
+    levels = 0
     for i in range(steps):
         if i % every == 0:
             bt.upload_world(world_index, wo.snapshot())
             wo.step(scenes.DT, 8, 3)
             bt.step(scenes.DT, 8, 3)
-            bad = parity.compare_large_step(wo.snapshot(), bt.download_world(world_index), wo.get_stats(), bt.stats()[world_index])
+            st = bt.stats()[world_index]
+            bad = parity.compare_large_step(wo.snapshot(), bt.download_world(world_index), wo.get_stats(), st)
             assert bad == [], "step %d: %s" % (i, bad[:6])
+            levels = max(levels, int(st["solver_levels"]))
         else:
             wo.step(scenes.DT, 8, 3)
+    return levels
 
 
 @pytest.mark.parametrize("name,every", [("hello_world", 1), ("pyramid", 2), ("mixed300", 2), ("pile400", 2), ("variety", 1),
@@ -188,3 +193,68 @@ def test_large_mode_exact_order_free_running(name, ctx):
                 [b for b in parity.compare_stats(wo.get_stats(), wg.get_stats()) if "island_bodies" not in b]
             assert bad == [], "step %d: %s" % (i, bad[:6])
     wg.close()
+
+
+# ---- level-scheduled sweeps of giant islands (b2g_levels.h).  The host simulator runs a CTA functor with one thread, so the
+# constraints of an island are visited in LEVEL order instead of list order: the commutation argument, tested bit for bit.
+@pytest.mark.parametrize("name,every", [("pyramid", 2), ("mixed300", 2), ("pile400", 2), ("variety", 1), ("addpair2000", 3), ("terrain", 2)])
+def test_level_order_teacher_forced(name, every, ctx):
+    wo, wg, steps = _pair(name, ctx)
+    bt = wg.batch(1, lane_block=1, solver='large')
+    bt.set_level_threshold(6)
+    assert teacher_forced(wo, bt, steps, every) > 0  # islands really took the level form
+    bt.close()
+    wg.close()
+
+
+@pytest.mark.parametrize("name", ["pyramid", "pile400", "mixed300"])
+def test_level_order_free_running(name, ctx):
+    """Mode 2 (reference contact order) with every island of >= 4 contacts swept level by level: the whole snapshot stays
+    bit-identical to the oracle free-running, through island rebuilds and cached islands alike."""
+    from box2d_rs_b200 import scenes
+    wo, wg, steps = _pair(name, ctx)
+    wg.set_large_mode(2)
+    wg.set_level_threshold(4)
+    used = 0
+    for i in range(steps):
+        wo.step(scenes.DT, 8, 3)
+        wg.step(scenes.DT, 8, 3)
+        if i < 2 or i % 40 == 39 or i == steps - 1:
+            bad = parity.compare_snapshots(wo.snapshot(), wg.snapshot()) + \
+                [b for b in parity.compare_stats(wo.get_stats(), wg.get_stats()) if "island_bodies" not in b]
+            assert bad == [], "step %d: %s" % (i, bad[:6])
+            used = max(used, int(wg.get_stats()["solver_levels"]))
+    assert used > 0
+    wg.close()
+
+
+def test_level_threshold_off_and_more_giants_than_slots(ctx):
+    """A negative threshold switches the level form off; with more eligible islands than CTA slots (16) the surplus keeps
+    the one-thread form — same bits either way."""
+    from box2d_rs_b200 import abi, scenes, world
+    from oracle import b2o
+
+    def build(w):
+        ground = w.create_body(abi.BodyDef())
+        ground.create_fixture_by_shape(w.shapes.edge_two_sided((-100.0, 0.0), (100.0, 0.0)), 0.0)
+        box = w.shapes.polygon_box(0.5, 0.5)
+        for s in range(24):  # 24 separate stacks of 4 boxes: 24 islands of 4 contacts once they rest
+            for i in range(4):
+                b = w.create_body(abi.BodyDef(type=abi.DYNAMIC_BODY, position=(-60.0 + 5.0 * s, 0.51 + 1.02 * i), allow_sleep=0))
+                b.create_fixture_by_shape(box, 1.0)
+
+    for thr in (-1, 3):
+        wo = b2o.B2world((0.0, -10.0))
+        build(wo)
+        wg = world.B2world((0.0, -10.0), ctx=ctx)
+        build(wg)
+        wg.set_large_mode(2)
+        wg.set_level_threshold(thr)
+        for i in range(40):
+            wo.step(scenes.DT, 8, 3)
+            wg.step(scenes.DT, 8, 3)
+        assert parity.compare_snapshots(wo.snapshot(), wg.snapshot()) == []
+        st = wg.get_stats()
+        assert int(st["islands"]) == 24
+        assert (int(st["solver_levels"]) > 0) == (thr > 0)
+        wg.close()
