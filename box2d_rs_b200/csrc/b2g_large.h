@@ -80,6 +80,8 @@ struct Large {  // device scratch of the large-world mode
   int* lv_start;      // [NC + NB + 2] first position of a level in lv_order, at first + island + level
   int* lv_order;      // [NC] constraints in level order, per island at its contact range
   int4* lv_ix;        // [NC] vc_idx of the constraint at each position of the level order (refreshed every step)
+  float4* lv_vrec;    // [NC * 8] velocity records q0..q7 in level order (refreshed every step; q6 follows the sweeps)
+  float4* lv_prec;    // [NC * 5] position records p0..p4 in level order (refreshed every step)
   // islands
   int* uf_parent;  // [NB]
   int* cnt_b;      // [NB] per root: non-static bodies

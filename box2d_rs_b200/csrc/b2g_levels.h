@@ -10,8 +10,8 @@
 // One thread per island (LwVelocity7K / LwPosition6K) pays (visits) x (latency of a visit).  Here ONE CTA sweeps the
 // island level by level: level(k) = max over its movable bodies of (level of the body's previous constraint + 1),
 // computed once per island rebuild by a sequential scan (LwLevelBuildK) and counting-sorted; a sweep then costs
-// (levels) x (latency of a level) with a __syncthreads between levels, the constraints of a level one per thread.  The
-// body state stays in the plain global arrays (L1 / L2: the CTA is one SM, its own writes are visible to it after the
+// (levels) x (latency of a level) with a barrier between levels, the constraints of a level one per thread.  The body
+// state stays in the plain global arrays (L1 / L2: the CTA is one SM, its own writes are visible to it after the
 // barrier).  Islands with joints keep the one-thread form (joint rows interleave with the contact rows per iteration).
 //
 // The functors take (cta, thread, threads); the host simulator runs them with one thread per CTA, i.e. it executes the
@@ -21,7 +21,8 @@
 
 namespace b2g {
 
-enum { LW_MAXG = 16, LW_LEVEL_NT = 256, LW_LEVEL_BUILD_NT = 1024, LW_LEVEL_MIN_DEFAULT = 1024 };
+enum { LW_MAXG = 16, LW_LEVEL_NT = 160, LW_LEVEL_BUILD_NT = 1024, LW_LEVEL_MIN_DEFAULT = 1024 };  // LW_LEVEL_NT: four consumer warps + the producer warp
+enum { LV_VQ = 8, LV_PQ = 5 };  // float4 per velocity / position record in the level-ordered copies
 // L.lv_meta: [0] giant islands chosen at the last island rebuild (may exceed LW_MAXG: the surplus keeps the one-thread form)
 
 B2G_HD void lv_cta_sync() {
@@ -46,12 +47,6 @@ B2G_HD int lv_slot(int tid, int nt) {
   const int nw = nt >> 5;
   return nw > 0 ? (tid & 31) * nw + (tid >> 5) : tid;
 }
-// lv_level entry of a constraint: its level, and per body whether the body's state is FRESH at that level — written by the
-// level just before (or level 0, which follows the last level of the previous sweep), so it can only be read after the
-// barrier.  A body that is not fresh was last written at least two levels earlier (or never: immovable) and may be
-// requested one level ahead.
-enum { LV_LEVEL_MASK = 0x1fffffff, LV_FRESH_A = 1 << 29, LV_FRESH_B = 1 << 30, LV_IX_FRESH_A = 1 << 8, LV_IX_FRESH_B = 1 << 9 };
-B2G_HD int lv_pack(int level, bool fresh_a, bool fresh_b) { return level | (fresh_a ? (int)LV_FRESH_A : 0) | (fresh_b ? (int)LV_FRESH_B : 0); }
 
 struct LwLevelResetK {  // one thread, before the selection
   Large L;
@@ -76,7 +71,7 @@ struct LwGiantSelectK {  // flat over islands: which islands take the level-sche
 };
 
 // Levels of one giant island: CTA g, after SolverInitK / LwVcIdxK of the step that rebuilt the islands.
-//   lv_level[first + k]   level of constraint k (island order) | LV_FRESH_A / LV_FRESH_B
+//   lv_level[first + k]   level of constraint k (island order)
 //   lv_start[first + isl + l]  first position of level l in lv_order (island-relative), l = 0 .. depth (at depth: n);
 //                              first + isl grows by more than an island's level count from one island to the next
 //   lv_order[first + p]   constraint (absolute index) at position p of the level order
@@ -115,7 +110,7 @@ struct LwLevelBuildK {
           const bool mov_a = q7[j].x != 0.0f || q7[j].y != 0.0f, mov_b = q7[j].z != 0.0f || q7[j].w != 0.0f;
           const int la = mov_a ? L.lv_last[ix[j].x] : 0, lb = mov_b ? L.lv_last[ix[j].y] : 0;
           const int lvl = imax(la, lb);
-          L.lv_level[first + k + j] = lv_pack(lvl, mov_a && (la == lvl), mov_b && (lb == lvl));
+          L.lv_level[first + k + j] = lvl;
           if (mov_a) L.lv_last[ix[j].x] = lvl + 1;
           if (mov_b) L.lv_last[ix[j].y] = lvl + 1;
           depth = imax(depth, lvl + 1);
@@ -127,7 +122,7 @@ struct LwLevelBuildK {
         const bool mov_a = q7.x != 0.0f || q7.y != 0.0f, mov_b = q7.z != 0.0f || q7.w != 0.0f;
         const int la = mov_a ? L.lv_last[ix.x] : 0, lb = mov_b ? L.lv_last[ix.y] : 0;
         const int lvl = imax(la, lb);
-        L.lv_level[first + k] = lv_pack(lvl, mov_a && (la == lvl), mov_b && (lb == lvl));
+        L.lv_level[first + k] = lvl;
         if (mov_a) L.lv_last[ix.x] = lvl + 1;
         if (mov_b) L.lv_last[ix.y] = lvl + 1;
         depth = imax(depth, lvl + 1);
@@ -136,7 +131,7 @@ struct LwLevelBuildK {
     }
     lv_cta_sync();
     const int depth = L.lv_info[g].w;
-    for (int k = tid; k < n; k += nt) lv_fetch_add(&L.lv_count[base + (L.lv_level[first + k] & LV_LEVEL_MASK)], 1);
+    for (int k = tid; k < n; k += nt) lv_fetch_add(&L.lv_count[base + L.lv_level[first + k]], 1);
     lv_cta_sync();
     // exclusive scan of the level sizes: a contiguous chunk per thread, the chunk sums scanned by thread 0
     const int per = (depth + 1 + nt - 1) / nt;
@@ -159,236 +154,354 @@ struct LwLevelBuildK {
     }
     lv_cta_sync();
     for (int k = tid; k < n; k += nt) {
-      const int lvl = L.lv_level[first + k] & LV_LEVEL_MASK;
+      const int lvl = L.lv_level[first + k];
       const int pos = L.lv_start[base + lvl] + lv_fetch_add(&L.lv_count[base + lvl], 1);
       L.lv_order[first + pos] = first + k;
     }
   }
 };
 
-// Indices of the giant islands' constraints in level order, every step after LwVcIdxK (the point counts in vc_idx follow the
-// manifolds): a sweep reads (constraint, bodies) of position i with two independent loads instead of a chain of three.
-struct LwLevelIdxK {  // flat over the island contact slots
+// Level-ordered copies of what a sweep reads, every step after SolverInitK / LwVcIdxK: position i of the level order gets its
+// constraint's indices, velocity record (q0..q7) and position record (p0..p4).  The sweeps then read
+// CONTIGUOUS streams in the order they visit them — no indirection between a position and its data.
+struct LwLevelGatherK {  // flat over the island contact slots
   Batch B;
   Large L;
   int n;
   B2G_HD void operator()(int i) const {
     if (i >= n || !L.lv_isl_giant[B.c_isl[i]]) return;
     const int k = L.lv_order[i];
-    int4 ix = L.vc_idx[k];
-    const int lv = L.lv_level[k];
-    ix.z |= ((lv & LV_FRESH_A) ? (int)LV_IX_FRESH_A : 0) | ((lv & LV_FRESH_B) ? (int)LV_IX_FRESH_B : 0);
-    L.lv_ix[i] = ix;
+    L.lv_ix[i] = L.vc_idx[k];
+    const float4* v = B.vc + (size_t)k * VC_Q;
+    float4* dv = L.lv_vrec + (size_t)i * LV_VQ;
+    for (int q = 0; q < LV_VQ; ++q) dv[q] = v[q];
+    const float4* c = B.pc + (size_t)k * PC_Q;
+    float4* dc = L.lv_prec + (size_t)i * LV_PQ;
+    for (int q = 0; q < LV_PQ; ++q) dc[q] = c[q];
   }
 };
 
-// A sweep costs (levels) x (latency of a level), so everything a level needs that does not depend on the level before it is
-// requested ahead: the bounds of level t+3, the (constraint, bodies) indices of level t+2 and the constraint record of level
-// t+1 are in flight while level t is solved; after the barrier only the two body loads stand before the arithmetic.  A
-// record's impulses are rewritten by its own visit one pass (= depth levels) earlier: with depth >= 3 that store is at least
-// two barriers old when the record is requested.  Shallower islands take the plain loop.
+// ------------------------------------------------------------------------------------------
+// The sweep engine.  A sweep costs (levels) x (latency of a level): a level must be nothing but "read two bodies, solve,
+// write two bodies, barrier".  What was measured on the way (profiles/r02_levels.md): with every thread running its own
+// prefetch pipeline the bookkeeping of the idle threads WAS the level time, and so was a producer warp that worked level by
+// level inside the CTA barrier; a register load in flight shares a scoreboard with the body loads of the level and makes
+// their first use wait for L2 (~550 cycles); cp.async.cg and prefetch.global.L1 do not fill L1, a plain load does
+// (41 cycles afterwards), and a body written by this SM is an L1 hit for the next reader.  So:
+//   * the CONSUMER warps sweep level by level with a barrier of their own (bar.sync 1): bounds of the next level requested a
+//     level ahead, position -> thread round the warps (lv_slot), the constraint from the ring when it is there (plain loads
+//     when not: the consumers never wait for the producer), its bodies by plain loads, arithmetic, stores, barrier;
+//   * one PRODUCER warp runs DECOUPLED from the levels: in chunks it streams the level-ordered indices and records of the
+//     positions ahead through a ring in shared memory (cp.async, contiguous source; the ring is indexed by the running
+//     position of the sweeps, pass * n + position) and then touches the bodies of those constraints with plain loads, which
+//     fills this SM's L1.  It follows the consumers' published position: a ring slot is reused only when the consumers are
+//     past it, and a record is requested only when its previous visit — one pass, n positions, earlier: it rewrites the
+//     record's impulses — is behind a consumer barrier:  position < consumers' position + min(ring, n).
+// Hand-over: producer  cp.async -> wait_group 0 -> __threadfence_block -> ready = position;  consumers  ready ->
+// __threadfence_block -> ring.  Host simulator: one thread plays both roles, the producer keeps the ring full.
+// ------------------------------------------------------------------------------------------
+enum { LV_RING = 256, LV_PRODUCER = 32, LV_CHUNK = 48 };
+#if defined(__CUDA_ARCH__)
+#define LW_CP4(dst, src) asm volatile("cp.async.ca.shared.global [%0], [%1], 4;\n" ::"r"((unsigned)__cvta_generic_to_shared(dst)), "l"(src) : "memory")
+#else
+#define LW_CP4(dst, src) (*(int*)(dst) = *(const int*)(src))
+#endif
+template <int Q> struct LvRing {
+  enum { RS = Q + 1 };  // record stride in float4 (one of padding: wide levels read with a stride of several records)
+  float4* rec;  // [LV_RING][RS]
+  int4* ix;     // [LV_RING]
+  int* k;       // [LV_RING]
+  int* ctl;     // [0] positions below this are in the ring (producer), [1] position the consumers are at
+  static B2G_HD size_t bytes() { return (size_t)LV_RING * (RS * 16 + 16 + 4) + 16; }
+  B2G_HD void carve(float4* smem) {
+    rec = smem;
+    ix = (int4*)(rec + (size_t)LV_RING * RS);
+    k = (int*)(ix + LV_RING);
+    ctl = k + LV_RING;
+  }
+};
+B2G_HD int lv_vload(const int* p) {
+#if defined(__CUDA_ARCH__)
+  return *(volatile const int*)p;
+#else
+  return *p;
+#endif
+}
+B2G_HD void lv_vstore(int* p, int v) {
+#if defined(__CUDA_ARCH__)
+  *(volatile int*)p = v;
+#else
+  *p = v;
+#endif
+}
+B2G_HD void lv_fence_block() {
+#if defined(__CUDA_ARCH__)
+  __threadfence_block();
+#endif
+}
+B2G_HD void lv_consumer_sync(int nc) {
+#if defined(__CUDA_ARCH__)
+  asm volatile("bar.sync 1, %0;" ::"r"(nc) : "memory");
+#endif
+}
+
+// POL: Q; stream(): level-ordered records of the island (Q float4 per position); touch(ix): plain loads of a constraint's
+// bodies, returns something that depends on them; ring(t, rel, k, ix, rec): solve a constraint from the ring;
+// direct(t, rel, k): solve it with plain loads only.
+template <class POL> struct LvProducer {  // the producer's state (host simulator: advanced between the consumers' levels)
+  int pf;        // positions requested (and landed) so far
+  float touched, pending;
+};
+template <class POL>
+B2G_HD void lv_produce(POL& pol, const Large& L, LvRing<POL::Q>& R, LvProducer<POL>& P, const float4* stream, int first, int n, int total_pos,
+                       int cons, int lane, int lanes) {
+  typedef LvRing<POL::Q> Ring;
+  const int lim = imin(total_pos, cons + imin((int)LV_RING, n));
+  if (lim <= P.pf) return;
+  const int pieces = POL::Q + 2;
+  for (int c = lane; c < (lim - P.pf) * pieces; c += lanes) {
+    const int gp = P.pf + c / pieces, part = c % pieces, rel = gp % n, rs = gp & (LV_RING - 1);
+    if (part < POL::Q) LW_CP16(R.rec + (size_t)rs * Ring::RS + part, stream + (size_t)rel * POL::Q + part);
+    else if (part == POL::Q) LW_CP16(R.ix + rs, &L.lv_ix[first + rel]);
+    else LW_CP4(R.k + rs, &L.lv_order[first + rel]);
+  }
+  LW_CP_COMMIT();
+  P.touched += P.pending;  // the loads of the previous chunk's touch are looked at only now
+  P.pending = 0.0f;
+  LW_CP_WAIT0();
+  lv_fence_block();
+#if defined(__CUDA_ARCH__)
+  __syncwarp();
+#endif
+  if (lane == 0) lv_vstore(&R.ctl[0], lim);
+  // touch the bodies of the chunk (its indices are in the ring now): plain loads fill this SM's L1
+  for (int gp = P.pf + lane; gp < lim; gp += lanes) P.pending += pol.touch(R.ix[gp & (LV_RING - 1)]);
+  P.pf = lim;
+}
+template <class POL>
+B2G_HD void lv_sweeps(POL& pol, const Large& L, float4* smem, int first, int n, int depth, int base, int passes, int tid, int nt) {
+  typedef LvRing<POL::Q> Ring;
+  Ring R;
+  R.carve(smem);
+#if defined(__CUDA_ARCH__)
+  const int nc = nt - LV_PRODUCER;          // consumer threads
+  const bool producer = tid >= nc;
+  const int lane = tid - nc, lanes = LV_PRODUCER;
+#else
+  const int nc = 1;
+  const int lane = 0, lanes = 1;
+#endif
+  const int total = passes * depth, total_pos = passes * n;
+  const float4* stream = pol.stream();
+  LvProducer<POL> P;
+  P.pf = 0;
+  P.touched = P.pending = 0.0f;
+  if (tid == 0) { lv_vstore(&R.ctl[0], 0); lv_vstore(&R.ctl[1], 0); }
+  lv_cta_sync();
+#if defined(__CUDA_ARCH__)
+  if (producer) {
+    while (P.pf < total_pos) {
+      const int cons = lv_vload(&R.ctl[1]);
+      lv_fence_block();
+      const int lim = imin(total_pos, cons + imin((int)LV_RING, n));
+      if (lim - P.pf < imin((int)LV_CHUNK, imax(1, n >> 1)) && lim < total_pos) { __nanosleep(100); continue; }  // wait for room: a chunk at a time
+      lv_produce(pol, L, R, P, stream, first, n, total_pos, cons, lane, lanes);
+    }
+    if (P.touched + P.pending == 12345.678f) L.lv_meta[3] = 1;  // keeps the touch loads alive
+    return;
+  }
+#endif
+  // ---- consumers
+  const int slot = lv_slot(tid, nc);
+  int lc = 0, pbc = 0;  // level index and pass base of level t
+  int s = L.lv_start[base], e = L.lv_start[base + 1];
+  for (int t = 0; t < total; ++t) {
+    // bounds of the next level, requested now
+    int ln = lc + 1, pbn = pbc;
+    if (ln == depth) { ln = 0; pbn += n; }
+    const int sn = L.lv_start[base + ln], en = L.lv_start[base + ln + 1];
+    if (tid == 0) {  // every position below is behind a barrier: publish (release) the consumers' position
+      lv_fence_block();
+      lv_vstore(&R.ctl[1], pbc + s);
+    }
+#if !defined(__CUDA_ARCH__)
+    lv_produce(pol, L, R, P, stream, first, n, total_pos, pbc + s, lane, lanes);
+#endif
+    const int rd = lv_vload(&R.ctl[0]);
+    lv_fence_block();
+    for (int rel = s + slot; rel < e; rel += nc) {
+      const int gp = pbc + rel;
+      if (gp < rd) {
+        const int rs = gp & (LV_RING - 1);
+        pol.ring(t, rel, R.k[rs], R.ix[rs], R.rec + (size_t)rs * Ring::RS);
+      } else {
+        pol.direct(t, rel, L.lv_order[first + rel]);
+#if defined(B2G_LV_DEBUG)
+        lv_fetch_add(&L.lv_meta[2], 1);
+#endif
+      }
+    }
+    lv_consumer_sync(nc);
+    lc = ln; pbc = pbn; s = sn; e = en;
+  }
+}
+template <class POL>
+B2G_HD void lv_sweeps_plain(POL& pol, const Large& L, int first, int depth, int base, int passes, int tid, int nt) {
+  const int slot = lv_slot(tid, nt);
+  for (int p = 0; p < passes; ++p) {
+    int s = L.lv_start[base];
+    for (int l = 0; l < depth; ++l) {
+      const int e = L.lv_start[base + l + 1];
+      for (int i = s + slot; i < e; i += nt) pol.direct(p * depth + l, i, L.lv_order[first + i]);
+      s = e;
+      lv_cta_sync();
+    }
+  }
+}
+
+// Warm start + velocity iterations of giant island g (the loops of LwVelocity7K, level by level).
 struct LwLevelVelocityK {
   Batch B;
   Large L;
   StepParams sp;
-  B2G_HD void solve(int k, const int4 ix, const float4 q0, const float4 q1, const float4 q2, const float4 q3, const float4 q4,
-                    const float4 q5, float4 q6, const float4 q7, bool warm_pass, bool block, const float4 ea, const float4 eb) const {
-    const int points = ix.z & 0xff;
-    if (points == 0) return;
-    // a fresh body is read now, after the barrier; the others were requested a level ago (ea / eb)
-    const float4 va = (ix.z & LV_IX_FRESH_A) ? B.b_vel[ix.x] : ea, vb = (ix.z & LV_IX_FRESH_B) ? B.b_vel[ix.y] : eb;
-    VelState s;
-    s.v_a = v2(va.x, va.y); s.w_a = va.z;
-    s.v_b = v2(vb.x, vb.y); s.w_b = vb.z;
-    if (warm_pass) {
-      warm_start_one(s, q0, q1, q2, q6, q7, points);
-    } else {
-      // the common case — two points, block solver — as its own call: the constants fold its branches away
-      if (points == 2 && block) solve_velocity_one(s, q0, q1, q2, q3, q4, q5, q6, q7, 2, true);
-      else solve_velocity_one(s, q0, q1, q2, q3, q4, q5, q6, q7, points, block);
-      B.vc[(size_t)k * VC_Q + 6] = q6;
+  static size_t smem_bytes() { return LvRing<LV_VQ>::bytes(); }
+  struct Pol {
+    enum { Q = LV_VQ };
+    const LwLevelVelocityK* K;
+    int first, depth;
+    bool warm, block;
+    B2G_HD const float4* stream() const { return K->L.lv_vrec + (size_t)first * LV_VQ; }
+    B2G_HD float touch(const int4 ix) const { return K->B.b_vel[ix.x].w + K->B.b_vel[ix.y].w; }
+    B2G_HD void solve(int t, int rel, int k, const int4 ix, const float4 q0, const float4 q1, const float4 q2, const float4 q3,
+                      const float4 q4, const float4 q5, float4 q6, const float4 q7) const {
+      const Batch& B = K->B;
+      const int points = ix.z & 0xff;
+      if (points == 0) return;
+      const float4 va = B.b_vel[ix.x], vb = B.b_vel[ix.y];  // L1: touched by the producer two levels ago, or written by this SM
+      VelState s;
+      s.v_a = v2(va.x, va.y); s.w_a = va.z;
+      s.v_b = v2(vb.x, vb.y); s.w_b = vb.z;
+      if (warm && t < depth) {
+        warm_start_one(s, q0, q1, q2, q6, q7, points);
+      } else {
+        // the common case — two points, block solver — as its own call: the constants fold its branches away
+        if (points == 2 && block) solve_velocity_one(s, q0, q1, q2, q3, q4, q5, q6, q7, 2, true);
+        else solve_velocity_one(s, q0, q1, q2, q3, q4, q5, q6, q7, points, block);
+        B.vc[(size_t)k * VC_Q + 6] = q6;                                 // what PostVelocityK stores into the manifold
+        K->L.lv_vrec[(size_t)(first + rel) * LV_VQ + 6] = q6;            // what the next pass reads
+      }
+      // a body without inverse mass and inertia may sit in several constraints of a level (and in several islands): never written
+      if (q7.x != 0.0f || q7.y != 0.0f) B.b_vel[ix.x] = make_float4(s.v_a.x, s.v_a.y, s.w_a, 0.0f);
+      if (q7.z != 0.0f || q7.w != 0.0f) B.b_vel[ix.y] = make_float4(s.v_b.x, s.v_b.y, s.w_b, 0.0f);
     }
-    // a body without inverse mass and inertia may sit in several constraints of a level (and in several islands): never written
-    if (q7.x != 0.0f || q7.y != 0.0f) B.b_vel[ix.x] = make_float4(s.v_a.x, s.v_a.y, s.w_a, 0.0f);
-    if (q7.z != 0.0f || q7.w != 0.0f) B.b_vel[ix.y] = make_float4(s.v_b.x, s.v_b.y, s.w_b, 0.0f);
-  }
-  B2G_HD void visit(int k, bool warm_pass, bool block) const {  // everything read now
-    const LwVcRec r = lw_load_vc(B.vc, k);
-    int4 ix = L.vc_idx[k];
-    ix.z |= LV_IX_FRESH_A | LV_IX_FRESH_B;
-    const float4 none = make_float4(0, 0, 0, 0);
-    solve(k, ix, r.q0, r.q1, r.q2, r.q3, r.q4, r.q5, r.q6, r.q7, warm_pass, block, none, none);
-  }
+    B2G_HD void ring(int t, int rel, int k, const int4 ix, const float4* r) const {
+      solve(t, rel, k, ix, r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7]);
+    }
+    B2G_HD void direct(int t, int rel, int k) const {  // everything read now
+      const float4* r = stream() + (size_t)rel * LV_VQ;
+      solve(t, rel, k, K->L.vc_idx[k], r[0], r[1], r[2], r[3], r[4], r[5], r[6], r[7]);
+    }
+  };
   B2G_HD void operator()(int g, int tid, int nt) const {
+#if defined(__CUDA_ARCH__)
+    extern __shared__ float4 lv_smem[];
+    float4* smem = lv_smem;
+#else
+    float4 host_ring[(LvRing<LV_VQ>::RS + 2) * LV_RING + 8];
+    float4* smem = host_ring;
+#endif
     if (g >= lv_giants(L)) return;
     const int4 info = L.lv_info[g];
-    const int first = info.y, depth = info.w, base = first + info.x;
-    const int slot = lv_slot(tid, nt);
-    const bool warm = (B.ws[WS_FLAGS] & B2GPU_WORLD_WARM_STARTING) != 0;
-    const bool block = (B.ws[WS_FLAGS] & B2GPU_WORLD_BLOCK_SOLVE) != 0;
-    const int passes = (warm ? 1 : 0) + sp.velocity_iterations;
+    const int first = info.y, n = info.z, depth = info.w, base = first + info.x;
+    Pol pol;
+    pol.K = this;
+    pol.first = first;
+    pol.depth = depth;
+    pol.warm = (B.ws[WS_FLAGS] & B2GPU_WORLD_WARM_STARTING) != 0;
+    pol.block = (B.ws[WS_FLAGS] & B2GPU_WORLD_BLOCK_SOLVE) != 0;
+    const int passes = (pol.warm ? 1 : 0) + sp.velocity_iterations;
     if (tid == 0) lv_fetch_add(&B.ws[WS_ST_LEVELS], depth);  // b2gpu_step_stats.solver_levels: levels of one sweep, summed over the giant islands
-    if (depth < 3) {
-      for (int p = 0; p < passes; ++p) {
-        int s = L.lv_start[base];
-        for (int l = 0; l < depth; ++l) {
-          const int e = L.lv_start[base + l + 1];
-          for (int i = s + slot; i < e; i += nt) visit(L.lv_order[first + i], warm && p == 0, block);
-          s = e;
-          lv_cta_sync();
-        }
-      }
-      return;
-    }
-    const long long total = (long long)passes * depth;
-    // level t: bounds (s0, e0), this thread's first constraint k0 / ix0 with its record; t+1: (s1, e1), k1 / ix1; t+2: (s2, e2)
-    int s0 = L.lv_start[base], e0 = L.lv_start[base + 1], s1 = e0, e1 = L.lv_start[base + 2], s2 = e1, e2 = L.lv_start[base + 3];
-    int l3 = 3 < depth ? 3 : 0;  // level index of t+3
-    int k0 = -1, k1 = -1;
-    int4 ix0 = make_int4(0, 0, 0, 0), ix1 = ix0;
-    if (s0 + slot < e0) { k0 = L.lv_order[first + s0 + slot]; ix0 = L.lv_ix[first + s0 + slot]; }
-    if (s1 + slot < e1) { k1 = L.lv_order[first + s1 + slot]; ix1 = L.lv_ix[first + s1 + slot]; }
-    float4 q0 = make_float4(0, 0, 0, 0), q1 = q0, q2 = q0, q3 = q0, q4 = q0, q5 = q0, q6 = q0, q7 = q0, ea = q0, eb = q0;
-    if (k0 >= 0) {
-      const float4* r = B.vc + (size_t)k0 * VC_Q;
-      q0 = r[0]; q1 = r[1]; q2 = r[2]; q3 = r[3]; q4 = r[4]; q5 = r[5]; q6 = r[6]; q7 = r[7];
-      ix0.z |= LV_IX_FRESH_A | LV_IX_FRESH_B;  // the first level of the stage: nothing was requested ahead
-    }
-    for (long long t = 0; t < total; ++t) {
-      // requests for the levels ahead
-      const int s3 = L.lv_start[base + l3], e3 = L.lv_start[base + l3 + 1];
-      int k2 = -1;
-      int4 ix2 = make_int4(0, 0, 0, 0);
-      if (s2 + slot < e2) { k2 = L.lv_order[first + s2 + slot]; ix2 = L.lv_ix[first + s2 + slot]; }
-      float4 n0 = make_float4(0, 0, 0, 0), n1 = n0, n2 = n0, n3 = n0, n4 = n0, n5 = n0, n6 = n0, n7 = n0;
-      if (k1 >= 0) {
-        const float4* r = B.vc + (size_t)k1 * VC_Q;
-        n0 = r[0]; n1 = r[1]; n2 = r[2]; n3 = r[3]; n4 = r[4]; n5 = r[5]; n6 = r[6]; n7 = r[7];
-      }
-      float4 fa = make_float4(0, 0, 0, 0), fb = fa;  // the bodies of level t+1 that level t does not write
-      if (k1 >= 0 && !(ix1.z & LV_IX_FRESH_A)) fa = B.b_vel[ix1.x];
-      if (k1 >= 0 && !(ix1.z & LV_IX_FRESH_B)) fb = B.b_vel[ix1.y];
-      // this level
-      const bool warm_pass = warm && t < depth;
-      if (k0 >= 0) solve(k0, ix0, q0, q1, q2, q3, q4, q5, q6, q7, warm_pass, block, ea, eb);
-      for (int i = s0 + slot + nt; i < e0; i += nt) visit(L.lv_order[first + i], warm_pass, block);
-      lv_cta_sync();
-      k0 = k1; ix0 = ix1; q0 = n0; q1 = n1; q2 = n2; q3 = n3; q4 = n4; q5 = n5; q6 = n6; q7 = n7; ea = fa; eb = fb;
-      k1 = k2; ix1 = ix2;
-      s0 = s1; e0 = e1; s1 = s2; e1 = e2; s2 = s3; e2 = e3;
-      if (++l3 == depth) l3 = 0;
-    }
+    if (depth < 3 || (long long)passes * n > 0x3fffffffLL) lv_sweeps_plain(pol, L, first, depth, base, passes, tid, nt);
+    else lv_sweeps(pol, L, smem, first, n, depth, base, passes, tid, nt);
   }
 };
 
 // Position iterations of giant island g (the loop of LwPosition6K, level by level; the running minimum separation of a
 // sweep is reduced over the CTA: a minimum does not depend on the order).  The position records do not change during the
-// stage, so the same requests ahead are always safe.
+// stage; every sweep runs the engine for one pass.
 struct LwLevelPositionK {
   Batch B;
   Large L;
   StepParams sp;
-  B2G_HD float solve(const int4 ix, const float4 p0, const float4 p1, const float4 p2, const float4 p3, const float4 p4,
-                     float min_separation, float4 pa, float4 ra, float4 pb, float4 rb) const {
-    const int ba = ix.x, bb = ix.y, packed = ix.w;
-    // a fresh body is read now, after the barrier; the others were requested a level ago
-    if (ix.z & LV_IX_FRESH_A) { pa = B.b_pos[ba]; ra = B.b_rot[ba]; }
-    if (ix.z & LV_IX_FRESH_B) { pb = B.b_pos[bb]; rb = B.b_rot[bb]; }
-    PosState s;
-    s.c_a = v2(pa.x, pa.y); s.a_a = pa.z; s.q_a.s = ra.x; s.q_a.c = ra.y;
-    s.c_b = v2(pb.x, pb.y); s.a_b = pb.z; s.q_b.s = rb.x; s.q_b.c = rb.y;
-    const int type = (packed >> 8) & 0xff, points = packed & 0xff;
-    bool done = false;
-    if (points == 2 && type != B2GPU_MANIFOLD_CIRCLES) {  // a face manifold with two points: the straight-line form of position_sl_kernel
-      const PosState s0 = s;
-      bool wide = false;
-      const float ms = solve_position_face2(s, p0, p1, p2, p3, type == B2GPU_MANIFOLD_FACE_A, p4.x, p4.y, min_separation, wide);
-      if (!wide) { min_separation = ms; done = true; }
-      else s = s0;  // an angle beyond +-120 rad: the general form
+  static size_t smem_bytes() { return LvRing<LV_PQ>::bytes(); }
+  struct Pol {
+    enum { Q = LV_PQ };
+    const LwLevelPositionK* K;
+    int first;
+    float ms;  // this thread's running minimum separation of the sweep
+    B2G_HD const float4* stream() const { return K->L.lv_prec + (size_t)first * LV_PQ; }
+    B2G_HD float touch(const int4 ix) const {
+      const Batch& B = K->B;
+      return B.b_pos[ix.x].w + B.b_rot[ix.x].w + B.b_pos[ix.y].w + B.b_rot[ix.y].w;
     }
-    if (!done) min_separation = solve_position_one(s, p0, p1, p2, p3, type, points, p4.x, p4.y, min_separation);
-    if (p0.x != 0.0f || p0.y != 0.0f) {
-      pa.x = s.c_a.x; pa.y = s.c_a.y; pa.z = s.a_a; ra.x = s.q_a.s; ra.y = s.q_a.c;
-      B.b_pos[ba] = pa;
-      B.b_rot[ba] = ra;
-    }
-    if (p0.z != 0.0f || p0.w != 0.0f) {
-      pb.x = s.c_b.x; pb.y = s.c_b.y; pb.z = s.a_b; rb.x = s.q_b.s; rb.y = s.q_b.c;
-      B.b_pos[bb] = pb;
-      B.b_rot[bb] = rb;
-    }
-    return min_separation;
-  }
-  B2G_HD float visit(int k, float min_separation) const {  // everything read now
-    const LwPcRec r = lw_load_pc(B.pc, k);
-    int4 ix = L.vc_idx[k];
-    ix.z |= LV_IX_FRESH_A | LV_IX_FRESH_B;
-    const float4 none = make_float4(0, 0, 0, 0);
-    return solve(ix, r.p0, r.p1, r.p2, r.p3, r.p4, min_separation, none, none, none, none);
-  }
-  // one sweep; returns this thread's minimum separation
-  B2G_HD float sweep(int first, int depth, int base, int tid, int nt) const {
-    float ms = 0.0f;
-    const int slot = lv_slot(tid, nt);
-    if (depth < 3) {
-      int s = L.lv_start[base];
-      for (int l = 0; l < depth; ++l) {
-        const int e = L.lv_start[base + l + 1];
-        for (int i = s + slot; i < e; i += nt) ms = visit(L.lv_order[first + i], ms);
-        s = e;
-        lv_cta_sync();
+    B2G_HD void solve(const int4 ix, const float4 p0, const float4 p1, const float4 p2, const float4 p3, const float4 p4) {
+      const Batch& B = K->B;
+      const int ba = ix.x, bb = ix.y, packed = ix.w;
+      float4 pa = B.b_pos[ba], ra = B.b_rot[ba], pb = B.b_pos[bb], rb = B.b_rot[bb];  // L1: touched by the producer, or written by this SM
+      PosState s;
+      s.c_a = v2(pa.x, pa.y); s.a_a = pa.z; s.q_a.s = ra.x; s.q_a.c = ra.y;
+      s.c_b = v2(pb.x, pb.y); s.a_b = pb.z; s.q_b.s = rb.x; s.q_b.c = rb.y;
+      const int type = (packed >> 8) & 0xff, points = packed & 0xff;
+      bool done = false;
+      if (points == 2 && type != B2GPU_MANIFOLD_CIRCLES) {  // a face manifold with two points: the straight-line form of position_sl_kernel
+        const PosState s0 = s;
+        bool wide = false;
+        const float m = solve_position_face2(s, p0, p1, p2, p3, type == B2GPU_MANIFOLD_FACE_A, p4.x, p4.y, ms, wide);
+        if (!wide) { ms = m; done = true; }
+        else s = s0;  // an angle beyond +-120 rad: the general form
       }
-      return ms;
-    }
-    int s0 = L.lv_start[base], e0 = L.lv_start[base + 1], s1 = e0, e1 = L.lv_start[base + 2], s2 = e1, e2 = L.lv_start[base + 3];
-    int k0 = -1, k1 = -1;
-    int4 ix0 = make_int4(0, 0, 0, 0), ix1 = ix0;
-    if (s0 + slot < e0) { k0 = L.lv_order[first + s0 + slot]; ix0 = L.lv_ix[first + s0 + slot]; }
-    if (s1 + slot < e1) { k1 = L.lv_order[first + s1 + slot]; ix1 = L.lv_ix[first + s1 + slot]; }
-    float4 p0 = make_float4(0, 0, 0, 0), p1 = p0, p2 = p0, p3 = p0, p4 = p0, epa = p0, era = p0, epb = p0, erb = p0;
-    if (k0 >= 0) {
-      const float4* r = B.pc + (size_t)k0 * PC_Q;
-      p0 = r[0]; p1 = r[1]; p2 = r[2]; p3 = r[3]; p4 = r[4];
-      ix0.z |= LV_IX_FRESH_A | LV_IX_FRESH_B;  // the first level of the sweep: nothing was requested ahead
-    }
-    for (int l = 0; l < depth; ++l) {
-      const int l3 = l + 3 < depth ? l + 3 : depth - 1;  // past the sweep's end: any valid level, the request is dropped
-      const int s3 = L.lv_start[base + l3], e3 = L.lv_start[base + l3 + 1];
-      int k2 = -1;
-      int4 ix2 = make_int4(0, 0, 0, 0);
-      if (l + 2 < depth && s2 + slot < e2) { k2 = L.lv_order[first + s2 + slot]; ix2 = L.lv_ix[first + s2 + slot]; }
-      float4 n0 = make_float4(0, 0, 0, 0), n1 = n0, n2 = n0, n3 = n0, n4 = n0;
-      if (k1 >= 0) {
-        const float4* r = B.pc + (size_t)k1 * PC_Q;
-        n0 = r[0]; n1 = r[1]; n2 = r[2]; n3 = r[3]; n4 = r[4];
+      if (!done) ms = solve_position_one(s, p0, p1, p2, p3, type, points, p4.x, p4.y, ms);
+      if (p0.x != 0.0f || p0.y != 0.0f) {
+        pa.x = s.c_a.x; pa.y = s.c_a.y; pa.z = s.a_a; ra.x = s.q_a.s; ra.y = s.q_a.c;
+        B.b_pos[ba] = pa;
+        B.b_rot[ba] = ra;
       }
-      float4 fpa = make_float4(0, 0, 0, 0), fra = fpa, fpb = fpa, frb = fpa;  // the bodies of level l+1 that level l does not write
-      if (k1 >= 0 && !(ix1.z & LV_IX_FRESH_A)) { fpa = B.b_pos[ix1.x]; fra = B.b_rot[ix1.x]; }
-      if (k1 >= 0 && !(ix1.z & LV_IX_FRESH_B)) { fpb = B.b_pos[ix1.y]; frb = B.b_rot[ix1.y]; }
-      if (k0 >= 0) ms = solve(ix0, p0, p1, p2, p3, p4, ms, epa, era, epb, erb);
-      for (int i = s0 + slot + nt; i < e0; i += nt) ms = visit(L.lv_order[first + i], ms);
-      lv_cta_sync();
-      k0 = k1; ix0 = ix1; p0 = n0; p1 = n1; p2 = n2; p3 = n3; p4 = n4; epa = fpa; era = fra; epb = fpb; erb = frb;
-      k1 = k2; ix1 = ix2;
-      s0 = s1; e0 = e1; s1 = s2; e1 = e2; s2 = s3; e2 = e3;
+      if (p0.z != 0.0f || p0.w != 0.0f) {
+        pb.x = s.c_b.x; pb.y = s.c_b.y; pb.z = s.a_b; rb.x = s.q_b.s; rb.y = s.q_b.c;
+        B.b_pos[bb] = pb;
+        B.b_rot[bb] = rb;
+      }
     }
-    return ms;
-  }
+    B2G_HD void ring(int, int, int, const int4 ix, const float4* r) { solve(ix, r[0], r[1], r[2], r[3], r[4]); }
+    B2G_HD void direct(int, int rel, int k) {  // everything read now
+      const float4* r = stream() + (size_t)rel * LV_PQ;
+      solve(K->L.vc_idx[k], r[0], r[1], r[2], r[3], r[4]);
+    }
+  };
   B2G_HD void operator()(int g, int tid, int nt) const {
 #if defined(__CUDA_ARCH__)
+    extern __shared__ float4 lv_smem[];
     __shared__ float red[LW_LEVEL_NT];
+    float4* smem = lv_smem;
 #else
+    float4 host_ring[(LvRing<LV_PQ>::RS + 2) * LV_RING + 8];
     float red[1];
+    float4* smem = host_ring;
 #endif
     if (g >= lv_giants(L)) return;
     const int4 info = L.lv_info[g];
-    const int isl = info.x, first = info.y, depth = info.w, base = first + isl;
+    const int isl = info.x, first = info.y, n = info.z, depth = info.w, base = first + isl;
+    Pol pol;
+    pol.K = this;
+    pol.first = first;
     for (int it = 0; it < sp.position_iterations; ++it) {
-      const float ms = sweep(first, depth, base, tid, nt);
-      red[tid] = ms;
+      pol.ms = 0.0f;
+      if (depth < 3) lv_sweeps_plain(pol, L, first, depth, base, 1, tid, nt);
+      else lv_sweeps(pol, L, smem, first, n, depth, base, 1, tid, nt);
+      red[tid] = pol.ms;
       lv_cta_sync();
-      for (int h = nt >> 1; h > 0; h >>= 1) {
-        if (tid < h) red[tid] = fmin_sel(red[tid], red[tid + h]);
+      for (int h = 128; h > 0; h >>= 1) {  // LW_LEVEL_NT <= 256
+        if (tid < h && tid + h < nt) red[tid] = fmin_sel(red[tid], red[tid + h]);
         lv_cta_sync();
       }
       const float m = red[0];

@@ -45,7 +45,7 @@ template <class K> static int launch(Ctx* ctx, const K& k, int n, int /*block*/,
 }
 template <class K> static int launch_occ(Ctx* ctx, const K& k, int n, int stage) { return launch(ctx, k, n, 128, stage); }
 // CTA functors k(cta, thread, threads): one thread per CTA here, so a barrier is the end of a loop
-template <class K> static int launch_cta(Ctx* ctx, const K& k, int n_cta, int /*threads*/, int stage) {
+template <class K> static int launch_cta(Ctx* ctx, const K& k, int n_cta, int /*threads*/, int stage, size_t /*smem_bytes*/ = 0) {
   for (int g = 0; g < n_cta; ++g) k(g, 0, 1);
   ctx->launches++;
   ctx->stage_launches[stage] += 1;
@@ -134,11 +134,18 @@ template <class K> static int launch_occ(Ctx* ctx, const K& k, int n, int stage)
 }
 // CTA functors k(cta, thread, threads) that synchronise their threads (b2g_levels.h)
 template <class K> __global__ void cta_kernel(const K k) { k((int)blockIdx.x, (int)threadIdx.x, (int)blockDim.x); }
-template <class K> static int launch_cta(Ctx* ctx, const K& k, int n_cta, int threads, int stage) {
+template <class K> static int launch_cta(Ctx* ctx, const K& k, int n_cta, int threads, int stage, size_t smem_bytes = 0) {
   if (n_cta <= 0) return 0;
+  if (smem_bytes > 48 * 1024) {  // opt in to the large dynamic shared memory once per kernel
+    static size_t allowed = 0;
+    if (smem_bytes > allowed) {
+      CU(cudaFuncSetAttribute(cta_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_bytes));
+      allowed = smem_bytes;
+    }
+  }
   LaunchScope ls = {ctx, stage};
   RC(ls.begin());
-  cta_kernel<K><<<n_cta, threads, 0, (cudaStream_t)ctx->stream>>>(k);
+  cta_kernel<K><<<n_cta, threads, smem_bytes, (cudaStream_t)ctx->stream>>>(k);
   return ls.end();
 }
 int ctx_collect_profile(Ctx* ctx) {
@@ -1086,7 +1093,7 @@ static int large_alloc(BatchHost* bh) {
   AL(L.first_idx, B.NN); AL(L.vc_idx, B.NC); AL(L.scratch4, 16);
   AL(L.wake_idx, B.NB + 1LL);
   AL(L.lv_meta, 4); AL(L.lv_info, LW_MAXG); AL(L.lv_isl_giant, B.NB + 1LL); AL(L.lv_last, B.NB + 1LL); AL(L.lv_level, B.NC + 1LL);
-  AL(L.lv_count, (long long)B.NC + B.NB + 2); AL(L.lv_start, (long long)B.NC + B.NB + 2); AL(L.lv_order, B.NC + 1LL); AL(L.lv_ix, B.NC + 1LL);
+  AL(L.lv_count, (long long)B.NC + B.NB + 2); AL(L.lv_start, (long long)B.NC + B.NB + 2); AL(L.lv_order, B.NC + 1LL); AL(L.lv_ix, B.NC + 1LL); AL(L.lv_vrec, (B.NC + 1LL) * LV_VQ); AL(L.lv_prec, (B.NC + 1LL) * LV_PQ);
   AL(L.state, B.NB); AL(L.adj, 2LL * B.NC); AL(L.eadj, 2LL * B.NC); AL(L.erow, B.NB); AL(L.row_start, B.NB); AL(L.row_end, B.NB);
 #undef AL
 #if defined(B2G_HOSTSIM)
@@ -1269,12 +1276,12 @@ static int step_large(BatchHost* bh, const StepParams& sp, int steps) {
         if (levels) { LwLevelBuildK k = {B, L}; RC(launch_cta(ctx, k, LW_MAXG, LW_LEVEL_BUILD_NT, STAGE_ISLAND)); }
       }
       if (levels) {
-        { LwLevelIdxK k = {B, L, nic}; RC(launch(ctx, k, nic, 256, STAGE_SOLVER_INIT)); }
-        { LwLevelVelocityK k = {B, L, sp}; RC(launch_cta(ctx, k, LW_MAXG, LW_LEVEL_NT, STAGE_VELOCITY)); }
+        { LwLevelGatherK k = {B, L, nic}; RC(launch(ctx, k, nic, 256, STAGE_SOLVER_INIT)); }
+        { LwLevelVelocityK k = {B, L, sp}; RC(launch_cta(ctx, k, LW_MAXG, LW_LEVEL_NT, STAGE_VELOCITY, LwLevelVelocityK::smem_bytes())); }
       }
       { LwVelocity7K k = {B, L, sp, ni}; RC(launch(ctx, k, ni, 32, STAGE_VELOCITY)); }
       { PostVelocityK k = {B, sp}; RC(launch(ctx, k, std::max(std::max(ni, nib), nic), 128, STAGE_POST_VELOCITY)); }
-      if (levels) { LwLevelPositionK k = {B, L, sp}; RC(launch_cta(ctx, k, LW_MAXG, LW_LEVEL_NT, STAGE_POSITION)); }
+      if (levels) { LwLevelPositionK k = {B, L, sp}; RC(launch_cta(ctx, k, LW_MAXG, LW_LEVEL_NT, STAGE_POSITION, LwLevelPositionK::smem_bytes())); }
       { LwPosition6K k = {B, L, sp, ni}; RC(launch(ctx, k, ni, 32, STAGE_POSITION)); }
       { FinalizeK k = {B, sp}; RC(launch(ctx, k, nib, 128, STAGE_FINALIZE)); }
       { SleepK k = {B}; RC(launch(ctx, k, ni, 128, STAGE_SLEEP)); }
@@ -1641,6 +1648,9 @@ int batch_get_stats(BatchHost* bh, int first, int count, b2gpu_step_stats* out) 
     s.islands = get(WS_ST_ISLANDS); s.island_bodies = get(WS_ST_ISL_BODIES); s.island_contacts = get(WS_ST_ISL_CONTACTS);
     s.moved = get(WS_ST_MOVED); s.pairs = get(WS_ST_PAIRS); s.created = get(WS_ST_CREATED); s.awake_bodies = get(WS_ST_AWAKE);
     s.solver_levels = get(WS_ST_LEVELS);
+#if defined(B2G_LV_DEBUG)
+    if (bh->large) { int dbg[4]; dev_d2h(bh->ctx, dbg, bh->L.lv_meta, 16); s.reserved[0] = dbg[2]; }
+#endif
   }
   return 0;
 }

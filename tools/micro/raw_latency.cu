@@ -4,7 +4,7 @@
 #include <cstdio>
 #include <cuda_runtime.h>
 #define ITERS 4096
-template <int MODE> __global__ void k(float4* buf, int n_slots, long long* cyc, float* out) {
+template <int MODE, int RD> __global__ void k(float4* buf, int n_slots, long long* cyc, float* out) {
   __shared__ float4 sm[1024];
   const int tid = threadIdx.x, nt = blockDim.x;
   float4 v = make_float4(tid, 1, 2, 3);
@@ -15,7 +15,7 @@ template <int MODE> __global__ void k(float4* buf, int n_slots, long long* cyc, 
   for (int i = 0; i < ITERS; ++i) {
     slot = slot * 1664525u + 1013904223u;
     const int s = (int)((slot >> 8) % (unsigned)n_slots);
-    const int writer = i % nt, reader = (i + 7) % nt;
+    const int writer = i % nt, reader = (i + RD) % nt;
     if (tid == writer) {
       v.x += 1.0f;
       if (MODE == 0) buf[s] = v;                                  // plain store
@@ -41,9 +41,9 @@ template <int MODE> __global__ void k(float4* buf, int n_slots, long long* cyc, 
   if (tid == 0) cyc[0] = t1 - t0;
   out[tid] = acc + v.y;
 }
-template <int MODE> void run(const char* name, float4* buf, int n_slots, long long* cyc, float* out) {
-  k<MODE><<<1, 256>>>(buf, n_slots, cyc, out);
-  k<MODE><<<1, 256>>>(buf, n_slots, cyc, out);
+template <int MODE, int RD = 7> void run(const char* name, float4* buf, int n_slots, long long* cyc, float* out) {
+  k<MODE, RD><<<1, 256>>>(buf, n_slots, cyc, out);
+  k<MODE, RD><<<1, 256>>>(buf, n_slots, cyc, out);
   cudaDeviceSynchronize();
   long long h;
   cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
@@ -61,6 +61,12 @@ int main() {
   run<1>("global, st.cg / ld.cg, 100k slots", buf, big, cyc, out);
   run<3>("global, plain st / volatile ld, 100k slots", buf, big, cyc, out);
   run<4>("global, st.wt / ld.cv, 100k slots", buf, big, cyc, out);
+  run<0, 0>("global plain, reader = writer (same thread), 100k slots", buf, big, cyc, out);
+  run<0, 1>("global plain, reader = writer + 1 (same warp mostly), 100k", buf, big, cyc, out);
+  run<0, 32>("global plain, reader = writer + 32 (next warp), 100k", buf, big, cyc, out);
+  run<0, 96>("global plain, reader = writer + 96 (another scheduler), 100k", buf, big, cyc, out);
+  run<2, 32>("shared, reader = writer + 32", buf, small, cyc, out);
+  run<1, 32>("global cg, reader = writer + 32, 100k", buf, big, cyc, out);
   printf("rc=%d\n", (int)cudaGetLastError());
   return 0;
 }
