@@ -71,6 +71,7 @@ struct Large {  // device scratch of the large-world mode
   int4* vc_idx;    // [NC] per island contact slot: (body A, body B, velocity points, -), see LwVelocity4K
   int* first_idx;  // [NN] first move-buffer index of a tree node (host edits can buffer a proxy more than once)
   // level schedule of giant islands (b2g_levels.h)
+  int* sleep_min;     // [NB] per island: bits of the minimum sleep time of its bodies (LwSleepK)
   int* lv_meta;       // [4] [0] = giant islands chosen at the last island rebuild
   int4* lv_info;      // [LW_MAXG] (island, first constraint, constraints, levels)
   int* lv_isl_giant;  // [NB] per island: 1 = swept by the level-scheduled kernels
@@ -1372,6 +1373,50 @@ struct LwPosition6K {
         break;
       }
     }
+  }
+};
+
+// SleepK for a large world (b2_island_private.rs:283-312): 32 threads per island instead of one — the settled 100k pile is
+// ONE island of 100k bodies.  phase 0 (flat over islands): minimum = max float; phase 1 (flat over 32 x islands): minimum of
+// the bodies' sleep times (non-negative floats order like their bit patterns: atomicMin on the bits); phase 2 (flat over
+// 32 x islands): set_awake(false) for every body of an island that is solved and has rested long enough.
+struct LwSleepK {
+  Batch B;
+  Large L;
+  int n_islands, phase;
+  B2G_HD void operator()(int t) const {
+    const int* ws = B.ws;
+    if (!(ws[WS_FLAGS] & B2GPU_WORLD_ALLOW_SLEEP)) return;
+    if (phase == 0) {
+      if (t < n_islands) L.sleep_min[t] = f2i(B2G_MAX_FLOAT);
+      return;
+    }
+    const int isl = t >> 5, lane = t & 31;
+    if (isl >= n_islands) return;
+    const int4 rg = B.isl_range[isl];
+    if (phase == 1) {
+      float m = B2G_MAX_FLOAT;
+      for (int k = rg.x + lane; k < rg.y; k += 32) {
+        const int bi = B.isl_body[k];
+        if (body_type(B.b_flags[bi]) == B2GPU_STATIC_BODY) continue;
+        m = fmin_sel(m, B.b_pos[bi].w);
+      }
+      if (m < B2G_MAX_FLOAT) B2G_ATOMIC_MIN(&L.sleep_min[isl], f2i(m));
+      return;
+    }
+    if (!(i2f(L.sleep_min[isl]) >= B2G_TIME_TO_SLEEP && (B.isl_flags[isl] & 1))) return;
+    for (int k = rg.x + lane; k < rg.y; k += 32) {  // set_awake(false), src/b2_body.rs:783-801
+      const int bi = B.isl_body[k];
+      const int bf = B.b_flags[bi];
+      if (body_type(bf) == B2GPU_STATIC_BODY) continue;
+      B.b_flags[bi] = bf & ~B2GPU_BODY_AWAKE;
+      B.b_pos[bi].w = 0.0f;
+      B.b_vel[bi] = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+      float4 fo = B.b_force[bi];
+      fo.x = 0.0f; fo.y = 0.0f; fo.z = 0.0f;
+      B.b_force[bi] = fo;
+    }
+    if (lane == 0) B.ws[WS_TOPO_DIRTY] = 1;
   }
 };
 

@@ -91,23 +91,30 @@ struct LwLevelBuildK {
     for (int i = rg.x + tid; i < rg.y; i += nt) L.lv_last[B.isl_body[i]] = 0;
     for (int i = tid; i <= n; i += nt) L.lv_count[base + i] = 0;
     lv_cta_sync();
+    // which bodies of a constraint move (inverse mass or inertia): flat, into lv_level, where the scan finds them as one
+    // contiguous word per constraint instead of a record row per constraint
+    for (int k = tid; k < n; k += nt) {
+      const float4 q7 = B.vc[(size_t)(first + k) * VC_Q + 7];
+      L.lv_level[first + k] = ((q7.x != 0.0f || q7.y != 0.0f) ? 1 : 0) | ((q7.z != 0.0f || q7.w != 0.0f) ? 2 : 0);
+    }
+    lv_cta_sync();
     if (tid == 0) {
-      // the scan is a chain through lv_last (a constraint's level needs its bodies' latest levels); the indices and masses of
-      // four constraints are requested ahead of it
+      // the scan is a chain through lv_last (a constraint's level needs its bodies' latest levels); the indices of eight
+      // constraints are requested ahead of it
       int depth = 0;
       int k = 0;
-      for (; k + 4 <= n; k += 4) {
-        int4 ix[4];
-        float4 q7[4];
+      for (; k + 8 <= n; k += 8) {
+        int4 ix[8];
+        int mv[8];
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-        for (int j = 0; j < 4; ++j) { ix[j] = L.vc_idx[first + k + j]; q7[j] = B.vc[(size_t)(first + k + j) * VC_Q + 7]; }
+        for (int j = 0; j < 8; ++j) { ix[j] = L.vc_idx[first + k + j]; mv[j] = L.lv_level[first + k + j]; }
 #if defined(__CUDA_ARCH__)
 #pragma unroll
 #endif
-        for (int j = 0; j < 4; ++j) {
-          const bool mov_a = q7[j].x != 0.0f || q7[j].y != 0.0f, mov_b = q7[j].z != 0.0f || q7[j].w != 0.0f;
+        for (int j = 0; j < 8; ++j) {
+          const bool mov_a = (mv[j] & 1) != 0, mov_b = (mv[j] & 2) != 0;
           const int la = mov_a ? L.lv_last[ix[j].x] : 0, lb = mov_b ? L.lv_last[ix[j].y] : 0;
           const int lvl = imax(la, lb);
           L.lv_level[first + k + j] = lvl;
@@ -118,8 +125,8 @@ struct LwLevelBuildK {
       }
       for (; k < n; ++k) {
         const int4 ix = L.vc_idx[first + k];
-        const float4 q7 = B.vc[(size_t)(first + k) * VC_Q + 7];
-        const bool mov_a = q7.x != 0.0f || q7.y != 0.0f, mov_b = q7.z != 0.0f || q7.w != 0.0f;
+        const int mv = L.lv_level[first + k];
+        const bool mov_a = (mv & 1) != 0, mov_b = (mv & 2) != 0;
         const int la = mov_a ? L.lv_last[ix.x] : 0, lb = mov_b ? L.lv_last[ix.y] : 0;
         const int lvl = imax(la, lb);
         L.lv_level[first + k] = lvl;

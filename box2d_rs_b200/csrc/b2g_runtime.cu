@@ -1092,7 +1092,7 @@ static int large_alloc(BatchHost* bh) {
   AL(L.keep_flag, B.NC + 1LL); AL(L.keep_pos, B.NC + 1LL);
   AL(L.first_idx, B.NN); AL(L.vc_idx, B.NC); AL(L.scratch4, 16);
   AL(L.wake_idx, B.NB + 1LL);
-  AL(L.lv_meta, 4); AL(L.lv_info, LW_MAXG); AL(L.lv_isl_giant, B.NB + 1LL); AL(L.lv_last, B.NB + 1LL); AL(L.lv_level, B.NC + 1LL);
+  AL(L.sleep_min, B.NB + 1LL); AL(L.lv_meta, 4); AL(L.lv_info, LW_MAXG); AL(L.lv_isl_giant, B.NB + 1LL); AL(L.lv_last, B.NB + 1LL); AL(L.lv_level, B.NC + 1LL);
   AL(L.lv_count, (long long)B.NC + B.NB + 2); AL(L.lv_start, (long long)B.NC + B.NB + 2); AL(L.lv_order, B.NC + 1LL); AL(L.lv_ix, B.NC + 1LL); AL(L.lv_vrec, (B.NC + 1LL) * LV_VQ); AL(L.lv_prec, (B.NC + 1LL) * LV_PQ);
   AL(L.state, B.NB); AL(L.adj, 2LL * B.NC); AL(L.eadj, 2LL * B.NC); AL(L.erow, B.NB); AL(L.row_start, B.NB); AL(L.row_end, B.NB);
 #undef AL
@@ -1284,7 +1284,7 @@ static int step_large(BatchHost* bh, const StepParams& sp, int steps) {
       if (levels) { LwLevelPositionK k = {B, L, sp}; RC(launch_cta(ctx, k, LW_MAXG, LW_LEVEL_NT, STAGE_POSITION, LwLevelPositionK::smem_bytes())); }
       { LwPosition6K k = {B, L, sp, ni}; RC(launch(ctx, k, ni, 32, STAGE_POSITION)); }
       { FinalizeK k = {B, sp}; RC(launch(ctx, k, nib, 128, STAGE_FINALIZE)); }
-      { SleepK k = {B}; RC(launch(ctx, k, ni, 128, STAGE_SLEEP)); }
+      for (int phase = 0; phase < 3; ++phase) { LwSleepK k = {B, L, ni, phase}; RC(launch(ctx, k, phase == 0 ? ni : 32 * ni, 256, STAGE_SLEEP)); }
       { SyncFixturesK k = {B}; RC(launch(ctx, k, B.NP, 128, STAGE_SYNC_FIXTURES)); }
       // ---- find_new_contacts
       RC(lw_read(bh, B.ws, WS_COUNT));
