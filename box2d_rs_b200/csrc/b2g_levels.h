@@ -21,7 +21,7 @@
 
 namespace b2g {
 
-enum { LW_MAXG = 16, LW_LEVEL_NT = 160, LW_LEVEL_BUILD_NT = 1024, LW_LEVEL_MIN_DEFAULT = 1024 };  // LW_LEVEL_NT: four consumer warps + the producer warp
+enum { LW_MAXG = 16, LW_LEVEL_NT = 288, LW_LEVEL_BUILD_NT = 1024, LW_LEVEL_MIN_DEFAULT = 1024 };  // LW_LEVEL_NT: eight consumer warps + the producer warp
 enum { LV_VQ = 8, LV_PQ = 5 };  // float4 per velocity / position record in the level-ordered copies
 // L.lv_meta: [0] giant islands chosen at the last island rebuild (may exceed LW_MAXG: the surplus keeps the one-thread form)
 
@@ -322,20 +322,24 @@ B2G_HD void lv_sweeps(POL& pol, const Large& L, float4* smem, int first, int n, 
   const int slot = lv_slot(tid, nc);
   int lc = 0, pbc = 0;  // level index and pass base of level t
   int s = L.lv_start[base], e = L.lv_start[base + 1];
+  int rd = 0;
   for (int t = 0; t < total; ++t) {
-    // bounds of the next level, requested now
-    int ln = lc + 1, pbn = pbc;
-    if (ln == depth) { ln = 0; pbn += n; }
-    const int sn = L.lv_start[base + ln], en = L.lv_start[base + ln + 1];
-    if (tid == 0) {  // every position below is behind a barrier: publish (release) the consumers' position
+    if ((t & 3) == 0 && tid == 0) {  // every position below is behind a barrier: publish (release) the consumers' position, every 4th level
       lv_fence_block();
       lv_vstore(&R.ctl[1], pbc + s);
     }
 #if !defined(__CUDA_ARCH__)
     lv_produce(pol, L, R, P, stream, first, n, total_pos, pbc + s, lane, lanes);
 #endif
-    const int rd = lv_vload(&R.ctl[0]);
-    lv_fence_block();
+    const int rd_now = lv_vload(&R.ctl[0]);
+    if (rd_now != rd) {  // the producer published a chunk: acquire it
+      lv_fence_block();
+      rd = rd_now;
+    }
+    // bounds of the next level, requested now
+    int ln = lc + 1, pbn = pbc;
+    if (ln == depth) { ln = 0; pbn += n; }
+    const int sn = L.lv_start[base + ln], en = L.lv_start[base + ln + 1];
     for (int rel = s + slot; rel < e; rel += nc) {
       const int gp = pbc + rel;
       if (gp < rd) {
@@ -507,7 +511,7 @@ struct LwLevelPositionK {
       else lv_sweeps(pol, L, smem, first, n, depth, base, 1, tid, nt);
       red[tid] = pol.ms;
       lv_cta_sync();
-      for (int h = 128; h > 0; h >>= 1) {  // LW_LEVEL_NT <= 256
+      for (int h = 256; h > 0; h >>= 1) {  // LW_LEVEL_NT <= 512
         if (tid < h && tid + h < nt) red[tid] = fmin_sel(red[tid], red[tid + h]);
         lv_cta_sync();
       }
