@@ -172,8 +172,9 @@ def single_world_leg(ctx, full=False):
                           "oracle's step of the same state; free-running trajectories are two valid Box2D runs)",
                      "2": "large-world mode keeping the reference's contact-creation order (sequential replica-tree "
                           "re-insertion); free-running state bit-identical to the oracle"},
-           "limit": "inside one island the exact Gauss-Seidel order is a dependency chain (profiles/r02_dag_depth.md: the "
-                    "settled pile's DAG allows 3-9x parallelism at best), so the settled 100k pile is slower than one CPU core"}
+           "limit": "inside one island the exact Gauss-Seidel order is a dependency DAG 3-9x wider than a chain "
+                    "(profiles/r02_dag_depth.md); islands of >= 1024 contacts are swept level by level by one CTA "
+                    "(b2g_levels.h, profiles/r02_levels.md: a level costs ~1.7 visit latencies), every other island by one thread"}
     for name, scene, n, gravity, first, count, window, modes in SINGLE_WORLD_CASES:
         if full:
             count = {"pile100k": 100, "addpair20k": 580, "mixed10k": 800}[name]
