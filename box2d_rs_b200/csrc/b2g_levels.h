@@ -307,11 +307,17 @@ B2G_HD void lv_sweeps(POL& pol, const Large& L, float4* smem, int first, int n, 
   lv_cta_sync();
 #if defined(__CUDA_ARCH__)
   if (producer) {
+    int spins = 0;
     while (P.pf < total_pos) {
       const int cons = lv_vload(&R.ctl[1]);
+      if (cons >= total_pos) break;  // the consumers are through (they publish total_pos when they leave)
       lv_fence_block();
       const int lim = imin(total_pos, cons + imin((int)LV_RING, n));
-      if (lim - P.pf < imin((int)LV_CHUNK, imax(1, n >> 1)) && lim < total_pos) { __nanosleep(100); continue; }  // wait for room: a chunk at a time
+      if (lim - P.pf < imin((int)LV_CHUNK, imax(1, n >> 1)) && lim < total_pos) {  // wait for room: a chunk at a time
+        if (++spins > (1 << 24)) break;  // never the reason a kernel does not end: the consumers do not need the producer
+        __nanosleep(100);
+        continue;
+      }
       lv_produce(pol, L, R, P, stream, first, n, total_pos, cons, lane, lanes);
     }
     if (P.touched + P.pending == 12345.678f) L.lv_meta[3] = 1;  // keeps the touch loads alive
@@ -355,6 +361,7 @@ B2G_HD void lv_sweeps(POL& pol, const Large& L, float4* smem, int first, int n, 
     lv_consumer_sync(nc);
     lc = ln; pbc = pbn; s = sn; e = en;
   }
+  if (tid == 0) lv_vstore(&R.ctl[1], total_pos);  // releases the producer, whatever it was waiting for
 }
 template <class POL>
 B2G_HD void lv_sweeps_plain(POL& pol, const Large& L, int first, int depth, int base, int passes, int tid, int nt) {

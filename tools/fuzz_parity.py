@@ -119,7 +119,7 @@ def build(world, rng):
     return n + 1
 
 
-def run_seed(seed, make_world, steps, batch_mode, large=False, events=False):
+def run_seed(seed, make_world, steps, batch_mode, large=False, events=False, level_threshold=0):
     import parity
     from oracle import b2o
     rng = np.random.default_rng(seed)
@@ -147,6 +147,8 @@ def run_seed(seed, make_world, steps, batch_mode, large=False, events=False):
         batch = wg.batch(int(rng.integers(33, 70)), max_contacts=40 * nb + 256)  # the reference grows its tables; a batch cannot
     if large:
         bt = wg.batch(1, lane_block=1, solver='large')
+        if level_threshold:
+            bt.set_level_threshold(level_threshold)
         for i in range(steps):
             dt = 0.0 if rng.integers(0, 40) == 0 else scenes.DT
             ev = rng.integers(0, 30)
@@ -247,6 +249,7 @@ def main():
     ap.add_argument("--gpu", action="store_true")
     ap.add_argument("--batch", action="store_true")
     ap.add_argument("--large", action="store_true")
+    ap.add_argument("--level-threshold", type=int, default=0, help="--large: islands of at least this many contacts take the level-scheduled sweeps (b2g_levels.h)")
     ap.add_argument("--events", action="store_true", help="also compare b2gpu_contact_events with the oracle's listener log every step")
     args = ap.parse_args()
     from box2d_rs_b200 import batch as batch_mod, world
@@ -254,13 +257,13 @@ def main():
     ctx = batch_mod.Context(0, lib_path=lib_path)
     fails = 0
     for seed in range(args.first, args.first + args.seeds):
-        r = run_seed(seed, lambda g: world.B2world(g, ctx=ctx), args.steps, args.batch, args.large, args.events)
+        r = run_seed(seed, lambda g: world.B2world(g, ctx=ctx), args.steps, args.batch, args.large, args.events, args.level_threshold)
         if r not in (None, "skip"):
             fails += 1
             print("seed %d: %s" % (seed, r), flush=True)
     print("fuzz: %d seeds, %d failures, %d runs ended early by a numerical explosion of the scene (%s%s%s)"
           % (args.seeds, fails, getattr(run_seed, "exploded", 0), "gpu" if args.gpu else "host simulator",
-                                                     ", batch" if args.batch else ", large-world mode teacher-forced" if args.large else "",
+                                                     ", batch" if args.batch else (", large-world mode teacher-forced" + (", level threshold %d" % args.level_threshold if args.level_threshold else "")) if args.large else "",
                                                      ", %d contact events compared" % getattr(run_seed, "event_total", 0) if args.events else ""))
     sys.exit(1 if fails else 0)
 
