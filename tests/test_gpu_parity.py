@@ -401,6 +401,41 @@ def test_level_scheduled_islands_free_running(name, ctx):
     wg.close()
 
 
+@pytest.mark.parametrize("warm", [True, False])
+def test_level_scheduled_shallow_islands(warm, ctx):
+    """Islands of three levels (a stack of three boxes), with and without warm starting: 9 or 8 passes over 3 levels.  (With 8
+    passes the consumers' last published position used to sit in the previous pass, and the producer warp waited for room
+    that never came.)"""
+    from box2d_rs_b200 import abi, scenes, world
+    from oracle import b2o
+
+    def build(w):
+        ground = w.create_body(abi.BodyDef())
+        ground.create_fixture_by_shape(w.shapes.edge_two_sided((-40.0, 0.0), (40.0, 0.0)), 0.0)
+        box = w.shapes.polygon_box(0.5, 0.5)
+        for s in range(6):
+            for i in range(3 + s % 3):
+                b = w.create_body(abi.BodyDef(type=abi.DYNAMIC_BODY, position=(-20.0 + 6.0 * s, 0.51 + 1.02 * i), allow_sleep=0))
+                b.create_fixture_by_shape(box, 1.0)
+
+    wo = b2o.B2world((0.0, -10.0))
+    build(wo)
+    wg = world.B2world((0.0, -10.0), ctx=ctx)
+    build(wg)
+    for w in (wo, wg):
+        w.set_warm_starting(warm)
+    wg.set_large_mode(2)
+    wg.set_level_threshold(3)
+    levels = 0
+    for i in range(60):
+        wo.step(scenes.DT, 8, 3)
+        wg.step(scenes.DT, 8, 3)
+        levels = max(levels, int(wg.get_stats()["solver_levels"]))
+    assert parity.compare_snapshots(wo.snapshot(), wg.snapshot()) == []
+    assert levels >= 3
+    wg.close()
+
+
 # ---------------------------------------------------------------------------------------------------------
 # BASELINE configs[1], [3], [4] at FULL size (10k mixed, 100k pile, AddPair-20k): teacher-forced single steps
 # ---------------------------------------------------------------------------------------------------------
