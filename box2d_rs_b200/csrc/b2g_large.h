@@ -468,77 +468,88 @@ struct LwAdjCompactK {  // flat over max(2 cc, NB): eligible entries packed in r
 // (AddPair: ~60 per circle) cost nothing.  "Contact already in the island" needs no contact flag: an
 // eligible contact was added when the first of its two movable bodies was listed, so it is skipped exactly when
 // the other body is already listed (state 2).  Body / contact ISLAND flags are set flat afterwards.
+struct LwDfsNoHook {
+  B2G_HD void pushed(int) const {}
+};
+// hook.pushed(body): called for every body put on the stack (the giant-island form hands it to a prefetching warp)
+template <class Hook>
+B2G_HD void lw_dfs_walk(const Batch& B, const Large& L, int* stack, int isl, Hook& hook) {
+  const int4 rg = B.isl_range[isl];
+  int* st = stack + rg.x;
+  int nb = rg.x, nc = rg.z, sp_ = 0;
+  int nj = B.NJ > 0 ? B.isl_jrange[isl].x : 0;
+  const int seed = L.isl_seed[isl];
+  st[sp_++] = seed;
+  L.state[seed] = 1;
+  while (sp_ > 0) {
+    const int b = st[--sp_];
+    B.isl_body[nb++] = b;
+    L.state[b] = 2;
+    const int2 row = L.erow[b];
+    const int r0 = row.x, r1 = row.y;
+    for (int i = r1 - 1; i >= r0; i -= 4) {
+      int e[4], info[4], sv[4];
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+      for (int j = 0; j < 4; ++j) {
+        const int2 ent = i - j >= r0 ? L.eadj[i - j] : make_int2(0, 0);
+        e[j] = ent.x;
+        info[j] = ent.y;
+      }
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+      for (int j = 0; j < 4; ++j) sv[j] = (info[j] < 0 && !(info[j] & 0x40000000)) ? L.state[info[j] & 0x3fffffff] : 0;
+      int pushed[4] = {-1, -1, -1, -1};
+#if defined(__CUDA_ARCH__)
+#pragma unroll
+#endif
+      for (int j = 0; j < 4; ++j) {
+        if (info[j] >= 0) continue;  // not eligible (or padding)
+        const int other = info[j] & 0x3fffffff;
+        const bool is_static = (info[j] & 0x40000000) != 0;
+        if (!is_static && sv[j] == 2) continue;  // added when `other` was listed
+        B.isl_contact[nc] = e[j] >> 1;
+        B.c_isl[nc] = isl;
+        ++nc;
+        if (is_static || sv[j] != 0) continue;  // static bodies never propagate; not listed in this mode
+        if (other == pushed[0] || other == pushed[1] || other == pushed[2]) continue;  // pushed by an earlier edge of this group
+        pushed[j] = other;
+        st[sp_++] = other;
+        L.state[other] = 1;
+        hook.pushed(other);
+      }
+    }
+    // joints of this body, newest edge first (b2_world.rs(private):461-483).  "Already in the island" needs no joint
+    // flag either: a joint is added when the first of its movable bodies is listed
+    if (B.NJ > 0)
+      for (int q = B.jadj_off[b]; q < B.jadj_off[b + 1]; ++q) {
+        const int je = B.jadj[q], jn = je >> 1;
+        const int other = (je & 1) ? B.joints[jn].body_a : B.joints[jn].body_b;
+        const int of = B.b_flags[other];
+        if (!(of & B2GPU_BODY_ENABLED)) continue;
+        const bool is_static = body_type(of) == B2GPU_STATIC_BODY;
+        const int so = is_static ? 0 : L.state[other];
+        if (!is_static && so == 2) continue;
+        B.isl_joint[nj++] = jn;
+        if (is_static || so != 0) continue;
+        st[sp_++] = other;
+        L.state[other] = 1;
+        hook.pushed(other);
+      }
+  }
+  if (nb != rg.y || nc != rg.w || (B.NJ > 0 && nj != B.isl_jrange[isl].y)) B.ws[WS_STATUS] = B2GPU_E_INTERNAL;
+}
 struct LwDfsK {
   Batch B;
   Large L;
   int* stack;  // [NB]: island i uses the slots of its body range
   int n_islands;
   B2G_HD void operator()(int isl) const {
-    if (isl >= n_islands) return;
-    const int4 rg = B.isl_range[isl];
-    int* st = stack + rg.x;
-    int nb = rg.x, nc = rg.z, sp_ = 0;
-    int nj = B.NJ > 0 ? B.isl_jrange[isl].x : 0;
-    const int seed = L.isl_seed[isl];
-    st[sp_++] = seed;
-    L.state[seed] = 1;
-    while (sp_ > 0) {
-      const int b = st[--sp_];
-      B.isl_body[nb++] = b;
-      L.state[b] = 2;
-      const int2 row = L.erow[b];
-      const int r0 = row.x, r1 = row.y;
-      for (int i = r1 - 1; i >= r0; i -= 4) {
-        int e[4], info[4], sv[4];
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-        for (int j = 0; j < 4; ++j) {
-          const int2 ent = i - j >= r0 ? L.eadj[i - j] : make_int2(0, 0);
-          e[j] = ent.x;
-          info[j] = ent.y;
-        }
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-        for (int j = 0; j < 4; ++j) sv[j] = (info[j] < 0 && !(info[j] & 0x40000000)) ? L.state[info[j] & 0x3fffffff] : 0;
-        int pushed[4] = {-1, -1, -1, -1};
-#if defined(__CUDA_ARCH__)
-#pragma unroll
-#endif
-        for (int j = 0; j < 4; ++j) {
-          if (info[j] >= 0) continue;  // not eligible (or padding)
-          const int other = info[j] & 0x3fffffff;
-          const bool is_static = (info[j] & 0x40000000) != 0;
-          if (!is_static && sv[j] == 2) continue;  // added when `other` was listed
-          B.isl_contact[nc] = e[j] >> 1;
-          B.c_isl[nc] = isl;
-          ++nc;
-          if (is_static || sv[j] != 0) continue;  // static bodies never propagate; not listed in this mode
-          if (other == pushed[0] || other == pushed[1] || other == pushed[2]) continue;  // pushed by an earlier edge of this group
-          pushed[j] = other;
-          st[sp_++] = other;
-          L.state[other] = 1;
-        }
-      }
-      // joints of this body, newest edge first (b2_world.rs(private):461-483).  "Already in the island" needs no joint
-      // flag either: a joint is added when the first of its movable bodies is listed
-      if (B.NJ > 0)
-        for (int q = B.jadj_off[b]; q < B.jadj_off[b + 1]; ++q) {
-          const int je = B.jadj[q], jn = je >> 1;
-          const int other = (je & 1) ? B.joints[jn].body_a : B.joints[jn].body_b;
-          const int of = B.b_flags[other];
-          if (!(of & B2GPU_BODY_ENABLED)) continue;
-          const bool is_static = body_type(of) == B2GPU_STATIC_BODY;
-          const int so = is_static ? 0 : L.state[other];
-          if (!is_static && so == 2) continue;
-          B.isl_joint[nj++] = jn;
-          if (is_static || so != 0) continue;
-          st[sp_++] = other;
-          L.state[other] = 1;
-        }
-    }
-    if (nb != rg.y || nc != rg.w || (B.NJ > 0 && nj != B.isl_jrange[isl].y)) B.ws[WS_STATUS] = B2GPU_E_INTERNAL;
+    if (isl >= n_islands || L.lv_isl_giant[isl]) return;  // a giant island is walked by LwDfsGiantK (b2g_levels.h)
+    LwDfsNoHook hook;
+    lw_dfs_walk(B, L, stack, isl, hook);
   }
 };
 struct LwIslFlagsK {  // flat over max(island bodies, island contacts): what the traversal leaves on bodies and contacts

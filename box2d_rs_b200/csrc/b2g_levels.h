@@ -70,6 +70,84 @@ struct LwGiantSelectK {  // flat over islands: which islands take the level-sche
   }
 };
 
+// The traversal of a giant island (LwDfsK's walk, 89 ms on the settled 100k pile: three dependent L2 misses per body — its
+// row, the row's entries, the states of the bodies they name).  The walk itself is the reference's lexicographic DFS and
+// stays one thread; a second warp reads along: every body the walker pushes is handed over through shared memory, and the
+// helper loads that body's row, the entries the walker will read first, the states of their bodies and those bodies' own
+// rows — plain loads whose values are thrown away, so that the walker finds the lines in this SM's L1 when it pops the body.  Nothing the helper
+// does can change a result (it writes nothing but its queue position); a lost or overwritten hand-over is a missed prefetch.
+struct LwDfsGiantK {
+  Batch B;
+  Large L;
+  int* stack;
+  struct Hook {
+    int* q;     // [64] bodies pushed, a ring
+    int* head;  // pushes so far
+    int h;
+    B2G_HD void pushed(int o) {
+#if defined(__CUDA_ARCH__)
+      *(volatile int*)(q + (h & 63)) = o;
+      *(volatile int*)head = ++h;
+#else
+      (void)o;
+#endif
+    }
+  };
+  B2G_HD void operator()(int g, int tid, int nt) const {
+#if defined(__CUDA_ARCH__)
+    __shared__ int q[64];
+    __shared__ int ctl[2];  // [0] pushes so far, [1] the walk is over
+#else
+    int q[1], ctl[2];
+#endif
+    if (g >= lv_giants(L)) return;
+    const int isl = L.lv_info[g].x;
+    if (tid == 0) { ctl[0] = 0; ctl[1] = 0; }
+    lv_cta_sync();
+    if (tid == 0) {
+      Hook hook;
+      hook.q = q; hook.head = &ctl[0]; hook.h = 0;
+      lw_dfs_walk(B, L, stack, isl, hook);
+#if defined(__CUDA_ARCH__)
+      *(volatile int*)&ctl[1] = 1;
+#endif
+    }
+#if defined(__CUDA_ARCH__)
+    else if (tid >= 32) {
+      const int lane = tid - 32, lanes = nt - 32;
+      int tail = 0, sink = 0;
+      for (;;) {
+        const int head = *(volatile int*)&ctl[0];
+        if (head == tail) {
+          if (*(volatile int*)&ctl[1]) break;
+          continue;
+        }
+        if (head - tail > 64) tail = head - 64;  // overrun: the oldest hand-overs are gone
+        // eight lanes per handed-over body, one per entry of its row (the walker reads a row from its end): the entry, the
+        // state of the body it names, and — one level further, for when that body is pushed and popped in turn — that
+        // body's own row and its last entry
+        for (int i = tail + (lane >> 3); i < head; i += (lanes >> 3)) {
+          const int o = *(volatile int*)(q + (i & 63));
+          const int2 row = L.erow[o];
+          const int j = row.y - 1 - (lane & 7);
+          if (j >= row.x) {
+            const int2 ent = L.eadj[j];
+            if (ent.y < 0 && !(ent.y & 0x40000000)) {
+              const int other = ent.y & 0x3fffffff;
+              sink += L.state[other];
+              const int2 r2 = L.erow[other];
+              if (r2.y > r2.x) sink += L.eadj[r2.y - 1].x;
+            }
+          }
+        }
+        tail = head;
+      }
+      if (sink == 0x7fffffff) L.lv_meta[3] = 1;  // keeps the loads alive
+    }
+#endif
+  }
+};
+
 // Levels of one giant island: CTA g, after SolverInitK / LwVcIdxK of the step that rebuilt the islands.
 //   lv_level[first + k]   level of constraint k (island order)
 //   lv_start[first + isl + l]  first position of level l in lv_order (island-relative), l = 0 .. depth (at depth: n);

@@ -1253,6 +1253,14 @@ static int step_large(BatchHost* bh, const StepParams& sp, int steps) {
         { LwAdjInfoK k = {B, L, 2 * cc}; RC(launch(ctx, k, 2 * cc + 1, 256, STAGE_ISLAND)); }
         RC(lw_scan_int(bh, L.cand_flag, L.cand_pos, 2 * cc + 1, STAGE_ISLAND));
         { LwAdjCompactK k = {B, L, 2 * cc}; RC(launch(ctx, k, std::max(2 * cc, B.NB), 256, STAGE_ISLAND)); }
+        // giant islands (>= lw_level_min contacts, no joints): chosen here — their traversal has a prefetching warp, their
+        // sweeps are level-scheduled (b2g_levels.h); every other island one thread
+        {
+          const bool lv = bh->lw_level_min > 0 && hw[WS_ISL_CONTACTS] >= bh->lw_level_min;
+          { LwLevelResetK k = {L}; RC(launch(ctx, k, 1, 32, STAGE_ISLAND)); }
+          { LwGiantSelectK k = {B, L, hw[WS_ISL_COUNT], lv ? bh->lw_level_min : 0}; RC(launch(ctx, k, hw[WS_ISL_COUNT], 256, STAGE_ISLAND)); }
+          if (lv) { LwDfsGiantK k = {B, L, bh->stack}; RC(launch_cta(ctx, k, LW_MAXG, 64, STAGE_ISLAND)); }
+        }
         { LwDfsK k = {B, L, bh->stack, hw[WS_ISL_COUNT]}; RC(launch(ctx, k, hw[WS_ISL_COUNT], 32, STAGE_ISLAND)); }
         { LwIslFlagsK k = {B, hw[WS_ISL_BODIES], hw[WS_ISL_CONTACTS]}; RC(launch(ctx, k, std::max(hw[WS_ISL_BODIES], hw[WS_ISL_CONTACTS]), 256, STAGE_ISLAND)); }
       } else {
@@ -1270,11 +1278,7 @@ static int step_large(BatchHost* bh, const StepParams& sp, int steps) {
       // giant islands without joints (>= lw_level_min contacts): level schedule rebuilt with the islands, one CTA per island
       // sweeps level by level (b2g_levels.h); every other island one thread
       const bool levels = bh->lw_level_min > 0 && nic >= bh->lw_level_min;
-      if (dirty) {
-        { LwLevelResetK k = {L}; RC(launch(ctx, k, 1, 32, STAGE_ISLAND)); }
-        { LwGiantSelectK k = {B, L, ni, levels ? bh->lw_level_min : 0}; RC(launch(ctx, k, ni, 256, STAGE_ISLAND)); }
-        if (levels) { LwLevelBuildK k = {B, L}; RC(launch_cta(ctx, k, LW_MAXG, LW_LEVEL_BUILD_NT, STAGE_ISLAND)); }
-      }
+      if (dirty && levels) { LwLevelBuildK k = {B, L}; RC(launch_cta(ctx, k, LW_MAXG, LW_LEVEL_BUILD_NT, STAGE_ISLAND)); }
       if (levels) {
         { LwLevelGatherK k = {B, L, nic}; RC(launch(ctx, k, nic, 256, STAGE_SOLVER_INIT)); }
         { LwLevelVelocityK k = {B, L, sp}; RC(launch_cta(ctx, k, LW_MAXG, LW_LEVEL_NT, STAGE_VELOCITY, LwLevelVelocityK::smem_bytes())); }
