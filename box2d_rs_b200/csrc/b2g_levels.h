@@ -175,13 +175,38 @@ struct LwLevelBuildK {
       const float4 q7 = B.vc[(size_t)(first + k) * VC_Q + 7];
       L.lv_level[first + k] = ((q7.x != 0.0f || q7.y != 0.0f) ? 1 : 0) | ((q7.z != 0.0f || q7.w != 0.0f) ? 2 : 0);
     }
+#if defined(__CUDA_ARCH__)
+    __shared__ int scan_at;  // constraint the scan has reached (published every eight)
+    if (tid == 0) scan_at = 0;
+#endif
     lv_cta_sync();
+#if defined(__CUDA_ARCH__)
+    if (tid >= 32 && tid < 64) {
+      // a second warp reads along ahead of the scan: lv_last of the bodies of the next few hundred constraints, plain loads
+      // whose values are thrown away — they fill this SM's L1 (the scan's own stores keep those lines current)
+      int done = 0, sink = 0;
+      for (;;) {
+        const int at = *(volatile int*)&scan_at;
+        if (at >= n) break;
+        const int lo = max(done, at + 32), hi = min(n, at + 32 + 512);
+        for (int c = lo + (tid - 32); c < hi; c += 32) {
+          const int4 ix = L.vc_idx[first + c];
+          sink += L.lv_last[ix.x] + L.lv_last[ix.y];
+        }
+        if (hi > done) done = hi;
+      }
+      if (sink == 0x7fffffff) L.lv_meta[3] = 1;  // keeps the loads alive
+    }
+#endif
     if (tid == 0) {
       // the scan is a chain through lv_last (a constraint's level needs its bodies' latest levels); the indices of eight
       // constraints are requested ahead of it
       int depth = 0;
       int k = 0;
       for (; k + 8 <= n; k += 8) {
+#if defined(__CUDA_ARCH__)
+        *(volatile int*)&scan_at = k;
+#endif
         int4 ix[8];
         int mv[8];
 #if defined(__CUDA_ARCH__)
@@ -213,6 +238,9 @@ struct LwLevelBuildK {
         depth = imax(depth, lvl + 1);
       }
       L.lv_info[g].w = depth;
+#if defined(__CUDA_ARCH__)
+      *(volatile int*)&scan_at = n;
+#endif
     }
     lv_cta_sync();
     const int depth = L.lv_info[g].w;
