@@ -435,8 +435,13 @@ B2G_HD void lv_sweeps(POL& pol, const Large& L, float4* smem, int first, int n, 
   int lc = 0, pbc = 0;  // level index and pass base of level t
   int s = L.lv_start[base], e = L.lv_start[base + 1];
   int rd = 0;
+#if defined(B2G_LV_DEBUG) && defined(__CUDA_ARCH__)
+  long long dbg_a = 0, dbg_b = 0, dbg_c = 0, dbg_t = clock64();
+#endif
   for (int t = 0; t < total; ++t) {
-    if ((t & 3) == 0 && tid == 0) {  // every position below is behind a barrier: publish (release) the consumers' position, every 4th level
+    if ((t & 3) == 0 && tid == nc - 1) {  // every position below is behind a barrier: publish (release) the consumers' position, every 4th
+                                          // level — by the thread of the LAST slot, which has a constraint only in the widest levels
+                                          // (the fence costs ~200 cycles; thread 0 has a constraint in every level)
       lv_fence_block();
       lv_vstore(&R.ctl[1], pbc + s);
     }
@@ -452,6 +457,9 @@ B2G_HD void lv_sweeps(POL& pol, const Large& L, float4* smem, int first, int n, 
     int ln = lc + 1, pbn = pbc;
     if (ln == depth) { ln = 0; pbn += n; }
     const int sn = L.lv_start[base + ln], en = L.lv_start[base + ln + 1];
+#if defined(B2G_LV_DEBUG) && defined(__CUDA_ARCH__)
+    { const long long c = clock64(); dbg_a += c - dbg_t; dbg_t = c; }
+#endif
     for (int rel = s + slot; rel < e; rel += nc) {
       const int gp = pbc + rel;
       if (gp < rd) {
@@ -459,15 +467,25 @@ B2G_HD void lv_sweeps(POL& pol, const Large& L, float4* smem, int first, int n, 
         pol.ring(t, rel, R.k[rs], R.ix[rs], R.rec + (size_t)rs * Ring::RS);
       } else {
         pol.direct(t, rel, L.lv_order[first + rel]);
-#if defined(B2G_LV_DEBUG)
-        lv_fetch_add(&L.lv_meta[2], 1);
-#endif
       }
     }
+#if defined(B2G_LV_DEBUG) && defined(__CUDA_ARCH__)
+    { const long long c = clock64(); dbg_b += c - dbg_t; dbg_t = c; }
+#endif
     lv_consumer_sync(nc);
+#if defined(B2G_LV_DEBUG) && defined(__CUDA_ARCH__)
+    { const long long c = clock64(); dbg_c += c - dbg_t; dbg_t = c; }
+#endif
     lc = ln; pbc = pbn; s = sn; e = en;
   }
-  if (tid == 0) lv_vstore(&R.ctl[1], total_pos);  // releases the producer, whatever it was waiting for
+#if defined(B2G_LV_DEBUG) && defined(__CUDA_ARCH__)
+  if (tid == 0) {  // thread 0 takes the first position of every level: cycles / 1024 before the visit, in it, at the barrier
+    atomicAdd(&L.lv_meta[1], (int)(dbg_a >> 10));
+    atomicAdd(&L.lv_meta[2], (int)(dbg_b >> 10));
+    atomicAdd(&L.lv_meta[3], (int)(dbg_c >> 10));
+  }
+#endif
+  if (tid == nc - 1) lv_vstore(&R.ctl[1], total_pos);  // releases the producer, whatever it was waiting for
 }
 template <class POL>
 B2G_HD void lv_sweeps_plain(POL& pol, const Large& L, int first, int depth, int base, int passes, int tid, int nt) {

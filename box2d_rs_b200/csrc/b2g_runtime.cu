@@ -1653,7 +1653,7 @@ int batch_get_stats(BatchHost* bh, int first, int count, b2gpu_step_stats* out) 
     s.moved = get(WS_ST_MOVED); s.pairs = get(WS_ST_PAIRS); s.created = get(WS_ST_CREATED); s.awake_bodies = get(WS_ST_AWAKE);
     s.solver_levels = get(WS_ST_LEVELS);
 #if defined(B2G_LV_DEBUG)
-    if (bh->large) { int dbg[4]; dev_d2h(bh->ctx, dbg, bh->L.lv_meta, 16); s.reserved[0] = dbg[2]; }
+    if (bh->large) { int dbg[4]; dev_d2h(bh->ctx, dbg, bh->L.lv_meta, 16); s.reserved[0] = dbg[1]; s.reserved[1] = dbg[2]; s.reserved[2] = dbg[3]; }
 #endif
   }
   return 0;
