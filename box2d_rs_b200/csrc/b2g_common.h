@@ -49,7 +49,7 @@ enum {
 // velocity-constraint record: VC_Q float4 per island contact
 enum { VC_Q = 9, PC_Q = 6 };
 // per-step joint scratch: JT_Q float4 per joint (see b2g_joint.h)
-enum { JT_Q = 4 };
+enum { JT_Q = 5 };
 
 struct Batch {
   int n_worlds, LB, lb_shift, n_wblocks;

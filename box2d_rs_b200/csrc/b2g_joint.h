@@ -1,4 +1,4 @@
-// b2g_joint.h — joints inside the island solve: revolute and distance joints.
+// b2g_joint.h — joints inside the island solve: revolute, distance and weld joints.
 //
 // Reference: B2jointTraitDyn::{init_velocity_constraints, solve_velocity_constraints, solve_position_constraints}
 // (src/b2_joint.rs:268-286) as driven by B2island::solve (src/private/dynamics/b2_island_private.rs:198-201 init after the
@@ -6,17 +6,19 @@
 // position iteration, early exit only when both are within tolerance);
 //   revolute: src/private/dynamics/joints/b2_revolute_joint.rs:22-123 / :125-217 / :219-301
 //   distance: src/private/dynamics/joints/b2_distance_joint.rs:80-184 / :186-277 / :279-320
+//   weld:     src/private/dynamics/joints/b2_weld_joint.rs:22-136 / :138-205 / :207-283
 // Expression shapes are kept operation for operation (one rounding per operation, no FMA), like the contact solver.
 //
 // Data: the static part of a joint (type, bodies, anchors, limits, lengths, COLLIDE_CONNECTED) is topology shared by the
 // worlds of a batch (Batch::joints); what the solver or the user changes per world lives in two float4 rows
-//   j_s0: impulse.x impulse.y motor_impulse lower_impulse     (distance: impulse, -, -, lower_impulse)
+//   j_s0: impulse.x impulse.y motor_impulse lower_impulse     (distance: impulse, -, -, lower_impulse; weld: impulse.x .y .z, -)
 //   j_s1: upper_impulse motor_speed max_motor_torque (int bits) ENABLE_LIMIT | ENABLE_MOTOR
 // and the per-step solver data (the reference's "solver temp" members) in JT_Q float4 rows of j_tmp:
 //   0: rA.xy rB.xy
-//   1: revolute K.ex.x K.ey.x K.ey.y axial_mass      | distance u.x u.y mass soft_mass
-//   2: revolute angle - - -                          | distance gamma bias current_length -
+//   1: revolute K.ex.x K.ey.x K.ey.y axial_mass      | distance u.x u.y mass soft_mass        | weld mass.ex.xyz mass.ey.x
+//   2: revolute angle - - -                          | distance gamma bias current_length -   | weld mass.ey.yz mass.ez.xy
 //   3: mA iA mB iB
+//   4: weld mass.ez.z gamma bias -
 // Joint visits are ordered work: they run in the island's joint order inside every form of the Gauss-Seidel stages
 // (VelocityK / PositionK generic; velocity_sl_kernel / position_sl_kernel for batches, through an accessor over their
 // shared-memory rows; LwVelocity7K / LwPosition6K in the large-world modes).
@@ -36,6 +38,61 @@ B2G_HD V2 mat22_solve(float exx, float eyx, float exy, float eyy, V2 b) {
   float det = a11 * a22 - a12 * a21;
   if (det != 0.0f) det = 1.0f / det;
   return v2(det * (a22 * b.x - a12 * b.y), det * (a11 * b.y - a21 * b.x));
+}
+
+// B2Mat33 (src/b2_math.rs:296-352, src/private/common/b2_math.rs:5-72) on a plain array: ex.xyz, ey.xyz, ez.xyz at [0..8].
+B2G_HD float vec3_dot(const float* a, const float* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }
+B2G_HD void vec3_cross(const float* a, const float* b, float* o) {
+  o[0] = a[1] * b[2] - a[2] * b[1];
+  o[1] = a[2] * b[0] - a[0] * b[2];
+  o[2] = a[0] * b[1] - a[1] * b[0];
+}
+B2G_HD void mat33_get_inverse22(const float* k, float* m) {
+  const float a = k[0], b = k[3], c = k[1], d = k[4];
+  float det = a * d - b * c;
+  if (det != 0.0f) det = 1.0f / det;
+  m[0] = det * d; m[3] = -det * b; m[2] = 0.0f;
+  m[1] = -det * c; m[4] = det * a; m[5] = 0.0f;
+  m[6] = 0.0f; m[7] = 0.0f; m[8] = 0.0f;
+}
+B2G_HD void mat33_get_sym_inverse33(const float* k, float* m) {
+  float cr[3];
+  vec3_cross(k + 3, k + 6, cr);
+  float det = vec3_dot(k, cr);
+  if (det != 0.0f) det = 1.0f / det;
+  const float a11 = k[0], a12 = k[3], a13 = k[6], a22 = k[4], a23 = k[7], a33 = k[8];
+  m[0] = det * (a22 * a33 - a23 * a23);
+  m[1] = det * (a13 * a23 - a12 * a33);
+  m[2] = det * (a12 * a23 - a13 * a22);
+  m[3] = m[1];
+  m[4] = det * (a11 * a33 - a13 * a13);
+  m[5] = det * (a13 * a12 - a11 * a23);
+  m[6] = m[2];
+  m[7] = m[5];
+  m[8] = det * (a11 * a22 - a12 * a12);
+}
+B2G_HD void mat33_solve33(const float* k, const float* b, float* x) {
+  float cr[3];
+  vec3_cross(k + 3, k + 6, cr);
+  float det = vec3_dot(k, cr);
+  if (det != 0.0f) det = 1.0f / det;
+  x[0] = det * vec3_dot(b, cr);
+  vec3_cross(b, k + 6, cr);
+  x[1] = det * vec3_dot(k, cr);
+  vec3_cross(k + 3, b, cr);
+  x[2] = det * vec3_dot(k, cr);
+}
+// K of the weld joint (b2_weld_joint.rs:66-75 and :238-247: the same expression in both places)
+B2G_HD void weld_k(float* k, V2 r_a, V2 r_b, float m_a, float i_a, float m_b, float i_b) {
+  k[0] = m_a + m_b + r_a.y * r_a.y * i_a + r_b.y * r_b.y * i_b;
+  k[3] = -r_a.y * r_a.x * i_a - r_b.y * r_b.x * i_b;
+  k[6] = -r_a.y * i_a - r_b.y * i_b;
+  k[1] = k[3];
+  k[4] = m_a + m_b + r_a.x * r_a.x * i_a + r_b.x * r_b.x * i_b;
+  k[7] = r_a.x * i_a + r_b.x * i_b;
+  k[2] = k[6];
+  k[5] = k[7];
+  k[8] = i_a + i_b;
 }
 
 // Does a joint of `self_` prevent collision with `other`? (B2body::should_collide, b2_body.rs(private):400-413)
@@ -88,8 +145,44 @@ B2G_HD void joint_init_velocity(const Batch& B, const WIdx& x, const S& st, int 
   const int ji = x.at(B.NJ, j);
   float4 s0 = B.j_s0[ji], s1 = B.j_s1[ji];
   const int jflags = f2i(s1.w);
-  float4 t1, t2 = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-  if (jr.type == B2GPU_JOINT_REVOLUTE) {
+  float4 t1, t2 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), t4 = t2;
+  if (jr.type == B2GPU_JOINT_WELD) {
+    float k[9], m[9];
+    weld_k(k, r_a, r_b, m_a, i_a, m_b, i_b);
+    const float stiffness = jr.param[3], damping = jr.param[4];
+    float gamma, bias;
+    if (stiffness > 0.0f) {
+      mat33_get_inverse22(k, m);
+      float inv_m = i_a + i_b;
+      const float c = a_b - a_a - jr.param[0];
+      gamma = h * (damping + h * stiffness);
+      gamma = gamma != 0.0f ? 1.0f / gamma : 0.0f;
+      bias = c * h * stiffness * gamma;
+      inv_m += gamma;
+      m[8] = inv_m != 0.0f ? 1.0f / inv_m : 0.0f;
+    } else if (k[8] == 0.0f) {
+      mat33_get_inverse22(k, m);
+      gamma = 0.0f;
+      bias = 0.0f;
+    } else {
+      mat33_get_sym_inverse33(k, m);
+      gamma = 0.0f;
+      bias = 0.0f;
+    }
+    if (warm_starting) {
+      s0.x *= dt_ratio; s0.y *= dt_ratio; s0.z *= dt_ratio;
+      const V2 p = v2(s0.x, s0.y);
+      v_a = v_a - m_a * p;
+      w_a -= i_a * (cross(r_a, p) + s0.z);
+      v_b = v_b + m_b * p;
+      w_b += i_b * (cross(r_b, p) + s0.z);
+    } else {
+      s0.x = 0.0f; s0.y = 0.0f; s0.z = 0.0f;
+    }
+    t1 = make_float4(m[0], m[1], m[2], m[3]);
+    t2 = make_float4(m[4], m[5], m[6], m[7]);
+    t4 = make_float4(m[8], gamma, bias, 0.0f);
+  } else if (jr.type == B2GPU_JOINT_REVOLUTE) {
     const float kxx = m_a + m_b + r_a.y * r_a.y * i_a + r_b.y * r_b.y * i_b;
     const float kyx = -r_a.y * r_a.x * i_a - r_b.y * r_b.x * i_b;
     const float kyy = m_a + m_b + r_a.x * r_a.x * i_a + r_b.x * r_b.x * i_b;
@@ -162,6 +255,7 @@ B2G_HD void joint_init_velocity(const Batch& B, const WIdx& x, const S& st, int 
   B.j_tmp[jt_at(B, x, j, 1)] = t1;
   B.j_tmp[jt_at(B, x, j, 2)] = t2;
   B.j_tmp[jt_at(B, x, j, 3)] = make_float4(m_a, i_a, m_b, i_b);
+  if (jr.type == B2GPU_JOINT_WELD) B.j_tmp[jt_at(B, x, j, 4)] = t4;
   // an immovable body may sit in several islands: its velocity never changes, leave it alone
   if (m_a != 0.0f || i_a != 0.0f) st.set_vel(jr.body_a, make_float4(v_a.x, v_a.y, w_a, 0.0f));
   if (m_b != 0.0f || i_b != 0.0f) st.set_vel(jr.body_b, make_float4(v_b.x, v_b.y, w_b, 0.0f));
@@ -180,7 +274,40 @@ B2G_HD void joint_solve_velocity(const Batch& B, const WIdx& x, const S& st, int
   const int ji = x.at(B.NJ, j);
   float4 s0 = B.j_s0[ji], s1 = B.j_s1[ji];
   const int jflags = f2i(s1.w);
-  if (jr.type == B2GPU_JOINT_REVOLUTE) {
+  if (jr.type == B2GPU_JOINT_WELD) {
+    const float4 t4 = B.j_tmp[jt_at(B, x, j, 4)];
+    const float m[9] = {t1.x, t1.y, t1.z, t1.w, t2.x, t2.y, t2.z, t2.w, t4.x};
+    const float gamma = t4.y, bias = t4.z;
+    if (jr.param[3] > 0.0f) {
+      const float cdot2 = w_b - w_a;
+      const float impulse2 = -m[8] * (cdot2 + bias + gamma * s0.z);
+      s0.z += impulse2;
+      w_a -= i_a * impulse2;
+      w_b += i_b * impulse2;
+      const V2 cdot1 = v_b + cross_sv(w_b, r_b) - v_a - cross_sv(w_a, r_a);
+      const V2 impulse1 = -v2(m[0] * cdot1.x + m[3] * cdot1.y, m[1] * cdot1.x + m[4] * cdot1.y);  // b2_mul22
+      s0.x += impulse1.x;
+      s0.y += impulse1.y;
+      const V2 p = impulse1;
+      v_a = v_a - m_a * p;
+      w_a -= i_a * cross(r_a, p);
+      v_b = v_b + m_b * p;
+      w_b += i_b * cross(r_b, p);
+    } else {
+      const V2 cdot1 = v_b + cross_sv(w_b, r_b) - v_a - cross_sv(w_a, r_a);
+      const float cdot2 = w_b - w_a;
+      // b2_mul_mat33 (src/b2_math.rs:601-603): v.x * ex + v.y * ey + v.z * ez, then the negation
+      const float ix = -((cdot1.x * m[0] + cdot1.y * m[3]) + cdot2 * m[6]);
+      const float iy = -((cdot1.x * m[1] + cdot1.y * m[4]) + cdot2 * m[7]);
+      const float iz = -((cdot1.x * m[2] + cdot1.y * m[5]) + cdot2 * m[8]);
+      s0.x += ix; s0.y += iy; s0.z += iz;
+      const V2 p = v2(ix, iy);
+      v_a = v_a - m_a * p;
+      w_a -= i_a * (cross(r_a, p) + iz);
+      v_b = v_b + m_b * p;
+      w_b += i_b * (cross(r_b, p) + iz);
+    }
+  } else if (jr.type == B2GPU_JOINT_REVOLUTE) {
     const float axial_mass = t1.w, angle = t2.x;
     const bool fixed_rotation = i_a + i_b == 0.0f;
     if ((jflags & B2GPU_JOINT_ENABLE_MOTOR) && fixed_rotation == false) {
@@ -308,7 +435,44 @@ B2G_HD bool joint_solve_position(const Batch& B, const WIdx& x, const S& st, int
   const V2 la = v2(jr.local_anchor_a[0], jr.local_anchor_a[1]) - v2(msa.z, msa.w);
   const V2 lb = v2(jr.local_anchor_b[0], jr.local_anchor_b[1]) - v2(msb.z, msb.w);
   bool okay;
-  if (jr.type == B2GPU_JOINT_REVOLUTE) {
+  if (jr.type == B2GPU_JOINT_WELD) {
+    const V2 r_a = rot_mul(q_a, la);
+    const V2 r_b = rot_mul(q_b, lb);
+    float k[9];
+    weld_k(k, r_a, r_b, m_a, i_a, m_b, i_b);
+    float position_error, angular_error;
+    if (jr.param[3] > 0.0f) {
+      const V2 c1 = c_b + r_b - c_a - r_a;
+      position_error = length(c1);
+      angular_error = 0.0f;
+      const V2 p = -mat22_solve(k[0], k[3], k[1], k[4], c1);  // B2Mat33::solve22
+      c_a = c_a - m_a * p;
+      a_a -= i_a * cross(r_a, p);
+      c_b = c_b + m_b * p;
+      a_b += i_b * cross(r_b, p);
+    } else {
+      const V2 c1 = c_b + r_b - c_a - r_a;
+      const float c2 = a_b - a_a - jr.param[0];
+      position_error = length(c1);
+      angular_error = fabsf(c2);
+      float imp[3];
+      if (k[8] > 0.0f) {
+        const float c[3] = {c1.x, c1.y, c2};
+        float xs[3];
+        mat33_solve33(k, c, xs);
+        imp[0] = -xs[0]; imp[1] = -xs[1]; imp[2] = -xs[2];
+      } else {
+        const V2 impulse2 = -mat22_solve(k[0], k[3], k[1], k[4], c1);
+        imp[0] = impulse2.x; imp[1] = impulse2.y; imp[2] = 0.0f;
+      }
+      const V2 p = v2(imp[0], imp[1]);
+      c_a = c_a - m_a * p;
+      a_a -= i_a * (cross(r_a, p) + imp[2]);
+      c_b = c_b + m_b * p;
+      a_b += i_b * (cross(r_b, p) + imp[2]);
+    }
+    okay = position_error <= B2G_LINEAR_SLOP && angular_error <= B2G_ANGULAR_SLOP;
+  } else if (jr.type == B2GPU_JOINT_REVOLUTE) {
     const float axial_mass = B.j_tmp[jt_at(B, x, j, 1)].w;
     const int jflags = f2i(B.j_s1[x.at(B.NJ, j)].w);
     float angular_error = 0.0f;

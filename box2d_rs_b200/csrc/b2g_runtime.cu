@@ -444,8 +444,8 @@ static int topology_build(const b2gpu_snapshot* s, Topology& T) {
   T.jadj_off.assign(n.body_count + 1, 0);
   T.jadj.assign(2 * (size_t)n.joint_count, 0);
   for (const b2gpu_joint_rec& j : T.joints) {
-    if (j.type != B2GPU_JOINT_REVOLUTE && j.type != B2GPU_JOINT_DISTANCE) {
-      set_error("joint type outside the supported set (revolute, distance)");
+    if (j.type != B2GPU_JOINT_REVOLUTE && j.type != B2GPU_JOINT_DISTANCE && j.type != B2GPU_JOINT_WELD) {
+      set_error("joint type outside the supported set (revolute, distance, weld)");
       return B2GPU_E_UNSUPPORTED;
     }
     if (j.body_a < 0 || j.body_a >= n.body_count || j.body_b < 0 || j.body_b >= n.body_count || j.body_a == j.body_b) {

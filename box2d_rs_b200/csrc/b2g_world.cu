@@ -819,6 +819,45 @@ int b2gpu_distance_joint_def(b2gpu_world* W, b2gpu_joint_def* def, int body_a, i
   return 0;
   GUARD_END
 }
+int b2gpu_weld_joint_def(b2gpu_world* W, b2gpu_joint_def* def, int body_a, int body_b, float ax, float ay) {
+  GUARD_BEGIN
+  int rc = check_body(W, body_a);
+  if (!rc) rc = check_body(W, body_b);
+  if (rc) return rc;
+  if (!def) { set_error("joint def is NULL"); return B2GPU_E_INVALID; }
+  rc = ensure_host(W);
+  if (rc) return rc;
+  joint_def_defaults(def, B2GPU_JOINT_WELD, body_a, body_b);
+  const b2gpu_body_rec &a = W->h.bodies[body_a], &b = W->h.bodies[body_b];
+  const V2 la = body_local_point(a, v2(ax, ay)), lb = body_local_point(b, v2(ax, ay));
+  def->local_anchor_a[0] = la.x; def->local_anchor_a[1] = la.y;
+  def->local_anchor_b[0] = lb.x; def->local_anchor_b[1] = lb.y;
+  def->reference_angle = b.a - a.a;
+  return 0;
+  GUARD_END
+}
+int b2gpu_angular_stiffness(b2gpu_world* W, float frequency_hertz, float damping_ratio, int body_a, int body_b, float* stiffness,
+                            float* damping) {  // src/private/dynamics/b2_joint.rs:47-70, B2body::get_inertia (src/b2_body.rs:708-711)
+  GUARD_BEGIN
+  int rc = check_body(W, body_a);
+  if (!rc) rc = check_body(W, body_b);
+  if (rc) return rc;
+  if (!stiffness || !damping) { set_error("angular_stiffness: NULL output"); return B2GPU_E_INVALID; }
+  rc = ensure_host(W);
+  if (rc) return rc;
+  const b2gpu_body_rec &a = W->h.bodies[body_a], &b = W->h.bodies[body_b];
+  const float ia = a.inertia + a.mass * dot(v2(a.lc_x, a.lc_y), v2(a.lc_x, a.lc_y));
+  const float ib = b.inertia + b.mass * dot(v2(b.lc_x, b.lc_y), v2(b.lc_x, b.lc_y));
+  float i;
+  if (ia > 0.0f && ib > 0.0f) i = ia * ib / (ia + ib);
+  else if (ia > 0.0f) i = ia;
+  else i = ib;
+  const float omega = 2.0f * B2G_PI * frequency_hertz;
+  *stiffness = i * omega * omega;
+  *damping = 2.0f * i * damping_ratio * omega;
+  return 0;
+  GUARD_END
+}
 int b2gpu_linear_stiffness(b2gpu_world* W, float frequency_hertz, float damping_ratio, int body_a, int body_b, float* stiffness,
                            float* damping) {  // src/private/dynamics/b2_joint.rs:22-45
   GUARD_BEGIN
@@ -846,8 +885,8 @@ int b2gpu_world_create_joint(b2gpu_world* W, const b2gpu_joint_def* def) {  // b
   if (!rc) rc = check_body(W, def->body_b);
   if (rc) return rc;
   if (def->body_a == def->body_b) { set_error("create_joint: body_a == body_b (the reference asserts)"); return B2GPU_E_INVALID; }
-  if (def->type != B2GPU_JOINT_REVOLUTE && def->type != B2GPU_JOINT_DISTANCE) {
-    set_error("create_joint: only revolute and distance joints are inside the accelerated path");
+  if (def->type != B2GPU_JOINT_REVOLUTE && def->type != B2GPU_JOINT_DISTANCE && def->type != B2GPU_JOINT_WELD) {
+    set_error("create_joint: only revolute, distance and weld joints are inside the accelerated path");
     return B2GPU_E_UNSUPPORTED;
   }
   rc = ensure_host(W);
@@ -864,6 +903,9 @@ int b2gpu_world_create_joint(b2gpu_world* W, const b2gpu_joint_def* def) {  // b
     j.param[3] = def->max_motor_torque; j.param[4] = def->motor_speed;
     if (def->enable_limit) j.flags |= B2GPU_JOINT_ENABLE_LIMIT;
     if (def->enable_motor) j.flags |= B2GPU_JOINT_ENABLE_MOTOR;
+  } else if (def->type == B2GPU_JOINT_WELD) {  // B2weldJoint::new (src/joints/b2_weld_joint.rs:152-185)
+    j.param[0] = def->reference_angle;
+    j.param[3] = def->stiffness; j.param[4] = def->damping;
   } else {  // b2_distance_joint_new (private b2_distance_joint.rs:43-78)
     const float min_length = fmax_sel(def->min_length, B2G_LINEAR_SLOP);
     j.param[0] = fmax_sel(def->length, B2G_LINEAR_SLOP);

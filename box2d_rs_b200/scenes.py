@@ -294,6 +294,55 @@ def bridge(world, count=30, testbed_ground_body=True):
         b.create_fixture(FixtureDef(density=1.0), ball)
 
 
+def cantilever(world, count=8, testbed_ground_body=True):
+    """examples/testbed/tests/cantilever.rs:60-243: four beams of planks chained by weld joints — rigid from the ground, soft
+    (5 Hz) from the ground, rigid and soft (8 Hz) free chains — with two triangles and two circles dropped on them."""
+    if testbed_ground_body:
+        world.create_body(BodyDef())
+    ground = world.create_body(BodyDef())
+    ground.create_fixture_by_shape(world.shapes.edge_two_sided((-40.0, 0.0), (40.0, 0.0)), 0.0)
+    plank = world.shapes.polygon_box(0.5, 0.125)
+    prev = ground
+    for i in range(count):
+        body = world.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(f32(-14.5 + 1.0 * i), 5.0)))
+        body.create_fixture(FixtureDef(density=20.0), plank)
+        world.create_joint(world.weld_joint_def(prev, body, (f32(-15.0 + 1.0 * i), 5.0)))
+        prev = body
+    long_plank = world.shapes.polygon_box(1.0, 0.125)
+    prev = ground
+    for i in range(3):
+        body = world.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(f32(-14.0 + 2.0 * i), 15.0)))
+        body.create_fixture(FixtureDef(density=20.0), long_plank)
+        jd = world.weld_joint_def(prev, body, (f32(-15.0 + 2.0 * i), 15.0))
+        jd.stiffness, jd.damping = world.angular_stiffness(5.0, 0.7, prev, body)
+        world.create_joint(jd)
+        prev = body
+    prev = ground
+    for i in range(count):
+        body = world.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(f32(-4.5 + 1.0 * i), 5.0)))
+        body.create_fixture(FixtureDef(density=20.0), plank)
+        if i > 0:
+            world.create_joint(world.weld_joint_def(prev, body, (f32(-5.0 + 1.0 * i), 5.0)))
+        prev = body
+    prev = ground
+    for i in range(count):
+        body = world.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(f32(5.5 + 1.0 * i), 10.0)))
+        body.create_fixture(FixtureDef(density=20.0), plank)
+        if i > 0:
+            jd = world.weld_joint_def(prev, body, (f32(5.0 + 1.0 * i), 10.0))
+            jd.stiffness, jd.damping = world.angular_stiffness(8.0, 0.7, prev, body)
+            world.create_joint(jd)
+        prev = body
+    tri = world.shapes.polygon([(-0.5, 0.0), (0.5, 0.0), (0.0, 1.5)])
+    for i in range(2):
+        b = world.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(f32(-8.0 + 8.0 * i), 12.0)))
+        b.create_fixture(FixtureDef(density=1.0), tri)
+    ball = world.shapes.circle(0.5)
+    for i in range(2):
+        b = world.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(f32(-6.0 + 6.0 * i), 10.0)))
+        b.create_fixture(FixtureDef(density=1.0), ball)
+
+
 def tumbler(world, n=200, seed=0xB2D + 21):
     """examples/testbed/tests/tumbler.rs:62-97: a hollow box of four plank fixtures turned by a revolute-joint motor
     (0.05 pi rad/s, torque 1e8) around a point of the ground body; the testbed drops one 0.125 box per step, here `n`

@@ -183,6 +183,20 @@ class B2world:
                                                       anchor_a[0], anchor_a[1], anchor_b[0], anchor_b[1]))
         return d
 
+    def weld_joint_def(self, body_a, body_b, anchor):
+        """B2weldJointDef::default() + initialize(body_a, body_b, anchor): rigid unless stiffness / damping are set."""
+        d = abi.JointDef()
+        check(self.L, self.L.b2gpu_weld_joint_def(self.h, C.byref(d), _body_index(body_a), _body_index(body_b),
+                                                  anchor[0], anchor[1]))
+        return d
+
+    def angular_stiffness(self, frequency_hertz, damping_ratio, body_a, body_b):
+        """b2_angular_stiffness: (stiffness, damping) of a soft weld joint."""
+        k, d = C.c_float(), C.c_float()
+        check(self.L, self.L.b2gpu_angular_stiffness(self.h, frequency_hertz, damping_ratio, _body_index(body_a),
+                                                     _body_index(body_b), C.byref(k), C.byref(d)))
+        return k.value, d.value
+
     def linear_stiffness(self, frequency_hertz, damping_ratio, body_a, body_b):
         """b2_linear_stiffness: (stiffness, damping) of a soft distance joint."""
         k, d = C.c_float(), C.c_float()
@@ -191,7 +205,7 @@ class B2world:
         return k.value, d.value
 
     def create_joint(self, joint_def):
-        """B2world::create_joint (revolute and distance joints)."""
+        """B2world::create_joint (revolute, distance and weld joints)."""
         return B2joint(self, check(self.L, self.L.b2gpu_world_create_joint(self.h, C.byref(joint_def))))
 
     def joint(self, index):

@@ -38,7 +38,7 @@ extern "C" {
 #define B2GPU_E_NO_DEVICE (-2) /* no CUDA device: there is no CPU fallback */
 #define B2GPU_E_CUDA (-3)      /* CUDA runtime error, see b2gpu_last_error */
 #define B2GPU_E_CAPACITY (-4)  /* a device-side capacity was exceeded */
-#define B2GPU_E_UNSUPPORTED (-5) /* feature outside the hot-path scope (TOI, joint types other than revolute / distance) */
+#define B2GPU_E_UNSUPPORTED (-5) /* feature outside the hot-path scope (TOI, joint types other than revolute / distance / weld) */
 #define B2GPU_E_LOCKED (-6)    /* world is locked (reference: is_locked() panic) */
 #define B2GPU_E_INTERNAL (-7)  /* a device-side consistency check failed (a bug: please report) */
 #define B2GPU_E_IO (-8)        /* a checkpoint file could not be opened, read or written */
@@ -84,6 +84,7 @@ extern "C" {
 /* joint types: B2jointType (src/b2_joint.rs:46-58), same numbering */
 #define B2GPU_JOINT_DISTANCE 1
 #define B2GPU_JOINT_REVOLUTE 8
+#define B2GPU_JOINT_WELD 9
 /* b2gpu_joint_rec.flags */
 #define B2GPU_JOINT_COLLIDE_CONNECTED 0x1u /* B2jointDef::collide_connected */
 #define B2GPU_JOINT_ENABLE_LIMIT 0x2u      /* revolute: m_enable_limit */
@@ -384,12 +385,18 @@ int b2gpu_revolute_joint_def(b2gpu_world* w, b2gpu_joint_def* def, int body_a, i
 /* B2distanceJointDef::default + ::initialize(b1, b2, anchor1, anchor2) (private b2_distance_joint.rs:26-41):
  * length = max(|anchor2 - anchor1|, linear slop), min_length = max_length = length. */
 int b2gpu_distance_joint_def(b2gpu_world* w, b2gpu_joint_def* def, int body_a, int body_b, float a1x, float a1y, float a2x, float a2y);
+/* B2weldJointDef::default + ::initialize(body_a, body_b, anchor) (src/joints/b2_weld_joint.rs:10-50): local anchors and
+ * reference angle from the bodies' current transforms; stiffness = damping = 0 (rigid). */
+int b2gpu_weld_joint_def(b2gpu_world* w, b2gpu_joint_def* def, int body_a, int body_b, float anchor_x, float anchor_y);
+/* b2_angular_stiffness (src/private/dynamics/b2_joint.rs:47-70): stiffness and damping of a soft weld joint. */
+int b2gpu_angular_stiffness(b2gpu_world* w, float frequency_hertz, float damping_ratio, int body_a, int body_b, float* stiffness,
+                            float* damping);
 /* b2_linear_stiffness (src/private/dynamics/b2_joint.rs:22-45): stiffness and damping of a soft distance joint. */
 int b2gpu_linear_stiffness(b2gpu_world* w, float frequency_hertz, float damping_ratio, int body_a, int body_b, float* stiffness,
                            float* damping);
 /* B2world::create_joint (src/private/dynamics/b2_world.rs:156-262): returns the joint index (>= 0); contacts between
  * the two bodies are flagged for filtering when collide_connected is false.  Does not wake the bodies.
- * Joint types other than revolute and distance: B2GPU_E_UNSUPPORTED. */
+ * Joint types other than revolute, distance and weld: B2GPU_E_UNSUPPORTED. */
 int b2gpu_world_create_joint(b2gpu_world* w, const b2gpu_joint_def* def);
 int b2gpu_world_get_joint_count(b2gpu_world* w);
 int b2gpu_world_get_joint(b2gpu_world* w, int joint, b2gpu_joint_rec* out);

@@ -55,6 +55,9 @@ def lib():
         L.b2o_revolute_joint_def.argtypes = [C.c_void_p, C.POINTER(abi.JointDef), C.c_int, C.c_int, C.c_float, C.c_float]
         L.b2o_distance_joint_def.argtypes = [C.c_void_p, C.POINTER(abi.JointDef), C.c_int, C.c_int, C.c_float, C.c_float,
                                              C.c_float, C.c_float]
+        L.b2o_weld_joint_def.argtypes = [C.c_void_p, C.POINTER(abi.JointDef), C.c_int, C.c_int, C.c_float, C.c_float]
+        L.b2o_angular_stiffness.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_int, C.POINTER(C.c_float),
+                                            C.POINTER(C.c_float)]
         L.b2o_linear_stiffness.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_int, C.POINTER(C.c_float),
                                            C.POINTER(C.c_float)]
         L.b2o_create_joint.argtypes = [C.c_void_p, C.POINTER(abi.JointDef)]
@@ -241,6 +244,19 @@ class B2world:
         lib().b2o_distance_joint_def(self.h, C.byref(d), _body_index(body_a), _body_index(body_b), anchor_a[0], anchor_a[1],
                                      anchor_b[0], anchor_b[1])
         return d
+
+    def weld_joint_def(self, body_a, body_b, anchor):
+        """B2weldJointDef::default() + initialize(body_a, body_b, anchor)."""
+        d = abi.JointDef()
+        lib().b2o_weld_joint_def(self.h, C.byref(d), _body_index(body_a), _body_index(body_b), anchor[0], anchor[1])
+        return d
+
+    def angular_stiffness(self, frequency_hertz, damping_ratio, body_a, body_b):
+        """b2_angular_stiffness: (stiffness, damping)."""
+        k, d = C.c_float(), C.c_float()
+        lib().b2o_angular_stiffness(self.h, frequency_hertz, damping_ratio, _body_index(body_a), _body_index(body_b),
+                                    C.byref(k), C.byref(d))
+        return k.value, d.value
 
     def linear_stiffness(self, frequency_hertz, damping_ratio, body_a, body_b):
         """b2_linear_stiffness: (stiffness, damping)."""

@@ -158,6 +158,14 @@ int b2o_distance_joint_def(void* w, b2gpu_joint_def* def, int body_a, int body_b
   joint_def_out(((World*)w)->distance_joint_def(body_a, body_b, Vec2(a1x, a1y), Vec2(a2x, a2y)), def);
   return 0;
 }
+int b2o_weld_joint_def(void* w, b2gpu_joint_def* def, int body_a, int body_b, float ax, float ay) {
+  joint_def_out(((World*)w)->weld_joint_def(body_a, body_b, Vec2(ax, ay)), def);
+  return 0;
+}
+int b2o_angular_stiffness(void* w, float hz, float ratio, int body_a, int body_b, float* stiffness, float* damping) {
+  ((World*)w)->angular_stiffness(*stiffness, *damping, hz, ratio, body_a, body_b);
+  return 0;
+}
 int b2o_linear_stiffness(void* w, float hz, float ratio, int body_a, int body_b, float* stiffness, float* damping) {
   ((World*)w)->linear_stiffness(*stiffness, *damping, hz, ratio, body_a, body_b);
   return 0;
@@ -326,6 +334,9 @@ int b2o_snapshot_export(void* w, b2gpu_snapshot* out) {
       r.param[0] = j.reference_angle; r.param[1] = j.lower_angle; r.param[2] = j.upper_angle;
       r.param[3] = j.max_motor_torque; r.param[4] = j.motor_speed;
       r.impulse[0] = j.impulse2.x; r.impulse[1] = j.impulse2.y; r.impulse[2] = j.motor_impulse;
+    } else if (j.type == J_WELD) {
+      r.param[0] = j.reference_angle; r.param[3] = j.stiffness; r.param[4] = j.damping;
+      r.impulse[0] = j.impulse3[0]; r.impulse[1] = j.impulse3[1]; r.impulse[2] = j.impulse3[2];
     } else {
       r.param[0] = j.length; r.param[1] = j.min_length; r.param[2] = j.max_length; r.param[3] = j.stiffness; r.param[4] = j.damping;
       r.impulse[0] = j.impulse;

@@ -66,6 +66,51 @@ inline Vec2 operator+(Vec2 a, Vec2 b) { return Vec2(a.x + b.x, a.y + b.y); }
 inline Vec2 operator-(Vec2 a, Vec2 b) { return Vec2(a.x - b.x, a.y - b.y); }
 inline Vec2 operator*(float s, Vec2 a) { return Vec2(s * a.x, s * a.y); }
 
+// B2Mat33 (src/b2_math.rs:296-352, src/private/common/b2_math.rs) on a plain array: ex.xyz, ey.xyz, ez.xyz at [0..8].
+inline float vec3_dot(const float* a, const float* b) { return a[0] * b[0] + a[1] * b[1] + a[2] * b[2]; }  // b2_dot_vec3 :569
+inline void vec3_cross(const float* a, const float* b, float* o) {  // b2_cross_vec3 :574-580
+  o[0] = a[1] * b[2] - a[2] * b[1];
+  o[1] = a[2] * b[0] - a[0] * b[2];
+  o[2] = a[0] * b[1] - a[1] * b[0];
+}
+// get_inverse22 (private b2_math.rs:32-48): the inverse of the upper 2x2 block, the rest zero
+inline void mat33_get_inverse22(const float* k, float* m) {
+  float a = k[0], b = k[3], c = k[1], d = k[4];
+  float det = a * d - b * c;
+  if (det != 0.0f) det = 1.0f / det;
+  m[0] = det * d; m[3] = -det * b; m[2] = 0.0f;
+  m[1] = -det * c; m[4] = det * a; m[5] = 0.0f;
+  m[6] = 0.0f; m[7] = 0.0f; m[8] = 0.0f;
+}
+// get_sym_inverse33 (private b2_math.rs:50-72): zero matrix if singular
+inline void mat33_get_sym_inverse33(const float* k, float* m) {
+  float cr[3];
+  vec3_cross(k + 3, k + 6, cr);
+  float det = vec3_dot(k, cr);
+  if (det != 0.0f) det = 1.0f / det;
+  float a11 = k[0], a12 = k[3], a13 = k[6], a22 = k[4], a23 = k[7], a33 = k[8];
+  m[0] = det * (a22 * a33 - a23 * a23);
+  m[1] = det * (a13 * a23 - a12 * a33);
+  m[2] = det * (a12 * a23 - a13 * a22);
+  m[3] = m[1];
+  m[4] = det * (a11 * a33 - a13 * a13);
+  m[5] = det * (a13 * a12 - a11 * a23);
+  m[6] = m[2];
+  m[7] = m[5];
+  m[8] = det * (a11 * a22 - a12 * a12);
+}
+// solve33 (private b2_math.rs:5-16)
+inline void mat33_solve33(const float* k, const float* b, float* x) {
+  float cr[3];
+  vec3_cross(k + 3, k + 6, cr);
+  float det = vec3_dot(k, cr);
+  if (det != 0.0f) det = 1.0f / det;
+  x[0] = det * vec3_dot(b, cr);
+  vec3_cross(b, k + 6, cr);
+  x[1] = det * vec3_dot(k, cr);
+  vec3_cross(k + 3, b, cr);
+  x[2] = det * vec3_dot(k, cr);
+}
 struct Mat22 {
   Vec2 ex, ey;
   void set_zero() { ex.set_zero(); ey.set_zero(); }

@@ -93,7 +93,7 @@ struct Contact {
 
 // Joints: B2jointDef + B2revoluteJointDef / B2distanceJointDef as one plain struct
 // (src/b2_joint.rs:112-122, src/joints/b2_revolute_joint.rs:10-72, src/joints/b2_distance_joint.rs:11-58).
-enum JointType { J_DISTANCE = 1, J_REVOLUTE = 8 };  // B2jointType numbering (src/b2_joint.rs:46-58)
+enum JointType { J_DISTANCE = 1, J_REVOLUTE = 8, J_WELD = 9 };  // B2jointType numbering (src/b2_joint.rs:46-58)
 struct JointDef {
   int type = 0, body_a = -1, body_b = -1;
   bool collide_connected = false;
@@ -115,6 +115,8 @@ struct Joint {  // B2joint + B2revoluteJoint (src/joints/b2_revolute_joint.rs:10
   float length = 0.0f, min_length = 0.0f, max_length = 0.0f, stiffness = 0.0f, damping = 0.0f, impulse = 0.0f;
   float gamma = 0.0f, bias = 0.0f, current_length = 0.0f, mass = 0.0f, soft_mass = 0.0f;
   Vec2 u;
+  // weld (src/joints/b2_weld_joint.rs:66-90): impulse (x, y, angular), effective mass B2Mat33 as ex.xyz ey.xyz ez.xyz
+  float impulse3[3] = {0.0f, 0.0f, 0.0f}, m33[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   // solver temp
   int index_a = 0, index_b = 0;
   Vec2 r_a, r_b, local_center_a, local_center_b;
@@ -447,6 +449,30 @@ struct World {
     d.max_length = d.length;
     return d;
   }
+  // B2weldJointDef::default + ::initialize (src/joints/b2_weld_joint.rs:10-50)
+  JointDef weld_joint_def(int body_a, int body_b, Vec2 anchor) const {
+    JointDef d;
+    d.type = J_WELD;
+    d.body_a = body_a; d.body_b = body_b;
+    d.local_anchor_a = b2_mul_t_xf(bodies[body_a].xf, anchor);
+    d.local_anchor_b = b2_mul_t_xf(bodies[body_b].xf, anchor);
+    d.reference_angle = bodies[body_b].sweep.a - bodies[body_a].sweep.a;
+    return d;
+  }
+  // b2_angular_stiffness (src/private/dynamics/b2_joint.rs:47-70); B2body::get_inertia (src/b2_body.rs:708-711)
+  void angular_stiffness(float& stiffness, float& damping, float frequency_hertz, float damping_ratio, int body_a, int body_b) const {
+    const Body& a = bodies[body_a];
+    const Body& b = bodies[body_b];
+    float ia = a.i + a.mass * b2_dot(a.sweep.local_center, a.sweep.local_center);
+    float ib = b.i + b.mass * b2_dot(b.sweep.local_center, b.sweep.local_center);
+    float i;
+    if (ia > 0.0f && ib > 0.0f) i = ia * ib / (ia + ib);
+    else if (ia > 0.0f) i = ia;
+    else i = ib;
+    float omega = 2.0f * PI * frequency_hertz;
+    stiffness = i * omega * omega;
+    damping = 2.0f * i * damping_ratio * omega;
+  }
   // b2_linear_stiffness (src/private/dynamics/b2_joint.rs:22-45)
   void linear_stiffness(float& stiffness, float& damping, float frequency_hertz, float damping_ratio, int body_a, int body_b) const {
     float mass_a = bodies[body_a].mass, mass_b = bodies[body_b].mass, mass;
@@ -470,6 +496,9 @@ struct World {
       j.min_length = b2_max(def.min_length, LINEAR_SLOP);
       j.length = b2_max(def.length, LINEAR_SLOP);
       j.max_length = b2_max(def.max_length, j.min_length);
+      j.stiffness = def.stiffness; j.damping = def.damping;
+    } else if (def.type == J_WELD) {  // B2weldJoint::new (src/joints/b2_weld_joint.rs:152-185)
+      j.reference_angle = def.reference_angle;
       j.stiffness = def.stiffness; j.damping = def.damping;
     } else {
       assert(false && "joint type outside the oracle's scope");
@@ -1100,6 +1129,47 @@ struct World {
         j.lower_impulse = 0.0f;
         j.upper_impulse = 0.0f;
       }
+    } else if (j.type == J_WELD) {  // private joints/b2_weld_joint.rs:22-136
+      float m_a = j.inv_mass_a, m_b = j.inv_mass_b, i_a = j.inv_ia, i_b = j.inv_ib;
+      float k[9];  // ex.x ex.y ex.z ey.x ey.y ey.z ez.x ez.y ez.z
+      k[0] = m_a + m_b + j.r_a.y * j.r_a.y * i_a + j.r_b.y * j.r_b.y * i_b;
+      k[3] = -j.r_a.y * j.r_a.x * i_a - j.r_b.y * j.r_b.x * i_b;
+      k[6] = -j.r_a.y * i_a - j.r_b.y * i_b;
+      k[1] = k[3];
+      k[4] = m_a + m_b + j.r_a.x * j.r_a.x * i_a + j.r_b.x * j.r_b.x * i_b;
+      k[7] = j.r_a.x * i_a + j.r_b.x * i_b;
+      k[2] = k[6];
+      k[5] = k[7];
+      k[8] = i_a + i_b;
+      if (j.stiffness > 0.0f) {
+        mat33_get_inverse22(k, j.m33);
+        float inv_m = i_a + i_b;
+        float c = a_b - a_a - j.reference_angle;
+        float d = j.damping, kk = j.stiffness, h = step.dt;
+        j.gamma = h * (d + h * kk);
+        j.gamma = j.gamma != 0.0f ? 1.0f / j.gamma : 0.0f;
+        j.bias = c * h * kk * j.gamma;
+        inv_m += j.gamma;
+        j.m33[8] = inv_m != 0.0f ? 1.0f / inv_m : 0.0f;
+      } else if (k[8] == 0.0f) {
+        mat33_get_inverse22(k, j.m33);
+        j.gamma = 0.0f;
+        j.bias = 0.0f;
+      } else {
+        mat33_get_sym_inverse33(k, j.m33);
+        j.gamma = 0.0f;
+        j.bias = 0.0f;
+      }
+      if (step.warm_starting) {
+        j.impulse3[0] *= step.dt_ratio; j.impulse3[1] *= step.dt_ratio; j.impulse3[2] *= step.dt_ratio;
+        Vec2 p(j.impulse3[0], j.impulse3[1]);
+        v_a -= m_a * p;
+        w_a -= i_a * (b2_cross(j.r_a, p) + j.impulse3[2]);
+        v_b += m_b * p;
+        w_b += i_b * (b2_cross(j.r_b, p) + j.impulse3[2]);
+      } else {
+        j.impulse3[0] = j.impulse3[1] = j.impulse3[2] = 0.0f;
+      }
     } else {  // distance: private joints/b2_distance_joint.rs:80-184
       j.u = c_b + j.r_b - c_a - j.r_a;
       j.current_length = j.u.length();
@@ -1195,6 +1265,38 @@ struct World {
         w_a -= i_a * b2_cross(j.r_a, impulse);
         v_b += m_b * impulse;
         w_b += i_b * b2_cross(j.r_b, impulse);
+      }
+    } else if (j.type == J_WELD) {  // private joints/b2_weld_joint.rs:138-205
+      float m_a = j.inv_mass_a, m_b = j.inv_mass_b, i_a = j.inv_ia, i_b = j.inv_ib;
+      const float* m = j.m33;
+      if (j.stiffness > 0.0f) {
+        float cdot2 = w_b - w_a;
+        float impulse2 = -m[8] * (cdot2 + j.bias + j.gamma * j.impulse3[2]);
+        j.impulse3[2] += impulse2;
+        w_a -= i_a * impulse2;
+        w_b += i_b * impulse2;
+        Vec2 cdot1 = v_b + b2_cross_sv(w_b, j.r_b) - v_a - b2_cross_sv(w_a, j.r_a);
+        Vec2 impulse1 = -Vec2(m[0] * cdot1.x + m[3] * cdot1.y, m[1] * cdot1.x + m[4] * cdot1.y);  // b2_mul22
+        j.impulse3[0] += impulse1.x;
+        j.impulse3[1] += impulse1.y;
+        Vec2 p = impulse1;
+        v_a -= m_a * p;
+        w_a -= i_a * b2_cross(j.r_a, p);
+        v_b += m_b * p;
+        w_b += i_b * b2_cross(j.r_b, p);
+      } else {
+        Vec2 cdot1 = v_b + b2_cross_sv(w_b, j.r_b) - v_a - b2_cross_sv(w_a, j.r_a);
+        float cdot2 = w_b - w_a;
+        // b2_mul_mat33 (src/b2_math.rs:601-603): v.x * ex + v.y * ey + v.z * ez, then the negation
+        float ix = -((cdot1.x * m[0] + cdot1.y * m[3]) + cdot2 * m[6]);
+        float iy = -((cdot1.x * m[1] + cdot1.y * m[4]) + cdot2 * m[7]);
+        float iz = -((cdot1.x * m[2] + cdot1.y * m[5]) + cdot2 * m[8]);
+        j.impulse3[0] += ix; j.impulse3[1] += iy; j.impulse3[2] += iz;
+        Vec2 p(ix, iy);
+        v_a -= m_a * p;
+        w_a -= i_a * (b2_cross(j.r_a, p) + iz);
+        v_b += m_b * p;
+        w_b += i_b * (b2_cross(j.r_b, p) + iz);
       }
     } else {  // distance: private joints/b2_distance_joint.rs:186-277
       if (j.min_length < j.max_length) {
@@ -1303,6 +1405,58 @@ struct World {
         a_a -= i_a * b2_cross(r_a, impulse);
         c_b += m_b * impulse;
         a_b += i_b * b2_cross(r_b, impulse);
+      }
+      okay = position_error <= LINEAR_SLOP && angular_error <= ANGULAR_SLOP;
+    } else if (j.type == J_WELD) {  // private joints/b2_weld_joint.rs:207-283
+      Rot q_a(a_a), q_b(a_b);
+      float m_a = j.inv_mass_a, m_b = j.inv_mass_b, i_a = j.inv_ia, i_b = j.inv_ib;
+      Vec2 r_a = b2_mul_rot(q_a, j.local_anchor_a - j.local_center_a);
+      Vec2 r_b = b2_mul_rot(q_b, j.local_anchor_b - j.local_center_b);
+      float position_error, angular_error;
+      float k[9];
+      k[0] = m_a + m_b + r_a.y * r_a.y * i_a + r_b.y * r_b.y * i_b;
+      k[3] = -r_a.y * r_a.x * i_a - r_b.y * r_b.x * i_b;
+      k[6] = -r_a.y * i_a - r_b.y * i_b;
+      k[1] = k[3];
+      k[4] = m_a + m_b + r_a.x * r_a.x * i_a + r_b.x * r_b.x * i_b;
+      k[7] = r_a.x * i_a + r_b.x * i_b;
+      k[2] = k[6];
+      k[5] = k[7];
+      k[8] = i_a + i_b;
+      auto solve22 = [&](Vec2 b) {  // B2Mat33::solve22 (private b2_math.rs:19-30)
+        float a11 = k[0], a12 = k[3], a21 = k[1], a22 = k[4];
+        float det = a11 * a22 - a12 * a21;
+        if (det != 0.0f) det = 1.0f / det;
+        return Vec2(det * (a22 * b.x - a12 * b.y), det * (a11 * b.y - a21 * b.x));
+      };
+      if (j.stiffness > 0.0f) {
+        Vec2 c1 = c_b + r_b - c_a - r_a;
+        position_error = c1.length();
+        angular_error = 0.0f;
+        Vec2 p = -solve22(c1);
+        c_a -= m_a * p;
+        a_a -= i_a * b2_cross(r_a, p);
+        c_b += m_b * p;
+        a_b += i_b * b2_cross(r_b, p);
+      } else {
+        Vec2 c1 = c_b + r_b - c_a - r_a;
+        float c2 = a_b - a_a - j.reference_angle;
+        position_error = c1.length();
+        angular_error = fabsf(c2);
+        float imp[3];
+        if (k[8] > 0.0f) {
+          float c[3] = {c1.x, c1.y, c2}, x[3];
+          mat33_solve33(k, c, x);
+          imp[0] = -x[0]; imp[1] = -x[1]; imp[2] = -x[2];
+        } else {
+          Vec2 impulse2 = -solve22(c1);
+          imp[0] = impulse2.x; imp[1] = impulse2.y; imp[2] = 0.0f;
+        }
+        Vec2 p(imp[0], imp[1]);
+        c_a -= m_a * p;
+        a_a -= i_a * (b2_cross(r_a, p) + imp[2]);
+        c_b += m_b * p;
+        a_b += i_b * (b2_cross(r_b, p) + imp[2]);
       }
       okay = position_error <= LINEAR_SLOP && angular_error <= ANGULAR_SLOP;
     } else {  // distance: private joints/b2_distance_joint.rs:279-320

@@ -40,9 +40,10 @@ SCENES = {
     "terrain": (lambda s, w: s.terrain(w), (0.0, -10.0), 260),
 }
 
-# scenes with joints (revolute / distance): the exact mode and batches; the large-world modes reject joints
+# scenes with joints (revolute / distance / weld)
 JOINT_SCENES = {
     "bridge": (lambda s, w: s.bridge(w), (0.0, -10.0), 240),
     "tumbler": (lambda s, w: s.tumbler(w, n=120), (0.0, -10.0), 240),
     "joints_mix": (lambda s, w: s.joints_mix(w), (0.0, -10.0), 400),
+    "cantilever": (lambda s, w: s.cantilever(w), (0.0, -10.0), 300),
 }

@@ -101,6 +101,92 @@ def test_oracle_revolute_motor_reaches_its_speed(built):
     assert abs(w.snapshot().bodies[1]["w"] + 1.0) < 1e-4
 
 
+def test_oracle_weld_joint_keeps_the_relative_pose(built):
+    """Two free bodies welded together and thrown: the anchor points stay together and the relative angle stays the
+    reference angle (b2_weld_joint.rs: rigid form, 3x3 solve); the soft form lets the angle oscillate and damps it out."""
+    from box2d_rs_b200 import abi, scenes
+    from box2d_rs_b200.abi import BodyDef
+    from oracle import b2o
+    for soft in (False, True):
+        w = b2o.B2world((0.0, -10.0))
+        a = w.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(0.0, 10.0), angle=0.3))
+        a.create_fixture_by_shape(w.shapes.polygon_box(1.0, 0.2), 2.0)
+        b = w.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(2.0, 10.5), angle=-0.4))
+        b.create_fixture_by_shape(w.shapes.polygon_box(0.5, 0.5), 1.0)
+        jd = w.weld_joint_def(a, b, (1.0, 10.3))
+        assert abs(jd.reference_angle - (-0.7)) < 1e-6
+        if soft:
+            jd.stiffness, jd.damping = w.angular_stiffness(3.0, 0.5, a, b)
+        w.create_joint(jd)
+        a.set_angular_velocity(2.0)
+        b.apply_linear_impulse_to_center((3.0, 4.0), True)
+        worst_angle = 0.0
+        for i in range(150):
+            w.step(scenes.DT, 8, 3)
+            ba, bb = w.snapshot().bodies[0], w.snapshot().bodies[1]
+
+            def world_point(body, lp):
+                return (body["xf"][0] + body["xf"][3] * lp[0] - body["xf"][2] * lp[1],
+                        body["xf"][1] + body["xf"][2] * lp[0] + body["xf"][3] * lp[1])
+            pa, pb = world_point(ba, jd.local_anchor_a), world_point(bb, jd.local_anchor_b)
+            assert math.hypot(pa[0] - pb[0], pa[1] - pb[1]) < 0.02
+            err = abs(float(bb["a"] - ba["a"]) - jd.reference_angle)
+            if i > 100:
+                worst_angle = max(worst_angle, err)
+            if not soft:
+                assert err < 0.02
+        assert worst_angle < (0.05 if soft else 0.01)
+
+
+def test_oracle_angular_stiffness_formula(built):
+    """b2_angular_stiffness (private b2_joint.rs:47-70): I = Ia Ib / (Ia + Ib) of B2body::get_inertia, omega = 2 pi f."""
+    from box2d_rs_b200 import abi
+    from box2d_rs_b200.abi import BodyDef
+    from oracle import b2o
+    w = b2o.B2world((0.0, 0.0))
+    ground = w.create_body(BodyDef())
+    a = w.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(0.0, 0.0)))
+    a.create_fixture_by_shape(w.shapes.polygon_box(1.0, 0.125), 20.0)   # mass 10, I = 10 (4 + 1/16) / 12
+    b = w.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(3.0, 0.0)))
+    b.create_fixture_by_shape(w.shapes.circle(0.5), 4.0)                # mass pi, I = pi / 8
+    ia, ib = 10.0 * (4.0 + 0.0625) / 12.0, math.pi * 0.125
+    k, d = w.angular_stiffness(5.0, 0.7, ground, a)
+    omega = 2.0 * math.pi * 5.0
+    assert abs(k - ia * omega * omega) / k < 1e-5 and abs(d - 2.0 * ia * 0.7 * omega) / d < 1e-5
+    k, d = w.angular_stiffness(2.0, 0.3, a, b)
+    i = ia * ib / (ia + ib)
+    omega = 2.0 * math.pi * 2.0
+    assert abs(k - i * omega * omega) / k < 1e-5 and abs(d - 2.0 * i * 0.3 * omega) / d < 1e-5
+
+
+def test_weld_defs_and_unsupported_types(built):
+    """b2gpu_weld_joint_def / b2gpu_angular_stiffness equal the oracle's bit for bit; a joint type outside the supported set
+    is refused with B2GPU_E_UNSUPPORTED."""
+    from box2d_rs_b200 import abi, batch, world
+    from box2d_rs_b200.abi import BodyDef
+    from box2d_rs_b200.lib import B2gpuError
+    from oracle import b2o
+    ctx = batch.Context(0, lib_path=HOSTSIM_SO)
+    ws = []
+    for mk in (lambda: b2o.B2world((0.0, -10.0)), lambda: world.B2world((0.0, -10.0), ctx=ctx)):
+        w = mk()
+        a = w.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(0.25, 1.5), angle=0.7))
+        a.create_fixture_by_shape(w.shapes.polygon_box(1.0, 0.125, center=(0.3, 0.1), angle=0.2), 20.0)
+        b = w.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(2.0, 1.0), angle=-1.1))
+        b.create_fixture_by_shape(w.shapes.circle(0.5), 3.0)
+        jd = w.weld_joint_def(a, b, (1.3, 1.2))
+        ws.append((w, jd, w.angular_stiffness(4.0, 0.6, a, b)))
+    (wo, jo, so), (wg, jg, sg) = ws
+    assert bytes(jo) == bytes(jg)
+    assert np.array_equal(np.float32(so).view(np.uint32), np.float32(sg).view(np.uint32))
+    jg.type = 6  # prismatic
+    with pytest.raises(B2gpuError) as e:
+        wg.create_joint(jg)
+    assert e.value.code == abi.E_UNSUPPORTED
+    wg.close()
+    ctx.close()
+
+
 def test_oracle_joint_prevents_collision_unless_collide_connected(built):
     from box2d_rs_b200 import abi, scenes
     from box2d_rs_b200.abi import BodyDef

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Differential fuzzing of the device stages (host simulator build by default, --gpu for the CUDA path) against
 the CPU oracle: random scenes (polygons of 3..8 vertices, circles, edges, chains, kinematic / fixed-rotation /
-multi-fixture bodies, sensors, filters, restitution, damping, revolute / distance joints with limits, motors and springs,
+multi-fixture bodies, sensors, filters, restitution, damping, revolute / distance / weld joints with limits, motors and springs,
 random world flags and iteration counts, dt = 0 steps,
 mid-run set_transform / set_linear_velocity / apply_force / apply_torque / apply_*_impulse / set_awake edits), stepped freely and compared bit for bit.
 
@@ -89,7 +89,7 @@ def build(world, rng):
                 ang = np.sort(rng.uniform(0, 2 * math.pi, nv))
                 shape = world.shapes.polygon([(f32(rad * math.cos(a)), f32(rad * math.sin(a) * rng.uniform(0.5, 1.0))) for a in ang])
             b.create_fixture(fd, shape)
-    # joints (revolute / distance) between random bodies, the ground included: limits, motors, soft springs, slack ranges,
+    # joints (revolute / distance / weld) between random bodies, the ground included: limits, motors, soft springs, slack ranges,
     # collide_connected, degenerate pairs (kinematic or fixed-rotation bodies, anchors far from the bodies)
     joints = []
     if rng.integers(0, 5) < 3:
@@ -97,7 +97,12 @@ def build(world, rng):
             a, b = int(rng.integers(0, n + 1)), int(rng.integers(0, n + 1))
             if a == b:
                 continue
-            if rng.integers(0, 2) == 0:
+            kind = int(rng.integers(0, 3))
+            if kind == 2:  # weld: rigid or soft; anchors far from the bodies and immovable partners included
+                jd = world.weld_joint_def(a, b, (f32(rng.uniform(-10, 10)), f32(rng.uniform(0.5, 14))))
+                if rng.integers(0, 2) == 0:
+                    jd.stiffness, jd.damping = world.angular_stiffness(f32(rng.uniform(0.5, 8)), f32(rng.uniform(0, 1)), a, b)
+            elif kind == 0:
                 jd = world.revolute_joint_def(a, b, (f32(rng.uniform(-10, 10)), f32(rng.uniform(0.5, 14))))
                 if rng.integers(0, 2) == 0:
                     lo = f32(rng.uniform(-1.5, 0.2))
