@@ -226,6 +226,13 @@ pub fn flatten<D: UserDataType>(world: &B2world<D>) -> Snapshot<D> {
                 r.param[3] = v.m_stiffness; r.param[4] = v.m_damping;
                 r.impulse[0] = v.m_impulse; r.impulse[3] = v.m_lower_impulse; r.impulse[4] = v.m_upper_impulse;
             }
+            JointAsDerived::EWeldJoint(v) => {
+                r.type_ = 9;
+                r.local_anchor_a = [v.m_local_anchor_a.x, v.m_local_anchor_a.y];
+                r.local_anchor_b = [v.m_local_anchor_b.x, v.m_local_anchor_b.y];
+                r.param[0] = v.m_reference_angle; r.param[3] = v.m_stiffness; r.param[4] = v.m_damping;
+                r.impulse[0] = v.m_impulse.x; r.impulse[1] = v.m_impulse.y; r.impulse[2] = v.m_impulse.z;
+            }
             _ => { r.type_ = 0; } // b2gpu_world_upload answers B2GPU_E_UNSUPPORTED: keep such worlds on the CPU path
         }
         r
@@ -436,6 +443,9 @@ pub fn write_back<D: UserDataType>(world: &mut B2world<D>, snap: &Snapshot<D>) {
                 v.m_impulse = r.impulse[0];
                 v.m_lower_impulse = r.impulse[3];
                 v.m_upper_impulse = r.impulse[4];
+            }
+            JointAsDerivedMut::EWeldJoint(v) => {
+                v.m_impulse.set(r.impulse[0], r.impulse[1], r.impulse[2]);
             }
             _ => {}
         }
