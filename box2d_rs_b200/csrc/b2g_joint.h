@@ -1,4 +1,4 @@
-// b2g_joint.h — joints inside the island solve: revolute, distance and weld joints.
+// b2g_joint.h — joints inside the island solve: revolute, prismatic, distance and weld joints.
 //
 // Reference: B2jointTraitDyn::{init_velocity_constraints, solve_velocity_constraints, solve_position_constraints}
 // (src/b2_joint.rs:268-286) as driven by B2island::solve (src/private/dynamics/b2_island_private.rs:198-201 init after the
@@ -7,6 +7,8 @@
 //   revolute: src/private/dynamics/joints/b2_revolute_joint.rs:22-123 / :125-217 / :219-301
 //   distance: src/private/dynamics/joints/b2_distance_joint.rs:80-184 / :186-277 / :279-320
 //   weld:     src/private/dynamics/joints/b2_weld_joint.rs:22-136 / :138-205 / :207-283
+//   prismatic: src/private/dynamics/joints/b2_prismatic_joint.rs:168-280 / :282-393 / :395-506 (impulses and switches laid
+//              out like the revolute joint's; param 1 / 2 = translation limits, 3 = max motor force, 5 / 6 = local x axis)
 // Expression shapes are kept operation for operation (one rounding per operation, no FMA), like the contact solver.
 //
 // Data: the static part of a joint (type, bodies, anchors, limits, lengths, COLLIDE_CONNECTED) is topology shared by the
@@ -19,6 +21,7 @@
 //   2: revolute angle - - -                          | distance gamma bias current_length -   | weld mass.ey.yz mass.ez.xy
 //   3: mA iA mB iB
 //   4: weld mass.ez.z gamma bias -
+// prismatic: 0: axis.xy perp.xy   1: s1 s2 a1 a2   2: K11 K12 K22 axial_mass   3: mA iA mB iB   4: translation - - -
 // Joint visits are ordered work: they run in the island's joint order inside every form of the Gauss-Seidel stages
 // (VelocityK / PositionK generic; velocity_sl_kernel / position_sl_kernel for batches, through an accessor over their
 // shared-memory rows; LwVelocity7K / LwPosition6K in the large-world modes).
@@ -146,7 +149,45 @@ B2G_HD void joint_init_velocity(const Batch& B, const WIdx& x, const S& st, int 
   float4 s0 = B.j_s0[ji], s1 = B.j_s1[ji];
   const int jflags = f2i(s1.w);
   float4 t1, t2 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), t4 = t2;
-  if (jr.type == B2GPU_JOINT_WELD) {
+  float4 t0 = make_float4(r_a.x, r_a.y, r_b.x, r_b.y);
+  if (jr.type == B2GPU_JOINT_PRISMATIC) {
+    const V2 d = (c_b - c_a) + r_b - r_a;
+    const V2 lx = v2(jr.param[5], jr.param[6]), ly = cross_sv(1.0f, lx);  // m_local_xaxis_a, m_local_yaxis_a
+    const V2 axis = rot_mul(q_a, lx);
+    const float a1 = cross(d + r_a, axis), a2 = cross(r_b, axis);
+    float axial_mass = m_a + m_b + i_a * a1 * a1 + i_b * a2 * a2;
+    if (axial_mass > 0.0f) axial_mass = 1.0f / axial_mass;
+    const V2 perp = rot_mul(q_a, ly);
+    const float ps1 = cross(d + r_a, perp), ps2 = cross(r_b, perp);
+    const float k11 = m_a + m_b + i_a * ps1 * ps1 + i_b * ps2 * ps2;
+    const float k12 = i_a * ps1 + i_b * ps2;
+    float k22 = i_a + i_b;
+    if (k22 == 0.0f) k22 = 1.0f;  // bodies with fixed rotation
+    float translation = 0.0f;
+    if (jflags & B2GPU_JOINT_ENABLE_LIMIT) translation = dot(axis, d);
+    else { s0.w = 0.0f; s1.x = 0.0f; }
+    if (!(jflags & B2GPU_JOINT_ENABLE_MOTOR)) s0.z = 0.0f;
+    if (warm_starting) {
+      s0.x *= dt_ratio; s0.y *= dt_ratio;
+      s0.z *= dt_ratio;
+      s0.w *= dt_ratio;
+      s1.x *= dt_ratio;
+      const float axial_impulse = s0.z + s0.w - s1.x;
+      const V2 p = s0.x * perp + axial_impulse * axis;
+      const float la = s0.x * ps1 + s0.y + axial_impulse * a1;
+      const float lb = s0.x * ps2 + s0.y + axial_impulse * a2;
+      v_a = v_a - m_a * p;
+      w_a -= i_a * la;
+      v_b = v_b + m_b * p;
+      w_b += i_b * lb;
+    } else {
+      s0.x = 0.0f; s0.y = 0.0f; s0.z = 0.0f; s0.w = 0.0f; s1.x = 0.0f;
+    }
+    t0 = make_float4(axis.x, axis.y, perp.x, perp.y);
+    t1 = make_float4(ps1, ps2, a1, a2);
+    t2 = make_float4(k11, k12, k22, axial_mass);
+    t4 = make_float4(translation, 0.0f, 0.0f, 0.0f);
+  } else if (jr.type == B2GPU_JOINT_WELD) {
     float k[9], m[9];
     weld_k(k, r_a, r_b, m_a, i_a, m_b, i_b);
     const float stiffness = jr.param[3], damping = jr.param[4];
@@ -251,11 +292,11 @@ B2G_HD void joint_init_velocity(const Batch& B, const WIdx& x, const S& st, int 
   }
   B.j_s0[ji] = s0;
   B.j_s1[ji] = s1;
-  B.j_tmp[jt_at(B, x, j, 0)] = make_float4(r_a.x, r_a.y, r_b.x, r_b.y);
+  B.j_tmp[jt_at(B, x, j, 0)] = t0;
   B.j_tmp[jt_at(B, x, j, 1)] = t1;
   B.j_tmp[jt_at(B, x, j, 2)] = t2;
   B.j_tmp[jt_at(B, x, j, 3)] = make_float4(m_a, i_a, m_b, i_b);
-  if (jr.type == B2GPU_JOINT_WELD) B.j_tmp[jt_at(B, x, j, 4)] = t4;
+  if (jr.type == B2GPU_JOINT_WELD || jr.type == B2GPU_JOINT_PRISMATIC) B.j_tmp[jt_at(B, x, j, 4)] = t4;
   // an immovable body may sit in several islands: its velocity never changes, leave it alone
   if (m_a != 0.0f || i_a != 0.0f) st.set_vel(jr.body_a, make_float4(v_a.x, v_a.y, w_a, 0.0f));
   if (m_b != 0.0f || i_b != 0.0f) st.set_vel(jr.body_b, make_float4(v_b.x, v_b.y, w_b, 0.0f));
@@ -274,7 +315,68 @@ B2G_HD void joint_solve_velocity(const Batch& B, const WIdx& x, const S& st, int
   const int ji = x.at(B.NJ, j);
   float4 s0 = B.j_s0[ji], s1 = B.j_s1[ji];
   const int jflags = f2i(s1.w);
-  if (jr.type == B2GPU_JOINT_WELD) {
+  if (jr.type == B2GPU_JOINT_PRISMATIC) {
+    const V2 axis = v2(t0.x, t0.y), perp = v2(t0.z, t0.w);
+    const float s1_ = t1.x, s2_ = t1.y, a1 = t1.z, a2 = t1.w, axial_mass = t2.w;
+    const float translation = B.j_tmp[jt_at(B, x, j, 4)].x;
+    if (jflags & B2GPU_JOINT_ENABLE_MOTOR) {  // linear motor
+      const float cdot = dot(axis, v_b - v_a) + a2 * w_b - a1 * w_a;
+      float impulse = axial_mass * (s1.y - cdot);
+      const float old_impulse = s0.z;
+      const float max_impulse = h * s1.z;
+      s0.z = fclamp_sel(s0.z + impulse, -max_impulse, max_impulse);
+      impulse = s0.z - old_impulse;
+      const V2 p = impulse * axis;
+      const float la = impulse * a1, lb = impulse * a2;
+      v_a = v_a - m_a * p;
+      w_a -= i_a * la;
+      v_b = v_b + m_b * p;
+      w_b += i_b * lb;
+    }
+    if (jflags & B2GPU_JOINT_ENABLE_LIMIT) {
+      {  // lower limit
+        const float c = translation - jr.param[1];
+        const float cdot = dot(axis, v_b - v_a) + a2 * w_b - a1 * w_a;
+        float impulse = -axial_mass * (cdot + fmax_sel(c, 0.0f) * inv_dt);
+        const float old_impulse = s0.w;
+        s0.w = fmax_sel(s0.w + impulse, 0.0f);
+        impulse = s0.w - old_impulse;
+        const V2 p = impulse * axis;
+        const float la = impulse * a1, lb = impulse * a2;
+        v_a = v_a - m_a * p;
+        w_a -= i_a * la;
+        v_b = v_b + m_b * p;
+        w_b += i_b * lb;
+      }
+      {  // upper limit: signs flipped to keep c positive when the constraint is satisfied
+        const float c = jr.param[2] - translation;
+        const float cdot = dot(axis, v_a - v_b) + a1 * w_a - a2 * w_b;
+        float impulse = -axial_mass * (cdot + fmax_sel(c, 0.0f) * inv_dt);
+        const float old_impulse = s1.x;
+        s1.x = fmax_sel(s1.x + impulse, 0.0f);
+        impulse = s1.x - old_impulse;
+        const V2 p = impulse * axis;
+        const float la = impulse * a1, lb = impulse * a2;
+        v_a = v_a + m_a * p;
+        w_a += i_a * la;
+        v_b = v_b - m_b * p;
+        w_b -= i_b * lb;
+      }
+    }
+    {  // prismatic constraint in 2D
+      const V2 cdot = v2(dot(perp, v_b - v_a) + s2_ * w_b - s1_ * w_a, w_b - w_a);
+      const V2 df = mat22_solve(t2.x, t2.y, t2.y, t2.z, -cdot);
+      s0.x += df.x;
+      s0.y += df.y;
+      const V2 p = df.x * perp;
+      const float la = df.x * s1_ + df.y;
+      const float lb = df.x * s2_ + df.y;
+      v_a = v_a - m_a * p;
+      w_a -= i_a * la;
+      v_b = v_b + m_b * p;
+      w_b += i_b * lb;
+    }
+  } else if (jr.type == B2GPU_JOINT_WELD) {
     const float4 t4 = B.j_tmp[jt_at(B, x, j, 4)];
     const float m[9] = {t1.x, t1.y, t1.z, t1.w, t2.x, t2.y, t2.z, t2.w, t4.x};
     const float gamma = t4.y, bias = t4.z;
@@ -435,7 +537,63 @@ B2G_HD bool joint_solve_position(const Batch& B, const WIdx& x, const S& st, int
   const V2 la = v2(jr.local_anchor_a[0], jr.local_anchor_a[1]) - v2(msa.z, msa.w);
   const V2 lb = v2(jr.local_anchor_b[0], jr.local_anchor_b[1]) - v2(msb.z, msb.w);
   bool okay;
-  if (jr.type == B2GPU_JOINT_WELD) {
+  if (jr.type == B2GPU_JOINT_PRISMATIC) {
+    const int jflags = f2i(B.j_s1[x.at(B.NJ, j)].w);
+    const V2 r_a = rot_mul(q_a, la);
+    const V2 r_b = rot_mul(q_b, lb);
+    const V2 d = c_b + r_b - c_a - r_a;
+    const V2 lx = v2(jr.param[5], jr.param[6]), ly = cross_sv(1.0f, lx);
+    const V2 axis = rot_mul(q_a, lx);
+    const float a1 = cross(d + r_a, axis), a2 = cross(r_b, axis);
+    const V2 perp = rot_mul(q_a, ly);
+    const float s1 = cross(d + r_a, perp), s2 = cross(r_b, perp);
+    const V2 c1 = v2(dot(perp, d), a_b - a_a - jr.param[0]);
+    float linear_error = fabsf(c1.x);
+    const float angular_error = fabsf(c1.y);
+    bool active = false;
+    float c2 = 0.0f;
+    if (jflags & B2GPU_JOINT_ENABLE_LIMIT) {
+      const float lower = jr.param[1], upper = jr.param[2];
+      const float translation = dot(axis, d);
+      if (fabsf(upper - lower) < 2.0f * B2G_LINEAR_SLOP) {
+        c2 = translation;
+        linear_error = fmax_sel(linear_error, fabsf(translation));
+        active = true;
+      } else if (translation <= lower) {
+        c2 = fmin_sel(translation - lower, 0.0f);
+        linear_error = fmax_sel(linear_error, lower - translation);
+        active = true;
+      } else if (translation >= upper) {
+        c2 = fmax_sel(translation - upper, 0.0f);
+        linear_error = fmax_sel(linear_error, translation - upper);
+        active = true;
+      }
+    }
+    float imp[3];
+    const float k11 = m_a + m_b + i_a * s1 * s1 + i_b * s2 * s2;
+    const float k12 = i_a * s1 + i_b * s2;
+    float k22 = i_a + i_b;
+    if (k22 == 0.0f) k22 = 1.0f;  // fixed rotation
+    if (active) {
+      const float k13 = i_a * s1 * a1 + i_b * s2 * a2;
+      const float k23 = i_a * a1 + i_b * a2;
+      const float k33 = m_a + m_b + i_a * a1 * a1 + i_b * a2 * a2;
+      const float k[9] = {k11, k12, k13, k12, k22, k23, k13, k23, k33};
+      const float c[3] = {-c1.x, -c1.y, -c2};
+      mat33_solve33(k, c, imp);
+    } else {
+      const V2 impulse1 = mat22_solve(k11, k12, k12, k22, -c1);
+      imp[0] = impulse1.x; imp[1] = impulse1.y; imp[2] = 0.0f;
+    }
+    const V2 p = imp[0] * perp + imp[2] * axis;
+    const float la_ = imp[0] * s1 + imp[1] + imp[2] * a1;
+    const float lb_ = imp[0] * s2 + imp[1] + imp[2] * a2;
+    c_a = c_a - m_a * p;
+    a_a -= i_a * la_;
+    c_b = c_b + m_b * p;
+    a_b += i_b * lb_;
+    okay = linear_error <= B2G_LINEAR_SLOP && angular_error <= B2G_ANGULAR_SLOP;
+  } else if (jr.type == B2GPU_JOINT_WELD) {
     const V2 r_a = rot_mul(q_a, la);
     const V2 r_b = rot_mul(q_b, lb);
     float k[9];

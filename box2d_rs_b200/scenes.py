@@ -343,6 +343,46 @@ def cantilever(world, count=8, testbed_ground_body=True):
         b.create_fixture(FixtureDef(density=1.0), ball)
 
 
+def sliders(world):
+    """Prismatic joints: examples/testbed/tests/prismatic_joint.rs:61-101 (a 2 x 2 box, turned a quarter, on a horizontal slider
+    from the ground with limits +-10 and a motor that is off), plus a vertical lift with its motor on against a stack it
+    carries, a slider between two dynamic bodies, and one with equal limits (a locked translation)."""
+    ground = world.create_body(BodyDef())
+    ground.create_fixture_by_shape(world.shapes.edge_two_sided((-40.0, 0.0), (40.0, 0.0)), 0.0)
+    body = world.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(0.0, 10.0), angle=f32(0.5 * math.pi), allow_sleep=0))
+    body.create_fixture_by_shape(world.shapes.polygon_box(1.0, 1.0), 5.0)
+    jd = world.prismatic_joint_def(ground, body, (0.0, 10.0), (1.0, 0.0))
+    jd.motor_speed, jd.max_motor_torque, jd.enable_motor = 10.0, 10000.0, 0
+    jd.lower_angle, jd.upper_angle, jd.enable_limit = -10.0, 10.0, 1
+    world.create_joint(jd)
+    body.set_linear_velocity((6.0, 0.0))
+    # a lift: platform on a vertical slider, motor on, two boxes riding it
+    lift = world.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(-12.0, 2.0)))
+    lift.create_fixture(FixtureDef(density=2.0, friction=0.6), world.shapes.polygon_box(2.0, 0.25))
+    jd = world.prismatic_joint_def(ground, lift, (-12.0, 2.0), (0.0, 1.0))
+    jd.motor_speed, jd.max_motor_torque, jd.enable_motor = 1.5, 2000.0, 1
+    jd.lower_angle, jd.upper_angle, jd.enable_limit = 0.0, 6.0, 1
+    world.create_joint(jd)
+    for i in range(2):
+        b = world.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(f32(-12.5 + 1.0 * i), f32(2.76 + 1.02 * i))))
+        b.create_fixture(FixtureDef(density=1.0, friction=0.6), world.shapes.polygon_box(0.5, 0.5))
+    # a slider between two dynamic bodies, along a slanted axis
+    a = world.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(10.0, 6.0), angle=0.3))
+    a.create_fixture_by_shape(world.shapes.polygon_box(1.5, 0.3), 1.0)
+    b = world.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(12.0, 7.0)))
+    b.create_fixture_by_shape(world.shapes.circle(0.5), 2.0)
+    jd = world.prismatic_joint_def(a, b, (11.0, 6.5), (2.0, 1.0))
+    jd.lower_angle, jd.upper_angle, jd.enable_limit = -0.5, 1.5, 1
+    jd.collide_connected = 1
+    world.create_joint(jd)
+    # equal limits: the translation is locked
+    c = world.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(20.0, 4.0)))
+    c.create_fixture_by_shape(world.shapes.polygon_box(0.5, 0.5), 1.0)
+    jd = world.prismatic_joint_def(ground, c, (20.0, 4.0), (0.0, 1.0))
+    jd.lower_angle, jd.upper_angle, jd.enable_limit = 0.0, 0.0, 1
+    world.create_joint(jd)
+
+
 def tumbler(world, n=200, seed=0xB2D + 21):
     """examples/testbed/tests/tumbler.rs:62-97: a hollow box of four plank fixtures turned by a revolute-joint motor
     (0.05 pi rad/s, torque 1e8) around a point of the ground body; the testbed drops one 0.125 box per step, here `n`

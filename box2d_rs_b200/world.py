@@ -183,6 +183,14 @@ class B2world:
                                                       anchor_a[0], anchor_a[1], anchor_b[0], anchor_b[1]))
         return d
 
+    def prismatic_joint_def(self, body_a, body_b, anchor, axis):
+        """B2prismaticJointDef::default() + initialize(body_a, body_b, anchor, axis).  In the shared def struct lower_angle /
+        upper_angle are the translation limits, max_motor_torque the maximum motor force, (length, min_length) the local axis."""
+        d = abi.JointDef()
+        check(self.L, self.L.b2gpu_prismatic_joint_def(self.h, C.byref(d), _body_index(body_a), _body_index(body_b),
+                                                       anchor[0], anchor[1], axis[0], axis[1]))
+        return d
+
     def weld_joint_def(self, body_a, body_b, anchor):
         """B2weldJointDef::default() + initialize(body_a, body_b, anchor): rigid unless stiffness / damping are set."""
         d = abi.JointDef()
@@ -205,7 +213,7 @@ class B2world:
         return k.value, d.value
 
     def create_joint(self, joint_def):
-        """B2world::create_joint (revolute, distance and weld joints)."""
+        """B2world::create_joint (revolute, prismatic, distance and weld joints)."""
         return B2joint(self, check(self.L, self.L.b2gpu_world_create_joint(self.h, C.byref(joint_def))))
 
     def joint(self, index):

@@ -38,7 +38,7 @@ extern "C" {
 #define B2GPU_E_NO_DEVICE (-2) /* no CUDA device: there is no CPU fallback */
 #define B2GPU_E_CUDA (-3)      /* CUDA runtime error, see b2gpu_last_error */
 #define B2GPU_E_CAPACITY (-4)  /* a device-side capacity was exceeded */
-#define B2GPU_E_UNSUPPORTED (-5) /* feature outside the hot-path scope (TOI, joint types other than revolute / distance / weld) */
+#define B2GPU_E_UNSUPPORTED (-5) /* feature outside the hot-path scope (TOI, joint types other than revolute / prismatic / distance / weld) */
 #define B2GPU_E_LOCKED (-6)    /* world is locked (reference: is_locked() panic) */
 #define B2GPU_E_INTERNAL (-7)  /* a device-side consistency check failed (a bug: please report) */
 #define B2GPU_E_IO (-8)        /* a checkpoint file could not be opened, read or written */
@@ -83,6 +83,7 @@ extern "C" {
 
 /* joint types: B2jointType (src/b2_joint.rs:46-58), same numbering */
 #define B2GPU_JOINT_DISTANCE 1
+#define B2GPU_JOINT_PRISMATIC 6
 #define B2GPU_JOINT_REVOLUTE 8
 #define B2GPU_JOINT_WELD 9
 /* b2gpu_joint_rec.flags */
@@ -385,6 +386,13 @@ int b2gpu_revolute_joint_def(b2gpu_world* w, b2gpu_joint_def* def, int body_a, i
 /* B2distanceJointDef::default + ::initialize(b1, b2, anchor1, anchor2) (private b2_distance_joint.rs:26-41):
  * length = max(|anchor2 - anchor1|, linear slop), min_length = max_length = length. */
 int b2gpu_distance_joint_def(b2gpu_world* w, b2gpu_joint_def* def, int body_a, int body_b, float a1x, float a1y, float a2x, float a2y);
+/* B2prismaticJointDef::default + ::initialize(body_a, body_b, anchor, axis) (src/joints/b2_prismatic_joint.rs:10-89).  The
+ * plain def struct is shared, so a prismatic def reads some fields under other names: lower_angle / upper_angle are the
+ * lower / upper TRANSLATION, max_motor_torque is the maximum motor FORCE, and (length, min_length) carry local_axis_a (x, y)
+ * — b2gpu_world_create_joint normalises it as B2prismaticJoint::new does; lower > upper is B2GPU_E_INVALID (the reference
+ * asserts).  The revolute setters below (motor speed, max motor torque = force, enable motor / limit, set_limits) apply. */
+int b2gpu_prismatic_joint_def(b2gpu_world* w, b2gpu_joint_def* def, int body_a, int body_b, float anchor_x, float anchor_y,
+                              float axis_x, float axis_y);
 /* B2weldJointDef::default + ::initialize(body_a, body_b, anchor) (src/joints/b2_weld_joint.rs:10-50): local anchors and
  * reference angle from the bodies' current transforms; stiffness = damping = 0 (rigid). */
 int b2gpu_weld_joint_def(b2gpu_world* w, b2gpu_joint_def* def, int body_a, int body_b, float anchor_x, float anchor_y);
@@ -396,7 +404,7 @@ int b2gpu_linear_stiffness(b2gpu_world* w, float frequency_hertz, float damping_
                            float* damping);
 /* B2world::create_joint (src/private/dynamics/b2_world.rs:156-262): returns the joint index (>= 0); contacts between
  * the two bodies are flagged for filtering when collide_connected is false.  Does not wake the bodies.
- * Joint types other than revolute, distance and weld: B2GPU_E_UNSUPPORTED. */
+ * Joint types other than revolute, prismatic, distance and weld: B2GPU_E_UNSUPPORTED. */
 int b2gpu_world_create_joint(b2gpu_world* w, const b2gpu_joint_def* def);
 int b2gpu_world_get_joint_count(b2gpu_world* w);
 int b2gpu_world_get_joint(b2gpu_world* w, int joint, b2gpu_joint_rec* out);

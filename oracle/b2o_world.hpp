@@ -93,7 +93,7 @@ struct Contact {
 
 // Joints: B2jointDef + B2revoluteJointDef / B2distanceJointDef as one plain struct
 // (src/b2_joint.rs:112-122, src/joints/b2_revolute_joint.rs:10-72, src/joints/b2_distance_joint.rs:11-58).
-enum JointType { J_DISTANCE = 1, J_REVOLUTE = 8, J_WELD = 9 };  // B2jointType numbering (src/b2_joint.rs:46-58)
+enum JointType { J_DISTANCE = 1, J_PRISMATIC = 6, J_REVOLUTE = 8, J_WELD = 9 };  // B2jointType numbering (src/b2_joint.rs:46-58)
 struct JointDef {
   int type = 0, body_a = -1, body_b = -1;
   bool collide_connected = false;
@@ -101,6 +101,9 @@ struct JointDef {
   float reference_angle = 0.0f, lower_angle = 0.0f, upper_angle = 0.0f, max_motor_torque = 0.0f, motor_speed = 0.0f;
   bool enable_limit = false, enable_motor = false;
   float length = 1.0f, min_length = 0.0f, max_length = MAX_FLOAT, stiffness = 0.0f, damping = 0.0f;
+  // prismatic (src/joints/b2_prismatic_joint.rs:10-72): lower_angle / upper_angle carry the translation limits,
+  // max_motor_torque the maximum motor force
+  Vec2 local_axis_a = Vec2(1.0f, 0.0f);
 };
 struct Joint {  // B2joint + B2revoluteJoint (src/joints/b2_revolute_joint.rs:104-136) / B2distanceJoint fields
   int type = 0, body_a = -1, body_b = -1;
@@ -115,6 +118,10 @@ struct Joint {  // B2joint + B2revoluteJoint (src/joints/b2_revolute_joint.rs:10
   float length = 0.0f, min_length = 0.0f, max_length = 0.0f, stiffness = 0.0f, damping = 0.0f, impulse = 0.0f;
   float gamma = 0.0f, bias = 0.0f, current_length = 0.0f, mass = 0.0f, soft_mass = 0.0f;
   Vec2 u;
+  // prismatic (src/joints/b2_prismatic_joint.rs:101-136): shares impulse2 / motor / limit impulses and switches with the
+  // revolute joint (lower_angle / upper_angle = translation limits, max_motor_torque = max motor force)
+  Vec2 local_xaxis_a, local_yaxis_a, axis, perp;
+  float s1 = 0.0f, s2 = 0.0f, a1 = 0.0f, a2 = 0.0f, translation = 0.0f;
   // weld (src/joints/b2_weld_joint.rs:66-90): impulse (x, y, angular), effective mass B2Mat33 as ex.xyz ey.xyz ez.xyz
   float impulse3[3] = {0.0f, 0.0f, 0.0f}, m33[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   // solver temp
@@ -449,6 +456,17 @@ struct World {
     d.max_length = d.length;
     return d;
   }
+  // B2prismaticJointDef::default + ::initialize (src/joints/b2_prismatic_joint.rs:10-89)
+  JointDef prismatic_joint_def(int body_a, int body_b, Vec2 anchor, Vec2 axis) const {
+    JointDef d;
+    d.type = J_PRISMATIC;
+    d.body_a = body_a; d.body_b = body_b;
+    d.local_anchor_a = b2_mul_t_xf(bodies[body_a].xf, anchor);
+    d.local_anchor_b = b2_mul_t_xf(bodies[body_b].xf, anchor);
+    d.local_axis_a = b2_mul_t_rot(bodies[body_a].xf.q, axis);  // get_local_vector (src/b2_body.rs:733-735)
+    d.reference_angle = bodies[body_b].sweep.a - bodies[body_a].sweep.a;
+    return d;
+  }
   // B2weldJointDef::default + ::initialize (src/joints/b2_weld_joint.rs:10-50)
   JointDef weld_joint_def(int body_a, int body_b, Vec2 anchor) const {
     JointDef d;
@@ -497,6 +515,15 @@ struct World {
       j.length = b2_max(def.length, LINEAR_SLOP);
       j.max_length = b2_max(def.max_length, j.min_length);
       j.stiffness = def.stiffness; j.damping = def.damping;
+    } else if (def.type == J_PRISMATIC) {  // private joints/b2_prismatic_joint.rs:99-166
+      j.local_xaxis_a = def.local_axis_a;
+      j.local_xaxis_a.normalize();
+      j.local_yaxis_a = b2_cross_sv(1.0f, j.local_xaxis_a);
+      j.reference_angle = def.reference_angle;
+      j.lower_angle = def.lower_angle; j.upper_angle = def.upper_angle;
+      assert(j.lower_angle <= j.upper_angle);
+      j.max_motor_torque = def.max_motor_torque; j.motor_speed = def.motor_speed;
+      j.enable_limit = def.enable_limit; j.enable_motor = def.enable_motor;
     } else if (def.type == J_WELD) {  // B2weldJoint::new (src/joints/b2_weld_joint.rs:152-185)
       j.reference_angle = def.reference_angle;
       j.stiffness = def.stiffness; j.damping = def.damping;
@@ -1129,6 +1156,53 @@ struct World {
         j.lower_impulse = 0.0f;
         j.upper_impulse = 0.0f;
       }
+    } else if (j.type == J_PRISMATIC) {  // private joints/b2_prismatic_joint.rs:168-280
+      float m_a = j.inv_mass_a, m_b = j.inv_mass_b, i_a = j.inv_ia, i_b = j.inv_ib;
+      Vec2 d = (c_b - c_a) + j.r_b - j.r_a;
+      {
+        j.axis = b2_mul_rot(q_a, j.local_xaxis_a);
+        j.a1 = b2_cross(d + j.r_a, j.axis);
+        j.a2 = b2_cross(j.r_b, j.axis);
+        j.axial_mass = m_a + m_b + i_a * j.a1 * j.a1 + i_b * j.a2 * j.a2;
+        if (j.axial_mass > 0.0f) j.axial_mass = 1.0f / j.axial_mass;
+      }
+      {
+        j.perp = b2_mul_rot(q_a, j.local_yaxis_a);
+        j.s1 = b2_cross(d + j.r_a, j.perp);
+        j.s2 = b2_cross(j.r_b, j.perp);
+        float k11 = m_a + m_b + i_a * j.s1 * j.s1 + i_b * j.s2 * j.s2;
+        float k12 = i_a * j.s1 + i_b * j.s2;
+        float k22 = i_a + i_b;
+        if (k22 == 0.0f) k22 = 1.0f;  // bodies with fixed rotation
+        j.k.ex.set(k11, k12);
+        j.k.ey.set(k12, k22);
+      }
+      if (j.enable_limit) {
+        j.translation = b2_dot(j.axis, d);
+      } else {
+        j.lower_impulse = 0.0f;
+        j.upper_impulse = 0.0f;
+      }
+      if (j.enable_motor == false) j.motor_impulse = 0.0f;
+      if (step.warm_starting) {
+        j.impulse2 *= step.dt_ratio;
+        j.motor_impulse *= step.dt_ratio;
+        j.lower_impulse *= step.dt_ratio;
+        j.upper_impulse *= step.dt_ratio;
+        float axial_impulse = j.motor_impulse + j.lower_impulse - j.upper_impulse;
+        Vec2 p = j.impulse2.x * j.perp + axial_impulse * j.axis;
+        float la = j.impulse2.x * j.s1 + j.impulse2.y + axial_impulse * j.a1;
+        float lb = j.impulse2.x * j.s2 + j.impulse2.y + axial_impulse * j.a2;
+        v_a -= m_a * p;
+        w_a -= i_a * la;
+        v_b += m_b * p;
+        w_b += i_b * lb;
+      } else {
+        j.impulse2.set_zero();
+        j.motor_impulse = 0.0f;
+        j.lower_impulse = 0.0f;
+        j.upper_impulse = 0.0f;
+      }
     } else if (j.type == J_WELD) {  // private joints/b2_weld_joint.rs:22-136
       float m_a = j.inv_mass_a, m_b = j.inv_mass_b, i_a = j.inv_ia, i_b = j.inv_ib;
       float k[9];  // ex.x ex.y ex.z ey.x ey.y ey.z ez.x ez.y ez.z
@@ -1265,6 +1339,64 @@ struct World {
         w_a -= i_a * b2_cross(j.r_a, impulse);
         v_b += m_b * impulse;
         w_b += i_b * b2_cross(j.r_b, impulse);
+      }
+    } else if (j.type == J_PRISMATIC) {  // private joints/b2_prismatic_joint.rs:282-393
+      float m_a = j.inv_mass_a, m_b = j.inv_mass_b, i_a = j.inv_ia, i_b = j.inv_ib;
+      if (j.enable_motor) {  // linear motor
+        float cdot = b2_dot(j.axis, v_b - v_a) + j.a2 * w_b - j.a1 * w_a;
+        float impulse = j.axial_mass * (j.motor_speed - cdot);
+        float old_impulse = j.motor_impulse;
+        float max_impulse = step.dt * j.max_motor_torque;
+        j.motor_impulse = b2_clamp(j.motor_impulse + impulse, -max_impulse, max_impulse);
+        impulse = j.motor_impulse - old_impulse;
+        Vec2 p = impulse * j.axis;
+        float la = impulse * j.a1, lb = impulse * j.a2;
+        v_a -= m_a * p;
+        w_a -= i_a * la;
+        v_b += m_b * p;
+        w_b += i_b * lb;
+      }
+      if (j.enable_limit) {
+        {  // lower limit
+          float c = j.translation - j.lower_angle;
+          float cdot = b2_dot(j.axis, v_b - v_a) + j.a2 * w_b - j.a1 * w_a;
+          float impulse = -j.axial_mass * (cdot + b2_max(c, 0.0f) * step.inv_dt);
+          float old_impulse = j.lower_impulse;
+          j.lower_impulse = b2_max(j.lower_impulse + impulse, 0.0f);
+          impulse = j.lower_impulse - old_impulse;
+          Vec2 p = impulse * j.axis;
+          float la = impulse * j.a1, lb = impulse * j.a2;
+          v_a -= m_a * p;
+          w_a -= i_a * la;
+          v_b += m_b * p;
+          w_b += i_b * lb;
+        }
+        {  // upper limit: signs flipped to keep c positive when the constraint is satisfied
+          float c = j.upper_angle - j.translation;
+          float cdot = b2_dot(j.axis, v_a - v_b) + j.a1 * w_a - j.a2 * w_b;
+          float impulse = -j.axial_mass * (cdot + b2_max(c, 0.0f) * step.inv_dt);
+          float old_impulse = j.upper_impulse;
+          j.upper_impulse = b2_max(j.upper_impulse + impulse, 0.0f);
+          impulse = j.upper_impulse - old_impulse;
+          Vec2 p = impulse * j.axis;
+          float la = impulse * j.a1, lb = impulse * j.a2;
+          v_a += m_a * p;
+          w_a += i_a * la;
+          v_b -= m_b * p;
+          w_b -= i_b * lb;
+        }
+      }
+      {  // prismatic constraint in 2D
+        Vec2 cdot(b2_dot(j.perp, v_b - v_a) + j.s2 * w_b - j.s1 * w_a, w_b - w_a);
+        Vec2 df = j.k.solve(-cdot);
+        j.impulse2 += df;
+        Vec2 p = df.x * j.perp;
+        float la = df.x * j.s1 + df.y;
+        float lb = df.x * j.s2 + df.y;
+        v_a -= m_a * p;
+        w_a -= i_a * la;
+        v_b += m_b * p;
+        w_b += i_b * lb;
       }
     } else if (j.type == J_WELD) {  // private joints/b2_weld_joint.rs:138-205
       float m_a = j.inv_mass_a, m_b = j.inv_mass_b, i_a = j.inv_ia, i_b = j.inv_ib;
@@ -1407,6 +1539,70 @@ struct World {
         a_b += i_b * b2_cross(r_b, impulse);
       }
       okay = position_error <= LINEAR_SLOP && angular_error <= ANGULAR_SLOP;
+    } else if (j.type == J_PRISMATIC) {  // private joints/b2_prismatic_joint.rs:395-506
+      Rot q_a(a_a), q_b(a_b);
+      float m_a = j.inv_mass_a, m_b = j.inv_mass_b, i_a = j.inv_ia, i_b = j.inv_ib;
+      Vec2 r_a = b2_mul_rot(q_a, j.local_anchor_a - j.local_center_a);
+      Vec2 r_b = b2_mul_rot(q_b, j.local_anchor_b - j.local_center_b);
+      Vec2 d = c_b + r_b - c_a - r_a;
+      Vec2 axis = b2_mul_rot(q_a, j.local_xaxis_a);
+      float a1 = b2_cross(d + r_a, axis);
+      float a2 = b2_cross(r_b, axis);
+      Vec2 perp = b2_mul_rot(q_a, j.local_yaxis_a);
+      float s1 = b2_cross(d + r_a, perp);
+      float s2 = b2_cross(r_b, perp);
+      float imp[3];
+      Vec2 c1(b2_dot(perp, d), a_b - a_a - j.reference_angle);
+      float linear_error = fabsf(c1.x);
+      float angular_error = fabsf(c1.y);
+      bool active = false;
+      float c2 = 0.0f;
+      if (j.enable_limit) {
+        float translation = b2_dot(axis, d);
+        if (fabsf(j.upper_angle - j.lower_angle) < 2.0f * LINEAR_SLOP) {
+          c2 = translation;
+          linear_error = b2_max(linear_error, fabsf(translation));
+          active = true;
+        } else if (translation <= j.lower_angle) {
+          c2 = b2_min(translation - j.lower_angle, 0.0f);
+          linear_error = b2_max(linear_error, j.lower_angle - translation);
+          active = true;
+        } else if (translation >= j.upper_angle) {
+          c2 = b2_max(translation - j.upper_angle, 0.0f);
+          linear_error = b2_max(linear_error, translation - j.upper_angle);
+          active = true;
+        }
+      }
+      if (active) {
+        float k11 = m_a + m_b + i_a * s1 * s1 + i_b * s2 * s2;
+        float k12 = i_a * s1 + i_b * s2;
+        float k13 = i_a * s1 * a1 + i_b * s2 * a2;
+        float k22 = i_a + i_b;
+        if (k22 == 0.0f) k22 = 1.0f;  // fixed rotation
+        float k23 = i_a * a1 + i_b * a2;
+        float k33 = m_a + m_b + i_a * a1 * a1 + i_b * a2 * a2;
+        float k[9] = {k11, k12, k13, k12, k22, k23, k13, k23, k33};
+        float c[3] = {-c1.x, -c1.y, -c2};
+        mat33_solve33(k, c, imp);
+      } else {
+        float k11 = m_a + m_b + i_a * s1 * s1 + i_b * s2 * s2;
+        float k12 = i_a * s1 + i_b * s2;
+        float k22 = i_a + i_b;
+        if (k22 == 0.0f) k22 = 1.0f;
+        Mat22 k;
+        k.ex.set(k11, k12);
+        k.ey.set(k12, k22);
+        Vec2 impulse1 = k.solve(-c1);
+        imp[0] = impulse1.x; imp[1] = impulse1.y; imp[2] = 0.0f;
+      }
+      Vec2 p = imp[0] * perp + imp[2] * axis;
+      float la = imp[0] * s1 + imp[1] + imp[2] * a1;
+      float lb = imp[0] * s2 + imp[1] + imp[2] * a2;
+      c_a -= m_a * p;
+      a_a -= i_a * la;
+      c_b += m_b * p;
+      a_b += i_b * lb;
+      okay = linear_error <= LINEAR_SLOP && angular_error <= ANGULAR_SLOP;
     } else if (j.type == J_WELD) {  // private joints/b2_weld_joint.rs:207-283
       Rot q_a(a_a), q_b(a_b);
       float m_a = j.inv_mass_a, m_b = j.inv_mass_b, i_a = j.inv_ia, i_b = j.inv_ib;

@@ -226,6 +226,18 @@ pub fn flatten<D: UserDataType>(world: &B2world<D>) -> Snapshot<D> {
                 r.param[3] = v.m_stiffness; r.param[4] = v.m_damping;
                 r.impulse[0] = v.m_impulse; r.impulse[3] = v.m_lower_impulse; r.impulse[4] = v.m_upper_impulse;
             }
+            JointAsDerived::EPrismaticJoint(v) => {
+                r.type_ = 6;
+                r.local_anchor_a = [v.m_local_anchor_a.x, v.m_local_anchor_a.y];
+                r.local_anchor_b = [v.m_local_anchor_b.x, v.m_local_anchor_b.y];
+                r.param[0] = v.m_reference_angle; r.param[1] = v.m_lower_translation; r.param[2] = v.m_upper_translation;
+                r.param[3] = v.m_max_motor_force; r.param[4] = v.m_motor_speed;
+                r.param[5] = v.m_local_xaxis_a.x; r.param[6] = v.m_local_xaxis_a.y;
+                if v.m_enable_limit { r.flags |= 2; }
+                if v.m_enable_motor { r.flags |= 4; }
+                r.impulse[0] = v.m_impulse.x; r.impulse[1] = v.m_impulse.y; r.impulse[2] = v.m_motor_impulse;
+                r.impulse[3] = v.m_lower_impulse; r.impulse[4] = v.m_upper_impulse;
+            }
             JointAsDerived::EWeldJoint(v) => {
                 r.type_ = 9;
                 r.local_anchor_a = [v.m_local_anchor_a.x, v.m_local_anchor_a.y];
@@ -441,6 +453,12 @@ pub fn write_back<D: UserDataType>(world: &mut B2world<D>, snap: &Snapshot<D>) {
             }
             JointAsDerivedMut::EDistanceJoint(v) => {
                 v.m_impulse = r.impulse[0];
+                v.m_lower_impulse = r.impulse[3];
+                v.m_upper_impulse = r.impulse[4];
+            }
+            JointAsDerivedMut::EPrismaticJoint(v) => {
+                v.m_impulse.set(r.impulse[0], r.impulse[1]);
+                v.m_motor_impulse = r.impulse[2];
                 v.m_lower_impulse = r.impulse[3];
                 v.m_upper_impulse = r.impulse[4];
             }

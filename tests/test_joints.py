@@ -138,6 +138,60 @@ def test_oracle_weld_joint_keeps_the_relative_pose(built):
         assert worst_angle < (0.05 if soft else 0.01)
 
 
+def test_oracle_prismatic_joint_slides_along_its_axis_only(built):
+    """examples/testbed/tests/prismatic_joint.rs: a box on a horizontal slider from the ground, gravity on, pushed along the
+    axis — it keeps its height and its angle, runs into the upper limit (10) and rests there; with the motor on it is driven
+    back at the motor speed."""
+    from box2d_rs_b200 import abi, scenes
+    from box2d_rs_b200.abi import BodyDef
+    from oracle import b2o
+    w = b2o.B2world((0.0, -10.0))
+    ground = w.create_body(BodyDef())
+    box = w.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(0.0, 10.0), angle=0.5 * math.pi, allow_sleep=0))
+    box.create_fixture_by_shape(w.shapes.polygon_box(1.0, 1.0), 5.0)
+    jd = w.prismatic_joint_def(ground, box, (0.0, 10.0), (1.0, 0.0))
+    assert abs(jd.length - 1.0) < 1e-7 and abs(jd.min_length) < 1e-7  # local axis of the (unrotated) ground body
+    jd.lower_angle, jd.upper_angle, jd.enable_limit = -10.0, 10.0, 1
+    jd.motor_speed, jd.max_motor_torque = -2.0, 10000.0
+    j = w.create_joint(jd)
+    box.set_linear_velocity((8.0, 0.0))
+    far = 0.0
+    for _ in range(240):
+        w.step(scenes.DT, 8, 3)
+        b = w.snapshot().bodies[1]
+        assert abs(b["c"][1] - 10.0) < 0.01 and abs(b["a"] - 0.5 * math.pi) < 0.01
+        assert b["c"][0] < 10.0 + 0.02
+        far = max(far, float(b["c"][0]))
+    assert far > 9.9  # it reached the limit
+    j.enable_motor(True)
+    for _ in range(60):
+        w.step(scenes.DT, 8, 3)
+    b = w.snapshot().bodies[1]
+    assert abs(b["v"][0] + 2.0) < 1e-3 and abs(b["v"][1]) < 1e-3
+
+
+def test_oracle_prismatic_motor_lifts_against_gravity_until_the_limit(built):
+    from box2d_rs_b200 import abi, scenes
+    from box2d_rs_b200.abi import BodyDef
+    from oracle import b2o
+    w = b2o.B2world((0.0, -10.0))
+    ground = w.create_body(BodyDef())
+    lift = w.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(0.0, 2.0), allow_sleep=0))
+    lift.create_fixture_by_shape(w.shapes.polygon_box(2.0, 0.25), 2.0)  # mass 4: weight 40 < max motor force
+    jd = w.prismatic_joint_def(ground, lift, (0.0, 2.0), (0.0, 1.0))
+    jd.motor_speed, jd.max_motor_torque, jd.enable_motor = 1.5, 2000.0, 1
+    jd.lower_angle, jd.upper_angle, jd.enable_limit = 0.0, 3.0, 1
+    w.create_joint(jd)
+    for i in range(60):
+        w.step(scenes.DT, 8, 3)
+    b = w.snapshot().bodies[1]
+    assert abs(b["v"][1] - 1.5) < 1e-3 and abs(b["c"][0]) < 1e-3  # rising at the motor speed, on the axis
+    for i in range(120):
+        w.step(scenes.DT, 8, 3)
+    b = w.snapshot().bodies[1]
+    assert abs(b["c"][1] - 5.0) < 0.02 and abs(b["v"][1]) < 1e-2  # held at the upper limit (2 + 3)
+
+
 def test_oracle_angular_stiffness_formula(built):
     """b2_angular_stiffness (private b2_joint.rs:47-70): I = Ia Ib / (Ia + Ib) of B2body::get_inertia, omega = 2 pi f."""
     from box2d_rs_b200 import abi
@@ -179,7 +233,14 @@ def test_weld_defs_and_unsupported_types(built):
     (wo, jo, so), (wg, jg, sg) = ws
     assert bytes(jo) == bytes(jg)
     assert np.array_equal(np.float32(so).view(np.uint32), np.float32(sg).view(np.uint32))
-    jg.type = 6  # prismatic
+    po = wo.prismatic_joint_def(wo.body(0), wo.body(1), (1.3, 1.2), (0.6, -0.8))
+    pg = wg.prismatic_joint_def(wg.body(0), wg.body(1), (1.3, 1.2), (0.6, -0.8))
+    assert bytes(po) == bytes(pg)
+    pg.lower_angle, pg.upper_angle = 1.0, 0.5  # lower > upper: the reference asserts
+    with pytest.raises(B2gpuError) as e:
+        wg.create_joint(pg)
+    assert e.value.code == abi.E_INVALID
+    jg.type = 10  # wheel
     with pytest.raises(B2gpuError) as e:
         wg.create_joint(jg)
     assert e.value.code == abi.E_UNSUPPORTED
