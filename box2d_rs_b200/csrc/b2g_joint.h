@@ -1,4 +1,4 @@
-// b2g_joint.h — joints inside the island solve: revolute, prismatic, distance and weld joints.
+// b2g_joint.h — joints inside the island solve: revolute, prismatic, wheel, distance and weld joints.
 //
 // Reference: B2jointTraitDyn::{init_velocity_constraints, solve_velocity_constraints, solve_position_constraints}
 // (src/b2_joint.rs:268-286) as driven by B2island::solve (src/private/dynamics/b2_island_private.rs:198-201 init after the
@@ -22,6 +22,9 @@
 //   3: mA iA mB iB
 //   4: weld mass.ez.z gamma bias -
 // prismatic: 0: axis.xy perp.xy   1: s1 s2 a1 a2   2: K11 K12 K22 axial_mass   3: mA iA mB iB   4: translation - - -
+// wheel (private joints/b2_wheel_joint.rs:19-170 / :172-282 / :284-380; j_s0 = impulse, spring_impulse, motor_impulse,
+//        lower_impulse; param 0 = stiffness, 1 / 2 = translation limits, 5 / 6 = local x axis (not normalised), 7 = damping):
+//        0: ax.xy ay.xy   1: sAx sBx sAy sBy   2: mass axial_mass spring_mass motor_mass   3: mA iA mB iB   4: bias gamma translation -
 // Joint visits are ordered work: they run in the island's joint order inside every form of the Gauss-Seidel stages
 // (VelocityK / PositionK generic; velocity_sl_kernel / position_sl_kernel for batches, through an accessor over their
 // shared-memory rows; LwVelocity7K / LwPosition6K in the large-world modes).
@@ -150,7 +153,61 @@ B2G_HD void joint_init_velocity(const Batch& B, const WIdx& x, const S& st, int 
   const int jflags = f2i(s1.w);
   float4 t1, t2 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), t4 = t2;
   float4 t0 = make_float4(r_a.x, r_a.y, r_b.x, r_b.y);
-  if (jr.type == B2GPU_JOINT_PRISMATIC) {
+  if (jr.type == B2GPU_JOINT_WHEEL) {
+    const V2 d = c_b + r_b - c_a - r_a;
+    const V2 lx = v2(jr.param[5], jr.param[6]), ly = cross_sv(1.0f, lx);
+    const V2 ay = rot_mul(q_a, ly);
+    const float s_ay = cross(d + r_a, ay), s_by = cross(r_b, ay);
+    float mass = m_a + m_b + i_a * s_ay * s_ay + i_b * s_by * s_by;
+    if (mass > 0.0f) mass = 1.0f / mass;
+    const V2 ax = rot_mul(q_a, lx);
+    const float s_ax = cross(d + r_a, ax), s_bx = cross(r_b, ax);
+    const float inv_mass = m_a + m_b + i_a * s_ax * s_ax + i_b * s_bx * s_bx;
+    const float axial_mass = inv_mass > 0.0f ? 1.0f / inv_mass : 0.0f;
+    float spring_mass = 0.0f, bias = 0.0f, gamma = 0.0f;
+    const float stiffness = jr.param[0], damping = jr.param[7];
+    if (stiffness > 0.0f && inv_mass > 0.0f) {
+      spring_mass = 1.0f / inv_mass;
+      const float c = dot(d, ax);
+      gamma = h * (damping + h * stiffness);
+      if (gamma > 0.0f) gamma = 1.0f / gamma;
+      bias = c * h * stiffness * gamma;
+      spring_mass = inv_mass + gamma;
+      if (spring_mass > 0.0f) spring_mass = 1.0f / spring_mass;
+    } else {
+      s0.y = 0.0f;
+    }
+    float translation = 0.0f;
+    if (jflags & B2GPU_JOINT_ENABLE_LIMIT) translation = dot(ax, d);
+    else { s0.w = 0.0f; s1.x = 0.0f; }
+    float motor_mass;
+    if (jflags & B2GPU_JOINT_ENABLE_MOTOR) {
+      motor_mass = i_a + i_b;
+      if (motor_mass > 0.0f) motor_mass = 1.0f / motor_mass;
+    } else {
+      motor_mass = 0.0f;
+      s0.z = 0.0f;
+    }
+    if (warm_starting) {
+      s0.x *= dt_ratio;  // the limit impulses are not scaled (b2_wheel_joint.rs:143-146)
+      s0.y *= dt_ratio;
+      s0.z *= dt_ratio;
+      const float axial_impulse = s0.y + s0.w - s1.x;
+      const V2 p = s0.x * ay + axial_impulse * ax;
+      const float la = s0.x * s_ay + axial_impulse * s_ax + s0.z;
+      const float lb = s0.x * s_by + axial_impulse * s_bx + s0.z;
+      v_a = v_a - m_a * p;
+      w_a -= i_a * la;
+      v_b = v_b + m_b * p;
+      w_b += i_b * lb;
+    } else {
+      s0.x = 0.0f; s0.y = 0.0f; s0.z = 0.0f; s0.w = 0.0f; s1.x = 0.0f;
+    }
+    t0 = make_float4(ax.x, ax.y, ay.x, ay.y);
+    t1 = make_float4(s_ax, s_bx, s_ay, s_by);
+    t2 = make_float4(mass, axial_mass, spring_mass, motor_mass);
+    t4 = make_float4(bias, gamma, translation, 0.0f);
+  } else if (jr.type == B2GPU_JOINT_PRISMATIC) {
     const V2 d = (c_b - c_a) + r_b - r_a;
     const V2 lx = v2(jr.param[5], jr.param[6]), ly = cross_sv(1.0f, lx);  // m_local_xaxis_a, m_local_yaxis_a
     const V2 axis = rot_mul(q_a, lx);
@@ -296,7 +353,7 @@ B2G_HD void joint_init_velocity(const Batch& B, const WIdx& x, const S& st, int 
   B.j_tmp[jt_at(B, x, j, 1)] = t1;
   B.j_tmp[jt_at(B, x, j, 2)] = t2;
   B.j_tmp[jt_at(B, x, j, 3)] = make_float4(m_a, i_a, m_b, i_b);
-  if (jr.type == B2GPU_JOINT_WELD || jr.type == B2GPU_JOINT_PRISMATIC) B.j_tmp[jt_at(B, x, j, 4)] = t4;
+  if (jr.type == B2GPU_JOINT_WELD || jr.type == B2GPU_JOINT_PRISMATIC || jr.type == B2GPU_JOINT_WHEEL) B.j_tmp[jt_at(B, x, j, 4)] = t4;
   // an immovable body may sit in several islands: its velocity never changes, leave it alone
   if (m_a != 0.0f || i_a != 0.0f) st.set_vel(jr.body_a, make_float4(v_a.x, v_a.y, w_a, 0.0f));
   if (m_b != 0.0f || i_b != 0.0f) st.set_vel(jr.body_b, make_float4(v_b.x, v_b.y, w_b, 0.0f));
@@ -315,7 +372,75 @@ B2G_HD void joint_solve_velocity(const Batch& B, const WIdx& x, const S& st, int
   const int ji = x.at(B.NJ, j);
   float4 s0 = B.j_s0[ji], s1 = B.j_s1[ji];
   const int jflags = f2i(s1.w);
-  if (jr.type == B2GPU_JOINT_PRISMATIC) {
+  if (jr.type == B2GPU_JOINT_WHEEL) {
+    const V2 ax = v2(t0.x, t0.y), ay = v2(t0.z, t0.w);
+    const float s_ax = t1.x, s_bx = t1.y, s_ay = t1.z, s_by = t1.w;
+    const float mass = t2.x, axial_mass = t2.y, spring_mass = t2.z, motor_mass = t2.w;
+    const float4 t4 = B.j_tmp[jt_at(B, x, j, 4)];
+    const float bias = t4.x, gamma = t4.y, translation = t4.z;
+    {  // spring constraint
+      const float cdot = dot(ax, v_b - v_a) + s_bx * w_b - s_ax * w_a;
+      const float impulse = -spring_mass * (cdot + bias + gamma * s0.y);
+      s0.y += impulse;
+      const V2 p = impulse * ax;
+      const float la = impulse * s_ax, lb = impulse * s_bx;
+      v_a = v_a - m_a * p;
+      w_a -= i_a * la;
+      v_b = v_b + m_b * p;
+      w_b += i_b * lb;
+    }
+    {  // rotational motor constraint (motor_mass is 0 when the motor is off)
+      const float cdot = w_b - w_a - s1.y;
+      float impulse = -motor_mass * cdot;
+      const float old_impulse = s0.z;
+      const float max_impulse = h * s1.z;
+      s0.z = fclamp_sel(s0.z + impulse, -max_impulse, max_impulse);
+      impulse = s0.z - old_impulse;
+      w_a -= i_a * impulse;
+      w_b += i_b * impulse;
+    }
+    if (jflags & B2GPU_JOINT_ENABLE_LIMIT) {
+      {  // lower limit
+        const float c = translation - jr.param[1];
+        const float cdot = dot(ax, v_b - v_a) + s_bx * w_b - s_ax * w_a;
+        float impulse = -axial_mass * (cdot + fmax_sel(c, 0.0f) * inv_dt);
+        const float old_impulse = s0.w;
+        s0.w = fmax_sel(s0.w + impulse, 0.0f);
+        impulse = s0.w - old_impulse;
+        const V2 p = impulse * ax;
+        const float la = impulse * s_ax, lb = impulse * s_bx;
+        v_a = v_a - m_a * p;
+        w_a -= i_a * la;
+        v_b = v_b + m_b * p;
+        w_b += i_b * lb;
+      }
+      {  // upper limit
+        const float c = jr.param[2] - translation;
+        const float cdot = dot(ax, v_a - v_b) + s_ax * w_a - s_bx * w_b;
+        float impulse = -axial_mass * (cdot + fmax_sel(c, 0.0f) * inv_dt);
+        const float old_impulse = s1.x;
+        s1.x = fmax_sel(s1.x + impulse, 0.0f);
+        impulse = s1.x - old_impulse;
+        const V2 p = impulse * ax;
+        const float la = impulse * s_ax, lb = impulse * s_bx;
+        v_a = v_a + m_a * p;
+        w_a += i_a * la;
+        v_b = v_b - m_b * p;
+        w_b -= i_b * lb;
+      }
+    }
+    {  // point to line constraint
+      const float cdot = dot(ay, v_b - v_a) + s_by * w_b - s_ay * w_a;
+      const float impulse = -mass * cdot;
+      s0.x += impulse;
+      const V2 p = impulse * ay;
+      const float la = impulse * s_ay, lb = impulse * s_by;
+      v_a = v_a - m_a * p;
+      w_a -= i_a * la;
+      v_b = v_b + m_b * p;
+      w_b += i_b * lb;
+    }
+  } else if (jr.type == B2GPU_JOINT_PRISMATIC) {
     const V2 axis = v2(t0.x, t0.y), perp = v2(t0.z, t0.w);
     const float s1_ = t1.x, s2_ = t1.y, a1 = t1.z, a2 = t1.w, axial_mass = t2.w;
     const float translation = B.j_tmp[jt_at(B, x, j, 4)].x;
@@ -537,7 +662,60 @@ B2G_HD bool joint_solve_position(const Batch& B, const WIdx& x, const S& st, int
   const V2 la = v2(jr.local_anchor_a[0], jr.local_anchor_a[1]) - v2(msa.z, msa.w);
   const V2 lb = v2(jr.local_anchor_b[0], jr.local_anchor_b[1]) - v2(msb.z, msb.w);
   bool okay;
-  if (jr.type == B2GPU_JOINT_PRISMATIC) {
+  if (jr.type == B2GPU_JOINT_WHEEL) {
+    const int jflags = f2i(B.j_s1[x.at(B.NJ, j)].w);
+    const float4 t0 = B.j_tmp[jt_at(B, x, j, 0)], t1 = B.j_tmp[jt_at(B, x, j, 1)];
+    const V2 lx = v2(jr.param[5], jr.param[6]), ly = cross_sv(1.0f, lx);
+    float linear_error = 0.0f;
+    if (jflags & B2GPU_JOINT_ENABLE_LIMIT) {
+      const V2 r_a = rot_mul(q_a, la);
+      const V2 r_b = rot_mul(q_b, lb);
+      const V2 d = (c_b - c_a) + r_b - r_a;
+      const V2 ax = rot_mul(q_a, lx);
+      const V2 ax0 = v2(t0.x, t0.y);  // m_ax of init_velocity_constraints: the reference crosses with it here
+      const float s_ax = cross(d + r_a, ax0), s_bx = cross(r_b, ax0);
+      float c = 0.0f;
+      const float translation = dot(ax, d);
+      const float lower = jr.param[1], upper = jr.param[2];
+      if (fabsf(upper - lower) < 2.0f * B2G_LINEAR_SLOP) c = translation;
+      else if (translation <= lower) c = fmin_sel(translation - lower, 0.0f);
+      else if (translation >= upper) c = fmax_sel(translation - upper, 0.0f);
+      if (c != 0.0f) {
+        const float inv_mass = m_a + m_b + i_a * s_ax * s_ax + i_b * s_bx * s_bx;
+        float impulse = 0.0f;
+        if (inv_mass != 0.0f) impulse = -c / inv_mass;
+        const V2 p = impulse * ax;
+        const float la_ = impulse * s_ax, lb_ = impulse * s_bx;
+        c_a = c_a - m_a * p;
+        const float na = a_a - i_a * la_;
+        c_b = c_b + m_b * p;
+        const float nb = a_b + i_b * lb_;
+        if (f2u(na) != f2u(a_a)) { a_a = na; q_a = rot_from_angle(na); }
+        if (f2u(nb) != f2u(a_b)) { a_b = nb; q_b = rot_from_angle(nb); }
+        linear_error = fabsf(c);
+      }
+    }
+    {  // perpendicular constraint (rotations of the angles as they are now)
+      const V2 r_a = rot_mul(q_a, la);
+      const V2 r_b = rot_mul(q_b, lb);
+      const V2 d = (c_b - c_a) + r_b - r_a;
+      const V2 ay = rot_mul(q_a, ly);
+      const float s_ay = cross(d + r_a, ay), s_by = cross(r_b, ay);
+      const float c = dot(d, ay);
+      // the reference uses m_s_ay / m_s_by of init_velocity_constraints in the effective mass
+      const float inv_mass = m_a + m_b + i_a * t1.z * t1.z + i_b * t1.w * t1.w;
+      float impulse = 0.0f;
+      if (inv_mass != 0.0f) impulse = -c / inv_mass;
+      const V2 p = impulse * ay;
+      const float la_ = impulse * s_ay, lb_ = impulse * s_by;
+      c_a = c_a - m_a * p;
+      a_a -= i_a * la_;
+      c_b = c_b + m_b * p;
+      a_b += i_b * lb_;
+      linear_error = fmax_sel(linear_error, fabsf(c));
+    }
+    okay = linear_error <= B2G_LINEAR_SLOP;
+  } else if (jr.type == B2GPU_JOINT_PRISMATIC) {
     const int jflags = f2i(B.j_s1[x.at(B.NJ, j)].w);
     const V2 r_a = rot_mul(q_a, la);
     const V2 r_b = rot_mul(q_b, lb);

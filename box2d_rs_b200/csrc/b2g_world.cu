@@ -838,6 +838,24 @@ int b2gpu_prismatic_joint_def(b2gpu_world* W, b2gpu_joint_def* def, int body_a, 
   return 0;
   GUARD_END
 }
+int b2gpu_wheel_joint_def(b2gpu_world* W, b2gpu_joint_def* def, int body_a, int body_b, float ax, float ay, float dx, float dy) {
+  GUARD_BEGIN
+  int rc = check_body(W, body_a);
+  if (!rc) rc = check_body(W, body_b);
+  if (rc) return rc;
+  if (!def) { set_error("joint def is NULL"); return B2GPU_E_INVALID; }
+  rc = ensure_host(W);
+  if (rc) return rc;
+  joint_def_defaults(def, B2GPU_JOINT_WHEEL, body_a, body_b);
+  const b2gpu_body_rec &a = W->h.bodies[body_a], &b = W->h.bodies[body_b];
+  const V2 la = body_local_point(a, v2(ax, ay)), lb = body_local_point(b, v2(ax, ay));
+  def->local_anchor_a[0] = la.x; def->local_anchor_a[1] = la.y;
+  def->local_anchor_b[0] = lb.x; def->local_anchor_b[1] = lb.y;
+  const V2 axis = rot_mul_t(body_xf(a).q, v2(dx, dy));  // get_local_vector (src/b2_body.rs:733-735)
+  def->length = axis.x; def->min_length = axis.y; def->max_length = 0.0f;  // local_axis_a (see b2gpu.h)
+  return 0;
+  GUARD_END
+}
 int b2gpu_weld_joint_def(b2gpu_world* W, b2gpu_joint_def* def, int body_a, int body_b, float ax, float ay) {
   GUARD_BEGIN
   int rc = check_body(W, body_a);
@@ -905,8 +923,8 @@ int b2gpu_world_create_joint(b2gpu_world* W, const b2gpu_joint_def* def) {  // b
   if (rc) return rc;
   if (def->body_a == def->body_b) { set_error("create_joint: body_a == body_b (the reference asserts)"); return B2GPU_E_INVALID; }
   if (def->type != B2GPU_JOINT_REVOLUTE && def->type != B2GPU_JOINT_DISTANCE && def->type != B2GPU_JOINT_WELD &&
-      def->type != B2GPU_JOINT_PRISMATIC) {
-    set_error("create_joint: only revolute, prismatic, distance and weld joints are inside the accelerated path");
+      def->type != B2GPU_JOINT_PRISMATIC && def->type != B2GPU_JOINT_WHEEL) {
+    set_error("create_joint: only revolute, prismatic, wheel, distance and weld joints are inside the accelerated path");
     return B2GPU_E_UNSUPPORTED;
   }
   if (def->type == B2GPU_JOINT_PRISMATIC && !(def->lower_angle <= def->upper_angle)) {
@@ -935,6 +953,12 @@ int b2gpu_world_create_joint(b2gpu_world* W, const b2gpu_joint_def* def) {  // b
     j.param[5] = axis.x; j.param[6] = axis.y;
     if (def->enable_limit) j.flags |= B2GPU_JOINT_ENABLE_LIMIT;
     if (def->enable_motor) j.flags |= B2GPU_JOINT_ENABLE_MOTOR;
+  } else if (def->type == B2GPU_JOINT_WHEEL) {  // B2wheelJoint::new (src/joints/b2_wheel_joint.rs:266-310): axis not normalised
+    j.param[0] = def->stiffness; j.param[1] = def->lower_angle; j.param[2] = def->upper_angle;
+    j.param[3] = def->max_motor_torque; j.param[4] = def->motor_speed;
+    j.param[5] = def->length; j.param[6] = def->min_length; j.param[7] = def->damping;
+    if (def->enable_limit) j.flags |= B2GPU_JOINT_ENABLE_LIMIT;
+    if (def->enable_motor) j.flags |= B2GPU_JOINT_ENABLE_MOTOR;
   } else if (def->type == B2GPU_JOINT_WELD) {  // B2weldJoint::new (src/joints/b2_weld_joint.rs:152-185)
     j.param[0] = def->reference_angle;
     j.param[3] = def->stiffness; j.param[4] = def->damping;
@@ -960,8 +984,8 @@ int b2gpu_world_get_joint_count(b2gpu_world* W) { return W ? (int)W->h.joints.si
 static int check_joint(b2gpu_world* W, int joint, int type) {
   if (!W) { set_error("world is NULL"); return B2GPU_E_INVALID; }
   if (joint < 0 || joint >= (int)W->h.joints.size()) { set_error("joint index out of range"); return B2GPU_E_INVALID; }
-  const int jt = W->h.joints[joint].type;  // the revolute setters edit prismatic joints too (same switches, force for torque)
-  if (type && jt != type && !(type == B2GPU_JOINT_REVOLUTE && jt == B2GPU_JOINT_PRISMATIC)) {
+  const int jt = W->h.joints[joint].type;  // the revolute setters edit prismatic and wheel joints too (same switches; force for torque on a slider)
+  if (type && jt != type && !(type == B2GPU_JOINT_REVOLUTE && (jt == B2GPU_JOINT_PRISMATIC || jt == B2GPU_JOINT_WHEEL))) {
     set_error("joint is not of the type this call edits");
     return B2GPU_E_INVALID;
   }

@@ -383,6 +383,50 @@ def sliders(world):
     world.create_joint(jd)
 
 
+def car(world, motor_speed=-20.0):
+    """The vehicle of examples/testbed/tests/car.rs:196-275 — a six-vertex chassis on two circle wheels hung on wheel joints
+    along the chassis' y axis (4 Hz, damping ratio 0.7, limits +-0.25, rear wheel motorised with 20 Nm) — on a short track:
+    flat ground, the testbed's first row of bumps (:88-101), a ramp and a stack of boxes to run into."""
+    ground = world.create_body(BodyDef())
+    gfd = FixtureDef(density=0.0, friction=0.6)
+    ground.create_fixture(gfd, world.shapes.edge_two_sided((-20.0, 0.0), (20.0, 0.0)))
+    hs = (0.25, 1.0, 4.0, 0.0, 0.0, -1.0, -2.0, -2.0, -1.25, 0.0)
+    x, y1, dx = 20.0, 0.0, 5.0
+    for i in range(10):
+        y2 = hs[i]
+        ground.create_fixture(gfd, world.shapes.edge_two_sided((f32(x), f32(y1)), (f32(x + dx), f32(y2))))
+        y1 = y2
+        x += dx
+    ground.create_fixture(gfd, world.shapes.edge_two_sided((f32(x), 0.0), (f32(x + 40.0), 0.0)))
+    x += 40.0
+    ground.create_fixture(gfd, world.shapes.edge_two_sided((f32(x), 0.0), (f32(x + 10.0), 5.0)))
+    box = world.shapes.polygon_box(0.5, 0.5)
+    for i in range(4):
+        b = world.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(12.0, f32(0.5 + 1.0 * i))))
+        b.create_fixture(FixtureDef(density=0.5), box)
+    chassis = world.shapes.polygon([(-1.5, -0.5), (1.5, -0.5), (1.5, 0.0), (0.0, 0.9), (-1.15, 0.9), (-1.5, 0.2)])
+    circle = world.shapes.circle(0.4)
+    car_body = world.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(0.0, 1.0)))
+    car_body.create_fixture_by_shape(chassis, 1.0)
+    wfd = FixtureDef(density=1.0, friction=0.9)
+    wheel1 = world.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(-1.0, 0.35)))
+    wheel1.create_fixture(wfd, circle)
+    wheel2 = world.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(1.0, 0.4)))
+    wheel2.create_fixture(wfd, circle)
+    hertz, ratio = f32(4.0), f32(0.7)
+    omega = f32(f32(2.0) * f32(math.pi) * hertz)
+    joints = []
+    for wheel, pos, torque, motor in ((wheel1, (-1.0, 0.35), 20.0, 1), (wheel2, (1.0, 0.4), 10.0, 0)):
+        mass = f32(f32(f32(f32(1.0) * f32(math.pi)) * f32(0.4)) * f32(0.4))  # B2circleShape::compute_mass: density * pi * r * r
+        jd = world.wheel_joint_def(car_body, wheel, pos, (0.0, 1.0))
+        jd.motor_speed, jd.max_motor_torque, jd.enable_motor = (motor_speed if motor else 0.0), torque, motor
+        jd.stiffness = f32(f32(mass * omega) * omega)
+        jd.damping = f32(f32(f32(f32(2.0) * mass) * ratio) * omega)
+        jd.lower_angle, jd.upper_angle, jd.enable_limit = -0.25, 0.25, 1
+        joints.append(world.create_joint(jd))
+    return joints
+
+
 def tumbler(world, n=200, seed=0xB2D + 21):
     """examples/testbed/tests/tumbler.rs:62-97: a hollow box of four plank fixtures turned by a revolute-joint motor
     (0.05 pi rad/s, torque 1e8) around a point of the ground body; the testbed drops one 0.125 box per step, here `n`

@@ -38,7 +38,7 @@ extern "C" {
 #define B2GPU_E_NO_DEVICE (-2) /* no CUDA device: there is no CPU fallback */
 #define B2GPU_E_CUDA (-3)      /* CUDA runtime error, see b2gpu_last_error */
 #define B2GPU_E_CAPACITY (-4)  /* a device-side capacity was exceeded */
-#define B2GPU_E_UNSUPPORTED (-5) /* feature outside the hot-path scope (TOI, joint types other than revolute / prismatic / distance / weld) */
+#define B2GPU_E_UNSUPPORTED (-5) /* feature outside the hot-path scope (TOI, joint types other than revolute / prismatic / wheel / distance / weld) */
 #define B2GPU_E_LOCKED (-6)    /* world is locked (reference: is_locked() panic) */
 #define B2GPU_E_INTERNAL (-7)  /* a device-side consistency check failed (a bug: please report) */
 #define B2GPU_E_IO (-8)        /* a checkpoint file could not be opened, read or written */
@@ -86,6 +86,7 @@ extern "C" {
 #define B2GPU_JOINT_PRISMATIC 6
 #define B2GPU_JOINT_REVOLUTE 8
 #define B2GPU_JOINT_WELD 9
+#define B2GPU_JOINT_WHEEL 10
 /* b2gpu_joint_rec.flags */
 #define B2GPU_JOINT_COLLIDE_CONNECTED 0x1u /* B2jointDef::collide_connected */
 #define B2GPU_JOINT_ENABLE_LIMIT 0x2u      /* revolute: m_enable_limit */
@@ -393,6 +394,12 @@ int b2gpu_distance_joint_def(b2gpu_world* w, b2gpu_joint_def* def, int body_a, i
  * asserts).  The revolute setters below (motor speed, max motor torque = force, enable motor / limit, set_limits) apply. */
 int b2gpu_prismatic_joint_def(b2gpu_world* w, b2gpu_joint_def* def, int body_a, int body_b, float anchor_x, float anchor_y,
                               float axis_x, float axis_y);
+/* B2wheelJointDef::default + ::initialize(body_a, body_b, anchor, axis) (src/joints/b2_wheel_joint.rs:10-90): a point of
+ * body B on a line of body A, with a spring (stiffness / damping: b2gpu_linear_stiffness), translation limits and a
+ * rotational motor.  Def overlay as for the prismatic joint: lower_angle / upper_angle are the translation limits,
+ * (length, min_length) carry local_axis_a, which B2wheelJoint::new does NOT normalise.  The revolute setters apply. */
+int b2gpu_wheel_joint_def(b2gpu_world* w, b2gpu_joint_def* def, int body_a, int body_b, float anchor_x, float anchor_y,
+                          float axis_x, float axis_y);
 /* B2weldJointDef::default + ::initialize(body_a, body_b, anchor) (src/joints/b2_weld_joint.rs:10-50): local anchors and
  * reference angle from the bodies' current transforms; stiffness = damping = 0 (rigid). */
 int b2gpu_weld_joint_def(b2gpu_world* w, b2gpu_joint_def* def, int body_a, int body_b, float anchor_x, float anchor_y);
@@ -404,7 +411,7 @@ int b2gpu_linear_stiffness(b2gpu_world* w, float frequency_hertz, float damping_
                            float* damping);
 /* B2world::create_joint (src/private/dynamics/b2_world.rs:156-262): returns the joint index (>= 0); contacts between
  * the two bodies are flagged for filtering when collide_connected is false.  Does not wake the bodies.
- * Joint types other than revolute, prismatic, distance and weld: B2GPU_E_UNSUPPORTED. */
+ * Joint types other than revolute, prismatic, wheel, distance and weld: B2GPU_E_UNSUPPORTED. */
 int b2gpu_world_create_joint(b2gpu_world* w, const b2gpu_joint_def* def);
 int b2gpu_world_get_joint_count(b2gpu_world* w);
 int b2gpu_world_get_joint(b2gpu_world* w, int joint, b2gpu_joint_rec* out);

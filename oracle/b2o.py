@@ -57,6 +57,8 @@ def lib():
                                              C.c_float, C.c_float]
         L.b2o_prismatic_joint_def.argtypes = [C.c_void_p, C.POINTER(abi.JointDef), C.c_int, C.c_int, C.c_float, C.c_float,
                                               C.c_float, C.c_float]
+        L.b2o_wheel_joint_def.argtypes = [C.c_void_p, C.POINTER(abi.JointDef), C.c_int, C.c_int, C.c_float, C.c_float,
+                                          C.c_float, C.c_float]
         L.b2o_weld_joint_def.argtypes = [C.c_void_p, C.POINTER(abi.JointDef), C.c_int, C.c_int, C.c_float, C.c_float]
         L.b2o_angular_stiffness.argtypes = [C.c_void_p, C.c_float, C.c_float, C.c_int, C.c_int, C.POINTER(C.c_float),
                                             C.POINTER(C.c_float)]
@@ -252,6 +254,13 @@ class B2world:
         d = abi.JointDef()
         lib().b2o_prismatic_joint_def(self.h, C.byref(d), _body_index(body_a), _body_index(body_b), anchor[0], anchor[1],
                                       axis[0], axis[1])
+        return d
+
+    def wheel_joint_def(self, body_a, body_b, anchor, axis):
+        """B2wheelJointDef::default() + initialize(body_a, body_b, anchor, axis)."""
+        d = abi.JointDef()
+        lib().b2o_wheel_joint_def(self.h, C.byref(d), _body_index(body_a), _body_index(body_b), anchor[0], anchor[1],
+                                  axis[0], axis[1])
         return d
 
     def weld_joint_def(self, body_a, body_b, anchor):

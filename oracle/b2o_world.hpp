@@ -93,7 +93,7 @@ struct Contact {
 
 // Joints: B2jointDef + B2revoluteJointDef / B2distanceJointDef as one plain struct
 // (src/b2_joint.rs:112-122, src/joints/b2_revolute_joint.rs:10-72, src/joints/b2_distance_joint.rs:11-58).
-enum JointType { J_DISTANCE = 1, J_PRISMATIC = 6, J_REVOLUTE = 8, J_WELD = 9 };  // B2jointType numbering (src/b2_joint.rs:46-58)
+enum JointType { J_DISTANCE = 1, J_PRISMATIC = 6, J_REVOLUTE = 8, J_WELD = 9, J_WHEEL = 10 };  // B2jointType numbering (src/b2_joint.rs:46-58)
 struct JointDef {
   int type = 0, body_a = -1, body_b = -1;
   bool collide_connected = false;
@@ -122,6 +122,10 @@ struct Joint {  // B2joint + B2revoluteJoint (src/joints/b2_revolute_joint.rs:10
   // revolute joint (lower_angle / upper_angle = translation limits, max_motor_torque = max motor force)
   Vec2 local_xaxis_a, local_yaxis_a, axis, perp;
   float s1 = 0.0f, s2 = 0.0f, a1 = 0.0f, a2 = 0.0f, translation = 0.0f;
+  // wheel (src/joints/b2_wheel_joint.rs:120-170): impulse (scalar, here `impulse`), spring_impulse; shares the motor / limit
+  // impulses and switches, local_xaxis_a / local_yaxis_a, translation, gamma, bias, mass, axial_mass
+  float spring_impulse = 0.0f, spring_mass = 0.0f, motor_mass = 0.0f, s_ax = 0.0f, s_bx = 0.0f, s_ay = 0.0f, s_by = 0.0f;
+  Vec2 ax, ay;
   // weld (src/joints/b2_weld_joint.rs:66-90): impulse (x, y, angular), effective mass B2Mat33 as ex.xyz ey.xyz ez.xyz
   float impulse3[3] = {0.0f, 0.0f, 0.0f}, m33[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   // solver temp
@@ -467,6 +471,16 @@ struct World {
     d.reference_angle = bodies[body_b].sweep.a - bodies[body_a].sweep.a;
     return d;
   }
+  // B2wheelJointDef::default + ::initialize (src/joints/b2_wheel_joint.rs:10-90)
+  JointDef wheel_joint_def(int body_a, int body_b, Vec2 anchor, Vec2 axis) const {
+    JointDef d;
+    d.type = J_WHEEL;
+    d.body_a = body_a; d.body_b = body_b;
+    d.local_anchor_a = b2_mul_t_xf(bodies[body_a].xf, anchor);
+    d.local_anchor_b = b2_mul_t_xf(bodies[body_b].xf, anchor);
+    d.local_axis_a = b2_mul_t_rot(bodies[body_a].xf.q, axis);
+    return d;
+  }
   // B2weldJointDef::default + ::initialize (src/joints/b2_weld_joint.rs:10-50)
   JointDef weld_joint_def(int body_a, int body_b, Vec2 anchor) const {
     JointDef d;
@@ -524,6 +538,13 @@ struct World {
       assert(j.lower_angle <= j.upper_angle);
       j.max_motor_torque = def.max_motor_torque; j.motor_speed = def.motor_speed;
       j.enable_limit = def.enable_limit; j.enable_motor = def.enable_motor;
+    } else if (def.type == J_WHEEL) {  // B2wheelJoint::new (src/joints/b2_wheel_joint.rs:266-310): the axis is NOT normalised
+      j.local_xaxis_a = def.local_axis_a;
+      j.local_yaxis_a = b2_cross_sv(1.0f, def.local_axis_a);
+      j.lower_angle = def.lower_angle; j.upper_angle = def.upper_angle;
+      j.max_motor_torque = def.max_motor_torque; j.motor_speed = def.motor_speed;
+      j.enable_limit = def.enable_limit; j.enable_motor = def.enable_motor;
+      j.stiffness = def.stiffness; j.damping = def.damping;
     } else if (def.type == J_WELD) {  // B2weldJoint::new (src/joints/b2_weld_joint.rs:152-185)
       j.reference_angle = def.reference_angle;
       j.stiffness = def.stiffness; j.damping = def.damping;
@@ -1203,6 +1224,71 @@ struct World {
         j.lower_impulse = 0.0f;
         j.upper_impulse = 0.0f;
       }
+    } else if (j.type == J_WHEEL) {  // private joints/b2_wheel_joint.rs:19-170
+      float m_a = j.inv_mass_a, m_b = j.inv_mass_b, i_a = j.inv_ia, i_b = j.inv_ib;
+      Vec2 d = c_b + j.r_b - c_a - j.r_a;
+      {  // point to line constraint
+        j.ay = b2_mul_rot(q_a, j.local_yaxis_a);
+        j.s_ay = b2_cross(d + j.r_a, j.ay);
+        j.s_by = b2_cross(j.r_b, j.ay);
+        j.mass = m_a + m_b + i_a * j.s_ay * j.s_ay + i_b * j.s_by * j.s_by;
+        if (j.mass > 0.0f) j.mass = 1.0f / j.mass;
+      }
+      // spring constraint
+      j.ax = b2_mul_rot(q_a, j.local_xaxis_a);
+      j.s_ax = b2_cross(d + j.r_a, j.ax);
+      j.s_bx = b2_cross(j.r_b, j.ax);
+      float inv_mass = m_a + m_b + i_a * j.s_ax * j.s_ax + i_b * j.s_bx * j.s_bx;
+      if (inv_mass > 0.0f) j.axial_mass = 1.0f / inv_mass;
+      else j.axial_mass = 0.0f;
+      j.spring_mass = 0.0f;
+      j.bias = 0.0f;
+      j.gamma = 0.0f;
+      if (j.stiffness > 0.0f && inv_mass > 0.0f) {
+        j.spring_mass = 1.0f / inv_mass;
+        float c = b2_dot(d, j.ax);
+        float h = step.dt;
+        j.gamma = h * (j.damping + h * j.stiffness);
+        if (j.gamma > 0.0f) j.gamma = 1.0f / j.gamma;
+        j.bias = c * h * j.stiffness * j.gamma;
+        j.spring_mass = inv_mass + j.gamma;
+        if (j.spring_mass > 0.0f) j.spring_mass = 1.0f / j.spring_mass;
+      } else {
+        j.spring_impulse = 0.0f;
+      }
+      if (j.enable_limit) {
+        j.translation = b2_dot(j.ax, d);
+      } else {
+        j.lower_impulse = 0.0f;
+        j.upper_impulse = 0.0f;
+      }
+      if (j.enable_motor) {
+        j.motor_mass = i_a + i_b;
+        if (j.motor_mass > 0.0f) j.motor_mass = 1.0f / j.motor_mass;
+      } else {
+        j.motor_mass = 0.0f;
+        j.motor_impulse = 0.0f;
+      }
+      if (step.warm_starting) {
+        // account for variable time step (the limit impulses are not scaled: b2_wheel_joint.rs:143-146)
+        j.impulse *= step.dt_ratio;
+        j.spring_impulse *= step.dt_ratio;
+        j.motor_impulse *= step.dt_ratio;
+        float axial_impulse = j.spring_impulse + j.lower_impulse - j.upper_impulse;
+        Vec2 p = j.impulse * j.ay + axial_impulse * j.ax;
+        float la = j.impulse * j.s_ay + axial_impulse * j.s_ax + j.motor_impulse;
+        float lb = j.impulse * j.s_by + axial_impulse * j.s_bx + j.motor_impulse;
+        v_a -= j.inv_mass_a * p;
+        w_a -= j.inv_ia * la;
+        v_b += j.inv_mass_b * p;
+        w_b += j.inv_ib * lb;
+      } else {
+        j.impulse = 0.0f;
+        j.spring_impulse = 0.0f;
+        j.motor_impulse = 0.0f;
+        j.lower_impulse = 0.0f;
+        j.upper_impulse = 0.0f;
+      }
     } else if (j.type == J_WELD) {  // private joints/b2_weld_joint.rs:22-136
       float m_a = j.inv_mass_a, m_b = j.inv_mass_b, i_a = j.inv_ia, i_b = j.inv_ib;
       float k[9];  // ex.x ex.y ex.z ey.x ey.y ey.z ez.x ez.y ez.z
@@ -1393,6 +1479,70 @@ struct World {
         Vec2 p = df.x * j.perp;
         float la = df.x * j.s1 + df.y;
         float lb = df.x * j.s2 + df.y;
+        v_a -= m_a * p;
+        w_a -= i_a * la;
+        v_b += m_b * p;
+        w_b += i_b * lb;
+      }
+    } else if (j.type == J_WHEEL) {  // private joints/b2_wheel_joint.rs:172-282
+      float m_a = j.inv_mass_a, m_b = j.inv_mass_b, i_a = j.inv_ia, i_b = j.inv_ib;
+      {  // spring constraint
+        float cdot = b2_dot(j.ax, v_b - v_a) + j.s_bx * w_b - j.s_ax * w_a;
+        float impulse = -j.spring_mass * (cdot + j.bias + j.gamma * j.spring_impulse);
+        j.spring_impulse += impulse;
+        Vec2 p = impulse * j.ax;
+        float la = impulse * j.s_ax, lb = impulse * j.s_bx;
+        v_a -= m_a * p;
+        w_a -= i_a * la;
+        v_b += m_b * p;
+        w_b += i_b * lb;
+      }
+      {  // rotational motor constraint (runs with motor_mass = 0 when the motor is off)
+        float cdot = w_b - w_a - j.motor_speed;
+        float impulse = -j.motor_mass * cdot;
+        float old_impulse = j.motor_impulse;
+        float max_impulse = step.dt * j.max_motor_torque;
+        j.motor_impulse = b2_clamp(j.motor_impulse + impulse, -max_impulse, max_impulse);
+        impulse = j.motor_impulse - old_impulse;
+        w_a -= i_a * impulse;
+        w_b += i_b * impulse;
+      }
+      if (j.enable_limit) {
+        {  // lower limit
+          float c = j.translation - j.lower_angle;
+          float cdot = b2_dot(j.ax, v_b - v_a) + j.s_bx * w_b - j.s_ax * w_a;
+          float impulse = -j.axial_mass * (cdot + b2_max(c, 0.0f) * step.inv_dt);
+          float old_impulse = j.lower_impulse;
+          j.lower_impulse = b2_max(j.lower_impulse + impulse, 0.0f);
+          impulse = j.lower_impulse - old_impulse;
+          Vec2 p = impulse * j.ax;
+          float la = impulse * j.s_ax, lb = impulse * j.s_bx;
+          v_a -= m_a * p;
+          w_a -= i_a * la;
+          v_b += m_b * p;
+          w_b += i_b * lb;
+        }
+        {  // upper limit
+          float c = j.upper_angle - j.translation;
+          float cdot = b2_dot(j.ax, v_a - v_b) + j.s_ax * w_a - j.s_bx * w_b;
+          float impulse = -j.axial_mass * (cdot + b2_max(c, 0.0f) * step.inv_dt);
+          float old_impulse = j.upper_impulse;
+          j.upper_impulse = b2_max(j.upper_impulse + impulse, 0.0f);
+          impulse = j.upper_impulse - old_impulse;
+          Vec2 p = impulse * j.ax;
+          float la = impulse * j.s_ax, lb = impulse * j.s_bx;
+          v_a += m_a * p;
+          w_a += i_a * la;
+          v_b -= m_b * p;
+          w_b -= i_b * lb;
+        }
+      }
+      {  // point to line constraint
+        float cdot = b2_dot(j.ay, v_b - v_a) + j.s_by * w_b - j.s_ay * w_a;
+        float impulse = -j.mass * cdot;
+        j.impulse += impulse;
+        Vec2 p = impulse * j.ay;
+        float la = impulse * j.s_ay, lb = impulse * j.s_by;
         v_a -= m_a * p;
         w_a -= i_a * la;
         v_b += m_b * p;
@@ -1603,6 +1753,56 @@ struct World {
       c_b += m_b * p;
       a_b += i_b * lb;
       okay = linear_error <= LINEAR_SLOP && angular_error <= ANGULAR_SLOP;
+    } else if (j.type == J_WHEEL) {  // private joints/b2_wheel_joint.rs:284-380
+      float linear_error = 0.0f;
+      if (j.enable_limit) {
+        Rot q_a(a_a), q_b(a_b);
+        Vec2 r_a = b2_mul_rot(q_a, j.local_anchor_a - j.local_center_a);
+        Vec2 r_b = b2_mul_rot(q_b, j.local_anchor_b - j.local_center_b);
+        Vec2 d = (c_b - c_a) + r_b - r_a;
+        Vec2 ax = b2_mul_rot(q_a, j.local_xaxis_a);
+        float s_ax = b2_cross(d + r_a, j.ax);  // the reference crosses with m_ax of init_velocity_constraints here
+        float s_bx = b2_cross(r_b, j.ax);
+        float c = 0.0f;
+        float translation = b2_dot(ax, d);
+        if (fabsf(j.upper_angle - j.lower_angle) < 2.0f * LINEAR_SLOP) c = translation;
+        else if (translation <= j.lower_angle) c = b2_min(translation - j.lower_angle, 0.0f);
+        else if (translation >= j.upper_angle) c = b2_max(translation - j.upper_angle, 0.0f);
+        if (c != 0.0f) {
+          float inv_mass = j.inv_mass_a + j.inv_mass_b + j.inv_ia * s_ax * s_ax + j.inv_ib * s_bx * s_bx;
+          float impulse = 0.0f;
+          if (inv_mass != 0.0f) impulse = -c / inv_mass;
+          Vec2 p = impulse * ax;
+          float la = impulse * s_ax, lb = impulse * s_bx;
+          c_a -= j.inv_mass_a * p;
+          a_a -= j.inv_ia * la;
+          c_b += j.inv_mass_b * p;
+          a_b += j.inv_ib * lb;
+          linear_error = fabsf(c);
+        }
+      }
+      {  // solve perpendicular constraint
+        Rot q_a(a_a), q_b(a_b);
+        Vec2 r_a = b2_mul_rot(q_a, j.local_anchor_a - j.local_center_a);
+        Vec2 r_b = b2_mul_rot(q_b, j.local_anchor_b - j.local_center_b);
+        Vec2 d = (c_b - c_a) + r_b - r_a;
+        Vec2 ay = b2_mul_rot(q_a, j.local_yaxis_a);
+        float s_ay = b2_cross(d + r_a, ay);
+        float s_by = b2_cross(r_b, ay);
+        float c = b2_dot(d, ay);
+        // the reference uses m_s_ay / m_s_by of init_velocity_constraints in the effective mass
+        float inv_mass = j.inv_mass_a + j.inv_mass_b + j.inv_ia * j.s_ay * j.s_ay + j.inv_ib * j.s_by * j.s_by;
+        float impulse = 0.0f;
+        if (inv_mass != 0.0f) impulse = -c / inv_mass;
+        Vec2 p = impulse * ay;
+        float la = impulse * s_ay, lb = impulse * s_by;
+        c_a -= j.inv_mass_a * p;
+        a_a -= j.inv_ia * la;
+        c_b += j.inv_mass_b * p;
+        a_b += j.inv_ib * lb;
+        linear_error = b2_max(linear_error, fabsf(c));
+      }
+      okay = linear_error <= LINEAR_SLOP;
     } else if (j.type == J_WELD) {  // private joints/b2_weld_joint.rs:207-283
       Rot q_a(a_a), q_b(a_b);
       float m_a = j.inv_mass_a, m_b = j.inv_mass_b, i_a = j.inv_ia, i_b = j.inv_ib;

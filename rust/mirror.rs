@@ -238,6 +238,18 @@ pub fn flatten<D: UserDataType>(world: &B2world<D>) -> Snapshot<D> {
                 r.impulse[0] = v.m_impulse.x; r.impulse[1] = v.m_impulse.y; r.impulse[2] = v.m_motor_impulse;
                 r.impulse[3] = v.m_lower_impulse; r.impulse[4] = v.m_upper_impulse;
             }
+            JointAsDerived::EWheelJoint(v) => {
+                r.type_ = 10;
+                r.local_anchor_a = [v.m_local_anchor_a.x, v.m_local_anchor_a.y];
+                r.local_anchor_b = [v.m_local_anchor_b.x, v.m_local_anchor_b.y];
+                r.param[0] = v.m_stiffness; r.param[1] = v.m_lower_translation; r.param[2] = v.m_upper_translation;
+                r.param[3] = v.m_max_motor_torque; r.param[4] = v.m_motor_speed;
+                r.param[5] = v.m_local_xaxis_a.x; r.param[6] = v.m_local_xaxis_a.y; r.param[7] = v.m_damping;
+                if v.m_enable_limit { r.flags |= 2; }
+                if v.m_enable_motor { r.flags |= 4; }
+                r.impulse[0] = v.m_impulse; r.impulse[1] = v.m_spring_impulse; r.impulse[2] = v.m_motor_impulse;
+                r.impulse[3] = v.m_lower_impulse; r.impulse[4] = v.m_upper_impulse;
+            }
             JointAsDerived::EWeldJoint(v) => {
                 r.type_ = 9;
                 r.local_anchor_a = [v.m_local_anchor_a.x, v.m_local_anchor_a.y];
@@ -458,6 +470,13 @@ pub fn write_back<D: UserDataType>(world: &mut B2world<D>, snap: &Snapshot<D>) {
             }
             JointAsDerivedMut::EPrismaticJoint(v) => {
                 v.m_impulse.set(r.impulse[0], r.impulse[1]);
+                v.m_motor_impulse = r.impulse[2];
+                v.m_lower_impulse = r.impulse[3];
+                v.m_upper_impulse = r.impulse[4];
+            }
+            JointAsDerivedMut::EWheelJoint(v) => {
+                v.m_impulse = r.impulse[0];
+                v.m_spring_impulse = r.impulse[1];
                 v.m_motor_impulse = r.impulse[2];
                 v.m_lower_impulse = r.impulse[3];
                 v.m_upper_impulse = r.impulse[4];

@@ -40,11 +40,12 @@ SCENES = {
     "terrain": (lambda s, w: s.terrain(w), (0.0, -10.0), 260),
 }
 
-# scenes with joints (revolute / prismatic / distance / weld)
+# scenes with joints (revolute / prismatic / wheel / distance / weld)
 JOINT_SCENES = {
     "bridge": (lambda s, w: s.bridge(w), (0.0, -10.0), 240),
     "tumbler": (lambda s, w: s.tumbler(w, n=120), (0.0, -10.0), 240),
     "joints_mix": (lambda s, w: s.joints_mix(w), (0.0, -10.0), 400),
     "cantilever": (lambda s, w: s.cantilever(w), (0.0, -10.0), 300),
     "sliders": (lambda s, w: s.sliders(w), (0.0, -10.0), 360),
+    "car": (lambda s, w: s.car(w), (0.0, -10.0), 420),
 }

@@ -192,6 +192,47 @@ def test_oracle_prismatic_motor_lifts_against_gravity_until_the_limit(built):
     assert abs(b["c"][1] - 5.0) < 0.02 and abs(b["v"][1]) < 1e-2  # held at the upper limit (2 + 3)
 
 
+def test_oracle_wheel_joints_carry_a_car(built):
+    """The vehicle of examples/testbed/tests/car.rs on flat ground: the rear wheel's motor (-20 rad/s, radius 0.4) brings the
+    car to 8 m/s; each wheel stays on its chassis axis (point-to-line constraint) within its translation limits."""
+    from box2d_rs_b200 import abi, scenes
+    from box2d_rs_b200.abi import BodyDef, FixtureDef
+    from oracle import b2o
+    w = b2o.B2world((0.0, -10.0))
+    ground = w.create_body(BodyDef())
+    ground.create_fixture(FixtureDef(density=0.0, friction=0.6), w.shapes.edge_two_sided((-20.0, 0.0), (400.0, 0.0)))
+    chassis = w.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(0.0, 1.0)))
+    chassis.create_fixture_by_shape(w.shapes.polygon([(-1.5, -0.5), (1.5, -0.5), (1.5, 0.0), (0.0, 0.9), (-1.15, 0.9), (-1.5, 0.2)]), 1.0)
+    wheels, defs = [], []
+    for pos, torque, motor in (((-1.0, 0.35), 20.0, 1), ((1.0, 0.4), 10.0, 0)):
+        wh = w.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=pos))
+        wh.create_fixture(FixtureDef(density=1.0, friction=0.9), w.shapes.circle(0.4))
+        jd = w.wheel_joint_def(chassis, wh, pos, (0.0, 1.0))
+        assert abs(jd.length) < 1e-7 and abs(jd.min_length - 1.0) < 1e-7  # local axis = (0, 1): the chassis is not rotated
+        jd.motor_speed, jd.max_motor_torque, jd.enable_motor = (-20.0 if motor else 0.0), torque, motor
+        jd.stiffness, jd.damping = w.linear_stiffness(4.0, 0.7, chassis, wh)
+        jd.lower_angle, jd.upper_angle, jd.enable_limit = -0.25, 0.25, 1
+        w.create_joint(jd)
+        wheels.append(wh)
+        defs.append(jd)
+    for i in range(300):
+        w.step(scenes.DT, 8, 3)
+        if i % 20 == 19:
+            b = w.snapshot().bodies
+            c = b[1]
+            for k, jd in enumerate(defs):
+                wh = b[2 + k]
+                # anchor on the chassis and the chassis' y axis in world space
+                ax = c["xf"][0] + c["xf"][3] * jd.local_anchor_a[0] - c["xf"][2] * jd.local_anchor_a[1]
+                ay = c["xf"][1] + c["xf"][2] * jd.local_anchor_a[0] + c["xf"][3] * jd.local_anchor_a[1]
+                ux, uy = -c["xf"][2], c["xf"][3]  # rotated (0, 1)
+                dx, dy = wh["xf"][0] - ax, wh["xf"][1] - ay
+                assert abs(dx * uy - dy * ux) < 0.02              # on the line
+                assert -0.25 - 0.02 <= dx * ux + dy * uy <= 0.25 + 0.02  # inside the limits
+    b = w.snapshot().bodies
+    assert abs(b[1]["v"][0] - 8.0) < 0.4 and abs(b[2]["w"] + 20.0) < 0.5 and b[1]["c"][0] > 25.0
+
+
 def test_oracle_angular_stiffness_formula(built):
     """b2_angular_stiffness (private b2_joint.rs:47-70): I = Ia Ib / (Ia + Ib) of B2body::get_inertia, omega = 2 pi f."""
     from box2d_rs_b200 import abi
@@ -236,11 +277,14 @@ def test_weld_defs_and_unsupported_types(built):
     po = wo.prismatic_joint_def(wo.body(0), wo.body(1), (1.3, 1.2), (0.6, -0.8))
     pg = wg.prismatic_joint_def(wg.body(0), wg.body(1), (1.3, 1.2), (0.6, -0.8))
     assert bytes(po) == bytes(pg)
+    qo = wo.wheel_joint_def(wo.body(0), wo.body(1), (1.3, 1.2), (0.6, -0.8))
+    qg = wg.wheel_joint_def(wg.body(0), wg.body(1), (1.3, 1.2), (0.6, -0.8))
+    assert bytes(qo) == bytes(qg)
     pg.lower_angle, pg.upper_angle = 1.0, 0.5  # lower > upper: the reference asserts
     with pytest.raises(B2gpuError) as e:
         wg.create_joint(pg)
     assert e.value.code == abi.E_INVALID
-    jg.type = 10  # wheel
+    jg.type = 7  # pulley
     with pytest.raises(B2gpuError) as e:
         wg.create_joint(jg)
     assert e.value.code == abi.E_UNSUPPORTED

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Differential fuzzing of the device stages (host simulator build by default, --gpu for the CUDA path) against
 the CPU oracle: random scenes (polygons of 3..8 vertices, circles, edges, chains, kinematic / fixed-rotation /
-multi-fixture bodies, sensors, filters, restitution, damping, revolute / prismatic / distance / weld joints with limits, motors and springs,
+multi-fixture bodies, sensors, filters, restitution, damping, revolute / prismatic / wheel / distance / weld joints with limits, motors and springs,
 random world flags and iteration counts, dt = 0 steps,
 mid-run set_transform / set_linear_velocity / apply_force / apply_torque / apply_*_impulse / set_awake edits), stepped freely and compared bit for bit.
 
@@ -89,7 +89,7 @@ def build(world, rng):
                 ang = np.sort(rng.uniform(0, 2 * math.pi, nv))
                 shape = world.shapes.polygon([(f32(rad * math.cos(a)), f32(rad * math.sin(a) * rng.uniform(0.5, 1.0))) for a in ang])
             b.create_fixture(fd, shape)
-    # joints (revolute / prismatic / distance / weld) between random bodies, the ground included: limits, motors, soft springs, slack ranges,
+    # joints (revolute / prismatic / wheel / distance / weld) between random bodies, the ground included: limits, motors, soft springs, slack ranges,
     # collide_connected, degenerate pairs (kinematic or fixed-rotation bodies, anchors far from the bodies)
     joints = []
     if rng.integers(0, 5) < 3:
@@ -97,8 +97,19 @@ def build(world, rng):
             a, b = int(rng.integers(0, n + 1)), int(rng.integers(0, n + 1))
             if a == b:
                 continue
-            kind = int(rng.integers(0, 4))
-            if kind == 3:  # prismatic: random axis, limits (sometimes equal), motor
+            kind = int(rng.integers(0, 5))
+            if kind == 4:  # wheel: random (unnormalised) axis, spring, limits, motor
+                th = rng.uniform(0, 2 * math.pi)
+                jd = world.wheel_joint_def(a, b, (f32(rng.uniform(-10, 10)), f32(rng.uniform(0.5, 14))),
+                                           (f32(math.cos(th) * rng.uniform(0.5, 2)), f32(math.sin(th) * rng.uniform(0.5, 2))))
+                if rng.integers(0, 3) > 0:
+                    jd.stiffness, jd.damping = world.linear_stiffness(f32(rng.uniform(0.5, 6)), f32(rng.uniform(0, 1)), a, b)
+                if rng.integers(0, 2) == 0:
+                    lo = f32(rng.uniform(-2, 0.2))
+                    jd.enable_limit, jd.lower_angle, jd.upper_angle = 1, lo, f32(lo + (0.0 if rng.integers(0, 5) == 0 else rng.uniform(0, 3)))
+                if rng.integers(0, 2) == 0:
+                    jd.enable_motor, jd.motor_speed, jd.max_motor_torque = 1, f32(rng.uniform(-10, 10)), f32(rng.uniform(0, 100))
+            elif kind == 3:  # prismatic: random axis, limits (sometimes equal), motor
                 th = rng.uniform(0, 2 * math.pi)
                 jd = world.prismatic_joint_def(a, b, (f32(rng.uniform(-10, 10)), f32(rng.uniform(0.5, 14))),
                                                (f32(math.cos(th) * rng.uniform(0.5, 2)), f32(math.sin(th) * rng.uniform(0.5, 2))))
@@ -195,7 +206,7 @@ def run_seed(seed, make_world, steps, batch_mode, large=False, events=False, lev
             wo.body(b).set_linear_velocity(v); wg.body(b).set_linear_velocity(v)
         if batch is None and ev == 8 and wo._fuzz_joints:  # B2revoluteJoint setters mid-run
             q = int(rng.integers(0, len(wo._fuzz_joints)))
-            if wo._fuzz_joints[q][1] in (abi.JOINT_REVOLUTE, abi.JOINT_PRISMATIC):
+            if wo._fuzz_joints[q][1] in (abi.JOINT_REVOLUTE, abi.JOINT_PRISMATIC, abi.JOINT_WHEEL):
                 op, val, flag = int(rng.integers(0, 5)), f32v(rng.uniform(-3, 3)), bool(rng.integers(0, 2))
                 for w in (wo, wg):
                     j = w._fuzz_joints[q][0]
