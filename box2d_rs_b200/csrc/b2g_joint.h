@@ -1,4 +1,5 @@
-// b2g_joint.h — joints inside the island solve: revolute, prismatic, wheel, distance and weld joints.
+// b2g_joint.h — joints inside the island solve: revolute, prismatic, wheel, distance, weld, friction and
+// motor joints.
 //
 // Reference: B2jointTraitDyn::{init_velocity_constraints, solve_velocity_constraints, solve_position_constraints}
 // (src/b2_joint.rs:268-286) as driven by B2island::solve (src/private/dynamics/b2_island_private.rs:198-201 init after the
@@ -25,6 +26,10 @@
 // wheel (private joints/b2_wheel_joint.rs:19-170 / :172-282 / :284-380; j_s0 = impulse, spring_impulse, motor_impulse,
 //        lower_impulse; param 0 = stiffness, 1 / 2 = translation limits, 5 / 6 = local x axis (not normalised), 7 = damping):
 //        0: ax.xy ay.xy   1: sAx sBx sAy sBy   2: mass axial_mass spring_mass motor_mass   3: mA iA mB iB   4: bias gamma translation -
+// friction / motor (private joints/b2_friction_joint.rs:8-72 / :74-128, b2_motor_joint.rs:8-96 / :98-160; no position rows;
+//        j_s0 = linear impulse x y, angular impulse; param 0 = max force, 1 = max torque, motor: 2 = angular offset,
+//        3 = correction factor, local_anchor_a = linear offset):
+//        0: rA.xy rB.xy   1: linear mass ex.x ex.y ey.x ey.y   2: angular mass, linear error x y, angular error   3: mA iA mB iB
 // Joint visits are ordered work: they run in the island's joint order inside every form of the Gauss-Seidel stages
 // (VelocityK / PositionK generic; velocity_sl_kernel / position_sl_kernel for batches, through an accessor over their
 // shared-memory rows; LwVelocity7K / LwPosition6K in the large-world modes).
@@ -153,7 +158,38 @@ B2G_HD void joint_init_velocity(const Batch& B, const WIdx& x, const S& st, int 
   const int jflags = f2i(s1.w);
   float4 t1, t2 = make_float4(0.0f, 0.0f, 0.0f, 0.0f), t4 = t2;
   float4 t0 = make_float4(r_a.x, r_a.y, r_b.x, r_b.y);
-  if (jr.type == B2GPU_JOINT_WHEEL) {
+  if (jr.type == B2GPU_JOINT_FRICTION || jr.type == B2GPU_JOINT_MOTOR) {
+    V2 fr_a = r_a, fr_b = r_b;
+    if (jr.type == B2GPU_JOINT_MOTOR) fr_b = rot_mul(q_b, -v2(msb.z, msb.w));  // from body B's origin: -local_center_b, not 0 - it
+    const float kxx = m_a + m_b + i_a * fr_a.y * fr_a.y + i_b * fr_b.y * fr_b.y;
+    const float kxy = -i_a * fr_a.x * fr_a.y - i_b * fr_b.x * fr_b.y;
+    const float kyy = m_a + m_b + i_a * fr_a.x * fr_a.x + i_b * fr_b.x * fr_b.x;
+    // B2Mat22::get_inverse (src/b2_math.rs:261-274) of [kxx kxy; kxy kyy]
+    float det = kxx * kyy - kxy * kxy;
+    if (det != 0.0f) det = 1.0f / det;
+    t1 = make_float4(det * kyy, -det * kxy, -det * kxy, det * kxx);
+    float angular_mass = i_a + i_b;
+    if (angular_mass > 0.0f) angular_mass = 1.0f / angular_mass;
+    V2 linear_error = v2(0.0f, 0.0f);
+    float angular_error = 0.0f;
+    if (jr.type == B2GPU_JOINT_MOTOR) {
+      linear_error = c_b + fr_b - c_a - fr_a;
+      angular_error = a_b - a_a - jr.param[2];
+    }
+    if (warm_starting) {
+      s0.x *= dt_ratio; s0.y *= dt_ratio;
+      s0.z *= dt_ratio;
+      const V2 p = v2(s0.x, s0.y);
+      v_a = v_a - m_a * p;
+      w_a -= i_a * (cross(fr_a, p) + s0.z);
+      v_b = v_b + m_b * p;
+      w_b += i_b * (cross(fr_b, p) + s0.z);
+    } else {
+      s0.x = 0.0f; s0.y = 0.0f; s0.z = 0.0f;
+    }
+    t0 = make_float4(fr_a.x, fr_a.y, fr_b.x, fr_b.y);
+    t2 = make_float4(angular_mass, linear_error.x, linear_error.y, angular_error);
+  } else if (jr.type == B2GPU_JOINT_WHEEL) {
     const V2 d = c_b + r_b - c_a - r_a;
     const V2 lx = v2(jr.param[5], jr.param[6]), ly = cross_sv(1.0f, lx);
     const V2 ay = rot_mul(q_a, ly);
@@ -372,7 +408,39 @@ B2G_HD void joint_solve_velocity(const Batch& B, const WIdx& x, const S& st, int
   const int ji = x.at(B.NJ, j);
   float4 s0 = B.j_s0[ji], s1 = B.j_s1[ji];
   const int jflags = f2i(s1.w);
-  if (jr.type == B2GPU_JOINT_WHEEL) {
+  if (jr.type == B2GPU_JOINT_FRICTION || jr.type == B2GPU_JOINT_MOTOR) {
+    const bool motor = jr.type == B2GPU_JOINT_MOTOR;
+    const float angular_mass = t2.x;
+    {  // angular
+      float cdot = w_b - w_a;
+      if (motor) cdot = w_b - w_a + inv_dt * jr.param[3] * t2.w;
+      float impulse = -angular_mass * cdot;
+      const float old_impulse = s0.z;
+      const float max_impulse = h * jr.param[1];
+      s0.z = fclamp_sel(s0.z + impulse, -max_impulse, max_impulse);
+      impulse = s0.z - old_impulse;
+      w_a -= i_a * impulse;
+      w_b += i_b * impulse;
+    }
+    {  // linear
+      V2 cdot = v_b + cross_sv(w_b, r_b) - v_a - cross_sv(w_a, r_a);
+      if (motor) cdot = cdot + (inv_dt * jr.param[3]) * v2(t2.y, t2.z);
+      V2 impulse = -v2(t1.x * cdot.x + t1.z * cdot.y, t1.y * cdot.x + t1.w * cdot.y);  // b2_mul(linear mass, cdot)
+      const V2 old_impulse = v2(s0.x, s0.y);
+      V2 li = old_impulse + impulse;
+      const float max_impulse = h * jr.param[0];
+      if (dot(li, li) > max_impulse * max_impulse) {
+        normalize(li);
+        li = max_impulse * li;
+      }
+      s0.x = li.x; s0.y = li.y;
+      impulse = li - old_impulse;
+      v_a = v_a - m_a * impulse;
+      w_a -= i_a * cross(r_a, impulse);
+      v_b = v_b + m_b * impulse;
+      w_b += i_b * cross(r_b, impulse);
+    }
+  } else if (jr.type == B2GPU_JOINT_WHEEL) {
     const V2 ax = v2(t0.x, t0.y), ay = v2(t0.z, t0.w);
     const float s_ax = t1.x, s_bx = t1.y, s_ay = t1.z, s_by = t1.w;
     const float mass = t2.x, axial_mass = t2.y, spring_mass = t2.z, motor_mass = t2.w;
@@ -652,6 +720,7 @@ B2G_HD void joint_solve_velocity(const Batch& B, const WIdx& x, const S& st, int
 template <class S>
 B2G_HD bool joint_solve_position(const Batch& B, const WIdx& x, const S& st, int j) {
   const b2gpu_joint_rec& jr = B.joints[j];
+  if (jr.type == B2GPU_JOINT_FRICTION || jr.type == B2GPU_JOINT_MOTOR) return true;  // no position rows
   const int bai = x.at(B.NB, jr.body_a), bbi = x.at(B.NB, jr.body_b);
   const float4 msa = B.b_mass[bai], msb = B.b_mass[bbi];
   const float m_a = msa.x, i_a = msa.y, m_b = msb.x, i_b = msb.y;

@@ -445,8 +445,8 @@ static int topology_build(const b2gpu_snapshot* s, Topology& T) {
   T.jadj.assign(2 * (size_t)n.joint_count, 0);
   for (const b2gpu_joint_rec& j : T.joints) {
     if (j.type != B2GPU_JOINT_REVOLUTE && j.type != B2GPU_JOINT_DISTANCE && j.type != B2GPU_JOINT_WELD && j.type != B2GPU_JOINT_PRISMATIC &&
-        j.type != B2GPU_JOINT_WHEEL) {
-      set_error("joint type outside the supported set (revolute, prismatic, wheel, distance, weld)");
+        j.type != B2GPU_JOINT_WHEEL && j.type != B2GPU_JOINT_FRICTION && j.type != B2GPU_JOINT_MOTOR) {
+      set_error("joint type outside the supported set (pulley, gear and mouse joints are not)");
       return B2GPU_E_UNSUPPORTED;
     }
     if (j.body_a < 0 || j.body_a >= n.body_count || j.body_b < 0 || j.body_b >= n.body_count || j.body_a == j.body_b) {

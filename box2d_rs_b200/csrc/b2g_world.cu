@@ -838,6 +838,41 @@ int b2gpu_prismatic_joint_def(b2gpu_world* W, b2gpu_joint_def* def, int body_a, 
   return 0;
   GUARD_END
 }
+int b2gpu_friction_joint_def(b2gpu_world* W, b2gpu_joint_def* def, int body_a, int body_b, float ax, float ay) {
+  GUARD_BEGIN
+  int rc = check_body(W, body_a);
+  if (!rc) rc = check_body(W, body_b);
+  if (rc) return rc;
+  if (!def) { set_error("joint def is NULL"); return B2GPU_E_INVALID; }
+  rc = ensure_host(W);
+  if (rc) return rc;
+  joint_def_defaults(def, B2GPU_JOINT_FRICTION, body_a, body_b);
+  const V2 la = body_local_point(W->h.bodies[body_a], v2(ax, ay)), lb = body_local_point(W->h.bodies[body_b], v2(ax, ay));
+  def->local_anchor_a[0] = la.x; def->local_anchor_a[1] = la.y;
+  def->local_anchor_b[0] = lb.x; def->local_anchor_b[1] = lb.y;
+  def->length = 0.0f; def->min_length = 0.0f; def->max_length = 0.0f;  // max_force (see b2gpu.h)
+  return 0;
+  GUARD_END
+}
+int b2gpu_motor_joint_def(b2gpu_world* W, b2gpu_joint_def* def, int body_a, int body_b) {
+  GUARD_BEGIN
+  int rc = check_body(W, body_a);
+  if (!rc) rc = check_body(W, body_b);
+  if (rc) return rc;
+  if (!def) { set_error("joint def is NULL"); return B2GPU_E_INVALID; }
+  rc = ensure_host(W);
+  if (rc) return rc;
+  joint_def_defaults(def, B2GPU_JOINT_MOTOR, body_a, body_b);
+  const b2gpu_body_rec &a = W->h.bodies[body_a], &b = W->h.bodies[body_b];
+  const V2 lo = body_local_point(a, v2(b.xf_px, b.xf_py));  // linear_offset = body A's local point of body B's position
+  def->local_anchor_a[0] = lo.x; def->local_anchor_a[1] = lo.y;
+  def->reference_angle = b.a - a.a;                          // angular_offset
+  def->length = 1.0f; def->min_length = 0.0f; def->max_length = 0.0f;  // max_force
+  def->max_motor_torque = 1.0f;                              // max_torque
+  def->stiffness = 0.3f;                                     // correction_factor
+  return 0;
+  GUARD_END
+}
 int b2gpu_wheel_joint_def(b2gpu_world* W, b2gpu_joint_def* def, int body_a, int body_b, float ax, float ay, float dx, float dy) {
   GUARD_BEGIN
   int rc = check_body(W, body_a);
@@ -923,8 +958,9 @@ int b2gpu_world_create_joint(b2gpu_world* W, const b2gpu_joint_def* def) {  // b
   if (rc) return rc;
   if (def->body_a == def->body_b) { set_error("create_joint: body_a == body_b (the reference asserts)"); return B2GPU_E_INVALID; }
   if (def->type != B2GPU_JOINT_REVOLUTE && def->type != B2GPU_JOINT_DISTANCE && def->type != B2GPU_JOINT_WELD &&
-      def->type != B2GPU_JOINT_PRISMATIC && def->type != B2GPU_JOINT_WHEEL) {
-    set_error("create_joint: only revolute, prismatic, wheel, distance and weld joints are inside the accelerated path");
+      def->type != B2GPU_JOINT_PRISMATIC && def->type != B2GPU_JOINT_WHEEL && def->type != B2GPU_JOINT_FRICTION &&
+      def->type != B2GPU_JOINT_MOTOR) {
+    set_error("create_joint: pulley, gear and mouse joints are outside the accelerated path");
     return B2GPU_E_UNSUPPORTED;
   }
   if (def->type == B2GPU_JOINT_PRISMATIC && !(def->lower_angle <= def->upper_angle)) {
@@ -953,6 +989,11 @@ int b2gpu_world_create_joint(b2gpu_world* W, const b2gpu_joint_def* def) {  // b
     j.param[5] = axis.x; j.param[6] = axis.y;
     if (def->enable_limit) j.flags |= B2GPU_JOINT_ENABLE_LIMIT;
     if (def->enable_motor) j.flags |= B2GPU_JOINT_ENABLE_MOTOR;
+  } else if (def->type == B2GPU_JOINT_FRICTION) {  // B2frictionJoint::new (src/joints/b2_friction_joint.rs:120-150)
+    j.param[0] = def->length; j.param[1] = def->max_motor_torque;
+  } else if (def->type == B2GPU_JOINT_MOTOR) {  // B2motorJoint::new (src/joints/b2_motor_joint.rs:175-205)
+    j.param[0] = def->length; j.param[1] = def->max_motor_torque;
+    j.param[2] = def->reference_angle; j.param[3] = def->stiffness;
   } else if (def->type == B2GPU_JOINT_WHEEL) {  // B2wheelJoint::new (src/joints/b2_wheel_joint.rs:266-310): axis not normalised
     j.param[0] = def->stiffness; j.param[1] = def->lower_angle; j.param[2] = def->upper_angle;
     j.param[3] = def->max_motor_torque; j.param[4] = def->motor_speed;

@@ -427,6 +427,39 @@ def car(world, motor_speed=-20.0):
     return joints
 
 
+def top_down(world):
+    """Zero-gravity, top-down: examples/testbed/tests/apply_force.rs:106-140 (boxes held back by friction joints to the ground:
+    max_force = m g, max_torque = 0.2 I g) kicked into each other, and examples/testbed/tests/motor_joint.rs:78-100 (a box driven
+    to an offset pose by a motor joint: max_force 1000, max_torque 1000) with a target away from where it starts."""
+    ground = world.create_body(BodyDef(position=(0.0, 20.0)))
+    for a, b in (((-20.0, -20.0), (-20.0, 20.0)), ((20.0, -20.0), (20.0, 20.0)), ((-20.0, 20.0), (20.0, 20.0)), ((-20.0, -20.0), (20.0, -20.0))):
+        ground.create_fixture(FixtureDef(density=0.0, restitution=0.4), world.shapes.edge_two_sided(a, b))
+    box = world.shapes.polygon_box(0.5, 0.5)
+    gravity = f32(10.0)
+    for i in range(10):
+        body = world.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(0.0, f32(7.0 + 1.54 * i))))
+        body.create_fixture(FixtureDef(density=1.0, friction=0.3), box)
+        mass = f32(1.0)                         # 1 x 1 box of density 1
+        inertia = f32(f32(1.0) * f32(f32(1.0 + 1.0) / f32(12.0)))  # m (w^2 + h^2) / 12
+        radius = f32(math.sqrt(f32(f32(2.0) * inertia) / mass))
+        jd = world.friction_joint_def(ground, body, (0.0, f32(7.0 + 1.54 * i)))
+        jd.local_anchor_a[0], jd.local_anchor_a[1] = 0.0, 0.0
+        jd.local_anchor_b[0], jd.local_anchor_b[1] = 0.0, 0.0
+        jd.collide_connected = 1
+        jd.length = f32(mass * gravity)                                   # max_force
+        jd.max_motor_torque = f32(f32(f32(0.2) * f32(mass * radius)) * gravity)  # max_torque
+        world.create_joint(jd)
+        body.set_linear_velocity((f32(26.0 - 6.0 * i), f32(-18.0 + 4.5 * i)))  # fast: they slide and collide for seconds
+        body.set_angular_velocity(f32(3.0 * i - 12.0))
+    puck = world.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(-8.0, 28.0)))
+    puck.create_fixture(FixtureDef(density=2.0, friction=0.6), world.shapes.polygon_box(2.0, 0.5))
+    jd = world.motor_joint_def(ground, puck)
+    jd.local_anchor_a[0], jd.local_anchor_a[1] = 6.0, 4.0   # linear_offset: where body B shall go, in the ground body's frame
+    jd.reference_angle = 1.0                                 # angular_offset
+    jd.length, jd.max_motor_torque = 1000.0, 1000.0
+    world.create_joint(jd)
+
+
 def tumbler(world, n=200, seed=0xB2D + 21):
     """examples/testbed/tests/tumbler.rs:62-97: a hollow box of four plank fixtures turned by a revolute-joint motor
     (0.05 pi rad/s, torque 1e8) around a point of the ground body; the testbed drops one 0.125 box per step, here `n`

@@ -191,6 +191,20 @@ class B2world:
                                                        anchor[0], anchor[1], axis[0], axis[1]))
         return d
 
+    def friction_joint_def(self, body_a, body_b, anchor):
+        """B2frictionJointDef::default() + initialize(body_a, body_b, anchor): `length` is max_force, `max_motor_torque` max_torque."""
+        d = abi.JointDef()
+        check(self.L, self.L.b2gpu_friction_joint_def(self.h, C.byref(d), _body_index(body_a), _body_index(body_b),
+                                                      anchor[0], anchor[1]))
+        return d
+
+    def motor_joint_def(self, body_a, body_b):
+        """B2motorJointDef::default() + initialize(body_a, body_b): local_anchor_a is linear_offset, reference_angle angular_offset,
+        `length` max_force, `max_motor_torque` max_torque, `stiffness` correction_factor."""
+        d = abi.JointDef()
+        check(self.L, self.L.b2gpu_motor_joint_def(self.h, C.byref(d), _body_index(body_a), _body_index(body_b)))
+        return d
+
     def wheel_joint_def(self, body_a, body_b, anchor, axis):
         """B2wheelJointDef::default() + initialize(body_a, body_b, anchor, axis): lower_angle / upper_angle are the translation
         limits, (length, min_length) the local axis; stiffness / damping as for a distance joint."""
@@ -221,7 +235,7 @@ class B2world:
         return k.value, d.value
 
     def create_joint(self, joint_def):
-        """B2world::create_joint (revolute, prismatic, wheel, distance and weld joints)."""
+        """B2world::create_joint (revolute, prismatic, wheel, distance, weld, friction and motor joints)."""
         return B2joint(self, check(self.L, self.L.b2gpu_world_create_joint(self.h, C.byref(joint_def))))
 
     def joint(self, index):

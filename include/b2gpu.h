@@ -38,7 +38,7 @@ extern "C" {
 #define B2GPU_E_NO_DEVICE (-2) /* no CUDA device: there is no CPU fallback */
 #define B2GPU_E_CUDA (-3)      /* CUDA runtime error, see b2gpu_last_error */
 #define B2GPU_E_CAPACITY (-4)  /* a device-side capacity was exceeded */
-#define B2GPU_E_UNSUPPORTED (-5) /* feature outside the hot-path scope (TOI, joint types other than revolute / prismatic / wheel / distance / weld) */
+#define B2GPU_E_UNSUPPORTED (-5) /* feature outside the hot-path scope (TOI, pulley, gear and mouse joints) */
 #define B2GPU_E_LOCKED (-6)    /* world is locked (reference: is_locked() panic) */
 #define B2GPU_E_INTERNAL (-7)  /* a device-side consistency check failed (a bug: please report) */
 #define B2GPU_E_IO (-8)        /* a checkpoint file could not be opened, read or written */
@@ -83,6 +83,8 @@ extern "C" {
 
 /* joint types: B2jointType (src/b2_joint.rs:46-58), same numbering */
 #define B2GPU_JOINT_DISTANCE 1
+#define B2GPU_JOINT_FRICTION 2
+#define B2GPU_JOINT_MOTOR 4
 #define B2GPU_JOINT_PRISMATIC 6
 #define B2GPU_JOINT_REVOLUTE 8
 #define B2GPU_JOINT_WELD 9
@@ -394,6 +396,13 @@ int b2gpu_distance_joint_def(b2gpu_world* w, b2gpu_joint_def* def, int body_a, i
  * asserts).  The revolute setters below (motor speed, max motor torque = force, enable motor / limit, set_limits) apply. */
 int b2gpu_prismatic_joint_def(b2gpu_world* w, b2gpu_joint_def* def, int body_a, int body_b, float anchor_x, float anchor_y,
                               float axis_x, float axis_y);
+/* B2frictionJointDef::default + ::initialize(body_a, body_b, anchor) (src/joints/b2_friction_joint.rs:9-50): top-down
+ * friction between two bodies.  Def overlay: `length` is max_force, `max_motor_torque` is max_torque (both default 0). */
+int b2gpu_friction_joint_def(b2gpu_world* w, b2gpu_joint_def* def, int body_a, int body_b, float anchor_x, float anchor_y);
+/* B2motorJointDef::default + ::initialize(body_a, body_b) (src/joints/b2_motor_joint.rs:9-59): drives body B towards an
+ * offset pose in body A's frame.  Def overlay: local_anchor_a is linear_offset, reference_angle is angular_offset, `length` is
+ * max_force (default 1), `max_motor_torque` is max_torque (default 1), `stiffness` is correction_factor (default 0.3). */
+int b2gpu_motor_joint_def(b2gpu_world* w, b2gpu_joint_def* def, int body_a, int body_b);
 /* B2wheelJointDef::default + ::initialize(body_a, body_b, anchor, axis) (src/joints/b2_wheel_joint.rs:10-90): a point of
  * body B on a line of body A, with a spring (stiffness / damping: b2gpu_linear_stiffness), translation limits and a
  * rotational motor.  Def overlay as for the prismatic joint: lower_angle / upper_angle are the translation limits,
@@ -411,7 +420,7 @@ int b2gpu_linear_stiffness(b2gpu_world* w, float frequency_hertz, float damping_
                            float* damping);
 /* B2world::create_joint (src/private/dynamics/b2_world.rs:156-262): returns the joint index (>= 0); contacts between
  * the two bodies are flagged for filtering when collide_connected is false.  Does not wake the bodies.
- * Joint types other than revolute, prismatic, wheel, distance and weld: B2GPU_E_UNSUPPORTED. */
+ * Joint types other than revolute, prismatic, wheel, distance, weld, friction and motor: B2GPU_E_UNSUPPORTED. */
 int b2gpu_world_create_joint(b2gpu_world* w, const b2gpu_joint_def* def);
 int b2gpu_world_get_joint_count(b2gpu_world* w);
 int b2gpu_world_get_joint(b2gpu_world* w, int joint, b2gpu_joint_rec* out);

@@ -57,6 +57,8 @@ def lib():
                                              C.c_float, C.c_float]
         L.b2o_prismatic_joint_def.argtypes = [C.c_void_p, C.POINTER(abi.JointDef), C.c_int, C.c_int, C.c_float, C.c_float,
                                               C.c_float, C.c_float]
+        L.b2o_friction_joint_def.argtypes = [C.c_void_p, C.POINTER(abi.JointDef), C.c_int, C.c_int, C.c_float, C.c_float]
+        L.b2o_motor_joint_def.argtypes = [C.c_void_p, C.POINTER(abi.JointDef), C.c_int, C.c_int]
         L.b2o_wheel_joint_def.argtypes = [C.c_void_p, C.POINTER(abi.JointDef), C.c_int, C.c_int, C.c_float, C.c_float,
                                           C.c_float, C.c_float]
         L.b2o_weld_joint_def.argtypes = [C.c_void_p, C.POINTER(abi.JointDef), C.c_int, C.c_int, C.c_float, C.c_float]
@@ -254,6 +256,18 @@ class B2world:
         d = abi.JointDef()
         lib().b2o_prismatic_joint_def(self.h, C.byref(d), _body_index(body_a), _body_index(body_b), anchor[0], anchor[1],
                                       axis[0], axis[1])
+        return d
+
+    def friction_joint_def(self, body_a, body_b, anchor):
+        """B2frictionJointDef::default() + initialize(body_a, body_b, anchor): set length (= max_force), max_motor_torque."""
+        d = abi.JointDef()
+        lib().b2o_friction_joint_def(self.h, C.byref(d), _body_index(body_a), _body_index(body_b), anchor[0], anchor[1])
+        return d
+
+    def motor_joint_def(self, body_a, body_b):
+        """B2motorJointDef::default() + initialize(body_a, body_b)."""
+        d = abi.JointDef()
+        lib().b2o_motor_joint_def(self.h, C.byref(d), _body_index(body_a), _body_index(body_b))
         return d
 
     def wheel_joint_def(self, body_a, body_b, anchor, axis):

@@ -149,6 +149,10 @@ static void joint_def_out(const JointDef& d, b2gpu_joint_def* o) {
   o->max_motor_torque = d.max_motor_torque; o->motor_speed = d.motor_speed;
   o->enable_limit = d.enable_limit ? 1 : 0; o->enable_motor = d.enable_motor ? 1 : 0;
   o->length = d.length; o->min_length = d.min_length; o->max_length = d.max_length; o->stiffness = d.stiffness; o->damping = d.damping;
+  if (d.type == J_FRICTION || d.type == J_MOTOR) {  // b2gpu.h: length = max_force, stiffness = correction_factor (motor)
+    o->length = d.max_force; o->min_length = 0.0f; o->max_length = 0.0f;
+    o->stiffness = d.type == J_MOTOR ? d.correction_factor : 0.0f;
+  }
   if (d.type == J_PRISMATIC || d.type == J_WHEEL) { o->length = d.local_axis_a.x; o->min_length = d.local_axis_a.y; o->max_length = 0.0f; }  // b2gpu.h: the def's overlay
 }
 int b2o_prismatic_joint_def(void* w, b2gpu_joint_def* def, int body_a, int body_b, float ax, float ay, float dx, float dy) {
@@ -161,6 +165,14 @@ int b2o_revolute_joint_def(void* w, b2gpu_joint_def* def, int body_a, int body_b
 }
 int b2o_distance_joint_def(void* w, b2gpu_joint_def* def, int body_a, int body_b, float a1x, float a1y, float a2x, float a2y) {
   joint_def_out(((World*)w)->distance_joint_def(body_a, body_b, Vec2(a1x, a1y), Vec2(a2x, a2y)), def);
+  return 0;
+}
+int b2o_friction_joint_def(void* w, b2gpu_joint_def* def, int body_a, int body_b, float ax, float ay) {
+  joint_def_out(((World*)w)->friction_joint_def(body_a, body_b, Vec2(ax, ay)), def);
+  return 0;
+}
+int b2o_motor_joint_def(void* w, b2gpu_joint_def* def, int body_a, int body_b) {
+  joint_def_out(((World*)w)->motor_joint_def(body_a, body_b), def);
   return 0;
 }
 int b2o_wheel_joint_def(void* w, b2gpu_joint_def* def, int body_a, int body_b, float ax, float ay, float dx, float dy) {
@@ -189,6 +201,7 @@ int b2o_create_joint(void* w, const b2gpu_joint_def* d) {
   jd.enable_limit = d->enable_limit != 0; jd.enable_motor = d->enable_motor != 0;
   jd.length = d->length; jd.min_length = d->min_length; jd.max_length = d->max_length; jd.stiffness = d->stiffness; jd.damping = d->damping;
   if (d->type == J_PRISMATIC || d->type == J_WHEEL) jd.local_axis_a = Vec2(d->length, d->min_length);
+  if (d->type == J_FRICTION || d->type == J_MOTOR) { jd.max_force = d->length; jd.correction_factor = d->stiffness; }
   return ((World*)w)->create_joint(jd);
 }
 int b2o_joint_count(void* w) { return (int)((World*)w)->joints.size(); }
@@ -348,6 +361,10 @@ int b2o_snapshot_export(void* w, b2gpu_snapshot* out) {
       r.param[0] = j.reference_angle; r.param[1] = j.lower_angle; r.param[2] = j.upper_angle;
       r.param[3] = j.max_motor_torque; r.param[4] = j.motor_speed;
       r.param[5] = j.local_xaxis_a.x; r.param[6] = j.local_xaxis_a.y;
+      r.impulse[0] = j.impulse2.x; r.impulse[1] = j.impulse2.y; r.impulse[2] = j.motor_impulse;
+    } else if (j.type == J_FRICTION || j.type == J_MOTOR) {
+      r.param[0] = j.max_force; r.param[1] = j.max_motor_torque;
+      if (j.type == J_MOTOR) { r.param[2] = j.reference_angle; r.param[3] = j.correction_factor; }
       r.impulse[0] = j.impulse2.x; r.impulse[1] = j.impulse2.y; r.impulse[2] = j.motor_impulse;
     } else if (j.type == J_WHEEL) {
       r.param[0] = j.stiffness; r.param[1] = j.lower_angle; r.param[2] = j.upper_angle;

@@ -93,7 +93,7 @@ struct Contact {
 
 // Joints: B2jointDef + B2revoluteJointDef / B2distanceJointDef as one plain struct
 // (src/b2_joint.rs:112-122, src/joints/b2_revolute_joint.rs:10-72, src/joints/b2_distance_joint.rs:11-58).
-enum JointType { J_DISTANCE = 1, J_PRISMATIC = 6, J_REVOLUTE = 8, J_WELD = 9, J_WHEEL = 10 };  // B2jointType numbering (src/b2_joint.rs:46-58)
+enum JointType { J_DISTANCE = 1, J_FRICTION = 2, J_MOTOR = 4, J_PRISMATIC = 6, J_REVOLUTE = 8, J_WELD = 9, J_WHEEL = 10 };  // B2jointType numbering (src/b2_joint.rs:46-58)
 struct JointDef {
   int type = 0, body_a = -1, body_b = -1;
   bool collide_connected = false;
@@ -104,6 +104,9 @@ struct JointDef {
   // prismatic (src/joints/b2_prismatic_joint.rs:10-72): lower_angle / upper_angle carry the translation limits,
   // max_motor_torque the maximum motor force
   Vec2 local_axis_a = Vec2(1.0f, 0.0f);
+  // friction (src/joints/b2_friction_joint.rs:9-50) / motor (src/joints/b2_motor_joint.rs:9-59): max_force, and for the motor
+  // joint linear_offset (in local_anchor_a), angular_offset (in reference_angle), correction_factor; max_motor_torque = max_torque
+  float max_force = 0.0f, correction_factor = 0.3f;
 };
 struct Joint {  // B2joint + B2revoluteJoint (src/joints/b2_revolute_joint.rs:104-136) / B2distanceJoint fields
   int type = 0, body_a = -1, body_b = -1;
@@ -126,6 +129,10 @@ struct Joint {  // B2joint + B2revoluteJoint (src/joints/b2_revolute_joint.rs:10
   // impulses and switches, local_xaxis_a / local_yaxis_a, translation, gamma, bias, mass, axial_mass
   float spring_impulse = 0.0f, spring_mass = 0.0f, motor_mass = 0.0f, s_ax = 0.0f, s_bx = 0.0f, s_ay = 0.0f, s_by = 0.0f;
   Vec2 ax, ay;
+  // friction / motor: impulse2 = linear impulse, motor_impulse = angular impulse, max_motor_torque = max torque;
+  // k = linear mass (inverse), axial_mass = angular mass
+  float max_force = 0.0f, correction_factor = 0.0f, angular_error = 0.0f;
+  Vec2 linear_error;
   // weld (src/joints/b2_weld_joint.rs:66-90): impulse (x, y, angular), effective mass B2Mat33 as ex.xyz ey.xyz ez.xyz
   float impulse3[3] = {0.0f, 0.0f, 0.0f}, m33[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   // solver temp
@@ -471,6 +478,26 @@ struct World {
     d.reference_angle = bodies[body_b].sweep.a - bodies[body_a].sweep.a;
     return d;
   }
+  // B2frictionJointDef::default + ::initialize (src/joints/b2_friction_joint.rs:9-50)
+  JointDef friction_joint_def(int body_a, int body_b, Vec2 anchor) const {
+    JointDef d;
+    d.type = J_FRICTION;
+    d.body_a = body_a; d.body_b = body_b;
+    d.local_anchor_a = b2_mul_t_xf(bodies[body_a].xf, anchor);
+    d.local_anchor_b = b2_mul_t_xf(bodies[body_b].xf, anchor);
+    d.max_force = 0.0f; d.max_motor_torque = 0.0f;
+    return d;
+  }
+  // B2motorJointDef::default + ::initialize (src/joints/b2_motor_joint.rs:9-59)
+  JointDef motor_joint_def(int body_a, int body_b) const {
+    JointDef d;
+    d.type = J_MOTOR;
+    d.body_a = body_a; d.body_b = body_b;
+    d.local_anchor_a = b2_mul_t_xf(bodies[body_a].xf, bodies[body_b].xf.p);  // linear_offset = get_local_point(body_b position)
+    d.reference_angle = bodies[body_b].sweep.a - bodies[body_a].sweep.a;     // angular_offset
+    d.max_force = 1.0f; d.max_motor_torque = 1.0f; d.correction_factor = 0.3f;
+    return d;
+  }
   // B2wheelJointDef::default + ::initialize (src/joints/b2_wheel_joint.rs:10-90)
   JointDef wheel_joint_def(int body_a, int body_b, Vec2 anchor, Vec2 axis) const {
     JointDef d;
@@ -538,6 +565,11 @@ struct World {
       assert(j.lower_angle <= j.upper_angle);
       j.max_motor_torque = def.max_motor_torque; j.motor_speed = def.motor_speed;
       j.enable_limit = def.enable_limit; j.enable_motor = def.enable_motor;
+    } else if (def.type == J_FRICTION) {  // B2frictionJoint::new (src/joints/b2_friction_joint.rs:120-150)
+      j.max_force = def.max_force; j.max_motor_torque = def.max_motor_torque;
+    } else if (def.type == J_MOTOR) {  // B2motorJoint::new (src/joints/b2_motor_joint.rs:175-205): local_anchor_a = linear offset
+      j.reference_angle = def.reference_angle;
+      j.max_force = def.max_force; j.max_motor_torque = def.max_motor_torque; j.correction_factor = def.correction_factor;
     } else if (def.type == J_WHEEL) {  // B2wheelJoint::new (src/joints/b2_wheel_joint.rs:266-310): the axis is NOT normalised
       j.local_xaxis_a = def.local_axis_a;
       j.local_yaxis_a = b2_cross_sv(1.0f, def.local_axis_a);
@@ -1224,6 +1256,38 @@ struct World {
         j.lower_impulse = 0.0f;
         j.upper_impulse = 0.0f;
       }
+    } else if (j.type == J_FRICTION || j.type == J_MOTOR) {
+      // private joints/b2_friction_joint.rs:8-72, b2_motor_joint.rs:8-96: the same rows; the motor joint measures from body
+      // B's origin to the linear offset on body A and carries position errors
+      float m_a = j.inv_mass_a, m_b = j.inv_mass_b, i_a = j.inv_ia, i_b = j.inv_ib;
+      if (j.type == J_MOTOR) {
+        j.r_a = b2_mul_rot(q_a, j.local_anchor_a - j.local_center_a);
+        j.r_b = b2_mul_rot(q_b, -j.local_center_b);
+      }
+      Mat22 k;
+      k.ex.x = m_a + m_b + i_a * j.r_a.y * j.r_a.y + i_b * j.r_b.y * j.r_b.y;
+      k.ex.y = -i_a * j.r_a.x * j.r_a.y - i_b * j.r_b.x * j.r_b.y;
+      k.ey.x = k.ex.y;
+      k.ey.y = m_a + m_b + i_a * j.r_a.x * j.r_a.x + i_b * j.r_b.x * j.r_b.x;
+      j.k = k.get_inverse();
+      j.axial_mass = i_a + i_b;
+      if (j.axial_mass > 0.0f) j.axial_mass = 1.0f / j.axial_mass;
+      if (j.type == J_MOTOR) {
+        j.linear_error = c_b + j.r_b - c_a - j.r_a;
+        j.angular_error = a_b - a_a - j.reference_angle;
+      }
+      if (step.warm_starting) {
+        j.impulse2 *= step.dt_ratio;
+        j.motor_impulse *= step.dt_ratio;
+        Vec2 p(j.impulse2.x, j.impulse2.y);
+        v_a -= m_a * p;
+        w_a -= i_a * (b2_cross(j.r_a, p) + j.motor_impulse);
+        v_b += m_b * p;
+        w_b += i_b * (b2_cross(j.r_b, p) + j.motor_impulse);
+      } else {
+        j.impulse2.set_zero();
+        j.motor_impulse = 0.0f;
+      }
     } else if (j.type == J_WHEEL) {  // private joints/b2_wheel_joint.rs:19-170
       float m_a = j.inv_mass_a, m_b = j.inv_mass_b, i_a = j.inv_ia, i_b = j.inv_ib;
       Vec2 d = c_b + j.r_b - c_a - j.r_a;
@@ -1483,6 +1547,37 @@ struct World {
         w_a -= i_a * la;
         v_b += m_b * p;
         w_b += i_b * lb;
+      }
+    } else if (j.type == J_FRICTION || j.type == J_MOTOR) {  // b2_friction_joint.rs:74-128, b2_motor_joint.rs:98-160
+      float m_a = j.inv_mass_a, m_b = j.inv_mass_b, i_a = j.inv_ia, i_b = j.inv_ib;
+      float h = step.dt, inv_h = step.inv_dt;
+      {  // angular
+        float cdot = w_b - w_a;
+        if (j.type == J_MOTOR) cdot = w_b - w_a + inv_h * j.correction_factor * j.angular_error;
+        float impulse = -j.axial_mass * cdot;
+        float old_impulse = j.motor_impulse;
+        float max_impulse = h * j.max_motor_torque;
+        j.motor_impulse = b2_clamp(j.motor_impulse + impulse, -max_impulse, max_impulse);
+        impulse = j.motor_impulse - old_impulse;
+        w_a -= i_a * impulse;
+        w_b += i_b * impulse;
+      }
+      {  // linear
+        Vec2 cdot = v_b + b2_cross_sv(w_b, j.r_b) - v_a - b2_cross_sv(w_a, j.r_a);
+        if (j.type == J_MOTOR) cdot = cdot + inv_h * j.correction_factor * j.linear_error;
+        Vec2 impulse = -Vec2(j.k.ex.x * cdot.x + j.k.ey.x * cdot.y, j.k.ex.y * cdot.x + j.k.ey.y * cdot.y);  // b2_mul(Mat22, v)
+        Vec2 old_impulse = j.impulse2;
+        j.impulse2 += impulse;
+        float max_impulse = h * j.max_force;
+        if (j.impulse2.length_squared() > max_impulse * max_impulse) {
+          j.impulse2.normalize();
+          j.impulse2 *= max_impulse;
+        }
+        impulse = j.impulse2 - old_impulse;
+        v_a -= m_a * impulse;
+        w_a -= i_a * b2_cross(j.r_a, impulse);
+        v_b += m_b * impulse;
+        w_b += i_b * b2_cross(j.r_b, impulse);
       }
     } else if (j.type == J_WHEEL) {  // private joints/b2_wheel_joint.rs:172-282
       float m_a = j.inv_mass_a, m_b = j.inv_mass_b, i_a = j.inv_ia, i_b = j.inv_ib;
@@ -1753,6 +1848,8 @@ struct World {
       c_b += m_b * p;
       a_b += i_b * lb;
       okay = linear_error <= LINEAR_SLOP && angular_error <= ANGULAR_SLOP;
+    } else if (j.type == J_FRICTION || j.type == J_MOTOR) {  // no position rows: always within tolerance
+      return true;
     } else if (j.type == J_WHEEL) {  // private joints/b2_wheel_joint.rs:284-380
       float linear_error = 0.0f;
       if (j.enable_limit) {

@@ -187,6 +187,8 @@ extern "C" {
     pub fn b2gpu_revolute_joint_def(w: *mut b2gpu_world, def: *mut b2gpu_joint_def, body_a: c_int, body_b: c_int, anchor_x: c_float, anchor_y: c_float) -> c_int;
     pub fn b2gpu_distance_joint_def(w: *mut b2gpu_world, def: *mut b2gpu_joint_def, body_a: c_int, body_b: c_int, a1x: c_float, a1y: c_float, a2x: c_float, a2y: c_float) -> c_int;
     pub fn b2gpu_prismatic_joint_def(w: *mut b2gpu_world, def: *mut b2gpu_joint_def, body_a: c_int, body_b: c_int, anchor_x: c_float, anchor_y: c_float, axis_x: c_float, axis_y: c_float) -> c_int;
+    pub fn b2gpu_friction_joint_def(w: *mut b2gpu_world, def: *mut b2gpu_joint_def, body_a: c_int, body_b: c_int, anchor_x: c_float, anchor_y: c_float) -> c_int;
+    pub fn b2gpu_motor_joint_def(w: *mut b2gpu_world, def: *mut b2gpu_joint_def, body_a: c_int, body_b: c_int) -> c_int;
     pub fn b2gpu_wheel_joint_def(w: *mut b2gpu_world, def: *mut b2gpu_joint_def, body_a: c_int, body_b: c_int, anchor_x: c_float, anchor_y: c_float, axis_x: c_float, axis_y: c_float) -> c_int;
     pub fn b2gpu_weld_joint_def(w: *mut b2gpu_world, def: *mut b2gpu_joint_def, body_a: c_int, body_b: c_int, anchor_x: c_float, anchor_y: c_float) -> c_int;
     pub fn b2gpu_angular_stiffness(w: *mut b2gpu_world, frequency_hertz: c_float, damping_ratio: c_float, body_a: c_int, body_b: c_int, stiffness: *mut c_float, damping: *mut c_float) -> c_int;

@@ -238,6 +238,20 @@ pub fn flatten<D: UserDataType>(world: &B2world<D>) -> Snapshot<D> {
                 r.impulse[0] = v.m_impulse.x; r.impulse[1] = v.m_impulse.y; r.impulse[2] = v.m_motor_impulse;
                 r.impulse[3] = v.m_lower_impulse; r.impulse[4] = v.m_upper_impulse;
             }
+            JointAsDerived::EFrictionJoint(v) => {
+                r.type_ = 2;
+                r.local_anchor_a = [v.m_local_anchor_a.x, v.m_local_anchor_a.y];
+                r.local_anchor_b = [v.m_local_anchor_b.x, v.m_local_anchor_b.y];
+                r.param[0] = v.m_max_force; r.param[1] = v.m_max_torque;
+                r.impulse[0] = v.m_linear_impulse.x; r.impulse[1] = v.m_linear_impulse.y; r.impulse[2] = v.m_angular_impulse;
+            }
+            JointAsDerived::EMotorJoint(v) => {
+                r.type_ = 4;
+                r.local_anchor_a = [v.m_linear_offset.x, v.m_linear_offset.y];
+                r.param[0] = v.m_max_force; r.param[1] = v.m_max_torque;
+                r.param[2] = v.m_angular_offset; r.param[3] = v.m_correction_factor;
+                r.impulse[0] = v.m_linear_impulse.x; r.impulse[1] = v.m_linear_impulse.y; r.impulse[2] = v.m_angular_impulse;
+            }
             JointAsDerived::EWheelJoint(v) => {
                 r.type_ = 10;
                 r.local_anchor_a = [v.m_local_anchor_a.x, v.m_local_anchor_a.y];
@@ -473,6 +487,14 @@ pub fn write_back<D: UserDataType>(world: &mut B2world<D>, snap: &Snapshot<D>) {
                 v.m_motor_impulse = r.impulse[2];
                 v.m_lower_impulse = r.impulse[3];
                 v.m_upper_impulse = r.impulse[4];
+            }
+            JointAsDerivedMut::EFrictionJoint(v) => {
+                v.m_linear_impulse.set(r.impulse[0], r.impulse[1]);
+                v.m_angular_impulse = r.impulse[2];
+            }
+            JointAsDerivedMut::EMotorJoint(v) => {
+                v.m_linear_impulse.set(r.impulse[0], r.impulse[1]);
+                v.m_angular_impulse = r.impulse[2];
             }
             JointAsDerivedMut::EWheelJoint(v) => {
                 v.m_impulse = r.impulse[0];

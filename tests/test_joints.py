@@ -233,6 +233,57 @@ def test_oracle_wheel_joints_carry_a_car(built):
     assert abs(b[1]["v"][0] - 8.0) < 0.4 and abs(b[2]["w"] + 20.0) < 0.5 and b[1]["c"][0] > 25.0
 
 
+def test_oracle_friction_joint_decelerates_at_max_force_over_mass(built):
+    """examples/testbed/tests/apply_force.rs: top-down friction, no gravity.  A sliding box loses max_force / m per second until
+    it stops (Coulomb friction in the plane), its spin loses max_torque / I per second."""
+    from box2d_rs_b200 import abi, scenes
+    from box2d_rs_b200.abi import BodyDef
+    from oracle import b2o
+    w = b2o.B2world((0.0, 0.0))
+    ground = w.create_body(BodyDef())
+    box = w.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(0.0, 0.0), allow_sleep=0))
+    box.create_fixture_by_shape(w.shapes.polygon_box(0.5, 0.5), 2.0)  # mass 2, I = 2 / 6
+    jd = w.friction_joint_def(ground, box, (0.0, 0.0))
+    jd.length, jd.max_motor_torque = 4.0, 0.5  # max_force, max_torque
+    w.create_joint(jd)
+    box.set_linear_velocity((3.0, 4.0))  # speed 5
+    box.set_angular_velocity(6.0)
+    for i in range(60):
+        w.step(scenes.DT, 8, 3)
+    b = w.snapshot().bodies[1]
+    speed = math.hypot(b["v"][0], b["v"][1])
+    assert abs(speed - (5.0 - 4.0 / 2.0 * 1.0)) < 0.02       # a = F / m = 2
+    assert abs(b["v"][0] / b["v"][1] - 0.75) < 1e-3          # straight line
+    assert abs(b["w"] - (6.0 - 0.5 / (2.0 / 6.0) * 1.0)) < 0.02  # alpha = T / I = 1.5
+    for i in range(120):
+        w.step(scenes.DT, 8, 3)
+    b = w.snapshot().bodies[1]
+    assert math.hypot(b["v"][0], b["v"][1]) < 1e-4           # stopped after 2.5 s
+
+
+def test_oracle_motor_joint_drives_to_its_offsets(built):
+    """examples/testbed/tests/motor_joint.rs: body B is driven to linear_offset / angular_offset in body A's frame."""
+    from box2d_rs_b200 import abi, scenes
+    from box2d_rs_b200.abi import BodyDef
+    from oracle import b2o
+    w = b2o.B2world((0.0, -10.0))
+    ground = w.create_body(BodyDef(position=(1.0, 2.0)))
+    box = w.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(3.0, 8.0), allow_sleep=0))
+    box.create_fixture_by_shape(w.shapes.polygon_box(2.0, 0.5), 2.0)  # mass 8: weight 80 < max_force
+    jd = w.motor_joint_def(ground, box)
+    assert abs(jd.local_anchor_a[0] - 2.0) < 1e-6 and abs(jd.local_anchor_a[1] - 6.0) < 1e-6  # body B's position in A's frame
+    assert abs(jd.length - 1.0) < 1e-7 and abs(jd.max_motor_torque - 1.0) < 1e-7 and abs(jd.stiffness - 0.3) < 1e-7  # defaults
+    jd.local_anchor_a[0], jd.local_anchor_a[1], jd.reference_angle = 5.0, 4.0, 0.8
+    jd.length, jd.max_motor_torque = 1000.0, 1000.0
+    w.create_joint(jd)
+    for i in range(240):
+        w.step(scenes.DT, 8, 3)
+    b = w.snapshot().bodies[1]
+    # the spring-like correction (factor 0.3) holds the box a little below the target: 8 kg x 10 m/s^2 against it
+    assert abs(b["c"][0] - 6.0) < 0.01 and 5.9 < b["c"][1] < 6.0 + 1e-3 and abs(b["a"] - 0.8) < 0.01
+    assert math.hypot(b["v"][0], b["v"][1]) < 1e-3
+
+
 def test_oracle_angular_stiffness_formula(built):
     """b2_angular_stiffness (private b2_joint.rs:47-70): I = Ia Ib / (Ia + Ib) of B2body::get_inertia, omega = 2 pi f."""
     from box2d_rs_b200 import abi
@@ -280,11 +331,13 @@ def test_weld_defs_and_unsupported_types(built):
     qo = wo.wheel_joint_def(wo.body(0), wo.body(1), (1.3, 1.2), (0.6, -0.8))
     qg = wg.wheel_joint_def(wg.body(0), wg.body(1), (1.3, 1.2), (0.6, -0.8))
     assert bytes(qo) == bytes(qg)
+    assert bytes(wo.friction_joint_def(wo.body(0), wo.body(1), (1.3, 1.2))) == bytes(wg.friction_joint_def(wg.body(0), wg.body(1), (1.3, 1.2)))
+    assert bytes(wo.motor_joint_def(wo.body(0), wo.body(1))) == bytes(wg.motor_joint_def(wg.body(0), wg.body(1)))
     pg.lower_angle, pg.upper_angle = 1.0, 0.5  # lower > upper: the reference asserts
     with pytest.raises(B2gpuError) as e:
         wg.create_joint(pg)
     assert e.value.code == abi.E_INVALID
-    jg.type = 7  # pulley
+    jg.type = 7  # pulley (gear and mouse joints likewise)
     with pytest.raises(B2gpuError) as e:
         wg.create_joint(jg)
     assert e.value.code == abi.E_UNSUPPORTED

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Differential fuzzing of the device stages (host simulator build by default, --gpu for the CUDA path) against
 the CPU oracle: random scenes (polygons of 3..8 vertices, circles, edges, chains, kinematic / fixed-rotation /
-multi-fixture bodies, sensors, filters, restitution, damping, revolute / prismatic / wheel / distance / weld joints with limits, motors and springs,
+multi-fixture bodies, sensors, filters, restitution, damping, revolute / prismatic / wheel / distance / weld / friction / motor joints with limits, motors and springs,
 random world flags and iteration counts, dt = 0 steps,
 mid-run set_transform / set_linear_velocity / apply_force / apply_torque / apply_*_impulse / set_awake edits), stepped freely and compared bit for bit.
 
@@ -89,7 +89,7 @@ def build(world, rng):
                 ang = np.sort(rng.uniform(0, 2 * math.pi, nv))
                 shape = world.shapes.polygon([(f32(rad * math.cos(a)), f32(rad * math.sin(a) * rng.uniform(0.5, 1.0))) for a in ang])
             b.create_fixture(fd, shape)
-    # joints (revolute / prismatic / wheel / distance / weld) between random bodies, the ground included: limits, motors, soft springs, slack ranges,
+    # joints (revolute / prismatic / wheel / distance / weld / friction / motor) between random bodies, the ground included: limits, motors, soft springs, slack ranges,
     # collide_connected, degenerate pairs (kinematic or fixed-rotation bodies, anchors far from the bodies)
     joints = []
     if rng.integers(0, 5) < 3:
@@ -97,8 +97,18 @@ def build(world, rng):
             a, b = int(rng.integers(0, n + 1)), int(rng.integers(0, n + 1))
             if a == b:
                 continue
-            kind = int(rng.integers(0, 5))
-            if kind == 4:  # wheel: random (unnormalised) axis, spring, limits, motor
+            kind = int(rng.integers(0, 7))
+            if kind == 6:  # motor joint: target pose, force / torque caps, correction factor
+                jd = world.motor_joint_def(a, b)
+                jd.local_anchor_a[0] = f32(jd.local_anchor_a[0] + rng.uniform(-2, 2))
+                jd.local_anchor_a[1] = f32(jd.local_anchor_a[1] + rng.uniform(-2, 2))
+                jd.reference_angle = f32(jd.reference_angle + rng.uniform(-1, 1))
+                jd.length, jd.max_motor_torque = f32(rng.uniform(0, 300)), f32(rng.uniform(0, 300))
+                jd.stiffness = f32(rng.uniform(0.0, 1.0))
+            elif kind == 5:  # friction joint
+                jd = world.friction_joint_def(a, b, (f32(rng.uniform(-10, 10)), f32(rng.uniform(0.5, 14))))
+                jd.length, jd.max_motor_torque = f32(rng.uniform(0, 60)), f32(rng.uniform(0, 30))
+            elif kind == 4:  # wheel: random (unnormalised) axis, spring, limits, motor
                 th = rng.uniform(0, 2 * math.pi)
                 jd = world.wheel_joint_def(a, b, (f32(rng.uniform(-10, 10)), f32(rng.uniform(0.5, 14))),
                                            (f32(math.cos(th) * rng.uniform(0.5, 2)), f32(math.sin(th) * rng.uniform(0.5, 2))))
