@@ -176,7 +176,7 @@ int b2gpu_snapshot_validate(const b2gpu_snapshot* s) {
   for (int i = 0; i < n.move_count; ++i) CHECK_RANGE(s->move_buffer[i] >= -1 && s->move_buffer[i] < nn, "move buffer entry", i);
   for (int i = 0; i < n.joint_count; ++i) {
     const b2gpu_joint_rec& j = s->joints[i];
-    CHECK_RANGE(j.type == B2GPU_JOINT_REVOLUTE || j.type == B2GPU_JOINT_DISTANCE || j.type == B2GPU_JOINT_WELD || j.type == B2GPU_JOINT_PRISMATIC || j.type == B2GPU_JOINT_WHEEL || j.type == B2GPU_JOINT_FRICTION || j.type == B2GPU_JOINT_MOTOR, "joint type", i);
+    CHECK_RANGE(j.type == B2GPU_JOINT_REVOLUTE || j.type == B2GPU_JOINT_DISTANCE || j.type == B2GPU_JOINT_WELD || j.type == B2GPU_JOINT_PRISMATIC || j.type == B2GPU_JOINT_WHEEL || j.type == B2GPU_JOINT_FRICTION || j.type == B2GPU_JOINT_MOTOR || j.type == B2GPU_JOINT_PULLEY || j.type == B2GPU_JOINT_MOUSE, "joint type", i);
     CHECK_RANGE(j.body_a >= 0 && j.body_a < nb && j.body_b >= 0 && j.body_b < nb && j.body_a != j.body_b, "joint body", i);
   }
   const b2gpu_world_rec& w = s->world;

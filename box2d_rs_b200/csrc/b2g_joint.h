@@ -15,7 +15,8 @@
 // Data: the static part of a joint (type, bodies, anchors, limits, lengths, COLLIDE_CONNECTED) is topology shared by the
 // worlds of a batch (Batch::joints); what the solver or the user changes per world lives in two float4 rows
 //   j_s0: impulse.x impulse.y motor_impulse lower_impulse     (distance: impulse, -, -, lower_impulse; weld: impulse.x .y .z, -)
-//   j_s1: upper_impulse motor_speed max_motor_torque (int bits) ENABLE_LIMIT | ENABLE_MOTOR
+//   j_s1: upper_impulse motor_speed max_motor_torque (int bits) ENABLE_LIMIT | ENABLE_MOTOR   (mouse: - target.y target.x -)
+//   pulley: j_s0.x = impulse; tmp rows r_a r_b | u_a u_b | mass.   mouse: j_s0.xy = impulse; tmp rows r_a r_b | mass 2x2 | gamma C.x C.y
 // and the per-step solver data (the reference's "solver temp" members) in JT_Q float4 rows of j_tmp:
 //   0: rA.xy rB.xy
 //   1: revolute K.ex.x K.ey.x K.ey.y axial_mass      | distance u.x u.y mass soft_mass        | weld mass.ex.xyz mass.ey.x
@@ -189,6 +190,54 @@ B2G_HD void joint_init_velocity(const Batch& B, const WIdx& x, const S& st, int 
     }
     t0 = make_float4(fr_a.x, fr_a.y, fr_b.x, fr_b.y);
     t2 = make_float4(angular_mass, linear_error.x, linear_error.y, angular_error);
+  } else if (jr.type == B2GPU_JOINT_PULLEY) {  // private joints/b2_pulley_joint.rs:46-137
+    const float ratio = jr.param[6];
+    V2 u_a = c_a + r_a - v2(jr.param[0], jr.param[1]);
+    V2 u_b = c_b + r_b - v2(jr.param[2], jr.param[3]);
+    const float length_a = length(u_a), length_b = length(u_b);
+    if (length_a > 10.0f * B2G_LINEAR_SLOP) u_a = (1.0f / length_a) * u_a; else u_a = v2(0.0f, 0.0f);
+    if (length_b > 10.0f * B2G_LINEAR_SLOP) u_b = (1.0f / length_b) * u_b; else u_b = v2(0.0f, 0.0f);
+    const float ru_a = cross(r_a, u_a), ru_b = cross(r_b, u_b);
+    const float pm_a = m_a + i_a * ru_a * ru_a;
+    const float pm_b = m_b + i_b * ru_b * ru_b;
+    float mass = pm_a + ratio * ratio * pm_b;
+    if (mass > 0.0f) mass = 1.0f / mass;
+    if (warm_starting) {
+      s0.x *= dt_ratio;
+      const V2 pa_ = (-s0.x) * u_a;
+      const V2 pb_ = (-ratio * s0.x) * u_b;
+      v_a = v_a + m_a * pa_;
+      w_a += i_a * cross(r_a, pa_);
+      v_b = v_b + m_b * pb_;
+      w_b += i_b * cross(r_b, pb_);
+    } else {
+      s0.x = 0.0f;
+    }
+    t1 = make_float4(u_a.x, u_a.y, u_b.x, u_b.y);
+    t2 = make_float4(mass, 0.0f, 0.0f, 0.0f);
+  } else if (jr.type == B2GPU_JOINT_MOUSE) {  // private joints/b2_mouse_joint.rs:7-67: body A is neither read nor changed
+    const float d = jr.param[2], k = jr.param[1];
+    float gamma = h * (d + h * k);
+    if (gamma != 0.0f) gamma = 1.0f / gamma;
+    const float beta = h * k * gamma;
+    const float kxx = m_b + i_b * r_b.y * r_b.y + gamma;
+    const float kxy = -i_b * r_b.x * r_b.y;
+    const float kyy = m_b + i_b * r_b.x * r_b.x + gamma;
+    float det = kxx * kyy - kxy * kxy;  // B2Mat22::get_inverse (src/b2_math.rs:261-274)
+    if (det != 0.0f) det = 1.0f / det;
+    t1 = make_float4(det * kyy, -det * kxy, -det * kxy, det * kxx);
+    V2 c = c_b + r_b - v2(s1.z, s1.y);  // the target lives in j_s1 (per world)
+    c = beta * c;
+    w_b *= 0.98f;
+    if (warm_starting) {
+      s0.x *= dt_ratio; s0.y *= dt_ratio;
+      const V2 p = v2(s0.x, s0.y);
+      v_b = v_b + m_b * p;
+      w_b += i_b * cross(r_b, p);
+    } else {
+      s0.x = 0.0f; s0.y = 0.0f;
+    }
+    t2 = make_float4(gamma, c.x, c.y, 0.0f);
   } else if (jr.type == B2GPU_JOINT_WHEEL) {
     const V2 d = c_b + r_b - c_a - r_a;
     const V2 lx = v2(jr.param[5], jr.param[6]), ly = cross_sv(1.0f, lx);
@@ -390,9 +439,11 @@ B2G_HD void joint_init_velocity(const Batch& B, const WIdx& x, const S& st, int 
   B.j_tmp[jt_at(B, x, j, 2)] = t2;
   B.j_tmp[jt_at(B, x, j, 3)] = make_float4(m_a, i_a, m_b, i_b);
   if (jr.type == B2GPU_JOINT_WELD || jr.type == B2GPU_JOINT_PRISMATIC || jr.type == B2GPU_JOINT_WHEEL) B.j_tmp[jt_at(B, x, j, 4)] = t4;
-  // an immovable body may sit in several islands: its velocity never changes, leave it alone
+  // an immovable body may sit in several islands: its velocity never changes, leave it alone — but for the mouse joint's
+  // damping of w_b, which the reference applies to a kinematic body B too (a kinematic body belongs to one island)
+  const bool mouse_kinematic = jr.type == B2GPU_JOINT_MOUSE && body_type(B.b_flags[bbi]) != B2GPU_STATIC_BODY;
   if (m_a != 0.0f || i_a != 0.0f) st.set_vel(jr.body_a, make_float4(v_a.x, v_a.y, w_a, 0.0f));
-  if (m_b != 0.0f || i_b != 0.0f) st.set_vel(jr.body_b, make_float4(v_b.x, v_b.y, w_b, 0.0f));
+  if (m_b != 0.0f || i_b != 0.0f || mouse_kinematic) st.set_vel(jr.body_b, make_float4(v_b.x, v_b.y, w_b, 0.0f));
 }
 
 template <class S>
@@ -440,6 +491,32 @@ B2G_HD void joint_solve_velocity(const Batch& B, const WIdx& x, const S& st, int
       v_b = v_b + m_b * impulse;
       w_b += i_b * cross(r_b, impulse);
     }
+  } else if (jr.type == B2GPU_JOINT_PULLEY) {  // private joints/b2_pulley_joint.rs:139-170
+    const V2 u_a = v2(t1.x, t1.y), u_b = v2(t1.z, t1.w);
+    const float ratio = jr.param[6];
+    const V2 vp_a = v_a + cross_sv(w_a, r_a);
+    const V2 vp_b = v_b + cross_sv(w_b, r_b);
+    const float cdot = -dot(u_a, vp_a) - ratio * dot(u_b, vp_b);
+    const float impulse = -t2.x * cdot;
+    s0.x += impulse;
+    const V2 pa_ = (-impulse) * u_a;
+    const V2 pb_ = (-ratio * impulse) * u_b;
+    v_a = v_a + m_a * pa_;
+    w_a += i_a * cross(r_a, pa_);
+    v_b = v_b + m_b * pb_;
+    w_b += i_b * cross(r_b, pb_);
+  } else if (jr.type == B2GPU_JOINT_MOUSE) {  // private joints/b2_mouse_joint.rs:69-92
+    const V2 cdot = v_b + cross_sv(w_b, r_b);
+    const V2 old_impulse = v2(s0.x, s0.y);
+    const V2 t = -(cdot + v2(t2.y, t2.z) + t2.x * old_impulse);
+    V2 impulse = v2(t1.x * t.x + t1.z * t.y, t1.y * t.x + t1.w * t.y);  // b2_mul(mass, t)
+    V2 li = old_impulse + impulse;
+    const float max_impulse = h * jr.param[0];
+    if (dot(li, li) > max_impulse * max_impulse) li = (max_impulse / length(li)) * li;
+    s0.x = li.x; s0.y = li.y;
+    impulse = li - old_impulse;
+    v_b = v_b + m_b * impulse;
+    w_b += i_b * cross(r_b, impulse);
   } else if (jr.type == B2GPU_JOINT_WHEEL) {
     const V2 ax = v2(t0.x, t0.y), ay = v2(t0.z, t0.w);
     const float s_ax = t1.x, s_bx = t1.y, s_ay = t1.z, s_by = t1.w;
@@ -720,7 +797,7 @@ B2G_HD void joint_solve_velocity(const Batch& B, const WIdx& x, const S& st, int
 template <class S>
 B2G_HD bool joint_solve_position(const Batch& B, const WIdx& x, const S& st, int j) {
   const b2gpu_joint_rec& jr = B.joints[j];
-  if (jr.type == B2GPU_JOINT_FRICTION || jr.type == B2GPU_JOINT_MOTOR) return true;  // no position rows
+  if (jr.type == B2GPU_JOINT_FRICTION || jr.type == B2GPU_JOINT_MOTOR || jr.type == B2GPU_JOINT_MOUSE) return true;  // no position rows
   const int bai = x.at(B.NB, jr.body_a), bbi = x.at(B.NB, jr.body_b);
   const float4 msa = B.b_mass[bai], msb = B.b_mass[bbi];
   const float m_a = msa.x, i_a = msa.y, m_b = msb.x, i_b = msb.y;
@@ -912,6 +989,29 @@ B2G_HD bool joint_solve_position(const Batch& B, const WIdx& x, const S& st, int
     c_b = c_b + m_b * impulse;
     a_b += i_b * cross(r_b, impulse);
     okay = position_error <= B2G_LINEAR_SLOP && angular_error <= B2G_ANGULAR_SLOP;
+  } else if (jr.type == B2GPU_JOINT_PULLEY) {  // private joints/b2_pulley_joint.rs:172-240
+    const float ratio = jr.param[6];
+    const V2 r_a = rot_mul(q_a, la);
+    const V2 r_b = rot_mul(q_b, lb);
+    V2 u_a = c_a + r_a - v2(jr.param[0], jr.param[1]);
+    V2 u_b = c_b + r_b - v2(jr.param[2], jr.param[3]);
+    const float length_a = length(u_a), length_b = length(u_b);
+    if (length_a > 10.0f * B2G_LINEAR_SLOP) u_a = (1.0f / length_a) * u_a; else u_a = v2(0.0f, 0.0f);
+    if (length_b > 10.0f * B2G_LINEAR_SLOP) u_b = (1.0f / length_b) * u_b; else u_b = v2(0.0f, 0.0f);
+    const float ru_a = cross(r_a, u_a), ru_b = cross(r_b, u_b);
+    const float pm_a = m_a + i_a * ru_a * ru_a;
+    const float pm_b = m_b + i_b * ru_b * ru_b;
+    float mass = pm_a + ratio * ratio * pm_b;
+    if (mass > 0.0f) mass = 1.0f / mass;
+    const float c = jr.param[7] - length_a - ratio * length_b;
+    const float impulse = -mass * c;
+    const V2 pa_ = (-impulse) * u_a;
+    const V2 pb_ = (-ratio * impulse) * u_b;
+    c_a = c_a + m_a * pa_;
+    a_a += i_a * cross(r_a, pa_);
+    c_b = c_b + m_b * pb_;
+    a_b += i_b * cross(r_b, pb_);
+    okay = fabsf(c) < B2G_LINEAR_SLOP;
   } else {  // distance
     const float mass = B.j_tmp[jt_at(B, x, j, 1)].z;
     const float min_length = jr.param[1], max_length = jr.param[2];

@@ -295,7 +295,8 @@ static int image_pack(const BatchHost* bh, const b2gpu_snapshot* s, WorldImage& 
     // revolute: param 3 = max_motor_torque, 4 = motor_speed are per world (an RL action); distance joints keep
     // everything static (their slots of j_s1 are unused)
     im.j_s0[i] = make_float4(j.impulse[0], j.impulse[1], j.impulse[2], j.impulse[3]);
-    const bool motorised = j.type == B2GPU_JOINT_REVOLUTE || j.type == B2GPU_JOINT_PRISMATIC || j.type == B2GPU_JOINT_WHEEL;
+    const bool motorised = j.type == B2GPU_JOINT_REVOLUTE || j.type == B2GPU_JOINT_PRISMATIC || j.type == B2GPU_JOINT_WHEEL ||
+                           j.type == B2GPU_JOINT_MOUSE;  // mouse: param 3, 4 = the target
     im.j_s1[i] = make_float4(j.impulse[4], motorised ? j.param[4] : 0.0f, motorised ? j.param[3] : 0.0f,
                              bitsf((int)(j.flags & (B2GPU_JOINT_ENABLE_LIMIT | B2GPU_JOINT_ENABLE_MOTOR))));
   }
@@ -399,7 +400,7 @@ static int image_unpack(const BatchHost* bh, const WorldImage& im, b2gpu_snapsho
     const float4 s0 = im.j_s0[i], s1 = im.j_s1[i];
     j.impulse[0] = s0.x; j.impulse[1] = s0.y; j.impulse[2] = s0.z; j.impulse[3] = s0.w; j.impulse[4] = s1.x;
     j.impulse[5] = j.impulse[6] = j.impulse[7] = 0.0f;
-    if (j.type == B2GPU_JOINT_REVOLUTE || j.type == B2GPU_JOINT_PRISMATIC || j.type == B2GPU_JOINT_WHEEL) {
+    if (j.type == B2GPU_JOINT_REVOLUTE || j.type == B2GPU_JOINT_PRISMATIC || j.type == B2GPU_JOINT_WHEEL || j.type == B2GPU_JOINT_MOUSE) {
       j.param[4] = s1.y;
       j.param[3] = s1.z;
       j.flags = (j.flags & B2GPU_JOINT_COLLIDE_CONNECTED) | ((uint32_t)fbits(s1.w) & (B2GPU_JOINT_ENABLE_LIMIT | B2GPU_JOINT_ENABLE_MOTOR));
@@ -445,8 +446,9 @@ static int topology_build(const b2gpu_snapshot* s, Topology& T) {
   T.jadj.assign(2 * (size_t)n.joint_count, 0);
   for (const b2gpu_joint_rec& j : T.joints) {
     if (j.type != B2GPU_JOINT_REVOLUTE && j.type != B2GPU_JOINT_DISTANCE && j.type != B2GPU_JOINT_WELD && j.type != B2GPU_JOINT_PRISMATIC &&
-        j.type != B2GPU_JOINT_WHEEL && j.type != B2GPU_JOINT_FRICTION && j.type != B2GPU_JOINT_MOTOR) {
-      set_error("joint type outside the supported set (pulley, gear and mouse joints are not)");
+        j.type != B2GPU_JOINT_WHEEL && j.type != B2GPU_JOINT_FRICTION && j.type != B2GPU_JOINT_MOTOR && j.type != B2GPU_JOINT_PULLEY &&
+        j.type != B2GPU_JOINT_MOUSE) {
+      set_error("joint type outside the supported set (the gear joint is not)");
       return B2GPU_E_UNSUPPORTED;
     }
     if (j.body_a < 0 || j.body_a >= n.body_count || j.body_b < 0 || j.body_b >= n.body_count || j.body_a == j.body_b) {
@@ -502,11 +504,13 @@ static bool topology_matches(const Topology& T, const b2gpu_snapshot* s) {
         (a.flags & B2GPU_JOINT_COLLIDE_CONNECTED) != (b.flags & B2GPU_JOINT_COLLIDE_CONNECTED) ||
         memcmp(a.local_anchor_a, b.local_anchor_a, 8) || memcmp(a.local_anchor_b, b.local_anchor_b, 8))
       return false;
-    const bool motorised = a.type == B2GPU_JOINT_REVOLUTE || a.type == B2GPU_JOINT_PRISMATIC || a.type == B2GPU_JOINT_WHEEL;
+    const bool motorised = a.type == B2GPU_JOINT_REVOLUTE || a.type == B2GPU_JOINT_PRISMATIC || a.type == B2GPU_JOINT_WHEEL ||
+                           a.type == B2GPU_JOINT_MOUSE;
     const int n_static = motorised ? 3 : 5;  // revolute / prismatic: motor torque (force) / speed are per world
     if (memcmp(a.param, b.param, 4 * n_static)) return false;
     if (a.type == B2GPU_JOINT_PRISMATIC && memcmp(a.param + 5, b.param + 5, 8)) return false;   // the local axis
     if (a.type == B2GPU_JOINT_WHEEL && memcmp(a.param + 5, b.param + 5, 12)) return false;      // the local axis, damping
+    if (a.type == B2GPU_JOINT_PULLEY && memcmp(a.param + 5, b.param + 5, 12)) return false;     // length_b, ratio, constant
   }
   return true;
 }

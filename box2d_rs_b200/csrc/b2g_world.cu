@@ -854,6 +854,41 @@ int b2gpu_friction_joint_def(b2gpu_world* W, b2gpu_joint_def* def, int body_a, i
   return 0;
   GUARD_END
 }
+int b2gpu_pulley_joint_def(b2gpu_world* W, b2gpu_joint_def* def, int body_a, int body_b, float gax, float gay, float gbx, float gby,
+                           float ax, float ay, float bx, float by, float ratio) {
+  GUARD_BEGIN
+  int rc = check_body(W, body_a);
+  if (!rc) rc = check_body(W, body_b);
+  if (rc) return rc;
+  if (!def) { set_error("joint def is NULL"); return B2GPU_E_INVALID; }
+  if (!(ratio > B2G_EPSILON)) { set_error("pulley_joint_def: ratio <= epsilon (the reference asserts)"); return B2GPU_E_INVALID; }
+  rc = ensure_host(W);
+  if (rc) return rc;
+  joint_def_defaults(def, B2GPU_JOINT_PULLEY, body_a, body_b);
+  def->collide_connected = 1;
+  const V2 la = body_local_point(W->h.bodies[body_a], v2(ax, ay)), lb = body_local_point(W->h.bodies[body_b], v2(bx, by));
+  def->local_anchor_a[0] = la.x; def->local_anchor_a[1] = la.y;
+  def->local_anchor_b[0] = lb.x; def->local_anchor_b[1] = lb.y;
+  def->lower_angle = gax; def->upper_angle = gay;       // ground_anchor_a (see b2gpu.h)
+  def->max_motor_torque = gbx; def->motor_speed = gby;  // ground_anchor_b
+  def->length = length(v2(ax, ay) - v2(gax, gay));      // length_a
+  def->min_length = length(v2(bx, by) - v2(gbx, gby));  // length_b
+  def->max_length = ratio;
+  return 0;
+  GUARD_END
+}
+int b2gpu_mouse_joint_def(b2gpu_world* W, b2gpu_joint_def* def, int body_a, int body_b, float tx, float ty) {
+  GUARD_BEGIN
+  int rc = check_body(W, body_a);
+  if (!rc) rc = check_body(W, body_b);
+  if (rc) return rc;
+  if (!def) { set_error("joint def is NULL"); return B2GPU_E_INVALID; }
+  joint_def_defaults(def, B2GPU_JOINT_MOUSE, body_a, body_b);
+  def->local_anchor_a[0] = tx; def->local_anchor_a[1] = ty;  // the target, in world coordinates (see b2gpu.h)
+  def->length = 0.0f; def->min_length = 0.0f; def->max_length = 0.0f;  // max_force
+  return 0;
+  GUARD_END
+}
 int b2gpu_motor_joint_def(b2gpu_world* W, b2gpu_joint_def* def, int body_a, int body_b) {
   GUARD_BEGIN
   int rc = check_body(W, body_a);
@@ -959,12 +994,16 @@ int b2gpu_world_create_joint(b2gpu_world* W, const b2gpu_joint_def* def) {  // b
   if (def->body_a == def->body_b) { set_error("create_joint: body_a == body_b (the reference asserts)"); return B2GPU_E_INVALID; }
   if (def->type != B2GPU_JOINT_REVOLUTE && def->type != B2GPU_JOINT_DISTANCE && def->type != B2GPU_JOINT_WELD &&
       def->type != B2GPU_JOINT_PRISMATIC && def->type != B2GPU_JOINT_WHEEL && def->type != B2GPU_JOINT_FRICTION &&
-      def->type != B2GPU_JOINT_MOTOR) {
-    set_error("create_joint: pulley, gear and mouse joints are outside the accelerated path");
+      def->type != B2GPU_JOINT_MOTOR && def->type != B2GPU_JOINT_PULLEY && def->type != B2GPU_JOINT_MOUSE) {
+    set_error("create_joint: the gear joint is outside the accelerated path");
     return B2GPU_E_UNSUPPORTED;
   }
   if (def->type == B2GPU_JOINT_PRISMATIC && !(def->lower_angle <= def->upper_angle)) {
     set_error("create_joint: prismatic lower translation > upper translation (the reference asserts)");
+    return B2GPU_E_INVALID;
+  }
+  if (def->type == B2GPU_JOINT_PULLEY && def->max_length == 0.0f) {
+    set_error("create_joint: pulley ratio is 0 (the reference asserts)");
     return B2GPU_E_INVALID;
   }
   rc = ensure_host(W);
@@ -991,6 +1030,17 @@ int b2gpu_world_create_joint(b2gpu_world* W, const b2gpu_joint_def* def) {  // b
     if (def->enable_motor) j.flags |= B2GPU_JOINT_ENABLE_MOTOR;
   } else if (def->type == B2GPU_JOINT_FRICTION) {  // B2frictionJoint::new (src/joints/b2_friction_joint.rs:120-150)
     j.param[0] = def->length; j.param[1] = def->max_motor_torque;
+  } else if (def->type == B2GPU_JOINT_PULLEY) {  // B2pulleyJoint::new (private joints/b2_pulley_joint.rs:8-44)
+    j.param[0] = def->lower_angle; j.param[1] = def->upper_angle; j.param[2] = def->max_motor_torque; j.param[3] = def->motor_speed;
+    j.param[4] = def->length; j.param[5] = def->min_length; j.param[6] = def->max_length;
+    j.param[7] = def->length + def->max_length * def->min_length;  // constant = length_a + ratio * length_b
+  } else if (def->type == B2GPU_JOINT_MOUSE) {  // B2mouseJoint::new (src/joints/b2_mouse_joint.rs:140-170)
+    const V2 target = v2(def->local_anchor_a[0], def->local_anchor_a[1]);
+    const V2 lb = body_local_point(h.bodies[def->body_b], target);
+    j.local_anchor_a[0] = 0.0f; j.local_anchor_a[1] = 0.0f;
+    j.local_anchor_b[0] = lb.x; j.local_anchor_b[1] = lb.y;
+    j.param[0] = def->length; j.param[1] = def->stiffness; j.param[2] = def->damping;
+    j.param[3] = target.x; j.param[4] = target.y;  // per world (j_s1), like the motor settings of a revolute joint
   } else if (def->type == B2GPU_JOINT_MOTOR) {  // B2motorJoint::new (src/joints/b2_motor_joint.rs:175-205)
     j.param[0] = def->length; j.param[1] = def->max_motor_torque;
     j.param[2] = def->reference_angle; j.param[3] = def->stiffness;
@@ -1055,6 +1105,20 @@ int b2gpu_joint_set_motor_speed(b2gpu_world* W, int joint, float speed) {
   if (rc) return rc;
   b2gpu_joint_rec& j = W->h.joints[joint];
   if (speed != j.param[4]) { joint_wake(W, j); j.param[4] = speed; W->host_dirty = true; }
+  return 0;
+  GUARD_END
+}
+int b2gpu_joint_set_target(b2gpu_world* W, int joint, float tx, float ty) {  // src/joints/b2_mouse_joint.rs:114-119
+  GUARD_BEGIN
+  int rc = check_joint(W, joint, B2GPU_JOINT_MOUSE);
+  if (!rc) rc = ensure_host(W);
+  if (rc) return rc;
+  b2gpu_joint_rec& j = W->h.joints[joint];
+  if (tx != j.param[3] || ty != j.param[4]) {
+    set_awake(W->h.bodies[j.body_b], true);
+    j.param[3] = tx; j.param[4] = ty;
+    W->host_dirty = true;
+  }
   return 0;
   GUARD_END
 }

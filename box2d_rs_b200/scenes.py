@@ -460,6 +460,41 @@ def top_down(world):
     world.create_joint(jd)
 
 
+def pulleys(world):
+    """examples/testbed/tests/pulley_joint.rs:55-115 (two 1 x 2 boxes of density 5 on a ratio-1.5 pulley under two ground
+    circles) next to a second, lighter pair over a floor so one side lands, and the testbed's mouse drag
+    (examples/testbed/test.rs:230-262: 5 Hz, damping ratio 0.7, max_force 1000 m) pulling a box sideways off the floor.
+    Returns the mouse joint so a test can move its target."""
+    y, l, a, b = 16.0, 12.0, 1.0, 2.0
+    ground = world.create_body(BodyDef())
+    for x in (-10.0, 10.0):
+        ground.create_fixture(FixtureDef(density=0.0), world.shapes.circle(2.0, (x, y + b + l)))
+    ground.create_fixture(FixtureDef(density=0.0), world.shapes.edge_two_sided((-60.0, 0.0), (60.0, 0.0)))
+    shape = world.shapes.polygon_box(a, b)
+    body1 = world.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(-10.0, y)))
+    body1.create_fixture_by_shape(shape, 5.0)
+    body2 = world.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(10.0, y)))
+    body2.create_fixture_by_shape(shape, 5.0)
+    world.create_joint(world.pulley_joint_def(body1, body2, (-10.0, y + b + l), (10.0, y + b + l), (-10.0, y + b), (10.0, y + b), 1.5))
+    # a lighter pair with a block-and-tackle ratio: the heavy side comes down on the floor, the rope goes slack-free
+    small, big = world.shapes.polygon_box(0.5, 0.5), world.shapes.polygon_box(1.0, 1.0)
+    body3 = world.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(24.0, 6.0), angle=0.2))
+    body3.create_fixture(FixtureDef(density=1.0, friction=0.4), small)
+    body4 = world.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(32.0, 9.0)))
+    body4.create_fixture(FixtureDef(density=2.0, friction=0.4), big)
+    world.create_joint(world.pulley_joint_def(body3, body4, (25.0, 20.0), (31.0, 20.0), (24.0, 6.5), (32.0, 10.0), 2.0))
+    # mouse drag
+    crate = world.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(-30.0, 1.0)))
+    crate.create_fixture(FixtureDef(density=1.0, friction=0.5), big)
+    jd = world.mouse_joint_def(ground, crate, (-29.5, 1.5))
+    jd.length = f32(1000.0 * 4.0)  # max_force = 1000 * mass (2 x 2 box of density 1)
+    jd.stiffness, jd.damping = world.linear_stiffness(5.0, 0.7, ground, crate)
+    mouse = world.create_joint(jd)
+    mouse.set_target((-22.0, 9.0))
+    crate.set_awake(True)
+    return mouse
+
+
 def tumbler(world, n=200, seed=0xB2D + 21):
     """examples/testbed/tests/tumbler.rs:62-97: a hollow box of four plank fixtures turned by a revolute-joint motor
     (0.05 pi rad/s, torque 1e8) around a point of the ground body; the testbed drops one 0.125 box per step, here `n`

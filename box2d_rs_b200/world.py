@@ -140,6 +140,10 @@ class B2joint:
     def set_limits(self, lower, upper):
         check(self.world.L, self.world.L.b2gpu_joint_set_limits(self.world.h, self.index, lower, upper))
 
+    def set_target(self, target):
+        """B2mouseJoint::set_target (src/joints/b2_mouse_joint.rs:114-119)."""
+        check(self.world.L, self.world.L.b2gpu_joint_set_target(self.world.h, self.index, target[0], target[1]))
+
     def record(self):
         out = np.zeros(1, abi.JOINT_DTYPE)
         check(self.world.L, self.world.L.b2gpu_world_get_joint(self.world.h, self.index, out.ctypes.data))
@@ -196,6 +200,22 @@ class B2world:
         d = abi.JointDef()
         check(self.L, self.L.b2gpu_friction_joint_def(self.h, C.byref(d), _body_index(body_a), _body_index(body_b),
                                                       anchor[0], anchor[1]))
+        return d
+
+    def pulley_joint_def(self, body_a, body_b, ground_a, ground_b, anchor_a, anchor_b, ratio):
+        """B2pulleyJointDef::default() + initialize(...) (src/joints/b2_pulley_joint.rs:10-78); overlay in b2gpu.h."""
+        d = abi.JointDef()
+        check(self.L, self.L.b2gpu_pulley_joint_def(self.h, C.byref(d), _body_index(body_a), _body_index(body_b), ground_a[0],
+                                                    ground_a[1], ground_b[0], ground_b[1], anchor_a[0], anchor_a[1],
+                                                    anchor_b[0], anchor_b[1], ratio))
+        return d
+
+    def mouse_joint_def(self, body_a, body_b, target):
+        """B2mouseJointDef::default() with `target` (src/joints/b2_mouse_joint.rs:8-21): set length (= max_force),
+        stiffness, damping."""
+        d = abi.JointDef()
+        check(self.L, self.L.b2gpu_mouse_joint_def(self.h, C.byref(d), _body_index(body_a), _body_index(body_b), target[0],
+                                                   target[1]))
         return d
 
     def motor_joint_def(self, body_a, body_b):

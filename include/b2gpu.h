@@ -85,7 +85,9 @@ extern "C" {
 #define B2GPU_JOINT_DISTANCE 1
 #define B2GPU_JOINT_FRICTION 2
 #define B2GPU_JOINT_MOTOR 4
+#define B2GPU_JOINT_MOUSE 5
 #define B2GPU_JOINT_PRISMATIC 6
+#define B2GPU_JOINT_PULLEY 7
 #define B2GPU_JOINT_REVOLUTE 8
 #define B2GPU_JOINT_WELD 9
 #define B2GPU_JOINT_WHEEL 10
@@ -403,6 +405,19 @@ int b2gpu_friction_joint_def(b2gpu_world* w, b2gpu_joint_def* def, int body_a, i
  * offset pose in body A's frame.  Def overlay: local_anchor_a is linear_offset, reference_angle is angular_offset, `length` is
  * max_force (default 1), `max_motor_torque` is max_torque (default 1), `stiffness` is correction_factor (default 0.3). */
 int b2gpu_motor_joint_def(b2gpu_world* w, b2gpu_joint_def* def, int body_a, int body_b);
+/* B2pulleyJointDef::default + ::initialize(body_a, body_b, ground_a, ground_b, anchor_a, anchor_b, ratio)
+ * (src/joints/b2_pulley_joint.rs:10-78): length_a + ratio * length_b stays constant.  collide_connected defaults to 1 here.
+ * Def overlay: (lower_angle, upper_angle) is ground_anchor_a, (max_motor_torque, motor_speed) is ground_anchor_b, `length` is
+ * length_a, `min_length` is length_b, `max_length` is the ratio.  ratio <= FLT_EPSILON here, or 0 at create: B2GPU_E_INVALID
+ * (the reference asserts). */
+int b2gpu_pulley_joint_def(b2gpu_world* w, b2gpu_joint_def* def, int body_a, int body_b, float ground_ax, float ground_ay,
+                           float ground_bx, float ground_by, float anchor_ax, float anchor_ay, float anchor_bx, float anchor_by,
+                           float ratio);
+/* B2mouseJointDef::default (src/joints/b2_mouse_joint.rs:8-21) with `target`: a soft constraint that drags a point of body B
+ * (the body-local point under the target at creation) towards a world target; body A is only the island link (use a static
+ * body).  Def overlay: local_anchor_a is the target in WORLD coordinates, `length` is max_force (default 0), stiffness and
+ * damping as named (b2gpu_linear_stiffness).  Move the target with b2gpu_joint_set_target. */
+int b2gpu_mouse_joint_def(b2gpu_world* w, b2gpu_joint_def* def, int body_a, int body_b, float target_x, float target_y);
 /* B2wheelJointDef::default + ::initialize(body_a, body_b, anchor, axis) (src/joints/b2_wheel_joint.rs:10-90): a point of
  * body B on a line of body A, with a spring (stiffness / damping: b2gpu_linear_stiffness), translation limits and a
  * rotational motor.  Def overlay as for the prismatic joint: lower_angle / upper_angle are the translation limits,
@@ -420,7 +435,7 @@ int b2gpu_linear_stiffness(b2gpu_world* w, float frequency_hertz, float damping_
                            float* damping);
 /* B2world::create_joint (src/private/dynamics/b2_world.rs:156-262): returns the joint index (>= 0); contacts between
  * the two bodies are flagged for filtering when collide_connected is false.  Does not wake the bodies.
- * Joint types other than revolute, prismatic, wheel, distance, weld, friction and motor: B2GPU_E_UNSUPPORTED. */
+ * The gear joint (it wraps two other joints) is the one type outside the path: B2GPU_E_UNSUPPORTED. */
 int b2gpu_world_create_joint(b2gpu_world* w, const b2gpu_joint_def* def);
 int b2gpu_world_get_joint_count(b2gpu_world* w);
 int b2gpu_world_get_joint(b2gpu_world* w, int joint, b2gpu_joint_rec* out);
@@ -432,6 +447,8 @@ int b2gpu_joint_set_max_motor_torque(b2gpu_world* w, int joint, float torque);
 int b2gpu_joint_enable_motor(b2gpu_world* w, int joint, int flag);
 int b2gpu_joint_enable_limit(b2gpu_world* w, int joint, int flag);
 int b2gpu_joint_set_limits(b2gpu_world* w, int joint, float lower, float upper);
+/* B2mouseJoint::set_target (src/joints/b2_mouse_joint.rs:114-119): wakes body B when the target changes. */
+int b2gpu_joint_set_target(b2gpu_world* w, int joint, float target_x, float target_y);
 /* B2world::set_allow_sleeping / set_warm_starting / set_continuous_physics */
 int b2gpu_world_set_allow_sleeping(b2gpu_world* w, int flag);
 int b2gpu_world_set_warm_starting(b2gpu_world* w, int flag);

@@ -59,6 +59,9 @@ def lib():
                                               C.c_float, C.c_float]
         L.b2o_friction_joint_def.argtypes = [C.c_void_p, C.POINTER(abi.JointDef), C.c_int, C.c_int, C.c_float, C.c_float]
         L.b2o_motor_joint_def.argtypes = [C.c_void_p, C.POINTER(abi.JointDef), C.c_int, C.c_int]
+        L.b2o_pulley_joint_def.argtypes = [C.c_void_p, C.POINTER(abi.JointDef), C.c_int, C.c_int] + [C.c_float] * 9
+        L.b2o_mouse_joint_def.argtypes = [C.c_void_p, C.POINTER(abi.JointDef), C.c_int, C.c_int, C.c_float, C.c_float]
+        L.b2o_joint_set_target.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float]
         L.b2o_wheel_joint_def.argtypes = [C.c_void_p, C.POINTER(abi.JointDef), C.c_int, C.c_int, C.c_float, C.c_float,
                                           C.c_float, C.c_float]
         L.b2o_weld_joint_def.argtypes = [C.c_void_p, C.POINTER(abi.JointDef), C.c_int, C.c_int, C.c_float, C.c_float]
@@ -213,6 +216,9 @@ class B2joint:
     def set_limits(self, lower, upper):
         lib().b2o_joint_set_limits(self.world.h, self.index, lower, upper)
 
+    def set_target(self, target):
+        lib().b2o_joint_set_target(self.world.h, self.index, target[0], target[1])
+
 
 def _body_index(b):
     return b.index if hasattr(b, "index") else int(b)
@@ -268,6 +274,19 @@ class B2world:
         """B2motorJointDef::default() + initialize(body_a, body_b)."""
         d = abi.JointDef()
         lib().b2o_motor_joint_def(self.h, C.byref(d), _body_index(body_a), _body_index(body_b))
+        return d
+
+    def pulley_joint_def(self, body_a, body_b, ground_a, ground_b, anchor_a, anchor_b, ratio):
+        """B2pulleyJointDef::default() + initialize(body_a, body_b, ground_a, ground_b, anchor_a, anchor_b, ratio)."""
+        d = abi.JointDef()
+        lib().b2o_pulley_joint_def(self.h, C.byref(d), _body_index(body_a), _body_index(body_b), ground_a[0], ground_a[1],
+                                   ground_b[0], ground_b[1], anchor_a[0], anchor_a[1], anchor_b[0], anchor_b[1], ratio)
+        return d
+
+    def mouse_joint_def(self, body_a, body_b, target):
+        """B2mouseJointDef::default() with `target`: set length (= max_force), stiffness, damping."""
+        d = abi.JointDef()
+        lib().b2o_mouse_joint_def(self.h, C.byref(d), _body_index(body_a), _body_index(body_b), target[0], target[1])
         return d
 
     def wheel_joint_def(self, body_a, body_b, anchor, axis):

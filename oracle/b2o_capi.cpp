@@ -153,6 +153,15 @@ static void joint_def_out(const JointDef& d, b2gpu_joint_def* o) {
     o->length = d.max_force; o->min_length = 0.0f; o->max_length = 0.0f;
     o->stiffness = d.type == J_MOTOR ? d.correction_factor : 0.0f;
   }
+  if (d.type == J_PULLEY) {  // b2gpu.h: ground anchors over (lower_angle, upper_angle) / (max_motor_torque, motor_speed)
+    o->lower_angle = d.ground_anchor_a.x; o->upper_angle = d.ground_anchor_a.y;
+    o->max_motor_torque = d.ground_anchor_b.x; o->motor_speed = d.ground_anchor_b.y;
+    o->length = d.length; o->min_length = d.length_b; o->max_length = d.ratio;
+  }
+  if (d.type == J_MOUSE) {  // b2gpu.h: local_anchor_a = target (world), length = max_force
+    o->local_anchor_a[0] = d.target.x; o->local_anchor_a[1] = d.target.y;
+    o->length = d.max_force; o->min_length = 0.0f; o->max_length = 0.0f;
+  }
   if (d.type == J_PRISMATIC || d.type == J_WHEEL) { o->length = d.local_axis_a.x; o->min_length = d.local_axis_a.y; o->max_length = 0.0f; }  // b2gpu.h: the def's overlay
 }
 int b2o_prismatic_joint_def(void* w, b2gpu_joint_def* def, int body_a, int body_b, float ax, float ay, float dx, float dy) {
@@ -169,6 +178,15 @@ int b2o_distance_joint_def(void* w, b2gpu_joint_def* def, int body_a, int body_b
 }
 int b2o_friction_joint_def(void* w, b2gpu_joint_def* def, int body_a, int body_b, float ax, float ay) {
   joint_def_out(((World*)w)->friction_joint_def(body_a, body_b, Vec2(ax, ay)), def);
+  return 0;
+}
+int b2o_pulley_joint_def(void* w, b2gpu_joint_def* def, int body_a, int body_b, float gax, float gay, float gbx, float gby,
+                         float ax, float ay, float bx, float by, float ratio) {
+  joint_def_out(((World*)w)->pulley_joint_def(body_a, body_b, Vec2(gax, gay), Vec2(gbx, gby), Vec2(ax, ay), Vec2(bx, by), ratio), def);
+  return 0;
+}
+int b2o_mouse_joint_def(void* w, b2gpu_joint_def* def, int body_a, int body_b, float tx, float ty) {
+  joint_def_out(((World*)w)->mouse_joint_def(body_a, body_b, Vec2(tx, ty)), def);
   return 0;
 }
 int b2o_motor_joint_def(void* w, b2gpu_joint_def* def, int body_a, int body_b) {
@@ -202,9 +220,15 @@ int b2o_create_joint(void* w, const b2gpu_joint_def* d) {
   jd.length = d->length; jd.min_length = d->min_length; jd.max_length = d->max_length; jd.stiffness = d->stiffness; jd.damping = d->damping;
   if (d->type == J_PRISMATIC || d->type == J_WHEEL) jd.local_axis_a = Vec2(d->length, d->min_length);
   if (d->type == J_FRICTION || d->type == J_MOTOR) { jd.max_force = d->length; jd.correction_factor = d->stiffness; }
+  if (d->type == J_PULLEY) {
+    jd.ground_anchor_a = Vec2(d->lower_angle, d->upper_angle); jd.ground_anchor_b = Vec2(d->max_motor_torque, d->motor_speed);
+    jd.length_b = d->min_length; jd.ratio = d->max_length;
+  }
+  if (d->type == J_MOUSE) { jd.target = jd.local_anchor_a; jd.max_force = d->length; }
   return ((World*)w)->create_joint(jd);
 }
 int b2o_joint_count(void* w) { return (int)((World*)w)->joints.size(); }
+void b2o_joint_set_target(void* w, int j, float x, float y) { ((World*)w)->joint_set_target(j, Vec2(x, y)); }
 void b2o_joint_set_motor_speed(void* w, int j, float v) { ((World*)w)->joint_set_motor_speed(j, v); }
 void b2o_joint_set_max_motor_torque(void* w, int j, float v) { ((World*)w)->joint_set_max_motor_torque(j, v); }
 void b2o_joint_enable_motor(void* w, int j, int f) { ((World*)w)->joint_enable_motor(j, f != 0); }
@@ -366,6 +390,14 @@ int b2o_snapshot_export(void* w, b2gpu_snapshot* out) {
       r.param[0] = j.max_force; r.param[1] = j.max_motor_torque;
       if (j.type == J_MOTOR) { r.param[2] = j.reference_angle; r.param[3] = j.correction_factor; }
       r.impulse[0] = j.impulse2.x; r.impulse[1] = j.impulse2.y; r.impulse[2] = j.motor_impulse;
+    } else if (j.type == J_PULLEY) {
+      r.param[0] = j.ground_anchor_a.x; r.param[1] = j.ground_anchor_a.y; r.param[2] = j.ground_anchor_b.x; r.param[3] = j.ground_anchor_b.y;
+      r.param[4] = j.length; r.param[5] = j.length_b; r.param[6] = j.ratio; r.param[7] = j.constant;
+      r.impulse[0] = j.impulse;
+    } else if (j.type == J_MOUSE) {
+      r.param[0] = j.max_force; r.param[1] = j.stiffness; r.param[2] = j.damping;
+      r.param[3] = j.ground_anchor_a.x; r.param[4] = j.ground_anchor_a.y;  // the target: per world, like the motor settings
+      r.impulse[0] = j.impulse2.x; r.impulse[1] = j.impulse2.y;
     } else if (j.type == J_WHEEL) {
       r.param[0] = j.stiffness; r.param[1] = j.lower_angle; r.param[2] = j.upper_angle;
       r.param[3] = j.max_motor_torque; r.param[4] = j.motor_speed;

@@ -93,7 +93,7 @@ struct Contact {
 
 // Joints: B2jointDef + B2revoluteJointDef / B2distanceJointDef as one plain struct
 // (src/b2_joint.rs:112-122, src/joints/b2_revolute_joint.rs:10-72, src/joints/b2_distance_joint.rs:11-58).
-enum JointType { J_DISTANCE = 1, J_FRICTION = 2, J_MOTOR = 4, J_PRISMATIC = 6, J_REVOLUTE = 8, J_WELD = 9, J_WHEEL = 10 };  // B2jointType numbering (src/b2_joint.rs:46-58)
+enum JointType { J_DISTANCE = 1, J_FRICTION = 2, J_MOTOR = 4, J_MOUSE = 5, J_PRISMATIC = 6, J_PULLEY = 7, J_REVOLUTE = 8, J_WELD = 9, J_WHEEL = 10 };  // B2jointType numbering (src/b2_joint.rs:46-58)
 struct JointDef {
   int type = 0, body_a = -1, body_b = -1;
   bool collide_connected = false;
@@ -107,6 +107,10 @@ struct JointDef {
   // friction (src/joints/b2_friction_joint.rs:9-50) / motor (src/joints/b2_motor_joint.rs:9-59): max_force, and for the motor
   // joint linear_offset (in local_anchor_a), angular_offset (in reference_angle), correction_factor; max_motor_torque = max_torque
   float max_force = 0.0f, correction_factor = 0.3f;
+  // pulley (src/joints/b2_pulley_joint.rs:10-78): ground anchors, rest lengths (length = length_a), ratio
+  // mouse (src/joints/b2_mouse_joint.rs:8-50): target (world point); max_force, stiffness, damping as named
+  Vec2 ground_anchor_a = Vec2(-1.0f, 1.0f), ground_anchor_b = Vec2(1.0f, 1.0f), target;
+  float length_b = 0.0f, ratio = 1.0f;
 };
 struct Joint {  // B2joint + B2revoluteJoint (src/joints/b2_revolute_joint.rs:104-136) / B2distanceJoint fields
   int type = 0, body_a = -1, body_b = -1;
@@ -133,6 +137,10 @@ struct Joint {  // B2joint + B2revoluteJoint (src/joints/b2_revolute_joint.rs:10
   // k = linear mass (inverse), axial_mass = angular mass
   float max_force = 0.0f, correction_factor = 0.0f, angular_error = 0.0f;
   Vec2 linear_error;
+  // pulley (private joints/b2_pulley_joint.rs:8-44): length = length_a; `constant` = length_a + ratio * length_b; u = u_a
+  // mouse (src/joints/b2_mouse_joint.rs:140-170): ground_anchor_a = target, impulse2, gamma, `beta`, linear_error = C, k = mass
+  Vec2 ground_anchor_a, ground_anchor_b, u_b;
+  float length_b = 0.0f, ratio = 1.0f, constant = 0.0f, beta = 0.0f;
   // weld (src/joints/b2_weld_joint.rs:66-90): impulse (x, y, angular), effective mass B2Mat33 as ex.xyz ey.xyz ez.xyz
   float impulse3[3] = {0.0f, 0.0f, 0.0f}, m33[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   // solver temp
@@ -488,6 +496,30 @@ struct World {
     d.max_force = 0.0f; d.max_motor_torque = 0.0f;
     return d;
   }
+  // B2pulleyJointDef::default + ::initialize (src/joints/b2_pulley_joint.rs:10-78): collide_connected defaults to true
+  JointDef pulley_joint_def(int body_a, int body_b, Vec2 ground_a, Vec2 ground_b, Vec2 anchor_a, Vec2 anchor_b, float r) const {
+    JointDef d;
+    d.type = J_PULLEY;
+    d.collide_connected = true;
+    d.body_a = body_a; d.body_b = body_b;
+    d.ground_anchor_a = ground_a; d.ground_anchor_b = ground_b;
+    d.local_anchor_a = b2_mul_t_xf(bodies[body_a].xf, anchor_a);
+    d.local_anchor_b = b2_mul_t_xf(bodies[body_b].xf, anchor_b);
+    d.length = (anchor_a - ground_a).length();
+    d.length_b = (anchor_b - ground_b).length();
+    d.ratio = r;
+    assert(r > EPSILON);
+    return d;
+  }
+  // B2mouseJointDef::default (src/joints/b2_mouse_joint.rs:8-21): target, max_force, stiffness, damping all zero
+  JointDef mouse_joint_def(int body_a, int body_b, Vec2 target) const {
+    JointDef d;
+    d.type = J_MOUSE;
+    d.body_a = body_a; d.body_b = body_b;
+    d.target = target;
+    d.length = 0.0f; d.min_length = 0.0f; d.max_length = 0.0f;
+    return d;
+  }
   // B2motorJointDef::default + ::initialize (src/joints/b2_motor_joint.rs:9-59)
   JointDef motor_joint_def(int body_a, int body_b) const {
     JointDef d;
@@ -567,6 +599,17 @@ struct World {
       j.enable_limit = def.enable_limit; j.enable_motor = def.enable_motor;
     } else if (def.type == J_FRICTION) {  // B2frictionJoint::new (src/joints/b2_friction_joint.rs:120-150)
       j.max_force = def.max_force; j.max_motor_torque = def.max_motor_torque;
+    } else if (def.type == J_PULLEY) {  // B2pulleyJoint::new (private joints/b2_pulley_joint.rs:8-44)
+      j.ground_anchor_a = def.ground_anchor_a; j.ground_anchor_b = def.ground_anchor_b;
+      j.length = def.length; j.length_b = def.length_b;
+      assert(def.ratio != 0.0f);
+      j.ratio = def.ratio;
+      j.constant = def.length + j.ratio * def.length_b;
+    } else if (def.type == J_MOUSE) {  // B2mouseJoint::new (src/joints/b2_mouse_joint.rs:140-170)
+      j.ground_anchor_a = def.target;
+      j.local_anchor_a.set_zero();  // unused: body A is only the island link
+      j.local_anchor_b = b2_mul_t_xf(bodies[def.body_b].xf, def.target);
+      j.max_force = def.max_force; j.stiffness = def.stiffness; j.damping = def.damping;
     } else if (def.type == J_MOTOR) {  // B2motorJoint::new (src/joints/b2_motor_joint.rs:175-205): local_anchor_a = linear offset
       j.reference_angle = def.reference_angle;
       j.max_force = def.max_force; j.max_motor_torque = def.max_motor_torque; j.correction_factor = def.correction_factor;
@@ -591,6 +634,11 @@ struct World {
       for (int e = bodies[def.body_b].contact_list; e != -1; e = edge(e).next)
         if (edge(e).other == def.body_a) contacts[e >> 1].flags |= CF_FILTER;
     return ji;  // creating a joint doesn't wake the bodies
+  }
+  // B2mouseJoint::set_target (src/joints/b2_mouse_joint.rs:114-119): wakes body B when the target moves
+  void joint_set_target(int ji, Vec2 t) {
+    Joint& j = joints[ji];
+    if (t.x != j.ground_anchor_a.x || t.y != j.ground_anchor_a.y) { set_awake(j.body_b, true); j.ground_anchor_a = t; }
   }
   // B2revoluteJoint setters (src/joints/b2_revolute_joint.rs:172-242)
   void joint_set_motor_speed(int ji, float speed) {
@@ -1256,6 +1304,49 @@ struct World {
         j.lower_impulse = 0.0f;
         j.upper_impulse = 0.0f;
       }
+    } else if (j.type == J_PULLEY) {  // private joints/b2_pulley_joint.rs:46-137
+      j.u = c_a + j.r_a - j.ground_anchor_a;
+      j.u_b = c_b + j.r_b - j.ground_anchor_b;
+      float length_a = j.u.length(), length_b = j.u_b.length();
+      if (length_a > 10.0f * LINEAR_SLOP) j.u *= 1.0f / length_a; else j.u.set_zero();
+      if (length_b > 10.0f * LINEAR_SLOP) j.u_b *= 1.0f / length_b; else j.u_b.set_zero();
+      float ru_a = b2_cross(j.r_a, j.u), ru_b = b2_cross(j.r_b, j.u_b);
+      float m_a = j.inv_mass_a + j.inv_ia * ru_a * ru_a;
+      float m_b = j.inv_mass_b + j.inv_ib * ru_b * ru_b;
+      j.mass = m_a + j.ratio * j.ratio * m_b;
+      if (j.mass > 0.0f) j.mass = 1.0f / j.mass;
+      if (step.warm_starting) {
+        j.impulse *= step.dt_ratio;
+        Vec2 pa = -(j.impulse) * j.u;
+        Vec2 pb = (-j.ratio * j.impulse) * j.u_b;
+        v_a += j.inv_mass_a * pa;
+        w_a += j.inv_ia * b2_cross(j.r_a, pa);
+        v_b += j.inv_mass_b * pb;
+        w_b += j.inv_ib * b2_cross(j.r_b, pb);
+      } else {
+        j.impulse = 0.0f;
+      }
+    } else if (j.type == J_MOUSE) {  // private joints/b2_mouse_joint.rs:7-67: body A is not read or written
+      float d = j.damping, k = j.stiffness, h = step.dt;
+      j.gamma = h * (d + h * k);
+      if (j.gamma != 0.0f) j.gamma = 1.0f / j.gamma;
+      j.beta = h * k * j.gamma;
+      Mat22 km;
+      km.ex.x = j.inv_mass_b + j.inv_ib * j.r_b.y * j.r_b.y + j.gamma;
+      km.ex.y = -j.inv_ib * j.r_b.x * j.r_b.y;
+      km.ey.x = km.ex.y;
+      km.ey.y = j.inv_mass_b + j.inv_ib * j.r_b.x * j.r_b.x + j.gamma;
+      j.k = km.get_inverse();
+      j.linear_error = c_b + j.r_b - j.ground_anchor_a;
+      j.linear_error *= j.beta;
+      w_b *= 0.98f;
+      if (step.warm_starting) {
+        j.impulse2 *= step.dt_ratio;
+        v_b += j.inv_mass_b * j.impulse2;
+        w_b += j.inv_ib * b2_cross(j.r_b, j.impulse2);
+      } else {
+        j.impulse2.set_zero();
+      }
     } else if (j.type == J_FRICTION || j.type == J_MOTOR) {
       // private joints/b2_friction_joint.rs:8-72, b2_motor_joint.rs:8-96: the same rows; the motor joint measures from body
       // B's origin to the linear offset on body A and carries position errors
@@ -1548,6 +1639,29 @@ struct World {
         v_b += m_b * p;
         w_b += i_b * lb;
       }
+    } else if (j.type == J_PULLEY) {  // private joints/b2_pulley_joint.rs:139-170
+      Vec2 vp_a = v_a + b2_cross_sv(w_a, j.r_a);
+      Vec2 vp_b = v_b + b2_cross_sv(w_b, j.r_b);
+      float cdot = -b2_dot(j.u, vp_a) - j.ratio * b2_dot(j.u_b, vp_b);
+      float impulse = -j.mass * cdot;
+      j.impulse += impulse;
+      Vec2 pa = -impulse * j.u;
+      Vec2 pb = -j.ratio * impulse * j.u_b;
+      v_a += j.inv_mass_a * pa;
+      w_a += j.inv_ia * b2_cross(j.r_a, pa);
+      v_b += j.inv_mass_b * pb;
+      w_b += j.inv_ib * b2_cross(j.r_b, pb);
+    } else if (j.type == J_MOUSE) {  // private joints/b2_mouse_joint.rs:69-92
+      Vec2 cdot = v_b + b2_cross_sv(w_b, j.r_b);
+      Vec2 t = -(cdot + j.linear_error + j.gamma * j.impulse2);
+      Vec2 impulse(j.k.ex.x * t.x + j.k.ey.x * t.y, j.k.ex.y * t.x + j.k.ey.y * t.y);  // b2_mul(Mat22, v)
+      Vec2 old_impulse = j.impulse2;
+      j.impulse2 += impulse;
+      float max_impulse = step.dt * j.max_force;
+      if (j.impulse2.length_squared() > max_impulse * max_impulse) j.impulse2 *= max_impulse / j.impulse2.length();
+      impulse = j.impulse2 - old_impulse;
+      v_b += j.inv_mass_b * impulse;
+      w_b += j.inv_ib * b2_cross(j.r_b, impulse);
     } else if (j.type == J_FRICTION || j.type == J_MOTOR) {  // b2_friction_joint.rs:74-128, b2_motor_joint.rs:98-160
       float m_a = j.inv_mass_a, m_b = j.inv_mass_b, i_a = j.inv_ia, i_b = j.inv_ib;
       float h = step.dt, inv_h = step.inv_dt;
@@ -1848,8 +1962,32 @@ struct World {
       c_b += m_b * p;
       a_b += i_b * lb;
       okay = linear_error <= LINEAR_SLOP && angular_error <= ANGULAR_SLOP;
-    } else if (j.type == J_FRICTION || j.type == J_MOTOR) {  // no position rows: always within tolerance
+    } else if (j.type == J_FRICTION || j.type == J_MOTOR || j.type == J_MOUSE) {  // no position rows: always within tolerance
       return true;
+    } else if (j.type == J_PULLEY) {  // private joints/b2_pulley_joint.rs:172-240
+      Rot q_a(a_a), q_b(a_b);
+      Vec2 r_a = b2_mul_rot(q_a, j.local_anchor_a - j.local_center_a);
+      Vec2 r_b = b2_mul_rot(q_b, j.local_anchor_b - j.local_center_b);
+      Vec2 u_a = c_a + r_a - j.ground_anchor_a;
+      Vec2 u_b = c_b + r_b - j.ground_anchor_b;
+      float length_a = u_a.length(), length_b = u_b.length();
+      if (length_a > 10.0f * LINEAR_SLOP) u_a *= 1.0f / length_a; else u_a.set_zero();
+      if (length_b > 10.0f * LINEAR_SLOP) u_b *= 1.0f / length_b; else u_b.set_zero();
+      float ru_a = b2_cross(r_a, u_a), ru_b = b2_cross(r_b, u_b);
+      float m_a = j.inv_mass_a + j.inv_ia * ru_a * ru_a;
+      float m_b = j.inv_mass_b + j.inv_ib * ru_b * ru_b;
+      float mass = m_a + j.ratio * j.ratio * m_b;
+      if (mass > 0.0f) mass = 1.0f / mass;
+      float c = j.constant - length_a - j.ratio * length_b;
+      float linear_error = fabsf(c);
+      float impulse = -mass * c;
+      Vec2 pa = -impulse * u_a;
+      Vec2 pb = -j.ratio * impulse * u_b;
+      c_a += j.inv_mass_a * pa;
+      a_a += j.inv_ia * b2_cross(r_a, pa);
+      c_b += j.inv_mass_b * pb;
+      a_b += j.inv_ib * b2_cross(r_b, pb);
+      okay = linear_error < LINEAR_SLOP;
     } else if (j.type == J_WHEEL) {  // private joints/b2_wheel_joint.rs:284-380
       float linear_error = 0.0f;
       if (j.enable_limit) {

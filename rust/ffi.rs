@@ -189,6 +189,12 @@ extern "C" {
     pub fn b2gpu_prismatic_joint_def(w: *mut b2gpu_world, def: *mut b2gpu_joint_def, body_a: c_int, body_b: c_int, anchor_x: c_float, anchor_y: c_float, axis_x: c_float, axis_y: c_float) -> c_int;
     pub fn b2gpu_friction_joint_def(w: *mut b2gpu_world, def: *mut b2gpu_joint_def, body_a: c_int, body_b: c_int, anchor_x: c_float, anchor_y: c_float) -> c_int;
     pub fn b2gpu_motor_joint_def(w: *mut b2gpu_world, def: *mut b2gpu_joint_def, body_a: c_int, body_b: c_int) -> c_int;
+    pub fn b2gpu_pulley_joint_def(w: *mut b2gpu_world, def: *mut b2gpu_joint_def, body_a: c_int, body_b: c_int,
+                                  ground_ax: c_float, ground_ay: c_float, ground_bx: c_float, ground_by: c_float,
+                                  anchor_ax: c_float, anchor_ay: c_float, anchor_bx: c_float, anchor_by: c_float,
+                                  ratio: c_float) -> c_int;
+    pub fn b2gpu_mouse_joint_def(w: *mut b2gpu_world, def: *mut b2gpu_joint_def, body_a: c_int, body_b: c_int,
+                                 target_x: c_float, target_y: c_float) -> c_int;
     pub fn b2gpu_wheel_joint_def(w: *mut b2gpu_world, def: *mut b2gpu_joint_def, body_a: c_int, body_b: c_int, anchor_x: c_float, anchor_y: c_float, axis_x: c_float, axis_y: c_float) -> c_int;
     pub fn b2gpu_weld_joint_def(w: *mut b2gpu_world, def: *mut b2gpu_joint_def, body_a: c_int, body_b: c_int, anchor_x: c_float, anchor_y: c_float) -> c_int;
     pub fn b2gpu_angular_stiffness(w: *mut b2gpu_world, frequency_hertz: c_float, damping_ratio: c_float, body_a: c_int, body_b: c_int, stiffness: *mut c_float, damping: *mut c_float) -> c_int;
@@ -201,6 +207,7 @@ extern "C" {
     pub fn b2gpu_joint_enable_motor(w: *mut b2gpu_world, joint: c_int, flag: c_int) -> c_int;
     pub fn b2gpu_joint_enable_limit(w: *mut b2gpu_world, joint: c_int, flag: c_int) -> c_int;
     pub fn b2gpu_joint_set_limits(w: *mut b2gpu_world, joint: c_int, lower: c_float, upper: c_float) -> c_int;
+    pub fn b2gpu_joint_set_target(w: *mut b2gpu_world, joint: c_int, target_x: c_float, target_y: c_float) -> c_int;
     pub fn b2gpu_world_set_allow_sleeping(w: *mut b2gpu_world, flag: c_int) -> c_int;
     pub fn b2gpu_world_set_warm_starting(w: *mut b2gpu_world, flag: c_int) -> c_int;
     pub fn b2gpu_world_set_continuous_physics(w: *mut b2gpu_world, flag: c_int) -> c_int;

@@ -196,7 +196,7 @@ pub fn flatten<D: UserDataType>(world: &B2world<D>) -> Snapshot<D> {
         }
     }).collect();
 
-    // ---- joints (world list reversed); only revolute and distance joints are inside the accelerated path
+    // ---- joints (world list reversed); every type but the gear joint is inside the accelerated path
     let mut joint_ptrs: Vec<B2jointPtr<D>> = world.m_joint_list.iter().collect();
     joint_ptrs.reverse();
     let joints: Vec<b2gpu_joint_rec> = joint_ptrs.iter().map(|j| {
@@ -251,6 +251,22 @@ pub fn flatten<D: UserDataType>(world: &B2world<D>) -> Snapshot<D> {
                 r.param[0] = v.m_max_force; r.param[1] = v.m_max_torque;
                 r.param[2] = v.m_angular_offset; r.param[3] = v.m_correction_factor;
                 r.impulse[0] = v.m_linear_impulse.x; r.impulse[1] = v.m_linear_impulse.y; r.impulse[2] = v.m_angular_impulse;
+            }
+            JointAsDerived::EPulleyJoint(v) => {
+                r.type_ = 7;
+                r.local_anchor_a = [v.m_local_anchor_a.x, v.m_local_anchor_a.y];
+                r.local_anchor_b = [v.m_local_anchor_b.x, v.m_local_anchor_b.y];
+                r.param[0] = v.m_ground_anchor_a.x; r.param[1] = v.m_ground_anchor_a.y;
+                r.param[2] = v.m_ground_anchor_b.x; r.param[3] = v.m_ground_anchor_b.y;
+                r.param[4] = v.m_length_a; r.param[5] = v.m_length_b; r.param[6] = v.m_ratio; r.param[7] = v.m_constant;
+                r.impulse[0] = v.m_impulse;
+            }
+            JointAsDerived::EMouseJoint(v) => {
+                r.type_ = 5;
+                r.local_anchor_b = [v.m_local_anchor_b.x, v.m_local_anchor_b.y];
+                r.param[0] = v.m_max_force; r.param[1] = v.m_stiffness; r.param[2] = v.m_damping;
+                r.param[3] = v.m_target_a.x; r.param[4] = v.m_target_a.y;
+                r.impulse[0] = v.m_impulse.x; r.impulse[1] = v.m_impulse.y;
             }
             JointAsDerived::EWheelJoint(v) => {
                 r.type_ = 10;
@@ -495,6 +511,12 @@ pub fn write_back<D: UserDataType>(world: &mut B2world<D>, snap: &Snapshot<D>) {
             JointAsDerivedMut::EMotorJoint(v) => {
                 v.m_linear_impulse.set(r.impulse[0], r.impulse[1]);
                 v.m_angular_impulse = r.impulse[2];
+            }
+            JointAsDerivedMut::EPulleyJoint(v) => {
+                v.m_impulse = r.impulse[0];
+            }
+            JointAsDerivedMut::EMouseJoint(v) => {
+                v.m_impulse.set(r.impulse[0], r.impulse[1]);
             }
             JointAsDerivedMut::EWheelJoint(v) => {
                 v.m_impulse = r.impulse[0];

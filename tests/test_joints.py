@@ -284,6 +284,84 @@ def test_oracle_motor_joint_drives_to_its_offsets(built):
     assert math.hypot(b["v"][0], b["v"][1]) < 1e-3
 
 
+def test_oracle_pulley_joint_keeps_length_a_plus_ratio_length_b(built):
+    """examples/testbed/tests/pulley_joint.rs: equal boxes on a ratio-1.5 pulley.  length_a + ratio * length_b stays at its
+    initial value (12 + 1.5 * 12 = 30) within the position solver's slop while the side with the mechanical advantage (B: its
+    rope carries ratio x the tension) rises."""
+    from box2d_rs_b200 import abi, scenes
+    from box2d_rs_b200.abi import BodyDef
+    from oracle import b2o
+    w = b2o.B2world((0.0, -10.0))
+    ground = w.create_body(BodyDef())
+    shape = w.shapes.polygon_box(1.0, 2.0)
+    b1 = w.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(-10.0, 16.0), allow_sleep=0))
+    b1.create_fixture_by_shape(shape, 5.0)
+    b2 = w.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(10.0, 16.0), allow_sleep=0))
+    b2.create_fixture_by_shape(shape, 5.0)
+    jd = w.pulley_joint_def(b1, b2, (-10.0, 30.0), (10.0, 30.0), (-10.0, 18.0), (10.0, 18.0), 1.5)
+    assert jd.collide_connected == 1 and abs(jd.length - 12.0) < 1e-6 and abs(jd.min_length - 12.0) < 1e-6 and jd.max_length == 1.5
+    assert (jd.lower_angle, jd.upper_angle, jd.max_motor_torque, jd.motor_speed) == (-10.0, 30.0, 10.0, 30.0)  # ground anchors
+    w.create_joint(jd)
+    for i in range(60):
+        w.step(scenes.DT, 8, 3)
+        ba, bb = w.snapshot().bodies[1], w.snapshot().bodies[2]
+        la = math.hypot(ba["c"][0] + 10.0, ba["c"][1] + 2.0 - 30.0)  # anchors stay above the centres: the boxes do not turn
+        lb = math.hypot(bb["c"][0] - 10.0, bb["c"][1] + 2.0 - 30.0)
+        assert abs(la + 1.5 * lb - 30.0) < 0.02
+    assert ba["c"][1] < 15.0 and bb["c"][1] > 16.5 and abs(ba["a"]) < 1e-4
+    # accelerations: T from m a1 = m g - T, m a2 = 1.5 T - m g, a1 = 1.5 a2  ->  a2 = g / 6.5: after 1 s body B rose ~0.77
+    assert abs((bb["c"][1] - 16.0) - 0.5 * 10.0 / 6.5) < 0.05
+    assert w.snapshot().joints[0]["impulse"][0] > 0.0  # rope in tension
+
+
+def test_oracle_mouse_joint_drags_the_body_to_its_target(built):
+    """examples/testbed/test.rs:230-262 (mouse_down / mouse_move): a soft constraint pulls the grabbed point to the target;
+    set_target wakes body B; the force never exceeds max_force."""
+    from box2d_rs_b200 import abi, scenes
+    from box2d_rs_b200.abi import BodyDef
+    from oracle import b2o
+    w = b2o.B2world((0.0, -10.0))
+    ground = w.create_body(BodyDef())
+    ground.create_fixture_by_shape(w.shapes.edge_two_sided((-40.0, 0.0), (40.0, 0.0)), 0.0)
+    box = w.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(0.0, 0.5)))
+    box.create_fixture_by_shape(w.shapes.polygon_box(0.5, 0.5), 1.0)
+    for i in range(120):
+        w.step(scenes.DT, 8, 3)
+    assert not w.snapshot().bodies[1]["flags"] & abi.BODY_AWAKE  # asleep on the floor
+    jd = w.mouse_joint_def(ground, box, (0.0, 0.5))
+    assert (jd.local_anchor_a[0], jd.local_anchor_a[1], jd.length) == (0.0, 0.5, 0.0)
+    jd.length = 1000.0  # max_force = 1000 * mass
+    jd.stiffness, jd.damping = w.linear_stiffness(5.0, 0.7, ground, box)
+    mouse = w.create_joint(jd)
+    rec = w.snapshot().joints[0]
+    assert abs(rec["local_anchor_b"][0]) < 1e-6 and abs(rec["local_anchor_b"][1]) < 0.02  # the grabbed point, body-local
+    assert not w.snapshot().bodies[1]["flags"] & abi.BODY_AWAKE  # creating the joint doesn't wake
+    mouse.set_target((0.0, 0.5))                                 # unchanged target: still asleep
+    assert not w.snapshot().bodies[1]["flags"] & abi.BODY_AWAKE
+    mouse.set_target((3.0, 4.0))
+    assert w.snapshot().bodies[1]["flags"] & abi.BODY_AWAKE
+    peak = 0.0
+    for i in range(180):
+        w.step(scenes.DT, 8, 3)
+        imp = w.snapshot().joints[0]["impulse"]
+        peak = max(peak, math.hypot(imp[0], imp[1]) * 60.0)
+    b = w.snapshot().bodies[1]
+    assert abs(b["c"][0] - 3.0) < 0.02 and 3.9 < b["c"][1] < 4.0 + 0.01  # hangs a little below: m g / k
+    assert peak <= 1000.0 + 1e-3
+    jd.length = 5.0  # weaker than the weight (10): cannot lift the box
+    w2 = b2o.B2world((0.0, -10.0))
+    g2 = w2.create_body(BodyDef())
+    g2.create_fixture_by_shape(w2.shapes.edge_two_sided((-40.0, 0.0), (40.0, 0.0)), 0.0)
+    box2 = w2.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(0.0, 0.5)))
+    box2.create_fixture_by_shape(w2.shapes.polygon_box(0.5, 0.5), 1.0)
+    w2.create_joint(jd).set_target((0.0, 6.0))
+    for i in range(120):
+        w2.step(scenes.DT, 8, 3)
+        imp = w2.snapshot().joints[0]["impulse"]
+        assert math.hypot(imp[0], imp[1]) * 60.0 <= 5.0 + 1e-4
+    assert w2.snapshot().bodies[1]["c"][1] < 0.6
+
+
 def test_oracle_angular_stiffness_formula(built):
     """b2_angular_stiffness (private b2_joint.rs:47-70): I = Ia Ib / (Ia + Ib) of B2body::get_inertia, omega = 2 pi f."""
     from box2d_rs_b200 import abi
@@ -333,11 +411,18 @@ def test_weld_defs_and_unsupported_types(built):
     assert bytes(qo) == bytes(qg)
     assert bytes(wo.friction_joint_def(wo.body(0), wo.body(1), (1.3, 1.2))) == bytes(wg.friction_joint_def(wg.body(0), wg.body(1), (1.3, 1.2)))
     assert bytes(wo.motor_joint_def(wo.body(0), wo.body(1))) == bytes(wg.motor_joint_def(wg.body(0), wg.body(1)))
+    args = (wo.body(0), wo.body(1), (0.5, 6.0), (2.5, 7.0), (0.4, 1.7), (2.1, 1.2), 2.5)
+    argsg = (wg.body(0), wg.body(1)) + args[2:]
+    assert bytes(wo.pulley_joint_def(*args)) == bytes(wg.pulley_joint_def(*argsg))
+    assert bytes(wo.mouse_joint_def(wo.body(0), wo.body(1), (2.2, 1.1))) == bytes(wg.mouse_joint_def(wg.body(0), wg.body(1), (2.2, 1.1)))
+    with pytest.raises(B2gpuError) as e:  # ratio <= epsilon: the reference asserts
+        wg.pulley_joint_def(*(argsg[:-1] + (0.0,)))
+    assert e.value.code == abi.E_INVALID
     pg.lower_angle, pg.upper_angle = 1.0, 0.5  # lower > upper: the reference asserts
     with pytest.raises(B2gpuError) as e:
         wg.create_joint(pg)
     assert e.value.code == abi.E_INVALID
-    jg.type = 7  # pulley (gear and mouse joints likewise)
+    jg.type = 3  # gear: the one joint type outside the path
     with pytest.raises(B2gpuError) as e:
         wg.create_joint(jg)
     assert e.value.code == abi.E_UNSUPPORTED
@@ -384,6 +469,9 @@ def _free_running(name, ctx, every):
                     m.enable_motor(False)
                     m.enable_limit(True)
                     m.set_limits(-0.5, 0.5)
+        if name == "pulleys" and i in (100, 200):  # the drag moves on (B2mouseJoint::set_target)
+            for m in (ro, rg):
+                m.set_target((-26.0, 5.0) if i == 100 else (-34.0, 12.0))
         wo.step(scenes.DT, 8, 3)
         wg.step(scenes.DT, 8, 3)
         if i < 3 or i % every == every - 1 or i == steps - 1:
@@ -525,7 +613,7 @@ def test_validate_rejects_bad_joint_records(built):
         s.joints[3]["body_b"] = s.joints[3]["body_a"]
 
     def unknown_type(s):
-        s.joints[0]["type"] = 5
+        s.joints[0]["type"] = 3  # gear
     broken(body_out_of_range)
     broken(same_body)
     broken(unknown_type)

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Differential fuzzing of the device stages (host simulator build by default, --gpu for the CUDA path) against
 the CPU oracle: random scenes (polygons of 3..8 vertices, circles, edges, chains, kinematic / fixed-rotation /
-multi-fixture bodies, sensors, filters, restitution, damping, revolute / prismatic / wheel / distance / weld / friction / motor joints with limits, motors and springs,
+multi-fixture bodies, sensors, filters, restitution, damping, revolute / prismatic / wheel / distance / weld / friction / motor / pulley / mouse joints with limits, motors and springs,
 random world flags and iteration counts, dt = 0 steps,
 mid-run set_transform / set_linear_velocity / apply_force / apply_torque / apply_*_impulse / set_awake edits), stepped freely and compared bit for bit.
 
@@ -89,7 +89,7 @@ def build(world, rng):
                 ang = np.sort(rng.uniform(0, 2 * math.pi, nv))
                 shape = world.shapes.polygon([(f32(rad * math.cos(a)), f32(rad * math.sin(a) * rng.uniform(0.5, 1.0))) for a in ang])
             b.create_fixture(fd, shape)
-    # joints (revolute / prismatic / wheel / distance / weld / friction / motor) between random bodies, the ground included: limits, motors, soft springs, slack ranges,
+    # joints (every type but gear) between random bodies, the ground included: limits, motors, soft springs, slack ranges,
     # collide_connected, degenerate pairs (kinematic or fixed-rotation bodies, anchors far from the bodies)
     joints = []
     if rng.integers(0, 5) < 3:
@@ -97,8 +97,19 @@ def build(world, rng):
             a, b = int(rng.integers(0, n + 1)), int(rng.integers(0, n + 1))
             if a == b:
                 continue
-            kind = int(rng.integers(0, 7))
-            if kind == 6:  # motor joint: target pose, force / torque caps, correction factor
+            kind = int(rng.integers(0, 9))
+            if kind == 8:  # mouse joint: soft drag to a world target (sometimes rigid: stiffness 0 -> gamma 0), weak or strong
+                jd = world.mouse_joint_def(a, b, (f32(rng.uniform(-10, 10)), f32(rng.uniform(0.5, 14))))
+                jd.length = f32(rng.uniform(0, 400))
+                if rng.integers(0, 4):
+                    jd.stiffness, jd.damping = f32(rng.uniform(0, 200)), f32(rng.uniform(0, 20))
+            elif kind == 7:  # pulley: random anchors and ground anchors (sometimes on top of each other), ratios around 1
+                pa, pb = (f32(rng.uniform(-10, 10)), f32(rng.uniform(0.5, 10))), (f32(rng.uniform(-10, 10)), f32(rng.uniform(0.5, 10)))
+                ga = pa if rng.integers(0, 6) == 0 else (f32(pa[0] + rng.uniform(-2, 2)), f32(pa[1] + rng.uniform(0, 8)))
+                gb = (f32(pb[0] + rng.uniform(-2, 2)), f32(pb[1] + rng.uniform(0, 8)))
+                jd = world.pulley_joint_def(a, b, ga, gb, pa, pb, f32(rng.uniform(0.3, 3.0)))
+                jd.collide_connected = int(rng.integers(0, 2))
+            elif kind == 6:  # motor joint: target pose, force / torque caps, correction factor
                 jd = world.motor_joint_def(a, b)
                 jd.local_anchor_a[0] = f32(jd.local_anchor_a[0] + rng.uniform(-2, 2))
                 jd.local_anchor_a[1] = f32(jd.local_anchor_a[1] + rng.uniform(-2, 2))
@@ -216,6 +227,10 @@ def run_seed(seed, make_world, steps, batch_mode, large=False, events=False, lev
             wo.body(b).set_linear_velocity(v); wg.body(b).set_linear_velocity(v)
         if batch is None and ev == 8 and wo._fuzz_joints:  # B2revoluteJoint setters mid-run
             q = int(rng.integers(0, len(wo._fuzz_joints)))
+            if wo._fuzz_joints[q][1] == abi.JOINT_MOUSE:  # B2mouseJoint::set_target
+                tgt = (f32v(rng.uniform(-10, 10)), f32v(rng.uniform(0.5, 14)))
+                for w in (wo, wg):
+                    w._fuzz_joints[q][0].set_target(tgt)
             if wo._fuzz_joints[q][1] in (abi.JOINT_REVOLUTE, abi.JOINT_PRISMATIC, abi.JOINT_WHEEL):
                 op, val, flag = int(rng.integers(0, 5)), f32v(rng.uniform(-3, 3)), bool(rng.integers(0, 2))
                 for w in (wo, wg):
