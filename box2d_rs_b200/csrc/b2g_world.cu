@@ -1082,6 +1082,26 @@ static int check_joint(b2gpu_world* W, int joint, int type) {
   }
   return 0;
 }
+int b2gpu_world_destroy_joint(b2gpu_world* W, int joint) {  // b2_world.rs(private):278-339
+  GUARD_BEGIN
+  int rc = check_joint(W, joint, 0);
+  if (!rc) rc = ensure_host(W);
+  if (rc) return rc;
+  HostWorld& h = W->h;
+  const b2gpu_joint_rec j = h.joints[joint];
+  set_awake(h.bodies[j.body_a], true);
+  set_awake(h.bodies[j.body_b], true);
+  h.joints.erase(h.joints.begin() + joint);
+  if (!(j.flags & B2GPU_JOINT_COLLIDE_CONNECTED)) {
+    for (b2gpu_contact_rec& c : h.contacts) {
+      const int ba = h.fixtures[c.fixture_a].body, bb = h.fixtures[c.fixture_b].body;
+      if ((ba == j.body_a && bb == j.body_b) || (ba == j.body_b && bb == j.body_a)) c.flags |= B2GPU_CONTACT_FILTER;
+    }
+  }
+  W->host_dirty = W->topo_dirty = true;
+  return 0;
+  GUARD_END
+}
 int b2gpu_world_get_joint(b2gpu_world* W, int joint, b2gpu_joint_rec* out) {
   GUARD_BEGIN
   int rc = check_joint(W, joint, 0);

@@ -161,6 +161,7 @@ class B2world:
         self.shapes = Shapes(self.L)
         self.h = C.c_void_p()
         check(self.L, self.L.b2gpu_world_create(self.ctx.h, gravity[0], gravity[1], C.byref(self.h)))
+        self._joint_handles = []
 
     def close(self):
         if self.h:
@@ -255,8 +256,21 @@ class B2world:
         return k.value, d.value
 
     def create_joint(self, joint_def):
-        """B2world::create_joint (revolute, prismatic, wheel, distance, weld, friction and motor joints)."""
-        return B2joint(self, check(self.L, self.L.b2gpu_world_create_joint(self.h, C.byref(joint_def))))
+        """B2world::create_joint (every joint type but gear)."""
+        j = B2joint(self, check(self.L, self.L.b2gpu_world_create_joint(self.h, C.byref(joint_def))))
+        self._joint_handles.append(j)
+        return j
+
+    def destroy_joint(self, joint):
+        """B2world::destroy_joint (src/private/dynamics/b2_world.rs:278-339): wakes both bodies; joints created later move
+        down one index (handles made by create_joint follow)."""
+        i = joint.index
+        check(self.L, self.L.b2gpu_world_destroy_joint(self.h, i))
+        self._joint_handles = [h for h in self._joint_handles if h is not joint]
+        joint.index = -1
+        for h in self._joint_handles:
+            if h.index > i:
+                h.index -= 1
 
     def joint(self, index):
         return B2joint(self, index)

@@ -437,6 +437,10 @@ int b2gpu_linear_stiffness(b2gpu_world* w, float frequency_hertz, float damping_
  * the two bodies are flagged for filtering when collide_connected is false.  Does not wake the bodies.
  * The gear joint (it wraps two other joints) is the one type outside the path: B2GPU_E_UNSUPPORTED. */
 int b2gpu_world_create_joint(b2gpu_world* w, const b2gpu_joint_def* def);
+/* B2world::destroy_joint (src/private/dynamics/b2_world.rs:278-339): wakes both bodies, removes the joint (the order of the
+ * others is kept) and, when it had collide_connected == false, flags the contacts between its bodies for filtering so that
+ * they may start to collide.  Joints created after it move down by one index. */
+int b2gpu_world_destroy_joint(b2gpu_world* w, int joint);
 int b2gpu_world_get_joint_count(b2gpu_world* w);
 int b2gpu_world_get_joint(b2gpu_world* w, int joint, b2gpu_joint_rec* out);
 /* B2revoluteJoint::set_motor_speed / set_max_motor_torque / enable_motor / enable_limit / set_limits

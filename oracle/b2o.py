@@ -71,6 +71,7 @@ def lib():
                                            C.POINTER(C.c_float)]
         L.b2o_create_joint.argtypes = [C.c_void_p, C.POINTER(abi.JointDef)]
         L.b2o_joint_count.argtypes = [C.c_void_p]
+        L.b2o_destroy_joint.argtypes = [C.c_void_p, C.c_int]
         L.b2o_joint_set_motor_speed.argtypes = [C.c_void_p, C.c_int, C.c_float]
         L.b2o_joint_set_max_motor_torque.argtypes = [C.c_void_p, C.c_int, C.c_float]
         L.b2o_joint_enable_motor.argtypes = [C.c_void_p, C.c_int, C.c_int]
@@ -229,6 +230,7 @@ class B2world:
 
     def __init__(self, gravity, _handle=None):
         self.h = C.c_void_p(_handle if _handle is not None else lib().b2o_world_create(gravity[0], gravity[1]))
+        self._joint_handles = []
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -317,7 +319,19 @@ class B2world:
         return k.value, d.value
 
     def create_joint(self, joint_def):
-        return B2joint(self, lib().b2o_create_joint(self.h, C.byref(joint_def)))
+        j = B2joint(self, lib().b2o_create_joint(self.h, C.byref(joint_def)))
+        self._joint_handles.append(j)
+        return j
+
+    def destroy_joint(self, joint):
+        """B2world::destroy_joint: later joints move down one index (live handles follow)."""
+        i = joint.index
+        lib().b2o_destroy_joint(self.h, i)
+        self._joint_handles = [h for h in self._joint_handles if h is not joint]
+        joint.index = -1
+        for h in self._joint_handles:
+            if h.index > i:
+                h.index -= 1
 
     def joint(self, index):
         return B2joint(self, index)

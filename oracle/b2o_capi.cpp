@@ -227,6 +227,7 @@ int b2o_create_joint(void* w, const b2gpu_joint_def* d) {
   if (d->type == J_MOUSE) { jd.target = jd.local_anchor_a; jd.max_force = d->length; }
   return ((World*)w)->create_joint(jd);
 }
+void b2o_destroy_joint(void* w, int j) { ((World*)w)->destroy_joint(j); }
 int b2o_joint_count(void* w) { return (int)((World*)w)->joints.size(); }
 void b2o_joint_set_target(void* w, int j, float x, float y) { ((World*)w)->joint_set_target(j, Vec2(x, y)); }
 void b2o_joint_set_motor_speed(void* w, int j, float v) { ((World*)w)->joint_set_motor_speed(j, v); }

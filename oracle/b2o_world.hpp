@@ -635,6 +635,27 @@ struct World {
         if (edge(e).other == def.body_a) contacts[e >> 1].flags |= CF_FILTER;
     return ji;  // creating a joint doesn't wake the bodies
   }
+  // B2world::destroy_joint (src/private/dynamics/b2_world.rs:278-339): both bodies wake, the joint leaves the world list and
+  // the two body lists (the order of the others is kept), contacts between the bodies are re-filtered when the joint had
+  // collide_connected == false.  Joints created after it move down by one index.
+  void destroy_joint(int ji) {
+    const Joint j = joints[ji];
+    set_awake(j.body_a, true);
+    set_awake(j.body_b, true);
+    joints.erase(joints.begin() + ji);
+    for (Body& b : bodies) {
+      std::vector<int>& je = b.joint_edges;
+      size_t o = 0;
+      for (size_t i = 0; i < je.size(); ++i) {
+        if ((je[i] >> 1) == ji) continue;
+        je[o++] = (je[i] >> 1) > ji ? je[i] - 2 : je[i];
+      }
+      je.resize(o);
+    }
+    if (!j.collide_connected)
+      for (int e = bodies[j.body_b].contact_list; e != -1; e = edge(e).next)
+        if (edge(e).other == j.body_a) contacts[e >> 1].flags |= CF_FILTER;
+  }
   // B2mouseJoint::set_target (src/joints/b2_mouse_joint.rs:114-119): wakes body B when the target moves
   void joint_set_target(int ji, Vec2 t) {
     Joint& j = joints[ji];

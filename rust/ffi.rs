@@ -207,6 +207,7 @@ extern "C" {
     pub fn b2gpu_joint_enable_motor(w: *mut b2gpu_world, joint: c_int, flag: c_int) -> c_int;
     pub fn b2gpu_joint_enable_limit(w: *mut b2gpu_world, joint: c_int, flag: c_int) -> c_int;
     pub fn b2gpu_joint_set_limits(w: *mut b2gpu_world, joint: c_int, lower: c_float, upper: c_float) -> c_int;
+    pub fn b2gpu_world_destroy_joint(w: *mut b2gpu_world, joint: c_int) -> c_int;
     pub fn b2gpu_joint_set_target(w: *mut b2gpu_world, joint: c_int, target_x: c_float, target_y: c_float) -> c_int;
     pub fn b2gpu_world_set_allow_sleeping(w: *mut b2gpu_world, flag: c_int) -> c_int;
     pub fn b2gpu_world_set_warm_starting(w: *mut b2gpu_world, flag: c_int) -> c_int;

@@ -536,6 +536,68 @@ def test_hostsim_teacher_forced(name, hctx):
     _teacher_forced(name, hctx)
 
 
+def _destroy_joints(ctx):
+    """B2world::destroy_joint between steps: a mouse grab released mid-flight (the testbed's mouse_up), a bridge cut in the
+    middle (later joints move down one index, handles follow), a hinge with collide_connected == false removed from two
+    overlapping boxes, which start to collide."""
+    from box2d_rs_b200 import abi, scenes
+    from box2d_rs_b200.abi import BodyDef, FixtureDef
+    wo, wg, _, _, _ = _pair("bridge", ctx)
+    extra = []
+    for w in (wo, wg):
+        ground = w.body(0)
+        crate = w.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(0.0, 8.0)))
+        crate.create_fixture(FixtureDef(density=1.0, friction=0.4), w.shapes.polygon_box(0.75, 0.75))
+        jd = w.mouse_joint_def(ground, crate, (0.25, 8.25))
+        jd.length = 1000.0 * 2.25
+        jd.stiffness, jd.damping = w.linear_stiffness(5.0, 0.7, ground, crate)
+        mouse = w.create_joint(jd)
+        mouse.set_target((6.0, 12.0))
+        a = w.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(-14.0, 14.0)))
+        a.create_fixture(FixtureDef(density=1.0, friction=0.3), w.shapes.polygon_box(1.0, 0.25))
+        b = w.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(-13.0, 14.0)))
+        b.create_fixture(FixtureDef(density=1.0, friction=0.3), w.shapes.polygon_box(1.0, 0.25))
+        hinge = w.create_joint(w.revolute_joint_def(a, b, (-13.5, 14.0)))  # overlapping boxes, no contact while hinged
+        extra.append((mouse, hinge))
+    n0 = wo.get_joint_count()
+    for i in range(200):
+        if i == 40:
+            for w, (mouse, hinge) in zip((wo, wg), extra):
+                w.destroy_joint(w.joint(10))     # cut the bridge
+                assert mouse.index == n0 - 3 and hinge.index == n0 - 2
+        if i == 70:
+            for w, (mouse, hinge) in zip((wo, wg), extra):
+                mouse.set_target((-6.0, 14.0))
+        if i == 90:
+            for w, (mouse, hinge) in zip((wo, wg), extra):
+                w.destroy_joint(mouse)           # mouse up
+                assert mouse.index == -1 and hinge.index == n0 - 3
+        if i == 120:
+            for w, (mouse, hinge) in zip((wo, wg), extra):
+                w.destroy_joint(hinge)
+            assert wo.get_joint_count() == wg.get_joint_count() == n0 - 3
+        wo.step(scenes.DT, 8, 3)
+        wg.step(scenes.DT, 8, 3)
+        if i in (119, 199):
+            so = wo.snapshot()
+            nb = len(so.bodies)
+            between = [c for c in so.contacts if {int(so.fixtures[c["fixture_a"]]["body"]), int(so.fixtures[c["fixture_b"]]["body"])} == {nb - 2, nb - 1}]
+            assert len(between) == (0 if i == 119 else 1)  # should_collide: no contact while hinged, one once the pair is found again
+        if i % 5 == 4 or i in (40, 41, 90, 91, 120, 121):
+            bad = parity.compare_snapshots(wo.snapshot(), wg.snapshot()) + parity.compare_stats(wo.get_stats(), wg.get_stats())
+            assert bad == [], "step %d: %s" % (i, bad[:6])
+    wg.close()
+
+
+def test_hostsim_destroy_joint(hctx):
+    _destroy_joints(hctx)
+
+
+@pytest.mark.gpu
+def test_gpu_destroy_joint(gctx):
+    _destroy_joints(gctx)
+
+
 def test_sleeping_island_with_joints(hctx):
     """Two boxes resting apart on the ground, tied by a distance joint, fall asleep as ONE island (the joint propagates
     the island DFS); an impulse on one wakes both in the same step."""

@@ -240,6 +240,10 @@ def run_seed(seed, make_world, steps, batch_mode, large=False, events=False, lev
                     elif op == 2: j.enable_motor(flag)
                     elif op == 3: j.enable_limit(flag)
                     else: j.set_limits(min(val, 0.0) - 0.3, max(val, 0.0) + 0.3)
+        if batch is None and ev == 9 and wo._fuzz_joints and rng.integers(0, 3) == 0:  # B2world::destroy_joint
+            q = int(rng.integers(0, len(wo._fuzz_joints)))
+            for w in (wo, wg):
+                w.destroy_joint(w._fuzz_joints.pop(q)[0])
         if batch is None and 2 <= ev <= 7:  # the rest of B2body's force / impulse API, sleeping bodies included
             b = int(rng.integers(1, nb))
             vec = (f32v(rng.uniform(-40, 40)), f32v(rng.uniform(-40, 40)))
