@@ -176,8 +176,13 @@ int b2gpu_snapshot_validate(const b2gpu_snapshot* s) {
   for (int i = 0; i < n.move_count; ++i) CHECK_RANGE(s->move_buffer[i] >= -1 && s->move_buffer[i] < nn, "move buffer entry", i);
   for (int i = 0; i < n.joint_count; ++i) {
     const b2gpu_joint_rec& j = s->joints[i];
-    CHECK_RANGE(j.type == B2GPU_JOINT_REVOLUTE || j.type == B2GPU_JOINT_DISTANCE || j.type == B2GPU_JOINT_WELD || j.type == B2GPU_JOINT_PRISMATIC || j.type == B2GPU_JOINT_WHEEL || j.type == B2GPU_JOINT_FRICTION || j.type == B2GPU_JOINT_MOTOR || j.type == B2GPU_JOINT_PULLEY || j.type == B2GPU_JOINT_MOUSE, "joint type", i);
+    CHECK_RANGE(j.type == B2GPU_JOINT_REVOLUTE || j.type == B2GPU_JOINT_DISTANCE || j.type == B2GPU_JOINT_WELD || j.type == B2GPU_JOINT_PRISMATIC || j.type == B2GPU_JOINT_WHEEL || j.type == B2GPU_JOINT_FRICTION || j.type == B2GPU_JOINT_MOTOR || j.type == B2GPU_JOINT_PULLEY || j.type == B2GPU_JOINT_MOUSE || j.type == B2GPU_JOINT_GEAR, "joint type", i);
     CHECK_RANGE(j.body_a >= 0 && j.body_a < nb && j.body_b >= 0 && j.body_b < nb && j.body_a != j.body_b, "joint body", i);
+    if (j.type == B2GPU_JOINT_GEAR) {
+      int32_t bc, bd;
+      memcpy(&bc, &j.impulse[5], 4); memcpy(&bd, &j.impulse[6], 4);
+      CHECK_RANGE(bc >= 0 && bc < nb && bd >= 0 && bd < nb, "gear joint body C / D", i);
+    }
   }
   const b2gpu_world_rec& w = s->world;
   if (w.tree_root < -1 || w.tree_root >= nn || w.tree_free_list < -1 || w.tree_free_list >= nn || w.tree_node_capacity != nn ||

@@ -133,11 +133,182 @@ struct BodyStateGlobal {
   B2G_HD void set_rot(int b, Rot q) const { float4 r = B.b_rot[x.at(B.NB, b)]; r.x = q.s; r.y = q.c; B.b_rot[x.at(B.NB, b)] = r; }
 };
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Gear joint (private joints/b2_gear_joint.rs:142-245 / :247-290 / :292-400): one row over FOUR bodies — A, B (the joint's
+// own) and C, D (body A of the two coupled revolute / prismatic joints; ids in impulse[5], [6] of the record).  Every body is
+// read first and written back in the order A, B, C, D as the reference does, so that when two of them are one body the later
+// store wins.  j_s0.x = impulse (not rescaled by dt_ratio); scratch rows 0: jv_ac jv_bd, 1: jw_a jw_b jw_c jw_d, 2: mass,
+// 3: mA iA mB iB, 4: mC iC mD iD.
+struct GearBodies {
+  int b[4];
+  float m[4], i[4];
+  V2 lc[4];
+};
+struct GearRows {
+  V2 jv_ac, jv_bd;
+  float jw_a, jw_b, jw_c, jw_d, mass, coordinate_a, coordinate_b;
+};
+B2G_HD GearBodies gear_bodies(const Batch& B, const WIdx& x, const b2gpu_joint_rec& jr) {
+  GearBodies g;
+  g.b[0] = jr.body_a; g.b[1] = jr.body_b; g.b[2] = f2i(jr.impulse[5]); g.b[3] = f2i(jr.impulse[6]);
+  for (int k = 0; k < 4; ++k) {
+    const float4 ms = B.b_mass[x.at(B.NB, g.b[k])];
+    g.m[k] = ms.x; g.i[k] = ms.y; g.lc[k] = v2(ms.z, ms.w);
+  }
+  return g;
+}
+B2G_HD GearRows gear_rows(const b2gpu_joint_rec& jr, const GearBodies& gb, const V2* c, const float* a, const Rot* q) {
+  GearRows g;
+  const float ratio = jr.impulse[4];
+  const V2 anchor_a = v2(jr.local_anchor_a[0], jr.local_anchor_a[1]), anchor_b = v2(jr.local_anchor_b[0], jr.local_anchor_b[1]);
+  const V2 anchor_c = v2(jr.param[0], jr.param[1]), anchor_d = v2(jr.param[2], jr.param[3]);
+  const V2 axis_c = v2(jr.param[4], jr.param[5]), axis_d = v2(jr.param[6], jr.param[7]);
+  g.mass = 0.0f;
+  if (!(jr.flags & B2GPU_JOINT_GEAR_PRISMATIC_1)) {
+    g.jv_ac = v2(0.0f, 0.0f);
+    g.jw_a = 1.0f; g.jw_c = 1.0f;
+    g.mass = g.mass + (gb.i[0] + gb.i[2]);
+    g.coordinate_a = a[0] - a[2] - jr.impulse[1];
+  } else {
+    const V2 u = rot_mul(q[2], axis_c);
+    const V2 r_c = rot_mul(q[2], anchor_c - gb.lc[2]);
+    const V2 r_a = rot_mul(q[0], anchor_a - gb.lc[0]);
+    g.jv_ac = u;
+    g.jw_c = cross(r_c, u);
+    g.jw_a = cross(r_a, u);
+    g.mass = g.mass + (gb.m[2] + gb.m[0] + gb.i[2] * g.jw_c * g.jw_c + gb.i[0] * g.jw_a * g.jw_a);
+    const V2 p_c = anchor_c - gb.lc[2];
+    const V2 p_a = rot_mul_t(q[2], r_a + (c[0] - c[2]));
+    g.coordinate_a = dot(p_a - p_c, axis_c);
+  }
+  if (!(jr.flags & B2GPU_JOINT_GEAR_PRISMATIC_2)) {
+    g.jv_bd = v2(0.0f, 0.0f);
+    g.jw_b = ratio; g.jw_d = ratio;
+    g.mass = g.mass + ratio * ratio * (gb.i[1] + gb.i[3]);
+    g.coordinate_b = a[1] - a[3] - jr.impulse[2];
+  } else {
+    const V2 u = rot_mul(q[3], axis_d);
+    const V2 r_d = rot_mul(q[3], anchor_d - gb.lc[3]);
+    const V2 r_b = rot_mul(q[1], anchor_b - gb.lc[1]);
+    g.jv_bd = ratio * u;
+    g.jw_d = ratio * cross(r_d, u);
+    g.jw_b = ratio * cross(r_b, u);
+    g.mass = g.mass + (ratio * ratio * (gb.m[3] + gb.m[1]) + gb.i[3] * g.jw_d * g.jw_d + gb.i[1] * g.jw_b * g.jw_b);
+    const V2 p_d = anchor_d - gb.lc[3];
+    const V2 p_b = rot_mul_t(q[3], r_b + (c[1] - c[3]));
+    g.coordinate_b = dot(p_b - p_d, axis_d);
+  }
+  return g;
+}
+template <class S>
+B2G_HD void gear_init_velocity(const Batch& B, const WIdx& x, const S& st, int j, bool warm_starting) {
+  const b2gpu_joint_rec& jr = B.joints[j];
+  const GearBodies gb = gear_bodies(B, x, jr);
+  V2 c[4], v[4];
+  float a[4], w[4];
+  Rot q[4];
+  for (int k = 0; k < 4; ++k) {
+    const float4 p = st.pos(gb.b[k]), vl = st.vel(gb.b[k]);
+    c[k] = v2(p.x, p.y); a[k] = p.z;
+    v[k] = v2(vl.x, vl.y); w[k] = vl.z;
+    q[k] = st.rot(gb.b[k]);
+  }
+  const GearRows g = gear_rows(jr, gb, c, a, q);
+  const float mass = g.mass > 0.0f ? 1.0f / g.mass : 0.0f;
+  const int ji = x.at(B.NJ, j);
+  float4 s0 = B.j_s0[ji];
+  if (warm_starting) {
+    const float imp = s0.x;
+    v[0] = v[0] + (gb.m[0] * imp) * g.jv_ac;
+    w[0] += gb.i[0] * imp * g.jw_a;
+    v[1] = v[1] + (gb.m[1] * imp) * g.jv_bd;
+    w[1] += gb.i[1] * imp * g.jw_b;
+    v[2] = v[2] - (gb.m[2] * imp) * g.jv_ac;
+    w[2] -= gb.i[2] * imp * g.jw_c;
+    v[3] = v[3] - (gb.m[3] * imp) * g.jv_bd;
+    w[3] -= gb.i[3] * imp * g.jw_d;
+  } else {
+    s0.x = 0.0f;
+  }
+  B.j_s0[ji] = s0;
+  B.j_tmp[jt_at(B, x, j, 0)] = make_float4(g.jv_ac.x, g.jv_ac.y, g.jv_bd.x, g.jv_bd.y);
+  B.j_tmp[jt_at(B, x, j, 1)] = make_float4(g.jw_a, g.jw_b, g.jw_c, g.jw_d);
+  B.j_tmp[jt_at(B, x, j, 2)] = make_float4(mass, 0.0f, 0.0f, 0.0f);
+  B.j_tmp[jt_at(B, x, j, 3)] = make_float4(gb.m[0], gb.i[0], gb.m[1], gb.i[1]);
+  B.j_tmp[jt_at(B, x, j, 4)] = make_float4(gb.m[2], gb.i[2], gb.m[3], gb.i[3]);
+  for (int k = 0; k < 4; ++k)
+    if (gb.m[k] != 0.0f || gb.i[k] != 0.0f) st.set_vel(gb.b[k], make_float4(v[k].x, v[k].y, w[k], 0.0f));
+}
+template <class S>
+B2G_HD void gear_solve_velocity(const Batch& B, const WIdx& x, const S& st, int j) {
+  const b2gpu_joint_rec& jr = B.joints[j];
+  const int b[4] = {jr.body_a, jr.body_b, f2i(jr.impulse[5]), f2i(jr.impulse[6])};
+  const float4 t0 = B.j_tmp[jt_at(B, x, j, 0)], t1 = B.j_tmp[jt_at(B, x, j, 1)], t2 = B.j_tmp[jt_at(B, x, j, 2)];
+  const float4 t3 = B.j_tmp[jt_at(B, x, j, 3)], t4 = B.j_tmp[jt_at(B, x, j, 4)];
+  const float m[4] = {t3.x, t3.z, t4.x, t4.z}, i[4] = {t3.y, t3.w, t4.y, t4.w};
+  const V2 jv_ac = v2(t0.x, t0.y), jv_bd = v2(t0.z, t0.w);
+  V2 v[4];
+  float w[4];
+  for (int k = 0; k < 4; ++k) {
+    const float4 vl = st.vel(b[k]);
+    v[k] = v2(vl.x, vl.y); w[k] = vl.z;
+  }
+  float cdot = dot(jv_ac, v[0] - v[2]) + dot(jv_bd, v[1] - v[3]);
+  cdot += (t1.x * w[0] - t1.z * w[2]) + (t1.y * w[1] - t1.w * w[3]);
+  const float impulse = -t2.x * cdot;
+  const int ji = x.at(B.NJ, j);
+  B.j_s0[ji].x += impulse;
+  v[0] = v[0] + (m[0] * impulse) * jv_ac;
+  w[0] += i[0] * impulse * t1.x;
+  v[1] = v[1] + (m[1] * impulse) * jv_bd;
+  w[1] += i[1] * impulse * t1.y;
+  v[2] = v[2] - (m[2] * impulse) * jv_ac;
+  w[2] -= i[2] * impulse * t1.z;
+  v[3] = v[3] - (m[3] * impulse) * jv_bd;
+  w[3] -= i[3] * impulse * t1.w;
+  for (int k = 0; k < 4; ++k)
+    if (m[k] != 0.0f || i[k] != 0.0f) st.set_vel(b[k], make_float4(v[k].x, v[k].y, w[k], 0.0f));
+}
+template <class S>
+B2G_HD bool gear_solve_position(const Batch& B, const WIdx& x, const S& st, int j) {
+  const b2gpu_joint_rec& jr = B.joints[j];
+  const GearBodies gb = gear_bodies(B, x, jr);
+  V2 c[4];
+  float a[4];
+  Rot q[4];
+  for (int k = 0; k < 4; ++k) {
+    const float4 p = st.pos(gb.b[k]);
+    c[k] = v2(p.x, p.y); a[k] = p.z;
+    q[k] = st.rot(gb.b[k]);
+  }
+  const GearRows g = gear_rows(jr, gb, c, a, q);
+  const float cc = (g.coordinate_a + jr.impulse[4] * g.coordinate_b) - jr.impulse[3];
+  float impulse = 0.0f;
+  if (g.mass > 0.0f) impulse = -cc / g.mass;
+  c[0] = c[0] + (gb.m[0] * impulse) * g.jv_ac;
+  a[0] += gb.i[0] * impulse * g.jw_a;
+  c[1] = c[1] + (gb.m[1] * impulse) * g.jv_bd;
+  a[1] += gb.i[1] * impulse * g.jw_b;
+  c[2] = c[2] - (gb.m[2] * impulse) * g.jv_ac;
+  a[2] -= gb.i[2] * impulse * g.jw_c;
+  c[3] = c[3] - (gb.m[3] * impulse) * g.jv_bd;
+  a[3] -= gb.i[3] * impulse * g.jw_d;
+  for (int k = 0; k < 4; ++k) {
+    if (gb.m[k] == 0.0f && gb.i[k] == 0.0f) continue;  // immovable bodies are shared between islands: never written
+    float4 cur = st.pos(gb.b[k]);                      // what an earlier store of this loop may have left (aliased bodies)
+    if (f2u(a[k]) != f2u(cur.z)) st.set_rot(gb.b[k], rot_from_angle(a[k]));
+    cur.x = c[k].x; cur.y = c[k].y; cur.z = a[k];
+    st.set_pos(gb.b[k], cur);
+  }
+  return true;  // linear_error stays 0 (b2_gear_joint.rs:311, :399)
+}
+
 // init_velocity_constraints of joint j: solver data into j_tmp, impulses scaled (or zeroed) in j_s0 / j_s1, the warm-start
 // impulse applied to the two bodies' velocities.
 template <class S>
 B2G_HD void joint_init_velocity(const Batch& B, const WIdx& x, const S& st, int j, bool warm_starting, float dt_ratio, float h) {
   const b2gpu_joint_rec& jr = B.joints[j];
+  if (jr.type == B2GPU_JOINT_GEAR) { gear_init_velocity(B, x, st, j, warm_starting); return; }
   const int bai = x.at(B.NB, jr.body_a), bbi = x.at(B.NB, jr.body_b);
   const float4 msa = B.b_mass[bai], msb = B.b_mass[bbi];
   const float m_a = msa.x, i_a = msa.y, m_b = msb.x, i_b = msb.y;
@@ -449,6 +620,7 @@ B2G_HD void joint_init_velocity(const Batch& B, const WIdx& x, const S& st, int 
 template <class S>
 B2G_HD void joint_solve_velocity(const Batch& B, const WIdx& x, const S& st, int j, float h, float inv_dt) {
   const b2gpu_joint_rec& jr = B.joints[j];
+  if (jr.type == B2GPU_JOINT_GEAR) { gear_solve_velocity(B, x, st, j); return; }
   const float4 va = st.vel(jr.body_a), vb = st.vel(jr.body_b);
   V2 v_a = v2(va.x, va.y), v_b = v2(vb.x, vb.y);
   float w_a = va.z, w_b = vb.z;
@@ -797,6 +969,7 @@ B2G_HD void joint_solve_velocity(const Batch& B, const WIdx& x, const S& st, int
 template <class S>
 B2G_HD bool joint_solve_position(const Batch& B, const WIdx& x, const S& st, int j) {
   const b2gpu_joint_rec& jr = B.joints[j];
+  if (jr.type == B2GPU_JOINT_GEAR) return gear_solve_position(B, x, st, j);
   if (jr.type == B2GPU_JOINT_FRICTION || jr.type == B2GPU_JOINT_MOTOR || jr.type == B2GPU_JOINT_MOUSE) return true;  // no position rows
   const int bai = x.at(B.NB, jr.body_a), bbi = x.at(B.NB, jr.body_b);
   const float4 msa = B.b_mass[bai], msb = B.b_mass[bbi];

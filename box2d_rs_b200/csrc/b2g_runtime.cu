@@ -294,6 +294,11 @@ static int image_pack(const BatchHost* bh, const b2gpu_snapshot* s, WorldImage& 
     const b2gpu_joint_rec& j = s->joints[i];
     // revolute: param 3 = max_motor_torque, 4 = motor_speed are per world (an RL action); distance joints keep
     // everything static (their slots of j_s1 are unused)
+    if (j.type == B2GPU_JOINT_GEAR) {  // one accumulated impulse; impulse[1..6] are static data
+      im.j_s0[i] = make_float4(j.impulse[0], 0.0f, 0.0f, 0.0f);
+      im.j_s1[i] = make_float4(0.0f, 0.0f, 0.0f, bitsf(0));
+      continue;
+    }
     im.j_s0[i] = make_float4(j.impulse[0], j.impulse[1], j.impulse[2], j.impulse[3]);
     const bool motorised = j.type == B2GPU_JOINT_REVOLUTE || j.type == B2GPU_JOINT_PRISMATIC || j.type == B2GPU_JOINT_WHEEL ||
                            j.type == B2GPU_JOINT_MOUSE;  // mouse: param 3, 4 = the target
@@ -398,6 +403,7 @@ static int image_unpack(const BatchHost* bh, const WorldImage& im, b2gpu_snapsho
     b2gpu_joint_rec& j = out->joints[i];
     j = T.joints[i];
     const float4 s0 = im.j_s0[i], s1 = im.j_s1[i];
+    if (j.type == B2GPU_JOINT_GEAR) { j.impulse[0] = s0.x; continue; }  // impulse[1..6] are static data of the record
     j.impulse[0] = s0.x; j.impulse[1] = s0.y; j.impulse[2] = s0.z; j.impulse[3] = s0.w; j.impulse[4] = s1.x;
     j.impulse[5] = j.impulse[6] = j.impulse[7] = 0.0f;
     if (j.type == B2GPU_JOINT_REVOLUTE || j.type == B2GPU_JOINT_PRISMATIC || j.type == B2GPU_JOINT_WHEEL || j.type == B2GPU_JOINT_MOUSE) {
@@ -447,9 +453,14 @@ static int topology_build(const b2gpu_snapshot* s, Topology& T) {
   for (const b2gpu_joint_rec& j : T.joints) {
     if (j.type != B2GPU_JOINT_REVOLUTE && j.type != B2GPU_JOINT_DISTANCE && j.type != B2GPU_JOINT_WELD && j.type != B2GPU_JOINT_PRISMATIC &&
         j.type != B2GPU_JOINT_WHEEL && j.type != B2GPU_JOINT_FRICTION && j.type != B2GPU_JOINT_MOTOR && j.type != B2GPU_JOINT_PULLEY &&
-        j.type != B2GPU_JOINT_MOUSE) {
-      set_error("joint type outside the supported set (the gear joint is not)");
+        j.type != B2GPU_JOINT_MOUSE && j.type != B2GPU_JOINT_GEAR) {
+      set_error("unknown joint type");
       return B2GPU_E_UNSUPPORTED;
+    }
+    if (j.type == B2GPU_JOINT_GEAR) {
+      int32_t bc, bd;
+      memcpy(&bc, &j.impulse[5], 4); memcpy(&bd, &j.impulse[6], 4);
+      if (bc < 0 || bc >= n.body_count || bd < 0 || bd >= n.body_count) { set_error("gear joint record: body C / D out of range"); return B2GPU_E_INVALID; }
     }
     if (j.body_a < 0 || j.body_a >= n.body_count || j.body_b < 0 || j.body_b >= n.body_count || j.body_a == j.body_b) {
       set_error("joint record out of range");
@@ -511,6 +522,8 @@ static bool topology_matches(const Topology& T, const b2gpu_snapshot* s) {
     if (a.type == B2GPU_JOINT_PRISMATIC && memcmp(a.param + 5, b.param + 5, 8)) return false;   // the local axis
     if (a.type == B2GPU_JOINT_WHEEL && memcmp(a.param + 5, b.param + 5, 12)) return false;      // the local axis, damping
     if (a.type == B2GPU_JOINT_PULLEY && memcmp(a.param + 5, b.param + 5, 12)) return false;     // length_b, ratio, constant
+    if (a.type == B2GPU_JOINT_GEAR && (memcmp(a.param + 5, b.param + 5, 12) || memcmp(a.impulse + 1, b.impulse + 1, 24) ||
+                                       ((a.flags ^ b.flags) & (B2GPU_JOINT_GEAR_PRISMATIC_1 | B2GPU_JOINT_GEAR_PRISMATIC_2)))) return false;
   }
   return true;
 }

@@ -877,6 +877,18 @@ int b2gpu_pulley_joint_def(b2gpu_world* W, b2gpu_joint_def* def, int body_a, int
   return 0;
   GUARD_END
 }
+static bool gear_couples(int type) { return type == B2GPU_JOINT_REVOLUTE || type == B2GPU_JOINT_PRISMATIC; }
+int b2gpu_gear_joint_def(b2gpu_world* W, b2gpu_joint_def* def, int joint1, int joint2, float ratio) {
+  GUARD_BEGIN
+  if (!W || !def) { set_error("gear_joint_def: bad argument"); return B2GPU_E_INVALID; }
+  const int nj = (int)W->h.joints.size();
+  if (joint1 < 0 || joint1 >= nj || joint2 < 0 || joint2 >= nj) { set_error("gear_joint_def: joint index out of range"); return B2GPU_E_INVALID; }
+  joint_def_defaults(def, B2GPU_JOINT_GEAR, W->h.joints[joint1].body_b, W->h.joints[joint2].body_b);
+  def->enable_limit = joint1; def->enable_motor = joint2;               // the coupled joints (see b2gpu.h)
+  def->length = ratio; def->min_length = 0.0f; def->max_length = 0.0f;
+  return 0;
+  GUARD_END
+}
 int b2gpu_mouse_joint_def(b2gpu_world* W, b2gpu_joint_def* def, int body_a, int body_b, float tx, float ty) {
   GUARD_BEGIN
   int rc = check_body(W, body_a);
@@ -994,13 +1006,27 @@ int b2gpu_world_create_joint(b2gpu_world* W, const b2gpu_joint_def* def) {  // b
   if (def->body_a == def->body_b) { set_error("create_joint: body_a == body_b (the reference asserts)"); return B2GPU_E_INVALID; }
   if (def->type != B2GPU_JOINT_REVOLUTE && def->type != B2GPU_JOINT_DISTANCE && def->type != B2GPU_JOINT_WELD &&
       def->type != B2GPU_JOINT_PRISMATIC && def->type != B2GPU_JOINT_WHEEL && def->type != B2GPU_JOINT_FRICTION &&
-      def->type != B2GPU_JOINT_MOTOR && def->type != B2GPU_JOINT_PULLEY && def->type != B2GPU_JOINT_MOUSE) {
-    set_error("create_joint: the gear joint is outside the accelerated path");
+      def->type != B2GPU_JOINT_MOTOR && def->type != B2GPU_JOINT_PULLEY && def->type != B2GPU_JOINT_MOUSE &&
+      def->type != B2GPU_JOINT_GEAR) {
+    set_error("create_joint: unknown joint type");
     return B2GPU_E_UNSUPPORTED;
   }
   if (def->type == B2GPU_JOINT_PRISMATIC && !(def->lower_angle <= def->upper_angle)) {
     set_error("create_joint: prismatic lower translation > upper translation (the reference asserts)");
     return B2GPU_E_INVALID;
+  }
+  if (def->type == B2GPU_JOINT_GEAR) {  // the asserts of private joints/b2_gear_joint.rs:8-30
+    const int nj = (int)W->h.joints.size(), j1 = def->enable_limit, j2 = def->enable_motor;
+    if (j1 < 0 || j1 >= nj || j2 < 0 || j2 >= nj || !gear_couples(W->h.joints[j1].type) || !gear_couples(W->h.joints[j2].type)) {
+      set_error("create_joint: a gear joint couples two revolute / prismatic joints of this world");
+      return B2GPU_E_INVALID;
+    }
+    rc = ensure_host(W);
+    if (rc) return rc;
+    if (W->h.bodies[W->h.joints[j1].body_b].type != B2GPU_DYNAMIC_BODY || W->h.bodies[W->h.joints[j2].body_b].type != B2GPU_DYNAMIC_BODY) {
+      set_error("create_joint: body B of a geared joint must be dynamic (the reference asserts)");
+      return B2GPU_E_INVALID;
+    }
   }
   if (def->type == B2GPU_JOINT_PULLEY && def->max_length == 0.0f) {
     set_error("create_joint: pulley ratio is 0 (the reference asserts)");
@@ -1034,6 +1060,36 @@ int b2gpu_world_create_joint(b2gpu_world* W, const b2gpu_joint_def* def) {  // b
     j.param[0] = def->lower_angle; j.param[1] = def->upper_angle; j.param[2] = def->max_motor_torque; j.param[3] = def->motor_speed;
     j.param[4] = def->length; j.param[5] = def->min_length; j.param[6] = def->max_length;
     j.param[7] = def->length + def->max_length * def->min_length;  // constant = length_a + ratio * length_b
+  } else if (def->type == B2GPU_JOINT_GEAR) {  // private joints/b2_gear_joint.rs:8-140
+    // bodies A / B stay the def's (B2joint::new(&def.base)); coordinates are measured on the coupled joints' own bodies
+    const b2gpu_joint_rec j1 = h.joints[def->enable_limit], j2 = h.joints[def->enable_motor];
+    const float ratio = def->length;
+    float coordinate[2];
+    const b2gpu_joint_rec* jn[2] = {&j1, &j2};
+    for (int s = 0; s < 2; ++s) {
+      const b2gpu_joint_rec& c = *jn[s];
+      const b2gpu_body_rec &bb = h.bodies[c.body_b], &bc = h.bodies[c.body_a];  // "A" / "B" of the gear, and C / D
+      const Xf xf_b = body_xf(bb), xf_c = body_xf(bc);
+      const V2 anchor_c = v2(c.local_anchor_a[0], c.local_anchor_a[1]), anchor_b = v2(c.local_anchor_b[0], c.local_anchor_b[1]);
+      memcpy(s == 0 ? j.local_anchor_a : j.local_anchor_b, c.local_anchor_b, 8);
+      j.param[2 * s] = anchor_c.x; j.param[2 * s + 1] = anchor_c.y;
+      j.impulse[1 + s] = c.param[0];  // reference angle
+      if (c.type == B2GPU_JOINT_REVOLUTE) {
+        j.param[4 + 2 * s] = 0.0f; j.param[5 + 2 * s] = 0.0f;
+        coordinate[s] = bb.a - bc.a - c.param[0];
+      } else {
+        const V2 axis = v2(c.param[5], c.param[6]);
+        j.param[4 + 2 * s] = axis.x; j.param[5 + 2 * s] = axis.y;
+        j.flags |= s == 0 ? B2GPU_JOINT_GEAR_PRISMATIC_1 : B2GPU_JOINT_GEAR_PRISMATIC_2;
+        const V2 p = rot_mul_t(xf_c.q, rot_mul(xf_b.q, anchor_b) + (xf_b.p - xf_c.p));
+        coordinate[s] = dot(p - anchor_c, axis);
+      }
+    }
+    j.impulse[3] = coordinate[0] + ratio * coordinate[1];  // constant
+    j.impulse[4] = ratio;
+    const int32_t body_c = j1.body_a, body_d = j2.body_a;
+    memcpy(&j.impulse[5], &body_c, 4);
+    memcpy(&j.impulse[6], &body_d, 4);
   } else if (def->type == B2GPU_JOINT_MOUSE) {  // B2mouseJoint::new (src/joints/b2_mouse_joint.rs:140-170)
     const V2 target = v2(def->local_anchor_a[0], def->local_anchor_a[1]);
     const V2 lb = body_local_point(h.bodies[def->body_b], target);

@@ -62,6 +62,7 @@ def load(path=None):
         "b2gpu_friction_joint_def": (i32, [vp, C.POINTER(abi.JointDef), i32, i32, f32, f32]),
         "b2gpu_motor_joint_def": (i32, [vp, C.POINTER(abi.JointDef), i32, i32]),
         "b2gpu_pulley_joint_def": (i32, [vp, C.POINTER(abi.JointDef), i32, i32] + [f32] * 9),
+        "b2gpu_gear_joint_def": (i32, [vp, C.POINTER(abi.JointDef), i32, i32, f32]),
         "b2gpu_mouse_joint_def": (i32, [vp, C.POINTER(abi.JointDef), i32, i32, f32, f32]),
         "b2gpu_joint_set_target": (i32, [vp, i32, f32, f32]),
         "b2gpu_world_destroy_joint": (i32, [vp, i32]),

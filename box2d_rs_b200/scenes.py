@@ -495,6 +495,44 @@ def pulleys(world):
     return mouse
 
 
+def gears(world):
+    """examples/testbed/tests/gear_joint.rs:66-205: a pendulum bar hinged on a static disc with a disc hinged on its end, the two
+    hinges geared 2 : 1 (the testbed hands the gear joint the STATIC disc as body A — kept: the port solves on the def's
+    bodies), and the ground-mounted train disc - disc - rack (two revolute joints and a prismatic joint with limits, gear
+    ratios 2 and -1/2).  A kick on the small disc and on the bar sets everything turning.  Returns the first train gear."""
+    ground = world.create_body(BodyDef())
+    ground.create_fixture_by_shape(world.shapes.edge_two_sided((50.0, 0.0), (-50.0, 0.0)), 0.0)
+    circle1, circle2, box = world.shapes.circle(1.0), world.shapes.circle(2.0), world.shapes.polygon_box(0.5, 5.0)
+    body1 = world.create_body(BodyDef(type=abi.STATIC_BODY, position=(10.0, 9.0)))
+    body1.create_fixture_by_shape(circle1, 5.0)
+    body2 = world.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(10.0, 8.0)))
+    body2.create_fixture_by_shape(box, 5.0)
+    body3 = world.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(10.0, 6.0)))
+    body3.create_fixture_by_shape(circle2, 5.0)
+    joint1 = world.create_joint(world.revolute_joint_def(body1, body2, (10.0, 9.0)))
+    joint2 = world.create_joint(world.revolute_joint_def(body2, body3, (10.0, 6.0)))
+    jd = world.gear_joint_def(joint1, joint2, 2.0)
+    jd.body_a, jd.body_b = body1.index, body3.index
+    world.create_joint(jd)
+    body2.set_angular_velocity(1.5)
+    # the train
+    b1 = world.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(-3.0, 12.0)))
+    b1.create_fixture_by_shape(circle1, 5.0)
+    j1 = world.create_joint(world.revolute_joint_def(ground, b1, (-3.0, 12.0)))
+    b2 = world.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(0.0, 12.0)))
+    b2.create_fixture_by_shape(circle2, 5.0)
+    j2 = world.create_joint(world.revolute_joint_def(ground, b2, (0.0, 12.0)))
+    b3 = world.create_body(BodyDef(type=abi.DYNAMIC_BODY, position=(2.5, 12.0)))
+    b3.create_fixture_by_shape(box, 5.0)
+    jd3 = world.prismatic_joint_def(ground, b3, (2.5, 12.0), (0.0, 1.0))
+    jd3.lower_angle, jd3.upper_angle, jd3.enable_limit = -5.0, 5.0, 1
+    j3 = world.create_joint(jd3)
+    train = world.create_joint(world.gear_joint_def(j1, j2, 2.0))
+    world.create_joint(world.gear_joint_def(j2, j3, -0.5))
+    b1.set_angular_velocity(6.0)
+    return train
+
+
 def tumbler(world, n=200, seed=0xB2D + 21):
     """examples/testbed/tests/tumbler.rs:62-97: a hollow box of four plank fixtures turned by a revolute-joint motor
     (0.05 pi rad/s, torque 1e8) around a point of the ground body; the testbed drops one 0.125 box per step, here `n`

@@ -211,6 +211,13 @@ class B2world:
                                                     anchor_b[0], anchor_b[1], ratio))
         return d
 
+    def gear_joint_def(self, joint1, joint2, ratio):
+        """B2gearJointDef::default() with joint1, joint2 (revolute / prismatic handles) and ratio
+        (src/joints/b2_gear_joint.rs:12-40); overlay in b2gpu.h."""
+        d = abi.JointDef()
+        check(self.L, self.L.b2gpu_gear_joint_def(self.h, C.byref(d), joint1.index, joint2.index, ratio))
+        return d
+
     def mouse_joint_def(self, body_a, body_b, target):
         """B2mouseJointDef::default() with `target` (src/joints/b2_mouse_joint.rs:8-21): set length (= max_force),
         stiffness, damping."""
@@ -256,7 +263,7 @@ class B2world:
         return k.value, d.value
 
     def create_joint(self, joint_def):
-        """B2world::create_joint (every joint type but gear)."""
+        """B2world::create_joint (all ten joint types)."""
         j = B2joint(self, check(self.L, self.L.b2gpu_world_create_joint(self.h, C.byref(joint_def))))
         self._joint_handles.append(j)
         return j

@@ -84,6 +84,7 @@ extern "C" {
 /* joint types: B2jointType (src/b2_joint.rs:46-58), same numbering */
 #define B2GPU_JOINT_DISTANCE 1
 #define B2GPU_JOINT_FRICTION 2
+#define B2GPU_JOINT_GEAR 3
 #define B2GPU_JOINT_MOTOR 4
 #define B2GPU_JOINT_MOUSE 5
 #define B2GPU_JOINT_PRISMATIC 6
@@ -95,6 +96,8 @@ extern "C" {
 #define B2GPU_JOINT_COLLIDE_CONNECTED 0x1u /* B2jointDef::collide_connected */
 #define B2GPU_JOINT_ENABLE_LIMIT 0x2u      /* revolute: m_enable_limit */
 #define B2GPU_JOINT_ENABLE_MOTOR 0x4u      /* revolute: m_enable_motor */
+#define B2GPU_JOINT_GEAR_PRISMATIC_1 0x100u /* gear: joint 1 is prismatic (else revolute) */
+#define B2GPU_JOINT_GEAR_PRISMATIC_2 0x200u /* gear: joint 2 is prismatic */
 
 #define B2GPU_NULL (-1)
 #define B2GPU_MAX_POLYGON_VERTICES 8
@@ -195,7 +198,11 @@ typedef struct b2gpu_contact_rec {
  *   param[]  revolute: 0 reference_angle, 1 lower_angle, 2 upper_angle, 3 max_motor_torque, 4 motor_speed
  *            distance: 0 length, 1 min_length, 2 max_length, 3 stiffness, 4 damping
  *   impulse[] revolute: 0,1 m_impulse.xy, 2 m_motor_impulse, 3 m_lower_impulse, 4 m_upper_impulse
- *            distance: 0 m_impulse, 3 m_lower_impulse, 4 m_upper_impulse */
+ *            distance: 0 m_impulse, 3 m_lower_impulse, 4 m_upper_impulse
+ *   gear (four bodies; src/joints/b2_gear_joint.rs:150-200): body_a / body_b as given, local_anchor_a / _b copied from the
+ *            coupled joints; param 0,1 local_anchor_c, 2,3 local_anchor_d, 4,5 local_axis_c, 6,7 local_axis_d; flags
+ *            GEAR_PRISMATIC_1 / _2 = the coupled joints' types; impulse 0 m_impulse, and the static rest overflows into
+ *            impulse 1 reference_angle_a, 2 reference_angle_b, 3 constant, 4 ratio, 5 / 6 body_c / body_d (int32 bits) */
 typedef struct b2gpu_joint_rec {
   int32_t type;             /* B2GPU_JOINT_* */
   int32_t body_a, body_b;
@@ -413,6 +420,12 @@ int b2gpu_motor_joint_def(b2gpu_world* w, b2gpu_joint_def* def, int body_a, int 
 int b2gpu_pulley_joint_def(b2gpu_world* w, b2gpu_joint_def* def, int body_a, int body_b, float ground_ax, float ground_ay,
                            float ground_bx, float ground_by, float anchor_ax, float anchor_ay, float anchor_bx, float anchor_by,
                            float ratio);
+/* B2gearJointDef::default (src/joints/b2_gear_joint.rs:12-40) with joint1, joint2 (revolute or prismatic joints of this
+ * world, by index) and ratio: coordinate1 + ratio * coordinate2 stays constant.  body_a / body_b are set to body B of joint 1 /
+ * joint 2, the bodies B2gearJoint::new measures on.  Def overlay: `enable_limit` / `enable_motor` carry the indices joint1 /
+ * joint2, `length` the ratio.  Create: a coupled joint of another type, or a body B that is not dynamic: B2GPU_E_INVALID (the
+ * reference asserts).  As in the reference, destroy the gear joint before either coupled joint. */
+int b2gpu_gear_joint_def(b2gpu_world* w, b2gpu_joint_def* def, int joint1, int joint2, float ratio);
 /* B2mouseJointDef::default (src/joints/b2_mouse_joint.rs:8-21) with `target`: a soft constraint that drags a point of body B
  * (the body-local point under the target at creation) towards a world target; body A is only the island link (use a static
  * body).  Def overlay: local_anchor_a is the target in WORLD coordinates, `length` is max_force (default 0), stiffness and
@@ -435,7 +448,7 @@ int b2gpu_linear_stiffness(b2gpu_world* w, float frequency_hertz, float damping_
                            float* damping);
 /* B2world::create_joint (src/private/dynamics/b2_world.rs:156-262): returns the joint index (>= 0); contacts between
  * the two bodies are flagged for filtering when collide_connected is false.  Does not wake the bodies.
- * The gear joint (it wraps two other joints) is the one type outside the path: B2GPU_E_UNSUPPORTED. */
+ * All ten joint types of B2jointType are inside the path; any other type value: B2GPU_E_UNSUPPORTED. */
 int b2gpu_world_create_joint(b2gpu_world* w, const b2gpu_joint_def* def);
 /* B2world::destroy_joint (src/private/dynamics/b2_world.rs:278-339): wakes both bodies, removes the joint (the order of the
  * others is kept) and, when it had collide_connected == false, flags the contacts between its bodies for filtering so that

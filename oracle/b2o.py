@@ -60,6 +60,7 @@ def lib():
         L.b2o_friction_joint_def.argtypes = [C.c_void_p, C.POINTER(abi.JointDef), C.c_int, C.c_int, C.c_float, C.c_float]
         L.b2o_motor_joint_def.argtypes = [C.c_void_p, C.POINTER(abi.JointDef), C.c_int, C.c_int]
         L.b2o_pulley_joint_def.argtypes = [C.c_void_p, C.POINTER(abi.JointDef), C.c_int, C.c_int] + [C.c_float] * 9
+        L.b2o_gear_joint_def.argtypes = [C.c_void_p, C.POINTER(abi.JointDef), C.c_int, C.c_int, C.c_float]
         L.b2o_mouse_joint_def.argtypes = [C.c_void_p, C.POINTER(abi.JointDef), C.c_int, C.c_int, C.c_float, C.c_float]
         L.b2o_joint_set_target.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float]
         L.b2o_wheel_joint_def.argtypes = [C.c_void_p, C.POINTER(abi.JointDef), C.c_int, C.c_int, C.c_float, C.c_float,
@@ -283,6 +284,12 @@ class B2world:
         d = abi.JointDef()
         lib().b2o_pulley_joint_def(self.h, C.byref(d), _body_index(body_a), _body_index(body_b), ground_a[0], ground_a[1],
                                    ground_b[0], ground_b[1], anchor_a[0], anchor_a[1], anchor_b[0], anchor_b[1], ratio)
+        return d
+
+    def gear_joint_def(self, joint1, joint2, ratio):
+        """B2gearJointDef::default() with joint1, joint2 (revolute / prismatic handles) and ratio."""
+        d = abi.JointDef()
+        lib().b2o_gear_joint_def(self.h, C.byref(d), joint1.index, joint2.index, ratio)
         return d
 
     def mouse_joint_def(self, body_a, body_b, target):

@@ -158,6 +158,10 @@ static void joint_def_out(const JointDef& d, b2gpu_joint_def* o) {
     o->max_motor_torque = d.ground_anchor_b.x; o->motor_speed = d.ground_anchor_b.y;
     o->length = d.length; o->min_length = d.length_b; o->max_length = d.ratio;
   }
+  if (d.type == J_GEAR) {  // b2gpu.h: enable_limit / enable_motor = joint1 / joint2 (indices), length = ratio
+    o->enable_limit = d.joint1; o->enable_motor = d.joint2;
+    o->length = d.ratio; o->min_length = 0.0f; o->max_length = 0.0f;
+  }
   if (d.type == J_MOUSE) {  // b2gpu.h: local_anchor_a = target (world), length = max_force
     o->local_anchor_a[0] = d.target.x; o->local_anchor_a[1] = d.target.y;
     o->length = d.max_force; o->min_length = 0.0f; o->max_length = 0.0f;
@@ -183,6 +187,10 @@ int b2o_friction_joint_def(void* w, b2gpu_joint_def* def, int body_a, int body_b
 int b2o_pulley_joint_def(void* w, b2gpu_joint_def* def, int body_a, int body_b, float gax, float gay, float gbx, float gby,
                          float ax, float ay, float bx, float by, float ratio) {
   joint_def_out(((World*)w)->pulley_joint_def(body_a, body_b, Vec2(gax, gay), Vec2(gbx, gby), Vec2(ax, ay), Vec2(bx, by), ratio), def);
+  return 0;
+}
+int b2o_gear_joint_def(void* w, b2gpu_joint_def* def, int joint1, int joint2, float ratio) {
+  joint_def_out(((World*)w)->gear_joint_def(joint1, joint2, ratio), def);
   return 0;
 }
 int b2o_mouse_joint_def(void* w, b2gpu_joint_def* def, int body_a, int body_b, float tx, float ty) {
@@ -225,6 +233,7 @@ int b2o_create_joint(void* w, const b2gpu_joint_def* d) {
     jd.length_b = d->min_length; jd.ratio = d->max_length;
   }
   if (d->type == J_MOUSE) { jd.target = jd.local_anchor_a; jd.max_force = d->length; }
+  if (d->type == J_GEAR) { jd.joint1 = d->enable_limit; jd.joint2 = d->enable_motor; jd.ratio = d->length; jd.enable_limit = jd.enable_motor = false; }
   return ((World*)w)->create_joint(jd);
 }
 void b2o_destroy_joint(void* w, int j) { ((World*)w)->destroy_joint(j); }
@@ -391,6 +400,13 @@ int b2o_snapshot_export(void* w, b2gpu_snapshot* out) {
       r.param[0] = j.max_force; r.param[1] = j.max_motor_torque;
       if (j.type == J_MOTOR) { r.param[2] = j.reference_angle; r.param[3] = j.correction_factor; }
       r.impulse[0] = j.impulse2.x; r.impulse[1] = j.impulse2.y; r.impulse[2] = j.motor_impulse;
+    } else if (j.type == J_GEAR) {  // b2gpu.h: the static part overflows into impulse[1..6]
+      r.flags |= (j.type_a == J_PRISMATIC ? B2GPU_JOINT_GEAR_PRISMATIC_1 : 0) | (j.type_b == J_PRISMATIC ? B2GPU_JOINT_GEAR_PRISMATIC_2 : 0);
+      r.param[0] = j.local_anchor_c.x; r.param[1] = j.local_anchor_c.y; r.param[2] = j.local_anchor_d.x; r.param[3] = j.local_anchor_d.y;
+      r.param[4] = j.local_axis_c.x; r.param[5] = j.local_axis_c.y; r.param[6] = j.local_axis_d.x; r.param[7] = j.local_axis_d.y;
+      r.impulse[0] = j.impulse; r.impulse[1] = j.reference_angle; r.impulse[2] = j.reference_angle_b;
+      r.impulse[3] = j.constant; r.impulse[4] = j.ratio;
+      std::memcpy(&r.impulse[5], &j.body_c, 4); std::memcpy(&r.impulse[6], &j.body_d, 4);
     } else if (j.type == J_PULLEY) {
       r.param[0] = j.ground_anchor_a.x; r.param[1] = j.ground_anchor_a.y; r.param[2] = j.ground_anchor_b.x; r.param[3] = j.ground_anchor_b.y;
       r.param[4] = j.length; r.param[5] = j.length_b; r.param[6] = j.ratio; r.param[7] = j.constant;
@@ -411,7 +427,7 @@ int b2o_snapshot_export(void* w, b2gpu_snapshot* out) {
       r.param[0] = j.length; r.param[1] = j.min_length; r.param[2] = j.max_length; r.param[3] = j.stiffness; r.param[4] = j.damping;
       r.impulse[0] = j.impulse;
     }
-    r.impulse[3] = j.lower_impulse; r.impulse[4] = j.upper_impulse;
+    if (j.type != J_GEAR) { r.impulse[3] = j.lower_impulse; r.impulse[4] = j.upper_impulse; }
   }
   b2gpu_world_rec& wr = out->world;
   std::memset(&wr, 0, sizeof(wr));

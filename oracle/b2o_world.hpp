@@ -93,7 +93,7 @@ struct Contact {
 
 // Joints: B2jointDef + B2revoluteJointDef / B2distanceJointDef as one plain struct
 // (src/b2_joint.rs:112-122, src/joints/b2_revolute_joint.rs:10-72, src/joints/b2_distance_joint.rs:11-58).
-enum JointType { J_DISTANCE = 1, J_FRICTION = 2, J_MOTOR = 4, J_MOUSE = 5, J_PRISMATIC = 6, J_PULLEY = 7, J_REVOLUTE = 8, J_WELD = 9, J_WHEEL = 10 };  // B2jointType numbering (src/b2_joint.rs:46-58)
+enum JointType { J_DISTANCE = 1, J_FRICTION = 2, J_GEAR = 3, J_MOTOR = 4, J_MOUSE = 5, J_PRISMATIC = 6, J_PULLEY = 7, J_REVOLUTE = 8, J_WELD = 9, J_WHEEL = 10 };  // B2jointType numbering (src/b2_joint.rs:46-58)
 struct JointDef {
   int type = 0, body_a = -1, body_b = -1;
   bool collide_connected = false;
@@ -111,6 +111,8 @@ struct JointDef {
   // mouse (src/joints/b2_mouse_joint.rs:8-50): target (world point); max_force, stiffness, damping as named
   Vec2 ground_anchor_a = Vec2(-1.0f, 1.0f), ground_anchor_b = Vec2(1.0f, 1.0f), target;
   float length_b = 0.0f, ratio = 1.0f;
+  // gear (src/joints/b2_gear_joint.rs:12-40): the two revolute / prismatic joints it couples (indices), `ratio`
+  int joint1 = -1, joint2 = -1;
 };
 struct Joint {  // B2joint + B2revoluteJoint (src/joints/b2_revolute_joint.rs:104-136) / B2distanceJoint fields
   int type = 0, body_a = -1, body_b = -1;
@@ -141,6 +143,11 @@ struct Joint {  // B2joint + B2revoluteJoint (src/joints/b2_revolute_joint.rs:10
   // mouse (src/joints/b2_mouse_joint.rs:140-170): ground_anchor_a = target, impulse2, gamma, `beta`, linear_error = C, k = mass
   Vec2 ground_anchor_a, ground_anchor_b, u_b;
   float length_b = 0.0f, ratio = 1.0f, constant = 0.0f, beta = 0.0f;
+  // gear (src/joints/b2_gear_joint.rs:150-200): bodies C, D = body A of joint 1 / 2 (A, B = their body B), the joints' types,
+  // anchors and axes copied at creation; reference_angle = reference_angle_a; solver temp jv_ac, jv_bd, jw_a..d, `mass`
+  int body_c = -1, body_d = -1, type_a = 0, type_b = 0;
+  Vec2 local_anchor_c, local_anchor_d, local_axis_c, local_axis_d, jv_ac, jv_bd;
+  float reference_angle_b = 0.0f, jw_a = 0.0f, jw_b = 0.0f, jw_c = 0.0f, jw_d = 0.0f;
   // weld (src/joints/b2_weld_joint.rs:66-90): impulse (x, y, angular), effective mass B2Mat33 as ex.xyz ey.xyz ez.xyz
   float impulse3[3] = {0.0f, 0.0f, 0.0f}, m33[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   // solver temp
@@ -511,6 +518,16 @@ struct World {
     assert(r > EPSILON);
     return d;
   }
+  // B2gearJointDef::default (src/joints/b2_gear_joint.rs:12-40) with joint1, joint2, ratio; bodies A / B as B2gearJoint::new
+  // takes them (body B of joint 1 / joint 2)
+  JointDef gear_joint_def(int joint1, int joint2, float r) const {
+    JointDef d;
+    d.type = J_GEAR;
+    d.joint1 = joint1; d.joint2 = joint2;
+    d.body_a = joints[joint1].body_b; d.body_b = joints[joint2].body_b;
+    d.ratio = r;
+    return d;
+  }
   // B2mouseJointDef::default (src/joints/b2_mouse_joint.rs:8-21): target, max_force, stiffness, damping all zero
   JointDef mouse_joint_def(int body_a, int body_b, Vec2 target) const {
     JointDef d;
@@ -605,6 +622,47 @@ struct World {
       assert(def.ratio != 0.0f);
       j.ratio = def.ratio;
       j.constant = def.length + j.ratio * def.length_b;
+    } else if (def.type == J_GEAR) {  // private joints/b2_gear_joint.rs:8-140
+      const Joint &j1 = joints[def.joint1], &j2 = joints[def.joint2];
+      j.type_a = j1.type; j.type_b = j2.type;
+      assert(j.type_a == J_REVOLUTE || j.type_a == J_PRISMATIC);
+      assert(j.type_b == J_REVOLUTE || j.type_b == J_PRISMATIC);
+      float coordinate_a, coordinate_b;
+      // the solver's bodies A / B stay the def's (B2joint::new(&def.base)); the coordinates are measured on the joints' own
+      j.body_c = j1.body_a;
+      const int jb_a = j1.body_b;
+      assert(bodies[jb_a].type == DYNAMIC_BODY);
+      const Transform xf_a = bodies[jb_a].xf, xf_c = bodies[j.body_c].xf;
+      const float a_a = bodies[jb_a].sweep.a, a_c = bodies[j.body_c].sweep.a;
+      j.local_anchor_c = j1.local_anchor_a; j.local_anchor_a = j1.local_anchor_b;
+      j.reference_angle = j1.reference_angle;
+      if (j.type_a == J_REVOLUTE) {
+        j.local_axis_c.set_zero();
+        coordinate_a = a_a - a_c - j.reference_angle;
+      } else {
+        j.local_axis_c = j1.local_xaxis_a;
+        Vec2 p_c = j.local_anchor_c;
+        Vec2 p_a = b2_mul_t_rot(xf_c.q, b2_mul_rot(xf_a.q, j.local_anchor_a) + (xf_a.p - xf_c.p));
+        coordinate_a = b2_dot(p_a - p_c, j.local_axis_c);
+      }
+      j.body_d = j2.body_a;
+      const int jb_b = j2.body_b;
+      assert(bodies[jb_b].type == DYNAMIC_BODY);
+      const Transform xf_b = bodies[jb_b].xf, xf_d = bodies[j.body_d].xf;
+      const float a_b = bodies[jb_b].sweep.a, a_d = bodies[j.body_d].sweep.a;
+      j.local_anchor_d = j2.local_anchor_a; j.local_anchor_b = j2.local_anchor_b;
+      j.reference_angle_b = j2.reference_angle;
+      if (j.type_b == J_REVOLUTE) {
+        j.local_axis_d.set_zero();
+        coordinate_b = a_b - a_d - j.reference_angle_b;
+      } else {
+        j.local_axis_d = j2.local_xaxis_a;
+        Vec2 p_d = j.local_anchor_d;
+        Vec2 p_b = b2_mul_t_rot(xf_d.q, b2_mul_rot(xf_b.q, j.local_anchor_b) + (xf_b.p - xf_d.p));
+        coordinate_b = b2_dot(p_b - p_d, j.local_axis_d);
+      }
+      j.ratio = def.ratio;
+      j.constant = coordinate_a + j.ratio * coordinate_b;
     } else if (def.type == J_MOUSE) {  // B2mouseJoint::new (src/joints/b2_mouse_joint.rs:140-170)
       j.ground_anchor_a = def.target;
       j.local_anchor_a.set_zero();  // unused: body A is only the island link
@@ -1226,7 +1284,117 @@ struct World {
   // -------------------------------------------------------------- joint solver
   // B2jointTraitDyn::init_velocity_constraints / solve_velocity_constraints / solve_position_constraints
   // (src/b2_joint.rs:268-286), dispatched on the joint type.
+  // The gear joint couples four bodies (private joints/b2_gear_joint.rs:142-245 / :247-290 / :292-400).  Every body is read
+  // first and written back in the order A, B, C, D, as the reference does: when two of them are one body (both joints on one
+  // carrier, or joint 2 hanging off body A) the later store wins.
+  struct GearRows { Vec2 jv_ac, jv_bd; float jw_a, jw_b, jw_c, jw_d, mass, coordinate_a, coordinate_b; };
+  GearRows gear_rows(const Joint& j, const Vec2 c[4], const float a[4], const Vec2 lc[4], const float m[4], const float i[4]) const {
+    GearRows g;
+    Rot q_a(a[0]), q_b(a[1]), q_c(a[2]), q_d(a[3]);
+    g.mass = 0.0f;
+    if (j.type_a == J_REVOLUTE) {
+      g.jv_ac.set_zero();
+      g.jw_a = 1.0f; g.jw_c = 1.0f;
+      g.mass += i[0] + i[2];
+      g.coordinate_a = a[0] - a[2] - j.reference_angle;
+    } else {
+      Vec2 u = b2_mul_rot(q_c, j.local_axis_c);
+      Vec2 r_c = b2_mul_rot(q_c, j.local_anchor_c - lc[2]);
+      Vec2 r_a = b2_mul_rot(q_a, j.local_anchor_a - lc[0]);
+      g.jv_ac = u;
+      g.jw_c = b2_cross(r_c, u);
+      g.jw_a = b2_cross(r_a, u);
+      g.mass += m[2] + m[0] + i[2] * g.jw_c * g.jw_c + i[0] * g.jw_a * g.jw_a;
+      Vec2 p_c = j.local_anchor_c - lc[2];
+      Vec2 p_a = b2_mul_t_rot(q_c, r_a + (c[0] - c[2]));
+      g.coordinate_a = b2_dot(p_a - p_c, j.local_axis_c);
+    }
+    if (j.type_b == J_REVOLUTE) {
+      g.jv_bd.set_zero();
+      g.jw_b = j.ratio; g.jw_d = j.ratio;
+      g.mass += j.ratio * j.ratio * (i[1] + i[3]);
+      g.coordinate_b = a[1] - a[3] - j.reference_angle_b;
+    } else {
+      Vec2 u = b2_mul_rot(q_d, j.local_axis_d);
+      Vec2 r_d = b2_mul_rot(q_d, j.local_anchor_d - lc[3]);
+      Vec2 r_b = b2_mul_rot(q_b, j.local_anchor_b - lc[1]);
+      g.jv_bd = j.ratio * u;
+      g.jw_d = j.ratio * b2_cross(r_d, u);
+      g.jw_b = j.ratio * b2_cross(r_b, u);
+      g.mass += j.ratio * j.ratio * (m[3] + m[1]) + i[3] * g.jw_d * g.jw_d + i[1] * g.jw_b * g.jw_b;
+      Vec2 p_d = j.local_anchor_d - lc[3];
+      Vec2 p_b = b2_mul_t_rot(q_d, r_b + (c[1] - c[3]));
+      g.coordinate_b = b2_dot(p_b - p_d, j.local_axis_d);
+    }
+    return g;
+  }
+  void gear_bodies(const Joint& j, int ix[4], Vec2 lc[4], float m[4], float i[4]) const {
+    const int b[4] = {j.body_a, j.body_b, j.body_c, j.body_d};
+    for (int k = 0; k < 4; ++k) {
+      ix[k] = bodies[b[k]].island_index; lc[k] = bodies[b[k]].sweep.local_center;
+      m[k] = bodies[b[k]].inv_mass; i[k] = bodies[b[k]].inv_i;
+    }
+  }
+  void gear_init_velocity(Joint& j, const TimeStep& step, Island& is) {
+    int ix[4]; Vec2 lc[4], c[4], v[4]; float m[4], i[4], a[4], w[4];
+    gear_bodies(j, ix, lc, m, i);
+    for (int k = 0; k < 4; ++k) { c[k] = is.positions[ix[k]].c; a[k] = is.positions[ix[k]].a; v[k] = is.velocities[ix[k]].v; w[k] = is.velocities[ix[k]].w; }
+    const GearRows g = gear_rows(j, c, a, lc, m, i);
+    j.jv_ac = g.jv_ac; j.jv_bd = g.jv_bd; j.jw_a = g.jw_a; j.jw_b = g.jw_b; j.jw_c = g.jw_c; j.jw_d = g.jw_d;
+    j.mass = g.mass > 0.0f ? 1.0f / g.mass : 0.0f;
+    if (step.warm_starting) {  // not rescaled by dt_ratio
+      v[0] += (m[0] * j.impulse) * j.jv_ac;
+      w[0] += i[0] * j.impulse * j.jw_a;
+      v[1] += (m[1] * j.impulse) * j.jv_bd;
+      w[1] += i[1] * j.impulse * j.jw_b;
+      v[2] -= (m[2] * j.impulse) * j.jv_ac;
+      w[2] -= i[2] * j.impulse * j.jw_c;
+      v[3] -= (m[3] * j.impulse) * j.jv_bd;
+      w[3] -= i[3] * j.impulse * j.jw_d;
+    } else {
+      j.impulse = 0.0f;
+    }
+    for (int k = 0; k < 4; ++k) { is.velocities[ix[k]].v = v[k]; is.velocities[ix[k]].w = w[k]; }
+  }
+  void gear_solve_velocity(Joint& j, Island& is) {
+    int ix[4]; Vec2 lc[4], v[4]; float m[4], i[4], w[4];
+    gear_bodies(j, ix, lc, m, i);
+    for (int k = 0; k < 4; ++k) { v[k] = is.velocities[ix[k]].v; w[k] = is.velocities[ix[k]].w; }
+    float cdot = b2_dot(j.jv_ac, v[0] - v[2]) + b2_dot(j.jv_bd, v[1] - v[3]);
+    cdot += (j.jw_a * w[0] - j.jw_c * w[2]) + (j.jw_b * w[1] - j.jw_d * w[3]);
+    float impulse = -j.mass * cdot;
+    j.impulse += impulse;
+    v[0] += (m[0] * impulse) * j.jv_ac;
+    w[0] += i[0] * impulse * j.jw_a;
+    v[1] += (m[1] * impulse) * j.jv_bd;
+    w[1] += i[1] * impulse * j.jw_b;
+    v[2] -= (m[2] * impulse) * j.jv_ac;
+    w[2] -= i[2] * impulse * j.jw_c;
+    v[3] -= (m[3] * impulse) * j.jv_bd;
+    w[3] -= i[3] * impulse * j.jw_d;
+    for (int k = 0; k < 4; ++k) { is.velocities[ix[k]].v = v[k]; is.velocities[ix[k]].w = w[k]; }
+  }
+  bool gear_solve_position(Joint& j, Island& is) {
+    int ix[4]; Vec2 lc[4], c[4]; float m[4], i[4], a[4];
+    gear_bodies(j, ix, lc, m, i);
+    for (int k = 0; k < 4; ++k) { c[k] = is.positions[ix[k]].c; a[k] = is.positions[ix[k]].a; }
+    const GearRows g = gear_rows(j, c, a, lc, m, i);
+    float cc = (g.coordinate_a + j.ratio * g.coordinate_b) - j.constant;
+    float impulse = 0.0f;
+    if (g.mass > 0.0f) impulse = -cc / g.mass;
+    c[0] += m[0] * impulse * g.jv_ac;
+    a[0] += i[0] * impulse * g.jw_a;
+    c[1] += m[1] * impulse * g.jv_bd;
+    a[1] += i[1] * impulse * g.jw_b;
+    c[2] -= m[2] * impulse * g.jv_ac;
+    a[2] -= i[2] * impulse * g.jw_c;
+    c[3] -= m[3] * impulse * g.jv_bd;
+    a[3] -= i[3] * impulse * g.jw_d;
+    for (int k = 0; k < 4; ++k) { is.positions[ix[k]].c = c[k]; is.positions[ix[k]].a = a[k]; }
+    return true;  // linear_error stays 0
+  }
   void joint_init_velocity_constraints(Joint& j, const TimeStep& step, Island& is) {
+    if (j.type == J_GEAR) { gear_init_velocity(j, step, is); return; }
     const Body& body_a = bodies[j.body_a];
     const Body& body_b = bodies[j.body_b];
     j.index_a = body_a.island_index;
@@ -1553,6 +1721,7 @@ struct World {
     is.velocities[j.index_b].w = w_b;
   }
   void joint_solve_velocity_constraints(Joint& j, const TimeStep& step, Island& is) {
+    if (j.type == J_GEAR) { gear_solve_velocity(j, is); return; }
     Vec2 v_a = is.velocities[j.index_a].v;
     float w_a = is.velocities[j.index_a].w;
     Vec2 v_b = is.velocities[j.index_b].v;
@@ -1875,6 +2044,7 @@ struct World {
     is.velocities[j.index_b].w = w_b;
   }
   bool joint_solve_position_constraints(Joint& j, Island& is) {
+    if (j.type == J_GEAR) return gear_solve_position(j, is);
     Vec2 c_a = is.positions[j.index_a].c;
     float a_a = is.positions[j.index_a].a;
     Vec2 c_b = is.positions[j.index_b].c;

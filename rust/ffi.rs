@@ -193,6 +193,7 @@ extern "C" {
                                   ground_ax: c_float, ground_ay: c_float, ground_bx: c_float, ground_by: c_float,
                                   anchor_ax: c_float, anchor_ay: c_float, anchor_bx: c_float, anchor_by: c_float,
                                   ratio: c_float) -> c_int;
+    pub fn b2gpu_gear_joint_def(w: *mut b2gpu_world, def: *mut b2gpu_joint_def, joint1: c_int, joint2: c_int, ratio: c_float) -> c_int;
     pub fn b2gpu_mouse_joint_def(w: *mut b2gpu_world, def: *mut b2gpu_joint_def, body_a: c_int, body_b: c_int,
                                  target_x: c_float, target_y: c_float) -> c_int;
     pub fn b2gpu_wheel_joint_def(w: *mut b2gpu_world, def: *mut b2gpu_joint_def, body_a: c_int, body_b: c_int, anchor_x: c_float, anchor_y: c_float, axis_x: c_float, axis_y: c_float) -> c_int;

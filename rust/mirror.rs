@@ -196,7 +196,7 @@ pub fn flatten<D: UserDataType>(world: &B2world<D>) -> Snapshot<D> {
         }
     }).collect();
 
-    // ---- joints (world list reversed); every type but the gear joint is inside the accelerated path
+    // ---- joints (world list reversed); all ten joint types are inside the accelerated path
     let mut joint_ptrs: Vec<B2jointPtr<D>> = world.m_joint_list.iter().collect();
     joint_ptrs.reverse();
     let joints: Vec<b2gpu_joint_rec> = joint_ptrs.iter().map(|j| {
@@ -252,6 +252,21 @@ pub fn flatten<D: UserDataType>(world: &B2world<D>) -> Snapshot<D> {
                 r.param[2] = v.m_angular_offset; r.param[3] = v.m_correction_factor;
                 r.impulse[0] = v.m_linear_impulse.x; r.impulse[1] = v.m_linear_impulse.y; r.impulse[2] = v.m_angular_impulse;
             }
+            JointAsDerived::EGearJoint(v) => {
+                // four bodies: C / D and the static rest of the record overflow into impulse[1..6] (include/b2gpu.h)
+                r.type_ = 3;
+                r.local_anchor_a = [v.m_local_anchor_a.x, v.m_local_anchor_a.y];
+                r.local_anchor_b = [v.m_local_anchor_b.x, v.m_local_anchor_b.y];
+                r.param = [v.m_local_anchor_c.x, v.m_local_anchor_c.y, v.m_local_anchor_d.x, v.m_local_anchor_d.y,
+                           v.m_local_axis_c.x, v.m_local_axis_c.y, v.m_local_axis_d.x, v.m_local_axis_d.y];
+                if v.m_type_a == B2jointType::EPrismaticJoint { r.flags |= 0x100; }
+                if v.m_type_b == B2jointType::EPrismaticJoint { r.flags |= 0x200; }
+                r.impulse[0] = v.m_impulse;
+                r.impulse[1] = v.m_reference_angle_a; r.impulse[2] = v.m_reference_angle_b;
+                r.impulse[3] = v.m_constant; r.impulse[4] = v.m_ratio;
+                r.impulse[5] = f32::from_bits(body_index[&addr(&v.m_body_c)] as u32);
+                r.impulse[6] = f32::from_bits(body_index[&addr(&v.m_body_d)] as u32);
+            }
             JointAsDerived::EPulleyJoint(v) => {
                 r.type_ = 7;
                 r.local_anchor_a = [v.m_local_anchor_a.x, v.m_local_anchor_a.y];
@@ -287,7 +302,8 @@ pub fn flatten<D: UserDataType>(world: &B2world<D>) -> Snapshot<D> {
                 r.param[0] = v.m_reference_angle; r.param[3] = v.m_stiffness; r.param[4] = v.m_damping;
                 r.impulse[0] = v.m_impulse.x; r.impulse[1] = v.m_impulse.y; r.impulse[2] = v.m_impulse.z;
             }
-            _ => { r.type_ = 0; } // b2gpu_world_upload answers B2GPU_E_UNSUPPORTED: keep such worlds on the CPU path
+            #[allow(unreachable_patterns)]
+            _ => { r.type_ = 0; } // an unknown joint type: b2gpu_world_upload answers B2GPU_E_UNSUPPORTED
         }
         r
     }).collect();
@@ -513,6 +529,9 @@ pub fn write_back<D: UserDataType>(world: &mut B2world<D>, snap: &Snapshot<D>) {
                 v.m_angular_impulse = r.impulse[2];
             }
             JointAsDerivedMut::EPulleyJoint(v) => {
+                v.m_impulse = r.impulse[0];
+            }
+            JointAsDerivedMut::EGearJoint(v) => {
                 v.m_impulse = r.impulse[0];
             }
             JointAsDerivedMut::EMouseJoint(v) => {

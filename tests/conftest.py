@@ -40,7 +40,7 @@ SCENES = {
     "terrain": (lambda s, w: s.terrain(w), (0.0, -10.0), 260),
 }
 
-# scenes with joints (revolute / prismatic / wheel / distance / weld / friction / motor / pulley / mouse)
+# scenes with joints (revolute / prismatic / wheel / distance / weld / friction / motor / pulley / mouse / gear)
 JOINT_SCENES = {
     "bridge": (lambda s, w: s.bridge(w), (0.0, -10.0), 240),
     "tumbler": (lambda s, w: s.tumbler(w, n=120), (0.0, -10.0), 240),
@@ -50,4 +50,5 @@ JOINT_SCENES = {
     "car": (lambda s, w: s.car(w), (0.0, -10.0), 420),
     "top_down": (lambda s, w: s.top_down(w), (0.0, 0.0), 150),
     "pulleys": (lambda s, w: s.pulleys(w), (0.0, -10.0), 300),
+    "gears": (lambda s, w: s.gears(w), (0.0, -10.0), 300),
 }

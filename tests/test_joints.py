@@ -362,6 +362,32 @@ def test_oracle_mouse_joint_drags_the_body_to_its_target(built):
     assert w2.snapshot().bodies[1]["c"][1] < 0.6
 
 
+def test_oracle_gear_joint_keeps_coordinate1_plus_ratio_coordinate2(built):
+    """examples/testbed/tests/gear_joint.rs (the ground-mounted train): disc 1 and disc 2 on revolute joints geared 2 : 1, disc 2
+    and a rack on a prismatic joint geared -1/2.  angle1 + 2 angle2 and angle2 - translation / 2 stay at their initial
+    values (0) while the train turns, until the rack reaches its limit and stops everything."""
+    from box2d_rs_b200 import abi, scenes
+    from oracle import b2o
+    w = b2o.B2world((0.0, -10.0))
+    train = scenes.gears(w)
+    jd = w.gear_joint_def(w.joint(3), w.joint(4), 2.0)
+    assert (jd.type, jd.body_a, jd.body_b, jd.enable_limit, jd.enable_motor, jd.length) == (abi.JOINT_GEAR, 4, 5, 3, 4, 2.0)
+    rec = w.snapshot().joints[train.index]
+    assert rec["type"] == abi.JOINT_GEAR and rec["flags"] & 0x300 == 0 and rec["impulse"][4] == 2.0 and rec["impulse"][3] == 0.0
+    assert np.array(rec["impulse"][5:7], np.float32).view(np.int32).tolist() == [0, 0]  # bodies C, D: the ground
+    rack = w.snapshot().joints[train.index + 1]
+    assert rack["flags"] & 0x300 == 0x200 and rack["impulse"][4] == -0.5 and tuple(rack["param"][6:8]) == (0.0, 1.0)
+    turned = 0.0
+    for i in range(120):
+        w.step(scenes.DT, 8, 3)
+        b = w.snapshot().bodies
+        a1, a2, y3 = float(b[4]["a"]), float(b[5]["a"]), float(b[6]["c"][1])
+        assert abs(a1 + 2.0 * a2) < 0.02 and abs(a2 - 0.5 * (y3 - 12.0)) < 0.02
+        turned = max(turned, abs(a1))
+    assert turned > 4.9 and abs(y3 - 7.0) < 0.02  # the rack came down to its lower limit (-5) and holds the train
+    assert abs(float(b[4]["w"])) < 1e-3
+
+
 def test_oracle_angular_stiffness_formula(built):
     """b2_angular_stiffness (private b2_joint.rs:47-70): I = Ia Ib / (Ia + Ib) of B2body::get_inertia, omega = 2 pi f."""
     from box2d_rs_b200 import abi
@@ -418,11 +444,22 @@ def test_weld_defs_and_unsupported_types(built):
     with pytest.raises(B2gpuError) as e:  # ratio <= epsilon: the reference asserts
         wg.pulley_joint_def(*(argsg[:-1] + (0.0,)))
     assert e.value.code == abi.E_INVALID
+    for w in (wo, wg):  # a gear over two joints of the world: the defs and the created records agree; bad couples are refused
+        w._r = w.create_joint(w.revolute_joint_def(w.body(0), w.body(1), (1.0, 1.0)))
+        w._p = w.create_joint(w.prismatic_joint_def(w.body(1), w.body(0), (1.3, 1.2), (0.6, -0.8)))
+        w._d = w.create_joint(w.distance_joint_def(w.body(0), w.body(1), (0.0, 1.0), (2.0, 1.0)))
+    assert bytes(wo.gear_joint_def(wo._r, wo._p, -1.5)) == bytes(wg.gear_joint_def(wg._r, wg._p, -1.5))
+    wo.create_joint(wo.gear_joint_def(wo._r, wo._p, -1.5))
+    wg.create_joint(wg.gear_joint_def(wg._r, wg._p, -1.5))
+    assert parity.compare_snapshots(wo.snapshot(), wg.snapshot()) == []
+    with pytest.raises(B2gpuError) as e:  # a distance joint cannot be geared: the reference asserts
+        wg.create_joint(wg.gear_joint_def(wg._r, wg._d, 1.0))
+    assert e.value.code == abi.E_INVALID
     pg.lower_angle, pg.upper_angle = 1.0, 0.5  # lower > upper: the reference asserts
     with pytest.raises(B2gpuError) as e:
         wg.create_joint(pg)
     assert e.value.code == abi.E_INVALID
-    jg.type = 3  # gear: the one joint type outside the path
+    jg.type = 11  # past the end of B2jointType
     with pytest.raises(B2gpuError) as e:
         wg.create_joint(jg)
     assert e.value.code == abi.E_UNSUPPORTED
@@ -526,7 +563,7 @@ def test_hostsim_free_running(name, hctx):
     _free_running(name, hctx, 20)
 
 
-@pytest.mark.parametrize("name,lane_block", [("bridge", 1), ("tumbler", 4), ("joints_mix", 32)])
+@pytest.mark.parametrize("name,lane_block", [("bridge", 1), ("tumbler", 4), ("joints_mix", 32), ("gears", 4), ("pulleys", 32)])
 def test_hostsim_batched(name, lane_block, hctx):
     _batched(name, hctx, 5 if lane_block < 32 else 34, lane_block)
 
@@ -675,7 +712,7 @@ def test_validate_rejects_bad_joint_records(built):
         s.joints[3]["body_b"] = s.joints[3]["body_a"]
 
     def unknown_type(s):
-        s.joints[0]["type"] = 3  # gear
+        s.joints[0]["type"] = 11
     broken(body_out_of_range)
     broken(same_body)
     broken(unknown_type)
@@ -733,7 +770,7 @@ def test_gpu_free_running(name, gctx):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("name,lane_block", [("bridge", 1), ("tumbler", 32), ("joints_mix", 32)])
+@pytest.mark.parametrize("name,lane_block", [("bridge", 1), ("tumbler", 32), ("joints_mix", 32), ("gears", 32), ("pulleys", 32)])
 def test_gpu_batched(name, lane_block, gctx):
     _batched(name, gctx, 5 if lane_block < 32 else 70, lane_block)
 

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Differential fuzzing of the device stages (host simulator build by default, --gpu for the CUDA path) against
 the CPU oracle: random scenes (polygons of 3..8 vertices, circles, edges, chains, kinematic / fixed-rotation /
-multi-fixture bodies, sensors, filters, restitution, damping, revolute / prismatic / wheel / distance / weld / friction / motor / pulley / mouse joints with limits, motors and springs,
+multi-fixture bodies, sensors, filters, restitution, damping, revolute / prismatic / wheel / distance / weld / friction / motor / pulley / mouse / gear joints with limits, motors and springs,
 random world flags and iteration counts, dt = 0 steps,
 mid-run set_transform / set_linear_velocity / apply_force / apply_torque / apply_*_impulse / set_awake edits), stepped freely and compared bit for bit.
 
@@ -11,6 +11,9 @@ mid-run set_transform / set_linear_velocity / apply_force / apply_torque / apply
 reproduce the oracle's step (contacts created in that step compared as a set).
 """
 import argparse
+import os
+
+EVERY = int(os.environ.get("FUZZ_EVERY", "16"))  # compare every n-th step (1 to locate a divergence)
 import math
 import os
 import sys
@@ -28,6 +31,7 @@ from box2d_rs_b200.abi import BodyDef, FixtureDef  # noqa: E402
 def build(world, rng):
     f32 = scenes.f32
     ground = world.create_body(BodyDef())
+    body_types = [abi.STATIC_BODY]
     kind = rng.integers(0, 3)
     if kind == 0:
         ground.create_fixture_by_shape(world.shapes.edge_two_sided((-15.0, 0.0), (15.0, 0.0)), 0.0)
@@ -64,6 +68,7 @@ def build(world, rng):
             bd.linear_velocity = (f32(rng.uniform(-150, 150)), f32(rng.uniform(-50, 150)))
             bd.angle = f32(rng.uniform(-200, 200))
         b = world.create_body(bd)
+        body_types.append(bd.type if bd.enabled else -1)  # -1: disabled (its joints stay out of the islands)
         for _ in range(1 + int(rng.integers(0, 3) == 0)):
             zero_mass = bd.type == abi.DYNAMIC_BODY and rng.integers(0, 25) == 0  # dynamic body nothing can push
             fd = FixtureDef(density=f32(rng.uniform(0.2, 4)) if (bd.type == abi.DYNAMIC_BODY and not zero_mass) else 0.0,
@@ -89,9 +94,9 @@ def build(world, rng):
                 ang = np.sort(rng.uniform(0, 2 * math.pi, nv))
                 shape = world.shapes.polygon([(f32(rad * math.cos(a)), f32(rad * math.sin(a) * rng.uniform(0.5, 1.0))) for a in ang])
             b.create_fixture(fd, shape)
-    # joints (every type but gear) between random bodies, the ground included: limits, motors, soft springs, slack ranges,
+    # joints (all ten types) between random bodies, the ground included: limits, motors, soft springs, slack ranges,
     # collide_connected, degenerate pairs (kinematic or fixed-rotation bodies, anchors far from the bodies)
-    joints = []
+    joints, ends, gears, coupled = [], [], [], []
     if rng.integers(0, 5) < 3:
         for _ in range(int(rng.integers(1, 9))):
             a, b = int(rng.integers(0, n + 1)), int(rng.integers(0, n + 1))
@@ -161,7 +166,29 @@ def build(world, rng):
                     jd.max_length = f32(jd.length + rng.uniform(0, 2))
             jd.collide_connected = int(rng.integers(0, 2))
             joints.append((world.create_joint(jd), jd.type))
-    world._fuzz_joints = joints
+            ends.append((a, b))
+        # gear joints over the revolute / prismatic joints made above (body B of each must be dynamic): any ratio sign, the
+        # joint's own bodies or — as the testbed does — other ones, a joint geared to itself's neighbour on a shared body
+        # (all four bodies must reach the gear's island through the coupled joints — a disabled one would leave the reference
+        # with a stale island index — so the optional other bodies are the coupled joints' own body A)
+        couples = [q for q, (h, t) in enumerate(joints) if t in (abi.JOINT_REVOLUTE, abi.JOINT_PRISMATIC)
+                   and body_types[ends[q][1]] == abi.DYNAMIC_BODY and body_types[ends[q][0]] >= 0]
+        for _ in range(int(rng.integers(0, 3))):
+            if len(couples) < 2:
+                break
+            q1, q2 = (int(v) for v in rng.choice(couples, 2, replace=False))
+            jd = world.gear_joint_def(joints[q1][0], joints[q2][0], f32(rng.uniform(0.3, 3.0) * (1 if rng.integers(0, 2) else -1)))
+            if rng.integers(0, 4) == 0:
+                jd.body_a = ends[q1][0]
+            if rng.integers(0, 4) == 0:
+                jd.body_b = ends[q2][0]
+            if jd.body_a == jd.body_b:
+                continue
+            jd.collide_connected = int(rng.integers(0, 2))
+            gears.append((world.create_joint(jd), jd.type))
+            coupled += [joints[q1][0], joints[q2][0]]
+    world._fuzz_joints = joints + gears
+    world._fuzz_coupled = coupled  # never destroyed: "destroy the gear joint first" (src/joints/b2_gear_joint.rs:116-117)
     return n + 1
 
 
@@ -217,6 +244,8 @@ def run_seed(seed, make_world, steps, batch_mode, large=False, events=False, lev
     for i in range(steps):
         dt = 0.0 if rng.integers(0, 40) == 0 else scenes.DT
         ev = rng.integers(0, 30)
+        if os.environ.get("FUZZ_TRACE"):
+            print("step %d: dt %g event %d" % (i, dt, ev))
         if batch is None and ev == 0:
             b = int(rng.integers(1, nb))
             p, a = (f32v(rng.uniform(-8, 8)), f32v(rng.uniform(1, 10))), f32v(rng.uniform(-3, 3))
@@ -242,8 +271,9 @@ def run_seed(seed, make_world, steps, batch_mode, large=False, events=False, lev
                     else: j.set_limits(min(val, 0.0) - 0.3, max(val, 0.0) + 0.3)
         if batch is None and ev == 9 and wo._fuzz_joints and rng.integers(0, 3) == 0:  # B2world::destroy_joint
             q = int(rng.integers(0, len(wo._fuzz_joints)))
-            for w in (wo, wg):
-                w.destroy_joint(w._fuzz_joints.pop(q)[0])
+            if not any(wo._fuzz_joints[q][0] is h for h in wo._fuzz_coupled):
+                for w in (wo, wg):
+                    w.destroy_joint(w._fuzz_joints.pop(q)[0])
         if batch is None and 2 <= ev <= 7:  # the rest of B2body's force / impulse API, sleeping bodies included
             b = int(rng.integers(1, nb))
             vec = (f32v(rng.uniform(-40, 40)), f32v(rng.uniform(-40, 40)))
@@ -273,7 +303,7 @@ def run_seed(seed, make_world, steps, batch_mode, large=False, events=False, lev
             wg.step(dt, vi, pi)
         else:
             batch.step(dt, vi, pi)
-        if i % 16 == 15 or i == steps - 1:
+        if i % EVERY == EVERY - 1 or i == steps - 1:
             got = wg.snapshot() if batch is None else batch.download_world(batch.n_worlds - 1)
             st = wg.get_stats() if batch is None else batch.stats()[batch.n_worlds - 1]
             bad = parity.compare_snapshots(wo.snapshot(), got) + parity.compare_stats(wo.get_stats(), st)
