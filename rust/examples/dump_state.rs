@@ -20,6 +20,10 @@ use box2d_rs::b2_math::*;
 use box2d_rs::b2_world::*;
 use box2d_rs::b2rs_common::UserDataType;
 use box2d_rs::joints::b2_distance_joint::*;
+use box2d_rs::joints::b2_gear_joint::*;
+use box2d_rs::joints::b2_mouse_joint::*;
+use box2d_rs::joints::b2_prismatic_joint::*;
+use box2d_rs::joints::b2_pulley_joint::*;
 use box2d_rs::joints::b2_revolute_joint::*;
 use box2d_rs::shapes::b2_circle_shape::*;
 use box2d_rs::shapes::b2_edge_shape::*;
@@ -85,7 +89,7 @@ fn container(world: &World, hw: f32, height: f32) -> Body {
     g
 }
 
-// ---- scenes.py: hello_world, pyramid, pile, add_pair, bridge, tumbler
+// ---- scenes.py: hello_world, pyramid, pile, add_pair, bridge, tumbler (gears and pulleys further down)
 fn hello_world(world: &World) {
     let g = body(world, false, 0.0, -10.0, 0.0);
     B2body::create_fixture_by_shape(g, boxed(50.0, 10.0), 0.0);
@@ -212,6 +216,100 @@ fn pendulum(world: &World) {
     world.borrow_mut().create_joint(&B2JointDefEnum::DistanceJoint(jd));
 }
 
+fn circle_at(r: f32, x: f32, y: f32) -> Rc<RefCell<B2circleShape>> {
+    let mut s = B2circleShape::default();
+    s.base.m_radius = r;
+    s.m_p.set(x, y);
+    Rc::new(RefCell::new(s))
+}
+fn revolute(world: &World, a: &Body, b: &Body, x: f32, y: f32) -> B2jointPtr<Ud> {
+    let mut jd = B2revoluteJointDef::default();
+    jd.initialize(a.clone(), b.clone(), B2vec2::new(x, y));
+    world.borrow_mut().create_joint(&B2JointDefEnum::RevoluteJoint(jd))
+}
+fn gear(world: &World, a: &Body, b: &Body, j1: &B2jointPtr<Ud>, j2: &B2jointPtr<Ud>, ratio: f32) {
+    let mut jd = B2gearJointDef::default();
+    jd.base.body_a = Some(a.clone());
+    jd.base.body_b = Some(b.clone());
+    jd.joint1 = Some(j1.clone());
+    jd.joint2 = Some(j2.clone());
+    jd.ratio = ratio;
+    world.borrow_mut().create_joint(&B2JointDefEnum::GearJoint(jd));
+}
+fn gears(world: &World) {
+    // scenes.py::gears — the testbed's GearJoint scene plus two kicks
+    let g = body(world, false, 0.0, 0.0, 0.0);
+    edge(world, &g, 50.0, 0.0, -50.0, 0.0);
+    let (circle1, circle2, bar) = (circle(1.0), circle(2.0), boxed(0.5, 5.0));
+    let body1 = body(world, false, 10.0, 9.0, 0.0);
+    B2body::create_fixture_by_shape(body1.clone(), circle1.clone(), 5.0);
+    let body2 = body(world, true, 10.0, 8.0, 0.0);
+    B2body::create_fixture_by_shape(body2.clone(), bar.clone(), 5.0);
+    let body3 = body(world, true, 10.0, 6.0, 0.0);
+    B2body::create_fixture_by_shape(body3.clone(), circle2.clone(), 5.0);
+    let joint1 = revolute(world, &body1, &body2, 10.0, 9.0);
+    let joint2 = revolute(world, &body2, &body3, 10.0, 6.0);
+    gear(world, &body1, &body3, &joint1, &joint2, 2.0); // the STATIC disc as body A, as the testbed does
+    body2.borrow_mut().set_angular_velocity(1.5);
+    let b1 = body(world, true, -3.0, 12.0, 0.0);
+    B2body::create_fixture_by_shape(b1.clone(), circle1, 5.0);
+    let j1 = revolute(world, &g, &b1, -3.0, 12.0);
+    let b2 = body(world, true, 0.0, 12.0, 0.0);
+    B2body::create_fixture_by_shape(b2.clone(), circle2, 5.0);
+    let j2 = revolute(world, &g, &b2, 0.0, 12.0);
+    let b3 = body(world, true, 2.5, 12.0, 0.0);
+    B2body::create_fixture_by_shape(b3.clone(), bar, 5.0);
+    let mut jd3 = B2prismaticJointDef::default();
+    jd3.initialize(g.clone(), b3.clone(), B2vec2::new(2.5, 12.0), B2vec2::new(0.0, 1.0));
+    jd3.lower_translation = -5.0;
+    jd3.upper_translation = 5.0;
+    jd3.enable_limit = true;
+    let j3 = world.borrow_mut().create_joint(&B2JointDefEnum::PrismaticJoint(jd3));
+    gear(world, &b1, &b2, &j1, &j2, 2.0);
+    gear(world, &b2, &b3, &j2, &j3, -0.5);
+    b1.borrow_mut().set_angular_velocity(6.0);
+}
+fn pulley(world: &World, a: &Body, b: &Body, ga: (f32, f32), gb: (f32, f32), pa: (f32, f32), pb: (f32, f32), ratio: f32) {
+    let mut jd = B2pulleyJointDef::default();
+    jd.initialize(a.clone(), b.clone(), B2vec2::new(ga.0, ga.1), B2vec2::new(gb.0, gb.1), B2vec2::new(pa.0, pa.1),
+                  B2vec2::new(pb.0, pb.1), ratio);
+    world.borrow_mut().create_joint(&B2JointDefEnum::PulleyJoint(jd));
+}
+fn pulleys(world: &World) {
+    // scenes.py::pulleys — the testbed's PulleyJoint scene, a block-and-tackle pair over a floor, a mouse drag
+    let (y, l, a, b) = (16.0f32, 12.0f32, 1.0f32, 2.0f32);
+    let g = body(world, false, 0.0, 0.0, 0.0);
+    for x in [-10.0f32, 10.0f32] {
+        B2body::create_fixture_by_shape(g.clone(), circle_at(2.0, x, y + b + l), 0.0);
+    }
+    edge(world, &g, -60.0, 0.0, 60.0, 0.0);
+    let shape = boxed(a, b);
+    let body1 = body(world, true, -10.0, y as f64, 0.0);
+    B2body::create_fixture_by_shape(body1.clone(), shape.clone(), 5.0);
+    let body2 = body(world, true, 10.0, y as f64, 0.0);
+    B2body::create_fixture_by_shape(body2.clone(), shape, 5.0);
+    pulley(world, &body1, &body2, (-10.0, y + b + l), (10.0, y + b + l), (-10.0, y + b), (10.0, y + b), 1.5);
+    let (small, big) = (boxed(0.5, 0.5), boxed(1.0, 1.0));
+    let body3 = body(world, true, 24.0, 6.0, 0.2);
+    fixture(&body3, small, 1.0, 0.4);
+    let body4 = body(world, true, 32.0, 9.0, 0.0);
+    fixture(&body4, big.clone(), 2.0, 0.4);
+    pulley(world, &body3, &body4, (25.0, 20.0), (31.0, 20.0), (24.0, 6.5), (32.0, 10.0), 2.0);
+    let crate_ = body(world, true, -30.0, 1.0, 0.0);
+    fixture(&crate_, big, 1.0, 0.5);
+    let mut jd = B2mouseJointDef::default();
+    jd.base.body_a = Some(g.clone());
+    jd.base.body_b = Some(crate_.clone());
+    jd.target.set(-29.5, 1.5);
+    jd.max_force = 4000.0; // 1000 * mass
+    b2_linear_stiffness(&mut jd.stiffness, &mut jd.damping, 5.0, 0.7, g.clone(), crate_.clone());
+    let mouse = world.borrow_mut().create_joint(&B2JointDefEnum::MouseJoint(jd));
+    if let JointAsDerivedMut::EMouseJoint(m) = mouse.borrow_mut().as_derived_mut() {
+        m.set_target(B2vec2::new(-22.0, 9.0));
+    }
+    crate_.borrow_mut().set_awake(true);
+}
+
 fn main() {
     let out = PathBuf::from(std::env::args().nth(1).unwrap_or_else(|| "reference_dump".to_string()));
     std::fs::create_dir_all(&out).unwrap();
@@ -225,6 +323,8 @@ fn main() {
         ("bridge", (0.0, -10.0), Box::new(bridge), vec![0, 1, 60, 240]),
         ("tumbler", (0.0, -10.0), Box::new(|w| tumbler(w, 120)), vec![0, 1, 60, 240]),
         ("pendulum", (0.0, -10.0), Box::new(pendulum), vec![0, 1, 60, 240]),
+        ("gears", (0.0, -10.0), Box::new(gears), vec![0, 1, 30, 120, 300]),
+        ("pulleys", (0.0, -10.0), Box::new(pulleys), vec![0, 1, 60, 150, 300]),
     ];
     let dt: f32 = 1.0 / 60.0;
     for (name, g, recipe, steps) in cases {

@@ -25,6 +25,8 @@ CASES = {
     "bridge": (lambda s, w: s.bridge(w), (0.0, -10.0)),
     "tumbler": (lambda s, w: s.tumbler(w, n=120), (0.0, -10.0)),
     "pendulum": (None, (0.0, -10.0)),
+    "gears": (lambda s, w: s.gears(w), (0.0, -10.0)),
+    "pulleys": (lambda s, w: s.pulleys(w), (0.0, -10.0)),
 }
 
 
