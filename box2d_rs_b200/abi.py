@@ -21,7 +21,8 @@ WORLD_ALLOW_SLEEP, WORLD_WARM_STARTING, WORLD_NEW_CONTACTS, WORLD_CLEAR_FORCES, 
     0x01, 0x02, 0x04, 0x08, 0x10)
 MAX_POLYGON_VERTICES = 8
 JOINT_DISTANCE, JOINT_FRICTION, JOINT_MOTOR, JOINT_PRISMATIC, JOINT_REVOLUTE, JOINT_WELD, JOINT_WHEEL = 1, 2, 4, 6, 8, 9, 10
-JOINT_GEAR, JOINT_MOUSE, JOINT_PULLEY = 3, 5, 7  # B2jointType (src/b2_joint.rs:46-58)
+JOINT_GEAR, JOINT_MOUSE, JOINT_PULLEY = 3, 5, 7
+JOINT_CONTROL_MOTOR_SPEED, JOINT_CONTROL_MAX_MOTOR_TORQUE, JOINT_CONTROL_TARGET = 0, 1, 2  # b2gpu_batch_set_joint_control  # B2jointType (src/b2_joint.rs:46-58)
 JOINT_COLLIDE_CONNECTED, JOINT_ENABLE_LIMIT, JOINT_ENABLE_MOTOR = 0x1, 0x2, 0x4
 POLYGON_RADIUS = float(np.float32(2.0) * np.float32(0.005))  # src/b2_common.rs:48
 

@@ -196,6 +196,22 @@ class Batch:
         assert f.shape[1:] == (self.body_count, 3)
         check(self.L, self.L.b2gpu_batch_set_forces(self.h, f.ctypes.data, first, f.shape[0]))
 
+    def _joint_control(self, joint, control, values, per, first):
+        v = np.ascontiguousarray(values, np.float32).reshape(-1, per)
+        check(self.L, self.L.b2gpu_batch_set_joint_control(self.h, getattr(joint, "index", joint), control, v.ctypes.data, first, v.shape[0]))
+
+    def set_motor_speeds(self, joint, speeds, first=0):
+        """B2revoluteJoint::set_motor_speed in worlds first .. first + len(speeds): one value per world (an RL action)."""
+        self._joint_control(joint, abi.JOINT_CONTROL_MOTOR_SPEED, speeds, 1, first)
+
+    def set_max_motor_torques(self, joint, torques, first=0):
+        """B2revoluteJoint::set_max_motor_torque per world (prismatic joints: the maximum motor force)."""
+        self._joint_control(joint, abi.JOINT_CONTROL_MAX_MOTOR_TORQUE, torques, 1, first)
+
+    def set_targets(self, joint, targets, first=0):
+        """B2mouseJoint::set_target per world: targets[n][2]."""
+        self._joint_control(joint, abi.JOINT_CONTROL_TARGET, targets, 2, first)
+
     def set_linear_velocity(self, body, vxvy, first=0):
         v = np.ascontiguousarray(vxvy, np.float32)
         check(self.L, self.L.b2gpu_batch_set_linear_velocity(self.h, body, v.ctypes.data, first, v.shape[0]))

@@ -928,6 +928,42 @@ struct VelScatterK {
   }
 };
 
+// b2gpu_batch_set_joint_control: the revolute / mouse setters in every world of a range (include/b2gpu.h)
+struct JointControlK {
+  Batch B;
+  const float* in;  // [count] or [count][2]
+  int joint, control, first, count;
+  B2G_HD void wake(const WIdx& x, int body) const {  // B2body::set_awake(true): static bodies stay as they are
+    const int bi = x.at(B.NB, body);
+    const int bf = B.b_flags[bi];
+    if (body_type(bf) == B2GPU_STATIC_BODY) return;
+    B.b_flags[bi] = bf | B2GPU_BODY_AWAKE;
+    B.b_pos[bi].w = 0.0f;
+    if (!(bf & B2GPU_BODY_AWAKE)) ws_of(B, x)[WS_TOPO_DIRTY] = 1;
+  }
+  B2G_HD void operator()(int i) const {
+    if (i >= count) return;
+    WIdx x = widx(B, first + i);
+    const b2gpu_joint_rec& jr = B.joints[joint];
+    const int ji = x.at(B.NJ, joint);
+    float4 s1 = B.j_s1[ji];
+    if (control == B2GPU_JOINT_CONTROL_TARGET) {
+      const float tx = in[2 * i], ty = in[2 * i + 1];
+      if (tx == s1.z && ty == s1.y) return;
+      wake(x, jr.body_b);
+      s1.z = tx; s1.y = ty;
+    } else {
+      const float v = in[i];
+      float& slot = control == B2GPU_JOINT_CONTROL_MOTOR_SPEED ? s1.y : s1.z;
+      if (v == slot) return;
+      wake(x, jr.body_a);
+      wake(x, jr.body_b);
+      slot = v;
+    }
+    B.j_s1[ji] = s1;
+  }
+};
+
 // Device-side failures (contact table / move buffer / island list full, unregistered shape pair, query stack
 // overflow) are recorded per world in WS_STATUS and stay set; this reduces them to one word so that every call that
 // already synchronises can return the first failure instead of 0 (the word is the most negative code of any world).
@@ -1714,6 +1750,25 @@ int batch_set_linear_velocity(BatchHost* bh, int body, const float* host_vxvy, i
   }
   RC(dev_h2d(bh->ctx, bh->vel_scratch, host_vxvy, (size_t)count * 2 * 4));  // its own scratch: forces_dev belongs to the caller
   { VelScatterK k = {bh->B, bh->vel_scratch, body, first, count}; RC(launch(bh->ctx, k, count, 128)); }
+  return 0;
+}
+int batch_set_joint_control(BatchHost* bh, int joint, int control, const float* host_values, int first, int count) {
+  if (!bh || !host_values || joint < 0 || joint >= bh->B.NJ || first < 0 || count < 0 || first + count > bh->B.n_worlds) {
+    set_error("set_joint_control: bad argument");
+    return B2GPU_E_INVALID;
+  }
+  const int type = bh->topo.joints[joint].type;
+  const bool motorised = type == B2GPU_JOINT_REVOLUTE || type == B2GPU_JOINT_PRISMATIC || type == B2GPU_JOINT_WHEEL;
+  const bool ok = control == B2GPU_JOINT_CONTROL_TARGET ? type == B2GPU_JOINT_MOUSE
+                  : (control == B2GPU_JOINT_CONTROL_MOTOR_SPEED || control == B2GPU_JOINT_CONTROL_MAX_MOTOR_TORQUE) && motorised;
+  if (!ok) { set_error("set_joint_control: the joint is not of a type this control edits"); return B2GPU_E_INVALID; }
+  if (count == 0) return 0;
+  const int per = control == B2GPU_JOINT_CONTROL_TARGET ? 2 : 1;
+  RC(dev_h2d(bh->ctx, bh->vel_scratch, host_values, (size_t)count * per * 4));  // [n_worlds][2] staging
+  Batch all = bh->B;
+  all.wb_first = 0;
+  all.wb_count = bh->B.n_wblocks;
+  { JointControlK k = {all, bh->vel_scratch, joint, control, first, count}; RC(launch(bh->ctx, k, count, 128)); }
   return 0;
 }
 // The device-pointer forms (zero-copy consumers, e.g. torch tensors over b2gpu_batch_forces_device /

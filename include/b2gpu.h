@@ -617,6 +617,16 @@ int b2gpu_batch_set_level_threshold(b2gpu_batch* b, int contacts);
 int b2gpu_batch_set_forces(b2gpu_batch* b, const float* host_fxfyt, int first_world, int count);
 /* Linear velocity of one body index in every world (B2body::set_linear_velocity). */
 int b2gpu_batch_set_linear_velocity(b2gpu_batch* b, int body, const float* host_vxvy, int first_world, int count);
+/* Per-world joint controls of a batch — the RL action on a jointed agent.  One joint index (shared topology), one value per
+ * world: host array [count] for MOTOR_SPEED / MAX_MOTOR_TORQUE (revolute, prismatic — there it is the maximum motor force —
+ * and wheel joints), [count][2] for TARGET (mouse joints).  Semantics of B2revoluteJoint::set_motor_speed /
+ * set_max_motor_torque (src/joints/b2_revolute_joint.rs:172-205) and B2mouseJoint::set_target
+ * (src/joints/b2_mouse_joint.rs:114-119) in every world: a value that differs from the world's current one wakes the joint's
+ * bodies (body B only for TARGET) and replaces it.  Another joint type: B2GPU_E_INVALID. */
+#define B2GPU_JOINT_CONTROL_MOTOR_SPEED 0
+#define B2GPU_JOINT_CONTROL_MAX_MOTOR_TORQUE 1
+#define B2GPU_JOINT_CONTROL_TARGET 2
+int b2gpu_batch_set_joint_control(b2gpu_batch* b, int joint, int control, const float* host_values, int first_world, int count);
 /* Body state of every world after the last step: host array [count][body_count][8] =
  * (c.x, c.y, a, v.x, v.y, w, xf.p.x, xf.p.y) — what get_world_center/get_angle/
  * get_linear_velocity/get_angular_velocity/get_position return. */

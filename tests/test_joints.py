@@ -541,6 +541,69 @@ def _batched(name, ctx, n, lane_block):
     wg.close()
 
 
+def _batch_joint_controls(ctx, lane_block):
+    """b2gpu_batch_set_joint_control: per-world motor speeds / torques / mouse targets of a batch (the RL action on a jointed
+    agent) against oracle worlds driven through the single-world setters, sleeping worlds woken by a changed value included."""
+    from box2d_rs_b200 import scenes
+    from box2d_rs_b200.lib import B2gpuError
+    n = 37
+    rng = np.random.default_rng(5)
+    for name, control in (("car", "speed"), ("joints_mix", "torque"), ("pulleys", "target")):
+        wo, wg, steps, ro, rg = _pair(name, ctx)
+        jo = ro[0] if name == "car" else ro     # the rear wheel's motor / the motorised arm / the mouse joint
+        ji = jo.index
+        bt = wg.batch(n, lane_block=lane_block)
+        picks = {0: wo.clone(), 5: wo.clone(), n - 1: wo.clone()}
+        for i in range(150):
+            if i % 30 == 10:  # a new action for every world; world 5 repeats its old one every other time (no wake, no change)
+                if control == "target":
+                    vals = rng.uniform(-30.0, -20.0, (n, 2)).astype(np.float32) + np.float32([0.0, 30.0])
+                else:
+                    vals = rng.uniform(-30.0, 30.0, n).astype(np.float32) if control == "speed" else rng.uniform(0.0, 80.0, n).astype(np.float32)
+                if i % 60 == 40:
+                    vals[5] = last[5]
+                last = vals.copy()
+                if control == "speed":
+                    bt.set_motor_speeds(ji, vals)
+                elif control == "torque":
+                    bt.set_max_motor_torques(ji, vals[:20])
+                    bt.set_max_motor_torques(ji, vals[20:], first=20)
+                else:
+                    bt.set_targets(ji, vals)
+                for w, o in picks.items():
+                    j = o.joint(ji)
+                    if control == "speed":
+                        j.set_motor_speed(float(vals[w]))
+                    elif control == "torque":
+                        j.set_max_motor_torque(float(vals[w]))
+                    else:
+                        j.set_target((float(vals[w][0]), float(vals[w][1])))
+            bt.step(scenes.DT, 8, 3)
+            for o in picks.values():
+                o.step(scenes.DT, 8, 3)
+            if i % 10 == 9:
+                for w, o in picks.items():
+                    bad = parity.compare_snapshots(o.snapshot(), bt.download_world(w)) + parity.compare_stats(o.get_stats(), bt.stats()[w])
+                    assert bad == [], "%s world %d step %d: %s" % (name, w, i, bad[:6])
+        with pytest.raises(B2gpuError):  # a control the joint type does not have
+            if control == "target":
+                bt.set_motor_speeds(ji, np.zeros(n, np.float32))
+            else:
+                bt.set_targets(ji, np.zeros((n, 2), np.float32))
+        bt.close()
+        wg.close()
+
+
+@pytest.mark.parametrize("lane_block", [1, 32])
+def test_hostsim_batch_joint_controls(lane_block, hctx):
+    _batch_joint_controls(hctx, lane_block)
+
+
+@pytest.mark.gpu
+def test_gpu_batch_joint_controls(gctx):
+    _batch_joint_controls(gctx, 32)
+
+
 def _teacher_forced(name, ctx):
     from box2d_rs_b200 import scenes
     wo, wg, steps, _, _ = _pair(name, ctx)
