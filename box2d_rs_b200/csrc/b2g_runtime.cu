@@ -691,6 +691,7 @@ int batch_create(Ctx* ctx, const b2gpu_snapshot* proto, int n_worlds, const b2gp
       }
     }
     if (const char* e = getenv("B2GPU_STREAM_GROUPS")) bh->stream_groups = atoi(e);  // tuning experiments
+    if (const char* e = getenv("B2GPU_STAGGER")) bh->stagger_groups = atoi(e) != 0;
     if (caps && caps->reserved[1] == 5) bh->stream_groups = 1;
     if (caps && caps->reserved[1] == 6) bh->use_graphs = false;
     bh->island_layout = island_smem_layout(B.NB, B.NF, (size_t)max_optin - 1024);
@@ -1562,7 +1563,7 @@ static int enqueue_steps(BatchHost* bh, const StepParams& sp, int steps, const f
       else { ForceScatterK k = {Bw, bh->forces_dev + off, w0, wn}; rc = launch(ctx, k, sg.wb_count * B.LB * B.NB, 128); }
     }
     // stagger: start behind the previous group's solver set-up of its first step
-    if (!rc && g > 0) {
+    if (!rc && g > 0 && bh->stagger_groups) {
       cudaError_t e = cudaStreamWaitEvent(gs, (cudaEvent_t)bh->groups[g - 1].ev_init, 0);
       if (e != cudaSuccess) { ctx->stream = (void*)main_s; return cuda_fail(e, "cudaStreamWaitEvent"); }
     }
