@@ -1471,7 +1471,11 @@ static StepParams make_params(float dt, int vi, int pi) {
 static int ensure_groups(BatchHost* bh) {
   if (!bh->groups.empty()) return 0;
   const Batch& B = bh->B;
-  int ng = (B.LB == 32 && B.n_wblocks >= 16 && bh->stream_groups != 1) ? (bh->stream_groups > 1 ? bh->stream_groups : (B.n_wblocks >= 64 ? 8 : 4)) : 1;
+  // automatic: 8 groups for >= 64 world blocks, 4 for >= 16 — but one stream for worlds of fewer than 96 bodies, whose step is
+  // ~20 short launches that eight staggered groups only multiply (profiles/r02_stream_groups.md: car 0.32 -> 0.12 ms/step,
+  // joints_mix 1.66 -> 0.64 at one step per call, and still ahead at 200 steps per call)
+  const int ng_auto = B.NB < 96 ? 1 : (B.n_wblocks >= 64 ? 8 : 4);
+  int ng = (B.LB == 32 && B.n_wblocks >= 16 && bh->stream_groups != 1) ? (bh->stream_groups > 1 ? bh->stream_groups : ng_auto) : 1;
   if (ng > B.n_wblocks) ng = B.n_wblocks;
   for (int g = 0; g < ng; ++g) {
     StreamGroup sg;

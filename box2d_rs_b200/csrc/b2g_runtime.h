@@ -100,7 +100,7 @@ struct BatchHost {
   std::vector<StepGraph> graphs;    // CUDA graphs per call signature (see run_steps)
   bool use_graphs = true;
   bool stagger_groups = true;       // group g starts behind group g-1's solver set-up (B2GPU_STAGGER=0: all start together)
-  int stream_groups = 0;            // 0 = automatic (4 for batches of >= 16 world blocks, 8 for >= 64), 1 = single stream
+  int stream_groups = 0;            // 0 = automatic (4 for batches of >= 16 world blocks, 8 for >= 64, 1 for worlds under 96 bodies), 1 = single stream
   bool stepped = false;          // at least one dt > 0 step ran: island arrays are meaningful
   bool pre_step_needed = true;   // some world may carry m_new_contacts / a non-empty move buffer
   long long total_bytes = 0;
