@@ -1276,6 +1276,21 @@ int b2gpu_world_set_allow_sleeping(b2gpu_world* W, int flag) {  // b2_world.rs(p
   return 0;
   GUARD_END
 }
+int b2gpu_world_set_gravity(b2gpu_world* W, float gx, float gy) {  // src/b2_world.rs:358-360: no waking, takes effect next step
+  GUARD_BEGIN
+  if (!W) { set_error("world is NULL"); return B2GPU_E_INVALID; }
+  int rc = ensure_host(W);
+  if (rc) return rc;
+  W->h.world.gravity_x = gx; W->h.world.gravity_y = gy;
+  W->host_dirty = true;
+  return 0;
+  GUARD_END
+}
+int b2gpu_world_get_gravity(b2gpu_world* W, float* gx, float* gy) {
+  if (!W || !gx || !gy) { set_error("get_gravity: bad argument"); return B2GPU_E_INVALID; }
+  *gx = W->h.world.gravity_x; *gy = W->h.world.gravity_y;  // only the host changes it
+  return 0;
+}
 int b2gpu_world_set_warm_starting(b2gpu_world* W, int flag) { return set_world_flag(W, B2GPU_WORLD_WARM_STARTING, flag); }
 int b2gpu_world_set_block_solve(b2gpu_world* W, int flag) { return set_world_flag(W, B2GPU_WORLD_BLOCK_SOLVE, flag); }
 int b2gpu_world_set_large_mode(b2gpu_world* W, int flag) {

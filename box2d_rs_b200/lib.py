@@ -66,6 +66,8 @@ def load(path=None):
         "b2gpu_mouse_joint_def": (i32, [vp, C.POINTER(abi.JointDef), i32, i32, f32, f32]),
         "b2gpu_joint_set_target": (i32, [vp, i32, f32, f32]),
         "b2gpu_world_destroy_joint": (i32, [vp, i32]),
+        "b2gpu_world_set_gravity": (i32, [vp, f32, f32]),
+        "b2gpu_world_get_gravity": (i32, [vp, C.POINTER(f32), C.POINTER(f32)]),
         "b2gpu_angular_stiffness": (i32, [vp, f32, f32, i32, i32, C.POINTER(f32), C.POINTER(f32)]),
         "b2gpu_world_create_joint": (i32, [vp, C.POINTER(abi.JointDef)]),
         "b2gpu_world_get_joint_count": (i32, [vp]),

@@ -288,6 +288,15 @@ class B2world:
     def set_allow_sleeping(self, flag):
         check(self.L, self.L.b2gpu_world_set_allow_sleeping(self.h, int(flag)))
 
+    def set_gravity(self, gravity):
+        """B2world::set_gravity."""
+        check(self.L, self.L.b2gpu_world_set_gravity(self.h, gravity[0], gravity[1]))
+
+    def get_gravity(self):
+        gx, gy = C.c_float(), C.c_float()
+        check(self.L, self.L.b2gpu_world_get_gravity(self.h, C.byref(gx), C.byref(gy)))
+        return (gx.value, gy.value)
+
     def set_warm_starting(self, flag):
         check(self.L, self.L.b2gpu_world_set_warm_starting(self.h, int(flag)))
 

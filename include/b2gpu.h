@@ -466,6 +466,9 @@ int b2gpu_joint_enable_limit(b2gpu_world* w, int joint, int flag);
 int b2gpu_joint_set_limits(b2gpu_world* w, int joint, float lower, float upper);
 /* B2mouseJoint::set_target (src/joints/b2_mouse_joint.rs:114-119): wakes body B when the target changes. */
 int b2gpu_joint_set_target(b2gpu_world* w, int joint, float target_x, float target_y);
+/* B2world::set_gravity / get_gravity (src/b2_world.rs:232-239): the next step integrates with it; nobody is woken. */
+int b2gpu_world_set_gravity(b2gpu_world* w, float gravity_x, float gravity_y);
+int b2gpu_world_get_gravity(b2gpu_world* w, float* gravity_x, float* gravity_y);
 /* B2world::set_allow_sleeping / set_warm_starting / set_continuous_physics */
 int b2gpu_world_set_allow_sleeping(b2gpu_world* w, int flag);
 int b2gpu_world_set_warm_starting(b2gpu_world* w, int flag);

@@ -73,6 +73,7 @@ def lib():
         L.b2o_create_joint.argtypes = [C.c_void_p, C.POINTER(abi.JointDef)]
         L.b2o_joint_count.argtypes = [C.c_void_p]
         L.b2o_destroy_joint.argtypes = [C.c_void_p, C.c_int]
+        L.b2o_set_gravity.argtypes = [C.c_void_p, C.c_float, C.c_float]
         L.b2o_joint_set_motor_speed.argtypes = [C.c_void_p, C.c_int, C.c_float]
         L.b2o_joint_set_max_motor_torque.argtypes = [C.c_void_p, C.c_int, C.c_float]
         L.b2o_joint_enable_motor.argtypes = [C.c_void_p, C.c_int, C.c_int]
@@ -348,6 +349,9 @@ class B2world:
 
     def set_allow_sleeping(self, flag):
         lib().b2o_set_allow_sleeping(self.h, int(flag))
+
+    def set_gravity(self, gravity):
+        lib().b2o_set_gravity(self.h, gravity[0], gravity[1])
 
     def set_warm_starting(self, flag):
         lib().b2o_set_warm_starting(self.h, int(flag))

@@ -251,6 +251,7 @@ void b2o_set_allow_sleeping(void* w, int f) {  // b2_world.rs(private):340-353
   if (!W->allow_sleep)
     for (int b = W->body_list; b != -1; b = W->bodies[b].next) W->set_awake(b, true);
 }
+void b2o_set_gravity(void* w, float gx, float gy) { ((World*)w)->gravity = Vec2(gx, gy); }  // src/b2_world.rs:358-360
 void b2o_set_warm_starting(void* w, int f) { ((World*)w)->warm_starting = f != 0; }
 void b2o_set_block_solve(void* w, int f) { ((World*)w)->block_solve = f != 0; }
 void b2o_set_collect_levels(void* w, int f) { ((World*)w)->collect_levels = f != 0; }

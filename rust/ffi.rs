@@ -208,6 +208,8 @@ extern "C" {
     pub fn b2gpu_joint_enable_motor(w: *mut b2gpu_world, joint: c_int, flag: c_int) -> c_int;
     pub fn b2gpu_joint_enable_limit(w: *mut b2gpu_world, joint: c_int, flag: c_int) -> c_int;
     pub fn b2gpu_joint_set_limits(w: *mut b2gpu_world, joint: c_int, lower: c_float, upper: c_float) -> c_int;
+    pub fn b2gpu_world_set_gravity(w: *mut b2gpu_world, gravity_x: c_float, gravity_y: c_float) -> c_int;
+    pub fn b2gpu_world_get_gravity(w: *mut b2gpu_world, gravity_x: *mut c_float, gravity_y: *mut c_float) -> c_int;
     pub fn b2gpu_world_destroy_joint(w: *mut b2gpu_world, joint: c_int) -> c_int;
     pub fn b2gpu_joint_set_target(w: *mut b2gpu_world, joint: c_int, target_x: c_float, target_y: c_float) -> c_int;
     pub fn b2gpu_world_set_allow_sleeping(w: *mut b2gpu_world, flag: c_int) -> c_int;

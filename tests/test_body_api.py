@@ -61,6 +61,62 @@ def _case(ctx):
     wg.close()
 
 
+def _gravity_case(ctx):
+    """B2world::set_gravity between steps (src/b2_world.rs:232-239): the next step integrates with the new vector; bodies
+    that sleep stay asleep (nobody is woken), in the plain and the large-world mode."""
+    from box2d_rs_b200 import abi, scenes, world
+    from oracle import b2o
+    for large in (0, 1):
+        wo = b2o.B2world((0.0, -10.0))
+        scenes.mixed(wo, n=40, width=10.0)
+        wg = world.B2world((0.0, -10.0), ctx=ctx)
+        scenes.mixed(wg, n=40, width=10.0)
+        if large:
+            wg.set_large_mode(1)
+        assert wg.get_gravity() == (0.0, -10.0)
+        for step in range(400):
+            if step in (120, 200, 330):
+                g = {120: (4.0, -6.0), 200: (0.0, 12.5), 330: (0.0, -10.0)}[step]
+                for w in (wo, wg):
+                    w.set_gravity(g)
+                assert wg.get_gravity() == g
+            if large:  # mode 1 is teacher-forced: every step starts from the oracle's state (contact order within a step differs)
+                wg.upload(wo.snapshot())
+                wo.step(scenes.DT, 8, 3)
+                wg.step(scenes.DT, 8, 3)
+                if step % 40 == 39 or step in (120, 121, 200, 201):
+                    assert parity.compare_large_step(wo.snapshot(), wg.snapshot(), wo.get_stats(), wg.get_stats()) == [], (large, step)
+            else:
+                wo.step(scenes.DT, 8, 3)
+                wg.step(scenes.DT, 8, 3)
+                if step % 40 == 39 or step in (120, 121, 200, 201):
+                    assert parity.compare_snapshots(wo.snapshot(), wg.snapshot()) == [], (large, step)
+        asleep = [i for i, b in enumerate(wo.snapshot().bodies) if b["type"] == abi.DYNAMIC_BODY and not (int(b["flags"]) & abi.BODY_AWAKE)]
+        if asleep:  # a sleeping body is not woken by a new gravity
+            for w in (wo, wg):
+                w.set_gravity((0.0, 30.0))
+            assert not (int(wg.body(asleep[0])._rec()["flags"]) & abi.BODY_AWAKE)
+        assert wg.L.b2gpu_world_set_gravity(None, 0.0, 0.0) == abi.E_INVALID
+        wg.close()
+
+
+def test_set_gravity_host_simulator(built):
+    from box2d_rs_b200 import batch
+    ctx = batch.Context(0, lib_path=HOSTSIM_SO)
+    _gravity_case(ctx)
+    ctx.close()
+
+
+@pytest.mark.gpu
+def test_set_gravity_gpu(built):
+    from box2d_rs_b200 import batch
+    ctx = batch.Context(0)
+    try:
+        _gravity_case(ctx)
+    finally:
+        ctx.close()
+
+
 def test_body_api_host_simulator(built):
     from box2d_rs_b200 import batch
     ctx = batch.Context(0, lib_path=HOSTSIM_SO)
