@@ -196,6 +196,11 @@ class Batch:
         assert f.shape[1:] == (self.body_count, 3)
         check(self.L, self.L.b2gpu_batch_set_forces(self.h, f.ctypes.data, first, f.shape[0]))
 
+    def set_gravity(self, gxgy, first=0):
+        """B2world::set_gravity per world: gxgy[n][2] (domain randomisation)."""
+        v = np.ascontiguousarray(gxgy, np.float32).reshape(-1, 2)
+        check(self.L, self.L.b2gpu_batch_set_gravity(self.h, v.ctypes.data, first, v.shape[0]))
+
     def _joint_control(self, joint, control, values, per, first):
         v = np.ascontiguousarray(values, np.float32).reshape(-1, per)
         check(self.L, self.L.b2gpu_batch_set_joint_control(self.h, getattr(joint, "index", joint), control, v.ctypes.data, first, v.shape[0]))

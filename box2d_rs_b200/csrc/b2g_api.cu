@@ -196,6 +196,12 @@ int b2gpu_batch_set_linear_velocity(b2gpu_batch* b, int body, const float* host_
   return batch_set_linear_velocity(b->h, body, host_vxvy, first, count);
   GUARD_END
 }
+int b2gpu_batch_set_gravity(b2gpu_batch* b, const float* host_gxgy, int first, int count) {
+  GUARD_BEGIN
+  if (!b) { set_error("batch is NULL"); return B2GPU_E_INVALID; }
+  return batch_set_gravity(b->h, host_gxgy, first, count);
+  GUARD_END
+}
 int b2gpu_batch_set_joint_control(b2gpu_batch* b, int joint, int control, const float* host_values, int first, int count) {
   GUARD_BEGIN
   if (!b) { set_error("batch is NULL"); return B2GPU_E_INVALID; }

@@ -929,6 +929,18 @@ struct VelScatterK {
   }
 };
 
+struct GravityScatterK {  // b2gpu_batch_set_gravity
+  Batch B;
+  const float* in;  // [count][2]
+  int first, count;
+  B2G_HD void operator()(int i) const {
+    if (i >= count) return;
+    WIdx x = widx(B, first + i);
+    Ws ws = ws_of(B, x);
+    ws[WS_GRAVITY_X] = f2i(in[2 * i]);
+    ws[WS_GRAVITY_Y] = f2i(in[2 * i + 1]);
+  }
+};
 // b2gpu_batch_set_joint_control: the revolute / mouse setters in every world of a range (include/b2gpu.h)
 struct JointControlK {
   Batch B;
@@ -1755,6 +1767,16 @@ int batch_set_linear_velocity(BatchHost* bh, int body, const float* host_vxvy, i
   }
   RC(dev_h2d(bh->ctx, bh->vel_scratch, host_vxvy, (size_t)count * 2 * 4));  // its own scratch: forces_dev belongs to the caller
   { VelScatterK k = {bh->B, bh->vel_scratch, body, first, count}; RC(launch(bh->ctx, k, count, 128)); }
+  return 0;
+}
+int batch_set_gravity(BatchHost* bh, const float* host_gxgy, int first, int count) {
+  if (!bh || !host_gxgy || first < 0 || count < 0 || first + count > bh->B.n_worlds) { set_error("set_gravity: bad argument"); return B2GPU_E_INVALID; }
+  if (count == 0) return 0;
+  RC(dev_h2d(bh->ctx, bh->vel_scratch, host_gxgy, (size_t)count * 2 * 4));
+  Batch all = bh->B;
+  all.wb_first = 0;
+  all.wb_count = bh->B.n_wblocks;
+  { GravityScatterK k = {all, bh->vel_scratch, first, count}; RC(launch(bh->ctx, k, count, 128)); }
   return 0;
 }
 int batch_set_joint_control(BatchHost* bh, int joint, int control, const float* host_values, int first, int count) {

@@ -143,6 +143,7 @@ int batch_dynamic_bodies(BatchHost* b, int* out, int capacity);
 int batch_get_body_state(BatchHost* b, float* host_out, int first, int count);
 int batch_set_forces(BatchHost* b, const float* host, int first, int count);
 int batch_set_linear_velocity(BatchHost* b, int body, const float* host_vxvy, int first, int count);
+int batch_set_gravity(BatchHost* b, const float* host_gxgy, int first, int count);
 int batch_set_joint_control(BatchHost* b, int joint, int control, const float* host_values, int first, int count);
 int batch_ray_cast_closest(BatchHost* b, const float* host_rays, int rays_per_world, b2gpu_ray_hit* host_out);
 int batch_query_aabb(BatchHost* b, const float* host_boxes, int n, int max_hits, int* host_counts, int* host_hits);

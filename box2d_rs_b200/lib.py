@@ -116,6 +116,7 @@ def load(path=None):
         "b2gpu_batch_set_forces": (i32, [vp, vp, i32, i32]),
         "b2gpu_batch_set_linear_velocity": (i32, [vp, i32, vp, i32, i32]),
         "b2gpu_batch_set_joint_control": (i32, [vp, i32, i32, vp, i32, i32]),
+        "b2gpu_batch_set_gravity": (i32, [vp, vp, i32, i32]),
         "b2gpu_batch_get_body_state": (i32, [vp, vp, i32, i32]),
         "b2gpu_batch_body_state_device": (vp, [vp, C.POINTER(i64)]),
         "b2gpu_batch_forces_device": (vp, [vp, C.POINTER(i64)]),

@@ -620,6 +620,9 @@ int b2gpu_batch_set_level_threshold(b2gpu_batch* b, int contacts);
 int b2gpu_batch_set_forces(b2gpu_batch* b, const float* host_fxfyt, int first_world, int count);
 /* Linear velocity of one body index in every world (B2body::set_linear_velocity). */
 int b2gpu_batch_set_linear_velocity(b2gpu_batch* b, int body, const float* host_vxvy, int first_world, int count);
+/* Gravity per world (B2world::set_gravity in worlds first_world .. first_world + count; domain randomisation): host array
+ * [count][2].  Takes effect at the next step, wakes nobody. */
+int b2gpu_batch_set_gravity(b2gpu_batch* b, const float* host_gxgy, int first_world, int count);
 /* Per-world joint controls of a batch — the RL action on a jointed agent.  One joint index (shared topology), one value per
  * world: host array [count] for MOTOR_SPEED / MAX_MOTOR_TORQUE (revolute, prismatic — there it is the maximum motor force —
  * and wheel joints), [count][2] for TARGET (mouse joints).  Semantics of B2revoluteJoint::set_motor_speed /

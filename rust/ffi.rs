@@ -251,6 +251,7 @@ extern "C" {
     pub fn b2gpu_batch_status(b: *mut b2gpu_batch) -> c_int;
     pub fn b2gpu_batch_set_level_threshold(b: *mut b2gpu_batch, contacts: c_int) -> c_int;
     pub fn b2gpu_batch_set_forces(b: *mut b2gpu_batch, host_fxfyt: *const c_float, first_world: c_int, count: c_int) -> c_int;
+    pub fn b2gpu_batch_set_gravity(b: *mut b2gpu_batch, host_gxgy: *const c_float, first_world: c_int, count: c_int) -> c_int;
     pub fn b2gpu_batch_set_joint_control(b: *mut b2gpu_batch, joint: c_int, control: c_int, host_values: *const c_float, first_world: c_int, count: c_int) -> c_int;
     pub fn b2gpu_batch_set_linear_velocity(b: *mut b2gpu_batch, body: c_int, host_vxvy: *const c_float, first_world: c_int, count: c_int) -> c_int;
     pub fn b2gpu_batch_get_body_state(b: *mut b2gpu_batch, host_out: *mut c_float, first_world: c_int, count: c_int) -> c_int;

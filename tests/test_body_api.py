@@ -100,10 +100,40 @@ def _gravity_case(ctx):
         wg.close()
 
 
+def _batch_gravity_case(ctx):
+    """b2gpu_batch_set_gravity: a different gravity per world of a batch, changed mid-run, against oracle worlds."""
+    from box2d_rs_b200 import scenes, world
+    from oracle import b2o
+    wo = b2o.B2world((0.0, -10.0))
+    scenes.mixed(wo, n=30, width=8.0)
+    wg = world.B2world((0.0, -10.0), ctx=ctx)
+    scenes.mixed(wg, n=30, width=8.0)
+    n = 35
+    bt = wg.batch(n)
+    rng = np.random.default_rng(3)
+    picks = {0: wo.clone(), 17: wo.clone(), n - 1: wo.clone()}
+    for step in range(160):
+        if step in (0, 70):
+            g = np.stack([rng.uniform(-3.0, 3.0, n), rng.uniform(-15.0, -5.0, n)], 1).astype(np.float32)
+            bt.set_gravity(g[:10])
+            bt.set_gravity(g[10:], first=10)
+            for w, o in picks.items():
+                o.set_gravity((float(g[w][0]), float(g[w][1])))
+        bt.step(scenes.DT, 8, 3)
+        for o in picks.values():
+            o.step(scenes.DT, 8, 3)
+        if step % 20 == 19:
+            for w, o in picks.items():
+                assert parity.compare_snapshots(o.snapshot(), bt.download_world(w)) == [], (w, step)
+    bt.close()
+    wg.close()
+
+
 def test_set_gravity_host_simulator(built):
     from box2d_rs_b200 import batch
     ctx = batch.Context(0, lib_path=HOSTSIM_SO)
     _gravity_case(ctx)
+    _batch_gravity_case(ctx)
     ctx.close()
 
 
@@ -113,6 +143,7 @@ def test_set_gravity_gpu(built):
     ctx = batch.Context(0)
     try:
         _gravity_case(ctx)
+        _batch_gravity_case(ctx)
     finally:
         ctx.close()
 
