@@ -681,6 +681,39 @@ int b2gpu_body_set_angular_velocity(b2gpu_world* W, int body, float w_) {
   return 0;
   GUARD_END
 }
+int b2gpu_body_set_damping(b2gpu_world* W, int body, float linear_damping, float angular_damping) {  // src/b2_body.rs:755-765
+  GUARD_BEGIN
+  int rc = check_body(W, body);
+  if (!rc) rc = ensure_host(W);
+  if (rc) return rc;
+  b2gpu_body_rec& b = W->h.bodies[body];
+  b.linear_damping = linear_damping; b.angular_damping = angular_damping;
+  W->host_dirty = true;
+  return 0;
+  GUARD_END
+}
+int b2gpu_body_set_gravity_scale(b2gpu_world* W, int body, float scale) {  // src/b2_body.rs:771-773
+  GUARD_BEGIN
+  int rc = check_body(W, body);
+  if (!rc) rc = ensure_host(W);
+  if (rc) return rc;
+  W->h.bodies[body].gravity_scale = scale;
+  W->host_dirty = true;
+  return 0;
+  GUARD_END
+}
+int b2gpu_body_set_sleeping_allowed(b2gpu_world* W, int body, int flag) {  // src/b2_body.rs:815-821
+  GUARD_BEGIN
+  int rc = check_body(W, body);
+  if (!rc) rc = ensure_host(W);
+  if (rc) return rc;
+  b2gpu_body_rec& b = W->h.bodies[body];
+  if (flag) b.flags |= B2GPU_BODY_AUTO_SLEEP;
+  else { b.flags &= ~B2GPU_BODY_AUTO_SLEEP; set_awake(b, true); }
+  W->host_dirty = true;
+  return 0;
+  GUARD_END
+}
 int b2gpu_body_apply_force_to_center(b2gpu_world* W, int body, float fx, float fy, int wake) {
   GUARD_BEGIN
   int rc = check_body(W, body);

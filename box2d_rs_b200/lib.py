@@ -53,6 +53,9 @@ def load(path=None):
         "b2gpu_body_apply_linear_impulse_to_center": (i32, [vp, i32, f32, f32, i32]),
         "b2gpu_body_apply_angular_impulse": (i32, [vp, i32, f32, i32]),
         "b2gpu_body_set_awake": (i32, [vp, i32, i32]),
+        "b2gpu_body_set_damping": (i32, [vp, i32, f32, f32]),
+        "b2gpu_body_set_gravity_scale": (i32, [vp, i32, f32]),
+        "b2gpu_body_set_sleeping_allowed": (i32, [vp, i32, i32]),
         "b2gpu_revolute_joint_def": (i32, [vp, C.POINTER(abi.JointDef), i32, i32, f32, f32]),
         "b2gpu_distance_joint_def": (i32, [vp, C.POINTER(abi.JointDef), i32, i32, f32, f32, f32, f32]),
         "b2gpu_linear_stiffness": (i32, [vp, f32, f32, i32, i32, C.POINTER(f32), C.POINTER(f32)]),

@@ -98,6 +98,19 @@ class B2body:
         w = self.world
         check(w.L, w.L.b2gpu_body_set_awake(w.h, self.index, int(flag)))
 
+    def set_damping(self, linear_damping, angular_damping):
+        """B2body::set_linear_damping + set_angular_damping."""
+        w = self.world
+        check(w.L, w.L.b2gpu_body_set_damping(w.h, self.index, linear_damping, angular_damping))
+
+    def set_gravity_scale(self, scale):
+        w = self.world
+        check(w.L, w.L.b2gpu_body_set_gravity_scale(w.h, self.index, scale))
+
+    def set_sleeping_allowed(self, flag):
+        w = self.world
+        check(w.L, w.L.b2gpu_body_set_sleeping_allowed(w.h, self.index, int(flag)))
+
     def _rec(self):
         w = self.world
         out = np.zeros(1, abi.BODY_DTYPE)

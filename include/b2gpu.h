@@ -392,6 +392,11 @@ int b2gpu_body_apply_linear_impulse(b2gpu_world* w, int body, float ix, float iy
 int b2gpu_body_apply_linear_impulse_to_center(b2gpu_world* w, int body, float ix, float iy, int wake);
 int b2gpu_body_apply_angular_impulse(b2gpu_world* w, int body, float impulse, int wake);
 int b2gpu_body_set_awake(b2gpu_world* w, int body, int flag);
+/* B2body::set_linear_damping / set_angular_damping / set_gravity_scale (src/b2_body.rs:755-775: plain stores) and
+ * set_sleeping_allowed (:815-821: clearing it wakes the body). */
+int b2gpu_body_set_damping(b2gpu_world* w, int body, float linear_damping, float angular_damping);
+int b2gpu_body_set_gravity_scale(b2gpu_world* w, int body, float scale);
+int b2gpu_body_set_sleeping_allowed(b2gpu_world* w, int body, int flag);
 /* Joints.  B2revoluteJointDef::default + ::initialize(body_a, body_b, anchor)
  * (src/joints/b2_revolute_joint.rs:10-86): local anchors and reference angle from the bodies' current transforms. */
 int b2gpu_revolute_joint_def(b2gpu_world* w, b2gpu_joint_def* def, int body_a, int body_b, float anchor_x, float anchor_y);

@@ -50,6 +50,9 @@ def lib():
         L.b2o_apply_torque.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_int]
         L.b2o_apply_angular_impulse.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_int]
         L.b2o_body_set_awake.argtypes = [C.c_void_p, C.c_int, C.c_int]
+        L.b2o_body_set_damping.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float]
+        L.b2o_body_set_gravity_scale.argtypes = [C.c_void_p, C.c_int, C.c_float]
+        L.b2o_body_set_sleeping_allowed.argtypes = [C.c_void_p, C.c_int, C.c_int]
         for f in ("b2o_set_allow_sleeping", "b2o_set_warm_starting", "b2o_set_block_solve", "b2o_set_collect_levels"):
             getattr(L, f).argtypes = [C.c_void_p, C.c_int]
         L.b2o_revolute_joint_def.argtypes = [C.c_void_p, C.POINTER(abi.JointDef), C.c_int, C.c_int, C.c_float, C.c_float]
@@ -186,6 +189,15 @@ class B2body:
 
     def set_awake(self, flag):
         lib().b2o_body_set_awake(self.world.h, self.index, int(flag))
+
+    def set_damping(self, linear_damping, angular_damping):
+        lib().b2o_body_set_damping(self.world.h, self.index, linear_damping, angular_damping)
+
+    def set_gravity_scale(self, scale):
+        lib().b2o_body_set_gravity_scale(self.world.h, self.index, scale)
+
+    def set_sleeping_allowed(self, flag):
+        lib().b2o_body_set_sleeping_allowed(self.world.h, self.index, int(flag))
 
     def _rec(self):
         return self.world.snapshot().bodies[self.index]

@@ -139,6 +139,13 @@ void b2o_apply_linear_impulse(void* w, int body, float ix, float iy, float px, f
 void b2o_apply_linear_impulse_to_center(void* w, int body, float ix, float iy, int wake) { ((World*)w)->apply_linear_impulse_to_center(body, Vec2(ix, iy), wake != 0); }
 void b2o_apply_angular_impulse(void* w, int body, float i, int wake) { ((World*)w)->apply_angular_impulse(body, i, wake != 0); }
 void b2o_body_set_awake(void* w, int body, int flag) { ((World*)w)->set_awake(body, flag != 0); }
+void b2o_body_set_damping(void* w, int body, float l, float a) { Body& b = ((World*)w)->bodies[body]; b.linear_damping = l; b.angular_damping = a; }  // src/b2_body.rs:755-765
+void b2o_body_set_gravity_scale(void* w, int body, float s) { ((World*)w)->bodies[body].gravity_scale = s; }  // :771-773
+void b2o_body_set_sleeping_allowed(void* w, int body, int flag) {  // :815-821
+  World* W = (World*)w;
+  if (flag) W->bodies[body].flags |= BF_AUTO_SLEEP;
+  else { W->bodies[body].flags &= ~BF_AUTO_SLEEP; W->set_awake(body, true); }
+}
 // ---- joints (b2gpu_joint_def in and out, so the scene recipes drive both engines)
 static void joint_def_out(const JointDef& d, b2gpu_joint_def* o) {
   std::memset(o, 0, sizeof(*o));

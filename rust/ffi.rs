@@ -184,6 +184,9 @@ extern "C" {
     pub fn b2gpu_body_apply_linear_impulse_to_center(w: *mut b2gpu_world, body: c_int, ix: c_float, iy: c_float, wake: c_int) -> c_int;
     pub fn b2gpu_body_apply_angular_impulse(w: *mut b2gpu_world, body: c_int, impulse: c_float, wake: c_int) -> c_int;
     pub fn b2gpu_body_set_awake(w: *mut b2gpu_world, body: c_int, flag: c_int) -> c_int;
+    pub fn b2gpu_body_set_damping(w: *mut b2gpu_world, body: c_int, linear_damping: c_float, angular_damping: c_float) -> c_int;
+    pub fn b2gpu_body_set_gravity_scale(w: *mut b2gpu_world, body: c_int, scale: c_float) -> c_int;
+    pub fn b2gpu_body_set_sleeping_allowed(w: *mut b2gpu_world, body: c_int, flag: c_int) -> c_int;
     pub fn b2gpu_revolute_joint_def(w: *mut b2gpu_world, def: *mut b2gpu_joint_def, body_a: c_int, body_b: c_int, anchor_x: c_float, anchor_y: c_float) -> c_int;
     pub fn b2gpu_distance_joint_def(w: *mut b2gpu_world, def: *mut b2gpu_joint_def, body_a: c_int, body_b: c_int, a1x: c_float, a1y: c_float, a2x: c_float, a2y: c_float) -> c_int;
     pub fn b2gpu_prismatic_joint_def(w: *mut b2gpu_world, def: *mut b2gpu_joint_def, body_a: c_int, body_b: c_int, anchor_x: c_float, anchor_y: c_float, axis_x: c_float, axis_y: c_float) -> c_int;

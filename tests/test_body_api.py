@@ -24,7 +24,7 @@ def _case(ctx):
     for step in range(260):
         for _ in range(int(rng.integers(0, 4))):
             b = int(rng.integers(0, nb))  # body 0 is the static container: calls must be ignored
-            kind = int(rng.integers(0, 6))
+            kind = int(rng.integers(0, 9))
             vec, pt, sc, wake = (f(-60, 60), f(-60, 60)), (f(-6, 6), f(0, 12)), f(-30, 30), bool(rng.integers(0, 2))
             for w in (wo, wg):
                 bd = w.body(b)
@@ -33,7 +33,10 @@ def _case(ctx):
                 elif kind == 2: bd.apply_linear_impulse((vec[0] * 0.05, vec[1] * 0.05), pt, wake)
                 elif kind == 3: bd.apply_linear_impulse_to_center((vec[0] * 0.05, vec[1] * 0.05), wake)
                 elif kind == 4: bd.apply_angular_impulse(sc * 0.02, wake)
-                else: bd.set_awake(wake)
+                elif kind == 5: bd.set_awake(wake)
+                elif kind == 6: bd.set_damping(abs(sc) * 0.02, abs(vec[0]) * 0.01)
+                elif kind == 7: bd.set_gravity_scale(sc * 0.05)
+                else: bd.set_sleeping_allowed(wake)
             ro, rg = wo.body(b)._rec(), wg.body(b)._rec()
             assert ro.tobytes() == rg.tobytes(), (step, b, kind)
             calls += 1
