@@ -38,7 +38,7 @@ extern "C" {
 #define B2GPU_E_NO_DEVICE (-2) /* no CUDA device: there is no CPU fallback */
 #define B2GPU_E_CUDA (-3)      /* CUDA runtime error, see b2gpu_last_error */
 #define B2GPU_E_CAPACITY (-4)  /* a device-side capacity was exceeded */
-#define B2GPU_E_UNSUPPORTED (-5) /* feature outside the hot-path scope (TOI, pulley, gear and mouse joints) */
+#define B2GPU_E_UNSUPPORTED (-5) /* feature outside the hot-path scope (TOI sub-stepping, an unknown joint type, an unregistered shape pair) */
 #define B2GPU_E_LOCKED (-6)    /* world is locked (reference: is_locked() panic) */
 #define B2GPU_E_INTERNAL (-7)  /* a device-side consistency check failed (a bug: please report) */
 #define B2GPU_E_IO (-8)        /* a checkpoint file could not be opened, read or written */
