@@ -815,7 +815,7 @@ def _large_exact_free_running(name, ctx):
     wg.close()
 
 
-@pytest.mark.parametrize("name,every", [("bridge", 3), ("tumbler", 4), ("joints_mix", 2)])
+@pytest.mark.parametrize("name,every", [("bridge", 3), ("tumbler", 4), ("joints_mix", 2), ("gears", 2), ("pulleys", 3), ("car", 5), ("top_down", 2)])
 def test_hostsim_large_mode_teacher_forced(name, every, hctx):
     _large_teacher_forced(name, hctx, every)
 
