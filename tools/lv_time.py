@@ -10,6 +10,7 @@ ap.add_argument("--n", type=int, default=0)
 ap.add_argument("--at", type=int, default=220)
 ap.add_argument("--steps", type=int, default=20)
 ap.add_argument("--threshold", type=int, default=0)
+ap.add_argument("--mode", type=int, default=1, help="large-world mode: 1 = LBVH order, 2 = replica tree kept (reference contact order)")
 a = ap.parse_args()
 from box2d_rs_b200 import scenes, world
 from box2d_rs_b200.batch import Context
@@ -17,7 +18,7 @@ ctx = Context(0, lib_path=os.environ.get("B2GPU_LIB"))
 gravity = (0.0, 0.0) if a.scene == "add_pair" else (0.0, -10.0)
 wg = world.B2world(gravity, ctx=ctx)
 getattr(scenes, a.scene)(wg, n=a.n or {"pile": 100000, "mixed": 10000, "add_pair": 20000}[a.scene])
-wg.set_large_mode(1)
+wg.set_large_mode(a.mode)
 if a.threshold:
     wg.set_level_threshold(a.threshold)
 for _ in range(a.at):
