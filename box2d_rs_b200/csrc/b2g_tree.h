@@ -145,6 +145,35 @@ struct Tree {
     return ia;
   }
 
+  // The walk from a changed node to the root (insert_leaf :261-288, remove_leaf :333-346): balance, then height and box from
+  // the two children.  Every node on it is internal.  balance() is entered only when the heights it would read ask for a
+  // rotation; otherwise the node, its children's links and boxes and — early — the parent's link are loaded in one round
+  // (the rotation-free level changes nothing the parent's link holds), so a level costs one dependent load instead of four.
+  // The values stored are those of the plain loop.
+  B2G_HD void refit_up(int index) {
+    if (index == -1) return;
+    int4 a = L(index);
+    for (;;) {
+      int4 b = L(a.y), c = L(a.z);
+      Box ab = A(a.y), ac = A(a.z);
+      int4 pa = a;
+      if (a.x != -1) pa = L(a.x);
+      if (a.w >= 2 && (c.w - b.w > 1 || c.w - b.w < -1)) {
+        index = balance(index);
+        a = L(index);
+        b = L(a.y); c = L(a.z);
+        ab = A(a.y); ac = A(a.z);
+        if (a.x != -1) pa = L(a.x);
+      }
+      a.w = 1 + imax(b.w, c.w);
+      setL(index, a);
+      setA(index, box_union(ab, ac));
+      if (a.x == -1) break;
+      index = a.x;
+      a = pa;
+    }
+  }
+
   B2G_HDN void insert_leaf(int leaf) {
     insertions() += 1;
     if (root() == -1) {
@@ -153,31 +182,34 @@ struct Tree {
       return;
     }
     Box leaf_box = A(leaf);
+    // The descent keeps the chosen child's link and box (loaded to price it) for the next level: one dependent load round per
+    // level instead of three.  Same arithmetic, same comparisons.
     int index = root();
+    int4 n = L(index);
+    Box nb = A(index);
     for (;;) {
-      int4 n = L(index);
       if (n.y == -1) break;
-      int child1 = n.y, child2 = n.z;
-      Box nb = A(index);
+      const int child1 = n.y, child2 = n.z;
+      const Box cb1 = A(child1), cb2 = A(child2);
+      const int4 l1 = L(child1), l2 = L(child2);
       float area = box_perimeter(nb);
       float combined_area = box_perimeter(box_union(nb, leaf_box));
       float cost = 2.0f * combined_area;
       float inheritance = 2.0f * (combined_area - area);
       float cost1, cost2;
       {
-        Box cb = A(child1);
-        float na = box_perimeter(box_union(leaf_box, cb));
-        if (L(child1).y == -1) cost1 = na + inheritance;
-        else cost1 = (na - box_perimeter(cb)) + inheritance;
+        float na = box_perimeter(box_union(leaf_box, cb1));
+        if (l1.y == -1) cost1 = na + inheritance;
+        else cost1 = (na - box_perimeter(cb1)) + inheritance;
       }
       {
-        Box cb = A(child2);
-        float na = box_perimeter(box_union(leaf_box, cb));
-        if (L(child2).y == -1) cost2 = na + inheritance;
-        else cost2 = na - box_perimeter(cb) + inheritance;
+        float na = box_perimeter(box_union(leaf_box, cb2));
+        if (l2.y == -1) cost2 = na + inheritance;
+        else cost2 = na - box_perimeter(cb2) + inheritance;
       }
       if (cost < cost1 && cost < cost2) break;
-      index = cost1 < cost2 ? child1 : child2;
+      if (cost1 < cost2) { index = child1; n = l1; nb = cb1; }
+      else { index = child2; n = l2; nb = cb2; }
     }
     int sibling = index;
     int old_parent = parent(sibling);
@@ -192,15 +224,7 @@ struct Tree {
     }
     set_parent(sibling, new_parent);
     set_parent(leaf, new_parent);
-    index = new_parent;
-    while (index != -1) {
-      index = balance(index);
-      int4 n = L(index);
-      n.w = 1 + imax(height(n.y), height(n.z));
-      setL(index, n);
-      setA(index, box_union(A(n.y), A(n.z)));
-      index = n.x;
-    }
+    refit_up(new_parent);
   }
 
   B2G_HDN void remove_leaf(int leaf) {
@@ -213,15 +237,7 @@ struct Tree {
       if (L(grand).y == par) set_child1(grand, sibling); else set_child2(grand, sibling);
       set_parent(sibling, grand);
       free_node(par);
-      int index = grand;
-      while (index != -1) {
-        index = balance(index);
-        int4 n = L(index);
-        setA(index, box_union(A(n.y), A(n.z)));
-        n.w = 1 + imax(height(n.y), height(n.z));
-        setL(index, n);
-        index = n.x;
-      }
+      refit_up(grand);
     } else {
       root() = sibling;
       set_parent(sibling, -1);
