@@ -218,6 +218,34 @@ def run_seed(seed, make_world, steps, batch_mode, large=False, events=False, lev
     batch = None
     if batch_mode:
         batch = wg.batch(int(rng.integers(33, 70)), max_contacts=40 * nb + 256)  # the reference grows its tables; a batch cannot
+    if large == 2:
+        # mode 2 (replica tree kept): FREE-RUNNING, every table including the tree compared; the state is re-uploaded only after
+        # a user edit of the oracle world (a batch has no set_transform)
+        bt = wg.batch(1, lane_block=1, solver='large_exact')
+        bt.upload_world(0, wo.snapshot())
+        for i in range(steps):
+            dt = 0.0 if rng.integers(0, 40) == 0 else scenes.DT
+            ev = rng.integers(0, 30)
+            if ev <= 1:
+                b = wo.body(int(rng.integers(1, nb)))
+                if ev == 0:
+                    b.set_transform((f32v(rng.uniform(-8, 8)), f32v(rng.uniform(1, 10))), f32v(rng.uniform(-3, 3)))
+                else:
+                    b.set_linear_velocity((f32v(rng.uniform(-6, 6)), f32v(rng.uniform(-6, 6))))
+                bt.upload_world(0, wo.snapshot())
+            wo.step(dt, vi, pi)
+            if exploded(wo):
+                run_seed.exploded = getattr(run_seed, "exploded", 0) + 1
+                break
+            bt.step(dt, vi, pi)
+            if i % EVERY == EVERY - 1 or i == steps - 1:
+                bad = parity.compare_snapshots(wo.snapshot(), bt.download_world(0))
+                bad += [b for b in parity.compare_stats(wo.get_stats(), bt.stats()[0]) if "island_bodies" not in b]
+                if bad:
+                    return "large exact, step %d (dt=%g vi=%d pi=%d flags=%s): %s" % (i, dt, vi, pi, flags, bad[:4])
+        bt.close()
+        wg.close()
+        return None
     if large:
         bt = wg.batch(1, lane_block=1, solver='large')
         if level_threshold:
@@ -333,6 +361,7 @@ def main():
     ap.add_argument("--gpu", action="store_true")
     ap.add_argument("--batch", action="store_true")
     ap.add_argument("--large", action="store_true")
+    ap.add_argument("--large-exact", action="store_true", help="large-world mode 2 (replica tree kept), free-running, the tree tables compared too")
     ap.add_argument("--level-threshold", type=int, default=0, help="--large: islands of at least this many contacts take the level-scheduled sweeps (b2g_levels.h)")
     ap.add_argument("--events", action="store_true", help="also compare b2gpu_contact_events with the oracle's listener log every step")
     args = ap.parse_args()
@@ -341,13 +370,13 @@ def main():
     ctx = batch_mod.Context(0, lib_path=lib_path)
     fails = 0
     for seed in range(args.first, args.first + args.seeds):
-        r = run_seed(seed, lambda g: world.B2world(g, ctx=ctx), args.steps, args.batch, args.large, args.events, args.level_threshold)
+        r = run_seed(seed, lambda g: world.B2world(g, ctx=ctx), args.steps, args.batch, 2 if args.large_exact else args.large, args.events, args.level_threshold)
         if r not in (None, "skip"):
             fails += 1
             print("seed %d: %s" % (seed, r), flush=True)
     print("fuzz: %d seeds, %d failures, %d runs ended early by a numerical explosion of the scene (%s%s%s)"
           % (args.seeds, fails, getattr(run_seed, "exploded", 0), "gpu" if args.gpu else "host simulator",
-                                                     ", batch" if args.batch else (", large-world mode teacher-forced" + (", level threshold %d" % args.level_threshold if args.level_threshold else "")) if args.large else "",
+                                                     ", batch" if args.batch else ", large-world mode 2 free-running" if args.large_exact else (", large-world mode teacher-forced" + (", level threshold %d" % args.level_threshold if args.level_threshold else "")) if args.large else "",
                                                      ", %d contact events compared" % getattr(run_seed, "event_total", 0) if args.events else ""))
     sys.exit(1 if fails else 0)
 
