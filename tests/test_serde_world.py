@@ -33,7 +33,7 @@ JOINTS = {  # src/joints/serialize/*.rs
 }
 ALL = dict(SCENES)
 ALL.update(JOINT_SCENES)
-NAMES = ["hello_world", "pyramid", "variety", "sensors", "bridge", "joints_mix", "cantilever", "sliders", "car", "top_down", "pulleys", "gears"]
+NAMES = ["hello_world", "pyramid", "variety", "sensors", "terrain", "bridge", "joints_mix", "cantilever", "sliders", "car", "top_down", "pulleys", "gears"]
 
 
 def _built(name):
